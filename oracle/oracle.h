@@ -1,0 +1,81 @@
+/* ORACLE — TEST INFRASTRUCTURE ONLY.
+ *
+ * C interface of the CPU restatement of the Illumina/canvas hot path (reference @ v1.40.0,
+ * CanvasClean -> CanvasPartition).  It exists to check libcanvasgpu.so and to be timed as the CPU
+ * baseline.  Only tests/, __graft_entry__.smoke() and bench.py (cpu_baseline / --impl reference legs)
+ * may load it.  The product path must never call into this library.
+ *
+ * Parity status: pinned by the reference's own known-answer tests
+ *   CanvasTest/CanvasPartition/WaveletTests.cs:9-90      (12 breakpoints)
+ *   CanvasTest/TestLoessInterpolator.cs:11-81            (R loess fitted values)
+ *   CanvasTest/TestUtilities.cs:33-41,195-206            (golden section, SortedList median rule)
+ *   CanvasTest/CanvasPartition/SegmentationResultsProcessorTests.cs:10-95
+ * Everything in CanvasClean except LOESS has no reference test: restated from source only.
+ */
+#ifndef CANVAS_ORACLE_H
+#define CANVAS_ORACLE_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct {
+    int size_filter;     /* -s */
+    int outlier_filter;  /* -r */
+    int gc_norm;         /* -g */
+    int gc_mode;         /* -m : 0 MedianByGC, 1 LOESS */
+    int want_local_sd;   /* --local-sd-metric-file given */
+    int min_bins_per_gc; /* -w, default 100 */
+} ora_clean_opts;
+
+int ora_clean(const ora_clean_opts* o, int64_t n, const uint8_t* chrom,
+              const uint8_t* chrom_is_autosome, const uint8_t* chrom_is_chrY, int n_chrom,
+              const int32_t* start, const int32_t* stop, const float* count, const uint8_t* gc,
+              int64_t* n_out, int32_t* kept_index, float* count_out, double* local_sd,
+              int* gc_norm_skipped);
+
+typedef struct {
+    int is_germline;
+    double mad_factor;  /* CanvasPartitionParameters.MadFactor, 5.0 */
+    double thr_lower;   /* WaveletsRunnerParams.ThresholdLower (= ThresholdLowerMaf 0.05) */
+    double thr_upper;   /* 80 */
+    int min_size;       /* 10 */
+    int evenness_window; /* EvennessScoreWindow 100000 */
+    int n_threads;      /* CPU threads for the per-chromosome fan-out (Parallel.ForEach) */
+} ora_wavelet_opts;
+
+int ora_partition_wavelet(const ora_wavelet_opts* o, int n_chrom, const int64_t* chrom_off,
+                          const double* coverage, int32_t* n_bp, int32_t* bp, double* evenness,
+                          int* evenness_ok, double* cv, int* cv_has_value, double* factor_of_three);
+
+/* Piecewise entry points used by the known-answer tests. */
+int ora_coverage_variability(int window, int n_chrom, const int64_t* chrom_off, const double* cov,
+                             double* cv);                                  /* returns has_value */
+void ora_factor_of_three(int n_chrom, const int64_t* chrom_off, const double* cov, double* f3 /*[9]*/);
+int ora_evenness_score(int window, int n_chrom, const int64_t* chrom_off, const double* cov,
+                       double* score);                                     /* returns ok */
+int ora_haar_wavelets(int64_t n, const double* ratio, double thr_lower, double thr_upper,
+                      int is_germline, double mad_factor, int has_cv, double cv, const double* f3,
+                      int n_f3, int32_t* bp /*[n]*/);                       /* returns n_bp */
+/* Unbalanced-Haar tree of one chromosome, flattened level by level: per node level, start, brk,
+ * end (1-based as in the reference) and coefficient.  Returns the node count. */
+int64_t ora_uh_tree(int64_t n, const double* x, int32_t* level, int32_t* start, int32_t* brk,
+                    int32_t* end, double* coef, double* smooth);
+
+int ora_loess_train(int n, const double* x, const double* y, double bandwidth, int robustness_iters,
+                    double x_step, double* fitted_orig_order, int n_query, const double* xq,
+                    double* yq);
+double ora_golden_section_quadratic(double a, double b);
+double ora_median_f32(int64_t n, const float* x);
+double ora_median_f64(int64_t n, const double* x);
+void ora_quartiles_f32(int64_t n, const float* x, float* q /*[3]*/);
+void ora_weighted_quantiles(int64_t n, const float* v, const float* w, int n_probs,
+                            const float* probs, double* q);
+/* .NET Core 2.0 Array.Sort(T[], Comparison<T>) introsort, restated; sorts indices 0..n-1 by
+ * descending counts the way WaveletSegmentation.HardThresh does (WaveletSegmentation.cs:87). */
+void ora_dotnet_sort_levels(int n, const int32_t* counts, int32_t* indices);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,216 @@
+"""ORACLE — TEST INFRASTRUCTURE ONLY.
+
+ctypes binding of oracle/_build/libcanvas_oracle.so (CPU restatement of the reference hot path).
+Importable only from tests/, __graft_entry__.smoke() and bench.py's CPU-baseline legs; nothing under
+canvas_b200/ may import this module.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "_build", "libcanvas_oracle.so")
+
+
+def build(force=False):
+    """Compile the oracle with the committed Makefile (g++, no dependencies)."""
+    if force or not os.path.exists(_SO) or any(
+        os.path.getmtime(os.path.join(_HERE, f)) > os.path.getmtime(_SO)
+        for f in os.listdir(_HERE) if f.endswith((".cpp", ".hpp", ".h", "Makefile"))
+    ):
+        subprocess.check_call(["make", "-C", _HERE, "-s"])
+    return _SO
+
+
+class CleanOpts(C.Structure):
+    _fields_ = [("size_filter", C.c_int), ("outlier_filter", C.c_int), ("gc_norm", C.c_int),
+                ("gc_mode", C.c_int), ("want_local_sd", C.c_int), ("min_bins_per_gc", C.c_int)]
+
+
+class WaveletOpts(C.Structure):
+    _fields_ = [("is_germline", C.c_int), ("mad_factor", C.c_double), ("thr_lower", C.c_double),
+                ("thr_upper", C.c_double), ("min_size", C.c_int), ("evenness_window", C.c_int),
+                ("n_threads", C.c_int)]
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        _lib = C.CDLL(_SO)
+        _lib.ora_golden_section_quadratic.restype = C.c_double
+        _lib.ora_golden_section_quadratic.argtypes = [C.c_double, C.c_double]
+        _lib.ora_median_f32.restype = C.c_double
+        _lib.ora_median_f64.restype = C.c_double
+        _lib.ora_uh_tree.restype = C.c_int64
+    return _lib
+
+
+def _p(a, t):
+    return a.ctypes.data_as(C.POINTER(t))
+
+
+def clean(chrom, is_auto, is_chry, start, stop, count, gc, size_filter=True, outlier_filter=True,
+          gc_norm=True, gc_mode=0, want_local_sd=True, min_bins_per_gc=100):
+    n = len(count)
+    chrom = np.ascontiguousarray(chrom, np.uint8)
+    is_auto = np.ascontiguousarray(is_auto, np.uint8)
+    is_chry = np.ascontiguousarray(is_chry, np.uint8)
+    start = np.ascontiguousarray(start, np.int32)
+    stop = np.ascontiguousarray(stop, np.int32)
+    count = np.ascontiguousarray(count, np.float32)
+    gc = np.ascontiguousarray(gc, np.uint8)
+    o = CleanOpts(int(size_filter), int(outlier_filter), int(gc_norm), int(gc_mode),
+                  int(want_local_sd), int(min_bins_per_gc))
+    n_out = C.c_int64(0)
+    kept = np.empty(max(n, 1), np.int32)
+    out = np.empty(max(n, 1), np.float32)
+    lsd = C.c_double(0)
+    skipped = C.c_int(0)
+    rc = lib().ora_clean(C.byref(o), C.c_int64(n), _p(chrom, C.c_uint8), _p(is_auto, C.c_uint8),
+                         _p(is_chry, C.c_uint8), C.c_int(len(is_auto)), _p(start, C.c_int32),
+                         _p(stop, C.c_int32), _p(count, C.c_float), _p(gc, C.c_uint8),
+                         C.byref(n_out), _p(kept, C.c_int32), _p(out, C.c_float), C.byref(lsd),
+                         C.byref(skipped))
+    assert rc == 0
+    k = n_out.value
+    return {"kept_index": kept[:k].copy(), "count": out[:k].copy(), "local_sd": lsd.value,
+            "gc_norm_skipped": bool(skipped.value)}
+
+
+def partition_wavelet(chrom_off, coverage, is_germline=True, mad_factor=5.0, thr_lower=0.05,
+                      thr_upper=80.0, min_size=10, evenness_window=100000, n_threads=1):
+    chrom_off = np.ascontiguousarray(chrom_off, np.int64)
+    coverage = np.ascontiguousarray(coverage, np.float64)
+    nc = len(chrom_off) - 1
+    n = int(chrom_off[-1])
+    o = WaveletOpts(int(is_germline), mad_factor, thr_lower, thr_upper, min_size, evenness_window,
+                    n_threads)
+    n_bp = np.zeros(nc, np.int32)
+    bp = np.zeros(max(n, 1), np.int32)
+    ev = C.c_double(0)
+    ev_ok = C.c_int(0)
+    cv = C.c_double(0)
+    cv_has = C.c_int(0)
+    f3 = np.zeros(9, np.float64)
+    rc = lib().ora_partition_wavelet(C.byref(o), C.c_int(nc), _p(chrom_off, C.c_int64),
+                                     _p(coverage, C.c_double), _p(n_bp, C.c_int32),
+                                     _p(bp, C.c_int32), C.byref(ev), C.byref(ev_ok), C.byref(cv),
+                                     C.byref(cv_has), _p(f3, C.c_double))
+    assert rc == 0
+    bps = [bp[chrom_off[c]:chrom_off[c] + n_bp[c]].copy() for c in range(nc)]
+    return {"breakpoints": bps, "evenness": ev.value if ev_ok.value else None,
+            "cv": cv.value if cv_has.value else None, "factor_of_three": f3}
+
+
+def coverage_variability(window, chrom_off, coverage):
+    chrom_off = np.ascontiguousarray(chrom_off, np.int64)
+    coverage = np.ascontiguousarray(coverage, np.float64)
+    cv = C.c_double(0)
+    has = lib().ora_coverage_variability(C.c_int(window), C.c_int(len(chrom_off) - 1),
+                                         _p(chrom_off, C.c_int64), _p(coverage, C.c_double),
+                                         C.byref(cv))
+    return cv.value if has else None
+
+
+def factor_of_three(chrom_off, coverage):
+    chrom_off = np.ascontiguousarray(chrom_off, np.int64)
+    coverage = np.ascontiguousarray(coverage, np.float64)
+    f3 = np.zeros(9, np.float64)
+    lib().ora_factor_of_three(C.c_int(len(chrom_off) - 1), _p(chrom_off, C.c_int64),
+                              _p(coverage, C.c_double), _p(f3, C.c_double))
+    return f3
+
+
+def evenness_score(window, chrom_off, coverage):
+    chrom_off = np.ascontiguousarray(chrom_off, np.int64)
+    coverage = np.ascontiguousarray(coverage, np.float64)
+    s = C.c_double(0)
+    ok = lib().ora_evenness_score(C.c_int(window), C.c_int(len(chrom_off) - 1),
+                                  _p(chrom_off, C.c_int64), _p(coverage, C.c_double), C.byref(s))
+    return s.value if ok else None
+
+
+def haar_wavelets(ratio, thr_lower, thr_upper, is_germline, mad_factor, cv, f3):
+    ratio = np.ascontiguousarray(ratio, np.float64)
+    f3 = np.ascontiguousarray(f3, np.float64)
+    bp = np.zeros(len(ratio), np.int32)
+    k = lib().ora_haar_wavelets(C.c_int64(len(ratio)), _p(ratio, C.c_double), C.c_double(thr_lower),
+                                C.c_double(thr_upper), C.c_int(int(is_germline)),
+                                C.c_double(mad_factor), C.c_int(cv is not None),
+                                C.c_double(cv if cv is not None else 0.0), _p(f3, C.c_double),
+                                C.c_int(len(f3)), _p(bp, C.c_int32))
+    return bp[:k].copy()
+
+
+def uh_tree(x):
+    x = np.ascontiguousarray(x, np.float64)
+    n = len(x)
+    level = np.zeros(n, np.int32)
+    start = np.zeros(n, np.int32)
+    brk = np.zeros(n, np.int32)
+    end = np.zeros(n, np.int32)
+    coef = np.zeros(n, np.float64)
+    smooth = C.c_double(0)
+    k = lib().ora_uh_tree(C.c_int64(n), _p(x, C.c_double), _p(level, C.c_int32), _p(start, C.c_int32),
+                          _p(brk, C.c_int32), _p(end, C.c_int32), _p(coef, C.c_double),
+                          C.byref(smooth))
+    return {"level": level[:k], "start": start[:k], "brk": brk[:k], "end": end[:k],
+            "coef": coef[:k], "smooth": smooth.value}
+
+
+def loess_train(x, y, bandwidth, robustness_iters, x_step, xq=None):
+    x = np.ascontiguousarray(x, np.float64)
+    y = np.ascontiguousarray(y, np.float64)
+    fitted = np.zeros(len(x), np.float64)
+    xq = np.ascontiguousarray(xq if xq is not None else [], np.float64)
+    yq = np.zeros(max(len(xq), 1), np.float64)
+    rc = lib().ora_loess_train(C.c_int(len(x)), _p(x, C.c_double), _p(y, C.c_double),
+                               C.c_double(bandwidth), C.c_int(robustness_iters), C.c_double(x_step),
+                               _p(fitted, C.c_double), C.c_int(len(xq)), _p(xq, C.c_double),
+                               _p(yq, C.c_double))
+    assert rc == 0
+    return fitted, yq[:len(xq)]
+
+
+def golden_section_quadratic(a, b):
+    return lib().ora_golden_section_quadratic(a, b)
+
+
+def median_f32(x):
+    x = np.ascontiguousarray(x, np.float32)
+    return lib().ora_median_f32(C.c_int64(len(x)), _p(x, C.c_float))
+
+
+def median_f64(x):
+    x = np.ascontiguousarray(x, np.float64)
+    return lib().ora_median_f64(C.c_int64(len(x)), _p(x, C.c_double))
+
+
+def quartiles_f32(x):
+    x = np.ascontiguousarray(x, np.float32)
+    q = np.zeros(3, np.float32)
+    lib().ora_quartiles_f32(C.c_int64(len(x)), _p(x, C.c_float), _p(q, C.c_float))
+    return q
+
+
+def weighted_quantiles(v, w, probs):
+    v = np.ascontiguousarray(v, np.float32)
+    w = np.ascontiguousarray(w, np.float32)
+    probs = np.ascontiguousarray(probs, np.float32)
+    q = np.zeros(len(probs), np.float64)
+    lib().ora_weighted_quantiles(C.c_int64(len(v)), _p(v, C.c_float), _p(w, C.c_float),
+                                 C.c_int(len(probs)), _p(probs, C.c_float), _p(q, C.c_double))
+    return q
+
+
+def dotnet_sort_levels(counts):
+    counts = np.ascontiguousarray(counts, np.int32)
+    idx = np.zeros(len(counts), np.int32)
+    lib().ora_dotnet_sort_levels(C.c_int(len(counts)), _p(counts, C.c_int32), _p(idx, C.c_int32))
+    return idx
