@@ -1,0 +1,54 @@
+// Context management of libcanvasgpu.
+#include "common.cuh"
+
+extern "C" int cg_create(int device, cg_ctx** out) {
+    if (!out) return CG_ERR_ARG;
+    *out = nullptr;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0 || device < 0 || device >= count)
+        return CG_ERR_CUDA;  // no CPU fallback: the engine needs a CUDA device
+    cg_ctx* ctx = new cg_ctx();
+    ctx->device = device;
+    if (cudaSetDevice(device) != cudaSuccess) { delete ctx; return CG_ERR_CUDA; }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete ctx; return CG_ERR_CUDA; }
+    ctx->num_sms = prop.multiProcessorCount;
+    char buf[512];
+    snprintf(buf, sizeof buf, "canvasgpu 0.1 sm_%d%d %s %d SMs", prop.major, prop.minor, prop.name, prop.multiProcessorCount);
+    ctx->desc = buf;
+    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess ||
+        cudaMallocHost((void**)&ctx->pinned, 1 << 16) != cudaSuccess) {
+        cg_destroy(ctx);
+        return CG_ERR_CUDA;
+    }
+    ctx->pinned_cap = 1 << 16;
+    *out = ctx;
+    return CG_OK;
+}
+
+extern "C" void cg_destroy(cg_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    if (ctx->arena) cudaFree(ctx->arena);
+    if (ctx->pinned) cudaFreeHost(ctx->pinned);
+    if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+    if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+extern "C" const char* cg_last_error(cg_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+extern "C" const char* cg_describe(cg_ctx* ctx) { return ctx ? ctx->desc.c_str() : ""; }
+extern "C" double cg_last_kernel_ms(cg_ctx* ctx) { return ctx ? ctx->last_kernel_ms : 0.0; }
+extern "C" int cg_last_launches(cg_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+extern "C" void* cg_host_alloc(size_t bytes) {
+    void* p = nullptr;
+    if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) return nullptr;
+    return p;
+}
+extern "C" void cg_host_free(void* p) {
+    if (p) cudaFreeHost(p);
+}

@@ -1,0 +1,773 @@
+// cg_clean: CanvasClean's numeric block on the device (reference CanvasClean.cs:474-530).
+#include "clean.cuh"
+
+// ---------------------------------------------------------------------------------------------
+// Views for the select engine
+// ---------------------------------------------------------------------------------------------
+struct SizeView {  // RemoveBigBins: bin sizes, one segment
+    const int32_t* start;
+    const int32_t* stop;
+    long long n;
+    __device__ long long size() const { return n; }
+    __device__ bool get(long long i, uint32_t& key, int& a, int& b) const {
+        key = i32_key(stop[i] - start[i]);
+        a = 0;
+        b = -1;
+        return true;
+    }
+};
+
+struct GcCountView {  // GetCountsByGC: autosomal alive bins, segment = GC bucket plus the global list
+    const float* count;
+    const uint8_t* gc;
+    const uint8_t* chrom;
+    const uint8_t* alive;
+    const uint8_t* is_auto;
+    const CleanCtl* ctl;
+    const int* enabled;
+    __device__ long long size() const { return *enabled ? ctl->n2 : 0; }
+    __device__ bool get(long long i, uint32_t& key, int& a, int& b) const {
+        if (!alive[i] || !is_auto[chrom[i]]) return false;
+        key = f32_key(count[i]);
+        a = gc[i];
+        b = GC_BINS;
+        return true;
+    }
+};
+
+struct WindowView {  // local-SD windows, segment = chromosome of the window's first bin
+    const double* wsd;
+    const uint8_t* wchrom;
+    const CleanCtl* ctl;
+    const double* center;  // nullptr: raw value; else |x - center[seg]|
+    __device__ long long size() const { return ctl->metric_on ? ctl->n_windows : 0; }
+    __device__ bool get(long long i, uint64_t& key, int& a, int& b) const {
+        a = wchrom[i];
+        b = -1;
+        double x = wsd[i];
+        if (center) x = fabs(x - center[a]);
+        key = f64_key(x);
+        return true;
+    }
+};
+
+// ---------------------------------------------------------------------------------------------
+// Kernels
+// ---------------------------------------------------------------------------------------------
+__global__ void clean_init_kernel(CleanCtl* ctl, int n) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        CleanCtl z;
+        memset(&z, 0, sizeof(z));
+        z.n0 = z.n1 = z.n2 = z.n3 = n;
+        z.local_sd = -1.0;
+        *ctl = z;
+    }
+}
+
+// input validation (chromosome runs, GC range)
+__global__ void clean_validate_kernel(const uint8_t* __restrict__ chrom, const uint8_t* __restrict__ gc,
+                                      int n, CleanCtl* ctl) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if ((i > 0 && chrom[i] < chrom[i - 1]) || gc[i] > 100) ctl->unsorted = 1;
+}
+
+// size request: rank (int)(0.98 n)  (CanvasClean.cs:338)
+__global__ void size_request_kernel(SelState<uint32_t> st, long long k, int on) {
+    st.nreq[0] = on ? 1 : 0;
+    st.req_k[0] = (unsigned long long)k;
+}
+
+__global__ void size_finish_kernel(SelState<uint32_t> st, CleanCtl* ctl, int on) {
+    ctl->size_filter_on = on;
+    ctl->size_thresh = on ? i32_unkey(st.req_key[0]) : 0x7fffffff;
+}
+
+struct SizePred {  // CanvasClean.cs:349-353
+    const int32_t* start;
+    const int32_t* stop;
+    const CleanCtl* ctl;
+    __device__ bool operator()(int i) const { return (stop[i] - start[i]) <= ctl->size_thresh; }
+};
+
+struct Emit1 {
+    const uint8_t* chrom;
+    const uint8_t* gc;
+    const float* count;
+    uint8_t* chrom1;
+    uint8_t* gc1;
+    float* count1;
+    int32_t* orig1;
+    __device__ void operator()(int src, int dst) const {
+        chrom1[dst] = chrom[src];
+        gc1[dst] = gc[src];
+        count1[dst] = count[src];
+        orig1[dst] = src;
+    }
+};
+
+// CanvasClean.cs:363-381
+__device__ inline bool significantly_different(float a, float b) {
+    double mu = __ddiv_rn(__dadd_rn((double)a, (double)b), 2.0);
+    if (__fadd_rn(a, b) == 0.0f) return false;
+    double da = __dsub_rn((double)a, mu), db = __dsub_rn((double)b, mu);
+    double chi2 = __ddiv_rn(__dadd_rn(__dmul_rn(da, da), __dmul_rn(db, db)), mu);
+    return chi2 > 6.635;
+}
+
+struct OutlierPred {  // CanvasClean.cs:387-413, on the size-filtered list
+    const uint8_t* chrom1;
+    const float* count1;
+    const CleanCtl* ctl;
+    int on;
+    __device__ bool operator()(int r) const {
+        if (!on) return true;
+        const int n1 = ctl->n1;
+        const bool has_prev = r > 0, has_next = r < n1 - 1;
+        const uint8_t c = chrom1[r];
+        const bool prev_same = has_prev && chrom1[r - 1] == c;
+        const bool next_same = has_next && chrom1[r + 1] == c;
+        if ((has_prev && !prev_same) && (has_next && !next_same)) return false;
+        const float x = count1[r];
+        return (prev_same && !significantly_different(x, count1[r - 1])) ||
+               (next_same && !significantly_different(x, count1[r + 1])) || (!has_prev && !has_next);
+    }
+};
+
+struct Emit2 {
+    const uint8_t* chrom1;
+    const uint8_t* gc1;
+    const float* count1;
+    const int32_t* orig1;
+    uint8_t* chrom2;
+    uint8_t* gc2;
+    float* count2;
+    int32_t* orig2;
+    __device__ void operator()(int src, int dst) const {
+        chrom2[dst] = chrom1[src];
+        gc2[dst] = gc1[src];
+        count2[dst] = count1[src];
+        orig2[dst] = orig1[src];
+    }
+};
+
+// decisions that depend on the length of the filtered list (CanvasClean.cs:483-486)
+__global__ void clean_decide_metric_kernel(CleanCtl* ctl, int want_local_sd) {
+    const int n2 = ctl->n2;
+    ctl->metric_on = (want_local_sd && n2 >= 50000) ? 1 : 0;
+    // windows of 20 differences while windowEnd < len(diffs) = n2 - 1  (:284)
+    ctl->n_windows = (ctl->metric_on && n2 >= 2) ? (n2 - 2) / LOCAL_SD_WINDOW : 0;
+}
+
+// CanvasClean.cs:268-293 — one thread per window; sequential sums as Utilities.Mean/StandardDeviation.
+__global__ void local_sd_windows_kernel(const float* __restrict__ count2, const uint8_t* __restrict__ chrom2,
+                                        const CleanCtl* __restrict__ ctl, double* __restrict__ wsd,
+                                        uint8_t* __restrict__ wchrom, unsigned* __restrict__ wcnt) {
+    const int nw = ctl->n_windows;
+    const int w = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool ok = w < nw;
+    int c = -1;
+    if (ok) {
+        const int ws = w * LOCAL_SD_WINDOW;
+        double d[LOCAL_SD_WINDOW];
+        float prev = count2[ws];
+        double sum = 0;
+#pragma unroll
+        for (int t = 0; t < LOCAL_SD_WINDOW; t++) {
+            float nxt = count2[ws + t + 1];
+            d[t] = (double)__fsub_rn(nxt, prev);
+            prev = nxt;
+            sum = __dadd_rn(sum, d[t]);
+        }
+        const double mu = __ddiv_rn(sum, (double)LOCAL_SD_WINDOW);
+        double ss = 0;
+#pragma unroll
+        for (int t = 0; t < LOCAL_SD_WINDOW; t++) {
+            double diff = __dsub_rn(d[t], mu);
+            ss = __dadd_rn(ss, __dmul_rn(diff, diff));
+        }
+        wsd[w] = sqrt(__ddiv_rn(ss, (double)(LOCAL_SD_WINDOW - 1)));
+        c = chrom2[ws];
+        wchrom[w] = (uint8_t)c;
+    }
+    // windows per chromosome (adjacent windows share the chromosome: aggregate per warp)
+    unsigned act = __ballot_sync(0xffffffffu, ok);
+    if (ok) {
+        unsigned m = __match_any_sync(act, c);
+        if ((int)(__ffs(m) - 1) == (int)(threadIdx.x & 31)) atomicAdd(&wcnt[c], (unsigned)__popc(m));
+    }
+}
+
+// median-style requests {lower middle, upper middle} for every segment with cnt > 0
+__global__ void median_request_u64_kernel(SelState<uint64_t> st, const unsigned* __restrict__ cnt, const int* on) {
+    int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= st.nseg) return;
+    unsigned n = *on ? cnt[s] : 0u;
+    if (n == 0) { st.nreq[s] = 0; return; }
+    st.nreq[s] = 2;
+    st.req_k[s * SEL_G + 0] = (n & 1u) ? n / 2 : n / 2 - 1;
+    st.req_k[s * SEL_G + 1] = n / 2;
+}
+
+// SortedList<double>.Median(): mean of the middles
+__global__ void median_finish_u64_kernel(SelState<uint64_t> st, double* __restrict__ out) {
+    int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= st.nseg) return;
+    if (st.nreq[s] == 0) { out[s] = 0.0; return; }
+    double a = f64_unkey(st.req_key[s * SEL_G + 0]), b = f64_unkey(st.req_key[s * SEL_G + 1]);
+    out[s] = st.req_key[s * SEL_G + 0] == st.req_key[s * SEL_G + 1] ? a : __ddiv_rn(__dadd_rn(a, b), 2.0);
+}
+
+// CanvasClean.cs:243-258 — average of the per-chromosome MADs, in chromosome order
+__global__ void local_sd_average_kernel(CleanCtl* ctl, const unsigned* __restrict__ wcnt,
+                                        const double* __restrict__ mad, int n_chrom) {
+    if (!ctl->metric_on) return;
+    double s = 0;
+    int k = 0;
+    for (int c = 0; c < n_chrom; c++)
+        if (wcnt[c] > 0) { s = __dadd_rn(s, mad[c]); k++; }
+    ctl->local_sd = k > 0 ? __ddiv_rn(s, (double)k) : __longlong_as_double(0x7ff8000000000000ll);
+}
+
+// CanvasClean.cs:213-224 — GC histograms of the outlier-filtered list
+__global__ void gc_hist_kernel(const uint8_t* __restrict__ gc2, const uint8_t* __restrict__ chrom2,
+                               const uint8_t* __restrict__ is_auto, CleanCtl* ctl) {
+    __shared__ unsigned h_auto[GC_BINS], h_all[GC_BINS];
+    for (int t = threadIdx.x; t < GC_BINS; t += blockDim.x) h_auto[t] = h_all[t] = 0u;
+    __syncthreads();
+    const int n2 = ctl->n2;
+    const int n_round = ((n2 + 31) / 32) * 32;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += gridDim.x * blockDim.x) {
+        const bool ok = i < n2;
+        int g = ok ? gc2[i] : 0;
+        bool au = ok && is_auto[chrom2[i]];
+        unsigned act = __ballot_sync(0xffffffffu, ok);
+        if (ok) {
+            unsigned m = __match_any_sync(act, g);
+            unsigned ma = __ballot_sync(m, au) & m;
+            if ((int)(__ffs(m) - 1) == (int)(threadIdx.x & 31)) {
+                atomicAdd(&h_all[g], (unsigned)__popc(m));
+                if (ma) atomicAdd(&h_auto[g], (unsigned)__popc(ma));
+            }
+        }
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < GC_BINS; t += blockDim.x) {
+        if (h_all[t]) atomicAdd(&ctl->hist_all[t], h_all[t]);
+        if (h_auto[t]) atomicAdd(&ctl->hist_auto[t], h_auto[t]);
+    }
+}
+
+// CanvasClean.cs:226-227 and the bookkeeping that follows from it
+__global__ void gc_threshold_kernel(CleanCtl* ctl, int gc_norm, int median_mode, int min_bins_weighted) {
+    unsigned total = 0;
+    for (int g = 0; g < GC_BINS; g++) total += ctl->hist_auto[g];
+    ctl->n_auto = total;
+    int thr = 0;
+    if (gc_norm && median_mode) {
+        int avg = max(min_bins_weighted, (int)((double)total / (double)GC_BINS));
+        thr = min(MIN_BINS_PER_GC, avg);
+    } else {
+        thr = -0x7fffffff;  // no GC filter: every bin stays
+    }
+    long long alive = 0, alive_auto = 0;
+    for (int g = 0; g < GC_BINS; g++) {
+        if ((long long)ctl->hist_auto[g] >= (long long)thr) {
+            alive += ctl->hist_all[g];
+            alive_auto += ctl->hist_auto[g];
+        }
+    }
+    ctl->do_norm = gc_norm;
+    if (gc_norm && alive == 0) {  // :502-505 — keep the unfiltered list and skip normalisation
+        ctl->gc_skipped = 1;
+        ctl->do_norm = 0;
+        thr = -0x7fffffff;
+        alive = ctl->n2;
+        alive_auto = total;
+    }
+    ctl->gc_thresh = thr;
+    ctl->n3 = (int)alive;
+    ctl->n_auto3 = (unsigned)alive_auto;
+    ctl->do_variance = (ctl->do_norm && ctl->metric_on && alive > 500000) ? 1 : 0;  // :512
+}
+
+__global__ void gc_alive_kernel(const uint8_t* __restrict__ gc2, const CleanCtl* __restrict__ ctl,
+                                uint8_t* __restrict__ alive) {
+    const int n2 = ctl->n2;
+    const int thr = ctl->gc_thresh;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += gridDim.x * blockDim.x)
+        alive[i] = (long long)ctl->hist_auto[gc2[i]] >= (long long)thr ? 1 : 0;
+}
+
+__device__ inline unsigned alive_auto_count(const CleanCtl* ctl, int g) {
+    return (long long)ctl->hist_auto[g] >= (long long)ctl->gc_thresh ? ctl->hist_auto[g] : 0u;
+}
+
+// NormalizeByGC requests (CanvasClean.cs:172-187): exact median per bucket with >= 100 bins + global
+__global__ void gc_median_request_kernel(SelState<uint32_t> st, CleanCtl* ctl, const int* enabled) {
+    int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= GC_SEGS) return;
+    st.nreq[s] = 0;
+    if (!*enabled) return;
+    unsigned n = s < GC_BINS ? alive_auto_count(ctl, s) : ctl->n_auto3;
+    if (s < GC_BINS && n < (unsigned)MIN_BINS_PER_GC) {
+        // weighted path: only matters when a surviving bin actually uses this bucket
+        bool used = (long long)ctl->hist_auto[s] >= (long long)ctl->gc_thresh && ctl->hist_all[s] > 0;
+        if (used) ctl->need_weighted = 1;
+        return;
+    }
+    if (n == 0) return;
+    st.nreq[s] = 2;
+    st.req_k[s * SEL_G + 0] = (n & 1u) ? n / 2 : n / 2 - 1;
+    st.req_k[s * SEL_G + 1] = n / 2;
+}
+
+// SortedList<float>.Median(): mean of the middles in single precision, widened to double
+__global__ void gc_median_finish_kernel(SelState<uint32_t> st, CleanCtl* ctl, const int* enabled) {
+    int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= GC_SEGS || !*enabled) return;
+    double m = 0.0;
+    if (st.nreq[s] == 2) {
+        float a = f32_unkey(st.req_key[s * SEL_G + 0]), b = f32_unkey(st.req_key[s * SEL_G + 1]);
+        unsigned n = s < GC_BINS ? alive_auto_count(ctl, s) : ctl->n_auto3;
+        m = (n & 1u) ? (double)a : (double)__fdiv_rn(__fadd_rn(a, b), 2.0f);
+    }
+    if (s < GC_BINS) ctl->med[s] = m;
+    else ctl->global_median = m;
+}
+
+// Quartile ranks of Utilities.Quartiles (Utilities.cs:361-419) as six requests
+// {Q1a, Q1b, Q2a, Q2b, Q3a, Q3b}
+__device__ inline void quartile_ranks(unsigned n, unsigned long long* k) {
+    const unsigned mid = n / 2;
+    if ((n & 1u) == 0) {
+        k[2] = mid - 1; k[3] = mid;
+        const unsigned mm = mid / 2;
+        if ((mid & 1u) == 0) { k[0] = mm - 1; k[1] = mm; k[4] = mid + mm - 1; k[5] = mid + mm; }
+        else { k[0] = k[1] = mm; k[4] = k[5] = mm + mid; }
+    } else {
+        k[2] = k[3] = mid;
+        if ((n - 1) % 4 == 0) { const unsigned q = (n - 1) / 4; k[0] = q - 1; k[1] = q; k[4] = 3 * q; k[5] = 3 * q + 1; }
+        else { const unsigned q = (n - 3) / 4; k[0] = q; k[1] = q + 1; k[4] = 3 * q + 1; k[5] = 3 * q + 2; }
+    }
+}
+
+__device__ inline void quartile_values(unsigned n, const float* v, float* q) {
+    const unsigned mid = n / 2;
+    if ((n & 1u) == 0) {
+        q[1] = __fdiv_rn(__fadd_rn(v[2], v[3]), 2.0f);
+        if ((mid & 1u) == 0) {
+            q[0] = __fdiv_rn(__fadd_rn(v[0], v[1]), 2.0f);
+            q[2] = __fdiv_rn(__fadd_rn(v[4], v[5]), 2.0f);
+        } else { q[0] = v[0]; q[2] = v[4]; }
+    } else {
+        q[1] = v[2];
+        if ((n - 1) % 4 == 0) {
+            q[0] = __fadd_rn(__fmul_rn(v[0], 0.25f), __fmul_rn(v[1], 0.75f));
+            q[2] = __fadd_rn(__fmul_rn(v[4], 0.75f), __fmul_rn(v[5], 0.25f));
+        } else {
+            q[0] = __fadd_rn(__fmul_rn(v[0], 0.75f), __fmul_rn(v[1], 0.25f));
+            q[2] = __fadd_rn(__fmul_rn(v[4], 0.25f), __fmul_rn(v[5], 0.75f));
+        }
+    }
+}
+
+__global__ void gc_quartile_request_kernel(SelState<uint32_t> st, CleanCtl* ctl, const int* enabled) {
+    int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= GC_SEGS) return;
+    st.nreq[s] = 0;
+    if (!*enabled) return;
+    unsigned n = s < GC_BINS ? alive_auto_count(ctl, s) : ctl->n_auto3;
+    if (s < GC_BINS && n > 0 && n < (unsigned)MIN_BINS_PER_GC) { ctl->need_weighted = 1; return; }
+    if (n < 2) return;
+    st.nreq[s] = 6;
+    quartile_ranks(n, st.req_k + s * SEL_G);
+}
+
+__global__ void gc_quartile_finish_kernel(SelState<uint32_t> st, CleanCtl* ctl, const int* enabled) {
+    int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= GC_SEGS || !*enabled) return;
+    unsigned n = s < GC_BINS ? alive_auto_count(ctl, s) : ctl->n_auto3;
+    float q[3] = {0.f, 0.f, 0.f};
+    if (st.nreq[s] == 6) {
+        float v[6];
+        for (int r = 0; r < 6; r++) v[r] = f32_unkey(st.req_key[s * SEL_G + r]);
+        quartile_values(n, v, q);
+    }
+    if (s < GC_BINS) {
+        if (n == 0) { ctl->iqr[s] = -1.f; ctl->q2[s] = -1.f; }   // CanvasClean.cs:52-56
+        else { ctl->iqr[s] = __fsub_rn(q[2], q[0]); ctl->q2[s] = q[1]; }
+    } else {
+        ctl->global_q[0] = q[0]; ctl->global_q[1] = q[1]; ctl->global_q[2] = q[2];
+        ctl->global_iqr = __fsub_rn(q[2], q[0]);
+    }
+}
+
+// CanvasClean.cs:71-82
+__global__ void variance_decide_kernel(CleanCtl* ctl) {
+    if (!ctl->do_variance) { ctl->variance_fired = 0; return; }
+    int significant = 0;
+    for (int g = 10; g < 90; g++)
+        if (__fmul_rn(ctl->global_iqr, 2.f) < ctl->iqr[g]) significant++;
+    ctl->variance_fired = significant > 0 ? 1 : 0;
+}
+
+// CanvasClean.cs:85-94 (single precision throughout)
+__global__ void variance_apply_kernel(float* __restrict__ count2, const uint8_t* __restrict__ gc2,
+                                      const uint8_t* __restrict__ alive, const CleanCtl* __restrict__ ctl) {
+    if (!ctl->variance_fired) return;
+    __shared__ float s_iqr[GC_BINS], s_q2[GC_BINS];
+    for (int t = threadIdx.x; t < GC_BINS; t += blockDim.x) { s_iqr[t] = ctl->iqr[t]; s_q2[t] = ctl->q2[t]; }
+    __syncthreads();
+    const float giqr = ctl->global_iqr;
+    const int n2 = ctl->n2;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += gridDim.x * blockDim.x) {
+        if (!alive[i]) continue;
+        const int g = gc2[i];
+        const float scaled = __fmul_rn(s_iqr[g], 0.8f);
+        if (giqr >= scaled) continue;
+        const float ratio = __fdiv_rn(scaled, giqr);
+        const float m = s_q2[g];
+        count2[i] = __fadd_rn(m, __fdiv_rn(__fsub_rn(count2[i], m), ratio));
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K8 — normalise apply (CanvasClean.cs:190-195): count = (float)(gMed * (double)count / med[gc]).
+// Pure stream: 4 B count + 1 B gc in, 4 B out per bin.  Four bins per thread per step through
+// 128-bit count accesses and 32-bit GC accesses, the 101-entry median table in shared memory.
+// `alive` (optional) masks bins removed by the GC filter; `tables` may hold one table per sample.
+// ---------------------------------------------------------------------------------------------
+template <int UNROLL>
+__global__ void __launch_bounds__(256)
+normalize_apply_kernel(const float* in, const uint8_t* __restrict__ gc,
+                       const uint8_t* __restrict__ alive, float* out,
+                       const int* __restrict__ n_ptr, long long n_fixed, const double* __restrict__ med_tab,
+                       const double* __restrict__ gmed_tab, const int* __restrict__ enabled, long long sample_stride) {
+    if (enabled && !*enabled) return;
+    __shared__ double s_med[GC_BINS];
+    const int sample = blockIdx.y;
+    for (int t = threadIdx.x; t < GC_BINS; t += blockDim.x) s_med[t] = med_tab[(size_t)sample * GC_BINS + t];
+    __syncthreads();
+    const double gmed = gmed_tab[sample];
+    const long long n = n_ptr ? (long long)*n_ptr : n_fixed;
+    in += sample * sample_stride;
+    out += sample * sample_stride;
+    gc += sample * sample_stride;
+    if (alive) alive += sample * sample_stride;
+    const long long nvec = n >> 2;
+    const float4* in4 = reinterpret_cast<const float4*>(in);
+    float4* out4 = reinterpret_cast<float4*>(out);
+    const uchar4* gc4 = reinterpret_cast<const uchar4*>(gc);
+    const uchar4* al4 = reinterpret_cast<const uchar4*>(alive);
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; v + (UNROLL - 1) * stride < nvec; v += UNROLL * stride) {
+        float4 c[UNROLL];
+        uchar4 g[UNROLL];
+        uchar4 a[UNROLL];
+#pragma unroll
+        for (int u = 0; u < UNROLL; u++) {
+            c[u] = __ldcs(in4 + v + u * stride);
+            g[u] = __ldcs(gc4 + v + u * stride);
+            a[u] = alive ? __ldcs(al4 + v + u * stride) : make_uchar4(1, 1, 1, 1);
+        }
+#pragma unroll
+        for (int u = 0; u < UNROLL; u++) {
+            double m;
+            m = s_med[g[u].x]; if (a[u].x && m > 0) c[u].x = (float)__ddiv_rn(__dmul_rn(gmed, (double)c[u].x), m);
+            m = s_med[g[u].y]; if (a[u].y && m > 0) c[u].y = (float)__ddiv_rn(__dmul_rn(gmed, (double)c[u].y), m);
+            m = s_med[g[u].z]; if (a[u].z && m > 0) c[u].z = (float)__ddiv_rn(__dmul_rn(gmed, (double)c[u].z), m);
+            m = s_med[g[u].w]; if (a[u].w && m > 0) c[u].w = (float)__ddiv_rn(__dmul_rn(gmed, (double)c[u].w), m);
+            __stcs(out4 + v + u * stride, c[u]);
+        }
+    }
+    for (; v < nvec; v += stride) {
+        float4 c = in4[v];
+        uchar4 g = gc4[v];
+        uchar4 a = alive ? al4[v] : make_uchar4(1, 1, 1, 1);
+        double m;
+        m = s_med[g.x]; if (a.x && m > 0) c.x = (float)__ddiv_rn(__dmul_rn(gmed, (double)c.x), m);
+        m = s_med[g.y]; if (a.y && m > 0) c.y = (float)__ddiv_rn(__dmul_rn(gmed, (double)c.y), m);
+        m = s_med[g.z]; if (a.z && m > 0) c.z = (float)__ddiv_rn(__dmul_rn(gmed, (double)c.z), m);
+        m = s_med[g.w]; if (a.w && m > 0) c.w = (float)__ddiv_rn(__dmul_rn(gmed, (double)c.w), m);
+        out4[v] = c;
+    }
+    // tail (n not a multiple of 4)
+    if (blockIdx.x == 0) {
+        for (long long i = (nvec << 2) + threadIdx.x; i < n; i += blockDim.x) {
+            float c = in[i];
+            double m = s_med[gc[i]];
+            if ((!alive || alive[i]) && m > 0) c = (float)__ddiv_rn(__dmul_rn(gmed, (double)c), m);
+            out[i] = c;
+        }
+    }
+}
+
+struct FinalPred {  // GC filter survivors minus RemoveBinsWithExtremeLocalSD (CanvasClean.cs:308-322)
+    const uint8_t* alive;
+    const double* wsd;
+    const CleanCtl* ctl;
+    __device__ bool operator()(int i) const {
+        if (!alive[i]) return false;
+        if (!ctl->metric_on) return true;
+        const int w = i / LOCAL_SD_WINDOW;
+        const double dev = w < ctl->n_windows ? wsd[w] : -1.0;
+        return !(dev > 20.0 * 2.0 && ctl->local_sd > 5.0);
+    }
+};
+
+struct EmitOut {
+    const float* count2;
+    const int32_t* orig2;
+    int32_t* kept;
+    float* count_out;
+    __device__ void operator()(int src, int dst) const {
+        kept[dst] = orig2[src];
+        count_out[dst] = count2[src];
+    }
+};
+
+// ---------------------------------------------------------------------------------------------
+// Device-side pipeline (shared by cg_clean and cg_clean_partition_wavelet)
+// ---------------------------------------------------------------------------------------------
+size_t clean_workspace_bytes(int64_t n, int n_chrom) {
+    size_t s = 0;
+    s += arena_need(n, 1) * 2 + arena_need(n, 4) * 3;          // inputs
+    s += arena_need(n, 1) * 2 + arena_need(n, 4) * 2;          // L1
+    s += arena_need(n, 1) * 3 + arena_need(n, 4) * 2;          // L2 + alive
+    s += arena_need(n / LOCAL_SD_WINDOW + 2, 8) + arena_need(n / LOCAL_SD_WINDOW + 2, 1);
+    s += arena_need(n, 4) * 2;                                  // outputs
+    s += arena_need(n / CMP_TILE + 2, 4);
+    s += arena_need(1, sizeof(CleanCtl)) + arena_need(256, 1) + arena_need(256, 4) + arena_need(256, 8) * 2;
+    s += sel_state_bytes<uint32_t>(1) + sel_state_bytes<uint32_t>(GC_SEGS) + sel_state_bytes<uint64_t>(std::max(n_chrom, 1));
+    return s + (1 << 16);
+}
+
+int clean_alloc(cg_ctx* ctx, int64_t n, int n_chrom, CleanDev& d) {
+    d.n = n;
+    d.n_chrom = n_chrom;
+    d.chrom = arena_take<uint8_t>(ctx, n);
+    d.gc = arena_take<uint8_t>(ctx, n);
+    d.start = arena_take<int32_t>(ctx, n);
+    d.stop = arena_take<int32_t>(ctx, n);
+    d.count = arena_take<float>(ctx, n);
+    d.chrom1 = arena_take<uint8_t>(ctx, n);
+    d.gc1 = arena_take<uint8_t>(ctx, n);
+    d.count1 = arena_take<float>(ctx, n);
+    d.orig1 = arena_take<int32_t>(ctx, n);
+    d.chrom2 = arena_take<uint8_t>(ctx, n);
+    d.gc2 = arena_take<uint8_t>(ctx, n);
+    d.alive = arena_take<uint8_t>(ctx, n);
+    d.count2 = arena_take<float>(ctx, n);
+    d.orig2 = arena_take<int32_t>(ctx, n);
+    d.wsd = arena_take<double>(ctx, n / LOCAL_SD_WINDOW + 2);
+    d.wchrom = arena_take<uint8_t>(ctx, n / LOCAL_SD_WINDOW + 2);
+    d.kept = arena_take<int32_t>(ctx, n);
+    d.count_out = arena_take<float>(ctx, n);
+    d.tiles = arena_take<int>(ctx, n / CMP_TILE + 2);
+    d.ctl = arena_take<CleanCtl>(ctx, 1);
+    d.is_auto = arena_take<uint8_t>(ctx, 256);
+    d.wcnt = arena_take<unsigned>(ctx, 256);
+    d.wmed = arena_take<double>(ctx, 256);
+    d.wmad = arena_take<double>(ctx, 256);
+    bool ok = d.chrom && d.gc && d.start && d.stop && d.count && d.chrom1 && d.gc1 && d.count1 && d.orig1 &&
+              d.chrom2 && d.gc2 && d.alive && d.count2 && d.orig2 && d.wsd && d.wchrom && d.kept &&
+              d.count_out && d.tiles && d.ctl && d.is_auto && d.wcnt && d.wmed && d.wmad;
+    ok = ok && sel_state_alloc<uint32_t>(ctx, 1, d.sel_size) && sel_state_alloc<uint32_t>(ctx, GC_SEGS, d.sel_gc) &&
+         sel_state_alloc<uint64_t>(ctx, std::max(n_chrom, 1), d.sel_win);
+    return ok ? CG_OK : cg_fail(ctx, CG_ERR_CUDA, "clean: device arena exhausted");
+}
+
+// Enqueue the whole CanvasClean pipeline on ctx->stream.  Inputs must already be in d.chrom/...;
+// results end in d.kept / d.count_out / d.ctl.
+int clean_enqueue(cg_ctx* ctx, const cg_clean_opts* o, CleanDev& d) {
+    const int n = (int)d.n;
+    const int nb = std::max(1, div_up(n, 256));
+    const int grid_stream = std::max(1, std::min(nb, ctx->num_sms * 8));
+    CleanCtl* ctl = d.ctl;
+    if (o->gc_norm && o->gc_mode != 0)
+        return cg_fail(ctx, CG_ERR_UNSUPPORTED, "cg_clean: LOESS GC normalisation (-m LOESS) is not implemented in this build");
+
+    CG_LAUNCH(ctx, clean_init_kernel, 1, 32, 0, ctl, n);
+    cudaMemsetAsync(d.wcnt, 0, 256 * sizeof(unsigned), ctx->stream);
+    cudaMemsetAsync(d.sel_size.hist, 0, (size_t)1 * SEL_G * SEL_BINS * sizeof(unsigned), ctx->stream);
+    cudaMemsetAsync(d.sel_gc.hist, 0, (size_t)GC_SEGS * SEL_G * SEL_BINS * sizeof(unsigned), ctx->stream);
+    cudaMemsetAsync(d.sel_win.hist, 0, (size_t)d.sel_win.nseg * SEL_G * SEL_BINS * sizeof(unsigned), ctx->stream);
+    CG_LAUNCH(ctx, clean_validate_kernel, nb, 256, 0, d.chrom, d.gc, n, ctl);
+
+    // --- RemoveBigBins (:328-355)
+    long long k98 = (long long)(0.98 * (double)n);
+    int size_on = (o->size_filter && k98 < n) ? 1 : 0;
+    CG_LAUNCH(ctx, size_request_kernel, 1, 1, 0, d.sel_size, k98, size_on);
+    if (size_on) {
+        SizeView sv{d.start, d.stop, n};
+        sel_run_scatter<uint32_t, SizeView>(ctx, sv, d.sel_size, n);
+    }
+    CG_LAUNCH(ctx, size_finish_kernel, 1, 1, 0, d.sel_size, ctl, size_on);
+    {
+        SizePred p{d.start, d.stop, ctl};
+        Emit1 e{d.chrom, d.gc, d.count, d.chrom1, d.gc1, d.count1, d.orig1};
+        compact_run(ctx, p, e, &ctl->n0, n, d.tiles, &ctl->n1);
+    }
+    // --- RemoveOutliers (:387-413)
+    {
+        OutlierPred p{d.chrom1, d.count1, ctl, o->outlier_filter};
+        Emit2 e{d.chrom1, d.gc1, d.count1, d.orig1, d.chrom2, d.gc2, d.count2, d.orig2};
+        compact_run(ctx, p, e, &ctl->n1, n, d.tiles, &ctl->n2);
+    }
+    // --- local SD metric (:483-494)
+    CG_LAUNCH(ctx, clean_decide_metric_kernel, 1, 1, 0, ctl, o->want_local_sd);
+    if (o->want_local_sd && n >= 50000) {
+        const int nwin_upper = n / LOCAL_SD_WINDOW + 1;
+        CG_LAUNCH(ctx, local_sd_windows_kernel, div_up(nwin_upper, 128), 128, 0, d.count2, d.chrom2, ctl, d.wsd,
+                  d.wchrom, d.wcnt);
+        WindowView wv{d.wsd, d.wchrom, ctl, nullptr};
+        CG_LAUNCH(ctx, median_request_u64_kernel, div_up(d.sel_win.nseg, 128), 128, 0, d.sel_win, d.wcnt, &ctl->metric_on);
+        sel_run_scatter<uint64_t, WindowView>(ctx, wv, d.sel_win, nwin_upper);
+        CG_LAUNCH(ctx, median_finish_u64_kernel, div_up(d.sel_win.nseg, 128), 128, 0, d.sel_win, d.wmed);
+        WindowView wv2{d.wsd, d.wchrom, ctl, d.wmed};
+        CG_LAUNCH(ctx, median_request_u64_kernel, div_up(d.sel_win.nseg, 128), 128, 0, d.sel_win, d.wcnt, &ctl->metric_on);
+        sel_run_scatter<uint64_t, WindowView>(ctx, wv2, d.sel_win, nwin_upper);
+        CG_LAUNCH(ctx, median_finish_u64_kernel, div_up(d.sel_win.nseg, 128), 128, 0, d.sel_win, d.wmad);
+        CG_LAUNCH(ctx, local_sd_average_kernel, 1, 1, 0, ctl, d.wcnt, d.wmad, d.n_chrom);
+    }
+    // --- RemoveBinsWithExtremeGC (:207-237) as an alive mask over the outlier-filtered list
+    CG_LAUNCH(ctx, gc_hist_kernel, grid_stream, 256, 0, d.gc2, d.chrom2, d.is_auto, ctl);
+    CG_LAUNCH(ctx, gc_threshold_kernel, 1, 1, 0, ctl, o->gc_norm, o->gc_mode == 0, o->min_bins_per_gc);
+    CG_LAUNCH(ctx, gc_alive_kernel, grid_stream, 256, 0, d.gc2, ctl, d.alive);
+    if (o->gc_norm) {
+        GcCountView gv{d.count2, d.gc2, d.chrom2, d.alive, d.is_auto, ctl, &ctl->do_norm};
+        // --- NormalizeByGC (:163-196)
+        CG_LAUNCH(ctx, gc_median_request_kernel, 1, 128, 0, d.sel_gc, ctl, &ctl->do_norm);
+        sel_run_scatter<uint32_t, GcCountView>(ctx, gv, d.sel_gc, n);
+        CG_LAUNCH(ctx, gc_median_finish_kernel, 1, 128, 0, d.sel_gc, ctl, &ctl->do_norm);
+        CG_LAUNCH(ctx, (normalize_apply_kernel<4>), dim3(grid_stream, 1), 256, 0, d.count2, d.gc2, d.alive, d.count2,
+                  &ctl->n2, 0LL, ctl->med, &ctl->global_median, &ctl->do_norm, 0LL);
+        // --- NormalizeVarianceByGC (:34-97), evaluated only when the metric is on and > 500000 bins
+        if (o->want_local_sd && n > 500000) {
+            GcCountView gq{d.count2, d.gc2, d.chrom2, d.alive, d.is_auto, ctl, &ctl->do_variance};
+            CG_LAUNCH(ctx, gc_quartile_request_kernel, 1, 128, 0, d.sel_gc, ctl, &ctl->do_variance);
+            sel_run_scatter<uint32_t, GcCountView>(ctx, gq, d.sel_gc, n);
+            CG_LAUNCH(ctx, gc_quartile_finish_kernel, 1, 128, 0, d.sel_gc, ctl, &ctl->do_variance);
+            CG_LAUNCH(ctx, variance_decide_kernel, 1, 1, 0, ctl);
+            CG_LAUNCH(ctx, variance_apply_kernel, grid_stream, 256, 0, d.count2, d.gc2, d.alive, ctl);
+            // second NormalizeByGC when the rescale fired (:516-517)
+            GcCountView gm{d.count2, d.gc2, d.chrom2, d.alive, d.is_auto, ctl, &ctl->variance_fired};
+            CG_LAUNCH(ctx, gc_median_request_kernel, 1, 128, 0, d.sel_gc, ctl, &ctl->variance_fired);
+            sel_run_scatter<uint32_t, GcCountView>(ctx, gm, d.sel_gc, n);
+            CG_LAUNCH(ctx, gc_median_finish_kernel, 1, 128, 0, d.sel_gc, ctl, &ctl->variance_fired);
+            CG_LAUNCH(ctx, (normalize_apply_kernel<4>), dim3(grid_stream, 1), 256, 0, d.count2, d.gc2, d.alive,
+                      d.count2, &ctl->n2, 0LL, ctl->med, &ctl->global_median, &ctl->variance_fired, 0LL);
+        }
+    }
+    // --- RemoveBinsWithExtremeLocalSD (:308-322) + final compaction
+    {
+        FinalPred p{d.alive, d.wsd, ctl};
+        EmitOut e{d.count2, d.orig2, d.kept, d.count_out};
+        compact_run(ctx, p, e, &ctl->n2, n, d.tiles, &ctl->n_out);
+    }
+    return CG_OK;
+}
+
+extern "C" int cg_clean(cg_ctx* ctx, const cg_clean_opts* opts, int64_t n, const uint8_t* chrom,
+                        const uint8_t* chrom_is_autosome, const uint8_t* chrom_is_chrY, int n_chrom,
+                        const int32_t* start, const int32_t* stop, const float* count, const uint8_t* gc,
+                        int64_t* n_out, int32_t* kept_index, float* count_out, double* local_sd,
+                        int* gc_norm_skipped) {
+    (void)chrom_is_chrY;
+    if (!ctx) return CG_ERR_ARG;
+    if (!opts || n < 0 || n > 0x7fff0000LL || n_chrom < 0 || n_chrom > 256 || !n_out || !local_sd || !gc_norm_skipped)
+        return cg_fail(ctx, CG_ERR_ARG, "cg_clean: bad argument");
+    ctx->launches = 0;
+    ctx->last_kernel_ms = 0;
+    *n_out = 0;
+    *local_sd = -1.0;
+    *gc_norm_skipped = 0;
+    if (n == 0) return CG_OK;
+    if (!chrom || !start || !stop || !count || !gc || !kept_index || !count_out || (n_chrom > 0 && !chrom_is_autosome))
+        return cg_fail(ctx, CG_ERR_ARG, "cg_clean: null array");
+    CG_CUDA(ctx, cudaSetDevice(ctx->device));
+    int rc = arena_reserve(ctx, clean_workspace_bytes(n, n_chrom));
+    if (rc) return rc;
+    CleanDev d;
+    rc = clean_alloc(ctx, n, n_chrom, d);
+    if (rc) return rc;
+    cudaStream_t s = ctx->stream;
+    CG_CUDA(ctx, cudaMemcpyAsync(d.chrom, chrom, n, cudaMemcpyHostToDevice, s));
+    CG_CUDA(ctx, cudaMemcpyAsync(d.gc, gc, n, cudaMemcpyHostToDevice, s));
+    CG_CUDA(ctx, cudaMemcpyAsync(d.start, start, n * 4, cudaMemcpyHostToDevice, s));
+    CG_CUDA(ctx, cudaMemcpyAsync(d.stop, stop, n * 4, cudaMemcpyHostToDevice, s));
+    CG_CUDA(ctx, cudaMemcpyAsync(d.count, count, n * 4, cudaMemcpyHostToDevice, s));
+    CG_CUDA(ctx, cudaMemsetAsync(d.is_auto, 0, 256, s));
+    if (n_chrom > 0) CG_CUDA(ctx, cudaMemcpyAsync(d.is_auto, chrom_is_autosome, n_chrom, cudaMemcpyHostToDevice, s));
+    CG_CUDA(ctx, cudaEventRecord(ctx->ev0, s));
+    rc = clean_enqueue(ctx, opts, d);
+    if (rc) return rc;
+    CG_CUDA(ctx, cudaEventRecord(ctx->ev1, s));
+    CleanCtl* h = (CleanCtl*)ctx->pinned;
+    CG_CUDA(ctx, cudaMemcpyAsync(h, d.ctl, sizeof(CleanCtl), cudaMemcpyDeviceToHost, s));
+    CG_CUDA(ctx, cudaStreamSynchronize(s));
+    CG_CUDA(ctx, cudaGetLastError());
+    float ms = 0;
+    cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+    ctx->last_kernel_ms = ms;
+    if (h->unsorted) return cg_fail(ctx, CG_ERR_UNSORTED, "cg_clean: chromosome ids must form non-decreasing runs and GC must be 0..100");
+    if (h->need_weighted)
+        return cg_fail(ctx, CG_ERR_UNSUPPORTED, "cg_clean: a GC bucket in use has < 100 autosomal bins (weighted-quantile path not implemented)");
+    const int64_t m = h->n_out;
+    if (m > 0) {
+        CG_CUDA(ctx, cudaMemcpyAsync(kept_index, d.kept, m * 4, cudaMemcpyDeviceToHost, s));
+        CG_CUDA(ctx, cudaMemcpyAsync(count_out, d.count_out, m * 4, cudaMemcpyDeviceToHost, s));
+        CG_CUDA(ctx, cudaStreamSynchronize(s));
+    }
+    *n_out = m;
+    *local_sd = h->local_sd;
+    *gc_norm_skipped = h->gc_skipped;
+    return CG_OK;
+}
+
+// Stand-alone K8 for the roofline measurement (see canvasgpu.h).
+extern "C" int cg_normalize_apply(cg_ctx* ctx, int batch, int64_t n, const float* count, const uint8_t* gc,
+                                  const double* median_by_gc, const double* global_median, float* count_out,
+                                  int repeats, double* kernel_ms) {
+    if (!ctx) return CG_ERR_ARG;
+    if (batch <= 0 || n <= 0 || (n & 3) || !count || !gc || !median_by_gc || !global_median || !count_out)
+        return cg_fail(ctx, CG_ERR_ARG, "cg_normalize_apply: bad argument (n must be a multiple of 4)");
+    CG_CUDA(ctx, cudaSetDevice(ctx->device));
+    ctx->launches = 0;
+    const size_t total = (size_t)batch * (size_t)n;
+    int rc = arena_reserve(ctx, arena_need(total, 4) * 2 + arena_need(total, 1) + arena_need((size_t)batch * GC_BINS, 8) +
+                                    arena_need(batch, 8) + 4096);
+    if (rc) return rc;
+    float* d_in = arena_take<float>(ctx, total);
+    float* d_out = arena_take<float>(ctx, total);
+    uint8_t* d_gc = arena_take<uint8_t>(ctx, total);
+    double* d_med = arena_take<double>(ctx, (size_t)batch * GC_BINS);
+    double* d_gmed = arena_take<double>(ctx, batch);
+    if (!d_in || !d_out || !d_gc || !d_med || !d_gmed) return cg_fail(ctx, CG_ERR_CUDA, "arena exhausted");
+    cudaStream_t s = ctx->stream;
+    CG_CUDA(ctx, cudaMemcpyAsync(d_in, count, total * 4, cudaMemcpyHostToDevice, s));
+    CG_CUDA(ctx, cudaMemcpyAsync(d_gc, gc, total, cudaMemcpyHostToDevice, s));
+    CG_CUDA(ctx, cudaMemcpyAsync(d_med, median_by_gc, (size_t)batch * GC_BINS * 8, cudaMemcpyHostToDevice, s));
+    CG_CUDA(ctx, cudaMemcpyAsync(d_gmed, global_median, (size_t)batch * 8, cudaMemcpyHostToDevice, s));
+    const int per_sample_blocks = std::max(1, std::min(div_up(n / 4, 256 * 4), (ctx->num_sms * 8 + batch - 1) / batch));
+    dim3 grid(per_sample_blocks, batch);
+    if (repeats < 1) repeats = 1;
+    // one untimed launch, then `repeats` timed ones
+    CG_LAUNCH(ctx, (normalize_apply_kernel<4>), grid, 256, 0, d_in, d_gc, (const uint8_t*)nullptr, d_out,
+              (const int*)nullptr, (long long)n, d_med, d_gmed, (const int*)nullptr, (long long)n);
+    CG_CUDA(ctx, cudaEventRecord(ctx->ev0, s));
+    for (int r = 0; r < repeats; r++)
+        CG_LAUNCH(ctx, (normalize_apply_kernel<4>), grid, 256, 0, d_in, d_gc, (const uint8_t*)nullptr, d_out,
+                  (const int*)nullptr, (long long)n, d_med, d_gmed, (const int*)nullptr, (long long)n);
+    CG_CUDA(ctx, cudaEventRecord(ctx->ev1, s));
+    CG_CUDA(ctx, cudaMemcpyAsync(count_out, d_out, total * 4, cudaMemcpyDeviceToHost, s));
+    CG_CUDA(ctx, cudaStreamSynchronize(s));
+    CG_CUDA(ctx, cudaGetLastError());
+    float ms = 0;
+    cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+    ctx->last_kernel_ms = ms / repeats;
+    if (kernel_ms) *kernel_ms = ms / repeats;
+    return CG_OK;
+}

@@ -1,0 +1,131 @@
+// Shared plumbing of libcanvasgpu: context, device arena, error handling, key mappings.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "canvasgpu.h"
+
+#define CG_NUM_SMS_FALLBACK 148
+
+struct cg_ctx {
+    int device = 0;
+    int num_sms = CG_NUM_SMS_FALLBACK;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    std::string err;
+    std::string desc;
+    double last_kernel_ms = 0;
+    int launches = 0;
+    // device arena, grown on demand and reused across calls
+    char* arena = nullptr;
+    size_t arena_cap = 0;
+    size_t arena_off = 0;
+    // small pinned staging block for scalars coming back from the device
+    char* pinned = nullptr;
+    size_t pinned_cap = 0;
+};
+
+inline int cg_fail(cg_ctx* ctx, int code, const std::string& msg) {
+    if (ctx) ctx->err = msg;
+    return code;
+}
+
+#define CG_CUDA(ctx, call)                                                                   \
+    do {                                                                                     \
+        cudaError_t e__ = (call);                                                            \
+        if (e__ != cudaSuccess)                                                              \
+            return cg_fail(ctx, CG_ERR_CUDA,                                                 \
+                           std::string(#call) + ": " + cudaGetErrorString(e__) + " (" +      \
+                               __FILE__ + ":" + std::to_string(__LINE__) + ")");             \
+    } while (0)
+
+// Arena: one cudaMalloc, bump allocation, 256-byte aligned.  reserve() is called once per API call
+// with the worst-case footprint, take() hands out slices.
+inline int arena_reserve(cg_ctx* ctx, size_t bytes) {
+    ctx->arena_off = 0;
+    if (bytes <= ctx->arena_cap) return CG_OK;
+    if (ctx->arena) {
+        CG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        CG_CUDA(ctx, cudaFree(ctx->arena));
+        ctx->arena = nullptr;
+        ctx->arena_cap = 0;
+    }
+    size_t cap = bytes + (bytes >> 3) + (1u << 20);
+    CG_CUDA(ctx, cudaMalloc((void**)&ctx->arena, cap));
+    ctx->arena_cap = cap;
+    return CG_OK;
+}
+
+template <typename T>
+inline T* arena_take(cg_ctx* ctx, size_t count) {
+    size_t bytes = (count * sizeof(T) + 255) & ~(size_t)255;
+    if (ctx->arena_off + bytes > ctx->arena_cap) return nullptr;
+    T* p = (T*)(ctx->arena + ctx->arena_off);
+    ctx->arena_off += bytes;
+    return p;
+}
+
+inline size_t arena_need(size_t count, size_t elem) { return ((count * elem + 255) & ~(size_t)255); }
+
+// ---------------------------------------------------------------------------------------------
+// Order-preserving key maps.  .NET orders NaN below every number (Double.CompareTo), so NaN maps
+// to key 0, which no other value produces.
+// ---------------------------------------------------------------------------------------------
+__host__ __device__ inline uint32_t f32_key(float x) {
+    if (x != x) return 0u;
+    uint32_t u;
+#ifdef __CUDA_ARCH__
+    u = __float_as_uint(x);
+#else
+    memcpy(&u, &x, 4);
+#endif
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__host__ __device__ inline float f32_unkey(uint32_t k) {
+    uint32_t u = (k & 0x80000000u) ? (k ^ 0x80000000u) : ~k;
+    if (k == 0u) u = 0x7fc00000u;
+    float x;
+#ifdef __CUDA_ARCH__
+    x = __uint_as_float(u);
+#else
+    memcpy(&x, &u, 4);
+#endif
+    return x;
+}
+__host__ __device__ inline uint64_t f64_key(double x) {
+    if (x != x) return 0ull;
+    uint64_t u;
+#ifdef __CUDA_ARCH__
+    u = (uint64_t)__double_as_longlong(x);
+#else
+    memcpy(&u, &x, 8);
+#endif
+    return (u & 0x8000000000000000ull) ? ~u : (u | 0x8000000000000000ull);
+}
+__host__ __device__ inline double f64_unkey(uint64_t k) {
+    uint64_t u = (k & 0x8000000000000000ull) ? (k ^ 0x8000000000000000ull) : ~k;
+    if (k == 0ull) u = 0x7ff8000000000000ull;
+    double x;
+#ifdef __CUDA_ARCH__
+    x = __longlong_as_double((long long)u);
+#else
+    memcpy(&x, &u, 8);
+#endif
+    return x;
+}
+__host__ __device__ inline uint32_t i32_key(int32_t x) { return (uint32_t)x ^ 0x80000000u; }
+__host__ __device__ inline int32_t i32_unkey(uint32_t k) { return (int32_t)(k ^ 0x80000000u); }
+
+static inline int div_up(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+
+// counted launch helper
+#define CG_LAUNCH(ctx, kernel, grid, block, smem, ...)                                 \
+    do {                                                                               \
+        kernel<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__);               \
+        (ctx)->launches++;                                                             \
+    } while (0)

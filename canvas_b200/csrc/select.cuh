@@ -1,0 +1,299 @@
+// Exact multi-segment, multi-rank order statistics by MSD radix select (8-bit digits).
+//
+// Every median / quartile / percentile of the reference is an exact element of a sorted list
+// (Utilities.cs:340-474), and the result feeds a division, so approximations are not acceptable.
+// Instead of sorting, each requested rank is resolved digit by digit: one histogram pass over the
+// data per digit, followed by a tiny "resolve" kernel that walks the histograms and narrows every
+// request to one bucket.  Requests of a segment that still share a prefix share one histogram row
+// ("group"), so asking for rank k and k+1 (even-length median) or all quartile ranks costs the same
+// passes as one rank.
+//
+// Layout: up to SEL_G requests and SEL_G groups per segment; row (seg, j) of `hist` has 256 bins.
+#pragma once
+#include <algorithm>
+
+#include "common.cuh"
+
+constexpr int SEL_G = 6;
+constexpr int SEL_BINS = 256;
+
+template <typename K>
+struct SelState {
+    int nseg;
+    int* nreq;                   // [nseg]        requests per segment (0..SEL_G)
+    unsigned long long* req_k;   // [nseg*SEL_G]  0-based rank, relative to the request's group
+    int* req_grp;                // [nseg*SEL_G]  group slot of the request
+    K* req_key;                  // [nseg*SEL_G]  result: key of the requested order statistic
+    int* ngrp;                   // [nseg]
+    K* gprefix;                  // [nseg*SEL_G]  decided high bits of each group
+    unsigned* hist;              // [nseg*SEL_G*256]
+};
+
+template <typename K>
+inline size_t sel_state_bytes(int nseg) {
+    size_t s = 0;
+    s += arena_need(nseg, sizeof(int)) * 2;
+    s += arena_need((size_t)nseg * SEL_G, sizeof(unsigned long long));
+    s += arena_need((size_t)nseg * SEL_G, sizeof(int));
+    s += arena_need((size_t)nseg * SEL_G, sizeof(K)) * 2;
+    s += arena_need((size_t)nseg * SEL_G * SEL_BINS, sizeof(unsigned));
+    return s;
+}
+
+template <typename K>
+inline bool sel_state_alloc(cg_ctx* ctx, int nseg, SelState<K>& st) {
+    st.nseg = nseg;
+    st.nreq = arena_take<int>(ctx, nseg);
+    st.ngrp = arena_take<int>(ctx, nseg);
+    st.req_k = arena_take<unsigned long long>(ctx, (size_t)nseg * SEL_G);
+    st.req_grp = arena_take<int>(ctx, (size_t)nseg * SEL_G);
+    st.req_key = arena_take<K>(ctx, (size_t)nseg * SEL_G);
+    st.gprefix = arena_take<K>(ctx, (size_t)nseg * SEL_G);
+    st.hist = arena_take<unsigned>(ctx, (size_t)nseg * SEL_G * SEL_BINS);
+    return st.nreq && st.ngrp && st.req_k && st.req_grp && st.req_key && st.gprefix && st.hist;
+}
+
+// After the caller filled nreq / req_k: one group per segment with an empty prefix.
+template <typename K>
+__global__ void sel_begin_kernel(SelState<K> st) {
+    int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= st.nseg) return;
+    int nr = st.nreq[s];
+    st.ngrp[s] = nr > 0 ? 1 : 0;
+    for (int j = 0; j < SEL_G; j++) {
+        st.gprefix[s * SEL_G + j] = (K)0;
+        st.req_grp[s * SEL_G + j] = 0;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Histogram pass, scattered segments: every element may belong to two segments (its own bucket and
+// a "global" one).  Row 0 of every segment is privatised in shared memory when it fits (PRIV) and
+// updates to it are warp-aggregated (degenerate digits — e.g. all bin sizes equal — would otherwise
+// serialise 32-way on one address); rows >= 1 only exist once ranks of a segment have diverged,
+// when few elements still match, and go straight to global atomics.
+//
+// View: __device__ long long size() const;
+//       __device__ bool get(long long i, K& key, int& segA, int& segB) const;  (seg < 0: none)
+// ---------------------------------------------------------------------------------------------
+template <typename K, class View, bool PRIV>
+__global__ void sel_hist_scatter_kernel(View v, SelState<K> st, int shift, int first) {
+    extern __shared__ unsigned char sel_smem[];
+    const int nseg = st.nseg;
+    K* s_prefix = (K*)sel_smem;
+    int* s_ngrp = (int*)(s_prefix + (size_t)nseg * SEL_G);
+    unsigned* s_hist = (unsigned*)(s_ngrp + nseg);
+    for (int t = threadIdx.x; t < nseg * SEL_G; t += blockDim.x) s_prefix[t] = st.gprefix[t];
+    for (int t = threadIdx.x; t < nseg; t += blockDim.x) s_ngrp[t] = st.ngrp[t];
+    if (PRIV)
+        for (int t = threadIdx.x; t < nseg * SEL_BINS; t += blockDim.x) s_hist[t] = 0u;
+    __syncthreads();
+
+    const long long n = v.size();
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const long long n_round = ((n + 31) / 32) * 32;
+    const int hi_shift = shift + 8;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += stride) {
+        K key = 0;
+        int seg[2] = {-1, -1};
+        bool ok = false;
+        if (i < n) ok = v.get(i, key, seg[0], seg[1]);
+        const int d = (int)((key >> shift) & (K)255);
+#pragma unroll
+        for (int a = 0; a < 2; a++) {
+            const int s = ok ? seg[a] : -1;
+            const int ng = s >= 0 ? s_ngrp[s] : 0;
+            bool hit0 = false;
+            if (ng > 0) hit0 = first || (((key ^ s_prefix[s * SEL_G]) >> hi_shift) == 0);
+            if (PRIV) {
+                unsigned act = __ballot_sync(0xffffffffu, hit0);
+                if (hit0) {
+                    int idx = s * SEL_BINS + d;
+                    unsigned m = __match_any_sync(act, idx);
+                    if ((int)(__ffs(m) - 1) == (int)(threadIdx.x & 31)) atomicAdd(&s_hist[idx], __popc(m));
+                }
+            } else if (hit0) {
+                atomicAdd(&st.hist[(size_t)(s * SEL_G) * SEL_BINS + d], 1u);
+            }
+            for (int j = 1; j < ng; j++)
+                if (((key ^ s_prefix[s * SEL_G + j]) >> hi_shift) == 0)
+                    atomicAdd(&st.hist[(size_t)(s * SEL_G + j) * SEL_BINS + d], 1u);
+        }
+    }
+    if (PRIV) {
+        __syncthreads();
+        for (int t = threadIdx.x; t < nseg * SEL_BINS; t += blockDim.x) {
+            unsigned c = s_hist[t];
+            if (c) atomicAdd(&st.hist[(size_t)((t / SEL_BINS) * SEL_G) * SEL_BINS + (t % SEL_BINS)], c);
+        }
+    }
+}
+
+template <typename K>
+inline size_t sel_scatter_smem(int nseg, bool priv) {
+    size_t s = (size_t)nseg * SEL_G * sizeof(K) + (size_t)nseg * sizeof(int);
+    if (priv) s += (size_t)nseg * SEL_BINS * sizeof(unsigned);
+    return s;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Histogram pass, contiguous segments: segment s owns elements [seg_off[s], seg_off[s+1]) of the
+// view; block (x, s) handles chunk x of segment s with all its group rows private in shared memory.
+// View: __device__ bool get(long long i, int seg, K& key) const;   (false: skip element)
+// ---------------------------------------------------------------------------------------------
+template <typename K, class View>
+__global__ void sel_hist_contig_kernel(View v, const long long* __restrict__ seg_off, long long chunk,
+                                       SelState<K> st, int shift, int first) {
+    __shared__ unsigned s_hist[SEL_G * SEL_BINS];
+    __shared__ K s_prefix[SEL_G];
+    const int s = blockIdx.y;
+    const int ng = st.ngrp[s];
+    if (ng == 0) return;
+    const long long lo = seg_off[s] + (long long)blockIdx.x * chunk;
+    const long long hi_seg = seg_off[s + 1];
+    if (lo >= hi_seg) return;
+    const long long hi = lo + chunk < hi_seg ? lo + chunk : hi_seg;
+    for (int t = threadIdx.x; t < ng * SEL_BINS; t += blockDim.x) s_hist[t] = 0u;
+    if (threadIdx.x < SEL_G) s_prefix[threadIdx.x] = st.gprefix[s * SEL_G + threadIdx.x];
+    __syncthreads();
+    const int hi_shift = shift + 8;
+    for (long long i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+        K key;
+        if (!v.get(i, s, key)) continue;
+        const int d = (int)((key >> shift) & (K)255);
+        for (int j = 0; j < ng; j++)
+            if (first || (((key ^ s_prefix[j]) >> hi_shift) == 0)) atomicAdd(&s_hist[j * SEL_BINS + d], 1u);
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < ng * SEL_BINS; t += blockDim.x) {
+        unsigned c = s_hist[t];
+        if (c) atomicAdd(&st.hist[(size_t)(s * SEL_G) * SEL_BINS + t], c);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Resolve: one warp per segment walks the rows of its groups, moves each request into the bucket
+// that holds its rank, regroups requests by their new prefix and clears the rows for the next pass.
+// ---------------------------------------------------------------------------------------------
+template <typename K>
+__global__ void sel_resolve_kernel(SelState<K> st, int shift, int last) {
+    const int lane = threadIdx.x & 31;
+    const int s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (s >= st.nseg) return;
+    const int nr = st.nreq[s];
+    const int ng = st.ngrp[s];
+    if (nr == 0 || ng == 0) return;
+    unsigned long long rk[SEL_G];
+    int rgrp[SEL_G], rnew[SEL_G];
+    K newpref[SEL_G];
+    int newng = 0;
+#pragma unroll
+    for (int r = 0; r < SEL_G; r++) {
+        rk[r] = r < nr ? st.req_k[s * SEL_G + r] : 0ull;
+        rgrp[r] = r < nr ? st.req_grp[s * SEL_G + r] : -1;
+        rnew[r] = 0;
+        newpref[r] = (K)0;
+    }
+    for (int j = 0; j < ng; j++) {
+        unsigned* row = st.hist + (size_t)(s * SEL_G + j) * SEL_BINS;
+        unsigned c[8];
+        unsigned long long sum = 0;
+#pragma unroll
+        for (int t = 0; t < 8; t++) {
+            c[t] = row[lane * 8 + t];
+            sum += c[t];
+            row[lane * 8 + t] = 0u;
+        }
+        unsigned long long incl = sum;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            unsigned long long t = __shfl_up_sync(0xffffffffu, incl, off);
+            if (lane >= off) incl += t;
+        }
+        const unsigned long long excl = incl - sum;
+        const K pref = st.gprefix[s * SEL_G + j];
+#pragma unroll
+        for (int r = 0; r < SEL_G; r++) {
+            if (rgrp[r] != j) continue;  // uniform across the warp
+            const unsigned long long k = rk[r];
+            const bool mine = sum > 0 && k >= excl && k < excl + sum;
+            unsigned b = __ballot_sync(0xffffffffu, mine);
+            if (b == 0u) {  // rank beyond the group (never for well-formed requests): clamp to the top bucket
+                const unsigned nz = __ballot_sync(0xffffffffu, sum > 0);
+                b = nz ? (1u << (31 - __clz(nz))) : 1u;
+            }
+            const int owner = __ffs(b) - 1;
+            int d = lane * 8 + 7;
+            unsigned long long cum = excl;
+            if (lane == owner) {
+                unsigned long long run = excl;
+                d = lane * 8 + 7;
+                cum = excl + sum - c[7];
+#pragma unroll
+                for (int t = 0; t < 8; t++) {
+                    if (k < run + c[t]) { d = lane * 8 + t; cum = run; break; }
+                    run += c[t];
+                }
+            }
+            d = __shfl_sync(0xffffffffu, d, owner);
+            cum = __shfl_sync(0xffffffffu, cum, owner);
+            rk[r] = k >= cum ? k - cum : 0ull;
+            const K np = pref | ((K)d << shift);
+            int idx = -1;
+            for (int q = 0; q < newng; q++)
+                if (newpref[q] == np) idx = q;
+            if (idx < 0) { idx = newng; newpref[newng++] = np; }
+            rnew[r] = idx;
+        }
+    }
+    if (lane == 0) {
+        for (int r = 0; r < nr; r++) {
+            st.req_k[s * SEL_G + r] = rk[r];
+            st.req_grp[s * SEL_G + r] = rnew[r];
+            if (last) st.req_key[s * SEL_G + r] = newpref[rnew[r]];
+        }
+        for (int q = 0; q < newng; q++) st.gprefix[s * SEL_G + q] = newpref[q];
+        st.ngrp[s] = newng;
+    }
+}
+
+// Host drivers.  The caller has already written nreq/req_k (device side) before calling.
+template <typename K, class View>
+inline void sel_run_scatter(cg_ctx* ctx, const View& v, SelState<K>& st, long long n_upper) {
+    const int bits = (int)sizeof(K) * 8;
+    CG_LAUNCH(ctx, sel_begin_kernel<K>, div_up(st.nseg, 128), 128, 0, st);
+    size_t smem_priv = sel_scatter_smem<K>(st.nseg, true);
+    const bool priv = smem_priv <= 200 * 1024;
+    size_t smem = priv ? smem_priv : sel_scatter_smem<K>(st.nseg, false);
+    int grid = (int)std::min<long long>(std::max<long long>(1, (n_upper + 1023) / 1024), (long long)ctx->num_sms * (priv ? 1 : 4));
+    if (priv) {
+        cudaFuncSetAttribute(sel_hist_scatter_kernel<K, View, true>,
+                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    }
+    for (int shift = bits - 8; shift >= 0; shift -= 8) {
+        int first = shift == bits - 8;
+        if (priv)
+            CG_LAUNCH(ctx, (sel_hist_scatter_kernel<K, View, true>), grid, 1024, smem, v, st, shift, first);
+        else
+            CG_LAUNCH(ctx, (sel_hist_scatter_kernel<K, View, false>), grid, 256, smem, v, st, shift, first);
+        CG_LAUNCH(ctx, sel_resolve_kernel<K>, div_up((long long)st.nseg * 32, 256), 256, 0, st, shift,
+                  shift == 0);
+    }
+}
+
+template <typename K, class View>
+inline void sel_run_contig(cg_ctx* ctx, const View& v, const long long* seg_off_dev, long long max_seg_len,
+                           SelState<K>& st) {
+    const int bits = (int)sizeof(K) * 8;
+    CG_LAUNCH(ctx, sel_begin_kernel<K>, div_up(st.nseg, 128), 128, 0, st);
+    if (max_seg_len <= 0) max_seg_len = 1;
+    // aim for >= ~4 blocks per SM overall without going below 2048 elements per block
+    long long chunk = 8192;
+    dim3 grid((unsigned)((max_seg_len + chunk - 1) / chunk), (unsigned)st.nseg);
+    for (int shift = bits - 8; shift >= 0; shift -= 8) {
+        int first = shift == bits - 8;
+        CG_LAUNCH(ctx, (sel_hist_contig_kernel<K, View>), grid, 256, 0, v, seg_off_dev, chunk, st, shift, first);
+        CG_LAUNCH(ctx, sel_resolve_kernel<K>, div_up((long long)st.nseg * 32, 256), 256, 0, st, shift,
+                  shift == 0);
+    }
+}

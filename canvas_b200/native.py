@@ -1,0 +1,235 @@
+"""ctypes binding of libcanvasgpu.so — the only way the Python host layer reaches the GPU.
+
+There is no CPU fallback: importing works anywhere (so the CPU test tier can check the exported
+symbols), but creating an Engine without the library or without a CUDA device raises.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "_build", "libcanvasgpu.so")
+
+CG_OK, CG_ERR_CUDA, CG_ERR_ARG, CG_ERR_UNSORTED, CG_ERR_UNSUPPORTED, CG_ERR_CAPACITY = 0, -1, -2, -3, -4, -5
+
+
+class CanvasGpuError(RuntimeError):
+    def __init__(self, code, message):
+        super().__init__(f"libcanvasgpu error {code}: {message}")
+        self.code = code
+
+
+class CleanOpts(C.Structure):
+    _fields_ = [("size_filter", C.c_int), ("outlier_filter", C.c_int), ("gc_norm", C.c_int),
+                ("gc_mode", C.c_int), ("want_local_sd", C.c_int), ("min_bins_per_gc", C.c_int)]
+
+
+class WaveletOpts(C.Structure):
+    _fields_ = [("is_germline", C.c_int), ("mad_factor", C.c_double), ("thr_lower", C.c_double),
+                ("thr_upper", C.c_double), ("min_size", C.c_int), ("evenness_window", C.c_int)]
+
+
+_P = C.POINTER
+_u8, _i32, _i64, _f32, _f64 = C.c_uint8, C.c_int32, C.c_int64, C.c_float, C.c_double
+
+# name -> (restype, argtypes); must list every symbol include/canvasgpu.h declares
+SIGNATURES = {
+    "cg_create": (C.c_int, [C.c_int, _P(C.c_void_p)]),
+    "cg_destroy": (None, [C.c_void_p]),
+    "cg_last_error": (C.c_char_p, [C.c_void_p]),
+    "cg_describe": (C.c_char_p, [C.c_void_p]),
+    "cg_host_alloc": (C.c_void_p, [C.c_size_t]),
+    "cg_host_free": (None, [C.c_void_p]),
+    "cg_last_kernel_ms": (C.c_double, [C.c_void_p]),
+    "cg_last_launches": (C.c_int, [C.c_void_p]),
+    "cg_clean": (C.c_int, [C.c_void_p, _P(CleanOpts), _i64, _P(_u8), _P(_u8), _P(_u8), C.c_int,
+                           _P(_i32), _P(_i32), _P(_f32), _P(_u8), _P(_i64), _P(_i32), _P(_f32),
+                           _P(_f64), _P(C.c_int)]),
+    "cg_partition_wavelet": (C.c_int, [C.c_void_p, _P(WaveletOpts), C.c_int, _P(_i64), _P(_f64),
+                                       _P(_i32), _P(_i32), _P(_f64), _P(C.c_int), _P(_f64),
+                                       _P(C.c_int), _P(_f64)]),
+    "cg_partition_wavelet_shard": (C.c_int, [C.c_void_p, _P(WaveletOpts), C.c_int, _P(_i64),
+                                             _P(_f64), _P(_u8), _P(_i32), _P(_i32), _P(_f64),
+                                             _P(C.c_int), _P(_f64), _P(C.c_int), _P(_f64)]),
+    "cg_clean_partition_wavelet": (C.c_int, [C.c_void_p, _P(CleanOpts), _P(WaveletOpts), _i64,
+                                             _P(_u8), _P(_u8), _P(_u8), C.c_int, _P(_i32), _P(_i32),
+                                             _P(_f32), _P(_u8), _P(_i64), _P(_i32), _P(_f32),
+                                             _P(_f64), _P(C.c_int), _P(_i64), _P(_i32), _P(_i32),
+                                             _P(_f64), _P(C.c_int), _P(_f64), _P(C.c_int), _P(_f64)]),
+    "cg_normalize_apply": (C.c_int, [C.c_void_p, C.c_int, _i64, _P(_f32), _P(_u8), _P(_f64),
+                                     _P(_f64), _P(_f32), C.c_int, _P(_f64)]),
+}
+
+_lib = None
+
+
+def load():
+    """Load the shared library and attach signatures.  Raises if it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise CanvasGpuError(CG_ERR_CUDA, f"{LIB_PATH} is missing: run `python -m canvas_b200.build` "
+                                 "(__graft_entry__.build()); there is no CPU fallback")
+        lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)  # AttributeError if the symbol is not exported
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+def _ptr(a, t):
+    return a.ctypes.data_as(_P(t))
+
+
+class PinnedPool:
+    """numpy arrays over page-locked memory from cg_host_alloc."""
+
+    def __init__(self, lib):
+        self._lib = lib
+        self._blocks = []
+
+    def empty(self, n, dtype):
+        dtype = np.dtype(dtype)
+        nbytes = max(1, int(n) * dtype.itemsize)
+        p = self._lib.cg_host_alloc(nbytes)
+        if not p:
+            raise CanvasGpuError(CG_ERR_CUDA, "cg_host_alloc failed")
+        self._blocks.append(p)
+        buf = (C.c_char * nbytes).from_address(p)
+        return np.frombuffer(buf, dtype=dtype, count=int(n))
+
+    def array(self, src, dtype=None):
+        src = np.asarray(src, dtype=dtype)
+        a = self.empty(src.size, src.dtype)
+        a[...] = src.ravel()
+        return a
+
+    def close(self):
+        for p in self._blocks:
+            self._lib.cg_host_free(p)
+        self._blocks = []
+
+
+class Engine:
+    """One cg_ctx (one GPU)."""
+
+    def __init__(self, device=0):
+        self.lib = load()
+        h = C.c_void_p()
+        rc = self.lib.cg_create(device, C.byref(h))
+        if rc != CG_OK or not h:
+            raise CanvasGpuError(rc, f"cg_create(device={device}) failed: no usable CUDA device "
+                                 "(libcanvasgpu has no CPU fallback)")
+        self.h = h
+        self.device = device
+        self.pinned = PinnedPool(self.lib)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.pinned.close()
+            self.lib.cg_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def describe(self):
+        return self.lib.cg_describe(self.h).decode()
+
+    def _check(self, rc):
+        if rc != CG_OK:
+            raise CanvasGpuError(rc, self.lib.cg_last_error(self.h).decode())
+
+    @property
+    def last_kernel_ms(self):
+        return self.lib.cg_last_kernel_ms(self.h)
+
+    @property
+    def last_launches(self):
+        return self.lib.cg_last_launches(self.h)
+
+    # ------------------------------------------------------------------ CanvasClean
+    def clean(self, chrom, is_autosome, is_chr_y, start, stop, count, gc, size_filter=True,
+              outlier_filter=True, gc_norm=True, gc_mode=0, want_local_sd=True, min_bins_per_gc=100,
+              out=None):
+        n = len(count)
+        chrom = np.ascontiguousarray(chrom, np.uint8)
+        is_autosome = np.ascontiguousarray(is_autosome, np.uint8)
+        is_chr_y = np.ascontiguousarray(is_chr_y, np.uint8)
+        start = np.ascontiguousarray(start, np.int32)
+        stop = np.ascontiguousarray(stop, np.int32)
+        count = np.ascontiguousarray(count, np.float32)
+        gc = np.ascontiguousarray(gc, np.uint8)
+        o = CleanOpts(int(size_filter), int(outlier_filter), int(gc_norm), int(gc_mode),
+                      int(want_local_sd), int(min_bins_per_gc))
+        if out is None:
+            kept = np.empty(max(n, 1), np.int32)
+            cnt = np.empty(max(n, 1), np.float32)
+        else:
+            kept, cnt = out
+        n_out = _i64(0)
+        lsd = _f64(0)
+        skipped = C.c_int(0)
+        rc = self.lib.cg_clean(self.h, C.byref(o), n, _ptr(chrom, _u8), _ptr(is_autosome, _u8),
+                               _ptr(is_chr_y, _u8), len(is_autosome), _ptr(start, _i32),
+                               _ptr(stop, _i32), _ptr(count, _f32), _ptr(gc, _u8), C.byref(n_out),
+                               _ptr(kept, _i32), _ptr(cnt, _f32), C.byref(lsd), C.byref(skipped))
+        self._check(rc)
+        k = n_out.value
+        return {"kept_index": kept[:k], "count": cnt[:k], "local_sd": lsd.value,
+                "gc_norm_skipped": bool(skipped.value)}
+
+    # ------------------------------------------------------------------ CanvasPartition (wavelets)
+    def partition_wavelet(self, chrom_off, coverage, is_germline=True, mad_factor=5.0,
+                          thr_lower=0.05, thr_upper=80.0, min_size=10, evenness_window=100000,
+                          chrom_selected=None, out=None):
+        chrom_off = np.ascontiguousarray(chrom_off, np.int64)
+        coverage = np.ascontiguousarray(coverage, np.float64)
+        nc = len(chrom_off) - 1
+        n = int(chrom_off[-1])
+        o = WaveletOpts(int(is_germline), mad_factor, thr_lower, thr_upper, min_size, evenness_window)
+        if out is None:
+            n_bp = np.zeros(max(nc, 1), np.int32)
+            bp = np.zeros(max(n, 1), np.int32)
+        else:
+            n_bp, bp = out
+        ev, cv = _f64(0), _f64(0)
+        ev_ok, cv_has = C.c_int(0), C.c_int(0)
+        f3 = np.zeros(9, np.float64)
+        if chrom_selected is None:
+            rc = self.lib.cg_partition_wavelet(self.h, C.byref(o), nc, _ptr(chrom_off, _i64),
+                                               _ptr(coverage, _f64), _ptr(n_bp, _i32), _ptr(bp, _i32),
+                                               C.byref(ev), C.byref(ev_ok), C.byref(cv),
+                                               C.byref(cv_has), _ptr(f3, _f64))
+        else:
+            sel = np.ascontiguousarray(chrom_selected, np.uint8)
+            rc = self.lib.cg_partition_wavelet_shard(self.h, C.byref(o), nc, _ptr(chrom_off, _i64),
+                                                     _ptr(coverage, _f64), _ptr(sel, _u8),
+                                                     _ptr(n_bp, _i32), _ptr(bp, _i32), C.byref(ev),
+                                                     C.byref(ev_ok), C.byref(cv), C.byref(cv_has),
+                                                     _ptr(f3, _f64))
+        self._check(rc)
+        bps = [bp[chrom_off[c]:chrom_off[c] + n_bp[c]].copy() for c in range(nc)]
+        return {"breakpoints": bps, "evenness": ev.value if ev_ok.value else None,
+                "cv": cv.value if cv_has.value else None, "factor_of_three": f3}
+
+    # ------------------------------------------------------------------ stand-alone K8
+    def normalize_apply(self, count, gc, median_by_gc, global_median, repeats=1):
+        count = np.ascontiguousarray(count, np.float32)
+        gc = np.ascontiguousarray(gc, np.uint8)
+        batch, n = count.shape
+        med = np.ascontiguousarray(median_by_gc, np.float64).reshape(batch, 101)
+        gmed = np.ascontiguousarray(global_median, np.float64).reshape(batch)
+        out = np.empty_like(count)
+        ms = _f64(0)
+        rc = self.lib.cg_normalize_apply(self.h, batch, n, _ptr(count, _f32), _ptr(gc, _u8),
+                                         _ptr(med, _f64), _ptr(gmed, _f64), _ptr(out, _f32),
+                                         repeats, C.byref(ms))
+        self._check(rc)
+        return out, ms.value

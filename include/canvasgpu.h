@@ -1,0 +1,143 @@
+/* libcanvasgpu — C-ABI of the B200-native coverage-to-segments engine.
+ *
+ * Drop-in boundary for the numeric blocks of the Illumina/canvas module executables
+ * (reference @ v1.40.0).  The reference has no FFI: its only interface is "process + gzip-TSV file"
+ * (Src/Canvas/CanvasClean/CanvasClean.cs:415-533, Src/Canvas/CanvasPartition/CanvasPartition.cs:24-187).
+ * Each entry point below replaces the in-memory computation between a module's file reader and its
+ * file writer; the C# hosts keep parsing flags and files and call these through [DllImport]
+ * (binding shown in INTEGRATION.md).
+ *
+ * Conventions
+ *  - every function returns 0 on success, <0 on error (CG_ERR_*); cg_last_error() gives the text;
+ *  - all pointers are HOST memory owned by the caller; the library copies host<->device inside the
+ *    call and never keeps a pointer after returning.  Buffers obtained from cg_host_alloc() are
+ *    page-locked, which makes those copies run at PCIe speed;
+ *  - outputs are caller-allocated at worst-case capacity (documented per argument);
+ *  - one cg_ctx per GPU; a ctx is not thread-safe; different ctxs may be used concurrently;
+ *  - calls are synchronous.  There is no CPU fallback: without a CUDA device cg_create fails.
+ */
+#ifndef CANVASGPU_H
+#define CANVASGPU_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct cg_ctx cg_ctx;
+
+enum {
+    CG_OK = 0,
+    CG_ERR_CUDA = -1,        /* CUDA runtime failure */
+    CG_ERR_ARG = -2,         /* invalid argument */
+    CG_ERR_UNSORTED = -3,    /* chromosome ids not grouped in non-decreasing runs */
+    CG_ERR_UNSUPPORTED = -4, /* option not implemented by this build */
+    CG_ERR_CAPACITY = -5     /* internal work queue overflow */
+};
+
+int cg_create(int device, cg_ctx** out);
+void cg_destroy(cg_ctx* ctx);
+const char* cg_last_error(cg_ctx* ctx);
+/* library + device description, e.g. "canvasgpu 0.1 sm_100 NVIDIA B200 148 SMs" */
+const char* cg_describe(cg_ctx* ctx);
+
+/* Page-locked host buffers (optional; plain malloc'ed memory is accepted everywhere). */
+void* cg_host_alloc(size_t bytes);
+void cg_host_free(void* p);
+
+/* Device time (ms, CUDA events on the ctx stream) of the kernels of the last call, excluding the
+ * host<->device copies; and the number of kernel launches it made. */
+double cg_last_kernel_ms(cg_ctx* ctx);
+int cg_last_launches(cg_ctx* ctx);
+
+/* ---------------------------------------------------------------------------------------------
+ * CanvasClean — replaces CanvasClean.Main between CanvasIO.ReadFromTextFile (CanvasClean.cs:474)
+ * and CanvasIO.WriteToTextFile (:530): RemoveBigBins :328-355, RemoveOutliers :387-413,
+ * GetLocalStandardDeviation :268-298, RemoveBinsWithExtremeGC :207-237, NormalizeByGC :163-196,
+ * NormalizeVarianceByGC :34-97, RemoveBinsWithExtremeLocalSD :308-322.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+    int size_filter;     /* -s|filtsize */
+    int outlier_filter;  /* -r|outliers */
+    int gc_norm;         /* -g|gcnorm */
+    int gc_mode;         /* -m|mode: 0 MedianByGC (default), 1 LOESS */
+    int want_local_sd;   /* --local-sd-metric-file given */
+    int min_bins_per_gc; /* -w|weightedmedian, default 100 */
+} cg_clean_opts;
+
+/* chrom[i]: dense id of the chromosome run bin i belongs to, in file order (non-decreasing);
+ * chrom_is_autosome / chrom_is_chrY: [n_chrom] flags decided by the host from the names
+ * (GenomeMetadata.SequenceMetadata.IsAutosome; LoessGCNormalizer.cs:52-53).
+ * Outputs: *n_out surviving bins; kept_index[0..n_out) their positions in the input (ascending);
+ * count_out[0..n_out) their normalised counts; *local_sd the "#localSD" metric (-1 when not
+ * computed, CanvasClean.cs:489); *gc_norm_skipped set when every bin was GC-filtered and
+ * normalisation was skipped (:502-505).  kept_index and count_out need capacity n. */
+int cg_clean(cg_ctx* ctx, const cg_clean_opts* opts, int64_t n, const uint8_t* chrom,
+             const uint8_t* chrom_is_autosome, const uint8_t* chrom_is_chrY, int n_chrom,
+             const int32_t* start, const int32_t* stop, const float* count, const uint8_t* gc,
+             int64_t* n_out, int32_t* kept_index, float* count_out, double* local_sd,
+             int* gc_norm_skipped);
+
+/* ---------------------------------------------------------------------------------------------
+ * CanvasPartition, wavelets — replaces WaveletsRunner.Run (WaveletsRunner.cs:52-72):
+ * GetCoverageVariability (Segmentation.cs:309-347), FactorOfThreeCoverageVariabilities (:364-429),
+ * GetEvennessScore (:260-297) and, per chromosome, WaveletSegmentation.HaarWavelets
+ * (WaveletSegmentation.cs:385-426).  Breakpoint -> segment conversion (Segmentation.cs:83-125) and
+ * SegmentationResultsProcessor stay on the host.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+    int is_germline;     /* -g */
+    double mad_factor;   /* CanvasPartitionParameters.MadFactor (5.0) */
+    double thr_lower;    /* ThresholdLowerMaf (0.05), WaveletsRunner.cs:35 */
+    double thr_upper;    /* 80 */
+    int min_size;        /* WaveletsRunnerParams.MinSize (10) */
+    int evenness_window; /* EvennessScoreWindow (100000) */
+} cg_wavelet_opts;
+
+/* coverage: all chromosomes concatenated; chrom_off[n_chrom + 1] their offsets.
+ * Outputs: n_bp[c] breakpoints of chromosome c written at bp[chrom_off[c] ...] (bin indices within
+ * the chromosome, ascending, first is 0; n_bp[c] = 0 when the chromosome has <= min_size bins);
+ * *evenness (x100 score) valid when *evenness_ok; *cv valid when *cv_has_value;
+ * factor_of_three[9].  bp needs capacity chrom_off[n_chrom]. */
+int cg_partition_wavelet(cg_ctx* ctx, const cg_wavelet_opts* opts, int n_chrom,
+                         const int64_t* chrom_off, const double* coverage, int32_t* n_bp,
+                         int32_t* bp, double* evenness, int* evenness_ok, double* cv,
+                         int* cv_has_value, double* factor_of_three);
+
+/* The same, for the chromosomes of one shard only (multi-GPU: each rank passes the full coverage
+ * array so that the genome-wide scalars are identical everywhere, and a 0/1 mask of the chromosomes
+ * it segments; n_bp of unselected chromosomes is 0). */
+int cg_partition_wavelet_shard(cg_ctx* ctx, const cg_wavelet_opts* opts, int n_chrom,
+                               const int64_t* chrom_off, const double* coverage,
+                               const uint8_t* chrom_selected, int32_t* n_bp, int32_t* bp,
+                               double* evenness, int* evenness_ok, double* cv, int* cv_has_value,
+                               double* factor_of_three);
+
+/* Clean followed by wavelet partition without leaving the device between the two: the cleaned
+ * counts are rounded exactly as the .cleaned file round trip does (IO.cs:21 "{3:F2}" then
+ * Convert.ToDouble, CanvasSegment.cs:1147) before segmentation.  Outputs of both stages as above;
+ * chrom_off_out[n_chrom + 1] receives the per-chromosome offsets of the surviving bins. */
+int cg_clean_partition_wavelet(cg_ctx* ctx, const cg_clean_opts* copts, const cg_wavelet_opts* wopts,
+                               int64_t n, const uint8_t* chrom, const uint8_t* chrom_is_autosome,
+                               const uint8_t* chrom_is_chrY, int n_chrom, const int32_t* start,
+                               const int32_t* stop, const float* count, const uint8_t* gc,
+                               int64_t* n_out, int32_t* kept_index, float* count_out,
+                               double* local_sd, int* gc_norm_skipped, int64_t* chrom_off_out,
+                               int32_t* n_bp, int32_t* bp, double* evenness, int* evenness_ok,
+                               double* cv, int* cv_has_value, double* factor_of_three);
+
+/* ---------------------------------------------------------------------------------------------
+ * Stand-alone normalise-apply stream (the kernel BASELINE.json's roofline target names):
+ * count_out[i] = (float)(global_median * (double)count[i] / median_by_gc[gc[i]]) when the bucket
+ * median is > 0, else count[i] (CanvasClean.cs:190-195).  `batch` independent samples of n bins laid
+ * out back to back; medians are [batch][101], global_median [batch].  Used by bench.py to measure
+ * the kernel on arrays larger than L2; *kernel_ms returns its device time.
+ * ------------------------------------------------------------------------------------------- */
+int cg_normalize_apply(cg_ctx* ctx, int batch, int64_t n, const float* count, const uint8_t* gc,
+                       const double* median_by_gc, const double* global_median, float* count_out,
+                       int repeats, double* kernel_ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,142 @@
+"""cg_clean (CUDA, through the C-ABI) against the oracle's restatement of CanvasClean.
+Bit-exact: kept bins, normalised counts (float32) and the local-SD metric (float64)."""
+import numpy as np
+import pytest
+
+from canvas_b200 import synth
+from oracle import pyoracle as ora
+
+pytestmark = pytest.mark.gpu
+
+
+def _run_both(engine, s, **kw):
+    a = engine.clean(s.chrom, s.is_autosome, s.is_chr_y, s.start, s.stop, s.count, s.gc, **kw)
+    b = ora.clean(s.chrom, s.is_autosome, s.is_chr_y, s.start, s.stop, s.count, s.gc, **kw)
+    return a, b
+
+
+def _assert_same(a, b):
+    assert len(a["kept_index"]) == len(b["kept_index"]), (len(a["kept_index"]), len(b["kept_index"]))
+    assert np.array_equal(a["kept_index"], b["kept_index"])
+    bad = np.nonzero(a["count"].view(np.uint32) != b["count"].view(np.uint32))[0]
+    assert len(bad) == 0, (len(bad), a["count"][bad[:5]], b["count"][bad[:5]])
+    assert a["gc_norm_skipped"] == b["gc_norm_skipped"]
+    if np.isnan(b["local_sd"]):
+        assert np.isnan(a["local_sd"])
+    else:
+        assert a["local_sd"] == b["local_sd"], (a["local_sd"], b["local_sd"])
+
+
+def test_chr20_config1(engine):
+    # BASELINE config 1: chr20 at 1 kb (~63k bins): local-SD on (>= 50000), variance step off
+    s = synth.make_sample(config=1, chromosomes=["chr20"])
+    a, b = _run_both(engine, s)
+    _assert_same(a, b)
+    assert b["local_sd"] > 0
+
+
+def test_scaled_genome_all_flag_combinations(engine):
+    s = synth.make_sample(config=2, sample=3, scale=0.08)  # ~250k bins, 24 chromosomes
+    for size_filter in (True, False):
+        for outlier_filter in (True, False):
+            for gc_norm in (True, False):
+                for want in (True, False):
+                    a, b = _run_both(engine, s, size_filter=size_filter, outlier_filter=outlier_filter,
+                                     gc_norm=gc_norm, want_local_sd=want)
+                    _assert_same(a, b)
+
+
+def test_full_genome_config2(engine):
+    # BASELINE config 2: ~3.1M bins; exercises the > 500000-bin variance branch
+    s = synth.make_sample(config=2)
+    a, b = _run_both(engine, s)
+    _assert_same(a, b)
+    assert len(a["kept_index"]) > 2_900_000
+
+
+def test_variance_normalisation_fires(engine):
+    # inflate the spread of a few GC buckets so NormalizeVarianceByGC rescales and the second
+    # NormalizeByGC runs (CanvasClean.cs:512-517)
+    s = synth.make_sample(config=2, sample=1, scale=0.25)
+    rng = np.random.default_rng(7)
+    hot = (s.gc >= 44) & (s.gc <= 47)
+    noise = rng.normal(0, 60, len(s)).astype(np.float32)
+    s.count = np.where(hot, np.maximum(0, s.count + noise), s.count).astype(np.float32)
+    a, b = _run_both(engine, s)
+    _assert_same(a, b)
+    # the oracle without the variance branch gives something else: the branch really ran
+    c = ora.clean(s.chrom, s.is_autosome, s.is_chr_y, s.start, s.stop, s.count, s.gc, want_local_sd=False)
+    common = np.intersect1d(c["kept_index"], b["kept_index"], return_indices=True)
+    assert not np.array_equal(c["count"][common[1]], b["count"][common[2]])
+
+
+def test_ffpe_like_sample_drops_local_sd_windows(engine):
+    # noisy stretches push the local-SD average above 5 so RemoveBinsWithExtremeLocalSD removes bins
+    s = synth.make_sample(config=2, sample=2, scale=0.1)
+    rng = np.random.default_rng(11)
+    cnt = s.count.copy()
+    for c in range(len(s.names)):
+        idx = np.nonzero(s.chrom == c)[0]
+        half = idx[: len(idx) // 2]
+        cnt[half] = np.maximum(0, cnt[half] + rng.normal(0, 45, len(half))).astype(np.float32)
+    s.count = np.rint(cnt).astype(np.float32)
+    a, b = _run_both(engine, s, outlier_filter=False)
+    _assert_same(a, b)
+    assert b["local_sd"] > 5.0
+    plain = ora.clean(s.chrom, s.is_autosome, s.is_chr_y, s.start, s.stop, s.count, s.gc,
+                      outlier_filter=False, want_local_sd=False)
+    assert len(b["kept_index"]) < len(plain["kept_index"])
+
+
+def test_edge_cases(engine):
+    names = ["chr1", "chrX"]
+    for n in (0, 1, 2, 3, 49, 50, 101, 5000):
+        rng = np.random.default_rng(n)
+        chrom = np.sort(rng.integers(0, 2, n)).astype(np.uint8)
+        start = (np.arange(n) * 1000).astype(np.int32)
+        stop = start + 1000 + (rng.integers(0, 3, n) * 500).astype(np.int32)
+        count = rng.poisson(100, n).astype(np.float32)
+        gc = np.full(n, 40, np.uint8)  # one bucket so the >= 100-bin rule is predictable
+        s = synth.Sample(names, chrom, start, stop, count, gc)
+        for kw in ({}, {"gc_norm": False}, {"size_filter": False, "outlier_filter": False}):
+            try:
+                a, b = _run_both(engine, s, **kw)
+            except Exception as e:  # weighted-quantile path is reported, not silently wrong
+                assert "weighted" in str(e), (n, kw, e)
+                continue
+            _assert_same(a, b)
+
+
+def test_all_zero_counts_and_constant_sizes(engine):
+    s = synth.make_sample(config=2, sample=4, scale=0.03)
+    s.count[:] = 0
+    s.stop = (s.start + 1000).astype(np.int32)
+    a, b = _run_both(engine, s)
+    _assert_same(a, b)
+
+
+def test_unsorted_chromosomes_rejected(engine):
+    from canvas_b200 import native
+    s = synth.make_sample(config=2, sample=5, scale=0.01)
+    s.chrom = s.chrom[::-1].copy()
+    with pytest.raises(native.CanvasGpuError) as e:
+        engine.clean(s.chrom, s.is_autosome, s.is_chr_y, s.start, s.stop, s.count, s.gc)
+    assert e.value.code == native.CG_ERR_UNSORTED
+
+
+def test_normalize_apply_stream_matches_formula(engine):
+    rng = np.random.default_rng(5)
+    batch, n = 3, 40_000
+    count = rng.poisson(100, (batch, n)).astype(np.float32)
+    gc = rng.integers(0, 101, (batch, n)).astype(np.uint8)
+    med = rng.uniform(50, 150, (batch, 101))
+    med[:, 7] = 0.0  # a disabled bucket leaves counts untouched
+    gmed = rng.uniform(90, 110, batch)
+    out, ms = engine.normalize_apply(count, gc, med, gmed, repeats=2)
+    exp = count.copy()
+    for b in range(batch):
+        m = med[b][gc[b]]
+        ok = m > 0
+        exp[b][ok] = (gmed[b] * count[b][ok].astype(np.float64) / m[ok]).astype(np.float32)
+    assert np.array_equal(out.view(np.uint32), exp.view(np.uint32))
+    assert ms > 0
