@@ -684,7 +684,10 @@ extern "C" int cg_clean(cg_ctx* ctx, const cg_clean_opts* opts, int64_t n, const
     *n_out = 0;
     *local_sd = -1.0;
     *gc_norm_skipped = 0;
-    if (n == 0) return CG_OK;
+    if (n == 0) {  // an empty list is "every bin GC-filtered" for the reference (:502-505)
+        *gc_norm_skipped = opts->gc_norm ? 1 : 0;
+        return CG_OK;
+    }
     if (!chrom || !start || !stop || !count || !gc || !kept_index || !count_out || (n_chrom > 0 && !chrom_is_autosome))
         return cg_fail(ctx, CG_ERR_ARG, "cg_clean: null array");
     CG_CUDA(ctx, cudaSetDevice(ctx->device));

@@ -101,7 +101,7 @@ __global__ void compact_count_kernel(Pred p, const int* __restrict__ n_ptr, int*
     if (threadIdx.x == 0) tile_counts[blockIdx.x] = total;
 }
 
-__global__ void compact_scan_kernel(int* __restrict__ tile_counts, int ntiles, int* __restrict__ total_out) {
+static __global__ void compact_scan_kernel(int* __restrict__ tile_counts, int ntiles, int* __restrict__ total_out) {
     __shared__ int s_carry;
     if (threadIdx.x == 0) s_carry = 0;
     __syncthreads();

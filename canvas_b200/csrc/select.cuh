@@ -137,27 +137,31 @@ inline size_t sel_scatter_smem(int nseg, bool priv) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// Histogram pass, contiguous segments: segment s owns elements [seg_off[s], seg_off[s+1]) of the
-// view; block (x, s) handles chunk x of segment s with all its group rows private in shared memory.
+// Histogram pass, contiguous segments: a host-built work list cuts every segment into chunks;
+// block b handles work[b] = {seg, lo, hi} with all group rows of that segment private in shared
+// memory.  Segments may overlap in the underlying arrays (windows and whole chromosomes).
 // View: __device__ bool get(long long i, int seg, K& key) const;   (false: skip element)
 // ---------------------------------------------------------------------------------------------
+struct SelWork {
+    int seg;
+    int pad;
+    long long lo, hi;
+};
+
 template <typename K, class View>
-__global__ void sel_hist_contig_kernel(View v, const long long* __restrict__ seg_off, long long chunk,
-                                       SelState<K> st, int shift, int first) {
+__global__ void sel_hist_contig_kernel(View v, const SelWork* __restrict__ work, SelState<K> st, int shift,
+                                       int first) {
     __shared__ unsigned s_hist[SEL_G * SEL_BINS];
     __shared__ K s_prefix[SEL_G];
-    const int s = blockIdx.y;
+    const SelWork w = work[blockIdx.x];
+    const int s = w.seg;
     const int ng = st.ngrp[s];
     if (ng == 0) return;
-    const long long lo = seg_off[s] + (long long)blockIdx.x * chunk;
-    const long long hi_seg = seg_off[s + 1];
-    if (lo >= hi_seg) return;
-    const long long hi = lo + chunk < hi_seg ? lo + chunk : hi_seg;
     for (int t = threadIdx.x; t < ng * SEL_BINS; t += blockDim.x) s_hist[t] = 0u;
     if (threadIdx.x < SEL_G) s_prefix[threadIdx.x] = st.gprefix[s * SEL_G + threadIdx.x];
     __syncthreads();
     const int hi_shift = shift + 8;
-    for (long long i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+    for (long long i = w.lo + threadIdx.x; i < w.hi; i += blockDim.x) {
         K key;
         if (!v.get(i, s, key)) continue;
         const int d = (int)((key >> shift) & (K)255);
@@ -282,17 +286,13 @@ inline void sel_run_scatter(cg_ctx* ctx, const View& v, SelState<K>& st, long lo
 }
 
 template <typename K, class View>
-inline void sel_run_contig(cg_ctx* ctx, const View& v, const long long* seg_off_dev, long long max_seg_len,
-                           SelState<K>& st) {
+inline void sel_run_contig(cg_ctx* ctx, const View& v, const SelWork* work_dev, int nwork, SelState<K>& st) {
     const int bits = (int)sizeof(K) * 8;
     CG_LAUNCH(ctx, sel_begin_kernel<K>, div_up(st.nseg, 128), 128, 0, st);
-    if (max_seg_len <= 0) max_seg_len = 1;
-    // aim for >= ~4 blocks per SM overall without going below 2048 elements per block
-    long long chunk = 8192;
-    dim3 grid((unsigned)((max_seg_len + chunk - 1) / chunk), (unsigned)st.nseg);
+    if (nwork <= 0) return;
     for (int shift = bits - 8; shift >= 0; shift -= 8) {
         int first = shift == bits - 8;
-        CG_LAUNCH(ctx, (sel_hist_contig_kernel<K, View>), grid, 256, 0, v, seg_off_dev, chunk, st, shift, first);
+        CG_LAUNCH(ctx, (sel_hist_contig_kernel<K, View>), nwork, 256, 0, v, work_dev, st, shift, first);
         CG_LAUNCH(ctx, sel_resolve_kernel<K>, div_up((long long)st.nseg * 32, 256), 256, 0, st, shift,
                   shift == 0);
     }

@@ -1,14 +1,428 @@
-// cg_partition_wavelet — placeholder until the wavelet kernels land.
-#include "common.cuh"
+// cg_partition_wavelet / cg_partition_wavelet_shard / cg_clean_partition_wavelet
+// (reference WaveletsRunner.Run, WaveletsRunner.cs:52-139).
+#include <cmath>
 
-extern "C" int cg_partition_wavelet(cg_ctx* ctx, const cg_wavelet_opts*, int, const int64_t*, const double*, int32_t*,
-                                    int32_t*, double*, int*, double*, int*, double*) {
-    return cg_fail(ctx, CG_ERR_UNSUPPORTED, "cg_partition_wavelet: not built yet");
+#include "clean.cuh"
+#include "wavelet.cuh"
+#include "wavelet_decompose.cuh"
+#include "wavelet_finish.cuh"
+#include "wavelet_scalars.cuh"
+
+namespace {
+
+struct WvPlan {
+    int n_chrom = 0;
+    long long N = 0;
+    std::vector<long long> off;
+    WvSegTable t{};
+    std::vector<long long> seg_len;
+    std::vector<SelWork> work;       // select work list (coverage windows, chromosomes, f3 pools)
+    std::vector<WvEvWork> ev_work;
+    std::vector<WvScanTile> tiles;
+    std::vector<int> tile_first;
+    WvF3Level f3lv[WV_F3_LEVELS];
+    long long f3_cnt[WV_F3_LEVELS];
+    long long f3_off[WV_F3_LEVELS];  // offset of level r's pool in cmad/tmed
+    long long f3_total = 0;
+    int f3_levels_run = 0;
+    int window = 100000;
+    int cv_possible = 0;
+};
+
+constexpr long long SEL_CHUNK = 8192;
+
+void add_work(std::vector<SelWork>& w, int seg, long long lo, long long hi) {
+    for (long long a = lo; a < hi; a += SEL_CHUNK) w.push_back(SelWork{seg, 0, a, std::min(hi, a + SEL_CHUNK)});
 }
-extern "C" int cg_partition_wavelet_shard(cg_ctx* ctx, const cg_wavelet_opts*, int, const int64_t*, const double*,
-                                          const uint8_t*, int32_t*, int32_t*, double*, int*, double*, int*, double*) {
-    return cg_fail(ctx, CG_ERR_UNSUPPORTED, "cg_partition_wavelet_shard: not built yet");
+
+void make_plan(WvPlan& pl, int n_chrom, const int64_t* chrom_off, int window) {
+    pl.n_chrom = n_chrom;
+    pl.off.assign(chrom_off, chrom_off + n_chrom + 1);
+    pl.N = pl.off[n_chrom];
+    pl.window = window;
+    pl.cv_possible = (pl.N >= 10LL * window) ? 1 : 0;  // Segmentation.cs:311
+    // windows: for (idx = 0; idx < len - w; idx += w)  (Segmentation.cs:281, :338)
+    auto nwin = [](long long len, long long w) { return len >= 1 ? (len - 1) / w : 0LL; };
+    long long n10 = 0, n100 = 0;
+    for (int c = 0; c < n_chrom; c++) {
+        long long len = pl.off[c + 1] - pl.off[c];
+        n10 += nwin(len, WV_WINDOW_IQR);
+        n100 += nwin(len, window);
+    }
+    WvSegTable& t = pl.t;
+    t.n_w10 = (int)n10; t.n_w100 = (int)n100; t.n_chrom = n_chrom;
+    t.base_w10 = 0; t.base_w100 = t.n_w10; t.base_chrom = t.base_w100 + t.n_w100;
+    t.base_f3 = t.base_chrom + n_chrom; t.base_ev10 = t.base_f3 + WV_F3_LEVELS; t.base_ev100 = t.base_ev10 + 1;
+    t.base_r10 = t.base_ev100 + 1; t.base_r100 = t.base_r10 + 1; t.nseg = t.base_r100 + 1;
+    pl.seg_len.assign(t.nseg, 0);
+    pl.work.clear();
+    pl.ev_work.clear();
+    int s10 = 0, s100 = 0;
+    for (int c = 0; c < n_chrom; c++) {
+        long long o = pl.off[c], len = pl.off[c + 1] - o;
+        for (long long idx = 0; idx < len - WV_WINDOW_IQR; idx += WV_WINDOW_IQR) {
+            int seg = t.base_w10 + s10;
+            pl.seg_len[seg] = WV_WINDOW_IQR;
+            add_work(pl.work, seg, o + idx, o + idx + WV_WINDOW_IQR);
+            pl.ev_work.push_back(WvEvWork{o + idx, WV_WINDOW_IQR - 1, s10, 0, 0});
+            s10++;
+        }
+        for (long long idx = 0; idx < len - window; idx += window) {
+            int seg = t.base_w100 + s100;
+            pl.seg_len[seg] = window;
+            add_work(pl.work, seg, o + idx, o + idx + window);
+            pl.ev_work.push_back(WvEvWork{o + idx, window - 1, s100, 1, 0});
+            s100++;
+        }
+        pl.seg_len[t.base_chrom + c] = len;
+        add_work(pl.work, t.base_chrom + c, o, o + len);
+    }
+    // factor-of-three cascade
+    std::vector<long long> cur_len(n_chrom), cur_off(n_chrom);
+    for (int c = 0; c < n_chrom; c++) { cur_len[c] = pl.off[c + 1] - pl.off[c]; cur_off[c] = pl.off[c]; }
+    long long pool = 0;
+    pl.f3_levels_run = 0;
+    for (int r = 0; r < WV_F3_LEVELS; r++) {
+        long long cnt = 0;
+        pl.f3_off[r] = pool;
+        for (int c = 0; c < n_chrom; c++) {
+            long long m = cur_len[c] / 3;
+            pl.f3lv[r].src_off[c] = cur_off[c];
+            pl.f3lv[r].dst_off[c] = pool + cnt;
+            pl.f3lv[r].cnt[c] = (int)m;
+            cur_off[c] = pool + cnt;  // next level reads this level's medians (tmed array)
+            cur_len[c] = m;
+            cnt += m;
+        }
+        pl.f3_cnt[r] = cnt;
+        pl.seg_len[t.base_f3 + r] = cnt;
+        if (cnt > 0) add_work(pl.work, t.base_f3 + r, pool, pool + cnt);
+        pool += cnt;
+        pl.f3_levels_run = r + 1;
+        if (cnt < 50) {  // the reference stops here (Segmentation.cs:393-397)
+            for (int q = r + 1; q < WV_F3_LEVELS; q++) { pl.f3_cnt[q] = 0; pl.f3_off[q] = pool; }
+            break;
+        }
+    }
+    pl.f3_total = pool;
+    // evenness / ratio segments: whole arrays
+    if (t.n_w10 > 0) add_work(pl.work, t.base_ev10, 0, t.n_w10);
+    if (t.n_w100 > 0) add_work(pl.work, t.base_ev100, 0, t.n_w100);
+    if (t.n_w10 > 0) add_work(pl.work, t.base_r10, 0, t.n_w10);
+    if (t.n_w100 > 0) add_work(pl.work, t.base_r100, 0, t.n_w100);
+    // scan tiles
+    pl.tiles.clear();
+    pl.tile_first.assign(n_chrom + 1, 0);
+    for (int c = 0; c < n_chrom; c++) {
+        pl.tile_first[c] = (int)pl.tiles.size();
+        long long o = pl.off[c], len = pl.off[c + 1] - o;
+        for (long long a = 0; a < len; a += WV_SCAN_TILE)
+            pl.tiles.push_back(WvScanTile{o + a, (int)std::min<long long>(WV_SCAN_TILE, len - a), c});
+    }
+    pl.tile_first[n_chrom] = (int)pl.tiles.size();
 }
+
+struct WvDev {
+    double* cov;
+    long long* off;
+    unsigned char* selected;
+    double* pz;
+    // scalars
+    SelState<uint64_t> sel;
+    long long* seg_len;
+    SelWork* work;
+    WvEvWork* ev_work;
+    WvScanTile* tiles;
+    int* tile_first;
+    double* tsum;
+    WvF3Level* f3lv;
+    double *tmed, *cmad, *ev10, *ev100;
+    float *r10, *r100;
+    double *med, *mad, *sigma, *cand_thr, *log3;
+    WvCtl* ctl;
+    // decomposition
+    unsigned* lvlcnt;
+    int* depth;
+    UhNode* bn;
+    int bn_cap;
+    unsigned long long* tickets;
+    UhSmallTask* small;
+    int small_cap;
+    UhCand* cand;
+    int cand_cap;
+    // finish scratch
+    int *lvl_idx, *sv, *piece, *prelim, *lvl_first;
+    unsigned long long* svkey;
+    unsigned* bitmap;
+    double* rec;
+    int *n_bp, *bp;
+};
+
+size_t wv_workspace_bytes(const WvPlan& pl) {
+    const size_t N = (size_t)pl.N, C = (size_t)pl.n_chrom;
+    size_t s = 0;
+    s += arena_need(N, 8) + arena_need(C + 1, 8) + arena_need(C + 1, 1) + arena_need(N + C + 1, 8);
+    s += sel_state_bytes<uint64_t>(pl.t.nseg) + arena_need(pl.t.nseg, 8);
+    s += arena_need(pl.work.size() + 1, sizeof(SelWork)) + arena_need(pl.ev_work.size() + 1, sizeof(WvEvWork));
+    s += arena_need(pl.tiles.size() + 1, sizeof(WvScanTile)) + arena_need(C + 2, 4) + arena_need(pl.tiles.size() + 1, 8);
+    s += arena_need(WV_F3_LEVELS, sizeof(WvF3Level));
+    s += arena_need(pl.f3_total + 1, 8) * 2 + arena_need(pl.t.n_w10 + 1, 8) + arena_need(pl.t.n_w100 + 1, 8);
+    s += arena_need(pl.t.n_w10 + 1, 4) + arena_need(pl.t.n_w100 + 1, 4);
+    s += arena_need(pl.t.nseg, 8) * 2 + arena_need(C + 1, 8) * 2 + arena_need(32, 8) + arena_need(1, sizeof(WvCtl));
+    s += arena_need(N + 1, 4) + arena_need(C + 1, 4);
+    s += arena_need(N / 4 + 4096, sizeof(UhNode)) + arena_need(UH_QCAP, 8) + arena_need(N / 2 + C + 64, sizeof(UhSmallTask));
+    s += arena_need(N / 4 + 4096, sizeof(UhCand));
+    s += arena_need(N + 1, 4) * 5 + arena_need(N + 1, 8) * 2 + arena_need(N / 32 + C + 2, 4);
+    s += arena_need(C + 1, 4) + arena_need(N + 1, 4);
+    return s + (1 << 16);
+}
+
+int wv_alloc(cg_ctx* ctx, const WvPlan& pl, WvDev& d, double* cov_dev_existing) {
+    const size_t N = (size_t)pl.N, C = (size_t)pl.n_chrom;
+    d.cov = cov_dev_existing ? cov_dev_existing : arena_take<double>(ctx, N);
+    d.off = arena_take<long long>(ctx, C + 1);
+    d.selected = arena_take<unsigned char>(ctx, C + 1);
+    d.pz = arena_take<double>(ctx, N + C + 1);
+    bool ok = sel_state_alloc<uint64_t>(ctx, pl.t.nseg, d.sel);
+    d.seg_len = arena_take<long long>(ctx, pl.t.nseg);
+    d.work = arena_take<SelWork>(ctx, pl.work.size() + 1);
+    d.ev_work = arena_take<WvEvWork>(ctx, pl.ev_work.size() + 1);
+    d.tiles = arena_take<WvScanTile>(ctx, pl.tiles.size() + 1);
+    d.tile_first = arena_take<int>(ctx, C + 2);
+    d.tsum = arena_take<double>(ctx, pl.tiles.size() + 1);
+    d.f3lv = arena_take<WvF3Level>(ctx, WV_F3_LEVELS);
+    d.tmed = arena_take<double>(ctx, pl.f3_total + 1);
+    d.cmad = arena_take<double>(ctx, pl.f3_total + 1);
+    d.ev10 = arena_take<double>(ctx, pl.t.n_w10 + 1);
+    d.ev100 = arena_take<double>(ctx, pl.t.n_w100 + 1);
+    d.r10 = arena_take<float>(ctx, pl.t.n_w10 + 1);
+    d.r100 = arena_take<float>(ctx, pl.t.n_w100 + 1);
+    d.med = arena_take<double>(ctx, pl.t.nseg);
+    d.mad = arena_take<double>(ctx, pl.t.nseg);
+    d.sigma = arena_take<double>(ctx, C + 1);
+    d.cand_thr = arena_take<double>(ctx, C + 1);
+    d.log3 = arena_take<double>(ctx, 32);
+    d.ctl = arena_take<WvCtl>(ctx, 1);
+    d.lvlcnt = arena_take<unsigned>(ctx, N + 1);
+    d.depth = arena_take<int>(ctx, C + 1);
+    d.bn_cap = (int)(N / 4 + 4096);
+    d.bn = arena_take<UhNode>(ctx, d.bn_cap);
+    d.tickets = arena_take<unsigned long long>(ctx, UH_QCAP);
+    d.small_cap = (int)(N / 2 + C + 64);
+    d.small = arena_take<UhSmallTask>(ctx, d.small_cap);
+    d.cand_cap = (int)(N / 4 + 4096);
+    d.cand = arena_take<UhCand>(ctx, d.cand_cap);
+    d.lvl_idx = arena_take<int>(ctx, N + 1);
+    d.sv = arena_take<int>(ctx, N + 1);
+    d.piece = arena_take<int>(ctx, N + 1);
+    d.prelim = arena_take<int>(ctx, N + 1);
+    d.lvl_first = arena_take<int>(ctx, N + 1);
+    d.svkey = arena_take<unsigned long long>(ctx, N + 1);
+    d.rec = arena_take<double>(ctx, N + 1);
+    d.bitmap = arena_take<unsigned>(ctx, N / 32 + C + 2);
+    d.n_bp = arena_take<int>(ctx, C + 1);
+    d.bp = arena_take<int>(ctx, N + 1);
+    ok = ok && d.cov && d.off && d.selected && d.pz && d.seg_len && d.work && d.ev_work && d.tiles && d.tile_first &&
+         d.tsum && d.f3lv && d.tmed && d.cmad && d.ev10 && d.ev100 && d.r10 && d.r100 && d.med && d.mad && d.sigma &&
+         d.cand_thr && d.log3 && d.ctl && d.lvlcnt && d.depth && d.bn && d.tickets && d.small && d.cand && d.lvl_idx &&
+         d.sv && d.piece && d.prelim && d.lvl_first && d.svkey && d.rec && d.bitmap && d.n_bp && d.bp;
+    return ok ? CG_OK : cg_fail(ctx, CG_ERR_CUDA, "partition: device arena exhausted");
+}
+
+// Upload the plan tables (small) and enqueue the whole partition pipeline.  d.cov must already hold
+// the coverage on the device (or be filled by an earlier kernel on the same stream).
+int wv_enqueue(cg_ctx* ctx, const cg_wavelet_opts* o, const WvPlan& pl, WvDev& d, const unsigned char* selected_host) {
+    cudaStream_t s = ctx->stream;
+    const int C = pl.n_chrom;
+    const WvSegTable& t = pl.t;
+    // ---- plan tables.  Host vectors live until the caller synchronises the stream.
+    CG_CUDA(ctx, cudaMemcpyAsync(d.off, pl.off.data(), (C + 1) * 8, cudaMemcpyHostToDevice, s));
+    CG_CUDA(ctx, cudaMemcpyAsync(d.selected, selected_host, C, cudaMemcpyHostToDevice, s));
+    CG_CUDA(ctx, cudaMemcpyAsync(d.seg_len, pl.seg_len.data(), t.nseg * 8, cudaMemcpyHostToDevice, s));
+    if (!pl.work.empty()) CG_CUDA(ctx, cudaMemcpyAsync(d.work, pl.work.data(), pl.work.size() * sizeof(SelWork), cudaMemcpyHostToDevice, s));
+    if (!pl.ev_work.empty()) CG_CUDA(ctx, cudaMemcpyAsync(d.ev_work, pl.ev_work.data(), pl.ev_work.size() * sizeof(WvEvWork), cudaMemcpyHostToDevice, s));
+    if (!pl.tiles.empty()) CG_CUDA(ctx, cudaMemcpyAsync(d.tiles, pl.tiles.data(), pl.tiles.size() * sizeof(WvScanTile), cudaMemcpyHostToDevice, s));
+    CG_CUDA(ctx, cudaMemcpyAsync(d.tile_first, pl.tile_first.data(), (C + 1) * 4, cudaMemcpyHostToDevice, s));
+    CG_CUDA(ctx, cudaMemcpyAsync(d.f3lv, pl.f3lv, sizeof(WvF3Level) * WV_F3_LEVELS, cudaMemcpyHostToDevice, s));
+    // ceil(log(3^k) / log(3)) as the host's libm evaluates it (WaveletSegmentation.cs:224)
+    static double log3_tab[32];
+    {
+        double pw = 1.0;
+        for (int k = 0; k < 20; k++) { log3_tab[k] = std::ceil(std::log(pw) / std::log(3.0)); pw *= 3.0; }
+    }
+    CG_CUDA(ctx, cudaMemcpyAsync(d.log3, log3_tab, 20 * 8, cudaMemcpyHostToDevice, s));
+    CG_CUDA(ctx, cudaMemsetAsync(d.ctl, 0, sizeof(WvCtl), s));
+    CG_CUDA(ctx, cudaMemsetAsync(d.sel.hist, 0, (size_t)t.nseg * SEL_G * SEL_BINS * sizeof(unsigned), s));
+    CG_CUDA(ctx, cudaMemsetAsync(d.lvlcnt, 0, (size_t)(pl.N + 1) * sizeof(unsigned), s));
+    CG_CUDA(ctx, cudaMemsetAsync(d.depth, 0, (size_t)(C + 1) * sizeof(int), s));
+    CG_CUDA(ctx, cudaMemsetAsync(d.tickets, 0, (size_t)UH_QCAP * 8, s));
+    CG_CUDA(ctx, cudaMemsetAsync(d.small, 0xff, (size_t)d.small_cap * sizeof(UhSmallTask), s));
+    CG_CUDA(ctx, cudaMemsetAsync(d.n_bp, 0, (size_t)(C + 1) * sizeof(int), s));
+    CG_CUDA(ctx, cudaMemsetAsync(d.med, 0, (size_t)t.nseg * 8, s));
+    CG_CUDA(ctx, cudaMemsetAsync(d.mad, 0, (size_t)t.nseg * 8, s));
+    if (pl.N == 0) return CG_OK;
+
+    WvScalarParams sp;
+    sp.t = t;
+    sp.seg_len = d.seg_len;
+    for (int r = 0; r < WV_F3_LEVELS; r++) sp.f3_cnt[r] = pl.f3_cnt[r];
+    sp.n_total = pl.N;
+    sp.window = pl.window;
+    sp.cv_possible = pl.cv_possible;
+    sp.is_germline = o->is_germline;
+    sp.mad_factor = o->mad_factor;
+    sp.thr_lower = o->thr_lower;
+    sp.thr_upper = o->thr_upper;
+
+    // ---- prefix sums
+    const int ntiles = (int)pl.tiles.size();
+    if (ntiles > 0) {
+        CG_LAUNCH(ctx, wv_scan_tile_sum_kernel, ntiles, 256, 0, d.cov, d.tiles, d.tsum);
+        CG_LAUNCH(ctx, wv_scan_tile_offsets_kernel, div_up(C, 64), 64, 0, d.tsum, d.tile_first, C);
+        CG_LAUNCH(ctx, wv_scan_apply_kernel, ntiles, 256, 0, d.cov, d.tiles, d.tsum, d.off, d.pz);
+    }
+    // ---- factor-of-three cascade
+    int max_len = 1;
+    for (int c = 0; c < C; c++) max_len = std::max<long long>(max_len, pl.off[c + 1] - pl.off[c]);
+    for (int r = 0; r < pl.f3_levels_run; r++) {
+        if (pl.f3_cnt[r] == 0) break;
+        long long per = std::max<long long>(1, max_len / 3);
+        for (int q = 0; q < r; q++) per = std::max<long long>(1, per / 3);
+        dim3 grid((unsigned)std::min<long long>(256, (per + 255) / 256), (unsigned)C);
+        CG_LAUNCH(ctx, wv_triplet_kernel, grid, 256, 0, r == 0 ? d.cov : d.tmed, d.tmed, d.cmad, d.f3lv + r);
+    }
+    // ---- evenness per window
+    if (!pl.ev_work.empty())
+        CG_LAUNCH(ctx, wv_evenness_kernel, (int)pl.ev_work.size(), 256, 0, d.cov, d.ev_work, d.ev10, d.ev100, d.ctl);
+    // ---- order statistics, three dependent waves
+    const int nwork = (int)pl.work.size();
+    const int rq_grid = div_up(t.nseg, 128);
+    PartView pv{d.cov, d.cmad, d.ev10, d.ev100, d.r10, d.r100, nullptr, t};
+    CG_LAUNCH(ctx, wv_request_kernel, rq_grid, 128, 0, d.sel, sp, d.ctl, 1);
+    sel_run_contig<uint64_t, PartView>(ctx, pv, d.work, nwork, d.sel);
+    CG_LAUNCH(ctx, wv_median_finish_kernel, rq_grid, 128, 0, d.sel, d.med);
+    CG_LAUNCH(ctx, wv_evenness_finish_kernel, 1, 1, 0, d.sel, t, d.ctl);
+    CG_LAUNCH(ctx, wv_f3_finish_kernel, 1, 1, 0, sp, d.med, d.ctl);
+    PartView pv2 = pv;
+    pv2.center = d.med;
+    CG_LAUNCH(ctx, wv_request_kernel, rq_grid, 128, 0, d.sel, sp, d.ctl, 2);
+    sel_run_contig<uint64_t, PartView>(ctx, pv2, d.work, nwork, d.sel);
+    CG_LAUNCH(ctx, wv_median_finish_kernel, rq_grid, 128, 0, d.sel, d.mad);
+    if (pl.cv_possible) {
+        if (t.base_chrom > 0) CG_LAUNCH(ctx, wv_ratio_kernel, div_up(t.base_chrom, 128), 128, 0, t, d.med, d.mad, d.r10, d.r100);
+        CG_LAUNCH(ctx, wv_request_kernel, rq_grid, 128, 0, d.sel, sp, d.ctl, 3);
+        sel_run_contig<uint64_t, PartView>(ctx, pv, d.work, nwork, d.sel);
+    }
+    CG_LAUNCH(ctx, wv_cv_sigma_kernel, 1, 128, 0, d.sel, sp, d.med, d.mad, d.off, d.ctl, d.sigma, d.cand_thr);
+
+    // ---- decomposition
+    UhParams up;
+    up.x = d.cov; up.pz = d.pz; up.off = d.off; up.cand_thr = d.cand_thr; up.lvlcnt = d.lvlcnt; up.depth = d.depth;
+    up.bn = d.bn; up.bn_cap = d.bn_cap; up.tickets = d.tickets; up.small = d.small; up.small_cap = d.small_cap;
+    up.cand = d.cand; up.cand_cap = d.cand_cap; up.ctl = d.ctl;
+    CG_LAUNCH(ctx, uh_seed_kernel, 1, 32, 0, up, d.selected, C, o->min_size);
+    int occ = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, uh_decompose_kernel, UH_THREADS, 0);
+    if (occ < 1) occ = 1;
+    if (occ > 4) occ = 4;
+    int grid = ctx->num_sms * occ;
+    grid = (grid / 4) * 4;
+    if (grid < 4) grid = 4;
+    CG_LAUNCH(ctx, uh_decompose_kernel, grid, UH_THREADS, 0, up);
+
+    // ---- per-chromosome finish
+    FinParams fp;
+    fp.x = d.cov; fp.pz = d.pz; fp.off = d.off; fp.selected = d.selected; fp.cand = d.cand; fp.ctl = d.ctl;
+    fp.lvlcnt = d.lvlcnt; fp.depth = d.depth; fp.sigma = d.sigma; fp.chrom_median = d.med + t.base_chrom;
+    fp.log3_scale_tab = d.log3;
+    fp.is_germline = o->is_germline; fp.min_size = o->min_size; fp.n_chrom = C; fp.pad = 0;
+    fp.lvl_idx = d.lvl_idx; fp.sv = d.sv; fp.svkey = d.svkey; fp.bitmap = d.bitmap; fp.piece = d.piece; fp.rec = d.rec;
+    fp.prelim = d.prelim; fp.lvl_first = d.lvl_first; fp.n_bp = d.n_bp; fp.bp = d.bp;
+    if (C > 0) CG_LAUNCH(ctx, uh_finish_kernel, C, FIN_THREADS, 0, fp);
+    return CG_OK;
+}
+
+int wv_collect(cg_ctx* ctx, const WvPlan& pl, WvDev& d, int32_t* n_bp, int32_t* bp, double* evenness, int* evenness_ok,
+               double* cv, int* cv_has_value, double* factor_of_three) {
+    cudaStream_t s = ctx->stream;
+    const int C = pl.n_chrom;
+    WvCtl* h = (WvCtl*)ctx->pinned;
+    int* h_nbp = (int*)(ctx->pinned + 4096);
+    CG_CUDA(ctx, cudaMemcpyAsync(h, d.ctl, sizeof(WvCtl), cudaMemcpyDeviceToHost, s));
+    CG_CUDA(ctx, cudaMemcpyAsync(h_nbp, d.n_bp, (size_t)C * 4, cudaMemcpyDeviceToHost, s));
+    CG_CUDA(ctx, cudaStreamSynchronize(s));
+    CG_CUDA(ctx, cudaGetLastError());
+    if (h->overflow) return cg_fail(ctx, CG_ERR_CAPACITY, "partition: internal queue capacity exceeded");
+    // breakpoints: one copy per chromosome that has any (they are few and short)
+    for (int c = 0; c < C; c++) {
+        n_bp[c] = h_nbp[c];
+        if (h_nbp[c] > 0)
+            CG_CUDA(ctx, cudaMemcpyAsync(bp + pl.off[c], d.bp + pl.off[c], (size_t)h_nbp[c] * 4, cudaMemcpyDeviceToHost, s));
+    }
+    CG_CUDA(ctx, cudaStreamSynchronize(s));
+    *evenness = h->evenness;
+    *evenness_ok = h->evenness_ok;
+    *cv = h->cv;
+    *cv_has_value = h->cv_has_value;
+    for (int i = 0; i <= WV_F3_LEVELS; i++) factor_of_three[i] = h->f3[i];
+    return CG_OK;
+}
+
+int check_args(cg_ctx* ctx, const cg_wavelet_opts* opts, int n_chrom, const int64_t* chrom_off) {
+    if (!opts || n_chrom < 0 || n_chrom > WV_MAX_CHROM || !chrom_off) return cg_fail(ctx, CG_ERR_ARG, "partition: bad argument");
+    if (opts->evenness_window <= 0) return cg_fail(ctx, CG_ERR_ARG, "partition: evenness_window must be positive");
+    if (chrom_off[0] != 0) return cg_fail(ctx, CG_ERR_ARG, "partition: chrom_off[0] must be 0");
+    for (int c = 0; c < n_chrom; c++)
+        if (chrom_off[c + 1] < chrom_off[c]) return cg_fail(ctx, CG_ERR_ARG, "partition: chrom_off must be non-decreasing");
+    if (chrom_off[n_chrom] > 0x7fff0000LL) return cg_fail(ctx, CG_ERR_ARG, "partition: too many bins");
+    return CG_OK;
+}
+
+}  // namespace
+
+extern "C" int cg_partition_wavelet_shard(cg_ctx* ctx, const cg_wavelet_opts* opts, int n_chrom,
+                                          const int64_t* chrom_off, const double* coverage,
+                                          const uint8_t* chrom_selected, int32_t* n_bp, int32_t* bp,
+                                          double* evenness, int* evenness_ok, double* cv, int* cv_has_value,
+                                          double* factor_of_three) {
+    if (!ctx) return CG_ERR_ARG;
+    int rc = check_args(ctx, opts, n_chrom, chrom_off);
+    if (rc) return rc;
+    if (!n_bp || !bp || !evenness || !evenness_ok || !cv || !cv_has_value || !factor_of_three || (chrom_off[n_chrom] > 0 && !coverage))
+        return cg_fail(ctx, CG_ERR_ARG, "partition: null output");
+    ctx->launches = 0;
+    ctx->last_kernel_ms = 0;
+    CG_CUDA(ctx, cudaSetDevice(ctx->device));
+    WvPlan pl;
+    make_plan(pl, n_chrom, chrom_off, opts->evenness_window);
+    rc = arena_reserve(ctx, wv_workspace_bytes(pl));
+    if (rc) return rc;
+    WvDev d;
+    rc = wv_alloc(ctx, pl, d, nullptr);
+    if (rc) return rc;
+    std::vector<unsigned char> sel(n_chrom + 1, 1);
+    if (chrom_selected)
+        for (int c = 0; c < n_chrom; c++) sel[c] = chrom_selected[c] ? 1 : 0;
+    cudaStream_t s = ctx->stream;
+    if (pl.N > 0) CG_CUDA(ctx, cudaMemcpyAsync(d.cov, coverage, (size_t)pl.N * 8, cudaMemcpyHostToDevice, s));
+    CG_CUDA(ctx, cudaEventRecord(ctx->ev0, s));
+    rc = wv_enqueue(ctx, opts, pl, d, sel.data());
+    if (rc) { cudaStreamSynchronize(s); return rc; }
+    CG_CUDA(ctx, cudaEventRecord(ctx->ev1, s));
+    rc = wv_collect(ctx, pl, d, n_bp, bp, evenness, evenness_ok, cv, cv_has_value, factor_of_three);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+    ctx->last_kernel_ms = ms;
+    return rc;
+}
+
+extern "C" int cg_partition_wavelet(cg_ctx* ctx, const cg_wavelet_opts* opts, int n_chrom, const int64_t* chrom_off,
+                                    const double* coverage, int32_t* n_bp, int32_t* bp, double* evenness,
+                                    int* evenness_ok, double* cv, int* cv_has_value, double* factor_of_three) {
+    return cg_partition_wavelet_shard(ctx, opts, n_chrom, chrom_off, coverage, nullptr, n_bp, bp, evenness, evenness_ok,
+                                      cv, cv_has_value, factor_of_three);
+}
+
 extern "C" int cg_clean_partition_wavelet(cg_ctx* ctx, const cg_clean_opts*, const cg_wavelet_opts*, int64_t,
                                           const uint8_t*, const uint8_t*, const uint8_t*, int, const int32_t*,
                                           const int32_t*, const float*, const uint8_t*, int64_t*, int32_t*, float*,

@@ -1,0 +1,543 @@
+// Per-chromosome tail of HaarWavelets (WaveletSegmentation.cs:406-425), one CTA per chromosome:
+//   HardThresh :72-115 on the candidate nodes, GetSegments :174-185 evaluated only on the pieces
+//   delimited by surviving nodes, GetBreakpointsAfterHealingBadSplits :194-232, RefineSegments
+//   :237-258.  Range medians are exact (block-wide radix select over the L2-resident coverage).
+#pragma once
+#include "wavelet.cuh"
+
+constexpr int FIN_THREADS = 256;
+constexpr int FIN_SORT_SMEM = 1024;  // survivors sorted in shared memory up to this many
+constexpr int BMS_R = 24;            // requests of one block multi-select
+constexpr int BMS_X = 12;            // "extra" bins per request beyond the shared core range
+
+struct FinParams {
+    const double* x;           // coverage
+    const double* pz;          // prefix sums (for the smooth term)
+    const long long* off;
+    const unsigned char* selected;
+    const UhCand* cand;
+    const WvCtl* ctl;
+    const unsigned* lvlcnt;
+    const int* depth;
+    const double* sigma;       // [n_chrom]
+    const double* chrom_median;  // [n_chrom] Median(ratio)
+    const double* log3_scale_tab;  // unused slot (kept for layout stability)
+    int is_germline, min_size, n_chrom, pad;
+    // scratch, all indexed per chromosome at off[c]
+    int* lvl_idx;              // [N]   introsort permutation of the levels
+    int* sv;                   // [N]   candidate indices of the survivors
+    unsigned long long* svkey; // [N]   sort keys (level << 32 | start)
+    unsigned* bitmap;          // [N/32 + n_chrom] boundary bitmap, chromosome c at (off[c] >> 5) + c
+    int* piece;                // [N]   piece start positions
+    double* rec;               // [N]   reconstructed value per piece
+    int* prelim;               // [N]   preliminary breakpoints
+    int* lvl_first;            // [N]   first survivor of each distinct level
+    // outputs
+    int* n_bp;                 // [n_chrom]
+    int* bp;                   // [N] at off[c]
+};
+
+// ------------------------------------------------------------------------------------------------
+// .NET Core 2.0 Array.Sort<int>(indices, (a, b) => counts[b].CompareTo(counts[a])) — the introspective
+// sort of ArraySortHelper<T> restated (unstable: the order of equal counts is part of the result).
+// ------------------------------------------------------------------------------------------------
+struct LevelSorter {
+    int* k;
+    const unsigned* counts;
+    __device__ int cmp(int a, int b) const {
+        const unsigned ca = counts[a], cb = counts[b];
+        return cb < ca ? -1 : (cb > ca ? 1 : 0);
+    }
+    __device__ void swap(int i, int j) { int t = k[i]; k[i] = k[j]; k[j] = t; }
+    __device__ void swap_if_greater(int a, int b) {
+        if (a != b && cmp(k[a], k[b]) > 0) swap(a, b);
+    }
+    __device__ void insertion(int lo, int hi) {
+        for (int i = lo; i < hi; i++) {
+            int j = i;
+            const int t = k[i + 1];
+            while (j >= lo && cmp(t, k[j]) < 0) { k[j + 1] = k[j]; j--; }
+            k[j + 1] = t;
+        }
+    }
+    __device__ void down_heap(int i, int n, int lo) {
+        const int d = k[lo + i - 1];
+        while (i <= n / 2) {
+            int child = 2 * i;
+            if (child < n && cmp(k[lo + child - 1], k[lo + child]) < 0) child++;
+            if (!(cmp(d, k[lo + child - 1]) < 0)) break;
+            k[lo + i - 1] = k[lo + child - 1];
+            i = child;
+        }
+        k[lo + i - 1] = d;
+    }
+    __device__ void heapsort(int lo, int hi) {
+        const int n = hi - lo + 1;
+        for (int i = n / 2; i >= 1; i--) down_heap(i, n, lo);
+        for (int i = n; i > 1; i--) { swap(lo, lo + i - 1); down_heap(1, i - 1, lo); }
+    }
+    __device__ int partition(int lo, int hi) {
+        const int mid = lo + (hi - lo) / 2;
+        swap_if_greater(lo, mid);
+        swap_if_greater(lo, hi);
+        swap_if_greater(mid, hi);
+        const int pivot = k[mid];
+        swap(mid, hi - 1);
+        int left = lo, right = hi - 1;
+        while (left < right) {
+            while (cmp(k[++left], pivot) < 0) {}
+            while (cmp(pivot, k[--right]) < 0) {}
+            if (left >= right) break;
+            swap(left, right);
+        }
+        swap(left, hi - 1);
+        return left;
+    }
+    __device__ void sort(int n) {
+        if (n < 2) return;
+        int depth0 = 0;
+        for (int t = n; t >= 1; t /= 2) depth0++;
+        depth0 *= 2;
+        // explicit stack replaces the recursion on the right part
+        int st_lo[96], st_hi[96], st_d[96];
+        int sp = 0;
+        st_lo[0] = 0; st_hi[0] = n - 1; st_d[0] = depth0; sp = 1;
+        while (sp > 0) {
+            sp--;
+            int lo = st_lo[sp], hi = st_hi[sp], depth = st_d[sp];
+            while (hi > lo) {
+                const int size = hi - lo + 1;
+                if (size <= 16) {
+                    if (size == 2) { swap_if_greater(lo, hi); }
+                    else if (size == 3) { swap_if_greater(lo, hi - 1); swap_if_greater(lo, hi); swap_if_greater(hi - 1, hi); }
+                    else if (size > 3) insertion(lo, hi);
+                    break;
+                }
+                if (depth == 0) { heapsort(lo, hi); break; }
+                depth--;
+                const int pv = partition(lo, hi);
+                // the reference recurses into [pv+1, hi] first and then loops on [lo, pv-1]; the two
+                // ranges are disjoint, so deferring the left one instead gives the same permutation
+                if (sp < 96) { st_lo[sp] = lo; st_hi[sp] = pv - 1; st_d[sp] = depth; sp++; }
+                lo = pv + 1;
+            }
+        }
+    }
+};
+
+// ------------------------------------------------------------------------------------------------
+// Block multi-select: exact order statistics of up to BMS_R requests.  Request r asks for rank rk[r]
+// of the bins  core(range id) ∪ [xlo, xhi)  (a few extra bins right after the core).  All requests
+// that still share (range, prefix) share one histogram.  8 radix passes over the core ranges.
+// ------------------------------------------------------------------------------------------------
+struct BmsState {
+    unsigned hist[BMS_R][256];
+    unsigned long long gprefix[BMS_R];
+    int grange[BMS_R];
+    int ngroups;
+    int nranges;
+    int rlo[2], rhi[2];
+    int nreq;
+    int rgrp[BMS_R];
+    unsigned long long rk[BMS_R];
+    int xlo[BMS_R], xhi[BMS_R];
+    unsigned long long rkey[BMS_R];
+    int newgrp[BMS_R];
+};
+
+// caller (thread 0) fills nranges, rlo/rhi, nreq, rk, xlo/xhi and rgrp = range id; then all threads call
+__device__ void bms_run(BmsState& st, const double* __restrict__ x) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        st.ngroups = st.nranges;
+        for (int g = 0; g < st.nranges; g++) { st.gprefix[g] = 0ull; st.grange[g] = g; }
+    }
+    __syncthreads();
+    for (int shift = 56; shift >= 0; shift -= 8) {
+        const int ng = st.ngroups;
+        const bool first = shift == 56;
+        for (int t = threadIdx.x; t < ng * 256; t += blockDim.x) st.hist[t >> 8][t & 255] = 0u;
+        __syncthreads();
+        for (int r = 0; r < st.nranges; r++) {
+            const int lo = st.rlo[r], hi = st.rhi[r];
+            for (int i = lo + (int)threadIdx.x; i < hi; i += blockDim.x) {
+                const unsigned long long key = f64_key(x[i]);
+                const int d = (int)((key >> shift) & 255ull);
+                for (int g = 0; g < ng; g++)
+                    if (st.grange[g] == r && (first || ((key ^ st.gprefix[g]) >> (shift + 8)) == 0ull))
+                        atomicAdd(&st.hist[g][d], 1u);
+            }
+        }
+        __syncthreads();
+        // resolve: one thread per request walks its histogram merged with its extra bins
+        if ((int)threadIdx.x < st.nreq) {
+            const int r = threadIdx.x;
+            const int g = st.rgrp[r];
+            const unsigned long long pref = st.gprefix[g];
+            int xd[BMS_X];
+            int nx = 0;
+            for (int i = st.xlo[r]; i < st.xhi[r] && nx < BMS_X; i++) {
+                const unsigned long long key = f64_key(x[i]);
+                if (first || ((key ^ pref) >> (shift + 8)) == 0ull) {
+                    const int d = (int)((key >> shift) & 255ull);
+                    int j = nx++;
+                    while (j > 0 && xd[j - 1] > d) { xd[j] = xd[j - 1]; j--; }
+                    xd[j] = d;
+                }
+            }
+            unsigned long long k = st.rk[r], cum = 0;
+            int xi = 0, dsel = 255;
+            for (int d = 0; d < 256; d++) {
+                unsigned long long cnt = st.hist[g][d];
+                while (xi < nx && xd[xi] == d) { cnt++; xi++; }
+                if (k < cum + cnt) { dsel = d; break; }
+                cum += cnt;
+            }
+            st.rk[r] = k >= cum ? k - cum : 0ull;
+            st.rkey[r] = pref | ((unsigned long long)dsel << shift);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            // regroup by (range, new prefix)
+            int nn = 0;
+            unsigned long long np[BMS_R];
+            int nr[BMS_R];
+            for (int r = 0; r < st.nreq; r++) {
+                const int range = st.grange[st.rgrp[r]];
+                int idx = -1;
+                for (int q = 0; q < nn; q++)
+                    if (np[q] == st.rkey[r] && nr[q] == range) idx = q;
+                if (idx < 0) { idx = nn; np[nn] = st.rkey[r]; nr[nn] = range; nn++; }
+                st.newgrp[r] = idx;
+            }
+            for (int q = 0; q < nn; q++) { st.gprefix[q] = np[q]; st.grange[q] = nr[q]; }
+            for (int r = 0; r < st.nreq; r++) st.rgrp[r] = st.newgrp[r];
+            st.ngroups = nn;
+        }
+        __syncthreads();
+    }
+}
+
+// median of x[lo, hi) from a pair of requests {lower middle, upper middle}
+__device__ inline void bms_add_median(BmsState& st, int range, int len_total, int xlo, int xhi) {
+    const int r = st.nreq;
+    st.rgrp[r] = range; st.rgrp[r + 1] = range;
+    st.rk[r] = (len_total & 1) ? len_total / 2 : len_total / 2 - 1;
+    st.rk[r + 1] = len_total / 2;
+    st.xlo[r] = st.xlo[r + 1] = xlo;
+    st.xhi[r] = st.xhi[r + 1] = xhi;
+    st.nreq = r + 2;
+}
+__device__ inline double bms_median_value(const BmsState& st, int r) {
+    const double a = f64_unkey(st.rkey[r]), b = f64_unkey(st.rkey[r + 1]);
+    return st.rkey[r] == st.rkey[r + 1] ? a : __ddiv_rn(__dadd_rn(a, b), 2.0);
+}
+
+__device__ inline int fin_block_scan(int v, int& total) {
+    __shared__ int s_warp[32];
+    __shared__ int s_total;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    int incl = v;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        int t = __shfl_up_sync(0xffffffffu, incl, off);
+        if (lane >= off) incl += t;
+    }
+    if (lane == 31) s_warp[w] = incl;
+    __syncthreads();
+    if (w == 0) {
+        const int nw = (blockDim.x + 31) >> 5;
+        int xv = lane < nw ? s_warp[lane] : 0;
+        int xi = xv;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            int t = __shfl_up_sync(0xffffffffu, xi, off);
+            if (lane >= off) xi += t;
+        }
+        s_warp[lane] = xi - xv;
+        if (lane == 31) s_total = xi;
+    }
+    __syncthreads();
+    const int r = s_warp[w] + incl - v;
+    total = s_total;
+    __syncthreads();
+    return r;
+}
+
+// bitonic sort of (key, value) pairs, n padded to a power of two by the caller with key = ~0
+__device__ void fin_bitonic(unsigned long long* key, int* val, int n2) {
+    for (int k = 2; k <= n2; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = threadIdx.x; i < n2; i += blockDim.x) {
+                const int l = i ^ j;
+                if (l > i) {
+                    const bool up = (i & k) == 0;
+                    const unsigned long long a = key[i], b = key[l];
+                    if ((a > b) == up) {
+                        key[i] = b; key[l] = a;
+                        const int t = val[i]; val[i] = val[l]; val[l] = t;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+__global__ void __launch_bounds__(FIN_THREADS)
+uh_finish_kernel(FinParams p) {
+    __shared__ BmsState s_bms;
+    __shared__ unsigned long long s_key[FIN_SORT_SMEM];
+    __shared__ int s_val[FIN_SORT_SMEM];
+    __shared__ int s_i[8];
+    __shared__ double s_d[4];
+    const int c = blockIdx.x;
+    const long long o = p.off[c];
+    const int n = (int)(p.off[c + 1] - o);
+    if (threadIdx.x == 0) p.n_bp[c] = 0;
+    if (!p.selected[c] || n <= p.min_size || n < 2) return;
+    const double* __restrict__ x = p.x + o;
+    int* lvl_idx = p.lvl_idx + o;
+    int* sv = p.sv + o;
+    unsigned long long* svkey = p.svkey + o;
+    unsigned* bitmap = p.bitmap + (o >> 5) + c;
+    int* piece = p.piece + o;
+    double* rec = p.rec + o;
+    int* prelim = p.prelim + o;
+    int* lvl_first = p.lvl_first + o;
+    int* bp = p.bp + o;
+    const unsigned* lvlcnt = p.lvlcnt + o;
+    const int T = p.depth[c];  // number of levels (tree.Count)
+    const int ncand_all = min(p.ctl->cand_count, 0x7fffffff);
+
+    // ---- HardThresh level weights (:78-91): germline only
+    if (p.is_germline && threadIdx.x == 0) {
+        for (int l = 0; l < T; l++) lvl_idx[l] = l;
+        LevelSorter ls{lvl_idx, lvlcnt};
+        ls.sort(T);
+    }
+    __syncthreads();
+
+    // ---- survivors of the threshold among this chromosome's candidates (:102-114)
+    const double sigma = p.sigma[c];
+    const double root = sqrt(2.0 * log((double)n));
+    int K = 0;
+    for (int base = 0; base < ncand_all; base += blockDim.x) {
+        const int i = base + threadIdx.x;
+        bool keep = false;
+        if (i < ncand_all && p.cand[i].c == c) {
+            const UhCand k = p.cand[i];
+            double w = 1.0;
+            if (p.is_germline) w = __dadd_rn(__ddiv_rn(__dmul_rn((double)(lvl_idx[k.level] + 1), 1.0 - 0.8), (double)T), 0.8);
+            const double thr = __dmul_rn(__dmul_rn(__dmul_rn(2.0, sigma), w), root);
+            keep = !(fabs(k.coef) <= thr);
+        }
+        int total;
+        const int ex = fin_block_scan(keep ? 1 : 0, total);
+        if (keep) {
+            sv[K + ex] = i;
+            svkey[K + ex] = ((unsigned long long)p.cand[i].level << 32) | (unsigned)p.cand[i].s;
+        }
+        K += total;
+    }
+    __syncthreads();
+
+    // ---- sort survivors by (level, start)
+    if (K > 1) {
+        int n2 = 1;
+        while (n2 < K) n2 <<= 1;
+        if (n2 <= FIN_SORT_SMEM) {
+            for (int i = threadIdx.x; i < n2; i += blockDim.x) {
+                s_key[i] = i < K ? svkey[i] : ~0ull;
+                s_val[i] = i < K ? sv[i] : -1;
+            }
+            __syncthreads();
+            fin_bitonic(s_key, s_val, n2);
+            for (int i = threadIdx.x; i < K; i += blockDim.x) { svkey[i] = s_key[i]; sv[i] = s_val[i]; }
+        } else if (n2 <= n) {
+            for (int i = K + threadIdx.x; i < n2; i += blockDim.x) { svkey[i] = ~0ull; sv[i] = -1; }
+            __syncthreads();
+            fin_bitonic(svkey, sv, n2);
+        } else {
+            // more survivors than fit the padded scratch: cannot happen (K <= n - 1, n2 < 2n) unless
+            // n2 > n; fall back to an odd-even transposition sort in place
+            for (int pass = 0; pass < K; pass++) {
+                for (int i = (pass & 1) + 2 * (int)threadIdx.x; i + 1 < K; i += 2 * blockDim.x)
+                    if (svkey[i] > svkey[i + 1]) {
+                        const unsigned long long a = svkey[i]; svkey[i] = svkey[i + 1]; svkey[i + 1] = a;
+                        const int t = sv[i]; sv[i] = sv[i + 1]; sv[i + 1] = t;
+                    }
+                __syncthreads();
+            }
+        }
+        __syncthreads();
+    }
+
+    // ---- pieces: positions where a surviving node starts, breaks or ends (+ position 0)
+    const int nwords = (n + 31) >> 5;
+    for (int i = threadIdx.x; i < nwords; i += blockDim.x) bitmap[i] = 0u;
+    __syncthreads();
+    if (threadIdx.x == 0) atomicOr(&bitmap[0], 1u);
+    for (int i = threadIdx.x; i < K; i += blockDim.x) {
+        const UhCand k = p.cand[sv[i]];
+        const int q[3] = {k.s, k.b + 1, k.e + 1};
+        for (int t = 0; t < 3; t++)
+            if (q[t] > 0 && q[t] < n) atomicOr(&bitmap[q[t] >> 5], 1u << (q[t] & 31));
+    }
+    __syncthreads();
+    int P = 0;
+    for (int base = 0; base < nwords; base += blockDim.x) {
+        const int i = base + threadIdx.x;
+        const unsigned wbits = i < nwords ? bitmap[i] : 0u;
+        int total;
+        int ex = fin_block_scan(__popc(wbits), total);
+        unsigned b = wbits;
+        while (b) {
+            const int bit = __ffs(b) - 1;
+            b &= b - 1;
+            piece[P + ex++] = (i << 5) + bit;
+        }
+        P += total;
+    }
+    __syncthreads();
+
+    // ---- distinct levels among the sorted survivors
+    int NL = 0;
+    for (int base = 0; base < K; base += blockDim.x) {
+        const int i = base + threadIdx.x;
+        const bool head = i < K && (i == 0 || (svkey[i] >> 32) != (svkey[i - 1] >> 32));
+        int total;
+        const int ex = fin_block_scan(head ? 1 : 0, total);
+        if (head) lvl_first[NL + ex] = i;
+        NL += total;
+    }
+    __syncthreads();
+
+    // ---- reconstruction on the pieces (:138-168): additions in level order, exactly one node per level
+    {
+        const long long p0 = o + c;
+        const double total_sum = p.pz[p0 + n] - p.pz[p0];
+        const double smooth = total_sum / sqrt((double)n);              // :376-378
+        const double base_val = __dmul_rn(__ddiv_rn(1.0, sqrt((double)n)), smooth);  // :146
+        for (int pi = threadIdx.x; pi < P; pi += blockDim.x) {
+            const int q = piece[pi];
+            double r = base_val;
+            for (int l = 0; l < NL; l++) {
+                const int lo = lvl_first[l], hi = (l + 1 < NL) ? lvl_first[l + 1] : K;
+                // last survivor of this level with start <= q
+                int a = lo, b = hi;
+                while (a < b) {
+                    const int mid = (a + b) >> 1;
+                    if ((int)(svkey[mid] & 0xffffffffu) <= q) a = mid + 1; else b = mid;
+                }
+                if (a == lo) continue;
+                const UhCand k = p.cand[sv[a - 1]];
+                if (q > k.e) continue;
+                const double nn = (double)(k.e - k.s + 1), m = (double)(k.b - k.s + 1);
+                const double v = q <= k.b ? sqrt(__dsub_rn(__ddiv_rn(1.0, m), __ddiv_rn(1.0, nn)))
+                                          : __ddiv_rn(-1.0, sqrt(__dsub_rn(__ddiv_rn(__dmul_rn(nn, nn), m), nn)));
+                r = __dadd_rn(r, __dmul_rn(v, k.coef));
+            }
+            rec[pi] = r;
+        }
+    }
+    __syncthreads();
+
+    // ---- preliminary breakpoints (:174-185)
+    int L = 0;
+    for (int base = 0; base < P; base += blockDim.x) {
+        const int pi = base + threadIdx.x;
+        const bool isbp = pi < P && (pi == 0 || __dsub_rn(rec[pi], rec[pi - 1]) != 0.0);
+        int total;
+        const int ex = fin_block_scan(isbp ? 1 : 0, total);
+        if (isbp) prelim[L + ex] = piece[pi];
+        L += total;
+    }
+    __syncthreads();
+
+    // ---- healing (:194-232): greedy left to right, exact medians of the two implied segments
+    int nb = 0;  // kept breakpoints so far (uniform across the block)
+    if (threadIdx.x == 0) bp[0] = prelim[0];
+    nb = 1;
+    {
+        double left_median_cache = 0.0;
+        int cache_lo = -1, cache_hi = -1;
+        for (int i = 1; i < L; i++) {
+            __syncthreads();
+            const int left_start = bp[nb - 1];
+            const int right_start = prelim[i];
+            const int right_end = (i < L - 1) ? prelim[i + 1] : n;
+            const int left_len = right_start - left_start, right_len = right_end - right_start;
+            const bool have_left = cache_lo == left_start && cache_hi == right_start;
+            if (threadIdx.x == 0) {
+                s_bms.nreq = 0;
+                s_bms.nranges = have_left ? 1 : 2;
+                s_bms.rlo[0] = right_start; s_bms.rhi[0] = right_end;
+                bms_add_median(s_bms, 0, right_len, 0, 0);
+                if (!have_left) {
+                    s_bms.rlo[1] = left_start; s_bms.rhi[1] = right_start;
+                    bms_add_median(s_bms, 1, left_len, 0, 0);
+                }
+            }
+            bms_run(s_bms, x);
+            const double rm = bms_median_value(s_bms, 0);
+            const double lm = have_left ? left_median_cache : bms_median_value(s_bms, 2);
+            const double wm = __ddiv_rn(__dadd_rn(__dmul_rn((double)left_len, lm), __dmul_rn((double)right_len, rm)),
+                                        (double)(right_end - left_start));
+            const int smaller = min(left_len, right_len);
+            int scale = (int)ceil(__ddiv_rn(log((double)smaller), log(3.0)));
+            // exact powers of three: log(3^k)/log(3) must not depend on the last bit of log()
+            {
+                int pw = 1, kk = 0;
+                while (pw < smaller && kk < 19) { pw *= 3; kk++; }
+                if (pw == smaller) scale = p.log3_scale_tab ? (int)p.log3_scale_tab[kk] : kk;
+            }
+            scale = min(WV_F3_LEVELS, scale);
+            const double cutoff = p.ctl->f3[scale];
+            const bool keep = fabs(__dsub_rn(lm, rm)) > __dmul_rn(__dmul_rn(cutoff, 4.0), fmax(wm, 50.0));
+            __syncthreads();
+            if (keep) {
+                if (threadIdx.x == 0) bp[nb] = right_start;
+                nb++;
+                // the right segment becomes the next left segment
+                left_median_cache = rm; cache_lo = right_start; cache_hi = right_end;
+            } else {
+                cache_lo = cache_hi = -1;
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- RefineSegments (:237-258), germline only
+    if (p.is_germline && nb > 2) {
+        const double total_median = p.chrom_median[c];
+        for (int i = 1; i < nb - 1; i++) {
+            __syncthreads();
+            const int prev = bp[i - 1], cur = bp[i], next = bp[i + 1];
+            const int li = min(5, (cur - prev) / 2), ri = min(5, (next - cur) / 2);
+            const int core_hi = cur - li;
+            if (threadIdx.x == 0) {
+                s_bms.nreq = 0;
+                s_bms.nranges = 1;
+                s_bms.rlo[0] = prev; s_bms.rhi[0] = core_hi;
+                bms_add_median(s_bms, 0, cur - prev, core_hi, cur);             // Median(coverage, prev, cur)
+                for (int j = cur - li; j < cur + ri; j++) bms_add_median(s_bms, 0, j - prev, core_hi, j);
+            }
+            bms_run(s_bms, x);
+            if (threadIdx.x == 0) {
+                double best = fabs(__dsub_rn(bms_median_value(s_bms, 0), total_median));
+                int best_bp = cur;
+                int r = 2;
+                for (int j = cur - li; j < cur + ri; j++, r += 2) {
+                    const double d = fabs(__dsub_rn(bms_median_value(s_bms, r), total_median));
+                    if (d > best) { best = d; best_bp = j; }
+                }
+                bp[i] = best_bp;
+            }
+            __syncthreads();
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) p.n_bp[c] = nb;
+    (void)s_i; (void)s_d;
+}

@@ -1,0 +1,410 @@
+// Genome-wide scalars of CanvasPartition's wavelet branch and the per-chromosome prefix sums.
+//   GetCoverageVariability / reportVariabilityByWindow   Segmentation.cs:309-347
+//   FactorOfThreeCoverageVariabilities / triplets        Segmentation.cs:364-429
+//   GetEvennessScore / reportScoresByWindow              Segmentation.cs:260-297
+//   per-chromosome median / MAD and the threshold        WaveletSegmentation.cs:406-417
+#pragma once
+#include "wavelet.cuh"
+
+// One view for every order statistic of the partition stage; the segment index selects the array.
+struct PartView {
+    const double* cov;
+    const double* cmad;
+    const double* ev10;
+    const double* ev100;
+    const float* r10;
+    const float* r100;
+    const double* center;  // per-segment centre for the MAD wave (nullptr otherwise)
+    WvSegTable t;
+    __device__ bool get(long long i, int seg, uint64_t& key) const {
+        double x;
+        if (seg < t.base_f3) {
+            x = cov[i];
+            if (center) x = fabs(x - center[seg]);
+        } else if (seg < t.base_ev10) {
+            x = cmad[i];
+        } else if (seg == t.base_ev10) {
+            x = ev10[i];
+            if (isnan(x) || isinf(x)) return false;  // Segmentation.cs:291
+            x = (double)(float)x;                     // Select(Convert.ToSingle), :265
+        } else if (seg == t.base_ev100) {
+            x = ev100[i];
+            if (isnan(x) || isinf(x)) return false;
+        } else if (seg == t.base_r10) {
+            x = (double)r10[i];
+        } else {
+            x = (double)r100[i];
+        }
+        key = f64_key(x);
+        return true;
+    }
+};
+
+struct WvScalarParams {
+    WvSegTable t;
+    const long long* seg_len;  // [nseg] host-known lengths (0 for the ev/ratio kinds)
+    long long f3_cnt[WV_F3_LEVELS];
+    long long n_total;
+    int window;        // EvennessScoreWindow
+    int cv_possible;   // N >= 10 * window  (Segmentation.cs:311)
+    int is_germline;
+    double mad_factor, thr_lower, thr_upper;
+};
+
+__device__ inline void median_pair(unsigned long long n, unsigned long long* k) {
+    k[0] = (n & 1ull) ? n / 2 : n / 2 - 1;
+    k[1] = n / 2;
+}
+
+// Quartile ranks of Utilities.Quartiles (Utilities.cs:361-419): {Q1a, Q1b, Q2a, Q2b, Q3a, Q3b}
+__device__ inline void wv_quartile_ranks(unsigned long long n, unsigned long long* k) {
+    const unsigned long long mid = n / 2;
+    if ((n & 1ull) == 0) {
+        k[2] = mid - 1; k[3] = mid;
+        const unsigned long long mm = mid / 2;
+        if ((mid & 1ull) == 0) { k[0] = mm - 1; k[1] = mm; k[4] = mid + mm - 1; k[5] = mid + mm; }
+        else { k[0] = k[1] = mm; k[4] = k[5] = mm + mid; }
+    } else {
+        k[2] = k[3] = mid;
+        if ((n - 1) % 4 == 0) { const unsigned long long q = (n - 1) / 4; k[0] = q - 1; k[1] = q; k[4] = 3 * q; k[5] = 3 * q + 1; }
+        else { const unsigned long long q = (n - 3) / 4; k[0] = q; k[1] = q + 1; k[4] = 3 * q + 1; k[5] = 3 * q + 2; }
+    }
+}
+
+__device__ inline void wv_quartile_values(unsigned long long n, const float* v, float* q) {
+    const unsigned long long mid = n / 2;
+    if ((n & 1ull) == 0) {
+        q[1] = __fdiv_rn(__fadd_rn(v[2], v[3]), 2.0f);
+        if ((mid & 1ull) == 0) {
+            q[0] = __fdiv_rn(__fadd_rn(v[0], v[1]), 2.0f);
+            q[2] = __fdiv_rn(__fadd_rn(v[4], v[5]), 2.0f);
+        } else { q[0] = v[0]; q[2] = v[4]; }
+    } else {
+        q[1] = v[2];
+        if ((n - 1) % 4 == 0) {
+            q[0] = __fadd_rn(__fmul_rn(v[0], 0.25f), __fmul_rn(v[1], 0.75f));
+            q[2] = __fadd_rn(__fmul_rn(v[4], 0.75f), __fmul_rn(v[5], 0.25f));
+        } else {
+            q[0] = __fadd_rn(__fmul_rn(v[0], 0.75f), __fmul_rn(v[1], 0.25f));
+            q[2] = __fadd_rn(__fmul_rn(v[4], 0.25f), __fmul_rn(v[5], 0.75f));
+        }
+    }
+}
+
+// wave 1: medians of coverage windows + chromosomes, of the factor-of-three CMAD pools, and the
+// evenness order statistics; wave 2: MADs (centre = wave-1 median); wave 3: the float statistics of
+// the per-window MAD/median ratios.
+__global__ void wv_request_kernel(SelState<uint64_t> st, WvScalarParams p, const WvCtl* ctl, int wave) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= st.nseg) return;
+    const WvSegTable& t = p.t;
+    st.nreq[s] = 0;
+    unsigned long long* k = st.req_k + (size_t)s * SEL_G;
+    if (wave == 1) {
+        if (s < t.base_f3) {
+            long long n = p.seg_len[s];
+            if (n > 0) { st.nreq[s] = 2; median_pair((unsigned long long)n, k); }
+        } else if (s < t.base_ev10) {
+            long long n = p.f3_cnt[s - t.base_f3];
+            if (n >= 50) { st.nreq[s] = 2; median_pair((unsigned long long)n, k); }  // Segmentation.cs:393
+        } else if (s == t.base_ev10) {
+            unsigned n = ctl->ev10_valid;
+            if (n >= 2) { st.nreq[s] = 6; wv_quartile_ranks(n, k); }
+        } else if (s == t.base_ev100) {
+            unsigned n = ctl->ev100_valid;
+            if (n >= 1) { st.nreq[s] = 2; median_pair(n, k); }
+        }
+    } else if (wave == 2) {
+        const bool window_seg = s < t.base_chrom;
+        const bool chrom_seg = s >= t.base_chrom && s < t.base_f3;
+        if ((window_seg && p.cv_possible) || (chrom_seg && !p.cv_possible)) {
+            long long n = p.seg_len[s];
+            if (n > 0) { st.nreq[s] = 2; median_pair((unsigned long long)n, k); }
+        }
+    } else {
+        if (!p.cv_possible) return;
+        if (s == t.base_r10 && p.window > WV_WINDOW_IQR && t.n_w10 >= 2) { st.nreq[s] = 6; wv_quartile_ranks(t.n_w10, k); }
+        if (s == t.base_r100 && t.n_w100 >= 1) { st.nreq[s] = 2; median_pair(t.n_w100, k); }
+    }
+}
+
+// SortedList<double>.Median() of every segment that had a median request
+__global__ void wv_median_finish_kernel(SelState<uint64_t> st, double* __restrict__ out) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= st.nseg) return;
+    if (st.nreq[s] != 2) return;
+    const uint64_t ka = st.req_key[s * SEL_G + 0], kb = st.req_key[s * SEL_G + 1];
+    const double a = f64_unkey(ka), b = f64_unkey(kb);
+    out[s] = ka == kb ? a : __ddiv_rn(__dadd_rn(a, b), 2.0);
+}
+
+// evenness order statistics are consumed right after wave 1 (the select state is reused by wave 2)
+__global__ void wv_evenness_finish_kernel(SelState<uint64_t> st, WvSegTable t, WvCtl* ctl) {
+    ctl->evenness_ok = 0;
+    ctl->evenness = 0.0;
+    const unsigned n10 = ctl->ev10_valid, n100 = ctl->ev100_valid;
+    if (n10 < 2 || n100 < 1) return;  // Quartiles()/Median() of an empty list throw; swallowed by WaveletsRunner.cs:56-66
+    float v[6], q[3];
+    for (int r = 0; r < 6; r++) v[r] = (float)f64_unkey(st.req_key[t.base_ev10 * SEL_G + r]);
+    wv_quartile_values(n10, v, q);
+    const uint64_t ka = st.req_key[t.base_ev100 * SEL_G + 0], kb = st.req_key[t.base_ev100 * SEL_G + 1];
+    const double a = f64_unkey(ka), b = f64_unkey(kb);
+    const double median = ka == kb ? a : __ddiv_rn(__dadd_rn(a, b), 2.0);
+    // Segmentation.cs:268
+    ctl->evenness = ((double)__fsub_rn(q[2], q[0]) > 0.015) ? __dmul_rn((double)q[2], 100.0) : __dmul_rn(median, 100.0);
+    ctl->evenness_ok = 1;
+}
+
+// factor-of-three list (Segmentation.cs:379-401) from the wave-1 medians
+__global__ void wv_f3_finish_kernel(WvScalarParams p, const double* __restrict__ med, WvCtl* ctl) {
+    double last = 0.0;
+    ctl->f3[0] = 0.0;
+    int r = 1;
+    for (; r <= WV_F3_LEVELS; r++) {
+        if (p.f3_cnt[r - 1] < 50) break;
+        last = med[p.t.base_f3 + r - 1];
+        ctl->f3[r] = last;
+    }
+    for (; r <= WV_F3_LEVELS; r++) ctl->f3[r] = last;
+}
+
+// per-window MAD / median as float (Segmentation.cs:340-346)
+__global__ void wv_ratio_kernel(WvSegTable t, const double* __restrict__ med, const double* __restrict__ mad,
+                                float* __restrict__ r10, float* __restrict__ r100) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= t.base_chrom) return;
+    const float r = (float)__ddiv_rn(mad[s], med[s]);
+    if (s < t.base_w100) r10[s - t.base_w10] = r;
+    else r100[s - t.base_w100] = r;
+}
+
+// CV decision (Segmentation.cs:309-327) and per-chromosome thresholds (WaveletSegmentation.cs:406-417)
+__global__ void wv_cv_sigma_kernel(SelState<uint64_t> st, WvScalarParams p, const double* __restrict__ med,
+                                   const double* __restrict__ mad, const long long* __restrict__ off, WvCtl* ctl,
+                                   double* __restrict__ sigma, double* __restrict__ cand_thr) {
+    __shared__ double s_cv;
+    __shared__ int s_has;
+    const WvSegTable& t = p.t;
+    if (threadIdx.x == 0) {
+        int has = 0;
+        double cv = 0.0;
+        if (p.cv_possible) {
+            has = 1;
+            bool done = false;
+            if (p.window > WV_WINDOW_IQR && t.n_w10 >= 2) {
+                float v[6], q[3];
+                for (int r = 0; r < 6; r++) v[r] = (float)f64_unkey(st.req_key[t.base_r10 * SEL_G + r]);
+                wv_quartile_values(t.n_w10, v, q);
+                if ((double)__fdiv_rn(__fsub_rn(q[2], q[0]), q[1]) > 0.015) { cv = (double)q[0]; done = true; }
+            }
+            if (!done) {
+                if (t.n_w100 >= 1) {
+                    const float a = (float)f64_unkey(st.req_key[t.base_r100 * SEL_G + 0]);
+                    const float b = (float)f64_unkey(st.req_key[t.base_r100 * SEL_G + 1]);
+                    cv = (t.n_w100 & 1) ? (double)a : (double)__fdiv_rn(__fadd_rn(a, b), 2.0f);
+                } else {
+                    cv = 0.0;  // Median of an empty list: unreachable for WGS-shaped input
+                }
+            }
+        }
+        ctl->cv = cv;
+        ctl->cv_has_value = has;
+        s_cv = cv;
+        s_has = has;
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < t.n_chrom; c += blockDim.x) {
+        const double median = med[t.base_chrom + c];
+        const double variability = s_has ? __dmul_rn(median, s_cv) : mad[t.base_chrom + c];
+        double thr = __dmul_rn(p.mad_factor, variability);
+        if (thr < p.thr_lower) thr = p.thr_lower;
+        if (thr > p.thr_upper) thr = p.thr_upper;
+        sigma[c] = thr;
+        const double n = (double)(off[c + 1] - off[c]);
+        const double wmin = p.is_germline ? 0.8 : 1.0;
+        // superset of the final test |coef| <= 2*sigma*w*sqrt(2 ln n), w > 0.8 (germline) or 1
+        cand_thr[c] = n > 1 ? 2.0 * thr * wmin * sqrt(2.0 * log(n)) * (1.0 - 1e-9) : 0.0;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Factor-of-three cascade (Segmentation.cs:404-429): level r holds the middle of every triplet of
+// level r-1; the scaled spread (c - a) / 2 / b goes to the level's CMAD pool.
+// ---------------------------------------------------------------------------------------------
+struct WvF3Level {
+    long long src_off[WV_MAX_CHROM];  // offset of chromosome c in the source array
+    long long dst_off[WV_MAX_CHROM];  // offset in tmed / cmad
+    int cnt[WV_MAX_CHROM];            // triplets of chromosome c at this level
+};
+
+__global__ void wv_triplet_kernel(const double* __restrict__ src, double* __restrict__ tmed,
+                                  double* __restrict__ cmad, const WvF3Level* __restrict__ lv) {
+    const int c = blockIdx.y;
+    const int n = lv->cnt[c];
+    const double* x = src + lv->src_off[c];
+    const long long d0 = lv->dst_off[c];
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        double a = x[3 * (long long)i], b = x[3 * (long long)i + 1], cc = x[3 * (long long)i + 2];
+        double t;
+        if (a > b) { t = a; a = b; b = t; }
+        if (a > cc) { t = a; a = cc; cc = t; }
+        if (b > cc) { t = b; b = cc; cc = t; }
+        tmed[d0 + i] = b;
+        cmad[d0 + i] = __ddiv_rn(__ddiv_rn(__dsub_rn(cc, a), 2.0), b);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Evenness of one window (Segmentation.cs:281-292): sum over integer depths c = 0..floor(mean) of
+// #{bin >= c} / sum(bins).  One block per window: block sum, histogram of floor(bin) clipped to the
+// mean, then the same left-to-right accumulation of quotients as the reference.
+// ---------------------------------------------------------------------------------------------
+struct WvEvWork {
+    long long lo;  // first bin (genome index)
+    int cnt;       // window - 1 bins (Take(windowSize - 1))
+    int out;       // index in ev10 (kind 0) or ev100 (kind 1)
+    int kind, pad;
+};
+constexpr int WV_EV_BINS = 8192;
+
+__device__ inline double block_sum_double(double v) {
+    __shared__ double s_w[32];
+    __shared__ double s_tot;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) v += __shfl_down_sync(0xffffffffu, v, off);
+    if (lane == 0) s_w[w] = v;
+    __syncthreads();
+    if (w == 0) {
+        const int nw = (blockDim.x + 31) >> 5;
+        double x = lane < nw ? s_w[lane] : 0.0;
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) x += __shfl_down_sync(0xffffffffu, x, off);
+        if (lane == 0) s_tot = x;
+    }
+    __syncthreads();
+    const double r = s_tot;
+    __syncthreads();
+    return r;
+}
+
+__global__ void wv_evenness_kernel(const double* __restrict__ cov, const WvEvWork* __restrict__ work,
+                                   double* __restrict__ ev10, double* __restrict__ ev100, WvCtl* ctl) {
+    __shared__ unsigned s_hist[WV_EV_BINS];
+    const WvEvWork w = work[blockIdx.x];
+    const double* x = cov + w.lo;
+    double part = 0.0;
+    for (int i = threadIdx.x; i < w.cnt; i += blockDim.x) part += x[i];
+    const double sum = block_sum_double(part);
+    const double average = sum / (double)w.cnt;
+    double ev;
+    if (!(average >= 0.0)) {
+        ev = 0.0;  // the loop `for (c = 0; c <= average; c++)` runs zero times (also for NaN)
+    } else if (isinf(average)) {
+        ev = average;  // the reference never terminates here; reported as a non-finite score
+    } else {
+        const long long cmax = (long long)floor(average);
+        if (cmax < WV_EV_BINS) {
+            for (int t = threadIdx.x; t <= (int)cmax; t += blockDim.x) s_hist[t] = 0u;
+            __syncthreads();
+            for (int i = threadIdx.x; i < w.cnt; i += blockDim.x) {
+                const double v = x[i];
+                if (v >= 0.0) {
+                    const double f = floor(v);
+                    const int t = f >= (double)cmax ? (int)cmax : (int)f;
+                    atomicAdd(&s_hist[t], 1u);
+                }
+            }
+            __syncthreads();
+            ev = 0.0;
+            if (threadIdx.x == 0) {
+                unsigned run = 0;
+                for (int t = (int)cmax; t >= 0; t--) { run += s_hist[t]; s_hist[t] = run; }  // #{bin >= t}
+                for (int t = 0; t <= (int)cmax; t++) ev = __dadd_rn(ev, __ddiv_rn((double)s_hist[t], sum));
+            }
+        } else {
+            // mean depth beyond the shared-memory histogram: closed form (differs from the
+            // reference's running sum of quotients only in the last bits)
+            double acc = 0.0;
+            for (int i = threadIdx.x; i < w.cnt; i += blockDim.x) {
+                const double v = x[i];
+                if (v >= 0.0) { const double f = floor(v); acc += (f >= (double)cmax ? (double)cmax : f) + 1.0; }
+            }
+            ev = block_sum_double(acc) / sum;
+        }
+    }
+    if (threadIdx.x == 0) {
+        if (w.kind == 0) ev10[w.out] = ev; else ev100[w.out] = ev;
+        if (!(isnan(ev) || isinf(ev))) atomicAdd(w.kind == 0 ? &ctl->ev10_valid : &ctl->ev100_valid, 1u);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Per-chromosome inclusive prefix sums with a leading zero: Pz[off[c] + c] = 0,
+// Pz[off[c] + c + 1 + i] = x[off[c]] + ... + x[off[c] + i].  Tiles never cross chromosomes.
+// ---------------------------------------------------------------------------------------------
+struct WvScanTile {
+    long long lo;  // genome index of the first element
+    int len;       // <= WV_SCAN_TILE
+    int c;         // chromosome
+};
+
+__global__ void wv_scan_tile_sum_kernel(const double* __restrict__ cov, const WvScanTile* __restrict__ tiles,
+                                        double* __restrict__ tsum) {
+    const WvScanTile t = tiles[blockIdx.x];
+    double part = 0.0;
+    for (int i = threadIdx.x; i < t.len; i += blockDim.x) part += cov[t.lo + i];
+    const double s = block_sum_double(part);
+    if (threadIdx.x == 0) tsum[blockIdx.x] = s;
+}
+
+// exclusive scan of the tile sums inside each chromosome (one thread per chromosome; <= a few
+// hundred tiles each)
+__global__ void wv_scan_tile_offsets_kernel(double* __restrict__ tsum, const int* __restrict__ tile_first, int n_chrom) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n_chrom) return;
+    double run = 0.0;
+    for (int t = tile_first[c]; t < tile_first[c + 1]; t++) {
+        const double v = tsum[t];
+        tsum[t] = run;
+        run += v;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+wv_scan_apply_kernel(const double* __restrict__ cov, const WvScanTile* __restrict__ tiles,
+                     const double* __restrict__ toff, const long long* __restrict__ off, double* __restrict__ pz) {
+    __shared__ double s_w[8];
+    const WvScanTile t = tiles[blockIdx.x];
+    constexpr int ITEMS = WV_SCAN_TILE / 256;
+    const int first = threadIdx.x * ITEMS;
+    double v[ITEMS];
+    double local = 0.0;
+#pragma unroll
+    for (int k = 0; k < ITEMS; k++) {
+        const int i = first + k;
+        v[k] = i < t.len ? cov[t.lo + i] : 0.0;
+        local += v[k];
+        v[k] = local;
+    }
+    // block exclusive scan of `local`
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    double incl = local;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const double u = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += u;
+    }
+    if (lane == 31) s_w[w] = incl;
+    __syncthreads();
+    double wbase = 0.0;
+    for (int k = 0; k < w; k++) wbase += s_w[k];
+    const double base = toff[blockIdx.x] + wbase + (incl - local);
+    const long long p0 = t.lo + t.c + 1;  // index of element t.lo in pz
+#pragma unroll
+    for (int k = 0; k < ITEMS; k++) {
+        const int i = first + k;
+        if (i < t.len) pz[p0 + i] = base + v[k];
+    }
+    if (threadIdx.x == 0 && t.lo == off[t.c]) pz[off[t.c] + t.c] = 0.0;
+}

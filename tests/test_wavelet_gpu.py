@@ -1,0 +1,132 @@
+"""cg_partition_wavelet (CUDA, through the C-ABI) against the oracle's restatement of
+CanvasPartition's wavelet branch.  Breakpoints are integer bin indices: compared exactly.  Scalars:
+factor-of-three and CV are exact order statistics (compared exactly); evenness sums 10^4-10^5 doubles
+in a different order than the reference's sequential LINQ Sum (1e-9 relative, north_star allows 1e-5)."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from canvas_b200 import synth
+from oracle import pyoracle as ora
+
+pytestmark = pytest.mark.gpu
+
+
+def _cleaned_coverage(s):
+    """Partition's input as the reference sees it: CanvasClean output rounded by the .cleaned file."""
+    r = ora.clean(s.chrom, s.is_autosome, s.is_chr_y, s.start, s.stop, s.count, s.gc)
+    chrom = s.chrom[r["kept_index"]]
+    off = synth.chrom_offsets(chrom, len(s.names))
+    cov = np.round(r["count"].astype(np.float64), 2)
+    return off, cov
+
+
+def _compare(a, b, label=""):
+    for c, (x, y) in enumerate(zip(a["breakpoints"], b["breakpoints"])):
+        assert x.tolist() == y.tolist(), (label, "chromosome", c, x.tolist()[:40], y.tolist()[:40])
+    assert (a["cv"] is None) == (b["cv"] is None)
+    if b["cv"] is not None:
+        assert a["cv"] == b["cv"], (a["cv"], b["cv"])
+    assert np.array_equal(a["factor_of_three"], b["factor_of_three"]), (a["factor_of_three"], b["factor_of_three"])
+    assert (a["evenness"] is None) == (b["evenness"] is None)
+    if b["evenness"] is not None:
+        assert abs(a["evenness"] - b["evenness"]) <= 1e-9 * abs(b["evenness"]), (a["evenness"], b["evenness"])
+
+
+def test_reference_golden_vector(engine, golden_dir):
+    # CanvasTest/CanvasPartition/WaveletTests.cs:9-90 through the C-ABI: the CV window of the test
+    # (11) is the evenness window; 550 bins >= 10 * 11 so CV has a value.
+    g = json.load(open(os.path.join(golden_dir, "wavelet_minimal.json")))
+    cov = np.array(g["coverage"], np.float64)
+    off = np.array([0, len(cov)], np.int64)
+    r = engine.partition_wavelet(off, cov, is_germline=False, mad_factor=5.0, thr_lower=5.0, thr_upper=80.0,
+                                 min_size=10, evenness_window=11)
+    assert r["breakpoints"][0].tolist() == g["breakpoints"]
+    o = ora.partition_wavelet(off, cov, is_germline=False, mad_factor=5.0, thr_lower=5.0, thr_upper=80.0,
+                              min_size=10, evenness_window=11)
+    _compare(r, o, "golden")
+
+
+@pytest.mark.parametrize("germline", [True, False])
+def test_chr20_config1(engine, germline):
+    s = synth.make_sample(config=1, chromosomes=["chr20"])
+    off, cov = _cleaned_coverage(s)
+    a = engine.partition_wavelet(off, cov, is_germline=germline)
+    b = ora.partition_wavelet(off, cov, is_germline=germline, n_threads=8)
+    _compare(a, b, "chr20")
+    assert b["cv"] is None  # < 10 windows of 100000: threshold falls back to the MAD
+
+
+@pytest.mark.parametrize("germline", [True, False])
+def test_scaled_genome(engine, germline):
+    s = synth.make_sample(config=2, sample=6, scale=0.12, n_events=300)
+    off, cov = _cleaned_coverage(s)
+    # small windows so that the CV / evenness branches that need >= 10 windows are exercised
+    a = engine.partition_wavelet(off, cov, is_germline=germline, evenness_window=12000)
+    b = ora.partition_wavelet(off, cov, is_germline=germline, evenness_window=12000, n_threads=8)
+    _compare(a, b, "scaled")
+    assert b["cv"] is not None and b["evenness"] is not None
+    assert sum(len(x) for x in b["breakpoints"]) > 40
+
+
+def test_full_genome_config2(engine):
+    s = synth.make_sample(config=2)
+    off, cov = _cleaned_coverage(s)
+    a = engine.partition_wavelet(off, cov, is_germline=True)
+    b = ora.partition_wavelet(off, cov, is_germline=True, n_threads=8)
+    _compare(a, b, "full")
+
+
+def test_tumour_like_config3(engine):
+    s = synth.make_sample(config=3, sample=0, scale=0.3, n_events=150, tumour=True)
+    off, cov = _cleaned_coverage(s)
+    a = engine.partition_wavelet(off, cov, is_germline=False, evenness_window=30000)
+    b = ora.partition_wavelet(off, cov, is_germline=False, evenness_window=30000, n_threads=8)
+    _compare(a, b, "tumour")
+
+
+def test_zero_runs_and_short_chromosomes(engine):
+    # runs of exact zeros (unmappable stretches, chrY of a female sample) make the reference peel one
+    # bin per level; chromosomes at or below MinSize are skipped
+    rng = np.random.default_rng(21)
+    lens = [5000, 10, 11, 3000, 1, 0, 2500]
+    parts = []
+    for i, n in enumerate(lens):
+        x = np.round(rng.normal(100, 10, n), 2)
+        if i == 0:
+            x[1200:2900] = 0.0
+            x[2900:3400] = np.round(rng.normal(150, 10, 500), 2)
+        if i == 3:
+            x[:] = 0.0
+        parts.append(x)
+    cov = np.concatenate(parts)
+    off = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    for germline in (False, True):
+        a = engine.partition_wavelet(off, cov, is_germline=germline, evenness_window=1000)
+        b = ora.partition_wavelet(off, cov, is_germline=germline, evenness_window=1000, n_threads=4)
+        _compare(a, b, "zeros")
+        assert len(b["breakpoints"][1]) == 0 and len(b["breakpoints"][2]) >= 1
+
+
+def test_shard_mask_matches_full_run(engine):
+    s = synth.make_sample(config=2, sample=7, scale=0.05, n_events=200)
+    off, cov = _cleaned_coverage(s)
+    full = engine.partition_wavelet(off, cov, is_germline=True, evenness_window=5000)
+    nc = len(off) - 1
+    for rank in range(2):
+        mask = np.array([1 if c % 2 == rank else 0 for c in range(nc)], np.uint8)
+        part = engine.partition_wavelet(off, cov, is_germline=True, evenness_window=5000, chrom_selected=mask)
+        assert part["cv"] == full["cv"] and part["evenness"] == full["evenness"]
+        for c in range(nc):
+            if mask[c]:
+                assert part["breakpoints"][c].tolist() == full["breakpoints"][c].tolist()
+            else:
+                assert len(part["breakpoints"][c]) == 0
+
+
+def test_empty_input(engine):
+    off = np.array([0, 0], np.int64)
+    r = engine.partition_wavelet(off, np.zeros(0), is_germline=True)
+    assert len(r["breakpoints"][0]) == 0 and r["cv"] is None and r["evenness"] is None
