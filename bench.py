@@ -1,0 +1,276 @@
+#!/usr/bin/env python
+"""Headline benchmark: Mbins/s through CanvasClean + CanvasPartition (wavelets) on a synthetic
+3.1 M-bin germline WGS coverage array (BASELINE.json config 2), 1..8 GPUs, one sample per GPU.
+
+  python bench.py --gpus 1 --steps 5 --warmup 3
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+         --master-port P bench.py --gpus N --steps K --warmup W
+  python bench.py --impl reference ...      # CPU restatement of the reference on the host cores
+
+One JSON line on stdout (rank 0).  `value` = bins of all ranks / device time of the kernels with the
+inputs already resident in HBM (CUDA events on the library's launch stream); `e2e` = the same metric
+through the C-ABI call with pinned HOST buffers (H2D + kernels + D2H, wall clock around the
+synchronous call, max over ranks); `roofline` = Unbalanced-Haar decomposition kernel against the
+measured HBM copy bandwidth; `cpu_baseline` = oracle (C++ restatement of the reference) on this box.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "Mbins/s through Clean+Partition on 3M-bin WGS array"
+UNIT = "Mbins/s"
+WORKLOAD = ("config2 germline-WGS 30x synthetic, ~3.1M x 1kb bins: CanvasClean (-g -s -r, local-SD metric, "
+            "MedianByGC) + CanvasPartition wavelets (-g); one sample per GPU")
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples = []
+        self.stop_flag = threading.Event()
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                f = [x.strip() for x in out.strip().split(",")]
+                if len(f) >= 6:
+                    self.samples.append(f)
+            except Exception:
+                pass
+            self.stop_flag.wait(0.2)
+
+    def summary(self):
+        self.stop_flag.set()
+        self.join(timeout=6)
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        sm = sorted(int(s[0]) for s in self.samples if s[0].isdigit())
+        mx = [int(s[1]) for s in self.samples if s[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for s in self.samples for i in range(4) if s[2 + i].lower().startswith("active")})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(self.samples)}
+
+
+def run_oracle_once(s, threads):
+    """The reference path on the CPU: CanvasClean (single thread, as the reference) -> .cleaned text
+    round trip -> CanvasPartition wavelets with one thread per chromosome up to `threads`."""
+    from canvas_b200 import synth
+    from oracle import pyoracle as ora
+    t0 = time.perf_counter()
+    r = ora.clean(s.chrom, s.is_autosome, s.is_chr_y, s.start, s.stop, s.count, s.gc)
+    t1 = time.perf_counter()
+    off = synth.chrom_offsets(s.chrom[r["kept_index"]], len(s.names))
+    cov = ora.f2_roundtrip(r["count"])
+    t2 = time.perf_counter()
+    p = ora.partition_wavelet(off, cov, is_germline=True, n_threads=threads)
+    t3 = time.perf_counter()
+    return {"clean_s": t1 - t0, "partition_s": t3 - t2, "total_s": (t1 - t0) + (t3 - t2),
+            "breakpoints": sum(len(b) for b in p["breakpoints"])}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="canvas_b200", choices=["canvas_b200", "reference"])
+    ap.add_argument("--scale", type=float, default=1.0, help="shrink the genome (debugging only; 1.0 = BASELINE config)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    W = max(args.warmup, 0)
+    K = max(args.steps, 1)
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    from canvas_b200 import synth
+
+    # ------------------------------------------------------------------ reference arm (CPU)
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        threads = os.cpu_count() or 1
+        s = synth.make_sample(config=2, sample=0, scale=args.scale)
+        nb = len(s)
+        for _ in range(max(W, 0)):
+            run_oracle_once(s, threads)
+        t = []
+        for _ in range(K):
+            t.append(run_oracle_once(s, threads))
+        sec = sum(x["total_s"] for x in t) / K
+        v = nb / sec / 1e6
+        line = {"metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": K, "warmup": W,
+                "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f64", "data": "synthetic", "impl": "reference",
+                "config": {"workload": WORKLOAD, "bins_per_sample": nb, "samples": 1},
+                "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
+                                 "sample": "one full config-2 sample per step (Clean on 1 thread as the reference, "
+                                           "Partition one thread per chromosome); C++ restatement, the C# build "
+                                           "needs private NuGet feeds"},
+                "clean_ms": 1e3 * sum(x["clean_s"] for x in t) / K,
+                "partition_ms": 1e3 * sum(x["partition_s"] for x in t) / K,
+                "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line))
+        return 0
+
+    # ------------------------------------------------------------------ GPU arm
+    import torch
+    import torch.distributed as dist
+    from canvas_b200 import native
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    else:
+        torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    eng = native.Engine(local_rank)
+    s = synth.make_sample(config=2, sample=rank, scale=args.scale)
+    nb = len(s)
+    nc = len(s.names)
+    pin = eng.pinned
+    inp = dict(chrom=pin.array(s.chrom), start=pin.array(s.start), stop=pin.array(s.stop), count=pin.array(s.count),
+               gc=pin.array(s.gc))
+    out = (pin.empty(nb, np.int32), pin.empty(nb, np.float32), pin.empty(max(nc, 1), np.int32), pin.empty(nb, np.int32))
+    h2d = nb * (1 + 4 + 4 + 4 + 1)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+    SEG_CAP = 8192
+    seg_local = torch.zeros(SEG_CAP, dtype=torch.int32, device=dev)
+    seg_all = torch.zeros(SEG_CAP * world, dtype=torch.int32, device=dev) if world > 1 else None
+
+    def step():
+        flush.fill_(1)
+        torch.cuda.synchronize()
+        r = eng.clean_partition_wavelet(inp["chrom"], s.is_autosome, s.is_chr_y, inp["start"], inp["stop"],
+                                        inp["count"], inp["gc"], is_germline=True, out=out)
+        nbp = sum(len(b) for b in r["breakpoints"])
+        if world > 1:
+            # config 5: gather the per-sample segment lists (chromosome, breakpoint) on every rank
+            flat = np.zeros(SEG_CAP, np.int32)
+            flat[0] = nbp
+            k = 1
+            for c, b in enumerate(r["breakpoints"]):
+                m = min(len(b), (SEG_CAP - k) // 2)
+                flat[k:k + 2 * m:2] = c
+                flat[k + 1:k + 2 * m:2] = b[:m]
+                k += 2 * m
+            seg_local.copy_(torch.from_numpy(flat))
+            dist.all_gather_into_tensor(seg_all, seg_local)
+            torch.cuda.synchronize()
+        return r, nbp
+
+    W = max(W, 3)  # timing rules: at least three warm-up steps
+    for _ in range(W):
+        step()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    dev_ms, launches, stage_acc, visits, d2h = [], 0, {}, 0.0, 0
+    t0 = time.perf_counter()
+    for _ in range(K):
+        r, nbp = step()
+        dev_ms.append(eng.last_kernel_ms)
+        launches += eng.last_launches
+        for k, v in eng.last_stage_ms().items():
+            stage_acc[k] = stage_acc.get(k, 0.0) + v
+        visits = eng.last_partition_stats()["visits"]
+        d2h = len(r["kept_index"]) * 8 + nbp * 4 + nc * 4 + 4096
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t1 = time.perf_counter()
+    clocks = sampler.summary() if rank == 0 else None
+    wall_ms = (t1 - t0) * 1e3 / K
+    kern_ms = sum(dev_ms) / K
+    tt = torch.tensor([wall_ms, kern_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    wall_ms, kern_ms = tt.tolist()
+    total_bins = nb * world if world == 1 else None
+    if world > 1:
+        nbt = torch.tensor([nb], dtype=torch.int64, device=dev)
+        dist.all_reduce(nbt)
+        total_bins = int(nbt.item())
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    hbm, peak_src = peaks()
+    stages = {k: v / K for k, v in stage_acc.items()}
+    dec_ms = stages.get("decompose", -1.0)
+    alg_bytes = 8.0 * visits  # one f64 prefix sum read per bin visit (8 * L_eff B/bin)
+    achieved = alg_bytes / (dec_ms * 1e-3) / 1e9 if dec_ms > 0 else None
+    line = {"metric": METRIC, "value": total_bins / (kern_ms * 1e-3) / 1e6, "unit": UNIT, "n_gpus": world, "steps": K,
+            "warmup": W, "ms_per_step": kern_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "bins_per_sample": nb, "samples": world,
+                       "l2": "flushed between steps (256 MiB device write)", "parallelism": f"sample-per-gpu x{world}",
+                       "exchange": "NCCL all-gather of per-sample segment lists" if world > 1 else "none"},
+            "e2e": {"value": total_bins / (wall_ms * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": wall_ms,
+                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": launches,
+            "stages_ms": stages,
+            "roofline": {"kernel": "uh_decompose_kernel", "bound": "hbm", "achieved": achieved, "peak": hbm,
+                         "unit": "GB/s", "frac": (achieved / hbm) if achieved else None, "traffic": None,
+                         "peak_source": peak_src, "algorithmic_bytes": alg_bytes,
+                         "l_eff": visits / max(1, len(r["kept_index"]))},
+            "clocks": clocks, "device": eng.describe()}
+    # K8 normalise stream on a batch larger than L2 (the kernel BASELINE.json's roofline target names)
+    try:
+        batch = 8
+        n4 = (nb // 4) * 4
+        rng = np.random.default_rng(1)
+        cnt = np.tile(s.count[:n4], (batch, 1))
+        gcb = np.tile(s.gc[:n4], (batch, 1))
+        med = rng.uniform(80, 120, (batch, 101))
+        _, k8_ms = eng.normalize_apply(cnt, gcb, med, np.full(batch, 100.0), repeats=20)
+        k8_bytes = 9.0 * batch * n4
+        line["roofline_normalize"] = {"kernel": "normalize_apply_kernel", "bound": "hbm",
+                                      "achieved": k8_bytes / (k8_ms * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s",
+                                      "frac": k8_bytes / (k8_ms * 1e-3) / 1e9 / hbm, "traffic": None,
+                                      "batch_bins": batch * n4, "ms": k8_ms}
+    except Exception as e:  # noqa
+        line["roofline_normalize"] = {"error": str(e)}
+    if world == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        o = run_oracle_once(s, threads)
+        line["cpu_baseline"] = {"value": nb / o["total_s"] / 1e6, "unit": UNIT, "cores": threads, "kind": "port",
+                                "sample": "one full config-2 sample (Clean 1 thread, Partition 1 thread per chromosome)",
+                                "clean_ms": o["clean_s"] * 1e3, "partition_ms": o["partition_s"] * 1e3}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

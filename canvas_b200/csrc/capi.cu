@@ -17,12 +17,16 @@ extern "C" int cg_create(int device, cg_ctx** out) {
     snprintf(buf, sizeof buf, "canvasgpu 0.1 sm_%d%d %s %d SMs", prop.major, prop.minor, prop.name, prop.multiProcessorCount);
     ctx->desc = buf;
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->ev_mid, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess ||
         cudaMallocHost((void**)&ctx->pinned, 1 << 16) != cudaSuccess) {
         cg_destroy(ctx);
         return CG_ERR_CUDA;
     }
     ctx->pinned_cap = 1 << 16;
+    for (int i = 0; i < 8; i++)
+        if (cudaEventCreate(&ctx->stage_ev[i]) != cudaSuccess) { cg_destroy(ctx); return CG_ERR_CUDA; }
     *out = ctx;
     return CG_OK;
 }
@@ -33,8 +37,12 @@ extern "C" void cg_destroy(cg_ctx* ctx) {
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     if (ctx->arena) cudaFree(ctx->arena);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
+    for (int i = 0; i < 8; i++)
+        if (ctx->stage_ev[i]) cudaEventDestroy(ctx->stage_ev[i]);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    if (ctx->ev_mid) cudaEventDestroy(ctx->ev_mid);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -43,6 +51,18 @@ extern "C" const char* cg_last_error(cg_ctx* ctx) { return ctx ? ctx->err.c_str(
 extern "C" const char* cg_describe(cg_ctx* ctx) { return ctx ? ctx->desc.c_str() : ""; }
 extern "C" double cg_last_kernel_ms(cg_ctx* ctx) { return ctx ? ctx->last_kernel_ms : 0.0; }
 extern "C" int cg_last_launches(cg_ctx* ctx) { return ctx ? ctx->launches : 0; }
+extern "C" double cg_last_stage_ms(cg_ctx* ctx, int stage) {
+    if (!ctx || stage < 0 || stage > 3 || !ctx->stage_used[stage]) return -1.0;
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, ctx->stage_ev[2 * stage], ctx->stage_ev[2 * stage + 1]) != cudaSuccess) return -1.0;
+    return ms;
+}
+extern "C" int cg_last_partition_stats(cg_ctx* ctx, double* out, int n) {
+    if (!ctx || !out) return 0;
+    int k = n < 4 ? n : 4;
+    for (int i = 0; i < k; i++) out[i] = ctx->stats[i];
+    return k;
+}
 
 extern "C" void* cg_host_alloc(size_t bytes) {
     void* p = nullptr;

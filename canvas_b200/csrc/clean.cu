@@ -589,6 +589,8 @@ int clean_enqueue(cg_ctx* ctx, const cg_clean_opts* o, CleanDev& d) {
     if (o->gc_norm && o->gc_mode != 0)
         return cg_fail(ctx, CG_ERR_UNSUPPORTED, "cg_clean: LOESS GC normalisation (-m LOESS) is not implemented in this build");
 
+    cudaEventRecord(ctx->stage_ev[0], ctx->stream);
+    ctx->stage_used[0] = true;
     CG_LAUNCH(ctx, clean_init_kernel, 1, 32, 0, ctl, n);
     cudaMemsetAsync(d.wcnt, 0, 256 * sizeof(unsigned), ctx->stream);
     cudaMemsetAsync(d.sel_size.hist, 0, (size_t)1 * SEL_G * SEL_BINS * sizeof(unsigned), ctx->stream);
@@ -667,6 +669,7 @@ int clean_enqueue(cg_ctx* ctx, const cg_clean_opts* o, CleanDev& d) {
         EmitOut e{d.count2, d.orig2, d.kept, d.count_out};
         compact_run(ctx, p, e, &ctl->n2, n, d.tiles, &ctl->n_out);
     }
+    cudaEventRecord(ctx->stage_ev[1], ctx->stream);
     return CG_OK;
 }
 
@@ -681,6 +684,7 @@ extern "C" int cg_clean(cg_ctx* ctx, const cg_clean_opts* opts, int64_t n, const
         return cg_fail(ctx, CG_ERR_ARG, "cg_clean: bad argument");
     ctx->launches = 0;
     ctx->last_kernel_ms = 0;
+    for (int i = 0; i < 4; i++) ctx->stage_used[i] = false;
     *n_out = 0;
     *local_sd = -1.0;
     *gc_norm_skipped = 0;

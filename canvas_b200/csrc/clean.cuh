@@ -151,6 +151,41 @@ inline void compact_run(cg_ctx* ctx, const Pred& p, const Emit& e, const int* n_
     CG_LAUNCH(ctx, (compact_scatter_kernel<Pred, Emit>), ntiles, CMP_THREADS, 0, p, e, n_ptr, tile_counts);
 }
 
+// float.ToString("F2") followed by Convert.ToDouble — what the .cleaned file does to a count on its way
+// to CanvasPartition (IO.cs:21, CanvasSegment.cs:1147).  .NET Core 2.0 formats a float from its 7
+// significant decimal digits (FLOAT_PRECISION) and then rounds that digit string half-up to two
+// decimals; parsing "ddd.dd" gives the double nearest to hundredths / 100.
+__host__ __device__ inline double dotnet_f2_roundtrip(float v) {
+    if (v != v || v - v != 0.0f) return (double)v;  // NaN / +-Infinity survive as such
+    double x = v < 0 ? -(double)v : (double)v;
+    if (x == 0.0) return 0.0;
+    const double p10[20] = {1e0, 1e1, 1e2, 1e3, 1e4, 1e5, 1e6, 1e7, 1e8, 1e9, 1e10, 1e11, 1e12, 1e13, 1e14, 1e15, 1e16, 1e17, 1e18, 1e19};
+    int e = 0;  // 10^e <= x < 10^(e+1)
+    if (x >= 1.0) { while (e < 18 && x >= p10[e + 1]) e++; }
+    else { e = -1; while (e > -19 && x * p10[-e] < 1.0) e--; }
+    // seven significant digits, round-half-even on the exact value (the product is exact: a 24-bit
+    // significand times 10^k, k <= 12, fits 53 bits)
+    double scaled = (6 - e >= 0) ? (6 - e < 20 ? x * p10[6 - e] : 0.0) : x / p10[e - 6];
+    double d7 = rint(scaled);
+    if (d7 >= 1e7) { d7 /= 10.0; e += 1; }
+    double hundredths;
+    if (e >= 4) {
+        hundredths = d7 * p10[e - 4 < 19 ? e - 4 : 19];
+    } else {
+        const int k = 4 - e;  // digits to drop
+        if (k > 7) hundredths = 0.0;
+        else {
+            const long long q = (long long)d7;
+            const long long p = (long long)p10[k];
+            long long h = q / p;
+            if ((q % p) * 2 >= p) h += 1;  // first dropped digit >= 5
+            hundredths = (double)h;
+        }
+    }
+    const double r = hundredths / 100.0;
+    return v < 0 ? -r : r;
+}
+
 // Device-side buffers of one cg_clean call (slices of the ctx arena).
 struct CleanDev {
     int64_t n;

@@ -16,11 +16,17 @@ struct cg_ctx {
     int device = 0;
     int num_sms = CG_NUM_SMS_FALLBACK;
     cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;  // overlaps result downloads with later kernels
+    cudaEvent_t ev_mid = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     std::string err;
     std::string desc;
     double last_kernel_ms = 0;
     int launches = 0;
+    // stage timers: events [2*i], [2*i+1] bracket stage i
+    cudaEvent_t stage_ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    bool stage_used[4] = {false, false, false, false};
+    double stats[4] = {0, 0, 0, 0};
     // device arena, grown on demand and reused across calls
     char* arena = nullptr;
     size_t arena_cap = 0;

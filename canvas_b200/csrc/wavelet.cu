@@ -146,6 +146,8 @@ struct WvDev {
     UhNode* bn;
     int bn_cap;
     unsigned long long* tickets;
+    double* part_score;
+    int* part_m;
     UhSmallTask* small;
     int small_cap;
     UhCand* cand;
@@ -170,7 +172,7 @@ size_t wv_workspace_bytes(const WvPlan& pl) {
     s += arena_need(pl.t.n_w10 + 1, 4) + arena_need(pl.t.n_w100 + 1, 4);
     s += arena_need(pl.t.nseg, 8) * 2 + arena_need(C + 1, 8) * 2 + arena_need(32, 8) + arena_need(1, sizeof(WvCtl));
     s += arena_need(N + 1, 4) + arena_need(C + 1, 4);
-    s += arena_need(N / 4 + 4096, sizeof(UhNode)) + arena_need(UH_QCAP, 8) + arena_need(N / 2 + C + 64, sizeof(UhSmallTask));
+    s += arena_need(UH_QCAP, sizeof(UhNode)) + arena_need(UH_QCAP, 8) * 2 + arena_need(UH_QCAP, 4) + arena_need(N / 2 + C + 64, sizeof(UhSmallTask));
     s += arena_need(N / 4 + 4096, sizeof(UhCand));
     s += arena_need(N + 1, 4) * 5 + arena_need(N + 1, 8) * 2 + arena_need(N / 32 + C + 2, 4);
     s += arena_need(C + 1, 4) + arena_need(N + 1, 4);
@@ -205,9 +207,11 @@ int wv_alloc(cg_ctx* ctx, const WvPlan& pl, WvDev& d, double* cov_dev_existing) 
     d.ctl = arena_take<WvCtl>(ctx, 1);
     d.lvlcnt = arena_take<unsigned>(ctx, N + 1);
     d.depth = arena_take<int>(ctx, C + 1);
-    d.bn_cap = (int)(N / 4 + 4096);
+    d.bn_cap = UH_QCAP;
     d.bn = arena_take<UhNode>(ctx, d.bn_cap);
     d.tickets = arena_take<unsigned long long>(ctx, UH_QCAP);
+    d.part_score = arena_take<double>(ctx, UH_QCAP);
+    d.part_m = arena_take<int>(ctx, UH_QCAP);
     d.small_cap = (int)(N / 2 + C + 64);
     d.small = arena_take<UhSmallTask>(ctx, d.small_cap);
     d.cand_cap = (int)(N / 4 + 4096);
@@ -224,7 +228,7 @@ int wv_alloc(cg_ctx* ctx, const WvPlan& pl, WvDev& d, double* cov_dev_existing) 
     d.bp = arena_take<int>(ctx, N + 1);
     ok = ok && d.cov && d.off && d.selected && d.pz && d.seg_len && d.work && d.ev_work && d.tiles && d.tile_first &&
          d.tsum && d.f3lv && d.tmed && d.cmad && d.ev10 && d.ev100 && d.r10 && d.r100 && d.med && d.mad && d.sigma &&
-         d.cand_thr && d.log3 && d.ctl && d.lvlcnt && d.depth && d.bn && d.tickets && d.small && d.cand && d.lvl_idx &&
+         d.cand_thr && d.log3 && d.ctl && d.lvlcnt && d.depth && d.bn && d.tickets && d.part_score && d.part_m && d.small && d.cand && d.lvl_idx &&
          d.sv && d.piece && d.prelim && d.lvl_first && d.svkey && d.rec && d.bitmap && d.n_bp && d.bp;
     return ok ? CG_OK : cg_fail(ctx, CG_ERR_CUDA, "partition: device arena exhausted");
 }
@@ -274,6 +278,8 @@ int wv_enqueue(cg_ctx* ctx, const cg_wavelet_opts* o, const WvPlan& pl, WvDev& d
     sp.thr_lower = o->thr_lower;
     sp.thr_upper = o->thr_upper;
 
+    cudaEventRecord(ctx->stage_ev[2], s);
+    ctx->stage_used[1] = true;
     // ---- prefix sums
     const int ntiles = (int)pl.tiles.size();
     if (ntiles > 0) {
@@ -315,12 +321,15 @@ int wv_enqueue(cg_ctx* ctx, const cg_wavelet_opts* o, const WvPlan& pl, WvDev& d
     }
     CG_LAUNCH(ctx, wv_cv_sigma_kernel, 1, 128, 0, d.sel, sp, d.med, d.mad, d.off, d.ctl, d.sigma, d.cand_thr);
 
+    cudaEventRecord(ctx->stage_ev[3], s);
+    cudaEventRecord(ctx->stage_ev[4], s);
+    ctx->stage_used[2] = true;
     // ---- decomposition
     UhParams up;
     up.x = d.cov; up.pz = d.pz; up.off = d.off; up.cand_thr = d.cand_thr; up.lvlcnt = d.lvlcnt; up.depth = d.depth;
-    up.bn = d.bn; up.bn_cap = d.bn_cap; up.tickets = d.tickets; up.small = d.small; up.small_cap = d.small_cap;
+    up.bn = d.bn; up.bn_cap = d.bn_cap; up.tickets = d.tickets; up.part_score = d.part_score; up.part_m = d.part_m; up.small = d.small; up.small_cap = d.small_cap;
     up.cand = d.cand; up.cand_cap = d.cand_cap; up.ctl = d.ctl;
-    CG_LAUNCH(ctx, uh_seed_kernel, 1, 32, 0, up, d.selected, C, o->min_size);
+    CG_LAUNCH(ctx, uh_seed_kernel, 1, 256, 0, up, d.selected, C, o->min_size);
     int occ = 0;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, uh_decompose_kernel, UH_THREADS, 0);
     if (occ < 1) occ = 1;
@@ -330,6 +339,9 @@ int wv_enqueue(cg_ctx* ctx, const cg_wavelet_opts* o, const WvPlan& pl, WvDev& d
     if (grid < 4) grid = 4;
     CG_LAUNCH(ctx, uh_decompose_kernel, grid, UH_THREADS, 0, up);
 
+    cudaEventRecord(ctx->stage_ev[5], s);
+    cudaEventRecord(ctx->stage_ev[6], s);
+    ctx->stage_used[3] = true;
     // ---- per-chromosome finish
     FinParams fp;
     fp.x = d.cov; fp.pz = d.pz; fp.off = d.off; fp.selected = d.selected; fp.cand = d.cand; fp.ctl = d.ctl;
@@ -339,6 +351,7 @@ int wv_enqueue(cg_ctx* ctx, const cg_wavelet_opts* o, const WvPlan& pl, WvDev& d
     fp.lvl_idx = d.lvl_idx; fp.sv = d.sv; fp.svkey = d.svkey; fp.bitmap = d.bitmap; fp.piece = d.piece; fp.rec = d.rec;
     fp.prelim = d.prelim; fp.lvl_first = d.lvl_first; fp.n_bp = d.n_bp; fp.bp = d.bp;
     if (C > 0) CG_LAUNCH(ctx, uh_finish_kernel, C, FIN_THREADS, 0, fp);
+    cudaEventRecord(ctx->stage_ev[7], s);
     return CG_OK;
 }
 
@@ -353,6 +366,10 @@ int wv_collect(cg_ctx* ctx, const WvPlan& pl, WvDev& d, int32_t* n_bp, int32_t* 
     CG_CUDA(ctx, cudaStreamSynchronize(s));
     CG_CUDA(ctx, cudaGetLastError());
     if (h->overflow) return cg_fail(ctx, CG_ERR_CAPACITY, "partition: internal queue capacity exceeded");
+    ctx->stats[0] = (double)(h->visits_big + h->visits_small + h->visits_tiny);
+    ctx->stats[1] = (double)(h->nodes_big + h->nodes_small + h->nodes_tiny);
+    ctx->stats[2] = (double)h->cand_count;
+    ctx->stats[3] = (double)pl.N;
     // breakpoints: one copy per chromosome that has any (they are few and short)
     for (int c = 0; c < C; c++) {
         n_bp[c] = h_nbp[c];
@@ -392,6 +409,7 @@ extern "C" int cg_partition_wavelet_shard(cg_ctx* ctx, const cg_wavelet_opts* op
         return cg_fail(ctx, CG_ERR_ARG, "partition: null output");
     ctx->launches = 0;
     ctx->last_kernel_ms = 0;
+    for (int i = 0; i < 4; i++) ctx->stage_used[i] = false;
     CG_CUDA(ctx, cudaSetDevice(ctx->device));
     WvPlan pl;
     make_plan(pl, n_chrom, chrom_off, opts->evenness_window);
@@ -423,10 +441,124 @@ extern "C" int cg_partition_wavelet(cg_ctx* ctx, const cg_wavelet_opts* opts, in
                                       cv, cv_has_value, factor_of_three);
 }
 
-extern "C" int cg_clean_partition_wavelet(cg_ctx* ctx, const cg_clean_opts*, const cg_wavelet_opts*, int64_t,
-                                          const uint8_t*, const uint8_t*, const uint8_t*, int, const int32_t*,
-                                          const int32_t*, const float*, const uint8_t*, int64_t*, int32_t*, float*,
-                                          double*, int*, int64_t*, int32_t*, int32_t*, double*, int*, double*, int*,
-                                          double*) {
-    return cg_fail(ctx, CG_ERR_UNSUPPORTED, "cg_clean_partition_wavelet: not built yet");
+// coverage for the partition stage = .cleaned round trip of the cleaned counts; per-chromosome bin counts
+__global__ void fused_coverage_kernel(const float* __restrict__ count_out, const int32_t* __restrict__ kept,
+                                      const uint8_t* __restrict__ chrom_in, const CleanCtl* __restrict__ ctl,
+                                      double* __restrict__ cov, unsigned* __restrict__ chrom_cnt) {
+    const int n = ctl->n_out;
+    const int n_round = ((n + 31) / 32) * 32;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += gridDim.x * blockDim.x) {
+        const bool ok = i < n;
+        int c = 0;
+        if (ok) {
+            cov[i] = dotnet_f2_roundtrip(count_out[i]);
+            c = chrom_in[kept[i]];
+        }
+        const unsigned act = __ballot_sync(0xffffffffu, ok);
+        if (ok) {
+            const unsigned m = __match_any_sync(act, c);
+            if ((int)(__ffs(m) - 1) == (int)(threadIdx.x & 31)) atomicAdd(&chrom_cnt[c], (unsigned)__popc(m));
+        }
+    }
+}
+
+extern "C" int cg_clean_partition_wavelet(cg_ctx* ctx, const cg_clean_opts* copts, const cg_wavelet_opts* wopts,
+                                          int64_t n, const uint8_t* chrom, const uint8_t* chrom_is_autosome,
+                                          const uint8_t* chrom_is_chrY, int n_chrom, const int32_t* start,
+                                          const int32_t* stop, const float* count, const uint8_t* gc,
+                                          int64_t* n_out, int32_t* kept_index, float* count_out,
+                                          double* local_sd, int* gc_norm_skipped, int64_t* chrom_off_out,
+                                          int32_t* n_bp, int32_t* bp, double* evenness, int* evenness_ok,
+                                          double* cv, int* cv_has_value, double* factor_of_three) {
+    (void)chrom_is_chrY;
+    if (!ctx) return CG_ERR_ARG;
+    if (!copts || !wopts || n < 0 || n > 0x7fff0000LL || n_chrom < 0 || n_chrom > WV_MAX_CHROM || !n_out || !local_sd ||
+        !gc_norm_skipped || !chrom_off_out || !n_bp || !evenness || !evenness_ok || !cv || !cv_has_value || !factor_of_three)
+        return cg_fail(ctx, CG_ERR_ARG, "cg_clean_partition_wavelet: bad argument");
+    if (wopts->evenness_window <= 0) return cg_fail(ctx, CG_ERR_ARG, "partition: evenness_window must be positive");
+    ctx->launches = 0;
+    ctx->last_kernel_ms = 0;
+    for (int i = 0; i < 4; i++) ctx->stage_used[i] = false;
+    *n_out = 0; *local_sd = -1.0; *gc_norm_skipped = 0; *evenness = 0; *evenness_ok = 0; *cv = 0; *cv_has_value = 0;
+    for (int i = 0; i <= WV_F3_LEVELS; i++) factor_of_three[i] = 0;
+    for (int c = 0; c <= n_chrom; c++) chrom_off_out[c] = 0;
+    for (int c = 0; c < n_chrom; c++) n_bp[c] = 0;
+    if (n == 0) { *gc_norm_skipped = copts->gc_norm ? 1 : 0; return CG_OK; }
+    if (!chrom || !start || !stop || !count || !gc || !kept_index || !count_out || !bp || !chrom_is_autosome)
+        return cg_fail(ctx, CG_ERR_ARG, "cg_clean_partition_wavelet: null array");
+    CG_CUDA(ctx, cudaSetDevice(ctx->device));
+    // chromosome runs of the input (ids are non-decreasing; the device validates that): binary search
+    std::vector<int64_t> in_off(n_chrom + 1, 0);
+    for (int c = 0; c < n_chrom; c++) {
+        int64_t lo = in_off[c], hi = n;
+        while (lo < hi) { int64_t mid = (lo + hi) >> 1; if (chrom[mid] <= (uint8_t)c) lo = mid + 1; else hi = mid; }
+        in_off[c + 1] = lo;
+    }
+    // workspace for both stages; the partition plan of the input lengths bounds the plan after cleaning
+    WvPlan worst;
+    make_plan(worst, n_chrom, in_off.data(), wopts->evenness_window);
+    size_t need = clean_workspace_bytes(n, n_chrom) + arena_need(n, 8) + arena_need(256, 4) + wv_workspace_bytes(worst);
+    need += need / 16;
+    int rc = arena_reserve(ctx, need);
+    if (rc) return rc;
+    CleanDev d;
+    rc = clean_alloc(ctx, n, n_chrom, d);
+    if (rc) return rc;
+    double* cov = arena_take<double>(ctx, n);
+    unsigned* chrom_cnt = arena_take<unsigned>(ctx, 256);
+    if (!cov || !chrom_cnt) return cg_fail(ctx, CG_ERR_CUDA, "arena exhausted");
+    cudaStream_t s = ctx->stream;
+    CG_CUDA(ctx, cudaMemcpyAsync(d.chrom, chrom, n, cudaMemcpyHostToDevice, s));
+    CG_CUDA(ctx, cudaMemcpyAsync(d.gc, gc, n, cudaMemcpyHostToDevice, s));
+    CG_CUDA(ctx, cudaMemcpyAsync(d.start, start, n * 4, cudaMemcpyHostToDevice, s));
+    CG_CUDA(ctx, cudaMemcpyAsync(d.stop, stop, n * 4, cudaMemcpyHostToDevice, s));
+    CG_CUDA(ctx, cudaMemcpyAsync(d.count, count, n * 4, cudaMemcpyHostToDevice, s));
+    CG_CUDA(ctx, cudaMemsetAsync(d.is_auto, 0, 256, s));
+    if (n_chrom > 0) CG_CUDA(ctx, cudaMemcpyAsync(d.is_auto, chrom_is_autosome, n_chrom, cudaMemcpyHostToDevice, s));
+    CG_CUDA(ctx, cudaMemsetAsync(chrom_cnt, 0, 256 * 4, s));
+    CG_CUDA(ctx, cudaEventRecord(ctx->ev0, s));
+    rc = clean_enqueue(ctx, copts, d);
+    if (rc) { cudaStreamSynchronize(s); return rc; }
+    CG_LAUNCH(ctx, fused_coverage_kernel, std::max(1, std::min(div_up(n, 256), ctx->num_sms * 8)), 256, 0, d.count_out,
+              d.kept, d.chrom, d.ctl, cov, chrom_cnt);
+    CleanCtl* h = (CleanCtl*)ctx->pinned;
+    unsigned* h_cnt = (unsigned*)(ctx->pinned + 8192);
+    CG_CUDA(ctx, cudaMemcpyAsync(h, d.ctl, sizeof(CleanCtl), cudaMemcpyDeviceToHost, s));
+    CG_CUDA(ctx, cudaMemcpyAsync(h_cnt, chrom_cnt, 256 * 4, cudaMemcpyDeviceToHost, s));
+    CG_CUDA(ctx, cudaEventRecord(ctx->ev_mid, s));
+    CG_CUDA(ctx, cudaStreamSynchronize(s));
+    CG_CUDA(ctx, cudaGetLastError());
+    if (h->unsorted) return cg_fail(ctx, CG_ERR_UNSORTED, "cg_clean: chromosome ids must form non-decreasing runs and GC must be 0..100");
+    if (h->need_weighted)
+        return cg_fail(ctx, CG_ERR_UNSUPPORTED, "cg_clean: a GC bucket in use has < 100 autosomal bins (weighted-quantile path not implemented)");
+    const int64_t m = h->n_out;
+    const double lsd = h->local_sd;
+    const int skipped = h->gc_skipped;
+    // clean outputs go back on the copy stream while the partition kernels run
+    if (m > 0) {
+        CG_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_mid, 0));
+        CG_CUDA(ctx, cudaMemcpyAsync(kept_index, d.kept, m * 4, cudaMemcpyDeviceToHost, ctx->copy_stream));
+        CG_CUDA(ctx, cudaMemcpyAsync(count_out, d.count_out, m * 4, cudaMemcpyDeviceToHost, ctx->copy_stream));
+    }
+    std::vector<int64_t> off(n_chrom + 1, 0);
+    for (int c = 0; c < n_chrom; c++) off[c + 1] = off[c] + h_cnt[c];
+    for (int c = 0; c <= n_chrom; c++) chrom_off_out[c] = off[c];
+    WvPlan pl;
+    make_plan(pl, n_chrom, off.data(), wopts->evenness_window);
+    WvDev wd;
+    rc = wv_alloc(ctx, pl, wd, cov);
+    if (rc) { cudaStreamSynchronize(ctx->copy_stream); return rc; }
+    std::vector<unsigned char> sel(n_chrom + 1, 1);
+    rc = wv_enqueue(ctx, wopts, pl, wd, sel.data());
+    if (rc) { cudaStreamSynchronize(s); cudaStreamSynchronize(ctx->copy_stream); return rc; }
+    CG_CUDA(ctx, cudaEventRecord(ctx->ev1, s));
+    rc = wv_collect(ctx, pl, wd, n_bp, bp, evenness, evenness_ok, cv, cv_has_value, factor_of_three);
+    CG_CUDA(ctx, cudaStreamSynchronize(ctx->copy_stream));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+    ctx->last_kernel_ms = ms;
+    *n_out = m;
+    *local_sd = lsd;
+    *gc_norm_skipped = skipped;
+    return rc;
 }

@@ -20,7 +20,7 @@ constexpr int WV_SCAN_TILE = 2048;
 // ---- decomposition tiers -------------------------------------------------------------------
 constexpr int UH_SMALL_MAX = 1024;  // nodes up to this size: a whole subtree is done by one warp
 constexpr int UH_TINY_MAX = 16;     // nodes up to this size: sequential reference recurrence per thread
-constexpr int UH_CHUNK = 4096;      // split positions per chunk ticket of a big node
+constexpr int UH_CHUNK = 16384;     // split positions per chunk ticket of a big node
 constexpr int UH_THREADS = 256;
 constexpr int UH_QCAP = 1 << 16;    // ticket ring capacity
 
@@ -31,11 +31,10 @@ struct WvSegTable {
     int nseg;
 };
 
-struct UhNode {  // big node record
+struct UhNode {  // big node record, stored in the ring slot of its first ticket
     int c, s, e, level;
-    int nchunks, done, lock, best_m;
-    double best_score;
-    double pad;
+    int nchunks, done;
+    unsigned long long pos;  // ring position of ticket 0
 };
 
 struct UhSmallTask {
@@ -52,7 +51,7 @@ struct UhCand {  // node whose coefficient may survive the hard threshold
 struct WvCtl {
     // queues
     unsigned long long q_head, q_tail;
-    int bn_count, small_head, small_tail, outstanding;
+    int bn_count_unused, small_head, small_tail, outstanding;
     int big_done, overflow, cand_count, pad0;
     // scalars
     int cv_has_value, evenness_ok;

@@ -31,6 +31,8 @@ struct UhParams {
     UhNode* bn;
     int bn_cap;
     unsigned long long* tickets;  // ring [UH_QCAP]; 0 = empty
+    double* part_score;           // ring [UH_QCAP]: per-ticket partial arg-max of a multi-chunk node
+    int* part_m;                  // ring [UH_QCAP]
     UhSmallTask* small;            // c < 0 = not published yet
     int small_cap;
     UhCand* cand;
@@ -57,28 +59,33 @@ __device__ inline void uh_push_small(const UhParams& p, int c, int s, int e, int
     *(volatile int*)&t->c = c;  // publish
 }
 
-__device__ inline void uh_push_big(const UhParams& p, int c, int s, int e, int level) {
-    const int id = atomicAdd(&p.ctl->bn_count, 1);
-    if (id >= p.bn_cap) { p.ctl->overflow = 1; return; }
+// A big node owns `nch` consecutive positions of the ticket ring: ticket i of the node sits at
+// position pos + i, its partial result at the same ring index, and the node record itself in slot
+// pos & mask.  One atomicAdd on q_tail therefore allocates all three.  `tid`/`nthr` let a whole CTA
+// write the tickets in parallel (the stores are independent); a single thread passes (0, 1).
+// The caller must make the node record visible (threadfence) before tickets are written; this
+// routine does that for the single-thread form.
+__device__ inline unsigned long long uh_big_alloc(const UhParams& p, int c, int s, int e, int level) {
     const int nsplit = e - s;  // n - 1 split positions
     const int nch = (nsplit + UH_CHUNK - 1) / UH_CHUNK;
-    UhNode* nd = p.bn + id;
-    nd->c = c; nd->s = s; nd->e = e; nd->level = level;
-    nd->nchunks = nch; nd->done = 0; nd->lock = 0; nd->best_m = 0x7fffffff; nd->best_score = -1.0;
-    __threadfence();
-    atomicAdd(&p.ctl->outstanding, 1);
     const unsigned long long pos = atomicAdd(&p.ctl->q_tail, (unsigned long long)nch);
-    for (int i = 0; i < nch; i++) {
+    UhNode* nd = p.bn + (pos & (UH_QCAP - 1));
+    nd->c = c; nd->s = s; nd->e = e; nd->level = level;
+    nd->nchunks = nch; nd->done = 0; nd->pos = pos;
+    __threadfence();
+    return pos;
+}
+
+__device__ inline void uh_big_publish(const UhParams& p, unsigned long long pos, int nch, int tid, int nthr) {
+    const unsigned long long slot1 = (pos & (UH_QCAP - 1)) + 1ull;
+    for (int i = tid; i < nch; i += nthr) {
         volatile unsigned long long* slot = p.tickets + ((pos + i) & (UH_QCAP - 1));
         while (*slot != 0ull) __nanosleep(64);
-        *slot = ((unsigned long long)(id + 1) << 32) | (unsigned)i;
+        *slot = (slot1 << 32) | (unsigned)i;
     }
 }
 
-__device__ inline void uh_route_child(const UhParams& p, int c, int s, int e, int level) {
-    if (e - s + 1 > UH_SMALL_MAX) uh_push_big(p, c, s, e, level);
-    else uh_push_small(p, c, s, e, level);
-}
+__device__ inline int uh_nchunks(int s, int e) { return (e - s + UH_CHUNK - 1) / UH_CHUNK; }
 
 // (score, m) arg-max inside a warp: largest score, smallest m among equals.  Scores are >= 0
 // (or NaN, mapped to 0), so their bit patterns order like unsigned integers.
@@ -273,27 +280,40 @@ uh_decompose_kernel(UhParams p) {
 
     if ((blockIdx.x & 3) == 0) {
         // ----------------------------------------------------------------- big worker
+        __shared__ int s_child[2][4];               // routed children {s, e, level, kind}
+        __shared__ unsigned long long s_child_pos[2];
+        bool have_local = false;                    // a single-chunk child continued without the queue
+        int lc = 0, ls = 0, le = 0, ll = 0;
         for (;;) {
-            if (threadIdx.x == 0) {
-                unsigned long long t = 0;
-                const unsigned long long pos = atomicAdd(&ctl->q_head, 1ull);
-                volatile unsigned long long* slot = p.tickets + (pos & (UH_QCAP - 1));
-                for (;;) {
-                    t = *slot;
-                    if (t != 0ull) { *slot = 0ull; break; }
-                    if (*(volatile int*)&ctl->big_done || *(volatile int*)&ctl->overflow) break;
-                    __nanosleep(100);
+            int c, s, e, level, nchunks, chunk;
+            unsigned long long npos = 0;
+            UhNode* nd = nullptr;
+            if (have_local) {
+                c = lc; s = ls; e = le; level = ll; nchunks = 1; chunk = 0;
+                have_local = false;
+            } else {
+                if (threadIdx.x == 0) {
+                    unsigned long long t = 0;
+                    const unsigned long long pos = atomicAdd(&ctl->q_head, 1ull);
+                    volatile unsigned long long* slot = p.tickets + (pos & (UH_QCAP - 1));
+                    for (;;) {
+                        t = *slot;
+                        if (t != 0ull) { *slot = 0ull; break; }
+                        if (*(volatile int*)&ctl->big_done || *(volatile int*)&ctl->overflow) break;
+                        __nanosleep(40);
+                    }
+                    s_ticket = t;
                 }
-                s_ticket = t;
+                __syncthreads();
+                const unsigned long long t = s_ticket;
+                __syncthreads();
+                if (t == 0ull) break;
+                nd = p.bn + ((t >> 32) - 1ull);
+                chunk = (int)(t & 0xffffffffu);
+                c = __ldcg(&nd->c); s = __ldcg(&nd->s); e = __ldcg(&nd->e); level = __ldcg(&nd->level);
+                nchunks = __ldcg(&nd->nchunks);
+                npos = __ldcg(&nd->pos);
             }
-            __syncthreads();
-            const unsigned long long t = s_ticket;
-            __syncthreads();
-            if (t == 0ull) break;
-            const int id = (int)(t >> 32) - 1, chunk = (int)(t & 0xffffffffu);
-            UhNode* nd = p.bn + id;
-            const int c = __ldcg(&nd->c), s = __ldcg(&nd->s), e = __ldcg(&nd->e), level = __ldcg(&nd->level);
-            const int nchunks = __ldcg(&nd->nchunks);
             const int n = e - s + 1;
             const long long p0 = p.off[c] + c;
             const double* __restrict__ pz = p.pz;
@@ -305,11 +325,29 @@ uh_decompose_kernel(UhParams p) {
             const int m1 = min(m0 + UH_CHUNK, n - 1);
             double best = -1.0;
             int best_m = 0x7fffffff;
-            for (int m = m0 + threadIdx.x; m < m1; m += UH_THREADS) {
-                const double a = (double)(m + 1);
-                const double D = (pz[p0 + s + m + 1] - base) - a * mu;
-                const double sc = D * D / (a * (nn - a));
-                if (sc > best) { best = sc; best_m = m; }
+            {
+                const double* __restrict__ q = pz + p0 + s + 1;
+                int m = m0 + threadIdx.x;
+                // four independent loads in flight per thread
+                for (; m + 3 * UH_THREADS < m1; m += 4 * UH_THREADS) {
+                    const double v0 = q[m], v1 = q[m + UH_THREADS], v2 = q[m + 2 * UH_THREADS], v3 = q[m + 3 * UH_THREADS];
+                    const double a0 = (double)(m + 1), a1 = (double)(m + UH_THREADS + 1);
+                    const double a2 = (double)(m + 2 * UH_THREADS + 1), a3 = (double)(m + 3 * UH_THREADS + 1);
+                    const double D0 = (v0 - base) - a0 * mu, D1 = (v1 - base) - a1 * mu;
+                    const double D2 = (v2 - base) - a2 * mu, D3 = (v3 - base) - a3 * mu;
+                    const double s0 = D0 * D0 / (a0 * (nn - a0)), s1 = D1 * D1 / (a1 * (nn - a1));
+                    const double s2 = D2 * D2 / (a2 * (nn - a2)), s3 = D3 * D3 / (a3 * (nn - a3));
+                    if (s0 > best) { best = s0; best_m = m; }
+                    if (s1 > best) { best = s1; best_m = m + UH_THREADS; }
+                    if (s2 > best) { best = s2; best_m = m + 2 * UH_THREADS; }
+                    if (s3 > best) { best = s3; best_m = m + 3 * UH_THREADS; }
+                }
+                for (; m < m1; m += UH_THREADS) {
+                    const double a = (double)(m + 1);
+                    const double D = (q[m] - base) - a * mu;
+                    const double sc = D * D / (a * (nn - a));
+                    if (sc > best) { best = sc; best_m = m; }
+                }
             }
             warp_argmax(best, best_m);
             if (lane == 0) { s_wscore[warp] = best; s_wm[warp] = best_m; }
@@ -317,53 +355,105 @@ uh_decompose_kernel(UhParams p) {
             if (threadIdx.x == 0) {
                 for (int w = 1; w < UH_THREADS / 32; w++)
                     if (s_wscore[w] > best || (s_wscore[w] == best && s_wm[w] < best_m)) { best = s_wscore[w]; best_m = s_wm[w]; }
-                // merge into the node under its lock
-                while (atomicCAS(&nd->lock, 0, 1) != 0) __nanosleep(32);
-                __threadfence();
-                const double cur = *(volatile double*)&nd->best_score;
-                const int cur_m = *(volatile int*)&nd->best_m;
-                if (best > cur || (best == cur && best_m < cur_m)) {
-                    *(volatile double*)&nd->best_score = best;
-                    *(volatile int*)&nd->best_m = best_m;
-                }
-                __threadfence();
-                atomicExch(&nd->lock, 0);
-                const int done = atomicAdd(&nd->done, 1);
-                s_flag = (done == nchunks - 1) ? 1 : 0;
                 v_big += (unsigned long long)(m1 - m0);
+                int fin = 1;
+                if (nchunks > 1) {
+                    const unsigned long long ri = (npos + (unsigned)chunk) & (UH_QCAP - 1);
+                    *(volatile double*)&p.part_score[ri] = best;
+                    *(volatile int*)&p.part_m[ri] = best_m;
+                    __threadfence();
+                    fin = (atomicAdd(&nd->done, 1) == nchunks - 1) ? 1 : 0;
+                }
+                s_flag = fin;
+                s_wscore[0] = best;
+                s_wm[0] = best_m;
             }
             __syncthreads();
             const int finalize = s_flag;
+            if (!finalize) { __syncthreads(); continue; }
+            // ---- last chunk: reduce the partials of a multi-chunk node (one ring read per thread)
+            double fbest = s_wscore[0];
+            int fm = s_wm[0];
             __syncthreads();
-            if (!finalize) continue;
-            // ---- last chunk: emit the node, route its children
-            __threadfence();
-            const double fbest = *(volatile double*)&nd->best_score;
-            int fm = *(volatile int*)&nd->best_m;
+            if (nchunks > 1) {
+                __threadfence();
+                double ps = -1.0;
+                int pm = 0x7fffffff;
+                for (int i = threadIdx.x; i < nchunks; i += UH_THREADS) {
+                    const unsigned long long ri = (npos + (unsigned)i) & (UH_QCAP - 1);
+                    const double sc = __ldcg(&p.part_score[ri]);
+                    const int mm = __ldcg(&p.part_m[ri]);
+                    if (sc > ps || (sc == ps && mm < pm)) { ps = sc; pm = mm; }
+                }
+                warp_argmax(ps, pm);
+                if (lane == 0) { s_wscore[warp] = ps; s_wm[warp] = pm; }
+                __syncthreads();
+                fbest = s_wscore[0]; fm = s_wm[0];
+                for (int w = 1; w < UH_THREADS / 32; w++)
+                    if (s_wscore[w] > fbest || (s_wscore[w] == fbest && s_wm[w] < fm)) { fbest = s_wscore[w]; fm = s_wm[w]; }
+                __syncthreads();
+            }
+            int nbig_children = 0;
             if (fbest == 0.0) {
                 // run of exact zeros: comb of n-1 nodes with coefficient 0 (see uh_small_subtree)
                 for (int k = threadIdx.x; k < n - 1; k += UH_THREADS) atomicAdd(&p.lvlcnt[p.off[c] + level + k], 1u);
                 if (threadIdx.x == 0) {
                     atomicMax(&p.depth[c], level + n - 1);
                     n_big += (unsigned long long)(n - 1);
+                    s_child[0][3] = 0; s_child[1][3] = 0;
                 }
-            } else if (threadIdx.x == 0) {
+                __syncthreads();
+            } else {
                 if (fm == 0x7fffffff || fm < 0 || fm > n - 2) fm = 0;
-                const double coef = uh_coef(pz, p0, s, n, fm, base, T);
-                atomicAdd(&p.lvlcnt[p.off[c] + level], 1u);
-                atomicMax(&p.depth[c], level + 1);
-                uh_emit_candidate(p, c, level, s, s + fm, e, coef);
-                n_big++;
-                const int ln = fm + 1, rn = n - fm - 1;
-                if (ln >= 2) uh_route_child(p, c, s, s + fm, level + 1);
-                if (rn >= 2) uh_route_child(p, c, s + fm + 1, e, level + 1);
+                // children: kind 0 none, 1 small, 2 big through the queue, 3 big continued locally
+                if (threadIdx.x < 2) {
+                    const int k = threadIdx.x;
+                    const int cs = k == 0 ? s : s + fm + 1, ce = k == 0 ? s + fm : e;
+                    const int cn = ce - cs + 1;
+                    int kind = 0;
+                    if (cn >= 2) {
+                        if (cn <= UH_SMALL_MAX) { uh_push_small(p, c, cs, ce, level + 1); kind = 1; }
+                        else {
+                            const int other_n = n - cn;
+                            const bool single = uh_nchunks(cs, ce) == 1;
+                            // continue locally with a single-chunk child; if both qualify, the larger (left on ties)
+                            const bool other_single_big = other_n > UH_SMALL_MAX && other_n - 1 <= UH_CHUNK;
+                            const bool prefer = !other_single_big || cn > other_n || (cn == other_n && k == 0);
+                            if (single && prefer) kind = 3;
+                            else { s_child_pos[k] = uh_big_alloc(p, c, cs, ce, level + 1); kind = 2; }
+                        }
+                    }
+                    s_child[k][0] = cs; s_child[k][1] = ce; s_child[k][2] = level + 1; s_child[k][3] = kind;
+                }
+                if (threadIdx.x == 2) {
+                    const double coef = uh_coef(pz, p0, s, n, fm, base, T);
+                    atomicAdd(&p.lvlcnt[p.off[c] + level], 1u);
+                    atomicMax(&p.depth[c], level + 1);
+                    uh_emit_candidate(p, c, level, s, s + fm, e, coef);
+                    n_big++;
+                }
+                __syncthreads();
+                for (int k = 0; k < 2; k++) {
+                    const int kind = s_child[k][3];
+                    if (kind == 2) {
+                        uh_big_publish(p, s_child_pos[k], uh_nchunks(s_child[k][0], s_child[k][1]), threadIdx.x, UH_THREADS);
+                        nbig_children++;
+                    } else if (kind == 3) {
+                        have_local = true;
+                        lc = c; ls = s_child[k][0]; le = s_child[k][1]; ll = s_child[k][2];
+                        nbig_children++;
+                    }
+                }
+            }
+            if (threadIdx.x == 0) {
+                const int delta = nbig_children - 1;
+                if (delta != 0) {
+                    __threadfence();
+                    const int now = atomicAdd(&ctl->outstanding, delta) + delta;
+                    if (now == 0) { __threadfence(); *(volatile int*)&ctl->big_done = 1; }
+                }
             }
             __syncthreads();
-            if (threadIdx.x == 0) {
-                __threadfence();
-                const int old = atomicSub(&ctl->outstanding, 1);
-                if (old == 1) { __threadfence(); *(volatile int*)&ctl->big_done = 1; }
-            }
         }
         __syncthreads();
     }
@@ -410,17 +500,25 @@ uh_decompose_kernel(UhParams p) {
     if (n_tiny) atomicAdd(&ctl->nodes_tiny, n_tiny);
 }
 
-// seeds: one root per selected chromosome with more than min_size bins
+// seeds: one root per selected chromosome with more than min_size bins (one thread per chromosome)
 __global__ void uh_seed_kernel(UhParams p, const unsigned char* __restrict__ selected, int n_chrom, int min_size) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    int roots = 0;
-    for (int c = 0; c < n_chrom; c++) {
+    __shared__ int s_big;
+    if (threadIdx.x == 0) s_big = 0;
+    __syncthreads();
+    for (int c = threadIdx.x; c < n_chrom; c += blockDim.x) {
         const long long len = p.off[c + 1] - p.off[c];
         if (!selected[c] || len <= (long long)min_size || len < 2) continue;
-        uh_route_child(p, c, 0, (int)len - 1, 0);
-        roots++;
+        const int e = (int)len - 1;
+        if (e + 1 > UH_SMALL_MAX) {
+            atomicAdd(&s_big, 1);
+            atomicAdd(&p.ctl->outstanding, 1);
+            const unsigned long long pos = uh_big_alloc(p, c, 0, e, 0);
+            uh_big_publish(p, pos, uh_nchunks(0, e), 0, 1);
+        } else {
+            uh_push_small(p, c, 0, e, 0);
+        }
     }
-    __threadfence();
+    __syncthreads();
     // no big node at all: the big phase is over before it starts
-    if (*(volatile int*)&p.ctl->outstanding == 0) *(volatile int*)&p.ctl->big_done = 1;
+    if (threadIdx.x == 0 && s_big == 0) { __threadfence(); *(volatile int*)&p.ctl->big_done = 1; }
 }

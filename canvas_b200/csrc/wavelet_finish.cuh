@@ -5,7 +5,7 @@
 #pragma once
 #include "wavelet.cuh"
 
-constexpr int FIN_THREADS = 256;
+constexpr int FIN_THREADS = 1024;
 constexpr int FIN_SORT_SMEM = 1024;  // survivors sorted in shared memory up to this many
 constexpr int BMS_R = 24;            // requests of one block multi-select
 constexpr int BMS_X = 12;            // "extra" bins per request beyond the shared core range
@@ -160,12 +160,22 @@ __device__ void bms_run(BmsState& st, const double* __restrict__ x) {
         __syncthreads();
         for (int r = 0; r < st.nranges; r++) {
             const int lo = st.rlo[r], hi = st.rhi[r];
-            for (int i = lo + (int)threadIdx.x; i < hi; i += blockDim.x) {
-                const unsigned long long key = f64_key(x[i]);
-                const int d = (int)((key >> shift) & 255ull);
-                for (int g = 0; g < ng; g++)
-                    if (st.grange[g] == r && (first || ((key ^ st.gprefix[g]) >> (shift + 8)) == 0ull))
-                        atomicAdd(&st.hist[g][d], 1u);
+            // four independent loads in flight per thread: the range is L2-resident and one CTA has
+            // to pull it through a single SM
+            const int B = blockDim.x;
+            for (int i0 = lo + (int)threadIdx.x; i0 < hi; i0 += 4 * B) {
+                double v[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) v[u] = (i0 + u * B < hi) ? __ldg(x + i0 + u * B) : 0.0;
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    if (i0 + u * B >= hi) break;
+                    const unsigned long long key = f64_key(v[u]);
+                    const int d = (int)((key >> shift) & 255ull);
+                    for (int g = 0; g < ng; g++)
+                        if (st.grange[g] == r && (first || ((key ^ st.gprefix[g]) >> (shift + 8)) == 0ull))
+                            atomicAdd(&st.hist[g][d], 1u);
+                }
             }
         }
         __syncthreads();
@@ -284,13 +294,11 @@ __device__ void fin_bitonic(unsigned long long* key, int* val, int n2) {
     }
 }
 
-__global__ void __launch_bounds__(FIN_THREADS)
+__global__ void __launch_bounds__(FIN_THREADS, 1)
 uh_finish_kernel(FinParams p) {
     __shared__ BmsState s_bms;
     __shared__ unsigned long long s_key[FIN_SORT_SMEM];
     __shared__ int s_val[FIN_SORT_SMEM];
-    __shared__ int s_i[8];
-    __shared__ double s_d[4];
     const int c = blockIdx.x;
     const long long o = p.off[c];
     const int n = (int)(p.off[c + 1] - o);
@@ -311,10 +319,23 @@ uh_finish_kernel(FinParams p) {
     const int ncand_all = min(p.ctl->cand_count, 0x7fffffff);
 
     // ---- HardThresh level weights (:78-91): germline only
-    if (p.is_germline && threadIdx.x == 0) {
-        for (int l = 0; l < T; l++) lvl_idx[l] = l;
-        LevelSorter ls{lvl_idx, lvlcnt};
-        ls.sort(T);
+    if (p.is_germline) {
+        if (T <= FIN_SORT_SMEM) {
+            // sort in shared memory (s_key doubles as the count table, s_val as the permutation)
+            unsigned* s_cnt = reinterpret_cast<unsigned*>(s_key);
+            for (int l = threadIdx.x; l < T; l += blockDim.x) { s_cnt[l] = lvlcnt[l]; s_val[l] = l; }
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                LevelSorter ls{s_val, s_cnt};
+                ls.sort(T);
+            }
+            __syncthreads();
+            for (int l = threadIdx.x; l < T; l += blockDim.x) lvl_idx[l] = s_val[l];
+        } else if (threadIdx.x == 0) {
+            for (int l = 0; l < T; l++) lvl_idx[l] = l;
+            LevelSorter ls{lvl_idx, lvlcnt};
+            ls.sort(T);
+        }
     }
     __syncthreads();
 
@@ -539,5 +560,4 @@ uh_finish_kernel(FinParams p) {
     }
     __syncthreads();
     if (threadIdx.x == 0) p.n_bp[c] = nb;
-    (void)s_i; (void)s_d;
 }

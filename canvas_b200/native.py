@@ -43,6 +43,8 @@ SIGNATURES = {
     "cg_host_free": (None, [C.c_void_p]),
     "cg_last_kernel_ms": (C.c_double, [C.c_void_p]),
     "cg_last_launches": (C.c_int, [C.c_void_p]),
+    "cg_last_stage_ms": (C.c_double, [C.c_void_p, C.c_int]),
+    "cg_last_partition_stats": (C.c_int, [C.c_void_p, _P(_f64), C.c_int]),
     "cg_clean": (C.c_int, [C.c_void_p, _P(CleanOpts), _i64, _P(_u8), _P(_u8), _P(_u8), C.c_int,
                            _P(_i32), _P(_i32), _P(_f32), _P(_u8), _P(_i64), _P(_i32), _P(_f32),
                            _P(_f64), _P(C.c_int)]),
@@ -154,6 +156,15 @@ class Engine:
     def last_launches(self):
         return self.lib.cg_last_launches(self.h)
 
+    def last_stage_ms(self):
+        names = ("clean", "scalars", "decompose", "finish")
+        return {k: self.lib.cg_last_stage_ms(self.h, i) for i, k in enumerate(names)}
+
+    def last_partition_stats(self):
+        out = np.zeros(4, np.float64)
+        self.lib.cg_last_partition_stats(self.h, _ptr(out, _f64), 4)
+        return {"visits": out[0], "nodes": out[1], "candidates": out[2], "bins": out[3]}
+
     # ------------------------------------------------------------------ CanvasClean
     def clean(self, chrom, is_autosome, is_chr_y, start, stop, count, gc, size_filter=True,
               outlier_filter=True, gc_norm=True, gc_mode=0, want_local_sd=True, min_bins_per_gc=100,
@@ -217,6 +228,52 @@ class Engine:
         self._check(rc)
         bps = [bp[chrom_off[c]:chrom_off[c] + n_bp[c]].copy() for c in range(nc)]
         return {"breakpoints": bps, "evenness": ev.value if ev_ok.value else None,
+                "cv": cv.value if cv_has.value else None, "factor_of_three": f3}
+
+    # ------------------------------------------------------------------ Clean + Partition, fused
+    def clean_partition_wavelet(self, chrom, is_autosome, is_chr_y, start, stop, count, gc,
+                                size_filter=True, outlier_filter=True, gc_norm=True, gc_mode=0,
+                                want_local_sd=True, min_bins_per_gc=100, is_germline=True,
+                                mad_factor=5.0, thr_lower=0.05, thr_upper=80.0, min_size=10,
+                                evenness_window=100000, out=None):
+        """cg_clean_partition_wavelet: both stages without leaving the device in between.
+        `out` = (kept_index, count_out, n_bp, bp) preallocated (e.g. pinned) arrays."""
+        n = len(count)
+        chrom = np.ascontiguousarray(chrom, np.uint8)
+        is_autosome = np.ascontiguousarray(is_autosome, np.uint8)
+        is_chr_y = np.ascontiguousarray(is_chr_y, np.uint8)
+        start = np.ascontiguousarray(start, np.int32)
+        stop = np.ascontiguousarray(stop, np.int32)
+        count = np.ascontiguousarray(count, np.float32)
+        gc = np.ascontiguousarray(gc, np.uint8)
+        nc = len(is_autosome)
+        co = CleanOpts(int(size_filter), int(outlier_filter), int(gc_norm), int(gc_mode),
+                       int(want_local_sd), int(min_bins_per_gc))
+        wo = WaveletOpts(int(is_germline), mad_factor, thr_lower, thr_upper, min_size, evenness_window)
+        if out is None:
+            kept = np.empty(max(n, 1), np.int32)
+            cnt = np.empty(max(n, 1), np.float32)
+            n_bp = np.zeros(max(nc, 1), np.int32)
+            bp = np.zeros(max(n, 1), np.int32)
+        else:
+            kept, cnt, n_bp, bp = out
+        n_out, lsd, skipped = _i64(0), _f64(0), C.c_int(0)
+        off = np.zeros(nc + 1, np.int64)
+        ev, cv = _f64(0), _f64(0)
+        ev_ok, cv_has = C.c_int(0), C.c_int(0)
+        f3 = np.zeros(9, np.float64)
+        rc = self.lib.cg_clean_partition_wavelet(
+            self.h, C.byref(co), C.byref(wo), n, _ptr(chrom, _u8), _ptr(is_autosome, _u8),
+            _ptr(is_chr_y, _u8), nc, _ptr(start, _i32), _ptr(stop, _i32), _ptr(count, _f32),
+            _ptr(gc, _u8), C.byref(n_out), _ptr(kept, _i32), _ptr(cnt, _f32), C.byref(lsd),
+            C.byref(skipped), _ptr(off, _i64), _ptr(n_bp, _i32), _ptr(bp, _i32), C.byref(ev),
+            C.byref(ev_ok), C.byref(cv), C.byref(cv_has), _ptr(f3, _f64))
+        self._check(rc)
+        k = n_out.value
+        bps = [bp[off[c]:off[c] + n_bp[c]].copy() for c in range(nc)]
+        return {"kept_index": kept[:k], "count": cnt[:k], "local_sd": lsd.value,
+                "gc_norm_skipped": bool(skipped.value), "chrom_off": off, "breakpoints": bps,
+                "evenness": ev.value if ev_ok.value else None,
                 "cv": cv.value if cv_has.value else None, "factor_of_three": f3}
 
     # ------------------------------------------------------------------ stand-alone K8

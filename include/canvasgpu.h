@@ -49,6 +49,14 @@ void cg_host_free(void* p);
  * host<->device copies; and the number of kernel launches it made. */
 double cg_last_kernel_ms(cg_ctx* ctx);
 int cg_last_launches(cg_ctx* ctx);
+/* Device time (ms) of one stage of the last call: 0 Clean pipeline, 1 partition scalars + prefix sums,
+ * 2 Unbalanced-Haar decomposition kernel, 3 per-chromosome finish kernel (threshold, reconstruction,
+ * healing, refinement).  -1 when the stage did not run. */
+double cg_last_stage_ms(cg_ctx* ctx, int stage);
+/* Work counters of the last partition call: out[0] = bin visits of the decomposition (sum over tree
+ * nodes of their length: L_eff * N), out[1] = tree nodes, out[2] = candidate nodes kept for the
+ * threshold, out[3] = bins.  Returns the number of values written (<= n). */
+int cg_last_partition_stats(cg_ctx* ctx, double* out, int n);
 
 /* ---------------------------------------------------------------------------------------------
  * CanvasClean — replaces CanvasClean.Main between CanvasIO.ReadFromTextFile (CanvasClean.cs:474)

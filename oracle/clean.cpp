@@ -238,6 +238,38 @@ static std::vector<Bin> remove_extreme_local_sd(const std::vector<Bin>& bins, do
 
 using namespace ora;
 
+// float.ToString("F2") then Convert.ToDouble (IO.cs:21 -> CanvasSegment.cs:1147) as .NET Core 2.0 does
+// it: 7 significant digits first (FLOAT_PRECISION; number.cpp DoubleToNumber), then the digit string
+// is rounded half-up to 2 decimals (RoundNumber).  Implemented on decimal strings, independently of
+// the arithmetic version in the product.  The runtime's formatter is not in the tree: parity unpinned.
+extern "C" void ora_f2_roundtrip(int64_t n, const float* in, double* out) {
+    for (int64_t i = 0; i < n; i++) {
+        float v = in[i];
+        if (std::isnan(v) || std::isinf(v)) { out[i] = (double)v; continue; }
+        char buf[64];
+        snprintf(buf, sizeof buf, "%.6e", (double)std::fabs(v));  // d.dddddde[+-]xx
+        int digits[7];
+        digits[0] = buf[0] - '0';
+        for (int k = 0; k < 6; k++) digits[k + 1] = buf[2 + k] - '0';
+        int exp10 = atoi(buf + 9);
+        // keep pos = exp10 + 3 digits (integer digits + 2 decimals)
+        int pos = exp10 + 3;
+        long long kept = 0;
+        if (pos >= 7) {
+            for (int k = 0; k < 7; k++) kept = kept * 10 + digits[k];
+            for (int k = 7; k < pos && k < 18; k++) kept *= 10;
+        } else if (pos >= 0) {
+            for (int k = 0; k < pos; k++) kept = kept * 10 + digits[k];
+            if (digits[pos] >= 5) kept += 1;
+        } else {
+            kept = 0;
+        }
+        char txt[64];
+        snprintf(txt, sizeof txt, "%s%lld.%02lld", (v < 0 && kept != 0) ? "-" : "", kept / 100, kept % 100);
+        out[i] = strtod(txt, nullptr);
+    }
+}
+
 // CanvasClean.cs:474-530 — everything between ReadFromTextFile and WriteToTextFile.
 extern "C" int ora_clean(const ora_clean_opts* o, int64_t n, const uint8_t* chrom,
                          const uint8_t* chrom_is_autosome, const uint8_t* chrom_is_chrY, int n_chrom,

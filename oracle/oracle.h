@@ -34,6 +34,9 @@ int ora_clean(const ora_clean_opts* o, int64_t n, const uint8_t* chrom,
               int64_t* n_out, int32_t* kept_index, float* count_out, double* local_sd,
               int* gc_norm_skipped);
 
+/* float.ToString("F2") then Convert.ToDouble: the .cleaned file round trip (IO.cs:21). */
+void ora_f2_roundtrip(int64_t n, const float* in, double* out);
+
 typedef struct {
     int is_germline;
     double mad_factor;  /* CanvasPartitionParameters.MadFactor, 5.0 */

@@ -214,3 +214,10 @@ def dotnet_sort_levels(counts):
     idx = np.zeros(len(counts), np.int32)
     lib().ora_dotnet_sort_levels(C.c_int(len(counts)), _p(counts, C.c_int32), _p(idx, C.c_int32))
     return idx
+
+
+def f2_roundtrip(x):
+    x = np.ascontiguousarray(x, np.float32)
+    out = np.zeros(len(x), np.float64)
+    lib().ora_f2_roundtrip(C.c_int64(len(x)), _p(x, C.c_float), _p(out, C.c_double))
+    return out

@@ -19,7 +19,7 @@ def _cleaned_coverage(s):
     r = ora.clean(s.chrom, s.is_autosome, s.is_chr_y, s.start, s.stop, s.count, s.gc)
     chrom = s.chrom[r["kept_index"]]
     off = synth.chrom_offsets(chrom, len(s.names))
-    cov = np.round(r["count"].astype(np.float64), 2)
+    cov = ora.f2_roundtrip(r["count"])
     return off, cov
 
 
@@ -130,3 +130,25 @@ def test_empty_input(engine):
     off = np.array([0, 0], np.int64)
     r = engine.partition_wavelet(off, np.zeros(0), is_germline=True)
     assert len(r["breakpoints"][0]) == 0 and r["cv"] is None and r["evenness"] is None
+
+
+def test_fused_clean_partition_matches_two_calls(engine):
+    # cg_clean_partition_wavelet == cg_clean, .cleaned text round trip on the host, cg_partition_wavelet
+    from canvas_b200 import textcodec
+    s = synth.make_sample(config=2, sample=8, scale=0.2, n_events=120)
+    fused = engine.clean_partition_wavelet(s.chrom, s.is_autosome, s.is_chr_y, s.start, s.stop, s.count, s.gc,
+                                           is_germline=True, evenness_window=20000)
+    o = ora.clean(s.chrom, s.is_autosome, s.is_chr_y, s.start, s.stop, s.count, s.gc)
+    assert np.array_equal(fused["kept_index"], o["kept_index"])
+    assert np.array_equal(fused["count"].view(np.uint32), o["count"].view(np.uint32))
+    assert fused["local_sd"] == o["local_sd"]
+    off = synth.chrom_offsets(s.chrom[o["kept_index"]], len(s.names))
+    assert np.array_equal(fused["chrom_off"], off)
+    cov = ora.f2_roundtrip(o["count"])
+    assert np.array_equal(cov, textcodec.f2_roundtrip(o["count"]))
+    p = ora.partition_wavelet(off, cov, is_germline=True, evenness_window=20000, n_threads=8)
+    _compare(fused, p, "fused")
+    stages = engine.last_stage_ms()
+    assert all(v > 0 for v in stages.values()), stages
+    st = engine.last_partition_stats()
+    assert st["bins"] == len(cov) and st["visits"] > 10 * len(cov)
