@@ -201,7 +201,8 @@ def main():
         launches += eng.last_launches
         for k, v in eng.last_stage_ms().items():
             stage_acc[k] = stage_acc.get(k, 0.0) + v
-        visits = eng.last_partition_stats()["visits"]
+        pstats = eng.last_partition_stats()
+        visits = pstats["visits"]
         d2h = len(r["kept_index"]) * 8 + nbp * 4 + nc * 4 + 4096
     torch.cuda.synchronize()
     if world > 1:
@@ -238,7 +239,7 @@ def main():
             "e2e": {"value": total_bins / (wall_ms * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": wall_ms,
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": launches,
-            "stages_ms": stages,
+            "stages_ms": stages, "partition_stats": pstats,
             "roofline": {"kernel": "uh_decompose_kernel", "bound": "hbm", "achieved": achieved, "peak": hbm,
                          "unit": "GB/s", "frac": (achieved / hbm) if achieved else None, "traffic": None,
                          "peak_source": peak_src, "algorithmic_bytes": alg_bytes,

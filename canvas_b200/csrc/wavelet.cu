@@ -331,13 +331,16 @@ int wv_enqueue(cg_ctx* ctx, const cg_wavelet_opts* o, const WvPlan& pl, WvDev& d
     up.cand = d.cand; up.cand_cap = d.cand_cap; up.ctl = d.ctl;
     CG_LAUNCH(ctx, uh_seed_kernel, 1, 256, 0, up, d.selected, C, o->min_size);
     int occ = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, uh_decompose_kernel, UH_THREADS, 0);
+    const size_t uh_smem = sizeof(UhWarpScratch) * (UH_THREADS / 32);
+    cudaFuncSetAttribute(uh_decompose_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)uh_smem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, uh_decompose_kernel, UH_THREADS, uh_smem);
     if (occ < 1) occ = 1;
-    if (occ > 4) occ = 4;
+    if (occ > 2) occ = 2;
+    // even CTAs are big-node workers, odd CTAs small-subtree workers: keep the grid even and resident
     int grid = ctx->num_sms * occ;
-    grid = (grid / 4) * 4;
-    if (grid < 4) grid = 4;
-    CG_LAUNCH(ctx, uh_decompose_kernel, grid, UH_THREADS, 0, up);
+    grid &= ~1;
+    if (grid < 2) grid = 2;
+    CG_LAUNCH(ctx, uh_decompose_kernel, grid, UH_THREADS, uh_smem, up);
 
     cudaEventRecord(ctx->stage_ev[5], s);
     cudaEventRecord(ctx->stage_ev[6], s);
@@ -350,7 +353,10 @@ int wv_enqueue(cg_ctx* ctx, const cg_wavelet_opts* o, const WvPlan& pl, WvDev& d
     fp.is_germline = o->is_germline; fp.min_size = o->min_size; fp.n_chrom = C; fp.pad = 0;
     fp.lvl_idx = d.lvl_idx; fp.sv = d.sv; fp.svkey = d.svkey; fp.bitmap = d.bitmap; fp.piece = d.piece; fp.rec = d.rec;
     fp.prelim = d.prelim; fp.lvl_first = d.lvl_first; fp.n_bp = d.n_bp; fp.bp = d.bp;
-    if (C > 0) CG_LAUNCH(ctx, uh_finish_kernel, C, FIN_THREADS, 0, fp);
+    if (C > 0) {
+        cudaFuncSetAttribute(uh_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fin_smem_bytes());
+        CG_LAUNCH(ctx, uh_finish_kernel, C, FIN_THREADS, fin_smem_bytes(), fp);
+    }
     cudaEventRecord(ctx->stage_ev[7], s);
     return CG_OK;
 }
@@ -370,6 +376,8 @@ int wv_collect(cg_ctx* ctx, const WvPlan& pl, WvDev& d, int32_t* n_bp, int32_t* 
     ctx->stats[1] = (double)(h->nodes_big + h->nodes_small + h->nodes_tiny);
     ctx->stats[2] = (double)h->cand_count;
     ctx->stats[3] = (double)pl.N;
+    ctx->stats[4] = (double)h->visits_big; ctx->stats[5] = (double)h->visits_small; ctx->stats[6] = (double)h->visits_tiny;
+    ctx->stats[7] = (double)h->nodes_big; ctx->stats[8] = (double)h->nodes_small; ctx->stats[9] = (double)h->nodes_tiny;
     // breakpoints: one copy per chromosome that has any (they are few and short)
     for (int c = 0; c < C; c++) {
         n_bp[c] = h_nbp[c];

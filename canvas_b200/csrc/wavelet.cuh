@@ -20,8 +20,8 @@ constexpr int WV_SCAN_TILE = 2048;
 // ---- decomposition tiers -------------------------------------------------------------------
 constexpr int UH_SMALL_MAX = 1024;  // nodes up to this size: a whole subtree is done by one warp
 constexpr int UH_TINY_MAX = 16;     // nodes up to this size: sequential reference recurrence per thread
-constexpr int UH_CHUNK = 16384;     // split positions per chunk ticket of a big node
-constexpr int UH_THREADS = 256;
+constexpr int UH_CHUNK = 8192;      // split positions per chunk ticket of a big node
+constexpr int UH_THREADS = 512;
 constexpr int UH_QCAP = 1 << 16;    // ticket ring capacity
 
 // Segment kinds of the partition select table (see wavelet.cu)
@@ -59,7 +59,7 @@ struct WvCtl {
     double f3[WV_F3_LEVELS + 1];
     unsigned ev10_valid, ev100_valid;
     double total_launch_dummy;
-    // statistics (bench / DESIGN): element visits of the decomposition, node counts
+    // statistics (bench / DESIGN): bin visits of the decomposition and node counts per tier
     unsigned long long visits_big, visits_small, visits_tiny;
     unsigned long long nodes_big, nodes_small, nodes_tiny;
 };

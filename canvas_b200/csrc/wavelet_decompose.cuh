@@ -267,9 +267,10 @@ __device__ void uh_small_subtree(const UhParams& p, UhWarpScratch& ws, int c, in
 // The persistent kernel.  blockIdx % 4 == 0: big worker (whole CTA per chunk ticket) until the big
 // phase ends, then joins the others; the rest: 8 independent warp workers on small subtrees.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(UH_THREADS)
+__global__ void __launch_bounds__(UH_THREADS, 2)
 uh_decompose_kernel(UhParams p) {
-    __shared__ UhWarpScratch s_ws[UH_THREADS / 32];
+    extern __shared__ __align__(16) unsigned char uh_smem[];
+    UhWarpScratch* s_ws = reinterpret_cast<UhWarpScratch*>(uh_smem);
     __shared__ unsigned long long s_ticket;
     __shared__ double s_wscore[UH_THREADS / 32];
     __shared__ int s_wm[UH_THREADS / 32];
@@ -278,7 +279,7 @@ uh_decompose_kernel(UhParams p) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     unsigned long long v_big = 0, v_small = 0, v_tiny = 0, n_big = 0, n_small = 0, n_tiny = 0;
 
-    if ((blockIdx.x & 3) == 0) {
+    if ((blockIdx.x & 1) == 0) {
         // ----------------------------------------------------------------- big worker
         __shared__ int s_child[2][4];               // routed children {s, e, level, kind}
         __shared__ unsigned long long s_child_pos[2];
@@ -328,19 +329,19 @@ uh_decompose_kernel(UhParams p) {
             {
                 const double* __restrict__ q = pz + p0 + s + 1;
                 int m = m0 + threadIdx.x;
-                // four independent loads in flight per thread
-                for (; m + 3 * UH_THREADS < m1; m += 4 * UH_THREADS) {
-                    const double v0 = q[m], v1 = q[m + UH_THREADS], v2 = q[m + 2 * UH_THREADS], v3 = q[m + 3 * UH_THREADS];
-                    const double a0 = (double)(m + 1), a1 = (double)(m + UH_THREADS + 1);
-                    const double a2 = (double)(m + 2 * UH_THREADS + 1), a3 = (double)(m + 3 * UH_THREADS + 1);
-                    const double D0 = (v0 - base) - a0 * mu, D1 = (v1 - base) - a1 * mu;
-                    const double D2 = (v2 - base) - a2 * mu, D3 = (v3 - base) - a3 * mu;
-                    const double s0 = D0 * D0 / (a0 * (nn - a0)), s1 = D1 * D1 / (a1 * (nn - a1));
-                    const double s2 = D2 * D2 / (a2 * (nn - a2)), s3 = D3 * D3 / (a3 * (nn - a3));
-                    if (s0 > best) { best = s0; best_m = m; }
-                    if (s1 > best) { best = s1; best_m = m + UH_THREADS; }
-                    if (s2 > best) { best = s2; best_m = m + 2 * UH_THREADS; }
-                    if (s3 > best) { best = s3; best_m = m + 3 * UH_THREADS; }
+                // eight independent loads in flight per thread (the prefix sums are L2-resident; a chunk
+                // is two round trips for the CTA)
+                for (; m + 7 * UH_THREADS < m1; m += 8 * UH_THREADS) {
+                    double v[8];
+#pragma unroll
+                    for (int u = 0; u < 8; u++) v[u] = q[m + u * UH_THREADS];
+#pragma unroll
+                    for (int u = 0; u < 8; u++) {
+                        const double a = (double)(m + u * UH_THREADS + 1);
+                        const double D = (v[u] - base) - a * mu;
+                        const double sc = D * D / (a * (nn - a));
+                        if (sc > best) { best = sc; best_m = m + u * UH_THREADS; }
+                    }
                 }
                 for (; m < m1; m += UH_THREADS) {
                     const double a = (double)(m + 1);
@@ -466,6 +467,7 @@ uh_decompose_kernel(UhParams p) {
             idx = atomicAdd(&ctl->small_head, 1);
             if (idx < p.small_cap) {
                 volatile int* ready = &p.small[idx].c;
+                unsigned backoff = 100;
                 for (;;) {
                     c = *ready;
                     if (c >= 0) break;
@@ -474,7 +476,8 @@ uh_decompose_kernel(UhParams p) {
                         c = *ready;  // every push happened before big_done was raised
                         break;
                     }
-                    __nanosleep(200);
+                    __nanosleep(backoff);
+                    if (backoff < 1600) backoff <<= 1;
                 }
                 if (c >= 0) {
                     __threadfence();

@@ -6,7 +6,7 @@
 #include "wavelet.cuh"
 
 constexpr int FIN_THREADS = 1024;
-constexpr int FIN_SORT_SMEM = 1024;  // survivors sorted in shared memory up to this many
+constexpr int FIN_SORT_SMEM = 4096;  // survivors sorted in shared memory up to this many
 constexpr int BMS_R = 24;            // requests of one block multi-select
 constexpr int BMS_X = 12;            // "extra" bins per request beyond the shared core range
 
@@ -128,12 +128,21 @@ struct LevelSorter {
 // ------------------------------------------------------------------------------------------------
 // Block multi-select: exact order statistics of up to BMS_R requests.  Request r asks for rank rk[r]
 // of the bins  core(range id) ∪ [xlo, xhi)  (a few extra bins right after the core).  All requests
-// that still share (range, prefix) share one histogram.  8 radix passes over the core ranges.
+// that still share (range, prefix) share one histogram.  MSD radix passes over the core ranges narrow
+// every request to one bucket; as soon as the buckets still in play hold <= BMS_GCAP bins in total
+// (immediately for short ranges, after ~3 passes for a whole chromosome arm) they are gathered into
+// shared memory, sorted there, and every request reads its answer from the sorted list.
 // ------------------------------------------------------------------------------------------------
+constexpr int BMS_GCAP = 1024;        // gathered candidates, all groups together
+constexpr int BMS_CAND = 2 * BMS_GCAP + 2 * BMS_R;  // slices are padded to powers of two
+
 struct BmsState {
     unsigned hist[BMS_R][256];
+    unsigned long long cand[BMS_CAND];
     unsigned long long gprefix[BMS_R];
     int grange[BMS_R];
+    int gcount[BMS_R], goff[BMS_R], gcap[BMS_R];
+    unsigned gcore[BMS_R];   // bins of the core range inside the group's current bucket
     int ngroups;
     int nranges;
     int rlo[2], rhi[2];
@@ -142,27 +151,62 @@ struct BmsState {
     unsigned long long rk[BMS_R];
     int xlo[BMS_R], xhi[BMS_R];
     unsigned long long rkey[BMS_R];
+    int rdig[BMS_R];
     int newgrp[BMS_R];
+    int mode;        // 0: keep histogramming, 1: gather + sort, 2: all digits decided
+    int match_all;   // gather without any decided digit
+    int shift;
 };
+
+__device__ inline bool bms_match(unsigned long long key, unsigned long long prefix, int low_bit, int match_all) {
+    return match_all || ((key ^ prefix) >> low_bit) == 0ull;
+}
+
+// thread 0: decide whether the buckets in play are small enough to gather
+__device__ inline void bms_plan_gather(BmsState& st) {
+    unsigned total = 0;
+    for (int g = 0; g < st.ngroups; g++) total += st.gcore[g];
+    if (total > (unsigned)BMS_GCAP) return;
+    int off = 0;
+    for (int g = 0; g < st.ngroups; g++) {
+        int cap = 1;
+        while (cap < (int)st.gcore[g]) cap <<= 1;
+        st.gcap[g] = cap;
+        st.goff[g] = off;
+        st.gcount[g] = 0;
+        off += cap;
+    }
+    st.mode = 1;
+}
 
 // caller (thread 0) fills nranges, rlo/rhi, nreq, rk, xlo/xhi and rgrp = range id; then all threads call
 __device__ void bms_run(BmsState& st, const double* __restrict__ x) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int B = blockDim.x;
     __syncthreads();
     if (threadIdx.x == 0) {
         st.ngroups = st.nranges;
-        for (int g = 0; g < st.nranges; g++) { st.gprefix[g] = 0ull; st.grange[g] = g; }
+        for (int g = 0; g < st.nranges; g++) {
+            st.gprefix[g] = 0ull;
+            st.grange[g] = g;
+            st.gcore[g] = (unsigned)max(0, st.rhi[g] - st.rlo[g]);
+        }
+        st.mode = 0;
+        st.match_all = 1;
+        st.shift = 56;
+        bms_plan_gather(st);  // short ranges: no histogram pass at all
     }
     __syncthreads();
-    for (int shift = 56; shift >= 0; shift -= 8) {
+    while (st.mode == 0) {
+        const int shift = st.shift;
         const int ng = st.ngroups;
         const bool first = shift == 56;
-        for (int t = threadIdx.x; t < ng * 256; t += blockDim.x) st.hist[t >> 8][t & 255] = 0u;
+        for (int t = threadIdx.x; t < ng * 256; t += B) st.hist[t >> 8][t & 255] = 0u;
         __syncthreads();
         for (int r = 0; r < st.nranges; r++) {
             const int lo = st.rlo[r], hi = st.rhi[r];
             // four independent loads in flight per thread: the range is L2-resident and one CTA has
             // to pull it through a single SM
-            const int B = blockDim.x;
             for (int i0 = lo + (int)threadIdx.x; i0 < hi; i0 += 4 * B) {
                 double v[4];
 #pragma unroll
@@ -179,53 +223,164 @@ __device__ void bms_run(BmsState& st, const double* __restrict__ x) {
             }
         }
         __syncthreads();
-        // resolve: one thread per request walks its histogram merged with its extra bins
-        if ((int)threadIdx.x < st.nreq) {
-            const int r = threadIdx.x;
+        // resolve: one warp per request; lane l owns bins 8l..8l+7 of the request's group, merged with
+        // the request's extra bins
+        for (int r = warp; r < st.nreq; r += (B >> 5)) {
             const int g = st.rgrp[r];
             const unsigned long long pref = st.gprefix[g];
-            int xd[BMS_X];
-            int nx = 0;
-            for (int i = st.xlo[r]; i < st.xhi[r] && nx < BMS_X; i++) {
+            unsigned c[8];
+            unsigned long long sum = 0;
+#pragma unroll
+            for (int t = 0; t < 8; t++) c[t] = st.hist[g][lane * 8 + t];
+            for (int i = st.xlo[r]; i < st.xhi[r]; i++) {
                 const unsigned long long key = f64_key(x[i]);
                 if (first || ((key ^ pref) >> (shift + 8)) == 0ull) {
                     const int d = (int)((key >> shift) & 255ull);
-                    int j = nx++;
-                    while (j > 0 && xd[j - 1] > d) { xd[j] = xd[j - 1]; j--; }
-                    xd[j] = d;
+                    if ((d >> 3) == lane) c[d & 7]++;
                 }
             }
-            unsigned long long k = st.rk[r], cum = 0;
-            int xi = 0, dsel = 255;
-            for (int d = 0; d < 256; d++) {
-                unsigned long long cnt = st.hist[g][d];
-                while (xi < nx && xd[xi] == d) { cnt++; xi++; }
-                if (k < cum + cnt) { dsel = d; break; }
-                cum += cnt;
+#pragma unroll
+            for (int t = 0; t < 8; t++) sum += c[t];
+            unsigned long long incl = sum;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned long long u = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += u;
             }
-            st.rk[r] = k >= cum ? k - cum : 0ull;
-            st.rkey[r] = pref | ((unsigned long long)dsel << shift);
+            const unsigned long long excl = incl - sum;
+            const unsigned long long k = st.rk[r];
+            const bool mine = sum > 0 && k >= excl && k < excl + sum;
+            unsigned b = __ballot_sync(0xffffffffu, mine);
+            if (b == 0u) {
+                const unsigned nz = __ballot_sync(0xffffffffu, sum > 0);
+                b = nz ? (1u << (31 - __clz(nz))) : 1u;
+            }
+            const int owner = __ffs(b) - 1;
+            if (lane == owner) {
+                unsigned long long run = excl;
+                int d = lane * 8 + 7;
+                unsigned long long cum = excl + sum - c[7];
+#pragma unroll
+                for (int t = 0; t < 8; t++) {
+                    if (k < run + c[t]) { d = lane * 8 + t; cum = run; break; }
+                    run += c[t];
+                }
+                st.rk[r] = k >= cum ? k - cum : 0ull;
+                st.rkey[r] = pref | ((unsigned long long)d << shift);
+                st.rdig[r] = d;
+            }
         }
         __syncthreads();
         if (threadIdx.x == 0) {
-            // regroup by (range, new prefix)
+            // regroup by (range, new prefix); the core count of a new group is one histogram bin
             int nn = 0;
             unsigned long long np[BMS_R];
             int nr[BMS_R];
+            unsigned ncore[BMS_R];
             for (int r = 0; r < st.nreq; r++) {
-                const int range = st.grange[st.rgrp[r]];
+                const int og = st.rgrp[r];
+                const int range = st.grange[og];
                 int idx = -1;
                 for (int q = 0; q < nn; q++)
                     if (np[q] == st.rkey[r] && nr[q] == range) idx = q;
-                if (idx < 0) { idx = nn; np[nn] = st.rkey[r]; nr[nn] = range; nn++; }
+                if (idx < 0) { idx = nn; np[nn] = st.rkey[r]; nr[nn] = range; ncore[nn] = st.hist[og][st.rdig[r]]; nn++; }
                 st.newgrp[r] = idx;
             }
-            for (int q = 0; q < nn; q++) { st.gprefix[q] = np[q]; st.grange[q] = nr[q]; }
+            for (int q = 0; q < nn; q++) { st.gprefix[q] = np[q]; st.grange[q] = nr[q]; st.gcore[q] = ncore[q]; }
             for (int r = 0; r < st.nreq; r++) st.rgrp[r] = st.newgrp[r];
             st.ngroups = nn;
+            st.match_all = 0;
+            if (shift == 0) st.mode = 2;
+            else {
+                bms_plan_gather(st);
+                if (st.mode == 0) st.shift = shift - 8;
+            }
         }
         __syncthreads();
     }
+    if (st.mode != 1) return;
+    // ---- gather the buckets in play, sort each group's slice, answer every request from it
+    const int low_bit = st.shift;
+    const int match_all = st.match_all;
+    const int ng = st.ngroups;
+    for (int g = 0; g < ng; g++)
+        for (int t = st.goff[g] + (int)threadIdx.x; t < st.goff[g] + st.gcap[g]; t += B) st.cand[t] = ~0ull;
+    __syncthreads();
+    for (int r = 0; r < st.nranges; r++) {
+        const int lo = st.rlo[r], hi = st.rhi[r];
+        for (int i0 = lo + (int)threadIdx.x; i0 < hi; i0 += 4 * B) {
+            double v[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) v[u] = (i0 + u * B < hi) ? __ldg(x + i0 + u * B) : 0.0;
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                if (i0 + u * B >= hi) break;
+                const unsigned long long key = f64_key(v[u]);
+                for (int g = 0; g < ng; g++)
+                    if (st.grange[g] == r && bms_match(key, st.gprefix[g], low_bit, match_all)) {
+                        const int idx = atomicAdd(&st.gcount[g], 1);
+                        if (idx < st.gcap[g]) st.cand[st.goff[g] + idx] = key;
+                    }
+            }
+        }
+    }
+    __syncthreads();
+    for (int g = 0; g < ng; g++) {
+        const int n2 = st.gcap[g];
+        unsigned long long* a = st.cand + st.goff[g];
+        for (int k = 2; k <= n2; k <<= 1)
+            for (int j = k >> 1; j > 0; j >>= 1) {
+                for (int i = threadIdx.x; i < n2; i += B) {
+                    const int l = i ^ j;
+                    if (l > i) {
+                        const bool up = (i & k) == 0;
+                        const unsigned long long p = a[i], q = a[l];
+                        if ((p > q) == up) { a[i] = q; a[l] = p; }
+                    }
+                }
+                __syncthreads();
+            }
+    }
+    __syncthreads();
+    if ((int)threadIdx.x < st.nreq) {
+        // k-th smallest of (sorted core candidates A) ∪ (extras E); ties: A before E
+        const int r = threadIdx.x;
+        const int g = st.rgrp[r];
+        const unsigned long long* a = st.cand + st.goff[g];
+        const int na = min(st.gcount[g], st.gcap[g]);
+        unsigned long long e[BMS_X];
+        int ne = 0;
+        for (int i = st.xlo[r]; i < st.xhi[r] && ne < BMS_X; i++) {
+            const unsigned long long key = f64_key(x[i]);
+            if (bms_match(key, st.gprefix[g], low_bit, match_all)) {
+                int j = ne++;
+                while (j > 0 && e[j - 1] > key) { e[j] = e[j - 1]; j--; }
+                e[j] = key;
+            }
+        }
+        const long long k = (long long)st.rk[r];
+        unsigned long long ans = na > 0 ? a[na - 1] : (ne > 0 ? e[ne - 1] : 0ull);
+        bool found = false;
+        for (int j = 0; j < ne && !found; j++) {
+            // rank of e[j] = j + #{a <= e[j]}
+            int lo = 0, hi = na;
+            while (lo < hi) { const int mid = (lo + hi) >> 1; if (a[mid] <= e[j]) lo = mid + 1; else hi = mid; }
+            if ((long long)j + lo == k) { ans = e[j]; found = true; }
+        }
+        if (!found) {
+            // rank of a[i] = i + #{e < a[i]}: monotone in i, find i with rank == k
+            int lo = 0, hi = na - 1;
+            while (lo < hi) {
+                const int mid = (lo + hi + 1) >> 1;
+                int less = 0;
+                for (int j = 0; j < ne; j++) less += e[j] < a[mid];
+                if ((long long)mid + less <= k) lo = mid; else hi = mid - 1;
+            }
+            if (na > 0) ans = a[lo];
+        }
+        st.rkey[r] = ans;
+    }
+    __syncthreads();
 }
 
 // median of x[lo, hi) from a pair of requests {lower middle, upper middle}
@@ -296,9 +451,10 @@ __device__ void fin_bitonic(unsigned long long* key, int* val, int n2) {
 
 __global__ void __launch_bounds__(FIN_THREADS, 1)
 uh_finish_kernel(FinParams p) {
-    __shared__ BmsState s_bms;
-    __shared__ unsigned long long s_key[FIN_SORT_SMEM];
-    __shared__ int s_val[FIN_SORT_SMEM];
+    extern __shared__ __align__(16) unsigned char fin_smem[];
+    BmsState& s_bms = *reinterpret_cast<BmsState*>(fin_smem);
+    unsigned long long* s_key = reinterpret_cast<unsigned long long*>(fin_smem + ((sizeof(BmsState) + 15) & ~(size_t)15));
+    int* s_val = reinterpret_cast<int*>(s_key + FIN_SORT_SMEM);
     const int c = blockIdx.x;
     const long long o = p.off[c];
     const int n = (int)(p.off[c + 1] - o);
@@ -560,4 +716,8 @@ uh_finish_kernel(FinParams p) {
     }
     __syncthreads();
     if (threadIdx.x == 0) p.n_bp[c] = nb;
+}
+
+inline size_t fin_smem_bytes() {
+    return ((sizeof(BmsState) + 15) & ~(size_t)15) + (size_t)FIN_SORT_SMEM * (sizeof(unsigned long long) + sizeof(int));
 }

@@ -55,7 +55,8 @@ int cg_last_launches(cg_ctx* ctx);
 double cg_last_stage_ms(cg_ctx* ctx, int stage);
 /* Work counters of the last partition call: out[0] = bin visits of the decomposition (sum over tree
  * nodes of their length: L_eff * N), out[1] = tree nodes, out[2] = candidate nodes kept for the
- * threshold, out[3] = bins.  Returns the number of values written (<= n). */
+ * threshold, out[3] = bins, out[4..6] = bin visits of the big / warp / per-thread tiers, out[7..9] = nodes of
+ * those tiers.  Returns the number of values written (<= min(n, 10)). */
 int cg_last_partition_stats(cg_ctx* ctx, double* out, int n);
 
 /* ---------------------------------------------------------------------------------------------

@@ -28,8 +28,8 @@ def _compare(a, b, label=""):
         assert x.tolist() == y.tolist(), (label, "chromosome", c, x.tolist()[:40], y.tolist()[:40])
     assert (a["cv"] is None) == (b["cv"] is None)
     if b["cv"] is not None:
-        assert a["cv"] == b["cv"], (a["cv"], b["cv"])
-    assert np.array_equal(a["factor_of_three"], b["factor_of_three"]), (a["factor_of_three"], b["factor_of_three"])
+        assert a["cv"] == b["cv"] or (np.isnan(a["cv"]) and np.isnan(b["cv"])), (a["cv"], b["cv"])
+    assert np.array_equal(a["factor_of_three"], b["factor_of_three"], equal_nan=True), (a["factor_of_three"], b["factor_of_three"])
     assert (a["evenness"] is None) == (b["evenness"] is None)
     if b["evenness"] is not None:
         assert abs(a["evenness"] - b["evenness"]) <= 1e-9 * abs(b["evenness"]), (a["evenness"], b["evenness"])
