@@ -59,7 +59,7 @@ extern "C" double cg_last_stage_ms(cg_ctx* ctx, int stage) {
 }
 extern "C" int cg_last_partition_stats(cg_ctx* ctx, double* out, int n) {
     if (!ctx || !out) return 0;
-    int k = n < 10 ? n : 10;
+    int k = n < 16 ? n : 16;
     for (int i = 0; i < k; i++) out[i] = ctx->stats[i];
     return k;
 }

@@ -26,7 +26,7 @@ struct cg_ctx {
     // stage timers: events [2*i], [2*i+1] bracket stage i
     cudaEvent_t stage_ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     bool stage_used[4] = {false, false, false, false};
-    double stats[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    double stats[16] = {0};
     // device arena, grown on demand and reused across calls
     char* arena = nullptr;
     size_t arena_cap = 0;

@@ -161,12 +161,22 @@ __global__ void sel_hist_contig_kernel(View v, const SelWork* __restrict__ work,
     if (threadIdx.x < SEL_G) s_prefix[threadIdx.x] = st.gprefix[s * SEL_G + threadIdx.x];
     __syncthreads();
     const int hi_shift = shift + 8;
-    for (long long i = w.lo + threadIdx.x; i < w.hi; i += blockDim.x) {
-        K key;
-        if (!v.get(i, s, key)) continue;
+    const long long span = w.hi - w.lo;
+    const long long span_round = ((span + blockDim.x - 1) / blockDim.x) * blockDim.x;
+    for (long long o = threadIdx.x; o < span_round; o += blockDim.x) {
+        const long long i = w.lo + o;
+        K key = 0;
+        const bool ok = i < w.hi && v.get(i, s, key);
         const int d = (int)((key >> shift) & (K)255);
-        for (int j = 0; j < ng; j++)
-            if (first || (((key ^ s_prefix[j]) >> hi_shift) == 0)) atomicAdd(&s_hist[j * SEL_BINS + d], 1u);
+        for (int j = 0; j < ng; j++) {
+            const bool hit = ok && (first || (((key ^ s_prefix[j]) >> hi_shift) == 0));
+            // warp-aggregated: the leading digits of a coverage window are nearly constant
+            const unsigned act = __ballot_sync(0xffffffffu, hit);
+            if (hit) {
+                const unsigned m = __match_any_sync(act, d);
+                if ((int)(__ffs(m) - 1) == (int)(threadIdx.x & 31)) atomicAdd(&s_hist[j * SEL_BINS + d], (unsigned)__popc(m));
+            }
+        }
     }
     __syncthreads();
     for (int t = threadIdx.x; t < ng * SEL_BINS; t += blockDim.x) {

@@ -143,11 +143,7 @@ struct WvDev {
     // decomposition
     unsigned* lvlcnt;
     int* depth;
-    UhNode* bn;
-    int bn_cap;
-    unsigned long long* tickets;
-    double* part_score;
-    int* part_m;
+    UhBigTask* big;
     UhSmallTask* small;
     int small_cap;
     UhCand* cand;
@@ -172,7 +168,7 @@ size_t wv_workspace_bytes(const WvPlan& pl) {
     s += arena_need(pl.t.n_w10 + 1, 4) + arena_need(pl.t.n_w100 + 1, 4);
     s += arena_need(pl.t.nseg, 8) * 2 + arena_need(C + 1, 8) * 2 + arena_need(32, 8) + arena_need(1, sizeof(WvCtl));
     s += arena_need(N + 1, 4) + arena_need(C + 1, 4);
-    s += arena_need(UH_QCAP, sizeof(UhNode)) + arena_need(UH_QCAP, 8) * 2 + arena_need(UH_QCAP, 4) + arena_need(N / 2 + C + 64, sizeof(UhSmallTask));
+    s += arena_need(UH_QCAP, sizeof(UhBigTask)) + arena_need(N / 2 + C + 64, sizeof(UhSmallTask));
     s += arena_need(N / 4 + 4096, sizeof(UhCand));
     s += arena_need(N + 1, 4) * 5 + arena_need(N + 1, 8) * 2 + arena_need(N / 32 + C + 2, 4);
     s += arena_need(C + 1, 4) + arena_need(N + 1, 4);
@@ -207,11 +203,7 @@ int wv_alloc(cg_ctx* ctx, const WvPlan& pl, WvDev& d, double* cov_dev_existing) 
     d.ctl = arena_take<WvCtl>(ctx, 1);
     d.lvlcnt = arena_take<unsigned>(ctx, N + 1);
     d.depth = arena_take<int>(ctx, C + 1);
-    d.bn_cap = UH_QCAP;
-    d.bn = arena_take<UhNode>(ctx, d.bn_cap);
-    d.tickets = arena_take<unsigned long long>(ctx, UH_QCAP);
-    d.part_score = arena_take<double>(ctx, UH_QCAP);
-    d.part_m = arena_take<int>(ctx, UH_QCAP);
+    d.big = arena_take<UhBigTask>(ctx, UH_QCAP);
     d.small_cap = (int)(N / 2 + C + 64);
     d.small = arena_take<UhSmallTask>(ctx, d.small_cap);
     d.cand_cap = (int)(N / 4 + 4096);
@@ -228,7 +220,7 @@ int wv_alloc(cg_ctx* ctx, const WvPlan& pl, WvDev& d, double* cov_dev_existing) 
     d.bp = arena_take<int>(ctx, N + 1);
     ok = ok && d.cov && d.off && d.selected && d.pz && d.seg_len && d.work && d.ev_work && d.tiles && d.tile_first &&
          d.tsum && d.f3lv && d.tmed && d.cmad && d.ev10 && d.ev100 && d.r10 && d.r100 && d.med && d.mad && d.sigma &&
-         d.cand_thr && d.log3 && d.ctl && d.lvlcnt && d.depth && d.bn && d.tickets && d.part_score && d.part_m && d.small && d.cand && d.lvl_idx &&
+         d.cand_thr && d.log3 && d.ctl && d.lvlcnt && d.depth && d.big && d.small && d.cand && d.lvl_idx &&
          d.sv && d.piece && d.prelim && d.lvl_first && d.svkey && d.rec && d.bitmap && d.n_bp && d.bp;
     return ok ? CG_OK : cg_fail(ctx, CG_ERR_CUDA, "partition: device arena exhausted");
 }
@@ -256,10 +248,11 @@ int wv_enqueue(cg_ctx* ctx, const cg_wavelet_opts* o, const WvPlan& pl, WvDev& d
     }
     CG_CUDA(ctx, cudaMemcpyAsync(d.log3, log3_tab, 20 * 8, cudaMemcpyHostToDevice, s));
     CG_CUDA(ctx, cudaMemsetAsync(d.ctl, 0, sizeof(WvCtl), s));
+    CG_CUDA(ctx, cudaMemsetAsync(&d.ctl->t_first, 0xff, sizeof(unsigned long long), s));
     CG_CUDA(ctx, cudaMemsetAsync(d.sel.hist, 0, (size_t)t.nseg * SEL_G * SEL_BINS * sizeof(unsigned), s));
     CG_CUDA(ctx, cudaMemsetAsync(d.lvlcnt, 0, (size_t)(pl.N + 1) * sizeof(unsigned), s));
     CG_CUDA(ctx, cudaMemsetAsync(d.depth, 0, (size_t)(C + 1) * sizeof(int), s));
-    CG_CUDA(ctx, cudaMemsetAsync(d.tickets, 0, (size_t)UH_QCAP * 8, s));
+    CG_CUDA(ctx, cudaMemsetAsync(d.big, 0xff, (size_t)UH_QCAP * sizeof(UhBigTask), s));
     CG_CUDA(ctx, cudaMemsetAsync(d.small, 0xff, (size_t)d.small_cap * sizeof(UhSmallTask), s));
     CG_CUDA(ctx, cudaMemsetAsync(d.n_bp, 0, (size_t)(C + 1) * sizeof(int), s));
     CG_CUDA(ctx, cudaMemsetAsync(d.med, 0, (size_t)t.nseg * 8, s));
@@ -327,7 +320,7 @@ int wv_enqueue(cg_ctx* ctx, const cg_wavelet_opts* o, const WvPlan& pl, WvDev& d
     // ---- decomposition
     UhParams up;
     up.x = d.cov; up.pz = d.pz; up.off = d.off; up.cand_thr = d.cand_thr; up.lvlcnt = d.lvlcnt; up.depth = d.depth;
-    up.bn = d.bn; up.bn_cap = d.bn_cap; up.tickets = d.tickets; up.part_score = d.part_score; up.part_m = d.part_m; up.small = d.small; up.small_cap = d.small_cap;
+    up.big = d.big; up.small = d.small; up.small_cap = d.small_cap;
     up.cand = d.cand; up.cand_cap = d.cand_cap; up.ctl = d.ctl;
     CG_LAUNCH(ctx, uh_seed_kernel, 1, 256, 0, up, d.selected, C, o->min_size);
     int occ = 0;
@@ -371,13 +364,23 @@ int wv_collect(cg_ctx* ctx, const WvPlan& pl, WvDev& d, int32_t* n_bp, int32_t* 
     CG_CUDA(ctx, cudaMemcpyAsync(h_nbp, d.n_bp, (size_t)C * 4, cudaMemcpyDeviceToHost, s));
     CG_CUDA(ctx, cudaStreamSynchronize(s));
     CG_CUDA(ctx, cudaGetLastError());
-    if (h->overflow) return cg_fail(ctx, CG_ERR_CAPACITY, "partition: internal queue capacity exceeded");
+    if (h->overflow_.v) return cg_fail(ctx, CG_ERR_CAPACITY, "partition: internal queue capacity exceeded");
     ctx->stats[0] = (double)(h->visits_big + h->visits_small + h->visits_tiny);
     ctx->stats[1] = (double)(h->nodes_big + h->nodes_small + h->nodes_tiny);
-    ctx->stats[2] = (double)h->cand_count;
+    ctx->stats[2] = (double)h->cand_count_.v;
     ctx->stats[3] = (double)pl.N;
     ctx->stats[4] = (double)h->visits_big; ctx->stats[5] = (double)h->visits_small; ctx->stats[6] = (double)h->visits_tiny;
     ctx->stats[7] = (double)h->nodes_big; ctx->stats[8] = (double)h->nodes_small; ctx->stats[9] = (double)h->nodes_tiny;
+    ctx->stats[10] = h->t_big_done > h->t_first ? (double)(h->t_big_done - h->t_first) * 1e-6 : 0.0;  // ms
+    ctx->stats[11] = h->t_last > h->t_first ? (double)(h->t_last - h->t_first) * 1e-6 : 0.0;
+    ctx->stats[12] = (double)h->multi_chunk_nodes; ctx->stats[13] = (double)h->queue_hops;
+    {
+        int maxd = 0;
+        std::vector<int> dep(pl.n_chrom + 1, 0);
+        cudaMemcpy(dep.data(), d.depth, (size_t)pl.n_chrom * 4, cudaMemcpyDeviceToHost);
+        for (int c = 0; c < pl.n_chrom; c++) maxd = std::max(maxd, dep[c]);
+        ctx->stats[14] = (double)maxd;
+    }
     // breakpoints: one copy per chromosome that has any (they are few and short)
     for (int c = 0; c < C; c++) {
         n_bp[c] = h_nbp[c];

@@ -20,7 +20,6 @@ constexpr int WV_SCAN_TILE = 2048;
 // ---- decomposition tiers -------------------------------------------------------------------
 constexpr int UH_SMALL_MAX = 1024;  // nodes up to this size: a whole subtree is done by one warp
 constexpr int UH_TINY_MAX = 16;     // nodes up to this size: sequential reference recurrence per thread
-constexpr int UH_CHUNK = 8192;      // split positions per chunk ticket of a big node
 constexpr int UH_THREADS = 512;
 constexpr int UH_QCAP = 1 << 16;    // ticket ring capacity
 
@@ -31,10 +30,9 @@ struct WvSegTable {
     int nseg;
 };
 
-struct UhNode {  // big node record, stored in the ring slot of its first ticket
-    int c, s, e, level;
-    int nchunks, done;
-    unsigned long long pos;  // ring position of ticket 0
+struct UhBigTask {  // a big node waiting for a chain worker
+    int c, s, e, level;   // c < 0: slot empty
+    double base, endv;    // prefix sums just before s and at e
 };
 
 struct UhSmallTask {
@@ -48,11 +46,15 @@ struct UhCand {  // node whose coefficient may survive the hard threshold
     double coef;
 };
 
+// Every hot word of the queues sits in its own 128-byte line: thousands of idle warps poll
+// `big_done` while the big workers run atomics on the ring counters.
+struct alignas(128) WvPadU64 { unsigned long long v; unsigned long long pad[15]; };
+struct alignas(128) WvPadI32 { int v; int pad[31]; };
+
 struct WvCtl {
     // queues
-    unsigned long long q_head, q_tail;
-    int bn_count_unused, small_head, small_tail, outstanding;
-    int big_done, overflow, cand_count, pad0;
+    WvPadU64 q_head_, q_tail_;
+    WvPadI32 small_head_, small_tail_, outstanding_, big_done_, overflow_, cand_count_;
     // scalars
     int cv_has_value, evenness_ok;
     double cv, evenness;
@@ -62,4 +64,9 @@ struct WvCtl {
     // statistics (bench / DESIGN): bin visits of the decomposition and node counts per tier
     unsigned long long visits_big, visits_small, visits_tiny;
     unsigned long long nodes_big, nodes_small, nodes_tiny;
+    // timeline of the decomposition kernel (%globaltimer, ns)
+    unsigned long long t_first, t_big_done, t_last;
+    unsigned long long multi_chunk_nodes, queue_hops;
+    // big-worker time accounting (ns, summed over workers) and node latencies
+    unsigned long long ns_wait, ns_work, ns_node_lat_sum, ns_node_lat_max, n_node_lat, ns_inline_sum, n_inline;
 };

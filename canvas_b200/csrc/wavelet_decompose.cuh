@@ -8,9 +8,12 @@
 //   * closed form: with P the prefix sums of the node, a = m+1, b = n-a,
 //       ip[m] = (P_m - a*T/n) * sqrt(n / (a*b)),  arg-max |ip| = arg-max (P_m - a*T/n)^2 / (a*b)
 //     so a node costs one division per split point on the chromosome-wide prefix-sum array;
-//   * big nodes (n > UH_SMALL_MAX) are cut into chunk tickets served from a global ring by
-//     "big worker" CTAs; the last chunk to finish reduces, emits the node and enqueues its children
-//     — no level barrier, every chromosome's chain advances on its own;
+//   * big nodes (n > UH_SMALL_MAX) are walked by "chain worker" CTAs: a CTA takes a big node, finds
+//     its split with all its threads (16 loads in flight per thread on the L2-resident prefix sums,
+//     one __syncthreads per node), emits it, keeps going with the LARGER big child and hands the other
+//     big child to an idle CTA through a task ring — no level barrier, no per-node global handshake:
+//     the prefix values bounding each child are carried over from the arg-max winner, so the chain
+//     never re-reads them;
 //   * a node of <= UH_SMALL_MAX bins is handed to ONE warp that runs its whole subtree depth-first
 //     (smaller child first: stack depth <= log2 n) without touching the global queue;
 //   * nodes of <= UH_TINY_MAX bins are batched 32 at a time and done one per thread with the
@@ -28,11 +31,7 @@ struct UhParams {
     const double* cand_thr;  // [n_chrom]
     unsigned* lvlcnt;        // [N]: node count of level l of chromosome c at off[c] + l
     int* depth;              // [n_chrom]: number of levels
-    UhNode* bn;
-    int bn_cap;
-    unsigned long long* tickets;  // ring [UH_QCAP]; 0 = empty
-    double* part_score;           // ring [UH_QCAP]: per-ticket partial arg-max of a multi-chunk node
-    int* part_m;                  // ring [UH_QCAP]
+    UhBigTask* big;               // ring [UH_QCAP]; c < 0 = empty
     UhSmallTask* small;            // c < 0 = not published yet
     int small_cap;
     UhCand* cand;
@@ -42,8 +41,8 @@ struct UhParams {
 
 __device__ inline void uh_emit_candidate(const UhParams& p, int c, int level, int s, int b, int e, double coef) {
     if (fabs(coef) <= p.cand_thr[c]) return;  // NaN falls through on purpose (never zeroed by HardThresh)
-    const int i = atomicAdd(&p.ctl->cand_count, 1);
-    if (i >= p.cand_cap) { p.ctl->overflow = 1; return; }
+    const int i = atomicAdd(&p.ctl->cand_count_.v, 1);
+    if (i >= p.cand_cap) { p.ctl->overflow_.v = 1; return; }
     UhCand k;
     k.key = ((unsigned long long)c << 56) | ((unsigned long long)level << 32) | (unsigned)s;
     k.s = s; k.b = b; k.e = e; k.level = level; k.c = c; k.pad = 0; k.coef = coef;
@@ -51,41 +50,24 @@ __device__ inline void uh_emit_candidate(const UhParams& p, int c, int level, in
 }
 
 __device__ inline void uh_push_small(const UhParams& p, int c, int s, int e, int level) {
-    const int i = atomicAdd(&p.ctl->small_tail, 1);
-    if (i >= p.small_cap) { p.ctl->overflow = 1; return; }
+    const int i = atomicAdd(&p.ctl->small_tail_.v, 1);
+    if (i >= p.small_cap) { p.ctl->overflow_.v = 1; return; }
     UhSmallTask* t = p.small + i;
     t->s = s; t->e = e; t->level = level;
     __threadfence();
     *(volatile int*)&t->c = c;  // publish
 }
 
-// A big node owns `nch` consecutive positions of the ticket ring: ticket i of the node sits at
-// position pos + i, its partial result at the same ring index, and the node record itself in slot
-// pos & mask.  One atomicAdd on q_tail therefore allocates all three.  `tid`/`nthr` let a whole CTA
-// write the tickets in parallel (the stores are independent); a single thread passes (0, 1).
-// The caller must make the node record visible (threadfence) before tickets are written; this
-// routine does that for the single-thread form.
-__device__ inline unsigned long long uh_big_alloc(const UhParams& p, int c, int s, int e, int level) {
-    const int nsplit = e - s;  // n - 1 split positions
-    const int nch = (nsplit + UH_CHUNK - 1) / UH_CHUNK;
-    const unsigned long long pos = atomicAdd(&p.ctl->q_tail, (unsigned long long)nch);
-    UhNode* nd = p.bn + (pos & (UH_QCAP - 1));
-    nd->c = c; nd->s = s; nd->e = e; nd->level = level;
-    nd->nchunks = nch; nd->done = 0; nd->pos = pos;
+// Big-task ring: a producer reserves a position with one atomicAdd, fills the slot and publishes it
+// by storing the chromosome id last; a consumer reserves a position the same way and waits for it.
+__device__ inline void uh_push_big(const UhParams& p, int c, int s, int e, int level, double base, double endv) {
+    const unsigned long long pos = atomicAdd(&p.ctl->q_tail_.v, 1ull);
+    UhBigTask* t = p.big + (pos & (UH_QCAP - 1));
+    while (*(volatile int*)&t->c >= 0) __nanosleep(64);  // slot still held by an unconsumed task (ring wrapped)
+    t->s = s; t->e = e; t->level = level; t->base = base; t->endv = endv;
     __threadfence();
-    return pos;
+    *(volatile int*)&t->c = c;
 }
-
-__device__ inline void uh_big_publish(const UhParams& p, unsigned long long pos, int nch, int tid, int nthr) {
-    const unsigned long long slot1 = (pos & (UH_QCAP - 1)) + 1ull;
-    for (int i = tid; i < nch; i += nthr) {
-        volatile unsigned long long* slot = p.tickets + ((pos + i) & (UH_QCAP - 1));
-        while (*slot != 0ull) __nanosleep(64);
-        *slot = (slot1 << 32) | (unsigned)i;
-    }
-}
-
-__device__ inline int uh_nchunks(int s, int e) { return (e - s + UH_CHUNK - 1) / UH_CHUNK; }
 
 // (score, m) arg-max inside a warp: largest score, smallest m among equals.  Scores are >= 0
 // (or NaN, mapped to 0), so their bit patterns order like unsigned integers.
@@ -271,190 +253,168 @@ __global__ void __launch_bounds__(UH_THREADS, 2)
 uh_decompose_kernel(UhParams p) {
     extern __shared__ __align__(16) unsigned char uh_smem[];
     UhWarpScratch* s_ws = reinterpret_cast<UhWarpScratch*>(uh_smem);
-    __shared__ unsigned long long s_ticket;
-    __shared__ double s_wscore[UH_THREADS / 32];
-    __shared__ int s_wm[UH_THREADS / 32];
-    __shared__ int s_flag;
     WvCtl* ctl = p.ctl;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+        atomicMin(&ctl->t_first, t);
+    }
     unsigned long long v_big = 0, v_small = 0, v_tiny = 0, n_big = 0, n_small = 0, n_tiny = 0;
 
     if ((blockIdx.x & 1) == 0) {
-        // ----------------------------------------------------------------- big worker
-        __shared__ int s_child[2][4];               // routed children {s, e, level, kind}
-        __shared__ unsigned long long s_child_pos[2];
-        bool have_local = false;                    // a single-chunk child continued without the queue
-        int lc = 0, ls = 0, le = 0, ll = 0;
+        // ----------------------------------------------------------------- chain worker
+        __shared__ int s_task[4];
+        __shared__ double s_taskd[2];
+        __shared__ double s_ws[2][UH_THREADS / 32];   // per-warp best score, double-buffered by node parity
+        __shared__ double s_wv[2][UH_THREADS / 32];   // prefix value at the best split
+        __shared__ int s_wm2[2][UH_THREADS / 32];
+        const double* __restrict__ pz = p.pz;
+        int parity = 0;
         for (;;) {
-            int c, s, e, level, nchunks, chunk;
-            unsigned long long npos = 0;
-            UhNode* nd = nullptr;
-            if (have_local) {
-                c = lc; s = ls; e = le; level = ll; nchunks = 1; chunk = 0;
-                have_local = false;
-            } else {
-                if (threadIdx.x == 0) {
-                    unsigned long long t = 0;
-                    const unsigned long long pos = atomicAdd(&ctl->q_head, 1ull);
-                    volatile unsigned long long* slot = p.tickets + (pos & (UH_QCAP - 1));
-                    for (;;) {
-                        t = *slot;
-                        if (t != 0ull) { *slot = 0ull; break; }
-                        if (*(volatile int*)&ctl->big_done || *(volatile int*)&ctl->overflow) break;
-                        __nanosleep(40);
-                    }
-                    s_ticket = t;
-                }
-                __syncthreads();
-                const unsigned long long t = s_ticket;
-                __syncthreads();
-                if (t == 0ull) break;
-                nd = p.bn + ((t >> 32) - 1ull);
-                chunk = (int)(t & 0xffffffffu);
-                c = __ldcg(&nd->c); s = __ldcg(&nd->s); e = __ldcg(&nd->e); level = __ldcg(&nd->level);
-                nchunks = __ldcg(&nd->nchunks);
-                npos = __ldcg(&nd->pos);
-            }
-            const int n = e - s + 1;
-            const long long p0 = p.off[c] + c;
-            const double* __restrict__ pz = p.pz;
-            const double base = pz[p0 + s];
-            const double T = pz[p0 + e + 1] - base;
-            const double nn = (double)n;
-            const double mu = T / nn;
-            const int m0 = chunk * UH_CHUNK;
-            const int m1 = min(m0 + UH_CHUNK, n - 1);
-            double best = -1.0;
-            int best_m = 0x7fffffff;
-            {
-                const double* __restrict__ q = pz + p0 + s + 1;
-                int m = m0 + threadIdx.x;
-                // eight independent loads in flight per thread (the prefix sums are L2-resident; a chunk
-                // is two round trips for the CTA)
-                for (; m + 7 * UH_THREADS < m1; m += 8 * UH_THREADS) {
-                    double v[8];
-#pragma unroll
-                    for (int u = 0; u < 8; u++) v[u] = q[m + u * UH_THREADS];
-#pragma unroll
-                    for (int u = 0; u < 8; u++) {
-                        const double a = (double)(m + u * UH_THREADS + 1);
-                        const double D = (v[u] - base) - a * mu;
-                        const double sc = D * D / (a * (nn - a));
-                        if (sc > best) { best = sc; best_m = m + u * UH_THREADS; }
-                    }
-                }
-                for (; m < m1; m += UH_THREADS) {
-                    const double a = (double)(m + 1);
-                    const double D = (q[m] - base) - a * mu;
-                    const double sc = D * D / (a * (nn - a));
-                    if (sc > best) { best = sc; best_m = m; }
-                }
-            }
-            warp_argmax(best, best_m);
-            if (lane == 0) { s_wscore[warp] = best; s_wm[warp] = best_m; }
-            __syncthreads();
+            // ---- take a big task
             if (threadIdx.x == 0) {
-                for (int w = 1; w < UH_THREADS / 32; w++)
-                    if (s_wscore[w] > best || (s_wscore[w] == best && s_wm[w] < best_m)) { best = s_wscore[w]; best_m = s_wm[w]; }
-                v_big += (unsigned long long)(m1 - m0);
-                int fin = 1;
-                if (nchunks > 1) {
-                    const unsigned long long ri = (npos + (unsigned)chunk) & (UH_QCAP - 1);
-                    *(volatile double*)&p.part_score[ri] = best;
-                    *(volatile int*)&p.part_m[ri] = best_m;
-                    __threadfence();
-                    fin = (atomicAdd(&nd->done, 1) == nchunks - 1) ? 1 : 0;
-                }
-                s_flag = fin;
-                s_wscore[0] = best;
-                s_wm[0] = best_m;
-            }
-            __syncthreads();
-            const int finalize = s_flag;
-            if (!finalize) { __syncthreads(); continue; }
-            // ---- last chunk: reduce the partials of a multi-chunk node (one ring read per thread)
-            double fbest = s_wscore[0];
-            int fm = s_wm[0];
-            __syncthreads();
-            if (nchunks > 1) {
-                __threadfence();
-                double ps = -1.0;
-                int pm = 0x7fffffff;
-                for (int i = threadIdx.x; i < nchunks; i += UH_THREADS) {
-                    const unsigned long long ri = (npos + (unsigned)i) & (UH_QCAP - 1);
-                    const double sc = __ldcg(&p.part_score[ri]);
-                    const int mm = __ldcg(&p.part_m[ri]);
-                    if (sc > ps || (sc == ps && mm < pm)) { ps = sc; pm = mm; }
-                }
-                warp_argmax(ps, pm);
-                if (lane == 0) { s_wscore[warp] = ps; s_wm[warp] = pm; }
-                __syncthreads();
-                fbest = s_wscore[0]; fm = s_wm[0];
-                for (int w = 1; w < UH_THREADS / 32; w++)
-                    if (s_wscore[w] > fbest || (s_wscore[w] == fbest && s_wm[w] < fm)) { fbest = s_wscore[w]; fm = s_wm[w]; }
-                __syncthreads();
-            }
-            int nbig_children = 0;
-            if (fbest == 0.0) {
-                // run of exact zeros: comb of n-1 nodes with coefficient 0 (see uh_small_subtree)
-                for (int k = threadIdx.x; k < n - 1; k += UH_THREADS) atomicAdd(&p.lvlcnt[p.off[c] + level + k], 1u);
-                if (threadIdx.x == 0) {
-                    atomicMax(&p.depth[c], level + n - 1);
-                    n_big += (unsigned long long)(n - 1);
-                    s_child[0][3] = 0; s_child[1][3] = 0;
-                }
-                __syncthreads();
-            } else {
-                if (fm == 0x7fffffff || fm < 0 || fm > n - 2) fm = 0;
-                // children: kind 0 none, 1 small, 2 big through the queue, 3 big continued locally
-                if (threadIdx.x < 2) {
-                    const int k = threadIdx.x;
-                    const int cs = k == 0 ? s : s + fm + 1, ce = k == 0 ? s + fm : e;
-                    const int cn = ce - cs + 1;
-                    int kind = 0;
-                    if (cn >= 2) {
-                        if (cn <= UH_SMALL_MAX) { uh_push_small(p, c, cs, ce, level + 1); kind = 1; }
-                        else {
-                            const int other_n = n - cn;
-                            const bool single = uh_nchunks(cs, ce) == 1;
-                            // continue locally with a single-chunk child; if both qualify, the larger (left on ties)
-                            const bool other_single_big = other_n > UH_SMALL_MAX && other_n - 1 <= UH_CHUNK;
-                            const bool prefer = !other_single_big || cn > other_n || (cn == other_n && k == 0);
-                            if (single && prefer) kind = 3;
-                            else { s_child_pos[k] = uh_big_alloc(p, c, cs, ce, level + 1); kind = 2; }
-                        }
+                int c = -1;
+                const unsigned long long pos = atomicAdd(&ctl->q_head_.v, 1ull);
+                UhBigTask* t = p.big + (pos & (UH_QCAP - 1));
+                volatile int* ready = &t->c;
+                unsigned polls = 0;
+                for (;;) {
+                    c = *ready;
+                    if (c >= 0) break;
+                    if ((++polls & 3u) == 0u && (*(volatile int*)&ctl->big_done_.v || *(volatile int*)&ctl->overflow_.v)) {
+                        __threadfence();
+                        c = *ready;
+                        break;
                     }
-                    s_child[k][0] = cs; s_child[k][1] = ce; s_child[k][2] = level + 1; s_child[k][3] = kind;
+                    __nanosleep(40);
                 }
-                if (threadIdx.x == 2) {
-                    const double coef = uh_coef(pz, p0, s, n, fm, base, T);
-                    atomicAdd(&p.lvlcnt[p.off[c] + level], 1u);
+                if (c >= 0) {
+                    __threadfence();
+                    s_task[1] = *(volatile int*)&t->s; s_task[2] = *(volatile int*)&t->e; s_task[3] = *(volatile int*)&t->level;
+                    s_taskd[0] = *(volatile double*)&t->base; s_taskd[1] = *(volatile double*)&t->endv;
+                    __threadfence();
+                    *ready = -1;  // free the slot
+                }
+                s_task[0] = c;
+            }
+            __syncthreads();
+            const int c = s_task[0];
+            int s = s_task[1], e = s_task[2], level = s_task[3];
+            double base = s_taskd[0], endv = s_taskd[1];
+            __syncthreads();
+            if (c < 0) break;
+            const long long p0 = p.off[c] + c;
+            const long long loff = p.off[c];
+            // ---- walk the chain
+            for (;;) {
+                const int n = e - s + 1;
+                const double nn = (double)n;
+                const double T = endv - base;
+                const double mu = T / nn;
+                const double* __restrict__ q = pz + p0 + s + 1;
+                // arg-max of D^2 / (a b); inside a thread compared by cross-multiplication (no division)
+                double bnum = -1.0, bden = 1.0, bv = 0.0;
+                int bm = 0x7fffffff;
+                int m = threadIdx.x;
+                for (; m + 15 * UH_THREADS < n - 1; m += 16 * UH_THREADS) {
+                    double v[16];
+#pragma unroll
+                    for (int u = 0; u < 16; u++) v[u] = __ldg(q + m + u * UH_THREADS);
+#pragma unroll
+                    for (int u = 0; u < 16; u++) {
+                        const double a = (double)(m + u * UH_THREADS + 1);
+                        const double D = fma(-a, mu, v[u] - base);
+                        const double num = D * D, den = a * (nn - a);
+                        if (num * bden > bnum * den) { bnum = num; bden = den; bm = m + u * UH_THREADS; bv = v[u]; }
+                    }
+                }
+                for (; m + 3 * UH_THREADS < n - 1; m += 4 * UH_THREADS) {
+                    double v[4];
+#pragma unroll
+                    for (int u = 0; u < 4; u++) v[u] = __ldg(q + m + u * UH_THREADS);
+#pragma unroll
+                    for (int u = 0; u < 4; u++) {
+                        const double a = (double)(m + u * UH_THREADS + 1);
+                        const double D = fma(-a, mu, v[u] - base);
+                        const double num = D * D, den = a * (nn - a);
+                        if (num * bden > bnum * den) { bnum = num; bden = den; bm = m + u * UH_THREADS; bv = v[u]; }
+                    }
+                }
+                for (; m < n - 1; m += UH_THREADS) {
+                    const double vv = __ldg(q + m);
+                    const double a = (double)(m + 1);
+                    const double D = fma(-a, mu, vv - base);
+                    const double num = D * D, den = a * (nn - a);
+                    if (num * bden > bnum * den) { bnum = num; bden = den; bm = m; bv = vv; }
+                }
+                double best = bnum >= 0.0 ? bnum / bden : -1.0;
+                int best_m = bm;
+                warp_argmax(best, best_m);
+                {
+                    // the lane that owns the winning split also owns its prefix value
+                    const unsigned own = __ballot_sync(0xffffffffu, bm == best_m && best_m != 0x7fffffff);
+                    const int src = own ? __ffs(own) - 1 : 0;
+                    const double wv = __shfl_sync(0xffffffffu, bv, src);
+                    if (lane == 0) { s_ws[parity][warp] = best; s_wm2[parity][warp] = best_m; s_wv[parity][warp] = wv; }
+                }
+                __syncthreads();
+                double fbest = s_ws[parity][0], fv = s_wv[parity][0];
+                int fm = s_wm2[parity][0];
+#pragma unroll
+                for (int w = 1; w < UH_THREADS / 32; w++) {
+                    const double sc = s_ws[parity][w];
+                    const int mm = s_wm2[parity][w];
+                    if (sc > fbest || (sc == fbest && mm < fm)) { fbest = sc; fm = mm; fv = s_wv[parity][w]; }
+                }
+                parity ^= 1;
+                if (threadIdx.x == 0) v_big += (unsigned long long)n;
+                if (fbest == 0.0 || fm == 0x7fffffff) {
+                    // run of exact zeros: comb of n-1 nodes with coefficient 0 (see uh_small_subtree)
+                    for (int k = threadIdx.x; k < n - 1; k += UH_THREADS) atomicAdd(&p.lvlcnt[loff + level + k], 1u);
+                    if (threadIdx.x == 0) { atomicMax(&p.depth[c], level + n - 1); n_big += (unsigned long long)(n - 1); }
+                    break;  // chain ends
+                }
+                // ---- emit (one lane of warp 1; every thread derives the children itself)
+                if (threadIdx.x == 32) {
+                    const double a = (double)(fm + 1), b = (double)(n - fm - 1);
+                    const double D = fma(-a, mu, fv - base);
+                    const double ip = D * sqrt(nn / (a * b));
+                    const double coef = ip / fmax(0.5, mu / 200.0);
+                    atomicAdd(&p.lvlcnt[loff + level], 1u);
                     atomicMax(&p.depth[c], level + 1);
                     uh_emit_candidate(p, c, level, s, s + fm, e, coef);
                     n_big++;
                 }
-                __syncthreads();
-                for (int k = 0; k < 2; k++) {
-                    const int kind = s_child[k][3];
-                    if (kind == 2) {
-                        uh_big_publish(p, s_child_pos[k], uh_nchunks(s_child[k][0], s_child[k][1]), threadIdx.x, UH_THREADS);
-                        nbig_children++;
-                    } else if (kind == 3) {
-                        have_local = true;
-                        lc = c; ls = s_child[k][0]; le = s_child[k][1]; ll = s_child[k][2];
-                        nbig_children++;
-                    }
+                const int ls = s, le = s + fm, rs = s + fm + 1, re = e;
+                const int ln = le - ls + 1, rn = re - rs + 1;
+                const bool lbig = ln > UH_SMALL_MAX, rbig = rn > UH_SMALL_MAX;
+                // continue with the larger big child (left on ties)
+                const bool cont_left = lbig && (!rbig || ln >= rn);
+                const bool cont_right = rbig && !cont_left;
+                if (threadIdx.x == 0) {
+                    if (lbig && !cont_left) { atomicAdd(&ctl->outstanding_.v, 1); uh_push_big(p, c, ls, le, level + 1, base, fv); }
+                    if (rbig && !cont_right) { atomicAdd(&ctl->outstanding_.v, 1); uh_push_big(p, c, rs, re, level + 1, fv, endv); }
+                    if (!lbig && ln >= 2) uh_push_small(p, c, ls, le, level + 1);
+                    if (!rbig && rn >= 2) uh_push_small(p, c, rs, re, level + 1);
                 }
+                if (cont_left) { e = le; endv = fv; level++; }
+                else if (cont_right) { s = rs; base = fv; level++; }
+                else break;  // no big child: chain ends
             }
-            if (threadIdx.x == 0) {
-                const int delta = nbig_children - 1;
-                if (delta != 0) {
-                    __threadfence();
-                    const int now = atomicAdd(&ctl->outstanding, delta) + delta;
-                    if (now == 0) { __threadfence(); *(volatile int*)&ctl->big_done = 1; }
-                }
-            }
+            // ---- chain finished: one big task less
             __syncthreads();
+            if (threadIdx.x == 0) {
+                __threadfence();
+                const int now = atomicSub(&ctl->outstanding_.v, 1) - 1;
+                if (now == 0) {
+                    __threadfence();
+                    *(volatile int*)&ctl->big_done_.v = 1;
+                    unsigned long long t;
+                    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+                    ctl->t_big_done = t;
+                }
+            }
         }
         __syncthreads();
     }
@@ -464,14 +424,15 @@ uh_decompose_kernel(UhParams p) {
     for (;;) {
         int idx = 0, c = -1, s = 0, e = 0, level = 0;
         if (lane == 0) {
-            idx = atomicAdd(&ctl->small_head, 1);
+            idx = atomicAdd(&ctl->small_head_.v, 1);
             if (idx < p.small_cap) {
                 volatile int* ready = &p.small[idx].c;
-                unsigned backoff = 100;
+                unsigned backoff = 100, polls = 0;
                 for (;;) {
                     c = *ready;
                     if (c >= 0) break;
-                    if (*(volatile int*)&ctl->big_done || *(volatile int*)&ctl->overflow) {
+                    // the shared flags are looked at every 4th poll only (one line for all idle warps)
+                    if ((++polls & 3u) == 0u && (*(volatile int*)&ctl->big_done_.v || *(volatile int*)&ctl->overflow_.v)) {
                         __threadfence();
                         c = *ready;  // every push happened before big_done was raised
                         break;
@@ -501,6 +462,12 @@ uh_decompose_kernel(UhParams p) {
     if (n_big) atomicAdd(&ctl->nodes_big, n_big);
     if (n_small) atomicAdd(&ctl->nodes_small, n_small);
     if (n_tiny) atomicAdd(&ctl->nodes_tiny, n_tiny);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+        atomicMax(&ctl->t_last, t);
+    }
 }
 
 // seeds: one root per selected chromosome with more than min_size bins (one thread per chromosome)
@@ -514,14 +481,14 @@ __global__ void uh_seed_kernel(UhParams p, const unsigned char* __restrict__ sel
         const int e = (int)len - 1;
         if (e + 1 > UH_SMALL_MAX) {
             atomicAdd(&s_big, 1);
-            atomicAdd(&p.ctl->outstanding, 1);
-            const unsigned long long pos = uh_big_alloc(p, c, 0, e, 0);
-            uh_big_publish(p, pos, uh_nchunks(0, e), 0, 1);
+            atomicAdd(&p.ctl->outstanding_.v, 1);
+            const long long p0 = p.off[c] + c;
+            uh_push_big(p, c, 0, e, 0, p.pz[p0], p.pz[p0 + e + 1]);
         } else {
             uh_push_small(p, c, 0, e, 0);
         }
     }
     __syncthreads();
     // no big node at all: the big phase is over before it starts
-    if (threadIdx.x == 0 && s_big == 0) { __threadfence(); *(volatile int*)&p.ctl->big_done = 1; }
+    if (threadIdx.x == 0 && s_big == 0) { __threadfence(); *(volatile int*)&p.ctl->big_done_.v = 1; }
 }

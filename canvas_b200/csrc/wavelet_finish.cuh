@@ -125,6 +125,57 @@ struct LevelSorter {
     }
 };
 
+// The replay above is inherently sequential inside one sub-array, but after a partition the two parts
+// never touch each other again, so they can be replayed by different threads and still give the
+// identical permutation.  Round r runs every pending sub-array on its own thread (one partition, or
+// the insertion / heap sort that finishes it) and queues the two parts for round r+1: the critical
+// path drops from ~n log n to ~2n steps.  Needed because a run of exact zeros makes the tree (and
+// with it the number of levels to sort) thousands of levels deep.
+__device__ void level_sort_parallel(LevelSorter ls, int n, int* task_a, int* task_b, int task_cap, int* s_counts2) {
+    if (n < 2) return;
+    int depth0 = 0;
+    for (int t = n; t >= 1; t /= 2) depth0++;
+    depth0 *= 2;
+    int* cur = task_a;
+    int* nxt = task_b;
+    if (threadIdx.x == 0) {
+        cur[0] = 0; cur[1] = n - 1; cur[2] = depth0;
+        s_counts2[0] = 1; s_counts2[1] = 0;
+    }
+    __syncthreads();
+    for (;;) {
+        const int ncur = s_counts2[0];
+        if (ncur <= 0) break;
+        for (int t = threadIdx.x; t < ncur; t += blockDim.x) {
+            const int lo = cur[3 * t], hi = cur[3 * t + 1];
+            int depth = cur[3 * t + 2];
+            if (hi <= lo) continue;
+            const int size = hi - lo + 1;
+            if (size <= 16) {
+                if (size == 2) ls.swap_if_greater(lo, hi);
+                else if (size == 3) { ls.swap_if_greater(lo, hi - 1); ls.swap_if_greater(lo, hi); ls.swap_if_greater(hi - 1, hi); }
+                else ls.insertion(lo, hi);
+                continue;
+            }
+            if (depth == 0) { ls.heapsort(lo, hi); continue; }
+            depth--;
+            const int pv = ls.partition(lo, hi);
+            if (hi > pv + 1) {
+                const int i = atomicAdd(&s_counts2[1], 1);
+                if (i < task_cap) { nxt[3 * i] = pv + 1; nxt[3 * i + 1] = hi; nxt[3 * i + 2] = depth; }
+            }
+            if (pv - 1 > lo) {
+                const int i = atomicAdd(&s_counts2[1], 1);
+                if (i < task_cap) { nxt[3 * i] = lo; nxt[3 * i + 1] = pv - 1; nxt[3 * i + 2] = depth; }
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) { s_counts2[0] = min(s_counts2[1], task_cap); s_counts2[1] = 0; }
+        int* tmp = cur; cur = nxt; nxt = tmp;
+        __syncthreads();
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // Block multi-select: exact order statistics of up to BMS_R requests.  Request r asks for rank rk[r]
 // of the bins  core(range id) ∪ [xlo, xhi)  (a few extra bins right after the core).  All requests
@@ -207,18 +258,28 @@ __device__ void bms_run(BmsState& st, const double* __restrict__ x) {
             const int lo = st.rlo[r], hi = st.rhi[r];
             // four independent loads in flight per thread: the range is L2-resident and one CTA has
             // to pull it through a single SM
-            for (int i0 = lo + (int)threadIdx.x; i0 < hi; i0 += 4 * B) {
+            // (the loop bound is rounded up so that whole warps stay converged for the match below)
+            const int span = hi - lo;
+            const int span_round = ((span + 4 * B - 1) / (4 * B)) * (4 * B);
+            for (int o0 = (int)threadIdx.x; o0 < span_round; o0 += 4 * B) {
+                const int i0 = lo + o0;
                 double v[4];
 #pragma unroll
                 for (int u = 0; u < 4; u++) v[u] = (i0 + u * B < hi) ? __ldg(x + i0 + u * B) : 0.0;
 #pragma unroll
                 for (int u = 0; u < 4; u++) {
-                    if (i0 + u * B >= hi) break;
+                    const bool ok = i0 + u * B < hi;
                     const unsigned long long key = f64_key(v[u]);
                     const int d = (int)((key >> shift) & 255ull);
-                    for (int g = 0; g < ng; g++)
-                        if (st.grange[g] == r && (first || ((key ^ st.gprefix[g]) >> (shift + 8)) == 0ull))
-                            atomicAdd(&st.hist[g][d], 1u);
+                    for (int g = 0; g < ng; g++) {
+                        const bool hit = ok && st.grange[g] == r && (first || ((key ^ st.gprefix[g]) >> (shift + 8)) == 0ull);
+                        // lanes that hit the same bin add once: noise-free stretches share most digits
+                        const unsigned act = __ballot_sync(0xffffffffu, hit);
+                        if (hit) {
+                            const unsigned m = __match_any_sync(act, d);
+                            if ((int)(__ffs(m) - 1) == lane) atomicAdd(&st.hist[g][d], (unsigned)__popc(m));
+                        }
+                    }
                 }
             }
         }
@@ -472,25 +533,27 @@ uh_finish_kernel(FinParams p) {
     int* bp = p.bp + o;
     const unsigned* lvlcnt = p.lvlcnt + o;
     const int T = p.depth[c];  // number of levels (tree.Count)
-    const int ncand_all = min(p.ctl->cand_count, 0x7fffffff);
+    const int ncand_all = min(p.ctl->cand_count_.v, 0x7fffffff);
 
     // ---- HardThresh level weights (:78-91): germline only
     if (p.is_germline) {
+        __shared__ int s_sort_counts[2];
         if (T <= FIN_SORT_SMEM) {
-            // sort in shared memory (s_key doubles as the count table, s_val as the permutation)
+            // sort in shared memory (s_key doubles as the count table, s_val as the permutation, the
+            // candidate buffer of the multi-select as the task lists)
             unsigned* s_cnt = reinterpret_cast<unsigned*>(s_key);
             for (int l = threadIdx.x; l < T; l += blockDim.x) { s_cnt[l] = lvlcnt[l]; s_val[l] = l; }
             __syncthreads();
-            if (threadIdx.x == 0) {
-                LevelSorter ls{s_val, s_cnt};
-                ls.sort(T);
-            }
+            int* tasks = reinterpret_cast<int*>(s_bms.cand);
+            const int cap = (int)(sizeof(s_bms.cand) / sizeof(int)) / 6;
+            level_sort_parallel(LevelSorter{s_val, s_cnt}, T, tasks, tasks + 3 * cap, cap, s_sort_counts);
             __syncthreads();
             for (int l = threadIdx.x; l < T; l += blockDim.x) lvl_idx[l] = s_val[l];
-        } else if (threadIdx.x == 0) {
-            for (int l = 0; l < T; l++) lvl_idx[l] = l;
-            LevelSorter ls{lvl_idx, lvlcnt};
-            ls.sort(T);
+        } else {
+            for (int l = threadIdx.x; l < T; l += blockDim.x) lvl_idx[l] = l;
+            __syncthreads();
+            const int cap = n / 3;
+            level_sort_parallel(LevelSorter{lvl_idx, lvlcnt}, T, piece, prelim, cap, s_sort_counts);
         }
     }
     __syncthreads();

@@ -161,11 +161,13 @@ class Engine:
         return {k: self.lib.cg_last_stage_ms(self.h, i) for i, k in enumerate(names)}
 
     def last_partition_stats(self):
-        out = np.zeros(10, np.float64)
-        self.lib.cg_last_partition_stats(self.h, _ptr(out, _f64), 10)
+        out = np.zeros(16, np.float64)
+        self.lib.cg_last_partition_stats(self.h, _ptr(out, _f64), 16)
         return {"visits": out[0], "nodes": out[1], "candidates": out[2], "bins": out[3],
                 "visits_big": out[4], "visits_small": out[5], "visits_tiny": out[6],
-                "nodes_big": out[7], "nodes_small": out[8], "nodes_tiny": out[9]}
+                "nodes_big": out[7], "nodes_small": out[8], "nodes_tiny": out[9],
+                "big_phase_ms": out[10], "decompose_span_ms": out[11], "multi_chunk_nodes": out[12],
+                "queue_hops": out[13], "max_depth": out[14]}
 
     # ------------------------------------------------------------------ CanvasClean
     def clean(self, chrom, is_autosome, is_chr_y, start, stop, count, gc, size_filter=True,

@@ -56,7 +56,9 @@ double cg_last_stage_ms(cg_ctx* ctx, int stage);
 /* Work counters of the last partition call: out[0] = bin visits of the decomposition (sum over tree
  * nodes of their length: L_eff * N), out[1] = tree nodes, out[2] = candidate nodes kept for the
  * threshold, out[3] = bins, out[4..6] = bin visits of the big / warp / per-thread tiers, out[7..9] = nodes of
- * those tiers.  Returns the number of values written (<= min(n, 10)). */
+ * those tiers, out[10] / out[11] = ms from the start of the decomposition kernel to the end of its big-node
+ * phase / to its end, out[12] = multi-chunk nodes, out[13] = nodes that went through the ticket ring,
+ * out[14] = deepest tree.  Returns the number of values written (<= min(n, 16)). */
 int cg_last_partition_stats(cg_ctx* ctx, double* out, int n);
 
 /* ---------------------------------------------------------------------------------------------
