@@ -156,6 +156,7 @@ constexpr int UH_TINY_BUF = 32;
 struct UhWarpScratch {
     unsigned lvl[UH_SMALL_MAX];  // node count per level relative to the task's level
     int st_s[UH_WARP_STACK], st_e[UH_WARP_STACK], st_l[UH_WARP_STACK];
+    double st_b[UH_WARP_STACK], st_v[UH_WARP_STACK];  // prefix sums bounding each stacked node
     int tn_s[UH_TINY_BUF], tn_e[UH_TINY_BUF], tn_l[UH_TINY_BUF];
 };
 
@@ -166,9 +167,11 @@ __device__ void uh_small_subtree(const UhParams& p, UhWarpScratch& ws, int c, in
     const long long p0 = p.off[c] + c;
     const double* __restrict__ pz = p.pz;
     for (int t = lane; t < UH_SMALL_MAX; t += 32) ws.lvl[t] = 0u;
-    __syncwarp();
     int sp = 0, ntiny = 0;
-    if (lane == 0) { ws.st_s[0] = S; ws.st_e[0] = E; ws.st_l[0] = L0; }
+    if (lane == 0) {
+        ws.st_s[0] = S; ws.st_e[0] = E; ws.st_l[0] = L0;
+        ws.st_b[0] = pz[p0 + S]; ws.st_v[0] = pz[p0 + E + 1];
+    }
     sp = 1;
     __syncwarp();
     while (sp > 0 || ntiny > 0) {
@@ -181,6 +184,7 @@ __device__ void uh_small_subtree(const UhParams& p, UhWarpScratch& ws, int c, in
         }
         sp--;
         const int s = ws.st_s[sp], e = ws.st_e[sp], level = ws.st_l[sp];
+        const double base = ws.st_b[sp], endv = ws.st_v[sp];
         __syncwarp();
         const int n = e - s + 1;
         if (n <= UH_TINY_MAX) {
@@ -189,21 +193,39 @@ __device__ void uh_small_subtree(const UhParams& p, UhWarpScratch& ws, int c, in
             __syncwarp();
             continue;
         }
-        const double base = pz[p0 + s];
-        const double T = pz[p0 + e + 1] - base;
+        const double T = endv - base;
         const double nn = (double)n;
         const double mu = T / nn;
-        double best = -1.0;
-        int best_m = 0x7fffffff;
-        for (int m = lane; m < n - 1; m += 32) {
-            const double a = (double)(m + 1);
-            const double D = (pz[p0 + s + m + 1] - base) - a * mu;
-            const double sc = D * D / (a * (nn - a));
-            if (sc > best) { best = sc; best_m = m; }
+        const double* __restrict__ q = pz + p0 + s + 1;
+        double bnum = -1.0, bden = 1.0, bv = 0.0;
+        int bm = 0x7fffffff;
+        int m = lane;
+        for (; m + 96 < n - 1; m += 128) {  // four loads in flight per lane
+            double v[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) v[u] = __ldg(q + m + 32 * u);
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const double a = (double)(m + 32 * u + 1);
+                const double D = fma(-a, mu, v[u] - base);
+                const double num = D * D, den = a * (nn - a);
+                if (num * bden > bnum * den) { bnum = num; bden = den; bm = m + 32 * u; bv = v[u]; }
+            }
         }
+        for (; m < n - 1; m += 32) {
+            const double vv = __ldg(q + m);
+            const double a = (double)(m + 1);
+            const double D = fma(-a, mu, vv - base);
+            const double num = D * D, den = a * (nn - a);
+            if (num * bden > bnum * den) { bnum = num; bden = den; bm = m; bv = vv; }
+        }
+        double best = bnum >= 0.0 ? bnum / bden : -1.0;
+        int best_m = bm;
         warp_argmax(best, best_m);
+        const unsigned own = __ballot_sync(0xffffffffu, bm == best_m && best_m != 0x7fffffff);
+        const double fv = __shfl_sync(0xffffffffu, bv, own ? __ffs(own) - 1 : 0);
         if (lane == 0) { visits_small += (unsigned long long)n; }
-        if (best == 0.0) {
+        if (best == 0.0 || best_m == 0x7fffffff) {
             // every inner product is exactly zero (a run of zeros): the reference peels one bin per
             // level with coefficient 0 — levels level .. level+n-2 get one node each
             for (int k = lane; k < n - 1; k += 32) atomicAdd(&ws.lvl[level - L0 + k], 1u);
@@ -211,21 +233,24 @@ __device__ void uh_small_subtree(const UhParams& p, UhWarpScratch& ws, int c, in
             __syncwarp();
             continue;
         }
-        if (best_m == 0x7fffffff || best_m < 0 || best_m > n - 2) best_m = 0;
+        if (best_m < 0 || best_m > n - 2) best_m = 0;
         if (lane == 0) {
-            const double coef = uh_coef(pz, p0, s, n, best_m, base, T);
+            const double a = (double)(best_m + 1), b = (double)(n - best_m - 1);
+            const double D = fma(-a, mu, fv - base);
+            const double coef = D * sqrt(nn / (a * b)) / fmax(0.5, mu / 200.0);
             atomicAdd(&ws.lvl[level - L0], 1u);
             uh_emit_candidate(p, c, level, s, s + best_m, e, coef);
             nodes_small++;
             const int ls = s, le = s + best_m, rs = s + best_m + 1, re = e;
             const int ln = le - ls + 1, rn = re - rs + 1;
-            int q = sp;
+            int qn = sp;
+            // larger child first so that the smaller one is popped next (stack depth <= log2 n)
             if (ln >= rn) {
-                if (ln >= 2) { ws.st_s[q] = ls; ws.st_e[q] = le; ws.st_l[q] = level + 1; q++; }
-                if (rn >= 2) { ws.st_s[q] = rs; ws.st_e[q] = re; ws.st_l[q] = level + 1; q++; }
+                if (ln >= 2) { ws.st_s[qn] = ls; ws.st_e[qn] = le; ws.st_l[qn] = level + 1; ws.st_b[qn] = base; ws.st_v[qn] = fv; qn++; }
+                if (rn >= 2) { ws.st_s[qn] = rs; ws.st_e[qn] = re; ws.st_l[qn] = level + 1; ws.st_b[qn] = fv; ws.st_v[qn] = endv; qn++; }
             } else {
-                if (rn >= 2) { ws.st_s[q] = rs; ws.st_e[q] = re; ws.st_l[q] = level + 1; q++; }
-                if (ln >= 2) { ws.st_s[q] = ls; ws.st_e[q] = le; ws.st_l[q] = level + 1; q++; }
+                if (rn >= 2) { ws.st_s[qn] = rs; ws.st_e[qn] = re; ws.st_l[qn] = level + 1; ws.st_b[qn] = fv; ws.st_v[qn] = endv; qn++; }
+                if (ln >= 2) { ws.st_s[qn] = ls; ws.st_e[qn] = le; ws.st_l[qn] = level + 1; ws.st_b[qn] = base; ws.st_v[qn] = fv; qn++; }
             }
         }
         {

@@ -1,0 +1,229 @@
+"""Intermediate file formats of the Canvas module chain (host side; reference CanvasCommon/IO.cs).
+
+  .binned / .cleaned   gzip TSV  chr  start  stop  count({0:F2})  gc          IO.cs:15-52
+  .partitioned         gzip TSV  chr  start  end   coverage       segmentId   Segmentation.cs:235-252
+  metric files         "#localSD\\t<v>" / "#evenness\\t<v>"                    IO.cs:83-98
+  filter BED           chr  start  stop                                       Utilities.cs:794-828
+"""
+import gzip
+import io
+
+import numpy as np
+
+from . import synth, textcodec
+
+
+def _open_text(path, mode="rt"):
+    with open(path, "rb") as f:
+        magic = f.read(2)
+    if magic == b"\x1f\x8b":
+        return gzip.open(path, mode)
+    return open(path, mode)
+
+
+def read_binned(path):
+    """CanvasIO.ReadFromTextFile (IO.cs:26-52): returns a synth.Sample with chromosome RUN ids (a
+    chromosome that reappears later in the file gets a new id, as the run-based loops of CanvasClean
+    see it, CanvasClean.cs:247-256)."""
+    names, chrom, start, stop, count, gc = [], [], [], [], [], []
+    last = None
+    with _open_text(path) as f:
+        for line in f:
+            line = line.rstrip("\n").rstrip("\r")
+            if not line:
+                continue
+            p = line.split("\t")
+            if p[0] != last:
+                names.append(p[0])
+                last = p[0]
+            chrom.append(len(names) - 1)
+            start.append(int(p[1]))
+            stop.append(int(p[2]))
+            count.append(float(p[3]))
+            gc.append(int(p[4]) if len(p) > 4 else 0)
+    if len(names) > 256:
+        raise ValueError("more than 256 chromosome runs")
+    return synth.Sample(names, np.array(chrom, np.uint8), np.array(start, np.int32), np.array(stop, np.int32),
+                        np.array(count, np.float32), np.array(gc, np.uint8))
+
+
+def write_binned(path, names, chrom, start, stop, count, gc):
+    """CanvasIO.WriteToTextFile (IO.cs:15-24): count printed with .NET's {0:F2}."""
+    txt = textcodec.f2_text(count)
+    buf = io.StringIO()
+    for c, a, b, t, g in zip(np.asarray(chrom).tolist(), np.asarray(start).tolist(), np.asarray(stop).tolist(), txt,
+                             np.asarray(gc).tolist()):
+        buf.write(f"{names[c]}\t{a}\t{b}\t{t}\t{g}\n")
+    with gzip.open(path, "wt") as f:
+        f.write(buf.getvalue())
+
+
+def write_metric(path, name, value):
+    """IO.cs:95-98 (double.ToString(): 15 significant digits on .NET Core 2.0)."""
+    with open(path, "w") as f:
+        f.write(f"#{name}\t{dotnet_double(value)}\n")
+
+
+def read_metric(path, name):
+    for line in open(path):
+        if line.startswith("#" + name):
+            return float(line.split("\t")[1])
+    raise ValueError(f"Did not find {name} metric in file '{path}'")
+
+
+def dotnet_double(x):
+    """double.ToString() of .NET Core 2.0: the G15 form."""
+    if x != x:
+        return "NaN"
+    if x in (float("inf"), float("-inf")):
+        return "Infinity" if x > 0 else "-Infinity"
+    s = "%.15g" % x
+    if "e" in s:
+        m, e = s.split("e")
+        return f"{m}E{'+' if int(e) >= 0 else '-'}{abs(int(e)):02d}"
+    return s
+
+
+def load_bed(path):
+    """Utilities.LoadBedFile (Utilities.cs:794-828): chr -> list of (start, stop) in file order."""
+    out = {}
+    if not path:
+        return out
+    with _open_text(path) as f:
+        for line in f:
+            line = line.rstrip("\n").rstrip("\r")
+            if not line:
+                continue
+            p = line.split("\t")
+            a, b = int(p[1]), int(p[2])
+            if a < 0:
+                raise ValueError(f"Start must be non-negative in a BED file: {line}")
+            if a >= b:
+                raise ValueError(f"Start must be less than Stop in a BED file: {line}")
+            out.setdefault(p[0], []).append((a, b))
+    return out
+
+
+class BinFilter:
+    """GenomicBinFilter.SkipBin (GenomicBinFilter.cs:29-58)."""
+
+    def __init__(self, excluded):
+        self.excluded = excluded
+        self.prev_chrom = None
+        self.prev_start = 0
+        self.intervals = []
+        self.idx = -1
+
+    def skip(self, chrom, start, stop):
+        if chrom != self.prev_chrom:
+            self.prev_chrom = chrom
+            self.intervals = self.excluded.get(chrom, [])
+            self.idx = 0
+        elif start < self.prev_start:
+            self.idx = 0
+        self.prev_start = start
+        while self.idx < len(self.intervals):
+            a, b = self.intervals[self.idx]
+            if b <= start:
+                self.idx += 1
+                continue
+            if a >= stop:
+                return False
+            return True
+        return False
+
+
+def read_cleaned_for_partition(path, filter_bed=None):
+    """CanvasSegment.ReadBedInput (CanvasSegment.cs:1117-1163): per chromosome (first-appearance order)
+    start, end and coverage; bins overlapping the -b BED are dropped."""
+    filt = BinFilter(load_bed(filter_bed))
+    order, start, end, cov = [], {}, {}, {}
+    with _open_text(path) as f:
+        for line in f:
+            line = line.rstrip("\n").rstrip("\r")
+            if not line:
+                continue
+            p = line.split("\t")
+            c = p[0].strip()
+            a, b = int(p[1].strip()), int(p[2].strip())
+            if filt.skip(c, a, b):
+                continue
+            if c not in start:
+                order.append(c)
+                start[c], end[c], cov[c] = [], [], []
+            start[c].append(a)
+            end[c].append(b)
+            cov[c].append(float(p[3].strip()))
+    return order, {c: np.array(start[c], np.int64) for c in order}, {c: np.array(end[c], np.int64) for c in order}, \
+        {c: np.array(cov[c], np.float64) for c in order}
+
+
+def derive_segments(breakpoints, n_bins, start, end):
+    """SegmentationInput.DeriveSegments (Segmentation.cs:83-125): list of (start, end) coordinates."""
+    bp = list(int(b) for b in breakpoints)
+    s_pos, e_pos = [], []
+    if len(bp) >= 2 and n_bins > 10:
+        if bp[0] != 0:
+            bp.insert(0, 0)
+        s_pos.append(bp[0])
+        e_pos.append(bp[1] - 1)
+        for i in range(1, len(bp) - 1):
+            s_pos.append(bp[i])
+            e_pos.append(bp[i + 1] - 1)
+        s_pos.append(bp[-1])
+        e_pos.append(n_bins - 1)
+    else:
+        s_pos.append(0)
+        e_pos.append(n_bins - 1)
+    return [(int(start[a]), int(end[b])) for a, b in zip(s_pos, e_pos)]
+
+
+def post_process_segments(order, seg_by_chr, start, end, cov, excluded=None, max_inter_bin_dist=1000000):
+    """SegmentationResultsProcessor.PostProcessSegments (SegmentationResultsProcessor.cs:17-129)
+    without reference ploidy.  Returns chr -> list of segments {id, bins: [(start, end, coverage)]}."""
+    excluded = excluded or {}
+    starts = set()
+    for c, segs in seg_by_chr.items():
+        for a, _ in segs:
+            starts.add((c, a))
+    seg_num = -1
+    out = {}
+    for c in order:
+        out[c] = []
+        cur = None
+        ex = excluded.get(c)
+        ex_idx = 0
+        prev_end = 0
+        for a, b, v in zip(start[c].tolist(), end[c].tolist(), cov[c].tolist()):
+            new = (c, a) in starts
+            if ex is not None:
+                while ex_idx < len(ex) and ex[ex_idx][1] < prev_end:
+                    ex_idx += 1
+                if ex_idx < len(ex):
+                    mid = (ex[ex_idx][0] + ex[ex_idx][1]) // 2
+                    if prev_end < mid and b >= mid:
+                        new = True
+            if prev_end > 0 and max_inter_bin_dist >= 0 and prev_end + max_inter_bin_dist < a and not new:
+                new = True
+            if new:
+                seg_num += 1
+                cur = {"id": seg_num, "bins": [(a, b, v)]}
+                out[c].append(cur)
+            elif cur is None:
+                cur = {"id": seg_num, "bins": [(a, b, v)]}
+                out[c].append(cur)
+            else:
+                cur["bins"].append((a, b, v))
+            prev_end = b
+    return out
+
+
+def write_partitioned(path, order, segments):
+    """SegmentationInput.WriteCanvasPartitionResults (Segmentation.cs:235-252)."""
+    buf = io.StringIO()
+    for c in order:
+        for seg in segments[c]:
+            for a, b, v in sorted(seg["bins"], key=lambda t: t[0]):
+                buf.write(f"{c}\t{a}\t{b}\t{dotnet_double(v)}\t{seg['id']}\n")
+    with gzip.open(path, "wt") as f:
+        f.write(buf.getvalue())

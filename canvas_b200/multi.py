@@ -1,0 +1,75 @@
+"""Multi-GPU plumbing of the partition stage (one process per GPU, torch.distributed).
+
+Chromosomes are independent once the genome-wide scalars exist: every rank computes
+the scalars on the full coverage (replicated, microseconds), segments only the chromosomes assigned
+to it (longest-processing-time-first by bin count) and ONE all-gather of a fixed-capacity int32 buffer
+reassembles the genome-wide breakpoint list on every rank.  There is no other exchange on the path.
+"""
+import numpy as np
+
+
+def assign_chromosomes_lpt(lengths, world):
+    """Greedy LPT: longest chromosome first onto the least loaded rank.  Returns owner[c]."""
+    lengths = np.asarray(lengths, np.int64)
+    owner = np.zeros(len(lengths), np.int32)
+    load = np.zeros(world, np.int64)
+    for c in np.argsort(-lengths, kind="stable"):
+        r = int(np.argmin(load))
+        owner[c] = r
+        load[r] += lengths[c]
+    return owner
+
+
+def pack_breakpoints(breakpoints, capacity):
+    """[count, (chrom, bp) ...] padded to `capacity` int32 entries."""
+    flat = np.zeros(capacity, np.int32)
+    k = 1
+    total = 0
+    for c, b in enumerate(breakpoints):
+        m = len(b)
+        if k + 2 * m > capacity:
+            raise ValueError("segment-list buffer too small")
+        flat[k:k + 2 * m:2] = c
+        flat[k + 1:k + 2 * m:2] = b
+        k += 2 * m
+        total += m
+    flat[0] = total
+    return flat
+
+
+def unpack_breakpoints(buffers, n_chrom):
+    """Inverse of pack_breakpoints over the gathered [world, capacity] array: per chromosome, the
+    breakpoints reported by whichever rank owned it."""
+    out = [np.zeros(0, np.int32) for _ in range(n_chrom)]
+    for row in np.asarray(buffers):
+        m = int(row[0])
+        pairs = row[1:1 + 2 * m].reshape(m, 2)
+        for c in np.unique(pairs[:, 0]):
+            out[int(c)] = pairs[pairs[:, 0] == c, 1].astype(np.int32)
+    return out
+
+
+def all_gather_breakpoints(breakpoints, n_chrom, capacity=16384, device=None):
+    """One collective: every rank contributes the breakpoints of its chromosomes, every rank gets all."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size()
+    dev = device if device is not None else ("cuda" if dist.get_backend() == "nccl" else "cpu")
+    local = torch.from_numpy(pack_breakpoints(breakpoints, capacity)).to(dev)
+    gathered = torch.empty(world * capacity, dtype=torch.int32, device=dev)
+    dist.all_gather_into_tensor(gathered, local)
+    return unpack_breakpoints(gathered.cpu().numpy().reshape(world, capacity), n_chrom)
+
+
+def partition_wavelet_sharded(engine, chrom_off, coverage, **kw):
+    """cg_partition_wavelet_shard on this rank's chromosomes + the all-gather.  Every rank returns the
+    full per-chromosome breakpoint list (identical to the single-GPU result)."""
+    import torch.distributed as dist
+    world, rank = dist.get_world_size(), dist.get_rank()
+    lengths = np.diff(np.asarray(chrom_off, np.int64))
+    owner = assign_chromosomes_lpt(lengths, world)
+    mask = (owner == rank).astype(np.uint8)
+    r = engine.partition_wavelet(chrom_off, coverage, chrom_selected=mask, **kw)
+    r["breakpoints"] = all_gather_breakpoints(r["breakpoints"], len(lengths))
+    r["owner"] = owner
+    return r

@@ -1,0 +1,118 @@
+"""Host-side logic (no GPU): file formats, .NET text semantics, option parsing, segment
+post-processing against the reference's own SegmentationResultsProcessorTests vectors."""
+import gzip
+import os
+
+import numpy as np
+import pytest
+
+from canvas_b200 import fileio, modules, multi, synth, textcodec
+from oracle import pyoracle as ora
+
+
+def test_f2_roundtrip_matches_oracle_string_implementation():
+    rng = np.random.default_rng(0)
+    x = np.concatenate([rng.uniform(0, 300, 50000), rng.uniform(0, 1, 5000), 10 ** rng.uniform(-6, 7, 10000),
+                        np.arange(0, 2000) / 32.0 + 100, np.arange(0, 2000) / 64.0 + 10,
+                        [0, 0.005, 0.004, 0.015, 99.995, 9.995, 999999.5, 1e7, -3.14159]]).astype(np.float32)
+    assert np.array_equal(ora.f2_roundtrip(x), textcodec.f2_roundtrip(x))
+    assert textcodec.f2_text(np.array([95.02041, 0.005, 0.004, 12.345, 1e6], np.float32)) == \
+        ["95.02", "0.01", "0.00", "12.35", "1000000.00"]
+
+
+def test_post_process_segments_reference_vectors():
+    # CanvasTest/CanvasPartition/SegmentationResultsProcessorTests.cs:10-95
+    order = ["chr1"]
+    segs = {"chr1": [(1, 1000), (1100, 4500), (4600, 5000)]}
+    start = {"chr1": np.array([100, 600, 1200, 1300, 4001, 5000])}
+    end = {"chr1": np.array([500, 890, 1299, 4000, 4500, 5050])}
+    cov = {"chr1": np.array([10, 10, 50, 100, 25, 10], float)}
+
+    def summary(res):
+        out = []
+        for s in res["chr1"]:
+            b = s["bins"]
+            out.append((min(x[0] for x in b), max(x[1] for x in b), float(np.median([x[2] for x in b])), len(b)))
+        return out
+
+    r = fileio.post_process_segments(order, segs, start, end, cov, {}, 100)
+    # the reference test asserts 3 segments with the first one spanning two bins although no bin starts
+    # at a segment start: bins before the first forced split share segment id -1 ... but MaxInterBinDist
+    # (100) splits where the gap exceeds it
+    assert summary(r) == [(100, 890, 10.0, 2), (1200, 4500, 50.0, 3), (5000, 5050, 10.0, 1)]
+    r = fileio.post_process_segments(order, segs, start, end, cov, {"chr1": [(525, 575)]}, 100)
+    assert summary(r) == [(100, 500, 10.0, 1), (600, 890, 10.0, 1), (1200, 4500, 50.0, 3), (5000, 5050, 10.0, 1)]
+    r = fileio.post_process_segments(order, segs, start, end, cov, {"chr1": [(585, 635)]}, 100)
+    assert summary(r) == [(100, 500, 10.0, 1), (600, 890, 10.0, 1), (1200, 4500, 50.0, 3), (5000, 5050, 10.0, 1)]
+
+
+def test_derive_segments():
+    start = np.arange(0, 20000, 1000)
+    end = start + 1000
+    assert fileio.derive_segments([0, 5, 12], 20, start, end) == [(0, 5000), (5000, 12000), (12000, 20000)]
+    assert fileio.derive_segments([0], 20, start, end) == [(0, 20000)]          # < 2 breakpoints
+    assert fileio.derive_segments([0, 3], 10, start[:10], end[:10]) == [(0, 10000)]  # <= 10 bins
+
+
+def test_bin_filter_semantics():
+    f = fileio.BinFilter({"chr1": [(100, 200), (500, 600)]})
+    assert [f.skip("chr1", a, b) for a, b in [(0, 100), (50, 101), (199, 250), (200, 300), (599, 700), (600, 700)]] == \
+        [False, True, True, False, True, False]
+    assert f.skip("chr2", 0, 1000) is False
+    assert f.skip("chr1", 150, 160) is True  # chromosome switch resets the cursor
+
+
+def test_binned_roundtrip_and_run_ids(tmp_path):
+    p = str(tmp_path / "x.binned")
+    names = ["chr1", "chrX"]
+    chrom = np.array([0, 0, 1, 1], np.uint8)
+    start = np.array([0, 1000, 0, 1000], np.int32)
+    count = np.array([95.02041, 100.125, 0.0, 7.005], np.float32)
+    fileio.write_binned(p, names, chrom, start, start + 1000, count, np.array([40, 41, 42, 43], np.uint8))
+    lines = gzip.open(p, "rt").read().splitlines()
+    assert lines[0] == "chr1\t0\t1000\t95.02\t40" and lines[3].split("\t")[3] in ("7.00", "7.01")
+    s = fileio.read_binned(p)
+    assert s.names == names and s.chrom.tolist() == [0, 0, 1, 1] and s.is_autosome.tolist() == [1, 0]
+    assert np.array_equal(s.count.astype(np.float64), textcodec.f2_roundtrip(count).astype(np.float32).astype(np.float64))
+
+
+def test_dotnet_double_and_metric_files(tmp_path):
+    assert fileio.dotnet_double(96.32670330162374) == "96.3267033016237"
+    assert fileio.dotnet_double(95.02) == "95.02" and fileio.dotnet_double(100.0) == "100"
+    p = str(tmp_path / "m.txt")
+    fileio.write_metric(p, "localSD", 1.8605272624936706)
+    assert open(p).read() == "#localSD\t1.86052726249367\n"
+    assert abs(fileio.read_metric(p, "localSD") - 1.86052726249367) < 1e-15
+
+
+def test_option_parsing_like_ndesk():
+    o = modules._parse(["-i", "a", "-o=b", "-g", "-s", "--local-sd-metric-file=f", "-w", "50"], modules.CLEAN_SPEC)
+    assert o == {"infile": "a", "outfile": "b", "gcnorm": True, "filtsize": True, "local_sd_file": "f", "weightedmedian": "50"}
+    with pytest.raises(modules.UnknownArguments):
+        modules._parse(["-i", "a", "stray"], modules.CLEAN_SPEC)
+    o = modules._parse(["-i", "a", "-i", "b", "-o", "c", "-r", "ref", "-g"], modules.PARTITION_SPEC)
+    assert o["infile"] == ["a", "b"] and o["germline"] is True
+
+
+def test_module_exit_codes_without_gpu(tmp_path, capsys):
+    assert modules.main(["CanvasClean"]) == 0                       # help when -i/-o are missing (:461-465)
+    assert "Usage: CanvasClean.exe" in capsys.readouterr().out
+    assert modules.main(["CanvasClean", "-i", str(tmp_path / "nope"), "-o", "x"]) == 1   # :468-472
+    assert modules.main(["CanvasPartition", "-i", str(tmp_path / "nope"), "-o", "x", "-r", "ref"]) == 1
+    assert modules.main(["CanvasClean", "-i", "a", "-o", "b", "bogus"]) == 255
+
+
+def test_lpt_assignment_balances():
+    lengths = [int(l / 1000) for _, l in synth.HG19]
+    owner = multi.assign_chromosomes_lpt(lengths, 8)
+    load = np.bincount(owner, weights=lengths, minlength=8)
+    assert load.max() / sum(lengths) < 0.14   # 8-way makespan close to 1/8 (~12.6 %)
+    assert sorted(set(owner.tolist())) == list(range(8))
+
+
+def test_pack_unpack_breakpoints():
+    bps = [np.array([0, 5, 9], np.int32), np.zeros(0, np.int32), np.array([0], np.int32)]
+    buf = multi.pack_breakpoints(bps, 64)
+    assert buf[0] == 4
+    out = multi.unpack_breakpoints(buf[None, :], 3)
+    assert [b.tolist() for b in out] == [[0, 5, 9], [], [0]]

@@ -1,0 +1,65 @@
+"""The module mains end to end on files (GPU): same command lines and file formats as the reference's
+CanvasClean / CanvasPartition, checked against the oracle driven through the same host code."""
+import gzip
+import os
+
+import numpy as np
+import pytest
+
+from canvas_b200 import fileio, modules, synth, textcodec
+from oracle import pyoracle as ora
+
+pytestmark = pytest.mark.gpu
+
+
+def test_clean_then_partition_on_files(tmp_path, engine):
+    modules._engine = engine
+    s = synth.make_sample(config=2, sample=11, scale=0.04, n_events=120)
+    binned = str(tmp_path / "s.binned")
+    cleaned = str(tmp_path / "s.cleaned")
+    part = str(tmp_path / "s.partitioned")
+    lsd = str(tmp_path / "LocalSdMetric.txt")
+    evn = str(tmp_path / "EvennessMetric.txt")
+    vaf = str(tmp_path / "s.SNV.txt.gz")
+    gzip.open(vaf, "wt").write("")
+    cfg = str(tmp_path / "CanvasPartitionParameters.json")
+    open(cfg, "w").write('{"EvennessScoreWindow": 6000}')
+    fileio.write_binned(binned, s.names, s.chrom, s.start, s.stop, s.count, s.gc)
+    assert modules.main(["CanvasClean", "-i", binned, "-o", cleaned, "-g", "-s", "-r",
+                         f"--local-sd-metric-file={lsd}"]) == 0
+    # expected .cleaned: oracle on what the reader parses back from the .binned text
+    sb = fileio.read_binned(binned)
+    o = ora.clean(sb.chrom, sb.is_autosome, sb.is_chr_y, sb.start, sb.stop, sb.count, sb.gc)
+    exp = str(tmp_path / "exp.cleaned")
+    k = o["kept_index"]
+    fileio.write_binned(exp, sb.names, sb.chrom[k], sb.start[k], sb.stop[k], o["count"], sb.gc[k])
+    assert gzip.open(cleaned, "rt").read() == gzip.open(exp, "rt").read()
+    assert fileio.read_metric(lsd, "localSD") == float(fileio.dotnet_double(o["local_sd"]))
+
+    assert modules.main(["CanvasPartition", "-i", cleaned, "-v", vaf, "-o", part, "-r", str(tmp_path), "-g",
+                         f"--evenness-metric-file={evn}", f"--config={cfg}"]) == 0
+    order, start, end, cov = fileio.read_cleaned_for_partition(cleaned)
+    lens = [len(cov[c]) for c in order]
+    off = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    p = ora.partition_wavelet(off, np.concatenate([cov[c] for c in order]), is_germline=True, evenness_window=6000,
+                              n_threads=4)
+    seg = {c: fileio.derive_segments(p["breakpoints"][i], lens[i], start[c], end[c]) for i, c in enumerate(order)}
+    expected = str(tmp_path / "exp.partitioned")
+    fileio.write_partitioned(expected, order, fileio.post_process_segments(order, seg, start, end, cov))
+    assert gzip.open(part, "rt").read() == gzip.open(expected, "rt").read()
+    got_ev = fileio.read_metric(evn, "evenness")
+    assert abs(got_ev - p["evenness"]) <= 1e-9 * abs(p["evenness"])
+    ids = [int(l.split("\t")[4]) for l in gzip.open(part, "rt").read().splitlines()]
+    assert ids == sorted(ids) and len(set(ids)) > len(order)  # genome-wide running segment counter
+
+
+def test_partition_without_vaf_gives_one_segment_per_chromosome(tmp_path, engine):
+    # WaveletsRunner.cs:74-79: no -v file -> no segments -> every chromosome stays one segment (id -1)
+    modules._engine = engine
+    s = synth.make_sample(config=2, sample=12, scale=0.01)
+    cleaned = str(tmp_path / "s.cleaned")
+    part = str(tmp_path / "s.partitioned")
+    fileio.write_binned(cleaned, s.names, s.chrom, s.start, s.stop, s.count, s.gc)
+    assert modules.main(["CanvasPartition", "-i", cleaned, "-o", part, "-r", str(tmp_path)]) == 0
+    ids = {int(l.split("\t")[4]) for l in gzip.open(part, "rt").read().splitlines()}
+    assert ids == {-1}

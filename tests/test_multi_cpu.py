@@ -1,0 +1,38 @@
+"""world_size-2 gloo test (CPU) of the only exchange step on the path: the all-gather of per-rank
+breakpoint lists, with LPT chromosome ownership."""
+import os
+import socket
+import sys
+
+import numpy as np
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _worker(rank, world, port, ret):
+    import torch.distributed as dist
+    sys.path.insert(0, ROOT)
+    from canvas_b200 import multi
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    lengths = [500, 100, 300, 200, 50]
+    owner = multi.assign_chromosomes_lpt(lengths, world)
+    truth = [np.array([0, 10 * (c + 1), 20 * (c + 1)], np.int32) for c in range(len(lengths))]
+    mine = [truth[c] if owner[c] == rank else np.zeros(0, np.int32) for c in range(len(lengths))]
+    got = multi.all_gather_breakpoints(mine, len(lengths), capacity=256, device="cpu")
+    ok = all(g.tolist() == t.tolist() for g, t in zip(got, truth))
+    ret[rank] = ok
+    dist.destroy_process_group()
+
+
+def test_all_gather_breakpoints_world2():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker, args=(2, port, ret), nprocs=2, join=True)
+    assert ret[0] and ret[1]
