@@ -1,11 +1,13 @@
 // cg_partition_wavelet / cg_partition_wavelet_shard / cg_clean_partition_wavelet
 // (reference WaveletsRunner.Run, WaveletsRunner.cs:52-139).
 #include <cmath>
+#include <cstdlib>
 
 #include "clean.cuh"
 #include "wavelet.cuh"
 #include "wavelet_decompose.cuh"
 #include "wavelet_finish.cuh"
+#include "wavelet_rqindex.cuh"
 #include "wavelet_scalars.cuh"
 
 namespace {
@@ -20,6 +22,8 @@ struct WvPlan {
     std::vector<WvEvWork> ev_work;
     std::vector<WvScanTile> tiles;
     std::vector<int> tile_first;
+    std::vector<int> rq_tfirst;   // first 256-bin index tile of each chromosome
+    int rq_ntiles = 0;
     WvF3Level f3lv[WV_F3_LEVELS];
     long long f3_cnt[WV_F3_LEVELS];
     long long f3_off[WV_F3_LEVELS];  // offset of level r's pool in cmad/tmed
@@ -120,6 +124,10 @@ void make_plan(WvPlan& pl, int n_chrom, const int64_t* chrom_off, int window) {
             pl.tiles.push_back(WvScanTile{o + a, (int)std::min<long long>(WV_SCAN_TILE, len - a), c});
     }
     pl.tile_first[n_chrom] = (int)pl.tiles.size();
+    pl.rq_tfirst.assign(n_chrom + 1, 0);
+    for (int c = 0; c < n_chrom; c++)
+        pl.rq_tfirst[c + 1] = pl.rq_tfirst[c] + (int)((pl.off[c + 1] - pl.off[c] + RQ_TILE - 1) / RQ_TILE);
+    pl.rq_ntiles = pl.rq_tfirst[n_chrom];
 }
 
 struct WvDev {
@@ -154,6 +162,12 @@ struct WvDev {
     unsigned* bitmap;
     double* rec;
     int *n_bp, *bp;
+    // range-quantile index
+    unsigned long long *rq_spl, *rq_sorted;
+    unsigned short *rq_hist, *rq_tstart;
+    unsigned* rq_cum;
+    int* rq_tfirst;
+    unsigned long long* phase_ns;
 };
 
 size_t wv_workspace_bytes(const WvPlan& pl) {
@@ -172,6 +186,8 @@ size_t wv_workspace_bytes(const WvPlan& pl) {
     s += arena_need(N / 4 + 4096, sizeof(UhCand));
     s += arena_need(N + 1, 4) * 5 + arena_need(N + 1, 8) * 2 + arena_need(N / 32 + C + 2, 4);
     s += arena_need(C + 1, 4) + arena_need(N + 1, 4);
+    s += arena_need((C + 1) * RQ_BUCKETS, 8) + arena_need(N + 1, 8) + arena_need((size_t)(pl.rq_ntiles + 1) * RQ_BUCKETS, 2) * 2;
+    s += arena_need((size_t)(pl.rq_ntiles + C + 2) * RQ_BUCKETS, 4) + arena_need(C + 2, 4) + arena_need((C + 1) * 8, 8);
     return s + (1 << 16);
 }
 
@@ -218,6 +234,14 @@ int wv_alloc(cg_ctx* ctx, const WvPlan& pl, WvDev& d, double* cov_dev_existing) 
     d.bitmap = arena_take<unsigned>(ctx, N / 32 + C + 2);
     d.n_bp = arena_take<int>(ctx, C + 1);
     d.bp = arena_take<int>(ctx, N + 1);
+    d.rq_spl = arena_take<unsigned long long>(ctx, (C + 1) * RQ_BUCKETS);
+    d.rq_sorted = arena_take<unsigned long long>(ctx, N + 1);
+    d.rq_hist = arena_take<unsigned short>(ctx, (size_t)(pl.rq_ntiles + 1) * RQ_BUCKETS);
+    d.rq_tstart = arena_take<unsigned short>(ctx, (size_t)(pl.rq_ntiles + 1) * RQ_BUCKETS);
+    d.rq_cum = arena_take<unsigned>(ctx, (size_t)(pl.rq_ntiles + C + 2) * RQ_BUCKETS);
+    d.rq_tfirst = arena_take<int>(ctx, C + 2);
+    d.phase_ns = arena_take<unsigned long long>(ctx, (C + 1) * 8);
+    ok = ok && d.rq_spl && d.rq_sorted && d.rq_hist && d.rq_tstart && d.rq_cum && d.rq_tfirst;
     ok = ok && d.cov && d.off && d.selected && d.pz && d.seg_len && d.work && d.ev_work && d.tiles && d.tile_first &&
          d.tsum && d.f3lv && d.tmed && d.cmad && d.ev10 && d.ev100 && d.r10 && d.r100 && d.med && d.mad && d.sigma &&
          d.cand_thr && d.log3 && d.ctl && d.lvlcnt && d.depth && d.big && d.small && d.cand && d.lvl_idx &&
@@ -240,6 +264,7 @@ int wv_enqueue(cg_ctx* ctx, const cg_wavelet_opts* o, const WvPlan& pl, WvDev& d
     if (!pl.tiles.empty()) CG_CUDA(ctx, cudaMemcpyAsync(d.tiles, pl.tiles.data(), pl.tiles.size() * sizeof(WvScanTile), cudaMemcpyHostToDevice, s));
     CG_CUDA(ctx, cudaMemcpyAsync(d.tile_first, pl.tile_first.data(), (C + 1) * 4, cudaMemcpyHostToDevice, s));
     CG_CUDA(ctx, cudaMemcpyAsync(d.f3lv, pl.f3lv, sizeof(WvF3Level) * WV_F3_LEVELS, cudaMemcpyHostToDevice, s));
+    CG_CUDA(ctx, cudaMemcpyAsync(d.rq_tfirst, pl.rq_tfirst.data(), (C + 1) * 4, cudaMemcpyHostToDevice, s));
     // ceil(log(3^k) / log(3)) as the host's libm evaluates it (WaveletSegmentation.cs:224)
     static double log3_tab[32];
     {
@@ -338,11 +363,22 @@ int wv_enqueue(cg_ctx* ctx, const cg_wavelet_opts* o, const WvPlan& pl, WvDev& d
     cudaEventRecord(ctx->stage_ev[5], s);
     cudaEventRecord(ctx->stage_ev[6], s);
     ctx->stage_used[3] = true;
+    // ---- range-quantile index for the medians of the finish stage
+    if (pl.rq_ntiles > 0 && C > 0) {
+        CG_LAUNCH(ctx, rq_splitter_kernel, C, 1024, 0, d.cov, d.off, d.selected, d.rq_spl);
+        CG_LAUNCH(ctx, rq_tile_kernel, pl.rq_ntiles, RQ_TILE, 0, d.cov, d.off, d.rq_tfirst, C, d.selected, d.rq_spl, d.rq_hist,
+                  d.rq_tstart, d.rq_sorted);
+        CG_LAUNCH(ctx, rq_cumulate_kernel, C, RQ_BUCKETS, 0, d.rq_tfirst, d.selected, d.rq_hist, d.rq_cum);
+    }
     // ---- per-chromosome finish
     FinParams fp;
     fp.x = d.cov; fp.pz = d.pz; fp.off = d.off; fp.selected = d.selected; fp.cand = d.cand; fp.ctl = d.ctl;
     fp.lvlcnt = d.lvlcnt; fp.depth = d.depth; fp.sigma = d.sigma; fp.chrom_median = d.med + t.base_chrom;
     fp.log3_scale_tab = d.log3;
+    fp.rq.spl = d.rq_spl; fp.rq.hist = d.rq_hist; fp.rq.tstart = d.rq_tstart; fp.rq.cum = d.rq_cum; fp.rq.sorted = d.rq_sorted;
+    fp.rq.tfirst = d.rq_tfirst;
+    fp.phase_ns = getenv("CANVAS_DEBUG") ? d.phase_ns : nullptr;
+    if (fp.phase_ns) cudaMemsetAsync(d.phase_ns, 0, (size_t)(C + 1) * 64, s);
     fp.is_germline = o->is_germline; fp.min_size = o->min_size; fp.n_chrom = C; fp.pad = 0;
     fp.lvl_idx = d.lvl_idx; fp.sv = d.sv; fp.svkey = d.svkey; fp.bitmap = d.bitmap; fp.piece = d.piece; fp.rec = d.rec;
     fp.prelim = d.prelim; fp.lvl_first = d.lvl_first; fp.n_bp = d.n_bp; fp.bp = d.bp;
@@ -369,6 +405,17 @@ int wv_collect(cg_ctx* ctx, const WvPlan& pl, WvDev& d, int32_t* n_bp, int32_t* 
     ctx->stats[1] = (double)(h->nodes_big + h->nodes_small + h->nodes_tiny);
     ctx->stats[2] = (double)h->cand_count_.v;
     ctx->stats[3] = (double)pl.N;
+    if (getenv("CANVAS_DEBUG")) {
+        std::vector<unsigned long long> ph((size_t)(pl.n_chrom + 1) * 8, 0);
+        cudaMemcpy(ph.data(), d.phase_ns, ph.size() * 8, cudaMemcpyDeviceToHost);
+        for (int c = 0; c < pl.n_chrom; c++) {
+            const unsigned long long* q = ph.data() + (size_t)c * 8;
+            if (!q[0]) continue;
+            fprintf(stderr, "[fin] chr %2d n=%7lld bp=%3d | sort %7.1f thr %7.1f sortsv %7.1f pieces+rec %7.1f heal %7.1f refine %7.1f us | idx ok %llu fallback %llu na_sum %llu na_max %llu\n", c,
+                    (long long)(pl.off[c + 1] - pl.off[c]), n_bp[c], (q[1] - q[0]) * 1e-3, (q[2] - q[1]) * 1e-3, 0.0, (q[3] - q[2]) * 1e-3,
+                    (q[4] - q[3]) * 1e-3, (q[5] - q[4]) * 1e-3, q[6] & 0xffffffffull, q[6] >> 32, q[7] & 0xffffffffull, q[7] >> 32);
+        }
+    }
     ctx->stats[4] = (double)h->visits_big; ctx->stats[5] = (double)h->visits_small; ctx->stats[6] = (double)h->visits_tiny;
     ctx->stats[7] = (double)h->nodes_big; ctx->stats[8] = (double)h->nodes_small; ctx->stats[9] = (double)h->nodes_tiny;
     ctx->stats[10] = h->t_big_done > h->t_first ? (double)(h->t_big_done - h->t_first) * 1e-6 : 0.0;  // ms

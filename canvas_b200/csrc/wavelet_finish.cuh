@@ -4,6 +4,7 @@
 //   :237-258.  Range medians are exact (block-wide radix select over the L2-resident coverage).
 #pragma once
 #include "wavelet.cuh"
+#include "wavelet_rqindex.cuh"
 
 constexpr int FIN_THREADS = 1024;
 constexpr int FIN_SORT_SMEM = 4096;  // survivors sorted in shared memory up to this many
@@ -21,7 +22,8 @@ struct FinParams {
     const int* depth;
     const double* sigma;       // [n_chrom]
     const double* chrom_median;  // [n_chrom] Median(ratio)
-    const double* log3_scale_tab;  // unused slot (kept for layout stability)
+    const double* log3_scale_tab;  // ceil(log(3^k)/log 3) as the host libm evaluates it
+    RqIndex rq;
     int is_germline, min_size, n_chrom, pad;
     // scratch, all indexed per chromosome at off[c]
     int* lvl_idx;              // [N]   introsort permutation of the levels
@@ -33,6 +35,7 @@ struct FinParams {
     int* prelim;               // [N]   preliminary breakpoints
     int* lvl_first;            // [N]   first survivor of each distinct level
     // outputs
+    unsigned long long* phase_ns;  // [n_chrom][8] debug timeline (nullable)
     int* n_bp;                 // [n_chrom]
     int* bp;                   // [N] at off[c]
 };
@@ -42,34 +45,39 @@ struct FinParams {
 // sort of ArraySortHelper<T> restated (unstable: the order of equal counts is part of the result).
 // ------------------------------------------------------------------------------------------------
 struct LevelSorter {
-    int* k;
-    const unsigned* counts;
-    __device__ int cmp(int a, int b) const {
-        const unsigned ca = counts[a], cb = counts[b];
-        return cb < ca ? -1 : (cb > ca ? 1 : 0);
+    int* k;            // level ids being permuted
+    unsigned* kc;      // count of the level currently at each position (moves with k)
+    __device__ static int cmpc(unsigned ca, unsigned cb) { return cb < ca ? -1 : (cb > ca ? 1 : 0); }  // counts[b].CompareTo(counts[a])
+    __device__ void swap(int i, int j) {
+        const int t = k[i]; k[i] = k[j]; k[j] = t;
+        const unsigned c = kc[i]; kc[i] = kc[j]; kc[j] = c;
     }
-    __device__ void swap(int i, int j) { int t = k[i]; k[i] = k[j]; k[j] = t; }
     __device__ void swap_if_greater(int a, int b) {
-        if (a != b && cmp(k[a], k[b]) > 0) swap(a, b);
+        if (a != b && cmpc(kc[a], kc[b]) > 0) swap(a, b);
     }
     __device__ void insertion(int lo, int hi) {
         for (int i = lo; i < hi; i++) {
             int j = i;
             const int t = k[i + 1];
-            while (j >= lo && cmp(t, k[j]) < 0) { k[j + 1] = k[j]; j--; }
+            const unsigned tc = kc[i + 1];
+            while (j >= lo && cmpc(tc, kc[j]) < 0) { k[j + 1] = k[j]; kc[j + 1] = kc[j]; j--; }
             k[j + 1] = t;
+            kc[j + 1] = tc;
         }
     }
     __device__ void down_heap(int i, int n, int lo) {
         const int d = k[lo + i - 1];
+        const unsigned dc = kc[lo + i - 1];
         while (i <= n / 2) {
             int child = 2 * i;
-            if (child < n && cmp(k[lo + child - 1], k[lo + child]) < 0) child++;
-            if (!(cmp(d, k[lo + child - 1]) < 0)) break;
+            if (child < n && cmpc(kc[lo + child - 1], kc[lo + child]) < 0) child++;
+            if (!(cmpc(dc, kc[lo + child - 1]) < 0)) break;
             k[lo + i - 1] = k[lo + child - 1];
+            kc[lo + i - 1] = kc[lo + child - 1];
             i = child;
         }
         k[lo + i - 1] = d;
+        kc[lo + i - 1] = dc;
     }
     __device__ void heapsort(int lo, int hi) {
         const int n = hi - lo + 1;
@@ -81,47 +89,17 @@ struct LevelSorter {
         swap_if_greater(lo, mid);
         swap_if_greater(lo, hi);
         swap_if_greater(mid, hi);
-        const int pivot = k[mid];
+        const unsigned pivot = kc[mid];
         swap(mid, hi - 1);
         int left = lo, right = hi - 1;
         while (left < right) {
-            while (cmp(k[++left], pivot) < 0) {}
-            while (cmp(pivot, k[--right]) < 0) {}
+            while (cmpc(kc[++left], pivot) < 0) {}
+            while (cmpc(pivot, kc[--right]) < 0) {}
             if (left >= right) break;
             swap(left, right);
         }
         swap(left, hi - 1);
         return left;
-    }
-    __device__ void sort(int n) {
-        if (n < 2) return;
-        int depth0 = 0;
-        for (int t = n; t >= 1; t /= 2) depth0++;
-        depth0 *= 2;
-        // explicit stack replaces the recursion on the right part
-        int st_lo[96], st_hi[96], st_d[96];
-        int sp = 0;
-        st_lo[0] = 0; st_hi[0] = n - 1; st_d[0] = depth0; sp = 1;
-        while (sp > 0) {
-            sp--;
-            int lo = st_lo[sp], hi = st_hi[sp], depth = st_d[sp];
-            while (hi > lo) {
-                const int size = hi - lo + 1;
-                if (size <= 16) {
-                    if (size == 2) { swap_if_greater(lo, hi); }
-                    else if (size == 3) { swap_if_greater(lo, hi - 1); swap_if_greater(lo, hi); swap_if_greater(hi - 1, hi); }
-                    else if (size > 3) insertion(lo, hi);
-                    break;
-                }
-                if (depth == 0) { heapsort(lo, hi); break; }
-                depth--;
-                const int pv = partition(lo, hi);
-                // the reference recurses into [pv+1, hi] first and then loops on [lo, pv-1]; the two
-                // ranges are disjoint, so deferring the left one instead gives the same permutation
-                if (sp < 96) { st_lo[sp] = lo; st_hi[sp] = pv - 1; st_d[sp] = depth; sp++; }
-                lo = pv + 1;
-            }
-        }
     }
 };
 
@@ -184,7 +162,7 @@ __device__ void level_sort_parallel(LevelSorter ls, int n, int* task_a, int* tas
 // (immediately for short ranges, after ~3 passes for a whole chromosome arm) they are gathered into
 // shared memory, sorted there, and every request reads its answer from the sorted list.
 // ------------------------------------------------------------------------------------------------
-constexpr int BMS_GCAP = 1024;        // gathered candidates, all groups together
+constexpr int BMS_GCAP = 4096;        // gathered candidates, all groups together
 constexpr int BMS_CAND = 2 * BMS_GCAP + 2 * BMS_R;  // slices are padded to powers of two
 
 struct BmsState {
@@ -194,6 +172,9 @@ struct BmsState {
     int grange[BMS_R];
     int gcount[BMS_R], goff[BMS_R], gcap[BMS_R];
     unsigned gcore[BMS_R];   // bins of the core range inside the group's current bucket
+    int gbucket[BMS_R];      // indexed path: value bucket of the group
+    int gpure[BMS_R];        // indexed path: the bucket holds one distinct key (answered from the splitter)
+    int r_tl[2], r_tr[2];    // indexed path: full tiles [tl, tr) of each range
     int ngroups;
     int nranges;
     int rlo[2], rhi[2];
@@ -204,6 +185,7 @@ struct BmsState {
     unsigned long long rkey[BMS_R];
     int rdig[BMS_R];
     int newgrp[BMS_R];
+    unsigned long long dbg_ok, dbg_fallback, dbg_na_sum, dbg_na_max;
     int mode;        // 0: keep histogramming, 1: gather + sort, 2: all digits decided
     int match_all;   // gather without any decided digit
     int shift;
@@ -228,6 +210,71 @@ __device__ inline void bms_plan_gather(BmsState& st) {
         off += cap;
     }
     st.mode = 1;
+}
+
+// Sort every group's gathered slice and answer each request: the k-th smallest of (sorted core
+// candidates A) ∪ (the request's extra bins E that fall into the group's bucket); ties: A before E.
+// Extras are matched by radix prefix (s_spl == nullptr) or by value bucket (indexed path).
+__device__ void bms_sort_and_answer(BmsState& st, const double* __restrict__ x, int low_bit, int match_all,
+                                    const unsigned long long* s_spl) {
+    const int B = blockDim.x;
+    const int ng = st.ngroups;
+    for (int g = 0; g < ng; g++) {
+        const int n2 = st.gcap[g];
+        unsigned long long* a = st.cand + st.goff[g];
+        for (int k = 2; k <= n2; k <<= 1)
+            for (int j = k >> 1; j > 0; j >>= 1) {
+                for (int i = threadIdx.x; i < n2; i += B) {
+                    const int l = i ^ j;
+                    if (l > i) {
+                        const bool up = (i & k) == 0;
+                        const unsigned long long p = a[i], q = a[l];
+                        if ((p > q) == up) { a[i] = q; a[l] = p; }
+                    }
+                }
+                __syncthreads();
+            }
+    }
+    __syncthreads();
+    if ((int)threadIdx.x < st.nreq) {
+        const int r = threadIdx.x;
+        const int g = st.rgrp[r];
+        const unsigned long long* a = st.cand + st.goff[g];
+        const int na = min(st.gcount[g], st.gcap[g]);
+        unsigned long long e[BMS_X];
+        int ne = 0;
+        for (int i = st.xlo[r]; i < st.xhi[r] && ne < BMS_X; i++) {
+            const unsigned long long key = f64_key(x[i]);
+            const bool in = s_spl ? (rq_bucket(s_spl, key) == st.gbucket[g]) : bms_match(key, st.gprefix[g], low_bit, match_all);
+            if (in) {
+                int j = ne++;
+                while (j > 0 && e[j - 1] > key) { e[j] = e[j - 1]; j--; }
+                e[j] = key;
+            }
+        }
+        const long long k = (long long)st.rk[r];
+        unsigned long long ans = na > 0 ? a[na - 1] : (ne > 0 ? e[ne - 1] : 0ull);
+        bool found = false;
+        for (int j = 0; j < ne && !found; j++) {
+            // rank of e[j] = j + #{a <= e[j]}
+            int lo = 0, hi = na;
+            while (lo < hi) { const int mid = (lo + hi) >> 1; if (a[mid] <= e[j]) lo = mid + 1; else hi = mid; }
+            if ((long long)j + lo == k) { ans = e[j]; found = true; }
+        }
+        if (!found) {
+            // rank of a[i] = i + #{e < a[i]}: monotone in i, find i with rank == k
+            int lo = 0, hi = na - 1;
+            while (lo < hi) {
+                const int mid = (lo + hi + 1) >> 1;
+                int less = 0;
+                for (int j = 0; j < ne; j++) less += e[j] < a[mid];
+                if ((long long)mid + less <= k) lo = mid; else hi = mid - 1;
+            }
+            if (na > 0) ans = a[lo];
+        }
+        st.rkey[r] = ans;
+    }
+    __syncthreads();
 }
 
 // caller (thread 0) fills nranges, rlo/rhi, nreq, rk, xlo/xhi and rgrp = range id; then all threads call
@@ -386,62 +433,203 @@ __device__ void bms_run(BmsState& st, const double* __restrict__ x) {
         }
     }
     __syncthreads();
-    for (int g = 0; g < ng; g++) {
-        const int n2 = st.gcap[g];
-        unsigned long long* a = st.cand + st.goff[g];
-        for (int k = 2; k <= n2; k <<= 1)
-            for (int j = k >> 1; j > 0; j >>= 1) {
-                for (int i = threadIdx.x; i < n2; i += B) {
-                    const int l = i ^ j;
-                    if (l > i) {
-                        const bool up = (i & k) == 0;
-                        const unsigned long long p = a[i], q = a[l];
-                        if ((p > q) == up) { a[i] = q; a[l] = p; }
-                    }
-                }
-                __syncthreads();
-            }
+    bms_sort_and_answer(st, x, low_bit, match_all, nullptr);
+}
+
+// ------------------------------------------------------------------------------------------------
+// The same requests answered from the range-quantile index (wavelet_rqindex.cuh): bucket counts of a
+// range = difference of two cumulative rows + the bins of its two partial tiles; the bucket holding a
+// wanted rank is gathered from the bucket-sorted tile copies.  Returns false (nothing answered) when
+// the buckets in play hold more than BMS_GCAP bins — heavy duplicates — and the caller falls back to
+// the radix passes of bms_run.
+// ------------------------------------------------------------------------------------------------
+struct RqChrom {  // index slices of one chromosome
+    const unsigned long long* spl;
+    const unsigned short* hist;
+    const unsigned short* tstart;
+    const unsigned* cum;
+    const unsigned long long* sorted;
+};
+
+__device__ bool bms_run_indexed(BmsState& st, const double* __restrict__ x, const RqChrom& rq,
+                                const unsigned long long* s_spl) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int B = blockDim.x;
+    unsigned* cnt = &st.hist[0][0];  // [nranges][RQ_BUCKETS] bucket counts (the radix histograms are idle here)
+    __syncthreads();
+    // ---- 1. bucket counts of every range
+    for (int r = 0; r < st.nranges; r++) {
+        const int lo = st.rlo[r], hi = st.rhi[r];
+        const int tl = (lo + RQ_TILE - 1) / RQ_TILE, tr = hi / RQ_TILE;
+        if (threadIdx.x == 0) { st.r_tl[r] = tl; st.r_tr[r] = tr; }
+        for (int b = threadIdx.x; b < RQ_BUCKETS; b += B)
+            cnt[r * RQ_BUCKETS + b] = tl < tr ? rq.cum[(size_t)tr * RQ_BUCKETS + b] - rq.cum[(size_t)tl * RQ_BUCKETS + b] : 0u;
     }
     __syncthreads();
-    if ((int)threadIdx.x < st.nreq) {
-        // k-th smallest of (sorted core candidates A) ∪ (extras E); ties: A before E
-        const int r = threadIdx.x;
+    for (int r = 0; r < st.nranges; r++) {
+        const int lo = st.rlo[r], hi = st.rhi[r];
+        const int tl = st.r_tl[r], tr = st.r_tr[r];
+        // partial pieces: [lo, min(hi, tl*T)) and, when a tile boundary lies inside, [max(lo, tr*T), hi)
+        const int a_end = tl <= tr ? min(hi, tl * RQ_TILE) : hi;
+        for (int i = lo + (int)threadIdx.x; i < a_end; i += B) atomicAdd(&cnt[r * RQ_BUCKETS + rq_bucket(s_spl, f64_key(x[i]))], 1u);
+        if (tl <= tr) {
+            const int b_start = max(max(lo, tr * RQ_TILE), a_end);
+            for (int i = b_start + (int)threadIdx.x; i < hi; i += B) atomicAdd(&cnt[r * RQ_BUCKETS + rq_bucket(s_spl, f64_key(x[i]))], 1u);
+        }
+    }
+    __syncthreads();
+    // ---- 2. one warp per request: bucket that holds its rank (extras merged in); lane l owns buckets 32l..32l+31
+    constexpr int PER = RQ_BUCKETS / 32;
+    for (int r = warp; r < st.nreq; r += (B >> 5)) {
+        const unsigned* row = cnt + st.rgrp[r] * RQ_BUCKETS + lane * PER;
+        int xb[BMS_X];
+        int nx = 0;
+        for (int i = st.xlo[r]; i < st.xhi[r] && nx < BMS_X; i++) xb[nx++] = rq_bucket(s_spl, f64_key(x[i]));
+        unsigned long long sum = 0;
+        for (int t = 0; t < PER; t++) sum += row[t];
+        for (int q = 0; q < nx; q++) sum += (xb[q] / PER) == lane;
+        unsigned long long incl = sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned long long u = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += u;
+        }
+        const unsigned long long excl = incl - sum;
+        const unsigned long long k = st.rk[r];
+        const bool mine = sum > 0 && k >= excl && k < excl + sum;
+        unsigned bal = __ballot_sync(0xffffffffu, mine);
+        if (bal == 0u) {
+            const unsigned nz = __ballot_sync(0xffffffffu, sum > 0);
+            bal = nz ? (1u << (31 - __clz(nz))) : 1u;
+        }
+        const int owner = __ffs(bal) - 1;
+        if (lane == owner) {
+            unsigned long long run = excl, cum = excl;
+            int d = lane * PER + PER - 1;
+            for (int t = 0; t < PER; t++) {
+                unsigned long long c = row[t];
+                for (int q = 0; q < nx; q++) c += xb[q] == lane * PER + t;
+                if (k < run + c) { d = lane * PER + t; cum = run; break; }
+                run += c;
+                cum = run;
+            }
+            st.rkey[r] = k >= cum ? k - cum : 0ull;  // rank inside the bucket (committed only if we go on)
+            st.rdig[r] = d;
+        }
+    }
+    __syncthreads();
+    // ---- 3. groups = distinct (range, bucket); plan the gather
+    if (threadIdx.x == 0) {
+        int nn = 0;
+        int nb[BMS_R], nr[BMS_R];
+        for (int r = 0; r < st.nreq; r++) {
+            const int range = st.rgrp[r];
+            int idx = -1;
+            for (int q = 0; q < nn; q++)
+                if (nb[q] == st.rdig[r] && nr[q] == range) idx = q;
+            if (idx < 0) { idx = nn; nb[nn] = st.rdig[r]; nr[nn] = range; nn++; }
+            st.newgrp[r] = idx;
+        }
+        unsigned total = 0;
+        int pure[BMS_R];
+        for (int q = 0; q < nn; q++) {
+            // bucket b = keys in (spl[b-1], spl[b]]: one distinct key when the two splitters are adjacent
+            pure[q] = nb[q] > 0 && s_spl[nb[q] - 1] + 1ull == s_spl[nb[q]];
+            if (!pure[q]) total += cnt[nr[q] * RQ_BUCKETS + nb[q]];
+        }
+        st.mode = 0;
+        if (total <= (unsigned)(BMS_CAND - 2 * BMS_R)) {
+            int off = 0;
+            for (int q = 0; q < nn; q++) {
+                st.gbucket[q] = nb[q]; st.grange[q] = nr[q]; st.gpure[q] = pure[q];
+                st.gcore[q] = pure[q] ? 0u : cnt[nr[q] * RQ_BUCKETS + nb[q]];
+                st.gcap[q] = (int)st.gcore[q]; st.goff[q] = off; st.gcount[q] = 0;
+                off += (int)st.gcore[q];
+            }
+            st.ngroups = nn;
+            for (int r = 0; r < st.nreq; r++) { st.rgrp[r] = st.newgrp[r]; st.rk[r] = st.rkey[r]; }
+            st.mode = 1;
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (st.mode == 1) { st.dbg_ok++; for (int q = 0; q < st.ngroups; q++) { if (st.gpure[q]) st.dbg_na_max += 1ull << 20; st.dbg_na_sum += st.gcore[q]; if (st.gcore[q] > st.dbg_na_max) st.dbg_na_max = st.gcore[q]; } }
+        else st.dbg_fallback++;
+    }
+    if (st.mode != 1) return false;  // requests untouched: the caller falls back to the radix passes
+    const int ng = st.ngroups;
+    // ---- 4. gather: bucket slices of the full tiles + matching bins of the partial tiles
+    for (int g = 0; g < ng; g++) {
+        if (st.gpure[g]) continue;
+        const int r = st.grange[g], b = st.gbucket[g];
+        const int lo = st.rlo[r], hi = st.rhi[r];
+        const int tl = st.r_tl[r], tr = st.r_tr[r];
+        for (int t = tl + (int)threadIdx.x; t < tr; t += B) {
+            const int c = rq.hist[(size_t)t * RQ_BUCKETS + b];
+            if (c) {
+                const int src = t * RQ_TILE + rq.tstart[(size_t)t * RQ_BUCKETS + b];
+                const int dst = atomicAdd(&st.gcount[g], c);
+                for (int q = 0; q < c; q++)
+                    if (dst + q < st.gcap[g]) st.cand[st.goff[g] + dst + q] = rq.sorted[src + q];
+            }
+        }
+        const int a_end = tl <= tr ? min(hi, tl * RQ_TILE) : hi;
+        for (int i = lo + (int)threadIdx.x; i < a_end; i += B) {
+            const unsigned long long key = f64_key(x[i]);
+            if (rq_bucket(s_spl, key) == b) { const int dst = atomicAdd(&st.gcount[g], 1); if (dst < st.gcap[g]) st.cand[st.goff[g] + dst] = key; }
+        }
+        if (tl <= tr) {
+            const int b_start = max(max(lo, tr * RQ_TILE), a_end);
+            for (int i = b_start + (int)threadIdx.x; i < hi; i += B) {
+                const unsigned long long key = f64_key(x[i]);
+                if (rq_bucket(s_spl, key) == b) { const int dst = atomicAdd(&st.gcount[g], 1); if (dst < st.gcap[g]) st.cand[st.goff[g] + dst] = key; }
+            }
+        }
+    }
+    __syncthreads();
+    // ---- 5. one warp per request: k-th smallest key of A ∪ E by binary radix descent over the gathered
+    //         candidates (only the bits in which they differ): linear in the candidate count, no sorting
+    for (int r = warp; r < st.nreq; r += (B >> 5)) {
         const int g = st.rgrp[r];
+        if (st.gpure[g]) {
+            if (lane == 0) st.rkey[r] = s_spl[st.gbucket[g]];
+            continue;
+        }
         const unsigned long long* a = st.cand + st.goff[g];
         const int na = min(st.gcount[g], st.gcap[g]);
         unsigned long long e[BMS_X];
         int ne = 0;
         for (int i = st.xlo[r]; i < st.xhi[r] && ne < BMS_X; i++) {
             const unsigned long long key = f64_key(x[i]);
-            if (bms_match(key, st.gprefix[g], low_bit, match_all)) {
-                int j = ne++;
-                while (j > 0 && e[j - 1] > key) { e[j] = e[j - 1]; j--; }
-                e[j] = key;
+            if (rq_bucket(s_spl, key) == st.gbucket[g]) e[ne++] = key;
+        }
+        unsigned long long vor = 0ull, vand = ~0ull;
+        for (int i = lane; i < na; i += 32) { const unsigned long long v = a[i]; vor |= v; vand &= v; }
+        for (int q = 0; q < ne; q++) { vor |= e[q]; vand &= e[q]; }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            vor |= __shfl_xor_sync(0xffffffffu, vor, o);
+            vand &= __shfl_xor_sync(0xffffffffu, vand, o);
+        }
+        const unsigned long long diff = vor ^ vand;   // bits that are not common to all keys
+        unsigned long long k = st.rk[r], mask = 0ull, value = 0ull;
+        for (int bit = 63; bit >= 0; bit--) {
+            if (!((diff >> bit) & 1ull)) continue;
+            const unsigned long long bm = 1ull << bit;
+            unsigned c0 = 0;
+            for (int i = lane; i < na; i += 32) {
+                const unsigned long long v = a[i];
+                c0 += (((v ^ value) & mask) == 0ull) && !(v & bm);
             }
+            c0 = __reduce_add_sync(0xffffffffu, c0);
+            for (int q = 0; q < ne; q++) c0 += (((e[q] ^ value) & mask) == 0ull) && !(e[q] & bm);
+            if (k >= c0) { k -= c0; value |= bm; }
+            mask |= bm;
         }
-        const long long k = (long long)st.rk[r];
-        unsigned long long ans = na > 0 ? a[na - 1] : (ne > 0 ? e[ne - 1] : 0ull);
-        bool found = false;
-        for (int j = 0; j < ne && !found; j++) {
-            // rank of e[j] = j + #{a <= e[j]}
-            int lo = 0, hi = na;
-            while (lo < hi) { const int mid = (lo + hi) >> 1; if (a[mid] <= e[j]) lo = mid + 1; else hi = mid; }
-            if ((long long)j + lo == k) { ans = e[j]; found = true; }
-        }
-        if (!found) {
-            // rank of a[i] = i + #{e < a[i]}: monotone in i, find i with rank == k
-            int lo = 0, hi = na - 1;
-            while (lo < hi) {
-                const int mid = (lo + hi + 1) >> 1;
-                int less = 0;
-                for (int j = 0; j < ne; j++) less += e[j] < a[mid];
-                if ((long long)mid + less <= k) lo = mid; else hi = mid - 1;
-            }
-            if (na > 0) ans = a[lo];
-        }
-        st.rkey[r] = ans;
+        if (lane == 0) st.rkey[r] = (vand & ~diff) | value;
     }
     __syncthreads();
+    return true;
 }
 
 // median of x[lo, hi) from a pair of requests {lower middle, upper middle}
@@ -510,12 +698,23 @@ __device__ void fin_bitonic(unsigned long long* key, int* val, int n2) {
     }
 }
 
+#define FIN_STAMP(k)                                                                         \
+    do {                                                                                     \
+        __syncthreads();                                                                     \
+        if (threadIdx.x == 0 && p.phase_ns) {                                                \
+            unsigned long long t__;                                                          \
+            asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t__));                          \
+            p.phase_ns[(size_t)blockIdx.x * 8 + (k)] = t__;                                  \
+        }                                                                                    \
+    } while (0)
+
 __global__ void __launch_bounds__(FIN_THREADS, 1)
 uh_finish_kernel(FinParams p) {
     extern __shared__ __align__(16) unsigned char fin_smem[];
     BmsState& s_bms = *reinterpret_cast<BmsState*>(fin_smem);
     unsigned long long* s_key = reinterpret_cast<unsigned long long*>(fin_smem + ((sizeof(BmsState) + 15) & ~(size_t)15));
     int* s_val = reinterpret_cast<int*>(s_key + FIN_SORT_SMEM);
+    unsigned long long* s_spl = reinterpret_cast<unsigned long long*>(s_val + FIN_SORT_SMEM);
     const int c = blockIdx.x;
     const long long o = p.off[c];
     const int n = (int)(p.off[c + 1] - o);
@@ -533,8 +732,20 @@ uh_finish_kernel(FinParams p) {
     int* bp = p.bp + o;
     const unsigned* lvlcnt = p.lvlcnt + o;
     const int T = p.depth[c];  // number of levels (tree.Count)
+    for (int j = threadIdx.x; j < RQ_BUCKETS; j += blockDim.x) s_spl[j] = p.rq.spl[(size_t)c * RQ_BUCKETS + j];
+    RqChrom rqc;
+    {
+        const int tf = p.rq.tfirst[c];
+        rqc.spl = p.rq.spl + (size_t)c * RQ_BUCKETS;
+        rqc.hist = p.rq.hist + (size_t)tf * RQ_BUCKETS;
+        rqc.tstart = p.rq.tstart + (size_t)tf * RQ_BUCKETS;
+        rqc.cum = p.rq.cum + (size_t)(tf + c) * RQ_BUCKETS;
+        rqc.sorted = p.rq.sorted + o;
+    }
     const int ncand_all = min(p.ctl->cand_count_.v, 0x7fffffff);
 
+    if (threadIdx.x == 0) { s_bms.dbg_ok = s_bms.dbg_fallback = s_bms.dbg_na_sum = s_bms.dbg_na_max = 0; }
+    FIN_STAMP(0);
     // ---- HardThresh level weights (:78-91): germline only
     if (p.is_germline) {
         __shared__ int s_sort_counts[2];
@@ -550,14 +761,18 @@ uh_finish_kernel(FinParams p) {
             __syncthreads();
             for (int l = threadIdx.x; l < T; l += blockDim.x) lvl_idx[l] = s_val[l];
         } else {
-            for (int l = threadIdx.x; l < T; l += blockDim.x) lvl_idx[l] = l;
+            // deeper than the shared-memory tables: same replay on global scratch (rec doubles as the
+            // moving count table)
+            unsigned* gcnt = reinterpret_cast<unsigned*>(rec);
+            for (int l = threadIdx.x; l < T; l += blockDim.x) { lvl_idx[l] = l; gcnt[l] = lvlcnt[l]; }
             __syncthreads();
             const int cap = n / 3;
-            level_sort_parallel(LevelSorter{lvl_idx, lvlcnt}, T, piece, prelim, cap, s_sort_counts);
+            level_sort_parallel(LevelSorter{lvl_idx, gcnt}, T, piece, prelim, cap, s_sort_counts);
         }
     }
     __syncthreads();
 
+    FIN_STAMP(1);
     // ---- survivors of the threshold among this chromosome's candidates (:102-114)
     const double sigma = p.sigma[c];
     const double root = sqrt(2.0 * log((double)n));
@@ -613,6 +828,7 @@ uh_finish_kernel(FinParams p) {
         __syncthreads();
     }
 
+    FIN_STAMP(2);
     // ---- pieces: positions where a surviving node starts, breaks or ends (+ position 0)
     const int nwords = (n + 31) >> 5;
     for (int i = threadIdx.x; i < nwords; i += blockDim.x) bitmap[i] = 0u;
@@ -695,6 +911,7 @@ uh_finish_kernel(FinParams p) {
     }
     __syncthreads();
 
+    FIN_STAMP(3);
     // ---- healing (:194-232): greedy left to right, exact medians of the two implied segments
     int nb = 0;  // kept breakpoints so far (uniform across the block)
     if (threadIdx.x == 0) bp[0] = prelim[0];
@@ -719,7 +936,7 @@ uh_finish_kernel(FinParams p) {
                     bms_add_median(s_bms, 1, left_len, 0, 0);
                 }
             }
-            bms_run(s_bms, x);
+            if (!bms_run_indexed(s_bms, x, rqc, s_spl)) bms_run(s_bms, x);
             const double rm = bms_median_value(s_bms, 0);
             const double lm = have_left ? left_median_cache : bms_median_value(s_bms, 2);
             const double wm = __ddiv_rn(__dadd_rn(__dmul_rn((double)left_len, lm), __dmul_rn((double)right_len, rm)),
@@ -748,6 +965,7 @@ uh_finish_kernel(FinParams p) {
     }
     __syncthreads();
 
+    FIN_STAMP(4);
     // ---- RefineSegments (:237-258), germline only
     if (p.is_germline && nb > 2) {
         const double total_median = p.chrom_median[c];
@@ -763,7 +981,7 @@ uh_finish_kernel(FinParams p) {
                 bms_add_median(s_bms, 0, cur - prev, core_hi, cur);             // Median(coverage, prev, cur)
                 for (int j = cur - li; j < cur + ri; j++) bms_add_median(s_bms, 0, j - prev, core_hi, j);
             }
-            bms_run(s_bms, x);
+            if (!bms_run_indexed(s_bms, x, rqc, s_spl)) bms_run(s_bms, x);
             if (threadIdx.x == 0) {
                 double best = fabs(__dsub_rn(bms_median_value(s_bms, 0), total_median));
                 int best_bp = cur;
@@ -777,10 +995,15 @@ uh_finish_kernel(FinParams p) {
             __syncthreads();
         }
     }
-    __syncthreads();
+    FIN_STAMP(5);
+    if (threadIdx.x == 0 && p.phase_ns) {
+        p.phase_ns[(size_t)blockIdx.x * 8 + 6] = (s_bms.dbg_fallback << 32) | s_bms.dbg_ok;
+        p.phase_ns[(size_t)blockIdx.x * 8 + 7] = (s_bms.dbg_na_max << 32) | s_bms.dbg_na_sum;
+    }
     if (threadIdx.x == 0) p.n_bp[c] = nb;
 }
 
 inline size_t fin_smem_bytes() {
-    return ((sizeof(BmsState) + 15) & ~(size_t)15) + (size_t)FIN_SORT_SMEM * (sizeof(unsigned long long) + sizeof(int));
+    return ((sizeof(BmsState) + 15) & ~(size_t)15) + (size_t)FIN_SORT_SMEM * (sizeof(unsigned long long) + sizeof(int)) +
+           (size_t)RQ_BUCKETS * sizeof(unsigned long long);
 }

@@ -14,7 +14,7 @@ pytestmark = pytest.mark.gpu
 
 def test_clean_then_partition_on_files(tmp_path, engine):
     modules._engine = engine
-    s = synth.make_sample(config=2, sample=11, scale=0.04, n_events=120)
+    s = synth.make_sample(config=2, sample=11, scale=0.07, n_events=120)
     binned = str(tmp_path / "s.binned")
     cleaned = str(tmp_path / "s.cleaned")
     part = str(tmp_path / "s.partitioned")
