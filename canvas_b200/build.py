@@ -19,7 +19,7 @@ NVCC_FLAGS = [
     # contraction would change results in the last bit
     "-fmad=false",
     "-Xcompiler", "-fPIC", "-I" + os.path.join(ROOT, "include"),
-]
+] + (["-DSEL_DEBUG"] if os.environ.get("CANVAS_SEL_DEBUG") else [])
 
 
 def _stale(target, deps):

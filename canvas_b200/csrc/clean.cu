@@ -683,6 +683,7 @@ extern "C" int cg_clean(cg_ctx* ctx, const cg_clean_opts* opts, int64_t n, const
     if (!opts || n < 0 || n > 0x7fff0000LL || n_chrom < 0 || n_chrom > 256 || !n_out || !local_sd || !gc_norm_skipped)
         return cg_fail(ctx, CG_ERR_ARG, "cg_clean: bad argument");
     ctx->launches = 0;
+    ctx->launch_err = cudaSuccess;
     ctx->last_kernel_ms = 0;
     for (int i = 0; i < 4; i++) ctx->stage_used[i] = false;
     *n_out = 0;
@@ -716,6 +717,7 @@ extern "C" int cg_clean(cg_ctx* ctx, const cg_clean_opts* opts, int64_t n, const
     CG_CUDA(ctx, cudaMemcpyAsync(h, d.ctl, sizeof(CleanCtl), cudaMemcpyDeviceToHost, s));
     CG_CUDA(ctx, cudaStreamSynchronize(s));
     CG_CUDA(ctx, cudaGetLastError());
+    CG_CHECK_LAUNCHES(ctx);
     float ms = 0;
     cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
     ctx->last_kernel_ms = ms;
@@ -743,6 +745,7 @@ extern "C" int cg_normalize_apply(cg_ctx* ctx, int batch, int64_t n, const float
         return cg_fail(ctx, CG_ERR_ARG, "cg_normalize_apply: bad argument (n must be a multiple of 4)");
     CG_CUDA(ctx, cudaSetDevice(ctx->device));
     ctx->launches = 0;
+    ctx->launch_err = cudaSuccess;
     const size_t total = (size_t)batch * (size_t)n;
     int rc = arena_reserve(ctx, arena_need(total, 4) * 2 + arena_need(total, 1) + arena_need((size_t)batch * GC_BINS, 8) +
                                     arena_need(batch, 8) + 4096);
@@ -772,6 +775,7 @@ extern "C" int cg_normalize_apply(cg_ctx* ctx, int batch, int64_t n, const float
     CG_CUDA(ctx, cudaMemcpyAsync(count_out, d_out, total * 4, cudaMemcpyDeviceToHost, s));
     CG_CUDA(ctx, cudaStreamSynchronize(s));
     CG_CUDA(ctx, cudaGetLastError());
+    CG_CHECK_LAUNCHES(ctx);
     float ms = 0;
     cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
     ctx->last_kernel_ms = ms / repeats;

@@ -23,6 +23,8 @@ struct cg_ctx {
     std::string desc;
     double last_kernel_ms = 0;
     int launches = 0;
+    cudaError_t launch_err = cudaSuccess;  // first failed kernel launch of the current call
+    const char* launch_err_kernel = "";
     // stage timers: events [2*i], [2*i+1] bracket stage i
     cudaEvent_t stage_ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     bool stage_used[4] = {false, false, false, false};
@@ -134,4 +136,20 @@ static inline int div_up(int64_t a, int64_t b) { return (int)((a + b - 1) / b); 
     do {                                                                               \
         kernel<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__);               \
         (ctx)->launches++;                                                             \
+        cudaError_t le__ = cudaGetLastError();                                         \
+        if (le__ != cudaSuccess && (ctx)->launch_err == cudaSuccess) {                 \
+            (ctx)->launch_err = le__;                                                  \
+            (ctx)->launch_err_kernel = #kernel;                                        \
+        }                                                                              \
+    } while (0)
+
+// to be called after the stream has been synchronised: a launch that failed is an error of the call
+#define CG_CHECK_LAUNCHES(ctx)                                                                         \
+    do {                                                                                               \
+        if ((ctx)->launch_err != cudaSuccess) {                                                        \
+            cudaError_t e__ = (ctx)->launch_err;                                                       \
+            (ctx)->launch_err = cudaSuccess;                                                           \
+            return cg_fail(ctx, CG_ERR_CUDA, std::string("kernel launch failed: ") + (ctx)->launch_err_kernel + ": " + \
+                                                 cudaGetErrorString(e__));                             \
+        }                                                                                              \
     } while (0)

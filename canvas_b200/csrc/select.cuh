@@ -27,6 +27,7 @@ struct SelState {
     int* ngrp;                   // [nseg]
     K* gprefix;                  // [nseg*SEL_G]  decided high bits of each group
     unsigned* hist;              // [nseg*SEL_G*256]
+    int* seg_done;               // [nseg + 1] blocks that finished the current pass (slot nseg: whole grid)
 };
 
 template <typename K>
@@ -37,6 +38,7 @@ inline size_t sel_state_bytes(int nseg) {
     s += arena_need((size_t)nseg * SEL_G, sizeof(int));
     s += arena_need((size_t)nseg * SEL_G, sizeof(K)) * 2;
     s += arena_need((size_t)nseg * SEL_G * SEL_BINS, sizeof(unsigned));
+    s += arena_need(nseg + 1, sizeof(int));
     return s;
 }
 
@@ -50,8 +52,12 @@ inline bool sel_state_alloc(cg_ctx* ctx, int nseg, SelState<K>& st) {
     st.req_key = arena_take<K>(ctx, (size_t)nseg * SEL_G);
     st.gprefix = arena_take<K>(ctx, (size_t)nseg * SEL_G);
     st.hist = arena_take<unsigned>(ctx, (size_t)nseg * SEL_G * SEL_BINS);
-    return st.nreq && st.ngrp && st.req_k && st.req_grp && st.req_key && st.gprefix && st.hist;
+    st.seg_done = arena_take<int>(ctx, nseg + 1);
+    return st.seg_done && st.nreq && st.ngrp && st.req_k && st.req_grp && st.req_key && st.gprefix && st.hist;
 }
+
+template <typename K>
+__device__ void sel_resolve_segment(SelState<K>& st, int s, int shift, int last);
 
 // After the caller filled nreq / req_k: one group per segment with an empty prefix.
 template <typename K>
@@ -60,6 +66,8 @@ __global__ void sel_begin_kernel(SelState<K> st) {
     if (s >= st.nseg) return;
     int nr = st.nreq[s];
     st.ngrp[s] = nr > 0 ? 1 : 0;
+    st.seg_done[s] = 0;
+    if (s == 0) st.seg_done[st.nseg] = 0;
     for (int j = 0; j < SEL_G; j++) {
         st.gprefix[s * SEL_G + j] = (K)0;
         st.req_grp[s * SEL_G + j] = 0;
@@ -77,7 +85,7 @@ __global__ void sel_begin_kernel(SelState<K> st) {
 //       __device__ bool get(long long i, K& key, int& segA, int& segB) const;  (seg < 0: none)
 // ---------------------------------------------------------------------------------------------
 template <typename K, class View, bool PRIV>
-__global__ void sel_hist_scatter_kernel(View v, SelState<K> st, int shift, int first) {
+__global__ void __launch_bounds__(1024) sel_hist_scatter_kernel(View v, SelState<K> st, int shift, int first, int last) {
     extern __shared__ unsigned char sel_smem[];
     const int nseg = st.nseg;
     K* s_prefix = (K*)sel_smem;
@@ -127,6 +135,26 @@ __global__ void sel_hist_scatter_kernel(View v, SelState<K> st, int shift, int f
             if (c) atomicAdd(&st.hist[(size_t)((t / SEL_BINS) * SEL_G) * SEL_BINS + (t % SEL_BINS)], c);
         }
     }
+    // the last block to finish the pass resolves every segment (one warp each); every thread fences its
+    // own histogram updates before the block reports completion
+    __shared__ int s_last_block;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        s_last_block = atomicAdd(&st.seg_done[nseg], 1) == (int)gridDim.x - 1;
+    }
+    __syncthreads();
+    if (s_last_block) {
+        __threadfence();
+        const int nwarps = blockDim.x >> 5;
+        for (int s = threadIdx.x >> 5; s < nseg; s += nwarps) sel_resolve_segment<K>(st, s, shift, last);
+        if (threadIdx.x == 0) st.seg_done[nseg] = 0;
+#ifdef SEL_DEBUG
+        __syncthreads();
+        if (threadIdx.x == 0 && sizeof(K) == 8) printf("[sel] shift=%d grid=%d last=%d nseg=%d nreq0=%d ngrp0=%d k0=%llu key0=%llx\n", shift, (int)gridDim.x, last, nseg, st.nreq[0], st.ngrp[0], st.req_k[0], (unsigned long long)st.req_key[0]);
+#endif
+    }
 }
 
 template <typename K>
@@ -149,8 +177,8 @@ struct SelWork {
 };
 
 template <typename K, class View>
-__global__ void sel_hist_contig_kernel(View v, const SelWork* __restrict__ work, SelState<K> st, int shift,
-                                       int first) {
+__global__ void sel_hist_contig_kernel(View v, const SelWork* __restrict__ work, const int* __restrict__ seg_nwork,
+                                       SelState<K> st, int shift, int first, int last) {
     __shared__ unsigned s_hist[SEL_G * SEL_BINS];
     __shared__ K s_prefix[SEL_G];
     const SelWork w = work[blockIdx.x];
@@ -183,17 +211,31 @@ __global__ void sel_hist_contig_kernel(View v, const SelWork* __restrict__ work,
         unsigned c = s_hist[t];
         if (c) atomicAdd(&st.hist[(size_t)(s * SEL_G) * SEL_BINS + t], c);
     }
+    // the last block of this segment resolves it (every thread fences its own updates first)
+    __shared__ int s_last_block;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        s_last_block = atomicAdd(&st.seg_done[s], 1) == seg_nwork[s] - 1;
+    }
+    __syncthreads();
+    if (s_last_block && threadIdx.x < 32) {
+        __threadfence();
+        sel_resolve_segment<K>(st, s, shift, last);
+        if (threadIdx.x == 0) st.seg_done[s] = 0;
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
 // Resolve: one warp per segment walks the rows of its groups, moves each request into the bucket
 // that holds its rank, regroups requests by their new prefix and clears the rows for the next pass.
 // ---------------------------------------------------------------------------------------------
+// Resolve one segment with one warp: walk the rows of its groups, move each request into the bucket
+// that holds its rank, regroup requests by their new prefix and clear the rows for the next pass.
 template <typename K>
-__global__ void sel_resolve_kernel(SelState<K> st, int shift, int last) {
+__device__ void sel_resolve_segment(SelState<K>& st, int s, int shift, int last) {
     const int lane = threadIdx.x & 31;
-    const int s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (s >= st.nseg) return;
     const int nr = st.nreq[s];
     const int ng = st.ngrp[s];
     if (nr == 0 || ng == 0) return;
@@ -214,7 +256,7 @@ __global__ void sel_resolve_kernel(SelState<K> st, int shift, int last) {
         unsigned long long sum = 0;
 #pragma unroll
         for (int t = 0; t < 8; t++) {
-            c[t] = row[lane * 8 + t];
+            c[t] = __ldcg(row + lane * 8 + t);
             sum += c[t];
             row[lane * 8 + t] = 0u;
         }
@@ -275,7 +317,7 @@ __global__ void sel_resolve_kernel(SelState<K> st, int shift, int last) {
 template <typename K, class View>
 inline void sel_run_scatter(cg_ctx* ctx, const View& v, SelState<K>& st, long long n_upper) {
     const int bits = (int)sizeof(K) * 8;
-    CG_LAUNCH(ctx, sel_begin_kernel<K>, div_up(st.nseg, 128), 128, 0, st);
+    CG_LAUNCH(ctx, sel_begin_kernel<K>, div_up(st.nseg + 1, 128), 128, 0, st);
     size_t smem_priv = sel_scatter_smem<K>(st.nseg, true);
     const bool priv = smem_priv <= 200 * 1024;
     size_t smem = priv ? smem_priv : sel_scatter_smem<K>(st.nseg, false);
@@ -287,23 +329,20 @@ inline void sel_run_scatter(cg_ctx* ctx, const View& v, SelState<K>& st, long lo
     for (int shift = bits - 8; shift >= 0; shift -= 8) {
         int first = shift == bits - 8;
         if (priv)
-            CG_LAUNCH(ctx, (sel_hist_scatter_kernel<K, View, true>), grid, 1024, smem, v, st, shift, first);
+            CG_LAUNCH(ctx, (sel_hist_scatter_kernel<K, View, true>), grid, 1024, smem, v, st, shift, first, shift == 0);
         else
-            CG_LAUNCH(ctx, (sel_hist_scatter_kernel<K, View, false>), grid, 256, smem, v, st, shift, first);
-        CG_LAUNCH(ctx, sel_resolve_kernel<K>, div_up((long long)st.nseg * 32, 256), 256, 0, st, shift,
-                  shift == 0);
+            CG_LAUNCH(ctx, (sel_hist_scatter_kernel<K, View, false>), grid, 256, smem, v, st, shift, first, shift == 0);
     }
 }
 
 template <typename K, class View>
-inline void sel_run_contig(cg_ctx* ctx, const View& v, const SelWork* work_dev, int nwork, SelState<K>& st) {
+inline void sel_run_contig(cg_ctx* ctx, const View& v, const SelWork* work_dev, const int* seg_nwork_dev, int nwork,
+                           SelState<K>& st) {
     const int bits = (int)sizeof(K) * 8;
-    CG_LAUNCH(ctx, sel_begin_kernel<K>, div_up(st.nseg, 128), 128, 0, st);
+    CG_LAUNCH(ctx, sel_begin_kernel<K>, div_up(st.nseg + 1, 128), 128, 0, st);
     if (nwork <= 0) return;
     for (int shift = bits - 8; shift >= 0; shift -= 8) {
         int first = shift == bits - 8;
-        CG_LAUNCH(ctx, (sel_hist_contig_kernel<K, View>), nwork, 256, 0, v, work_dev, st, shift, first);
-        CG_LAUNCH(ctx, sel_resolve_kernel<K>, div_up((long long)st.nseg * 32, 256), 256, 0, st, shift,
-                  shift == 0);
+        CG_LAUNCH(ctx, (sel_hist_contig_kernel<K, View>), nwork, 256, 0, v, work_dev, seg_nwork_dev, st, shift, first, shift == 0);
     }
 }

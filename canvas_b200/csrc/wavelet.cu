@@ -19,6 +19,7 @@ struct WvPlan {
     WvSegTable t{};
     std::vector<long long> seg_len;
     std::vector<SelWork> work;       // select work list (coverage windows, chromosomes, f3 pools)
+    std::vector<int> seg_nwork;      // work items of every segment
     std::vector<WvEvWork> ev_work;
     std::vector<WvScanTile> tiles;
     std::vector<int> tile_first;
@@ -114,6 +115,8 @@ void make_plan(WvPlan& pl, int n_chrom, const int64_t* chrom_off, int window) {
     if (t.n_w100 > 0) add_work(pl.work, t.base_ev100, 0, t.n_w100);
     if (t.n_w10 > 0) add_work(pl.work, t.base_r10, 0, t.n_w10);
     if (t.n_w100 > 0) add_work(pl.work, t.base_r100, 0, t.n_w100);
+    pl.seg_nwork.assign(t.nseg, 0);
+    for (const SelWork& wk : pl.work) pl.seg_nwork[wk.seg]++;
     // scan tiles
     pl.tiles.clear();
     pl.tile_first.assign(n_chrom + 1, 0);
@@ -139,6 +142,7 @@ struct WvDev {
     SelState<uint64_t> sel;
     long long* seg_len;
     SelWork* work;
+    int* seg_nwork;
     WvEvWork* ev_work;
     WvScanTile* tiles;
     int* tile_first;
@@ -152,8 +156,9 @@ struct WvDev {
     unsigned* lvlcnt;
     int* depth;
     UhBigTask* big;
-    UhSmallTask* small;
-    int small_cap;
+    UhTask *mid, *small;
+    UhTinyTask* tiny;
+    int mid_cap, small_cap, tiny_cap;
     UhCand* cand;
     int cand_cap;
     // finish scratch
@@ -168,6 +173,7 @@ struct WvDev {
     unsigned* rq_cum;
     int* rq_tfirst;
     unsigned long long* phase_ns;
+    UhTinyTab* tiny_tab;
 };
 
 size_t wv_workspace_bytes(const WvPlan& pl) {
@@ -175,19 +181,20 @@ size_t wv_workspace_bytes(const WvPlan& pl) {
     size_t s = 0;
     s += arena_need(N, 8) + arena_need(C + 1, 8) + arena_need(C + 1, 1) + arena_need(N + C + 1, 8);
     s += sel_state_bytes<uint64_t>(pl.t.nseg) + arena_need(pl.t.nseg, 8);
-    s += arena_need(pl.work.size() + 1, sizeof(SelWork)) + arena_need(pl.ev_work.size() + 1, sizeof(WvEvWork));
+    s += arena_need(pl.t.nseg + 1, 4) + arena_need(pl.work.size() + 1, sizeof(SelWork)) + arena_need(pl.ev_work.size() + 1, sizeof(WvEvWork));
     s += arena_need(pl.tiles.size() + 1, sizeof(WvScanTile)) + arena_need(C + 2, 4) + arena_need(pl.tiles.size() + 1, 8);
     s += arena_need(WV_F3_LEVELS, sizeof(WvF3Level));
     s += arena_need(pl.f3_total + 1, 8) * 2 + arena_need(pl.t.n_w10 + 1, 8) + arena_need(pl.t.n_w100 + 1, 8);
     s += arena_need(pl.t.n_w10 + 1, 4) + arena_need(pl.t.n_w100 + 1, 4);
     s += arena_need(pl.t.nseg, 8) * 2 + arena_need(C + 1, 8) * 2 + arena_need(32, 8) + arena_need(1, sizeof(WvCtl));
     s += arena_need(N + 1, 4) + arena_need(C + 1, 4);
-    s += arena_need(UH_QCAP, sizeof(UhBigTask)) + arena_need(N / 2 + C + 64, sizeof(UhSmallTask));
+    s += arena_need(UH_QCAP, sizeof(UhBigTask)) + arena_need(N / UH_SMALL_MAX + C + 64, sizeof(UhTask)) +
+         arena_need(N / UH_TINY_MAX + C + 64, sizeof(UhTask)) + arena_need(N / 2 + C + 64, sizeof(UhTinyTask));
     s += arena_need(N / 4 + 4096, sizeof(UhCand));
     s += arena_need(N + 1, 4) * 5 + arena_need(N + 1, 8) * 2 + arena_need(N / 32 + C + 2, 4);
     s += arena_need(C + 1, 4) + arena_need(N + 1, 4);
     s += arena_need((C + 1) * RQ_BUCKETS, 8) + arena_need(N + 1, 8) + arena_need((size_t)(pl.rq_ntiles + 1) * RQ_BUCKETS, 2) * 2;
-    s += arena_need((size_t)(pl.rq_ntiles + C + 2) * RQ_BUCKETS, 4) + arena_need(C + 2, 4) + arena_need((C + 1) * 8, 8);
+    s += arena_need((size_t)(pl.rq_ntiles + C + 2) * RQ_BUCKETS, 4) + arena_need(C + 2, 4) + arena_need((C + 1) * 8, 8) + arena_need(1, sizeof(UhTinyTab));
     return s + (1 << 16);
 }
 
@@ -200,6 +207,7 @@ int wv_alloc(cg_ctx* ctx, const WvPlan& pl, WvDev& d, double* cov_dev_existing) 
     bool ok = sel_state_alloc<uint64_t>(ctx, pl.t.nseg, d.sel);
     d.seg_len = arena_take<long long>(ctx, pl.t.nseg);
     d.work = arena_take<SelWork>(ctx, pl.work.size() + 1);
+    d.seg_nwork = arena_take<int>(ctx, pl.t.nseg + 1);
     d.ev_work = arena_take<WvEvWork>(ctx, pl.ev_work.size() + 1);
     d.tiles = arena_take<WvScanTile>(ctx, pl.tiles.size() + 1);
     d.tile_first = arena_take<int>(ctx, C + 2);
@@ -220,8 +228,14 @@ int wv_alloc(cg_ctx* ctx, const WvPlan& pl, WvDev& d, double* cov_dev_existing) 
     d.lvlcnt = arena_take<unsigned>(ctx, N + 1);
     d.depth = arena_take<int>(ctx, C + 1);
     d.big = arena_take<UhBigTask>(ctx, UH_QCAP);
-    d.small_cap = (int)(N / 2 + C + 64);
-    d.small = arena_take<UhSmallTask>(ctx, d.small_cap);
+    // a node of stage M / S / T has more than UH_SMALL_MAX / UH_TINY_MAX / 1 bins and the roots of one
+    // stage are disjoint, which bounds the list lengths
+    d.mid_cap = (int)(N / UH_SMALL_MAX + C + 64);
+    d.mid = arena_take<UhTask>(ctx, d.mid_cap);
+    d.small_cap = (int)(N / UH_TINY_MAX + C + 64);
+    d.small = arena_take<UhTask>(ctx, d.small_cap);
+    d.tiny_cap = (int)(N / 2 + C + 64);
+    d.tiny = arena_take<UhTinyTask>(ctx, d.tiny_cap);
     d.cand_cap = (int)(N / 4 + 4096);
     d.cand = arena_take<UhCand>(ctx, d.cand_cap);
     d.lvl_idx = arena_take<int>(ctx, N + 1);
@@ -241,10 +255,11 @@ int wv_alloc(cg_ctx* ctx, const WvPlan& pl, WvDev& d, double* cov_dev_existing) 
     d.rq_cum = arena_take<unsigned>(ctx, (size_t)(pl.rq_ntiles + C + 2) * RQ_BUCKETS);
     d.rq_tfirst = arena_take<int>(ctx, C + 2);
     d.phase_ns = arena_take<unsigned long long>(ctx, (C + 1) * 8);
+    d.tiny_tab = arena_take<UhTinyTab>(ctx, 1);
     ok = ok && d.rq_spl && d.rq_sorted && d.rq_hist && d.rq_tstart && d.rq_cum && d.rq_tfirst;
-    ok = ok && d.cov && d.off && d.selected && d.pz && d.seg_len && d.work && d.ev_work && d.tiles && d.tile_first &&
+    ok = ok && d.cov && d.off && d.selected && d.pz && d.seg_len && d.work && d.seg_nwork && d.ev_work && d.tiles && d.tile_first &&
          d.tsum && d.f3lv && d.tmed && d.cmad && d.ev10 && d.ev100 && d.r10 && d.r100 && d.med && d.mad && d.sigma &&
-         d.cand_thr && d.log3 && d.ctl && d.lvlcnt && d.depth && d.big && d.small && d.cand && d.lvl_idx &&
+         d.cand_thr && d.log3 && d.ctl && d.lvlcnt && d.depth && d.big && d.mid && d.small && d.tiny && d.cand && d.lvl_idx &&
          d.sv && d.piece && d.prelim && d.lvl_first && d.svkey && d.rec && d.bitmap && d.n_bp && d.bp;
     return ok ? CG_OK : cg_fail(ctx, CG_ERR_CUDA, "partition: device arena exhausted");
 }
@@ -259,6 +274,7 @@ int wv_enqueue(cg_ctx* ctx, const cg_wavelet_opts* o, const WvPlan& pl, WvDev& d
     CG_CUDA(ctx, cudaMemcpyAsync(d.off, pl.off.data(), (C + 1) * 8, cudaMemcpyHostToDevice, s));
     CG_CUDA(ctx, cudaMemcpyAsync(d.selected, selected_host, C, cudaMemcpyHostToDevice, s));
     CG_CUDA(ctx, cudaMemcpyAsync(d.seg_len, pl.seg_len.data(), t.nseg * 8, cudaMemcpyHostToDevice, s));
+    CG_CUDA(ctx, cudaMemcpyAsync(d.seg_nwork, pl.seg_nwork.data(), (size_t)t.nseg * 4, cudaMemcpyHostToDevice, s));
     if (!pl.work.empty()) CG_CUDA(ctx, cudaMemcpyAsync(d.work, pl.work.data(), pl.work.size() * sizeof(SelWork), cudaMemcpyHostToDevice, s));
     if (!pl.ev_work.empty()) CG_CUDA(ctx, cudaMemcpyAsync(d.ev_work, pl.ev_work.data(), pl.ev_work.size() * sizeof(WvEvWork), cudaMemcpyHostToDevice, s));
     if (!pl.tiles.empty()) CG_CUDA(ctx, cudaMemcpyAsync(d.tiles, pl.tiles.data(), pl.tiles.size() * sizeof(WvScanTile), cudaMemcpyHostToDevice, s));
@@ -278,7 +294,6 @@ int wv_enqueue(cg_ctx* ctx, const cg_wavelet_opts* o, const WvPlan& pl, WvDev& d
     CG_CUDA(ctx, cudaMemsetAsync(d.lvlcnt, 0, (size_t)(pl.N + 1) * sizeof(unsigned), s));
     CG_CUDA(ctx, cudaMemsetAsync(d.depth, 0, (size_t)(C + 1) * sizeof(int), s));
     CG_CUDA(ctx, cudaMemsetAsync(d.big, 0xff, (size_t)UH_QCAP * sizeof(UhBigTask), s));
-    CG_CUDA(ctx, cudaMemsetAsync(d.small, 0xff, (size_t)d.small_cap * sizeof(UhSmallTask), s));
     CG_CUDA(ctx, cudaMemsetAsync(d.n_bp, 0, (size_t)(C + 1) * sizeof(int), s));
     CG_CUDA(ctx, cudaMemsetAsync(d.med, 0, (size_t)t.nseg * 8, s));
     CG_CUDA(ctx, cudaMemsetAsync(d.mad, 0, (size_t)t.nseg * 8, s));
@@ -323,19 +338,19 @@ int wv_enqueue(cg_ctx* ctx, const cg_wavelet_opts* o, const WvPlan& pl, WvDev& d
     const int rq_grid = div_up(t.nseg, 128);
     PartView pv{d.cov, d.cmad, d.ev10, d.ev100, d.r10, d.r100, nullptr, t};
     CG_LAUNCH(ctx, wv_request_kernel, rq_grid, 128, 0, d.sel, sp, d.ctl, 1);
-    sel_run_contig<uint64_t, PartView>(ctx, pv, d.work, nwork, d.sel);
+    sel_run_contig<uint64_t, PartView>(ctx, pv, d.work, d.seg_nwork, nwork, d.sel);
     CG_LAUNCH(ctx, wv_median_finish_kernel, rq_grid, 128, 0, d.sel, d.med);
     CG_LAUNCH(ctx, wv_evenness_finish_kernel, 1, 1, 0, d.sel, t, d.ctl);
     CG_LAUNCH(ctx, wv_f3_finish_kernel, 1, 1, 0, sp, d.med, d.ctl);
     PartView pv2 = pv;
     pv2.center = d.med;
     CG_LAUNCH(ctx, wv_request_kernel, rq_grid, 128, 0, d.sel, sp, d.ctl, 2);
-    sel_run_contig<uint64_t, PartView>(ctx, pv2, d.work, nwork, d.sel);
+    sel_run_contig<uint64_t, PartView>(ctx, pv2, d.work, d.seg_nwork, nwork, d.sel);
     CG_LAUNCH(ctx, wv_median_finish_kernel, rq_grid, 128, 0, d.sel, d.mad);
     if (pl.cv_possible) {
         if (t.base_chrom > 0) CG_LAUNCH(ctx, wv_ratio_kernel, div_up(t.base_chrom, 128), 128, 0, t, d.med, d.mad, d.r10, d.r100);
         CG_LAUNCH(ctx, wv_request_kernel, rq_grid, 128, 0, d.sel, sp, d.ctl, 3);
-        sel_run_contig<uint64_t, PartView>(ctx, pv, d.work, nwork, d.sel);
+        sel_run_contig<uint64_t, PartView>(ctx, pv, d.work, d.seg_nwork, nwork, d.sel);
     }
     CG_LAUNCH(ctx, wv_cv_sigma_kernel, 1, 128, 0, d.sel, sp, d.med, d.mad, d.off, d.ctl, d.sigma, d.cand_thr);
 
@@ -344,22 +359,46 @@ int wv_enqueue(cg_ctx* ctx, const cg_wavelet_opts* o, const WvPlan& pl, WvDev& d
     ctx->stage_used[2] = true;
     // ---- decomposition
     UhParams up;
-    up.x = d.cov; up.pz = d.pz; up.off = d.off; up.cand_thr = d.cand_thr; up.lvlcnt = d.lvlcnt; up.depth = d.depth;
-    up.big = d.big; up.small = d.small; up.small_cap = d.small_cap;
+    up.x = d.cov; up.pz = d.pz; up.off = d.off; up.cand_thr = d.cand_thr; up.lvlcnt = d.lvlcnt;
+    up.big = d.big; up.mid = d.mid; up.mid_cap = d.mid_cap; up.small = d.small; up.small_cap = d.small_cap; up.tiny = d.tiny;
+    up.tiny_cap = d.tiny_cap;
     up.cand = d.cand; up.cand_cap = d.cand_cap; up.ctl = d.ctl;
     CG_LAUNCH(ctx, uh_seed_kernel, 1, 256, 0, up, d.selected, C, o->min_size);
-    int occ = 0;
-    const size_t uh_smem = sizeof(UhWarpScratch) * (UH_THREADS / 32);
-    cudaFuncSetAttribute(uh_decompose_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)uh_smem);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, uh_decompose_kernel, UH_THREADS, uh_smem);
-    if (occ < 1) occ = 1;
-    if (occ > 2) occ = 2;
-    // even CTAs are big-node workers, odd CTAs small-subtree workers: keep the grid even and resident
-    int grid = ctx->num_sms * occ;
-    grid &= ~1;
-    if (grid < 2) grid = 2;
-    CG_LAUNCH(ctx, uh_decompose_kernel, grid, UH_THREADS, uh_smem, up);
-
+    {
+        // kernel A: as many co-resident clusters as the device takes (the grid must stay resident: idle
+        // clusters wait on the task ring)
+        cudaLaunchConfig_t cfg = {};
+        cfg.blockDim = dim3(UH_THREADS);
+        cfg.dynamicSmemBytes = 0;
+        cfg.stream = s;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = UH_CLUSTER; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        cfg.gridDim = dim3(UH_CLUSTER * 64);
+        int ncl = 0;
+        if (cudaOccupancyMaxActiveClusters(&ncl, uh_chain_kernel, &cfg) != cudaSuccess || ncl < 1) { cudaGetLastError(); ncl = ctx->num_sms / UH_CLUSTER / 2; }
+        if (ncl > 64) ncl = 64;
+        if (ncl < 1) ncl = 1;
+        cfg.gridDim = dim3(UH_CLUSTER * ncl);
+        cudaError_t le = cudaLaunchKernelEx(&cfg, uh_chain_kernel, up);
+        if (le != cudaSuccess) return cg_fail(ctx, CG_ERR_CUDA, std::string("uh_chain_kernel launch: ") + cudaGetErrorString(le));
+        ctx->launches++;
+        // stages M, S, T: each consumes the list the earlier stages filled
+        int occ = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, uh_mid_kernel, UH_MID_THREADS, 0);
+        if (occ < 1) occ = 1;
+        CG_LAUNCH(ctx, uh_mid_kernel, ctx->num_sms * std::min(occ, 4), UH_MID_THREADS, 0, up);
+        const size_t uh_smem = sizeof(UhWarpScratch) * (UH_SMALL_THREADS / 32);
+        cudaFuncSetAttribute(uh_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)uh_smem);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, uh_small_kernel, UH_SMALL_THREADS, uh_smem);
+        if (occ < 1) occ = 1;
+        CG_LAUNCH(ctx, uh_small_kernel, ctx->num_sms * std::min(occ, 6), UH_SMALL_THREADS, uh_smem, up);
+        CG_LAUNCH(ctx, uh_tiny_table_kernel, UH_TINY_MAX - 1, UH_TINY_MAX, 0, d.tiny_tab);
+        CG_LAUNCH(ctx, uh_tiny_kernel, ctx->num_sms * 16, 128, 0, up, d.tiny_tab);
+        if (C > 0) CG_LAUNCH(ctx, uh_depth_kernel, dim3(32, C), 256, 0, d.lvlcnt, d.off, d.depth);
+    }
     cudaEventRecord(ctx->stage_ev[5], s);
     cudaEventRecord(ctx->stage_ev[6], s);
     ctx->stage_used[3] = true;
@@ -400,6 +439,7 @@ int wv_collect(cg_ctx* ctx, const WvPlan& pl, WvDev& d, int32_t* n_bp, int32_t* 
     CG_CUDA(ctx, cudaMemcpyAsync(h_nbp, d.n_bp, (size_t)C * 4, cudaMemcpyDeviceToHost, s));
     CG_CUDA(ctx, cudaStreamSynchronize(s));
     CG_CUDA(ctx, cudaGetLastError());
+    CG_CHECK_LAUNCHES(ctx);
     if (h->overflow_.v) return cg_fail(ctx, CG_ERR_CAPACITY, "partition: internal queue capacity exceeded");
     ctx->stats[0] = (double)(h->visits_big + h->visits_small + h->visits_tiny);
     ctx->stats[1] = (double)(h->nodes_big + h->nodes_small + h->nodes_tiny);
@@ -466,6 +506,7 @@ extern "C" int cg_partition_wavelet_shard(cg_ctx* ctx, const cg_wavelet_opts* op
     if (!n_bp || !bp || !evenness || !evenness_ok || !cv || !cv_has_value || !factor_of_three || (chrom_off[n_chrom] > 0 && !coverage))
         return cg_fail(ctx, CG_ERR_ARG, "partition: null output");
     ctx->launches = 0;
+    ctx->launch_err = cudaSuccess;
     ctx->last_kernel_ms = 0;
     for (int i = 0; i < 4; i++) ctx->stage_used[i] = false;
     CG_CUDA(ctx, cudaSetDevice(ctx->device));
@@ -535,6 +576,7 @@ extern "C" int cg_clean_partition_wavelet(cg_ctx* ctx, const cg_clean_opts* copt
         return cg_fail(ctx, CG_ERR_ARG, "cg_clean_partition_wavelet: bad argument");
     if (wopts->evenness_window <= 0) return cg_fail(ctx, CG_ERR_ARG, "partition: evenness_window must be positive");
     ctx->launches = 0;
+    ctx->launch_err = cudaSuccess;
     ctx->last_kernel_ms = 0;
     for (int i = 0; i < 4; i++) ctx->stage_used[i] = false;
     *n_out = 0; *local_sd = -1.0; *gc_norm_skipped = 0; *evenness = 0; *evenness_ok = 0; *cv = 0; *cv_has_value = 0;
@@ -586,6 +628,7 @@ extern "C" int cg_clean_partition_wavelet(cg_ctx* ctx, const cg_clean_opts* copt
     CG_CUDA(ctx, cudaEventRecord(ctx->ev_mid, s));
     CG_CUDA(ctx, cudaStreamSynchronize(s));
     CG_CUDA(ctx, cudaGetLastError());
+    CG_CHECK_LAUNCHES(ctx);
     if (h->unsorted) return cg_fail(ctx, CG_ERR_UNSORTED, "cg_clean: chromosome ids must form non-decreasing runs and GC must be 0..100");
     if (h->need_weighted)
         return cg_fail(ctx, CG_ERR_UNSUPPORTED, "cg_clean: a GC bucket in use has < 100 autosomal bins (weighted-quantile path not implemented)");

@@ -18,9 +18,13 @@ constexpr int WV_WINDOW_IQR = 10000;   // Segmentation.cs:263,313
 constexpr int WV_SCAN_TILE = 2048;
 
 // ---- decomposition tiers -------------------------------------------------------------------
-constexpr int UH_SMALL_MAX = 1024;  // nodes up to this size: a whole subtree is done by one warp
-constexpr int UH_TINY_MAX = 16;     // nodes up to this size: sequential reference recurrence per thread
+constexpr int UH_MID_MAX = 16384;   // nodes above this size: stage A (thread-block clusters)
+constexpr int UH_SMALL_MAX = 1024;  // nodes up to this size: a whole subtree is done by one warp (stage S)
+constexpr int UH_TINY_MAX = 16;     // nodes up to this size: sequential reference recurrence per thread (stage T)
+constexpr int UH_MID_THREADS = 256;
+constexpr int UH_SMALL_THREADS = 256;
 constexpr int UH_THREADS = 512;
+constexpr int UH_CLUSTER = 8;        // CTAs (SMs) cooperating on one chain of big nodes
 constexpr int UH_QCAP = 1 << 16;    // ticket ring capacity
 
 // Segment kinds of the partition select table (see wavelet.cu)
@@ -35,7 +39,12 @@ struct UhBigTask {  // a big node waiting for a chain worker
     double base, endv;    // prefix sums just before s and at e
 };
 
-struct UhSmallTask {
+struct UhTask {  // a node waiting for stage M or S
+    int c, s, e, level;
+    double base, endv;  // prefix sums just before s and at e
+};
+
+struct UhTinyTask {  // a node waiting for stage T (it reads the coverage itself)
     int c, s, e, level;
 };
 
@@ -55,6 +64,7 @@ struct WvCtl {
     // queues
     WvPadU64 q_head_, q_tail_;
     WvPadI32 small_head_, small_tail_, outstanding_, big_done_, overflow_, cand_count_;
+    WvPadI32 mid_head_, mid_tail_, tiny_tail_;
     // scalars
     int cv_has_value, evenness_ok;
     double cv, evenness;

@@ -1,27 +1,31 @@
-// Unbalanced-Haar top-down decomposition (WaveletSegmentation.cs:264-379) as ONE persistent kernel.
+// Unbalanced-Haar top-down decomposition (WaveletSegmentation.cs:264-379) as a pipeline of four
+// kernels, one per node granularity, connected by task lists (a kernel boundary is the only
+// synchronisation between stages; inside a stage nothing waits for another SM except stage A's ring).
 //
 // The reference walks the tree level by level and, for every node, evaluates the inner products
 // with all n-1 Unbalanced-Haar vectors by a sequential recurrence (GetInnerProdIter :19-48), then
-// takes the first arg-max of |ip| (:54-67).  The tree is ~100-130 levels deep on WGS data because
-// noise splits are lopsided, so the work is a long chain of big nodes with small subtrees peeling
-// off.  Here:
-//   * closed form: with P the prefix sums of the node, a = m+1, b = n-a,
-//       ip[m] = (P_m - a*T/n) * sqrt(n / (a*b)),  arg-max |ip| = arg-max (P_m - a*T/n)^2 / (a*b)
-//     so a node costs one division per split point on the chromosome-wide prefix-sum array;
-//   * big nodes (n > UH_SMALL_MAX) are walked by "chain worker" CTAs: a CTA takes a big node, finds
-//     its split with all its threads (16 loads in flight per thread on the L2-resident prefix sums,
-//     one __syncthreads per node), emits it, keeps going with the LARGER big child and hands the other
-//     big child to an idle CTA through a task ring — no level barrier, no per-node global handshake:
-//     the prefix values bounding each child are carried over from the arg-max winner, so the chain
-//     never re-reads them;
-//   * a node of <= UH_SMALL_MAX bins is handed to ONE warp that runs its whole subtree depth-first
-//     (smaller child first: stack depth <= log2 n) without touching the global queue;
-//   * nodes of <= UH_TINY_MAX bins are batched 32 at a time and done one per thread with the
-//     reference's own recurrence, operation for operation, so exact ties in tiny nodes (symmetric
-//     patterns on 2-decimal data) break exactly as in the reference.
-// Nodes are not stored: only per-level node counts (HardThresh's germline weights need them) and
-// the few nodes whose coefficient can survive the threshold ("candidates").
+// takes the first arg-max of |ip| (:54-67).  The tree is 130-220 levels deep on WGS data because
+// noise splits are lopsided: a long chain of big nodes with small subtrees peeling off.  Closed form:
+// with P the prefix sums of the node, a = m+1, b = n-a,
+//     ip[m] = (P_m - a*T/n) * sqrt(n / (a*b)),   arg-max |ip| = arg-max (P_m - a*T/n)^2 / (a*b)
+// so a node costs one pass over its slice of the chromosome-wide prefix-sum array (L2-resident).
+//
+//   A  uh_chain_kernel  n > UH_MID_MAX      one thread-block CLUSTER per chain of big nodes: every CTA
+//        scans a slice (16 loads in flight per thread; one SM alone gets ~80-120 GB/s out of L2), posts
+//        its best to all CTAs through distributed shared memory, one barrier.cluster per node; the
+//        prefix values bounding the children are carried from the arg-max winner, never re-read
+//   M  uh_mid_kernel    UH_SMALL_MAX < n <= UH_MID_MAX   one CTA per subtree, depth first on a small
+//        shared-memory stack, one __syncthreads per node
+//   S  uh_small_kernel  UH_TINY_MAX < n <= UH_SMALL_MAX  one warp per subtree, depth first
+//   T  uh_tiny_kernel   n <= UH_TINY_MAX    one thread per subtree, the reference's own recurrence
+//        operation for operation, so exact ties in tiny nodes (symmetric patterns on 2-decimal data)
+//        break exactly as in the reference
+// A run of exact zeros is emitted at once as the reference's one-bin-per-level comb.  Nodes are not
+// stored: only per-level node counts (HardThresh's germline weights need them) and the few nodes
+// whose coefficient can survive the threshold ("candidates").
 #pragma once
+#include <cooperative_groups.h>
+
 #include "wavelet.cuh"
 
 struct UhParams {
@@ -30,10 +34,13 @@ struct UhParams {
     const long long* off;    // [n_chrom + 1]
     const double* cand_thr;  // [n_chrom]
     unsigned* lvlcnt;        // [N]: node count of level l of chromosome c at off[c] + l
-    int* depth;              // [n_chrom]: number of levels
-    UhBigTask* big;               // ring [UH_QCAP]; c < 0 = empty
-    UhSmallTask* small;            // c < 0 = not published yet
+    UhBigTask* big;          // stage A ring [UH_QCAP]; c < 0 = empty
+    UhTask* mid;             // stage M list
+    int mid_cap;
+    UhTask* small;           // stage S list
     int small_cap;
+    UhTinyTask* tiny;        // stage T list
+    int tiny_cap;
     UhCand* cand;
     int cand_cap;
     WvCtl* ctl;
@@ -49,17 +56,8 @@ __device__ inline void uh_emit_candidate(const UhParams& p, int c, int level, in
     p.cand[i] = k;
 }
 
-__device__ inline void uh_push_small(const UhParams& p, int c, int s, int e, int level) {
-    const int i = atomicAdd(&p.ctl->small_tail_.v, 1);
-    if (i >= p.small_cap) { p.ctl->overflow_.v = 1; return; }
-    UhSmallTask* t = p.small + i;
-    t->s = s; t->e = e; t->level = level;
-    __threadfence();
-    *(volatile int*)&t->c = c;  // publish
-}
-
-// Big-task ring: a producer reserves a position with one atomicAdd, fills the slot and publishes it
-// by storing the chromosome id last; a consumer reserves a position the same way and waits for it.
+// Stage-A ring: a producer reserves a position with one atomicAdd, fills the slot and publishes it by
+// storing the chromosome id last; a consumer reserves a position the same way and waits for it.
 __device__ inline void uh_push_big(const UhParams& p, int c, int s, int e, int level, double base, double endv) {
     const unsigned long long pos = atomicAdd(&p.ctl->q_tail_.v, 1ull);
     UhBigTask* t = p.big + (pos & (UH_QCAP - 1));
@@ -67,6 +65,32 @@ __device__ inline void uh_push_big(const UhParams& p, int c, int s, int e, int l
     t->s = s; t->e = e; t->level = level; t->base = base; t->endv = endv;
     __threadfence();
     *(volatile int*)&t->c = c;
+}
+
+// Lists for the later stages are only read after the producing kernel has finished: no publication
+// protocol, and producers batch their appends in shared memory (one atomicAdd per flush).
+template <typename T, int CAP>
+struct UhOutBuf {
+    T item[CAP];
+    int count;
+};
+
+template <typename T, int CAP>
+__device__ inline void uh_buf_flush(UhOutBuf<T, CAP>& b, T* list, int list_cap, int* tail, WvCtl* ctl) {
+    const int n = b.count;
+    if (n == 0) return;
+    const int base = atomicAdd(tail, n);
+    for (int i = 0; i < n; i++) {
+        if (base + i < list_cap) list[base + i] = b.item[i];
+        else ctl->overflow_.v = 1;
+    }
+    b.count = 0;
+}
+
+template <typename T, int CAP>
+__device__ inline void uh_buf_push(UhOutBuf<T, CAP>& b, const T& t, T* list, int list_cap, int* tail, WvCtl* ctl) {
+    if (b.count == CAP) uh_buf_flush(b, list, list_cap, tail, ctl);
+    b.item[b.count++] = t;
 }
 
 // (score, m) arg-max inside a warp: largest score, smallest m among equals.  Scores are >= 0
@@ -84,415 +108,534 @@ __device__ inline void warp_argmax(double& score, int& m) {
     m = (int)mm;
 }
 
-// inner product and coefficient of the chosen split (closed form of :36-45, scaling of :282-283)
-__device__ inline double uh_coef(const double* __restrict__ pz, long long p0, int s, int n, int m, double base, double T) {
-    const double a = (double)(m + 1), b = (double)(n - m - 1), nn = (double)n;
-    const double mu = T / nn;
-    const double D = (pz[p0 + s + m + 1] - base) - a * mu;
-    const double ip = D * sqrt(nn / (a * b));
-    return ip / fmax(0.5, mu / 200.0);
-}
-
-// ---------------------------------------------------------------------------------------------
-// Tiny subtree (n <= UH_TINY_MAX), one thread, the reference recurrence verbatim.
-// ---------------------------------------------------------------------------------------------
-__device__ void uh_tiny_subtree(const UhParams& p, int c, int s0, int e0, int level0, unsigned* s_lvl, int lvl_base,
-                                unsigned long long& visits, unsigned long long& nodes) {
-    const double* __restrict__ xc = p.x + p.off[c];
-    int st_s[6], st_e[6], st_l[6];
-    int sp = 0;
-    st_s[0] = s0; st_e[0] = e0; st_l[0] = level0; sp = 1;
-    while (sp > 0) {
-        sp--;
-        const int s = st_s[sp], e = st_e[sp], level = st_l[sp];
-        const int n = e - s + 1;
-        double xl[UH_TINY_MAX];
+// Scan split positions [m_lo, m_hi) of a node with NT cooperating threads, U loads in flight each.
+// Candidates are compared inside a thread by cross-multiplication (no division in the loop).
+template <int NT, int U>
+__device__ inline void uh_scan(const double* __restrict__ q, int m_lo, int m_hi, int tid, double base, double mu, double nn,
+                               double& bnum, double& bden, int& bm, double& bv) {
+    int m = m_lo + tid;
+    for (; m + (U - 1) * NT < m_hi; m += U * NT) {
+        double v[U];
 #pragma unroll
-        for (int i = 0; i < UH_TINY_MAX; i++) xl[i] = i < n ? xc[s + i] : 0.0;
-        const double nn = (double)n;
-        double sum_x = 0.0;
-        for (int i = 1; i < n; i++) sum_x = __dadd_rn(sum_x, xl[i]);
-        const double mean = __ddiv_rn(__dadd_rn(xl[0], sum_x), nn);
-        double plus = __dmul_rn(sqrt(__dsub_rn(1.0, __ddiv_rn(1.0, nn))), xl[0]);
-        double minus = __dmul_rn(__ddiv_rn(1.0, sqrt((double)((long long)n * (long long)(n - 1)))), sum_x);
-        double best_ip = __dsub_rn(plus, minus);
-        double best_abs = fabs(best_ip);
-        if (!(best_abs >= 0.0)) best_abs = -1.0;
-        int best_m = 0;
-        for (int m = 1; m < n - 1; m++) {
-            const double factor = sqrt(__ddiv_rn(__ddiv_rn(__dmul_rn((double)(n - m - 1), (double)m), (double)(m + 1)), (double)(n - m)));
-            plus = __dadd_rn(__dmul_rn(plus, factor),
-                             __dmul_rn(xl[m], sqrt(__dsub_rn(__ddiv_rn(1.0, (double)(m + 1)), __ddiv_rn(1.0, nn)))));
-            minus = __dsub_rn(__ddiv_rn(minus, factor),
-                              __ddiv_rn(xl[m], sqrt(__dsub_rn(__ddiv_rn(__dmul_rn(nn, nn), (double)(m + 1)), nn))));
-            const double ip = __dsub_rn(plus, minus);
-            const double a = fabs(ip);
-            if (a > best_abs) { best_abs = a; best_m = m; best_ip = ip; }
+        for (int u = 0; u < U; u++) v[u] = __ldg(q + m + u * NT);
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const double a = (double)(m + u * NT + 1);
+            const double D = fma(-a, mu, v[u] - base);
+            const double num = D * D, den = a * (nn - a);
+            if (num * bden > bnum * den) { bnum = num; bden = den; bm = m + u * NT; bv = v[u]; }
         }
-        const double coef = __ddiv_rn(best_ip, fmax(0.5, __ddiv_rn(mean, 200.0)));
-        atomicAdd(&s_lvl[level - lvl_base], 1u);
-        uh_emit_candidate(p, c, level, s, s + best_m, e, coef);
-        visits += (unsigned long long)n;
-        nodes++;
-        // children: left [s, s+m] needs >= 2 bins, right [s+m+1, e] needs >= 2 bins; larger first
-        const int ls = s, le = s + best_m, rs = s + best_m + 1, re = e;
-        const int ln = le - ls + 1, rn = re - rs + 1;
-        if (ln >= rn) {
-            if (ln >= 2) { st_s[sp] = ls; st_e[sp] = le; st_l[sp] = level + 1; sp++; }
-            if (rn >= 2) { st_s[sp] = rs; st_e[sp] = re; st_l[sp] = level + 1; sp++; }
-        } else {
-            if (rn >= 2) { st_s[sp] = rs; st_e[sp] = re; st_l[sp] = level + 1; sp++; }
-            if (ln >= 2) { st_s[sp] = ls; st_e[sp] = le; st_l[sp] = level + 1; sp++; }
-        }
+    }
+    for (; m < m_hi; m += NT) {
+        const double vv = __ldg(q + m);
+        const double a = (double)(m + 1);
+        const double D = fma(-a, mu, vv - base);
+        const double num = D * D, den = a * (nn - a);
+        if (num * bden > bnum * den) { bnum = num; bden = den; bm = m; bv = vv; }
     }
 }
 
-// ---------------------------------------------------------------------------------------------
-// Small subtree (n <= UH_SMALL_MAX): one warp, depth first.
-// ---------------------------------------------------------------------------------------------
-constexpr int UH_WARP_STACK = 16;
-constexpr int UH_TINY_BUF = 32;
+// coefficient of the chosen split (closed form of :36-45, scaling of :282-283)
+__device__ inline double uh_coef_from(double fv, double base, double T, int n, int fm) {
+    const double nn = (double)n, a = (double)(fm + 1), b = (double)(n - fm - 1);
+    const double mu = T / nn;
+    const double D = fma(-a, mu, fv - base);
+    return D * sqrt(nn / (a * b)) / fmax(0.5, mu / 200.0);
+}
 
-struct UhWarpScratch {
-    unsigned lvl[UH_SMALL_MAX];  // node count per level relative to the task's level
-    int st_s[UH_WARP_STACK], st_e[UH_WARP_STACK], st_l[UH_WARP_STACK];
-    double st_b[UH_WARP_STACK], st_v[UH_WARP_STACK];  // prefix sums bounding each stacked node
-    int tn_s[UH_TINY_BUF], tn_e[UH_TINY_BUF], tn_l[UH_TINY_BUF];
+// which stage a node of n bins belongs to
+enum { UH_TIER_NONE = 0, UH_TIER_TINY, UH_TIER_SMALL, UH_TIER_MID, UH_TIER_BIG };
+__device__ inline int uh_tier(int n) {
+    if (n < 2) return UH_TIER_NONE;
+    if (n <= UH_TINY_MAX) return UH_TIER_TINY;
+    if (n <= UH_SMALL_MAX) return UH_TIER_SMALL;
+    if (n <= UH_MID_MAX) return UH_TIER_MID;
+    return UH_TIER_BIG;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Stage A — chains of big nodes on thread-block clusters
+// ---------------------------------------------------------------------------------------------
+struct UhMail {
+    double score, v;
+    int m, pad;
 };
 
-__device__ void uh_small_subtree(const UhParams& p, UhWarpScratch& ws, int c, int S, int E, int L0,
-                                 unsigned long long& visits_small, unsigned long long& visits_tiny,
-                                 unsigned long long& nodes_small, unsigned long long& nodes_tiny) {
-    const int lane = threadIdx.x & 31;
-    const long long p0 = p.off[c] + c;
+__global__ void __cluster_dims__(UH_CLUSTER, 1, 1) __launch_bounds__(UH_THREADS, 2)
+uh_chain_kernel(UhParams p) {
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    const int crank = (int)cluster.block_rank();
+    __shared__ UhMail s_mail[2][UH_CLUSTER];  // written by every CTA of the cluster (DSMEM)
+    __shared__ int s_task[4];                  // the leader's copy is the authoritative one
+    __shared__ double s_taskd[2];
+    __shared__ double s_ws[UH_THREADS / 32], s_wv[UH_THREADS / 32];
+    __shared__ int s_wm2[UH_THREADS / 32];
+    __shared__ UhOutBuf<UhTask, 32> s_mid_out, s_small_out;
+    __shared__ UhOutBuf<UhTinyTask, 32> s_tiny_out;
+    WvCtl* ctl = p.ctl;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const double* __restrict__ pz = p.pz;
-    for (int t = lane; t < UH_SMALL_MAX; t += 32) ws.lvl[t] = 0u;
-    int sp = 0, ntiny = 0;
-    if (lane == 0) {
-        ws.st_s[0] = S; ws.st_e[0] = E; ws.st_l[0] = L0;
-        ws.st_b[0] = pz[p0 + S]; ws.st_v[0] = pz[p0 + E + 1];
+    unsigned long long v_big = 0, n_big = 0;
+    if (threadIdx.x == 0) {
+        s_mid_out.count = 0; s_small_out.count = 0; s_tiny_out.count = 0;
+        if (crank == 0) {
+            unsigned long long t;
+            asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+            atomicMin(&ctl->t_first, t);
+        }
     }
-    sp = 1;
-    __syncwarp();
-    while (sp > 0 || ntiny > 0) {
-        if (sp == 0 || ntiny == UH_TINY_BUF) {
-            // flush the tiny batch: one subtree per lane
-            if (lane < ntiny) uh_tiny_subtree(p, c, ws.tn_s[lane], ws.tn_e[lane], ws.tn_l[lane], ws.lvl, L0, visits_tiny, nodes_tiny);
-            __syncwarp();
-            ntiny = 0;
-            continue;
-        }
-        sp--;
-        const int s = ws.st_s[sp], e = ws.st_e[sp], level = ws.st_l[sp];
-        const double base = ws.st_b[sp], endv = ws.st_v[sp];
-        __syncwarp();
-        const int n = e - s + 1;
-        if (n <= UH_TINY_MAX) {
-            if (lane == 0) { ws.tn_s[ntiny] = s; ws.tn_e[ntiny] = e; ws.tn_l[ntiny] = level; }
-            ntiny++;
-            __syncwarp();
-            continue;
-        }
-        const double T = endv - base;
-        const double nn = (double)n;
-        const double mu = T / nn;
-        const double* __restrict__ q = pz + p0 + s + 1;
-        double bnum = -1.0, bden = 1.0, bv = 0.0;
-        int bm = 0x7fffffff;
-        int m = lane;
-        for (; m + 96 < n - 1; m += 128) {  // four loads in flight per lane
-            double v[4];
-#pragma unroll
-            for (int u = 0; u < 4; u++) v[u] = __ldg(q + m + 32 * u);
-#pragma unroll
-            for (int u = 0; u < 4; u++) {
-                const double a = (double)(m + 32 * u + 1);
-                const double D = fma(-a, mu, v[u] - base);
-                const double num = D * D, den = a * (nn - a);
-                if (num * bden > bnum * den) { bnum = num; bden = den; bm = m + 32 * u; bv = v[u]; }
+    int parity = 0;
+    for (;;) {
+        // ---- the leader CTA takes a big task; everybody reads it from the leader's shared memory
+        if (crank == 0 && threadIdx.x == 0) {
+            int c = -1;
+            const unsigned long long pos = atomicAdd(&ctl->q_head_.v, 1ull);
+            UhBigTask* t = p.big + (pos & (UH_QCAP - 1));
+            volatile int* ready = &t->c;
+            unsigned polls = 0;
+            for (;;) {
+                c = *ready;
+                if (c >= 0) break;
+                if ((++polls & 3u) == 0u && (*(volatile int*)&ctl->big_done_.v || *(volatile int*)&ctl->overflow_.v)) {
+                    __threadfence();
+                    c = *ready;
+                    break;
+                }
+                __nanosleep(40);
             }
+            if (c >= 0) {
+                __threadfence();
+                s_task[1] = *(volatile int*)&t->s; s_task[2] = *(volatile int*)&t->e; s_task[3] = *(volatile int*)&t->level;
+                s_taskd[0] = *(volatile double*)&t->base; s_taskd[1] = *(volatile double*)&t->endv;
+                __threadfence();
+                *ready = -1;  // free the slot
+            }
+            s_task[0] = c;
         }
-        for (; m < n - 1; m += 32) {
-            const double vv = __ldg(q + m);
-            const double a = (double)(m + 1);
-            const double D = fma(-a, mu, vv - base);
-            const double num = D * D, den = a * (nn - a);
-            if (num * bden > bnum * den) { bnum = num; bden = den; bm = m; bv = vv; }
-        }
-        double best = bnum >= 0.0 ? bnum / bden : -1.0;
-        int best_m = bm;
-        warp_argmax(best, best_m);
-        const unsigned own = __ballot_sync(0xffffffffu, bm == best_m && best_m != 0x7fffffff);
-        const double fv = __shfl_sync(0xffffffffu, bv, own ? __ffs(own) - 1 : 0);
-        if (lane == 0) { visits_small += (unsigned long long)n; }
-        if (best == 0.0 || best_m == 0x7fffffff) {
-            // every inner product is exactly zero (a run of zeros): the reference peels one bin per
-            // level with coefficient 0 — levels level .. level+n-2 get one node each
-            for (int k = lane; k < n - 1; k += 32) atomicAdd(&ws.lvl[level - L0 + k], 1u);
-            if (lane == 0) nodes_small += (unsigned long long)(n - 1);
-            __syncwarp();
-            continue;
-        }
-        if (best_m < 0 || best_m > n - 2) best_m = 0;
-        if (lane == 0) {
-            const double a = (double)(best_m + 1), b = (double)(n - best_m - 1);
-            const double D = fma(-a, mu, fv - base);
-            const double coef = D * sqrt(nn / (a * b)) / fmax(0.5, mu / 200.0);
-            atomicAdd(&ws.lvl[level - L0], 1u);
-            uh_emit_candidate(p, c, level, s, s + best_m, e, coef);
-            nodes_small++;
-            const int ls = s, le = s + best_m, rs = s + best_m + 1, re = e;
+        cluster.sync();
+        const int* lt = cluster.map_shared_rank(s_task, 0);
+        const double* ltd = cluster.map_shared_rank(s_taskd, 0);
+        const int c = lt[0];
+        int s = lt[1], e = lt[2], level = lt[3];
+        double base = ltd[0], endv = ltd[1];
+        cluster.sync();  // the leader may overwrite its task slot only after everybody has read it
+        if (c < 0) break;
+        const long long p0 = p.off[c] + c;
+        const long long loff = p.off[c];
+        // ---- walk the chain
+        for (;;) {
+            const int n = e - s + 1;
+            const double nn = (double)n;
+            const double T = endv - base;
+            const double mu = T / nn;
+            const double* __restrict__ q = pz + p0 + s + 1;
+            int per = (n - 1 + UH_CLUSTER - 1) / UH_CLUSTER;
+            per = (per + UH_THREADS - 1) / UH_THREADS * UH_THREADS;
+            const int m_lo = crank * per;
+            const int m_hi = min(n - 1, m_lo + per);
+            double bnum = -1.0, bden = 1.0, bv = 0.0;
+            int bm = 0x7fffffff;
+            uh_scan<UH_THREADS, 16>(q, m_lo, m_hi, threadIdx.x, base, mu, nn, bnum, bden, bm, bv);
+            double best = bnum >= 0.0 ? bnum / bden : -1.0;
+            int best_m = bm;
+            warp_argmax(best, best_m);
+            {
+                const unsigned own = __ballot_sync(0xffffffffu, bm == best_m && best_m != 0x7fffffff);
+                const double wv = __shfl_sync(0xffffffffu, bv, own ? __ffs(own) - 1 : 0);
+                if (lane == 0) { s_ws[warp] = best; s_wm2[warp] = best_m; s_wv[warp] = wv; }
+            }
+            __syncthreads();
+            if (warp == 0) {
+                // CTA best, then post it to every CTA of the cluster (lane d writes to CTA d)
+                double cb = lane < UH_THREADS / 32 ? s_ws[lane] : 0.0;
+                int cm = lane < UH_THREADS / 32 ? s_wm2[lane] : 0x7fffffff;
+                const int mine_m = cm;
+                warp_argmax(cb, cm);
+                const unsigned own = __ballot_sync(0xffffffffu, lane < UH_THREADS / 32 && mine_m == cm && cm != 0x7fffffff);
+                const int src = own ? __ffs(own) - 1 : 0;
+                const double cv = s_wv[src < UH_THREADS / 32 ? src : 0];
+                if (lane < UH_CLUSTER) {
+                    UhMail* dst = cluster.map_shared_rank(&s_mail[parity][crank], lane);
+                    dst->score = cb; dst->v = cv; dst->m = cm;
+                }
+            }
+            cluster.sync();
+            double fbest = s_mail[parity][0].score, fv = s_mail[parity][0].v;
+            int fm = s_mail[parity][0].m;
+#pragma unroll
+            for (int w = 1; w < UH_CLUSTER; w++) {
+                const double sc = s_mail[parity][w].score;
+                const int mm = s_mail[parity][w].m;
+                if (sc > fbest || (sc == fbest && mm < fm)) { fbest = sc; fm = mm; fv = s_mail[parity][w].v; }
+            }
+            parity ^= 1;
+            if (threadIdx.x == 0 && crank == 0) v_big += (unsigned long long)n;
+            if (fbest == 0.0 || fm == 0x7fffffff) {
+                // run of exact zeros: comb of n-1 nodes with coefficient 0 — one node per level
+                for (int k = crank * UH_THREADS + threadIdx.x; k < n - 1; k += UH_CLUSTER * UH_THREADS)
+                    atomicAdd(&p.lvlcnt[loff + level + k], 1u);
+                if (threadIdx.x == 0 && crank == 0) n_big += (unsigned long long)(n - 1);
+                break;  // chain ends
+            }
+            const int ls = s, le = s + fm, rs = s + fm + 1, re = e;
             const int ln = le - ls + 1, rn = re - rs + 1;
-            int qn = sp;
-            // larger child first so that the smaller one is popped next (stack depth <= log2 n)
-            if (ln >= rn) {
-                if (ln >= 2) { ws.st_s[qn] = ls; ws.st_e[qn] = le; ws.st_l[qn] = level + 1; ws.st_b[qn] = base; ws.st_v[qn] = fv; qn++; }
-                if (rn >= 2) { ws.st_s[qn] = rs; ws.st_e[qn] = re; ws.st_l[qn] = level + 1; ws.st_b[qn] = fv; ws.st_v[qn] = endv; qn++; }
-            } else {
-                if (rn >= 2) { ws.st_s[qn] = rs; ws.st_e[qn] = re; ws.st_l[qn] = level + 1; ws.st_b[qn] = fv; ws.st_v[qn] = endv; qn++; }
-                if (ln >= 2) { ws.st_s[qn] = ls; ws.st_e[qn] = le; ws.st_l[qn] = level + 1; ws.st_b[qn] = base; ws.st_v[qn] = fv; qn++; }
+            const int lt_ = uh_tier(ln), rt_ = uh_tier(rn);
+            const bool lbig = lt_ == UH_TIER_BIG, rbig = rt_ == UH_TIER_BIG;
+            const bool cont_left = lbig && (!rbig || ln >= rn);  // larger big child, left on ties
+            const bool cont_right = rbig && !cont_left;
+            if (crank == 0 && threadIdx.x == 32) {
+                atomicAdd(&p.lvlcnt[loff + level], 1u);
+                uh_emit_candidate(p, c, level, s, s + fm, e, uh_coef_from(fv, base, T, n, fm));
+                n_big++;
+            }
+            if (crank == 0 && threadIdx.x == 0) {
+                // children that are not continued: other big child -> ring, the rest -> stage lists
+                if (lbig && !cont_left) { atomicAdd(&ctl->outstanding_.v, 1); uh_push_big(p, c, ls, le, level + 1, base, fv); }
+                if (rbig && !cont_right) { atomicAdd(&ctl->outstanding_.v, 1); uh_push_big(p, c, rs, re, level + 1, fv, endv); }
+                const UhTask tl = {c, ls, le, level + 1, base, fv}, tr = {c, rs, re, level + 1, fv, endv};
+                if (lt_ == UH_TIER_MID) uh_buf_push(s_mid_out, tl, p.mid, p.mid_cap, &ctl->mid_tail_.v, ctl);
+                if (rt_ == UH_TIER_MID) uh_buf_push(s_mid_out, tr, p.mid, p.mid_cap, &ctl->mid_tail_.v, ctl);
+                if (lt_ == UH_TIER_SMALL) uh_buf_push(s_small_out, tl, p.small, p.small_cap, &ctl->small_tail_.v, ctl);
+                if (rt_ == UH_TIER_SMALL) uh_buf_push(s_small_out, tr, p.small, p.small_cap, &ctl->small_tail_.v, ctl);
+                const UhTinyTask yl = {c, ls, le, level + 1}, yr = {c, rs, re, level + 1};
+                if (lt_ == UH_TIER_TINY) uh_buf_push(s_tiny_out, yl, p.tiny, p.tiny_cap, &ctl->tiny_tail_.v, ctl);
+                if (rt_ == UH_TIER_TINY) uh_buf_push(s_tiny_out, yr, p.tiny, p.tiny_cap, &ctl->tiny_tail_.v, ctl);
+            }
+            if (cont_left) { e = le; endv = fv; level++; }
+            else if (cont_right) { s = rs; base = fv; level++; }
+            else break;  // no big child: chain ends
+        }
+        // ---- chain finished: one big task less
+        if (crank == 0 && threadIdx.x == 0) {
+            __threadfence();
+            const int now = atomicSub(&ctl->outstanding_.v, 1) - 1;
+            if (now == 0) {
+                __threadfence();
+                *(volatile int*)&ctl->big_done_.v = 1;
+                unsigned long long t;
+                asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+                ctl->t_big_done = t;
             }
         }
-        {
-            const int ln = best_m + 1, rn = n - best_m - 1;
-            sp += (ln >= 2) + (rn >= 2);
-        }
-        __syncwarp();
     }
-    // flush level counts
-    int maxrel = -1;
-    for (int t = lane; t < UH_SMALL_MAX; t += 32) {
-        const unsigned v = ws.lvl[t];
-        if (v) { atomicAdd(&p.lvlcnt[p.off[c] + L0 + t], v); maxrel = t; }
+    if (crank == 0 && threadIdx.x == 0) {
+        uh_buf_flush(s_mid_out, p.mid, p.mid_cap, &ctl->mid_tail_.v, ctl);
+        uh_buf_flush(s_small_out, p.small, p.small_cap, &ctl->small_tail_.v, ctl);
+        uh_buf_flush(s_tiny_out, p.tiny, p.tiny_cap, &ctl->tiny_tail_.v, ctl);
     }
-    maxrel = (int)__reduce_max_sync(0xffffffffu, (unsigned)(maxrel + 1));
-    if (lane == 0 && maxrel > 0) atomicMax(&p.depth[c], L0 + maxrel);
-    __syncwarp();
+    if (v_big) atomicAdd(&ctl->visits_big, v_big);
+    if (n_big) atomicAdd(&ctl->nodes_big, n_big);
 }
 
 // ---------------------------------------------------------------------------------------------
-// The persistent kernel.  blockIdx % 4 == 0: big worker (whole CTA per chunk ticket) until the big
-// phase ends, then joins the others; the rest: 8 independent warp workers on small subtrees.
+// Stage M — subtrees of UH_SMALL_MAX < n <= UH_MID_MAX bins: one CTA each, depth first
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(UH_THREADS, 2)
-uh_decompose_kernel(UhParams p) {
-    extern __shared__ __align__(16) unsigned char uh_smem[];
-    UhWarpScratch* s_ws = reinterpret_cast<UhWarpScratch*>(uh_smem);
+constexpr int UH_MID_STACK = 32;
+
+__global__ void __launch_bounds__(UH_MID_THREADS, 4)
+uh_mid_kernel(UhParams p) {
+    __shared__ UhTask s_stack[UH_MID_STACK];
+    __shared__ double s_ws[2][UH_MID_THREADS / 32], s_wv[2][UH_MID_THREADS / 32];
+    __shared__ int s_wm2[2][UH_MID_THREADS / 32];
+    __shared__ UhOutBuf<UhTask, 32> s_small_out;
+    __shared__ UhOutBuf<UhTinyTask, 32> s_tiny_out;
+    __shared__ int s_idx;
     WvCtl* ctl = p.ctl;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (threadIdx.x == 0) {
-        unsigned long long t;
-        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
-        atomicMin(&ctl->t_first, t);
-    }
-    unsigned long long v_big = 0, v_small = 0, v_tiny = 0, n_big = 0, n_small = 0, n_tiny = 0;
-
-    if ((blockIdx.x & 1) == 0) {
-        // ----------------------------------------------------------------- chain worker
-        __shared__ int s_task[4];
-        __shared__ double s_taskd[2];
-        __shared__ double s_ws[2][UH_THREADS / 32];   // per-warp best score, double-buffered by node parity
-        __shared__ double s_wv[2][UH_THREADS / 32];   // prefix value at the best split
-        __shared__ int s_wm2[2][UH_THREADS / 32];
-        const double* __restrict__ pz = p.pz;
-        int parity = 0;
-        for (;;) {
-            // ---- take a big task
-            if (threadIdx.x == 0) {
-                int c = -1;
-                const unsigned long long pos = atomicAdd(&ctl->q_head_.v, 1ull);
-                UhBigTask* t = p.big + (pos & (UH_QCAP - 1));
-                volatile int* ready = &t->c;
-                unsigned polls = 0;
-                for (;;) {
-                    c = *ready;
-                    if (c >= 0) break;
-                    if ((++polls & 3u) == 0u && (*(volatile int*)&ctl->big_done_.v || *(volatile int*)&ctl->overflow_.v)) {
-                        __threadfence();
-                        c = *ready;
-                        break;
-                    }
-                    __nanosleep(40);
-                }
-                if (c >= 0) {
-                    __threadfence();
-                    s_task[1] = *(volatile int*)&t->s; s_task[2] = *(volatile int*)&t->e; s_task[3] = *(volatile int*)&t->level;
-                    s_taskd[0] = *(volatile double*)&t->base; s_taskd[1] = *(volatile double*)&t->endv;
-                    __threadfence();
-                    *ready = -1;  // free the slot
-                }
-                s_task[0] = c;
-            }
-            __syncthreads();
-            const int c = s_task[0];
-            int s = s_task[1], e = s_task[2], level = s_task[3];
-            double base = s_taskd[0], endv = s_taskd[1];
-            __syncthreads();
-            if (c < 0) break;
+    const double* __restrict__ pz = p.pz;
+    unsigned long long v_mid = 0, n_mid = 0;
+    const int total = min(*(volatile int*)&ctl->mid_tail_.v, p.mid_cap);
+    if (threadIdx.x == 0) { s_small_out.count = 0; s_tiny_out.count = 0; }
+    int parity = 0;
+    for (;;) {
+        if (threadIdx.x == 0) {
+            s_idx = atomicAdd(&ctl->mid_head_.v, 1);
+            if (s_idx < total) s_stack[0] = p.mid[s_idx];
+        }
+        __syncthreads();
+        if (s_idx >= total) break;
+        // every thread mirrors the stack pointer; thread 0 alone writes the stack
+        int sp = 1;
+        while (sp > 0) {
+            sp--;
+            const UhTask t = s_stack[sp];
+            const int c = t.c, s = t.s, e = t.e, level = t.level;
+            const double base = t.base, endv = t.endv;
             const long long p0 = p.off[c] + c;
             const long long loff = p.off[c];
-            // ---- walk the chain
-            for (;;) {
-                const int n = e - s + 1;
-                const double nn = (double)n;
-                const double T = endv - base;
-                const double mu = T / nn;
-                const double* __restrict__ q = pz + p0 + s + 1;
-                // arg-max of D^2 / (a b); inside a thread compared by cross-multiplication (no division)
-                double bnum = -1.0, bden = 1.0, bv = 0.0;
-                int bm = 0x7fffffff;
-                int m = threadIdx.x;
-                for (; m + 15 * UH_THREADS < n - 1; m += 16 * UH_THREADS) {
-                    double v[16];
-#pragma unroll
-                    for (int u = 0; u < 16; u++) v[u] = __ldg(q + m + u * UH_THREADS);
-#pragma unroll
-                    for (int u = 0; u < 16; u++) {
-                        const double a = (double)(m + u * UH_THREADS + 1);
-                        const double D = fma(-a, mu, v[u] - base);
-                        const double num = D * D, den = a * (nn - a);
-                        if (num * bden > bnum * den) { bnum = num; bden = den; bm = m + u * UH_THREADS; bv = v[u]; }
-                    }
-                }
-                for (; m + 3 * UH_THREADS < n - 1; m += 4 * UH_THREADS) {
-                    double v[4];
-#pragma unroll
-                    for (int u = 0; u < 4; u++) v[u] = __ldg(q + m + u * UH_THREADS);
-#pragma unroll
-                    for (int u = 0; u < 4; u++) {
-                        const double a = (double)(m + u * UH_THREADS + 1);
-                        const double D = fma(-a, mu, v[u] - base);
-                        const double num = D * D, den = a * (nn - a);
-                        if (num * bden > bnum * den) { bnum = num; bden = den; bm = m + u * UH_THREADS; bv = v[u]; }
-                    }
-                }
-                for (; m < n - 1; m += UH_THREADS) {
-                    const double vv = __ldg(q + m);
-                    const double a = (double)(m + 1);
-                    const double D = fma(-a, mu, vv - base);
-                    const double num = D * D, den = a * (nn - a);
-                    if (num * bden > bnum * den) { bnum = num; bden = den; bm = m; bv = vv; }
-                }
-                double best = bnum >= 0.0 ? bnum / bden : -1.0;
-                int best_m = bm;
-                warp_argmax(best, best_m);
-                {
-                    // the lane that owns the winning split also owns its prefix value
-                    const unsigned own = __ballot_sync(0xffffffffu, bm == best_m && best_m != 0x7fffffff);
-                    const int src = own ? __ffs(own) - 1 : 0;
-                    const double wv = __shfl_sync(0xffffffffu, bv, src);
-                    if (lane == 0) { s_ws[parity][warp] = best; s_wm2[parity][warp] = best_m; s_wv[parity][warp] = wv; }
-                }
-                __syncthreads();
-                double fbest = s_ws[parity][0], fv = s_wv[parity][0];
-                int fm = s_wm2[parity][0];
-#pragma unroll
-                for (int w = 1; w < UH_THREADS / 32; w++) {
-                    const double sc = s_ws[parity][w];
-                    const int mm = s_wm2[parity][w];
-                    if (sc > fbest || (sc == fbest && mm < fm)) { fbest = sc; fm = mm; fv = s_wv[parity][w]; }
-                }
-                parity ^= 1;
-                if (threadIdx.x == 0) v_big += (unsigned long long)n;
-                if (fbest == 0.0 || fm == 0x7fffffff) {
-                    // run of exact zeros: comb of n-1 nodes with coefficient 0 (see uh_small_subtree)
-                    for (int k = threadIdx.x; k < n - 1; k += UH_THREADS) atomicAdd(&p.lvlcnt[loff + level + k], 1u);
-                    if (threadIdx.x == 0) { atomicMax(&p.depth[c], level + n - 1); n_big += (unsigned long long)(n - 1); }
-                    break;  // chain ends
-                }
-                // ---- emit (one lane of warp 1; every thread derives the children itself)
-                if (threadIdx.x == 32) {
-                    const double a = (double)(fm + 1), b = (double)(n - fm - 1);
-                    const double D = fma(-a, mu, fv - base);
-                    const double ip = D * sqrt(nn / (a * b));
-                    const double coef = ip / fmax(0.5, mu / 200.0);
-                    atomicAdd(&p.lvlcnt[loff + level], 1u);
-                    atomicMax(&p.depth[c], level + 1);
-                    uh_emit_candidate(p, c, level, s, s + fm, e, coef);
-                    n_big++;
-                }
-                const int ls = s, le = s + fm, rs = s + fm + 1, re = e;
-                const int ln = le - ls + 1, rn = re - rs + 1;
-                const bool lbig = ln > UH_SMALL_MAX, rbig = rn > UH_SMALL_MAX;
-                // continue with the larger big child (left on ties)
-                const bool cont_left = lbig && (!rbig || ln >= rn);
-                const bool cont_right = rbig && !cont_left;
-                if (threadIdx.x == 0) {
-                    if (lbig && !cont_left) { atomicAdd(&ctl->outstanding_.v, 1); uh_push_big(p, c, ls, le, level + 1, base, fv); }
-                    if (rbig && !cont_right) { atomicAdd(&ctl->outstanding_.v, 1); uh_push_big(p, c, rs, re, level + 1, fv, endv); }
-                    if (!lbig && ln >= 2) uh_push_small(p, c, ls, le, level + 1);
-                    if (!rbig && rn >= 2) uh_push_small(p, c, rs, re, level + 1);
-                }
-                if (cont_left) { e = le; endv = fv; level++; }
-                else if (cont_right) { s = rs; base = fv; level++; }
-                else break;  // no big child: chain ends
+            const int n = e - s + 1;
+            const double nn = (double)n;
+            const double T = endv - base;
+            const double mu = T / nn;
+            double bnum = -1.0, bden = 1.0, bv = 0.0;
+            int bm = 0x7fffffff;
+            uh_scan<UH_MID_THREADS, 8>(pz + p0 + s + 1, 0, n - 1, threadIdx.x, base, mu, nn, bnum, bden, bm, bv);
+            double best = bnum >= 0.0 ? bnum / bden : -1.0;
+            int best_m = bm;
+            warp_argmax(best, best_m);
+            {
+                const unsigned own = __ballot_sync(0xffffffffu, bm == best_m && best_m != 0x7fffffff);
+                const double wv = __shfl_sync(0xffffffffu, bv, own ? __ffs(own) - 1 : 0);
+                if (lane == 0) { s_ws[parity][warp] = best; s_wm2[parity][warp] = best_m; s_wv[parity][warp] = wv; }
             }
-            // ---- chain finished: one big task less
-            __syncthreads();
+            __syncthreads();  // everybody has read s_stack[sp]; the per-warp bests are visible
+            double fbest = s_ws[parity][0], fv = s_wv[parity][0];
+            int fm = s_wm2[parity][0];
+#pragma unroll
+            for (int w = 1; w < UH_MID_THREADS / 32; w++) {
+                const double sc = s_ws[parity][w];
+                const int mm = s_wm2[parity][w];
+                if (sc > fbest || (sc == fbest && mm < fm)) { fbest = sc; fm = mm; fv = s_wv[parity][w]; }
+            }
+            parity ^= 1;
+            if (threadIdx.x == 0) v_mid += (unsigned long long)n;
+            if (fbest == 0.0 || fm == 0x7fffffff) {
+                for (int k = threadIdx.x; k < n - 1; k += UH_MID_THREADS) atomicAdd(&p.lvlcnt[loff + level + k], 1u);
+                if (threadIdx.x == 0) n_mid += (unsigned long long)(n - 1);
+                continue;
+            }
+            const int ls = s, le = s + fm, rs = s + fm + 1, re = e;
+            const int ln = le - ls + 1, rn = re - rs + 1;
+            const int lt_ = uh_tier(ln), rt_ = uh_tier(rn);
+            const bool lmid = lt_ >= UH_TIER_MID, rmid = rt_ >= UH_TIER_MID;  // a child of a mid node is never BIG
+            if (threadIdx.x == 32) {
+                atomicAdd(&p.lvlcnt[loff + level], 1u);
+                uh_emit_candidate(p, c, level, s, s + fm, e, uh_coef_from(fv, base, T, n, fm));
+                n_mid++;
+            }
             if (threadIdx.x == 0) {
-                __threadfence();
-                const int now = atomicSub(&ctl->outstanding_.v, 1) - 1;
-                if (now == 0) {
-                    __threadfence();
-                    *(volatile int*)&ctl->big_done_.v = 1;
-                    unsigned long long t;
-                    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
-                    ctl->t_big_done = t;
-                }
+                const UhTask tl = {c, ls, le, level + 1, base, fv}, tr = {c, rs, re, level + 1, fv, endv};
+                // larger child first so that the smaller one is popped next (stack depth <= log2)
+                int q = sp;
+                if (ln >= rn) { if (lmid) s_stack[q++] = tl; if (rmid) s_stack[q++] = tr; }
+                else { if (rmid) s_stack[q++] = tr; if (lmid) s_stack[q++] = tl; }
+                if (lt_ == UH_TIER_SMALL) uh_buf_push(s_small_out, tl, p.small, p.small_cap, &ctl->small_tail_.v, ctl);
+                if (rt_ == UH_TIER_SMALL) uh_buf_push(s_small_out, tr, p.small, p.small_cap, &ctl->small_tail_.v, ctl);
+                const UhTinyTask yl = {c, ls, le, level + 1}, yr = {c, rs, re, level + 1};
+                if (lt_ == UH_TIER_TINY) uh_buf_push(s_tiny_out, yl, p.tiny, p.tiny_cap, &ctl->tiny_tail_.v, ctl);
+                if (rt_ == UH_TIER_TINY) uh_buf_push(s_tiny_out, yr, p.tiny, p.tiny_cap, &ctl->tiny_tail_.v, ctl);
             }
+            sp += (lmid ? 1 : 0) + (rmid ? 1 : 0);
+            __syncthreads();  // thread 0's stack writes before the next pop
         }
         __syncthreads();
     }
+    if (threadIdx.x == 0) {
+        uh_buf_flush(s_small_out, p.small, p.small_cap, &ctl->small_tail_.v, ctl);
+        uh_buf_flush(s_tiny_out, p.tiny, p.tiny_cap, &ctl->tiny_tail_.v, ctl);
+    }
+    if (v_mid) atomicAdd(&ctl->visits_big, v_mid);
+    if (n_mid) atomicAdd(&ctl->nodes_big, n_mid);
+}
 
-    // --------------------------------------------------------------------- small workers (per warp)
-    UhWarpScratch& ws = s_ws[warp];
+// ---------------------------------------------------------------------------------------------
+// Stage S — subtrees of UH_TINY_MAX < n <= UH_SMALL_MAX bins: one warp each, depth first
+// ---------------------------------------------------------------------------------------------
+constexpr int UH_WARP_STACK = 16;
+
+struct UhWarpScratch {
+    unsigned lvl[UH_SMALL_MAX];  // node count per level relative to the task's level
+    UhTask st[UH_WARP_STACK];
+    UhOutBuf<UhTinyTask, 32> tiny_out;
+};
+
+__global__ void __launch_bounds__(UH_SMALL_THREADS, 4)
+uh_small_kernel(UhParams p) {
+    extern __shared__ __align__(16) unsigned char uh_smem[];
+    UhWarpScratch& ws = reinterpret_cast<UhWarpScratch*>(uh_smem)[threadIdx.x >> 5];
+    WvCtl* ctl = p.ctl;
+    const int lane = threadIdx.x & 31;
+    const double* __restrict__ pz = p.pz;
+    unsigned long long v_small = 0, n_small = 0;
+    const int total = min(*(volatile int*)&ctl->small_tail_.v, p.small_cap);
+    if (lane == 0) ws.tiny_out.count = 0;
     for (;;) {
-        int idx = 0, c = -1, s = 0, e = 0, level = 0;
-        if (lane == 0) {
-            idx = atomicAdd(&ctl->small_head_.v, 1);
-            if (idx < p.small_cap) {
-                volatile int* ready = &p.small[idx].c;
-                unsigned backoff = 100, polls = 0;
-                for (;;) {
-                    c = *ready;
-                    if (c >= 0) break;
-                    // the shared flags are looked at every 4th poll only (one line for all idle warps)
-                    if ((++polls & 3u) == 0u && (*(volatile int*)&ctl->big_done_.v || *(volatile int*)&ctl->overflow_.v)) {
-                        __threadfence();
-                        c = *ready;  // every push happened before big_done was raised
-                        break;
-                    }
-                    __nanosleep(backoff);
-                    if (backoff < 1600) backoff <<= 1;
-                }
-                if (c >= 0) {
-                    __threadfence();
-                    s = *(volatile int*)&p.small[idx].s;
-                    e = *(volatile int*)&p.small[idx].e;
-                    level = *(volatile int*)&p.small[idx].level;
-                }
+        int idx = 0;
+        if (lane == 0) idx = atomicAdd(&ctl->small_head_.v, 1);
+        idx = __shfl_sync(0xffffffffu, idx, 0);
+        if (idx >= total) break;
+        const UhTask root = p.small[idx];
+        const int c = root.c, L0 = root.level;
+        const long long p0 = p.off[c] + c;
+        for (int t = lane; t < UH_SMALL_MAX; t += 32) ws.lvl[t] = 0u;
+        if (lane == 0) ws.st[0] = root;
+        __syncwarp();
+        int sp = 1;
+        while (sp > 0) {
+            sp--;
+            const UhTask t = ws.st[sp];
+            __syncwarp();
+            const int s = t.s, e = t.e, level = t.level;
+            const double base = t.base, endv = t.endv;
+            const int n = e - s + 1;
+            const double nn = (double)n;
+            const double T = endv - base;
+            const double mu = T / nn;
+            double bnum = -1.0, bden = 1.0, bv = 0.0;
+            int bm = 0x7fffffff;
+            uh_scan<32, 4>(pz + p0 + s + 1, 0, n - 1, lane, base, mu, nn, bnum, bden, bm, bv);
+            double best = bnum >= 0.0 ? bnum / bden : -1.0;
+            int best_m = bm;
+            warp_argmax(best, best_m);
+            const unsigned own = __ballot_sync(0xffffffffu, bm == best_m && best_m != 0x7fffffff);
+            const double fv = __shfl_sync(0xffffffffu, bv, own ? __ffs(own) - 1 : 0);
+            if (lane == 0) v_small += (unsigned long long)n;
+            if (best == 0.0 || best_m == 0x7fffffff) {
+                for (int k = lane; k < n - 1; k += 32) atomicAdd(&ws.lvl[level - L0 + k], 1u);
+                if (lane == 0) n_small += (unsigned long long)(n - 1);
+                __syncwarp();
+                continue;
+            }
+            const int fm = best_m;
+            const int ls = s, le = s + fm, rs = s + fm + 1, re = e;
+            const int ln = le - ls + 1, rn = re - rs + 1;
+            const int lt_ = uh_tier(ln), rt_ = uh_tier(rn);
+            const bool lsm = lt_ >= UH_TIER_SMALL, rsm = rt_ >= UH_TIER_SMALL;
+            // the serial part is spread over two lanes: 0 pushes, 1 emits
+            if (lane == 1) {
+                atomicAdd(&ws.lvl[level - L0], 1u);
+                uh_emit_candidate(p, c, level, s, s + fm, e, uh_coef_from(fv, base, T, n, fm));
+                n_small++;
+            }
+            if (lane == 0) {
+                const UhTask tl = {c, ls, le, level + 1, base, fv}, tr = {c, rs, re, level + 1, fv, endv};
+                int q = sp;
+                if (ln >= rn) { if (lsm) ws.st[q++] = tl; if (rsm) ws.st[q++] = tr; }
+                else { if (rsm) ws.st[q++] = tr; if (lsm) ws.st[q++] = tl; }
+                const UhTinyTask yl = {c, ls, le, level + 1}, yr = {c, rs, re, level + 1};
+                if (lt_ == UH_TIER_TINY) uh_buf_push(ws.tiny_out, yl, p.tiny, p.tiny_cap, &ctl->tiny_tail_.v, ctl);
+                if (rt_ == UH_TIER_TINY) uh_buf_push(ws.tiny_out, yr, p.tiny, p.tiny_cap, &ctl->tiny_tail_.v, ctl);
+            }
+            sp += (lsm ? 1 : 0) + (rsm ? 1 : 0);
+            __syncwarp();
+        }
+        // flush the level counts of this subtree
+        for (int t = lane; t < UH_SMALL_MAX; t += 32) {
+            const unsigned v = ws.lvl[t];
+            if (v) atomicAdd(&p.lvlcnt[p.off[c] + L0 + t], v);
+        }
+        __syncwarp();
+    }
+    if (lane == 0) uh_buf_flush(ws.tiny_out, p.tiny, p.tiny_cap, &ctl->tiny_tail_.v, ctl);
+    if (v_small) atomicAdd(&ctl->visits_small, v_small);
+    if (n_small) atomicAdd(&ctl->nodes_small, n_small);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Stage T — subtrees of <= UH_TINY_MAX bins: one thread each, the reference recurrence verbatim
+// (GetInnerProdIter :19-48, GetInnerProdMax :54-67; Enumerable.Max skips NaN)
+// ---------------------------------------------------------------------------------------------
+// The recurrence's constants depend on (n, m) only.  They are tabulated once with the same IEEE
+// operations the reference performs (sqrt and division are correctly rounded on both sides), so using
+// the table instead of recomputing them per node changes no bit.
+struct UhTinyTab {
+    double first_plus[UH_TINY_MAX + 1];    // sqrt(1 - 1/n)
+    double first_minus[UH_TINY_MAX + 1];   // 1 / sqrt(n (n - 1))
+    double factor[UH_TINY_MAX + 1][UH_TINY_MAX];
+    double cplus[UH_TINY_MAX + 1][UH_TINY_MAX];   // sqrt(1/(m+1) - 1/n)
+    double cminus[UH_TINY_MAX + 1][UH_TINY_MAX];  // sqrt(n n/(m+1) - n)
+};
+
+__global__ void uh_tiny_table_kernel(UhTinyTab* tab) {
+    const int n = blockIdx.x + 2;  // 2..UH_TINY_MAX
+    const int m = threadIdx.x;
+    const double nn = (double)n;
+    if (m == 0) {
+        tab->first_plus[n] = sqrt(__dsub_rn(1.0, __ddiv_rn(1.0, nn)));
+        tab->first_minus[n] = __ddiv_rn(1.0, sqrt((double)((long long)n * (long long)(n - 1))));
+    }
+    if (m >= 1 && m < n - 1) {
+        tab->factor[n][m] = sqrt(__ddiv_rn(__ddiv_rn(__dmul_rn((double)(n - m - 1), (double)m), (double)(m + 1)), (double)(n - m)));
+        tab->cplus[n][m] = sqrt(__dsub_rn(__ddiv_rn(1.0, (double)(m + 1)), __ddiv_rn(1.0, nn)));
+        tab->cminus[n][m] = sqrt(__dsub_rn(__ddiv_rn(__dmul_rn(nn, nn), (double)(m + 1)), nn));
+    }
+}
+
+__global__ void __launch_bounds__(128)
+uh_tiny_kernel(UhParams p, const UhTinyTab* __restrict__ gtab) {
+    __shared__ UhTinyTab s_tab;
+    {
+        const double* src = reinterpret_cast<const double*>(gtab);
+        double* dst = reinterpret_cast<double*>(&s_tab);
+        for (int i = threadIdx.x; i < (int)(sizeof(UhTinyTab) / sizeof(double)); i += blockDim.x) dst[i] = src[i];
+    }
+    __syncthreads();
+    WvCtl* ctl = p.ctl;
+    const int total = min(*(volatile int*)&ctl->tiny_tail_.v, p.tiny_cap);
+    unsigned visits = 0, nodes = 0;
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+        const UhTinyTask root = p.tiny[idx];
+        const int c = root.c;
+        const double* __restrict__ xc = p.x + p.off[c];
+        unsigned* __restrict__ lv = p.lvlcnt + p.off[c];
+        int st_s[6], st_e[6], st_l[6];
+        int sp = 1;
+        st_s[0] = root.s; st_e[0] = root.e; st_l[0] = root.level;
+        while (sp > 0) {
+            sp--;
+            const int s = st_s[sp], e = st_e[sp], level = st_l[sp];
+            const int n = e - s + 1;
+            double xl[UH_TINY_MAX];
+#pragma unroll
+            for (int i = 0; i < UH_TINY_MAX; i++) xl[i] = i < n ? xc[s + i] : 0.0;
+            const double nn = (double)n;
+            double sum_x = 0.0;
+            for (int i = 1; i < n; i++) sum_x = __dadd_rn(sum_x, xl[i]);
+            const double mean = __ddiv_rn(__dadd_rn(xl[0], sum_x), nn);
+            double plus = __dmul_rn(s_tab.first_plus[n], xl[0]);
+            double minus = __dmul_rn(s_tab.first_minus[n], sum_x);
+            double best_ip = __dsub_rn(plus, minus);
+            double best_abs = fabs(best_ip);
+            if (!(best_abs >= 0.0)) best_abs = -1.0;
+            int best_m = 0;
+            for (int m = 1; m < n - 1; m++) {
+                const double factor = s_tab.factor[n][m];
+                plus = __dadd_rn(__dmul_rn(plus, factor), __dmul_rn(xl[m], s_tab.cplus[n][m]));
+                minus = __dsub_rn(__ddiv_rn(minus, factor), __ddiv_rn(xl[m], s_tab.cminus[n][m]));
+                const double ip = __dsub_rn(plus, minus);
+                const double a = fabs(ip);
+                if (a > best_abs) { best_abs = a; best_m = m; best_ip = ip; }
+            }
+            const double coef = __ddiv_rn(best_ip, fmax(0.5, __ddiv_rn(mean, 200.0)));
+            atomicAdd(&lv[level], 1u);
+            uh_emit_candidate(p, c, level, s, s + best_m, e, coef);
+            visits += (unsigned)n;
+            nodes++;
+            // children: left [s, s+m] and right [s+m+1, e], each needs >= 2 bins; larger first
+            const int ls = s, le = s + best_m, rs = s + best_m + 1, re = e;
+            const int ln = le - ls + 1, rn = re - rs + 1;
+            if (ln >= rn) {
+                if (ln >= 2) { st_s[sp] = ls; st_e[sp] = le; st_l[sp] = level + 1; sp++; }
+                if (rn >= 2) { st_s[sp] = rs; st_e[sp] = re; st_l[sp] = level + 1; sp++; }
+            } else {
+                if (rn >= 2) { st_s[sp] = rs; st_e[sp] = re; st_l[sp] = level + 1; sp++; }
+                if (ln >= 2) { st_s[sp] = ls; st_e[sp] = le; st_l[sp] = level + 1; sp++; }
             }
         }
-        c = __shfl_sync(0xffffffffu, c, 0);
-        if (c < 0) break;
-        s = __shfl_sync(0xffffffffu, s, 0);
-        e = __shfl_sync(0xffffffffu, e, 0);
-        level = __shfl_sync(0xffffffffu, level, 0);
-        uh_small_subtree(p, ws, c, s, e, level, v_small, v_tiny, n_small, n_tiny);
     }
-    // statistics
-    if (v_big) atomicAdd(&ctl->visits_big, v_big);
-    if (v_small) atomicAdd(&ctl->visits_small, v_small);
-    if (v_tiny) atomicAdd(&ctl->visits_tiny, v_tiny);
-    if (n_big) atomicAdd(&ctl->nodes_big, n_big);
-    if (n_small) atomicAdd(&ctl->nodes_small, n_small);
-    if (n_tiny) atomicAdd(&ctl->nodes_tiny, n_tiny);
-    __syncthreads();
-    if (threadIdx.x == 0) {
+    // statistics: one atomic per warp
+    visits = __reduce_add_sync(0xffffffffu, visits);
+    nodes = __reduce_add_sync(0xffffffffu, nodes);
+    if ((threadIdx.x & 31) == 0) {
+        if (visits) atomicAdd(&ctl->visits_tiny, (unsigned long long)visits);
+        if (nodes) atomicAdd(&ctl->nodes_tiny, (unsigned long long)nodes);
         unsigned long long t;
         asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
         atomicMax(&ctl->t_last, t);
     }
+}
+
+// number of levels of every chromosome = highest level with a node + 1 (depth[] zeroed by the host)
+__global__ void uh_depth_kernel(const unsigned* __restrict__ lvlcnt, const long long* __restrict__ off, int* __restrict__ depth) {
+    const int c = blockIdx.y;
+    const long long o = off[c];
+    const int n = (int)(off[c + 1] - o);
+    int mx = 0;
+    for (int l = blockIdx.x * blockDim.x + threadIdx.x; l < n; l += gridDim.x * blockDim.x)
+        if (lvlcnt[o + l]) mx = l + 1;
+    mx = (int)__reduce_max_sync(0xffffffffu, (unsigned)mx);
+    if ((threadIdx.x & 31) == 0 && mx > 0) atomicMax(&depth[c], mx);
 }
 
 // seeds: one root per selected chromosome with more than min_size bins (one thread per chromosome)
@@ -500,20 +643,30 @@ __global__ void uh_seed_kernel(UhParams p, const unsigned char* __restrict__ sel
     __shared__ int s_big;
     if (threadIdx.x == 0) s_big = 0;
     __syncthreads();
+    WvCtl* ctl = p.ctl;
     for (int c = threadIdx.x; c < n_chrom; c += blockDim.x) {
         const long long len = p.off[c + 1] - p.off[c];
         if (!selected[c] || len <= (long long)min_size || len < 2) continue;
         const int e = (int)len - 1;
-        if (e + 1 > UH_SMALL_MAX) {
+        const long long p0 = p.off[c] + c;
+        const double base = p.pz[p0], endv = p.pz[p0 + e + 1];
+        const int tier = uh_tier(e + 1);
+        if (tier == UH_TIER_BIG) {
             atomicAdd(&s_big, 1);
-            atomicAdd(&p.ctl->outstanding_.v, 1);
-            const long long p0 = p.off[c] + c;
-            uh_push_big(p, c, 0, e, 0, p.pz[p0], p.pz[p0 + e + 1]);
-        } else {
-            uh_push_small(p, c, 0, e, 0);
+            atomicAdd(&ctl->outstanding_.v, 1);
+            uh_push_big(p, c, 0, e, 0, base, endv);
+        } else if (tier == UH_TIER_MID) {
+            const int i = atomicAdd(&ctl->mid_tail_.v, 1);
+            if (i < p.mid_cap) p.mid[i] = UhTask{c, 0, e, 0, base, endv};
+        } else if (tier == UH_TIER_SMALL) {
+            const int i = atomicAdd(&ctl->small_tail_.v, 1);
+            if (i < p.small_cap) p.small[i] = UhTask{c, 0, e, 0, base, endv};
+        } else if (tier == UH_TIER_TINY) {
+            const int i = atomicAdd(&ctl->tiny_tail_.v, 1);
+            if (i < p.tiny_cap) p.tiny[i] = UhTinyTask{c, 0, e, 0};
         }
     }
     __syncthreads();
-    // no big node at all: the big phase is over before it starts
-    if (threadIdx.x == 0 && s_big == 0) { __threadfence(); *(volatile int*)&p.ctl->big_done_.v = 1; }
+    // no big node at all: stage A has nothing to wait for
+    if (threadIdx.x == 0 && s_big == 0) { __threadfence(); *(volatile int*)&ctl->big_done_.v = 1; }
 }
