@@ -1,0 +1,80 @@
+"""Host side of CanvasBin's counting step (reference CanvasBin/FragmentBinner.cs, HitArray.cs).
+
+BAM decoding and the read-name bookkeeping stay on the host; the geometric part — which bin a fragment
+overlaps most — and the per-bin counting run on the GPU through cg_bin_fragments / cg_bin_hits.
+
+Alignments are expected in coordinate order (a sorted, indexed BAM is what BinTask.DoIt jumps into,
+FragmentBinner.cs:204-243); that is what makes the reference's monotone `binIndexStart` scan equal to
+the kernel's binary search, and what lets the pairing below run without knowing the geometric outcome.
+"""
+import numpy as np
+
+# filter bits (the same encoding the tests use)
+MAPPED, MATE_MAPPED, PRIMARY, PAIRED, PROPER, DUPLICATE, FAILED_QC = 1, 2, 4, 8, 16, 32, 64
+MAPQ_NOT_AVAILABLE = 255  # FragmentBinnerConstants.MappingQualityNotAvailable
+
+
+def flags_from_sam(sam_flag):
+    """SAM FLAG -> the filter bits BinOneAlignment looks at (FragmentBinner.cs:259-262, :322-326)."""
+    f = np.asarray(sam_flag, np.int64)
+    out = np.zeros(f.shape, np.uint8)
+    out |= np.where(f & 0x4, 0, MAPPED).astype(np.uint8)
+    out |= np.where(f & 0x8, 0, MATE_MAPPED).astype(np.uint8)
+    out |= np.where(f & 0x100, 0, PRIMARY).astype(np.uint8)
+    out |= np.where(f & 0x1, PAIRED, 0).astype(np.uint8)
+    out |= np.where(f & 0x2, PROPER, 0).astype(np.uint8)
+    out |= np.where(f & 0x400, DUPLICATE, 0).astype(np.uint8)
+    out |= np.where(f & 0x200, FAILED_QC, 0).astype(np.uint8)
+    return out
+
+
+def hit_array(length, positions):
+    """HitArray.Set (HitArray.cs:61-64): one saturating byte counter per position."""
+    h = np.bincount(np.asarray(positions, np.int64), minlength=length)[:length]
+    return np.minimum(h, 255).astype(np.uint8)
+
+
+def pair_fragments(flags, pos, mate_pos, ref_id, mate_ref_id, frag_len, mapq, names, quality_threshold):
+    """The name-dictionary half of BinOneAlignment (FragmentBinner.cs:256-295).
+
+    Returns (frag_start, frag_stop, undo_index): the fragments the left read of every usable pair
+    defines, and the indices (into those fragments) whose mate later failed the filters."""
+    flags = np.asarray(flags, np.uint8)
+    need = MAPPED | MATE_MAPPED | PRIMARY | PAIRED | PROPER
+    ok = (flags & need) == need
+    mq = np.asarray(mapq, np.int64)
+    bad = ((flags & (DUPLICATE | FAILED_QC)) != 0) | (mq == MAPQ_NOT_AVAILABLE) | (mq < quality_threshold)
+    fs, fe, undo = [], [], []
+    name_to_frag = {}
+    same_pos = set()
+    pos = np.asarray(pos, np.int64); mate_pos = np.asarray(mate_pos, np.int64)
+    for i in np.nonzero(ok)[0].tolist():
+        nm = names[i]
+        if nm in name_to_frag:
+            if bad[i]:
+                undo.append(name_to_frag[nm])
+            del name_to_frag[nm]
+            continue
+        if bad[i] or ref_id[i] != mate_ref_id[i] or pos[i] > mate_pos[i]:
+            continue
+        if pos[i] == mate_pos[i]:
+            if nm in same_pos:
+                same_pos.remove(nm)
+                continue
+            same_pos.add(nm)
+        if frag_len[i] == 0:
+            continue
+        name_to_frag[nm] = len(fs)
+        fs.append(int(pos[i]))
+        fe.append(int(pos[i]) + int(frag_len[i]))
+    return np.array(fs, np.int32), np.array(fe, np.int32), np.array(undo, np.int32)
+
+
+def bin_paired_alignments(engine, flags, pos, mate_pos, ref_id, mate_ref_id, frag_len, mapq, names, quality_threshold,
+                          bin_start, bin_stop):
+    """BinTask.DoIt's counting for one chromosome: per-bin fragment counts and usableFragmentCount."""
+    fs, fe, undo = pair_fragments(flags, pos, mate_pos, ref_id, mate_ref_id, frag_len, mapq, names, quality_threshold)
+    r = engine.bin_fragments(fs, fe, bin_start, bin_stop, undo)
+    best = r["best_bin"]
+    usable = int((best >= 0).sum()) - int((best[undo] >= 0).sum()) if len(best) else 0
+    return {"count": r["count"], "usable": usable}

@@ -1,0 +1,328 @@
+// CanvasBin counting kernels (reference Src/Canvas/CanvasBin/):
+//   cg_bin_hits       BinCountsForChromosome, CanvasBin.cs:568-661 (bins of `bin_size` possible positions;
+//                     TruncatedDynamicRange :618-625 and GCContentWeighted :626-636 counts, GC% :638)
+//   cg_bin_fragments  FragmentBinner.BinOneAlignment / FindBestBin, FragmentBinner.cs:296-311, :353-371
+// BAM decoding, read-name pairing and the unique-kmer FASTA stay on the host; integers are bit-exact.
+#include "common.cuh"
+
+namespace {
+
+constexpr int BIN_TILE_WORDS = 1024;  // 64-bit words of the possible-alignment bitmap per scan tile
+
+struct BinCtl {
+    unsigned long long first_pos;   // first base that is not 'n' (CanvasBin.cs:582-583)
+    unsigned long long total_possible;
+    int n_bins;
+    int pad;
+};
+
+__global__ void bin_init_kernel(BinCtl* ctl) {
+    ctl->first_pos = ~0ull;
+    ctl->total_possible = 0ull;
+    ctl->n_bins = 0;
+}
+
+// "Skip past leading Ns": the first position whose base is not a lower-case 'n' (:582-583)
+__global__ void bin_first_base_kernel(const char* __restrict__ bases, long long len, BinCtl* ctl) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    unsigned long long best = ~0ull;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += stride) {
+        if (bases[i] != 'n') { best = (unsigned long long)i; break; }
+        if ((unsigned long long)i > *(volatile unsigned long long*)&ctl->first_pos) break;
+    }
+    if (best != ~0ull) atomicMin(&ctl->first_pos, best);
+}
+
+__device__ inline unsigned long long masked_word(const unsigned long long* __restrict__ bits, long long w, long long nwords,
+                                                  unsigned long long first_pos, long long len) {
+    if (w >= nwords) return 0ull;
+    unsigned long long v = bits[w];
+    const long long lo = w * 64;
+    if ((long long)first_pos > lo) {
+        const long long k = (long long)first_pos - lo;
+        v = k >= 64 ? 0ull : (v & (~0ull << k));
+    }
+    if (lo + 64 > len) {
+        const long long k = len - lo;
+        v = k <= 0 ? 0ull : (v & (~0ull >> (64 - k)));
+    }
+    return v;
+}
+
+// possible positions per tile of the bitmap (only positions >= first_pos count)
+__global__ void bin_tile_count_kernel(const unsigned long long* __restrict__ bits, long long nwords, long long len,
+                                      const BinCtl* __restrict__ ctl, unsigned* __restrict__ tile_cnt) {
+    __shared__ unsigned s_w[32];
+    const unsigned long long first = ctl->first_pos;
+    const long long w0 = (long long)blockIdx.x * BIN_TILE_WORDS;
+    unsigned c = 0;
+    for (int i = threadIdx.x; i < BIN_TILE_WORDS; i += blockDim.x) c += __popcll(masked_word(bits, w0 + i, nwords, first, len));
+    c = __reduce_add_sync(0xffffffffu, c);
+    if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned t = 0;
+        for (int k = 0; k < (int)(blockDim.x >> 5); k++) t += s_w[k];
+        tile_cnt[blockIdx.x] = t;
+    }
+}
+
+// exclusive scan of the tile counts (single block) -> tile_off (u64); number of complete bins
+__global__ void bin_tile_scan_kernel(const unsigned* __restrict__ tile_cnt, int ntiles, unsigned long long* __restrict__ tile_off,
+                                     int bin_size, BinCtl* ctl) {
+    __shared__ unsigned long long s_carry;
+    __shared__ unsigned long long s_w[32];
+    if (threadIdx.x == 0) s_carry = 0ull;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    for (int base = 0; base < ntiles; base += blockDim.x) {
+        const int i = base + threadIdx.x;
+        const unsigned long long v = i < ntiles ? tile_cnt[i] : 0ull;
+        unsigned long long incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const unsigned long long u = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += u; }
+        if (lane == 31) s_w[w] = incl;
+        __syncthreads();
+        unsigned long long wb = 0;
+        for (int k = 0; k < w; k++) wb += s_w[k];
+        if (i < ntiles) tile_off[i] = s_carry + wb + incl - v;
+        __syncthreads();
+        if (threadIdx.x == blockDim.x - 1) s_carry += wb + incl;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        tile_off[ntiles] = s_carry;
+        ctl->total_possible = s_carry;
+        ctl->n_bins = bin_size > 0 ? (int)(s_carry / (unsigned long long)bin_size) : 0;
+    }
+}
+
+// end position of bin k = position of the ((k+1) * bin_size)-th possible position (:611-612)
+__global__ void bin_end_kernel(const unsigned long long* __restrict__ bits, long long nwords, long long len,
+                               const unsigned long long* __restrict__ tile_off, int ntiles, int bin_size,
+                               const BinCtl* __restrict__ ctl, int max_bins, int* __restrict__ end_pos) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    const int nb = min(ctl->n_bins, max_bins);
+    if (k >= nb) return;
+    const unsigned long long target = (unsigned long long)(k + 1) * (unsigned long long)bin_size;  // 1-based rank
+    int lo = 0, hi = ntiles - 1;  // last tile with tile_off < target
+    while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (tile_off[mid] < target) lo = mid; else hi = mid - 1; }
+    unsigned long long need = target - tile_off[lo];
+    const unsigned long long first = ctl->first_pos;
+    long long w = (long long)lo * BIN_TILE_WORDS;
+    unsigned long long word = 0;
+    for (int i = 0; i < BIN_TILE_WORDS; i++, w++) {
+        word = masked_word(bits, w, nwords, first, len);
+        const unsigned c = __popcll(word);
+        if (need <= c) break;
+        need -= c;
+    }
+    // position of the need-th set bit of `word`
+    for (unsigned long long r = 1; r < need; r++) word &= word - 1;
+    end_pos[k] = (int)(w * 64 + (__ffsll((long long)word) - 1));
+}
+
+// per-bin sums, one warp per bin: count = sum of min(10, hits) over possible positions (:618-625),
+// gc = (int)(100f * GC / nucleotides) with every base counted as a nucleotide (:592-593, :638)
+__global__ void bin_sum_kernel(const unsigned char* __restrict__ hits, const unsigned long long* __restrict__ bits,
+                               const char* __restrict__ bases, const BinCtl* __restrict__ ctl, const int* __restrict__ end_pos,
+                               int max_bins, int32_t* __restrict__ start, int32_t* __restrict__ stop, int32_t* __restrict__ count,
+                               unsigned char* __restrict__ gc) {
+    const int k = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    const int nb = min(ctl->n_bins, max_bins);
+    if (k >= nb) return;
+    const int s = k == 0 ? (int)ctl->first_pos : end_pos[k - 1] + 1;
+    const int e = end_pos[k];  // inclusive
+    unsigned obs = 0, gcc = 0;
+    for (int p = s + lane; p <= e; p += 32) {
+        const char b = bases[p];
+        gcc += (b == 'C' || b == 'c' || b == 'G' || b == 'g');
+        if ((bits[p >> 6] >> (p & 63)) & 1ull) obs += min(10u, (unsigned)hits[p]);
+    }
+    obs = __reduce_add_sync(0xffffffffu, obs);
+    gcc = __reduce_add_sync(0xffffffffu, gcc);
+    if (lane == 0) {
+        start[k] = s;
+        stop[k] = e + 1;  // "pos + 1 to conform to bed specification" (:652)
+        count[k] = (int)obs;
+        gc[k] = (unsigned char)(int)__fdiv_rn(__fmul_rn(100.0f, (float)gcc), (float)(e - s + 1));
+    }
+}
+
+// GCContentWeighted (:626-636): float accumulation in position order, Math.Round (half to even)
+__global__ void bin_sum_weighted_kernel(const unsigned char* __restrict__ hits, const unsigned long long* __restrict__ bits,
+                                        const unsigned char* __restrict__ read_gc, const float* __restrict__ obs_vs_exp,
+                                        const BinCtl* __restrict__ ctl, const int* __restrict__ end_pos, int max_bins,
+                                        int32_t* __restrict__ count) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    const int nb = min(ctl->n_bins, max_bins);
+    if (k >= nb) return;
+    const int s = k == 0 ? (int)ctl->first_pos : end_pos[k - 1] + 1;
+    const int e = end_pos[k];
+    float acc = 0.0f;
+    for (int p = s; p <= e; p++)
+        if ((bits[p >> 6] >> (p & 63)) & 1ull)
+            acc = __fadd_rn(acc, fminf(10.0f, __fdiv_rn((float)hits[p], obs_vs_exp[read_gc[p]])));
+    count[k] = (int)rint((double)acc);
+}
+
+// FragmentBinner.cs:296-311 + FindBestBin :353-371: first bin whose Stop is right of the fragment start,
+// then the bin with the largest overlap (the first one on ties)
+__global__ void bin_fragments_kernel(const int32_t* __restrict__ fstart, const int32_t* __restrict__ fstop, long long nfrag,
+                                     const int32_t* __restrict__ bstart, const int32_t* __restrict__ bstop, int nbins,
+                                     int32_t* __restrict__ best_bin, int32_t* __restrict__ count) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nfrag) return;
+    const int fs = fstart[i], fe = fstop[i];
+    int lo = 0, hi = nbins;  // first bin with stop > fs
+    while (lo < hi) { const int mid = (lo + hi) >> 1; if (bstop[mid] <= fs) lo = mid + 1; else hi = mid; }
+    int best = -1, best_ov = 0;
+    for (int b = lo; b < nbins; b++) {
+        const int ov = min(bstop[b], fe) - max(bstart[b], fs);
+        if (ov <= 0) break;
+        if (ov > best_ov) { best_ov = ov; best = b; }
+    }
+    best_bin[i] = best;
+    if (best >= 0) atomicAdd(&count[best], 1);
+}
+
+// a fragment whose mate later fails the duplicate / QC / MAPQ filters is taken out again (:279-284)
+__global__ void bin_fragments_undo_kernel(const int32_t* __restrict__ undo, long long nundo, const int32_t* __restrict__ best_bin,
+                                          int32_t* __restrict__ count) {
+    const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= nundo) return;
+    const int b = best_bin[undo[j]];
+    if (b >= 0) atomicSub(&count[b], 1);
+}
+
+}  // namespace
+
+extern "C" int cg_bin_hits(cg_ctx* ctx, int64_t chr_len, const uint8_t* hits, const uint64_t* possible_bits, const char* bases,
+                           int bin_size, int mode, const uint8_t* read_gc, const float* obs_vs_exp_gc, int64_t max_bins,
+                           int64_t* n_bins, int32_t* start, int32_t* stop, int32_t* count, uint8_t* gc) {
+    if (!ctx) return CG_ERR_ARG;
+    if (chr_len < 0 || chr_len > 0x7fff0000LL || bin_size <= 0 || max_bins < 0 || !n_bins || (mode != 0 && mode != 1) ||
+        (mode == 1 && (!read_gc || !obs_vs_exp_gc)))
+        return cg_fail(ctx, CG_ERR_ARG, "cg_bin_hits: bad argument");
+    *n_bins = 0;
+    ctx->launches = 0;
+    ctx->launch_err = cudaSuccess;
+    for (int i = 0; i < 4; i++) ctx->stage_used[i] = false;
+    if (chr_len == 0) return CG_OK;
+    if (!hits || !possible_bits || !bases || (max_bins > 0 && (!start || !stop || !count || !gc)))
+        return cg_fail(ctx, CG_ERR_ARG, "cg_bin_hits: null array");
+    CG_CUDA(ctx, cudaSetDevice(ctx->device));
+    const long long nwords = (chr_len + 63) / 64;
+    const int ntiles = (int)((nwords + BIN_TILE_WORDS - 1) / BIN_TILE_WORDS);
+    const long long cap = std::min<long long>(max_bins, chr_len / bin_size + 1);
+    size_t need = arena_need(chr_len, 1) * 3 + arena_need(nwords, 8) + arena_need(ntiles + 1, 4) + arena_need(ntiles + 2, 8) +
+                  arena_need(cap + 1, 4) * 4 + arena_need(cap + 1, 1) + arena_need(256, 4) + arena_need(1, sizeof(BinCtl)) + (1 << 16);
+    int rc = arena_reserve(ctx, need);
+    if (rc) return rc;
+    unsigned char* d_hits = arena_take<unsigned char>(ctx, chr_len);
+    char* d_bases = arena_take<char>(ctx, chr_len);
+    unsigned char* d_rgc = arena_take<unsigned char>(ctx, chr_len);
+    unsigned long long* d_bits = arena_take<unsigned long long>(ctx, nwords);
+    unsigned* d_tcnt = arena_take<unsigned>(ctx, ntiles + 1);
+    unsigned long long* d_toff = arena_take<unsigned long long>(ctx, ntiles + 2);
+    int* d_end = arena_take<int>(ctx, cap + 1);
+    int32_t* d_start = arena_take<int32_t>(ctx, cap + 1);
+    int32_t* d_stop = arena_take<int32_t>(ctx, cap + 1);
+    int32_t* d_count = arena_take<int32_t>(ctx, cap + 1);
+    unsigned char* d_gc = arena_take<unsigned char>(ctx, cap + 1);
+    float* d_ratio = arena_take<float>(ctx, 256);
+    BinCtl* d_ctl = arena_take<BinCtl>(ctx, 1);
+    if (!d_hits || !d_bases || !d_rgc || !d_bits || !d_tcnt || !d_toff || !d_end || !d_start || !d_stop || !d_count || !d_gc || !d_ratio || !d_ctl)
+        return cg_fail(ctx, CG_ERR_CUDA, "cg_bin_hits: device arena exhausted");
+    cudaStream_t s = ctx->stream;
+    CG_CUDA(ctx, cudaMemcpyAsync(d_hits, hits, chr_len, cudaMemcpyHostToDevice, s));
+    CG_CUDA(ctx, cudaMemcpyAsync(d_bases, bases, chr_len, cudaMemcpyHostToDevice, s));
+    CG_CUDA(ctx, cudaMemcpyAsync(d_bits, possible_bits, nwords * 8, cudaMemcpyHostToDevice, s));
+    if (mode == 1) {
+        CG_CUDA(ctx, cudaMemcpyAsync(d_rgc, read_gc, chr_len, cudaMemcpyHostToDevice, s));
+        CG_CUDA(ctx, cudaMemcpyAsync(d_ratio, obs_vs_exp_gc, 101 * sizeof(float), cudaMemcpyHostToDevice, s));
+    }
+    CG_CUDA(ctx, cudaEventRecord(ctx->ev0, s));
+    CG_LAUNCH(ctx, bin_init_kernel, 1, 1, 0, d_ctl);
+    CG_LAUNCH(ctx, bin_first_base_kernel, ctx->num_sms, 256, 0, d_bases, (long long)chr_len, d_ctl);
+    CG_LAUNCH(ctx, bin_tile_count_kernel, ntiles, 256, 0, d_bits, nwords, (long long)chr_len, d_ctl, d_tcnt);
+    CG_LAUNCH(ctx, bin_tile_scan_kernel, 1, 1024, 0, d_tcnt, ntiles, d_toff, bin_size, d_ctl);
+    if (cap > 0) {
+        CG_LAUNCH(ctx, bin_end_kernel, div_up(cap, 128), 128, 0, d_bits, nwords, (long long)chr_len, d_toff, ntiles, bin_size, d_ctl,
+                  (int)cap, d_end);
+        CG_LAUNCH(ctx, bin_sum_kernel, div_up(cap * 32, 256), 256, 0, d_hits, d_bits, d_bases, d_ctl, d_end, (int)cap, d_start, d_stop,
+                  d_count, d_gc);
+        if (mode == 1)
+            CG_LAUNCH(ctx, bin_sum_weighted_kernel, div_up(cap, 128), 128, 0, d_hits, d_bits, d_rgc, d_ratio, d_ctl, d_end, (int)cap, d_count);
+    }
+    CG_CUDA(ctx, cudaEventRecord(ctx->ev1, s));
+    BinCtl* h = (BinCtl*)ctx->pinned;
+    CG_CUDA(ctx, cudaMemcpyAsync(h, d_ctl, sizeof(BinCtl), cudaMemcpyDeviceToHost, s));
+    CG_CUDA(ctx, cudaStreamSynchronize(s));
+    CG_CUDA(ctx, cudaGetLastError());
+    CG_CHECK_LAUNCHES(ctx);
+    const long long nb = h->n_bins;
+    if (nb > max_bins) return cg_fail(ctx, CG_ERR_CAPACITY, "cg_bin_hits: max_bins too small");
+    if (nb > 0) {
+        CG_CUDA(ctx, cudaMemcpyAsync(start, d_start, nb * 4, cudaMemcpyDeviceToHost, s));
+        CG_CUDA(ctx, cudaMemcpyAsync(stop, d_stop, nb * 4, cudaMemcpyDeviceToHost, s));
+        CG_CUDA(ctx, cudaMemcpyAsync(count, d_count, nb * 4, cudaMemcpyDeviceToHost, s));
+        CG_CUDA(ctx, cudaMemcpyAsync(gc, d_gc, nb, cudaMemcpyDeviceToHost, s));
+        CG_CUDA(ctx, cudaStreamSynchronize(s));
+    }
+    float ms = 0;
+    cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+    ctx->last_kernel_ms = ms;
+    *n_bins = nb;
+    return CG_OK;
+}
+
+extern "C" int cg_bin_fragments(cg_ctx* ctx, int64_t n_frag, const int32_t* frag_start, const int32_t* frag_stop, int64_t n_undo,
+                                const int32_t* undo_index, int64_t n_bins, const int32_t* bin_start, const int32_t* bin_stop,
+                                int32_t* best_bin, int32_t* count) {
+    if (!ctx) return CG_ERR_ARG;
+    if (n_frag < 0 || n_undo < 0 || n_bins < 0 || n_bins > 0x7fff0000LL || (n_bins > 0 && (!bin_start || !bin_stop || !count)) ||
+        (n_frag > 0 && (!frag_start || !frag_stop || !best_bin)) || (n_undo > 0 && !undo_index))
+        return cg_fail(ctx, CG_ERR_ARG, "cg_bin_fragments: bad argument");
+    ctx->launches = 0;
+    ctx->launch_err = cudaSuccess;
+    for (int i = 0; i < 4; i++) ctx->stage_used[i] = false;
+    if (n_bins == 0) {
+        for (int64_t i = 0; i < n_frag; i++) best_bin[i] = -1;
+        return CG_OK;
+    }
+    CG_CUDA(ctx, cudaSetDevice(ctx->device));
+    int rc = arena_reserve(ctx, arena_need(n_frag + 1, 4) * 3 + arena_need(n_undo + 1, 4) + arena_need(n_bins + 1, 4) * 3 + (1 << 16));
+    if (rc) return rc;
+    int32_t* d_fs = arena_take<int32_t>(ctx, n_frag + 1);
+    int32_t* d_fe = arena_take<int32_t>(ctx, n_frag + 1);
+    int32_t* d_best = arena_take<int32_t>(ctx, n_frag + 1);
+    int32_t* d_undo = arena_take<int32_t>(ctx, n_undo + 1);
+    int32_t* d_bs = arena_take<int32_t>(ctx, n_bins + 1);
+    int32_t* d_be = arena_take<int32_t>(ctx, n_bins + 1);
+    int32_t* d_cnt = arena_take<int32_t>(ctx, n_bins + 1);
+    if (!d_fs || !d_fe || !d_best || !d_undo || !d_bs || !d_be || !d_cnt) return cg_fail(ctx, CG_ERR_CUDA, "cg_bin_fragments: device arena exhausted");
+    cudaStream_t s = ctx->stream;
+    if (n_frag > 0) {
+        CG_CUDA(ctx, cudaMemcpyAsync(d_fs, frag_start, n_frag * 4, cudaMemcpyHostToDevice, s));
+        CG_CUDA(ctx, cudaMemcpyAsync(d_fe, frag_stop, n_frag * 4, cudaMemcpyHostToDevice, s));
+    }
+    if (n_undo > 0) CG_CUDA(ctx, cudaMemcpyAsync(d_undo, undo_index, n_undo * 4, cudaMemcpyHostToDevice, s));
+    CG_CUDA(ctx, cudaMemcpyAsync(d_bs, bin_start, n_bins * 4, cudaMemcpyHostToDevice, s));
+    CG_CUDA(ctx, cudaMemcpyAsync(d_be, bin_stop, n_bins * 4, cudaMemcpyHostToDevice, s));
+    CG_CUDA(ctx, cudaMemsetAsync(d_cnt, 0, n_bins * 4, s));
+    CG_CUDA(ctx, cudaEventRecord(ctx->ev0, s));
+    if (n_frag > 0) CG_LAUNCH(ctx, bin_fragments_kernel, div_up(n_frag, 256), 256, 0, d_fs, d_fe, (long long)n_frag, d_bs, d_be, (int)n_bins, d_best, d_cnt);
+    if (n_undo > 0) CG_LAUNCH(ctx, bin_fragments_undo_kernel, div_up(n_undo, 256), 256, 0, d_undo, (long long)n_undo, d_best, d_cnt);
+    CG_CUDA(ctx, cudaEventRecord(ctx->ev1, s));
+    if (n_frag > 0) CG_CUDA(ctx, cudaMemcpyAsync(best_bin, d_best, n_frag * 4, cudaMemcpyDeviceToHost, s));
+    CG_CUDA(ctx, cudaMemcpyAsync(count, d_cnt, n_bins * 4, cudaMemcpyDeviceToHost, s));
+    CG_CUDA(ctx, cudaStreamSynchronize(s));
+    CG_CUDA(ctx, cudaGetLastError());
+    CG_CHECK_LAUNCHES(ctx);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+    ctx->last_kernel_ms = ms;
+    return CG_OK;
+}

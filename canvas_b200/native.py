@@ -59,6 +59,10 @@ SIGNATURES = {
                                              _P(_f32), _P(_u8), _P(_i64), _P(_i32), _P(_f32),
                                              _P(_f64), _P(C.c_int), _P(_i64), _P(_i32), _P(_i32),
                                              _P(_f64), _P(C.c_int), _P(_f64), _P(C.c_int), _P(_f64)]),
+    "cg_bin_hits": (C.c_int, [C.c_void_p, _i64, _P(_u8), _P(C.c_uint64), C.c_char_p, C.c_int, C.c_int, _P(_u8),
+                              _P(_f32), _i64, _P(_i64), _P(_i32), _P(_i32), _P(_i32), _P(_u8)]),
+    "cg_bin_fragments": (C.c_int, [C.c_void_p, _i64, _P(_i32), _P(_i32), _i64, _P(_i32), _i64, _P(_i32), _P(_i32),
+                                   _P(_i32), _P(_i32)]),
     "cg_normalize_apply": (C.c_int, [C.c_void_p, C.c_int, _i64, _P(_f32), _P(_u8), _P(_f64),
                                      _P(_f64), _P(_f32), C.c_int, _P(_f64)]),
 }
@@ -279,6 +283,40 @@ class Engine:
                 "gc_norm_skipped": bool(skipped.value), "chrom_off": off, "breakpoints": bps,
                 "evenness": ev.value if ev_ok.value else None,
                 "cv": cv.value if cv_has.value else None, "factor_of_three": f3}
+
+    # ------------------------------------------------------------------ CanvasBin counting
+    def bin_hits(self, hits, possible, bases, bin_size, mode=0, read_gc=None, obs_vs_exp_gc=None):
+        """hits: uint8[len]; possible: bool[len]; bases: bytes of length len."""
+        hits = np.ascontiguousarray(hits, np.uint8)
+        n = len(hits)
+        bits = np.packbits(np.asarray(possible, bool), bitorder="little")
+        pad = (-len(bits)) % 8
+        words = np.frombuffer(np.concatenate([bits, np.zeros(pad, np.uint8)]).tobytes(), dtype=np.uint64).copy()
+        if len(words) == 0:
+            words = np.zeros(1, np.uint64)
+        cap = n // max(bin_size, 1) + 1
+        start = np.zeros(cap, np.int32); stop = np.zeros(cap, np.int32); count = np.zeros(cap, np.int32)
+        gc = np.zeros(cap, np.uint8)
+        nb = _i64(0)
+        rgc = np.ascontiguousarray(read_gc if read_gc is not None else np.zeros(1), np.uint8)
+        ratio = np.ascontiguousarray(obs_vs_exp_gc if obs_vs_exp_gc is not None else np.ones(101), np.float32)
+        rc = self.lib.cg_bin_hits(self.h, n, _ptr(hits, _u8), _ptr(words, C.c_uint64), bytes(bases), int(bin_size), int(mode),
+                                  _ptr(rgc, _u8), _ptr(ratio, _f32), cap, C.byref(nb), _ptr(start, _i32), _ptr(stop, _i32),
+                                  _ptr(count, _i32), _ptr(gc, _u8))
+        self._check(rc)
+        k = nb.value
+        return {"start": start[:k], "stop": stop[:k], "count": count[:k], "gc": gc[:k]}
+
+    def bin_fragments(self, frag_start, frag_stop, bin_start, bin_stop, undo_index=None):
+        fs = np.ascontiguousarray(frag_start, np.int32); fe = np.ascontiguousarray(frag_stop, np.int32)
+        bs = np.ascontiguousarray(bin_start, np.int32); be = np.ascontiguousarray(bin_stop, np.int32)
+        undo = np.ascontiguousarray(undo_index if undo_index is not None else [], np.int32)
+        best = np.full(max(len(fs), 1), -1, np.int32)
+        count = np.zeros(max(len(bs), 1), np.int32)
+        rc = self.lib.cg_bin_fragments(self.h, len(fs), _ptr(fs, _i32), _ptr(fe, _i32), len(undo), _ptr(undo, _i32), len(bs),
+                                       _ptr(bs, _i32), _ptr(be, _i32), _ptr(best, _i32), _ptr(count, _i32))
+        self._check(rc)
+        return {"best_bin": best[:len(fs)], "count": count[:len(bs)]}
 
     # ------------------------------------------------------------------ stand-alone K8
     def normalize_apply(self, count, gc, median_by_gc, global_median, repeats=1):

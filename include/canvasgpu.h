@@ -138,6 +138,29 @@ int cg_clean_partition_wavelet(cg_ctx* ctx, const cg_clean_opts* copts, const cg
                                double* cv, int* cv_has_value, double* factor_of_three);
 
 /* ---------------------------------------------------------------------------------------------
+ * CanvasBin counting (BAM decoding, read pairing and FASTA handling stay on the host).
+ *
+ * cg_bin_hits — BinCountsForChromosome (CanvasBin.cs:568-661) for one chromosome without predefined
+ * bins: hits[p] saturating per-position hit counts (HitArray.cs:61-64), possible_bits bit p of word
+ * p/64 = unique-kmer start (:183-200), bases the FASTA characters.  A bin closes at its bin_size-th
+ * possible position; count = sum of min(10, hits) over possible positions (mode 0, TruncatedDynamicRange
+ * :618-625) or round(sum of min(10, hits / obs_vs_exp_gc[read_gc[p]])) accumulated in single precision
+ * in position order (mode 1, GCContentWeighted :626-636); gc = (int)(100f * GC / length) (:638).  The
+ * trailing incomplete bin is dropped as in the reference.  Outputs need capacity max_bins.
+ *
+ * cg_bin_fragments — FragmentBinner.BinOneAlignment / FindBestBin (FragmentBinner.cs:296-311, :353-371):
+ * fragment i = [frag_start, frag_stop) goes to the bin (sorted, non-overlapping) with the largest
+ * overlap, the first one on ties; best_bin[i] = -1 when none.  undo_index lists fragments whose mate
+ * later failed the duplicate / QC / MAPQ filters (:279-284): their bin is decremented again.
+ * ------------------------------------------------------------------------------------------- */
+int cg_bin_hits(cg_ctx* ctx, int64_t chr_len, const uint8_t* hits, const uint64_t* possible_bits, const char* bases,
+                int bin_size, int mode, const uint8_t* read_gc, const float* obs_vs_exp_gc, int64_t max_bins,
+                int64_t* n_bins, int32_t* start, int32_t* stop, int32_t* count, uint8_t* gc);
+int cg_bin_fragments(cg_ctx* ctx, int64_t n_frag, const int32_t* frag_start, const int32_t* frag_stop, int64_t n_undo,
+                     const int32_t* undo_index, int64_t n_bins, const int32_t* bin_start, const int32_t* bin_stop,
+                     int32_t* best_bin, int32_t* count);
+
+/* ---------------------------------------------------------------------------------------------
  * Stand-alone normalise-apply stream (the kernel BASELINE.json's roofline target names):
  * count_out[i] = (float)(global_median * (double)count[i] / median_by_gc[gc[i]]) when the bucket
  * median is > 0, else count[i] (CanvasClean.cs:190-195).  `batch` independent samples of n bins laid

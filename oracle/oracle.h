@@ -34,6 +34,16 @@ int ora_clean(const ora_clean_opts* o, int64_t n, const uint8_t* chrom,
               int64_t* n_out, int32_t* kept_index, float* count_out, double* local_sd,
               int* gc_norm_skipped);
 
+/* CanvasBin counting loops (oracle/bin.cpp). possible: one byte per position. Returns the number of bins. */
+int64_t ora_bin_hits(int64_t len, const uint8_t* hits, const uint8_t* possible, const char* bases, int bin_size, int mode,
+                     const uint8_t* read_gc, const float* obs_vs_exp, int64_t max_bins, int32_t* start, int32_t* stop,
+                     int32_t* count, uint8_t* gc);
+/* flags: bit0 mapped, 1 mate mapped, 2 primary, 3 paired, 4 proper pair, 5 duplicate, 6 failed QC. Returns usableFragmentCount. */
+int64_t ora_bin_alignments(int64_t n, const uint8_t* flags, const int32_t* pos, const int32_t* mate_pos, const int32_t* ref_id,
+                           const int32_t* mate_ref_id, const int32_t* frag_len, const uint32_t* mapq, const int64_t* name_id,
+                           uint32_t quality_threshold, int64_t n_bins, const int32_t* bin_start, const int32_t* bin_stop,
+                           int32_t* count);
+
 /* float.ToString("F2") then Convert.ToDouble: the .cleaned file round trip (IO.cs:21). */
 void ora_f2_roundtrip(int64_t n, const float* in, double* out);
 

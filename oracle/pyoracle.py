@@ -221,3 +221,34 @@ def f2_roundtrip(x):
     out = np.zeros(len(x), np.float64)
     lib().ora_f2_roundtrip(C.c_int64(len(x)), _p(x, C.c_float), _p(out, C.c_double))
     return out
+
+
+def bin_hits(hits, possible, bases, bin_size, mode=0, read_gc=None, obs_vs_exp=None):
+    hits = np.ascontiguousarray(hits, np.uint8)
+    poss = np.ascontiguousarray(possible, np.uint8)
+    n = len(hits)
+    cap = n // max(bin_size, 1) + 1
+    start = np.zeros(cap, np.int32); stop = np.zeros(cap, np.int32); count = np.zeros(cap, np.int32)
+    gc = np.zeros(cap, np.uint8)
+    rgc = np.ascontiguousarray(read_gc if read_gc is not None else np.zeros(max(n, 1)), np.uint8)
+    ratio = np.ascontiguousarray(obs_vs_exp if obs_vs_exp is not None else np.ones(101), np.float32)
+    f = lib().ora_bin_hits
+    f.restype = C.c_int64
+    nb = f(C.c_int64(n), _p(hits, C.c_uint8), _p(poss, C.c_uint8), C.c_char_p(bytes(bases)), C.c_int(bin_size), C.c_int(mode),
+           _p(rgc, C.c_uint8), _p(ratio, C.c_float), C.c_int64(cap), _p(start, C.c_int32), _p(stop, C.c_int32),
+           _p(count, C.c_int32), _p(gc, C.c_uint8))
+    return {"start": start[:nb], "stop": stop[:nb], "count": count[:nb], "gc": gc[:nb]}
+
+
+def bin_alignments(flags, pos, mate_pos, ref_id, mate_ref_id, frag_len, mapq, name_id, quality_threshold, bin_start, bin_stop):
+    a = lambda x, t: np.ascontiguousarray(x, t)
+    flags = a(flags, np.uint8); pos = a(pos, np.int32); mate_pos = a(mate_pos, np.int32); ref_id = a(ref_id, np.int32)
+    mate_ref_id = a(mate_ref_id, np.int32); frag_len = a(frag_len, np.int32); mapq = a(mapq, np.uint32); name_id = a(name_id, np.int64)
+    bs = a(bin_start, np.int32); be = a(bin_stop, np.int32)
+    count = np.zeros(max(len(bs), 1), np.int32)
+    f = lib().ora_bin_alignments
+    f.restype = C.c_int64
+    usable = f(C.c_int64(len(flags)), _p(flags, C.c_uint8), _p(pos, C.c_int32), _p(mate_pos, C.c_int32), _p(ref_id, C.c_int32),
+               _p(mate_ref_id, C.c_int32), _p(frag_len, C.c_int32), _p(mapq, C.c_uint32), _p(name_id, C.c_int64),
+               C.c_uint32(quality_threshold), C.c_int64(len(bs)), _p(bs, C.c_int32), _p(be, C.c_int32), _p(count, C.c_int32))
+    return {"count": count[:len(bs)], "usable": int(usable)}
