@@ -53,7 +53,7 @@ __device__ inline unsigned long long masked_word(const unsigned long long* __res
 __global__ void bin_tile_count_kernel(const unsigned long long* __restrict__ bits, long long nwords, long long len,
                                       const BinCtl* __restrict__ ctl, unsigned* __restrict__ tile_cnt) {
     __shared__ unsigned s_w[32];
-    const unsigned long long first = ctl->first_pos;
+    const unsigned long long first = min(ctl->first_pos, (unsigned long long)len);  // all 'n': nothing is possible
     const long long w0 = (long long)blockIdx.x * BIN_TILE_WORDS;
     unsigned c = 0;
     for (int i = threadIdx.x; i < BIN_TILE_WORDS; i += blockDim.x) c += __popcll(masked_word(bits, w0 + i, nwords, first, len));
@@ -108,7 +108,7 @@ __global__ void bin_end_kernel(const unsigned long long* __restrict__ bits, long
     int lo = 0, hi = ntiles - 1;  // last tile with tile_off < target
     while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (tile_off[mid] < target) lo = mid; else hi = mid - 1; }
     unsigned long long need = target - tile_off[lo];
-    const unsigned long long first = ctl->first_pos;
+    const unsigned long long first = min(ctl->first_pos, (unsigned long long)len);
     long long w = (long long)lo * BIN_TILE_WORDS;
     unsigned long long word = 0;
     for (int i = 0; i < BIN_TILE_WORDS; i++, w++) {

@@ -59,6 +59,9 @@ SIGNATURES = {
                                              _P(_f32), _P(_u8), _P(_i64), _P(_i32), _P(_f32),
                                              _P(_f64), _P(C.c_int), _P(_i64), _P(_i32), _P(_i32),
                                              _P(_f64), _P(C.c_int), _P(_f64), _P(C.c_int), _P(_f64)]),
+    "cg_partition_cbs": (C.c_int, [C.c_void_p, C.c_void_p, _P(C.c_uint32), _i64, C.c_int, _P(_i64), _P(C.c_double), _P(_i32),
+                                   _P(_i32), _P(C.c_double), _P(_i64)]),
+    "cg_cbs_boundary": (_i64, [C.c_uint32, C.c_double, C.c_double, _P(C.c_uint32), _i64]),
     "cg_bin_hits": (C.c_int, [C.c_void_p, _i64, _P(_u8), _P(C.c_uint64), C.c_char_p, C.c_int, C.c_int, _P(_u8),
                               _P(_f32), _i64, _P(_i64), _P(_i32), _P(_i32), _P(_i32), _P(_u8)]),
     "cg_bin_fragments": (C.c_int, [C.c_void_p, _i64, _P(_i32), _P(_i32), _i64, _P(_i32), _i64, _P(_i32), _P(_i32),
@@ -117,6 +120,12 @@ class PinnedPool:
         for p in self._blocks:
             self._lib.cg_host_free(p)
         self._blocks = []
+
+
+class CbsOpts(C.Structure):
+    _fields_ = [("alpha", C.c_double), ("n_perm", C.c_uint32), ("hybrid", C.c_int), ("min_width", C.c_int), ("k_max", C.c_int),
+                ("n_min", C.c_uint32), ("eta", C.c_double), ("trim", C.c_double), ("undo", C.c_int), ("undo_prune", C.c_double),
+                ("undo_sd", C.c_double), ("seed", C.c_uint32)]
 
 
 class Engine:
@@ -283,6 +292,45 @@ class Engine:
                 "gc_norm_skipped": bool(skipped.value), "chrom_off": off, "breakpoints": bps,
                 "evenness": ev.value if ev_ok.value else None,
                 "cv": cv.value if cv_has.value else None, "factor_of_three": f3}
+
+    # ------------------------------------------------------------------ CBS segmentation
+    def cbs_boundary(self, n_perm=10000, alpha=0.01, eta=0.05):
+        key = (n_perm, alpha, eta)
+        cache = self.__dict__.setdefault("_bdry", {})
+        if key not in cache:
+            k = self.lib.cg_cbs_boundary(n_perm, alpha, eta, None, 0)
+            if k < 0:
+                raise ValueError("cg_cbs_boundary: bad arguments")
+            out = np.zeros(k, np.uint32)
+            self.lib.cg_cbs_boundary(n_perm, alpha, eta, _ptr(out, C.c_uint32), k)
+            cache[key] = out
+        return cache[key]
+
+    def partition_cbs(self, chrom_off, coverage, alpha=0.01, n_perm=10000, hybrid=True, min_width=2, k_max=25, n_min=200,
+                      eta=0.05, undo=0, seed=0, sbdry=None):
+        """CBSRunner.Run: per chromosome the segment lengths (bins) and means."""
+        off = np.ascontiguousarray(chrom_off, np.int64)
+        cov = np.ascontiguousarray(coverage, np.float64)
+        nc = len(off) - 1
+        if sbdry is None:
+            sbdry = self.cbs_boundary(n_perm, alpha, eta)
+        sbdry = np.ascontiguousarray(sbdry, np.uint32)
+        o = CbsOpts(alpha, n_perm, int(hybrid), min_width, k_max, n_min, eta, 0.025, undo, 0.05, 3.0, seed)
+        n = max(len(cov), 1)
+        n_seg = np.zeros(max(nc, 1), np.int32)
+        seg_len = np.zeros(n, np.int32)
+        seg_mean = np.zeros(n, np.float64)
+        stats = np.zeros(4, np.int64)
+        rc = self.lib.cg_partition_cbs(self.h, C.byref(o), _ptr(sbdry, C.c_uint32), len(sbdry), nc, _ptr(off, _i64),
+                                       _ptr(cov, C.c_double), _ptr(n_seg, _i32), _ptr(seg_len, _i32), _ptr(seg_mean, C.c_double),
+                                       _ptr(stats, _i64))
+        self._check(rc)
+        segs = []
+        for c in range(nc):
+            a, k = int(off[c]), int(n_seg[c])
+            segs.append({"len": seg_len[a:a + k].copy(), "mean": seg_mean[a:a + k].copy()})
+        return {"segments": segs, "tests": int(stats[0]), "perms": int(stats[1]), "perm_steps": int(stats[2]),
+                "edge_steps": int(stats[3]), "kernel_ms": self.lib.cg_last_kernel_ms(self.h)}
 
     # ------------------------------------------------------------------ CanvasBin counting
     def bin_hits(self, hits, possible, bases, bin_size, mode=0, read_gc=None, obs_vs_exp_gc=None):

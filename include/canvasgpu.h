@@ -138,6 +138,37 @@ int cg_clean_partition_wavelet(cg_ctx* ctx, const cg_clean_opts* copts, const cg
                                double* cv, int* cv_has_value, double* factor_of_three);
 
 /* ---------------------------------------------------------------------------------------------
+ * CanvasPartition -m CBS: circular binary segmentation, CBSRunner.Run (CBSRunner.cs:40-151) with
+ * ChangePoint.ChangePoints (ChangePoint.cs:44-153) per chromosome on its own MersenneTwister stream
+ * (seeds drawn from MersenneTwister(seed) in chromosome order, :107-112).  Coverage must be finite.
+ * sbdry = the sequential boundary of GetBoundary.ComputeBoundary (GetBoundary.cs:19-160); NULL makes
+ * the library compute it (cg_cbs_boundary) from n_perm, alpha, eta.  Outputs per chromosome c at
+ * chrom_off[c]: n_seg[c] segment lengths (in bins) and means (lengthSeg / segmentMeans, :140-152).
+ * stats (optional, [4]) = tests run, permutations consumed, permuted bins, edge-test draws.
+ * Supported: hybrid p-value method, undo = none, k_max <= 32, n_min <= 256 (the CanvasPartition defaults
+ * are hybrid / none / 25 / 200); anything else returns CG_ERR_UNSUPPORTED.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+    double alpha;      /* CanvasPartitionParameters.CBSalpha, 0.01 */
+    uint32_t n_perm;   /* 10000 */
+    int hybrid;        /* 1 */
+    int min_width;     /* 2 */
+    int k_max;         /* 25 */
+    uint32_t n_min;    /* 200 */
+    double eta;        /* 0.05 */
+    double trim;       /* 0.025 (only used by the sdundo method) */
+    int undo;          /* 0 none, 1 prune, 2 sdundo */
+    double undo_prune; /* 0.05 */
+    double undo_sd;    /* 3 */
+    uint32_t seed;     /* 0 = the reference's seed generator */
+} cg_cbs_opts;
+int cg_partition_cbs(cg_ctx* ctx, const cg_cbs_opts* opts, const uint32_t* sbdry, int64_t n_sbdry, int n_chrom,
+                     const int64_t* chrom_off, const double* coverage, int32_t* n_seg, int32_t* seg_len, double* seg_mean,
+                     int64_t* stats);
+/* Sequential boundary table; returns its length maxOnes (maxOnes + 1) / 2 (out may be NULL), < 0 on bad arguments. */
+int64_t cg_cbs_boundary(uint32_t n_perm, double alpha, double eta, uint32_t* out, int64_t cap);
+
+/* ---------------------------------------------------------------------------------------------
  * CanvasBin counting (BAM decoding, read pairing and FASTA handling stay on the host).
  *
  * cg_bin_hits — BinCountsForChromosome (CanvasBin.cs:568-661) for one chromosome without predefined

@@ -34,6 +34,26 @@ int ora_clean(const ora_clean_opts* o, int64_t n, const uint8_t* chrom,
               int64_t* n_out, int32_t* kept_index, float* count_out, double* local_sd,
               int* gc_norm_skipped);
 
+/* Circular binary segmentation (oracle/cbs.cpp). */
+typedef struct {
+    double alpha;      /* CanvasPartitionParameters.CBSalpha, 0.01 */
+    uint32_t n_perm;   /* 10000 */
+    int hybrid;        /* pMethod == "hybrid" */
+    int min_width;     /* 2 */
+    int k_max;         /* 25 */
+    uint32_t n_min;    /* 200 */
+    int undo;          /* 0 none (the only one restated) */
+    uint32_t seed;     /* seed of the per-chromosome seed generator; 0 in the reference */
+} ora_cbs_opts;
+int64_t ora_cbs_boundary(uint32_t n_perm, double alpha, double eta, uint32_t* out, int64_t cap);
+double ora_cbs_tailp(double b, double delta, int m);
+void ora_mt19937(uint32_t seed, int64_t n, uint32_t* out);
+double ora_cbs_tmaxo(const double* x, int n, int al0, int* seg);
+double ora_cbs_htmaxp(const double* px, int n, int k, double tss, int al0);
+int ora_partition_cbs(const ora_cbs_opts* o, const uint32_t* sbdry, int64_t n_sbdry, int n_chrom, const int64_t* chrom_off,
+                      const double* coverage, int32_t* n_seg, int32_t* seg_len, double* seg_mean, int32_t* seg_first,
+                      int32_t* seg_last, int64_t* stats);
+
 /* CanvasBin counting loops (oracle/bin.cpp). possible: one byte per position. Returns the number of bins. */
 int64_t ora_bin_hits(int64_t len, const uint8_t* hits, const uint8_t* possible, const char* bases, int bin_size, int mode,
                      const uint8_t* read_gc, const float* obs_vs_exp, int64_t max_bins, int32_t* start, int32_t* stop,

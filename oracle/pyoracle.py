@@ -252,3 +252,79 @@ def bin_alignments(flags, pos, mate_pos, ref_id, mate_ref_id, frag_len, mapq, na
                _p(mate_ref_id, C.c_int32), _p(frag_len, C.c_int32), _p(mapq, C.c_uint32), _p(name_id, C.c_int64),
                C.c_uint32(quality_threshold), C.c_int64(len(bs)), _p(bs, C.c_int32), _p(be, C.c_int32), _p(count, C.c_int32))
     return {"count": count[:len(bs)], "usable": int(usable)}
+
+
+class CbsOpts(C.Structure):
+    _fields_ = [("alpha", C.c_double), ("n_perm", C.c_uint32), ("hybrid", C.c_int), ("min_width", C.c_int), ("k_max", C.c_int),
+                ("n_min", C.c_uint32), ("undo", C.c_int), ("seed", C.c_uint32)]
+
+
+_BDRY = {}
+
+
+def cbs_boundary(n_perm=10000, alpha=0.01, eta=0.05):
+    key = (n_perm, alpha, eta)
+    if key not in _BDRY:
+        m = int(np.floor(n_perm * alpha) + 1)
+        out = np.zeros(m * (m + 1) // 2, np.uint32)
+        f = lib().ora_cbs_boundary
+        f.restype = C.c_int64
+        k = f(C.c_uint32(n_perm), C.c_double(alpha), C.c_double(eta), _p(out, C.c_uint32), C.c_int64(len(out)))
+        assert k == len(out)
+        _BDRY[key] = out
+    return _BDRY[key]
+
+
+def cbs_tailp(b, delta, m):
+    f = lib().ora_cbs_tailp
+    f.restype = C.c_double
+    return f(C.c_double(b), C.c_double(delta), C.c_int(m))
+
+
+def mt19937(seed, n):
+    out = np.zeros(n, np.uint32)
+    lib().ora_mt19937(C.c_uint32(seed), C.c_int64(n), _p(out, C.c_uint32))
+    return out
+
+
+def cbs_tmaxo(x, al0=2):
+    x = np.ascontiguousarray(x, np.float64)
+    seg = np.zeros(2, np.int32)
+    f = lib().ora_cbs_tmaxo
+    f.restype = C.c_double
+    v = f(_p(x, C.c_double), C.c_int(len(x)), C.c_int(al0), _p(seg, C.c_int32))
+    return v, int(seg[0]), int(seg[1])
+
+
+def cbs_htmaxp(px, k, tss, al0=2):
+    px = np.ascontiguousarray(px, np.float64)
+    f = lib().ora_cbs_htmaxp
+    f.restype = C.c_double
+    return f(_p(px, C.c_double), C.c_int(len(px)), C.c_int(k), C.c_double(tss), C.c_int(al0))
+
+
+def partition_cbs(chrom_off, coverage, alpha=0.01, n_perm=10000, hybrid=True, min_width=2, k_max=25, n_min=200, seed=0,
+                  sbdry=None):
+    off = np.ascontiguousarray(chrom_off, np.int64)
+    cov = np.ascontiguousarray(coverage, np.float64)
+    nc = len(off) - 1
+    n = max(len(cov), 1)
+    if sbdry is None:
+        sbdry = cbs_boundary(n_perm, alpha, 0.05)
+    sbdry = np.ascontiguousarray(sbdry, np.uint32)
+    o = CbsOpts(alpha, n_perm, int(hybrid), min_width, k_max, n_min, 0, seed)
+    n_seg = np.zeros(max(nc, 1), np.int32)
+    seg_len = np.zeros(n, np.int32); seg_mean = np.zeros(n, np.float64)
+    first = np.zeros(n, np.int32); last = np.zeros(n, np.int32)
+    stats = np.zeros(4, np.int64)
+    rc = lib().ora_partition_cbs(C.byref(o), _p(sbdry, C.c_uint32), C.c_int64(len(sbdry)), C.c_int(nc), _p(off, C.c_int64),
+                                 _p(cov, C.c_double), _p(n_seg, C.c_int32), _p(seg_len, C.c_int32), _p(seg_mean, C.c_double),
+                                 _p(first, C.c_int32), _p(last, C.c_int32), _p(stats, C.c_int64))
+    assert rc == 0
+    segs = []
+    for c in range(nc):
+        a = int(off[c]); k = int(n_seg[c])
+        segs.append({"len": seg_len[a:a + k].copy(), "mean": seg_mean[a:a + k].copy(), "first": first[a:a + k].copy(),
+                     "last": last[a:a + k].copy()})
+    return {"segments": segs, "tests": int(stats[0]), "perms": int(stats[1]), "perm_steps": int(stats[2]),
+            "edge_steps": int(stats[3])}

@@ -19,7 +19,7 @@ def _chromosome(rng, n, n_lead=1000, p_possible=0.8):
     # long unmappable stretches as well as speckle
     possible = rng.random(n) < p_possible
     for s in rng.integers(0, n, 20):
-        possible[s:s + int(rng.integers(100, 20000))] = False
+        possible[s:s + int(rng.integers(1, max(2, n // 100)))] = False
     hits = np.minimum(rng.poisson(3.0, n), 255).astype(np.uint8)
     hits[rng.integers(0, n, 50)] = 255
     return bases.tobytes(), possible, hits
@@ -71,7 +71,7 @@ def _alignments(rng, n_pairs, chr_len):
         rec.append((int(left[i]), 0, f1, int(right[i]), mref, int(tlen[i]), q1, i))
         rec.append((int(right[i]), 1, f2, int(left[i]), mref, -int(tlen[i]), q2, i))
     rec.sort(key=lambda r: (r[0], r[1]))
-    a = np.array([(r[0], r[2], r[3], r[4], r[5], r[6], r[7]) for r in rec], np.int64)
+    a = np.array([(r[0], r[2], r[3], r[4], r[5], r[6], r[7]) for r in rec], np.int64).reshape(-1, 7)
     return dict(pos=a[:, 0], flags=binning.flags_from_sam(a[:, 1]), mate_pos=a[:, 2], ref_id=np.zeros(len(a), np.int64),
                 mate_ref_id=a[:, 3], frag_len=a[:, 4], mapq=a[:, 5], name_id=a[:, 6], names=[names[j] for j in a[:, 6]])
 
