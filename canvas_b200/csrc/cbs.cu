@@ -33,7 +33,6 @@ constexpr int CBS_TILE = 2048;        // doubles staged per step of a sequential
 constexpr int CBS_KMAX = 32;          // largest supported k_max (arc length of the hybrid statistic)
 constexpr int CBS_NMIN_MAX = 256;     // largest supported n_min (segments up to this size use the full permuted search)
 constexpr int CBS_NB_SMALL = 16;      // round(sqrt(256))
-constexpr int CBS_U = 8;              // shuffle steps in flight per thread
 
 struct CbsOpts {
     double alpha;
@@ -74,6 +73,7 @@ struct CbsCtl {
     double xbar, t_ostat, rm1;
     int t_mode, t_m1, t_nrej, pad2;
     long long st_tests, st_perms, st_steps, st_edge;
+    long long ph[8];  // ns per phase: 0 passes, 1 observed search, 2 tail p, 3 stream, 4 shuffle+statistic, 5 edge tests, 6 total
     double tailp_term[128];
 };
 
@@ -101,6 +101,7 @@ struct CbsParams {
     int* seg_len;     // at chrom_off
     double* seg_mean;
     long long* stats;  // [n_chrom][4]
+    long long* phase_ns;  // [n_chrom][8]
 };
 
 struct Grp {
@@ -118,6 +119,20 @@ struct Grp {
         __threadfence();  // acquire side: later plain loads must not be served from a stale L1 line
     }
 };
+
+__device__ inline long long gtime() {
+    long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+#define CBS_PHASE(ctl, G, k, t0)                       \
+    do {                                               \
+        if ((G).rank == 0) {                           \
+            const long long now__ = gtime();           \
+            (ctl)->ph[k] += now__ - (t0);              \
+            (t0) = now__;                              \
+        }                                              \
+    } while (0)
 
 __device__ inline double ldd(const double* p) { return __ldcg(p); }
 __device__ inline int ldi(const int* p) { return __ldcg(p); }
@@ -153,9 +168,11 @@ __device__ void mt_ensure(MtShared& m, const CbsScratch& S, unsigned long long n
     CbsCtl* ctl = S.ctl;
     unsigned long long pos = vol(&ctl->gen_pos);
     const int t = threadIdx.x;
+    int cur = m.cur;
+    __syncthreads();
     while (pos < need) {
-        const unsigned* o = m.s[m.cur];
-        unsigned* w = m.s[m.cur ^ 1];
+        const unsigned* o = m.s[cur];
+        unsigned* w = m.s[cur ^ 1];
         if (t < 227) {
             const unsigned v = o[t + 397] ^ mt_mix(o[t], o[t + 1]);
             w[t] = v;
@@ -176,11 +193,11 @@ __device__ void mt_ensure(MtShared& m, const CbsScratch& S, unsigned long long n
             S.ring[(unsigned)((pos + k) & S.ring_mask)] = mt_temper(v);
         }
         __syncthreads();
-        if (t == 0) m.cur ^= 1;
+        cur ^= 1;
         pos += 624;
-        __syncthreads();
     }
-    if (t == 0) ctl->gen_pos = pos;
+    if (t == 0) { ctl->gen_pos = pos; m.cur = cur; }
+    __syncthreads();
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -438,17 +455,35 @@ __device__ void tmaxo(Grp& G, const CbsScratch& S, const CbsOpts& o, int n) {
 // ---------------------------------------------------------------------------------------------
 __device__ inline double dev_pnorm(double x) { return 0.5 * erfc(-x / sqrt(2.0)); }
 
-__device__ double dev_nu(double x, double tol) {
+// Nu (TailProbability.cs:46-82): the series is summed chunk by chunk (2, 2, 4, 8, ... terms, the reference's
+// convergence checkpoints); a warp computes the terms of a chunk in parallel.
+__device__ double warp_nu(double x, double tol, int lane) {
     double l1;
     if (x > 0.01) {
         l1 = log(2.0) - 2 * log(x);
-        double l0 = l1, dk = 0;
+        double l0;
+        long long done = 0;
         int k = 2;
-        for (int i = 0; i < k; i++) { dk += 1; l1 -= 2.0 * dev_pnorm(-x * sqrt(dk) / 2.0) / dk; }
-        while (fabs((l1 - l0) / l1) > tol) {
+        bool first = true;
+        while (true) {
             l0 = l1;
-            for (int i = 0; i < k; i++) { dk += 1; l1 -= 2.0 * dev_pnorm(-x * sqrt(dk) / 2.0) / dk; }
-            k *= 2;
+            double part = 0.0;
+            for (long long q = lane; q < k; q += 32) {
+                const double dk = (double)(done + q + 1);
+                part += 2.0 * dev_pnorm(-x * sqrt(dk) / 2.0) / dk;
+            }
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) part += __shfl_xor_sync(0xffffffffu, part, d);
+            l1 -= part;
+            done += k;
+            if (!first) k *= 2;
+            if (!first && !(fabs((l1 - l0) / l1) > tol)) break;
+            if (first) {
+                first = false;
+                // after the initial two terms the reference enters the while loop only if the test holds
+                // against lnu0 = the value before them
+                if (!(fabs((l1 - l0) / l1) > tol)) break;
+            }
         }
     } else {
         l1 = -0.583 * x;
@@ -464,25 +499,25 @@ __device__ double dev_integral(double x, double a) {
     return v;
 }
 
-// CTA 0
-__device__ void tailp_cta(CbsCtl* ctl, double b, double delta, int m) {
-    const int t = threadIdx.x;
+// whole group; the caller syncs afterwards and rank 0 adds the terms up in order
+__device__ void tailp_terms(Grp& G, CbsCtl* ctl, double b, double delta, int m) {
     const int ngrid = 100;
+    const int lane = threadIdx.x & 31;
+    const int warp = G.rank >> 5, nwarps = G.size >> 5;
     const double dincr = (0.5 - delta) / ngrid, bsqrtm = b / sqrt((double)m);
-    if (t < ngrid) {
+    for (int g = warp; g < ngrid; g += nwarps) {
         double tl = 0.5 - dincr, tt = 0.5 - 0.5 * dincr;
-        for (int i = 0; i <= t; i++) { tl += dincr; tt += dincr; }
-        const double v = dev_nu(bsqrtm / sqrt(tt * (1 - tt)), 1e-6);
-        ctl->tailp_term[t] = (v * v) * dev_integral(tl, dincr);
+        for (int i = 0; i <= g; i++) { tl += dincr; tt += dincr; }
+        const double v = warp_nu(bsqrtm / sqrt(tt * (1 - tt)), 1e-6, lane);
+        if (lane == 0) ctl->tailp_term[g] = (v * v) * dev_integral(tl, dincr);
     }
-    __syncthreads();
-    if (t == 0) {
-        double acc = 0.0;
-        for (int i = 0; i < ngrid; i++) acc += ctl->tailp_term[i];
-        acc = 9.973557E-2 * (b * b * b) * exp(-(b * b) / 2) * acc;
-        ctl->p1 = 2.0 * acc;
-    }
-    __syncthreads();
+}
+
+__device__ double tailp_finish(const CbsCtl* ctl, double b) {
+    double acc = 0.0;
+    for (int i = 0; i < 100; i++) acc += vol(&ctl->tailp_term[i]);
+    acc = 9.973557E-2 * (b * b * b) * exp(-(b * b) / 2) * acc;
+    return 2.0 * acc;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -490,9 +525,18 @@ __device__ void tailp_cta(CbsCtl* ctl, double b, double delta, int m) {
 // ---------------------------------------------------------------------------------------------
 __device__ inline unsigned ring_at(const CbsScratch& S, unsigned long long pos) { return __ldcg(S.ring + (unsigned)(pos & S.ring_mask)); }
 
-// XPerm (ChangePoint.cs:407-421): j = (int)(NextDouble() * (i + 1)) = (u32 * (i + 1)) >> 32 exactly
+// XPerm (ChangePoint.cs:407-421): j = (int)(NextDouble() * (i + 1)) = (u32 * (i + 1)) >> 32 exactly.
+// CBS_U steps are in flight per thread: their loads are issued together (with the next group's random
+// numbers), then the group is replayed in order on the loaded values, patching every value that an
+// earlier step of the same group has moved.
 __device__ void shuffle_column(const CbsScratch& S, double* col, int n, unsigned long long start) {
+    constexpr int CBS_U = 16;
+    unsigned rv[CBS_U];
     int t0 = 0;
+    if (n >= CBS_U) {
+#pragma unroll
+        for (int k = 0; k < CBS_U; k++) rv[k] = ring_at(S, start + k);
+    }
     for (; t0 + CBS_U <= n; t0 += CBS_U) {
         int iv[CBS_U], jv[CBS_U];
         double a[CBS_U], b[CBS_U];
@@ -500,14 +544,17 @@ __device__ void shuffle_column(const CbsScratch& S, double* col, int n, unsigned
         for (int k = 0; k < CBS_U; k++) {
             const int i = n - 1 - (t0 + k);
             iv[k] = i;
-            jv[k] = (int)(((unsigned long long)ring_at(S, start + t0 + k) * (unsigned long long)(i + 1)) >> 32);
+            jv[k] = (int)(((unsigned long long)rv[k] * (unsigned long long)(i + 1)) >> 32);
         }
 #pragma unroll
         for (int k = 0; k < CBS_U; k++) {
             a[k] = col[(size_t)iv[k] * CBS_PT];
             b[k] = col[(size_t)jv[k] * CBS_PT];
         }
-        // replay the group in order on the loaded values
+        if (t0 + 2 * CBS_U <= n) {
+#pragma unroll
+            for (int k = 0; k < CBS_U; k++) rv[k] = ring_at(S, start + t0 + CBS_U + k);
+        }
 #pragma unroll
         for (int k = 0; k < CBS_U; k++) {
             double av = a[k];
@@ -541,7 +588,11 @@ __device__ void shuffle_column(const CbsScratch& S, double* col, int n, unsigned
 // pruning of the reference never changes the maximum (its bounds hold exactly in floating point), so
 // the arcs are simply enumerated: M[j] = max_p |S_p - S_{p-j}|, p - j >= 1.  The running sums of the last
 // K positions rotate through registers; the ring starts as NaN so that arcs reaching before S_1 drop out.
-template <int K, int AL0, bool CHECK>
+// Four threads share one permutation: each of them runs the (identical) running sum and owns every
+// fourth arc length.
+constexpr int CBS_PARTS = CBS_THREADS / CBS_PT;
+
+template <int K, int AL0, int PART, bool CHECK>
 __device__ __forceinline__ void ht_group(const double* col, int p, int n, int k, int al0, double& run, double (&M)[K + 1], double (&h)[K],
                                          double* first, double* last) {
 #pragma unroll
@@ -550,11 +601,12 @@ __device__ __forceinline__ void ht_group(const double* col, int p, int n, int k,
             run += col[(size_t)(p + q - 1) * CBS_PT];
 #pragma unroll
             for (int j = 2; j <= K; j++) {
+                if ((j & (CBS_PARTS - 1)) != PART) continue;
                 const bool on = AL0 > 0 ? (j >= AL0) : (j >= al0 && j <= k);
                 if (on) M[j] = fmax(M[j], fabs(run - h[(q - j + 2 * K) % K]));
             }
             h[q] = run;
-            if (CHECK) {
+            if (CHECK && PART == 0) {
                 if (p + q <= k) first[(p + q) * CBS_PT] = run;
                 if (p + q > n - k) last[(p + q - (n - k)) * CBS_PT] = run;
             }
@@ -562,8 +614,9 @@ __device__ __forceinline__ void ht_group(const double* col, int p, int n, int k,
     }
 }
 
-template <int K, int AL0>
-__device__ double htmaxp_column(const double* col, int n, int k, int al0, double tss, double* first, double* last) {
+// called by all threads of the CTA (barrier inside); returns the largest c_j * M_j^2 over the thread's arc lengths
+template <int K, int AL0, int PART>
+__device__ double htmaxp_part(const double* col, bool active, int n, int k, int al0, double* first, double* last) {
     const double rn = (double)n;
     double M[K + 1];
     double h[K];
@@ -571,25 +624,40 @@ __device__ double htmaxp_column(const double* col, int n, int k, int al0, double
     for (int j = 0; j <= K; j++) M[j] = 0.0;
 #pragma unroll
     for (int q = 0; q < K; q++) h[q] = __longlong_as_double(0x7ff8000000000000ll);
-    double run = 0.0;
-    int p = 1;
-    ht_group<K, AL0, true>(col, p, n, k, al0, run, M, h, first, last);
-    p += K;
-    for (; p + K - 1 <= n - k; p += K) ht_group<K, AL0, false>(col, p, n, k, al0, run, M, h, first, last);
-    for (; p <= n; p += K) ht_group<K, AL0, true>(col, p, n, k, al0, run, M, h, first, last);
+    if (active) {
+        double run = 0.0;
+        int p = 1;
+        ht_group<K, AL0, PART, true>(col, p, n, k, al0, run, M, h, first, last);
+        p += K;
+        for (; p + K - 1 <= n - k; p += K) ht_group<K, AL0, PART, false>(col, p, n, k, al0, run, M, h, first, last);
+        for (; p <= n; p += K) ht_group<K, AL0, PART, true>(col, p, n, k, al0, run, M, h, first, last);
+    }
+    __syncthreads();
     double best = 0.0;
+    if (active) {
 #pragma unroll
-    for (int j = 2; j <= K; j++) {
-        const bool on = AL0 > 0 ? (j >= AL0) : (j >= al0 && j <= k);
-        if (on) {
-            double mx = M[j];
-            // arcs through the end (CBSTStatistic.cs:459-485): |S_{n-j+i} - S_i|, i = 1..j
-            for (int i = 1; i <= j; i++) mx = fmax(mx, fabs(last[(k - j + i) * CBS_PT] - first[i * CBS_PT]));
-            best = fmax(best, arc_scale(rn, (double)j) * (mx * mx));
+        for (int j = 2; j <= K; j++) {
+            if ((j & (CBS_PARTS - 1)) != PART) continue;
+            const bool on = AL0 > 0 ? (j >= AL0) : (j >= al0 && j <= k);
+            if (on) {
+                double mx = M[j];
+                // arcs through the end (CBSTStatistic.cs:459-485): |S_{n-j+i} - S_i|, i = 1..j
+                for (int i = 1; i <= j; i++) mx = fmax(mx, fabs(last[(k - j + i) * CBS_PT] - first[i * CBS_PT]));
+                best = fmax(best, arc_scale(rn, (double)j) * (mx * mx));
+            }
         }
     }
-    if (tss <= best + 0.0001) tss = best + 1.0;
-    return best / ((tss - best) / (rn - 2.0));
+    return best;
+}
+
+template <int K, int AL0>
+__device__ double htmaxp_parts(int part, const double* col, bool active, int n, int k, int al0, double* first, double* last) {
+    switch (part) {
+        case 0: return htmaxp_part<K, AL0, 0>(col, active, n, k, al0, first, last);
+        case 1: return htmaxp_part<K, AL0, 1>(col, active, n, k, al0, first, last);
+        case 2: return htmaxp_part<K, AL0, 2>(col, active, n, k, al0, first, last);
+        default: return htmaxp_part<K, AL0, 3>(col, active, n, k, al0, first, last);
+    }
 }
 
 // TMaxP for the short segments (n <= n_min): the full search on the permuted column, which is turned into its
@@ -733,7 +801,7 @@ __device__ int tp_run_block(const CbsScratch& S, const TpBlock& B, int H, int n1
 
 union CbsShared {
     SeqShared seq;
-    struct { double first[(CBS_KMAX + 1) * CBS_PT]; double last[(CBS_KMAX + 1) * CBS_PT]; } ht;
+    struct { double first[(CBS_KMAX + 1) * CBS_PT]; double last[(CBS_KMAX + 1) * CBS_PT]; double part[CBS_THREADS]; } ht;
 };
 
 // group-wide; result in ctl->t_nrej (count of permutations at least as extreme), p = t_nrej / n_perm
@@ -867,64 +935,89 @@ __device__ void find_change_points(Grp& G, const CbsScratch& S, const CbsParams&
     CbsCtl* ctl = S.ctl;
     const CbsOpts& o = P.o;
     const int t = threadIdx.x;
+    long long tph = gtime();
     tmaxo(G, S, o, n);
+    CBS_PHASE(ctl, G, 1, tph);
     const bool hybrid = o.n_min < (unsigned)n;
-    if (G.cta == 0) {
-        // 0 = no change point, 1 = permutations needed, 2 = split without permutations
-        if (t == 0) {
-            const double ostat1 = sqrt(ctl->ostat);
-            const int l = min(ctl->seg1 - ctl->seg0, n - ctl->seg1 + ctl->seg0);
-            int verdict;
-            if (ostat1 <= 0.1) verdict = 0;
-            else if (ostat1 >= 7.0 && l >= 10) verdict = 2;
-            else verdict = 1;
-            ctl->verdict = verdict;
-            ctl->st_tests++;
+    // 0 = no change point, 1 = permutations needed, 2 = split without permutations
+    if (G.rank == 0) {
+        const double ostat1 = sqrt(ctl->ostat);
+        const int l = min(ctl->seg1 - ctl->seg0, n - ctl->seg1 + ctl->seg0);
+        int verdict;
+        if (ostat1 <= 0.1) verdict = 0;
+        else if (ostat1 >= 7.0 && l >= 10) verdict = 2;
+        else verdict = 1;
+        ctl->verdict = verdict;
+        ctl->st_tests++;
+    }
+    G.sync();
+    if (vol(&ctl->verdict) == 1) {
+        const double ostat1 = sqrt(vol(&ctl->ostat));
+        if (hybrid) {
+            tailp_terms(G, ctl, ostat1, (o.k_max + 1.0) / n, n);
+            G.sync();
         }
-        __syncthreads();
-        if (ctl->verdict == 1) {
+        if (G.rank == 0) {
+            int nrejc;
             if (hybrid) {
-                const double delta = (o.k_max + 1.0) / n;
-                tailp_cta(ctl, sqrt(ctl->ostat), delta, n);
+                const double p1 = tailp_finish(ctl, ostat1);
+                ctl->p1 = p1;
+                if (p1 > o.alpha) ctl->verdict = 0;
+                nrejc = (int)((o.alpha - p1) * o.n_perm);
+            } else {
+                nrejc = (int)(o.alpha * o.n_perm);
             }
-            if (t == 0) {
-                int nrejc;
-                if (hybrid) {
-                    if (ctl->p1 > o.alpha) ctl->verdict = 0;
-                    nrejc = (int)((o.alpha - ctl->p1) * o.n_perm);
-                } else {
-                    nrejc = (int)(o.alpha * o.n_perm);
-                }
-                ctl->nrejc = nrejc;
-                ctl->kk = nrejc * (nrejc + 1) / 2 + 1;
-                ctl->nrej = 0;
-                ctl->np_done = 0;
-            }
+            ctl->nrejc = nrejc;
+            ctl->kk = nrejc * (nrejc + 1) / 2 + 1;
+            ctl->nrej = 0;
+            ctl->np_done = 0;
         }
     }
     G.sync();
+    CBS_PHASE(ctl, G, 2, tph);
     const double ostat = vol(&ctl->ostat) * 0.99999;
     const double tss = vol(&ctl->tss);
     const int batch = CBS_PT * (int)G.nctas;
+    // Every batch is the cluster's full capacity: a batch costs the same time whatever its size (the shuffle is
+    // bound by per-SM sector bandwidth and latency), so smaller first batches only add rounds (measured).
+    int grow = batch;
     while (vol(&ctl->verdict) == 1) {
         const int np_done = vol(&ctl->np_done);
-        const int nb = min(batch, (int)o.n_perm - np_done);
+        const int nb = min(grow, (int)o.n_perm - np_done);
+        grow = min(batch, grow * 2);
         const unsigned long long ubase = vol(&ctl->use_pos);
         if (G.cta == 0) mt_ensure(mt, S, ubase + (unsigned long long)nb * n);
         G.sync();
-        const int b = (int)G.cta * CBS_PT + t;
-        if (t < CBS_PT && b < nb) {
-            double* col = S.px + (size_t)G.cta * CBS_PT * S.n_alloc + t;
-            for (int i = 0; i < n; i++) col[(size_t)i * CBS_PT] = ldd(S.cur + i);
-            shuffle_column(S, col, n, ubase + (unsigned long long)b * n);
-            double ps;
-            if (hybrid) {
-                if (o.k_max == 25 && o.min_width == 2) ps = htmaxp_column<25, 2>(col, n, 25, 2, tss, sh.ht.first + t, sh.ht.last + t);
-                else ps = htmaxp_column<CBS_KMAX, 0>(col, n, o.k_max, o.min_width, tss, sh.ht.first + t, sh.ht.last + t);
-            } else {
-                ps = tmaxp_column(col, n, o.min_width, tss);
+        CBS_PHASE(ctl, G, 3, tph);
+        {
+            const int pt = t & (CBS_PT - 1), part = t / CBS_PT;
+            const int b = pt * (int)G.nctas + (int)G.cta;  // permutation b of the batch: spread over the CTAs
+            const bool active = b < nb;
+            double* col = S.px + (size_t)G.cta * CBS_PT * S.n_alloc + pt;
+            if (active)
+                for (int i = part; i < n; i += CBS_PARTS) col[(size_t)i * CBS_PT] = ldd(S.cur + i);
+            __syncthreads();
+            if (active && part == 0) {
+                const long long ts0 = gtime();
+                shuffle_column(S, col, n, ubase + (unsigned long long)b * n);
+                if (G.rank == 0) ctl->ph[7] += gtime() - ts0;
             }
-            S.pstat[b] = ps;
+            __syncthreads();
+            if (hybrid) {
+                double best;
+                if (o.k_max == 25 && o.min_width == 2) best = htmaxp_parts<25, 2>(part, col, active, n, 25, 2, sh.ht.first + pt, sh.ht.last + pt);
+                else best = htmaxp_parts<CBS_KMAX, 0>(part, col, active, n, o.k_max, o.min_width, sh.ht.first + pt, sh.ht.last + pt);
+                sh.ht.part[t] = best;
+                __syncthreads();
+                if (active && part == 0) {
+                    for (int r = 1; r < CBS_PARTS; r++) best = fmax(best, sh.ht.part[r * CBS_PT + pt]);
+                    double ts = tss;
+                    if (ts <= best + 0.0001) ts = best + 1.0;
+                    S.pstat[b] = best / ((ts - best) / ((double)n - 2.0));
+                }
+            } else if (active && part == 0) {
+                S.pstat[b] = tmaxp_column(col, n, o.min_width, tss);
+            }
         }
         G.sync();
         if (G.rank == 0) {
@@ -944,6 +1037,7 @@ __device__ void find_change_points(Grp& G, const CbsScratch& S, const CbsParams&
             ctl->st_steps += (long long)consumed * n;
         }
         G.sync();
+        CBS_PHASE(ctl, G, 4, tph);
     }
     if (vol(&ctl->verdict) == 0) {
         if (G.rank == 0) ctl->ncp = 0;
@@ -968,6 +1062,7 @@ __device__ void find_change_points(Grp& G, const CbsScratch& S, const CbsParams&
     G.sync();
     if (G.rank == 0) { ctl->ncp = ncp; ctl->cp[0] = cp0; ctl->cp[1] = cp1; }
     G.sync();
+    CBS_PHASE(ctl, G, 5, tph);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -991,10 +1086,13 @@ __device__ void run_chromosome(Grp& G, const CbsScratch& S, const CbsParams& P, 
             ctl->sp = 2;
             ctl->nloc = 0;
             ctl->st_tests = ctl->st_perms = ctl->st_steps = ctl->st_edge = 0;
+            for (int k = 0; k < 8; k++) ctl->ph[k] = 0;
         }
         __syncthreads();
     }
     G.sync();
+    long long tph = gtime();
+    const long long tstart = tph;
     while (true) {
         const int sp = vol(&ctl->sp);
         if (sp <= 1) break;
@@ -1006,7 +1104,9 @@ __device__ void run_chromosome(Grp& G, const CbsScratch& S, const CbsParams& P, 
             if (!vol(&ctl->same)) {
                 if (G.cta == 0) pass_centre(sh.seq, g + a, cn, vol(&ctl->avg), S.cur, S.sx, ctl);
                 G.sync();
+                CBS_PHASE(ctl, G, 0, tph);
                 find_change_points(G, S, P, sh, mt, cn);
+                tph = gtime();
                 tested = true;
             }
         }
@@ -1041,6 +1141,8 @@ __device__ void run_chromosome(Grp& G, const CbsScratch& S, const CbsParams& P, 
         P.stats[w.chrom * 4 + 1] = ctl->st_perms;
         P.stats[w.chrom * 4 + 2] = ctl->st_steps;
         P.stats[w.chrom * 4 + 3] = ctl->st_edge;
+        ctl->ph[6] = gtime() - tstart;
+        for (int k = 0; k < 8; k++) P.phase_ns[w.chrom * 8 + k] = ctl->ph[k];
     }
     G.sync();
 }
@@ -1238,7 +1340,7 @@ extern "C" int cg_partition_cbs(cg_ctx* ctx, const cg_cbs_opts* o, const uint32_
     struct Sizes { size_t n, nb, nb2, ring; };
     std::vector<Sizes> sz(nclusters);
     size_t need = arena_need(N, 8) + arena_need(nwork, sizeof(CbsWork)) + arena_need(n_sbdry, 4) + arena_need(nclusters, sizeof(CbsScratch)) +
-                  arena_need(n_chrom, 4) + arena_need(N, 4) + arena_need(N, 8) + arena_need((size_t)n_chrom * 4, 8) + 4096;
+                  arena_need(n_chrom, 4) + arena_need(N, 4) + arena_need(N, 8) + arena_need((size_t)n_chrom * 4, 8) + arena_need((size_t)n_chrom * 8, 8) + 4096;
     for (int k = 0; k < nclusters; k++) {
         const size_t n = (size_t)work[k].n;
         size_t nb = (size_t)std::llround(std::sqrt((double)n)) + 2;
@@ -1260,8 +1362,9 @@ extern "C" int cg_partition_cbs(cg_ctx* ctx, const cg_cbs_opts* o, const uint32_
     double* d_mean = arena_take<double>(ctx, N);
     long long* d_stats = arena_take<long long>(ctx, (size_t)n_chrom * 4);
     int* d_queue = arena_take<int>(ctx, 64);
+    long long* d_phase = arena_take<long long>(ctx, (size_t)n_chrom * 8);
     std::vector<CbsScratch> scr(nclusters);
-    bool ok = d_cov && d_work && d_sb && d_scr && d_nseg && d_len && d_mean && d_stats && d_queue;
+    bool ok = d_cov && d_work && d_sb && d_scr && d_nseg && d_len && d_mean && d_stats && d_queue && d_phase;
     for (int k = 0; k < nclusters && ok; k++) {
         CbsScratch& s = scr[k];
         const Sizes& z = sz[k];
@@ -1296,10 +1399,11 @@ extern "C" int cg_partition_cbs(cg_ctx* ctx, const cg_cbs_opts* o, const uint32_
     CG_CUDA(ctx, cudaMemsetAsync(d_nseg, 0, n_chrom * 4, st));
     CG_CUDA(ctx, cudaMemsetAsync(d_stats, 0, (size_t)n_chrom * 32, st));
     CG_CUDA(ctx, cudaMemsetAsync(d_queue, 0, 256, st));
+    CG_CUDA(ctx, cudaMemsetAsync(d_phase, 0, (size_t)n_chrom * 64, st));
     CbsParams P;
     P.o = CbsOpts{o->alpha, o->n_perm, o->min_width, o->k_max, o->n_min};
     P.cov = d_cov; P.work = d_work; P.nwork = nwork; P.queue = d_queue; P.sbdry = d_sb; P.scratch = d_scr;
-    P.n_seg = d_nseg; P.seg_len = d_len; P.seg_mean = d_mean; P.stats = d_stats;
+    P.n_seg = d_nseg; P.seg_len = d_len; P.seg_mean = d_mean; P.stats = d_stats; P.phase_ns = d_phase;
     CG_CUDA(ctx, cudaEventRecord(ctx->ev0, st));
     {
         cudaLaunchConfig_t cfg = {};
@@ -1322,11 +1426,21 @@ extern "C" int cg_partition_cbs(cg_ctx* ctx, const cg_cbs_opts* o, const uint32_
     CG_CUDA(ctx, cudaMemcpyAsync(seg_len, d_len, N * 4, cudaMemcpyDeviceToHost, st));
     CG_CUDA(ctx, cudaMemcpyAsync(seg_mean, d_mean, N * 8, cudaMemcpyDeviceToHost, st));
     CG_CUDA(ctx, cudaMemcpyAsync(h_stats.data(), d_stats, (size_t)n_chrom * 32, cudaMemcpyDeviceToHost, st));
+    std::vector<long long> h_phase((size_t)n_chrom * 8);
+    CG_CUDA(ctx, cudaMemcpyAsync(h_phase.data(), d_phase, (size_t)n_chrom * 64, cudaMemcpyDeviceToHost, st));
     CG_CUDA(ctx, cudaStreamSynchronize(st));
     CG_CUDA(ctx, cudaGetLastError());
     float ms = 0;
     cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
     ctx->last_kernel_ms = ms;
+    {
+        // phase times (ms) of the chromosome that took longest: cg_last_partition_stats slots 0..6
+        int worst = 0;
+        for (int c = 0; c < n_chrom; c++)
+            if (h_phase[(size_t)c * 8 + 6] > h_phase[(size_t)worst * 8 + 6]) worst = c;
+        for (int k = 0; k < 8; k++) ctx->stats[k] = (double)h_phase[(size_t)worst * 8 + k] * 1e-6;
+        ctx->stats[8] = worst;
+    }
     if (stats) {
         stats[0] = stats[1] = stats[2] = stats[3] = 0;
         for (int c = 0; c < n_chrom; c++)

@@ -330,7 +330,17 @@ class Engine:
             a, k = int(off[c]), int(n_seg[c])
             segs.append({"len": seg_len[a:a + k].copy(), "mean": seg_mean[a:a + k].copy()})
         return {"segments": segs, "tests": int(stats[0]), "perms": int(stats[1]), "perm_steps": int(stats[2]),
-                "edge_steps": int(stats[3]), "kernel_ms": self.lib.cg_last_kernel_ms(self.h)}
+                "edge_steps": int(stats[3]), "kernel_ms": self.lib.cg_last_kernel_ms(self.h), "phase_ms": self._cbs_phases()}
+
+    def _cbs_phases(self):
+        """Phase times (ms) of the slowest chromosome of the last cg_partition_cbs call."""
+        out = np.zeros(16, np.float64)
+        self.lib.cg_last_partition_stats(self.h, _ptr(out, _f64), 16)
+        names = ("passes", "observed", "tailp", "stream", "perms", "edge", "total")
+        d = {k: round(float(out[i]), 3) for i, k in enumerate(names)}
+        d["shuffle"] = round(float(out[7]), 3)
+        d["chrom"] = int(out[8])
+        return d
 
     # ------------------------------------------------------------------ CanvasBin counting
     def bin_hits(self, hits, possible, bases, bin_size, mode=0, read_gc=None, obs_vs_exp_gc=None):

@@ -12,6 +12,8 @@
 // int32 * 2^-32, NextFullRangeInt32 = the raw 32-bit draw), Normal CDF (0.5 erfc(-x/sqrt 2)), BinomialLn
 // (lgamma), R's phyper (direct summation of the mass function).
 #include <algorithm>
+#include <atomic>
+#include <thread>
 #include <cmath>
 #include <cstdint>
 #include <cstring>
@@ -517,22 +519,23 @@ extern "C" double ora_cbs_htmaxp(const double* px, int n, int k, double tss, int
 // finite-value index list (:122-138).  stats[0..3] = tests, permutations, permuted bins, edge-test bins.
 extern "C" int ora_partition_cbs(const ora_cbs_opts* o, const uint32_t* sbdry, int64_t n_sbdry, int n_chrom, const int64_t* chrom_off,
                                  const double* coverage, int32_t* n_seg, int32_t* seg_len, double* seg_mean, int32_t* seg_first,
-                                 int32_t* seg_last, int64_t* stats) {
+                                 int32_t* seg_last, int64_t* stats, int n_threads) {
     if (o->undo != 0) return -4;  // prune / sdundo are not restated
     std::vector<uint32_t> sb(sbdry, sbdry + n_sbdry);
     Mt seeder(o->seed);
-    CbsStats st;
-    for (int c = 0; c < n_chrom; c++) {
-        const uint32_t chrom_seed = seeder.u32();  // NextFullRangeInt32 -> MersenneTwister(int)
+    std::vector<uint32_t> seeds(n_chrom);
+    for (int c = 0; c < n_chrom; c++) seeds[c] = seeder.u32();  // NextFullRangeInt32 -> MersenneTwister(int)
+    std::vector<CbsStats> st(n_chrom);
+    auto one = [&](int c) {
         const double* g = coverage + chrom_off[c];
         const int n = (int)(chrom_off[c + 1] - chrom_off[c]);
         n_seg[c] = 0;
         std::vector<int> ina;
         for (int i = 0; i < n; i++)
             if (std::isfinite(g[i])) ina.push_back(i);
-        if (n == 0) continue;
-        Mt rnd(chrom_seed);
-        std::vector<int> len = change_points(g, n, *o, sb, rnd, st);
+        if (n == 0) return;
+        Mt rnd(seeds[c]);
+        std::vector<int> len = change_points(g, n, *o, sb, rnd, st[c]);
         int lo = 0, cs1 = 0, cs2 = -1;
         for (size_t i = 0; i < len.size(); i++) {
             cs2 += len[i];
@@ -547,7 +550,22 @@ extern "C" int ora_partition_cbs(const ora_cbs_opts* o, const uint32_t* sbdry, i
             lo += len[i];
         }
         n_seg[c] = (int)len.size();
+    };
+    // chromosomes are independent tasks (Parallel.ForEach, CBSRunner.cs:149); largest first
+    std::vector<int> order(n_chrom);
+    std::iota(order.begin(), order.end(), 0);
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return chrom_off[a + 1] - chrom_off[a] > chrom_off[b + 1] - chrom_off[b]; });
+    std::atomic<int> next{0};
+    auto worker = [&]() { for (int k; (k = next.fetch_add(1)) < n_chrom;) one(order[k]); };
+    if (n_threads <= 1) worker();
+    else {
+        std::vector<std::thread> pool;
+        for (int t = 0; t < n_threads; t++) pool.emplace_back(worker);
+        for (auto& th : pool) th.join();
     }
-    if (stats) { stats[0] = st.tests; stats[1] = st.perms; stats[2] = st.perm_steps; stats[3] = st.edge_steps; }
+    if (stats) {
+        stats[0] = stats[1] = stats[2] = stats[3] = 0;
+        for (auto& s : st) { stats[0] += s.tests; stats[1] += s.perms; stats[2] += s.perm_steps; stats[3] += s.edge_steps; }
+    }
     return 0;
 }

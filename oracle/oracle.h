@@ -52,7 +52,7 @@ double ora_cbs_tmaxo(const double* x, int n, int al0, int* seg);
 double ora_cbs_htmaxp(const double* px, int n, int k, double tss, int al0);
 int ora_partition_cbs(const ora_cbs_opts* o, const uint32_t* sbdry, int64_t n_sbdry, int n_chrom, const int64_t* chrom_off,
                       const double* coverage, int32_t* n_seg, int32_t* seg_len, double* seg_mean, int32_t* seg_first,
-                      int32_t* seg_last, int64_t* stats);
+                      int32_t* seg_last, int64_t* stats, int n_threads);
 
 /* CanvasBin counting loops (oracle/bin.cpp). possible: one byte per position. Returns the number of bins. */
 int64_t ora_bin_hits(int64_t len, const uint8_t* hits, const uint8_t* possible, const char* bases, int bin_size, int mode,

@@ -304,7 +304,7 @@ def cbs_htmaxp(px, k, tss, al0=2):
 
 
 def partition_cbs(chrom_off, coverage, alpha=0.01, n_perm=10000, hybrid=True, min_width=2, k_max=25, n_min=200, seed=0,
-                  sbdry=None):
+                  sbdry=None, n_threads=1):
     off = np.ascontiguousarray(chrom_off, np.int64)
     cov = np.ascontiguousarray(coverage, np.float64)
     nc = len(off) - 1
@@ -319,7 +319,7 @@ def partition_cbs(chrom_off, coverage, alpha=0.01, n_perm=10000, hybrid=True, mi
     stats = np.zeros(4, np.int64)
     rc = lib().ora_partition_cbs(C.byref(o), _p(sbdry, C.c_uint32), C.c_int64(len(sbdry)), C.c_int(nc), _p(off, C.c_int64),
                                  _p(cov, C.c_double), _p(n_seg, C.c_int32), _p(seg_len, C.c_int32), _p(seg_mean, C.c_double),
-                                 _p(first, C.c_int32), _p(last, C.c_int32), _p(stats, C.c_int64))
+                                 _p(first, C.c_int32), _p(last, C.c_int32), _p(stats, C.c_int64), C.c_int(n_threads))
     assert rc == 0
     segs = []
     for c in range(nc):
