@@ -1,5 +1,6 @@
 // cg_clean: CanvasClean's numeric block on the device (reference CanvasClean.cs:474-530).
 #include "clean.cuh"
+#include "clean_loess.cuh"
 
 // ---------------------------------------------------------------------------------------------
 // Views for the select engine
@@ -531,7 +532,7 @@ struct EmitOut {
 // ---------------------------------------------------------------------------------------------
 // Device-side pipeline (shared by cg_clean and cg_clean_partition_wavelet)
 // ---------------------------------------------------------------------------------------------
-size_t clean_workspace_bytes(int64_t n, int n_chrom) {
+size_t clean_workspace_bytes(int64_t n, int n_chrom, bool loess) {
     size_t s = 0;
     s += arena_need(n, 1) * 2 + arena_need(n, 4) * 3;          // inputs
     s += arena_need(n, 1) * 2 + arena_need(n, 4) * 2;          // L1
@@ -539,12 +540,13 @@ size_t clean_workspace_bytes(int64_t n, int n_chrom) {
     s += arena_need(n / LOCAL_SD_WINDOW + 2, 8) + arena_need(n / LOCAL_SD_WINDOW + 2, 1);
     s += arena_need(n, 4) * 2;                                  // outputs
     s += arena_need(n / CMP_TILE + 2, 4);
-    s += arena_need(1, sizeof(CleanCtl)) + arena_need(256, 1) + arena_need(256, 4) + arena_need(256, 8) * 2;
+    s += arena_need(1, sizeof(CleanCtl)) + arena_need(256, 1) * 2 + arena_need(256, 4) + arena_need(256, 8) * 2;
     s += sel_state_bytes<uint32_t>(1) + sel_state_bytes<uint32_t>(GC_SEGS) + sel_state_bytes<uint64_t>(std::max(n_chrom, 1));
+    if (loess) s += loess_workspace_bytes(n);
     return s + (1 << 16);
 }
 
-int clean_alloc(cg_ctx* ctx, int64_t n, int n_chrom, CleanDev& d) {
+int clean_alloc(cg_ctx* ctx, int64_t n, int n_chrom, CleanDev& d, bool loess) {
     d.n = n;
     d.n_chrom = n_chrom;
     d.chrom = arena_take<uint8_t>(ctx, n);
@@ -568,14 +570,20 @@ int clean_alloc(cg_ctx* ctx, int64_t n, int n_chrom, CleanDev& d) {
     d.tiles = arena_take<int>(ctx, n / CMP_TILE + 2);
     d.ctl = arena_take<CleanCtl>(ctx, 1);
     d.is_auto = arena_take<uint8_t>(ctx, 256);
+    d.is_chry = arena_take<uint8_t>(ctx, 256);
     d.wcnt = arena_take<unsigned>(ctx, 256);
     d.wmed = arena_take<double>(ctx, 256);
     d.wmad = arena_take<double>(ctx, 256);
     bool ok = d.chrom && d.gc && d.start && d.stop && d.count && d.chrom1 && d.gc1 && d.count1 && d.orig1 &&
               d.chrom2 && d.gc2 && d.alive && d.count2 && d.orig2 && d.wsd && d.wchrom && d.kept &&
-              d.count_out && d.tiles && d.ctl && d.is_auto && d.wcnt && d.wmed && d.wmad;
+              d.count_out && d.tiles && d.ctl && d.is_auto && d.is_chry && d.wcnt && d.wmed && d.wmad;
     ok = ok && sel_state_alloc<uint32_t>(ctx, 1, d.sel_size) && sel_state_alloc<uint32_t>(ctx, GC_SEGS, d.sel_gc) &&
          sel_state_alloc<uint64_t>(ctx, std::max(n_chrom, 1), d.sel_win);
+    if (ok && loess) {
+        d.lo = std::make_shared<LoessDev>();
+        ok = loess_alloc(ctx, n, *d.lo);
+        d.lo->is_chry = d.is_chry;
+    }
     return ok ? CG_OK : cg_fail(ctx, CG_ERR_CUDA, "clean: device arena exhausted");
 }
 
@@ -586,8 +594,8 @@ int clean_enqueue(cg_ctx* ctx, const cg_clean_opts* o, CleanDev& d) {
     const int nb = std::max(1, div_up(n, 256));
     const int grid_stream = std::max(1, std::min(nb, ctx->num_sms * 8));
     CleanCtl* ctl = d.ctl;
-    if (o->gc_norm && o->gc_mode != 0)
-        return cg_fail(ctx, CG_ERR_UNSUPPORTED, "cg_clean: LOESS GC normalisation (-m LOESS) is not implemented in this build");
+    const bool loess = o->gc_norm && o->gc_mode != 0;
+    if (loess && !d.lo) return cg_fail(ctx, CG_ERR_ARG, "clean: LOESS buffers were not allocated");
 
     cudaEventRecord(ctx->stage_ev[0], ctx->stream);
     ctx->stage_used[0] = true;
@@ -639,13 +647,18 @@ int clean_enqueue(cg_ctx* ctx, const cg_clean_opts* o, CleanDev& d) {
     CG_LAUNCH(ctx, gc_threshold_kernel, 1, 1, 0, ctl, o->gc_norm, o->gc_mode == 0, o->min_bins_per_gc);
     CG_LAUNCH(ctx, gc_alive_kernel, grid_stream, 256, 0, d.gc2, ctl, d.alive);
     if (o->gc_norm) {
-        GcCountView gv{d.count2, d.gc2, d.chrom2, d.alive, d.is_auto, ctl, &ctl->do_norm};
-        // --- NormalizeByGC (:163-196)
-        CG_LAUNCH(ctx, gc_median_request_kernel, 1, 128, 0, d.sel_gc, ctl, &ctl->do_norm);
-        sel_run_scatter<uint32_t, GcCountView>(ctx, gv, d.sel_gc, n);
-        CG_LAUNCH(ctx, gc_median_finish_kernel, 1, 128, 0, d.sel_gc, ctl, &ctl->do_norm);
-        CG_LAUNCH(ctx, (normalize_apply_kernel<4>), dim3(grid_stream, 1), 256, 0, d.count2, d.gc2, d.alive, d.count2,
-                  &ctl->n2, 0LL, ctl->med, &ctl->global_median, &ctl->do_norm, 0LL);
+        if (loess) {
+            // --- LoessGCNormalizer.Normalize (LoessGCNormalizer.cs:61-82)
+            loess_enqueue(ctx, *d.lo, d.count2, d.gc2, d.chrom2, d.alive, ctl, &ctl->do_norm, n, grid_stream);
+        } else {
+            GcCountView gv{d.count2, d.gc2, d.chrom2, d.alive, d.is_auto, ctl, &ctl->do_norm};
+            // --- NormalizeByGC (:163-196)
+            CG_LAUNCH(ctx, gc_median_request_kernel, 1, 128, 0, d.sel_gc, ctl, &ctl->do_norm);
+            sel_run_scatter<uint32_t, GcCountView>(ctx, gv, d.sel_gc, n);
+            CG_LAUNCH(ctx, gc_median_finish_kernel, 1, 128, 0, d.sel_gc, ctl, &ctl->do_norm);
+            CG_LAUNCH(ctx, (normalize_apply_kernel<4>), dim3(grid_stream, 1), 256, 0, d.count2, d.gc2, d.alive, d.count2,
+                      &ctl->n2, 0LL, ctl->med, &ctl->global_median, &ctl->do_norm, 0LL);
+        }
         // --- NormalizeVarianceByGC (:34-97), evaluated only when the metric is on and > 500000 bins
         if (o->want_local_sd && n > 500000) {
             GcCountView gq{d.count2, d.gc2, d.chrom2, d.alive, d.is_auto, ctl, &ctl->do_variance};
@@ -654,13 +667,17 @@ int clean_enqueue(cg_ctx* ctx, const cg_clean_opts* o, CleanDev& d) {
             CG_LAUNCH(ctx, gc_quartile_finish_kernel, 1, 128, 0, d.sel_gc, ctl, &ctl->do_variance);
             CG_LAUNCH(ctx, variance_decide_kernel, 1, 1, 0, ctl);
             CG_LAUNCH(ctx, variance_apply_kernel, grid_stream, 256, 0, d.count2, d.gc2, d.alive, ctl);
-            // second NormalizeByGC when the rescale fired (:516-517)
-            GcCountView gm{d.count2, d.gc2, d.chrom2, d.alive, d.is_auto, ctl, &ctl->variance_fired};
-            CG_LAUNCH(ctx, gc_median_request_kernel, 1, 128, 0, d.sel_gc, ctl, &ctl->variance_fired);
-            sel_run_scatter<uint32_t, GcCountView>(ctx, gm, d.sel_gc, n);
-            CG_LAUNCH(ctx, gc_median_finish_kernel, 1, 128, 0, d.sel_gc, ctl, &ctl->variance_fired);
-            CG_LAUNCH(ctx, (normalize_apply_kernel<4>), dim3(grid_stream, 1), 256, 0, d.count2, d.gc2, d.alive,
-                      d.count2, &ctl->n2, 0LL, ctl->med, &ctl->global_median, &ctl->variance_fired, 0LL);
+            // second normalisation when the rescale fired (:516-517)
+            if (loess) {
+                loess_enqueue(ctx, *d.lo, d.count2, d.gc2, d.chrom2, d.alive, ctl, &ctl->variance_fired, n, grid_stream);
+            } else {
+                GcCountView gm{d.count2, d.gc2, d.chrom2, d.alive, d.is_auto, ctl, &ctl->variance_fired};
+                CG_LAUNCH(ctx, gc_median_request_kernel, 1, 128, 0, d.sel_gc, ctl, &ctl->variance_fired);
+                sel_run_scatter<uint32_t, GcCountView>(ctx, gm, d.sel_gc, n);
+                CG_LAUNCH(ctx, gc_median_finish_kernel, 1, 128, 0, d.sel_gc, ctl, &ctl->variance_fired);
+                CG_LAUNCH(ctx, (normalize_apply_kernel<4>), dim3(grid_stream, 1), 256, 0, d.count2, d.gc2, d.alive,
+                          d.count2, &ctl->n2, 0LL, ctl->med, &ctl->global_median, &ctl->variance_fired, 0LL);
+            }
         }
     }
     // --- RemoveBinsWithExtremeLocalSD (:308-322) + final compaction
@@ -678,7 +695,6 @@ extern "C" int cg_clean(cg_ctx* ctx, const cg_clean_opts* opts, int64_t n, const
                         const int32_t* start, const int32_t* stop, const float* count, const uint8_t* gc,
                         int64_t* n_out, int32_t* kept_index, float* count_out, double* local_sd,
                         int* gc_norm_skipped) {
-    (void)chrom_is_chrY;
     if (!ctx) return CG_ERR_ARG;
     if (!opts || n < 0 || n > 0x7fff0000LL || n_chrom < 0 || n_chrom > 256 || !n_out || !local_sd || !gc_norm_skipped)
         return cg_fail(ctx, CG_ERR_ARG, "cg_clean: bad argument");
@@ -696,10 +712,11 @@ extern "C" int cg_clean(cg_ctx* ctx, const cg_clean_opts* opts, int64_t n, const
     if (!chrom || !start || !stop || !count || !gc || !kept_index || !count_out || (n_chrom > 0 && !chrom_is_autosome))
         return cg_fail(ctx, CG_ERR_ARG, "cg_clean: null array");
     CG_CUDA(ctx, cudaSetDevice(ctx->device));
-    int rc = arena_reserve(ctx, clean_workspace_bytes(n, n_chrom));
+    const bool loess = opts->gc_norm && opts->gc_mode != 0;
+    int rc = arena_reserve(ctx, clean_workspace_bytes(n, n_chrom, loess));
     if (rc) return rc;
     CleanDev d;
-    rc = clean_alloc(ctx, n, n_chrom, d);
+    rc = clean_alloc(ctx, n, n_chrom, d, loess);
     if (rc) return rc;
     cudaStream_t s = ctx->stream;
     CG_CUDA(ctx, cudaMemcpyAsync(d.chrom, chrom, n, cudaMemcpyHostToDevice, s));
@@ -709,6 +726,8 @@ extern "C" int cg_clean(cg_ctx* ctx, const cg_clean_opts* opts, int64_t n, const
     CG_CUDA(ctx, cudaMemcpyAsync(d.count, count, n * 4, cudaMemcpyHostToDevice, s));
     CG_CUDA(ctx, cudaMemsetAsync(d.is_auto, 0, 256, s));
     if (n_chrom > 0) CG_CUDA(ctx, cudaMemcpyAsync(d.is_auto, chrom_is_autosome, n_chrom, cudaMemcpyHostToDevice, s));
+    CG_CUDA(ctx, cudaMemsetAsync(d.is_chry, 0, 256, s));
+    if (n_chrom > 0 && chrom_is_chrY) CG_CUDA(ctx, cudaMemcpyAsync(d.is_chry, chrom_is_chrY, n_chrom, cudaMemcpyHostToDevice, s));
     CG_CUDA(ctx, cudaEventRecord(ctx->ev0, s));
     rc = clean_enqueue(ctx, opts, d);
     if (rc) return rc;

@@ -4,6 +4,7 @@
 // (list lengths after a filter, "metric enabled", "variance normalisation fired", ...) lives in a
 // device-side CleanCtl block that later kernels read.
 #pragma once
+#include <memory>
 #include "common.cuh"
 #include "select.cuh"
 
@@ -186,6 +187,8 @@ __host__ __device__ inline double dotnet_f2_roundtrip(float v) {
     return v < 0 ? -r : r;
 }
 
+struct LoessDev;
+
 // Device-side buffers of one cg_clean call (slices of the ctx arena).
 struct CleanDev {
     int64_t n;
@@ -214,10 +217,12 @@ struct CleanDev {
     int* tiles;
     CleanCtl* ctl;
     uint8_t* is_auto;
+    uint8_t* is_chry;
     SelState<uint32_t> sel_size, sel_gc;
     SelState<uint64_t> sel_win;
+    std::shared_ptr<LoessDev> lo;  // buffers of the LOESS mode (clean_loess.cuh), only allocated for -m LOESS
 };
 
-size_t clean_workspace_bytes(int64_t n, int n_chrom);
-int clean_alloc(cg_ctx* ctx, int64_t n, int n_chrom, CleanDev& d);
+size_t clean_workspace_bytes(int64_t n, int n_chrom, bool loess = false);
+int clean_alloc(cg_ctx* ctx, int64_t n, int n_chrom, CleanDev& d, bool loess = false);
 int clean_enqueue(cg_ctx* ctx, const cg_clean_opts* o, CleanDev& d);

@@ -569,7 +569,6 @@ extern "C" int cg_clean_partition_wavelet(cg_ctx* ctx, const cg_clean_opts* copt
                                           double* local_sd, int* gc_norm_skipped, int64_t* chrom_off_out,
                                           int32_t* n_bp, int32_t* bp, double* evenness, int* evenness_ok,
                                           double* cv, int* cv_has_value, double* factor_of_three) {
-    (void)chrom_is_chrY;
     if (!ctx) return CG_ERR_ARG;
     if (!copts || !wopts || n < 0 || n > 0x7fff0000LL || n_chrom < 0 || n_chrom > WV_MAX_CHROM || !n_out || !local_sd ||
         !gc_norm_skipped || !chrom_off_out || !n_bp || !evenness || !evenness_ok || !cv || !cv_has_value || !factor_of_three)
@@ -597,12 +596,13 @@ extern "C" int cg_clean_partition_wavelet(cg_ctx* ctx, const cg_clean_opts* copt
     // workspace for both stages; the partition plan of the input lengths bounds the plan after cleaning
     WvPlan worst;
     make_plan(worst, n_chrom, in_off.data(), wopts->evenness_window);
-    size_t need = clean_workspace_bytes(n, n_chrom) + arena_need(n, 8) + arena_need(256, 4) + wv_workspace_bytes(worst);
+    const bool loess = copts->gc_norm && copts->gc_mode != 0;
+    size_t need = clean_workspace_bytes(n, n_chrom, loess) + arena_need(n, 8) + arena_need(256, 4) + wv_workspace_bytes(worst);
     need += need / 16;
     int rc = arena_reserve(ctx, need);
     if (rc) return rc;
     CleanDev d;
-    rc = clean_alloc(ctx, n, n_chrom, d);
+    rc = clean_alloc(ctx, n, n_chrom, d, loess);
     if (rc) return rc;
     double* cov = arena_take<double>(ctx, n);
     unsigned* chrom_cnt = arena_take<unsigned>(ctx, 256);
@@ -615,6 +615,8 @@ extern "C" int cg_clean_partition_wavelet(cg_ctx* ctx, const cg_clean_opts* copt
     CG_CUDA(ctx, cudaMemcpyAsync(d.count, count, n * 4, cudaMemcpyHostToDevice, s));
     CG_CUDA(ctx, cudaMemsetAsync(d.is_auto, 0, 256, s));
     if (n_chrom > 0) CG_CUDA(ctx, cudaMemcpyAsync(d.is_auto, chrom_is_autosome, n_chrom, cudaMemcpyHostToDevice, s));
+    CG_CUDA(ctx, cudaMemsetAsync(d.is_chry, 0, 256, s));
+    if (n_chrom > 0 && chrom_is_chrY) CG_CUDA(ctx, cudaMemcpyAsync(d.is_chry, chrom_is_chrY, n_chrom, cudaMemcpyHostToDevice, s));
     CG_CUDA(ctx, cudaMemsetAsync(chrom_cnt, 0, 256 * 4, s));
     CG_CUDA(ctx, cudaEventRecord(ctx->ev0, s));
     rc = clean_enqueue(ctx, copts, d);

@@ -178,6 +178,39 @@ def derive_segments(breakpoints, n_bins, start, end):
     return [(int(start[a]), int(end[b])) for a, b in zip(s_pos, e_pos)]
 
 
+def cbs_segments(seg_len, start, end):
+    """CBSRunner.Run (CBSRunner.cs:127-138): segment lengths in bins -> (genomic start, genomic end) pairs.
+    Coverage is finite on this path, so the finite-index list is the identity."""
+    out, at = [], 0
+    for ln in np.asarray(seg_len).tolist():
+        out.append((int(start[at]), int(end[at + ln - 1])))
+        at += ln
+    return out
+
+
+def split_overlapping_segments(per_sample):
+    """GenomeSegmentationResults.SplitOverlappingSegments (GenomeSegmentationResults.cs:18-55): the union of
+    all samples' segment boundaries per chromosome.  per_sample: list of {chr: [(start, end), ...]}."""
+    if len(per_sample) == 1:
+        return per_sample[0]
+    result = {}
+    for c in per_sample[0]:
+        events = []
+        for sample in per_sample:
+            for a, b in sample[c]:
+                events.append((a, 0))
+                events.append((b, 1))
+        events.sort(key=lambda e: e[0])  # stable merge by position only
+        segs, depth, cur = [], 0, 0
+        for pos, is_end in events:
+            if depth > 0 and cur != pos:
+                segs.append((cur, pos))
+            cur = pos
+            depth += -1 if is_end else 1
+        result[c] = segs
+    return result
+
+
 def post_process_segments(order, seg_by_chr, start, end, cov, excluded=None, max_inter_bin_dist=1000000):
     """SegmentationResultsProcessor.PostProcessSegments (SegmentationResultsProcessor.cs:17-129)
     without reference ploidy.  Returns chr -> list of segments {id, bins: [(start, end, coverage)]}."""

@@ -140,3 +140,37 @@ def test_normalize_apply_stream_matches_formula(engine):
         exp[b][ok] = (gmed[b] * count[b][ok].astype(np.float64) / m[ok]).astype(np.float32)
     assert np.array_equal(out.view(np.uint32), exp.view(np.uint32))
     assert ms > 0
+
+
+# ---------------------------------------------------------------------------------------------
+# -m LOESS: floating point; the contract is 1e-5 relative on the normalised counts (bucket-wise instead of
+# point-wise summation order, device log / exp), kept bins identical
+# ---------------------------------------------------------------------------------------------
+LOESS_RTOL = 1e-5
+
+
+def _assert_close_loess(a, b):
+    assert np.array_equal(a["kept_index"], b["kept_index"])
+    assert a["gc_norm_skipped"] == b["gc_norm_skipped"]
+    x, y = a["count"].astype(np.float64), b["count"].astype(np.float64)
+    rel = np.abs(x - y) / np.maximum(np.abs(y), 1e-30)
+    rel[(x == y)] = 0
+    assert np.nanmax(rel) <= LOESS_RTOL, (np.nanmax(rel), int(np.nanargmax(rel)))
+    assert np.array_equal(np.isnan(x), np.isnan(y))
+
+
+@pytest.mark.parametrize("scale,sample", [(0.02, 5), (0.004, 6)])
+def test_loess_mode_matches_oracle(engine, scale, sample):
+    s = synth.make_sample(config=2, sample=sample, scale=scale)
+    a, b = _run_both(engine, s, gc_mode=1, want_local_sd=False)
+    _assert_close_loess(a, b)
+    # the normalisation did something: counts moved, and low / high GC bins moved in opposite directions to the middle
+    assert np.abs(a["count"] - s.count[a["kept_index"]]).max() > 1
+
+
+def test_loess_mode_with_metric_and_zero_counts(engine):
+    s = synth.make_sample(config=1, chromosomes=["chr20"], sample=2)
+    s.count[::977] = 0  # log(0) = -Infinity: dropped from the fit, written back as exp(-inf) = 0
+    a, b = _run_both(engine, s, gc_mode=1, outlier_filter=False)
+    _assert_close_loess(a, b)
+    assert (a["count"] == 0).sum() > 10 and a["local_sd"] == b["local_sd"]

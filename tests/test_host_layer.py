@@ -116,3 +116,25 @@ def test_pack_unpack_breakpoints():
     assert buf[0] == 4
     out = multi.unpack_breakpoints(buf[None, :], 3)
     assert [b.tolist() for b in out] == [[0, 5, 9], [], [0]]
+
+
+def test_split_overlapping_segments_reference_vectors():
+    # CanvasTest/CanvasPartition/GenomeSegmentationResultsTests.cs
+    f = fileio.split_overlapping_segments
+    one = {"chr1": [(1, 200)]}
+    assert f([one]) == one
+    assert f([one, {"chr1": [(1, 200)]}]) == one
+    assert f([{"chr1": [(1, 300)]}, {"chr1": [(1, 200), (200, 300)]}]) == {"chr1": [(1, 200), (200, 300)]}
+    assert f([{"chr1": [(0, 200)]}, {"chr1": [(100, 300)]}]) == {"chr1": [(0, 100), (100, 200), (200, 300)]}
+    assert f([{"chr1": [(0, 100)]}, {"chr1": [(0, 200)]}]) == {"chr1": [(0, 100), (100, 200)]}
+    assert f([{"chr1": [(0, 300)]}, {"chr1": [(100, 200)]}]) == {"chr1": [(0, 100), (100, 200), (200, 300)]}
+    assert f([{"chr1": [(0, 600)]}, {"chr1": [(100, 200), (200, 300), (500, 700), (800, 900)]}]) == {
+        "chr1": [(0, 100), (100, 200), (200, 300), (300, 500), (500, 600), (600, 700), (800, 900)]}
+    assert f([{"chr1": [(0, 100)]}, {"chr1": [(100, 200)]}]) == {"chr1": [(0, 100), (100, 200)]}
+    assert f([{"chr1": [(0, 100)], "chr2": [(300, 400)]}, {"chr1": [(100, 200)], "chr2": [(500, 600)]}]) == {
+        "chr1": [(0, 100), (100, 200)], "chr2": [(300, 400), (500, 600)]}
+
+
+def test_cbs_segments_from_lengths():
+    start = np.array([0, 10, 20, 30, 40]); end = start + 10
+    assert fileio.cbs_segments([2, 3], start, end) == [(0, 20), (20, 50)]

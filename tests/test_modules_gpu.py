@@ -63,3 +63,32 @@ def test_partition_without_vaf_gives_one_segment_per_chromosome(tmp_path, engine
     assert modules.main(["CanvasPartition", "-i", cleaned, "-o", part, "-r", str(tmp_path)]) == 0
     ids = {int(l.split("\t")[4]) for l in gzip.open(part, "rt").read().splitlines()}
     assert ids == {-1}
+
+
+def test_partition_cbs_on_files(tmp_path, engine):
+    # CanvasPartition -m CBS on two samples (CanvasPartition.cs:130-149): per-sample CBS, merged boundaries
+    modules._engine = engine
+    cleaned, parts, per_sample, inputs = [], [], [], []
+    for k in range(2):
+        s = synth.make_sample(config=2, sample=20 + k, scale=0.004, n_events=4000, chromosomes=["chr1", "chr2", "chrX"])
+        path = str(tmp_path / f"s{k}.cleaned")
+        fileio.write_binned(path, s.names, s.chrom, s.start, s.stop, s.count.astype(np.float32), s.gc)
+        cleaned.append(path)
+        parts.append(str(tmp_path / f"s{k}.partitioned"))
+        order, start, end, cov = fileio.read_cleaned_for_partition(path)
+        lens = [len(cov[c]) for c in order]
+        off = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+        r = ora.partition_cbs(off, np.concatenate([cov[c] for c in order]))
+        per_sample.append({c: [(int(start[c][a]), int(end[c][b])) for a, b in zip(r["segments"][i]["first"], r["segments"][i]["last"])]
+                           for i, c in enumerate(order)})
+        inputs.append((order, start, end, cov))
+    argv = ["CanvasPartition", "-m", "CBS", "-r", str(tmp_path)]
+    for c, p in zip(cleaned, parts):
+        argv += ["-i", c, "-o", p]
+    assert modules.main(argv) == 0
+    merged = fileio.split_overlapping_segments(per_sample)
+    assert sum(len(v) for v in merged.values()) > max(sum(len(v) for v in ps.values()) for ps in per_sample) > 3
+    for (order, start, end, cov), p in zip(inputs, parts):
+        expected = str(tmp_path / "exp.partitioned")
+        fileio.write_partitioned(expected, order, fileio.post_process_segments(order, merged, start, end, cov))
+        assert gzip.open(p, "rt").read() == gzip.open(expected, "rt").read()
