@@ -312,10 +312,7 @@ __global__ void gc_median_request_kernel(SelState<uint32_t> st, CleanCtl* ctl, c
     if (!*enabled) return;
     unsigned n = s < GC_BINS ? alive_auto_count(ctl, s) : ctl->n_auto3;
     if (s < GC_BINS && n < (unsigned)MIN_BINS_PER_GC) {
-        // weighted path: only matters when a surviving bin actually uses this bucket
-        bool used = (long long)ctl->hist_auto[s] >= (long long)ctl->gc_thresh && ctl->hist_all[s] > 0;
-        if (used) ctl->need_weighted = 1;
-        return;
+        return;  // weighted median of the neighbouring buckets: gc_weighted_kernel
     }
     if (n == 0) return;
     st.nreq[s] = 2;
@@ -379,7 +376,7 @@ __global__ void gc_quartile_request_kernel(SelState<uint32_t> st, CleanCtl* ctl,
     st.nreq[s] = 0;
     if (!*enabled) return;
     unsigned n = s < GC_BINS ? alive_auto_count(ctl, s) : ctl->n_auto3;
-    if (s < GC_BINS && n > 0 && n < (unsigned)MIN_BINS_PER_GC) { ctl->need_weighted = 1; return; }
+    if (s < GC_BINS && n > 0 && n < (unsigned)MIN_BINS_PER_GC) return;  // weighted quantiles: gc_weighted_kernel
     if (n < 2) return;
     st.nreq[s] = 6;
     quartile_ranks(n, st.req_k + s * SEL_G);
@@ -401,6 +398,91 @@ __global__ void gc_quartile_finish_kernel(SelState<uint32_t> st, CleanCtl* ctl, 
     } else {
         ctl->global_q[0] = q[0]; ctl->global_q[1] = q[1]; ctl->global_q[2] = q[2];
         ctl->global_iqr = __fsub_rn(q[2], q[0]);
+    }
+}
+
+// GC buckets with fewer than 100 autosomal bins borrow their neighbours (GetWeightedCounts, CanvasClean.cs:107-132:
+// buckets gc +- r with weight 2^-r until 100 values are collected) and take weighted quantiles
+// (Utilities.WeightedQuantiles, Utilities.cs:493-515: the last value, in stable value order, whose cumulative
+// weight / total weight is <= p).  One CTA per such bucket gathers the (value, radius) pairs, sorts them in
+// shared memory and walks them in order.  Weights are powers of two, so the running sums are exact.
+constexpr int WQ_CAP = 16384;
+
+__global__ void __launch_bounds__(256) gc_weighted_kernel(const float* __restrict__ count2, const uint8_t* __restrict__ gc2,
+                                                          const uint8_t* __restrict__ chrom2, const uint8_t* __restrict__ alive,
+                                                          const uint8_t* __restrict__ is_auto, CleanCtl* ctl, int mode,
+                                                          const int* enabled) {
+    extern __shared__ unsigned long long wq_key[];
+    __shared__ signed char s_rad[GC_BINS];
+    __shared__ int s_total, s_cnt, s_go;
+    if (!*enabled) return;
+    const int g = blockIdx.x, t = threadIdx.x;
+    const unsigned ng = alive_auto_count(ctl, g);
+    bool needed;
+    if (mode == 0) needed = ng < (unsigned)MIN_BINS_PER_GC && (long long)ctl->hist_auto[g] >= (long long)ctl->gc_thresh && ctl->hist_all[g] > 0;
+    else needed = ng > 0 && ng < (unsigned)MIN_BINS_PER_GC;
+    if (!needed) return;
+    if (t < GC_BINS) s_rad[t] = -1;
+    __syncthreads();
+    if (t == 0) {
+        long long total = 0;
+        int r = 0;
+        while (total < MIN_BINS_PER_GC) {
+            const int hi = g + r, lo = g - r;
+            if (hi >= GC_BINS && lo < 0) break;
+            if (hi < GC_BINS) { s_rad[hi] = (signed char)r; total += alive_auto_count(ctl, hi); }
+            if (lo != hi && lo >= 0) { s_rad[lo] = (signed char)r; total += alive_auto_count(ctl, lo); }
+            r++;
+        }
+        s_total = (int)min(total, (long long)0x7fffffff);
+        s_cnt = 0;
+        s_go = total <= WQ_CAP ? 1 : 0;
+        if (!s_go) ctl->need_weighted = 1;  // more neighbours than the shared-memory sorter holds: reported as unsupported
+    }
+    __syncthreads();
+    if (!s_go) return;
+    const int T = s_total;
+    int pad = 1;
+    while (pad < T) pad <<= 1;
+    for (int k = t; k < pad; k += blockDim.x) wq_key[k] = ~0ull;
+    __syncthreads();
+    const int n2 = ctl->n2;
+    for (int i = t; i < n2; i += blockDim.x) {
+        const int r = s_rad[gc2[i]];
+        if (r >= 0 && alive[i] && is_auto[chrom2[i]]) {
+            const int slot = atomicAdd(&s_cnt, 1);
+            if (slot < pad) wq_key[slot] = ((unsigned long long)f32_key(count2[i]) << 8) | (unsigned long long)r;
+        }
+    }
+    __syncthreads();
+    for (int k = 2; k <= pad; k <<= 1)
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = t; i < pad; i += blockDim.x) {
+                const int l = i ^ j;
+                if (l > i) {
+                    const bool up = (i & k) == 0;
+                    const unsigned long long a = wq_key[i], b = wq_key[l];
+                    if ((a > b) == up) { wq_key[i] = b; wq_key[l] = a; }
+                }
+            }
+            __syncthreads();
+        }
+    if (t == 0) {
+        double acc = 0.0;
+        for (int i = 0; i < T; i++) acc += ldexp(1.0, -(int)(wq_key[i] & 0xffull));
+        const double total_w = (double)(float)acc;  // Enumerable.Sum over float weights returns a float
+        const double probs[3] = {0.25, 0.5, 0.75};
+        double q[3] = {0.0, 0.0, 0.0};
+        double cw = 0.0;
+        for (int i = 0; i < T; i++) {
+            cw += ldexp(1.0, -(int)(wq_key[i] & 0xffull));
+            const double cp = cw / total_w;
+            const double v = (double)f32_unkey((uint32_t)(wq_key[i] >> 8));
+            for (int p = 0; p < 3; p++)
+                if (cp <= probs[p]) q[p] = v;
+        }
+        if (mode == 0) ctl->med[g] = q[1];
+        else { ctl->q2[g] = (float)q[1]; ctl->iqr[g] = (float)(q[2] - q[0]); }
     }
 }
 
@@ -597,6 +679,7 @@ int clean_enqueue(cg_ctx* ctx, const cg_clean_opts* o, CleanDev& d) {
     const bool loess = o->gc_norm && o->gc_mode != 0;
     if (loess && !d.lo) return cg_fail(ctx, CG_ERR_ARG, "clean: LOESS buffers were not allocated");
 
+    cudaFuncSetAttribute(gc_weighted_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WQ_CAP * 8);
     cudaEventRecord(ctx->stage_ev[0], ctx->stream);
     ctx->stage_used[0] = true;
     CG_LAUNCH(ctx, clean_init_kernel, 1, 32, 0, ctl, n);
@@ -656,6 +739,7 @@ int clean_enqueue(cg_ctx* ctx, const cg_clean_opts* o, CleanDev& d) {
             CG_LAUNCH(ctx, gc_median_request_kernel, 1, 128, 0, d.sel_gc, ctl, &ctl->do_norm);
             sel_run_scatter<uint32_t, GcCountView>(ctx, gv, d.sel_gc, n);
             CG_LAUNCH(ctx, gc_median_finish_kernel, 1, 128, 0, d.sel_gc, ctl, &ctl->do_norm);
+            CG_LAUNCH(ctx, gc_weighted_kernel, GC_BINS, 256, WQ_CAP * 8, d.count2, d.gc2, d.chrom2, d.alive, d.is_auto, ctl, 0, &ctl->do_norm);
             CG_LAUNCH(ctx, (normalize_apply_kernel<4>), dim3(grid_stream, 1), 256, 0, d.count2, d.gc2, d.alive, d.count2,
                       &ctl->n2, 0LL, ctl->med, &ctl->global_median, &ctl->do_norm, 0LL);
         }
@@ -665,6 +749,7 @@ int clean_enqueue(cg_ctx* ctx, const cg_clean_opts* o, CleanDev& d) {
             CG_LAUNCH(ctx, gc_quartile_request_kernel, 1, 128, 0, d.sel_gc, ctl, &ctl->do_variance);
             sel_run_scatter<uint32_t, GcCountView>(ctx, gq, d.sel_gc, n);
             CG_LAUNCH(ctx, gc_quartile_finish_kernel, 1, 128, 0, d.sel_gc, ctl, &ctl->do_variance);
+            CG_LAUNCH(ctx, gc_weighted_kernel, GC_BINS, 256, WQ_CAP * 8, d.count2, d.gc2, d.chrom2, d.alive, d.is_auto, ctl, 1, &ctl->do_variance);
             CG_LAUNCH(ctx, variance_decide_kernel, 1, 1, 0, ctl);
             CG_LAUNCH(ctx, variance_apply_kernel, grid_stream, 256, 0, d.count2, d.gc2, d.alive, ctl);
             // second normalisation when the rescale fired (:516-517)
@@ -675,6 +760,7 @@ int clean_enqueue(cg_ctx* ctx, const cg_clean_opts* o, CleanDev& d) {
                 CG_LAUNCH(ctx, gc_median_request_kernel, 1, 128, 0, d.sel_gc, ctl, &ctl->variance_fired);
                 sel_run_scatter<uint32_t, GcCountView>(ctx, gm, d.sel_gc, n);
                 CG_LAUNCH(ctx, gc_median_finish_kernel, 1, 128, 0, d.sel_gc, ctl, &ctl->variance_fired);
+                CG_LAUNCH(ctx, gc_weighted_kernel, GC_BINS, 256, WQ_CAP * 8, d.count2, d.gc2, d.chrom2, d.alive, d.is_auto, ctl, 0, &ctl->variance_fired);
                 CG_LAUNCH(ctx, (normalize_apply_kernel<4>), dim3(grid_stream, 1), 256, 0, d.count2, d.gc2, d.alive,
                           d.count2, &ctl->n2, 0LL, ctl->med, &ctl->global_median, &ctl->variance_fired, 0LL);
             }
@@ -742,7 +828,7 @@ extern "C" int cg_clean(cg_ctx* ctx, const cg_clean_opts* opts, int64_t n, const
     ctx->last_kernel_ms = ms;
     if (h->unsorted) return cg_fail(ctx, CG_ERR_UNSORTED, "cg_clean: chromosome ids must form non-decreasing runs and GC must be 0..100");
     if (h->need_weighted)
-        return cg_fail(ctx, CG_ERR_UNSUPPORTED, "cg_clean: a GC bucket in use has < 100 autosomal bins (weighted-quantile path not implemented)");
+        return cg_fail(ctx, CG_ERR_UNSUPPORTED, "cg_clean: a GC bucket with < 100 autosomal bins needs more than 16384 neighbouring values for its weighted quantiles");
     const int64_t m = h->n_out;
     if (m > 0) {
         CG_CUDA(ctx, cudaMemcpyAsync(kept_index, d.kept, m * 4, cudaMemcpyDeviceToHost, s));

@@ -633,7 +633,7 @@ extern "C" int cg_clean_partition_wavelet(cg_ctx* ctx, const cg_clean_opts* copt
     CG_CHECK_LAUNCHES(ctx);
     if (h->unsorted) return cg_fail(ctx, CG_ERR_UNSORTED, "cg_clean: chromosome ids must form non-decreasing runs and GC must be 0..100");
     if (h->need_weighted)
-        return cg_fail(ctx, CG_ERR_UNSUPPORTED, "cg_clean: a GC bucket in use has < 100 autosomal bins (weighted-quantile path not implemented)");
+        return cg_fail(ctx, CG_ERR_UNSUPPORTED, "cg_clean: a GC bucket with < 100 autosomal bins needs more than 16384 neighbouring values for its weighted quantiles");
     const int64_t m = h->n_out;
     const double lsd = h->local_sd;
     const int skipped = h->gc_skipped;

@@ -174,3 +174,27 @@ def test_loess_mode_with_metric_and_zero_counts(engine):
     a, b = _run_both(engine, s, gc_mode=1, outlier_filter=False)
     _assert_close_loess(a, b)
     assert (a["count"] == 0).sum() > 10 and a["local_sd"] == b["local_sd"]
+
+
+def test_weighted_quantiles_for_small_gc_buckets(engine):
+    # -w 10 on a small sample: buckets with 10..99 autosomal bins stay and take the weighted median of
+    # their neighbours (GetWeightedCounts / WeightedMedian); bit-exact like the rest of the median mode
+    s = synth.make_sample(config=2, sample=8, scale=0.002)
+    auto = np.array(s.is_autosome, bool)[s.chrom]
+    h = np.bincount(s.gc[auto], minlength=101)
+    assert ((h >= 10) & (h < 100)).sum() >= 5
+    for w in (10, 70, 100):
+        a, b = _run_both(engine, s, min_bins_per_gc=w, outlier_filter=False)
+        _assert_same(a, b)
+
+
+def test_loess_with_variance_step_uses_weighted_quartiles(engine):
+    # > 500000 bins with the metric on: NormalizeVarianceByGC runs on unfiltered GC buckets, the sparse
+    # ones through WeightedQuantiles (CanvasClean.cs:57-66)
+    s = synth.make_sample(config=2, sample=9, scale=0.18)
+    auto = np.array(s.is_autosome, bool)[s.chrom]
+    h = np.bincount(s.gc[auto], minlength=101)
+    assert ((h[10:90] > 0) & (h[10:90] < 100)).sum() >= 2
+    a, b = _run_both(engine, s, gc_mode=1)
+    _assert_close_loess(a, b)
+    assert a["local_sd"] == b["local_sd"]
