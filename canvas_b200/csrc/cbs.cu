@@ -1249,6 +1249,82 @@ std::vector<unsigned> h_boundary_compute(unsigned n_perm, double alpha, double e
     return sb;
 }
 
+// ---------------------------------------------------------------------------------------------
+// -s SDUndo (ChangePoint.cs:155-196, :423-474): host-side post-processing of the segment list, as in the
+// reference (a handful of medians per chromosome; the trimmed SD is one sort of the genome's |differences|).
+// ---------------------------------------------------------------------------------------------
+double h_std_normal_quantile(double p) {
+    double lo = -40.0, hi = 40.0;  // bisection on Phi, then it is exact to the last bits
+    for (int it = 0; it < 200; it++) {
+        const double mid = 0.5 * (lo + hi);
+        if (0.5 * erfc(-mid / sqrt(2.0)) < p) lo = mid; else hi = mid;
+    }
+    double x = 0.5 * (lo + hi);
+    for (int it = 0; it < 4; it++) x -= (0.5 * erfc(-x / sqrt(2.0)) - p) / (exp(-0.5 * x * x) / sqrt(2.0 * M_PI));
+    return x;
+}
+
+double h_trimmed_sd(int n_chrom, const int64_t* off, const double* cov, double trim) {
+    std::vector<double> d;
+    d.reserve((size_t)std::max<int64_t>(off[n_chrom] - 1, 0));
+    bool have = false;
+    double last = 0.0;
+    for (int c = 0; c < n_chrom; c++)
+        for (int64_t i = off[c]; i < off[c + 1]; i++) {
+            if (!std::isfinite(cov[i])) continue;
+            if (have) d.push_back(fabs(cov[i] - last));
+            last = cov[i];
+            have = true;
+        }
+    const long keep = (long)nearbyint((1 - 2 * trim) * (double)d.size());
+    std::sort(d.begin(), d.end());
+    double ss = 0.0;
+    for (long i = 0; i < keep && i < (long)d.size(); i++) ss += d[i] * d[i];
+    // inflation factor: 1 / E[X^2] of N(0,1) truncated to its central 1 - 2 trim, midpoint rule on 10000 points
+    const double a = h_std_normal_quantile(1 - trim);
+    const double step = 2 * a / 10000, from = -a + step / 2, to = a - step / 2, inc = (to - from) / 9999;
+    double e = 0.0, x = from;
+    for (int i = 0; i < 10000; i++) {
+        const double xi = i == 9999 ? to : x;
+        e += (xi * xi) * (exp(-0.5 * xi * xi) / sqrt(2.0 * M_PI));
+        x += inc;
+    }
+    e = e * step / (1 - 2 * trim);
+    return sqrt((1 / e) * ss / (2 * keep));
+}
+
+double h_segment_median(const double* g, int a, int b) {
+    std::vector<double> y(g + a, g + b);
+    const size_t mid = y.size() / 2;
+    std::nth_element(y.begin(), y.begin() + mid, y.end());
+    if (y.size() & 1) return y[mid];
+    return (y[mid] + *std::max_element(y.begin(), y.begin() + mid)) / 2;
+}
+
+// merge the two neighbours whose medians are closest while that distance is below the threshold
+void h_sd_undo(const double* g, std::vector<int>& len, double threshold) {
+    std::vector<int> end;
+    int at = 0;
+    for (int l : len) { at += l; end.push_back(at); }
+    std::vector<double> med(end.size());
+    for (size_t i = 0; i < end.size(); i++) med[i] = h_segment_median(g, i ? end[i - 1] : 0, end[i]);
+    while (end.size() > 1) {
+        size_t best = 0;
+        double mn = fabs(med[1] - med[0]);
+        for (size_t i = 1; i + 1 < end.size(); i++) {
+            const double dv = fabs(med[i + 1] - med[i]);
+            if (dv < mn) { mn = dv; best = i; }
+        }
+        if (!(mn < threshold)) break;
+        end.erase(end.begin() + (long)best);
+        med.erase(med.begin() + (long)best);
+        med[best] = h_segment_median(g, best ? end[best - 1] : 0, end[best]);
+    }
+    len.clear();
+    int prev = 0;
+    for (int e : end) { len.push_back(e - prev); prev = e; }
+}
+
 unsigned mt_first_outputs(unsigned seed, int count, std::vector<unsigned>& out) {
     unsigned s[624];
     s[0] = seed;
@@ -1283,12 +1359,13 @@ extern "C" int64_t cg_cbs_boundary(uint32_t n_perm, double alpha, double eta, ui
     return (int64_t)sb.size();
 }
 
-extern "C" int cg_partition_cbs(cg_ctx* ctx, const cg_cbs_opts* o, const uint32_t* sbdry, int64_t n_sbdry, int n_chrom,
-                                const int64_t* chrom_off, const double* coverage, int32_t* n_seg, int32_t* seg_len, double* seg_mean,
-                                int64_t* stats) {
+static int partition_cbs_impl(cg_ctx* ctx, const cg_cbs_opts* o, const uint32_t* sbdry, int64_t n_sbdry, int n_chrom,
+                              const int64_t* chrom_off, const double* coverage, const uint8_t* chrom_selected, int32_t* n_seg,
+                              int32_t* seg_len, double* seg_mean, int64_t* stats) {
     if (!ctx) return CG_ERR_ARG;
     if (!o || n_chrom < 0 || (n_chrom > 0 && (!chrom_off || !n_seg))) return cg_fail(ctx, CG_ERR_ARG, "cg_partition_cbs: bad argument");
-    if (o->undo != 0) return cg_fail(ctx, CG_ERR_UNSUPPORTED, "cg_partition_cbs: undo methods (prune / sdundo) are host-side post-processing not in this build");
+    if (o->undo != 0 && o->undo != 2)
+        return cg_fail(ctx, CG_ERR_UNSUPPORTED, "cg_partition_cbs: the prune undo method (an exhaustive search over change-point subsets) is not in this build");
     if (!o->hybrid) return cg_fail(ctx, CG_ERR_UNSUPPORTED, "cg_partition_cbs: only the hybrid p-value method (the one CanvasPartition uses) is supported");
     if (o->min_width < 2 || o->min_width > 5) return cg_fail(ctx, CG_ERR_ARG, "Minimum segment width should be between 2 and 5");
     if (o->n_min < 4u * (unsigned)o->k_max) return cg_fail(ctx, CG_ERR_ARG, "nMin should be >= 4 * kMax");
@@ -1316,7 +1393,8 @@ extern "C" int cg_partition_cbs(cg_ctx* ctx, const cg_cbs_opts* o, const uint32_
     }
     if (N == 0) return CG_OK;
     if (!coverage || !seg_len || !seg_mean) return cg_fail(ctx, CG_ERR_ARG, "cg_partition_cbs: null array");
-    for (int64_t i = 0; i < N; i++)
+    for (int c = 0; c < n_chrom; c++)
+        for (int64_t i = chrom_off[c]; i < chrom_off[c + 1] && (!chrom_selected || chrom_selected[c]); i++)
         if (!std::isfinite(coverage[i]))
             return cg_fail(ctx, CG_ERR_UNSUPPORTED, "cg_partition_cbs: non-finite coverage (the reference feeds it to ChangePoints unfiltered, CBSRunner.cs:118)");
     CG_CUDA(ctx, cudaSetDevice(ctx->device));
@@ -1327,10 +1405,11 @@ extern "C" int cg_partition_cbs(cg_ctx* ctx, const cg_cbs_opts* o, const uint32_
     std::vector<CbsWork> work;
     for (int c = 0; c < n_chrom; c++) {
         const int n = (int)(chrom_off[c + 1] - chrom_off[c]);
-        if (n > 0) work.push_back(CbsWork{chrom_off[c], n, c, seeds[c], 0});
+        if (n > 0 && (!chrom_selected || chrom_selected[c])) work.push_back(CbsWork{chrom_off[c], n, c, seeds[c], 0});
     }
     std::stable_sort(work.begin(), work.end(), [](const CbsWork& a, const CbsWork& b) { return a.n > b.n; });
     const int nwork = (int)work.size();
+    if (nwork == 0) return CG_OK;
     int G = 8;
     while (G > 1 && nwork * G > ctx->num_sms) G >>= 1;
     int nclusters = std::min(nwork, std::max(1, ctx->num_sms / G));
@@ -1446,5 +1525,36 @@ extern "C" int cg_partition_cbs(cg_ctx* ctx, const cg_cbs_opts* o, const uint32_
         for (int c = 0; c < n_chrom; c++)
             for (int k = 0; k < 4; k++) stats[k] += h_stats[(size_t)c * 4 + k];
     }
+    if (o->undo == 2) {
+        const double threshold = o->undo_sd * h_trimmed_sd(n_chrom, chrom_off, coverage, o->trim);
+        for (int c = 0; c < n_chrom; c++) {
+            if (n_seg[c] <= 1) continue;
+            const double* g = coverage + chrom_off[c];
+            std::vector<int> len(seg_len + chrom_off[c], seg_len + chrom_off[c] + n_seg[c]);
+            h_sd_undo(g, len, threshold);
+            int at = 0;
+            for (size_t i = 0; i < len.size(); i++) {
+                double sum = 0.0, w = 0.0;
+                for (int p2 = at; p2 < at + len[i]; p2++) { w += 1.0; sum += g[p2] * 1.0; }
+                seg_len[chrom_off[c] + (int64_t)i] = len[i];
+                seg_mean[chrom_off[c] + (int64_t)i] = sum / w;
+                at += len[i];
+            }
+            n_seg[c] = (int)len.size();
+        }
+    }
     return CG_OK;
+}
+
+extern "C" int cg_partition_cbs(cg_ctx* ctx, const cg_cbs_opts* o, const uint32_t* sbdry, int64_t n_sbdry, int n_chrom,
+                                const int64_t* chrom_off, const double* coverage, int32_t* n_seg, int32_t* seg_len, double* seg_mean,
+                                int64_t* stats) {
+    return partition_cbs_impl(ctx, o, sbdry, n_sbdry, n_chrom, chrom_off, coverage, nullptr, n_seg, seg_len, seg_mean, stats);
+}
+
+extern "C" int cg_partition_cbs_shard(cg_ctx* ctx, const cg_cbs_opts* o, const uint32_t* sbdry, int64_t n_sbdry, int n_chrom,
+                                      const int64_t* chrom_off, const double* coverage, const uint8_t* chrom_selected, int32_t* n_seg,
+                                      int32_t* seg_len, double* seg_mean, int64_t* stats) {
+    if (!chrom_selected && n_chrom > 0) return cg_fail(ctx, CG_ERR_ARG, "cg_partition_cbs_shard: chrom_selected is required");
+    return partition_cbs_impl(ctx, o, sbdry, n_sbdry, n_chrom, chrom_off, coverage, chrom_selected, n_seg, seg_len, seg_mean, stats);
 }

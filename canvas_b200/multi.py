@@ -73,3 +73,19 @@ def partition_wavelet_sharded(engine, chrom_off, coverage, **kw):
     r["breakpoints"] = all_gather_breakpoints(r["breakpoints"], len(lengths))
     r["owner"] = owner
     return r
+
+
+def partition_cbs_sharded(engine, chrom_off, coverage, **kw):
+    """cg_partition_cbs_shard on this rank's chromosomes + the same single all-gather: segment lengths travel
+    as (chromosome, cumulative end) pairs.  Every chromosome keeps its own random stream, so the merged result
+    equals the single-GPU call on every rank."""
+    import torch.distributed as dist
+    world, rank = dist.get_world_size(), dist.get_rank()
+    lengths = np.diff(np.asarray(chrom_off, np.int64))
+    owner = assign_chromosomes_lpt(lengths, world)
+    r = engine.partition_cbs(chrom_off, coverage, chrom_selected=(owner == rank).astype(np.uint8), **kw)
+    ends = [np.cumsum(s["len"]).astype(np.int32) for s in r["segments"]]
+    merged = all_gather_breakpoints(ends, len(lengths))
+    r["segments"] = [{"len": np.diff(np.concatenate([[0], e])).astype(np.int32)} for e in merged]
+    r["owner"] = owner
+    return r

@@ -61,6 +61,8 @@ SIGNATURES = {
                                              _P(_f64), _P(C.c_int), _P(_f64), _P(C.c_int), _P(_f64)]),
     "cg_partition_cbs": (C.c_int, [C.c_void_p, C.c_void_p, _P(C.c_uint32), _i64, C.c_int, _P(_i64), _P(C.c_double), _P(_i32),
                                    _P(_i32), _P(C.c_double), _P(_i64)]),
+    "cg_partition_cbs_shard": (C.c_int, [C.c_void_p, C.c_void_p, _P(C.c_uint32), _i64, C.c_int, _P(_i64), _P(C.c_double), _P(_u8),
+                                         _P(_i32), _P(_i32), _P(C.c_double), _P(_i64)]),
     "cg_cbs_boundary": (_i64, [C.c_uint32, C.c_double, C.c_double, _P(C.c_uint32), _i64]),
     "cg_bin_hits": (C.c_int, [C.c_void_p, _i64, _P(_u8), _P(C.c_uint64), C.c_char_p, C.c_int, C.c_int, _P(_u8),
                               _P(_f32), _i64, _P(_i64), _P(_i32), _P(_i32), _P(_i32), _P(_u8)]),
@@ -307,7 +309,7 @@ class Engine:
         return cache[key]
 
     def partition_cbs(self, chrom_off, coverage, alpha=0.01, n_perm=10000, hybrid=True, min_width=2, k_max=25, n_min=200,
-                      eta=0.05, undo=0, seed=0, sbdry=None):
+                      eta=0.05, undo=0, seed=0, sbdry=None, chrom_selected=None, trim=0.025, undo_sd=3.0):
         """CBSRunner.Run: per chromosome the segment lengths (bins) and means."""
         off = np.ascontiguousarray(chrom_off, np.int64)
         cov = np.ascontiguousarray(coverage, np.float64)
@@ -315,15 +317,21 @@ class Engine:
         if sbdry is None:
             sbdry = self.cbs_boundary(n_perm, alpha, eta)
         sbdry = np.ascontiguousarray(sbdry, np.uint32)
-        o = CbsOpts(alpha, n_perm, int(hybrid), min_width, k_max, n_min, eta, 0.025, undo, 0.05, 3.0, seed)
+        o = CbsOpts(alpha, n_perm, int(hybrid), min_width, k_max, n_min, eta, trim, undo, 0.05, undo_sd, seed)
         n = max(len(cov), 1)
         n_seg = np.zeros(max(nc, 1), np.int32)
         seg_len = np.zeros(n, np.int32)
         seg_mean = np.zeros(n, np.float64)
         stats = np.zeros(4, np.int64)
-        rc = self.lib.cg_partition_cbs(self.h, C.byref(o), _ptr(sbdry, C.c_uint32), len(sbdry), nc, _ptr(off, _i64),
-                                       _ptr(cov, C.c_double), _ptr(n_seg, _i32), _ptr(seg_len, _i32), _ptr(seg_mean, C.c_double),
-                                       _ptr(stats, _i64))
+        if chrom_selected is None:
+            rc = self.lib.cg_partition_cbs(self.h, C.byref(o), _ptr(sbdry, C.c_uint32), len(sbdry), nc, _ptr(off, _i64),
+                                           _ptr(cov, C.c_double), _ptr(n_seg, _i32), _ptr(seg_len, _i32),
+                                           _ptr(seg_mean, C.c_double), _ptr(stats, _i64))
+        else:
+            mask = np.ascontiguousarray(chrom_selected, np.uint8)
+            rc = self.lib.cg_partition_cbs_shard(self.h, C.byref(o), _ptr(sbdry, C.c_uint32), len(sbdry), nc, _ptr(off, _i64),
+                                                 _ptr(cov, C.c_double), _ptr(mask, _u8), _ptr(n_seg, _i32), _ptr(seg_len, _i32),
+                                                 _ptr(seg_mean, C.c_double), _ptr(stats, _i64))
         self._check(rc)
         segs = []
         for c in range(nc):

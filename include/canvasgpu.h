@@ -165,6 +165,11 @@ typedef struct {
 int cg_partition_cbs(cg_ctx* ctx, const cg_cbs_opts* opts, const uint32_t* sbdry, int64_t n_sbdry, int n_chrom,
                      const int64_t* chrom_off, const double* coverage, int32_t* n_seg, int32_t* seg_len, double* seg_mean,
                      int64_t* stats);
+/* Multi-GPU: segment only the chromosomes with chrom_selected[c] != 0 (the others get n_seg = 0).  Every chromosome
+ * keeps the random stream it has in the whole-genome call, so the union over ranks equals cg_partition_cbs. */
+int cg_partition_cbs_shard(cg_ctx* ctx, const cg_cbs_opts* opts, const uint32_t* sbdry, int64_t n_sbdry, int n_chrom,
+                           const int64_t* chrom_off, const double* coverage, const uint8_t* chrom_selected, int32_t* n_seg,
+                           int32_t* seg_len, double* seg_mean, int64_t* stats);
 /* Sequential boundary table; returns its length maxOnes (maxOnes + 1) / 2 (out may be NULL), < 0 on bad arguments. */
 int64_t cg_cbs_boundary(uint32_t n_perm, double alpha, double eta, uint32_t* out, int64_t cap);
 

@@ -483,7 +483,89 @@ std::vector<int> change_points(const double* g, int n, const ora_cbs_opts& o, co
     return len;
 }
 
+// Normal(0,1).InverseCumulativeDistribution: Newton steps on the erfc form of the distribution function
+double qnorm(double p) {
+    double x = 0.0;
+    for (int it = 0; it < 200; it++) {
+        const double f = pnorm(x) - p;
+        const double d = std::exp(-0.5 * x * x) / std::sqrt(2.0 * M_PI);
+        const double nx = x - f / d;
+        if (nx == x) break;
+        x = nx;
+    }
+    return x;
+}
+
+// ChangePoint.InflationFactor (:460-474): midpoint rule with 10000 points on the truncated normal
+double inflation_factor(double trim) {
+    const double a = qnorm(1 - trim);
+    const double step = 2 * a / 10000;
+    const double from = -a + step / 2, to = a - step / 2;
+    std::vector<double> xs(10000);
+    const double inc = (to - from) / (10000 - 1);  // Helper.Seq
+    xs[0] = from;
+    xs[9999] = to;
+    for (int i = 1; i < 9999; i++) xs[i] = xs[i - 1] + inc;
+    double e = 0.0;
+    for (double x : xs) e += (x * x) * (std::exp(-0.5 * x * x) / std::sqrt(2.0 * M_PI));
+    e = e * step / (1 - 2 * trim);
+    return 1 / e;
+}
+
+// ChangePoint.TrimmedVariance (:423-452) over the concatenated finite scores
+double trimmed_variance(const std::vector<double>& all, double trim) {
+    const long n = (long)all.size();
+    std::vector<double> d((size_t)std::max<long>(n - 1, 0));
+    for (long i = 0; i + 1 < n; i++) d[i] = std::fabs(all[i + 1] - all[i]);
+    const int keep = round_even((1 - 2 * trim) * (double)(n - 1));
+    std::sort(d.begin(), d.end());
+    double s = 0.0;
+    for (int i = 0; i < keep; i++) s += d[i] * d[i];
+    return inflation_factor(trim) * s / (2 * keep);
+}
+
+double helper_median(const double* x, int a, int b) {  // Helper.Median (Helper.cs:31-44)
+    std::vector<double> y(x + a, x + b);
+    const int mid = (int)y.size() / 2;
+    std::nth_element(y.begin(), y.begin() + mid, y.end());
+    double m = y[mid];
+    if (y.size() % 2 == 0) {
+        const double lo = *std::max_element(y.begin(), y.begin() + mid);
+        m = (m + lo) / 2;
+    }
+    return m;
+}
+
+// ChangePointsSDUndo (:155-196)
+std::vector<int> sd_undo(const double* g, const std::vector<int>& len, double trimmed_sd, double change_sd) {
+    change_sd *= trimmed_sd;
+    std::vector<int> locs;
+    int at = 0;
+    for (int l : len) { at += l; locs.push_back(at); }
+    while (locs.size() > 1) {
+        const size_t k = locs.size();
+        std::vector<double> med(k);
+        for (size_t i = 0; i < k; i++) med[i] = helper_median(g, i == 0 ? 0 : locs[i - 1], locs[i]);
+        size_t imin = 0;
+        double mn = std::fabs(med[1] - med[0]);
+        for (size_t i = 1; i + 1 < k; i++) {
+            const double dv = std::fabs(med[i + 1] - med[i]);
+            if (dv < mn) { mn = dv; imin = i; }
+        }
+        if (mn < change_sd) locs.erase(locs.begin() + (long)imin); else break;
+    }
+    std::vector<int> out;
+    int prev = 0;
+    for (int e : locs) { out.push_back(e - prev); prev = e; }
+    return out;
+}
+
 }  // namespace
+
+extern "C" double ora_cbs_inflation_factor(double trim) { return inflation_factor(trim); }
+extern "C" double ora_cbs_trimmed_variance(const double* x, int64_t n, double trim) {
+    return trimmed_variance(std::vector<double>(x, x + n), trim);
+}
 
 extern "C" int64_t ora_cbs_boundary(uint32_t n_perm, double alpha, double eta, uint32_t* out, int64_t cap) {
     auto sb = compute_boundary(n_perm, alpha, eta);
@@ -520,7 +602,15 @@ extern "C" double ora_cbs_htmaxp(const double* px, int n, int k, double tss, int
 extern "C" int ora_partition_cbs(const ora_cbs_opts* o, const uint32_t* sbdry, int64_t n_sbdry, int n_chrom, const int64_t* chrom_off,
                                  const double* coverage, int32_t* n_seg, int32_t* seg_len, double* seg_mean, int32_t* seg_first,
                                  int32_t* seg_last, int64_t* stats, int n_threads) {
-    if (o->undo != 0) return -4;  // prune / sdundo are not restated
+    if (o->undo != 0 && o->undo != 2) return -4;  // prune is not restated
+    double trimmed_sd = 0.0;
+    if (o->undo == 2) {
+        std::vector<double> all;
+        for (int c = 0; c < n_chrom; c++)
+            for (int64_t i = chrom_off[c]; i < chrom_off[c + 1]; i++)
+                if (std::isfinite(coverage[i])) all.push_back(coverage[i]);
+        trimmed_sd = std::sqrt(trimmed_variance(all, o->trim));
+    }
     std::vector<uint32_t> sb(sbdry, sbdry + n_sbdry);
     Mt seeder(o->seed);
     std::vector<uint32_t> seeds(n_chrom);
@@ -536,6 +626,7 @@ extern "C" int ora_partition_cbs(const ora_cbs_opts* o, const uint32_t* sbdry, i
         if (n == 0) return;
         Mt rnd(seeds[c]);
         std::vector<int> len = change_points(g, n, *o, sb, rnd, st[c]);
+        if (o->undo == 2 && len.size() > 1) len = sd_undo(g, len, trimmed_sd, o->undo_sd);
         int lo = 0, cs1 = 0, cs2 = -1;
         for (size_t i = 0; i < len.size(); i++) {
             cs2 += len[i];

@@ -42,11 +42,15 @@ typedef struct {
     int min_width;     /* 2 */
     int k_max;         /* 25 */
     uint32_t n_min;    /* 200 */
-    int undo;          /* 0 none (the only one restated) */
+    int undo;          /* 0 none, 2 sdundo (prune is not restated) */
     uint32_t seed;     /* seed of the per-chromosome seed generator; 0 in the reference */
+    double trim;       /* 0.025 */
+    double undo_sd;    /* 3 */
 } ora_cbs_opts;
 int64_t ora_cbs_boundary(uint32_t n_perm, double alpha, double eta, uint32_t* out, int64_t cap);
 double ora_cbs_tailp(double b, double delta, int m);
+double ora_cbs_inflation_factor(double trim);
+double ora_cbs_trimmed_variance(const double* x, int64_t n, double trim);
 void ora_mt19937(uint32_t seed, int64_t n, uint32_t* out);
 double ora_cbs_tmaxo(const double* x, int n, int al0, int* seg);
 double ora_cbs_htmaxp(const double* px, int n, int k, double tss, int al0);

@@ -256,7 +256,7 @@ def bin_alignments(flags, pos, mate_pos, ref_id, mate_ref_id, frag_len, mapq, na
 
 class CbsOpts(C.Structure):
     _fields_ = [("alpha", C.c_double), ("n_perm", C.c_uint32), ("hybrid", C.c_int), ("min_width", C.c_int), ("k_max", C.c_int),
-                ("n_min", C.c_uint32), ("undo", C.c_int), ("seed", C.c_uint32)]
+                ("n_min", C.c_uint32), ("undo", C.c_int), ("seed", C.c_uint32), ("trim", C.c_double), ("undo_sd", C.c_double)]
 
 
 _BDRY = {}
@@ -304,7 +304,7 @@ def cbs_htmaxp(px, k, tss, al0=2):
 
 
 def partition_cbs(chrom_off, coverage, alpha=0.01, n_perm=10000, hybrid=True, min_width=2, k_max=25, n_min=200, seed=0,
-                  sbdry=None, n_threads=1):
+                  sbdry=None, n_threads=1, undo=0, trim=0.025, undo_sd=3.0):
     off = np.ascontiguousarray(chrom_off, np.int64)
     cov = np.ascontiguousarray(coverage, np.float64)
     nc = len(off) - 1
@@ -312,7 +312,7 @@ def partition_cbs(chrom_off, coverage, alpha=0.01, n_perm=10000, hybrid=True, mi
     if sbdry is None:
         sbdry = cbs_boundary(n_perm, alpha, 0.05)
     sbdry = np.ascontiguousarray(sbdry, np.uint32)
-    o = CbsOpts(alpha, n_perm, int(hybrid), min_width, k_max, n_min, 0, seed)
+    o = CbsOpts(alpha, n_perm, int(hybrid), min_width, k_max, n_min, undo, seed, trim, undo_sd)
     n_seg = np.zeros(max(nc, 1), np.int32)
     seg_len = np.zeros(n, np.int32); seg_mean = np.zeros(n, np.float64)
     first = np.zeros(n, np.int32); last = np.zeros(n, np.int32)
@@ -328,3 +328,16 @@ def partition_cbs(chrom_off, coverage, alpha=0.01, n_perm=10000, hybrid=True, mi
                      "last": last[a:a + k].copy()})
     return {"segments": segs, "tests": int(stats[0]), "perms": int(stats[1]), "perm_steps": int(stats[2]),
             "edge_steps": int(stats[3])}
+
+
+def cbs_inflation_factor(trim=0.025):
+    f = lib().ora_cbs_inflation_factor
+    f.restype = C.c_double
+    return f(C.c_double(trim))
+
+
+def cbs_trimmed_variance(x, trim=0.025):
+    x = np.ascontiguousarray(x, np.float64)
+    f = lib().ora_cbs_trimmed_variance
+    f.restype = C.c_double
+    return f(_p(x, C.c_double), C.c_int64(len(x)), C.c_double(trim))

@@ -66,6 +66,18 @@ def test_cbs_other_parameters(eng):
     _compare(eng, off, cov, alpha=0.05, n_perm=1000, k_max=20, min_width=3, n_min=150)
 
 
+def test_cbs_sdundo_matches_oracle(eng):
+    # -s SDUndo: neighbours whose medians differ by less than 3 trimmed SDs are merged again
+    rng = np.random.default_rng(9)
+    lens = [6000, 3000]
+    cov = np.concatenate([_chrom(rng, n) for n in lens])
+    cov[3000:3300] += 6  # a weak event that CBS finds and the undo step removes
+    off = np.concatenate([[0], np.cumsum(lens)])
+    plain = po.partition_cbs(off, cov)
+    want = _compare(eng, off, cov, undo=2)
+    assert sum(len(s["len"]) for s in want["segments"]) < sum(len(s["len"]) for s in plain["segments"])
+
+
 def test_cbs_degenerate_inputs(eng):
     cov = np.concatenate([[1.0, 2.0, 3.0], np.full(10, 7.0), np.arange(30.0)])
     want = _compare(eng, [0, 3, 3, 13, 43], cov)
@@ -84,3 +96,21 @@ def test_cbs_rejects_what_it_does_not_implement(eng):
     bad[5] = np.nan
     with pytest.raises(native.CanvasGpuError):
         eng.partition_cbs([0, 100], bad)
+
+
+def test_cbs_shards_union_equals_whole(eng):
+    # every chromosome keeps its own random stream: two disjoint shard calls give the whole-genome answer
+    rng = np.random.default_rng(21)
+    lens = [3000, 50, 2000, 700, 1500]
+    cov = np.concatenate([_chrom(rng, n) for n in lens])
+    off = np.concatenate([[0], np.cumsum(lens)])
+    whole = eng.partition_cbs(off, cov)
+    a = eng.partition_cbs(off, cov, chrom_selected=[1, 0, 0, 1, 0])
+    b = eng.partition_cbs(off, cov, chrom_selected=[0, 1, 1, 0, 1])
+    for c in range(len(lens)):
+        pick = a if c in (0, 3) else b
+        other = b if c in (0, 3) else a
+        assert np.array_equal(pick["segments"][c]["len"], whole["segments"][c]["len"])
+        assert np.array_equal(pick["segments"][c]["mean"], whole["segments"][c]["mean"])
+        assert len(other["segments"][c]["len"]) == 0
+    assert a["perms"] + b["perms"] == whole["perms"]

@@ -55,3 +55,19 @@ def test_short_and_constant_chromosomes():
     r = po.partition_cbs([0, 3, 3, 13, 43], np.concatenate([[1.0, 2.0, 3.0], np.full(10, 7.0), np.arange(30.0)]))
     assert [s["len"].tolist() for s in r["segments"][:3]] == [[3], [], [10]]
     assert sum(r["segments"][3]["len"]) == 30
+
+
+def test_inflation_factor_and_trimmed_variance():
+    # DNAcopy's inflfact(0.025) = 1.3178; the trimmed variance of white noise recovers sigma^2
+    assert abs(po.cbs_inflation_factor(0.025) - 1.3178) < 1e-4
+    x = np.random.default_rng(0).normal(0, 3, 200000)
+    assert abs(po.cbs_trimmed_variance(x) - 9.0) < 0.15
+
+
+def test_sdundo_merges_a_weak_event():
+    rng = np.random.default_rng(0)
+    x = np.round(100 + rng.normal(0, 5, 6000), 2)
+    x[1000:1400] += 50
+    x[3000:3300] += 6
+    assert len(po.partition_cbs([0, 6000], x)["segments"][0]["len"]) > 3
+    assert po.partition_cbs([0, 6000], x, undo=2)["segments"][0]["len"].tolist() == [1000, 400, 4600]

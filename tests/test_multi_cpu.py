@@ -36,3 +36,39 @@ def test_all_gather_breakpoints_world2():
     ret = mgr.dict()
     mp.spawn(_worker, args=(2, port, ret), nprocs=2, join=True)
     assert ret[0] and ret[1]
+
+
+class _FakeEngine:
+    """Stands in for the GPU engine: returns the known segmentation of the chromosomes it is asked for."""
+
+    def __init__(self, truth):
+        self.truth = truth
+
+    def partition_cbs(self, chrom_off, coverage, chrom_selected=None, **kw):
+        segs = [{"len": np.asarray(t, np.int32) if chrom_selected[c] else np.zeros(0, np.int32)} for c, t in enumerate(self.truth)]
+        return {"segments": segs}
+
+
+def _cbs_worker(rank, world, port, ret):
+    import torch.distributed as dist
+    sys.path.insert(0, ROOT)
+    from canvas_b200 import multi
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    truth = [[100, 250, 150], [100], [40, 260], [], [5, 45]]
+    off = np.concatenate([[0], np.cumsum([sum(t) for t in truth])])
+    r = multi.partition_cbs_sharded(_FakeEngine(truth), off, np.zeros(int(off[-1])))
+    ret[rank] = [s["len"].tolist() for s in r["segments"]] == truth and sorted(set(r["owner"].tolist())) == [0, 1]
+    dist.destroy_process_group()
+
+
+def test_partition_cbs_sharded_world2():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_cbs_worker, args=(2, port, ret), nprocs=2, join=True)
+    assert ret[0] and ret[1]
