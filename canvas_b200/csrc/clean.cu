@@ -1,6 +1,7 @@
 // cg_clean: CanvasClean's numeric block on the device (reference CanvasClean.cs:474-530).
 #include "clean.cuh"
 #include "clean_loess.cuh"
+#include "clean_stream.cuh"
 
 // ---------------------------------------------------------------------------------------------
 // Views for the select engine
@@ -515,78 +516,6 @@ __global__ void variance_apply_kernel(float* __restrict__ count2, const uint8_t*
     }
 }
 
-// ---------------------------------------------------------------------------------------------
-// K8 — normalise apply (CanvasClean.cs:190-195): count = (float)(gMed * (double)count / med[gc]).
-// Pure stream: 4 B count + 1 B gc in, 4 B out per bin.  Four bins per thread per step through
-// 128-bit count accesses and 32-bit GC accesses, the 101-entry median table in shared memory.
-// `alive` (optional) masks bins removed by the GC filter; `tables` may hold one table per sample.
-// ---------------------------------------------------------------------------------------------
-template <int UNROLL>
-__global__ void __launch_bounds__(256)
-normalize_apply_kernel(const float* in, const uint8_t* __restrict__ gc,
-                       const uint8_t* __restrict__ alive, float* out,
-                       const int* __restrict__ n_ptr, long long n_fixed, const double* __restrict__ med_tab,
-                       const double* __restrict__ gmed_tab, const int* __restrict__ enabled, long long sample_stride) {
-    if (enabled && !*enabled) return;
-    __shared__ double s_med[GC_BINS];
-    const int sample = blockIdx.y;
-    for (int t = threadIdx.x; t < GC_BINS; t += blockDim.x) s_med[t] = med_tab[(size_t)sample * GC_BINS + t];
-    __syncthreads();
-    const double gmed = gmed_tab[sample];
-    const long long n = n_ptr ? (long long)*n_ptr : n_fixed;
-    in += sample * sample_stride;
-    out += sample * sample_stride;
-    gc += sample * sample_stride;
-    if (alive) alive += sample * sample_stride;
-    const long long nvec = n >> 2;
-    const float4* in4 = reinterpret_cast<const float4*>(in);
-    float4* out4 = reinterpret_cast<float4*>(out);
-    const uchar4* gc4 = reinterpret_cast<const uchar4*>(gc);
-    const uchar4* al4 = reinterpret_cast<const uchar4*>(alive);
-    const long long stride = (long long)gridDim.x * blockDim.x;
-    long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    for (; v + (UNROLL - 1) * stride < nvec; v += UNROLL * stride) {
-        float4 c[UNROLL];
-        uchar4 g[UNROLL];
-        uchar4 a[UNROLL];
-#pragma unroll
-        for (int u = 0; u < UNROLL; u++) {
-            c[u] = __ldcs(in4 + v + u * stride);
-            g[u] = __ldcs(gc4 + v + u * stride);
-            a[u] = alive ? __ldcs(al4 + v + u * stride) : make_uchar4(1, 1, 1, 1);
-        }
-#pragma unroll
-        for (int u = 0; u < UNROLL; u++) {
-            double m;
-            m = s_med[g[u].x]; if (a[u].x && m > 0) c[u].x = (float)__ddiv_rn(__dmul_rn(gmed, (double)c[u].x), m);
-            m = s_med[g[u].y]; if (a[u].y && m > 0) c[u].y = (float)__ddiv_rn(__dmul_rn(gmed, (double)c[u].y), m);
-            m = s_med[g[u].z]; if (a[u].z && m > 0) c[u].z = (float)__ddiv_rn(__dmul_rn(gmed, (double)c[u].z), m);
-            m = s_med[g[u].w]; if (a[u].w && m > 0) c[u].w = (float)__ddiv_rn(__dmul_rn(gmed, (double)c[u].w), m);
-            __stcs(out4 + v + u * stride, c[u]);
-        }
-    }
-    for (; v < nvec; v += stride) {
-        float4 c = in4[v];
-        uchar4 g = gc4[v];
-        uchar4 a = alive ? al4[v] : make_uchar4(1, 1, 1, 1);
-        double m;
-        m = s_med[g.x]; if (a.x && m > 0) c.x = (float)__ddiv_rn(__dmul_rn(gmed, (double)c.x), m);
-        m = s_med[g.y]; if (a.y && m > 0) c.y = (float)__ddiv_rn(__dmul_rn(gmed, (double)c.y), m);
-        m = s_med[g.z]; if (a.z && m > 0) c.z = (float)__ddiv_rn(__dmul_rn(gmed, (double)c.z), m);
-        m = s_med[g.w]; if (a.w && m > 0) c.w = (float)__ddiv_rn(__dmul_rn(gmed, (double)c.w), m);
-        out4[v] = c;
-    }
-    // tail (n not a multiple of 4)
-    if (blockIdx.x == 0) {
-        for (long long i = (nvec << 2) + threadIdx.x; i < n; i += blockDim.x) {
-            float c = in[i];
-            double m = s_med[gc[i]];
-            if ((!alive || alive[i]) && m > 0) c = (float)__ddiv_rn(__dmul_rn(gmed, (double)c), m);
-            out[i] = c;
-        }
-    }
-}
-
 struct FinalPred {  // GC filter survivors minus RemoveBinsWithExtremeLocalSD (CanvasClean.cs:308-322)
     const uint8_t* alive;
     const double* wsd;
@@ -675,6 +604,8 @@ int clean_enqueue(cg_ctx* ctx, const cg_clean_opts* o, CleanDev& d) {
     const int n = (int)d.n;
     const int nb = std::max(1, div_up(n, 256));
     const int grid_stream = std::max(1, std::min(nb, ctx->num_sms * 8));
+    const int grid_k8 = std::max(1, std::min(div_up(n, K8_TILE), ctx->num_sms * K8_CTAS_PER_SM));
+    cudaFuncSetAttribute(normalize_apply_bulk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k8_smem_bytes());
     CleanCtl* ctl = d.ctl;
     const bool loess = o->gc_norm && o->gc_mode != 0;
     if (loess && !d.lo) return cg_fail(ctx, CG_ERR_ARG, "clean: LOESS buffers were not allocated");
@@ -740,7 +671,7 @@ int clean_enqueue(cg_ctx* ctx, const cg_clean_opts* o, CleanDev& d) {
             sel_run_scatter<uint32_t, GcCountView>(ctx, gv, d.sel_gc, n);
             CG_LAUNCH(ctx, gc_median_finish_kernel, 1, 128, 0, d.sel_gc, ctl, &ctl->do_norm);
             CG_LAUNCH(ctx, gc_weighted_kernel, GC_BINS, 256, WQ_CAP * 8, d.count2, d.gc2, d.chrom2, d.alive, d.is_auto, ctl, 0, &ctl->do_norm);
-            CG_LAUNCH(ctx, (normalize_apply_kernel<4>), dim3(grid_stream, 1), 256, 0, d.count2, d.gc2, d.alive, d.count2,
+            CG_LAUNCH(ctx, normalize_apply_bulk_kernel, dim3(grid_k8, 1), K8_THREADS, k8_smem_bytes(), d.count2, d.gc2, d.alive, d.count2,
                       &ctl->n2, 0LL, ctl->med, &ctl->global_median, &ctl->do_norm, 0LL);
         }
         // --- NormalizeVarianceByGC (:34-97), evaluated only when the metric is on and > 500000 bins
@@ -761,7 +692,7 @@ int clean_enqueue(cg_ctx* ctx, const cg_clean_opts* o, CleanDev& d) {
                 sel_run_scatter<uint32_t, GcCountView>(ctx, gm, d.sel_gc, n);
                 CG_LAUNCH(ctx, gc_median_finish_kernel, 1, 128, 0, d.sel_gc, ctl, &ctl->variance_fired);
                 CG_LAUNCH(ctx, gc_weighted_kernel, GC_BINS, 256, WQ_CAP * 8, d.count2, d.gc2, d.chrom2, d.alive, d.is_auto, ctl, 0, &ctl->variance_fired);
-                CG_LAUNCH(ctx, (normalize_apply_kernel<4>), dim3(grid_stream, 1), 256, 0, d.count2, d.gc2, d.alive,
+                CG_LAUNCH(ctx, normalize_apply_bulk_kernel, dim3(grid_k8, 1), K8_THREADS, k8_smem_bytes(), d.count2, d.gc2, d.alive,
                           d.count2, &ctl->n2, 0LL, ctl->med, &ctl->global_median, &ctl->variance_fired, 0LL);
             }
         }
@@ -866,16 +797,16 @@ extern "C" int cg_normalize_apply(cg_ctx* ctx, int batch, int64_t n, const float
     CG_CUDA(ctx, cudaMemcpyAsync(d_gc, gc, total, cudaMemcpyHostToDevice, s));
     CG_CUDA(ctx, cudaMemcpyAsync(d_med, median_by_gc, (size_t)batch * GC_BINS * 8, cudaMemcpyHostToDevice, s));
     CG_CUDA(ctx, cudaMemcpyAsync(d_gmed, global_median, (size_t)batch * 8, cudaMemcpyHostToDevice, s));
-    const int per_sample_blocks = std::max(1, std::min(div_up(n / 4, 256 * 4), (ctx->num_sms * 8 + batch - 1) / batch));
-    dim3 grid(per_sample_blocks, batch);
     if (repeats < 1) repeats = 1;
-    // one untimed launch, then `repeats` timed ones
-    CG_LAUNCH(ctx, (normalize_apply_kernel<4>), grid, 256, 0, d_in, d_gc, (const uint8_t*)nullptr, d_out,
-              (const int*)nullptr, (long long)n, d_med, d_gmed, (const int*)nullptr, (long long)n);
-    CG_CUDA(ctx, cudaEventRecord(ctx->ev0, s));
-    for (int r = 0; r < repeats; r++)
-        CG_LAUNCH(ctx, (normalize_apply_kernel<4>), grid, 256, 0, d_in, d_gc, (const uint8_t*)nullptr, d_out,
+    // one untimed launch, then `repeats` timed ones; the grid fills every SM exactly once (no second wave)
+    CG_CUDA(ctx, cudaFuncSetAttribute(normalize_apply_bulk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k8_smem_bytes()));
+    const int per_sample_blocks = std::max(1, std::min(div_up(n, K8_TILE), ctx->num_sms * K8_CTAS_PER_SM / batch));
+    dim3 grid(per_sample_blocks, batch);
+    for (int r = 0; r <= repeats; r++) {
+        if (r == 1) CG_CUDA(ctx, cudaEventRecord(ctx->ev0, s));
+        CG_LAUNCH(ctx, normalize_apply_bulk_kernel, grid, K8_THREADS, k8_smem_bytes(), d_in, d_gc, (const uint8_t*)nullptr, d_out,
                   (const int*)nullptr, (long long)n, d_med, d_gmed, (const int*)nullptr, (long long)n);
+    }
     CG_CUDA(ctx, cudaEventRecord(ctx->ev1, s));
     CG_CUDA(ctx, cudaMemcpyAsync(count_out, d_out, total * 4, cudaMemcpyDeviceToHost, s));
     CG_CUDA(ctx, cudaStreamSynchronize(s));

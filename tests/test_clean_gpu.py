@@ -124,9 +124,12 @@ def test_unsorted_chromosomes_rejected(engine):
     assert e.value.code == native.CG_ERR_UNSORTED
 
 
-def test_normalize_apply_stream_matches_formula(engine):
+@pytest.mark.parametrize("n", [40_000, 40_004, 1_000_000 + 12, 2044])
+def test_normalize_apply_stream_matches_formula(engine, n):
+    # 40_004: the GC array of sample 1 is not 16-byte aligned (plain-load path); 1_000_012: many tiles per CTA
+    # plus a ragged end; 2044: shorter than one tile
     rng = np.random.default_rng(5)
-    batch, n = 3, 40_000
+    batch = 3
     count = rng.poisson(100, (batch, n)).astype(np.float32)
     gc = rng.integers(0, 101, (batch, n)).astype(np.uint8)
     med = rng.uniform(50, 150, (batch, 101))
