@@ -36,6 +36,9 @@ struct cg_ctx {
     // small pinned staging block for scalars coming back from the device
     char* pinned = nullptr;
     size_t pinned_cap = 0;
+    // pinned staging block for the partition plan tables (one host-to-device copy per call)
+    char* plan_pinned = nullptr;
+    size_t plan_pinned_cap = 0;
 };
 
 inline int cg_fail(cg_ctx* ctx, int code, const std::string& msg) {

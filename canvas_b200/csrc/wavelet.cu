@@ -152,6 +152,7 @@ struct WvDev {
     float *r10, *r100;
     double *med, *mad, *sigma, *cand_thr, *log3;
     WvCtl* ctl;
+    char* plan_end;  // end of the contiguous block of uploaded plan tables that starts at `off`
     // decomposition
     unsigned* lvlcnt;
     int* depth;
@@ -174,6 +175,10 @@ struct WvDev {
     int* rq_tfirst;
     unsigned long long* phase_ns;
     UhTinyTab* tiny_tab;
+    // sizes the arrays were allocated for (wv_alloc); a plan run on them must not exceed any
+    long long cap_N;
+    size_t cap_work, cap_ev, cap_tiles;
+    int cap_nseg, cap_f3, cap_w10, cap_w100, cap_rq, cap_C;
 };
 
 size_t wv_workspace_bytes(const WvPlan& pl) {
@@ -201,18 +206,23 @@ size_t wv_workspace_bytes(const WvPlan& pl) {
 int wv_alloc(cg_ctx* ctx, const WvPlan& pl, WvDev& d, double* cov_dev_existing) {
     const size_t N = (size_t)pl.N, C = (size_t)pl.n_chrom;
     d.cov = cov_dev_existing ? cov_dev_existing : arena_take<double>(ctx, N);
+    // plan tables uploaded by wv_enqueue: one contiguous block [d.off, d.plan_end) so that a single copy from a
+    // pinned staging buffer fills all of them
     d.off = arena_take<long long>(ctx, C + 1);
     d.selected = arena_take<unsigned char>(ctx, C + 1);
-    d.pz = arena_take<double>(ctx, N + C + 1);
-    bool ok = sel_state_alloc<uint64_t>(ctx, pl.t.nseg, d.sel);
     d.seg_len = arena_take<long long>(ctx, pl.t.nseg);
     d.work = arena_take<SelWork>(ctx, pl.work.size() + 1);
     d.seg_nwork = arena_take<int>(ctx, pl.t.nseg + 1);
     d.ev_work = arena_take<WvEvWork>(ctx, pl.ev_work.size() + 1);
     d.tiles = arena_take<WvScanTile>(ctx, pl.tiles.size() + 1);
     d.tile_first = arena_take<int>(ctx, C + 2);
-    d.tsum = arena_take<double>(ctx, pl.tiles.size() + 1);
     d.f3lv = arena_take<WvF3Level>(ctx, WV_F3_LEVELS);
+    d.rq_tfirst = arena_take<int>(ctx, C + 2);
+    d.log3 = arena_take<double>(ctx, 32);
+    d.plan_end = ctx->arena + ctx->arena_off;
+    d.pz = arena_take<double>(ctx, N + C + 1);
+    bool ok = sel_state_alloc<uint64_t>(ctx, pl.t.nseg, d.sel);
+    d.tsum = arena_take<double>(ctx, pl.tiles.size() + 1);
     d.tmed = arena_take<double>(ctx, pl.f3_total + 1);
     d.cmad = arena_take<double>(ctx, pl.f3_total + 1);
     d.ev10 = arena_take<double>(ctx, pl.t.n_w10 + 1);
@@ -223,7 +233,6 @@ int wv_alloc(cg_ctx* ctx, const WvPlan& pl, WvDev& d, double* cov_dev_existing) 
     d.mad = arena_take<double>(ctx, pl.t.nseg);
     d.sigma = arena_take<double>(ctx, C + 1);
     d.cand_thr = arena_take<double>(ctx, C + 1);
-    d.log3 = arena_take<double>(ctx, 32);
     d.ctl = arena_take<WvCtl>(ctx, 1);
     d.lvlcnt = arena_take<unsigned>(ctx, N + 1);
     d.depth = arena_take<int>(ctx, C + 1);
@@ -253,7 +262,6 @@ int wv_alloc(cg_ctx* ctx, const WvPlan& pl, WvDev& d, double* cov_dev_existing) 
     d.rq_hist = arena_take<unsigned short>(ctx, (size_t)(pl.rq_ntiles + 1) * RQ_BUCKETS);
     d.rq_tstart = arena_take<unsigned short>(ctx, (size_t)(pl.rq_ntiles + 1) * RQ_BUCKETS);
     d.rq_cum = arena_take<unsigned>(ctx, (size_t)(pl.rq_ntiles + C + 2) * RQ_BUCKETS);
-    d.rq_tfirst = arena_take<int>(ctx, C + 2);
     d.phase_ns = arena_take<unsigned long long>(ctx, (C + 1) * 8);
     d.tiny_tab = arena_take<UhTinyTab>(ctx, 1);
     ok = ok && d.rq_spl && d.rq_sorted && d.rq_hist && d.rq_tstart && d.rq_cum && d.rq_tfirst;
@@ -261,7 +269,26 @@ int wv_alloc(cg_ctx* ctx, const WvPlan& pl, WvDev& d, double* cov_dev_existing) 
          d.tsum && d.f3lv && d.tmed && d.cmad && d.ev10 && d.ev100 && d.r10 && d.r100 && d.med && d.mad && d.sigma &&
          d.cand_thr && d.log3 && d.ctl && d.lvlcnt && d.depth && d.big && d.mid && d.small && d.tiny && d.cand && d.lvl_idx &&
          d.sv && d.piece && d.prelim && d.lvl_first && d.svkey && d.rec && d.bitmap && d.n_bp && d.bp;
+    d.cap_N = pl.N; d.cap_nseg = pl.t.nseg; d.cap_work = pl.work.size(); d.cap_ev = pl.ev_work.size(); d.cap_tiles = pl.tiles.size();
+    d.cap_f3 = pl.f3_total; d.cap_w10 = pl.t.n_w10; d.cap_w100 = pl.t.n_w100; d.cap_rq = pl.rq_ntiles; d.cap_C = pl.n_chrom;
     return ok ? CG_OK : cg_fail(ctx, CG_ERR_CUDA, "partition: device arena exhausted");
+}
+
+// Clear the accumulators of one partition run.  Sized by the plan the arrays were allocated for, so that it can
+// be enqueued before the final plan is known (fused call: while the host still waits for the Clean results).
+int wv_clear(cg_ctx* ctx, WvDev& d) {
+    cudaStream_t s = ctx->stream;
+    const size_t C = (size_t)d.cap_C;
+    CG_CUDA(ctx, cudaMemsetAsync(d.ctl, 0, sizeof(WvCtl), s));
+    CG_CUDA(ctx, cudaMemsetAsync(&d.ctl->t_first, 0xff, sizeof(unsigned long long), s));
+    CG_CUDA(ctx, cudaMemsetAsync(d.sel.hist, 0, (size_t)d.cap_nseg * SEL_G * SEL_BINS * sizeof(unsigned), s));
+    CG_CUDA(ctx, cudaMemsetAsync(d.lvlcnt, 0, (size_t)(d.cap_N + 1) * sizeof(unsigned), s));
+    CG_CUDA(ctx, cudaMemsetAsync(d.depth, 0, (C + 1) * sizeof(int), s));
+    CG_CUDA(ctx, cudaMemsetAsync(d.big, 0xff, (size_t)UH_QCAP * sizeof(UhBigTask), s));
+    CG_CUDA(ctx, cudaMemsetAsync(d.n_bp, 0, (C + 1) * sizeof(int), s));
+    CG_CUDA(ctx, cudaMemsetAsync(d.med, 0, (size_t)d.cap_nseg * 8, s));
+    CG_CUDA(ctx, cudaMemsetAsync(d.mad, 0, (size_t)d.cap_nseg * 8, s));
+    return CG_OK;
 }
 
 // Upload the plan tables (small) and enqueue the whole partition pipeline.  d.cov must already hold
@@ -270,33 +297,43 @@ int wv_enqueue(cg_ctx* ctx, const cg_wavelet_opts* o, const WvPlan& pl, WvDev& d
     cudaStream_t s = ctx->stream;
     const int C = pl.n_chrom;
     const WvSegTable& t = pl.t;
-    // ---- plan tables.  Host vectors live until the caller synchronises the stream.
-    CG_CUDA(ctx, cudaMemcpyAsync(d.off, pl.off.data(), (C + 1) * 8, cudaMemcpyHostToDevice, s));
-    CG_CUDA(ctx, cudaMemcpyAsync(d.selected, selected_host, C, cudaMemcpyHostToDevice, s));
-    CG_CUDA(ctx, cudaMemcpyAsync(d.seg_len, pl.seg_len.data(), t.nseg * 8, cudaMemcpyHostToDevice, s));
-    CG_CUDA(ctx, cudaMemcpyAsync(d.seg_nwork, pl.seg_nwork.data(), (size_t)t.nseg * 4, cudaMemcpyHostToDevice, s));
-    if (!pl.work.empty()) CG_CUDA(ctx, cudaMemcpyAsync(d.work, pl.work.data(), pl.work.size() * sizeof(SelWork), cudaMemcpyHostToDevice, s));
-    if (!pl.ev_work.empty()) CG_CUDA(ctx, cudaMemcpyAsync(d.ev_work, pl.ev_work.data(), pl.ev_work.size() * sizeof(WvEvWork), cudaMemcpyHostToDevice, s));
-    if (!pl.tiles.empty()) CG_CUDA(ctx, cudaMemcpyAsync(d.tiles, pl.tiles.data(), pl.tiles.size() * sizeof(WvScanTile), cudaMemcpyHostToDevice, s));
-    CG_CUDA(ctx, cudaMemcpyAsync(d.tile_first, pl.tile_first.data(), (C + 1) * 4, cudaMemcpyHostToDevice, s));
-    CG_CUDA(ctx, cudaMemcpyAsync(d.f3lv, pl.f3lv, sizeof(WvF3Level) * WV_F3_LEVELS, cudaMemcpyHostToDevice, s));
-    CG_CUDA(ctx, cudaMemcpyAsync(d.rq_tfirst, pl.rq_tfirst.data(), (C + 1) * 4, cudaMemcpyHostToDevice, s));
-    // ceil(log(3^k) / log(3)) as the host's libm evaluates it (WaveletSegmentation.cs:224)
-    static double log3_tab[32];
+    if (pl.N > d.cap_N || t.nseg > d.cap_nseg || pl.work.size() > d.cap_work || pl.ev_work.size() > d.cap_ev ||
+        pl.tiles.size() > d.cap_tiles || pl.f3_total > d.cap_f3 || t.n_w10 > d.cap_w10 || t.n_w100 > d.cap_w100 ||
+        pl.rq_ntiles > d.cap_rq || C != d.cap_C)
+        return cg_fail(ctx, CG_ERR_CAPACITY, "partition: plan exceeds the workspace it was allocated for");
+    d.sel.nseg = t.nseg;
+    // ---- plan tables: packed into the pinned staging block with the device layout, one copy
     {
+        char* base = (char*)d.off;
+        const size_t bytes = (size_t)(d.plan_end - base);
+        if (bytes > ctx->plan_pinned_cap) {
+            if (ctx->plan_pinned) cudaFreeHost(ctx->plan_pinned);
+            ctx->plan_pinned = nullptr;
+            ctx->plan_pinned_cap = 0;
+            CG_CUDA(ctx, cudaMallocHost((void**)&ctx->plan_pinned, bytes + (bytes >> 2)));
+            ctx->plan_pinned_cap = bytes + (bytes >> 2);
+        }
+        char* h = ctx->plan_pinned;
+        auto put = [&](const void* dev_ptr, const void* src, size_t nbytes) {
+            if (nbytes) memcpy(h + ((const char*)dev_ptr - base), src, nbytes);
+        };
+        put(d.off, pl.off.data(), (size_t)(C + 1) * 8);
+        put(d.selected, selected_host, (size_t)C);
+        put(d.seg_len, pl.seg_len.data(), (size_t)t.nseg * 8);
+        put(d.seg_nwork, pl.seg_nwork.data(), (size_t)t.nseg * 4);
+        put(d.work, pl.work.data(), pl.work.size() * sizeof(SelWork));
+        put(d.ev_work, pl.ev_work.data(), pl.ev_work.size() * sizeof(WvEvWork));
+        put(d.tiles, pl.tiles.data(), pl.tiles.size() * sizeof(WvScanTile));
+        put(d.tile_first, pl.tile_first.data(), (size_t)(C + 1) * 4);
+        put(d.f3lv, pl.f3lv, sizeof(WvF3Level) * WV_F3_LEVELS);
+        put(d.rq_tfirst, pl.rq_tfirst.data(), (size_t)(C + 1) * 4);
+        // ceil(log(3^k) / log(3)) as the host's libm evaluates it (WaveletSegmentation.cs:224)
+        double log3_tab[32] = {0};
         double pw = 1.0;
         for (int k = 0; k < 20; k++) { log3_tab[k] = std::ceil(std::log(pw) / std::log(3.0)); pw *= 3.0; }
+        put(d.log3, log3_tab, 20 * 8);
+        CG_CUDA(ctx, cudaMemcpyAsync(base, h, bytes, cudaMemcpyHostToDevice, s));
     }
-    CG_CUDA(ctx, cudaMemcpyAsync(d.log3, log3_tab, 20 * 8, cudaMemcpyHostToDevice, s));
-    CG_CUDA(ctx, cudaMemsetAsync(d.ctl, 0, sizeof(WvCtl), s));
-    CG_CUDA(ctx, cudaMemsetAsync(&d.ctl->t_first, 0xff, sizeof(unsigned long long), s));
-    CG_CUDA(ctx, cudaMemsetAsync(d.sel.hist, 0, (size_t)t.nseg * SEL_G * SEL_BINS * sizeof(unsigned), s));
-    CG_CUDA(ctx, cudaMemsetAsync(d.lvlcnt, 0, (size_t)(pl.N + 1) * sizeof(unsigned), s));
-    CG_CUDA(ctx, cudaMemsetAsync(d.depth, 0, (size_t)(C + 1) * sizeof(int), s));
-    CG_CUDA(ctx, cudaMemsetAsync(d.big, 0xff, (size_t)UH_QCAP * sizeof(UhBigTask), s));
-    CG_CUDA(ctx, cudaMemsetAsync(d.n_bp, 0, (size_t)(C + 1) * sizeof(int), s));
-    CG_CUDA(ctx, cudaMemsetAsync(d.med, 0, (size_t)t.nseg * 8, s));
-    CG_CUDA(ctx, cudaMemsetAsync(d.mad, 0, (size_t)t.nseg * 8, s));
     if (pl.N == 0) return CG_OK;
 
     WvScalarParams sp;
@@ -523,6 +560,8 @@ extern "C" int cg_partition_wavelet_shard(cg_ctx* ctx, const cg_wavelet_opts* op
     cudaStream_t s = ctx->stream;
     if (pl.N > 0) CG_CUDA(ctx, cudaMemcpyAsync(d.cov, coverage, (size_t)pl.N * 8, cudaMemcpyHostToDevice, s));
     CG_CUDA(ctx, cudaEventRecord(ctx->ev0, s));
+    rc = wv_clear(ctx, d);
+    if (rc) return rc;
     rc = wv_enqueue(ctx, opts, pl, d, sel.data());
     if (rc) { cudaStreamSynchronize(s); return rc; }
     CG_CUDA(ctx, cudaEventRecord(ctx->ev1, s));
@@ -628,6 +667,13 @@ extern "C" int cg_clean_partition_wavelet(cg_ctx* ctx, const cg_clean_opts* copt
     CG_CUDA(ctx, cudaMemcpyAsync(h, d.ctl, sizeof(CleanCtl), cudaMemcpyDeviceToHost, s));
     CG_CUDA(ctx, cudaMemcpyAsync(h_cnt, chrom_cnt, 256 * 4, cudaMemcpyDeviceToHost, s));
     CG_CUDA(ctx, cudaEventRecord(ctx->ev_mid, s));
+    // partition workspace sized for the input lengths (an upper bound of the cleaned ones); its accumulators are
+    // cleared on the device while the host waits for the per-chromosome survivor counts
+    WvDev wd;
+    rc = wv_alloc(ctx, worst, wd, cov);
+    if (rc) { cudaStreamSynchronize(s); return rc; }
+    rc = wv_clear(ctx, wd);
+    if (rc) { cudaStreamSynchronize(s); return rc; }
     CG_CUDA(ctx, cudaStreamSynchronize(s));
     CG_CUDA(ctx, cudaGetLastError());
     CG_CHECK_LAUNCHES(ctx);
@@ -648,9 +694,6 @@ extern "C" int cg_clean_partition_wavelet(cg_ctx* ctx, const cg_clean_opts* copt
     for (int c = 0; c <= n_chrom; c++) chrom_off_out[c] = off[c];
     WvPlan pl;
     make_plan(pl, n_chrom, off.data(), wopts->evenness_window);
-    WvDev wd;
-    rc = wv_alloc(ctx, pl, wd, cov);
-    if (rc) { cudaStreamSynchronize(ctx->copy_stream); return rc; }
     std::vector<unsigned char> sel(n_chrom + 1, 1);
     rc = wv_enqueue(ctx, wopts, pl, wd, sel.data());
     if (rc) { cudaStreamSynchronize(s); cudaStreamSynchronize(ctx->copy_stream); return rc; }

@@ -58,6 +58,20 @@ int ora_partition_cbs(const ora_cbs_opts* o, const uint32_t* sbdry, int64_t n_sb
                       const double* coverage, int32_t* n_seg, int32_t* seg_len, double* seg_mean, int32_t* seg_first,
                       int32_t* seg_last, int64_t* stats, int n_threads);
 
+/* HMM segmentation (oracle/hmm.cpp): `-m HMM` (per_sample = 0, all samples jointly) and `-m PerSampleHMM`
+ * (per_sample = 1, called with one sample).  coverage is [n_samples][N]; breakpoints per chromosome at
+ * bp[chrom_off[c] ...] as for the wavelets; states (optional, [N]) the Viterbi path. */
+typedef struct {
+    int n_states;   /* 5 */
+    int per_sample; /* isPerSample: whole-genome median / pseudo-variance, all states distinct */
+    int min_size;   /* 10 */
+    int n_threads;
+} ora_hmm_opts;
+int ora_partition_hmm(const ora_hmm_opts* o, int n_samples, int n_chrom, const int64_t* chrom_off, const double* coverage,
+                      int32_t* n_bp, int32_t* bp, uint8_t* states);
+double ora_gamma_ln(double z);
+int ora_negative_binomial(double mean, double variance, int max_value, double* out);
+
 /* CanvasBin counting loops (oracle/bin.cpp). possible: one byte per position. Returns the number of bins. */
 int64_t ora_bin_hits(int64_t len, const uint8_t* hits, const uint8_t* possible, const char* bases, int bin_size, int mode,
                      const uint8_t* read_gc, const float* obs_vs_exp, int64_t max_bins, int32_t* start, int32_t* stop,

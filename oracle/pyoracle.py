@@ -341,3 +341,37 @@ def cbs_trimmed_variance(x, trim=0.025):
     f = lib().ora_cbs_trimmed_variance
     f.restype = C.c_double
     return f(_p(x, C.c_double), C.c_int64(len(x)), C.c_double(trim))
+
+
+class HmmOpts(C.Structure):
+    _fields_ = [("n_states", C.c_int), ("per_sample", C.c_int), ("min_size", C.c_int), ("n_threads", C.c_int)]
+
+
+def partition_hmm(chrom_off, coverage, per_sample=True, min_size=10, n_threads=1):
+    """HiddenMarkovModelsRunner.Run.  coverage: [N] (one sample) or [n_samples, N]."""
+    chrom_off = np.ascontiguousarray(chrom_off, np.int64)
+    cov = np.ascontiguousarray(np.atleast_2d(np.asarray(coverage, np.float64)))
+    ns, n = cov.shape
+    nc = len(chrom_off) - 1
+    assert n == int(chrom_off[-1])
+    o = HmmOpts(5, int(per_sample), min_size, n_threads)
+    n_bp = np.zeros(max(nc, 1), np.int32)
+    bp = np.zeros(max(n, 1), np.int32)
+    states = np.zeros(max(n, 1), np.uint8)
+    rc = lib().ora_partition_hmm(C.byref(o), C.c_int(ns), C.c_int(nc), _p(chrom_off, C.c_int64), _p(cov, C.c_double),
+                                 _p(n_bp, C.c_int32), _p(bp, C.c_int32), _p(states, C.c_uint8))
+    assert rc == 0
+    return {"breakpoints": [bp[chrom_off[c]:chrom_off[c] + n_bp[c]].copy() for c in range(nc)], "states": states[:n]}
+
+
+def gamma_ln(z):
+    f = lib().ora_gamma_ln
+    f.restype = C.c_double
+    f.argtypes = [C.c_double]
+    return f(float(z))
+
+
+def negative_binomial(mean, variance, max_value):
+    out = np.zeros(max(max_value, 1), np.float64)
+    k = lib().ora_negative_binomial(C.c_double(mean), C.c_double(variance), C.c_int(max_value), _p(out, C.c_double))
+    return out[:k]
