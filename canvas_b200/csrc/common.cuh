@@ -39,6 +39,9 @@ struct cg_ctx {
     // pinned staging block for the partition plan tables (one host-to-device copy per call)
     char* plan_pinned = nullptr;
     size_t plan_pinned_cap = 0;
+    // second device block for tables whose size is only known in the middle of a call (HMM emission tables)
+    char* aux = nullptr;
+    size_t aux_cap = 0;
 };
 
 inline int cg_fail(cg_ctx* ctx, int code, const std::string& msg) {
@@ -69,6 +72,21 @@ inline int arena_reserve(cg_ctx* ctx, size_t bytes) {
     size_t cap = bytes + (bytes >> 3) + (1u << 20);
     CG_CUDA(ctx, cudaMalloc((void**)&ctx->arena, cap));
     ctx->arena_cap = cap;
+    return CG_OK;
+}
+
+// grow-only side block; contents do not survive the call that filled them
+inline int aux_reserve(cg_ctx* ctx, size_t bytes) {
+    if (bytes <= ctx->aux_cap) return CG_OK;
+    if (ctx->aux) {
+        CG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        CG_CUDA(ctx, cudaFree(ctx->aux));
+        ctx->aux = nullptr;
+        ctx->aux_cap = 0;
+    }
+    const size_t cap = bytes + (bytes >> 2) + (1u << 16);
+    CG_CUDA(ctx, cudaMalloc((void**)&ctx->aux, cap));
+    ctx->aux_cap = cap;
     return CG_OK;
 }
 

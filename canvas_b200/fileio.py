@@ -260,3 +260,47 @@ def write_partitioned(path, order, segments):
                 buf.write(f"{c}\t{a}\t{b}\t{dotnet_double(v)}\t{seg['id']}\n")
     with gzip.open(path, "wt") as f:
         f.write(buf.getvalue())
+
+
+def read_cleaned_columns(path):
+    """chr, start, stop, count columns of a .cleaned file as parsed by MergeMultiSampleCleanedBedFile
+    (Utilities.cs:876-891: int.Parse, float.Parse)."""
+    chrom, start, stop, count = [], [], [], []
+    with _open_text(path) as f:
+        for line in f:
+            p = line.rstrip("\n").rstrip("\r").split("\t")
+            if len(p) < 4:
+                continue
+            chrom.append(p[0])
+            start.append(int(p[1]))
+            stop.append(int(p[2]))
+            count.append(float(p[3]))
+    return chrom, np.array(start, np.int32), np.array(stop, np.int32), np.array(count, np.float32)
+
+
+def normalize_canvas_clean(engine, cleaned_paths):
+    """CanvasRunner.NormalizeCanvasClean (CanvasRunner.cs:883-903): rewrite every sample's .cleaned file with the bins
+    common to all samples — four columns, the count printed by float.ToString().  The set intersection runs on the
+    GPU (cg_merge_common_bins); rows must be in (chromosome, start) order, which CanvasClean's output is."""
+    cols = [read_cleaned_columns(p) for p in cleaned_paths]
+    names = []
+    for chrom, _, _, _ in cols:  # chromosome ids by first appearance over all files (the reference's HashSet order)
+        for c in chrom:
+            if not names or (c != names[-1] and c not in names):
+                names.append(c)
+    ids = {c: i for i, c in enumerate(names)}
+    if len(names) > 256:
+        raise ValueError("more than 256 chromosomes")
+    samples = [(np.array([ids[c] for c in chrom], np.uint8), a, b, v) for chrom, a, b, v in cols]
+    r = engine.merge_common_bins(samples)
+    chrom0 = cols[0][0]
+    start0 = cols[0][1]
+    kept = r["kept_index"]
+    for k, path in enumerate(cleaned_paths):
+        txt = textcodec.float_default_text(r["count"][k])
+        buf = io.StringIO()
+        for i, b, t in zip(kept.tolist(), r["stop"].tolist(), txt):
+            buf.write(f"{chrom0[i]}\t{int(start0[i])}\t{b}\t{t}\n")
+        with gzip.open(path, "wt") as f:
+            f.write(buf.getvalue())
+    return len(kept)

@@ -30,6 +30,10 @@ class WaveletOpts(C.Structure):
                 ("thr_upper", C.c_double), ("min_size", C.c_int), ("evenness_window", C.c_int)]
 
 
+class HmmOpts(C.Structure):
+    _fields_ = [("n_states", C.c_int), ("per_sample", C.c_int), ("min_size", C.c_int), ("exact_sequential", C.c_int)]
+
+
 _P = C.POINTER
 _u8, _i32, _i64, _f32, _f64 = C.c_uint8, C.c_int32, C.c_int64, C.c_float, C.c_double
 
@@ -63,6 +67,11 @@ SIGNATURES = {
                                    _P(_i32), _P(C.c_double), _P(_i64)]),
     "cg_partition_cbs_shard": (C.c_int, [C.c_void_p, C.c_void_p, _P(C.c_uint32), _i64, C.c_int, _P(_i64), _P(C.c_double), _P(_u8),
                                          _P(_i32), _P(_i32), _P(C.c_double), _P(_i64)]),
+    "cg_partition_hmm": (C.c_int, [C.c_void_p, _P(HmmOpts), C.c_int, C.c_int, _P(_i64), _P(_f64), _P(_i32), _P(_i32), _P(_u8)]),
+    "cg_partition_hmm_shard": (C.c_int, [C.c_void_p, _P(HmmOpts), C.c_int, C.c_int, _P(_i64), _P(_f64), _P(_u8), _P(_i32),
+                                         _P(_i32), _P(_u8)]),
+    "cg_merge_common_bins": (C.c_int, [C.c_void_p, C.c_int, _P(_i64), _P(C.c_void_p), _P(C.c_void_p), _P(C.c_void_p),
+                                       _P(C.c_void_p), _P(_i64), _P(_i32), _P(_i32), _P(_f32)]),
     "cg_cbs_boundary": (_i64, [C.c_uint32, C.c_double, C.c_double, _P(C.c_uint32), _i64]),
     "cg_bin_hits": (C.c_int, [C.c_void_p, _i64, _P(_u8), _P(C.c_uint64), C.c_char_p, C.c_int, C.c_int, _P(_u8),
                               _P(_f32), _i64, _P(_i64), _P(_i32), _P(_i32), _P(_i32), _P(_u8)]),
@@ -339,6 +348,48 @@ class Engine:
             segs.append({"len": seg_len[a:a + k].copy(), "mean": seg_mean[a:a + k].copy()})
         return {"segments": segs, "tests": int(stats[0]), "perms": int(stats[1]), "perm_steps": int(stats[2]),
                 "edge_steps": int(stats[3]), "kernel_ms": self.lib.cg_last_kernel_ms(self.h), "phase_ms": self._cbs_phases()}
+
+    def partition_hmm(self, chrom_off, coverage, per_sample=True, min_size=10, exact_sequential=False, chrom_selected=None):
+        """HiddenMarkovModelsRunner.Run: breakpoints and Viterbi states.  coverage: [N] or [n_samples, N]."""
+        off = np.ascontiguousarray(chrom_off, np.int64)
+        cov = np.ascontiguousarray(np.atleast_2d(np.asarray(coverage, np.float64)))
+        ns, n = cov.shape
+        nc = len(off) - 1
+        if nc > 0 and n != int(off[-1]):
+            raise ValueError("coverage length does not match the chromosome offsets")
+        o = HmmOpts(5, int(per_sample), min_size, int(exact_sequential))
+        n_bp = np.zeros(max(nc, 1), np.int32)
+        bp = np.zeros(max(n, 1), np.int32)
+        states = np.zeros(max(n, 1), np.uint8)
+        if chrom_selected is None:
+            rc = self.lib.cg_partition_hmm(self.h, C.byref(o), ns, nc, _ptr(off, _i64), _ptr(cov, _f64), _ptr(n_bp, _i32),
+                                           _ptr(bp, _i32), _ptr(states, _u8))
+        else:
+            mask = np.ascontiguousarray(chrom_selected, np.uint8)
+            rc = self.lib.cg_partition_hmm_shard(self.h, C.byref(o), ns, nc, _ptr(off, _i64), _ptr(cov, _f64), _ptr(mask, _u8),
+                                                 _ptr(n_bp, _i32), _ptr(bp, _i32), _ptr(states, _u8))
+        self._check(rc)
+        return {"breakpoints": [bp[off[c]:off[c] + n_bp[c]].copy() for c in range(nc)], "states": states[:n],
+                "kernel_ms": self.lib.cg_last_kernel_ms(self.h), "launches": self.lib.cg_last_launches(self.h)}
+
+    def merge_common_bins(self, samples):
+        """MergeMultiSampleCleanedBedFile: samples = [(chrom_id u8, start i32, stop i32, count f32), ...] ordered by
+        (chromosome id, start).  Returns kept_index (into sample 0), stop and counts [n_samples, n_common]."""
+        ns = len(samples)
+        cols = [[np.ascontiguousarray(a, t) for a, t in zip(smp, (np.uint8, np.int32, np.int32, np.float32))] for smp in samples]
+        n = np.array([len(c[0]) for c in cols], np.int64)
+        n0 = int(n[0]) if ns else 0
+        arr = lambda k: (C.c_void_p * ns)(*[c[k].ctypes.data for c in cols])  # noqa: E731
+        kept = np.zeros(max(n0, 1), np.int32)
+        stop = np.zeros(max(n0, 1), np.int32)
+        cnt = np.zeros((max(ns, 1), max(n0, 1)), np.float32)
+        m = _i64(0)
+        rc = self.lib.cg_merge_common_bins(self.h, ns, _ptr(n, _i64), arr(0), arr(1), arr(2), arr(3), C.byref(m), _ptr(kept, _i32),
+                                           _ptr(stop, _i32), _ptr(cnt, _f32))
+        self._check(rc)
+        k = m.value
+        return {"kept_index": kept[:k].copy(), "stop": stop[:k].copy(), "count": cnt[:ns, :k].copy(),
+                "kernel_ms": self.lib.cg_last_kernel_ms(self.h)}
 
     def _cbs_phases(self):
         """Phase times (ms) of the slowest chromosome of the last cg_partition_cbs call."""

@@ -58,3 +58,40 @@ def f2_text(count):
     h = f2_hundredths(v)
     neg = (v < 0) & (h != 0)
     return [("-" if n else "") + f"{a // 100}.{a % 100:02d}" for a, n in zip(h.tolist(), neg.tolist())]
+
+
+def float_default_text(count):
+    """float.ToString() of .NET Core 2.0 — general format with 7 significant digits, scientific from 1E+07 up and
+    below 1E-04 — as NormalizeCanvasClean interpolates the merged counts (CanvasRunner.cs:895-897)."""
+    out = []
+    for v in np.asarray(count, np.float32).tolist():
+        if v != v:
+            out.append("NaN")
+        elif v in (float("inf"), float("-inf")):
+            out.append("Infinity" if v > 0 else "-Infinity")
+        else:
+            t = "%.7g" % v
+            if "e" in t:
+                m, e = t.split("e")
+                t = f"{m}E{'-' if e[0] == '-' else '+'}{abs(int(e)):02d}"
+            out.append(t)
+    return out
+
+
+def float_default_roundtrip(count):
+    """float32 counts -> the doubles CanvasPartition parses from the merged (4-column) .cleaned file."""
+    v = np.asarray(count, np.float32)
+    x = np.abs(v.astype(np.float64))
+    out = np.zeros(x.shape, np.float64)
+    ok = np.isfinite(x) & (x > 0)
+    xs = x[ok]
+    e = np.floor(np.log10(xs)).astype(np.int64)
+    e = np.where(xs < 10.0 ** e.astype(np.float64), e - 1, e)
+    e = np.where(xs >= 10.0 ** (e + 1).astype(np.float64), e + 1, e)
+    k = 6 - e  # decimal shift that leaves seven significant digits before the point
+    scaled = np.where(k >= 0, xs * 10.0 ** np.clip(k, 0, 22).astype(np.float64), xs / 10.0 ** np.clip(-k, 0, 22).astype(np.float64))
+    d7 = np.rint(scaled)
+    out[ok] = np.where(k >= 0, d7 / 10.0 ** np.clip(k, 0, 22).astype(np.float64), d7 * 10.0 ** np.clip(-k, 0, 22).astype(np.float64))
+    out = np.where(v < 0, -out, out)
+    bad = ~np.isfinite(v)
+    return np.where(bad, v.astype(np.float64), out)

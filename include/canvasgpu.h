@@ -174,6 +174,47 @@ int cg_partition_cbs_shard(cg_ctx* ctx, const cg_cbs_opts* opts, const uint32_t*
 int64_t cg_cbs_boundary(uint32_t n_perm, double alpha, double eta, uint32_t* out, int64_t cap);
 
 /* ---------------------------------------------------------------------------------------------
+ * CanvasPartition -m HMM / -m PerSampleHMM (the SmallPedigree default, CanvasRunner.cs:927):
+ * HiddenMarkovModelsRunner.Run (HiddenMarkovModelsRunner.cs:23-109) — negative-binomial emissions for copy
+ * numbers 0..4 (InitializeNegativeBinomialEmission :111-153, Distributions.cs:206-217), outliers clipped at
+ * 5 x the largest haploid mean (:155-163), HiddenMarkovModel.BestPathViterbi (HMM.cs:62-130) per chromosome,
+ * breakpoints where the state changes.  coverage is [n_samples][N] (sample-major, all chromosomes concatenated,
+ * chrom_off[n_chrom + 1]); finite and >= 0.  per_sample = 1 (PerSampleHMM): one sample per call, whole-genome
+ * median and IQR-based pseudo-variance, five distinct states; per_sample = 0 (HMM): up to 4 samples jointly,
+ * per-chromosome median and variance, states 0|1 and 3|4 share their emission.  Outputs as for the wavelets:
+ * n_bp[c] breakpoints at bp[chrom_off[c] ...] (first is 0; none when the chromosome has <= min_size bins);
+ * states (optional, [N]) the Viterbi path.  SegmentationInput.DeriveSegments and SplitOverlappingSegments
+ * stay on the host.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+    int n_states;         /* 5 */
+    int per_sample;       /* isPerSample */
+    int min_size;         /* 10 */
+    int exact_sequential; /* 1: one thread per chromosome replays the reference loop (cross-check; slow) */
+} cg_hmm_opts;
+int cg_partition_hmm(cg_ctx* ctx, const cg_hmm_opts* opts, int n_samples, int n_chrom, const int64_t* chrom_off,
+                     const double* coverage, int32_t* n_bp, int32_t* bp, uint8_t* states);
+/* Multi-GPU: only the chromosomes with chrom_selected[c] != 0 are segmented (the statistics of the emission
+ * model are whole-genome in per-sample mode, so every rank passes the full coverage). */
+int cg_partition_hmm_shard(cg_ctx* ctx, const cg_hmm_opts* opts, int n_samples, int n_chrom, const int64_t* chrom_off,
+                           const double* coverage, const uint8_t* chrom_selected, int32_t* n_bp, int32_t* bp,
+                           uint8_t* states);
+
+/* ---------------------------------------------------------------------------------------------
+ * Pedigree step between CanvasClean and CanvasPartition: keep the bins that survived CanvasClean in EVERY
+ * sample — Utilities.MergeMultiSampleCleanedBedFile (CanvasCommon/Utilities.cs:834-920), written back per
+ * sample by CanvasRunner.NormalizeCanvasClean (Canvas/CanvasRunner.cs:883-903).  Sample s has n[s] bins in the
+ * columns chrom[s] (dense chromosome ids shared by all samples), start[s], stop[s], count[s], ordered by
+ * (chromosome id, start) without duplicates (CG_ERR_UNSORTED otherwise).  Outputs, capacity n[0]: *n_out common
+ * bins in the first sample's order; kept_index = their positions in sample 0; stop_out = the stop of the last
+ * sample (the reference overwrites it per file, :885); count_out[s * n[0] + k] = sample s's count of common bin k.
+ * A kept bin with start < 0 or start >= stop is the reference's IlluminaException (CG_ERR_ARG, same message).
+ * ------------------------------------------------------------------------------------------- */
+int cg_merge_common_bins(cg_ctx* ctx, int n_samples, const int64_t* n, const uint8_t* const* chrom,
+                         const int32_t* const* start, const int32_t* const* stop, const float* const* count,
+                         int64_t* n_out, int32_t* kept_index, int32_t* stop_out, float* count_out);
+
+/* ---------------------------------------------------------------------------------------------
  * CanvasBin counting (BAM decoding, read pairing and FASTA handling stay on the host).
  *
  * cg_bin_hits — BinCountsForChromosome (CanvasBin.cs:568-661) for one chromosome without predefined

@@ -375,3 +375,34 @@ def negative_binomial(mean, variance, max_value):
     out = np.zeros(max(max_value, 1), np.float64)
     k = lib().ora_negative_binomial(C.c_double(mean), C.c_double(variance), C.c_int(max_value), _p(out, C.c_double))
     return out[:k]
+
+
+def merge_multi_sample_cleaned(samples):
+    """Utilities.MergeMultiSampleCleanedBedFile (CanvasCommon/Utilities.cs:834-920), dictionary for dictionary
+    (pure Python: small cases only).  samples: list of lists of (chr, start, stop, count) rows in file order.
+    Returns rows (chr, start, stop, [count per sample]) in the reference's output order: chromosomes by first
+    appearance over all files, positions by first appearance, kept when every file listed them."""
+    chromosomes = []
+    for rows in samples:
+        for r in rows:
+            if r[0] not in chromosomes:
+                chromosomes.append(r[0])
+    start = {c: {} for c in chromosomes}
+    stop = {c: {} for c in chromosomes}
+    counts = {c: {} for c in chromosomes}
+    for rows in samples:
+        for c, a, b, v in rows:
+            start[c][a] = a
+            stop[c][a] = b
+            counts[c].setdefault(a, []).append(np.float32(v))
+    out = []
+    for c in chromosomes:
+        for a in list(start[c].keys()):
+            if len(counts[c][a]) < len(samples):
+                continue
+            if a < 0:
+                raise ValueError("Start must be non-negative")
+            if a >= stop[c][a]:
+                raise ValueError("Start must be less than Stop")
+            out.append((c, a, stop[c][a], list(counts[c][a])))
+    return out

@@ -138,3 +138,25 @@ def test_split_overlapping_segments_reference_vectors():
 def test_cbs_segments_from_lengths():
     start = np.array([0, 10, 20, 30, 40]); end = start + 10
     assert fileio.cbs_segments([2, 3], start, end) == [(0, 20), (20, 50)]
+
+
+def test_float_default_text_and_roundtrip():
+    """float.ToString() of .NET Core 2.0 (7 significant digits) as used by NormalizeCanvasClean."""
+    from canvas_b200 import textcodec
+    v = np.array([0.0, 1.0, 99.46, 123.45, 12345.68, 123456.78, 1234567.0, 12345678.0, 0.0001, 0.00001234, 100.0], np.float32)
+    txt = textcodec.float_default_text(v)
+    assert txt == ["0", "1", "99.46", "123.45", "12345.68", "123456.8", "1234567", "1.234568E+07", "0.0001", "1.234E-05", "100"]
+    rt = textcodec.float_default_roundtrip(v)
+    assert rt.tolist() == [float(t) for t in txt]
+    rng = np.random.default_rng(0)
+    w = np.round(rng.gamma(2, 3000, 20000), 2).astype(np.float32)
+    assert textcodec.float_default_roundtrip(w).tolist() == [float(t) for t in textcodec.float_default_text(w)]
+
+
+def test_merge_oracle_follows_dictionary_semantics():
+    from oracle import pyoracle as ora
+    a = [("chr1", 0, 10, 1.0), ("chr1", 10, 20, 2.0), ("chr2", 0, 10, 3.0)]
+    b = [("chr1", 10, 25, 5.0), ("chr2", 0, 10, 6.0), ("chr3", 0, 10, 7.0)]
+    out = ora.merge_multi_sample_cleaned([a, b])
+    assert [(c, s, e) for c, s, e, _ in out] == [("chr1", 10, 25), ("chr2", 0, 10)]  # the last file's stop wins
+    assert [[float(x) for x in v] for *_, v in out] == [[2.0, 5.0], [3.0, 6.0]]
