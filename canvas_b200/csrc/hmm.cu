@@ -28,7 +28,8 @@
 namespace {
 
 constexpr int HMM_NS = 5;
-constexpr int HMM_BLOCK = 256;
+constexpr int HMM_BLOCK = 64;    // bins per block (thread granularity of steps A and C)
+constexpr int HMM_GROUP = 64;    // blocks per group (second level of the scan and of the back tracking)
 constexpr int HMM_MAX_SAMPLES = 4;
 constexpr int HMM_MAX_CHROM = 256;
 
@@ -38,9 +39,16 @@ struct HmmBlk {
     int last;          // last block of its chromosome
 };
 
+struct HmmGrp {
+    int b0, b1;        // block range of the group
+    int chrom;
+    int pad;
+};
+
 struct HmmChromInfo {
     long long a, b;    // global bin range
     int first_blk, n_blk;
+    int first_grp, n_grp;
     int active;        // selected and longer than min_size
     int tab;           // emission table index
     double max_thr;    // RemoveOutliers threshold
@@ -236,8 +244,19 @@ __global__ void __launch_bounds__(128) hmm_block_kernel(const double* __restrict
 #pragma unroll
             for (int j = 0; j < HMM_NS; j++) A[i][j] = fmax(-DBL_MAX, __dadd_rn(e[j], i == j ? ls : lo));
     }
+    double en[HMM_NS];  // emissions of the next bin, loaded one step ahead
+    if (bk.t0 + 1 < bk.t1) {
+#pragma unroll
+        for (int j = 0; j < HMM_NS; j++) en[j] = le[(size_t)(bk.t0 + 1) * HMM_NS + j];
+    }
     for (long long t = bk.t0 + 1; t < bk.t1; t++) {
-        const double* e = le + (size_t)t * HMM_NS;
+        double e[HMM_NS];
+#pragma unroll
+        for (int j = 0; j < HMM_NS; j++) e[j] = en[j];
+        if (t + 1 < bk.t1) {
+#pragma unroll
+            for (int j = 0; j < HMM_NS; j++) en[j] = le[(size_t)(t + 1) * HMM_NS + j];
+        }
         double cs[HMM_NS], co[HMM_NS];
 #pragma unroll
         for (int j = 0; j < HMM_NS; j++) { cs[j] = __dadd_rn(e[j], ls); co[j] = __dadd_rn(e[j], lo); }
@@ -289,47 +308,94 @@ __device__ inline int hmm_best_final(const double* s) {
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// step B: start vector of every block (one thread per chromosome, next matrix prefetched)
+// step B: start vector of every block, in two levels.  B1: one warp per group multiplies the group's block
+// matrices ((max,+) product, lane (i,j) owns one entry); B2: per chromosome the group matrices are applied in order
+// from the first-bin scores (staged in shared memory, one thread walks them); B3: one thread per group walks its
+// blocks from the group's start vector.
 // ---------------------------------------------------------------------------------------------------------------
-__global__ void hmm_scan_kernel(const double* __restrict__ le, const HmmChromInfo* __restrict__ ci, int C, const double* __restrict__ mats,
-                                double log_start, double ls, double lo, double* __restrict__ svec, int* __restrict__ end_state,
-                                HmmCtl* ctl) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= C) return;
-    const HmmChromInfo ch = ci[c];
+__global__ void __launch_bounds__(128) hmm_group_kernel(const HmmGrp* __restrict__ grp, int n_grp, const double* __restrict__ mats,
+                                                        double* __restrict__ gmats) {
+    const int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (g >= n_grp) return;
+    const HmmGrp gr = grp[g];
+    const int L = lane < 25 ? lane : 0;
+    const int i = L / HMM_NS, j = L % HMM_NS;
+    double P = mats[(size_t)gr.b0 * 25 + L];
+    double nxt = gr.b0 + 1 < gr.b1 ? mats[(size_t)(gr.b0 + 1) * 25 + L] : 0.0;
+    for (int b = gr.b0 + 1; b < gr.b1; b++) {
+        const double M = nxt;
+        if (b + 1 < gr.b1) nxt = mats[(size_t)(b + 1) * 25 + L];
+        double acc = -DBL_MAX;
+#pragma unroll
+        for (int k = 0; k < HMM_NS; k++) {
+            const double pk = __shfl_sync(0xffffffffu, P, i * HMM_NS + k);
+            const double mk = __shfl_sync(0xffffffffu, M, k * HMM_NS + j);
+            acc = fmax(acc, __dadd_rn(pk, mk));
+        }
+        P = acc;
+    }
+    if (lane < 25) gmats[(size_t)g * 25 + lane] = P;
+}
+
+__device__ inline void hmm_apply(double* s, const double* A) {  // s <- s (x) A with the reference's Double.MinValue floor
+    double ns[HMM_NS];
+#pragma unroll
+    for (int j = 0; j < HMM_NS; j++) {
+        double mx = -DBL_MAX;
+#pragma unroll
+        for (int i = 0; i < HMM_NS; i++) mx = fmax(mx, __dadd_rn(s[i], A[i * HMM_NS + j]));
+        ns[j] = mx;
+    }
+#pragma unroll
+    for (int j = 0; j < HMM_NS; j++) s[j] = ns[j];
+}
+
+__global__ void __launch_bounds__(128) hmm_scan_groups_kernel(const double* __restrict__ le, const HmmChromInfo* __restrict__ ci,
+                                                              const double* __restrict__ gmats, double log_start, double ls, double lo,
+                                                              double* __restrict__ gvec, int* __restrict__ end_state) {
+    extern __shared__ double s_gm[];
+    const HmmChromInfo ch = ci[blockIdx.x];
     if (!ch.active) return;
+    for (int q = threadIdx.x; q < ch.n_grp * 25; q += blockDim.x) s_gm[q] = gmats[(size_t)ch.first_grp * 25 + q];
+    __syncthreads();
+    if (threadIdx.x != 0) return;
     double s[HMM_NS];
     hmm_init_scores(le + (size_t)ch.a * HMM_NS, log_start, ls, lo, s);
-    if (ch.n_blk == 0) { end_state[c] = hmm_best_final(s); return; }
-    double nxt[25];
-    const double* m = mats + (size_t)ch.first_blk * 25;
+    if (ch.n_blk == 0) { end_state[blockIdx.x] = hmm_best_final(s); return; }
+    for (int g = 0; g < ch.n_grp; g++) {
+        double* gv = gvec + (size_t)(ch.first_grp + g) * HMM_NS;
 #pragma unroll
-    for (int q = 0; q < 25; q++) nxt[q] = m[q];
+        for (int j = 0; j < HMM_NS; j++) gv[j] = s[j];
+        hmm_apply(s, s_gm + g * 25);
+    }
+}
+
+__global__ void __launch_bounds__(64) hmm_scan_blocks_kernel(const HmmGrp* __restrict__ grp, int n_grp, const double* __restrict__ mats,
+                                                             const double* __restrict__ gvec, double* __restrict__ svec, HmmCtl* ctl) {
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n_grp) return;
+    const HmmGrp gr = grp[g];
+    double s[HMM_NS];
+#pragma unroll
+    for (int j = 0; j < HMM_NS; j++) s[j] = gvec[(size_t)g * HMM_NS + j];
+    double nxt[25];
+#pragma unroll
+    for (int q = 0; q < 25; q++) nxt[q] = mats[(size_t)gr.b0 * 25 + q];
     bool degenerate = false;
-    for (int b = 0; b < ch.n_blk; b++) {
+    for (int b = gr.b0; b < gr.b1; b++) {
         double A[25];
 #pragma unroll
         for (int q = 0; q < 25; q++) A[q] = nxt[q];
-        if (b + 1 < ch.n_blk) {
-            const double* mn = mats + (size_t)(ch.first_blk + b + 1) * 25;
+        if (b + 1 < gr.b1) {
 #pragma unroll
-            for (int q = 0; q < 25; q++) nxt[q] = mn[q];
+            for (int q = 0; q < 25; q++) nxt[q] = mats[(size_t)(b + 1) * 25 + q];
         }
-        double* sv = svec + (size_t)(ch.first_blk + b) * HMM_NS;
         bool any_alive = false;
 #pragma unroll
-        for (int j = 0; j < HMM_NS; j++) { sv[j] = s[j]; if (s[j] > -DBL_MAX) any_alive = true; }
+        for (int j = 0; j < HMM_NS; j++) { svec[(size_t)b * HMM_NS + j] = s[j]; if (s[j] > -DBL_MAX) any_alive = true; }
         if (!any_alive) degenerate = true;  // every state at Double.MinValue: only the sequential order is defined
-        double ns[HMM_NS];
-#pragma unroll
-        for (int j = 0; j < HMM_NS; j++) {
-            double mx = -DBL_MAX;
-#pragma unroll
-            for (int i = 0; i < HMM_NS; i++) mx = fmax(mx, __dadd_rn(s[i], A[i * HMM_NS + j]));
-            ns[j] = mx;
-        }
-#pragma unroll
-        for (int j = 0; j < HMM_NS; j++) s[j] = ns[j];
+        hmm_apply(s, A);
     }
     if (degenerate) ctl->degenerate = 1;
 }
@@ -370,8 +436,18 @@ __global__ void __launch_bounds__(128) hmm_replay_kernel(const double* __restric
 #pragma unroll
     for (int j = 0; j < HMM_NS; j++) s[j] = svec[(size_t)b * HMM_NS + j];
     unsigned origin = 0;  // origin[j] = state at the bin before the block on the best path into state j
+    double en[HMM_NS];  // emissions of the next bin, loaded one step ahead
+#pragma unroll
+    for (int j = 0; j < HMM_NS; j++) en[j] = le[(size_t)bk.t0 * HMM_NS + j];
     for (long long t = bk.t0; t < bk.t1; t++) {
-        const unsigned p = hmm_step(le + (size_t)t * HMM_NS, ls, lo, s);
+        double e[HMM_NS];
+#pragma unroll
+        for (int j = 0; j < HMM_NS; j++) e[j] = en[j];
+        if (t + 1 < bk.t1) {
+#pragma unroll
+            for (int j = 0; j < HMM_NS; j++) en[j] = le[(size_t)(t + 1) * HMM_NS + j];
+        }
+        const unsigned p = hmm_step(e, ls, lo, s);
         back[t] = (unsigned short)p;
         if (t == bk.t0) origin = p;
         else {
@@ -385,22 +461,54 @@ __global__ void __launch_bounds__(128) hmm_replay_kernel(const double* __restric
     if (bk.last) end_state[bk.chrom] = hmm_best_final(s);
 }
 
-// back tracking over the blocks of a chromosome: state at the last bin of every block, and at the first bin
-__global__ void __launch_bounds__(256) hmm_backtrack_kernel(const HmmChromInfo* __restrict__ ci, const unsigned short* __restrict__ map,
-                                                            const int* __restrict__ end_state, uint8_t* __restrict__ blk_end,
-                                                            uint8_t* __restrict__ states) {
+// back tracking over blocks, in two levels: D1 composes the maps of a group's blocks, D2 walks the groups of a
+// chromosome from its end state (state at the last bin of every group, and at the chromosome's first bin), D3 walks
+// the blocks of every group
+__global__ void __launch_bounds__(64) hmm_group_map_kernel(const HmmGrp* __restrict__ grp, int n_grp, const unsigned short* __restrict__ map,
+                                                           unsigned short* __restrict__ gmap) {
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n_grp) return;
+    const HmmGrp gr = grp[g];
+    unsigned cur = 0;
+#pragma unroll
+    for (int e = 0; e < HMM_NS; e++) cur |= (unsigned)e << (3 * e);
+    for (int b = gr.b1 - 1; b >= gr.b0; b--) {
+        const unsigned m = map[b];
+        unsigned nx = 0;
+#pragma unroll
+        for (int e = 0; e < HMM_NS; e++) nx |= ((m >> (3 * ((cur >> (3 * e)) & 7u))) & 7u) << (3 * e);
+        cur = nx;
+    }
+    gmap[g] = (unsigned short)cur;
+}
+
+__global__ void __launch_bounds__(128) hmm_backtrack_groups_kernel(const HmmChromInfo* __restrict__ ci, const unsigned short* __restrict__ gmap,
+                                                                   const int* __restrict__ end_state, uint8_t* __restrict__ grp_end,
+                                                                   uint8_t* __restrict__ states) {
     extern __shared__ unsigned short s_map[];
     const HmmChromInfo ch = ci[blockIdx.x];
     if (!ch.active) return;
-    for (int b = threadIdx.x; b < ch.n_blk; b += blockDim.x) s_map[b] = map[ch.first_blk + b];
+    for (int g = threadIdx.x; g < ch.n_grp; g += blockDim.x) s_map[g] = gmap[ch.first_grp + g];
     __syncthreads();
     if (threadIdx.x == 0) {
         unsigned e = (unsigned)end_state[blockIdx.x];
-        for (int b = ch.n_blk - 1; b >= 0; b--) {
-            blk_end[ch.first_blk + b] = (uint8_t)e;
-            e = (s_map[b] >> (3 * e)) & 7u;
+        for (int g = ch.n_grp - 1; g >= 0; g--) {
+            grp_end[ch.first_grp + g] = (uint8_t)e;
+            e = (s_map[g] >> (3 * e)) & 7u;
         }
         states[ch.a] = (uint8_t)e;
+    }
+}
+
+__global__ void __launch_bounds__(64) hmm_backtrack_blocks_kernel(const HmmGrp* __restrict__ grp, int n_grp, const unsigned short* __restrict__ map,
+                                                                  const uint8_t* __restrict__ grp_end, uint8_t* __restrict__ blk_end) {
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n_grp) return;
+    const HmmGrp gr = grp[g];
+    unsigned e = grp_end[g];
+    for (int b = gr.b1 - 1; b >= gr.b0; b--) {
+        blk_end[b] = (uint8_t)e;
+        e = (map[b] >> (3 * e)) & 7u;
     }
 }
 
@@ -588,16 +696,30 @@ extern "C" int cg_partition_hmm_shard(cg_ctx* ctx, const cg_hmm_opts* o, int n_s
             }
     }
     const int n_blk = (int)blks.size();
-    int max_chrom_blk = 1;
-    for (int c = 0; c < C; c++) max_chrom_blk = std::max(max_chrom_blk, ci[(size_t)c].n_blk);
-    if ((size_t)max_chrom_blk * 2 > 200 * 1024) return cg_fail(ctx, CG_ERR_UNSUPPORTED, "cg_partition_hmm: chromosome too long");
+    std::vector<HmmGrp> grps;
+    int max_chrom_grp = 1;
+    for (int c = 0; c < C; c++) {
+        HmmChromInfo& h = ci[(size_t)c];
+        h.first_grp = (int)grps.size();
+        h.n_grp = 0;
+        for (int b = h.first_blk; b < h.first_blk + h.n_blk; b += HMM_GROUP) {
+            HmmGrp g;
+            g.b0 = b; g.b1 = std::min(h.first_blk + h.n_blk, b + HMM_GROUP); g.chrom = c; g.pad = 0;
+            grps.push_back(g);
+            h.n_grp++;
+        }
+        max_chrom_grp = std::max(max_chrom_grp, h.n_grp);
+    }
+    const int n_grp = (int)grps.size();
+    if ((size_t)max_chrom_grp * 200 > 200 * 1024) return cg_fail(ctx, CG_ERR_UNSUPPORTED, "cg_partition_hmm: chromosome too long");
 
     // ---- workspace
     const int nseg_q = S, nseg_m = S * C;
     size_t need = arena_need((size_t)S * N, 8) + arena_need((size_t)N * HMM_NS, 8) + arena_need(N, 1) * 2 + arena_need(N, 2) + arena_need(N, 4) +
                   arena_need(C + 1, sizeof(HmmChromInfo)) + arena_need(n_blk + 1, sizeof(HmmBlk)) + arena_need((size_t)(n_blk + 1) * 25, 8) +
                   arena_need((size_t)(n_blk + 1) * HMM_NS, 8) + arena_need(n_blk + 1, 2) + arena_need(n_blk + 1, 1) + arena_need(n_blk + 1, 4) * 2 +
-                  arena_need(C + 1, 4) * 2 + arena_need(1, sizeof(HmmCtl)) + sel_state_bytes<uint32_t>(nseg_q) + sel_state_bytes<uint64_t>(nseg_m) +
+                  arena_need(n_grp + 1, sizeof(HmmGrp)) + arena_need((size_t)(n_grp + 1) * 25, 8) + arena_need((size_t)(n_grp + 1) * HMM_NS, 8) +
+                  arena_need(n_grp + 1, 2) + arena_need(n_grp + 1, 1) + arena_need(C + 1, 4) * 2 + arena_need(1, sizeof(HmmCtl)) + sel_state_bytes<uint32_t>(nseg_q) + sel_state_bytes<uint64_t>(nseg_m) +
                   arena_need((size_t)nseg_m + 1, 8) + (8u << 20);
     int rc = arena_reserve(ctx, need);
     if (rc) return rc;
@@ -615,6 +737,11 @@ extern "C" int cg_partition_hmm_shard(cg_ctx* ctx, const cg_hmm_opts* o, int n_s
     uint8_t* d_blk_end = arena_take<uint8_t>(ctx, n_blk + 1);
     int* d_blk_cnt = arena_take<int>(ctx, n_blk + 1);
     int* d_blk_off = arena_take<int>(ctx, n_blk + 1);
+    HmmGrp* d_grp = arena_take<HmmGrp>(ctx, n_grp + 1);
+    double* d_gmats = arena_take<double>(ctx, (size_t)(n_grp + 1) * 25);
+    double* d_gvec = arena_take<double>(ctx, (size_t)(n_grp + 1) * HMM_NS);
+    unsigned short* d_gmap = arena_take<unsigned short>(ctx, n_grp + 1);
+    uint8_t* d_grp_end = arena_take<uint8_t>(ctx, n_grp + 1);
     int* d_end_state = arena_take<int>(ctx, C + 1);
     int* d_nbp = arena_take<int>(ctx, C + 1);
     HmmCtl* d_ctl = arena_take<HmmCtl>(ctx, 1);
@@ -623,7 +750,7 @@ extern "C" int cg_partition_hmm_shard(cg_ctx* ctx, const cg_hmm_opts* o, int n_s
     SelState<uint64_t> sel_m;
     bool ok = sel_state_alloc<uint32_t>(ctx, nseg_q, sel_q) && sel_state_alloc<uint64_t>(ctx, nseg_m, sel_m);
     if (!ok || !d_cov || !d_le || !d_chrom_id || !d_states || !d_back || !d_bp || !d_ci || !d_blk || !d_mats || !d_svec || !d_map ||
-        !d_blk_end || !d_blk_cnt || !d_blk_off || !d_end_state || !d_nbp || !d_ctl || !d_var)
+        !d_grp || !d_gmats || !d_gvec || !d_gmap || !d_grp_end || !d_blk_end || !d_blk_cnt || !d_blk_off || !d_end_state || !d_nbp || !d_ctl || !d_var)
         return cg_fail(ctx, CG_ERR_CUDA, "cg_partition_hmm: device arena exhausted");
     cudaStream_t s = ctx->stream;
     CG_CUDA(ctx, cudaMemcpyAsync(d_cov, coverage, (size_t)S * N * 8, cudaMemcpyHostToDevice, s));
@@ -750,6 +877,7 @@ extern "C" int cg_partition_hmm_shard(cg_ctx* ctx, const cg_hmm_opts* o, int n_s
     CG_CUDA(ctx, cudaMemcpyAsync(d_tab, tab.data(), tab.size() * 8, cudaMemcpyHostToDevice, s));
     CG_CUDA(ctx, cudaMemcpyAsync(d_ci, ci.data(), (size_t)C * sizeof(HmmChromInfo), cudaMemcpyHostToDevice, s));
     if (n_blk > 0) CG_CUDA(ctx, cudaMemcpyAsync(d_blk, blks.data(), (size_t)n_blk * sizeof(HmmBlk), cudaMemcpyHostToDevice, s));
+    if (n_grp > 0) CG_CUDA(ctx, cudaMemcpyAsync(d_grp, grps.data(), (size_t)n_grp * sizeof(HmmGrp), cudaMemcpyHostToDevice, s));
     const double self_t = 0.99;
     const double ls = std::log(self_t), lo = std::log((1.0 - self_t) / (HMM_NS - 1));
     const double log_start = std::log((double)(1.0f / HMM_NS));
@@ -763,23 +891,28 @@ extern "C" int cg_partition_hmm_shard(cg_ctx* ctx, const cg_hmm_opts* o, int n_s
     ctx->stage_used[2] = true;
     dbg("emission");
     bool sequential = o->exact_sequential != 0;
-    if ((size_t)max_chrom_blk * 2 > 48 * 1024)
-        CG_CUDA(ctx, cudaFuncSetAttribute(hmm_backtrack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_chrom_blk * 2));
+    if ((size_t)max_chrom_grp * 200 > 48 * 1024)
+        CG_CUDA(ctx, cudaFuncSetAttribute(hmm_scan_groups_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_chrom_grp * 200));
     HmmCtl h_ctl = {0, 0};
     for (int attempt = 0; attempt < 2; attempt++) {
         if (!sequential) {
             if (n_blk > 0) {
                 CG_LAUNCH(ctx, hmm_block_kernel, div_up(n_blk, 128), 128, 0, d_le, d_blk, n_blk, ls, lo, d_mats);
+                CG_LAUNCH(ctx, hmm_group_kernel, div_up(n_grp * 32, 128), 128, 0, d_grp, n_grp, d_mats, d_gmats);
             }
-            CG_LAUNCH(ctx, hmm_scan_kernel, div_up(C, 32), 32, 0, d_le, d_ci, C, d_mats, log_start, ls, lo, d_svec, d_end_state, d_ctl);
-            if (n_blk > 0)
+            CG_LAUNCH(ctx, hmm_scan_groups_kernel, C, 128, (size_t)max_chrom_grp * 200, d_le, d_ci, d_gmats, log_start, ls, lo, d_gvec, d_end_state);
+            if (n_blk > 0) {
+                CG_LAUNCH(ctx, hmm_scan_blocks_kernel, div_up(n_grp, 64), 64, 0, d_grp, n_grp, d_mats, d_gvec, d_svec, d_ctl);
                 CG_LAUNCH(ctx, hmm_replay_kernel, div_up(n_blk, 128), 128, 0, d_le, d_blk, n_blk, d_svec, ls, lo, d_back, d_map, d_end_state);
-            CG_LAUNCH(ctx, hmm_backtrack_kernel, C, 256, (size_t)max_chrom_blk * 2, d_ci, d_map, d_end_state, d_blk_end, d_states);
+                CG_LAUNCH(ctx, hmm_group_map_kernel, div_up(n_grp, 64), 64, 0, d_grp, n_grp, d_map, d_gmap);
+            }
+            CG_LAUNCH(ctx, hmm_backtrack_groups_kernel, C, 128, (size_t)max_chrom_grp * 2, d_ci, d_gmap, d_end_state, d_grp_end, d_states);
+            if (n_blk > 0) CG_LAUNCH(ctx, hmm_backtrack_blocks_kernel, div_up(n_grp, 64), 64, 0, d_grp, n_grp, d_map, d_grp_end, d_blk_end);
             if (n_blk > 0) CG_LAUNCH(ctx, hmm_states_kernel, div_up(n_blk, 128), 128, 0, d_blk, n_blk, d_back, d_blk_end, d_states, d_blk_cnt);
             CG_LAUNCH(ctx, hmm_bp_scan_kernel, C, 256, 0, d_ci, d_blk_cnt, d_blk_off, d_nbp, d_bp);
             if (n_blk > 0) CG_LAUNCH(ctx, hmm_bp_write_kernel, div_up(n_blk, 128), 128, 0, d_blk, n_blk, d_ci, d_states, d_blk_off, d_bp);
         } else {
-            CG_LAUNCH(ctx, hmm_sequential_kernel, div_up(C, 32), 32, 0, d_le, d_ci, C, log_start, ls, lo, d_back, d_states, d_nbp, d_bp);
+            CG_LAUNCH(ctx, hmm_sequential_kernel, C, 1, 0, d_le, d_ci, C, log_start, ls, lo, d_back, d_states, d_nbp, d_bp);
         }
         CG_CUDA(ctx, cudaMemcpyAsync(&h_ctl, d_ctl, sizeof(HmmCtl), cudaMemcpyDeviceToHost, s));
         CG_CUDA(ctx, cudaStreamSynchronize(s));
