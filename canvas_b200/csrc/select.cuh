@@ -99,35 +99,41 @@ __global__ void __launch_bounds__(1024) sel_hist_scatter_kernel(View v, SelState
 
     const long long n = v.size();
     const long long stride = (long long)gridDim.x * blockDim.x;
-    const long long n_round = ((n + 31) / 32) * 32;
     const int hi_shift = shift + 8;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += stride) {
+    // Row-0 updates are aggregated per thread as run lengths: the leading digits of a data set are nearly constant
+    // (one flush per thread instead of one atomic per element), the trailing digits only concern the few elements
+    // that still match a prefix.  One run per segment slot (own bucket / global list).
+    int run_idx[2] = {-1, -1};
+    unsigned run_len[2] = {0u, 0u};
+    auto flush = [&](int a) {
+        if (run_len[a]) {
+            if (PRIV) atomicAdd(&s_hist[run_idx[a]], run_len[a]);
+            else atomicAdd(&st.hist[(size_t)(run_idx[a] / SEL_BINS * SEL_G) * SEL_BINS + (run_idx[a] % SEL_BINS)], run_len[a]);
+        }
+    };
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         K key = 0;
         int seg[2] = {-1, -1};
-        bool ok = false;
-        if (i < n) ok = v.get(i, key, seg[0], seg[1]);
+        if (!v.get(i, key, seg[0], seg[1])) continue;
         const int d = (int)((key >> shift) & (K)255);
 #pragma unroll
         for (int a = 0; a < 2; a++) {
-            const int s = ok ? seg[a] : -1;
-            const int ng = s >= 0 ? s_ngrp[s] : 0;
-            bool hit0 = false;
-            if (ng > 0) hit0 = first || (((key ^ s_prefix[s * SEL_G]) >> hi_shift) == 0);
-            if (PRIV) {
-                unsigned act = __ballot_sync(0xffffffffu, hit0);
-                if (hit0) {
-                    int idx = s * SEL_BINS + d;
-                    unsigned m = __match_any_sync(act, idx);
-                    if ((int)(__ffs(m) - 1) == (int)(threadIdx.x & 31)) atomicAdd(&s_hist[idx], __popc(m));
-                }
-            } else if (hit0) {
-                atomicAdd(&st.hist[(size_t)(s * SEL_G) * SEL_BINS + d], 1u);
+            const int s = seg[a];
+            if (s < 0) continue;
+            const int ng = s_ngrp[s];
+            if (ng <= 0) continue;
+            if (first || (((key ^ s_prefix[s * SEL_G]) >> hi_shift) == 0)) {
+                const int idx = s * SEL_BINS + d;
+                if (idx == run_idx[a]) run_len[a]++;
+                else { flush(a); run_idx[a] = idx; run_len[a] = 1u; }
             }
             for (int j = 1; j < ng; j++)
                 if (((key ^ s_prefix[s * SEL_G + j]) >> hi_shift) == 0)
                     atomicAdd(&st.hist[(size_t)(s * SEL_G + j) * SEL_BINS + d], 1u);
         }
     }
+    flush(0);
+    flush(1);
     if (PRIV) {
         __syncthreads();
         for (int t = threadIdx.x; t < nseg * SEL_BINS; t += blockDim.x) {
@@ -190,22 +196,28 @@ __global__ void sel_hist_contig_kernel(View v, const SelWork* __restrict__ work,
     __syncthreads();
     const int hi_shift = shift + 8;
     const long long span = w.hi - w.lo;
-    const long long span_round = ((span + blockDim.x - 1) / blockDim.x) * blockDim.x;
-    for (long long o = threadIdx.x; o < span_round; o += blockDim.x) {
-        const long long i = w.lo + o;
+    // per-thread run-length aggregation (see the scattered kernel); an element matches at most one group
+    int run_idx = -1;
+    unsigned run_len = 0u;
+    for (long long o = threadIdx.x; o < span; o += blockDim.x) {
         K key = 0;
-        const bool ok = i < w.hi && v.get(i, s, key);
+        if (!v.get(w.lo + o, s, key)) continue;
         const int d = (int)((key >> shift) & (K)255);
-        for (int j = 0; j < ng; j++) {
-            const bool hit = ok && (first || (((key ^ s_prefix[j]) >> hi_shift) == 0));
-            // warp-aggregated: the leading digits of a coverage window are nearly constant
-            const unsigned act = __ballot_sync(0xffffffffu, hit);
-            if (hit) {
-                const unsigned m = __match_any_sync(act, d);
-                if ((int)(__ffs(m) - 1) == (int)(threadIdx.x & 31)) atomicAdd(&s_hist[j * SEL_BINS + d], (unsigned)__popc(m));
-            }
+        int idx = -1;
+        if (first) idx = d;
+        else {
+            for (int j = 0; j < ng; j++)
+                if (((key ^ s_prefix[j]) >> hi_shift) == 0) { idx = j * SEL_BINS + d; break; }
+        }
+        if (idx < 0) continue;
+        if (idx == run_idx) run_len++;
+        else {
+            if (run_len) atomicAdd(&s_hist[run_idx], run_len);
+            run_idx = idx;
+            run_len = 1u;
         }
     }
+    if (run_len) atomicAdd(&s_hist[run_idx], run_len);
     __syncthreads();
     for (int t = threadIdx.x; t < ng * SEL_BINS; t += blockDim.x) {
         unsigned c = s_hist[t];

@@ -369,7 +369,7 @@ int wv_enqueue(cg_ctx* ctx, const cg_wavelet_opts* o, const WvPlan& pl, WvDev& d
     }
     // ---- evenness per window
     if (!pl.ev_work.empty())
-        CG_LAUNCH(ctx, wv_evenness_kernel, (int)pl.ev_work.size(), 256, 0, d.cov, d.ev_work, d.ev10, d.ev100, d.ctl);
+        CG_LAUNCH(ctx, wv_evenness_kernel, (int)pl.ev_work.size(), 1024, 0, d.cov, d.ev_work, d.ev10, d.ev100, d.ctl);
     // ---- order statistics, three dependent waves
     const int nwork = (int)pl.work.size();
     const int rq_grid = div_up(t.nseg, 128);

@@ -106,24 +106,141 @@ struct LevelSorter {
 // The replay above is inherently sequential inside one sub-array, but after a partition the two parts
 // never touch each other again, so they can be replayed by different threads and still give the
 // identical permutation.  Round r runs every pending sub-array on its own thread (one partition, or
-// the insertion / heap sort that finishes it) and queues the two parts for round r+1: the critical
-// path drops from ~n log n to ~2n steps.  Needed because a run of exact zeros makes the tree (and
-// with it the number of levels to sort) thousands of levels deep.
-__device__ void level_sort_parallel(LevelSorter ls, int n, int* task_a, int* task_b, int task_cap, int* s_counts2) {
+// the insertion / heap sort that finishes it) and queues the two parts for round r+1.  Needed because a
+// run of exact zeros makes the tree (and with it the number of levels to sort) thousands of levels deep.
+//
+// Large sub-arrays are partitioned by the whole block instead (level_partition_block): the sequential
+// Hoare loop swaps the t-th element from the left that is not below the pivot with the t-th element from
+// the right that is not above it for as long as the former lies left of the latter, so ranking both kinds
+// of "stops" with a block scan gives every swap pair at once.  In detail, with l_0 < l_1 < ... the stops
+// of the left scan over (lo, hi-1] and r_0 > r_1 > ... those of the right scan over [lo, hi-1) — the pivot
+// parked at hi-1 and the median-of-three minimum at lo are the sentinels — iteration t of the loop finds
+// left = min(l_t, r_{t-1}) and right = max(r_t, l_{t-1}): untouched positions keep their original
+// elements and an already swapped position holds a stop.  Hence pairs (l_t, r_t) are swapped while
+// l_t < r_t, a prefix property, and the loop exits with left = min(l_T, r_{T-1}) for the first T with
+// l_T >= r_T (r_{-1} = hi-1).
+constexpr int FIN_SORT_PAR_MIN = 160;  // sub-arrays longer than this are partitioned by the block
+constexpr int FIN_SORT_BIG_CAP = 64;   // pending large sub-arrays (disjoint, each > FIN_SORT_PAR_MIN of <= 4096)
+
+__device__ int level_partition_block(LevelSorter ls, int lo, int hi, int* Lpos, int* Rpos) {
+    __shared__ unsigned s_pivot;
+    __shared__ int s_wl[32], s_wr[32];
+    __shared__ int s_totl, s_totr, s_left;
+    const int tid = threadIdx.x, P = blockDim.x;
+    if (tid == 0) {
+        const int mid = lo + (hi - lo) / 2;
+        ls.swap_if_greater(lo, mid);
+        ls.swap_if_greater(lo, hi);
+        ls.swap_if_greater(mid, hi);
+        s_pivot = ls.kc[mid];
+        ls.swap(mid, hi - 1);
+    }
+    __syncthreads();
+    const unsigned pivot = s_pivot;
+    const int size = hi - lo + 1;
+    const int E = (size + P - 1) / P;
+    const int p0 = lo + tid * E, p1 = min(p0 + E, hi + 1);
+    int cl = 0, cr = 0;
+    for (int q = p0; q < p1; q++) {
+        const unsigned v = ls.kc[q];
+        if (q > lo && q <= hi - 1 && !(LevelSorter::cmpc(v, pivot) < 0)) cl++;
+        if (q >= lo && q < hi - 1 && !(LevelSorter::cmpc(pivot, v) < 0)) cr++;
+    }
+    // block-wide exclusive scan of (cl, cr)
+    int il = cl, ir = cr;
+    for (int o = 1; o < 32; o <<= 1) {
+        const int a = __shfl_up_sync(0xffffffffu, il, o), b2 = __shfl_up_sync(0xffffffffu, ir, o);
+        if ((tid & 31) >= o) { il += a; ir += b2; }
+    }
+    if ((tid & 31) == 31) { s_wl[tid >> 5] = il; s_wr[tid >> 5] = ir; }
+    __syncthreads();
+    if (tid < 32) {
+        const int nw = (P + 31) >> 5;
+        int a = tid < nw ? s_wl[tid] : 0, b2 = tid < nw ? s_wr[tid] : 0;
+        int ia = a, ib = b2;
+        for (int o = 1; o < 32; o <<= 1) {
+            const int x = __shfl_up_sync(0xffffffffu, ia, o), y = __shfl_up_sync(0xffffffffu, ib, o);
+            if (tid >= o) { ia += x; ib += y; }
+        }
+        s_wl[tid] = ia - a;
+        s_wr[tid] = ib - b2;
+        if (tid == 31) { s_totl = ia; s_totr = ib; }
+    }
+    __syncthreads();
+    const int totl = s_totl, totr = s_totr;
+    int rl = s_wl[tid >> 5] + il - cl;  // rank of this thread's first left stop
+    int rr = s_wr[tid >> 5] + ir - cr;  // ascending rank of its first right stop
+    for (int q = p0; q < p1; q++) {
+        const unsigned v = ls.kc[q];
+        if (q > lo && q <= hi - 1 && !(LevelSorter::cmpc(v, pivot) < 0)) Lpos[rl++] = q;
+        if (q >= lo && q < hi - 1 && !(LevelSorter::cmpc(pivot, v) < 0)) { Rpos[totr - 1 - rr] = q; rr++; }
+    }
+    __syncthreads();
+    // number of swapped pairs: l_t < r_t holds for a prefix of t
+    int a = 0, b2 = min(totl, totr);
+    while (a < b2) {
+        const int m = (a + b2) >> 1;
+        if (Lpos[m] < Rpos[m]) a = m + 1; else b2 = m;
+    }
+    const int nswap = a;
+    for (int t = tid; t < nswap; t += P) ls.swap(Lpos[t], Rpos[t]);
+    if (tid == 0) s_left = min(Lpos[nswap], nswap > 0 ? Rpos[nswap - 1] : hi - 1);
+    __syncthreads();
+    const int left = s_left;
+    if (tid == 0) ls.swap(left, hi - 1);
+    __syncthreads();
+    return left;
+}
+
+// Lpos / Rpos: scratch for the block partition (n ints each) or nullptr (every sub-array on one thread).
+__device__ void level_sort_parallel(LevelSorter ls, int n, int* task_a, int* task_b, int task_cap, int* s_counts2,
+                                    int* Lpos = nullptr, int* Rpos = nullptr) {
     if (n < 2) return;
+    __shared__ int s_big[2][3 * FIN_SORT_BIG_CAP];
+    __shared__ int s_nbig[2];
+    const bool coop = Lpos != nullptr && Rpos != nullptr;
     int depth0 = 0;
     for (int t = n; t >= 1; t /= 2) depth0++;
     depth0 *= 2;
     int* cur = task_a;
     int* nxt = task_b;
+    int bc = 0;  // index of the current big list
     if (threadIdx.x == 0) {
-        cur[0] = 0; cur[1] = n - 1; cur[2] = depth0;
-        s_counts2[0] = 1; s_counts2[1] = 0;
+        s_nbig[0] = s_nbig[1] = 0;
+        s_counts2[0] = 0; s_counts2[1] = 0;
+        if (coop && n > FIN_SORT_PAR_MIN) { s_big[0][0] = 0; s_big[0][1] = n - 1; s_big[0][2] = depth0; s_nbig[0] = 1; }
+        else { cur[0] = 0; cur[1] = n - 1; cur[2] = depth0; s_counts2[0] = 1; }
     }
     __syncthreads();
+    // queue a sub-array for the next round (any thread)
+    auto push = [&](int lo, int hi, int depth) {
+        if (coop && hi - lo + 1 > FIN_SORT_PAR_MIN) {
+            const int i = atomicAdd(&s_nbig[bc ^ 1], 1);
+            if (i < FIN_SORT_BIG_CAP) { s_big[bc ^ 1][3 * i] = lo; s_big[bc ^ 1][3 * i + 1] = hi; s_big[bc ^ 1][3 * i + 2] = depth; }
+        } else {
+            const int i = atomicAdd(&s_counts2[1], 1);
+            if (i < task_cap) { nxt[3 * i] = lo; nxt[3 * i + 1] = hi; nxt[3 * i + 2] = depth; }
+        }
+    };
     for (;;) {
         const int ncur = s_counts2[0];
-        if (ncur <= 0) break;
+        const int nbig = min(s_nbig[bc], FIN_SORT_BIG_CAP);
+        if (ncur <= 0 && nbig <= 0) break;
+        // large sub-arrays: one after the other, all threads
+        for (int b = 0; b < nbig; b++) {
+            const int lo = s_big[bc][3 * b], hi = s_big[bc][3 * b + 1];
+            int depth = s_big[bc][3 * b + 2];
+            if (depth == 0) {
+                if (threadIdx.x == 0) ls.heapsort(lo, hi);
+                continue;
+            }
+            depth--;
+            const int pv = level_partition_block(ls, lo, hi, Lpos, Rpos);
+            if (threadIdx.x == 0) {
+                if (hi > pv + 1) push(pv + 1, hi, depth);
+                if (pv - 1 > lo) push(lo, pv - 1, depth);
+            }
+        }
         for (int t = threadIdx.x; t < ncur; t += blockDim.x) {
             const int lo = cur[3 * t], hi = cur[3 * t + 1];
             int depth = cur[3 * t + 2];
@@ -138,18 +255,13 @@ __device__ void level_sort_parallel(LevelSorter ls, int n, int* task_a, int* tas
             if (depth == 0) { ls.heapsort(lo, hi); continue; }
             depth--;
             const int pv = ls.partition(lo, hi);
-            if (hi > pv + 1) {
-                const int i = atomicAdd(&s_counts2[1], 1);
-                if (i < task_cap) { nxt[3 * i] = pv + 1; nxt[3 * i + 1] = hi; nxt[3 * i + 2] = depth; }
-            }
-            if (pv - 1 > lo) {
-                const int i = atomicAdd(&s_counts2[1], 1);
-                if (i < task_cap) { nxt[3 * i] = lo; nxt[3 * i + 1] = pv - 1; nxt[3 * i + 2] = depth; }
-            }
+            if (hi > pv + 1) push(pv + 1, hi, depth);
+            if (pv - 1 > lo) push(lo, pv - 1, depth);
         }
         __syncthreads();
-        if (threadIdx.x == 0) { s_counts2[0] = min(s_counts2[1], task_cap); s_counts2[1] = 0; }
+        if (threadIdx.x == 0) { s_counts2[0] = min(s_counts2[1], task_cap); s_counts2[1] = 0; s_nbig[bc] = 0; }
         int* tmp = cur; cur = nxt; nxt = tmp;
+        bc ^= 1;
         __syncthreads();
     }
 }
@@ -757,7 +869,11 @@ uh_finish_kernel(FinParams p) {
             __syncthreads();
             int* tasks = reinterpret_cast<int*>(s_bms.cand);
             const int cap = (int)(sizeof(s_bms.cand) / sizeof(int)) / 6;
-            level_sort_parallel(LevelSorter{s_val, s_cnt}, T, tasks, tasks + 3 * cap, cap, s_sort_counts);
+            // scratch of the block partition: the upper half of s_key (s_cnt takes the lower) and the multi-select's histograms
+            int* lpos = reinterpret_cast<int*>(s_key) + FIN_SORT_SMEM;
+            int* rpos = reinterpret_cast<int*>(&s_bms.hist[0][0]);
+            static_assert(sizeof(s_bms.hist) >= FIN_SORT_SMEM * sizeof(int), "right-stop scratch does not fit");
+            level_sort_parallel(LevelSorter{s_val, s_cnt}, T, tasks, tasks + 3 * cap, cap, s_sort_counts, lpos, rpos);
             __syncthreads();
             for (int l = threadIdx.x; l < T; l += blockDim.x) lvl_idx[l] = s_val[l];
         } else {

@@ -293,8 +293,17 @@ __global__ void wv_evenness_kernel(const double* __restrict__ cov, const WvEvWor
     __shared__ unsigned s_hist[WV_EV_BINS];
     const WvEvWork w = work[blockIdx.x];
     const double* x = cov + w.lo;
+    // four loads in flight per thread: a 100 000-bin window is one CTA's work and would otherwise be a chain of
+    // dependent L2 round trips
     double part = 0.0;
-    for (int i = threadIdx.x; i < w.cnt; i += blockDim.x) part += x[i];
+    {
+        double p0 = 0.0, p1 = 0.0, p2 = 0.0, p3 = 0.0;
+        const int bd = blockDim.x;
+        int i = threadIdx.x;
+        for (; i + 3 * bd < w.cnt; i += 4 * bd) { p0 += x[i]; p1 += x[i + bd]; p2 += x[i + 2 * bd]; p3 += x[i + 3 * bd]; }
+        for (; i < w.cnt; i += bd) p0 += x[i];
+        part = (p0 + p1) + (p2 + p3);
+    }
     const double sum = block_sum_double(part);
     const double average = sum / (double)w.cnt;
     double ev;
@@ -307,6 +316,7 @@ __global__ void wv_evenness_kernel(const double* __restrict__ cov, const WvEvWor
         if (cmax < WV_EV_BINS) {
             for (int t = threadIdx.x; t <= (int)cmax; t += blockDim.x) s_hist[t] = 0u;
             __syncthreads();
+#pragma unroll 4
             for (int i = threadIdx.x; i < w.cnt; i += blockDim.x) {
                 const double v = x[i];
                 if (v >= 0.0) {
