@@ -207,6 +207,7 @@ extern "C" int cg_bin_hits(cg_ctx* ctx, int64_t chr_len, const uint8_t* hits, co
         return cg_fail(ctx, CG_ERR_ARG, "cg_bin_hits: bad argument");
     *n_bins = 0;
     ctx->launches = 0;
+    ctx->tl = nullptr;
     ctx->launch_err = cudaSuccess;
     for (int i = 0; i < 4; i++) ctx->stage_used[i] = false;
     if (chr_len == 0) return CG_OK;
@@ -286,6 +287,7 @@ extern "C" int cg_bin_fragments(cg_ctx* ctx, int64_t n_frag, const int32_t* frag
         (n_frag > 0 && (!frag_start || !frag_stop || !best_bin)) || (n_undo > 0 && !undo_index))
         return cg_fail(ctx, CG_ERR_ARG, "cg_bin_fragments: bad argument");
     ctx->launches = 0;
+    ctx->tl = nullptr;
     ctx->launch_err = cudaSuccess;
     for (int i = 0; i < 4; i++) ctx->stage_used[i] = false;
     if (n_bins == 0) {

@@ -1373,6 +1373,7 @@ static int partition_cbs_impl(cg_ctx* ctx, const cg_cbs_opts* o, const uint32_t*
         return cg_fail(ctx, CG_ERR_UNSUPPORTED, "cg_partition_cbs: k_max <= 32 and n_min <= 256 are supported");
     if (o->n_perm == 0 || !(o->alpha > 0)) return cg_fail(ctx, CG_ERR_ARG, "cg_partition_cbs: n_perm and alpha must be positive");
     ctx->launches = 0;
+    ctx->tl = nullptr;
     ctx->launch_err = cudaSuccess;
     for (int i = 0; i < 4; i++) ctx->stage_used[i] = false;
     std::vector<unsigned> table;

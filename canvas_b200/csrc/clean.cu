@@ -29,11 +29,15 @@ struct GcCountView {  // GetCountsByGC: autosomal alive bins, segment = GC bucke
     const int* enabled;
     __device__ long long size() const { return *enabled ? ctl->n2 : 0; }
     __device__ bool get(long long i, uint32_t& key, int& a, int& b) const {
-        if (!alive[i] || !is_auto[chrom[i]]) return false;
-        key = f32_key(count[i]);
-        a = gc[i];
+        // every column is loaded before anything is tested: the loads of one element (and of the other elements of
+        // the caller's batch) go out together instead of one L2 round trip after the other
+        const uint8_t al = alive[i], ch = chrom[i], g = gc[i];
+        const float c = count[i];
+        const uint8_t au = is_auto[ch];
+        key = f32_key(c);
+        a = g;
         b = GC_BINS;
-        return true;
+        return al != 0 && au != 0;
     }
 };
 
@@ -198,6 +202,81 @@ __global__ void local_sd_windows_kernel(const float* __restrict__ count2, const 
         unsigned m = __match_any_sync(act, c);
         if ((int)(__ffs(m) - 1) == (int)(threadIdx.x & 31)) atomicAdd(&wcnt[c], (unsigned)__popc(m));
     }
+}
+
+// Median and MAD of one chromosome's window SDs (CanvasClean.cs:243-258) in one CTA: the list (<= LSD_SORT_CAP values)
+// is staged in shared memory and the order statistics of SortedList<double>.Median() are radix-selected there, first
+// on the values, then on the deviations |x - median|.  Replaces two 8-pass grid-wide selections over ~N/20 values.
+constexpr int LSD_SORT_CAP = 16384;
+
+// k-th smallest (0-based) of k[0..n) in shared memory: MSD radix select, 8-bit digits, block-wide
+__device__ unsigned long long block_radix_select_u64(const unsigned long long* k, int n, int rank) {
+    __shared__ unsigned s_h[256];
+    __shared__ unsigned long long s_prefix;
+    __shared__ int s_rank;
+    if (threadIdx.x == 0) { s_prefix = 0ull; s_rank = rank; }
+    for (int shift = 56; shift >= 0; shift -= 8) {
+        if (threadIdx.x < 256) s_h[threadIdx.x] = 0u;
+        __syncthreads();
+        const unsigned long long prefix = s_prefix;
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {
+            const unsigned long long key = k[i];
+            if (shift == 56 || ((key ^ prefix) >> (shift + 8)) == 0ull) atomicAdd(&s_h[(unsigned)(key >> shift) & 255u], 1u);
+        }
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            const int lane = threadIdx.x;
+            unsigned c[8], sum = 0;
+#pragma unroll
+            for (int t = 0; t < 8; t++) { c[t] = s_h[lane * 8 + t]; sum += c[t]; }
+            unsigned incl = sum;
+            for (int o = 1; o < 32; o <<= 1) { const unsigned v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+            const unsigned excl = incl - sum;
+            const unsigned r = (unsigned)s_rank;
+            if (r >= excl && r < excl + sum) {  // exactly one lane
+                unsigned run = excl;
+#pragma unroll
+                for (int t = 0; t < 8; t++) {
+                    if (r < run + c[t]) { s_prefix = prefix | ((unsigned long long)(lane * 8 + t) << shift); s_rank = (int)(r - run); break; }
+                    run += c[t];
+                }
+            }
+        }
+        __syncthreads();
+    }
+    const unsigned long long out = s_prefix;
+    __syncthreads();
+    return out;
+}
+
+// SortedList<double>.Median() of the keys in shared memory
+__device__ double block_median_u64(const unsigned long long* k, int n) {
+    const unsigned long long kb = block_radix_select_u64(k, n, n / 2);
+    const unsigned long long ka = (n & 1) ? kb : block_radix_select_u64(k, n, n / 2 - 1);
+    const double a = f64_unkey(ka), b = f64_unkey(kb);
+    return ka == kb ? a : __ddiv_rn(__dadd_rn(a, b), 2.0);
+}
+
+__global__ void __launch_bounds__(1024) local_sd_mad_kernel(const double* __restrict__ wsd, const unsigned* __restrict__ wcnt,
+                                                            const CleanCtl* __restrict__ ctl, double* __restrict__ wmed,
+                                                            double* __restrict__ wmad) {
+    extern __shared__ unsigned long long lsd_k[];
+    if (!ctl->metric_on) return;
+    const int c = blockIdx.x;
+    const int n = (int)wcnt[c];
+    if (n == 0 || n > LSD_SORT_CAP) {  // the host only takes this path when no chromosome can exceed the capacity
+        if (threadIdx.x == 0) { wmed[c] = 0.0; wmad[c] = 0.0; }
+        return;
+    }
+    long long first = 0;
+    for (int q = 0; q < c; q++) first += wcnt[q];
+    for (int i = threadIdx.x; i < n; i += blockDim.x) lsd_k[i] = f64_key(wsd[first + i]);
+    __syncthreads();
+    const double med = block_median_u64(lsd_k, n);
+    for (int i = threadIdx.x; i < n; i += blockDim.x) lsd_k[i] = f64_key(fabs(f64_unkey(lsd_k[i]) - med));
+    __syncthreads();
+    const double mad = block_median_u64(lsd_k, n);
+    if (threadIdx.x == 0) { wmed[c] = med; wmad[c] = mad; }
 }
 
 // median-style requests {lower middle, upper middle} for every segment with cnt > 0
@@ -634,32 +713,42 @@ int clean_enqueue(cg_ctx* ctx, const cg_clean_opts* o, CleanDev& d) {
         Emit1 e{d.chrom, d.gc, d.count, d.chrom1, d.gc1, d.count1, d.orig1};
         compact_run(ctx, p, e, &ctl->n0, n, d.tiles, &ctl->n1);
     }
+    CG_TL(ctx, "size filter");
     // --- RemoveOutliers (:387-413)
     {
         OutlierPred p{d.chrom1, d.count1, ctl, o->outlier_filter};
         Emit2 e{d.chrom1, d.gc1, d.count1, d.orig1, d.chrom2, d.gc2, d.count2, d.orig2};
         compact_run(ctx, p, e, &ctl->n1, n, d.tiles, &ctl->n2);
     }
+    CG_TL(ctx, "outlier filter");
     // --- local SD metric (:483-494)
     CG_LAUNCH(ctx, clean_decide_metric_kernel, 1, 1, 0, ctl, o->want_local_sd);
     if (o->want_local_sd && n >= 50000) {
         const int nwin_upper = n / LOCAL_SD_WINDOW + 1;
         CG_LAUNCH(ctx, local_sd_windows_kernel, div_up(nwin_upper, 128), 128, 0, d.count2, d.chrom2, ctl, d.wsd,
                   d.wchrom, d.wcnt);
-        WindowView wv{d.wsd, d.wchrom, ctl, nullptr};
-        CG_LAUNCH(ctx, median_request_u64_kernel, div_up(d.sel_win.nseg, 128), 128, 0, d.sel_win, d.wcnt, &ctl->metric_on);
-        sel_run_scatter<uint64_t, WindowView>(ctx, wv, d.sel_win, nwin_upper);
-        CG_LAUNCH(ctx, median_finish_u64_kernel, div_up(d.sel_win.nseg, 128), 128, 0, d.sel_win, d.wmed);
-        WindowView wv2{d.wsd, d.wchrom, ctl, d.wmed};
-        CG_LAUNCH(ctx, median_request_u64_kernel, div_up(d.sel_win.nseg, 128), 128, 0, d.sel_win, d.wcnt, &ctl->metric_on);
-        sel_run_scatter<uint64_t, WindowView>(ctx, wv2, d.sel_win, nwin_upper);
-        CG_LAUNCH(ctx, median_finish_u64_kernel, div_up(d.sel_win.nseg, 128), 128, 0, d.sel_win, d.wmad);
+        if (d.max_chrom_bins >= 0 && d.max_chrom_bins / LOCAL_SD_WINDOW + 2 <= LSD_SORT_CAP && d.n_chrom > 0) {
+            // every chromosome's window list fits one CTA's shared memory: sort there
+            cudaFuncSetAttribute(local_sd_mad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LSD_SORT_CAP * 8);
+            CG_LAUNCH(ctx, local_sd_mad_kernel, d.n_chrom, 1024, LSD_SORT_CAP * 8, d.wsd, d.wcnt, ctl, d.wmed, d.wmad);
+        } else {
+            WindowView wv{d.wsd, d.wchrom, ctl, nullptr};
+            CG_LAUNCH(ctx, median_request_u64_kernel, div_up(d.sel_win.nseg, 128), 128, 0, d.sel_win, d.wcnt, &ctl->metric_on);
+            sel_run_scatter<uint64_t, WindowView>(ctx, wv, d.sel_win, nwin_upper);
+            CG_LAUNCH(ctx, median_finish_u64_kernel, div_up(d.sel_win.nseg, 128), 128, 0, d.sel_win, d.wmed);
+            WindowView wv2{d.wsd, d.wchrom, ctl, d.wmed};
+            CG_LAUNCH(ctx, median_request_u64_kernel, div_up(d.sel_win.nseg, 128), 128, 0, d.sel_win, d.wcnt, &ctl->metric_on);
+            sel_run_scatter<uint64_t, WindowView>(ctx, wv2, d.sel_win, nwin_upper);
+            CG_LAUNCH(ctx, median_finish_u64_kernel, div_up(d.sel_win.nseg, 128), 128, 0, d.sel_win, d.wmad);
+        }
         CG_LAUNCH(ctx, local_sd_average_kernel, 1, 1, 0, ctl, d.wcnt, d.wmad, d.n_chrom);
     }
+    CG_TL(ctx, "local sd");
     // --- RemoveBinsWithExtremeGC (:207-237) as an alive mask over the outlier-filtered list
     CG_LAUNCH(ctx, gc_hist_kernel, grid_stream, 256, 0, d.gc2, d.chrom2, d.is_auto, ctl);
     CG_LAUNCH(ctx, gc_threshold_kernel, 1, 1, 0, ctl, o->gc_norm, o->gc_mode == 0, o->min_bins_per_gc);
     CG_LAUNCH(ctx, gc_alive_kernel, grid_stream, 256, 0, d.gc2, ctl, d.alive);
+    CG_TL(ctx, "gc filter");
     if (o->gc_norm) {
         if (loess) {
             // --- LoessGCNormalizer.Normalize (LoessGCNormalizer.cs:61-82)
@@ -674,6 +763,7 @@ int clean_enqueue(cg_ctx* ctx, const cg_clean_opts* o, CleanDev& d) {
             CG_LAUNCH(ctx, normalize_apply_bulk_kernel, dim3(grid_k8, 1), K8_THREADS, k8_smem_bytes(), d.count2, d.gc2, d.alive, d.count2,
                       &ctl->n2, 0LL, ctl->med, &ctl->global_median, &ctl->do_norm, 0LL);
         }
+    CG_TL(ctx, "normalize 1");
         // --- NormalizeVarianceByGC (:34-97), evaluated only when the metric is on and > 500000 bins
         if (o->want_local_sd && n > 500000) {
             GcCountView gq{d.count2, d.gc2, d.chrom2, d.alive, d.is_auto, ctl, &ctl->do_variance};
@@ -697,12 +787,14 @@ int clean_enqueue(cg_ctx* ctx, const cg_clean_opts* o, CleanDev& d) {
             }
         }
     }
+    CG_TL(ctx, "variance + normalize 2");
     // --- RemoveBinsWithExtremeLocalSD (:308-322) + final compaction
     {
         FinalPred p{d.alive, d.wsd, ctl};
         EmitOut e{d.count2, d.orig2, d.kept, d.count_out};
         compact_run(ctx, p, e, &ctl->n2, n, d.tiles, &ctl->n_out);
     }
+    CG_TL(ctx, "final compaction");
     cudaEventRecord(ctx->stage_ev[1], ctx->stream);
     return CG_OK;
 }
@@ -716,6 +808,7 @@ extern "C" int cg_clean(cg_ctx* ctx, const cg_clean_opts* opts, int64_t n, const
     if (!opts || n < 0 || n > 0x7fff0000LL || n_chrom < 0 || n_chrom > 256 || !n_out || !local_sd || !gc_norm_skipped)
         return cg_fail(ctx, CG_ERR_ARG, "cg_clean: bad argument");
     ctx->launches = 0;
+    ctx->tl = nullptr;
     ctx->launch_err = cudaSuccess;
     ctx->last_kernel_ms = 0;
     for (int i = 0; i < 4; i++) ctx->stage_used[i] = false;
@@ -735,6 +828,17 @@ extern "C" int cg_clean(cg_ctx* ctx, const cg_clean_opts* opts, int64_t n, const
     CleanDev d;
     rc = clean_alloc(ctx, n, n_chrom, d, loess);
     if (rc) return rc;
+    {
+        // longest chromosome run (ids are non-decreasing; the device rejects anything else): sizes the local-SD sort
+        int64_t prev = 0, longest = 0;
+        for (int c = 0; c < n_chrom; c++) {
+            int64_t lo = prev, hi = n;
+            while (lo < hi) { const int64_t mid = (lo + hi) >> 1; if (chrom[mid] <= (uint8_t)c) lo = mid + 1; else hi = mid; }
+            longest = std::max(longest, lo - prev);
+            prev = lo;
+        }
+        d.max_chrom_bins = prev == n ? longest : -1;
+    }
     cudaStream_t s = ctx->stream;
     CG_CUDA(ctx, cudaMemcpyAsync(d.chrom, chrom, n, cudaMemcpyHostToDevice, s));
     CG_CUDA(ctx, cudaMemcpyAsync(d.gc, gc, n, cudaMemcpyHostToDevice, s));
@@ -781,6 +885,7 @@ extern "C" int cg_normalize_apply(cg_ctx* ctx, int batch, int64_t n, const float
         return cg_fail(ctx, CG_ERR_ARG, "cg_normalize_apply: bad argument (n must be a multiple of 4)");
     CG_CUDA(ctx, cudaSetDevice(ctx->device));
     ctx->launches = 0;
+    ctx->tl = nullptr;
     ctx->launch_err = cudaSuccess;
     const size_t total = (size_t)batch * (size_t)n;
     int rc = arena_reserve(ctx, arena_need(total, 4) * 2 + arena_need(total, 1) + arena_need((size_t)batch * GC_BINS, 8) +

@@ -193,6 +193,7 @@ struct LoessDev;
 struct CleanDev {
     int64_t n;
     int n_chrom;
+    int64_t max_chrom_bins = -1;  // longest chromosome run of the input when the host knows it (-1: unknown)
     // input
     uint8_t *chrom, *gc;
     int32_t *start, *stop;

@@ -4,7 +4,9 @@
 #include <stdint.h>
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
+#include <utility>
 #include <string>
 #include <vector>
 
@@ -12,6 +14,7 @@
 
 #define CG_NUM_SMS_FALLBACK 148
 
+struct CgTimeline;
 struct cg_ctx {
     int device = 0;
     int num_sms = CG_NUM_SMS_FALLBACK;
@@ -42,6 +45,7 @@ struct cg_ctx {
     // second device block for tables whose size is only known in the middle of a call (HMM emission tables)
     char* aux = nullptr;
     size_t aux_cap = 0;
+    CgTimeline* tl = nullptr;  // debug timeline of the current call (CANVAS_DEBUG)
 };
 
 inline int cg_fail(cg_ctx* ctx, int code, const std::string& msg) {
@@ -151,6 +155,34 @@ __host__ __device__ inline uint32_t i32_key(int32_t x) { return (uint32_t)x ^ 0x
 __host__ __device__ inline int32_t i32_unkey(uint32_t k) { return (int32_t)(k ^ 0x80000000u); }
 
 static inline int div_up(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+
+// Debug timeline (CANVAS_DEBUG): named CUDA events on the ctx stream, printed after the call's last sync.
+struct CgTimeline {
+    bool on = false;
+    cudaStream_t s = nullptr;
+    std::vector<std::pair<const char*, cudaEvent_t>> ev;
+    void begin(cudaStream_t stream) { on = getenv("CANVAS_DEBUG") != nullptr; s = stream; mark("start"); }
+    void mark(const char* name) {
+        if (!on) return;
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        cudaEventRecord(e, s);
+        ev.emplace_back(name, e);
+    }
+    void print(const char* tag) {
+        if (!on) return;
+        cudaStreamSynchronize(s);
+        for (size_t i = 1; i < ev.size(); i++) {
+            float ms = 0;
+            cudaEventElapsedTime(&ms, ev[i - 1].second, ev[i].second);
+            fprintf(stderr, "[%s] %-16s %8.1f us\n", tag, ev[i].first, ms * 1e3);
+        }
+        for (auto& e : ev) cudaEventDestroy(e.second);
+        ev.clear();
+    }
+};
+
+#define CG_TL(ctx, name) do { if ((ctx)->tl) (ctx)->tl->mark(name); } while (0)
 
 // counted launch helper
 #define CG_LAUNCH(ctx, kernel, grid, block, smem, ...)                                 \

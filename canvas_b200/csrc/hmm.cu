@@ -659,6 +659,7 @@ extern "C" int cg_partition_hmm_shard(cg_ctx* ctx, const cg_hmm_opts* o, int n_s
     if (C > 0 && chrom_off[0] != 0) return cg_fail(ctx, CG_ERR_ARG, "cg_partition_hmm: chrom_off[0] must be 0");
     for (int c = 0; c < C; c++) n_bp[c] = 0;
     ctx->launches = 0;
+    ctx->tl = nullptr;
     ctx->launch_err = cudaSuccess;
     ctx->last_kernel_ms = 0;
     for (int i = 0; i < 4; i++) ctx->stage_used[i] = false;

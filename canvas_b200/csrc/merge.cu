@@ -115,6 +115,7 @@ extern "C" int cg_merge_common_bins(cg_ctx* ctx, int n_samples, const int64_t* n
     }
     *n_out = 0;
     ctx->launches = 0;
+    ctx->tl = nullptr;
     ctx->launch_err = cudaSuccess;
     ctx->last_kernel_ms = 0;
     for (int i = 0; i < 4; i++) ctx->stage_used[i] = false;

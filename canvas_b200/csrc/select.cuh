@@ -84,17 +84,20 @@ __global__ void sel_begin_kernel(SelState<K> st) {
 // View: __device__ long long size() const;
 //       __device__ bool get(long long i, K& key, int& segA, int& segB) const;  (seg < 0: none)
 // ---------------------------------------------------------------------------------------------
-template <typename K, class View, bool PRIV>
+template <typename K, class View, int PRIV>
 __global__ void __launch_bounds__(1024) sel_hist_scatter_kernel(View v, SelState<K> st, int shift, int first, int last) {
     extern __shared__ unsigned char sel_smem[];
     const int nseg = st.nseg;
     K* s_prefix = (K*)sel_smem;
     int* s_ngrp = (int*)(s_prefix + (size_t)nseg * SEL_G);
     unsigned* s_hist = (unsigned*)(s_ngrp + nseg);
+    // PRIV == 2: rows 1 and 2 (the other quartile / median-pair groups once ranks have diverged) as two 16-bit
+    // counters per word; a block sees fewer than 65536 elements (checked by the host driver)
+    unsigned* s_hist12 = s_hist + (size_t)nseg * SEL_BINS;
     for (int t = threadIdx.x; t < nseg * SEL_G; t += blockDim.x) s_prefix[t] = st.gprefix[t];
     for (int t = threadIdx.x; t < nseg; t += blockDim.x) s_ngrp[t] = st.ngrp[t];
     if (PRIV)
-        for (int t = threadIdx.x; t < nseg * SEL_BINS; t += blockDim.x) s_hist[t] = 0u;
+        for (int t = threadIdx.x; t < nseg * SEL_BINS * (PRIV == 2 ? 2 : 1); t += blockDim.x) s_hist[t] = 0u;
     __syncthreads();
 
     const long long n = v.size();
@@ -111,10 +114,7 @@ __global__ void __launch_bounds__(1024) sel_hist_scatter_kernel(View v, SelState
             else atomicAdd(&st.hist[(size_t)(run_idx[a] / SEL_BINS * SEL_G) * SEL_BINS + (run_idx[a] % SEL_BINS)], run_len[a]);
         }
     };
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        K key = 0;
-        int seg[2] = {-1, -1};
-        if (!v.get(i, key, seg[0], seg[1])) continue;
+    auto update = [&](K key, const int* seg) {
         const int d = (int)((key >> shift) & (K)255);
 #pragma unroll
         for (int a = 0; a < 2; a++) {
@@ -128,9 +128,32 @@ __global__ void __launch_bounds__(1024) sel_hist_scatter_kernel(View v, SelState
                 else { flush(a); run_idx[a] = idx; run_len[a] = 1u; }
             }
             for (int j = 1; j < ng; j++)
-                if (((key ^ s_prefix[s * SEL_G + j]) >> hi_shift) == 0)
-                    atomicAdd(&st.hist[(size_t)(s * SEL_G + j) * SEL_BINS + d], 1u);
+                if (((key ^ s_prefix[s * SEL_G + j]) >> hi_shift) == 0) {
+                    if (PRIV == 2 && j <= 2) atomicAdd(&s_hist12[s * SEL_BINS + d], j == 1 ? 1u : 0x10000u);
+                    else atomicAdd(&st.hist[(size_t)(s * SEL_G + j) * SEL_BINS + d], 1u);
+                }
         }
+    };
+    // four elements per step: their (dependent) loads overlap
+    constexpr int SEL_U = 4;
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; i + (SEL_U - 1) * stride < n; i += SEL_U * stride) {
+        K key[SEL_U];
+        int seg[SEL_U][2];
+        bool ok[SEL_U];
+#pragma unroll
+        for (int u = 0; u < SEL_U; u++) {
+            key[u] = 0; seg[u][0] = -1; seg[u][1] = -1;
+            ok[u] = v.get(i + u * stride, key[u], seg[u][0], seg[u][1]);
+        }
+#pragma unroll
+        for (int u = 0; u < SEL_U; u++)
+            if (ok[u]) update(key[u], seg[u]);
+    }
+    for (; i < n; i += stride) {
+        K key = 0;
+        int seg[2] = {-1, -1};
+        if (v.get(i, key, seg[0], seg[1])) update(key, seg);
     }
     flush(0);
     flush(1);
@@ -139,6 +162,11 @@ __global__ void __launch_bounds__(1024) sel_hist_scatter_kernel(View v, SelState
         for (int t = threadIdx.x; t < nseg * SEL_BINS; t += blockDim.x) {
             unsigned c = s_hist[t];
             if (c) atomicAdd(&st.hist[(size_t)((t / SEL_BINS) * SEL_G) * SEL_BINS + (t % SEL_BINS)], c);
+            if (PRIV == 2) {
+                const unsigned c12 = s_hist12[t];
+                if (c12 & 0xffffu) atomicAdd(&st.hist[(size_t)((t / SEL_BINS) * SEL_G + 1) * SEL_BINS + (t % SEL_BINS)], c12 & 0xffffu);
+                if (c12 >> 16) atomicAdd(&st.hist[(size_t)((t / SEL_BINS) * SEL_G + 2) * SEL_BINS + (t % SEL_BINS)], c12 >> 16);
+            }
         }
     }
     // the last block to finish the pass resolves every segment (one warp each); every thread fences its
@@ -164,9 +192,9 @@ __global__ void __launch_bounds__(1024) sel_hist_scatter_kernel(View v, SelState
 }
 
 template <typename K>
-inline size_t sel_scatter_smem(int nseg, bool priv) {
+inline size_t sel_scatter_smem(int nseg, int priv) {
     size_t s = (size_t)nseg * SEL_G * sizeof(K) + (size_t)nseg * sizeof(int);
-    if (priv) s += (size_t)nseg * SEL_BINS * sizeof(unsigned);
+    s += (size_t)priv * nseg * SEL_BINS * sizeof(unsigned);
     return s;
 }
 
@@ -175,6 +203,8 @@ inline size_t sel_scatter_smem(int nseg, bool priv) {
 // block b handles work[b] = {seg, lo, hi} with all group rows of that segment private in shared
 // memory.  Segments may overlap in the underlying arrays (windows and whole chromosomes).
 // View: __device__ bool get(long long i, int seg, K& key) const;   (false: skip element)
+//       __device__ bool plain(int seg, const double*& base, double& centre, bool& has_centre) const;
+//         (true: the segment's elements are base[i], or |base[i] - centre|, every one of them valid)
 // ---------------------------------------------------------------------------------------------
 struct SelWork {
     int seg;
@@ -183,7 +213,7 @@ struct SelWork {
 };
 
 template <typename K, class View>
-__global__ void sel_hist_contig_kernel(View v, const SelWork* __restrict__ work, const int* __restrict__ seg_nwork,
+__global__ void __launch_bounds__(256, 4) sel_hist_contig_kernel(View v, const SelWork* __restrict__ work, const int* __restrict__ seg_nwork,
                                        SelState<K> st, int shift, int first, int last) {
     __shared__ unsigned s_hist[SEL_G * SEL_BINS];
     __shared__ K s_prefix[SEL_G];
@@ -199,9 +229,7 @@ __global__ void sel_hist_contig_kernel(View v, const SelWork* __restrict__ work,
     // per-thread run-length aggregation (see the scattered kernel); an element matches at most one group
     int run_idx = -1;
     unsigned run_len = 0u;
-    for (long long o = threadIdx.x; o < span; o += blockDim.x) {
-        K key = 0;
-        if (!v.get(w.lo + o, s, key)) continue;
+    auto update = [&](K key) {
         const int d = (int)((key >> shift) & (K)255);
         int idx = -1;
         if (first) idx = d;
@@ -209,13 +237,51 @@ __global__ void sel_hist_contig_kernel(View v, const SelWork* __restrict__ work,
             for (int j = 0; j < ng; j++)
                 if (((key ^ s_prefix[j]) >> hi_shift) == 0) { idx = j * SEL_BINS + d; break; }
         }
-        if (idx < 0) continue;
+        if (idx < 0) return;
         if (idx == run_idx) run_len++;
         else {
             if (run_len) atomicAdd(&s_hist[run_idx], run_len);
             run_idx = idx;
             run_len = 1u;
         }
+    };
+    constexpr int SEL_U = 4;  // loads of four elements in flight
+    const long long bd = blockDim.x;
+    long long o = threadIdx.x;
+    if constexpr (sizeof(K) == 8) {
+        // a segment that is a plain double array (optionally |x - centre|): one load per element, no per-element
+        // dispatch on the segment kind
+        const double* fp = nullptr;
+        double centre = 0.0;
+        bool has_centre = false;
+        if (v.plain(s, fp, centre, has_centre)) {
+            fp += w.lo;
+            for (; o + (SEL_U - 1) * bd < span; o += SEL_U * bd) {
+                double x[SEL_U];
+#pragma unroll
+                for (int u = 0; u < SEL_U; u++) x[u] = fp[o + u * bd];
+#pragma unroll
+                for (int u = 0; u < SEL_U; u++) update((K)f64_key(has_centre ? fabs(x[u] - centre) : x[u]));
+            }
+            for (; o < span; o += bd) {
+                const double x = fp[o];
+                update((K)f64_key(has_centre ? fabs(x - centre) : x));
+            }
+            o = span;  // the generic loops below have nothing left
+        }
+    }
+    for (; o + (SEL_U - 1) * bd < span; o += SEL_U * bd) {
+        K key[SEL_U];
+        bool ok[SEL_U];
+#pragma unroll
+        for (int u = 0; u < SEL_U; u++) { key[u] = 0; ok[u] = v.get(w.lo + o + u * bd, s, key[u]); }
+#pragma unroll
+        for (int u = 0; u < SEL_U; u++)
+            if (ok[u]) update(key[u]);
+    }
+    for (; o < span; o += bd) {
+        K key = 0;
+        if (v.get(w.lo + o, s, key)) update(key);
     }
     if (run_len) atomicAdd(&s_hist[run_idx], run_len);
     __syncthreads();
@@ -330,20 +396,24 @@ template <typename K, class View>
 inline void sel_run_scatter(cg_ctx* ctx, const View& v, SelState<K>& st, long long n_upper) {
     const int bits = (int)sizeof(K) * 8;
     CG_LAUNCH(ctx, sel_begin_kernel<K>, div_up(st.nseg + 1, 128), 128, 0, st);
-    size_t smem_priv = sel_scatter_smem<K>(st.nseg, true);
-    const bool priv = smem_priv <= 200 * 1024;
-    size_t smem = priv ? smem_priv : sel_scatter_smem<K>(st.nseg, false);
+    // histogram rows in shared memory: rows 0..2 when they fit next to each other (a block must then see fewer
+    // than 65536 elements: rows 1 and 2 are 16-bit counters), else row 0, else none
+    const long long per_block = (n_upper + ctx->num_sms - 1) / std::max(1, ctx->num_sms);
+    int priv = 0;
+    if (sel_scatter_smem<K>(st.nseg, 2) <= 220 * 1024 && per_block < 60000 && n_upper >= (long long)ctx->num_sms * 1024) priv = 2;
+    else if (sel_scatter_smem<K>(st.nseg, 1) <= 200 * 1024) priv = 1;
+    const size_t smem = sel_scatter_smem<K>(st.nseg, priv);
     int grid = (int)std::min<long long>(std::max<long long>(1, (n_upper + 1023) / 1024), (long long)ctx->num_sms * (priv ? 1 : 4));
-    if (priv) {
-        cudaFuncSetAttribute(sel_hist_scatter_kernel<K, View, true>,
-                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    }
+    if (priv == 2) cudaFuncSetAttribute(sel_hist_scatter_kernel<K, View, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (priv == 1) cudaFuncSetAttribute(sel_hist_scatter_kernel<K, View, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     for (int shift = bits - 8; shift >= 0; shift -= 8) {
         int first = shift == bits - 8;
-        if (priv)
-            CG_LAUNCH(ctx, (sel_hist_scatter_kernel<K, View, true>), grid, 1024, smem, v, st, shift, first, shift == 0);
+        if (priv == 2)
+            CG_LAUNCH(ctx, (sel_hist_scatter_kernel<K, View, 2>), grid, 1024, smem, v, st, shift, first, shift == 0);
+        else if (priv == 1)
+            CG_LAUNCH(ctx, (sel_hist_scatter_kernel<K, View, 1>), grid, 1024, smem, v, st, shift, first, shift == 0);
         else
-            CG_LAUNCH(ctx, (sel_hist_scatter_kernel<K, View, false>), grid, 256, smem, v, st, shift, first, shift == 0);
+            CG_LAUNCH(ctx, (sel_hist_scatter_kernel<K, View, 0>), grid, 256, smem, v, st, shift, first, shift == 0);
     }
 }
 

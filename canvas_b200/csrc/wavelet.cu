@@ -37,7 +37,8 @@ struct WvPlan {
 constexpr long long SEL_CHUNK = 8192;
 
 void add_work(std::vector<SelWork>& w, int seg, long long lo, long long hi) {
-    for (long long a = lo; a < hi; a += SEL_CHUNK) w.push_back(SelWork{seg, 0, a, std::min(hi, a + SEL_CHUNK)});
+    static const long long chunk = getenv("CANVAS_SEL_CHUNK") ? std::max(1024, atoi(getenv("CANVAS_SEL_CHUNK"))) : SEL_CHUNK;
+    for (long long a = lo; a < hi; a += chunk) w.push_back(SelWork{seg, 0, a, std::min(hi, a + chunk)});
 }
 
 void make_plan(WvPlan& pl, int n_chrom, const int64_t* chrom_off, int window) {
@@ -348,6 +349,7 @@ int wv_enqueue(cg_ctx* ctx, const cg_wavelet_opts* o, const WvPlan& pl, WvDev& d
     sp.thr_lower = o->thr_lower;
     sp.thr_upper = o->thr_upper;
 
+    CG_TL(ctx, "plan upload");
     cudaEventRecord(ctx->stage_ev[2], s);
     ctx->stage_used[1] = true;
     // ---- prefix sums
@@ -357,6 +359,7 @@ int wv_enqueue(cg_ctx* ctx, const cg_wavelet_opts* o, const WvPlan& pl, WvDev& d
         CG_LAUNCH(ctx, wv_scan_tile_offsets_kernel, div_up(C, 64), 64, 0, d.tsum, d.tile_first, C);
         CG_LAUNCH(ctx, wv_scan_apply_kernel, ntiles, 256, 0, d.cov, d.tiles, d.tsum, d.off, d.pz);
     }
+    CG_TL(ctx, "scan");
     // ---- factor-of-three cascade
     int max_len = 1;
     for (int c = 0; c < C; c++) max_len = std::max<long long>(max_len, pl.off[c + 1] - pl.off[c]);
@@ -367,15 +370,18 @@ int wv_enqueue(cg_ctx* ctx, const cg_wavelet_opts* o, const WvPlan& pl, WvDev& d
         dim3 grid((unsigned)std::min<long long>(256, (per + 255) / 256), (unsigned)C);
         CG_LAUNCH(ctx, wv_triplet_kernel, grid, 256, 0, r == 0 ? d.cov : d.tmed, d.tmed, d.cmad, d.f3lv + r);
     }
+    CG_TL(ctx, "triplets");
     // ---- evenness per window
     if (!pl.ev_work.empty())
         CG_LAUNCH(ctx, wv_evenness_kernel, (int)pl.ev_work.size(), 1024, 0, d.cov, d.ev_work, d.ev10, d.ev100, d.ctl);
+    CG_TL(ctx, "evenness");
     // ---- order statistics, three dependent waves
     const int nwork = (int)pl.work.size();
     const int rq_grid = div_up(t.nseg, 128);
     PartView pv{d.cov, d.cmad, d.ev10, d.ev100, d.r10, d.r100, nullptr, t};
     CG_LAUNCH(ctx, wv_request_kernel, rq_grid, 128, 0, d.sel, sp, d.ctl, 1);
     sel_run_contig<uint64_t, PartView>(ctx, pv, d.work, d.seg_nwork, nwork, d.sel);
+    CG_TL(ctx, "wave1 medians");
     CG_LAUNCH(ctx, wv_median_finish_kernel, rq_grid, 128, 0, d.sel, d.med);
     CG_LAUNCH(ctx, wv_evenness_finish_kernel, 1, 1, 0, d.sel, t, d.ctl);
     CG_LAUNCH(ctx, wv_f3_finish_kernel, 1, 1, 0, sp, d.med, d.ctl);
@@ -383,14 +389,20 @@ int wv_enqueue(cg_ctx* ctx, const cg_wavelet_opts* o, const WvPlan& pl, WvDev& d
     pv2.center = d.med;
     CG_LAUNCH(ctx, wv_request_kernel, rq_grid, 128, 0, d.sel, sp, d.ctl, 2);
     sel_run_contig<uint64_t, PartView>(ctx, pv2, d.work, d.seg_nwork, nwork, d.sel);
+    CG_TL(ctx, "wave2 mads");
     CG_LAUNCH(ctx, wv_median_finish_kernel, rq_grid, 128, 0, d.sel, d.mad);
     if (pl.cv_possible) {
         if (t.base_chrom > 0) CG_LAUNCH(ctx, wv_ratio_kernel, div_up(t.base_chrom, 128), 128, 0, t, d.med, d.mad, d.r10, d.r100);
-        CG_LAUNCH(ctx, wv_request_kernel, rq_grid, 128, 0, d.sel, sp, d.ctl, 3);
-        sel_run_contig<uint64_t, PartView>(ctx, pv, d.work, d.seg_nwork, nwork, d.sel);
+        if (t.n_w10 <= WV_RATIO_SORT_MAX && t.n_w100 <= WV_RATIO_SORT_MAX) {
+            CG_LAUNCH(ctx, wv_ratio_stats_kernel, 2, 1024, 0, d.sel, sp, d.r10, d.r100);
+        } else {
+            CG_LAUNCH(ctx, wv_request_kernel, rq_grid, 128, 0, d.sel, sp, d.ctl, 3);
+            sel_run_contig<uint64_t, PartView>(ctx, pv, d.work, d.seg_nwork, nwork, d.sel);
+        }
     }
     CG_LAUNCH(ctx, wv_cv_sigma_kernel, 1, 128, 0, d.sel, sp, d.med, d.mad, d.off, d.ctl, d.sigma, d.cand_thr);
 
+    CG_TL(ctx, "wave3 + cv");
     cudaEventRecord(ctx->stage_ev[3], s);
     cudaEventRecord(ctx->stage_ev[4], s);
     ctx->stage_used[2] = true;
@@ -426,16 +438,20 @@ int wv_enqueue(cg_ctx* ctx, const cg_wavelet_opts* o, const WvPlan& pl, WvDev& d
         int occ = 0;
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, uh_mid_kernel, UH_MID_THREADS, 0);
         if (occ < 1) occ = 1;
+        CG_TL(ctx, "uh_chain");
         CG_LAUNCH(ctx, uh_mid_kernel, ctx->num_sms * std::min(occ, 4), UH_MID_THREADS, 0, up);
         const size_t uh_smem = sizeof(UhWarpScratch) * (UH_SMALL_THREADS / 32);
         cudaFuncSetAttribute(uh_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)uh_smem);
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, uh_small_kernel, UH_SMALL_THREADS, uh_smem);
         if (occ < 1) occ = 1;
+        CG_TL(ctx, "uh_mid");
         CG_LAUNCH(ctx, uh_small_kernel, ctx->num_sms * std::min(occ, 6), UH_SMALL_THREADS, uh_smem, up);
+        CG_TL(ctx, "uh_small");
         CG_LAUNCH(ctx, uh_tiny_table_kernel, UH_TINY_MAX - 1, UH_TINY_MAX, 0, d.tiny_tab);
         CG_LAUNCH(ctx, uh_tiny_kernel, ctx->num_sms * 16, 128, 0, up, d.tiny_tab);
         if (C > 0) CG_LAUNCH(ctx, uh_depth_kernel, dim3(32, C), 256, 0, d.lvlcnt, d.off, d.depth);
     }
+    CG_TL(ctx, "uh_tiny + depth");
     cudaEventRecord(ctx->stage_ev[5], s);
     cudaEventRecord(ctx->stage_ev[6], s);
     ctx->stage_used[3] = true;
@@ -446,6 +462,7 @@ int wv_enqueue(cg_ctx* ctx, const cg_wavelet_opts* o, const WvPlan& pl, WvDev& d
                   d.rq_tstart, d.rq_sorted);
         CG_LAUNCH(ctx, rq_cumulate_kernel, C, RQ_BUCKETS, 0, d.rq_tfirst, d.selected, d.rq_hist, d.rq_cum);
     }
+    CG_TL(ctx, "rq index");
     // ---- per-chromosome finish
     FinParams fp;
     fp.x = d.cov; fp.pz = d.pz; fp.off = d.off; fp.selected = d.selected; fp.cand = d.cand; fp.ctl = d.ctl;
@@ -462,6 +479,7 @@ int wv_enqueue(cg_ctx* ctx, const cg_wavelet_opts* o, const WvPlan& pl, WvDev& d
         cudaFuncSetAttribute(uh_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fin_smem_bytes());
         CG_LAUNCH(ctx, uh_finish_kernel, C, FIN_THREADS, fin_smem_bytes(), fp);
     }
+    CG_TL(ctx, "uh_finish");
     cudaEventRecord(ctx->stage_ev[7], s);
     return CG_OK;
 }
@@ -543,6 +561,7 @@ extern "C" int cg_partition_wavelet_shard(cg_ctx* ctx, const cg_wavelet_opts* op
     if (!n_bp || !bp || !evenness || !evenness_ok || !cv || !cv_has_value || !factor_of_three || (chrom_off[n_chrom] > 0 && !coverage))
         return cg_fail(ctx, CG_ERR_ARG, "partition: null output");
     ctx->launches = 0;
+    ctx->tl = nullptr;
     ctx->launch_err = cudaSuccess;
     ctx->last_kernel_ms = 0;
     for (int i = 0; i < 4; i++) ctx->stage_used[i] = false;
@@ -559,6 +578,9 @@ extern "C" int cg_partition_wavelet_shard(cg_ctx* ctx, const cg_wavelet_opts* op
         for (int c = 0; c < n_chrom; c++) sel[c] = chrom_selected[c] ? 1 : 0;
     cudaStream_t s = ctx->stream;
     if (pl.N > 0) CG_CUDA(ctx, cudaMemcpyAsync(d.cov, coverage, (size_t)pl.N * 8, cudaMemcpyHostToDevice, s));
+    CgTimeline tl;
+    tl.begin(s);
+    ctx->tl = tl.on ? &tl : nullptr;
     CG_CUDA(ctx, cudaEventRecord(ctx->ev0, s));
     rc = wv_clear(ctx, d);
     if (rc) return rc;
@@ -566,6 +588,8 @@ extern "C" int cg_partition_wavelet_shard(cg_ctx* ctx, const cg_wavelet_opts* op
     if (rc) { cudaStreamSynchronize(s); return rc; }
     CG_CUDA(ctx, cudaEventRecord(ctx->ev1, s));
     rc = wv_collect(ctx, pl, d, n_bp, bp, evenness, evenness_ok, cv, cv_has_value, factor_of_three);
+    tl.print("partition");
+    ctx->tl = nullptr;
     float ms = 0;
     cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
     ctx->last_kernel_ms = ms;
@@ -614,6 +638,7 @@ extern "C" int cg_clean_partition_wavelet(cg_ctx* ctx, const cg_clean_opts* copt
         return cg_fail(ctx, CG_ERR_ARG, "cg_clean_partition_wavelet: bad argument");
     if (wopts->evenness_window <= 0) return cg_fail(ctx, CG_ERR_ARG, "partition: evenness_window must be positive");
     ctx->launches = 0;
+    ctx->tl = nullptr;
     ctx->launch_err = cudaSuccess;
     ctx->last_kernel_ms = 0;
     for (int i = 0; i < 4; i++) ctx->stage_used[i] = false;
@@ -643,6 +668,11 @@ extern "C" int cg_clean_partition_wavelet(cg_ctx* ctx, const cg_clean_opts* copt
     CleanDev d;
     rc = clean_alloc(ctx, n, n_chrom, d, loess);
     if (rc) return rc;
+    d.max_chrom_bins = -1;
+    if (in_off[n_chrom] == n) {
+        d.max_chrom_bins = 0;
+        for (int c = 0; c < n_chrom; c++) d.max_chrom_bins = std::max<int64_t>(d.max_chrom_bins, in_off[c + 1] - in_off[c]);
+    }
     double* cov = arena_take<double>(ctx, n);
     unsigned* chrom_cnt = arena_take<unsigned>(ctx, 256);
     if (!cov || !chrom_cnt) return cg_fail(ctx, CG_ERR_CUDA, "arena exhausted");
@@ -657,11 +687,15 @@ extern "C" int cg_clean_partition_wavelet(cg_ctx* ctx, const cg_clean_opts* copt
     CG_CUDA(ctx, cudaMemsetAsync(d.is_chry, 0, 256, s));
     if (n_chrom > 0 && chrom_is_chrY) CG_CUDA(ctx, cudaMemcpyAsync(d.is_chry, chrom_is_chrY, n_chrom, cudaMemcpyHostToDevice, s));
     CG_CUDA(ctx, cudaMemsetAsync(chrom_cnt, 0, 256 * 4, s));
+    CgTimeline tl;
+    tl.begin(s);
+    ctx->tl = tl.on ? &tl : nullptr;
     CG_CUDA(ctx, cudaEventRecord(ctx->ev0, s));
     rc = clean_enqueue(ctx, copts, d);
     if (rc) { cudaStreamSynchronize(s); return rc; }
     CG_LAUNCH(ctx, fused_coverage_kernel, std::max(1, std::min(div_up(n, 256), ctx->num_sms * 8)), 256, 0, d.count_out,
               d.kept, d.chrom, d.ctl, cov, chrom_cnt);
+    CG_TL(ctx, "coverage f2");
     CleanCtl* h = (CleanCtl*)ctx->pinned;
     unsigned* h_cnt = (unsigned*)(ctx->pinned + 8192);
     CG_CUDA(ctx, cudaMemcpyAsync(h, d.ctl, sizeof(CleanCtl), cudaMemcpyDeviceToHost, s));
@@ -699,6 +733,8 @@ extern "C" int cg_clean_partition_wavelet(cg_ctx* ctx, const cg_clean_opts* copt
     if (rc) { cudaStreamSynchronize(s); cudaStreamSynchronize(ctx->copy_stream); return rc; }
     CG_CUDA(ctx, cudaEventRecord(ctx->ev1, s));
     rc = wv_collect(ctx, pl, wd, n_bp, bp, evenness, evenness_ok, cv, cv_has_value, factor_of_three);
+    tl.print("fused");
+    ctx->tl = nullptr;
     CG_CUDA(ctx, cudaStreamSynchronize(ctx->copy_stream));
     float ms = 0;
     cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);

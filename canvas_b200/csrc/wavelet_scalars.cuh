@@ -38,6 +38,17 @@ struct PartView {
         key = f64_key(x);
         return true;
     }
+    // coverage windows / chromosomes and the factor-of-three pools are plain double arrays
+    __device__ bool plain(int seg, const double*& base, double& centre, bool& has_centre) const {
+        if (seg < t.base_f3) {
+            base = cov;
+            has_centre = center != nullptr;
+            centre = has_centre ? center[seg] : 0.0;
+            return true;
+        }
+        if (seg < t.base_ev10) { base = cmad; has_centre = false; centre = 0.0; return true; }
+        return false;
+    }
 };
 
 struct WvScalarParams {
@@ -176,6 +187,46 @@ __global__ void wv_ratio_kernel(WvSegTable t, const double* __restrict__ med, co
     const float r = (float)__ddiv_rn(mad[s], med[s]);
     if (s < t.base_w100) r10[s - t.base_w10] = r;
     else r100[s - t.base_w100] = r;
+}
+
+// Wave 3 without the radix passes: the per-window ratio lists are a few hundred floats, so one CTA per list sorts
+// the keys in shared memory (bitonic) and writes the requested order statistics where the select engine would
+// have left them (quartile ranks of the 10 000-bin windows, median pair of the evenness-size windows).
+constexpr int WV_RATIO_SORT_MAX = 4096;
+__global__ void __launch_bounds__(1024) wv_ratio_stats_kernel(SelState<uint64_t> st, WvScalarParams p, const float* __restrict__ r10,
+                                                              const float* __restrict__ r100) {
+    __shared__ unsigned long long s_k[WV_RATIO_SORT_MAX];
+    const WvSegTable& t = p.t;
+    const bool ten = blockIdx.x == 0;
+    const int n = ten ? t.n_w10 : t.n_w100;
+    const int seg = ten ? t.base_r10 : t.base_r100;
+    const float* src = ten ? r10 : r100;
+    if (!p.cv_possible) return;
+    if (ten && !(p.window > WV_WINDOW_IQR && n >= 2)) return;
+    if (!ten && n < 1) return;
+    int n2 = 1;
+    while (n2 < n) n2 <<= 1;
+    for (int i = threadIdx.x; i < n2; i += blockDim.x) s_k[i] = i < n ? f64_key((double)src[i]) : ~0ull;
+    __syncthreads();
+    for (int k = 2; k <= n2; k <<= 1)
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = threadIdx.x; i < n2; i += blockDim.x) {
+                const int l = i ^ j;
+                if (l > i) {
+                    const unsigned long long a = s_k[i], b = s_k[l];
+                    const bool up = (i & k) == 0;
+                    if ((a > b) == up) { s_k[i] = b; s_k[l] = a; }
+                }
+            }
+            __syncthreads();
+        }
+    if (threadIdx.x == 0) {
+        unsigned long long rk[SEL_G];
+        int nr;
+        if (ten) { nr = 6; wv_quartile_ranks((unsigned long long)n, rk); }
+        else { nr = 2; median_pair((unsigned long long)n, rk); }
+        for (int r = 0; r < nr; r++) st.req_key[(size_t)seg * SEL_G + r] = s_k[rk[r] < (unsigned long long)n ? rk[r] : n - 1];
+    }
 }
 
 // CV decision (Segmentation.cs:309-327) and per-chromosome thresholds (WaveletSegmentation.cs:406-417)
