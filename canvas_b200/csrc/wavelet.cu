@@ -352,6 +352,19 @@ int wv_enqueue(cg_ctx* ctx, const cg_wavelet_opts* o, const WvPlan& pl, WvDev& d
     CG_TL(ctx, "plan upload");
     cudaEventRecord(ctx->stage_ev[2], s);
     ctx->stage_used[1] = true;
+    // ---- range-quantile index for the medians of the finish stage: needs only the coverage, and is enqueued first so
+    // that the device has work while the host is still launching the many small kernels of the scalars
+    if (pl.rq_ntiles > 0 && C > 0) {
+        CG_LAUNCH(ctx, rq_splitter_kernel, C, 1024, 0, d.cov, d.off, d.selected, d.rq_spl);
+        CG_LAUNCH(ctx, rq_tile_kernel, pl.rq_ntiles, RQ_TILE, 0, d.cov, d.off, d.rq_tfirst, C, d.selected, d.rq_spl, d.rq_hist,
+                  d.rq_tstart, d.rq_sorted);
+        CG_LAUNCH(ctx, rq_cumulate_kernel, C, RQ_BUCKETS, 0, d.rq_tfirst, d.selected, d.rq_hist, d.rq_cum);
+    }
+    CG_TL(ctx, "rq index");
+    // ---- evenness per window (coverage only: early, for the same reason)
+    if (!pl.ev_work.empty())
+        CG_LAUNCH(ctx, wv_evenness_kernel, (int)pl.ev_work.size(), 1024, 0, d.cov, d.ev_work, d.ev10, d.ev100, d.ctl);
+    CG_TL(ctx, "evenness");
     // ---- prefix sums
     const int ntiles = (int)pl.tiles.size();
     if (ntiles > 0) {
@@ -371,10 +384,6 @@ int wv_enqueue(cg_ctx* ctx, const cg_wavelet_opts* o, const WvPlan& pl, WvDev& d
         CG_LAUNCH(ctx, wv_triplet_kernel, grid, 256, 0, r == 0 ? d.cov : d.tmed, d.tmed, d.cmad, d.f3lv + r);
     }
     CG_TL(ctx, "triplets");
-    // ---- evenness per window
-    if (!pl.ev_work.empty())
-        CG_LAUNCH(ctx, wv_evenness_kernel, (int)pl.ev_work.size(), 1024, 0, d.cov, d.ev_work, d.ev10, d.ev100, d.ctl);
-    CG_TL(ctx, "evenness");
     // ---- order statistics, three dependent waves
     const int nwork = (int)pl.work.size();
     const int rq_grid = div_up(t.nseg, 128);
@@ -455,14 +464,6 @@ int wv_enqueue(cg_ctx* ctx, const cg_wavelet_opts* o, const WvPlan& pl, WvDev& d
     cudaEventRecord(ctx->stage_ev[5], s);
     cudaEventRecord(ctx->stage_ev[6], s);
     ctx->stage_used[3] = true;
-    // ---- range-quantile index for the medians of the finish stage
-    if (pl.rq_ntiles > 0 && C > 0) {
-        CG_LAUNCH(ctx, rq_splitter_kernel, C, 1024, 0, d.cov, d.off, d.selected, d.rq_spl);
-        CG_LAUNCH(ctx, rq_tile_kernel, pl.rq_ntiles, RQ_TILE, 0, d.cov, d.off, d.rq_tfirst, C, d.selected, d.rq_spl, d.rq_hist,
-                  d.rq_tstart, d.rq_sorted);
-        CG_LAUNCH(ctx, rq_cumulate_kernel, C, RQ_BUCKETS, 0, d.rq_tfirst, d.selected, d.rq_hist, d.rq_cum);
-    }
-    CG_TL(ctx, "rq index");
     // ---- per-chromosome finish
     FinParams fp;
     fp.x = d.cov; fp.pz = d.pz; fp.off = d.off; fp.selected = d.selected; fp.cand = d.cand; fp.ctl = d.ctl;

@@ -72,6 +72,7 @@ SIGNATURES = {
                                          _P(_i32), _P(_u8)]),
     "cg_merge_common_bins": (C.c_int, [C.c_void_p, C.c_int, _P(_i64), _P(C.c_void_p), _P(C.c_void_p), _P(C.c_void_p),
                                        _P(C.c_void_p), _P(_i64), _P(_i32), _P(_i32), _P(_f32)]),
+    "cg_smooth": (C.c_int, [C.c_void_p, C.c_int, C.c_int, _P(_i64), _P(_f32), _P(_i64), _P(_f32)]),
     "cg_cbs_boundary": (_i64, [C.c_uint32, C.c_double, C.c_double, _P(C.c_uint32), _i64]),
     "cg_bin_hits": (C.c_int, [C.c_void_p, _i64, _P(_u8), _P(C.c_uint64), C.c_char_p, C.c_int, C.c_int, _P(_u8),
                               _P(_f32), _i64, _P(_i64), _P(_i32), _P(_i32), _P(_i32), _P(_u8)]),
@@ -390,6 +391,17 @@ class Engine:
         k = m.value
         return {"kept_index": kept[:k].copy(), "stop": stop[:k].copy(), "count": cnt[:ns, :k].copy(),
                 "kernel_ms": self.lib.cg_last_kernel_ms(self.h)}
+
+    def smooth(self, chrom_off, count, max_half_window):
+        """RepeatedMedianSmoother.Smooth per chromosome: list of smoothed count arrays (possibly shorter than the input)."""
+        off = np.ascontiguousarray(chrom_off, np.int64)
+        cnt = np.ascontiguousarray(count, np.float32)
+        nc = len(off) - 1
+        n_out = np.zeros(max(nc, 1), np.int64)
+        out = np.zeros(max(len(cnt), 1), np.float32)
+        rc = self.lib.cg_smooth(self.h, int(max_half_window), nc, _ptr(off, _i64), _ptr(cnt, _f32), _ptr(n_out, _i64), _ptr(out, _f32))
+        self._check(rc)
+        return [out[off[c]:off[c] + n_out[c]].copy() for c in range(nc)]
 
     def _cbs_phases(self):
         """Phase times (ms) of the slowest chromosome of the last cg_partition_cbs call."""

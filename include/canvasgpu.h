@@ -215,6 +215,16 @@ int cg_merge_common_bins(cg_ctx* ctx, int n_samples, const int64_t* n, const uin
                          int64_t* n_out, int32_t* kept_index, int32_t* stop_out, float* count_out);
 
 /* ---------------------------------------------------------------------------------------------
+ * CanvasSmooth — RepeatedMedianSmoother.Smooth (CanvasSmooth/CanvasSmooth.cs:44-77) over every chromosome:
+ * Utilities.MedianFilter (CanvasCommon/Utilities.cs:767-791) with half windows 1 .. max_half_window, each pass on
+ * the previous output.  count is all chromosomes concatenated (chrom_off[n_chrom + 1]).  n_out[c] smoothed counts of
+ * chromosome c are written at count_out[chrom_off[c] ...]; a chromosome shorter than 2h + 1 bins loses bins exactly
+ * as the reference's streaming window does (its first n_out[c] bins keep their coordinates, Enumerable.Zip :61).
+ * ------------------------------------------------------------------------------------------- */
+int cg_smooth(cg_ctx* ctx, int max_half_window, int n_chrom, const int64_t* chrom_off, const float* count,
+              int64_t* n_out, float* count_out);
+
+/* ---------------------------------------------------------------------------------------------
  * CanvasBin counting (BAM decoding, read pairing and FASTA handling stay on the host).
  *
  * cg_bin_hits — BinCountsForChromosome (CanvasBin.cs:568-661) for one chromosome without predefined

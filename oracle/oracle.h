@@ -72,6 +72,10 @@ int ora_partition_hmm(const ora_hmm_opts* o, int n_samples, int n_chrom, const i
 double ora_gamma_ln(double z);
 int ora_negative_binomial(double mean, double variance, int max_value, double* out);
 
+/* CanvasSmooth (oracle/smooth.cpp): Utilities.MedianFilter and the repeated filter; return the output length (<= n). */
+int64_t ora_median_filter(int64_t n, const float* in, uint32_t half_window, float* out);
+int64_t ora_repeated_median_filter(int64_t n, const float* in, uint32_t max_half_window, float* out);
+
 /* CanvasBin counting loops (oracle/bin.cpp). possible: one byte per position. Returns the number of bins. */
 int64_t ora_bin_hits(int64_t len, const uint8_t* hits, const uint8_t* possible, const char* bases, int bin_size, int mode,
                      const uint8_t* read_gc, const float* obs_vs_exp, int64_t max_bins, int32_t* start, int32_t* stop,

@@ -406,3 +406,23 @@ def merge_multi_sample_cleaned(samples):
                 raise ValueError("Start must be less than Stop")
             out.append((c, a, stop[c][a], list(counts[c][a])))
     return out
+
+
+def median_filter(values, half_window):
+    """Utilities.MedianFilter (Utilities.cs:767-791)."""
+    v = np.ascontiguousarray(values, np.float32)
+    out = np.zeros(max(len(v), 1), np.float32)
+    f = lib().ora_median_filter
+    f.restype = C.c_int64
+    m = f(C.c_int64(len(v)), _p(v, C.c_float), C.c_uint32(half_window), _p(out, C.c_float))
+    return out[:m].copy()
+
+
+def repeated_median_filter(values, max_half_window):
+    """RepeatedMedianSmoother (CanvasSmooth.cs:66-77)."""
+    v = np.ascontiguousarray(values, np.float32)
+    out = np.zeros(max(len(v), 1), np.float32)
+    f = lib().ora_repeated_median_filter
+    f.restype = C.c_int64
+    m = f(C.c_int64(len(v)), _p(v, C.c_float), C.c_uint32(max_half_window), _p(out, C.c_float))
+    return out[:m].copy()

@@ -110,3 +110,13 @@ def test_dotnet_introsort_is_a_descending_sort():
     # small arrays go through insertion sort, which is stable
     counts = np.array([3, 1, 3, 2, 1, 3], np.int32)
     assert ora.dotnet_sort_levels(counts).tolist() == [0, 2, 5, 3, 1, 4]
+
+
+def test_median_filter_streaming_restatement(golden_dir):
+    # CanvasTest/TestUtilities.cs:195-206 through the statement-for-statement restatement of the streaming filter,
+    # plus its behaviour on sequences shorter than the window (fewer outputs than inputs)
+    g = _load(golden_dir, "utilities.json")["median_filter"]
+    assert ora.median_filter(g["values"], g["half_window"]).tolist() == g["expected"]
+    assert [len(ora.median_filter(np.arange(n, dtype=np.float32), 3)) for n in range(9)] == [0, 0, 0, 0, 1, 3, 5, 7, 8]
+    x = np.arange(20, dtype=np.float32)
+    assert ora.repeated_median_filter(x, 0).tolist() == x.tolist()
