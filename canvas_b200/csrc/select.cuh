@@ -206,8 +206,10 @@ inline size_t sel_scatter_smem(int nseg, int priv) {
 //       __device__ bool plain(int seg, const double*& base, double& centre, bool& has_centre) const;
 //         (true: the segment's elements are base[i], or |base[i] - centre|, every one of them valid)
 // ---------------------------------------------------------------------------------------------
+constexpr int SEL_WSEG = 3;  // segments one work item can feed (e.g. chromosome + the two windows containing the chunk)
+
 struct SelWork {
-    int seg;
+    int seg[SEL_WSEG];  // seg[0] >= 0; unused slots are -1.  All of them cover [lo, hi) completely.
     int pad;
     long long lo, hi;
 };
@@ -215,93 +217,123 @@ struct SelWork {
 template <typename K, class View>
 __global__ void __launch_bounds__(256, 4) sel_hist_contig_kernel(View v, const SelWork* __restrict__ work, const int* __restrict__ seg_nwork,
                                        SelState<K> st, int shift, int first, int last) {
-    __shared__ unsigned s_hist[SEL_G * SEL_BINS];
-    __shared__ K s_prefix[SEL_G];
+    __shared__ unsigned s_hist[SEL_WSEG][SEL_G * SEL_BINS];
+    __shared__ K s_prefix[SEL_WSEG][SEL_G];
+    __shared__ int s_last_block[SEL_WSEG];
     const SelWork w = work[blockIdx.x];
-    const int s = w.seg;
-    const int ng = st.ngrp[s];
-    if (ng == 0) return;
-    for (int t = threadIdx.x; t < ng * SEL_BINS; t += blockDim.x) s_hist[t] = 0u;
-    if (threadIdx.x < SEL_G) s_prefix[threadIdx.x] = st.gprefix[s * SEL_G + threadIdx.x];
+    int ng[SEL_WSEG];
+    bool any = false;
+#pragma unroll
+    for (int a = 0; a < SEL_WSEG; a++) {
+        ng[a] = w.seg[a] >= 0 ? st.ngrp[w.seg[a]] : 0;
+        any = any || ng[a] > 0;
+    }
+    if (!any) return;
+#pragma unroll
+    for (int a = 0; a < SEL_WSEG; a++) {
+        for (int t = threadIdx.x; t < ng[a] * SEL_BINS; t += blockDim.x) s_hist[a][t] = 0u;
+        if (ng[a] > 0 && threadIdx.x < SEL_G) s_prefix[a][threadIdx.x] = st.gprefix[w.seg[a] * SEL_G + threadIdx.x];
+    }
     __syncthreads();
     const int hi_shift = shift + 8;
     const long long span = w.hi - w.lo;
-    // per-thread run-length aggregation (see the scattered kernel); an element matches at most one group
-    int run_idx = -1;
-    unsigned run_len = 0u;
-    auto update = [&](K key) {
+    // per-thread run-length aggregation (see the scattered kernel); an element matches at most one group of a segment
+    int run_idx[SEL_WSEG];
+    unsigned run_len[SEL_WSEG];
+#pragma unroll
+    for (int a = 0; a < SEL_WSEG; a++) { run_idx[a] = -1; run_len[a] = 0u; }
+    auto update = [&](int a, K key) {  // a is a compile-time constant at every call site
         const int d = (int)((key >> shift) & (K)255);
         int idx = -1;
         if (first) idx = d;
         else {
-            for (int j = 0; j < ng; j++)
-                if (((key ^ s_prefix[j]) >> hi_shift) == 0) { idx = j * SEL_BINS + d; break; }
+            for (int j = 0; j < ng[a]; j++)
+                if (((key ^ s_prefix[a][j]) >> hi_shift) == 0) { idx = j * SEL_BINS + d; break; }
         }
         if (idx < 0) return;
-        if (idx == run_idx) run_len++;
+        if (idx == run_idx[a]) run_len[a]++;
         else {
-            if (run_len) atomicAdd(&s_hist[run_idx], run_len);
-            run_idx = idx;
-            run_len = 1u;
+            if (run_len[a]) atomicAdd(&s_hist[a][run_idx[a]], run_len[a]);
+            run_idx[a] = idx;
+            run_len[a] = 1u;
         }
     };
     constexpr int SEL_U = 4;  // loads of four elements in flight
     const long long bd = blockDim.x;
     long long o = threadIdx.x;
     if constexpr (sizeof(K) == 8) {
-        // a segment that is a plain double array (optionally |x - centre|): one load per element, no per-element
-        // dispatch on the segment kind
+        // segments that are a plain double array (optionally |x - centre|): one load per element feeds every segment
+        // of the work item, no per-element dispatch on the segment kind
         const double* fp = nullptr;
-        double centre = 0.0;
+        double centre[SEL_WSEG] = {0.0, 0.0, 0.0};
         bool has_centre = false;
-        if (v.plain(s, fp, centre, has_centre)) {
+        bool plain = true;
+#pragma unroll
+        for (int a = 0; a < SEL_WSEG; a++)
+            if (ng[a] > 0) {
+                const double* base = nullptr;
+                bool hc = false;
+                if (!v.plain(w.seg[a], base, centre[a], hc)) plain = false;
+                else if (fp && (fp != base || hc != has_centre)) plain = false;
+                else { fp = base; has_centre = hc; }
+            }
+        if (plain && fp) {
             fp += w.lo;
+            auto feed = [&](double x) {
+                if (!has_centre) {
+                    const K key = (K)f64_key(x);
+#pragma unroll
+                    for (int a = 0; a < SEL_WSEG; a++)
+                        if (ng[a] > 0) update(a, key);
+                } else {
+#pragma unroll
+                    for (int a = 0; a < SEL_WSEG; a++)
+                        if (ng[a] > 0) update(a, (K)f64_key(fabs(x - centre[a])));
+                }
+            };
             for (; o + (SEL_U - 1) * bd < span; o += SEL_U * bd) {
                 double x[SEL_U];
 #pragma unroll
                 for (int u = 0; u < SEL_U; u++) x[u] = fp[o + u * bd];
 #pragma unroll
-                for (int u = 0; u < SEL_U; u++) update((K)f64_key(has_centre ? fabs(x[u] - centre) : x[u]));
+                for (int u = 0; u < SEL_U; u++) feed(x[u]);
             }
-            for (; o < span; o += bd) {
-                const double x = fp[o];
-                update((K)f64_key(has_centre ? fabs(x - centre) : x));
-            }
-            o = span;  // the generic loops below have nothing left
+            for (; o < span; o += bd) feed(fp[o]);
+            o = span;  // the generic loop below has nothing left
         }
     }
-    for (; o + (SEL_U - 1) * bd < span; o += SEL_U * bd) {
-        K key[SEL_U];
-        bool ok[SEL_U];
-#pragma unroll
-        for (int u = 0; u < SEL_U; u++) { key[u] = 0; ok[u] = v.get(w.lo + o + u * bd, s, key[u]); }
-#pragma unroll
-        for (int u = 0; u < SEL_U; u++)
-            if (ok[u]) update(key[u]);
-    }
     for (; o < span; o += bd) {
-        K key = 0;
-        if (v.get(w.lo + o, s, key)) update(key);
+#pragma unroll
+        for (int a = 0; a < SEL_WSEG; a++)
+            if (ng[a] > 0) {
+                K key = 0;
+                if (v.get(w.lo + o, w.seg[a], key)) update(a, key);
+            }
     }
-    if (run_len) atomicAdd(&s_hist[run_idx], run_len);
+#pragma unroll
+    for (int a = 0; a < SEL_WSEG; a++)
+        if (run_len[a]) atomicAdd(&s_hist[a][run_idx[a]], run_len[a]);
     __syncthreads();
-    for (int t = threadIdx.x; t < ng * SEL_BINS; t += blockDim.x) {
-        unsigned c = s_hist[t];
-        if (c) atomicAdd(&st.hist[(size_t)(s * SEL_G) * SEL_BINS + t], c);
-    }
-    // the last block of this segment resolves it (every thread fences its own updates first)
-    __shared__ int s_last_block;
+#pragma unroll
+    for (int a = 0; a < SEL_WSEG; a++)
+        for (int t = threadIdx.x; t < ng[a] * SEL_BINS; t += blockDim.x) {
+            unsigned c = s_hist[a][t];
+            if (c) atomicAdd(&st.hist[(size_t)(w.seg[a] * SEL_G) * SEL_BINS + t], c);
+        }
+    // the last block of a segment resolves it (every thread fences its own updates first); warp a takes slot a
     __threadfence();
     __syncthreads();
-    if (threadIdx.x == 0) {
+    if (threadIdx.x < SEL_WSEG) {
+        const int a = threadIdx.x;
         __threadfence();
-        s_last_block = atomicAdd(&st.seg_done[s], 1) == seg_nwork[s] - 1;
+        s_last_block[a] = ng[a] > 0 && atomicAdd(&st.seg_done[w.seg[a]], 1) == seg_nwork[w.seg[a]] - 1;
     }
     __syncthreads();
-    if (s_last_block && threadIdx.x < 32) {
+    const int wid = threadIdx.x >> 5;
+    if (wid < SEL_WSEG && s_last_block[wid]) {
         __threadfence();
-        sel_resolve_segment<K>(st, s, shift, last);
-        if (threadIdx.x == 0) st.seg_done[s] = 0;
+        sel_resolve_segment<K>(st, w.seg[wid], shift, last);
+        if ((threadIdx.x & 31) == 0) st.seg_done[w.seg[wid]] = 0;
     }
 }
 

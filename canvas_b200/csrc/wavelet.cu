@@ -36,9 +36,8 @@ struct WvPlan {
 
 constexpr long long SEL_CHUNK = 8192;
 
-void add_work(std::vector<SelWork>& w, int seg, long long lo, long long hi) {
-    static const long long chunk = getenv("CANVAS_SEL_CHUNK") ? std::max(1024, atoi(getenv("CANVAS_SEL_CHUNK"))) : SEL_CHUNK;
-    for (long long a = lo; a < hi; a += chunk) w.push_back(SelWork{seg, 0, a, std::min(hi, a + chunk)});
+void add_work(std::vector<SelWork>& w, int seg, long long lo, long long hi, int seg_b = -1, int seg_c = -1) {
+    for (long long a = lo; a < hi; a += SEL_CHUNK) w.push_back(SelWork{{seg, seg_b, seg_c}, 0, a, std::min(hi, a + SEL_CHUNK)});
 }
 
 void make_plan(WvPlan& pl, int n_chrom, const int64_t* chrom_off, int window) {
@@ -64,24 +63,38 @@ void make_plan(WvPlan& pl, int n_chrom, const int64_t* chrom_off, int window) {
     pl.work.clear();
     pl.ev_work.clear();
     int s10 = 0, s100 = 0;
+    std::vector<long long> cuts;
     for (int c = 0; c < n_chrom; c++) {
         long long o = pl.off[c], len = pl.off[c + 1] - o;
+        const int first10 = s10, first100 = s100;
         for (long long idx = 0; idx < len - WV_WINDOW_IQR; idx += WV_WINDOW_IQR) {
-            int seg = t.base_w10 + s10;
-            pl.seg_len[seg] = WV_WINDOW_IQR;
-            add_work(pl.work, seg, o + idx, o + idx + WV_WINDOW_IQR);
+            pl.seg_len[t.base_w10 + s10] = WV_WINDOW_IQR;
             pl.ev_work.push_back(WvEvWork{o + idx, WV_WINDOW_IQR - 1, s10, 0, 0});
             s10++;
         }
         for (long long idx = 0; idx < len - window; idx += window) {
-            int seg = t.base_w100 + s100;
-            pl.seg_len[seg] = window;
-            add_work(pl.work, seg, o + idx, o + idx + window);
+            pl.seg_len[t.base_w100 + s100] = window;
             pl.ev_work.push_back(WvEvWork{o + idx, window - 1, s100, 1, 0});
             s100++;
         }
         pl.seg_len[t.base_chrom + c] = len;
-        add_work(pl.work, t.base_chrom + c, o, o + len);
+        // One pass over the chromosome feeds all three families: cut it at every window boundary, so that a piece lies
+        // in at most one window of each size (pieces past the last full window belong to the chromosome only).
+        const long long cov10 = (long long)(s10 - first10) * WV_WINDOW_IQR, cov100 = (long long)(s100 - first100) * window;
+        cuts.clear();
+        cuts.push_back(0);
+        cuts.push_back(len);
+        for (long long b = WV_WINDOW_IQR; b <= cov10; b += WV_WINDOW_IQR) cuts.push_back(b);
+        for (long long b = window; b <= cov100; b += window) cuts.push_back(b);
+        std::sort(cuts.begin(), cuts.end());
+        cuts.erase(std::unique(cuts.begin(), cuts.end()), cuts.end());
+        for (size_t q = 0; q + 1 < cuts.size(); q++) {
+            const long long a = cuts[q], b = cuts[q + 1];
+            if (b <= a || a >= len) continue;
+            const int seg10 = a < cov10 ? t.base_w10 + first10 + (int)(a / WV_WINDOW_IQR) : -1;
+            const int seg100 = a < cov100 ? t.base_w100 + first100 + (int)(a / window) : -1;
+            add_work(pl.work, t.base_chrom + c, o + a, o + std::min(b, len), seg10, seg100);
+        }
     }
     // factor-of-three cascade
     std::vector<long long> cur_len(n_chrom), cur_off(n_chrom);
@@ -117,7 +130,9 @@ void make_plan(WvPlan& pl, int n_chrom, const int64_t* chrom_off, int window) {
     if (t.n_w10 > 0) add_work(pl.work, t.base_r10, 0, t.n_w10);
     if (t.n_w100 > 0) add_work(pl.work, t.base_r100, 0, t.n_w100);
     pl.seg_nwork.assign(t.nseg, 0);
-    for (const SelWork& wk : pl.work) pl.seg_nwork[wk.seg]++;
+    for (const SelWork& wk : pl.work)
+        for (int a = 0; a < SEL_WSEG; a++)
+            if (wk.seg[a] >= 0) pl.seg_nwork[wk.seg[a]]++;
     // scan tiles
     pl.tiles.clear();
     pl.tile_first.assign(n_chrom + 1, 0);
@@ -187,7 +202,7 @@ size_t wv_workspace_bytes(const WvPlan& pl) {
     size_t s = 0;
     s += arena_need(N, 8) + arena_need(C + 1, 8) + arena_need(C + 1, 1) + arena_need(N + C + 1, 8);
     s += sel_state_bytes<uint64_t>(pl.t.nseg) + arena_need(pl.t.nseg, 8);
-    s += arena_need(pl.t.nseg + 1, 4) + arena_need(pl.work.size() + 1, sizeof(SelWork)) + arena_need(pl.ev_work.size() + 1, sizeof(WvEvWork));
+    s += arena_need(pl.t.nseg + 1, 4) + arena_need(pl.work.size() + pl.work.size() / 8 + 64, sizeof(SelWork)) + arena_need(pl.ev_work.size() + 1, sizeof(WvEvWork));
     s += arena_need(pl.tiles.size() + 1, sizeof(WvScanTile)) + arena_need(C + 2, 4) + arena_need(pl.tiles.size() + 1, 8);
     s += arena_need(WV_F3_LEVELS, sizeof(WvF3Level));
     s += arena_need(pl.f3_total + 1, 8) * 2 + arena_need(pl.t.n_w10 + 1, 8) + arena_need(pl.t.n_w100 + 1, 8);
@@ -212,7 +227,7 @@ int wv_alloc(cg_ctx* ctx, const WvPlan& pl, WvDev& d, double* cov_dev_existing) 
     d.off = arena_take<long long>(ctx, C + 1);
     d.selected = arena_take<unsigned char>(ctx, C + 1);
     d.seg_len = arena_take<long long>(ctx, pl.t.nseg);
-    d.work = arena_take<SelWork>(ctx, pl.work.size() + 1);
+    d.work = arena_take<SelWork>(ctx, pl.work.size() + pl.work.size() / 8 + 64);
     d.seg_nwork = arena_take<int>(ctx, pl.t.nseg + 1);
     d.ev_work = arena_take<WvEvWork>(ctx, pl.ev_work.size() + 1);
     d.tiles = arena_take<WvScanTile>(ctx, pl.tiles.size() + 1);
@@ -270,7 +285,7 @@ int wv_alloc(cg_ctx* ctx, const WvPlan& pl, WvDev& d, double* cov_dev_existing) 
          d.tsum && d.f3lv && d.tmed && d.cmad && d.ev10 && d.ev100 && d.r10 && d.r100 && d.med && d.mad && d.sigma &&
          d.cand_thr && d.log3 && d.ctl && d.lvlcnt && d.depth && d.big && d.mid && d.small && d.tiny && d.cand && d.lvl_idx &&
          d.sv && d.piece && d.prelim && d.lvl_first && d.svkey && d.rec && d.bitmap && d.n_bp && d.bp;
-    d.cap_N = pl.N; d.cap_nseg = pl.t.nseg; d.cap_work = pl.work.size(); d.cap_ev = pl.ev_work.size(); d.cap_tiles = pl.tiles.size();
+    d.cap_N = pl.N; d.cap_nseg = pl.t.nseg; d.cap_work = pl.work.size() + pl.work.size() / 8 + 63; d.cap_ev = pl.ev_work.size(); d.cap_tiles = pl.tiles.size();
     d.cap_f3 = pl.f3_total; d.cap_w10 = pl.t.n_w10; d.cap_w100 = pl.t.n_w100; d.cap_rq = pl.rq_ntiles; d.cap_C = pl.n_chrom;
     return ok ? CG_OK : cg_fail(ctx, CG_ERR_CUDA, "partition: device arena exhausted");
 }
@@ -625,14 +640,14 @@ __global__ void fused_coverage_kernel(const float* __restrict__ count_out, const
     }
 }
 
-extern "C" int cg_clean_partition_wavelet(cg_ctx* ctx, const cg_clean_opts* copts, const cg_wavelet_opts* wopts,
-                                          int64_t n, const uint8_t* chrom, const uint8_t* chrom_is_autosome,
-                                          const uint8_t* chrom_is_chrY, int n_chrom, const int32_t* start,
-                                          const int32_t* stop, const float* count, const uint8_t* gc,
-                                          int64_t* n_out, int32_t* kept_index, float* count_out,
-                                          double* local_sd, int* gc_norm_skipped, int64_t* chrom_off_out,
-                                          int32_t* n_bp, int32_t* bp, double* evenness, int* evenness_ok,
-                                          double* cv, int* cv_has_value, double* factor_of_three) {
+extern "C" int cg_clean_partition_wavelet_shard(cg_ctx* ctx, const cg_clean_opts* copts, const cg_wavelet_opts* wopts,
+                                                int64_t n, const uint8_t* chrom, const uint8_t* chrom_is_autosome,
+                                                const uint8_t* chrom_is_chrY, int n_chrom, const int32_t* start,
+                                                const int32_t* stop, const float* count, const uint8_t* gc,
+                                                const uint8_t* chrom_selected, int64_t* n_out, int32_t* kept_index,
+                                                float* count_out, double* local_sd, int* gc_norm_skipped,
+                                                int64_t* chrom_off_out, int32_t* n_bp, int32_t* bp, double* evenness,
+                                                int* evenness_ok, double* cv, int* cv_has_value, double* factor_of_three) {
     if (!ctx) return CG_ERR_ARG;
     if (!copts || !wopts || n < 0 || n > 0x7fff0000LL || n_chrom < 0 || n_chrom > WV_MAX_CHROM || !n_out || !local_sd ||
         !gc_norm_skipped || !chrom_off_out || !n_bp || !evenness || !evenness_ok || !cv || !cv_has_value || !factor_of_three)
@@ -730,6 +745,8 @@ extern "C" int cg_clean_partition_wavelet(cg_ctx* ctx, const cg_clean_opts* copt
     WvPlan pl;
     make_plan(pl, n_chrom, off.data(), wopts->evenness_window);
     std::vector<unsigned char> sel(n_chrom + 1, 1);
+    if (chrom_selected)
+        for (int c = 0; c < n_chrom; c++) sel[c] = chrom_selected[c] ? 1 : 0;
     rc = wv_enqueue(ctx, wopts, pl, wd, sel.data());
     if (rc) { cudaStreamSynchronize(s); cudaStreamSynchronize(ctx->copy_stream); return rc; }
     CG_CUDA(ctx, cudaEventRecord(ctx->ev1, s));
@@ -744,4 +761,17 @@ extern "C" int cg_clean_partition_wavelet(cg_ctx* ctx, const cg_clean_opts* copt
     *local_sd = lsd;
     *gc_norm_skipped = skipped;
     return rc;
+}
+
+extern "C" int cg_clean_partition_wavelet(cg_ctx* ctx, const cg_clean_opts* copts, const cg_wavelet_opts* wopts,
+                                          int64_t n, const uint8_t* chrom, const uint8_t* chrom_is_autosome,
+                                          const uint8_t* chrom_is_chrY, int n_chrom, const int32_t* start,
+                                          const int32_t* stop, const float* count, const uint8_t* gc,
+                                          int64_t* n_out, int32_t* kept_index, float* count_out,
+                                          double* local_sd, int* gc_norm_skipped, int64_t* chrom_off_out,
+                                          int32_t* n_bp, int32_t* bp, double* evenness, int* evenness_ok,
+                                          double* cv, int* cv_has_value, double* factor_of_three) {
+    return cg_clean_partition_wavelet_shard(ctx, copts, wopts, n, chrom, chrom_is_autosome, chrom_is_chrY, n_chrom, start, stop,
+                                            count, gc, nullptr, n_out, kept_index, count_out, local_sd, gc_norm_skipped,
+                                            chrom_off_out, n_bp, bp, evenness, evenness_ok, cv, cv_has_value, factor_of_three);
 }

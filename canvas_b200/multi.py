@@ -89,3 +89,16 @@ def partition_cbs_sharded(engine, chrom_off, coverage, **kw):
     r["segments"] = [{"len": np.diff(np.concatenate([[0], e])).astype(np.int32)} for e in merged]
     r["owner"] = owner
     return r
+
+
+def clean_partition_wavelet_sharded(engine, sample_arrays, lengths_hint, **kw):
+    """Fused Clean + wavelet partition of ONE sample over all ranks: every rank cleans the whole sample (genome-wide
+    order statistics), segments the chromosomes LPT assigns to it (by input bin count: `lengths_hint`), and one
+    all-gather reassembles the breakpoint lists.  sample_arrays = (chrom, is_autosome, is_chr_y, start, stop, count, gc)."""
+    import torch.distributed as dist
+    world, rank = dist.get_world_size(), dist.get_rank()
+    owner = assign_chromosomes_lpt(lengths_hint, world)
+    r = engine.clean_partition_wavelet(*sample_arrays, chrom_selected=(owner == rank).astype(np.uint8), **kw)
+    r["breakpoints"] = all_gather_breakpoints(r["breakpoints"], len(lengths_hint))
+    r["owner"] = owner
+    return r

@@ -63,6 +63,11 @@ SIGNATURES = {
                                              _P(_f32), _P(_u8), _P(_i64), _P(_i32), _P(_f32),
                                              _P(_f64), _P(C.c_int), _P(_i64), _P(_i32), _P(_i32),
                                              _P(_f64), _P(C.c_int), _P(_f64), _P(C.c_int), _P(_f64)]),
+    "cg_clean_partition_wavelet_shard": (C.c_int, [C.c_void_p, _P(CleanOpts), _P(WaveletOpts), _i64,
+                                                   _P(_u8), _P(_u8), _P(_u8), C.c_int, _P(_i32), _P(_i32),
+                                                   _P(_f32), _P(_u8), _P(_u8), _P(_i64), _P(_i32), _P(_f32),
+                                                   _P(_f64), _P(C.c_int), _P(_i64), _P(_i32), _P(_i32),
+                                                   _P(_f64), _P(C.c_int), _P(_f64), _P(C.c_int), _P(_f64)]),
     "cg_partition_cbs": (C.c_int, [C.c_void_p, C.c_void_p, _P(C.c_uint32), _i64, C.c_int, _P(_i64), _P(C.c_double), _P(_i32),
                                    _P(_i32), _P(C.c_double), _P(_i64)]),
     "cg_partition_cbs_shard": (C.c_int, [C.c_void_p, C.c_void_p, _P(C.c_uint32), _i64, C.c_int, _P(_i64), _P(C.c_double), _P(_u8),
@@ -264,9 +269,10 @@ class Engine:
                                 size_filter=True, outlier_filter=True, gc_norm=True, gc_mode=0,
                                 want_local_sd=True, min_bins_per_gc=100, is_germline=True,
                                 mad_factor=5.0, thr_lower=0.05, thr_upper=80.0, min_size=10,
-                                evenness_window=100000, out=None):
+                                evenness_window=100000, out=None, chrom_selected=None):
         """cg_clean_partition_wavelet: both stages without leaving the device in between.
-        `out` = (kept_index, count_out, n_bp, bp) preallocated (e.g. pinned) arrays."""
+        `out` = (kept_index, count_out, n_bp, bp) preallocated (e.g. pinned) arrays; `chrom_selected` = 0/1 mask of
+        the chromosomes this rank segments (multi-GPU)."""
         n = len(count)
         chrom = np.ascontiguousarray(chrom, np.uint8)
         is_autosome = np.ascontiguousarray(is_autosome, np.uint8)
@@ -291,10 +297,11 @@ class Engine:
         ev, cv = _f64(0), _f64(0)
         ev_ok, cv_has = C.c_int(0), C.c_int(0)
         f3 = np.zeros(9, np.float64)
-        rc = self.lib.cg_clean_partition_wavelet(
+        mask = None if chrom_selected is None else np.ascontiguousarray(chrom_selected, np.uint8)
+        rc = self.lib.cg_clean_partition_wavelet_shard(
             self.h, C.byref(co), C.byref(wo), n, _ptr(chrom, _u8), _ptr(is_autosome, _u8),
             _ptr(is_chr_y, _u8), nc, _ptr(start, _i32), _ptr(stop, _i32), _ptr(count, _f32),
-            _ptr(gc, _u8), C.byref(n_out), _ptr(kept, _i32), _ptr(cnt, _f32), C.byref(lsd),
+            _ptr(gc, _u8), None if mask is None else _ptr(mask, _u8), C.byref(n_out), _ptr(kept, _i32), _ptr(cnt, _f32), C.byref(lsd),
             C.byref(skipped), _ptr(off, _i64), _ptr(n_bp, _i32), _ptr(bp, _i32), C.byref(ev),
             C.byref(ev_ok), C.byref(cv), C.byref(cv_has), _ptr(f3, _f64))
         self._check(rc)

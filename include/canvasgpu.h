@@ -137,6 +137,17 @@ int cg_clean_partition_wavelet(cg_ctx* ctx, const cg_clean_opts* copts, const cg
                                int32_t* n_bp, int32_t* bp, double* evenness, int* evenness_ok,
                                double* cv, int* cv_has_value, double* factor_of_three);
 
+/* Multi-GPU form of the fused call: Clean and the genome-wide scalars run on every rank (they need genome-wide order
+ * statistics), only the chromosomes with chrom_selected[c] != 0 are segmented (n_bp = 0 for the others). */
+int cg_clean_partition_wavelet_shard(cg_ctx* ctx, const cg_clean_opts* copts, const cg_wavelet_opts* wopts,
+                                     int64_t n, const uint8_t* chrom, const uint8_t* chrom_is_autosome,
+                                     const uint8_t* chrom_is_chrY, int n_chrom, const int32_t* start,
+                                     const int32_t* stop, const float* count, const uint8_t* gc,
+                                     const uint8_t* chrom_selected, int64_t* n_out, int32_t* kept_index,
+                                     float* count_out, double* local_sd, int* gc_norm_skipped, int64_t* chrom_off_out,
+                                     int32_t* n_bp, int32_t* bp, double* evenness, int* evenness_ok, double* cv,
+                                     int* cv_has_value, double* factor_of_three);
+
 /* ---------------------------------------------------------------------------------------------
  * CanvasPartition -m CBS: circular binary segmentation, CBSRunner.Run (CBSRunner.cs:40-151) with
  * ChangePoint.ChangePoints (ChangePoint.cs:44-153) per chromosome on its own MersenneTwister stream

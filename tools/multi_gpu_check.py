@@ -32,6 +32,13 @@ def main():
     shard = multi.partition_wavelet_sharded(eng, off, cov, is_germline=True, evenness_window=ew)
     ok_w = all(a.tolist() == b.tolist() for a, b in zip(full["breakpoints"], shard["breakpoints"]))
     ok_w = ok_w and full["cv"] == shard["cv"] and np.array_equal(full["factor_of_three"], shard["factor_of_three"])
+    # the fused Clean + partition call, sharded: equals the single-GPU fused call
+    fused = eng.clean_partition_wavelet(s.chrom, s.is_autosome, s.is_chr_y, s.start, s.stop, s.count, s.gc, is_germline=True,
+                                        evenness_window=ew)
+    fs = multi.clean_partition_wavelet_sharded(eng, (s.chrom, s.is_autosome, s.is_chr_y, s.start, s.stop, s.count, s.gc),
+                                               np.bincount(s.chrom, minlength=len(s.names)), is_germline=True, evenness_window=ew)
+    ok_w = ok_w and all(a.tolist() == b.tolist() for a, b in zip(fused["breakpoints"], fs["breakpoints"]))
+    ok_w = ok_w and all(a.tolist() == b.tolist() for a, b in zip(fused["breakpoints"], full["breakpoints"]))
     # CBS on a few chromosomes' worth of bins (permutation tests are heavier)
     ncb = min(len(off) - 1, 6)
     off_c = off[:ncb + 1]
