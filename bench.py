@@ -93,6 +93,28 @@ def run_oracle_once(s, threads):
             "breakpoints": sum(len(b) for b in p["breakpoints"])}
 
 
+_REAL_STDOUT = None
+
+
+def _claim_stdout():
+    """Everything a library prints on fd 1 (NCCL's version banner, for one) goes to stderr from here on; the JSON
+    line is written to the original stdout by _emit()."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def _emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -108,6 +130,7 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     from canvas_b200 import synth
+    _claim_stdout()
 
     # ------------------------------------------------------------------ reference arm (CPU)
     if args.impl == "reference":
@@ -135,7 +158,7 @@ def main():
                 "partition_ms": 1e3 * sum(x["partition_s"] for x in t) / K,
                 "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
-        print(json.dumps(line))
+        _emit(line)
         return 0
 
     # ------------------------------------------------------------------ GPU arm
@@ -316,7 +339,7 @@ def main():
         line["cpu_baseline"] = {"value": nb / o["total_s"] / 1e6, "unit": UNIT, "cores": threads, "kind": "port",
                                 "sample": "one full config-2 sample (Clean 1 thread, Partition 1 thread per chromosome)",
                                 "clean_ms": o["clean_s"] * 1e3, "partition_ms": o["partition_s"] * 1e3}
-    print(json.dumps(line))
+    _emit(line)
     if world > 1:
         dist.destroy_process_group()
     return 0

@@ -36,6 +36,7 @@ extern "C" void cg_destroy(cg_ctx* ctx) {
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     if (ctx->arena) cudaFree(ctx->arena);
+    cg_graphs_clear(ctx);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
     if (ctx->plan_pinned) cudaFreeHost(ctx->plan_pinned);
     if (ctx->aux) cudaFree(ctx->aux);

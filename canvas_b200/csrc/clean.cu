@@ -679,7 +679,62 @@ int clean_alloc(cg_ctx* ctx, int64_t n, int n_chrom, CleanDev& d, bool loess) {
 
 // Enqueue the whole CanvasClean pipeline on ctx->stream.  Inputs must already be in d.chrom/...;
 // results end in d.kept / d.count_out / d.ctl.
+static int clean_enqueue_body(cg_ctx* ctx, const cg_clean_opts* o, CleanDev& d);
+
+// The Clean pipeline is ~90 short launches whose arguments depend only on the problem shape (n, options, arena
+// placement): every data-dependent decision is taken on the device.  The sequence is therefore captured once per
+// shape into a CUDA graph and replayed — one launch instead of ninety, no host-side gaps between the kernels.
 int clean_enqueue(cg_ctx* ctx, const cg_clean_opts* o, CleanDev& d) {
+    cudaStream_t s = ctx->stream;
+    cudaEventRecord(ctx->stage_ev[0], s);
+    ctx->stage_used[0] = true;
+    static const bool no_graph = getenv("CANVAS_NO_GRAPH") != nullptr;
+    int rc = CG_OK;
+    if (no_graph || ctx->tl) {
+        rc = clean_enqueue_body(ctx, o, d);
+    } else {
+        CgGraphEntry want{};
+        const long long key[12] = {(long long)(uintptr_t)ctx->arena, (long long)(uintptr_t)d.ctl, d.n, d.n_chrom, d.max_chrom_bins,
+                                   o->size_filter, o->outlier_filter, o->gc_norm, o->gc_mode, o->want_local_sd, o->min_bins_per_gc,
+                                   (long long)(uintptr_t)d.count};
+        for (int i = 0; i < 12; i++) want.key[i] = key[i];
+        const CgGraphEntry* hit = nullptr;
+        for (const auto& g : ctx->clean_graphs)
+            if (!memcmp(g.key, want.key, sizeof(want.key))) { hit = &g; break; }
+        if (!hit) {
+            const int launches_before = ctx->launches;
+            cudaGraph_t graph = nullptr;
+            if (cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+                cudaGetLastError();
+                rc = clean_enqueue_body(ctx, o, d);  // capture unavailable: plain launches
+                cudaEventRecord(ctx->stage_ev[1], s);
+                return rc;
+            }
+            rc = clean_enqueue_body(ctx, o, d);
+            const cudaError_t ce = cudaStreamEndCapture(s, &graph);
+            want.launches = ctx->launches - launches_before;
+            ctx->launches = launches_before;
+            if (rc != CG_OK || ce != cudaSuccess || !graph) {
+                if (graph) cudaGraphDestroy(graph);
+                cudaGetLastError();
+                return rc != CG_OK ? rc : cg_fail(ctx, CG_ERR_CUDA, std::string("clean: graph capture failed: ") + cudaGetErrorString(ce));
+            }
+            const cudaError_t ie = cudaGraphInstantiate(&want.exec, graph, 0);
+            cudaGraphDestroy(graph);
+            if (ie != cudaSuccess) return cg_fail(ctx, CG_ERR_CUDA, std::string("clean: graph instantiation failed: ") + cudaGetErrorString(ie));
+            if (ctx->clean_graphs.size() >= 16) cg_graphs_clear(ctx);
+            ctx->clean_graphs.push_back(want);
+            hit = &ctx->clean_graphs.back();
+        }
+        const cudaError_t le = cudaGraphLaunch(hit->exec, s);
+        if (le != cudaSuccess) return cg_fail(ctx, CG_ERR_CUDA, std::string("clean: graph launch failed: ") + cudaGetErrorString(le));
+        ctx->launches += hit->launches;
+    }
+    cudaEventRecord(ctx->stage_ev[1], s);
+    return rc;
+}
+
+static int clean_enqueue_body(cg_ctx* ctx, const cg_clean_opts* o, CleanDev& d) {
     const int n = (int)d.n;
     const int nb = std::max(1, div_up(n, 256));
     const int grid_stream = std::max(1, std::min(nb, ctx->num_sms * 8));
@@ -690,8 +745,6 @@ int clean_enqueue(cg_ctx* ctx, const cg_clean_opts* o, CleanDev& d) {
     if (loess && !d.lo) return cg_fail(ctx, CG_ERR_ARG, "clean: LOESS buffers were not allocated");
 
     cudaFuncSetAttribute(gc_weighted_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WQ_CAP * 8);
-    cudaEventRecord(ctx->stage_ev[0], ctx->stream);
-    ctx->stage_used[0] = true;
     CG_LAUNCH(ctx, clean_init_kernel, 1, 32, 0, ctl, n);
     cudaMemsetAsync(d.wcnt, 0, 256 * sizeof(unsigned), ctx->stream);
     cudaMemsetAsync(d.sel_size.hist, 0, (size_t)1 * SEL_G * SEL_BINS * sizeof(unsigned), ctx->stream);
@@ -795,7 +848,6 @@ int clean_enqueue(cg_ctx* ctx, const cg_clean_opts* o, CleanDev& d) {
         compact_run(ctx, p, e, &ctl->n2, n, d.tiles, &ctl->n_out);
     }
     CG_TL(ctx, "final compaction");
-    cudaEventRecord(ctx->stage_ev[1], ctx->stream);
     return CG_OK;
 }
 

@@ -156,30 +156,47 @@ inline void compact_run(cg_ctx* ctx, const Pred& p, const Emit& e, const int* n_
 // to CanvasPartition (IO.cs:21, CanvasSegment.cs:1147).  .NET Core 2.0 formats a float from its 7
 // significant decimal digits (FLOAT_PRECISION) and then rounds that digit string half-up to two
 // decimals; parsing "ddd.dd" gives the double nearest to hundredths / 100.
+__host__ __device__ inline double cg_pow10(int k) {  // literals instead of a per-thread table in local memory
+    switch (k) {
+        case 0: return 1e0; case 1: return 1e1; case 2: return 1e2; case 3: return 1e3; case 4: return 1e4;
+        case 5: return 1e5; case 6: return 1e6; case 7: return 1e7; case 8: return 1e8; case 9: return 1e9;
+        case 10: return 1e10; case 11: return 1e11; case 12: return 1e12; case 13: return 1e13; case 14: return 1e14;
+        case 15: return 1e15; case 16: return 1e16; case 17: return 1e17; case 18: return 1e18; default: return 1e19;
+    }
+}
+
 __host__ __device__ inline double dotnet_f2_roundtrip(float v) {
     if (v != v || v - v != 0.0f) return (double)v;  // NaN / +-Infinity survive as such
     double x = v < 0 ? -(double)v : (double)v;
     if (x == 0.0) return 0.0;
-    const double p10[20] = {1e0, 1e1, 1e2, 1e3, 1e4, 1e5, 1e6, 1e7, 1e8, 1e9, 1e10, 1e11, 1e12, 1e13, 1e14, 1e15, 1e16, 1e17, 1e18, 1e19};
     int e = 0;  // 10^e <= x < 10^(e+1)
-    if (x >= 1.0) { while (e < 18 && x >= p10[e + 1]) e++; }
-    else { e = -1; while (e > -19 && x * p10[-e] < 1.0) e--; }
+    if (x >= 1.0) { while (e < 18 && x >= cg_pow10(e + 1)) e++; }
+    else { e = -1; while (e > -19 && x * cg_pow10(-e) < 1.0) e--; }
     // seven significant digits, round-half-even on the exact value (the product is exact: a 24-bit
     // significand times 10^k, k <= 12, fits 53 bits)
-    double scaled = (6 - e >= 0) ? (6 - e < 20 ? x * p10[6 - e] : 0.0) : x / p10[e - 6];
+    double scaled = (6 - e >= 0) ? (6 - e < 20 ? x * cg_pow10(6 - e) : 0.0) : x / cg_pow10(e - 6);
     double d7 = rint(scaled);
     if (d7 >= 1e7) { d7 /= 10.0; e += 1; }
     double hundredths;
     if (e >= 4) {
-        hundredths = d7 * p10[e - 4 < 19 ? e - 4 : 19];
+        hundredths = d7 * cg_pow10(e - 4 < 19 ? e - 4 : 19);
     } else {
         const int k = 4 - e;  // digits to drop
         if (k > 7) hundredths = 0.0;
         else {
             const long long q = (long long)d7;
-            const long long p = (long long)p10[k];
-            long long h = q / p;
-            if ((q % p) * 2 >= p) h += 1;  // first dropped digit >= 5
+            long long h, rem, p;
+            // constant divisors: the compiler turns these into multiplications
+            switch (k) {
+                case 1: p = 10LL; h = q / 10LL; rem = q % 10LL; break;
+                case 2: p = 100LL; h = q / 100LL; rem = q % 100LL; break;
+                case 3: p = 1000LL; h = q / 1000LL; rem = q % 1000LL; break;
+                case 4: p = 10000LL; h = q / 10000LL; rem = q % 10000LL; break;
+                case 5: p = 100000LL; h = q / 100000LL; rem = q % 100000LL; break;
+                case 6: p = 1000000LL; h = q / 1000000LL; rem = q % 1000000LL; break;
+                default: p = 10000000LL; h = q / 10000000LL; rem = q % 10000000LL; break;
+            }
+            if (rem * 2 >= p) h += 1;  // first dropped digit >= 5
             hundredths = (double)h;
         }
     }

@@ -15,6 +15,12 @@
 #define CG_NUM_SMS_FALLBACK 148
 
 struct CgTimeline;
+// an instantiated CUDA graph of one launch sequence, valid for one exact problem shape and arena placement
+struct CgGraphEntry {
+    long long key[12];
+    cudaGraphExec_t exec;
+    int launches;
+};
 struct cg_ctx {
     int device = 0;
     int num_sms = CG_NUM_SMS_FALLBACK;
@@ -46,7 +52,13 @@ struct cg_ctx {
     char* aux = nullptr;
     size_t aux_cap = 0;
     CgTimeline* tl = nullptr;  // debug timeline of the current call (CANVAS_DEBUG)
+    std::vector<CgGraphEntry> clean_graphs;  // Clean pipeline graphs (clean.cu), dropped when the arena moves
 };
+
+inline void cg_graphs_clear(cg_ctx* ctx) {
+    for (auto& g : ctx->clean_graphs) cudaGraphExecDestroy(g.exec);
+    ctx->clean_graphs.clear();
+}
 
 inline int cg_fail(cg_ctx* ctx, int code, const std::string& msg) {
     if (ctx) ctx->err = msg;
@@ -69,6 +81,7 @@ inline int arena_reserve(cg_ctx* ctx, size_t bytes) {
     if (bytes <= ctx->arena_cap) return CG_OK;
     if (ctx->arena) {
         CG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        cg_graphs_clear(ctx);  // they hold pointers into the old arena
         CG_CUDA(ctx, cudaFree(ctx->arena));
         ctx->arena = nullptr;
         ctx->arena_cap = 0;
