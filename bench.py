@@ -313,13 +313,13 @@ def main():
                                  "the stage is bound by the dependent chain of big nodes, not by HBM"},
             "clocks": clocks, "device": eng.describe()}
     # K8 normalise stream on batches larger than L2 (the kernel BASELINE.json's roofline target names):
-    # 8 samples = config 5 (223 MB), and 16 samples (446 MB)
+    # 8 samples = config 5 (223 MB), 16 samples (446 MB) and 32 samples (892 MB)
     if strong is not None:
         line["strong_scaling_single_sample"] = strong
     try:
         n16 = (nb // 16) * 16
         rng = np.random.default_rng(1)
-        for batch, key in ((8, "roofline_normalize"), (16, "roofline_normalize_16")):
+        for batch, key in ((8, "roofline_normalize"), (16, "roofline_normalize_16"), (32, "roofline_normalize_32")):
             cnt = np.tile(s.count[:n16], (batch, 1))
             gcb = np.tile(s.gc[:n16], (batch, 1))
             med = rng.uniform(80, 120, (batch, 101))

@@ -955,6 +955,7 @@ extern "C" int cg_normalize_apply(cg_ctx* ctx, int batch, int64_t n, const float
     CG_CUDA(ctx, cudaMemcpyAsync(d_med, median_by_gc, (size_t)batch * GC_BINS * 8, cudaMemcpyHostToDevice, s));
     CG_CUDA(ctx, cudaMemcpyAsync(d_gmed, global_median, (size_t)batch * 8, cudaMemcpyHostToDevice, s));
     if (repeats < 1) repeats = 1;
+    const int exact_divide = getenv("CANVAS_K8_EXACT_DIV") ? 1 : 0;  // experiments: FP64 divide on every element
     // one untimed launch, then `repeats` timed ones; the grid fills every SM exactly once (no second wave)
     CG_CUDA(ctx, cudaFuncSetAttribute(normalize_apply_bulk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k8_smem_bytes()));
     const int per_sample_blocks = std::max(1, std::min(div_up(n, K8_TILE), ctx->num_sms * K8_CTAS_PER_SM / batch));
@@ -962,7 +963,7 @@ extern "C" int cg_normalize_apply(cg_ctx* ctx, int batch, int64_t n, const float
     for (int r = 0; r <= repeats; r++) {
         if (r == 1) CG_CUDA(ctx, cudaEventRecord(ctx->ev0, s));
         CG_LAUNCH(ctx, normalize_apply_bulk_kernel, grid, K8_THREADS, k8_smem_bytes(), d_in, d_gc, (const uint8_t*)nullptr, d_out,
-                  (const int*)nullptr, (long long)n, d_med, d_gmed, (const int*)nullptr, (long long)n);
+                  (const int*)nullptr, (long long)n, d_med, d_gmed, (const int*)nullptr, (long long)n, exact_divide);
     }
     CG_CUDA(ctx, cudaEventRecord(ctx->ev1, s));
     CG_CUDA(ctx, cudaMemcpyAsync(count_out, d_out, total * 4, cudaMemcpyDeviceToHost, s));

@@ -1,7 +1,7 @@
 // K8, bulk-copy form — normalise apply (CanvasClean.cs:190-195) as a persistent stream kernel.
 //
 // count = (float)(gMed * (double)count / med[gc]) is 9 algorithmic bytes per bin (4 B count + 1 B GC in,
-// 4 B out) and ~40 FP64 instructions: an HBM stream.  Each CTA walks tiles of K8_TILE bins; one elected
+// 4 B out): an HBM stream, once the FP64 divide is kept off the common path (k8_norm).  Each CTA walks tiles of K8_TILE bins; one elected
 // thread feeds a ring of K8_STAGES shared-memory stages with 1-D bulk copies (cp.async.bulk, the TMA
 // engine: SASS UBLKCP) that complete on an mbarrier per stage, so the loads of the next K8_STAGES-1 tiles
 // are in flight while the CTA divides the current one; results leave as coalesced 128-bit streaming stores.
@@ -24,6 +24,7 @@ struct K8Smem {
     K8Stage st[K8_STAGES];
     alignas(8) unsigned long long full[K8_STAGES];
     double med[GC_BINS];
+    double rcp[GC_BINS];  // RN(1 / med)
 };
 
 __device__ __forceinline__ uint32_t k8_smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -51,9 +52,20 @@ __device__ __forceinline__ void k8_bulk_load(uint32_t dst, const void* src, uint
                  : "memory");
 }
 
-__device__ __forceinline__ float k8_norm(float c, unsigned g, unsigned a, const double* med, double gmed) {
+// (float)(gmed * c / m) without the FP64 divide in the common case.  With r = RN(1/m), q' = RN(p * r) is within 1.5 ulp
+// of the reference quotient RN(p / m) (p = RN(gmed * c) as in the reference), so both round to the same float unless a
+// float rounding boundary — a double whose low 29 mantissa bits are 1000...0 — lies within a few ulp of q'.  Those
+// elements (one in ~2^25), non-normal float ranges and non-finite values take the exact divide.
+__device__ __forceinline__ float k8_norm(float c, unsigned g, unsigned a, const double* med, const double* rcp, double gmed) {
     const double m = med[g];
-    return (a && m > 0) ? (float)__ddiv_rn(__dmul_rn(gmed, (double)c), m) : c;
+    if (!(a && m > 0)) return c;
+    const double p = __dmul_rn(gmed, (double)c);
+    if (rcp == nullptr) return (float)__ddiv_rn(p, m);  // experiment switch: always the exact divide
+    const double q = __dmul_rn(p, rcp[g]);
+    const int low = __double2loint(q) & 0x1fffffff;
+    const double aq = fabs(q);
+    const bool safe = (unsigned)abs(low - 0x10000000) > 8u && aq > 1e-30 && aq < 1e30;
+    return safe ? (float)q : (float)__ddiv_rn(p, m);
 }
 
 // grid = (CTAs per sample, samples).  n comes from the device (pipeline: survivors of the filters) or is fixed.
@@ -61,14 +73,19 @@ __global__ void __launch_bounds__(K8_THREADS)
 normalize_apply_bulk_kernel(const float* in, const uint8_t* __restrict__ gc, const uint8_t* __restrict__ alive,
                             float* out, const int* __restrict__ n_ptr, long long n_fixed,
                             const double* __restrict__ med_tab, const double* __restrict__ gmed_tab,
-                            const int* __restrict__ enabled, long long sample_stride) {
+                            const int* __restrict__ enabled, long long sample_stride, int exact_divide = 0) {
     if (enabled && !*enabled) return;
     extern __shared__ unsigned char k8_raw[];
     K8Smem& sm = *reinterpret_cast<K8Smem*>(((uintptr_t)k8_raw + 127) & ~(uintptr_t)127);
     const int sample = blockIdx.y;
     const int tid = threadIdx.x;
-    for (int t = tid; t < GC_BINS; t += K8_THREADS) sm.med[t] = med_tab[(size_t)sample * GC_BINS + t];
+    for (int t = tid; t < GC_BINS; t += K8_THREADS) {
+        const double m = med_tab[(size_t)sample * GC_BINS + t];
+        sm.med[t] = m;
+        sm.rcp[t] = m > 0 ? __ddiv_rn(1.0, m) : 0.0;
+    }
     const double gmed = gmed_tab[sample];
+    const double* rcp_tab = exact_divide ? nullptr : sm.rcp;
     const long long n = n_ptr ? (long long)*n_ptr : n_fixed;
     in += sample * sample_stride;
     out += sample * sample_stride;
@@ -123,17 +140,17 @@ normalize_apply_bulk_kernel(const float* in, const uint8_t* __restrict__ gc, con
         }
 #pragma unroll
         for (int u = 0; u < PER; u++) {
-            c[u].x = k8_norm(c[u].x, g[u].x, a[u].x, sm.med, gmed);
-            c[u].y = k8_norm(c[u].y, g[u].y, a[u].y, sm.med, gmed);
-            c[u].z = k8_norm(c[u].z, g[u].z, a[u].z, sm.med, gmed);
-            c[u].w = k8_norm(c[u].w, g[u].w, a[u].w, sm.med, gmed);
+            c[u].x = k8_norm(c[u].x, g[u].x, a[u].x, sm.med, rcp_tab, gmed);
+            c[u].y = k8_norm(c[u].y, g[u].y, a[u].y, sm.med, rcp_tab, gmed);
+            c[u].z = k8_norm(c[u].z, g[u].z, a[u].z, sm.med, rcp_tab, gmed);
+            c[u].w = k8_norm(c[u].w, g[u].w, a[u].w, sm.med, rcp_tab, gmed);
             __stcs(o4 + tid + u * K8_THREADS, c[u]);
         }
     }
     // ragged end (and unaligned arrays): plain loads, spread over the sample's CTAs
     for (long long i = (long long)tiles * K8_TILE + (long long)blockIdx.x * K8_THREADS + tid; i < n;
          i += (long long)gridDim.x * K8_THREADS)
-        out[i] = k8_norm(in[i], gc[i], alive ? alive[i] : 1u, sm.med, gmed);
+        out[i] = k8_norm(in[i], gc[i], alive ? alive[i] : 1u, sm.med, rcp_tab, gmed);
 }
 
 inline size_t k8_smem_bytes() { return sizeof(K8Smem) + 128; }

@@ -102,3 +102,17 @@ def clean_partition_wavelet_sharded(engine, sample_arrays, lengths_hint, **kw):
     r["breakpoints"] = all_gather_breakpoints(r["breakpoints"], len(lengths_hint))
     r["owner"] = owner
     return r
+
+
+def partition_hmm_sharded(engine, chrom_off, coverage, **kw):
+    """cg_partition_hmm_shard on this rank's chromosomes + the single all-gather.  The emission statistics are
+    whole-genome (per-sample mode) or per chromosome (joint mode), so the union over ranks equals the single-GPU call."""
+    import torch.distributed as dist
+    world, rank = dist.get_world_size(), dist.get_rank()
+    lengths = np.diff(np.asarray(chrom_off, np.int64))
+    owner = assign_chromosomes_lpt(lengths, world)
+    r = engine.partition_hmm(chrom_off, coverage, chrom_selected=(owner == rank).astype(np.uint8), **kw)
+    r["breakpoints"] = all_gather_breakpoints(r["breakpoints"], len(lengths))
+    r["owner"] = owner
+    r.pop("states", None)  # the Viterbi path stays on the rank that computed it
+    return r

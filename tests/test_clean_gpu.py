@@ -145,6 +145,34 @@ def test_normalize_apply_stream_matches_formula(engine, n):
     assert ms > 0
 
 
+def test_normalize_apply_near_float_rounding_boundaries(engine):
+    """The stream kernel multiplies by a rounded reciprocal and falls back to the exact divide near float rounding
+    boundaries: quotients placed within +-50 double ulps of float midpoints (and exactly on them) must still round
+    as gMed * count / median does in double (CanvasClean.cs:194)."""
+    rng = np.random.default_rng(11)
+    batch, n = 64, 4096
+    f = rng.uniform(0.5, 5000.0, batch).astype(np.float32)
+    mid = (f.astype(np.float64) + np.nextafter(f, np.float32(np.inf)).astype(np.float64)) / 2.0  # exact in double
+    gmed = rng.uniform(50.0, 150.0, batch)
+    base = gmed / mid
+    med = np.empty((batch, 101))
+    for g in range(101):
+        m = base.copy()
+        for _ in range(abs(g - 50)):
+            m = np.nextafter(m, np.inf if g > 50 else -np.inf)
+        med[:, g] = m
+    # one sample where the quotient is exactly a midpoint: 3 * (1 + 2^-24) / 3
+    gmed[0] = 3.0 * (1.0 + 2.0 ** -24)
+    med[0, :] = 3.0
+    count = np.ones((batch, n), np.float32)
+    gc = np.tile(np.arange(n) % 101, (batch, 1)).astype(np.uint8)
+    out, _ = engine.normalize_apply(count, gc, med, gmed, repeats=1)
+    exp = (gmed[:, None] * count.astype(np.float64) / np.take_along_axis(med, gc.astype(np.int64), axis=1)).astype(np.float32)
+    assert np.array_equal(out.view(np.uint32), exp.view(np.uint32))
+    assert out[0, 0] == np.float32(1.0)  # the tie rounds to even
+    assert len(np.unique(exp[1])) >= 2  # the perturbations do straddle a boundary
+
+
 # ---------------------------------------------------------------------------------------------
 # -m LOESS: floating point; the contract is 1e-5 relative on the normalised counts (bucket-wise instead of
 # point-wise summation order, device log / exp), kept bins identical

@@ -72,3 +72,37 @@ def test_partition_cbs_sharded_world2():
     ret = mgr.dict()
     mp.spawn(_cbs_worker, args=(2, port, ret), nprocs=2, join=True)
     assert ret[0] and ret[1]
+
+
+class _FakeHmmEngine:
+    def __init__(self, truth):
+        self.truth = truth
+
+    def partition_hmm(self, chrom_off, coverage, chrom_selected=None, **kw):
+        bps = [np.asarray(t, np.int32) if chrom_selected[c] else np.zeros(0, np.int32) for c, t in enumerate(self.truth)]
+        return {"breakpoints": bps, "states": np.zeros(int(chrom_off[-1]), np.uint8)}
+
+
+def _hmm_worker(rank, world, port, ret):
+    import torch.distributed as dist
+    sys.path.insert(0, ROOT)
+    from canvas_b200 import multi
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    truth = [[0, 40, 90], [0], [0, 7], [], [0, 3, 5, 9]]
+    off = np.array([0, 500, 600, 900, 905, 1000])
+    r = multi.partition_hmm_sharded(_FakeHmmEngine(truth), off, np.zeros(1000))
+    ret[rank] = [b.tolist() for b in r["breakpoints"]] == truth and "states" not in r
+    dist.destroy_process_group()
+
+
+def test_partition_hmm_sharded_world2():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_hmm_worker, args=(2, port, ret), nprocs=2, join=True)
+    assert ret[0] and ret[1]

@@ -24,8 +24,12 @@ def main():
         gcb = np.tile(s.gc[:n], (batch, 1))
         med = rng.uniform(80, 120, (batch, 101))
         gm = np.full(batch, 100.0)
-        for variant in ["bulk"]:
+        for variant in ["reciprocal", "divide", "reciprocal", "divide"]:
             for cps in [4]:
+                if variant == "divide":
+                    os.environ["CANVAS_K8_EXACT_DIV"] = "1"
+                else:
+                    os.environ.pop("CANVAS_K8_EXACT_DIV", None)
                 out, ms = eng.normalize_apply(cnt, gcb, med, gm, repeats=int(os.environ.get('K8_REPEATS', '20')))
                 if batch == 8:
                     if ref is None:

@@ -46,15 +46,18 @@ def main():
     full_c = eng.partition_cbs(off_c, cov_c)
     shard_c = multi.partition_cbs_sharded(eng, off_c, cov_c)
     ok_c = all(a["len"].tolist() == b["len"].tolist() for a, b in zip(full_c["segments"], shard_c["segments"]))
-    flag = torch.tensor([int(ok_w), int(ok_c)], device="cuda")
+    full_h = eng.partition_hmm(off, cov, per_sample=True)
+    shard_h = multi.partition_hmm_sharded(eng, off, cov, per_sample=True)
+    ok_h = all(a.tolist() == b.tolist() for a, b in zip(full_h["breakpoints"], shard_h["breakpoints"]))
+    flag = torch.tensor([int(ok_w), int(ok_c and ok_h)], device="cuda")
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0:
-        print("multi-gpu check: world", world, "bins", len(cov), "wavelet", bool(flag[0].item()), "cbs", bool(flag[1].item()),
+        print("multi-gpu check: world", world, "bins", len(cov), "wavelet", bool(flag[0].item()), "cbs+hmm", bool(flag[1].item()),
               "breakpoints", sum(len(b) for b in full["breakpoints"]), "cbs segments", sum(len(x["len"]) for x in full_c["segments"]),
               "owners", shard["owner"].tolist())
     dist.destroy_process_group()
     eng.close()
-    return 0 if (ok_w and ok_c) else 1
+    return 0 if (ok_w and ok_c and ok_h) else 1
 
 
 if __name__ == "__main__":
