@@ -21,41 +21,27 @@ def _open_text(path, mode="rt"):
     return open(path, mode)
 
 
+def _read_bytes(path):
+    with open(path, "rb") as f:
+        data = f.read()
+    return gzip.decompress(data) if data[:2] == b"\x1f\x8b" else data
+
+
 def read_binned(path):
     """CanvasIO.ReadFromTextFile (IO.cs:26-52): returns a synth.Sample with chromosome RUN ids (a
     chromosome that reappears later in the file gets a new id, as the run-based loops of CanvasClean
-    see it, CanvasClean.cs:247-256)."""
-    names, chrom, start, stop, count, gc = [], [], [], [], [], []
-    last = None
-    with _open_text(path) as f:
-        for line in f:
-            line = line.rstrip("\n").rstrip("\r")
-            if not line:
-                continue
-            p = line.split("\t")
-            if p[0] != last:
-                names.append(p[0])
-                last = p[0]
-            chrom.append(len(names) - 1)
-            start.append(int(p[1]))
-            stop.append(int(p[2]))
-            count.append(float(p[3]))
-            gc.append(int(p[4]) if len(p) > 4 else 0)
-    if len(names) > 256:
-        raise ValueError("more than 256 chromosome runs")
-    return synth.Sample(names, np.array(chrom, np.uint8), np.array(start, np.int32), np.array(stop, np.int32),
-                        np.array(count, np.float32), np.array(gc, np.uint8))
+    see it, CanvasClean.cs:247-256).  The lines are parsed by the library's native codec (cg_parse_bins)."""
+    from . import native
+    names, chrom, start, stop, count, gc = native.parse_bins(_read_bytes(path))
+    return synth.Sample(names, chrom, start, stop, count, gc)
 
 
 def write_binned(path, names, chrom, start, stop, count, gc):
-    """CanvasIO.WriteToTextFile (IO.cs:15-24): count printed with .NET's {0:F2}."""
-    txt = textcodec.f2_text(count)
-    buf = io.StringIO()
-    for c, a, b, t, g in zip(np.asarray(chrom).tolist(), np.asarray(start).tolist(), np.asarray(stop).tolist(), txt,
-                             np.asarray(gc).tolist()):
-        buf.write(f"{names[c]}\t{a}\t{b}\t{t}\t{g}\n")
-    with gzip.open(path, "wt") as f:
-        f.write(buf.getvalue())
+    """CanvasIO.WriteToTextFile (IO.cs:15-24): count printed with .NET's {0:F2} (native codec, cg_format_bins)."""
+    from . import native
+    text = native.format_bins(names, chrom, start, stop, count, gc)
+    with open(path, "wb") as f:
+        f.write(gzip.compress(text, compresslevel=6))
 
 
 def write_metric(path, name, value):

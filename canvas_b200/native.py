@@ -78,6 +78,10 @@ SIGNATURES = {
     "cg_merge_common_bins": (C.c_int, [C.c_void_p, C.c_int, _P(_i64), _P(C.c_void_p), _P(C.c_void_p), _P(C.c_void_p),
                                        _P(C.c_void_p), _P(_i64), _P(_i32), _P(_i32), _P(_f32)]),
     "cg_smooth": (C.c_int, [C.c_void_p, C.c_int, C.c_int, _P(_i64), _P(_f32), _P(_i64), _P(_f32)]),
+    "cg_format_bins": (_i64, [_i64, C.c_int, _P(C.c_char_p), _P(_u8), _P(_i32), _P(_i32), _P(_f32), _P(_u8), C.c_int,
+                              C.c_char_p, _i64, C.c_int]),
+    "cg_parse_bins": (_i64, [C.c_char_p, _i64, _i64, _P(_u8), _P(_i32), _P(_i32), _P(_f32), _P(_u8), _P(C.c_int),
+                             C.c_char_p, _i64, C.c_int]),
     "cg_cbs_boundary": (_i64, [C.c_uint32, C.c_double, C.c_double, _P(C.c_uint32), _i64]),
     "cg_bin_hits": (C.c_int, [C.c_void_p, _i64, _P(_u8), _P(C.c_uint64), C.c_char_p, C.c_int, C.c_int, _P(_u8),
                               _P(_f32), _i64, _P(_i64), _P(_i32), _P(_i32), _P(_i32), _P(_u8)]),
@@ -108,6 +112,52 @@ def load():
 
 def _ptr(a, t):
     return a.ctypes.data_as(_P(t))
+
+
+def format_bins(names, chrom, start, stop, count, gc=None, four_columns=False, n_threads=0):
+    """cg_format_bins: the text of a .binned / .cleaned file (bytes)."""
+    lib = load()
+    chrom = np.ascontiguousarray(chrom, np.uint8)
+    start = np.ascontiguousarray(start, np.int32)
+    stop = np.ascontiguousarray(stop, np.int32)
+    count = np.ascontiguousarray(count, np.float32)
+    n = len(count)
+    g = None if gc is None else np.ascontiguousarray(gc, np.uint8)
+    if g is None and not four_columns:
+        raise ValueError("the five-column layout needs GC")
+    arr = (C.c_char_p * max(len(names), 1))(*[str(x).encode() for x in names])
+    args = (n, len(names), arr, _ptr(chrom, _u8), _ptr(start, _i32), _ptr(stop, _i32), _ptr(count, _f32),
+            None if g is None else _ptr(g, _u8), int(four_columns))
+    cap = n * (max([len(str(x)) for x in names] + [1]) + 64) + 1  # a line is at most name + 2 x 11 + 48 + 3 + 5 characters
+    buf = C.create_string_buffer(cap)
+    got = lib.cg_format_bins(*args, buf, cap, n_threads)
+    if got < 0 or got > cap:
+        raise CanvasGpuError(CG_ERR_ARG, "cg_format_bins: bad argument (chromosome id outside the name table?)")
+    return buf.raw[:got]
+
+
+def parse_bins(text, n_threads=0):
+    """cg_parse_bins: (run names, chrom run ids u8, start i32, stop i32, count f32, gc u8) of a .binned / .cleaned text."""
+    lib = load()
+    data = bytes(text)
+    cap = data.count(b"\n") + 1
+    chrom = np.zeros(cap, np.uint8)
+    start = np.zeros(cap, np.int32)
+    stop = np.zeros(cap, np.int32)
+    count = np.zeros(cap, np.float32)
+    gc = np.zeros(cap, np.uint8)
+    n_names = C.c_int(0)
+    names = C.create_string_buffer(1 << 16)
+    n = lib.cg_parse_bins(data, len(data), cap, _ptr(chrom, _u8), _ptr(start, _i32), _ptr(stop, _i32), _ptr(count, _f32),
+                          _ptr(gc, _u8), C.byref(n_names), names, len(names), n_threads)
+    if n == -2:
+        raise ValueError("malformed line in bin file")
+    if n == -3:
+        raise ValueError("more than 256 chromosome runs")
+    if n < 0 or n > cap:
+        raise CanvasGpuError(CG_ERR_ARG, "cg_parse_bins failed")
+    parts = names.raw.split(b"\0")[:n_names.value]
+    return [p.decode() for p in parts], chrom[:n], start[:n], stop[:n], count[:n], gc[:n]
 
 
 class PinnedPool:

@@ -269,6 +269,27 @@ int cg_normalize_apply(cg_ctx* ctx, int batch, int64_t n, const float* count, co
                        const double* median_by_gc, const double* global_median, float* count_out,
                        int repeats, double* kernel_ms);
 
+/* ---------------------------------------------------------------------------------------------
+ * Text codecs of the .binned / .cleaned files (host code, multi-threaded; no ctx, no device work) — the per-line
+ * loops of CanvasIO.WriteToTextFile / ReadFromTextFile (CanvasCommon/IO.cs:15-52) on the uncompressed text; gzip stays
+ * with the caller.
+ *
+ * cg_format_bins: "chr \t start \t stop \t count \t gc \n" per bin, count as .NET Core 2.0 prints {0:F2} (IO.cs:21);
+ * four_columns != 0: "chr \t start \t stop \t count \n" with float.ToString() (CanvasRunner.cs:895-897; gc may be
+ * NULL).  names[chrom[i]] is the chromosome of bin i.  Returns the text length; when out is NULL or cap is too small
+ * nothing is written (size query).  < 0: bad argument.
+ *
+ * cg_parse_bins: columns of every non-empty line (4 or 5 columns; gc = 0 when absent); chrom[i] = id of the
+ * chromosome RUN of line i (a name that reappears later starts a new run); the run names are written back to back,
+ * NUL-terminated, into names.  Returns the number of rows (if > max_rows the buffers were too small and nothing is
+ * complete); -1 bad argument, -2 malformed line, -3 more than 256 runs or names_cap too small.
+ * ------------------------------------------------------------------------------------------- */
+int64_t cg_format_bins(int64_t n, int n_names, const char* const* names, const uint8_t* chrom, const int32_t* start,
+                       const int32_t* stop, const float* count, const uint8_t* gc, int four_columns, char* out,
+                       int64_t cap, int n_threads);
+int64_t cg_parse_bins(const char* text, int64_t len, int64_t max_rows, uint8_t* chrom, int32_t* start, int32_t* stop,
+                      float* count, uint8_t* gc, int* n_names, char* names, int64_t names_cap, int n_threads);
+
 #ifdef __cplusplus
 }
 #endif

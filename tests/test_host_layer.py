@@ -160,3 +160,42 @@ def test_merge_oracle_follows_dictionary_semantics():
     out = ora.merge_multi_sample_cleaned([a, b])
     assert [(c, s, e) for c, s, e, _ in out] == [("chr1", 10, 25), ("chr2", 0, 10)]  # the last file's stop wins
     assert [[float(x) for x in v] for *_, v in out] == [[2.0, 5.0], [3.0, 6.0]]
+
+
+def test_native_text_codec_matches_python_codec(tmp_path):
+    """cg_format_bins / cg_parse_bins (host code of the library) against the Python restatement of .NET's formats."""
+    from canvas_b200 import fileio, native, textcodec
+    rng = np.random.default_rng(3)
+    n = 60000
+    names = ["chr1", "chr2", "chrX", "chr1"]  # chr1 reappears: a new run
+    chrom = np.sort(rng.integers(0, 4, n)).astype(np.uint8)
+    start = (np.arange(n) * 1000).astype(np.int32)
+    stop = start + 1000
+    count = np.concatenate([rng.gamma(2, 60, n - 8), [0.0, 0.005, 0.015, 1e7, 123456.785, 2.5e-5, 99.995, 1234567.9]]).astype(np.float32)
+    gc = rng.integers(0, 101, n).astype(np.uint8)
+    txt = native.format_bins(names, chrom, start, stop, count, gc, n_threads=3)
+    lines = txt.decode().splitlines()
+    assert len(lines) == n
+    want = textcodec.f2_text(count)
+    for i in list(range(0, n, 997)) + list(range(n - 8, n)):
+        assert lines[i] == f"{names[chrom[i]]}\t{start[i]}\t{stop[i]}\t{want[i]}\t{gc[i]}"
+    t4 = native.format_bins(names, chrom, start, stop, count, None, four_columns=True).decode().splitlines()
+    g7 = textcodec.float_default_text(count)
+    for i in list(range(0, n, 997)) + list(range(n - 8, n)):
+        assert t4[i].split("\t")[3] == g7[i]
+    rn, rc, ra, rb, rv, rg = native.parse_bins(txt, n_threads=4)
+    assert rn == ["chr1", "chr2", "chrX", "chr1"][:len(rn)] and len(rn) == len(np.unique(chrom))
+    assert np.array_equal(ra, start) and np.array_equal(rb, stop) and np.array_equal(rg, gc)
+    assert np.array_equal(rv, np.array([float(x) for x in want]).astype(np.float32))
+    assert np.array_equal(np.diff(rc.astype(int)) != 0, np.diff(chrom.astype(int)) != 0)
+    # through the file layer (gzip) and with CRLF / blank lines / four columns
+    p = tmp_path / "x.binned"
+    fileio.write_binned(str(p), names, chrom, start, stop, count, gc)
+    s = fileio.read_binned(str(p))
+    assert np.array_equal(s.start, start) and np.array_equal(s.gc, gc) and len(s.names) == len(rn)
+    rn2, rc2, ra2, rb2, rv2, rg2 = native.parse_bins(b"chr1\t0\t10\t1.50\r\n\nchr2\t10\t20\t2.25\t7\n")
+    assert rn2 == ["chr1", "chr2"] and ra2.tolist() == [0, 10] and rv2.tolist() == [1.5, 2.25] and rg2.tolist() == [0, 7]
+    with pytest.raises(ValueError):
+        native.parse_bins(b"chr1\t0\t10\n")
+    with pytest.raises(ValueError):
+        native.parse_bins(b"chr1\t0\tx\t1.0\t3\n")
