@@ -105,14 +105,25 @@ extern "C" int64_t cg_format_bins(int64_t n, int n_names, const char* const* nam
     std::vector<size_t> name_len((size_t)n_names);
     for (int i = 0; i < n_names; i++) { name_len[(size_t)i] = names[i] ? strlen(names[i]) : 0; max_name = std::max(max_name, name_len[(size_t)i]); }
     const int T = codec_threads(n, n_threads);
-    std::vector<std::string> parts((size_t)T);
+    const size_t max_line = max_name + 96;  // name + two ints + a float in fixed notation + gc + separators
+    struct Part { char* buf = nullptr; size_t len = 0; };
+    std::vector<Part> parts((size_t)T);
     std::vector<int> bad((size_t)T, 0);
     auto work = [&](int t) {
         const int64_t lo = n * t / T, hi = n * (t + 1) / T;
-        std::string& s = parts[(size_t)t];
-        s.resize((size_t)(hi - lo) * (max_name + 96));
-        char* p = &s[0];
+        size_t cap = (size_t)(hi - lo) * (max_name + 36) + max_line;  // typical line; grown when a thread runs ahead of it
+        char* buf = (char*)malloc(cap);
+        if (!buf) { bad[(size_t)t] = 2; return; }
+        char* p = buf;
         for (int64_t i = lo; i < hi; i++) {
+            if ((size_t)(buf + cap - p) < max_line) {
+                const size_t used = (size_t)(p - buf);
+                cap = cap + cap / 2 + max_line;
+                char* nb = (char*)realloc(buf, cap);
+                if (!nb) { free(buf); bad[(size_t)t] = 2; return; }
+                buf = nb;
+                p = buf + used;
+            }
             const int c = chrom[i];
             if (c >= n_names) { bad[(size_t)t] = 1; continue; }
             memcpy(p, names[c], name_len[(size_t)c]);
@@ -130,18 +141,27 @@ extern "C" int64_t cg_format_bins(int64_t n, int n_names, const char* const* nam
             }
             *p++ = '\n';
         }
-        s.resize((size_t)(p - &s[0]));
+        parts[(size_t)t].buf = buf;
+        parts[(size_t)t].len = (size_t)(p - buf);
     };
     std::vector<std::thread> th;
     for (int t = 1; t < T; t++) th.emplace_back(work, t);
     work(0);
     for (auto& x : th) x.join();
     int64_t total = 0;
-    for (int t = 0; t < T; t++) { if (bad[(size_t)t]) return -1; total += (int64_t)parts[(size_t)t].size(); }
-    if (!out || cap < total) return total;  // size query
-    char* p = out;
-    for (int t = 0; t < T; t++) { memcpy(p, parts[(size_t)t].data(), parts[(size_t)t].size()); p += parts[(size_t)t].size(); }
-    return total;
+    bool failed = false;
+    for (int t = 0; t < T; t++) { failed = failed || bad[(size_t)t]; total += (int64_t)parts[(size_t)t].len; }
+    if (!failed && out && cap >= total) {
+        // the pieces are copied to their places side by side as well
+        std::vector<size_t> at((size_t)T, 0);
+        for (int t = 1; t < T; t++) at[(size_t)t] = at[(size_t)t - 1] + parts[(size_t)t - 1].len;
+        std::vector<std::thread> cp;
+        for (int t = 1; t < T; t++) cp.emplace_back([&, t] { memcpy(out + at[(size_t)t], parts[(size_t)t].buf, parts[(size_t)t].len); });
+        memcpy(out, parts[0].buf, parts[0].len);
+        for (auto& x : cp) x.join();
+    }
+    for (int t = 0; t < T; t++) free(parts[(size_t)t].buf);
+    return failed ? -1 : total;  // out == NULL or cap < total: size query
 }
 
 // Returns the number of rows (> max_rows: buffers too small, nothing complete), or < 0: -1 bad argument, -2 malformed

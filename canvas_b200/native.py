@@ -129,11 +129,11 @@ def format_bins(names, chrom, start, stop, count, gc=None, four_columns=False, n
     args = (n, len(names), arr, _ptr(chrom, _u8), _ptr(start, _i32), _ptr(stop, _i32), _ptr(count, _f32),
             None if g is None else _ptr(g, _u8), int(four_columns))
     cap = n * (max([len(str(x)) for x in names] + [1]) + 64) + 1  # a line is at most name + 2 x 11 + 48 + 3 + 5 characters
-    buf = C.create_string_buffer(cap)
-    got = lib.cg_format_bins(*args, buf, cap, n_threads)
+    buf = np.empty(cap, np.uint8)  # not zero-filled
+    got = lib.cg_format_bins(*args, buf.ctypes.data_as(C.c_char_p), cap, n_threads)
     if got < 0 or got > cap:
         raise CanvasGpuError(CG_ERR_ARG, "cg_format_bins: bad argument (chromosome id outside the name table?)")
-    return buf.raw[:got]
+    return buf[:got].tobytes()
 
 
 def parse_bins(text, n_threads=0):
