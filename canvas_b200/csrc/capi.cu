@@ -20,11 +20,11 @@ extern "C" int cg_create(int device, cg_ctx** out) {
         cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreateWithFlags(&ctx->ev_mid, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess ||
-        cudaMallocHost((void**)&ctx->pinned, 1 << 16) != cudaSuccess) {
+        cudaMallocHost((void**)&ctx->pinned, 1 << 18) != cudaSuccess) {
         cg_destroy(ctx);
         return CG_ERR_CUDA;
     }
-    ctx->pinned_cap = 1 << 16;
+    ctx->pinned_cap = 1 << 18;
     for (int i = 0; i < 8; i++)
         if (cudaEventCreate(&ctx->stage_ev[i]) != cudaSuccess) { cg_destroy(ctx); return CG_ERR_CUDA; }
     *out = ctx;

@@ -191,11 +191,33 @@ struct WvDev {
     int* rq_tfirst;
     unsigned long long* phase_ns;
     UhTinyTab* tiny_tab;
+    int* pack;  // results packed for one download: n_bp[C], depth[C], total, then the breakpoint lists back to back
     // sizes the arrays were allocated for (wv_alloc); a plan run on them must not exceed any
     long long cap_N;
     size_t cap_work, cap_ev, cap_tiles;
     int cap_nseg, cap_f3, cap_w10, cap_w100, cap_rq, cap_C;
 };
+
+// Results of one partition run packed for a single download (the host used to issue one copy per chromosome):
+// [0, C) n_bp, [C, 2C) tree depth, [2C] total breakpoints, then the lists in chromosome order while they fit.
+constexpr int WV_PACK_INTS = 16384;
+__global__ void __launch_bounds__(256) wv_pack_kernel(const int* __restrict__ n_bp, const int* __restrict__ depth, const int* __restrict__ bp,
+                                                      const long long* __restrict__ off, int C, int* __restrict__ pack) {
+    __shared__ int s_at[WV_MAX_CHROM + 1];
+    if (threadIdx.x == 0) {
+        int run = 0;
+        for (int c = 0; c < C; c++) { s_at[c] = run; run += n_bp[c]; }
+        s_at[C] = run;
+        pack[2 * C] = run;
+    }
+    for (int c = threadIdx.x; c < C; c += blockDim.x) { pack[c] = n_bp[c]; pack[C + c] = depth[c]; }
+    __syncthreads();
+    const int room = WV_PACK_INTS - (2 * C + 1);
+    for (int c = 0; c < C; c++) {
+        const int at = s_at[c], n = n_bp[c];
+        for (int i = threadIdx.x; i < n && at + i < room; i += blockDim.x) pack[2 * C + 1 + at + i] = bp[off[c] + i];
+    }
+}
 
 size_t wv_workspace_bytes(const WvPlan& pl) {
     const size_t N = (size_t)pl.N, C = (size_t)pl.n_chrom;
@@ -215,7 +237,7 @@ size_t wv_workspace_bytes(const WvPlan& pl) {
     s += arena_need(N + 1, 4) * 5 + arena_need(N + 1, 8) * 2 + arena_need(N / 32 + C + 2, 4);
     s += arena_need(C + 1, 4) + arena_need(N + 1, 4);
     s += arena_need((C + 1) * RQ_BUCKETS, 8) + arena_need(N + 1, 8) + arena_need((size_t)(pl.rq_ntiles + 1) * RQ_BUCKETS, 2) * 2;
-    s += arena_need((size_t)(pl.rq_ntiles + C + 2) * RQ_BUCKETS, 4) + arena_need(C + 2, 4) + arena_need((C + 1) * 8, 8) + arena_need(1, sizeof(UhTinyTab));
+    s += arena_need((size_t)(pl.rq_ntiles + C + 2) * RQ_BUCKETS, 4) + arena_need(C + 2, 4) + arena_need((C + 1) * 8, 8) + arena_need(1, sizeof(UhTinyTab)) + arena_need(WV_PACK_INTS, 4);
     return s + (1 << 16);
 }
 
@@ -279,11 +301,12 @@ int wv_alloc(cg_ctx* ctx, const WvPlan& pl, WvDev& d, double* cov_dev_existing) 
     d.rq_tstart = arena_take<unsigned short>(ctx, (size_t)(pl.rq_ntiles + 1) * RQ_BUCKETS);
     d.rq_cum = arena_take<unsigned>(ctx, (size_t)(pl.rq_ntiles + C + 2) * RQ_BUCKETS);
     d.phase_ns = arena_take<unsigned long long>(ctx, (C + 1) * 8);
+    d.pack = arena_take<int>(ctx, WV_PACK_INTS);
     d.tiny_tab = arena_take<UhTinyTab>(ctx, 1);
     ok = ok && d.rq_spl && d.rq_sorted && d.rq_hist && d.rq_tstart && d.rq_cum && d.rq_tfirst;
     ok = ok && d.cov && d.off && d.selected && d.pz && d.seg_len && d.work && d.seg_nwork && d.ev_work && d.tiles && d.tile_first &&
          d.tsum && d.f3lv && d.tmed && d.cmad && d.ev10 && d.ev100 && d.r10 && d.r100 && d.med && d.mad && d.sigma &&
-         d.cand_thr && d.log3 && d.ctl && d.lvlcnt && d.depth && d.big && d.mid && d.small && d.tiny && d.cand && d.lvl_idx &&
+         d.cand_thr && d.log3 && d.ctl && d.pack && d.lvlcnt && d.depth && d.big && d.mid && d.small && d.tiny && d.cand && d.lvl_idx &&
          d.sv && d.piece && d.prelim && d.lvl_first && d.svkey && d.rec && d.bitmap && d.n_bp && d.bp;
     d.cap_N = pl.N; d.cap_nseg = pl.t.nseg; d.cap_work = pl.work.size() + pl.work.size() / 8 + 63; d.cap_ev = pl.ev_work.size(); d.cap_tiles = pl.tiles.size();
     d.cap_f3 = pl.f3_total; d.cap_w10 = pl.t.n_w10; d.cap_w100 = pl.t.n_w100; d.cap_rq = pl.rq_ntiles; d.cap_C = pl.n_chrom;
@@ -497,6 +520,7 @@ int wv_enqueue(cg_ctx* ctx, const cg_wavelet_opts* o, const WvPlan& pl, WvDev& d
     }
     CG_TL(ctx, "uh_finish");
     cudaEventRecord(ctx->stage_ev[7], s);
+    CG_LAUNCH(ctx, wv_pack_kernel, 1, 256, 0, d.n_bp, d.depth, d.bp, d.off, C, d.pack);
     return CG_OK;
 }
 
@@ -505,9 +529,14 @@ int wv_collect(cg_ctx* ctx, const WvPlan& pl, WvDev& d, int32_t* n_bp, int32_t* 
     cudaStream_t s = ctx->stream;
     const int C = pl.n_chrom;
     WvCtl* h = (WvCtl*)ctx->pinned;
-    int* h_nbp = (int*)(ctx->pinned + 4096);
+    int* h_pack = (int*)(ctx->pinned + 8192);
+    static_assert(sizeof(WvCtl) <= 8192, "control block does not fit its pinned slot");
+    // one download: control block + packed results (counts, depths and the first breakpoints; the rest, if any, follows)
+    const int head = 2 * C + 1;
+    const int first = std::min<int>(WV_PACK_INTS, head + 4096);
     CG_CUDA(ctx, cudaMemcpyAsync(h, d.ctl, sizeof(WvCtl), cudaMemcpyDeviceToHost, s));
-    CG_CUDA(ctx, cudaMemcpyAsync(h_nbp, d.n_bp, (size_t)C * 4, cudaMemcpyDeviceToHost, s));
+    if (pl.N > 0) CG_CUDA(ctx, cudaMemcpyAsync(h_pack, d.pack, (size_t)first * 4, cudaMemcpyDeviceToHost, s));
+    else memset(h_pack, 0, (size_t)first * 4);  // nothing was enqueued for an empty genome
     CG_CUDA(ctx, cudaStreamSynchronize(s));
     CG_CUDA(ctx, cudaGetLastError());
     CG_CHECK_LAUNCHES(ctx);
@@ -516,6 +545,8 @@ int wv_collect(cg_ctx* ctx, const WvPlan& pl, WvDev& d, int32_t* n_bp, int32_t* 
     ctx->stats[1] = (double)(h->nodes_big + h->nodes_small + h->nodes_tiny);
     ctx->stats[2] = (double)h->cand_count_.v;
     ctx->stats[3] = (double)pl.N;
+    const int* h_nbp = h_pack;
+    for (int c = 0; c < C; c++) n_bp[c] = h_nbp[c];
     if (getenv("CANVAS_DEBUG")) {
         std::vector<unsigned long long> ph((size_t)(pl.n_chrom + 1) * 8, 0);
         cudaMemcpy(ph.data(), d.phase_ns, ph.size() * 8, cudaMemcpyDeviceToHost);
@@ -534,18 +565,23 @@ int wv_collect(cg_ctx* ctx, const WvPlan& pl, WvDev& d, int32_t* n_bp, int32_t* 
     ctx->stats[12] = (double)h->multi_chunk_nodes; ctx->stats[13] = (double)h->queue_hops;
     {
         int maxd = 0;
-        std::vector<int> dep(pl.n_chrom + 1, 0);
-        cudaMemcpy(dep.data(), d.depth, (size_t)pl.n_chrom * 4, cudaMemcpyDeviceToHost);
-        for (int c = 0; c < pl.n_chrom; c++) maxd = std::max(maxd, dep[c]);
+        for (int c = 0; c < C; c++) maxd = std::max(maxd, h_pack[C + c]);
         ctx->stats[14] = (double)maxd;
     }
-    // breakpoints: one copy per chromosome that has any (they are few and short)
-    for (int c = 0; c < C; c++) {
-        n_bp[c] = h_nbp[c];
-        if (h_nbp[c] > 0)
-            CG_CUDA(ctx, cudaMemcpyAsync(bp + pl.off[c], d.bp + pl.off[c], (size_t)h_nbp[c] * 4, cudaMemcpyDeviceToHost, s));
+    // breakpoints: from the packed block when they all arrived with it, else one copy per chromosome
+    const long long total = h_pack[2 * C];
+    if (head + total <= first) {
+        const int* src = h_pack + head;
+        for (int c = 0; c < C; c++) {
+            if (h_nbp[c] > 0) memcpy(bp + pl.off[c], src, (size_t)h_nbp[c] * 4);
+            src += h_nbp[c];
+        }
+    } else {
+        for (int c = 0; c < C; c++)
+            if (h_nbp[c] > 0)
+                CG_CUDA(ctx, cudaMemcpyAsync(bp + pl.off[c], d.bp + pl.off[c], (size_t)h_nbp[c] * 4, cudaMemcpyDeviceToHost, s));
+        CG_CUDA(ctx, cudaStreamSynchronize(s));
     }
-    CG_CUDA(ctx, cudaStreamSynchronize(s));
     *evenness = h->evenness;
     *evenness_ok = h->evenness_ok;
     *cv = h->cv;
