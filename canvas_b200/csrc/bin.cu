@@ -210,6 +210,7 @@ extern "C" int cg_bin_hits(cg_ctx* ctx, int64_t chr_len, const uint8_t* hits, co
     ctx->tl = nullptr;
     ctx->launch_err = cudaSuccess;
     for (int i = 0; i < 4; i++) ctx->stage_used[i] = false;
+    ctx->gap_used = false;
     if (chr_len == 0) return CG_OK;
     if (!hits || !possible_bits || !bases || (max_bins > 0 && (!start || !stop || !count || !gc)))
         return cg_fail(ctx, CG_ERR_ARG, "cg_bin_hits: null array");
@@ -290,6 +291,7 @@ extern "C" int cg_bin_fragments(cg_ctx* ctx, int64_t n_frag, const int32_t* frag
     ctx->tl = nullptr;
     ctx->launch_err = cudaSuccess;
     for (int i = 0; i < 4; i++) ctx->stage_used[i] = false;
+    ctx->gap_used = false;
     if (n_bins == 0) {
         for (int64_t i = 0; i < n_frag; i++) best_bin[i] = -1;
         return CG_OK;

@@ -27,6 +27,7 @@ extern "C" int cg_create(int device, cg_ctx** out) {
     ctx->pinned_cap = 1 << 18;
     for (int i = 0; i < 8; i++)
         if (cudaEventCreate(&ctx->stage_ev[i]) != cudaSuccess) { cg_destroy(ctx); return CG_ERR_CUDA; }
+    if (cudaEventCreate(&ctx->gap_ev) != cudaSuccess) { cg_destroy(ctx); return CG_ERR_CUDA; }
     *out = ctx;
     return CG_OK;
 }
@@ -37,6 +38,7 @@ extern "C" void cg_destroy(cg_ctx* ctx) {
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     if (ctx->arena) cudaFree(ctx->arena);
     cg_graphs_clear(ctx);
+    if (ctx->gap_ev) cudaEventDestroy(ctx->gap_ev);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
     if (ctx->plan_pinned) cudaFreeHost(ctx->plan_pinned);
     if (ctx->aux) cudaFree(ctx->aux);
@@ -55,8 +57,15 @@ extern "C" const char* cg_describe(cg_ctx* ctx) { return ctx ? ctx->desc.c_str()
 extern "C" double cg_last_kernel_ms(cg_ctx* ctx) { return ctx ? ctx->last_kernel_ms : 0.0; }
 extern "C" int cg_last_launches(cg_ctx* ctx) { return ctx ? ctx->launches : 0; }
 extern "C" double cg_last_stage_ms(cg_ctx* ctx, int stage) {
-    if (!ctx || stage < 0 || stage > 3 || !ctx->stage_used[stage]) return -1.0;
+    if (!ctx) return -1.0;
     float ms = 0;
+    if (stage == 4 || stage == 5) {  // fused call: 4 = Clean end -> end of the pre-wait work, 5 = that -> start of the scalars
+        if (!ctx->gap_used || !ctx->stage_used[0] || !ctx->stage_used[1]) return -1.0;
+        const cudaError_t e = stage == 4 ? cudaEventElapsedTime(&ms, ctx->stage_ev[1], ctx->gap_ev)
+                                         : cudaEventElapsedTime(&ms, ctx->gap_ev, ctx->stage_ev[2]);
+        return e == cudaSuccess ? ms : -1.0;
+    }
+    if (stage < 0 || stage > 3 || !ctx->stage_used[stage]) return -1.0;
     if (cudaEventElapsedTime(&ms, ctx->stage_ev[2 * stage], ctx->stage_ev[2 * stage + 1]) != cudaSuccess) return -1.0;
     return ms;
 }

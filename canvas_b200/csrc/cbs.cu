@@ -1376,6 +1376,7 @@ static int partition_cbs_impl(cg_ctx* ctx, const cg_cbs_opts* o, const uint32_t*
     ctx->tl = nullptr;
     ctx->launch_err = cudaSuccess;
     for (int i = 0; i < 4; i++) ctx->stage_used[i] = false;
+    ctx->gap_used = false;
     std::vector<unsigned> table;
     if (!sbdry) {
         table = h_boundary(o->n_perm, o->alpha, o->eta > 0 ? o->eta : 0.05);

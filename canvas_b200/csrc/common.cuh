@@ -37,6 +37,8 @@ struct cg_ctx {
     // stage timers: events [2*i], [2*i+1] bracket stage i
     cudaEvent_t stage_ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     bool stage_used[4] = {false, false, false, false};
+    cudaEvent_t gap_ev = nullptr;  // fused call: end of the work enqueued before the mid-call wait (see cg_last_stage_ms 4, 5)
+    bool gap_used = false;
     double stats[16] = {0};
     // device arena, grown on demand and reused across calls
     char* arena = nullptr;

@@ -663,6 +663,7 @@ extern "C" int cg_partition_hmm_shard(cg_ctx* ctx, const cg_hmm_opts* o, int n_s
     ctx->launch_err = cudaSuccess;
     ctx->last_kernel_ms = 0;
     for (int i = 0; i < 4; i++) ctx->stage_used[i] = false;
+    ctx->gap_used = false;
     if (N == 0) return CG_OK;
     if (!coverage || !bp) return cg_fail(ctx, CG_ERR_ARG, "cg_partition_hmm: null array");
     if (N > 0x7fff0000LL) return cg_fail(ctx, CG_ERR_UNSUPPORTED, "cg_partition_hmm: too many bins");

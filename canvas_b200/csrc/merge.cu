@@ -119,6 +119,7 @@ extern "C" int cg_merge_common_bins(cg_ctx* ctx, int n_samples, const int64_t* n
     ctx->launch_err = cudaSuccess;
     ctx->last_kernel_ms = 0;
     for (int i = 0; i < 4; i++) ctx->stage_used[i] = false;
+    ctx->gap_used = false;
     const int n0 = (int)n[0];
     if (n0 == 0) return CG_OK;
     if (!kept_index || !stop_out || !count_out) return cg_fail(ctx, CG_ERR_ARG, "cg_merge_common_bins: null output");

@@ -66,6 +66,7 @@ extern "C" int cg_smooth(cg_ctx* ctx, int max_half_window, int n_chrom, const in
     ctx->launch_err = cudaSuccess;
     ctx->last_kernel_ms = 0;
     for (int i = 0; i < 4; i++) ctx->stage_used[i] = false;
+    ctx->gap_used = false;
     const long long N = n_chrom > 0 ? chrom_off[n_chrom] - chrom_off[0] : 0;
     for (int c = 0; c < n_chrom; c++) n_out[c] = chrom_off[c + 1] - chrom_off[c];
     if (N == 0) return CG_OK;

@@ -332,7 +332,34 @@ int wv_clear(cg_ctx* ctx, WvDev& d) {
 
 // Upload the plan tables (small) and enqueue the whole partition pipeline.  d.cov must already hold
 // the coverage on the device (or be filled by an earlier kernel on the same stream).
-int wv_enqueue(cg_ctx* ctx, const cg_wavelet_opts* o, const WvPlan& pl, WvDev& d, const unsigned char* selected_host) {
+// The range-quantile index of the finish stage needs only the coverage and the chromosome offsets.
+static void wv_enqueue_rq_index(cg_ctx* ctx, WvDev& d, int C, int rq_ntiles_upper) {
+    if (rq_ntiles_upper <= 0 || C <= 0) return;
+    CG_LAUNCH(ctx, rq_splitter_kernel, C, 1024, 0, d.cov, d.off, d.selected, d.rq_spl);
+    CG_LAUNCH(ctx, rq_tile_kernel, rq_ntiles_upper, RQ_TILE, 0, d.cov, d.off, d.rq_tfirst, C, d.selected, d.rq_spl, d.rq_hist,
+              d.rq_tstart, d.rq_sorted);
+    CG_LAUNCH(ctx, rq_cumulate_kernel, C, RQ_BUCKETS, 0, d.rq_tfirst, d.selected, d.rq_hist, d.rq_cum);
+}
+
+// chromosome offsets and first index tiles from the per-chromosome bin counts, on the device (fused call: lets the index
+// be built while the host is still waiting for those counts)
+__global__ void wv_device_offsets_kernel(const unsigned* __restrict__ chrom_cnt, int C, long long* __restrict__ off, int* __restrict__ rq_tfirst) {
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    long long o = 0;
+    int t = 0;
+    for (int c = 0; c < C; c++) {
+        off[c] = o;
+        rq_tfirst[c] = t;
+        const long long n = chrom_cnt[c];
+        o += n;
+        t += (int)((n + RQ_TILE - 1) / RQ_TILE);
+    }
+    off[C] = o;
+    rq_tfirst[C] = t;
+}
+
+int wv_enqueue(cg_ctx* ctx, const cg_wavelet_opts* o, const WvPlan& pl, WvDev& d, const unsigned char* selected_host,
+               bool rq_index_done = false) {
     cudaStream_t s = ctx->stream;
     const int C = pl.n_chrom;
     const WvSegTable& t = pl.t;
@@ -392,12 +419,7 @@ int wv_enqueue(cg_ctx* ctx, const cg_wavelet_opts* o, const WvPlan& pl, WvDev& d
     ctx->stage_used[1] = true;
     // ---- range-quantile index for the medians of the finish stage: needs only the coverage, and is enqueued first so
     // that the device has work while the host is still launching the many small kernels of the scalars
-    if (pl.rq_ntiles > 0 && C > 0) {
-        CG_LAUNCH(ctx, rq_splitter_kernel, C, 1024, 0, d.cov, d.off, d.selected, d.rq_spl);
-        CG_LAUNCH(ctx, rq_tile_kernel, pl.rq_ntiles, RQ_TILE, 0, d.cov, d.off, d.rq_tfirst, C, d.selected, d.rq_spl, d.rq_hist,
-                  d.rq_tstart, d.rq_sorted);
-        CG_LAUNCH(ctx, rq_cumulate_kernel, C, RQ_BUCKETS, 0, d.rq_tfirst, d.selected, d.rq_hist, d.rq_cum);
-    }
+    if (!rq_index_done) wv_enqueue_rq_index(ctx, d, C, pl.rq_ntiles);
     CG_TL(ctx, "rq index");
     // ---- evenness per window (coverage only: early, for the same reason)
     if (!pl.ev_work.empty())
@@ -617,6 +639,7 @@ extern "C" int cg_partition_wavelet_shard(cg_ctx* ctx, const cg_wavelet_opts* op
     ctx->launch_err = cudaSuccess;
     ctx->last_kernel_ms = 0;
     for (int i = 0; i < 4; i++) ctx->stage_used[i] = false;
+    ctx->gap_used = false;
     CG_CUDA(ctx, cudaSetDevice(ctx->device));
     WvPlan pl;
     make_plan(pl, n_chrom, chrom_off, opts->evenness_window);
@@ -694,6 +717,7 @@ extern "C" int cg_clean_partition_wavelet_shard(cg_ctx* ctx, const cg_clean_opts
     ctx->launch_err = cudaSuccess;
     ctx->last_kernel_ms = 0;
     for (int i = 0; i < 4; i++) ctx->stage_used[i] = false;
+    ctx->gap_used = false;
     *n_out = 0; *local_sd = -1.0; *gc_norm_skipped = 0; *evenness = 0; *evenness_ok = 0; *cv = 0; *cv_has_value = 0;
     for (int i = 0; i <= WV_F3_LEVELS; i++) factor_of_three[i] = 0;
     for (int c = 0; c <= n_chrom; c++) chrom_off_out[c] = 0;
@@ -760,7 +784,24 @@ extern "C" int cg_clean_partition_wavelet_shard(cg_ctx* ctx, const cg_clean_opts
     if (rc) { cudaStreamSynchronize(s); return rc; }
     rc = wv_clear(ctx, wd);
     if (rc) { cudaStreamSynchronize(s); return rc; }
-    CG_CUDA(ctx, cudaStreamSynchronize(s));
+    // ... and the range-quantile index of the finish stage is built there too: offsets come from the device-side counts
+    std::vector<unsigned char> sel(n_chrom + 1, 1);
+    if (chrom_selected)
+        for (int c = 0; c < n_chrom; c++) sel[c] = chrom_selected[c] ? 1 : 0;
+    if (n_chrom > 0) {
+        CG_CUDA(ctx, cudaMemcpyAsync(wd.selected, sel.data(), n_chrom, cudaMemcpyHostToDevice, s));
+        CG_LAUNCH(ctx, wv_device_offsets_kernel, 1, 32, 0, chrom_cnt, n_chrom, wd.off, wd.rq_tfirst);
+        wv_enqueue_rq_index(ctx, wd, n_chrom, worst.rq_ntiles);
+    }
+    cudaEventRecord(ctx->gap_ev, s);
+    ctx->gap_used = true;
+    {
+        // the counts have landed when ev_mid completes; the index kernels keep the device busy meanwhile.  Polling the
+        // event returns as soon as it fires (a blocking wait on an event in the middle of a busy stream does not).
+        cudaError_t q;
+        while ((q = cudaEventQuery(ctx->ev_mid)) == cudaErrorNotReady) {}
+        if (q != cudaSuccess) return cg_fail(ctx, CG_ERR_CUDA, std::string("cg_clean_partition_wavelet: ") + cudaGetErrorString(q));
+    }
     CG_CUDA(ctx, cudaGetLastError());
     CG_CHECK_LAUNCHES(ctx);
     if (h->unsorted) return cg_fail(ctx, CG_ERR_UNSORTED, "cg_clean: chromosome ids must form non-decreasing runs and GC must be 0..100");
@@ -780,10 +821,7 @@ extern "C" int cg_clean_partition_wavelet_shard(cg_ctx* ctx, const cg_clean_opts
     for (int c = 0; c <= n_chrom; c++) chrom_off_out[c] = off[c];
     WvPlan pl;
     make_plan(pl, n_chrom, off.data(), wopts->evenness_window);
-    std::vector<unsigned char> sel(n_chrom + 1, 1);
-    if (chrom_selected)
-        for (int c = 0; c < n_chrom; c++) sel[c] = chrom_selected[c] ? 1 : 0;
-    rc = wv_enqueue(ctx, wopts, pl, wd, sel.data());
+    rc = wv_enqueue(ctx, wopts, pl, wd, sel.data(), n_chrom > 0);
     if (rc) { cudaStreamSynchronize(s); cudaStreamSynchronize(ctx->copy_stream); return rc; }
     CG_CUDA(ctx, cudaEventRecord(ctx->ev1, s));
     rc = wv_collect(ctx, pl, wd, n_bp, bp, evenness, evenness_ok, cv, cv_has_value, factor_of_three);

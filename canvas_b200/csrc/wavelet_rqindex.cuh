@@ -97,6 +97,7 @@ rq_tile_kernel(const double* __restrict__ cov, const long long* __restrict__ off
     __shared__ int s_cnt[RQ_BUCKETS], s_start[RQ_BUCKETS], s_fill[RQ_BUCKETS];
     __shared__ int s_warp[32];
     const int tile = blockIdx.x;
+    if (tile >= tfirst[n_chrom]) return;  // the grid may be sized for an upper bound of the tile count
     // chromosome of this tile
     int lo = 0, hi = n_chrom - 1;
     while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (tfirst[mid] <= tile) lo = mid; else hi = mid - 1; }

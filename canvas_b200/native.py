@@ -237,8 +237,9 @@ class Engine:
         return self.lib.cg_last_launches(self.h)
 
     def last_stage_ms(self):
-        names = ("clean", "scalars", "decompose", "finish")
-        return {k: self.lib.cg_last_stage_ms(self.h, i) for i, k in enumerate(names)}
+        names = ("clean", "scalars", "decompose", "finish", "between_clean_and_wait", "host_wait_gap")
+        out = {k: self.lib.cg_last_stage_ms(self.h, i) for i, k in enumerate(names)}
+        return {k: v for k, v in out.items() if v >= 0 or k in names[:4]}
 
     def last_partition_stats(self):
         out = np.zeros(16, np.float64)

@@ -51,7 +51,9 @@ double cg_last_kernel_ms(cg_ctx* ctx);
 int cg_last_launches(cg_ctx* ctx);
 /* Device time (ms) of one stage of the last call: 0 Clean pipeline, 1 partition scalars + prefix sums,
  * 2 Unbalanced-Haar decomposition kernel, 3 per-chromosome finish kernel (threshold, reconstruction,
- * healing, refinement).  -1 when the stage did not run. */
+ * healing, refinement).  -1 when the stage did not run.  Fused call only: 4 = from the end of Clean to the end of
+ * the work enqueued before the mid-call wait (coverage round trip, clears, range-quantile index), 5 = from there to the
+ * start of the scalars (device idle while the host plans the partition, plus the plan upload). */
 double cg_last_stage_ms(cg_ctx* ctx, int stage);
 /* Work counters of the last partition call: out[0] = bin visits of the decomposition (sum over tree
  * nodes of their length: L_eff * N), out[1] = tree nodes, out[2] = candidate nodes kept for the
