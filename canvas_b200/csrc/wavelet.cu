@@ -414,13 +414,15 @@ int wv_enqueue(cg_ctx* ctx, const cg_wavelet_opts* o, const WvPlan& pl, WvDev& d
     sp.thr_lower = o->thr_lower;
     sp.thr_upper = o->thr_upper;
 
-    CG_TL(ctx, "plan upload");
+    CG_TL(ctx, "host wait + plan");
     cudaEventRecord(ctx->stage_ev[2], s);
     ctx->stage_used[1] = true;
     // ---- range-quantile index for the medians of the finish stage: needs only the coverage, and is enqueued first so
     // that the device has work while the host is still launching the many small kernels of the scalars
-    if (!rq_index_done) wv_enqueue_rq_index(ctx, d, C, pl.rq_ntiles);
-    CG_TL(ctx, "rq index");
+    if (!rq_index_done) {
+        wv_enqueue_rq_index(ctx, d, C, pl.rq_ntiles);
+        CG_TL(ctx, "rq index");
+    }
     // ---- evenness per window (coverage only: early, for the same reason)
     if (!pl.ev_work.empty())
         CG_LAUNCH(ctx, wv_evenness_kernel, (int)pl.ev_work.size(), 1024, 0, d.cov, d.ev_work, d.ev10, d.ev100, d.ctl);
@@ -793,6 +795,7 @@ extern "C" int cg_clean_partition_wavelet_shard(cg_ctx* ctx, const cg_clean_opts
         CG_LAUNCH(ctx, wv_device_offsets_kernel, 1, 32, 0, chrom_cnt, n_chrom, wd.off, wd.rq_tfirst);
         wv_enqueue_rq_index(ctx, wd, n_chrom, worst.rq_ntiles);
     }
+    CG_TL(ctx, "clears + rq index");
     cudaEventRecord(ctx->gap_ev, s);
     ctx->gap_used = true;
     {
