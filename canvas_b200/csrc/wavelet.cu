@@ -315,23 +315,50 @@ int wv_alloc(cg_ctx* ctx, const WvPlan& pl, WvDev& d, double* cov_dev_existing) 
 
 // Clear the accumulators of one partition run.  Sized by the plan the arrays were allocated for, so that it can
 // be enqueued before the final plan is known (fused call: while the host still waits for the Clean results).
+// One kernel fills all nine regions (separate memsets cost a few microseconds of stream latency each).
+struct WvFillTable {
+    void* ptr[10];
+    unsigned long long words[10];  // 32-bit words
+    unsigned value[10];
+    int n;
+};
+
+__global__ void __launch_bounds__(256) wv_fill_kernel(WvFillTable t) {
+    for (int e = 0; e < t.n; e++) {
+        unsigned* p = static_cast<unsigned*>(t.ptr[e]);
+        const unsigned long long w = t.words[e];
+        const unsigned v = t.value[e];
+        const unsigned long long w4 = w >> 2;  // regions start 256-byte aligned: 128-bit stores for the bulk
+        uint4* p4 = reinterpret_cast<uint4*>(p);
+        const uint4 v4 = make_uint4(v, v, v, v);
+        for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < w4; i += (unsigned long long)gridDim.x * blockDim.x)
+            p4[i] = v4;
+        if (blockIdx.x == 0 && threadIdx.x < (w & 3ull)) p[(w4 << 2) + threadIdx.x] = v;
+    }
+}
+
 int wv_clear(cg_ctx* ctx, WvDev& d) {
-    cudaStream_t s = ctx->stream;
     const size_t C = (size_t)d.cap_C;
-    CG_CUDA(ctx, cudaMemsetAsync(d.ctl, 0, sizeof(WvCtl), s));
-    CG_CUDA(ctx, cudaMemsetAsync(&d.ctl->t_first, 0xff, sizeof(unsigned long long), s));
-    CG_CUDA(ctx, cudaMemsetAsync(d.sel.hist, 0, (size_t)d.cap_nseg * SEL_G * SEL_BINS * sizeof(unsigned), s));
-    CG_CUDA(ctx, cudaMemsetAsync(d.lvlcnt, 0, (size_t)(d.cap_N + 1) * sizeof(unsigned), s));
-    CG_CUDA(ctx, cudaMemsetAsync(d.depth, 0, (C + 1) * sizeof(int), s));
-    CG_CUDA(ctx, cudaMemsetAsync(d.big, 0xff, (size_t)UH_QCAP * sizeof(UhBigTask), s));
-    CG_CUDA(ctx, cudaMemsetAsync(d.n_bp, 0, (C + 1) * sizeof(int), s));
-    CG_CUDA(ctx, cudaMemsetAsync(d.med, 0, (size_t)d.cap_nseg * 8, s));
-    CG_CUDA(ctx, cudaMemsetAsync(d.mad, 0, (size_t)d.cap_nseg * 8, s));
+    WvFillTable t;
+    t.n = 0;
+    auto add = [&](void* p, size_t bytes, unsigned value) {
+        t.ptr[t.n] = p; t.words[t.n] = (bytes + 3) / 4; t.value[t.n] = value; t.n++;
+    };
+    add(d.ctl, sizeof(WvCtl), 0u);
+    add(d.sel.hist, (size_t)d.cap_nseg * SEL_G * SEL_BINS * sizeof(unsigned), 0u);
+    add(d.lvlcnt, (size_t)(d.cap_N + 1) * sizeof(unsigned), 0u);
+    add(d.depth, (C + 1) * sizeof(int), 0u);
+    add(d.big, (size_t)UH_QCAP * sizeof(UhBigTask), 0xffffffffu);
+    add(d.n_bp, (C + 1) * sizeof(int), 0u);
+    add(d.med, (size_t)d.cap_nseg * 8, 0u);
+    add(d.mad, (size_t)d.cap_nseg * 8, 0u);
+    static_assert(sizeof(WvCtl) % 4 == 0 && sizeof(UhBigTask) % 4 == 0, "fill regions are whole 32-bit words");
+    CG_LAUNCH(ctx, wv_fill_kernel, ctx->num_sms * 4, 256, 0, t);
+    // t_first = all ones (a minimum is taken over it); it lies inside the control block cleared above
+    CG_CUDA(ctx, cudaMemsetAsync(&d.ctl->t_first, 0xff, sizeof(unsigned long long), ctx->stream));
     return CG_OK;
 }
 
-// Upload the plan tables (small) and enqueue the whole partition pipeline.  d.cov must already hold
-// the coverage on the device (or be filled by an earlier kernel on the same stream).
 // The range-quantile index of the finish stage needs only the coverage and the chromosome offsets.
 static void wv_enqueue_rq_index(cg_ctx* ctx, WvDev& d, int C, int rq_ntiles_upper) {
     if (rq_ntiles_upper <= 0 || C <= 0) return;
