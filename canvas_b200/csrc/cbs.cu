@@ -1325,6 +1325,110 @@ void h_sd_undo(const double* g, std::vector<int>& len, double threshold) {
     for (int e : end) { len.push_back(e - prev); prev = e; }
 }
 
+// ---------------------------------------------------------------------------------------------
+// -s Prune (ChangePoint.cs:205-271, Prune.cs:18-76): host-side post-processing like SDUndo.  The reference scores
+// every j-subset of the K change points for j = K-1 .. 1 from scratch (O(K) per subset).  Here the term of every
+// possible merged group [a, b) of segments, (sum of the segments' sums, added left to right)^2 / length, is
+// tabulated once, and the subsets are walked depth-first in the same lexicographic order carrying the partial sum
+// of terms, which is the reference's own left-to-right sum: the same doubles, O(1) amortised per subset.
+// `<=` keeps the LAST of equally good subsets.  Returns false when more than `budget` subsets would be scored
+// (the search is exponential in K; the reference does not terminate in practice there either).
+// ---------------------------------------------------------------------------------------------
+constexpr long long CG_PRUNE_BUDGET = 1LL << 28;
+bool h_prune_undo(const double* g, int n, std::vector<int>& len, double cutoff, long long budget, long long* scored) {
+    if (budget <= 0) budget = CG_PRUNE_BUDGET;
+    const int S = (int)len.size(), K = S - 1;  // segments, change points
+    if (K > 4096) return false;
+    std::vector<double> sx(S);
+    double ssq = 0.0;
+    for (int i = 0; i < n; i++) ssq += pow(g[i], 2);
+    int at = 0;
+    for (int i = 0; i < S; i++) {
+        double s = 0.0;
+        for (int p2 = at; p2 < at + len[i]; p2++) s += g[p2];
+        sx[i] = s;
+        at += len[i];
+    }
+    // term[a * (S + 1) + b] for 0 <= a < b <= S
+    std::vector<double> term((size_t)(S + 1) * (S + 1), 0.0);
+    for (int a = 0; a < S; a++) {
+        double s = 0.0;
+        int cnt = 0;
+        for (int b = a + 1; b <= S; b++) {
+            s += sx[b - 1];
+            cnt += len[b - 1];
+            term[(size_t)a * (S + 1) + b] = pow(s, 2) / cnt;
+        }
+    }
+    auto T = [&](int a, int b) { return term[(size_t)a * (S + 1) + b]; };
+    std::vector<double> tail(S + 1);  // the last group [l, S)
+    for (int l = 0; l < S; l++) tail[l] = T(l, S);
+    double full = 0.0;  // all K change points kept
+    for (int i = 0; i < S; i++) full += T(i, i + 1);
+    const double wssqk = ssq - full;
+    std::vector<int> loc(K > 0 ? K : 1), best(K > 0 ? K : 1), best_prev(K > 0 ? K : 1);
+    std::vector<double> part(K + 1);
+    for (int i = 0; i < K; i++) best_prev[i] = i + 1;
+    int pruned = 0;
+    long long count = 0;
+    for (int j = K - 1; j > 0; j--) {
+        // depth-first over loc[0] < loc[1] < ... < loc[j-1] in 1..K; loc[d] <= K - (j - 1 - d); the last level is
+        // a plain loop over one row of the table
+        double wssqj = 0.0;
+        bool first = true;
+        int d = 0;
+        loc[0] = 1;
+        while (d >= 0) {
+            if (d < j - 1) {
+                if (loc[d] > K - (j - 1 - d)) {  // level exhausted
+                    d--;
+                    if (d >= 0) loc[d]++;
+                    continue;
+                }
+                part[d] = (d == 0 ? 0.0 + T(0, loc[0]) : part[d - 1] + T(loc[d - 1], loc[d]));
+                loc[d + 1] = loc[d] + 1;
+                d++;
+                continue;
+            }
+            const int from = loc[d], prev = d == 0 ? 0 : loc[d - 1];
+            const double base = d == 0 ? 0.0 : part[d - 1];
+            const double* row = &term[(size_t)prev * (S + 1)];
+            int arg = -1;
+            for (int l = from; l <= K; l++) {
+                const double w1 = ssq - ((base + row[l]) + tail[l]);
+                if (first || w1 <= wssqj) { first = false; wssqj = w1; arg = l; }
+            }
+            if (arg >= 0) {
+                for (int i = 0; i < d; i++) best[i] = loc[i];
+                best[d] = arg;
+            }
+            count += K - from + 1;
+            if (count > budget) return false;
+            d--;
+            if (d >= 0) loc[d]++;
+        }
+        if (wssqj / wssqk > 1 + cutoff) {
+            pruned = j + 1;
+            break;
+        }
+        for (int i = 0; i < j; i++) best_prev[i] = best[i];
+    }
+    if (scored) *scored = count;
+    std::vector<int> cum(S);
+    cum[0] = len[0];
+    for (int i = 1; i < S; i++) cum[i] = cum[i - 1] + len[i];
+    std::vector<int> out;
+    int prev = 0;
+    for (int i = 0; i < pruned; i++) {
+        const int e = cum[best_prev[i] - 1];
+        out.push_back(e - prev);
+        prev = e;
+    }
+    out.push_back(n - prev);
+    len.swap(out);
+    return true;
+}
+
 unsigned mt_first_outputs(unsigned seed, int count, std::vector<unsigned>& out) {
     unsigned s[624];
     s[0] = seed;
@@ -1351,6 +1455,23 @@ unsigned mt_first_outputs(unsigned seed, int count, std::vector<unsigned>& out) 
 
 }  // namespace
 
+extern "C" int cg_cbs_prune(const double* g, int64_t n, const int32_t* seg_len, int n_seg, double cutoff, int64_t max_subsets,
+                            int32_t* seg_len_out, int64_t* subsets_scored) {
+    if (!g || !seg_len || !seg_len_out || n_seg < 2 || n <= 0 || n > 0x3fffffffLL) return CG_ERR_ARG;
+    int64_t total = 0;
+    for (int i = 0; i < n_seg; i++) {
+        if (seg_len[i] <= 0) return CG_ERR_ARG;
+        total += seg_len[i];
+    }
+    if (total != n) return CG_ERR_ARG;
+    std::vector<int> len(seg_len, seg_len + n_seg);
+    long long scored = 0;
+    if (!h_prune_undo(g, (int)n, len, cutoff, max_subsets, &scored)) return CG_ERR_UNSUPPORTED;
+    for (size_t i = 0; i < len.size(); i++) seg_len_out[i] = len[i];
+    if (subsets_scored) *subsets_scored = scored;
+    return (int)len.size();
+}
+
 extern "C" int64_t cg_cbs_boundary(uint32_t n_perm, double alpha, double eta, uint32_t* out, int64_t cap) {
     if (n_perm == 0 || !(alpha > 0) || !(eta > 0)) return -1;
     const std::vector<unsigned>& sb = h_boundary(n_perm, alpha, eta);
@@ -1364,8 +1485,7 @@ static int partition_cbs_impl(cg_ctx* ctx, const cg_cbs_opts* o, const uint32_t*
                               int32_t* seg_len, double* seg_mean, int64_t* stats) {
     if (!ctx) return CG_ERR_ARG;
     if (!o || n_chrom < 0 || (n_chrom > 0 && (!chrom_off || !n_seg))) return cg_fail(ctx, CG_ERR_ARG, "cg_partition_cbs: bad argument");
-    if (o->undo != 0 && o->undo != 2)
-        return cg_fail(ctx, CG_ERR_UNSUPPORTED, "cg_partition_cbs: the prune undo method (an exhaustive search over change-point subsets) is not in this build");
+    if (o->undo < 0 || o->undo > 2) return cg_fail(ctx, CG_ERR_ARG, "cg_partition_cbs: undo must be 0 (none), 1 (prune) or 2 (sdundo)");
     if (!o->hybrid) return cg_fail(ctx, CG_ERR_UNSUPPORTED, "cg_partition_cbs: only the hybrid p-value method (the one CanvasPartition uses) is supported");
     if (o->min_width < 2 || o->min_width > 5) return cg_fail(ctx, CG_ERR_ARG, "Minimum segment width should be between 2 and 5");
     if (o->n_min < 4u * (unsigned)o->k_max) return cg_fail(ctx, CG_ERR_ARG, "nMin should be >= 4 * kMax");
@@ -1527,13 +1647,15 @@ static int partition_cbs_impl(cg_ctx* ctx, const cg_cbs_opts* o, const uint32_t*
         for (int c = 0; c < n_chrom; c++)
             for (int k = 0; k < 4; k++) stats[k] += h_stats[(size_t)c * 4 + k];
     }
-    if (o->undo == 2) {
-        const double threshold = o->undo_sd * h_trimmed_sd(n_chrom, chrom_off, coverage, o->trim);
+    if (o->undo == 1 || o->undo == 2) {
+        const double threshold = o->undo == 2 ? o->undo_sd * h_trimmed_sd(n_chrom, chrom_off, coverage, o->trim) : 0.0;
         for (int c = 0; c < n_chrom; c++) {
             if (n_seg[c] <= 1) continue;
             const double* g = coverage + chrom_off[c];
             std::vector<int> len(seg_len + chrom_off[c], seg_len + chrom_off[c] + n_seg[c]);
-            h_sd_undo(g, len, threshold);
+            if (o->undo == 2) h_sd_undo(g, len, threshold);
+            else if (!h_prune_undo(g, (int)(chrom_off[c + 1] - chrom_off[c]), len, o->undo_prune, CG_PRUNE_BUDGET, nullptr))
+                return cg_fail(ctx, CG_ERR_UNSUPPORTED, "cg_partition_cbs: the prune undo would score more than 2^28 change-point subsets on one chromosome (the search is exponential in the number of change points)");
             int at = 0;
             for (size_t i = 0; i < len.size(); i++) {
                 double sum = 0.0, w = 0.0;

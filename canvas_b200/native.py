@@ -83,6 +83,7 @@ SIGNATURES = {
     "cg_parse_bins": (_i64, [C.c_char_p, _i64, _i64, _P(_u8), _P(_i32), _P(_i32), _P(_f32), _P(_u8), _P(C.c_int),
                              C.c_char_p, _i64, C.c_int]),
     "cg_cbs_boundary": (_i64, [C.c_uint32, C.c_double, C.c_double, _P(C.c_uint32), _i64]),
+    "cg_cbs_prune": (C.c_int, [_P(_f64), _i64, _P(_i32), C.c_int, C.c_double, _i64, _P(_i32), _P(_i64)]),
     "cg_bin_hits": (C.c_int, [C.c_void_p, _i64, _P(_u8), _P(C.c_uint64), C.c_char_p, C.c_int, C.c_int, _P(_u8),
                               _P(_f32), _i64, _P(_i64), _P(_i32), _P(_i32), _P(_i32), _P(_u8)]),
     "cg_bin_fragments": (C.c_int, [C.c_void_p, _i64, _P(_i32), _P(_i32), _i64, _P(_i32), _i64, _P(_i32), _P(_i32),
@@ -158,6 +159,20 @@ def parse_bins(text, n_threads=0):
         raise CanvasGpuError(CG_ERR_ARG, "cg_parse_bins failed")
     parts = names.raw.split(b"\0")[:n_names.value]
     return [p.decode() for p in parts], chrom[:n], start[:n], stop[:n], count[:n], gc[:n]
+
+
+def cbs_prune(g, seg_len, cutoff=0.05, max_subsets=0):
+    """ChangePointsPrune (ChangePoint.cs:205-271) on one chromosome; host code in the library, no device needed.
+    Returns (new segment lengths, subsets scored)."""
+    g = np.ascontiguousarray(g, np.float64)
+    ln = np.ascontiguousarray(seg_len, np.int32)
+    out = np.zeros(len(ln), np.int32)
+    scored = C.c_int64(0)
+    k = load().cg_cbs_prune(_ptr(g, _f64), len(g), _ptr(ln, _i32), len(ln), cutoff, max_subsets,
+                            _ptr(out, _i32), C.byref(scored))
+    if k < 1:
+        raise CanvasGpuError(k, "cg_cbs_prune: bad arguments" if k != CG_ERR_UNSUPPORTED else "cg_cbs_prune: more change-point subsets to score than allowed")
+    return out[:k].copy(), int(scored.value)
 
 
 class PinnedPool:
@@ -377,7 +392,7 @@ class Engine:
         return cache[key]
 
     def partition_cbs(self, chrom_off, coverage, alpha=0.01, n_perm=10000, hybrid=True, min_width=2, k_max=25, n_min=200,
-                      eta=0.05, undo=0, seed=0, sbdry=None, chrom_selected=None, trim=0.025, undo_sd=3.0):
+                      eta=0.05, undo=0, seed=0, sbdry=None, chrom_selected=None, trim=0.025, undo_sd=3.0, undo_prune=0.05):
         """CBSRunner.Run: per chromosome the segment lengths (bins) and means."""
         off = np.ascontiguousarray(chrom_off, np.int64)
         cov = np.ascontiguousarray(coverage, np.float64)
@@ -385,7 +400,7 @@ class Engine:
         if sbdry is None:
             sbdry = self.cbs_boundary(n_perm, alpha, eta)
         sbdry = np.ascontiguousarray(sbdry, np.uint32)
-        o = CbsOpts(alpha, n_perm, int(hybrid), min_width, k_max, n_min, eta, trim, undo, 0.05, undo_sd, seed)
+        o = CbsOpts(alpha, n_perm, int(hybrid), min_width, k_max, n_min, eta, trim, undo, undo_prune, undo_sd, seed)
         n = max(len(cov), 1)
         n_seg = np.zeros(max(nc, 1), np.int32)
         seg_len = np.zeros(n, np.int32)

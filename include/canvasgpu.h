@@ -158,8 +158,9 @@ int cg_clean_partition_wavelet_shard(cg_ctx* ctx, const cg_clean_opts* copts, co
  * the library compute it (cg_cbs_boundary) from n_perm, alpha, eta.  Outputs per chromosome c at
  * chrom_off[c]: n_seg[c] segment lengths (in bins) and means (lengthSeg / segmentMeans, :140-152).
  * stats (optional, [4]) = tests run, permutations consumed, permuted bins, edge-test draws.
- * Supported: hybrid p-value method, undo = none, k_max <= 32, n_min <= 256 (the CanvasPartition defaults
- * are hybrid / none / 25 / 200); anything else returns CG_ERR_UNSUPPORTED.
+ * Supported: hybrid p-value method, every undo method (prune up to 2^28 scored subsets per chromosome),
+ * k_max <= 32, n_min <= 256 (the CanvasPartition defaults are hybrid / none / 25 / 200); anything else
+ * returns CG_ERR_UNSUPPORTED.
  * ------------------------------------------------------------------------------------------- */
 typedef struct {
     double alpha;      /* CanvasPartitionParameters.CBSalpha, 0.01 */
@@ -183,6 +184,12 @@ int cg_partition_cbs(cg_ctx* ctx, const cg_cbs_opts* opts, const uint32_t* sbdry
 int cg_partition_cbs_shard(cg_ctx* ctx, const cg_cbs_opts* opts, const uint32_t* sbdry, int64_t n_sbdry, int n_chrom,
                            const int64_t* chrom_off, const double* coverage, const uint8_t* chrom_selected, int32_t* n_seg,
                            int32_t* seg_len, double* seg_mean, int64_t* stats);
+/* -s Prune on one chromosome (ChangePoint.ChangePointsPrune, ChangePoint.cs:205-271; Prune.cs:18-76), the host-side
+ * step cg_partition_cbs applies with undo = 1: seg_len[n_seg] (n_seg >= 2, summing to n) -> seg_len_out, returns the
+ * new segment count (>= 1) or an error code; CG_ERR_UNSUPPORTED when more than max_subsets (0 = the 2^28 that
+ * cg_partition_cbs allows) subsets would be scored.  Host code only (no device needed). */
+int cg_cbs_prune(const double* g, int64_t n, const int32_t* seg_len, int n_seg, double cutoff, int64_t max_subsets,
+                 int32_t* seg_len_out, int64_t* subsets_scored);
 /* Sequential boundary table; returns its length maxOnes (maxOnes + 1) / 2 (out may be NULL), < 0 on bad arguments. */
 int64_t cg_cbs_boundary(uint32_t n_perm, double alpha, double eta, uint32_t* out, int64_t cap);
 

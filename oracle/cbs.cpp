@@ -560,7 +560,92 @@ std::vector<int> sd_undo(const double* g, const std::vector<int>& len, double tr
     return out;
 }
 
+// ChangePointsPrune (ChangePoint.cs:205-271) with Prune.ErrorSumOfSquares / Prune.Combination (Prune.cs:18-76):
+// for j = K-1 .. 1 change points, every j-subset of the K found ones is scored (AS 88 enumeration, the last of
+// equally good subsets wins through `<=`); stops at the first j whose best residual exceeds (1 + cutoff) times the
+// full model's and returns the best subset of size j + 1.  Falling through the loop returns NO change point (:264).
+double prune_errssq(const std::vector<int>& len, const std::vector<double>& sx, int k, const std::vector<int>& loc) {
+    double ess = 0.0, segsx = 0.0;
+    int segnx = 0;
+    for (int i = 0; i < loc[0]; i++) { segsx += sx[i]; segnx += len[i]; }
+    ess += std::pow(segsx, 2) / segnx;
+    for (int j = 1; j < k; j++) {
+        segsx = 0.0;
+        segnx = 0;
+        for (int i = loc[j - 1]; i < loc[j]; i++) { segsx += sx[i]; segnx += len[i]; }
+        ess += std::pow(segsx, 2) / segnx;
+    }
+    segsx = 0.0;
+    segnx = 0;
+    for (int i = loc[k - 1]; i < (int)len.size(); i++) { segsx += sx[i]; segnx += len[i]; }
+    ess += std::pow(segsx, 2) / segnx;
+    return ess;
+}
+
+void prune_combination(int r, int nmr, std::vector<int>& loc, bool& rleft) {
+    int i = r - 1;
+    while (loc[i] == nmr + i + 1) i--;
+    loc[i]++;
+    for (int j = i + 1; j < r; j++) loc[j] = loc[j - 1] + 1;
+    if (loc[0] == nmr + 1) rleft = false;
+}
+
+std::vector<int> prune_undo(const double* g, int n, const std::vector<int>& len, double cutoff) {
+    const int nseg = (int)len.size(), K = nseg - 1;
+    std::vector<double> sx(nseg);
+    std::vector<int> loc(K), best_j(K), best_prev(K);
+    double ssq = 0.0;
+    for (int i = 0; i < n; i++) ssq += std::pow(g[i], 2);
+    int at = 0;
+    for (int i = 0; i < nseg; i++) {
+        double s = 0.0;
+        for (int p = at; p < at + len[i]; p++) s += std::pow(g[p], 1);
+        sx[i] = s;
+        at += len[i];
+    }
+    for (int i = 0; i < K; i++) { loc[i] = i + 1; best_prev[i] = i + 1; }
+    const double wssqk = ssq - prune_errssq(len, sx, K, loc);
+    int pruned = 0;
+    for (int j = K - 1; j > 0; j--) {
+        const int kmj = K - j;
+        bool jleft = true;
+        for (int i = 0; i < j; i++) { loc[i] = i + 1; best_j[i] = i + 1; }
+        double wssqj = ssq - prune_errssq(len, sx, j, loc);
+        while (jleft) {
+            prune_combination(j, kmj, loc, jleft);
+            const double w1 = ssq - prune_errssq(len, sx, j, loc);
+            if (w1 <= wssqj) {
+                wssqj = w1;
+                for (int i = 0; i < j; i++) best_j[i] = loc[i];
+            }
+        }
+        if (wssqj / wssqk > 1 + cutoff) {
+            pruned = j + 1;
+            for (int i = 0; i < pruned; i++) loc[i] = best_prev[i];
+            break;
+        }
+        for (int i = 0; i < j; i++) best_prev[i] = best_j[i];
+    }
+    std::vector<int> cum(nseg);
+    cum[0] = len[0];
+    for (int i = 1; i < nseg; i++) cum[i] = cum[i - 1] + len[i];
+    std::vector<int> pts(pruned + 2);
+    pts[0] = 0;
+    for (int i = 0; i < pruned; i++) pts[i + 1] = cum[loc[i] - 1];
+    pts[pruned + 1] = n;
+    std::vector<int> out(pruned + 1);
+    for (int i = 0; i <= pruned; i++) out[i] = pts[i + 1] - pts[i];
+    return out;
+}
+
 }  // namespace
+
+extern "C" int ora_cbs_prune(const double* g, int n, const int32_t* len, int n_seg, double cutoff, int32_t* len_out) {
+    if (n_seg < 2) return -2;
+    std::vector<int> out = prune_undo(g, n, std::vector<int>(len, len + n_seg), cutoff);
+    for (size_t i = 0; i < out.size(); i++) len_out[i] = out[i];
+    return (int)out.size();
+}
 
 extern "C" double ora_cbs_inflation_factor(double trim) { return inflation_factor(trim); }
 extern "C" double ora_cbs_trimmed_variance(const double* x, int64_t n, double trim) {
@@ -602,7 +687,7 @@ extern "C" double ora_cbs_htmaxp(const double* px, int n, int k, double tss, int
 extern "C" int ora_partition_cbs(const ora_cbs_opts* o, const uint32_t* sbdry, int64_t n_sbdry, int n_chrom, const int64_t* chrom_off,
                                  const double* coverage, int32_t* n_seg, int32_t* seg_len, double* seg_mean, int32_t* seg_first,
                                  int32_t* seg_last, int64_t* stats, int n_threads) {
-    if (o->undo != 0 && o->undo != 2) return -4;  // prune is not restated
+    if (o->undo < 0 || o->undo > 2) return -2;
     double trimmed_sd = 0.0;
     if (o->undo == 2) {
         std::vector<double> all;
@@ -626,6 +711,7 @@ extern "C" int ora_partition_cbs(const ora_cbs_opts* o, const uint32_t* sbdry, i
         if (n == 0) return;
         Mt rnd(seeds[c]);
         std::vector<int> len = change_points(g, n, *o, sb, rnd, st[c]);
+        if (o->undo == 1 && len.size() > 1) len = prune_undo(g, n, len, o->undo_prune);
         if (o->undo == 2 && len.size() > 1) len = sd_undo(g, len, trimmed_sd, o->undo_sd);
         int lo = 0, cs1 = 0, cs2 = -1;
         for (size_t i = 0; i < len.size(); i++) {

@@ -42,10 +42,11 @@ typedef struct {
     int min_width;     /* 2 */
     int k_max;         /* 25 */
     uint32_t n_min;    /* 200 */
-    int undo;          /* 0 none, 2 sdundo (prune is not restated) */
+    int undo;          /* 0 none, 1 prune, 2 sdundo */
     uint32_t seed;     /* seed of the per-chromosome seed generator; 0 in the reference */
     double trim;       /* 0.025 */
     double undo_sd;    /* 3 */
+    double undo_prune; /* 0.05 */
 } ora_cbs_opts;
 int64_t ora_cbs_boundary(uint32_t n_perm, double alpha, double eta, uint32_t* out, int64_t cap);
 double ora_cbs_tailp(double b, double delta, int m);
@@ -54,6 +55,8 @@ double ora_cbs_trimmed_variance(const double* x, int64_t n, double trim);
 void ora_mt19937(uint32_t seed, int64_t n, uint32_t* out);
 double ora_cbs_tmaxo(const double* x, int n, int al0, int* seg);
 double ora_cbs_htmaxp(const double* px, int n, int k, double tss, int al0);
+/* ChangePointsPrune on one chromosome's segment lengths (n_seg >= 2); returns the new segment count. */
+int ora_cbs_prune(const double* g, int n, const int32_t* len, int n_seg, double cutoff, int32_t* len_out);
 int ora_partition_cbs(const ora_cbs_opts* o, const uint32_t* sbdry, int64_t n_sbdry, int n_chrom, const int64_t* chrom_off,
                       const double* coverage, int32_t* n_seg, int32_t* seg_len, double* seg_mean, int32_t* seg_first,
                       int32_t* seg_last, int64_t* stats, int n_threads);

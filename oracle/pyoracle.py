@@ -256,7 +256,7 @@ def bin_alignments(flags, pos, mate_pos, ref_id, mate_ref_id, frag_len, mapq, na
 
 class CbsOpts(C.Structure):
     _fields_ = [("alpha", C.c_double), ("n_perm", C.c_uint32), ("hybrid", C.c_int), ("min_width", C.c_int), ("k_max", C.c_int),
-                ("n_min", C.c_uint32), ("undo", C.c_int), ("seed", C.c_uint32), ("trim", C.c_double), ("undo_sd", C.c_double)]
+                ("n_min", C.c_uint32), ("undo", C.c_int), ("seed", C.c_uint32), ("trim", C.c_double), ("undo_sd", C.c_double), ("undo_prune", C.c_double)]
 
 
 _BDRY = {}
@@ -303,8 +303,19 @@ def cbs_htmaxp(px, k, tss, al0=2):
     return f(_p(px, C.c_double), C.c_int(len(px)), C.c_int(k), C.c_double(tss), C.c_int(al0))
 
 
+def cbs_prune(g, seg_len, cutoff=0.05):
+    """ChangePointsPrune (ChangePoint.cs:205-271) on one chromosome: new segment lengths."""
+    g = np.ascontiguousarray(g, np.float64)
+    ln = np.ascontiguousarray(seg_len, np.int32)
+    out = np.zeros(len(ln), np.int32)
+    k = lib().ora_cbs_prune(_p(g, C.c_double), C.c_int(len(g)), _p(ln, C.c_int32), C.c_int(len(ln)), C.c_double(cutoff),
+                            _p(out, C.c_int32))
+    assert k >= 1
+    return out[:k].copy()
+
+
 def partition_cbs(chrom_off, coverage, alpha=0.01, n_perm=10000, hybrid=True, min_width=2, k_max=25, n_min=200, seed=0,
-                  sbdry=None, n_threads=1, undo=0, trim=0.025, undo_sd=3.0):
+                  sbdry=None, n_threads=1, undo=0, trim=0.025, undo_sd=3.0, undo_prune=0.05):
     off = np.ascontiguousarray(chrom_off, np.int64)
     cov = np.ascontiguousarray(coverage, np.float64)
     nc = len(off) - 1
@@ -312,7 +323,7 @@ def partition_cbs(chrom_off, coverage, alpha=0.01, n_perm=10000, hybrid=True, mi
     if sbdry is None:
         sbdry = cbs_boundary(n_perm, alpha, 0.05)
     sbdry = np.ascontiguousarray(sbdry, np.uint32)
-    o = CbsOpts(alpha, n_perm, int(hybrid), min_width, k_max, n_min, undo, seed, trim, undo_sd)
+    o = CbsOpts(alpha, n_perm, int(hybrid), min_width, k_max, n_min, undo, seed, trim, undo_sd, undo_prune)
     n_seg = np.zeros(max(nc, 1), np.int32)
     seg_len = np.zeros(n, np.int32); seg_mean = np.zeros(n, np.float64)
     first = np.zeros(n, np.int32); last = np.zeros(n, np.int32)

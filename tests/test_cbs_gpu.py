@@ -78,6 +78,20 @@ def test_cbs_sdundo_matches_oracle(eng):
     assert sum(len(s["len"]) for s in want["segments"]) < sum(len(s["len"]) for s in plain["segments"])
 
 
+def test_cbs_prune_matches_oracle(eng):
+    # -s Prune: the subset search over the found change points (ChangePoint.cs:205-271), several chromosomes
+    rng = np.random.default_rng(12)
+    parts = [_chrom(rng, n) for n in (6000, 2500, 9000, 300)]
+    weak = parts[0]
+    weak[3000:3300] += 6
+    off = np.concatenate([[0], np.cumsum([len(p) for p in parts])])
+    cov = np.concatenate(parts)
+    plain = eng.partition_cbs(off, cov)
+    want = _compare(eng, off, cov, undo=1)
+    assert sum(len(s["len"]) for s in want["segments"]) < sum(len(s["len"]) for s in plain["segments"])
+    _compare(eng, off, cov, undo=1, undo_prune=0.5)
+
+
 def test_cbs_degenerate_inputs(eng):
     cov = np.concatenate([[1.0, 2.0, 3.0], np.full(10, 7.0), np.arange(30.0)])
     want = _compare(eng, [0, 3, 3, 13, 43], cov)
@@ -89,7 +103,7 @@ def test_cbs_degenerate_inputs(eng):
 def test_cbs_rejects_what_it_does_not_implement(eng):
     cov = np.arange(100.0)
     with pytest.raises(native.CanvasGpuError):
-        eng.partition_cbs([0, 100], cov, undo=1)
+        eng.partition_cbs([0, 100], cov, undo=3)
     with pytest.raises(native.CanvasGpuError):
         eng.partition_cbs([0, 100], cov, hybrid=False)
     bad = cov.copy()
