@@ -1,0 +1,285 @@
+// CanvasNormalize on the device: the weighted-average reference of the control samples and the sample / reference
+// ratio step with its conversion back to counts.
+//
+//   cg_normalize_reference   WeightedAverageReferenceGenerator.Run (WeightedAverageReferenceGenerator.cs:33-70) with
+//                            BinCounts.OnTargetMedianBinCount (BinCounts.cs:24-62)
+//   cg_normalize_ratio       LSNormRatioCalculator.Run (LSNormRatioCalculator.cs:22-48), RawRatioCalculator.Run
+//                            (RawRatioCalculator.cs:24-47), CanvasNormalizeUtilities.RatiosToCounts
+//                            (CanvasNormalizeUtilities.cs:22-31)
+//
+// Both are one exact order-statistics step (the medians, select.cuh) followed by one stream over the bins:
+// 8 S + 8 B/bin for the reference of S controls, 8 B/bin in and 12 B per kept bin out for the ratio step.
+// Arithmetic follows the C# expressions operation by operation (float division, then double factors, float store).
+#include <algorithm>
+#include <vector>
+
+#include "clean.cuh"
+#include "select.cuh"
+
+namespace {
+
+// counts[s * n + bin], segment = control sample; bins off target are not part of any median
+struct ControlCountView {
+    const double* counts;
+    const uint8_t* on_target;  // nullptr: every bin
+    long long n;
+    int n_samples;
+    __device__ long long size() const { return n * n_samples; }
+    __device__ bool get(long long i, uint64_t& key, int& a, int& b) const {
+        const long long bin = i % n;
+        if (on_target && !on_target[bin]) return false;
+        a = (int)(i / n);
+        b = -1;
+        key = f64_key(counts[i]);
+        return true;
+    }
+};
+
+// segment 0 = the sample's counts, segment 1 = the reference's; float order = order of the widened doubles
+struct PairCountView {
+    const float* sample;
+    const float* reference;
+    const uint8_t* on_target;
+    long long n;
+    __device__ long long size() const { return 2 * n; }
+    __device__ bool get(long long i, uint32_t& key, int& a, int& b) const {
+        const int which = i >= n;
+        const long long bin = which ? i - n : i;
+        if (on_target && !on_target[bin]) return false;
+        a = which;
+        b = -1;
+        key = f32_key(which ? reference[bin] : sample[bin]);
+        return true;
+    }
+};
+
+__global__ void count_on_target_kernel(const uint8_t* __restrict__ on_target, long long n, unsigned long long* __restrict__ out) {
+    unsigned long long c = 0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) c += on_target[i] != 0;
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_down_sync(0xffffffffu, c, o);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(out, c);
+}
+
+// SortedList<T>.Median(): ranks of the two middles (the same rank twice for an odd count)
+template <typename K>
+__global__ void middle_request_kernel(SelState<K> st, const unsigned long long* __restrict__ cnt_ptr, unsigned long long cnt_all) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= st.nseg) return;
+    const unsigned long long m = cnt_ptr ? *cnt_ptr : cnt_all;
+    if (m == 0) { st.nreq[s] = 0; return; }
+    st.nreq[s] = 2;
+    st.req_k[s * SEL_G + 0] = (m & 1ull) ? m / 2 : m / 2 - 1;
+    st.req_k[s * SEL_G + 1] = m / 2;
+}
+
+// medians as doubles (mean of the middles in double); an empty list gives 0 (default(T) of the empty SortedList)
+__global__ void control_weights_kernel(SelState<uint64_t> st, double* __restrict__ median, double* __restrict__ weight) {
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    double sum = 0.0;
+    for (int s = 0; s < st.nseg; s++) {
+        double m = 0.0;
+        if (st.nreq[s]) {
+            const double a = f64_unkey(st.req_key[s * SEL_G + 0]), b = f64_unkey(st.req_key[s * SEL_G + 1]);
+            m = st.req_key[s * SEL_G + 0] == st.req_key[s * SEL_G + 1] ? a : __ddiv_rn(__dadd_rn(a, b), 2.0);
+        }
+        median[s] = m;
+        const double w = m > 0 ? __ddiv_rn(1.0, m) : 0.0;  // WeightedAverageReferenceGenerator.cs:52
+        weight[s] = w;
+        sum = __dadd_rn(sum, w);                            // weights.Sum()
+    }
+    for (int s = 0; s < st.nseg; s++) weight[s] = __ddiv_rn(weight[s], sum);  // :56
+}
+
+// weightedBinCount = sum_i weights[i] * counts[i][bin], added in sample order (:70)
+__global__ void __launch_bounds__(256) weighted_average_kernel(const double* __restrict__ counts, const double* __restrict__ weight,
+                                                               int n_samples, long long n, double* __restrict__ out) {
+    extern __shared__ double s_w[];
+    for (int t = threadIdx.x; t < n_samples; t += blockDim.x) s_w[t] = weight[t];
+    __syncthreads();
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        double acc = 0.0;
+        for (int s = 0; s < n_samples; s++) acc = __dadd_rn(acc, __dmul_rn(s_w[s], __ldcs(counts + (size_t)s * n + i)));
+        __stcs(out + i, acc);
+    }
+}
+
+struct RatioCtl {
+    double sample_median, reference_median, library_size_factor;
+    int n, n_kept;
+};
+
+__global__ void ratio_factor_kernel(SelState<uint32_t> st, RatioCtl* ctl, int lsnorm, int n) {
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    double med[2] = {0.0, 0.0};
+    for (int s = 0; s < 2; s++)
+        if (lsnorm && st.nreq[s]) {
+            const double a = (double)f32_unkey(st.req_key[s * SEL_G + 0]), b = (double)f32_unkey(st.req_key[s * SEL_G + 1]);
+            med[s] = st.req_key[s * SEL_G + 0] == st.req_key[s * SEL_G + 1] ? a : __ddiv_rn(__dadd_rn(a, b), 2.0);
+        }
+    ctl->sample_median = med[0];
+    ctl->reference_median = med[1];
+    // LSNormRatioCalculator.cs:31
+    ctl->library_size_factor = (lsnorm && med[0] > 0 && med[1] > 0) ? __ddiv_rn(med[1], med[0]) : 1.0;
+    ctl->n = n;
+    ctl->n_kept = 0;
+}
+
+// a bin is skipped when its reference count is outside [min_ref, max_ref] (NaN compares false: kept, as in C#)
+struct RatioKeep {
+    const float* reference;
+    double min_ref, max_ref;
+    __device__ bool operator()(int i) const {
+        const double r = (double)reference[i];
+        return !(r < min_ref) && !(r > max_ref);
+    }
+};
+
+struct RatioEmit {
+    const float* sample;
+    const float* reference;
+    const int32_t* ploidy;  // nullptr: 2
+    const RatioCtl* ctl;
+    int32_t* kept_index;
+    float* ratio;
+    float* count;
+    __device__ void operator()(int src, int dst) const {
+        // `sampleBin.Count / referenceBin.Count` is a float division; the product with the double factor is a double
+        const float q = __fdiv_rn(sample[src], reference[src]);
+        const float r = (float)__dmul_rn((double)q, ctl->library_size_factor);
+        // RatiosToCounts: factor = 40 * ploidy / 2.0; count = (float)(ratio * factor)
+        const int p = ploidy ? ploidy[src] : 2;
+        const double factor = __ddiv_rn(__dmul_rn(40.0, (double)p), 2.0);
+        kept_index[dst] = src;
+        ratio[dst] = r;
+        count[dst] = (float)__dmul_rn((double)r, factor);
+    }
+};
+
+void reset_call(cg_ctx* ctx) {
+    ctx->launches = 0;
+    ctx->tl = nullptr;
+    ctx->launch_err = cudaSuccess;
+    ctx->last_kernel_ms = 0;
+    for (int i = 0; i < 4; i++) ctx->stage_used[i] = false;
+    ctx->gap_used = false;
+}
+
+}  // namespace
+
+extern "C" int cg_normalize_reference(cg_ctx* ctx, int n_samples, int64_t n, const double* counts, const uint8_t* on_target,
+                                      double* median, double* weight, double* reference) {
+    if (!ctx) return CG_ERR_ARG;
+    if (n_samples < 1 || n < 0 || !median || !weight || (n > 0 && (!counts || !reference)))
+        return cg_fail(ctx, CG_ERR_ARG, "cg_normalize_reference: bad argument");
+    if (n_samples > 1024) return cg_fail(ctx, CG_ERR_UNSUPPORTED, "cg_normalize_reference: more than 1024 control samples");
+    if (n > 0x7fff0000LL) return cg_fail(ctx, CG_ERR_UNSUPPORTED, "cg_normalize_reference: too many bins");
+    reset_call(ctx);
+    CG_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t total = (size_t)n_samples * (size_t)n;
+    int rc = arena_reserve(ctx, arena_need(total, 8) + arena_need(n, 8) + arena_need(n, 1) + arena_need(n_samples, 8) * 2 +
+                                    sel_state_bytes<uint64_t>(n_samples) + (1u << 16));
+    if (rc) return rc;
+    double* d_counts = arena_take<double>(ctx, std::max<size_t>(total, 1));
+    double* d_ref = arena_take<double>(ctx, std::max<int64_t>(n, 1));
+    uint8_t* d_on = on_target ? arena_take<uint8_t>(ctx, std::max<int64_t>(n, 1)) : nullptr;
+    double* d_med = arena_take<double>(ctx, n_samples);
+    double* d_w = arena_take<double>(ctx, n_samples);
+    unsigned long long* d_cnt = arena_take<unsigned long long>(ctx, 1);
+    SelState<uint64_t> st;
+    if (!d_counts || !d_ref || (on_target && !d_on) || !d_med || !d_w || !d_cnt || !sel_state_alloc<uint64_t>(ctx, n_samples, st))
+        return cg_fail(ctx, CG_ERR_CUDA, "arena exhausted");
+    cudaStream_t s = ctx->stream;
+    if (total) CG_CUDA(ctx, cudaMemcpyAsync(d_counts, counts, total * 8, cudaMemcpyHostToDevice, s));
+    if (on_target && n) CG_CUDA(ctx, cudaMemcpyAsync(d_on, on_target, (size_t)n, cudaMemcpyHostToDevice, s));
+    CG_CUDA(ctx, cudaEventRecord(ctx->ev0, s));
+    CG_CUDA(ctx, cudaMemsetAsync(st.hist, 0, (size_t)n_samples * SEL_G * SEL_BINS * sizeof(unsigned), s));
+    CG_CUDA(ctx, cudaMemsetAsync(d_cnt, 0, 8, s));
+    if (on_target && n) CG_LAUNCH(ctx, count_on_target_kernel, std::min<long long>(ctx->num_sms * 4, div_up(n, 256)), 256, 0, d_on, (long long)n, d_cnt);
+    CG_LAUNCH(ctx, middle_request_kernel<uint64_t>, div_up(n_samples, 128), 128, 0, st, on_target ? d_cnt : nullptr, (unsigned long long)n);
+    ControlCountView v{d_counts, d_on, (long long)n, n_samples};
+    sel_run_scatter<uint64_t, ControlCountView>(ctx, v, st, (long long)total);
+    CG_LAUNCH(ctx, control_weights_kernel, 1, 32, 0, st, d_med, d_w);
+    if (n) CG_LAUNCH(ctx, weighted_average_kernel, std::min<long long>(ctx->num_sms * 8, div_up(n, 256)), 256, (size_t)n_samples * 8, d_counts, d_w, n_samples, (long long)n, d_ref);
+    CG_CUDA(ctx, cudaEventRecord(ctx->ev1, s));
+    CG_CUDA(ctx, cudaMemcpyAsync(median, d_med, (size_t)n_samples * 8, cudaMemcpyDeviceToHost, s));
+    CG_CUDA(ctx, cudaMemcpyAsync(weight, d_w, (size_t)n_samples * 8, cudaMemcpyDeviceToHost, s));
+    if (n) CG_CUDA(ctx, cudaMemcpyAsync(reference, d_ref, (size_t)n * 8, cudaMemcpyDeviceToHost, s));
+    CG_CUDA(ctx, cudaStreamSynchronize(s));
+    CG_CUDA(ctx, cudaGetLastError());
+    CG_CHECK_LAUNCHES(ctx);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+    ctx->last_kernel_ms = ms;
+    return CG_OK;
+}
+
+extern "C" int cg_normalize_ratio(cg_ctx* ctx, int64_t n, const float* sample, const float* reference, const uint8_t* on_target,
+                                  int mode, double min_ref, double max_ref, const int32_t* ploidy, int64_t* n_out,
+                                  int32_t* kept_index, float* ratio, float* count, double* library_size_factor) {
+    if (!ctx) return CG_ERR_ARG;
+    if (n < 0 || !n_out || (mode != 0 && mode != 1) || (n > 0 && (!sample || !reference || !kept_index || !ratio || !count)))
+        return cg_fail(ctx, CG_ERR_ARG, "cg_normalize_ratio: bad argument");
+    if (n > 0x3fff0000LL) return cg_fail(ctx, CG_ERR_UNSUPPORTED, "cg_normalize_ratio: too many bins");
+    reset_call(ctx);
+    *n_out = 0;
+    const int lsnorm = mode == 1;
+    if (lsnorm) { min_ref = 1.0; max_ref = __builtin_inf(); }  // LSNormRatioCalculator.cs:44 drops reference counts below 1 only
+    CG_CUDA(ctx, cudaSetDevice(ctx->device));
+    const int ntiles = std::max(1, div_up((int)n, CMP_TILE));
+    int rc = arena_reserve(ctx, arena_need(n, 4) * 6 + arena_need(n, 1) + arena_need(ntiles, 4) + sel_state_bytes<uint32_t>(2) + (1u << 16));
+    if (rc) return rc;
+    const size_t n1 = (size_t)std::max<int64_t>(n, 1);
+    float* d_s = arena_take<float>(ctx, n1);
+    float* d_r = arena_take<float>(ctx, n1);
+    int32_t* d_p = ploidy ? arena_take<int32_t>(ctx, n1) : nullptr;
+    uint8_t* d_on = on_target ? arena_take<uint8_t>(ctx, n1) : nullptr;
+    // kept index, ratio and count of the kept bins lie next to each other: one download
+    int32_t* d_idx = arena_take<int32_t>(ctx, n1);
+    float* d_ratio = arena_take<float>(ctx, n1);
+    float* d_count = arena_take<float>(ctx, n1);
+    int* d_tiles = arena_take<int>(ctx, ntiles);
+    RatioCtl* d_ctl = arena_take<RatioCtl>(ctx, 1);
+    unsigned long long* d_cnt = arena_take<unsigned long long>(ctx, 1);
+    SelState<uint32_t> st;
+    if (!d_s || !d_r || (ploidy && !d_p) || (on_target && !d_on) || !d_idx || !d_ratio || !d_count || !d_tiles || !d_ctl || !d_cnt ||
+        !sel_state_alloc<uint32_t>(ctx, 2, st))
+        return cg_fail(ctx, CG_ERR_CUDA, "arena exhausted");
+    cudaStream_t s = ctx->stream;
+    if (n) {
+        CG_CUDA(ctx, cudaMemcpyAsync(d_s, sample, (size_t)n * 4, cudaMemcpyHostToDevice, s));
+        CG_CUDA(ctx, cudaMemcpyAsync(d_r, reference, (size_t)n * 4, cudaMemcpyHostToDevice, s));
+        if (ploidy) CG_CUDA(ctx, cudaMemcpyAsync(d_p, ploidy, (size_t)n * 4, cudaMemcpyHostToDevice, s));
+        if (on_target) CG_CUDA(ctx, cudaMemcpyAsync(d_on, on_target, (size_t)n, cudaMemcpyHostToDevice, s));
+    }
+    CG_CUDA(ctx, cudaEventRecord(ctx->ev0, s));
+    CG_CUDA(ctx, cudaMemsetAsync(st.hist, 0, (size_t)2 * SEL_G * SEL_BINS * sizeof(unsigned), s));
+    CG_CUDA(ctx, cudaMemsetAsync(d_cnt, 0, 8, s));
+    if (lsnorm) {
+        if (on_target && n) CG_LAUNCH(ctx, count_on_target_kernel, std::min<long long>(ctx->num_sms * 4, div_up(n, 256)), 256, 0, d_on, (long long)n, d_cnt);
+        CG_LAUNCH(ctx, middle_request_kernel<uint32_t>, 1, 128, 0, st, on_target ? d_cnt : nullptr, (unsigned long long)n);
+        PairCountView v{d_s, d_r, d_on, (long long)n};
+        sel_run_scatter<uint32_t, PairCountView>(ctx, v, st, 2 * (long long)n);
+    }
+    CG_LAUNCH(ctx, ratio_factor_kernel, 1, 32, 0, st, d_ctl, lsnorm, (int)n);
+    RatioKeep keep{d_r, min_ref, max_ref};
+    RatioEmit emit{d_s, d_r, d_p, d_ctl, d_idx, d_ratio, d_count};
+    compact_run(ctx, keep, emit, &d_ctl->n, (int)n, d_tiles, &d_ctl->n_kept);
+    CG_CUDA(ctx, cudaEventRecord(ctx->ev1, s));
+    RatioCtl h;
+    CG_CUDA(ctx, cudaMemcpyAsync(&h, d_ctl, sizeof(h), cudaMemcpyDeviceToHost, s));
+    CG_CUDA(ctx, cudaStreamSynchronize(s));
+    CG_CHECK_LAUNCHES(ctx);
+    if (h.n_kept > 0) {
+        CG_CUDA(ctx, cudaMemcpyAsync(kept_index, d_idx, (size_t)h.n_kept * 4, cudaMemcpyDeviceToHost, s));
+        CG_CUDA(ctx, cudaMemcpyAsync(ratio, d_ratio, (size_t)h.n_kept * 4, cudaMemcpyDeviceToHost, s));
+        CG_CUDA(ctx, cudaMemcpyAsync(count, d_count, (size_t)h.n_kept * 4, cudaMemcpyDeviceToHost, s));
+        CG_CUDA(ctx, cudaStreamSynchronize(s));
+    }
+    CG_CUDA(ctx, cudaGetLastError());
+    *n_out = h.n_kept;
+    if (library_size_factor) *library_size_factor = h.library_size_factor;
+    float ms = 0;
+    cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+    ctx->last_kernel_ms = ms;
+    return CG_OK;
+}

@@ -82,6 +82,9 @@ SIGNATURES = {
                               C.c_char_p, _i64, C.c_int]),
     "cg_parse_bins": (_i64, [C.c_char_p, _i64, _i64, _P(_u8), _P(_i32), _P(_i32), _P(_f32), _P(_u8), _P(C.c_int),
                              C.c_char_p, _i64, C.c_int]),
+    "cg_normalize_reference": (C.c_int, [C.c_void_p, C.c_int, _i64, _P(_f64), _P(_u8), _P(_f64), _P(_f64), _P(_f64)]),
+    "cg_normalize_ratio": (C.c_int, [C.c_void_p, _i64, _P(_f32), _P(_f32), _P(_u8), C.c_int, C.c_double, C.c_double, _P(_i32),
+                                     _P(_i64), _P(_i32), _P(_f32), _P(_f32), _P(_f64)]),
     "cg_cbs_boundary": (_i64, [C.c_uint32, C.c_double, C.c_double, _P(C.c_uint32), _i64]),
     "cg_cbs_prune": (C.c_int, [_P(_f64), _i64, _P(_i32), C.c_int, C.c_double, _i64, _P(_i32), _P(_i64)]),
     "cg_bin_hits": (C.c_int, [C.c_void_p, _i64, _P(_u8), _P(C.c_uint64), C.c_char_p, C.c_int, C.c_int, _P(_u8),
@@ -475,6 +478,44 @@ class Engine:
         rc = self.lib.cg_smooth(self.h, int(max_half_window), nc, _ptr(off, _i64), _ptr(cnt, _f32), _ptr(n_out, _i64), _ptr(out, _f32))
         self._check(rc)
         return [out[off[c]:off[c] + n_out[c]].copy() for c in range(nc)]
+
+    # ------------------------------------------------------------------ CanvasNormalize
+    def normalize_reference(self, counts, on_target=None):
+        """WeightedAverageReferenceGenerator.Run: counts [n_samples, n] (doubles) -> medians, weights, weighted bin counts."""
+        c = np.ascontiguousarray(np.atleast_2d(np.asarray(counts, np.float64)))
+        s, n = c.shape
+        on = None if on_target is None else np.ascontiguousarray(on_target, np.uint8)
+        if on is not None and len(on) != n:
+            raise ValueError("on_target must have one flag per bin")
+        med, w, ref = np.zeros(s), np.zeros(s), np.zeros(max(n, 1))
+        rc = self.lib.cg_normalize_reference(self.h, s, n, _ptr(c, _f64), _ptr(on, _u8) if on is not None else None,
+                                             _ptr(med, _f64), _ptr(w, _f64), _ptr(ref, _f64))
+        self._check(rc)
+        return {"median": med, "weight": w, "reference": ref[:n], "kernel_ms": self.lib.cg_last_kernel_ms(self.h)}
+
+    def normalize_ratio(self, sample, reference, on_target=None, mode="lsnorm", min_ref=1.0, max_ref=float("inf"), ploidy=None):
+        """LSNormRatioCalculator.Run ("lsnorm") or RawRatioCalculator.Run ("raw") + RatiosToCounts on the bins both lists
+        share (the enumeration stops at the shorter one): kept bin indices, ratios, counts."""
+        a = np.ascontiguousarray(sample, np.float32)
+        b = np.ascontiguousarray(reference, np.float32)
+        n = min(len(a), len(b))
+        on = None if on_target is None else np.ascontiguousarray(on_target, np.uint8)
+        pl = None if ploidy is None else np.ascontiguousarray(ploidy, np.int32)
+        if (on is not None and len(on) < n) or (pl is not None and len(pl) < n):
+            raise ValueError("on_target / ploidy must cover every bin")
+        idx = np.zeros(max(n, 1), np.int32)
+        ratio = np.zeros(max(n, 1), np.float32)
+        count = np.zeros(max(n, 1), np.float32)
+        k = C.c_int64(0)
+        lsf = C.c_double(0)
+        rc = self.lib.cg_normalize_ratio(self.h, n, _ptr(a, _f32), _ptr(b, _f32), _ptr(on, _u8) if on is not None else None,
+                                         {"raw": 0, "lsnorm": 1}[mode], min_ref, max_ref,
+                                         _ptr(pl, _i32) if pl is not None else None, C.byref(k), _ptr(idx, _i32),
+                                         _ptr(ratio, _f32), _ptr(count, _f32), C.byref(lsf))
+        self._check(rc)
+        k = int(k.value)
+        return {"kept_index": idx[:k].copy(), "ratio": ratio[:k].copy(), "count": count[:k].copy(),
+                "library_size_factor": lsf.value, "kernel_ms": self.lib.cg_last_kernel_ms(self.h)}
 
     def _cbs_phases(self):
         """Phase times (ms) of the slowest chromosome of the last cg_partition_cbs call."""

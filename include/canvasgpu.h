@@ -299,6 +299,25 @@ int64_t cg_format_bins(int64_t n, int n_names, const char* const* names, const u
 int64_t cg_parse_bins(const char* text, int64_t len, int64_t max_rows, uint8_t* chrom, int32_t* start, int32_t* stop,
                       float* count, uint8_t* gc, int* n_names, char* names, int64_t names_cap, int n_threads);
 
+/* ---------------------------------------------------------------------------------------------
+ * CanvasNormalize (tumour / control-panel coverage ratio; enrichment workflows).
+ * cg_normalize_reference = WeightedAverageReferenceGenerator.Run (CanvasNormalize/WeightedAverageReferenceGenerator.cs:43-70):
+ *   counts[n_samples][n] (doubles: double.Parse of column 4, or the widened float when a manifest is given,
+ *   BinCounts.cs:86-100 / :102-160), on_target[n] (bins overlapping the manifest regions; NULL = every bin);
+ *   out: median[s] = OnTargetMedianBinCount (BinCounts.cs:41-62), weight[s] = (1 / median or 0) / sum, reference[n] = the
+ *   weighted bin counts.  The single-control case is a file copy in the reference (:37-41) and stays with the host.
+ * cg_normalize_ratio = LSNormRatioCalculator.Run (mode 1, LSNormRatioCalculator.cs:22-48; min_ref / max_ref ignored, bins
+ *   with a reference count < 1 are skipped) or RawRatioCalculator.Run (mode 0, RawRatioCalculator.cs:24-47; bins with a
+ *   reference count outside [min_ref, max_ref] are skipped), followed by CanvasNormalizeUtilities.RatiosToCounts
+ *   (CanvasNormalizeUtilities.cs:22-31) with the reference ploidy of every bin (ploidy[n]; NULL = 2).  Outputs for the
+ *   *n_out kept bins, in order: kept_index (into the input), ratio (the .cnd column) and count (the output file's column 4).
+ * ------------------------------------------------------------------------------------------- */
+int cg_normalize_reference(cg_ctx* ctx, int n_samples, int64_t n, const double* counts, const uint8_t* on_target,
+                           double* median, double* weight, double* reference);
+int cg_normalize_ratio(cg_ctx* ctx, int64_t n, const float* sample, const float* reference, const uint8_t* on_target,
+                       int mode, double min_ref, double max_ref, const int32_t* ploidy, int64_t* n_out,
+                       int32_t* kept_index, float* ratio, float* count, double* library_size_factor);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,68 @@
+// ORACLE — TEST INFRASTRUCTURE ONLY.  Never linked into, imported by, or executed from the product path.
+//
+// CPU restatement of CanvasNormalize's weighted-average reference and ratio steps (reference @ v1.40.0):
+//   CanvasNormalize/BinCounts.cs:24-62                         OnTargetMedianBinCount: Utilities.Median of the (on-target) counts as doubles
+//   CanvasNormalize/WeightedAverageReferenceGenerator.cs:43-70 weights 1 / median (0 when the median is not positive), divided by their
+//                                                              sum; weighted bin count = sum of weight * count in sample order
+//   CanvasNormalize/LSNormRatioCalculator.cs:28-47             library size factor = reference median / sample median when both are
+//                                                              positive, else 1; bins with a reference count below 1 are skipped;
+//                                                              ratio = (float division) * factor, stored as float
+//   CanvasNormalize/RawRatioCalculator.cs:36-45                bins with a reference count outside [min, max] are skipped; ratio = float division
+//   CanvasNormalize/CanvasNormalizeUtilities.cs:22-31          RatiosToCounts: count = (float)(ratio * (40 * ploidy / 2.0))
+// Parity unpinned: the reference has no test for CanvasNormalize; restated from source only.
+#include <cstdint>
+#include <vector>
+
+#include "oracle.h"
+#include "ref_stats.hpp"
+
+extern "C" void ora_normalize_reference(int n_samples, int64_t n, const double* counts, const uint8_t* on_target, double* median,
+                                        double* weight, double* reference) {
+    for (int s = 0; s < n_samples; s++) {
+        std::vector<double> on;
+        for (int64_t i = 0; i < n; i++)
+            if (!on_target || on_target[i]) on.push_back(counts[(size_t)s * n + i]);
+        median[s] = ora::median_d(on);
+        weight[s] = median[s] > 0 ? 1.0 / median[s] : 0;
+    }
+    double sum = 0;
+    for (int s = 0; s < n_samples; s++) sum += weight[s];
+    for (int s = 0; s < n_samples; s++) weight[s] /= sum;
+    for (int64_t i = 0; i < n; i++) {
+        double w = 0;
+        for (int s = 0; s < n_samples; s++) w += weight[s] * counts[(size_t)s * n + i];
+        reference[i] = w;
+    }
+}
+
+extern "C" int64_t ora_normalize_ratio(int64_t n, const float* sample, const float* reference, const uint8_t* on_target, int lsnorm,
+                                       double min_ref, double max_ref, const int32_t* ploidy, int32_t* kept_index, float* ratio,
+                                       float* count, double* library_size_factor) {
+    double factor = 1;
+    if (lsnorm) {
+        std::vector<double> a, b;
+        for (int64_t i = 0; i < n; i++)
+            if (!on_target || on_target[i]) { a.push_back((double)sample[i]); b.push_back((double)reference[i]); }
+        const double sample_median = ora::median_d(a), reference_median = ora::median_d(b);
+        factor = (sample_median > 0 && reference_median > 0) ? reference_median / sample_median : 1;
+    }
+    int64_t k = 0;
+    for (int64_t i = 0; i < n; i++) {
+        if (lsnorm) {
+            if (reference[i] < 1) continue;
+        } else {
+            if ((double)reference[i] < min_ref) continue;
+            if ((double)reference[i] > max_ref) continue;
+        }
+        const float q = sample[i] / reference[i];
+        const double r = lsnorm ? (double)q * factor : (double)q;
+        const float rf = (float)r;
+        const double f = 40.0 * (ploidy ? ploidy[i] : 2) / 2.0;
+        kept_index[k] = (int32_t)i;
+        ratio[k] = rf;
+        count[k] = (float)((double)rf * f);
+        k++;
+    }
+    if (library_size_factor) *library_size_factor = factor;
+    return k;
+}

@@ -75,6 +75,12 @@ int ora_partition_hmm(const ora_hmm_opts* o, int n_samples, int n_chrom, const i
 double ora_gamma_ln(double z);
 int ora_negative_binomial(double mean, double variance, int max_value, double* out);
 
+/* CanvasNormalize (oracle/normalize.cpp): weighted-average reference of the controls; ratio + RatiosToCounts (returns kept bins). */
+void ora_normalize_reference(int n_samples, int64_t n, const double* counts, const uint8_t* on_target, double* median, double* weight,
+                             double* reference);
+int64_t ora_normalize_ratio(int64_t n, const float* sample, const float* reference, const uint8_t* on_target, int lsnorm, double min_ref,
+                            double max_ref, const int32_t* ploidy, int32_t* kept_index, float* ratio, float* count,
+                            double* library_size_factor);
 /* CanvasSmooth (oracle/smooth.cpp): Utilities.MedianFilter and the repeated filter; return the output length (<= n). */
 int64_t ora_median_filter(int64_t n, const float* in, uint32_t half_window, float* out);
 int64_t ora_repeated_median_filter(int64_t n, const float* in, uint32_t max_half_window, float* out);

@@ -437,3 +437,31 @@ def repeated_median_filter(values, max_half_window):
     f.restype = C.c_int64
     m = f(C.c_int64(len(v)), _p(v, C.c_float), C.c_uint32(max_half_window), _p(out, C.c_float))
     return out[:m].copy()
+
+
+def normalize_reference(counts, on_target=None):
+    """WeightedAverageReferenceGenerator.Run (:43-70): counts [n_samples, n] doubles -> medians, weights, reference."""
+    c = np.ascontiguousarray(np.atleast_2d(np.asarray(counts, np.float64)))
+    s, n = c.shape
+    on = None if on_target is None else np.ascontiguousarray(on_target, np.uint8)
+    med = np.zeros(s); w = np.zeros(s); ref = np.zeros(max(n, 1))
+    lib().ora_normalize_reference(C.c_int(s), C.c_int64(n), _p(c, C.c_double), _p(on, C.c_uint8) if on is not None else None,
+                                  _p(med, C.c_double), _p(w, C.c_double), _p(ref, C.c_double))
+    return {"median": med, "weight": w, "reference": ref[:n]}
+
+
+def normalize_ratio(sample, reference, on_target=None, mode="lsnorm", min_ref=1.0, max_ref=np.inf, ploidy=None):
+    """LSNormRatioCalculator / RawRatioCalculator + RatiosToCounts: kept bin indices, ratios and counts (float)."""
+    a = np.ascontiguousarray(sample, np.float32)
+    b = np.ascontiguousarray(reference, np.float32)
+    n = min(len(a), len(b))
+    on = None if on_target is None else np.ascontiguousarray(on_target, np.uint8)
+    pl = None if ploidy is None else np.ascontiguousarray(ploidy, np.int32)
+    idx = np.zeros(max(n, 1), np.int32); ratio = np.zeros(max(n, 1), np.float32); count = np.zeros(max(n, 1), np.float32)
+    lsf = C.c_double(0)
+    f = lib().ora_normalize_ratio
+    f.restype = C.c_int64
+    k = f(C.c_int64(n), _p(a, C.c_float), _p(b, C.c_float), _p(on, C.c_uint8) if on is not None else None,
+          C.c_int(mode == "lsnorm"), C.c_double(min_ref), C.c_double(max_ref), _p(pl, C.c_int32) if pl is not None else None,
+          _p(idx, C.c_int32), _p(ratio, C.c_float), _p(count, C.c_float), C.byref(lsf))
+    return {"kept_index": idx[:k].copy(), "ratio": ratio[:k].copy(), "count": count[:k].copy(), "library_size_factor": lsf.value}

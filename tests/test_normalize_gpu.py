@@ -1,0 +1,128 @@
+"""cg_normalize_reference / cg_normalize_ratio against the oracle: bit-identical medians, weights, reference counts,
+kept bins, ratios and counts; the CanvasNormalize module end to end on files."""
+import gzip
+import os
+
+import numpy as np
+import pytest
+
+from canvas_b200 import modules, native, textcodec
+from oracle import pyoracle as po
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def eng():
+    return native.Engine(0)
+
+
+def _controls(rng, s, n, integer=True):
+    depth = rng.uniform(40, 160, (s, 1))
+    shape = rng.gamma(8, 1 / 8, (1, n))
+    c = rng.poisson(depth * shape).astype(np.float64)
+    return c if integer else np.round(c + rng.normal(0, 0.3, c.shape), 2)
+
+
+@pytest.mark.parametrize("s,n,integer,masked", [(2, 1000, True, False), (5, 70001, True, True), (3, 4096, False, True),
+                                                (8, 300000, True, False), (1, 17, True, False), (4, 2, False, False)])
+def test_reference_matches_oracle(eng, s, n, integer, masked):
+    rng = np.random.default_rng(s * 1000 + n)
+    c = _controls(rng, s, n, integer)
+    on = (rng.random(n) < 0.3).astype(np.uint8) if masked else None
+    want = po.normalize_reference(c, on)
+    got = eng.normalize_reference(c, on)
+    for k in ("median", "weight", "reference"):
+        assert np.array_equal(want[k], got[k], equal_nan=True), k
+
+
+def test_reference_degenerate_cases(eng):
+    c = np.array([[0.0, 0.0, 5.0], [2.0, 4.0, 8.0]])
+    for on in (None, [0, 0, 0], [0, 1, 0]):
+        want, got = po.normalize_reference(c, on), eng.normalize_reference(c, on)
+        for k in ("median", "weight", "reference"):
+            assert np.array_equal(want[k], got[k], equal_nan=True), (on, k)
+    z = eng.normalize_reference(np.zeros((3, 0)))
+    assert len(z["reference"]) == 0 and z["median"].tolist() == [0, 0, 0]
+    with pytest.raises(ValueError):
+        eng.normalize_reference(c, on_target=[1, 1])
+
+
+@pytest.mark.parametrize("n,mode,masked,ploidy", [(1000, "lsnorm", False, False), (250001, "lsnorm", True, True),
+                                                  (65536, "raw", False, True), (3, "lsnorm", False, False),
+                                                  (3100000, "lsnorm", False, False)])
+def test_ratio_matches_oracle(eng, n, mode, masked, ploidy):
+    rng = np.random.default_rng(n)
+    sample = rng.poisson(rng.gamma(8, 12, n)).astype(np.float32)
+    ref = np.round(rng.gamma(8, 10, n), 3).astype(np.float32)
+    ref[rng.random(n) < 0.02] = np.float32(0.4)
+    ref[rng.random(n) < 0.001] = 0
+    on = (rng.random(n) < 0.5).astype(np.uint8) if masked else None
+    pl = rng.choice([0, 1, 2, 3], n).astype(np.int32) if ploidy else None
+    kw = dict(mode=mode, min_ref=20.0, max_ref=150.0) if mode == "raw" else dict(mode=mode)
+    want = po.normalize_ratio(sample, ref, on, ploidy=pl, **kw)
+    got = eng.normalize_ratio(sample, ref, on, ploidy=pl, **kw)
+    assert want["library_size_factor"] == got["library_size_factor"]
+    assert 0 < len(want["kept_index"]) < n or n == 3
+    for k in ("kept_index", "ratio", "count"):
+        assert np.array_equal(want[k], got[k], equal_nan=True), k
+
+
+def test_ratio_special_values(eng):
+    sample = np.array([1, np.nan, 3, 0, 5, np.inf, 7], np.float32)
+    ref = np.array([np.nan, 2, np.inf, 0.99, 1, 1, -3], np.float32)
+    for mode in ("lsnorm", "raw"):
+        want, got = po.normalize_ratio(sample, ref, mode=mode), eng.normalize_ratio(sample, ref, mode=mode)
+        for k in ("kept_index", "ratio", "count"):
+            assert np.array_equal(want[k], got[k], equal_nan=True), (mode, k)
+    assert len(eng.normalize_ratio(np.zeros(0), np.zeros(0))["ratio"]) == 0
+    # the shorter list ends the enumeration (eSampleBins.MoveNext() && eReferenceBins.MoveNext())
+    assert len(eng.normalize_ratio(np.ones(10), np.ones(4))["ratio"]) == 4
+
+
+def _write_binned(path, chrom, start, count, fmt="{:.0f}"):
+    lines = [f"{c}\t{s}\t{s + 1000}\t{fmt.format(v)}\t{40 + i % 20}" for i, (c, s, v) in enumerate(zip(chrom, start, count))]
+    with open(path, "wb") as f:
+        f.write(gzip.compress(("\n".join(lines) + "\n").encode()))
+
+
+def test_canvas_normalize_module(tmp_path):
+    rng = np.random.default_rng(4)
+    n = 5000
+    chrom = ["chr1"] * 3000 + ["chrX"] * 2000
+    start = list(range(0, 3000000, 1000)) + list(range(0, 2000000, 1000))
+    controls = _controls(rng, 3, n)
+    controls[:, 100:110] = 0  # reference below 1: dropped
+    tumor = rng.poisson(90, n).astype(np.float64)
+    tumor[3000:3500] *= 2
+    paths = []
+    for k in range(3):
+        p = str(tmp_path / f"normal{k}.binned")
+        _write_binned(p, chrom, start, controls[k])
+        paths.append(p)
+    t = str(tmp_path / "tumor.binned")
+    _write_binned(t, chrom, start, tumor)
+    out, w = str(tmp_path / "out.binned"), str(tmp_path / "ref.binned")
+    argv = ["-t", t, "-o", out, "-w", w]
+    for p in paths:
+        argv += ["-n", p]
+    assert modules.canvas_normalize_main(argv) == 0
+    ref = po.normalize_reference(controls)["reference"]
+    ref_lines = gzip.open(w, "rt").read().splitlines()
+    assert len(ref_lines) == n
+    ref_text = [ln.split("\t")[3] for ln in ref_lines]
+    assert all(abs(float(a) - b) <= 1e-14 * max(1.0, abs(b)) for a, b in zip(ref_text, ref.tolist()))
+    ref_f = np.array([float(a) for a in ref_text]).astype(np.float32)
+    want = po.normalize_ratio(tumor.astype(np.float32), ref_f)
+    got = [ln.split("\t") for ln in gzip.open(out, "rt").read().splitlines()]
+    assert len(got) == len(want["kept_index"]) == n - 10
+    assert [int(g[1]) for g in got] == [start[i] for i in want["kept_index"]]
+    assert [g[3] for g in got] == textcodec.f2_text(want["count"])
+    cnd = open(out + ".cnd").read().splitlines()
+    assert cnd[0] == "Fragment Count,Reference Count,Chromosome,Start,End,Unsmoothed Log Ratio" and len(cnd) == len(got) + 1
+    # a single control is copied; missing files and missing options are reported as the reference does
+    out2, w2 = str(tmp_path / "out2.binned"), str(tmp_path / "ref2.binned")
+    assert modules.canvas_normalize_main(["-t", t, "-n", paths[0], "-o", out2, "-w", w2]) == 0
+    assert open(w2, "rb").read() == open(paths[0], "rb").read()
+    assert modules.canvas_normalize_main(["-t", t, "-n", str(tmp_path / "nope"), "-o", out2, "-w", w2]) == 1
+    assert modules.canvas_normalize_main(["-n", paths[0], "-o", out2]) == 1

@@ -1,0 +1,41 @@
+"""CanvasNormalize oracle (weighted-average reference, ratio step): hand-computed cases.  The reference has no test
+for CanvasNormalize: parity is unpinned beyond the source restatement."""
+import numpy as np
+
+from oracle import pyoracle as po
+
+
+def test_weighted_average_reference_by_hand():
+    # medians 2 and 4 -> weights (1/2, 1/4) / (3/4) = (2/3, 1/3)
+    counts = np.array([[1.0, 2.0, 3.0], [2.0, 4.0, 8.0]])
+    r = po.normalize_reference(counts)
+    assert r["median"].tolist() == [2.0, 4.0]
+    w = np.array([0.5, 0.25]) / 0.75
+    assert r["weight"].tolist() == w.tolist()
+    assert r["reference"].tolist() == [(0.0 + w[0] * a) + w[1] * b for a, b in zip(counts[0], counts[1])]
+    # on-target bins only feed the medians; an even count takes the mean of the middles
+    r = po.normalize_reference(counts, on_target=[1, 0, 1])
+    assert r["median"].tolist() == [2.0, 5.0]
+    # a control whose median is not positive gets weight 0
+    r = po.normalize_reference(np.array([[0.0, 0.0, 5.0], [2.0, 4.0, 8.0]]))
+    assert r["weight"].tolist() == [0.0, 1.0] and r["reference"].tolist() == [2.0, 4.0, 8.0]
+
+
+def test_ratio_steps_by_hand():
+    sample = np.array([10, 20, 30, 40, 50], np.float32)
+    ref = np.array([20, 0.5, 30, 10, 25], np.float32)
+    r = po.normalize_ratio(sample, ref, mode="lsnorm")
+    # medians 30 and 20 -> factor 2/3; the bin with reference 0.5 < 1 is dropped
+    assert r["library_size_factor"] == 20.0 / 30.0
+    assert r["kept_index"].tolist() == [0, 2, 3, 4]
+    q = (sample / ref)[[0, 2, 3, 4]]
+    want = (q.astype(np.float64) * (20.0 / 30.0)).astype(np.float32)
+    assert np.array_equal(r["ratio"], want)
+    assert np.array_equal(r["count"], (want.astype(np.float64) * 40.0).astype(np.float32))
+    # raw mode: range filter on the reference count, no library size factor; ploidy 1 halves the count
+    r = po.normalize_ratio(sample, ref, mode="raw", min_ref=10, max_ref=25, ploidy=[2, 2, 2, 1, 2])
+    assert r["kept_index"].tolist() == [0, 3, 4] and r["library_size_factor"] == 1.0
+    assert r["ratio"].tolist() == [0.5, 4.0, 2.0] and r["count"].tolist() == [20.0, 80.0, 80.0]
+    # a sample median of zero leaves the factor at 1
+    assert po.normalize_ratio(np.zeros(4, np.float32), np.full(4, 3, np.float32))["library_size_factor"] == 1.0
+    assert len(po.normalize_ratio(np.zeros(0, np.float32), np.zeros(0, np.float32))["ratio"]) == 0
