@@ -197,9 +197,80 @@ def split_overlapping_segments(per_sample):
     return result
 
 
-def post_process_segments(order, seg_by_chr, start, end, cov, excluded=None, max_inter_bin_dist=1000000):
-    """SegmentationResultsProcessor.PostProcessSegments (SegmentationResultsProcessor.cs:17-129)
-    without reference ploidy.  Returns chr -> list of segments {id, bins: [(start, end, coverage)]}."""
+class PloidyInfo:
+    """CanvasCommon.PloidyInfo (PloidyInfo.cs:12-178): reference ploidy intervals per chromosome from a ploidy VCF
+    (END in INFO, CN in the single genotype column; "." = 2)."""
+
+    def __init__(self):
+        self.by_chr = {}  # chromosome -> [(one-based start, one-based end, ploidy)]
+
+    @staticmethod
+    def load_vcf_no_sample_id(path):
+        """LoadPloidyFromVcfFileNoSampleId (:112-127) + LoadPloidyFromVcfFile (:129-165)."""
+        info = PloidyInfo()
+        samples = None
+        with _open_text(path) as f:
+            for line in f:
+                line = line.rstrip("\r\n")
+                if line.startswith("##") or not line:
+                    continue
+                if line.startswith("#"):
+                    samples = line.split("\t")[9:]
+                    if len(samples) == 0:
+                        raise ValueError(f"File '{path}' does not contain any genotype column")
+                    if len(samples) > 1:
+                        raise ValueError(f"File '{path}' cannot have more than one genotype columns when no sample ID provided'")
+                    continue
+                if samples is None:
+                    raise ValueError(f"File '{path}' does not contain any genotype column")
+                t = line.split("\t")
+                fields = dict(kv.split("=", 1) for kv in t[7].split(";") if "=" in kv)
+                genotype = dict(zip(t[8].split(":"), t[9].split(":")))
+                if "CN" not in genotype:
+                    raise ValueError(f"File '{path}' must contain one genotype CN column!")
+                cn = 2 if genotype["CN"] == "." else int(genotype["CN"])
+                info.by_chr.setdefault(t[0], []).append((int(t[1]), int(fields["END"]), cn))
+        if samples is None:
+            raise ValueError(f"File '{path}' does not contain any genotype column")
+        return info
+
+    def _counts(self, chrom, one_based_start, one_based_end):
+        """getPloidyCounts (:92-109): bases of the query at each ploidy 0..4."""
+        counts = [0, 0, one_based_end - one_based_start + 1, 0, 0]
+        for a, b, ploidy in self.by_chr[chrom]:
+            if ploidy == 2:
+                continue
+            lo = max(one_based_start - 1, a - 1)
+            if lo > b:
+                continue
+            n = min(one_based_end, b) - lo
+            if n <= 0:
+                continue
+            counts[2] -= n
+            counts[ploidy] += n  # IndexError above 4, as the reference's int[5]
+        return counts
+
+    def reference_copy_number(self, chrom, begin, end):
+        """GetReferenceCopyNumber (:56-72) of a segment [begin, end) in bed coordinates: the ploidy covering most bases,
+        the lowest on ties, 2 when nothing is covered."""
+        if chrom not in self.by_chr:
+            return 2
+        best, cn = 0, 2
+        for k, v in enumerate(self._counts(chrom, begin + 1, end)):
+            if v > best:
+                best, cn = v, k
+        return cn
+
+    def is_uniform(self, chrom, one_based_start, one_based_end):
+        """IsUniformReferencePloidy (:78-90)."""
+        if chrom not in self.by_chr:
+            return True
+        return sum(1 for v in self._counts(chrom, one_based_start, one_based_end) if v > 0) < 2
+
+
+def post_process_segments(order, seg_by_chr, start, end, cov, excluded=None, max_inter_bin_dist=1000000, ploidy=None):
+    """SegmentationResultsProcessor.PostProcessSegments (SegmentationResultsProcessor.cs:17-129); `ploidy` is a
+    PloidyInfo or None.  Returns chr -> list of segments {id, bins: [(start, end, coverage)]}."""
     excluded = excluded or {}
     starts = set()
     for c, segs in seg_by_chr.items():
@@ -223,6 +294,9 @@ def post_process_segments(order, seg_by_chr, start, end, cov, excluded=None, max
                     if prev_end < mid and b >= mid:
                         new = True
             if prev_end > 0 and max_inter_bin_dist >= 0 and prev_end + max_inter_bin_dist < a and not new:
+                new = True
+            # a change of reference ploidy between the end of the last bin and the end of this one (:116-125)
+            if not new and ploidy is not None and not ploidy.is_uniform(c, prev_end if prev_end > 0 else 1, b):
                 new = True
             if new:
                 seg_num += 1

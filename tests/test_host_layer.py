@@ -199,3 +199,35 @@ def test_native_text_codec_matches_python_codec(tmp_path):
         native.parse_bins(b"chr1\t0\t10\n")
     with pytest.raises(ValueError):
         native.parse_bins(b"chr1\t0\tx\t1.0\t3\n")
+
+
+def test_ploidy_info_and_ploidy_splits(tmp_path):
+    # PloidyInfo.cs:56-109 and the ploidy rule of SegmentationResultsProcessor.IsNewSegment (:116-125)
+    vcf = tmp_path / "ploidy.vcf"
+    vcf.write_text("##fileformat=VCFv4.1\n#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT\tS1\n"
+                   "chrX\t1\t.\tN\t<CNV>\t.\tPASS\tEND=2500\tCN\t1\n"
+                   "chrX\t2501\t.\tN\t<CNV>\t.\tPASS\tEND=9000\tCN\t.\n"
+                   "chrY\t1\t.\tN\t<CNV>\t.\tPASS\tEND=100000\tGT:CN\t0:0\n")
+    p = fileio.PloidyInfo.load_vcf_no_sample_id(str(vcf))
+    assert p.by_chr == {"chrX": [(1, 2500, 1), (2501, 9000, 2)], "chrY": [(1, 100000, 0)]}
+    assert p.reference_copy_number("chr1", 0, 1000) == 2          # chromosome not listed
+    assert p.reference_copy_number("chrX", 0, 1000) == 1
+    assert p.reference_copy_number("chrX", 2000, 3000) == 1        # 500 bases each: the first best count wins
+    assert p.reference_copy_number("chrX", 2001, 3000) == 2        # 499 against 500
+    assert p.reference_copy_number("chrY", 500, 600) == 0
+    assert p.is_uniform("chr1", 1, 10 ** 6) and p.is_uniform("chrX", 1, 2500) and not p.is_uniform("chrX", 2500, 2501)
+    # an empty PloidyInfo (what the reference's tests pass) never splits
+    order = ["chrX"]
+    start = {"chrX": np.array([0, 1000, 2000, 3000, 4000])}
+    end = {"chrX": np.array([1000, 2000, 3000, 4000, 5000])}
+    cov = {"chrX": np.arange(5.0)}
+    ids = lambda r: [[b[0] for b in s["bins"]] for s in r["chrX"]]
+    assert ids(fileio.post_process_segments(order, {}, start, end, cov, {}, 10 ** 6, fileio.PloidyInfo())) == [[0, 1000, 2000, 3000, 4000]]
+    # the bin [2000, 3000) spans the change at 2500/2501: it opens a new segment; the next bin is checked from the
+    # previous bin's end (3000) and is uniform again
+    assert ids(fileio.post_process_segments(order, {}, start, end, cov, {}, 10 ** 6, p)) == [[0, 1000], [2000, 3000, 4000]]
+    # two genotype columns are refused when no sample id is given
+    bad = tmp_path / "two.vcf"
+    bad.write_text("#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT\tS1\tS2\n")
+    with pytest.raises(ValueError):
+        fileio.PloidyInfo.load_vcf_no_sample_id(str(bad))
