@@ -309,9 +309,21 @@ def main():
                          "traffic": traffic.get("uh_decompose"), "traffic_source": traffic.get("source"),
                          "peak_source": peak_src, "algorithmic_bytes": alg_bytes,
                          "l_eff": visits / max(1, len(r["kept_index"])),
-                         "note": "the prefix sums (24 MB) stay in L2: DRAM traffic is ~1/17 of the algorithmic bytes; "
-                                 "the stage is bound by the dependent chain of big nodes, not by HBM"},
+                         "note": "the prefix sums (24 MB) stay in L2: DRAM traffic (cold-cache ncu, each of the four stage kernels "
+                                 "re-reading them once) is ~1/%d of the algorithmic bytes; the stage is bound by the dependent "
+                                 "chain of big nodes, not by HBM" % max(1, round(alg_bytes / max(1, traffic.get("uh_decompose", 1))))},
             "clocks": clocks, "device": eng.describe()}
+    # Clean / Partition totals against the HBM roofline with SURVEY.md 8(d)'s accounting: Clean = 101 B per input bin,
+    # wavelet Partition = 8 * L_eff + 72 B per cleaned bin
+    kept = max(1, len(r["kept_index"]))
+    l_eff = visits / kept
+    part_ms = sum(stages.get(k, 0.0) for k in ("scalars", "decompose", "finish"))
+    totals = {}
+    for name, nbytes, ms in (("clean", 101.0 * nb, stages.get("clean", 0.0)), ("partition_wavelet", (8.0 * l_eff + 72.0) * kept, part_ms)):
+        if ms > 0:
+            ach = nbytes / (ms * 1e-3) / 1e9
+            totals[name] = {"algorithmic_bytes": nbytes, "ms": ms, "achieved": ach, "unit": "GB/s", "frac": ach / hbm}
+    line["roofline_totals"] = totals
     # K8 normalise stream on batches larger than L2 (the kernel BASELINE.json's roofline target names):
     # 8 samples = config 5 (223 MB), 16 samples (446 MB) and 32 samples (892 MB)
     if strong is not None:
