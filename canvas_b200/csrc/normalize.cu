@@ -155,6 +155,73 @@ struct RatioEmit {
     }
 };
 
+// BestLR2: squared log ratios of the median-normalised sample (row n_controls of `counts`) against every control over
+// the on-target bins.  Block (chunk, control) adds its chunk in index order; the chunk sums are added in chunk order by
+// lr2_finish_kernel: deterministic, but not the reference's single left-to-right sum (agreement better than 1e-9 relative).
+constexpr int LR2_CHUNK = 8192;
+struct Lr2Partial {
+    double sum;
+    long long used, ignored;
+};
+
+__global__ void __launch_bounds__(256) lr2_partial_kernel(const double* __restrict__ counts, const uint8_t* __restrict__ on_target,
+                                                          const double* __restrict__ median, int n_controls, long long n,
+                                                          Lr2Partial* __restrict__ part) {
+    const int ctrl = blockIdx.y;
+    const long long lo = (long long)blockIdx.x * LR2_CHUNK, hi = min(n, lo + LR2_CHUNK);
+    const double mt = median[n_controls], mc = median[ctrl];
+    const double wt = mt > 0 ? __ddiv_rn(1.0, mt) : 0.0, wc = mc > 0 ? __ddiv_rn(1.0, mc) : 0.0;
+    const double* __restrict__ t = counts + (size_t)n_controls * n;
+    const double* __restrict__ c = counts + (size_t)ctrl * n;
+    // thread k owns a contiguous run of the chunk: its partial is a left-to-right sum, and so is the sum over threads
+    constexpr int PER = LR2_CHUNK / 256;
+    double sum = 0.0;
+    long long used = 0, ign = 0;
+    const long long a = lo + (long long)threadIdx.x * PER;
+    for (long long i = a; i < min(hi, a + PER); i++) {
+        if (on_target && !on_target[i]) continue;
+        const double normal = __dmul_rn(c[i], wc);
+        if (normal <= 0) { ign++; continue; }  // NaN is not <= 0: it goes on and is dropped by the test below
+        const double lr = log(__ddiv_rn(__dmul_rn(t[i], wt), normal));
+        const double sq = __dmul_rn(lr, lr);
+        if (isinf(sq) || isnan(sq)) { ign++; continue; }
+        sum = __dadd_rn(sum, sq);
+        used++;
+    }
+    __shared__ double s_sum[256];
+    __shared__ long long s_used[256], s_ign[256];
+    s_sum[threadIdx.x] = sum; s_used[threadIdx.x] = used; s_ign[threadIdx.x] = ign;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double ts = 0.0;
+        long long tu = 0, ti = 0;
+        for (int k = 0; k < 256; k++) { ts = __dadd_rn(ts, s_sum[k]); tu += s_used[k]; ti += s_ign[k]; }
+        part[(size_t)ctrl * gridDim.x + blockIdx.x] = Lr2Partial{ts, tu, ti};
+    }
+}
+
+// mean squared log ratio per control and the first strict minimum (BestLR2ReferenceGenerator.cs:62-78); -1 when no
+// control beats +infinity
+__global__ void lr2_finish_kernel(const Lr2Partial* __restrict__ part, int n_controls, int n_chunks, double* __restrict__ mean,
+                                  long long* __restrict__ ignored, int* __restrict__ best) {
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    int b = -1;
+    double mn = __longlong_as_double(0x7ff0000000000000ll);
+    for (int c = 0; c < n_controls; c++) {
+        double s = 0.0;
+        long long u = 0, ig = 0;
+        for (int k = 0; k < n_chunks; k++) {
+            const Lr2Partial p = part[(size_t)c * n_chunks + k];
+            s = __dadd_rn(s, p.sum); u += p.used; ig += p.ignored;
+        }
+        const double m = u > 0 ? __ddiv_rn(s, (double)u) : s;
+        mean[c] = m;
+        ignored[c] = ig;
+        if (m < mn) { mn = m; b = c; }
+    }
+    *best = b;
+}
+
 void reset_call(cg_ctx* ctx) {
     ctx->launches = 0;
     ctx->tl = nullptr;
@@ -278,6 +345,67 @@ extern "C" int cg_normalize_ratio(cg_ctx* ctx, int64_t n, const float* sample, c
     CG_CUDA(ctx, cudaGetLastError());
     *n_out = h.n_kept;
     if (library_size_factor) *library_size_factor = h.library_size_factor;
+    float ms = 0;
+    cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+    ctx->last_kernel_ms = ms;
+    return CG_OK;
+}
+
+extern "C" int cg_normalize_best_lr2(cg_ctx* ctx, int n_controls, int64_t n, const double* sample, const double* controls,
+                                     const uint8_t* on_target, int* best_index, double* mean_sq_log_ratio, int64_t* ignored) {
+    if (!ctx) return CG_ERR_ARG;
+    if (n_controls < 1 || n < 0 || !best_index || !mean_sq_log_ratio || !ignored || (n > 0 && (!sample || !controls)))
+        return cg_fail(ctx, CG_ERR_ARG, "cg_normalize_best_lr2: bad argument");
+    if (n_controls > 1023) return cg_fail(ctx, CG_ERR_UNSUPPORTED, "cg_normalize_best_lr2: more than 1023 control samples");
+    if (n > 0x7fff0000LL) return cg_fail(ctx, CG_ERR_UNSUPPORTED, "cg_normalize_best_lr2: too many bins");
+    reset_call(ctx);
+    CG_CUDA(ctx, cudaSetDevice(ctx->device));
+    const int rows = n_controls + 1;  // the sample is the last row
+    const size_t total = (size_t)rows * (size_t)n;
+    const int n_chunks = std::max<int>(1, (int)div_up((long long)n, (long long)LR2_CHUNK));
+    int rc = arena_reserve(ctx, arena_need(total, 8) + arena_need(n, 1) + arena_need(rows, 8) * 3 +
+                                    arena_need((size_t)n_controls * n_chunks, sizeof(Lr2Partial)) + sel_state_bytes<uint64_t>(rows) + (1u << 16));
+    if (rc) return rc;
+    double* d_counts = arena_take<double>(ctx, std::max<size_t>(total, 1));
+    uint8_t* d_on = on_target ? arena_take<uint8_t>(ctx, std::max<int64_t>(n, 1)) : nullptr;
+    double* d_med = arena_take<double>(ctx, rows);
+    double* d_w = arena_take<double>(ctx, rows);
+    double* d_mean = arena_take<double>(ctx, rows);
+    long long* d_ign = arena_take<long long>(ctx, rows);
+    int* d_best = arena_take<int>(ctx, 1);
+    unsigned long long* d_cnt = arena_take<unsigned long long>(ctx, 1);
+    Lr2Partial* d_part = arena_take<Lr2Partial>(ctx, (size_t)n_controls * n_chunks);
+    SelState<uint64_t> st;
+    if (!d_counts || (on_target && !d_on) || !d_med || !d_w || !d_mean || !d_ign || !d_best || !d_cnt || !d_part ||
+        !sel_state_alloc<uint64_t>(ctx, rows, st))
+        return cg_fail(ctx, CG_ERR_CUDA, "arena exhausted");
+    cudaStream_t s = ctx->stream;
+    if (n) {
+        CG_CUDA(ctx, cudaMemcpyAsync(d_counts, controls, (size_t)n_controls * n * 8, cudaMemcpyHostToDevice, s));
+        CG_CUDA(ctx, cudaMemcpyAsync(d_counts + (size_t)n_controls * n, sample, (size_t)n * 8, cudaMemcpyHostToDevice, s));
+        if (on_target) CG_CUDA(ctx, cudaMemcpyAsync(d_on, on_target, (size_t)n, cudaMemcpyHostToDevice, s));
+    }
+    CG_CUDA(ctx, cudaEventRecord(ctx->ev0, s));
+    CG_CUDA(ctx, cudaMemsetAsync(st.hist, 0, (size_t)rows * SEL_G * SEL_BINS * sizeof(unsigned), s));
+    CG_CUDA(ctx, cudaMemsetAsync(d_cnt, 0, 8, s));
+    if (on_target && n) CG_LAUNCH(ctx, count_on_target_kernel, std::min<long long>(ctx->num_sms * 4, div_up(n, 256)), 256, 0, d_on, (long long)n, d_cnt);
+    CG_LAUNCH(ctx, middle_request_kernel<uint64_t>, div_up(rows, 128), 128, 0, st, on_target ? d_cnt : nullptr, (unsigned long long)n);
+    ControlCountView v{d_counts, d_on, (long long)n, rows};
+    sel_run_scatter<uint64_t, ControlCountView>(ctx, v, st, (long long)total);
+    CG_LAUNCH(ctx, control_weights_kernel, 1, 32, 0, st, d_med, d_w);  // medians; the weights are formed per pair below
+    CG_LAUNCH(ctx, lr2_partial_kernel, dim3(n_chunks, n_controls), 256, 0, d_counts, d_on, d_med, n_controls, (long long)n, d_part);
+    CG_LAUNCH(ctx, lr2_finish_kernel, 1, 32, 0, d_part, n_controls, n_chunks, d_mean, d_ign, d_best);
+    CG_CUDA(ctx, cudaEventRecord(ctx->ev1, s));
+    int h_best = -1;
+    std::vector<long long> h_ign(n_controls);
+    CG_CUDA(ctx, cudaMemcpyAsync(mean_sq_log_ratio, d_mean, (size_t)n_controls * 8, cudaMemcpyDeviceToHost, s));
+    CG_CUDA(ctx, cudaMemcpyAsync(h_ign.data(), d_ign, (size_t)n_controls * 8, cudaMemcpyDeviceToHost, s));
+    CG_CUDA(ctx, cudaMemcpyAsync(&h_best, d_best, 4, cudaMemcpyDeviceToHost, s));
+    CG_CUDA(ctx, cudaStreamSynchronize(s));
+    CG_CUDA(ctx, cudaGetLastError());
+    CG_CHECK_LAUNCHES(ctx);
+    for (int c = 0; c < n_controls; c++) ignored[c] = h_ign[c];
+    *best_index = h_best;
     float ms = 0;
     cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
     ctx->last_kernel_ms = ms;

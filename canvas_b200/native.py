@@ -83,6 +83,7 @@ SIGNATURES = {
     "cg_parse_bins": (_i64, [C.c_char_p, _i64, _i64, _P(_u8), _P(_i32), _P(_i32), _P(_f32), _P(_u8), _P(C.c_int),
                              C.c_char_p, _i64, C.c_int]),
     "cg_normalize_reference": (C.c_int, [C.c_void_p, C.c_int, _i64, _P(_f64), _P(_u8), _P(_f64), _P(_f64), _P(_f64)]),
+    "cg_normalize_best_lr2": (C.c_int, [C.c_void_p, C.c_int, _i64, _P(_f64), _P(_f64), _P(_u8), _P(C.c_int), _P(_f64), _P(_i64)]),
     "cg_normalize_ratio": (C.c_int, [C.c_void_p, _i64, _P(_f32), _P(_f32), _P(_u8), C.c_int, C.c_double, C.c_double, _P(_i32),
                                      _P(_i64), _P(_i32), _P(_f32), _P(_f32), _P(_f64)]),
     "cg_cbs_boundary": (_i64, [C.c_uint32, C.c_double, C.c_double, _P(C.c_uint32), _i64]),
@@ -492,6 +493,20 @@ class Engine:
                                              _ptr(med, _f64), _ptr(w, _f64), _ptr(ref, _f64))
         self._check(rc)
         return {"median": med, "weight": w, "reference": ref[:n], "kernel_ms": self.lib.cg_last_kernel_ms(self.h)}
+
+    def normalize_best_lr2(self, sample, controls, on_target=None):
+        """BestLR2ReferenceGenerator.Run: the control closest to the sample in mean squared log ratio."""
+        t = np.ascontiguousarray(sample, np.float64)
+        c = np.ascontiguousarray(np.atleast_2d(np.asarray(controls, np.float64)))
+        s, n = c.shape
+        if len(t) != n:
+            raise ValueError("sample and controls must have the same number of bins")
+        on = None if on_target is None else np.ascontiguousarray(on_target, np.uint8)
+        mean, ign, best = np.zeros(s), np.zeros(s, np.int64), C.c_int(-1)
+        rc = self.lib.cg_normalize_best_lr2(self.h, s, n, _ptr(t, _f64), _ptr(c, _f64), _ptr(on, _u8) if on is not None else None,
+                                            C.byref(best), _ptr(mean, _f64), _ptr(ign, _i64))
+        self._check(rc)
+        return {"best": int(best.value), "mean_sq_log_ratio": mean, "ignored": ign, "kernel_ms": self.lib.cg_last_kernel_ms(self.h)}
 
     def normalize_ratio(self, sample, reference, on_target=None, mode="lsnorm", min_ref=1.0, max_ref=float("inf"), ploidy=None):
         """LSNormRatioCalculator.Run ("lsnorm") or RawRatioCalculator.Run ("raw") + RatiosToCounts on the bins both lists

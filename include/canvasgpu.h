@@ -312,6 +312,13 @@ int64_t cg_parse_bins(const char* text, int64_t len, int64_t max_rows, uint8_t* 
  *   (CanvasNormalizeUtilities.cs:22-31) with the reference ploidy of every bin (ploidy[n]; NULL = 2).  Outputs for the
  *   *n_out kept bins, in order: kept_index (into the input), ratio (the .cnd column) and count (the output file's column 4).
  * ------------------------------------------------------------------------------------------- */
+/* BestLR2ReferenceGenerator.Run (CanvasNormalize/BestLR2ReferenceGenerator.cs:32-125): sample[n] and controls[n_controls][n]
+ * as doubles; every vector is divided by the median of its on-target counts, and *best_index is the control with the
+ * smallest mean squared log ratio over the on-target bins (first strict minimum; -1 when none is below +infinity, where
+ * the reference throws).  mean_sq_log_ratio / ignored: [n_controls].  The sums are added chunk-wise on the device:
+ * they agree with the reference's left-to-right sum to better than 1e-9 relative, not bit for bit. */
+int cg_normalize_best_lr2(cg_ctx* ctx, int n_controls, int64_t n, const double* sample, const double* controls,
+                          const uint8_t* on_target, int* best_index, double* mean_sq_log_ratio, int64_t* ignored);
 int cg_normalize_reference(cg_ctx* ctx, int n_samples, int64_t n, const double* counts, const uint8_t* on_target,
                            double* median, double* weight, double* reference);
 int cg_normalize_ratio(cg_ctx* ctx, int64_t n, const float* sample, const float* reference, const uint8_t* on_target,

@@ -9,8 +9,12 @@
 //                                                              ratio = (float division) * factor, stored as float
 //   CanvasNormalize/RawRatioCalculator.cs:36-45                bins with a reference count outside [min, max] are skipped; ratio = float division
 //   CanvasNormalize/CanvasNormalizeUtilities.cs:22-31          RatiosToCounts: count = (float)(ratio * (40 * ploidy / 2.0))
+//   CanvasNormalize/BestLR2ReferenceGenerator.cs:32-125        the control with the smallest mean squared log ratio of the median-normalised
+//                                                              on-target counts (first strict minimum; -1 when none is below +infinity)
 // Parity unpinned: the reference has no test for CanvasNormalize; restated from source only.
+#include <cmath>
 #include <cstdint>
+#include <limits>
 #include <vector>
 
 #include "oracle.h"
@@ -65,4 +69,38 @@ extern "C" int64_t ora_normalize_ratio(int64_t n, const float* sample, const flo
     }
     if (library_size_factor) *library_size_factor = factor;
     return k;
+}
+
+extern "C" int ora_normalize_best_lr2(int n_controls, int64_t n, const double* sample, const double* controls, const uint8_t* on_target,
+                                      double* mean_sq_log_ratio, int64_t* ignored) {
+    auto normalised = [&](const double* x) {
+        std::vector<double> on;
+        for (int64_t i = 0; i < n; i++)
+            if (!on_target || on_target[i]) on.push_back(x[i]);
+        const double median = ora::median_d(on);
+        const double weight = median > 0 ? 1.0 / median : 0;
+        for (double& v : on) v = v * weight;
+        return on;
+    };
+    const std::vector<double> tumor = normalised(sample);
+    int best = -1;
+    double mn = std::numeric_limits<double>::infinity();
+    for (int c = 0; c < n_controls; c++) {
+        const std::vector<double> normal = normalised(controls + (size_t)c * n);
+        double sum = 0;
+        int64_t ign = 0, used = 0;
+        for (size_t i = 0; i < tumor.size(); i++) {
+            if (normal[i] <= 0) { ign++; continue; }
+            const double lr = std::log(tumor[i] / normal[i]);
+            const double sq = lr * lr;
+            if (std::isinf(sq) || std::isnan(sq)) { ign++; continue; }
+            sum += sq;
+            used++;
+        }
+        const double mean = used > 0 ? sum / used : sum;
+        mean_sq_log_ratio[c] = mean;
+        ignored[c] = ign;
+        if (mean < mn) { mn = mean; best = c; }
+    }
+    return best;
 }

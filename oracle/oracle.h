@@ -81,6 +81,9 @@ void ora_normalize_reference(int n_samples, int64_t n, const double* counts, con
 int64_t ora_normalize_ratio(int64_t n, const float* sample, const float* reference, const uint8_t* on_target, int lsnorm, double min_ref,
                             double max_ref, const int32_t* ploidy, int32_t* kept_index, float* ratio, float* count,
                             double* library_size_factor);
+/* BestLR2ReferenceGenerator: returns the index of the best control (-1: none). */
+int ora_normalize_best_lr2(int n_controls, int64_t n, const double* sample, const double* controls, const uint8_t* on_target,
+                           double* mean_sq_log_ratio, int64_t* ignored);
 /* CanvasSmooth (oracle/smooth.cpp): Utilities.MedianFilter and the repeated filter; return the output length (<= n). */
 int64_t ora_median_filter(int64_t n, const float* in, uint32_t half_window, float* out);
 int64_t ora_repeated_median_filter(int64_t n, const float* in, uint32_t max_half_window, float* out);

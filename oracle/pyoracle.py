@@ -465,3 +465,15 @@ def normalize_ratio(sample, reference, on_target=None, mode="lsnorm", min_ref=1.
           C.c_int(mode == "lsnorm"), C.c_double(min_ref), C.c_double(max_ref), _p(pl, C.c_int32) if pl is not None else None,
           _p(idx, C.c_int32), _p(ratio, C.c_float), _p(count, C.c_float), C.byref(lsf))
     return {"kept_index": idx[:k].copy(), "ratio": ratio[:k].copy(), "count": count[:k].copy(), "library_size_factor": lsf.value}
+
+
+def normalize_best_lr2(sample, controls, on_target=None):
+    """BestLR2ReferenceGenerator.Run (:32-90): index of the best control, mean squared log ratios, ignored bins."""
+    t = np.ascontiguousarray(sample, np.float64)
+    c = np.ascontiguousarray(np.atleast_2d(np.asarray(controls, np.float64)))
+    s, n = c.shape
+    on = None if on_target is None else np.ascontiguousarray(on_target, np.uint8)
+    mean = np.zeros(s); ign = np.zeros(s, np.int64)
+    best = lib().ora_normalize_best_lr2(C.c_int(s), C.c_int64(n), _p(t, C.c_double), _p(c, C.c_double),
+                                        _p(on, C.c_uint8) if on is not None else None, _p(mean, C.c_double), _p(ign, C.c_int64))
+    return {"best": int(best), "mean_sq_log_ratio": mean, "ignored": ign}

@@ -80,6 +80,30 @@ def test_ratio_special_values(eng):
     assert len(eng.normalize_ratio(np.ones(10), np.ones(4))["ratio"]) == 4
 
 
+@pytest.mark.parametrize("s,n,masked", [(2, 1000, False), (6, 200001, True), (3, 3100000, False), (4, 5, False)])
+def test_best_lr2_matches_oracle(eng, s, n, masked):
+    rng = np.random.default_rng(s * 7 + n)
+    c = _controls(rng, s, n)
+    sample = np.round(c[rng.integers(0, s)] * rng.uniform(0.5, 2.0) + rng.normal(0, 3, n))
+    sample[rng.random(n) < 0.01] = 0
+    c[:, rng.random(n) < 0.005] = 0
+    on = (rng.random(n) < 0.4).astype(np.uint8) if masked else None
+    want, got = po.normalize_best_lr2(sample, c, on), eng.normalize_best_lr2(sample, c, on)
+    assert want["best"] == got["best"] and np.array_equal(want["ignored"], got["ignored"])
+    # chunk-wise sums on the device, one left-to-right sum of up to 3 M terms in the reference (and libm against CUDA log): 1e-9 relative is far inside 1e-5
+    assert np.allclose(want["mean_sq_log_ratio"], got["mean_sq_log_ratio"], rtol=1e-9, atol=0)
+
+
+def test_best_lr2_degenerate(eng):
+    sample = np.array([10.0, 20.0, 30.0, 40.0])
+    for controls in ([[0.0, 0.0, 0.0, 9.0], [20.0, 20.0, 20.0, 20.0]], [[np.nan] * 4, [1.0, 2.0, 3.0, 4.0]], [[5.0, 10.0, 15.0, 20.0]]):
+        want, got = po.normalize_best_lr2(sample, controls), eng.normalize_best_lr2(sample, controls)
+        assert want["best"] == got["best"] and np.array_equal(want["ignored"], got["ignored"])
+        assert np.allclose(want["mean_sq_log_ratio"], got["mean_sq_log_ratio"], rtol=1e-9, atol=0, equal_nan=True)
+    with pytest.raises(ValueError):
+        eng.normalize_best_lr2(sample, np.ones((2, 3)))
+
+
 def _write_binned(path, chrom, start, count, fmt="{:.0f}"):
     lines = [f"{c}\t{s}\t{s + 1000}\t{fmt.format(v)}\t{40 + i % 20}" for i, (c, s, v) in enumerate(zip(chrom, start, count))]
     with open(path, "wb") as f:
@@ -124,5 +148,10 @@ def test_canvas_normalize_module(tmp_path):
     out2, w2 = str(tmp_path / "out2.binned"), str(tmp_path / "ref2.binned")
     assert modules.canvas_normalize_main(["-t", t, "-n", paths[0], "-o", out2, "-w", w2]) == 0
     assert open(w2, "rb").read() == open(paths[0], "rb").read()
+    # BestLR2: the reference is a copy of the control closest to the tumour
+    out3, w3 = str(tmp_path / "out3.binned"), str(tmp_path / "ref3.binned")
+    assert modules.canvas_normalize_main(argv[:2] + ["-o", out3, "-w", w3, "-m", "BestLR2"] + argv[6:]) == 0
+    best = po.normalize_best_lr2(tumor, controls)["best"]
+    assert open(w3, "rb").read() == open(paths[best], "rb").read()
     assert modules.canvas_normalize_main(["-t", t, "-n", str(tmp_path / "nope"), "-o", out2, "-w", w2]) == 1
     assert modules.canvas_normalize_main(["-n", paths[0], "-o", out2]) == 1

@@ -39,3 +39,22 @@ def test_ratio_steps_by_hand():
     # a sample median of zero leaves the factor at 1
     assert po.normalize_ratio(np.zeros(4, np.float32), np.full(4, 3, np.float32))["library_size_factor"] == 1.0
     assert len(po.normalize_ratio(np.zeros(0, np.float32), np.zeros(0, np.float32))["ratio"]) == 0
+
+
+def test_best_lr2_by_hand():
+    import math
+    sample = np.array([10.0, 20.0, 30.0, 40.0])
+    controls = np.array([[5.0, 10.0, 15.0, 20.0],      # the sample's shape: every normalised ratio is 1, log ratio 0
+                         [20.0, 20.0, 20.0, 20.0],
+                         [10.0, 0.0, 30.0, 41.0]])
+    r = po.normalize_best_lr2(sample, controls)
+    assert r["best"] == 0 and r["mean_sq_log_ratio"][0] == 0.0 and r["ignored"].tolist() == [0, 0, 1]
+    t = sample / 25.0
+    want1 = sum(math.log(a / 1.0) ** 2 for a in t) / 4
+    assert abs(r["mean_sq_log_ratio"][1] - want1) < 1e-15
+    # only on-target bins count, for the medians too
+    r = po.normalize_best_lr2(sample, controls, on_target=[0, 1, 1, 1])
+    assert r["ignored"].tolist() == [0, 0, 1]
+    # a control whose median is not positive normalises to zeros: every bin is ignored, its mean is the empty sum 0 and it wins
+    r = po.normalize_best_lr2(sample, np.array([[0.0, 0.0, 0.0, 9.0], [20.0, 20.0, 20.0, 20.0]]))
+    assert r["best"] == 0 and r["ignored"][0] == 4 and r["mean_sq_log_ratio"][0] == 0.0
