@@ -222,6 +222,127 @@ __global__ void lr2_finish_kernel(const Lr2Partial* __restrict__ part, int n_con
     *best = b;
 }
 
+// ---------------------------------------------------------------------------------------------
+// PCA reference (PCAReferenceGenerator.cs:37-78).  Dot products are chunk-wise device sums added in chunk order
+// (deterministic; the reference adds left to right: agreement ~1e-13 relative, far inside the 1e-5 the path allows).
+// ---------------------------------------------------------------------------------------------
+constexpr int DOT_CHUNK = 8192;
+
+// part[pair * n_chunks + chunk] = sum over the chunk of a[i] * b[i]; pair p reads rows ia[p], ib[p] of `rows` (row -1 =
+// the centred sample: (double)max(1, sample) - (double)mu)
+struct DotPairs {
+    int ia[64], ib[64];
+};
+
+__device__ inline double pca_centred(const float* sample, const float* mu, long long i) {
+    return __dsub_rn((double)fmaxf(1.0f, sample[i]), (double)mu[i]);
+}
+
+__global__ void __launch_bounds__(256) dot_partial_kernel(const double* __restrict__ rows, long long n, DotPairs pairs,
+                                                          const float* __restrict__ sample, const float* __restrict__ mu,
+                                                          double* __restrict__ part) {
+    const int pr = blockIdx.y;
+    const int ia = pairs.ia[pr], ib = pairs.ib[pr];
+    const long long lo = (long long)blockIdx.x * DOT_CHUNK, hi = min(n, lo + DOT_CHUNK);
+    constexpr int PER = DOT_CHUNK / 256;
+    const long long a0 = lo + (long long)threadIdx.x * PER;
+    double sum = 0.0;
+    for (long long i = a0; i < min(hi, a0 + PER); i++) {
+        const double x = ia < 0 ? pca_centred(sample, mu, i) : rows[(size_t)ia * n + i];
+        const double y = ib < 0 ? pca_centred(sample, mu, i) : rows[(size_t)ib * n + i];
+        sum = __dadd_rn(sum, __dmul_rn(x, y));
+    }
+    __shared__ double s_sum[256];
+    s_sum[threadIdx.x] = sum;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int k = 0; k < 256; k++) t = __dadd_rn(t, s_sum[k]);
+        part[(size_t)pr * gridDim.x + blockIdx.x] = t;
+    }
+}
+
+__global__ void dot_finish_kernel(const double* __restrict__ part, int n_pairs, int n_chunks, double* __restrict__ out) {
+    const int pr = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pr >= n_pairs) return;
+    double t = 0.0;
+    for (int k = 0; k < n_chunks; k++) t = __dadd_rn(t, part[(size_t)pr * n_chunks + k]);
+    out[pr] = t;
+}
+
+// NormalizeBy2Norm (Utilities.cs:650-667): v / sqrt(sum of squares), unchanged when the norm is zero
+__global__ void __launch_bounds__(256) axes_normalize_kernel(double* __restrict__ rows, long long n, int n_axes, const double* __restrict__ sumsq) {
+    const int k = blockIdx.y;
+    const double size = sqrt(sumsq[k]);
+    if (size == 0) return;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        rows[(size_t)k * n + i] = __ddiv_rn(rows[(size_t)k * n + i], size);
+}
+
+// AreOrthogonal (:685-692) over all pairs; gram[] holds the pair dot products after the K axis projections
+__global__ void pca_check_kernel(const double* __restrict__ gram, int n_pairs, int* __restrict__ bad) {
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    int b = 0;
+    for (int p = 0; p < n_pairs; p++)
+        if (fabs(gram[p]) > 1e-4) b = 1;
+    *bad = b;
+}
+
+// reference vector, the temporary reference file's F2 round trip, the raw ratio and its keep flag (:49-63,
+// RawRatioCalculator.cs:36-45)
+__global__ void __launch_bounds__(256) pca_reference_kernel(const double* __restrict__ rows, long long n, int n_axes,
+                                                            const double* __restrict__ size, const float* __restrict__ sample,
+                                                            const float* __restrict__ mu, double min_ref, double max_ref,
+                                                            double* __restrict__ ref_d, float* __restrict__ ratio,
+                                                            uint8_t* __restrict__ kept) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        double proj = __dmul_rn(size[0], rows[i]);
+        for (int k = 1; k < n_axes; k++) proj = __dadd_rn(proj, __dmul_rn(size[k], rows[(size_t)k * n + i]));
+        const double r = fmax(1.0, __dadd_rn((double)mu[i], proj));
+        ref_d[i] = r;
+        const float rf = (float)dotnet_f2_roundtrip((float)r);  // written with {0:F2}, read back with float.Parse
+        const double rd = (double)rf;
+        kept[i] = !(rd < min_ref) && !(rd > max_ref);
+        ratio[i] = __fdiv_rn(sample[i], rf);
+    }
+}
+
+struct RatioListView {  // the kept (and on-target) ratios: one list
+    const float* ratio;
+    const uint8_t* kept;
+    const uint8_t* on_target;
+    long long n;
+    __device__ long long size() const { return n; }
+    __device__ bool get(long long i, uint32_t& key, int& a, int& b) const {
+        if (!kept[i] || (on_target && !on_target[i])) return false;
+        a = 0;
+        b = -1;
+        key = f32_key(ratio[i]);
+        return true;
+    }
+};
+
+__global__ void count_kept_kernel(const uint8_t* __restrict__ kept, const uint8_t* __restrict__ on_target, long long n,
+                                  unsigned long long* __restrict__ out) {
+    unsigned long long c = 0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        c += kept[i] && (!on_target || on_target[i]);
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_down_sync(0xffffffffu, c, o);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(out, c);
+}
+
+__global__ void __launch_bounds__(256) pca_scale_kernel(const double* __restrict__ ref_d, long long n, SelState<uint32_t> st,
+                                                        double* __restrict__ median_out, float* __restrict__ out) {
+    double med = 0.0;  // Median of an empty list
+    if (st.nreq[0]) {
+        const double a = (double)f32_unkey(st.req_key[0]), b = (double)f32_unkey(st.req_key[1]);
+        med = st.req_key[0] == st.req_key[1] ? a : __ddiv_rn(__dadd_rn(a, b), 2.0);
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) *median_out = med;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        out[i] = (float)__dmul_rn(ref_d[i], med);
+}
+
 void reset_call(cg_ctx* ctx) {
     ctx->launches = 0;
     ctx->tl = nullptr;
@@ -409,5 +530,93 @@ extern "C" int cg_normalize_best_lr2(cg_ctx* ctx, int n_controls, int64_t n, con
     float ms = 0;
     cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
     ctx->last_kernel_ms = ms;
+    return CG_OK;
+}
+
+extern "C" int cg_normalize_pca_reference(cg_ctx* ctx, int64_t n, int n_axes, const float* sample, const float* mu, const double* axes,
+                                          const uint8_t* on_target, double min_ref, double max_ref, float* reference,
+                                          double* median_ratio) {
+    if (!ctx) return CG_ERR_ARG;
+    if (n < 0 || n_axes < 1 || !median_ratio || (n > 0 && (!sample || !mu || !axes || !reference)))
+        return cg_fail(ctx, CG_ERR_ARG, n_axes < 1 ? "No axes to project onto." : "cg_normalize_pca_reference: bad argument");
+    if (n_axes > 10) return cg_fail(ctx, CG_ERR_UNSUPPORTED, "cg_normalize_pca_reference: more than 10 axes");
+    if (n > 0x7fff0000LL) return cg_fail(ctx, CG_ERR_UNSUPPORTED, "cg_normalize_pca_reference: too many bins");
+    reset_call(ctx);
+    *median_ratio = 0.0;
+    if (n == 0) return CG_OK;
+    CG_CUDA(ctx, cudaSetDevice(ctx->device));
+    const int K = n_axes, n_gram = K * (K - 1) / 2;
+    const int n_chunks = (int)div_up((long long)n, (long long)DOT_CHUNK);
+    const int max_pairs = std::max(K, std::max(n_gram, 1));
+    int rc = arena_reserve(ctx, arena_need((size_t)K * n, 8) + arena_need(n, 8) + arena_need(n, 4) * 4 + arena_need(n, 1) * 2 +
+                                    arena_need((size_t)max_pairs * n_chunks, 8) + arena_need(64, 8) * 3 + sel_state_bytes<uint32_t>(1) + (1u << 16));
+    if (rc) return rc;
+    double* d_rows = arena_take<double>(ctx, (size_t)K * n);
+    double* d_ref = arena_take<double>(ctx, n);
+    float* d_sample = arena_take<float>(ctx, n);
+    float* d_mu = arena_take<float>(ctx, n);
+    float* d_ratio = arena_take<float>(ctx, n);
+    float* d_out = arena_take<float>(ctx, n);
+    uint8_t* d_kept = arena_take<uint8_t>(ctx, n);
+    uint8_t* d_on = on_target ? arena_take<uint8_t>(ctx, n) : nullptr;
+    double* d_part = arena_take<double>(ctx, (size_t)max_pairs * n_chunks);
+    double* d_sumsq = arena_take<double>(ctx, 64);
+    double* d_gram = arena_take<double>(ctx, 64);
+    double* d_size = arena_take<double>(ctx, 64);
+    int* d_bad = arena_take<int>(ctx, 1);
+    double* d_med = arena_take<double>(ctx, 1);
+    unsigned long long* d_cnt = arena_take<unsigned long long>(ctx, 1);
+    SelState<uint32_t> st;
+    if (!d_rows || !d_ref || !d_sample || !d_mu || !d_ratio || !d_out || !d_kept || (on_target && !d_on) || !d_part || !d_sumsq || !d_gram ||
+        !d_size || !d_bad || !d_med || !d_cnt || !sel_state_alloc<uint32_t>(ctx, 1, st))
+        return cg_fail(ctx, CG_ERR_CUDA, "arena exhausted");
+    cudaStream_t s = ctx->stream;
+    CG_CUDA(ctx, cudaMemcpyAsync(d_rows, axes, (size_t)K * n * 8, cudaMemcpyHostToDevice, s));
+    CG_CUDA(ctx, cudaMemcpyAsync(d_sample, sample, (size_t)n * 4, cudaMemcpyHostToDevice, s));
+    CG_CUDA(ctx, cudaMemcpyAsync(d_mu, mu, (size_t)n * 4, cudaMemcpyHostToDevice, s));
+    if (on_target) CG_CUDA(ctx, cudaMemcpyAsync(d_on, on_target, (size_t)n, cudaMemcpyHostToDevice, s));
+    CG_CUDA(ctx, cudaEventRecord(ctx->ev0, s));
+    CG_CUDA(ctx, cudaMemsetAsync(st.hist, 0, (size_t)SEL_G * SEL_BINS * sizeof(unsigned), s));
+    CG_CUDA(ctx, cudaMemsetAsync(d_cnt, 0, 8, s));
+    const int grid_stream = (int)std::min<long long>(ctx->num_sms * 8, div_up((long long)n, 256LL));
+    DotPairs pairs;
+    // norms of the axes as read from the model file, then the unit axes
+    for (int k = 0; k < K; k++) { pairs.ia[k] = k; pairs.ib[k] = k; }
+    CG_LAUNCH(ctx, dot_partial_kernel, dim3(n_chunks, K), 256, 0, d_rows, (long long)n, pairs, d_sample, d_mu, d_part);
+    CG_LAUNCH(ctx, dot_finish_kernel, 1, 64, 0, d_part, K, n_chunks, d_sumsq);
+    CG_LAUNCH(ctx, axes_normalize_kernel, dim3(grid_stream, K), 256, 0, d_rows, (long long)n, K, d_sumsq);
+    // pairwise orthogonality of the unit axes
+    if (n_gram > 0) {
+        int q = 0;
+        for (int i = 0; i < K; i++)
+            for (int j = i + 1; j < K; j++) { pairs.ia[q] = i; pairs.ib[q] = j; q++; }
+        CG_LAUNCH(ctx, dot_partial_kernel, dim3(n_chunks, n_gram), 256, 0, d_rows, (long long)n, pairs, d_sample, d_mu, d_part);
+        CG_LAUNCH(ctx, dot_finish_kernel, 1, 64, 0, d_part, n_gram, n_chunks, d_gram);
+    }
+    CG_LAUNCH(ctx, pca_check_kernel, 1, 32, 0, d_gram, n_gram, d_bad);
+    // sizes of the projections of the centred sample
+    for (int k = 0; k < K; k++) { pairs.ia[k] = -1; pairs.ib[k] = k; }
+    CG_LAUNCH(ctx, dot_partial_kernel, dim3(n_chunks, K), 256, 0, d_rows, (long long)n, pairs, d_sample, d_mu, d_part);
+    CG_LAUNCH(ctx, dot_finish_kernel, 1, 64, 0, d_part, K, n_chunks, d_size);
+    CG_LAUNCH(ctx, pca_reference_kernel, grid_stream, 256, 0, d_rows, (long long)n, K, d_size, d_sample, d_mu, min_ref, max_ref, d_ref,
+              d_ratio, d_kept);
+    // median of the kept (on-target) ratios, then the scaled reference
+    CG_LAUNCH(ctx, count_kept_kernel, grid_stream, 256, 0, d_kept, d_on, (long long)n, d_cnt);
+    CG_LAUNCH(ctx, middle_request_kernel<uint32_t>, 1, 32, 0, st, d_cnt, 0ull);
+    RatioListView v{d_ratio, d_kept, d_on, (long long)n};
+    sel_run_scatter<uint32_t, RatioListView>(ctx, v, st, (long long)n);
+    CG_LAUNCH(ctx, pca_scale_kernel, grid_stream, 256, 0, d_ref, (long long)n, st, d_med, d_out);
+    CG_CUDA(ctx, cudaEventRecord(ctx->ev1, s));
+    int h_bad = 0;
+    CG_CUDA(ctx, cudaMemcpyAsync(&h_bad, d_bad, 4, cudaMemcpyDeviceToHost, s));
+    CG_CUDA(ctx, cudaMemcpyAsync(median_ratio, d_med, 8, cudaMemcpyDeviceToHost, s));
+    CG_CUDA(ctx, cudaMemcpyAsync(reference, d_out, (size_t)n * 4, cudaMemcpyDeviceToHost, s));
+    CG_CUDA(ctx, cudaStreamSynchronize(s));
+    CG_CUDA(ctx, cudaGetLastError());
+    CG_CHECK_LAUNCHES(ctx);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+    ctx->last_kernel_ms = ms;
+    if (h_bad) return cg_fail(ctx, CG_ERR_ARG, "Axes are not orthogonal to each other.");
     return CG_OK;
 }

@@ -84,6 +84,8 @@ SIGNATURES = {
                              C.c_char_p, _i64, C.c_int]),
     "cg_normalize_reference": (C.c_int, [C.c_void_p, C.c_int, _i64, _P(_f64), _P(_u8), _P(_f64), _P(_f64), _P(_f64)]),
     "cg_normalize_best_lr2": (C.c_int, [C.c_void_p, C.c_int, _i64, _P(_f64), _P(_f64), _P(_u8), _P(C.c_int), _P(_f64), _P(_i64)]),
+    "cg_normalize_pca_reference": (C.c_int, [C.c_void_p, _i64, C.c_int, _P(_f32), _P(_f32), _P(_f64), _P(_u8), C.c_double, C.c_double,
+                                             _P(_f32), _P(_f64)]),
     "cg_normalize_ratio": (C.c_int, [C.c_void_p, _i64, _P(_f32), _P(_f32), _P(_u8), C.c_int, C.c_double, C.c_double, _P(_i32),
                                      _P(_i64), _P(_i32), _P(_f32), _P(_f32), _P(_f64)]),
     "cg_cbs_boundary": (_i64, [C.c_uint32, C.c_double, C.c_double, _P(C.c_uint32), _i64]),
@@ -507,6 +509,23 @@ class Engine:
                                             C.byref(best), _ptr(mean, _f64), _ptr(ign, _i64))
         self._check(rc)
         return {"best": int(best.value), "mean_sq_log_ratio": mean, "ignored": ign, "kernel_ms": self.lib.cg_last_kernel_ms(self.h)}
+
+    def normalize_pca_reference(self, sample, mu, axes, on_target=None, min_ref=1.0, max_ref=float("inf")):
+        """PCAReferenceGenerator.Run: reference counts (float) and the median sample / reference ratio."""
+        a = np.ascontiguousarray(sample, np.float32)
+        m = np.ascontiguousarray(mu, np.float32)
+        ax = np.ascontiguousarray(np.atleast_2d(np.asarray(axes, np.float64)))
+        k, n = ax.shape
+        if len(a) != n or len(m) != n:
+            raise ValueError("sample, mean and axes must have the same number of bins")
+        on = None if on_target is None else np.ascontiguousarray(on_target, np.uint8)
+        ref = np.zeros(max(n, 1), np.float32)
+        med = C.c_double(0)
+        rc = self.lib.cg_normalize_pca_reference(self.h, n, k, _ptr(a, _f32), _ptr(m, _f32), _ptr(ax, _f64),
+                                                 _ptr(on, _u8) if on is not None else None, min_ref, max_ref, _ptr(ref, _f32),
+                                                 C.byref(med))
+        self._check(rc)
+        return {"reference": ref[:n], "median_ratio": med.value, "kernel_ms": self.lib.cg_last_kernel_ms(self.h)}
 
     def normalize_ratio(self, sample, reference, on_target=None, mode="lsnorm", min_ref=1.0, max_ref=float("inf"), ploidy=None):
         """LSNormRatioCalculator.Run ("lsnorm") or RawRatioCalculator.Run ("raw") + RatiosToCounts on the bins both lists

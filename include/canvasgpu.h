@@ -319,6 +319,15 @@ int64_t cg_parse_bins(const char* text, int64_t len, int64_t max_rows, uint8_t* 
  * they agree with the reference's left-to-right sum to better than 1e-9 relative, not bit for bit. */
 int cg_normalize_best_lr2(cg_ctx* ctx, int n_controls, int64_t n, const double* sample, const double* controls,
                           const uint8_t* on_target, int* best_index, double* mean_sq_log_ratio, int64_t* ignored);
+/* PCAReferenceGenerator.Run (CanvasNormalize/PCAReferenceGenerator.cs:37-78): sample[n] (the file's counts), the model's
+ * mean mu[n] and axes[n_axes][n] as read from the model file (they are scaled to unit length and checked for pairwise
+ * orthogonality as PCAModel.LoadModel does, :113-146: CG_ERR_ARG "Axes are not orthogonal to each other."); reference[n] =
+ * (float)(max(1, mu + projection of the centred sample) * median ratio), the median taken over the raw sample / reference
+ * ratios of the bins whose (two-decimal) reference count lies in [min_ref, max_ref].  Dot products are chunk-wise device
+ * sums: results agree with the reference's left-to-right sums to ~1e-12 relative (an occasional last-bit difference in the
+ * float outputs), not bit for bit.  n_axes <= 10. */
+int cg_normalize_pca_reference(cg_ctx* ctx, int64_t n, int n_axes, const float* sample, const float* mu, const double* axes,
+                               const uint8_t* on_target, double min_ref, double max_ref, float* reference, double* median_ratio);
 int cg_normalize_reference(cg_ctx* ctx, int n_samples, int64_t n, const double* counts, const uint8_t* on_target,
                            double* median, double* weight, double* reference);
 int cg_normalize_ratio(cg_ctx* ctx, int64_t n, const float* sample, const float* reference, const uint8_t* on_target,

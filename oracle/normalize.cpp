@@ -11,6 +11,10 @@
 //   CanvasNormalize/CanvasNormalizeUtilities.cs:22-31          RatiosToCounts: count = (float)(ratio * (40 * ploidy / 2.0))
 //   CanvasNormalize/BestLR2ReferenceGenerator.cs:32-125        the control with the smallest mean squared log ratio of the median-normalised
 //                                                              on-target counts (first strict minimum; -1 when none is below +infinity)
+//   CanvasNormalize/PCAReferenceGenerator.cs:37-78, :113-146    unit axes (Utilities.NormalizeBy2Norm :650-667), pairwise orthogonality
+//                                                              (AreOrthogonal :685-692, tolerance 1e-4), projection of the centred
+//                                                              sample (Project :700-745), F2 round trip of the temporary reference,
+//                                                              raw ratios, their median, scaled reference
 // Parity unpinned: the reference has no test for CanvasNormalize; restated from source only.
 #include <cmath>
 #include <cstdint>
@@ -103,4 +107,49 @@ extern "C" int ora_normalize_best_lr2(int n_controls, int64_t n, const double* s
         if (mean < mn) { mn = mean; best = c; }
     }
     return best;
+}
+
+// returns 0, or -1 when the axes are not orthogonal
+extern "C" int ora_normalize_pca_reference(int64_t n, int n_axes, const float* sample, const float* mu, const double* axes,
+                                           const uint8_t* on_target, double min_ref, double max_ref, float* reference,
+                                           double* median_ratio) {
+    std::vector<std::vector<double>> ax(n_axes, std::vector<double>(n));
+    for (int k = 0; k < n_axes; k++) {
+        double norm2 = 0;
+        for (int64_t i = 0; i < n; i++) norm2 += axes[(size_t)k * n + i] * axes[(size_t)k * n + i];
+        const double size = std::sqrt(norm2);
+        for (int64_t i = 0; i < n; i++) ax[k][i] = size == 0 ? axes[(size_t)k * n + i] : axes[(size_t)k * n + i] / size;
+    }
+    for (int a = 0; a < n_axes; a++)
+        for (int b = a + 1; b < n_axes; b++) {
+            double dot = 0;
+            for (int64_t i = 0; i < n; i++) dot += ax[a][i] * ax[b][i];
+            if (std::fabs(dot) > 1e-4) return -1;
+        }
+    std::vector<double> centred(n), projected(n, 0.0), ref(n);
+    for (int64_t i = 0; i < n; i++) centred[i] = (double)std::max(1.0f, sample[i]) - (double)mu[i];
+    for (int k = 0; k < n_axes; k++) {
+        double size = 0;
+        for (int64_t i = 0; i < n; i++) size += centred[i] * ax[k][i];
+        for (int64_t i = 0; i < n; i++) {
+            const double t = size * ax[k][i];
+            projected[i] = k == 0 ? t : projected[i] + t;
+        }
+    }
+    std::vector<double> ratios;
+    for (int64_t i = 0; i < n; i++) {
+        ref[i] = std::max(1.0, (double)mu[i] + projected[i]);
+        const float as_float = (float)ref[i];
+        double back = 0;
+        ora_f2_roundtrip(1, &as_float, &back);
+        const float rf = (float)back;  // float.Parse of the two-decimal text
+        if ((double)rf < min_ref) continue;
+        if ((double)rf > max_ref) continue;
+        const float ratio = sample[i] / rf;
+        if (!on_target || on_target[i]) ratios.push_back((double)ratio);
+    }
+    const double med = ora::median_d(ratios);
+    *median_ratio = med;
+    for (int64_t i = 0; i < n; i++) reference[i] = (float)(ref[i] * med);
+    return 0;
 }

@@ -84,6 +84,9 @@ int64_t ora_normalize_ratio(int64_t n, const float* sample, const float* referen
 /* BestLR2ReferenceGenerator: returns the index of the best control (-1: none). */
 int ora_normalize_best_lr2(int n_controls, int64_t n, const double* sample, const double* controls, const uint8_t* on_target,
                            double* mean_sq_log_ratio, int64_t* ignored);
+/* PCAReferenceGenerator.Run; -1 when the axes are not orthogonal. */
+int ora_normalize_pca_reference(int64_t n, int n_axes, const float* sample, const float* mu, const double* axes, const uint8_t* on_target,
+                                double min_ref, double max_ref, float* reference, double* median_ratio);
 /* CanvasSmooth (oracle/smooth.cpp): Utilities.MedianFilter and the repeated filter; return the output length (<= n). */
 int64_t ora_median_filter(int64_t n, const float* in, uint32_t half_window, float* out);
 int64_t ora_repeated_median_filter(int64_t n, const float* in, uint32_t max_half_window, float* out);

@@ -477,3 +477,20 @@ def normalize_best_lr2(sample, controls, on_target=None):
     best = lib().ora_normalize_best_lr2(C.c_int(s), C.c_int64(n), _p(t, C.c_double), _p(c, C.c_double),
                                         _p(on, C.c_uint8) if on is not None else None, _p(mean, C.c_double), _p(ign, C.c_int64))
     return {"best": int(best), "mean_sq_log_ratio": mean, "ignored": ign}
+
+
+def normalize_pca_reference(sample, mu, axes, on_target=None, min_ref=1.0, max_ref=np.inf):
+    """PCAReferenceGenerator.Run (:37-78): reference counts (float) and the median ratio; None when the axes are not orthogonal."""
+    a = np.ascontiguousarray(sample, np.float32)
+    m = np.ascontiguousarray(mu, np.float32)
+    ax = np.ascontiguousarray(np.atleast_2d(np.asarray(axes, np.float64)))
+    k, n = ax.shape
+    on = None if on_target is None else np.ascontiguousarray(on_target, np.uint8)
+    ref = np.zeros(max(n, 1), np.float32)
+    med = C.c_double(0)
+    rc = lib().ora_normalize_pca_reference(C.c_int64(n), C.c_int(k), _p(a, C.c_float), _p(m, C.c_float), _p(ax, C.c_double),
+                                           _p(on, C.c_uint8) if on is not None else None, C.c_double(min_ref), C.c_double(max_ref),
+                                           _p(ref, C.c_float), C.byref(med))
+    if rc != 0:
+        return None
+    return {"reference": ref[:n], "median_ratio": med.value}

@@ -104,6 +104,40 @@ def test_best_lr2_degenerate(eng):
         eng.normalize_best_lr2(sample, np.ones((2, 3)))
 
 
+def _pca_case(rng, n, k):
+    mu = rng.gamma(8, 12, n).astype(np.float32)
+    q, _ = np.linalg.qr(rng.normal(size=(n, k)))          # orthonormal columns, then arbitrary lengths
+    axes = (q.T * rng.uniform(0.5, 30, (k, 1))).copy()
+    sample = np.round(mu * rng.uniform(0.7, 1.3) + (axes * rng.normal(0, 40, (k, 1))).sum(0) + rng.normal(0, 4, n)).astype(np.float32)
+    sample[rng.random(n) < 0.01] = 0
+    return sample, mu, axes
+
+
+@pytest.mark.parametrize("n,k,masked", [(1000, 1, False), (70001, 3, True), (500000, 5, False), (9, 2, False)])
+def test_pca_reference_matches_oracle(eng, n, k, masked):
+    rng = np.random.default_rng(n + k)
+    sample, mu, axes = _pca_case(rng, n, k)
+    on = (rng.random(n) < 0.5).astype(np.uint8) if masked else None
+    want = po.normalize_pca_reference(sample, mu, axes, on, 5.0, 400.0)
+    got = eng.normalize_pca_reference(sample, mu, axes, on, 5.0, 400.0)
+    # dot products are chunk-wise device sums against the reference's left-to-right sums: tolerance 1e-6 relative on the
+    # float outputs (one float ulp is 6e-8), inside the 1e-5 the path allows
+    assert abs(want["median_ratio"] - got["median_ratio"]) <= 1e-6 * abs(want["median_ratio"])
+    assert np.allclose(want["reference"], got["reference"], rtol=1e-6, atol=0)
+    assert np.mean(want["reference"] == got["reference"]) > 0.99
+
+
+def test_pca_reference_refuses_skewed_axes(eng):
+    rng = np.random.default_rng(3)
+    sample, mu, axes = _pca_case(rng, 5000, 2)
+    axes[1] += 0.01 * axes[0]
+    assert po.normalize_pca_reference(sample, mu, axes) is None
+    with pytest.raises(native.CanvasGpuError):
+        eng.normalize_pca_reference(sample, mu, axes)
+    with pytest.raises(ValueError):
+        eng.normalize_pca_reference(sample[:10], mu, axes)
+
+
 def _write_binned(path, chrom, start, count, fmt="{:.0f}"):
     lines = [f"{c}\t{s}\t{s + 1000}\t{fmt.format(v)}\t{40 + i % 20}" for i, (c, s, v) in enumerate(zip(chrom, start, count))]
     with open(path, "wb") as f:
@@ -153,5 +187,22 @@ def test_canvas_normalize_module(tmp_path):
     assert modules.canvas_normalize_main(argv[:2] + ["-o", out3, "-w", w3, "-m", "BestLR2"] + argv[6:]) == 0
     best = po.normalize_best_lr2(tumor, controls)["best"]
     assert open(w3, "rb").read() == open(paths[best], "rb").read()
+    # PCA: model file = chr, start, stop, mean, axes...; raw ratios against the projected reference
+    rng2 = np.random.default_rng(9)
+    mu = controls.mean(0).astype(np.float32)
+    q, _ = np.linalg.qr(rng2.normal(size=(n, 2)))
+    axes = (q.T * 25.0).copy()
+    model = str(tmp_path / "model.txt.gz")
+    with open(model, "wb") as f:
+        f.write(gzip.compress(("\n".join(f"{c}\t{s_}\t{s_ + 1000}\t{m!r}\t{a!r}\t{b!r}" for c, s_, m, a, b in
+                                          zip(chrom, start, mu.tolist(), axes[0].tolist(), axes[1].tolist())) + "\n").encode()))
+    out4, w4 = str(tmp_path / "out4.binned"), str(tmp_path / "ref4.binned")
+    assert modules.canvas_normalize_main(["-t", t, "-n", model, "-o", out4, "-w", w4, "-m", "PCA", "-r", "1", "-r", "100000"]) == 0
+    want_ref = po.normalize_pca_reference(tumor.astype(np.float32), mu, axes, None, 1.0, 100000.0)
+    got_ref = [ln.split("\t")[3] for ln in gzip.open(w4, "rt").read().splitlines()]
+    assert len(got_ref) == n
+    assert np.mean(np.array(got_ref) == np.array(textcodec.f2_text(want_ref["reference"]))) > 0.99
+    assert len(gzip.open(out4, "rt").read().splitlines()) > 0.9 * n
+    assert modules.canvas_normalize_main(["-t", t, "-n", model, "-n", model, "-o", out4, "-w", w4, "-m", "PCA"]) == 1
     assert modules.canvas_normalize_main(["-t", t, "-n", str(tmp_path / "nope"), "-o", out2, "-w", w2]) == 1
     assert modules.canvas_normalize_main(["-n", paths[0], "-o", out2]) == 1

@@ -58,3 +58,17 @@ def test_best_lr2_by_hand():
     # a control whose median is not positive normalises to zeros: every bin is ignored, its mean is the empty sum 0 and it wins
     r = po.normalize_best_lr2(sample, np.array([[0.0, 0.0, 0.0, 9.0], [20.0, 20.0, 20.0, 20.0]]))
     assert r["best"] == 0 and r["ignored"][0] == 4 and r["mean_sq_log_ratio"][0] == 0.0
+
+
+def test_pca_reference_by_hand():
+    # one axis along (1, 1, 0, 0) / sqrt 2: the projection replaces the first two centred values by their mean
+    mu = np.array([100, 100, 100, 100], np.float32)
+    sample = np.array([120, 140, 90, 0.5], np.float32)
+    r = po.normalize_pca_reference(sample, mu, [[3.0, 3.0, 0.0, 0.0]])
+    ref = np.array([130.0, 130.0, 100.0, 100.0])          # mu + projection; the last two are untouched
+    ratios = sample / ref.astype(np.float32)
+    med = float(np.median(ratios.astype(np.float64)))
+    assert abs(r["median_ratio"] - med) < 1e-12
+    assert np.allclose(r["reference"], (ref * med).astype(np.float32), rtol=1e-6)
+    # axes that are not orthogonal are refused (PCAModel.LoadModel)
+    assert po.normalize_pca_reference(sample, mu, [[1.0, 1.0, 0.0, 0.0], [1.0, 0.0, 0.0, 0.0]]) is None
