@@ -78,3 +78,21 @@ def bin_paired_alignments(engine, flags, pos, mate_pos, ref_id, mate_ref_id, fra
     best = r["best_bin"]
     usable = int((best >= 0).sum()) - int((best[undo] >= 0).sum()) if len(best) else 0
     return {"count": r["count"], "usable": usable}
+
+
+def bin_size_from_rates(counts_per_bin, rates):
+    """SampleHitArrays.GetBinSize (CanvasBin.cs:79-83): (int)(countsPerBin / Median(rates)); rates = observed / possible of
+    every autosome (GetRates, :30-71, from Engine.bin_screen's counts).  Median = mean of the middles for an even count."""
+    import numpy as np
+    r = np.sort(np.asarray(rates, np.float64))
+    if len(r) == 0:
+        med = 0.0
+    elif len(r) % 2:
+        med = float(r[len(r) // 2])
+    else:
+        med = (float(r[len(r) // 2 - 1]) + float(r[len(r) // 2])) / 2
+    with np.errstate(divide="ignore", invalid="ignore"):
+        q = float(np.float64(counts_per_bin) / np.float64(med))
+    if q != q or abs(q) >= 2.0 ** 31:
+        return -2 ** 31  # (int) of NaN, an infinity or an out-of-range double: 0x80000000 on x64 .NET
+    return int(q)

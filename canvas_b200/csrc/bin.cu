@@ -1,4 +1,5 @@
 // CanvasBin counting kernels (reference Src/Canvas/CanvasBin/):
+//   cg_bin_screen     ExcludeTagsOverlappingFilterFile + ScreenObservedTags + the counts of GetRates, CanvasBin.cs:668-716, :56-58
 //   cg_bin_hits       BinCountsForChromosome, CanvasBin.cs:568-661 (bins of `bin_size` possible positions;
 //                     TruncatedDynamicRange :618-625 and GCContentWeighted :626-636 counts, GC% :638)
 //   cg_bin_fragments  FragmentBinner.BinOneAlignment / FindBestBin, FragmentBinner.cs:296-311, :353-371
@@ -196,7 +197,130 @@ __global__ void bin_fragments_undo_kernel(const int32_t* __restrict__ undo, long
     if (b >= 0) atomicSub(&count[b], 1);
 }
 
+// ---------------------------------------------------------------------------------------------
+// cg_bin_screen: the passes over the genome positions that precede the binning (CanvasBin.cs:777-780, :30-76).
+// ---------------------------------------------------------------------------------------------
+// ExcludeTagsOverlappingFilterFile (:668-692): possible[i] = false for i in [start, stop).  One warp per interval:
+// whole words are stored as zero (idempotent when intervals overlap), the two edge words are cleared atomically.
+__global__ void bin_filter_clear_kernel(unsigned long long* __restrict__ bits, const int32_t* __restrict__ fstart,
+                                        const int32_t* __restrict__ fstop, long long n_filter) {
+    const long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (w >= n_filter) return;
+    const long long a = fstart[w], b = fstop[w];  // validated by the host: 0 <= a, b <= length
+    if (a >= b) return;
+    const long long wa = a >> 6, wb = (b - 1) >> 6;
+    const unsigned long long head = ~0ull << (a & 63);                    // bits >= a inside word wa
+    const unsigned long long tail = ~0ull >> (63 - ((b - 1) & 63));       // bits <= b-1 inside word wb
+    if (wa == wb) {
+        if (lane == 0) atomicAnd(&bits[wa], ~(head & tail));
+        return;
+    }
+    if (lane == 0) atomicAnd(&bits[wa], ~head);
+    if (lane == 1) atomicAnd(&bits[wb], ~tail);
+    for (long long k = wa + 1 + lane; k < wb; k += 32) bits[k] = 0ull;
+}
+
+// ScreenObservedTags (:699-716): hits[i] = 0 where position i is not possible; and the two counts of GetRates (:56-58):
+// positions with a hit left (HitArray.CountSetBits, HitArray.cs:24-32) and possible positions.  A thread takes one
+// 64-position word: 8 eight-byte loads of hits, masked by the word's bits spread to bytes.
+__global__ void __launch_bounds__(256) bin_screen_kernel(unsigned long long* __restrict__ hits8, const unsigned long long* __restrict__ bits,
+                                                         long long nwords, long long len, unsigned long long* __restrict__ counts) {
+    unsigned long long obs = 0, pos = 0;
+    for (long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x; w < nwords; w += (long long)gridDim.x * blockDim.x) {
+        unsigned long long m = bits[w];
+        const long long base = w << 6;
+        if (base + 64 > len) m &= (len - base >= 64) ? ~0ull : ((1ull << (len - base)) - 1ull);  // bits past the end do not exist
+        pos += (unsigned long long)__popcll(m);
+        if (base + 64 <= len) {
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                const unsigned b8 = (unsigned)(m >> (8 * k)) & 0xffu;
+                // spread 8 bits to 8 byte masks: bit j -> byte j = 0xff
+                unsigned long long spread = (unsigned long long)b8 * 0x0101010101010101ull & 0x8040201008040201ull;
+                spread = ((spread + 0x7f7f7f7f7f7f7f7full) >> 7) & 0x0101010101010101ull;  // non-zero byte -> 1
+                const unsigned long long mask = spread * 0xffull;
+                const unsigned long long h = hits8[(base >> 3) + k];
+                const unsigned long long kept = h & mask;
+                if (kept != h) hits8[(base >> 3) + k] = kept;
+                // count non-zero bytes
+                unsigned long long nz = ((kept & 0x7f7f7f7f7f7f7f7full) + 0x7f7f7f7f7f7f7f7full) | kept;
+                obs += (unsigned long long)__popcll(nz & 0x8080808080808080ull);
+            }
+        } else {
+            unsigned char* hb = reinterpret_cast<unsigned char*>(hits8);
+            for (long long i = base; i < len; i++) {
+                if (!((m >> (i - base)) & 1ull)) { if (hb[i]) hb[i] = 0; }
+                else if (hb[i]) obs++;
+            }
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        obs += __shfl_down_sync(0xffffffffu, obs, o);
+        pos += __shfl_down_sync(0xffffffffu, pos, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (obs) atomicAdd(&counts[0], obs);
+        if (pos) atomicAdd(&counts[1], pos);
+    }
+}
+
 }  // namespace
+
+extern "C" int cg_bin_screen(cg_ctx* ctx, int64_t chr_len, uint8_t* hits, uint64_t* possible_bits, int64_t n_filter,
+                             const int32_t* filter_start, const int32_t* filter_stop, int64_t* n_observed, int64_t* n_possible) {
+    if (!ctx) return CG_ERR_ARG;
+    if (chr_len < 0 || chr_len > 0x7fff0000LL || n_filter < 0 || !n_observed || !n_possible || (n_filter > 0 && (!filter_start || !filter_stop)))
+        return cg_fail(ctx, CG_ERR_ARG, "cg_bin_screen: bad argument");
+    *n_observed = *n_possible = 0;
+    ctx->launches = 0;
+    ctx->tl = nullptr;
+    ctx->launch_err = cudaSuccess;
+    for (int i = 0; i < 4; i++) ctx->stage_used[i] = false;
+    ctx->gap_used = false;
+    if (chr_len == 0) return CG_OK;
+    if (!hits || !possible_bits) return cg_fail(ctx, CG_ERR_ARG, "cg_bin_screen: null array");
+    // `tags[chr][i] = false` throws past the end of the BitArray (and for a negative index)
+    for (int64_t k = 0; k < n_filter; k++)
+        if (filter_start[k] < filter_stop[k] && (filter_start[k] < 0 || filter_stop[k] > chr_len))
+            return cg_fail(ctx, CG_ERR_ARG, "Index was out of range. Must be non-negative and less than the size of the collection.");
+    CG_CUDA(ctx, cudaSetDevice(ctx->device));
+    const long long nwords = (chr_len + 63) / 64;
+    int rc = arena_reserve(ctx, arena_need(nwords * 64, 1) + arena_need(nwords, 8) + arena_need(n_filter + 1, 4) * 2 + (1 << 16));
+    if (rc) return rc;
+    unsigned long long* d_hits8 = arena_take<unsigned long long>(ctx, nwords * 8);
+    unsigned long long* d_bits = arena_take<unsigned long long>(ctx, nwords);
+    int32_t* d_fs = arena_take<int32_t>(ctx, n_filter + 1);
+    int32_t* d_fe = arena_take<int32_t>(ctx, n_filter + 1);
+    unsigned long long* d_counts = arena_take<unsigned long long>(ctx, 2);
+    if (!d_hits8 || !d_bits || !d_fs || !d_fe || !d_counts) return cg_fail(ctx, CG_ERR_CUDA, "cg_bin_screen: device arena exhausted");
+    cudaStream_t s = ctx->stream;
+    CG_CUDA(ctx, cudaMemcpyAsync(d_hits8, hits, chr_len, cudaMemcpyHostToDevice, s));
+    CG_CUDA(ctx, cudaMemcpyAsync(d_bits, possible_bits, nwords * 8, cudaMemcpyHostToDevice, s));
+    if (n_filter) {
+        CG_CUDA(ctx, cudaMemcpyAsync(d_fs, filter_start, n_filter * 4, cudaMemcpyHostToDevice, s));
+        CG_CUDA(ctx, cudaMemcpyAsync(d_fe, filter_stop, n_filter * 4, cudaMemcpyHostToDevice, s));
+    }
+    CG_CUDA(ctx, cudaMemsetAsync(d_counts, 0, 16, s));
+    CG_CUDA(ctx, cudaEventRecord(ctx->ev0, s));
+    if (n_filter) CG_LAUNCH(ctx, bin_filter_clear_kernel, div_up(n_filter * 32, 256), 256, 0, d_bits, d_fs, d_fe, (long long)n_filter);
+    CG_LAUNCH(ctx, bin_screen_kernel, (int)std::min<long long>(ctx->num_sms * 8, div_up(nwords, 256)), 256, 0, d_hits8, d_bits, nwords,
+              (long long)chr_len, d_counts);
+    CG_CUDA(ctx, cudaEventRecord(ctx->ev1, s));
+    unsigned long long h_counts[2] = {0, 0};
+    CG_CUDA(ctx, cudaMemcpyAsync(hits, d_hits8, chr_len, cudaMemcpyDeviceToHost, s));
+    CG_CUDA(ctx, cudaMemcpyAsync(possible_bits, d_bits, nwords * 8, cudaMemcpyDeviceToHost, s));
+    CG_CUDA(ctx, cudaMemcpyAsync(h_counts, d_counts, 16, cudaMemcpyDeviceToHost, s));
+    CG_CUDA(ctx, cudaStreamSynchronize(s));
+    CG_CUDA(ctx, cudaGetLastError());
+    CG_CHECK_LAUNCHES(ctx);
+    *n_observed = (int64_t)h_counts[0];
+    *n_possible = (int64_t)h_counts[1];
+    float ms = 0;
+    cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+    ctx->last_kernel_ms = ms;
+    return CG_OK;
+}
 
 extern "C" int cg_bin_hits(cg_ctx* ctx, int64_t chr_len, const uint8_t* hits, const uint64_t* possible_bits, const char* bases,
                            int bin_size, int mode, const uint8_t* read_gc, const float* obs_vs_exp_gc, int64_t max_bins,

@@ -90,6 +90,7 @@ SIGNATURES = {
                                      _P(_i64), _P(_i32), _P(_f32), _P(_f32), _P(_f64)]),
     "cg_cbs_boundary": (_i64, [C.c_uint32, C.c_double, C.c_double, _P(C.c_uint32), _i64]),
     "cg_cbs_prune": (C.c_int, [_P(_f64), _i64, _P(_i32), C.c_int, C.c_double, _i64, _P(_i32), _P(_i64)]),
+    "cg_bin_screen": (C.c_int, [C.c_void_p, _i64, _P(_u8), _P(C.c_uint64), _i64, _P(_i32), _P(_i32), _P(_i64), _P(_i64)]),
     "cg_bin_hits": (C.c_int, [C.c_void_p, _i64, _P(_u8), _P(C.c_uint64), C.c_char_p, C.c_int, C.c_int, _P(_u8),
                               _P(_f32), _i64, _P(_i64), _P(_i32), _P(_i32), _P(_i32), _P(_u8)]),
     "cg_bin_fragments": (C.c_int, [C.c_void_p, _i64, _P(_i32), _P(_i32), _i64, _P(_i32), _i64, _P(_i32), _P(_i32),
@@ -562,6 +563,25 @@ class Engine:
         return d
 
     # ------------------------------------------------------------------ CanvasBin counting
+    def bin_screen(self, hits, possible, filter_start=(), filter_stop=()):
+        """ExcludeTagsOverlappingFilterFile + ScreenObservedTags + the counts of GetRates on one chromosome.
+        hits: uint8[len]; possible: bool[len].  Returns the screened copies and the two counts."""
+        h = np.array(hits, np.uint8)
+        n = len(h)
+        pos = np.asarray(possible, bool)
+        if len(pos) != n:
+            raise ValueError("hits and possible must have one entry per position")
+        words = np.packbits(np.concatenate([pos, np.zeros((-n) % 64, bool)]), bitorder="little").view(np.uint64).copy() if n else np.zeros(1, np.uint64)
+        fs = np.ascontiguousarray(filter_start, np.int32)
+        fe = np.ascontiguousarray(filter_stop, np.int32)
+        obs, npos = C.c_int64(0), C.c_int64(0)
+        rc = self.lib.cg_bin_screen(self.h, n, _ptr(h, _u8), _ptr(words, C.c_uint64), len(fs), _ptr(fs, _i32), _ptr(fe, _i32),
+                                    C.byref(obs), C.byref(npos))
+        self._check(rc)
+        out_pos = np.unpackbits(words.view(np.uint8), bitorder="little")[:n].astype(bool)
+        return {"hits": h, "possible": out_pos, "observed": obs.value, "n_possible": npos.value,
+                "kernel_ms": self.lib.cg_last_kernel_ms(self.h)}
+
     def bin_hits(self, hits, possible, bases, bin_size, mode=0, read_gc=None, obs_vs_exp_gc=None):
         """hits: uint8[len]; possible: bool[len]; bases: bytes of length len."""
         hits = np.ascontiguousarray(hits, np.uint8)

@@ -255,11 +255,20 @@ int cg_smooth(cg_ctx* ctx, int max_half_window, int n_chrom, const int64_t* chro
  * in position order (mode 1, GCContentWeighted :626-636); gc = (int)(100f * GC / length) (:638).  The
  * trailing incomplete bin is dropped as in the reference.  Outputs need capacity max_bins.
  *
+ * cg_bin_screen — the passes over one chromosome's positions that precede the binning: ExcludeTagsOverlappingFilterFile
+ * (CanvasBin.cs:668-692: possible[i] = false inside every filter interval [start, stop); an interval reaching past the
+ * chromosome is the reference's ArgumentOutOfRangeException -> CG_ERR_ARG), ScreenObservedTags (:699-716: hits[i] = 0
+ * where position i is not possible) and the two counts behind the chromosome's rate in GetRates (:56-58): positions with
+ * hits[i] > 0 and possible positions.  hits and possible_bits are updated in place.  The host takes the median of
+ * observed / possible over the autosomes and bin size = (int)(countsPerBin / median) (:79-83).
+ *
  * cg_bin_fragments — FragmentBinner.BinOneAlignment / FindBestBin (FragmentBinner.cs:296-311, :353-371):
  * fragment i = [frag_start, frag_stop) goes to the bin (sorted, non-overlapping) with the largest
  * overlap, the first one on ties; best_bin[i] = -1 when none.  undo_index lists fragments whose mate
  * later failed the duplicate / QC / MAPQ filters (:279-284): their bin is decremented again.
  * ------------------------------------------------------------------------------------------- */
+int cg_bin_screen(cg_ctx* ctx, int64_t chr_len, uint8_t* hits, uint64_t* possible_bits, int64_t n_filter,
+                  const int32_t* filter_start, const int32_t* filter_stop, int64_t* n_observed, int64_t* n_possible);
 int cg_bin_hits(cg_ctx* ctx, int64_t chr_len, const uint8_t* hits, const uint64_t* possible_bits, const char* bases,
                 int bin_size, int mode, const uint8_t* read_gc, const float* obs_vs_exp_gc, int64_t max_bins,
                 int64_t* n_bins, int32_t* start, int32_t* stop, int32_t* count, uint8_t* gc);

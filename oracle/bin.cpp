@@ -1,5 +1,7 @@
 // ORACLE — test infrastructure only (never linked into or called by the product path).
 // CPU restatement of CanvasBin's two counting loops:
+//   ora_bin_screen      CanvasBin.cs:668-692 (ExcludeTagsOverlappingFilterFile), :699-716 (ScreenObservedTags), :56-58 with
+//                       HitArray.cs:24-32 and CanvasBin.cs:147-157 (the two counts behind a chromosome's rate)
 //   ora_bin_hits        CanvasBin.cs:568-661  (BinCountsForChromosome, no predefined bins)
 //   ora_bin_alignments  FragmentBinner.cs:256-371 (BinOneAlignment + FindBestBin, sequential, with the
 //                       read-name dictionary exactly as the reference keeps it)
@@ -95,4 +97,19 @@ extern "C" int64_t ora_bin_alignments(int64_t n, const uint8_t* flags, const int
         if (best >= 0) { usable++; count[best]++; name_to_bin[name_id[i]] = best; }
     }
     return usable;
+}
+
+extern "C" void ora_bin_screen(int64_t len, uint8_t* hits, uint8_t* possible, int64_t n_filter, const int32_t* filter_start,
+                               const int32_t* filter_stop, int64_t* n_observed, int64_t* n_possible) {
+    for (int64_t k = 0; k < n_filter; k++)
+        for (int64_t i = filter_start[k]; i < filter_stop[k]; i++) possible[i] = 0;
+    for (int64_t i = 0; i < len; i++)
+        if (!possible[i]) hits[i] = 0;
+    int64_t obs = 0, pos = 0;
+    for (int64_t i = 0; i < len; i++) {
+        if (hits[i] > 0) obs++;
+        if (possible[i]) pos++;
+    }
+    *n_observed = obs;
+    *n_possible = pos;
 }

@@ -87,6 +87,9 @@ int ora_normalize_best_lr2(int n_controls, int64_t n, const double* sample, cons
 /* PCAReferenceGenerator.Run; -1 when the axes are not orthogonal. */
 int ora_normalize_pca_reference(int64_t n, int n_axes, const float* sample, const float* mu, const double* axes, const uint8_t* on_target,
                                 double min_ref, double max_ref, float* reference, double* median_ratio);
+/* CanvasBin pre-binning passes on one chromosome (possible = one byte per position); arrays are modified in place. */
+void ora_bin_screen(int64_t len, uint8_t* hits, uint8_t* possible, int64_t n_filter, const int32_t* filter_start,
+                    const int32_t* filter_stop, int64_t* n_observed, int64_t* n_possible);
 /* CanvasSmooth (oracle/smooth.cpp): Utilities.MedianFilter and the repeated filter; return the output length (<= n). */
 int64_t ora_median_filter(int64_t n, const float* in, uint32_t half_window, float* out);
 int64_t ora_repeated_median_filter(int64_t n, const float* in, uint32_t max_half_window, float* out);

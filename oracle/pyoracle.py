@@ -494,3 +494,15 @@ def normalize_pca_reference(sample, mu, axes, on_target=None, min_ref=1.0, max_r
     if rc != 0:
         return None
     return {"reference": ref[:n], "median_ratio": med.value}
+
+
+def bin_screen(hits, possible, filter_start=(), filter_stop=()):
+    """ExcludeTagsOverlappingFilterFile + ScreenObservedTags + the counts of GetRates on one chromosome."""
+    h = np.array(hits, np.uint8)
+    p = np.array(possible, np.uint8)
+    fs = np.ascontiguousarray(filter_start, np.int32)
+    fe = np.ascontiguousarray(filter_stop, np.int32)
+    obs, pos = C.c_int64(0), C.c_int64(0)
+    lib().ora_bin_screen(C.c_int64(len(h)), _p(h, C.c_uint8), _p(p, C.c_uint8), C.c_int64(len(fs)), _p(fs, C.c_int32), _p(fe, C.c_int32),
+                         C.byref(obs), C.byref(pos))
+    return {"hits": h, "possible": p.astype(bool), "observed": obs.value, "n_possible": pos.value}

@@ -103,3 +103,27 @@ def test_bin_fragments_reference_cases(eng):
             got = binning.bin_paired_alignments(eng, flags, [pos1, pos2], [pos2, pos1], [0, 0], [0, 0], [100, -100], [mq1, mq2],
                                                 ["ReadName", "ReadName"], 3, [100], [200])
             assert got["count"].tolist() == [expect]
+
+
+@pytest.mark.parametrize("n,n_filter", [(1000, 0), (64, 3), (100003, 40), (5000000, 2000), (7, 1)])
+def test_bin_screen_matches_oracle(eng, n, n_filter):
+    rng = np.random.default_rng(n + n_filter)
+    hits = np.where(rng.random(n) < 0.3, rng.integers(1, 256, n), 0).astype(np.uint8)
+    possible = rng.random(n) < 0.8
+    fs = rng.integers(0, n, n_filter).astype(np.int32)
+    fe = np.minimum(n, fs + rng.integers(0, max(2, min(n, 700)), n_filter)).astype(np.int32)
+    if n_filter > 2:
+        fe[1] = fs[1]                      # empty interval
+        fs[2], fe[2] = 0, min(n, 200)      # overlaps whatever else starts there
+    want = pyoracle.bin_screen(hits, possible, fs, fe)
+    got = eng.bin_screen(hits, possible, fs, fe)
+    assert np.array_equal(want["possible"], got["possible"])
+    assert np.array_equal(want["hits"], got["hits"])
+    assert (want["observed"], want["n_possible"]) == (got["observed"], got["n_possible"])
+
+
+def test_bin_screen_rejects_intervals_past_the_end(eng):
+    with pytest.raises(native.CanvasGpuError):
+        eng.bin_screen(np.zeros(100, np.uint8), np.ones(100, bool), [90], [101])
+    r = eng.bin_screen(np.zeros(0, np.uint8), np.zeros(0, bool))
+    assert (r["observed"], r["n_possible"]) == (0, 0)

@@ -66,3 +66,16 @@ def test_bin_hits_weighted_rounding():
 def test_hit_array_saturates():
     h = binning.hit_array(4, [1] * 300 + [3])
     assert h.tolist() == [0, 255, 0, 1]
+
+
+def test_bin_screen_by_hand():
+    hits = np.array([1, 0, 3, 2, 0, 5, 1, 1], np.uint8)
+    possible = np.array([1, 1, 0, 1, 1, 1, 0, 1], bool)
+    r = pyoracle.bin_screen(hits, possible, [4], [6])           # the filter interval [4, 6) removes two possible positions
+    assert r["possible"].tolist() == [True, True, False, True, False, False, False, True]
+    assert r["hits"].tolist() == [1, 0, 0, 2, 0, 0, 0, 1]
+    assert (r["observed"], r["n_possible"]) == (3, 4)
+    # GetBinSize (CanvasBin.cs:79-83): (int)(countsPerBin / median rate), mean of the middles for an even count
+    assert binning.bin_size_from_rates(100, [0.5, 0.25, 0.1]) == 400
+    assert binning.bin_size_from_rates(100, [0.5, 0.25]) == 266
+    assert binning.bin_size_from_rates(100, [0.0]) == -2 ** 31
