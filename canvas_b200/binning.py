@@ -96,3 +96,23 @@ def bin_size_from_rates(counts_per_bin, rates):
     if q != q or abs(q) >= 2.0 ** 31:
         return -2 ** 31  # (int) of NaN, an infinity or an out-of-range double: 0x80000000 on x64 .NET
     return int(q)
+
+
+def mean_fragment_size(stats):
+    """MeanFragmentSize (CanvasBin.cs:164-174): NonZeroMean over the chromosomes of their NonZeroMean fragment length;
+    stats = [(sum, count)] per chromosome from Engine.bin_fragment_stats."""
+    means = [s // c if c else 0 for s, c in stats]       # Convert.ToInt16(sum / counter): integer division of longs
+    pos = [m for m in means if m > 0]
+    return sum(pos) // len(pos) if pos else 0
+
+
+def observed_vs_expected_gc(expected, observed):
+    """The ratio table of ComputeObservedVsExpectedGC (CanvasBin.cs:374-387), single precision as in the reference."""
+    import numpy as np
+    exp = np.array(expected, np.int64)
+    obs = np.array(observed, np.int64)
+    sum_obs, sum_exp = int(obs.sum()), int(exp.sum())      # taken before the zero counts are replaced by 1
+    exp[exp == 0] = 1
+    obs[obs == 0] = 1
+    with np.errstate(divide="ignore", invalid="ignore"):
+        return (obs.astype(np.float32) / exp.astype(np.float32)) * (np.float32(sum_exp) / np.float32(sum_obs))

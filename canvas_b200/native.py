@@ -91,6 +91,8 @@ SIGNATURES = {
     "cg_cbs_boundary": (_i64, [C.c_uint32, C.c_double, C.c_double, _P(C.c_uint32), _i64]),
     "cg_cbs_prune": (C.c_int, [_P(_f64), _i64, _P(_i32), C.c_int, C.c_double, _i64, _P(_i32), _P(_i64)]),
     "cg_bin_screen": (C.c_int, [C.c_void_p, _i64, _P(_u8), _P(C.c_uint64), _i64, _P(_i32), _P(_i32), _P(_i64), _P(_i64)]),
+    "cg_bin_fragment_stats": (C.c_int, [C.c_void_p, _i64, _P(C.c_int16), _P(_i64), _P(_i64)]),
+    "cg_bin_read_gc": (C.c_int, [C.c_void_p, _i64, C.c_char_p, _P(C.c_int16), C.c_int, _P(_u8), _P(_u8), _P(_i64), _P(_i64)]),
     "cg_bin_hits": (C.c_int, [C.c_void_p, _i64, _P(_u8), _P(C.c_uint64), C.c_char_p, C.c_int, C.c_int, _P(_u8),
                               _P(_f32), _i64, _P(_i64), _P(_i32), _P(_i32), _P(_i32), _P(_u8)]),
     "cg_bin_fragments": (C.c_int, [C.c_void_p, _i64, _P(_i32), _P(_i32), _i64, _P(_i32), _i64, _P(_i32), _P(_i32),
@@ -581,6 +583,30 @@ class Engine:
         out_pos = np.unpackbits(words.view(np.uint8), bitorder="little")[:n].astype(bool)
         return {"hits": h, "possible": out_pos, "observed": obs.value, "n_possible": npos.value,
                 "kernel_ms": self.lib.cg_last_kernel_ms(self.h)}
+
+    def bin_fragment_stats(self, frag_len):
+        """Sum and number of the positive fragment lengths of one chromosome (Utilities.NonZeroMean)."""
+        f = np.ascontiguousarray(frag_len, np.int16)
+        s, c = C.c_int64(0), C.c_int64(0)
+        self._check(self.lib.cg_bin_fragment_stats(self.h, len(f), _ptr(f, C.c_int16), C.byref(s), C.byref(c)))
+        return s.value, c.value
+
+    def bin_read_gc(self, bases, frag_len, mean_frag, hits, expected=None, observed=None):
+        """Read GC content per position and the chromosome's expected / observed read counts per GC bin, added to the
+        int64[101] arrays passed in (new ones when omitted)."""
+        b = bytes(bases)
+        f = np.ascontiguousarray(frag_len, np.int16)
+        h = np.ascontiguousarray(hits, np.uint8)
+        n = len(b)
+        if len(f) != n or len(h) != n:
+            raise ValueError("bases, fragment lengths and hits must have one entry per position")
+        gc = np.zeros(max(n, 1), np.uint8)
+        exp = np.zeros(101, np.int64) if expected is None else expected
+        obs = np.zeros(101, np.int64) if observed is None else observed
+        rc = self.lib.cg_bin_read_gc(self.h, n, b, _ptr(f, C.c_int16), int(mean_frag), _ptr(h, _u8), _ptr(gc, _u8), _ptr(exp, _i64),
+                                     _ptr(obs, _i64))
+        self._check(rc)
+        return {"read_gc": gc[:n], "expected": exp, "observed": obs, "kernel_ms": self.lib.cg_last_kernel_ms(self.h)}
 
     def bin_hits(self, hits, possible, bases, bin_size, mode=0, read_gc=None, obs_vs_exp_gc=None):
         """hits: uint8[len]; possible: bool[len]; bases: bytes of length len."""

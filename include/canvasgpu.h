@@ -262,6 +262,14 @@ int cg_smooth(cg_ctx* ctx, int max_half_window, int n_chrom, const int64_t* chro
  * hits[i] > 0 and possible positions.  hits and possible_bits are updated in place.  The host takes the median of
  * observed / possible over the autosomes and bin size = (int)(countsPerBin / median) (:79-83).
  *
+ * cg_bin_fragment_stats / cg_bin_read_gc — the tables of the GCContentWeighted mode.  fragment_stats: sum and number of the
+ * positive fragment lengths of one chromosome (Utilities.NonZeroMean, CanvasCommon/Utilities.cs:136-151; MeanFragmentSize,
+ * CanvasBin.cs:164-174, is the host's integer division of the two, then the same mean over the chromosomes' means).
+ * read_gc: GC content (0..100) of the read that starts at every position — fragment length frag_len[p], or mean_frag where
+ * it is 0, at most 3 * mean_frag; positions from len - 3 * mean_frag - 1 on stay 0 (:450-497) — written to read_gc[len], and
+ * this chromosome's share of expectedReadCountsByGC / observedReadCountsByGC ADDED to expected[101] / observed[101]
+ * (ComputeObservedVsExpectedGC :341-358; the 101 ratios are host arithmetic, :374-387).  mean_frag in 1..10922.
+ *
  * cg_bin_fragments — FragmentBinner.BinOneAlignment / FindBestBin (FragmentBinner.cs:296-311, :353-371):
  * fragment i = [frag_start, frag_stop) goes to the bin (sorted, non-overlapping) with the largest
  * overlap, the first one on ties; best_bin[i] = -1 when none.  undo_index lists fragments whose mate
@@ -269,6 +277,9 @@ int cg_smooth(cg_ctx* ctx, int max_half_window, int n_chrom, const int64_t* chro
  * ------------------------------------------------------------------------------------------- */
 int cg_bin_screen(cg_ctx* ctx, int64_t chr_len, uint8_t* hits, uint64_t* possible_bits, int64_t n_filter,
                   const int32_t* filter_start, const int32_t* filter_stop, int64_t* n_observed, int64_t* n_possible);
+int cg_bin_fragment_stats(cg_ctx* ctx, int64_t len, const int16_t* frag_len, int64_t* sum, int64_t* count);
+int cg_bin_read_gc(cg_ctx* ctx, int64_t len, const char* bases, const int16_t* frag_len, int mean_frag, const uint8_t* hits,
+                   uint8_t* read_gc, int64_t* expected, int64_t* observed);
 int cg_bin_hits(cg_ctx* ctx, int64_t chr_len, const uint8_t* hits, const uint64_t* possible_bits, const char* bases,
                 int bin_size, int mode, const uint8_t* read_gc, const float* obs_vs_exp_gc, int64_t max_bins,
                 int64_t* n_bins, int32_t* start, int32_t* stop, int32_t* count, uint8_t* gc);

@@ -2,6 +2,8 @@
 // CPU restatement of CanvasBin's two counting loops:
 //   ora_bin_screen      CanvasBin.cs:668-692 (ExcludeTagsOverlappingFilterFile), :699-716 (ScreenObservedTags), :56-58 with
 //                       HitArray.cs:24-32 and CanvasBin.cs:147-157 (the two counts behind a chromosome's rate)
+//   ora_bin_read_gc     CanvasBin.cs:450-497 (GC content of the read at every position, counted base by base as the reference does)
+//                       and :341-358 (expected / observed read counts per GC bin)
 //   ora_bin_hits        CanvasBin.cs:568-661  (BinCountsForChromosome, no predefined bins)
 //   ora_bin_alignments  FragmentBinner.cs:256-371 (BinOneAlignment + FindBestBin, sequential, with the
 //                       read-name dictionary exactly as the reference keeps it)
@@ -112,4 +114,29 @@ extern "C" void ora_bin_screen(int64_t len, uint8_t* hits, uint8_t* possible, in
     }
     *n_observed = obs;
     *n_possible = pos;
+}
+
+extern "C" void ora_bin_read_gc(int64_t len, const char* bases, const int16_t* frag_len, int mean_frag, const uint8_t* hits, uint8_t* read_gc,
+                                int64_t* expected, int64_t* observed) {
+    const int cutoff = 3;
+    for (int64_t i = 0; i < len; i++) read_gc[i] = 0;
+    uint32_t gc_counter = 0;
+    for (int64_t pos = 0; pos < len - (int64_t)mean_frag * cutoff - 1; pos++) {
+        int16_t current = 0;
+        if (frag_len[pos] == 0) current = (int16_t)mean_frag;
+        else current = (int16_t)std::min<int>(frag_len[pos], mean_frag * cutoff);
+        for (int64_t i = pos; i < pos + current; i++) {
+            switch (bases[i]) {
+                case 'C': case 'c': case 'G': case 'g': gc_counter++; break;
+                default: break;
+            }
+        }
+        const int64_t v = (int64_t)100 * (int64_t)gc_counter / (int64_t)current;
+        read_gc[pos] = (uint8_t)std::min<int64_t>(v, 101);
+        gc_counter = 0;
+    }
+    for (int64_t i = 0; i < len; i++) {
+        expected[read_gc[i]]++;
+        observed[read_gc[i]] += hits[i];
+    }
 }

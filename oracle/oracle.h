@@ -90,6 +90,9 @@ int ora_normalize_pca_reference(int64_t n, int n_axes, const float* sample, cons
 /* CanvasBin pre-binning passes on one chromosome (possible = one byte per position); arrays are modified in place. */
 void ora_bin_screen(int64_t len, uint8_t* hits, uint8_t* possible, int64_t n_filter, const int32_t* filter_start,
                     const int32_t* filter_stop, int64_t* n_observed, int64_t* n_possible);
+/* GCContentWeighted tables of one chromosome: read GC per position; expected / observed [101] are accumulated (+=). */
+void ora_bin_read_gc(int64_t len, const char* bases, const int16_t* frag_len, int mean_frag, const uint8_t* hits, uint8_t* read_gc,
+                     int64_t* expected, int64_t* observed);
 /* CanvasSmooth (oracle/smooth.cpp): Utilities.MedianFilter and the repeated filter; return the output length (<= n). */
 int64_t ora_median_filter(int64_t n, const float* in, uint32_t half_window, float* out);
 int64_t ora_repeated_median_filter(int64_t n, const float* in, uint32_t max_half_window, float* out);

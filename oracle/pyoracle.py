@@ -506,3 +506,16 @@ def bin_screen(hits, possible, filter_start=(), filter_stop=()):
     lib().ora_bin_screen(C.c_int64(len(h)), _p(h, C.c_uint8), _p(p, C.c_uint8), C.c_int64(len(fs)), _p(fs, C.c_int32), _p(fe, C.c_int32),
                          C.byref(obs), C.byref(pos))
     return {"hits": h, "possible": p.astype(bool), "observed": obs.value, "n_possible": pos.value}
+
+
+def bin_read_gc(bases, frag_len, mean_frag, hits):
+    """Read GC content per position (CanvasBin.cs:450-497) and the chromosome's expected / observed counts per GC bin (:341-358)."""
+    b = bytes(bases)
+    f = np.ascontiguousarray(frag_len, np.int16)
+    h = np.ascontiguousarray(hits, np.uint8)
+    n = len(b)
+    gc = np.zeros(max(n, 1), np.uint8)
+    exp = np.zeros(101, np.int64); obs = np.zeros(101, np.int64)
+    lib().ora_bin_read_gc(C.c_int64(n), b, _p(f, C.c_int16), C.c_int(mean_frag), _p(h, C.c_uint8), _p(gc, C.c_uint8),
+                          _p(exp, C.c_int64), _p(obs, C.c_int64))
+    return {"read_gc": gc[:n], "expected": exp, "observed": obs}

@@ -127,3 +127,29 @@ def test_bin_screen_rejects_intervals_past_the_end(eng):
         eng.bin_screen(np.zeros(100, np.uint8), np.ones(100, bool), [90], [101])
     r = eng.bin_screen(np.zeros(0, np.uint8), np.zeros(0, bool))
     assert (r["observed"], r["n_possible"]) == (0, 0)
+
+
+@pytest.mark.parametrize("n,mean", [(5000, 150), (100003, 300), (4097, 1), (2000000, 420), (700, 400)])
+def test_read_gc_matches_oracle(eng, n, mean):
+    rng = np.random.default_rng(n + mean)
+    bases = rng.choice(np.frombuffer(b"ACGTacgtNn", np.uint8), size=n, p=[.2, .2, .2, .2, .04, .04, .04, .04, .02, .02]).tobytes()
+    frag = np.where(rng.random(n) < 0.3, rng.integers(-20, 5 * mean + 2, n), 0).astype(np.int16)
+    hits = np.where(rng.random(n) < 0.3, rng.integers(1, 256, n), 0).astype(np.uint8)
+    if n > 200000:  # the oracle counts every fragment base by base: keep it to seconds
+        frag = np.minimum(frag, 60).astype(np.int16)
+        mean = 20
+    want = pyoracle.bin_read_gc(bases, frag, mean, hits)
+    got = eng.bin_read_gc(bases, frag, mean, hits)
+    assert np.array_equal(want["read_gc"], got["read_gc"])
+    assert np.array_equal(want["expected"], got["expected"]) and np.array_equal(want["observed"], got["observed"])
+    # the histograms accumulate over chromosomes
+    again = eng.bin_read_gc(bases, frag, mean, hits, got["expected"], got["observed"])
+    assert np.array_equal(again["expected"], 2 * want["expected"]) and np.array_equal(again["observed"], 2 * want["observed"])
+    s, c = eng.bin_fragment_stats(frag)
+    assert (s, c) == (int(frag[frag > 0].astype(np.int64).sum()), int((frag > 0).sum()))
+
+
+def test_read_gc_rejects_bad_mean(eng):
+    with pytest.raises(native.CanvasGpuError):
+        eng.bin_read_gc(b"ACGT", np.zeros(4, np.int16), 0, np.zeros(4, np.uint8))
+    assert eng.bin_fragment_stats(np.zeros(0, np.int16)) == (0, 0)

@@ -79,3 +79,20 @@ def test_bin_screen_by_hand():
     assert binning.bin_size_from_rates(100, [0.5, 0.25, 0.1]) == 400
     assert binning.bin_size_from_rates(100, [0.5, 0.25]) == 266
     assert binning.bin_size_from_rates(100, [0.0]) == -2 ** 31
+
+
+def test_read_gc_by_hand():
+    # mean fragment 2, cutoff 3: positions 0 .. len - 7 - 1 get a value
+    bases = b"GGCCAATTGCATATATAT"
+    frag = np.zeros(len(bases), np.int16)
+    frag[1] = 4      # own length
+    frag[2] = 100    # capped at 3 * mean = 6
+    frag[3] = -5     # negative: no base is counted
+    r = pyoracle.bin_read_gc(bases, frag, 2, np.ones(len(bases), np.uint8))
+    n_set = len(bases) - 2 * 3 - 1
+    assert r["read_gc"][:4].tolist() == [100, 75, 33, 0]          # GG | GCCA | CCAATT -> 2/6 | nothing
+    assert r["read_gc"][n_set:].tolist() == [0] * (len(bases) - n_set)
+    assert r["expected"].sum() == len(bases) and r["observed"].sum() == len(bases)
+    assert binning.mean_fragment_size([(1000, 4), (0, 0), (900, 3)]) == 275
+    t = binning.observed_vs_expected_gc(r["expected"], 2 * r["expected"])
+    assert t.dtype == np.float32 and np.allclose(t[r["expected"] > 0], 1.0) and np.allclose(t[r["expected"] == 0], 0.5)
