@@ -156,7 +156,7 @@ struct RatioEmit {
 };
 
 // BestLR2: squared log ratios of the median-normalised sample (row n_controls of `counts`) against every control over
-// the on-target bins.  Block (chunk, control) adds its chunk in index order; the chunk sums are added in chunk order by
+// the on-target bins.  Block (chunk, control) adds its chunk in a fixed order; the chunk sums are added in chunk order by
 // lr2_finish_kernel: deterministic, but not the reference's single left-to-right sum (agreement better than 1e-9 relative).
 constexpr int LR2_CHUNK = 8192;
 struct Lr2Partial {
@@ -173,12 +173,11 @@ __global__ void __launch_bounds__(256) lr2_partial_kernel(const double* __restri
     const double wt = mt > 0 ? __ddiv_rn(1.0, mt) : 0.0, wc = mc > 0 ? __ddiv_rn(1.0, mc) : 0.0;
     const double* __restrict__ t = counts + (size_t)n_controls * n;
     const double* __restrict__ c = counts + (size_t)ctrl * n;
-    // thread k owns a contiguous run of the chunk: its partial is a left-to-right sum, and so is the sum over threads
-    constexpr int PER = LR2_CHUNK / 256;
+    // thread k takes every 256th element of the chunk (coalesced rows); its partial and the sum over threads are added in
+    // a fixed order
     double sum = 0.0;
     long long used = 0, ign = 0;
-    const long long a = lo + (long long)threadIdx.x * PER;
-    for (long long i = a; i < min(hi, a + PER); i++) {
+    for (long long i = lo + threadIdx.x; i < hi; i += 256) {
         if (on_target && !on_target[i]) continue;
         const double normal = __dmul_rn(c[i], wc);
         if (normal <= 0) { ign++; continue; }  // NaN is not <= 0: it goes on and is dropped by the test below
@@ -244,10 +243,8 @@ __global__ void __launch_bounds__(256) dot_partial_kernel(const double* __restri
     const int pr = blockIdx.y;
     const int ia = pairs.ia[pr], ib = pairs.ib[pr];
     const long long lo = (long long)blockIdx.x * DOT_CHUNK, hi = min(n, lo + DOT_CHUNK);
-    constexpr int PER = DOT_CHUNK / 256;
-    const long long a0 = lo + (long long)threadIdx.x * PER;
     double sum = 0.0;
-    for (long long i = a0; i < min(hi, a0 + PER); i++) {
+    for (long long i = lo + threadIdx.x; i < hi; i += 256) {  // coalesced rows; fixed order of additions
         const double x = ia < 0 ? pca_centred(sample, mu, i) : rows[(size_t)ia * n + i];
         const double y = ib < 0 ? pca_centred(sample, mu, i) : rows[(size_t)ib * n + i];
         sum = __dadd_rn(sum, __dmul_rn(x, y));
