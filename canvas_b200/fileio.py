@@ -197,6 +197,29 @@ def split_overlapping_segments(per_sample):
     return result
 
 
+def on_target_mask(names, chrom, start, stop, regions_by_chrom):
+    """The on-target flags of BinCounts.LoadBinCounts (CanvasNormalize/BinCounts.cs:102-160): bins in file order, manifest
+    regions per chromosome as sorted 1-based (start, end) pairs.  A bin is on target when the first region of its chromosome
+    that does not end before the bin's first base (End >= bin.Start + 1) starts at or before its last base
+    (Start <= bin.Stop); the region cursor only moves forward and restarts when the chromosome NAME changes.  The result is
+    the `on_target` argument of cg_normalize_reference / cg_normalize_best_lr2 / cg_normalize_ratio."""
+    import numpy as np
+    out = np.zeros(len(chrom), np.uint8)
+    cur, regions, idx = None, None, -1
+    for i, (c, a, b) in enumerate(zip(np.asarray(chrom).tolist(), np.asarray(start).tolist(), np.asarray(stop).tolist())):
+        name = names[c]
+        if name != cur:
+            cur = name
+            regions = regions_by_chrom.get(name)
+            if regions is not None:
+                idx = 0
+        while regions is not None and idx < len(regions) and regions[idx][1] < a + 1:
+            idx += 1
+        if regions is not None and idx < len(regions) and regions[idx][0] <= b:
+            out[i] = 1
+    return out
+
+
 class PloidyInfo:
     """CanvasCommon.PloidyInfo (PloidyInfo.cs:12-178): reference ploidy intervals per chromosome from a ploidy VCF
     (END in INFO, CN in the single genotype column; "." = 2)."""

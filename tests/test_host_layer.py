@@ -231,3 +231,36 @@ def test_ploidy_info_and_ploidy_splits(tmp_path):
     bad.write_text("#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT\tS1\tS2\n")
     with pytest.raises(ValueError):
         fileio.PloidyInfo.load_vcf_no_sample_id(str(bad))
+
+
+def test_on_target_mask_follows_the_reference_walk():
+    # BinCounts.LoadBinCounts (BinCounts.cs:102-160): 1-based regions, 0-based half-open bins
+    names = ["chr1", "chr2", "chr3"]
+    chrom = [0, 0, 0, 0, 1, 1, 2, 0]
+    start = [0, 100, 200, 300, 0, 100, 0, 400]
+    stop = [100, 200, 300, 400, 100, 200, 100, 500]
+    regions = {"chr1": [(150, 180), (301, 310), (450, 460)], "chr3": [(101, 200)]}
+    m = fileio.on_target_mask(names, chrom, start, stop, regions)
+    # chr1: [100,200) holds 150-180; [200,300): the next region starts at 301 > 300 (off); [300,400) holds 301;
+    # chr2 has no regions; chr3's region starts after the bin's last base; the chromosome reappearing restarts its cursor
+    assert m.tolist() == [0, 1, 0, 1, 0, 0, 0, 1]
+    # a region ending exactly on the bin's first base (End == Start + 1) still overlaps; one ending before does not
+    assert fileio.on_target_mask(["c"], [0, 0], [10, 20], [20, 30], {"c": [(5, 11), (12, 20)]}).tolist() == [1, 0]
+
+
+def test_canvas_normalize_argument_handling(tmp_path, capsys):
+    # the checks of CanvasNormalizeParameters.ParseCommandLine (CanvasNormalize/Program.cs:45-148) run before any device work
+    t = tmp_path / "t.binned"
+    t.write_text("chr1\t0\t100\t5\t40\n")
+    assert modules.canvas_normalize_main(["-n", str(t), "-o", str(tmp_path / "o")]) == 1            # no tumour file
+    assert modules.canvas_normalize_main(["-t", str(t), "-o", str(tmp_path / "o")]) == 1            # no normal file
+    assert modules.canvas_normalize_main(["-t", str(t), "-n", str(t)]) == 1                         # no output
+    assert modules.canvas_normalize_main(["-t", str(t), "-n", str(t), "-o", "o", "-r", "5"]) == 1   # -r once
+    assert modules.canvas_normalize_main(["-t", str(tmp_path / "nope"), "-n", str(t), "-o", "o"]) == 1
+    assert modules.canvas_normalize_main(["-t", str(t), "-n", str(t), "-n", str(t), "-o", "o", "-m", "PCA"]) == 1
+    with pytest.raises(modules.UnknownArguments):
+        modules.canvas_normalize_main(["-t", str(t), "--bogus"])
+    with pytest.raises(ValueError):
+        modules.canvas_normalize_main(["-t", str(t), "-n", str(t), "-o", "o", "-m", "Nonsense"])
+    out = capsys.readouterr()
+    assert "Please specify the tumor bed file." in out.err and "does not exist! Exiting." in out.out
