@@ -15,7 +15,9 @@
 //                                                              (AreOrthogonal :685-692, tolerance 1e-4), projection of the centred
 //                                                              sample (Project :700-745), F2 round trip of the temporary reference,
 //                                                              raw ratios, their median, scaled reference
-// Parity unpinned: the reference has no test for CanvasNormalize; restated from source only.
+// Pinned in part: the projection helpers behind the PCA mode (TwoNorm, NormalizeBy2Norm, DotProduct, AreOrthogonal, Project)
+// by CanvasTest/TestUtilities.cs:53-169 through tests/test_normalize_oracle.py.  Parity unpinned for the rest: the reference
+// has no test of the CanvasNormalize classes themselves; restated from source only.
 #include <cmath>
 #include <cstdint>
 #include <limits>

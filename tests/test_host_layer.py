@@ -264,3 +264,21 @@ def test_canvas_normalize_argument_handling(tmp_path, capsys):
         modules.canvas_normalize_main(["-t", str(t), "-n", str(t), "-o", "o", "-m", "Nonsense"])
     out = capsys.readouterr()
     assert "Please specify the tumor bed file." in out.err and "does not exist! Exiting." in out.out
+
+
+def test_ploidy_counts_on_the_reference_ploidy_test_scenarios():
+    # The interval scenarios of CanvasTest/CanvasCommon/ReferencePloidyTests.cs (they exercise the sibling class
+    # ReferencePloidy; PloidyInfo.getPloidyCounts, PloidyInfo.cs:92-109, must split the same one-based intervals the same way)
+    def info(*intervals):
+        p = fileio.PloidyInfo()
+        p.by_chr["chrX"] = list(intervals)
+        return p
+    assert fileio.PloidyInfo().is_uniform("chrX", 1, 2)                                   # EmptyVcf_ReferencePloidyIs2
+    assert info((1, 2, 1))._counts("chrX", 1, 2) == [0, 2, 0, 0, 0]                        # VcfPloidy1AndSameQueryInterval
+    assert info((1, 1, 1))._counts("chrX", 1, 2) == [0, 1, 1, 0, 0]                        # PartialOverlap: ploidy 1 and 2
+    assert not info((1, 1, 1)).is_uniform("chrX", 1, 2)
+    assert info((1, 1, 1), (2, 2, 1)).is_uniform("chrX", 1, 2)                             # two adjacent ploidy-1 intervals
+    assert info((1, 1, 1), (2, 2, 1), (3, 3, 1), (4, 4, 1))._counts("chrX", 1, 4) == [0, 4, 0, 0, 0]
+    assert info((2, 2, 1), (4, 4, 3))._counts("chrX", 1, 5) == [0, 1, 3, 1, 0]             # MultiplePloidyAndLargeQuery
+    assert info((1, 4, 1)).reference_copy_number("chrX", 1, 3) == 1                        # query (2, 3) inside a ploidy-1 region
+    assert info((1, 4, 1)).is_uniform("chrX", 2, 3)

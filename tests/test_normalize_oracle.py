@@ -72,3 +72,43 @@ def test_pca_reference_by_hand():
     assert np.allclose(r["reference"], (ref * med).astype(np.float32), rtol=1e-6)
     # axes that are not orthogonal are refused (PCAModel.LoadModel)
     assert po.normalize_pca_reference(sample, mu, [[1.0, 1.0, 0.0, 0.0], [1.0, 0.0, 0.0, 0.0]]) is None
+
+
+def _helmert_basis(p):
+    # CanvasTest/TestUtilities.cs:125-142 (GetHelmertBasis)
+    axes = []
+    for i in range(1, p + 1):
+        v = np.zeros(p)
+        size = np.sqrt(i + i * i if i < p else i)
+        v[:i] = 1 / size
+        if i < p:
+            v[i] = -i / size
+        axes.append(v)
+    return np.array(axes)
+
+
+def test_pca_projection_pinned_by_the_reference_projection_tests():
+    # TestProject2 (TestUtilities.cs:144-169): projecting onto the complete Helmert basis returns the vector.  Through the
+    # PCA reference generator: mu = 0, so the reference vector is max(1, max(1, sample)) and every raw ratio that survives
+    # the [1, inf) filter is sample / max(1, sample)
+    u = np.arange(10, dtype=np.float32)
+    r = po.normalize_pca_reference(u, np.zeros(10, np.float32), _helmert_basis(10))
+    want = np.maximum(1.0, u)
+    ratios = u / want
+    assert abs(r["median_ratio"] - np.median(ratios.astype(np.float64))) < 1e-12
+    assert np.allclose(r["reference"], want * r["median_ratio"], rtol=1e-6)
+    # axes of any length are scaled to unit length first (TestNormalizeBy2Norm, :65-78): the same answer
+    r2 = po.normalize_pca_reference(u, np.zeros(10, np.float32), _helmert_basis(10) * np.arange(1, 11)[:, None])
+    assert np.allclose(r2["reference"], r["reference"], rtol=1e-6)
+    # TestProject (:106-123): one axis (1, .., 1) / sqrt(10) and the vector e0 project to 1/10 everywhere.
+    # mu = 1 and sample = (2, 1, .., 1) centre to e0: reference vector 1.1, written as "1.10"
+    sample = np.ones(10, np.float32)
+    sample[0] = 2
+    r = po.normalize_pca_reference(sample, np.ones(10, np.float32), [np.ones(10)])
+    ratios = (sample / np.float32(1.1)).astype(np.float64)
+    assert abs(r["median_ratio"] - np.median(ratios)) < 1e-12
+    assert np.allclose(r["reference"], np.float32(1.1 * r["median_ratio"]), rtol=1e-6)
+    # TestAreOrthogonal (:96-104)
+    two = np.array([3.0, 4.0], np.float32)
+    assert po.normalize_pca_reference(two, two, [[1.0, 1.0], [1.0, -1.0]]) is not None
+    assert po.normalize_pca_reference(two, two, [[1.0, 1.0], [1.0, 1.0]]) is None
