@@ -21,6 +21,37 @@ def _open_text(path, mode="rt"):
     return open(path, mode)
 
 
+def gzip_bytes(data, level=6, threads=None, chunk=8 << 20):
+    """One standard single-member gzip stream, deflated by several threads: the reference's writers spend most of a
+    module's wall clock inside zlib (7 s for a 108 MB .binned file at level 6 against milliseconds of device work).
+    Every chunk is deflated on its own (zlib releases the GIL) and ended with a sync flush, which byte-aligns it without
+    a final block, so the pieces concatenate into ONE valid deflate stream (the construction pigz uses); the CRC-32 and
+    length of the whole text close the member.  Any gzip reader (.NET's GZipStream included) reads it as usual."""
+    import os
+    import struct
+    import zlib
+    from concurrent.futures import ThreadPoolExecutor
+    data = bytes(data) if not isinstance(data, (bytes, bytearray, memoryview)) else data
+    n = len(data)
+    threads = threads or min(16, os.cpu_count() or 1)
+    if n <= chunk or threads <= 1:
+        return gzip.compress(bytes(data), compresslevel=level, mtime=0)
+    mv = memoryview(data)
+    cuts = list(range(0, n, chunk)) + [n]
+
+    def deflate(k):
+        c = zlib.compressobj(level, zlib.DEFLATED, -15)
+        out = c.compress(mv[cuts[k]:cuts[k + 1]])
+        return out + c.flush(zlib.Z_FINISH if k == len(cuts) - 2 else zlib.Z_SYNC_FLUSH)
+
+    with ThreadPoolExecutor(max_workers=threads) as ex:
+        crc = ex.submit(zlib.crc32, mv)
+        parts = list(ex.map(deflate, range(len(cuts) - 1)))
+        crc = crc.result()
+    header = b"\x1f\x8b\x08\x00" + struct.pack("<I", 0) + b"\x00\xff"  # deflate, no flags, no mtime, unknown OS
+    return b"".join([header] + parts + [struct.pack("<II", crc & 0xffffffff, n & 0xffffffff)])
+
+
 def _read_bytes(path):
     with open(path, "rb") as f:
         data = f.read()
@@ -41,7 +72,7 @@ def write_binned(path, names, chrom, start, stop, count, gc):
     from . import native
     text = native.format_bins(names, chrom, start, stop, count, gc)
     with open(path, "wb") as f:
-        f.write(gzip.compress(text, compresslevel=6))
+        f.write(gzip_bytes(text))
 
 
 def write_metric(path, name, value):
@@ -341,8 +372,8 @@ def write_partitioned(path, order, segments):
         for seg in segments[c]:
             for a, b, v in sorted(seg["bins"], key=lambda t: t[0]):
                 buf.write(f"{c}\t{a}\t{b}\t{dotnet_double(v)}\t{seg['id']}\n")
-    with gzip.open(path, "wt") as f:
-        f.write(buf.getvalue())
+    with open(path, "wb") as f:
+        f.write(gzip_bytes(buf.getvalue().encode()))
 
 
 def read_cleaned_columns(path):
@@ -384,6 +415,6 @@ def normalize_canvas_clean(engine, cleaned_paths):
         buf = io.StringIO()
         for i, b, t in zip(kept.tolist(), r["stop"].tolist(), txt):
             buf.write(f"{chrom0[i]}\t{int(start0[i])}\t{b}\t{t}\n")
-        with gzip.open(path, "wt") as f:
-            f.write(buf.getvalue())
+        with open(path, "wb") as f:
+            f.write(gzip_bytes(buf.getvalue().encode()))
     return len(kept)

@@ -282,3 +282,25 @@ def test_ploidy_counts_on_the_reference_ploidy_test_scenarios():
     assert info((2, 2, 1), (4, 4, 3))._counts("chrX", 1, 5) == [0, 1, 3, 1, 0]             # MultiplePloidyAndLargeQuery
     assert info((1, 4, 1)).reference_copy_number("chrX", 1, 3) == 1                        # query (2, 3) inside a ploidy-1 region
     assert info((1, 4, 1)).is_uniform("chrX", 2, 3)
+
+
+def test_parallel_gzip_is_one_standard_member():
+    import subprocess
+    import zlib
+    rng = np.random.default_rng(0)
+    lines = [f"chr{1 + i % 22}\t{i * 1000}\t{i * 1000 + 1000}\t{rng.integers(0, 300)}.{rng.integers(0, 100):02d}\t{rng.integers(20, 70)}\n"
+             for i in range(60000)]
+    text = "".join(lines).encode()
+    for chunk, threads in ((1 << 16, 4), (100000, 3), (1 << 30, 4), (1 << 16, 1)):
+        z = fileio.gzip_bytes(text, chunk=chunk, threads=threads)
+        assert gzip.decompress(z) == text
+        d = zlib.decompressobj(31)                 # a single gzip member: nothing is left over after it
+        assert d.decompress(z) == text and d.eof and d.unused_data == b""
+        assert z[:4] == b"\x1f\x8b\x08\x00"
+    assert gzip.decompress(fileio.gzip_bytes(b"")) == b""
+    # the system gzip agrees (when there is one)
+    try:
+        p = subprocess.run(["gzip", "-t"], input=fileio.gzip_bytes(text, chunk=1 << 16, threads=4), capture_output=True)
+        assert p.returncode == 0, p.stderr
+    except FileNotFoundError:
+        pass
