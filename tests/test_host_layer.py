@@ -304,3 +304,44 @@ def test_parallel_gzip_is_one_standard_member():
         assert p.returncode == 0, p.stderr
     except FileNotFoundError:
         pass
+
+
+def test_fast_cleaned_reader_equals_the_line_loop(tmp_path):
+    rng = np.random.default_rng(5)
+    n = 20000
+    chrom = np.sort(rng.integers(0, 5, n))
+    names = ["chr1", "chr2", "chrX", "chrY", "chrM"]
+    start = np.arange(n) * 1000
+    cov_text = [f"{rng.integers(0, 400)}.{rng.integers(0, 100):02d}" for _ in range(n)]
+    cov_text[5], cov_text[6], cov_text[7], cov_text[8] = "1E-05", "1.234568E+07", "0", "123456.78"
+    five = "".join(f"{names[c]}\t{a}\t{a + 1000}\t{t}\t{40 + a % 7}\n" for c, a, t in zip(chrom, start, cov_text))
+    four = "".join(f"{names[c]}\t{a}\t{a + 1000}\t{t}\n" for c, a, t in zip(chrom, start, cov_text))
+    # chromosome that reappears later in the file, CRLF line ends, a blank line
+    tricky = five + "chr1\t0\t10\t5.5\t40\r\n\nchr2\t20\t30\t6.25\t41\n"
+    for k, (body, gz) in enumerate(((five, True), (four, False), (tricky, True))):
+        p = tmp_path / f"f{k}"
+        p.write_bytes(gzip.compress(body.encode()) if gz else body.encode())
+        want = fileio._read_cleaned_rows(str(p))
+        got = fileio.read_cleaned_for_partition(str(p))
+        assert want[0] == got[0]
+        for w, g in zip(want[1:], got[1:]):
+            assert list(w) == list(g)
+            for c in w:
+                assert w[c].dtype == g[c].dtype and np.array_equal(w[c], g[c]), c
+    # padded fields and a -b filter take the line loop; a malformed line raises as before
+    p = tmp_path / "padded"
+    p.write_text(" chr1 \t0\t10\t5.5\t40\n")
+    assert fileio.read_cleaned_for_partition(str(p))[0] == ["chr1"]
+    p.write_text("chr1\tx\t10\t5.5\t40\n")
+    with pytest.raises(ValueError):
+        fileio.read_cleaned_for_partition(str(p))
+
+
+def test_write_partitioned_text(tmp_path):
+    order = ["chr1", "chr2"]
+    segs = {"chr1": [{"id": 0, "bins": [(1000, 2000, 95.5), (0, 1000, 95.02)]}, {"id": 1, "bins": [(2000, 3000, 1e-05)]}],
+            "chr2": [{"id": 2, "bins": [(0, 1000, 100.0), (1000, 2000, 95.02), (2000, 3000, float("nan"))]}]}
+    p = tmp_path / "x.partitioned"
+    fileio.write_partitioned(str(p), order, segs)
+    assert gzip.open(p, "rt").read() == ("chr1\t0\t1000\t95.02\t0\nchr1\t1000\t2000\t95.5\t0\nchr1\t2000\t3000\t1E-05\t1\n"
+                                         "chr2\t0\t1000\t100\t2\nchr2\t1000\t2000\t95.02\t2\nchr2\t2000\t3000\tNaN\t2\n")
