@@ -32,7 +32,7 @@ def test_all_gather_breakpoints_world2():
     s.bind(("127.0.0.1", 0))
     port = s.getsockname()[1]
     s.close()
-    mgr = mp.Manager()
+    mgr = mp.get_context("spawn").Manager()  # no fork() of a process that already runs threads
     ret = mgr.dict()
     mp.spawn(_worker, args=(2, port, ret), nprocs=2, join=True)
     assert ret[0] and ret[1]
@@ -68,7 +68,7 @@ def test_partition_cbs_sharded_world2():
     s.bind(("127.0.0.1", 0))
     port = s.getsockname()[1]
     s.close()
-    mgr = mp.Manager()
+    mgr = mp.get_context("spawn").Manager()  # no fork() of a process that already runs threads
     ret = mgr.dict()
     mp.spawn(_cbs_worker, args=(2, port, ret), nprocs=2, join=True)
     assert ret[0] and ret[1]
@@ -102,7 +102,7 @@ def test_partition_hmm_sharded_world2():
     s.bind(("127.0.0.1", 0))
     port = s.getsockname()[1]
     s.close()
-    mgr = mp.Manager()
+    mgr = mp.get_context("spawn").Manager()  # no fork() of a process that already runs threads
     ret = mgr.dict()
     mp.spawn(_hmm_worker, args=(2, port, ret), nprocs=2, join=True)
     assert ret[0] and ret[1]
