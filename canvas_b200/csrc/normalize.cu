@@ -356,7 +356,8 @@ extern "C" int cg_normalize_reference(cg_ctx* ctx, int n_samples, int64_t n, con
     if (!ctx) return CG_ERR_ARG;
     if (n_samples < 1 || n < 0 || !median || !weight || (n > 0 && (!counts || !reference)))
         return cg_fail(ctx, CG_ERR_ARG, "cg_normalize_reference: bad argument");
-    if (n_samples > 1024) return cg_fail(ctx, CG_ERR_UNSUPPORTED, "cg_normalize_reference: more than 1024 control samples");
+    if (n_samples > 256)  // the selection pass keeps one prefix row per sample in shared memory (48 KB without opt-in)
+        return cg_fail(ctx, CG_ERR_UNSUPPORTED, "cg_normalize_reference: more than 256 control samples");
     if (n > 0x7fff0000LL) return cg_fail(ctx, CG_ERR_UNSUPPORTED, "cg_normalize_reference: too many bins");
     reset_call(ctx);
     CG_CUDA(ctx, cudaSetDevice(ctx->device));
@@ -474,7 +475,7 @@ extern "C" int cg_normalize_best_lr2(cg_ctx* ctx, int n_controls, int64_t n, con
     if (!ctx) return CG_ERR_ARG;
     if (n_controls < 1 || n < 0 || !best_index || !mean_sq_log_ratio || !ignored || (n > 0 && (!sample || !controls)))
         return cg_fail(ctx, CG_ERR_ARG, "cg_normalize_best_lr2: bad argument");
-    if (n_controls > 1023) return cg_fail(ctx, CG_ERR_UNSUPPORTED, "cg_normalize_best_lr2: more than 1023 control samples");
+    if (n_controls > 255) return cg_fail(ctx, CG_ERR_UNSUPPORTED, "cg_normalize_best_lr2: more than 255 control samples");
     if (n > 0x7fff0000LL) return cg_fail(ctx, CG_ERR_UNSUPPORTED, "cg_normalize_best_lr2: too many bins");
     reset_call(ctx);
     CG_CUDA(ctx, cudaSetDevice(ctx->device));
