@@ -15,3 +15,5 @@ bash tools/gpu_timeline.sh ${tag} > /dev/null
 timeout 600 python tools/hmm_bench.py 1.0 > gpurun_out/${tag}_hmm_bench.json 2> gpurun_out/${tag}_hmm_bench.err
 cat gpurun_out/${tag}_hmm_bench.json
 python __graft_entry__.py smoke 2>&1 | tail -1
+timeout 300 python tools/aux_bench.py > gpurun_out/${tag}_aux_kernels.jsonl 2> gpurun_out/${tag}_aux.err
+cut -c1-160 gpurun_out/${tag}_aux_kernels.jsonl
