@@ -345,3 +345,23 @@ def test_write_partitioned_text(tmp_path):
     fileio.write_partitioned(str(p), order, segs)
     assert gzip.open(p, "rt").read() == ("chr1\t0\t1000\t95.02\t0\nchr1\t1000\t2000\t95.5\t0\nchr1\t2000\t3000\t1E-05\t1\n"
                                          "chr2\t0\t1000\t100\t2\nchr2\t1000\t2000\t95.02\t2\nchr2\t2000\t3000\tNaN\t2\n")
+
+
+def test_bench_reference_arm_contract():
+    # `bench.py --impl reference` needs no GPU: one JSON line with the contract's keys (a shrunken genome keeps it to seconds)
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    p = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                        "--scale", "0.05"], capture_output=True, text=True, timeout=300)
+    assert p.returncode == 0, p.stderr[-2000:]
+    lines = [ln for ln in p.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "Mbins/s" and d["higher_is_better"] is True and d["value"] > 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    for k in ("metric", "n_gpus", "steps", "warmup", "ms_per_step", "scaling", "vs_baseline", "dtype", "data", "config"):
+        assert k in d, k
+    assert "workload" in d["config"]
