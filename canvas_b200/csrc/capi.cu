@@ -36,6 +36,7 @@ extern "C" void cg_destroy(cg_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    cg_comm_destroy(ctx);
     if (ctx->arena) cudaFree(ctx->arena);
     cg_graphs_clear(ctx);
     if (ctx->gap_ev) cudaEventDestroy(ctx->gap_ev);

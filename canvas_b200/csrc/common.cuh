@@ -15,6 +15,7 @@
 #define CG_NUM_SMS_FALLBACK 148
 
 struct CgTimeline;
+struct CgComm;  // NCCL communicator + exchange buffers of this context (comm.cuh); nullptr until cg_comm_init
 // an instantiated CUDA graph of one launch sequence, valid for one exact problem shape and arena placement
 struct CgGraphEntry {
     long long key[12];
@@ -55,6 +56,7 @@ struct cg_ctx {
     size_t aux_cap = 0;
     CgTimeline* tl = nullptr;  // debug timeline of the current call (CANVAS_DEBUG)
     std::vector<CgGraphEntry> clean_graphs;  // Clean pipeline graphs (clean.cu), dropped when the arena moves
+    CgComm* comm = nullptr;
 };
 
 inline void cg_graphs_clear(cg_ctx* ctx) {

@@ -4,6 +4,7 @@
 #include <cstdlib>
 
 #include "clean.cuh"
+#include "comm.cuh"
 #include "wavelet.cuh"
 #include "wavelet_decompose.cuh"
 #include "wavelet_finish.cuh"
@@ -219,6 +220,26 @@ __global__ void __launch_bounds__(256) wv_pack_kernel(const int* __restrict__ n_
     }
 }
 
+// Sharded runs: this rank's results packed for the all-gather as [length, n_bp[0..C), lists of the chromosomes in order]
+// (length = C + total breakpoints; lists beyond the capacity are left out and travel in the exact second round).
+__global__ void __launch_bounds__(256) wv_pack_comm_kernel(const int* __restrict__ n_bp, const int* __restrict__ bp,
+                                                           const long long* __restrict__ off, int C, int* __restrict__ pack, int cap) {
+    __shared__ int s_at[WV_MAX_CHROM + 1];
+    if (threadIdx.x == 0) {
+        int run = 0;
+        for (int c = 0; c < C; c++) { s_at[c] = run; run += n_bp[c]; }
+        s_at[C] = run;
+        pack[0] = C + run;
+    }
+    for (int c = threadIdx.x; c < C; c += blockDim.x) pack[1 + c] = n_bp[c];
+    __syncthreads();
+    const int room = cap - (1 + C);
+    for (int c = 0; c < C; c++) {
+        const int at = s_at[c], n = n_bp[c];
+        for (int i = threadIdx.x; i < n && at + i < room; i += blockDim.x) pack[1 + C + at + i] = bp[off[c] + i];
+    }
+}
+
 size_t wv_workspace_bytes(const WvPlan& pl) {
     const size_t N = (size_t)pl.N, C = (size_t)pl.n_chrom;
     size_t s = 0;
@@ -386,7 +407,7 @@ __global__ void wv_device_offsets_kernel(const unsigned* __restrict__ chrom_cnt,
 }
 
 int wv_enqueue(cg_ctx* ctx, const cg_wavelet_opts* o, const WvPlan& pl, WvDev& d, const unsigned char* selected_host,
-               bool rq_index_done = false) {
+               bool rq_index_done = false, int* comm_pack = nullptr) {
     cudaStream_t s = ctx->stream;
     const int C = pl.n_chrom;
     const WvSegTable& t = pl.t;
@@ -427,7 +448,10 @@ int wv_enqueue(cg_ctx* ctx, const cg_wavelet_opts* o, const WvPlan& pl, WvDev& d
         put(d.log3, log3_tab, 20 * 8);
         CG_CUDA(ctx, cudaMemcpyAsync(base, h, bytes, cudaMemcpyHostToDevice, s));
     }
-    if (pl.N == 0) return CG_OK;
+    if (pl.N == 0) {
+        if (comm_pack) CG_LAUNCH(ctx, wv_pack_comm_kernel, 1, 256, 0, d.n_bp, d.bp, d.off, C, comm_pack, CG_COMM_PACK_INTS);
+        return CG_OK;
+    }
 
     WvScalarParams sp;
     sp.t = t;
@@ -572,11 +596,12 @@ int wv_enqueue(cg_ctx* ctx, const cg_wavelet_opts* o, const WvPlan& pl, WvDev& d
     CG_TL(ctx, "uh_finish");
     cudaEventRecord(ctx->stage_ev[7], s);
     CG_LAUNCH(ctx, wv_pack_kernel, 1, 256, 0, d.n_bp, d.depth, d.bp, d.off, C, d.pack);
+    if (comm_pack) CG_LAUNCH(ctx, wv_pack_comm_kernel, 1, 256, 0, d.n_bp, d.bp, d.off, C, comm_pack, CG_COMM_PACK_INTS);
     return CG_OK;
 }
 
 int wv_collect(cg_ctx* ctx, const WvPlan& pl, WvDev& d, int32_t* n_bp, int32_t* bp, double* evenness, int* evenness_ok,
-               double* cv, int* cv_has_value, double* factor_of_three) {
+               double* cv, int* cv_has_value, double* factor_of_three, bool exchange = false) {
     cudaStream_t s = ctx->stream;
     const int C = pl.n_chrom;
     WvCtl* h = (WvCtl*)ctx->pinned;
@@ -588,7 +613,26 @@ int wv_collect(cg_ctx* ctx, const WvPlan& pl, WvDev& d, int32_t* n_bp, int32_t* 
     CG_CUDA(ctx, cudaMemcpyAsync(h, d.ctl, sizeof(WvCtl), cudaMemcpyDeviceToHost, s));
     if (pl.N > 0) CG_CUDA(ctx, cudaMemcpyAsync(h_pack, d.pack, (size_t)first * 4, cudaMemcpyDeviceToHost, s));
     else memset(h_pack, 0, (size_t)first * 4);  // nothing was enqueued for an empty genome
-    CG_CUDA(ctx, cudaStreamSynchronize(s));
+    // sharded run: the all-gather of every rank's packed lists rides on the same stream (its first wait covers the copies above)
+    std::vector<int64_t> x_counts;
+    std::vector<int32_t> x_all, x_full;
+    if (exchange) {
+        auto fetch = [&]() -> const int32_t* {  // this rank's lists did not fit the fixed-capacity round: all of them, from the device
+            x_full.assign((size_t)C, 0);
+            if (C > 0) cudaMemcpy(x_full.data(), d.n_bp, (size_t)C * 4, cudaMemcpyDeviceToHost);
+            for (int c = 0; c < C; c++) {
+                const size_t at = x_full.size();
+                const int n = x_full[c];
+                x_full.resize(at + (size_t)n);
+                if (n > 0) cudaMemcpy(x_full.data() + at, d.bp + pl.off[c], (size_t)n * 4, cudaMemcpyDeviceToHost);
+            }
+            return x_full.data();
+        };
+        int rc = comm_allgatherv(ctx, nullptr, 0, fetch, x_counts, x_all);
+        if (rc) return rc;
+    } else {
+        CG_CUDA(ctx, cudaStreamSynchronize(s));
+    }
     CG_CUDA(ctx, cudaGetLastError());
     CG_CHECK_LAUNCHES(ctx);
     if (h->overflow_.v) return cg_fail(ctx, CG_ERR_CAPACITY, "partition: internal queue capacity exceeded");
@@ -621,7 +665,24 @@ int wv_collect(cg_ctx* ctx, const WvPlan& pl, WvDev& d, int32_t* n_bp, int32_t* 
     }
     // breakpoints: from the packed block when they all arrived with it, else one copy per chromosome
     const long long total = h_pack[2 * C];
-    if (head + total <= first) {
+    if (exchange) {
+        // every rank's block is [n_bp[0..C), lists in chromosome order]; a chromosome has breakpoints on its owner only
+        for (int c = 0; c < C; c++) n_bp[c] = 0;
+        size_t at = 0;
+        for (size_t r = 0; r < x_counts.size(); r++) {
+            const int32_t* blk = x_all.data() + at;
+            if (x_counts[r] < C) return cg_fail(ctx, CG_ERR_CUDA, "partition: malformed block in the all-gather");
+            const int32_t* src = blk + C;
+            for (int c = 0; c < C; c++) {
+                const int n = blk[c];
+                if (n < 0 || (src - blk) + n > x_counts[r] || n > pl.off[c + 1] - pl.off[c])
+                    return cg_fail(ctx, CG_ERR_CUDA, "partition: malformed block in the all-gather");
+                if (n > 0) { n_bp[c] = n; memcpy(bp + pl.off[c], src, (size_t)n * 4); }
+                src += n;
+            }
+            at += (size_t)x_counts[r];
+        }
+    } else if (head + total <= first) {
         const int* src = h_pack + head;
         for (int c = 0; c < C; c++) {
             if (h_nbp[c] > 0) memcpy(bp + pl.off[c], src, (size_t)h_nbp[c] * 4);
@@ -653,14 +714,26 @@ int check_args(cg_ctx* ctx, const cg_wavelet_opts* opts, int n_chrom, const int6
 
 }  // namespace
 
-extern "C" int cg_partition_wavelet_shard(cg_ctx* ctx, const cg_wavelet_opts* opts, int n_chrom,
-                                          const int64_t* chrom_off, const double* coverage,
-                                          const uint8_t* chrom_selected, int32_t* n_bp, int32_t* bp,
-                                          double* evenness, int* evenness_ok, double* cv, int* cv_has_value,
-                                          double* factor_of_three) {
+// exchange: this rank segments the chromosomes the LPT assignment gives it and the all-gather completes the lists
+static int partition_wavelet_impl(cg_ctx* ctx, const cg_wavelet_opts* opts, int n_chrom,
+                                  const int64_t* chrom_off, const double* coverage,
+                                  const uint8_t* chrom_selected, int32_t* n_bp, int32_t* bp,
+                                  double* evenness, int* evenness_ok, double* cv, int* cv_has_value,
+                                  double* factor_of_three, bool exchange, int32_t* owner) {
     if (!ctx) return CG_ERR_ARG;
     int rc = check_args(ctx, opts, n_chrom, chrom_off);
     if (rc) return rc;
+    std::vector<uint8_t> x_mask;
+    if (exchange) {
+        if (!ctx->comm) return cg_fail(ctx, CG_ERR_ARG, "cg_partition_wavelet_sharded: no communicator (cg_comm_init)");
+        std::vector<int64_t> w(n_chrom);
+        std::vector<int32_t> own(n_chrom);
+        for (int c = 0; c < n_chrom; c++) w[c] = chrom_off[c + 1] - chrom_off[c];
+        comm_assign_lpt(n_chrom, w.data(), ctx->comm->size, own.data());
+        x_mask.assign(n_chrom + 1, 0);
+        for (int c = 0; c < n_chrom; c++) { x_mask[c] = own[c] == ctx->comm->rank; if (owner) owner[c] = own[c]; }
+        chrom_selected = x_mask.data();
+    }
     if (!n_bp || !bp || !evenness || !evenness_ok || !cv || !cv_has_value || !factor_of_three || (chrom_off[n_chrom] > 0 && !coverage))
         return cg_fail(ctx, CG_ERR_ARG, "partition: null output");
     ctx->launches = 0;
@@ -688,16 +761,33 @@ extern "C" int cg_partition_wavelet_shard(cg_ctx* ctx, const cg_wavelet_opts* op
     CG_CUDA(ctx, cudaEventRecord(ctx->ev0, s));
     rc = wv_clear(ctx, d);
     if (rc) return rc;
-    rc = wv_enqueue(ctx, opts, pl, d, sel.data());
+    rc = wv_enqueue(ctx, opts, pl, d, sel.data(), false, exchange ? ctx->comm->d_send : nullptr);
     if (rc) { cudaStreamSynchronize(s); return rc; }
     CG_CUDA(ctx, cudaEventRecord(ctx->ev1, s));
-    rc = wv_collect(ctx, pl, d, n_bp, bp, evenness, evenness_ok, cv, cv_has_value, factor_of_three);
+    rc = wv_collect(ctx, pl, d, n_bp, bp, evenness, evenness_ok, cv, cv_has_value, factor_of_three, exchange);
     tl.print("partition");
     ctx->tl = nullptr;
     float ms = 0;
     cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
     ctx->last_kernel_ms = ms;
     return rc;
+}
+
+extern "C" int cg_partition_wavelet_shard(cg_ctx* ctx, const cg_wavelet_opts* opts, int n_chrom,
+                                          const int64_t* chrom_off, const double* coverage,
+                                          const uint8_t* chrom_selected, int32_t* n_bp, int32_t* bp,
+                                          double* evenness, int* evenness_ok, double* cv, int* cv_has_value,
+                                          double* factor_of_three) {
+    return partition_wavelet_impl(ctx, opts, n_chrom, chrom_off, coverage, chrom_selected, n_bp, bp, evenness, evenness_ok, cv,
+                                  cv_has_value, factor_of_three, false, nullptr);
+}
+
+extern "C" int cg_partition_wavelet_sharded(cg_ctx* ctx, const cg_wavelet_opts* opts, int n_chrom, const int64_t* chrom_off,
+                                            const double* coverage, int32_t* n_bp, int32_t* bp, double* evenness,
+                                            int* evenness_ok, double* cv, int* cv_has_value, double* factor_of_three,
+                                            int32_t* owner) {
+    return partition_wavelet_impl(ctx, opts, n_chrom, chrom_off, coverage, nullptr, n_bp, bp, evenness, evenness_ok, cv,
+                                  cv_has_value, factor_of_three, true, owner);
 }
 
 extern "C" int cg_partition_wavelet(cg_ctx* ctx, const cg_wavelet_opts* opts, int n_chrom, const int64_t* chrom_off,
@@ -728,15 +818,17 @@ __global__ void fused_coverage_kernel(const float* __restrict__ count_out, const
     }
 }
 
-extern "C" int cg_clean_partition_wavelet_shard(cg_ctx* ctx, const cg_clean_opts* copts, const cg_wavelet_opts* wopts,
-                                                int64_t n, const uint8_t* chrom, const uint8_t* chrom_is_autosome,
-                                                const uint8_t* chrom_is_chrY, int n_chrom, const int32_t* start,
-                                                const int32_t* stop, const float* count, const uint8_t* gc,
-                                                const uint8_t* chrom_selected, int64_t* n_out, int32_t* kept_index,
-                                                float* count_out, double* local_sd, int* gc_norm_skipped,
-                                                int64_t* chrom_off_out, int32_t* n_bp, int32_t* bp, double* evenness,
-                                                int* evenness_ok, double* cv, int* cv_has_value, double* factor_of_three) {
+static int clean_partition_wavelet_impl(cg_ctx* ctx, const cg_clean_opts* copts, const cg_wavelet_opts* wopts,
+                                        int64_t n, const uint8_t* chrom, const uint8_t* chrom_is_autosome,
+                                        const uint8_t* chrom_is_chrY, int n_chrom, const int32_t* start,
+                                        const int32_t* stop, const float* count, const uint8_t* gc,
+                                        const uint8_t* chrom_selected, int64_t* n_out, int32_t* kept_index,
+                                        float* count_out, double* local_sd, int* gc_norm_skipped,
+                                        int64_t* chrom_off_out, int32_t* n_bp, int32_t* bp, double* evenness,
+                                        int* evenness_ok, double* cv, int* cv_has_value, double* factor_of_three,
+                                        bool exchange, int32_t* owner) {
     if (!ctx) return CG_ERR_ARG;
+    if (exchange && !ctx->comm) return cg_fail(ctx, CG_ERR_ARG, "cg_clean_partition_wavelet_sharded: no communicator (cg_comm_init)");
     if (!copts || !wopts || n < 0 || n > 0x7fff0000LL || n_chrom < 0 || n_chrom > WV_MAX_CHROM || !n_out || !local_sd ||
         !gc_norm_skipped || !chrom_off_out || !n_bp || !evenness || !evenness_ok || !cv || !cv_has_value || !factor_of_three)
         return cg_fail(ctx, CG_ERR_ARG, "cg_clean_partition_wavelet: bad argument");
@@ -751,7 +843,14 @@ extern "C" int cg_clean_partition_wavelet_shard(cg_ctx* ctx, const cg_clean_opts
     for (int i = 0; i <= WV_F3_LEVELS; i++) factor_of_three[i] = 0;
     for (int c = 0; c <= n_chrom; c++) chrom_off_out[c] = 0;
     for (int c = 0; c < n_chrom; c++) n_bp[c] = 0;
-    if (n == 0) { *gc_norm_skipped = copts->gc_norm ? 1 : 0; return CG_OK; }
+    if (n == 0 && !exchange) { *gc_norm_skipped = copts->gc_norm ? 1 : 0; return CG_OK; }
+    if (n == 0) {  // still a collective: every rank enters the all-gather
+        *gc_norm_skipped = copts->gc_norm ? 1 : 0;
+        std::vector<int32_t> none((size_t)n_chrom + 1, 0), all;
+        std::vector<int64_t> counts;
+        if (owner) for (int c = 0; c < n_chrom; c++) owner[c] = 0;
+        return comm_allgatherv(ctx, none.data(), n_chrom, nullptr, counts, all);
+    }
     if (!chrom || !start || !stop || !count || !gc || !kept_index || !count_out || !bp || !chrom_is_autosome)
         return cg_fail(ctx, CG_ERR_ARG, "cg_clean_partition_wavelet: null array");
     CG_CUDA(ctx, cudaSetDevice(ctx->device));
@@ -815,7 +914,13 @@ extern "C" int cg_clean_partition_wavelet_shard(cg_ctx* ctx, const cg_clean_opts
     if (rc) { cudaStreamSynchronize(s); return rc; }
     // ... and the range-quantile index of the finish stage is built there too: offsets come from the device-side counts
     std::vector<unsigned char> sel(n_chrom + 1, 1);
-    if (chrom_selected)
+    if (exchange) {  // LPT over the chromosome run lengths of the input: known before Clean, identical on every rank
+        std::vector<int64_t> w(n_chrom);
+        std::vector<int32_t> own(n_chrom);
+        for (int c = 0; c < n_chrom; c++) w[c] = in_off[c + 1] - in_off[c];
+        comm_assign_lpt(n_chrom, w.data(), ctx->comm->size, own.data());
+        for (int c = 0; c < n_chrom; c++) { sel[c] = own[c] == ctx->comm->rank; if (owner) owner[c] = own[c]; }
+    } else if (chrom_selected)
         for (int c = 0; c < n_chrom; c++) sel[c] = chrom_selected[c] ? 1 : 0;
     if (n_chrom > 0) {
         CG_CUDA(ctx, cudaMemcpyAsync(wd.selected, sel.data(), n_chrom, cudaMemcpyHostToDevice, s));
@@ -851,10 +956,10 @@ extern "C" int cg_clean_partition_wavelet_shard(cg_ctx* ctx, const cg_clean_opts
     for (int c = 0; c <= n_chrom; c++) chrom_off_out[c] = off[c];
     WvPlan pl;
     make_plan(pl, n_chrom, off.data(), wopts->evenness_window);
-    rc = wv_enqueue(ctx, wopts, pl, wd, sel.data(), n_chrom > 0);
+    rc = wv_enqueue(ctx, wopts, pl, wd, sel.data(), n_chrom > 0, exchange ? ctx->comm->d_send : nullptr);
     if (rc) { cudaStreamSynchronize(s); cudaStreamSynchronize(ctx->copy_stream); return rc; }
     CG_CUDA(ctx, cudaEventRecord(ctx->ev1, s));
-    rc = wv_collect(ctx, pl, wd, n_bp, bp, evenness, evenness_ok, cv, cv_has_value, factor_of_three);
+    rc = wv_collect(ctx, pl, wd, n_bp, bp, evenness, evenness_ok, cv, cv_has_value, factor_of_three, exchange);
     tl.print("fused");
     ctx->tl = nullptr;
     CG_CUDA(ctx, cudaStreamSynchronize(ctx->copy_stream));
@@ -865,6 +970,32 @@ extern "C" int cg_clean_partition_wavelet_shard(cg_ctx* ctx, const cg_clean_opts
     *local_sd = lsd;
     *gc_norm_skipped = skipped;
     return rc;
+}
+
+extern "C" int cg_clean_partition_wavelet_shard(cg_ctx* ctx, const cg_clean_opts* copts, const cg_wavelet_opts* wopts,
+                                                int64_t n, const uint8_t* chrom, const uint8_t* chrom_is_autosome,
+                                                const uint8_t* chrom_is_chrY, int n_chrom, const int32_t* start,
+                                                const int32_t* stop, const float* count, const uint8_t* gc,
+                                                const uint8_t* chrom_selected, int64_t* n_out, int32_t* kept_index,
+                                                float* count_out, double* local_sd, int* gc_norm_skipped,
+                                                int64_t* chrom_off_out, int32_t* n_bp, int32_t* bp, double* evenness,
+                                                int* evenness_ok, double* cv, int* cv_has_value, double* factor_of_three) {
+    return clean_partition_wavelet_impl(ctx, copts, wopts, n, chrom, chrom_is_autosome, chrom_is_chrY, n_chrom, start, stop, count, gc,
+                                        chrom_selected, n_out, kept_index, count_out, local_sd, gc_norm_skipped, chrom_off_out, n_bp,
+                                        bp, evenness, evenness_ok, cv, cv_has_value, factor_of_three, false, nullptr);
+}
+
+extern "C" int cg_clean_partition_wavelet_sharded(cg_ctx* ctx, const cg_clean_opts* copts, const cg_wavelet_opts* wopts, int64_t n,
+                                                  const uint8_t* chrom, const uint8_t* chrom_is_autosome,
+                                                  const uint8_t* chrom_is_chrY, int n_chrom, const int32_t* start,
+                                                  const int32_t* stop, const float* count, const uint8_t* gc, int64_t* n_out,
+                                                  int32_t* kept_index, float* count_out, double* local_sd, int* gc_norm_skipped,
+                                                  int64_t* chrom_off_out, int32_t* n_bp, int32_t* bp, double* evenness,
+                                                  int* evenness_ok, double* cv, int* cv_has_value, double* factor_of_three,
+                                                  int32_t* owner) {
+    return clean_partition_wavelet_impl(ctx, copts, wopts, n, chrom, chrom_is_autosome, chrom_is_chrY, n_chrom, start, stop, count, gc,
+                                        nullptr, n_out, kept_index, count_out, local_sd, gc_norm_skipped, chrom_off_out, n_bp, bp,
+                                        evenness, evenness_ok, cv, cv_has_value, factor_of_three, true, owner);
 }
 
 extern "C" int cg_clean_partition_wavelet(cg_ctx* ctx, const cg_clean_opts* copts, const cg_wavelet_opts* wopts,

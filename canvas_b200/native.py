@@ -99,6 +99,29 @@ SIGNATURES = {
                                    _P(_i32), _P(_i32)]),
     "cg_normalize_apply": (C.c_int, [C.c_void_p, C.c_int, _i64, _P(_f32), _P(_u8), _P(_f64),
                                      _P(_f64), _P(_f32), C.c_int, _P(_f64)]),
+    # multi-GPU (NCCL communicator per context)
+    "cg_comm_unique_id": (C.c_int, [_P(_u8)]),
+    "cg_comm_init": (C.c_int, [C.c_void_p, C.c_int, C.c_int, _P(_u8)]),
+    "cg_comm_init_all": (C.c_int, [C.c_int, _P(C.c_void_p)]),
+    "cg_comm_destroy": (C.c_int, [C.c_void_p]),
+    "cg_comm_rank": (C.c_int, [C.c_void_p]),
+    "cg_comm_size": (C.c_int, [C.c_void_p]),
+    "cg_comm_nccl_version": (C.c_int, []),
+    "cg_comm_last_exchange_ms": (C.c_double, [C.c_void_p]),
+    "cg_shard_assign": (C.c_int, [C.c_int, _P(_i64), C.c_int, _P(_i32)]),
+    "cg_comm_allgather_lists": (C.c_int, [C.c_void_p, _i64, _P(_i32), _P(_i64), _P(_i32), _i64, _P(_i64)]),
+    "cg_comm_broadcast": (C.c_int, [C.c_void_p, C.c_void_p, _i64, C.c_int]),
+    "cg_partition_wavelet_sharded": (C.c_int, [C.c_void_p, _P(WaveletOpts), C.c_int, _P(_i64), _P(_f64), _P(_i32), _P(_i32),
+                                               _P(_f64), _P(C.c_int), _P(_f64), _P(C.c_int), _P(_f64), _P(_i32)]),
+    "cg_clean_partition_wavelet_sharded": (C.c_int, [C.c_void_p, _P(CleanOpts), _P(WaveletOpts), _i64,
+                                                     _P(_u8), _P(_u8), _P(_u8), C.c_int, _P(_i32), _P(_i32),
+                                                     _P(_f32), _P(_u8), _P(_i64), _P(_i32), _P(_f32),
+                                                     _P(_f64), _P(C.c_int), _P(_i64), _P(_i32), _P(_i32),
+                                                     _P(_f64), _P(C.c_int), _P(_f64), _P(C.c_int), _P(_f64), _P(_i32)]),
+    "cg_partition_cbs_sharded": (C.c_int, [C.c_void_p, C.c_void_p, _P(C.c_uint32), _i64, C.c_int, _P(_i64), _P(C.c_double),
+                                           _P(_i32), _P(_i32), _P(C.c_double), _P(_i64), _P(_i32)]),
+    "cg_partition_hmm_sharded": (C.c_int, [C.c_void_p, _P(HmmOpts), C.c_int, C.c_int, _P(_i64), _P(_f64), _P(_i32), _P(_i32),
+                                           _P(_u8), _P(_i32)]),
 }
 
 _lib = None
@@ -122,6 +145,25 @@ def load():
 
 def _ptr(a, t):
     return a.ctypes.data_as(_P(t))
+
+
+def shard_assign(weights, n_ranks):
+    """cg_shard_assign: longest-processing-time-first owner of every unit (host code; no device needed)."""
+    w = np.ascontiguousarray(weights, np.int64)
+    owner = np.zeros(max(len(w), 1), np.int32)
+    rc = load().cg_shard_assign(len(w), _ptr(w, _i64), int(n_ranks), _ptr(owner, _i32))
+    if rc != CG_OK:
+        raise CanvasGpuError(rc, "cg_shard_assign: bad argument")
+    return owner[:len(w)]
+
+
+def comm_unique_id():
+    """cg_comm_unique_id (ncclGetUniqueId): 128 bytes rank 0 creates and the host hands to every rank."""
+    ident = np.zeros(128, np.uint8)
+    rc = load().cg_comm_unique_id(_ptr(ident, _u8))
+    if rc != CG_OK:
+        raise CanvasGpuError(rc, "cg_comm_unique_id: libnccl.so.2 could not be bound")
+    return ident
 
 
 def format_bins(names, chrom, start, stop, count, gc=None, four_columns=False, n_threads=0):
@@ -248,6 +290,64 @@ class Engine:
     def describe(self):
         return self.lib.cg_describe(self.h).decode()
 
+    # ------------------------------------------------------------------ multi-GPU communicator
+    def comm_init(self, n_ranks, rank, unique_id=None):
+        """cg_comm_init: this context joins an NCCL communicator of n_ranks (unique_id from comm_unique_id() on rank 0,
+        handed over by the host; n_ranks == 1 is a loopback communicator that never calls NCCL)."""
+        ident = None if unique_id is None else np.ascontiguousarray(unique_id, np.uint8)
+        self._check(self.lib.cg_comm_init(self.h, int(n_ranks), int(rank), None if ident is None else _ptr(ident, _u8)))
+
+    def comm_init_torch(self):
+        """One process per GPU under torchrun: rank 0 creates the id, torch.distributed only carries its 128 bytes."""
+        import torch
+        import torch.distributed as dist
+        world, rank = dist.get_world_size(), dist.get_rank()
+        if world == 1:
+            return self.comm_init(1, 0)
+        ident = comm_unique_id() if rank == 0 else np.zeros(128, np.uint8)
+        dev = f"cuda:{self.device}" if dist.get_backend() == "nccl" else "cpu"
+        t = torch.from_numpy(ident).to(dev)
+        dist.broadcast(t, 0)
+        self.comm_init(world, rank, t.cpu().numpy())
+
+    @property
+    def comm_size(self):
+        return self.lib.cg_comm_size(self.h)
+
+    @property
+    def comm_rank(self):
+        return self.lib.cg_comm_rank(self.h)
+
+    @property
+    def last_exchange_ms(self):
+        return self.lib.cg_comm_last_exchange_ms(self.h)
+
+    def allgather_lists(self, local):
+        """cg_comm_allgather_lists: one int32 list per rank -> the list of every rank, on every rank."""
+        loc = np.ascontiguousarray(local, np.int32)
+        size = max(self.comm_size, 1)
+        counts = np.zeros(size, np.int64)
+        total = _i64(0)
+
+        def gather(lst, cap):
+            out = np.zeros(max(cap, 1), np.int32)
+            self._check(self.lib.cg_comm_allgather_lists(self.h, len(lst), _ptr(lst, _i32), _ptr(counts, _i64), _ptr(out, _i32),
+                                                         cap, C.byref(total)))
+            return out
+
+        # the output capacity has to be right on every rank at once (a retry would be a collective of its own), so the
+        # lengths travel first
+        lens = gather(np.array([len(loc)], np.int32), size)[:size]
+        out = gather(loc, int(lens.sum()))
+        ends = np.cumsum(counts)
+        return [out[e - c:e].copy() for c, e in zip(counts, ends)]
+
+    def broadcast(self, array, root):
+        """cg_comm_broadcast of a contiguous numpy array, in place."""
+        a = np.ascontiguousarray(array)
+        self._check(self.lib.cg_comm_broadcast(self.h, a.ctypes.data_as(C.c_void_p), a.nbytes, int(root)))
+        return a
+
     def _check(self, rc):
         if rc != CG_OK:
             raise CanvasGpuError(rc, self.lib.cg_last_error(self.h).decode())
@@ -308,7 +408,8 @@ class Engine:
     # ------------------------------------------------------------------ CanvasPartition (wavelets)
     def partition_wavelet(self, chrom_off, coverage, is_germline=True, mad_factor=5.0,
                           thr_lower=0.05, thr_upper=80.0, min_size=10, evenness_window=100000,
-                          chrom_selected=None, out=None):
+                          chrom_selected=None, out=None, sharded=False):
+        """sharded=True: cg_partition_wavelet_sharded (LPT over the communicator's ranks + NCCL all-gather inside the call)."""
         chrom_off = np.ascontiguousarray(chrom_off, np.int64)
         coverage = np.ascontiguousarray(coverage, np.float64)
         nc = len(chrom_off) - 1
@@ -322,7 +423,12 @@ class Engine:
         ev, cv = _f64(0), _f64(0)
         ev_ok, cv_has = C.c_int(0), C.c_int(0)
         f3 = np.zeros(9, np.float64)
-        if chrom_selected is None:
+        owner = np.zeros(max(nc, 1), np.int32)
+        if sharded:
+            rc = self.lib.cg_partition_wavelet_sharded(self.h, C.byref(o), nc, _ptr(chrom_off, _i64), _ptr(coverage, _f64),
+                                                       _ptr(n_bp, _i32), _ptr(bp, _i32), C.byref(ev), C.byref(ev_ok), C.byref(cv),
+                                                       C.byref(cv_has), _ptr(f3, _f64), _ptr(owner, _i32))
+        elif chrom_selected is None:
             rc = self.lib.cg_partition_wavelet(self.h, C.byref(o), nc, _ptr(chrom_off, _i64),
                                                _ptr(coverage, _f64), _ptr(n_bp, _i32), _ptr(bp, _i32),
                                                C.byref(ev), C.byref(ev_ok), C.byref(cv),
@@ -336,15 +442,18 @@ class Engine:
                                                      _ptr(f3, _f64))
         self._check(rc)
         bps = [bp[chrom_off[c]:chrom_off[c] + n_bp[c]].copy() for c in range(nc)]
-        return {"breakpoints": bps, "evenness": ev.value if ev_ok.value else None,
-                "cv": cv.value if cv_has.value else None, "factor_of_three": f3}
+        r = {"breakpoints": bps, "evenness": ev.value if ev_ok.value else None,
+             "cv": cv.value if cv_has.value else None, "factor_of_three": f3}
+        if sharded:
+            r["owner"] = owner[:nc]
+        return r
 
     # ------------------------------------------------------------------ Clean + Partition, fused
     def clean_partition_wavelet(self, chrom, is_autosome, is_chr_y, start, stop, count, gc,
                                 size_filter=True, outlier_filter=True, gc_norm=True, gc_mode=0,
                                 want_local_sd=True, min_bins_per_gc=100, is_germline=True,
                                 mad_factor=5.0, thr_lower=0.05, thr_upper=80.0, min_size=10,
-                                evenness_window=100000, out=None, chrom_selected=None):
+                                evenness_window=100000, out=None, chrom_selected=None, sharded=False):
         """cg_clean_partition_wavelet: both stages without leaving the device in between.
         `out` = (kept_index, count_out, n_bp, bp) preallocated (e.g. pinned) arrays; `chrom_selected` = 0/1 mask of
         the chromosomes this rank segments (multi-GPU)."""
@@ -373,7 +482,16 @@ class Engine:
         ev_ok, cv_has = C.c_int(0), C.c_int(0)
         f3 = np.zeros(9, np.float64)
         mask = None if chrom_selected is None else np.ascontiguousarray(chrom_selected, np.uint8)
-        rc = self.lib.cg_clean_partition_wavelet_shard(
+        owner = np.zeros(max(nc, 1), np.int32)
+        if sharded:
+            rc = self.lib.cg_clean_partition_wavelet_sharded(
+                self.h, C.byref(co), C.byref(wo), n, _ptr(chrom, _u8), _ptr(is_autosome, _u8),
+                _ptr(is_chr_y, _u8), nc, _ptr(start, _i32), _ptr(stop, _i32), _ptr(count, _f32),
+                _ptr(gc, _u8), C.byref(n_out), _ptr(kept, _i32), _ptr(cnt, _f32), C.byref(lsd),
+                C.byref(skipped), _ptr(off, _i64), _ptr(n_bp, _i32), _ptr(bp, _i32), C.byref(ev),
+                C.byref(ev_ok), C.byref(cv), C.byref(cv_has), _ptr(f3, _f64), _ptr(owner, _i32))
+        else:
+          rc = self.lib.cg_clean_partition_wavelet_shard(
             self.h, C.byref(co), C.byref(wo), n, _ptr(chrom, _u8), _ptr(is_autosome, _u8),
             _ptr(is_chr_y, _u8), nc, _ptr(start, _i32), _ptr(stop, _i32), _ptr(count, _f32),
             _ptr(gc, _u8), None if mask is None else _ptr(mask, _u8), C.byref(n_out), _ptr(kept, _i32), _ptr(cnt, _f32), C.byref(lsd),
@@ -382,10 +500,13 @@ class Engine:
         self._check(rc)
         k = n_out.value
         bps = [bp[off[c]:off[c] + n_bp[c]].copy() for c in range(nc)]
-        return {"kept_index": kept[:k], "count": cnt[:k], "local_sd": lsd.value,
-                "gc_norm_skipped": bool(skipped.value), "chrom_off": off, "breakpoints": bps,
-                "evenness": ev.value if ev_ok.value else None,
-                "cv": cv.value if cv_has.value else None, "factor_of_three": f3}
+        r = {"kept_index": kept[:k], "count": cnt[:k], "local_sd": lsd.value,
+             "gc_norm_skipped": bool(skipped.value), "chrom_off": off, "breakpoints": bps,
+             "evenness": ev.value if ev_ok.value else None,
+             "cv": cv.value if cv_has.value else None, "factor_of_three": f3}
+        if sharded:
+            r["owner"] = owner[:nc]
+        return r
 
     # ------------------------------------------------------------------ CBS segmentation
     def cbs_boundary(self, n_perm=10000, alpha=0.01, eta=0.05):
@@ -401,7 +522,7 @@ class Engine:
         return cache[key]
 
     def partition_cbs(self, chrom_off, coverage, alpha=0.01, n_perm=10000, hybrid=True, min_width=2, k_max=25, n_min=200,
-                      eta=0.05, undo=0, seed=0, sbdry=None, chrom_selected=None, trim=0.025, undo_sd=3.0, undo_prune=0.05):
+                      eta=0.05, undo=0, seed=0, sbdry=None, chrom_selected=None, trim=0.025, undo_sd=3.0, undo_prune=0.05, sharded=False):
         """CBSRunner.Run: per chromosome the segment lengths (bins) and means."""
         off = np.ascontiguousarray(chrom_off, np.int64)
         cov = np.ascontiguousarray(coverage, np.float64)
@@ -415,7 +536,12 @@ class Engine:
         seg_len = np.zeros(n, np.int32)
         seg_mean = np.zeros(n, np.float64)
         stats = np.zeros(4, np.int64)
-        if chrom_selected is None:
+        owner = np.zeros(max(nc, 1), np.int32)
+        if sharded:
+            rc = self.lib.cg_partition_cbs_sharded(self.h, C.byref(o), _ptr(sbdry, C.c_uint32), len(sbdry), nc, _ptr(off, _i64),
+                                                   _ptr(cov, C.c_double), _ptr(n_seg, _i32), _ptr(seg_len, _i32),
+                                                   _ptr(seg_mean, C.c_double), _ptr(stats, _i64), _ptr(owner, _i32))
+        elif chrom_selected is None:
             rc = self.lib.cg_partition_cbs(self.h, C.byref(o), _ptr(sbdry, C.c_uint32), len(sbdry), nc, _ptr(off, _i64),
                                            _ptr(cov, C.c_double), _ptr(n_seg, _i32), _ptr(seg_len, _i32),
                                            _ptr(seg_mean, C.c_double), _ptr(stats, _i64))
@@ -432,7 +558,7 @@ class Engine:
         return {"segments": segs, "tests": int(stats[0]), "perms": int(stats[1]), "perm_steps": int(stats[2]),
                 "edge_steps": int(stats[3]), "kernel_ms": self.lib.cg_last_kernel_ms(self.h), "phase_ms": self._cbs_phases()}
 
-    def partition_hmm(self, chrom_off, coverage, per_sample=True, min_size=10, exact_sequential=False, chrom_selected=None):
+    def partition_hmm(self, chrom_off, coverage, per_sample=True, min_size=10, exact_sequential=False, chrom_selected=None, sharded=False):
         """HiddenMarkovModelsRunner.Run: breakpoints and Viterbi states.  coverage: [N] or [n_samples, N]."""
         off = np.ascontiguousarray(chrom_off, np.int64)
         cov = np.ascontiguousarray(np.atleast_2d(np.asarray(coverage, np.float64)))
@@ -444,7 +570,11 @@ class Engine:
         n_bp = np.zeros(max(nc, 1), np.int32)
         bp = np.zeros(max(n, 1), np.int32)
         states = np.zeros(max(n, 1), np.uint8)
-        if chrom_selected is None:
+        if sharded:
+            owner = np.zeros(max(nc, 1), np.int32)
+            rc = self.lib.cg_partition_hmm_sharded(self.h, C.byref(o), ns, nc, _ptr(off, _i64), _ptr(cov, _f64), _ptr(n_bp, _i32),
+                                                   _ptr(bp, _i32), _ptr(states, _u8), _ptr(owner, _i32))
+        elif chrom_selected is None:
             rc = self.lib.cg_partition_hmm(self.h, C.byref(o), ns, nc, _ptr(off, _i64), _ptr(cov, _f64), _ptr(n_bp, _i32),
                                            _ptr(bp, _i32), _ptr(states, _u8))
         else:

@@ -221,6 +221,63 @@ int cg_partition_hmm_shard(cg_ctx* ctx, const cg_hmm_opts* opts, int n_samples, 
                            uint8_t* states);
 
 /* ---------------------------------------------------------------------------------------------
+ * Multi-GPU: chromosomes are independent once the genome-wide scalars exist, so every rank
+ * segments the chromosomes a longest-processing-time-first assignment gives it, and ONE NCCL all-gather over NVLink
+ * reassembles the whole-genome result on every rank.  This replaces the lock-protected dictionary merges of the
+ * reference's Parallel.ForEach over chromosomes (WaveletsRunner.cs:128-131, CBSRunner.cs:140-143,
+ * HiddenMarkovModelsRunner.cs:90-105).  One communicator per context:
+ *   one process per GPU  : rank 0 calls cg_comm_unique_id, the host hands the 128 bytes to every rank (any channel),
+ *                          every rank calls cg_comm_init(ctx, n_ranks, rank, id)  (ncclCommInitRank);
+ *   one process, n GPUs  : cg_comm_init_all(n, ctxs) (ncclCommInitAll); the sharded calls of the n contexts must then be
+ *                          issued from n host threads, because each blocks in the all-gather until every rank arrives.
+ * n_ranks = 1 gives a loopback communicator (no NCCL call; the sharded entry points then equal the plain ones).
+ * libnccl.so.2 is bound at run time on the first cg_comm_* call (the one already loaded in the process, if any).
+ * The *_sharded entry points take the arguments of their single-GPU forms on EVERY rank (the genome-wide scalars and
+ * Clean need the whole sample) and return the whole-genome result on every rank; owner (optional, [n_chrom]) receives
+ * the chromosome -> rank assignment (cg_shard_assign on the chromosome lengths).  The exchange carries, per rank, a
+ * packed int32 list [length, payload]: one fixed-capacity all-gather (64 KiB per rank); lists that do not fit travel in a
+ * second, exactly sized round that all ranks enter together (the decision is taken from the gathered lengths, so no rank
+ * can be left waiting in a collective).
+ * ------------------------------------------------------------------------------------------- */
+#define CG_COMM_ID_BYTES 128
+int cg_comm_unique_id(uint8_t* id /* [CG_COMM_ID_BYTES] */);
+int cg_comm_init(cg_ctx* ctx, int n_ranks, int rank, const uint8_t* id);
+int cg_comm_init_all(int n, cg_ctx* const* ctxs);
+int cg_comm_destroy(cg_ctx* ctx);
+int cg_comm_rank(cg_ctx* ctx);               /* -1 without a communicator */
+int cg_comm_size(cg_ctx* ctx);               /* 0 without a communicator */
+int cg_comm_nccl_version(void);              /* e.g. 22809; -1 when libnccl cannot be bound */
+double cg_comm_last_exchange_ms(cg_ctx* ctx); /* device time of the collectives of the last exchange */
+/* LPT: heaviest unit first onto the least loaded rank (ties: earlier unit, lower rank).  Host code. */
+int cg_shard_assign(int n_units, const int64_t* weight, int n_ranks, int32_t* owner);
+/* All-gather of one int32 list per rank (BASELINE config 5: per-sample segment lists of independent samples):
+ * counts[n_ranks] receives the list lengths, all[0 .. *n_total) the lists back to back in rank order. */
+int cg_comm_allgather_lists(cg_ctx* ctx, int64_t n_local, const int32_t* local, int64_t* counts, int32_t* all, int64_t cap,
+                            int64_t* n_total);
+/* Broadcast of a host buffer from rank `root` (staged through the device, NCCL broadcast over NVLink): pedigree mode,
+ * where the rank that cleaned a sample hands the cleaned bins to the ranks that segment its chromosomes. */
+int cg_comm_broadcast(cg_ctx* ctx, void* buf, int64_t bytes, int root);
+
+int cg_partition_wavelet_sharded(cg_ctx* ctx, const cg_wavelet_opts* opts, int n_chrom, const int64_t* chrom_off,
+                                 const double* coverage, int32_t* n_bp, int32_t* bp, double* evenness, int* evenness_ok,
+                                 double* cv, int* cv_has_value, double* factor_of_three, int32_t* owner);
+/* LPT weights = the chromosome run lengths of the INPUT (known before Clean, identical on every rank). */
+int cg_clean_partition_wavelet_sharded(cg_ctx* ctx, const cg_clean_opts* copts, const cg_wavelet_opts* wopts, int64_t n,
+                                       const uint8_t* chrom, const uint8_t* chrom_is_autosome, const uint8_t* chrom_is_chrY,
+                                       int n_chrom, const int32_t* start, const int32_t* stop, const float* count,
+                                       const uint8_t* gc, int64_t* n_out, int32_t* kept_index, float* count_out,
+                                       double* local_sd, int* gc_norm_skipped, int64_t* chrom_off_out, int32_t* n_bp,
+                                       int32_t* bp, double* evenness, int* evenness_ok, double* cv, int* cv_has_value,
+                                       double* factor_of_three, int32_t* owner);
+/* stats (optional, [4]) are those of this rank's chromosomes. */
+int cg_partition_cbs_sharded(cg_ctx* ctx, const cg_cbs_opts* opts, const uint32_t* sbdry, int64_t n_sbdry, int n_chrom,
+                             const int64_t* chrom_off, const double* coverage, int32_t* n_seg, int32_t* seg_len,
+                             double* seg_mean, int64_t* stats, int32_t* owner);
+/* states (optional, [N]): the Viterbi path of every chromosome, gathered like the breakpoints. */
+int cg_partition_hmm_sharded(cg_ctx* ctx, const cg_hmm_opts* opts, int n_samples, int n_chrom, const int64_t* chrom_off,
+                             const double* coverage, int32_t* n_bp, int32_t* bp, uint8_t* states, int32_t* owner);
+
+/* ---------------------------------------------------------------------------------------------
  * Pedigree step between CanvasClean and CanvasPartition: keep the bins that survived CanvasClean in EVERY
  * sample — Utilities.MergeMultiSampleCleanedBedFile (CanvasCommon/Utilities.cs:834-920), written back per
  * sample by CanvasRunner.NormalizeCanvasClean (Canvas/CanvasRunner.cs:883-903).  Sample s has n[s] bins in the

@@ -1,64 +1,118 @@
-"""Multi-GPU parity on real hardware (run under torchrun, one rank per GPU, NCCL):
-chromosome-sharded wavelet and CBS partition + the single all-gather must equal the single-GPU call.
+"""Multi-GPU parity on real hardware: the *_sharded entry points of the C-ABI (LPT chromosome assignment + NCCL all-gather
+inside libcanvasgpu) must return, on every rank, exactly what the single-GPU call returns.
 
-  python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 \
-      tools/multi_gpu_check.py [scale]
+  one process per GPU (torchrun; torch.distributed only carries the 128-byte NCCL id):
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 \
+        tools/multi_gpu_check.py [scale]
+  one process, N GPUs, one host thread per context (cg_comm_init_all — how a single C# host would drive a box):
+    python tools/multi_gpu_check.py --single-process 2 [scale]
 """
 import os
 import sys
+import threading
 
 import numpy as np
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 
-def main():
+def same_bp(a, b):
+    return all(x.tolist() == y.tolist() for x, y in zip(a, b))
+
+
+def checks(eng, rank, world, scale):
+    """Every comparison of one rank; returns (dict of booleans, info)."""
+    from canvas_b200 import synth, textcodec
+    s = synth.make_sample(config=2, sample=3, scale=scale, n_events=60)
+    ew = max(2000, int(100000 * scale))
+    ok = {}
+    fused = eng.clean_partition_wavelet(s.chrom, s.is_autosome, s.is_chr_y, s.start, s.stop, s.count, s.gc, evenness_window=ew)
+    fs = eng.clean_partition_wavelet(s.chrom, s.is_autosome, s.is_chr_y, s.start, s.stop, s.count, s.gc, evenness_window=ew,
+                                     sharded=True)
+    ok["fused"] = (same_bp(fused["breakpoints"], fs["breakpoints"]) and fused["cv"] == fs["cv"]
+                   and np.array_equal(fused["kept_index"], fs["kept_index"]))
+    x_ms = eng.last_exchange_ms
+    off = fused["chrom_off"]
+    cov = textcodec.f2_roundtrip(fused["count"])
+    full = eng.partition_wavelet(off, cov, evenness_window=ew)
+    shard = eng.partition_wavelet(off, cov, evenness_window=ew, sharded=True)
+    ok["wavelet"] = same_bp(full["breakpoints"], shard["breakpoints"]) and np.array_equal(full["factor_of_three"], shard["factor_of_three"])
+    ok["owners_cover_ranks"] = sorted(set(shard["owner"].tolist())) == list(range(min(world, len(off) - 1)))
+    # more breakpoints than the fixed first round holds: the exact second round
+    rng = np.random.default_rng(3)
+    n = 300_000
+    stair = np.round(100.0 + 60.0 * ((np.arange(n) // 12) % 2) + rng.normal(0, 0.5, n), 2)
+    soff = np.array([0, 120_000, 200_000, n])
+    a, b = eng.partition_wavelet(soff, stair, evenness_window=20000), eng.partition_wavelet(soff, stair, evenness_window=20000, sharded=True)
+    ok["wavelet_overflow_round"] = same_bp(a["breakpoints"], b["breakpoints"]) and sum(len(x) for x in a["breakpoints"]) > 17000
+    # CBS on a few chromosomes' worth of bins (permutation tests are heavier)
+    ncb = min(len(off) - 1, 6)
+    off_c = off[:ncb + 1]
+    cov_c = cov[:off_c[-1]]
+    fc, sc = eng.partition_cbs(off_c, cov_c), eng.partition_cbs(off_c, cov_c, sharded=True)
+    ok["cbs"] = all(np.array_equal(x["len"], y["len"]) and np.array_equal(x["mean"], y["mean"]) for x, y in zip(fc["segments"], sc["segments"]))
+    fh, sh = eng.partition_hmm(off, cov, per_sample=True), eng.partition_hmm(off, cov, per_sample=True, sharded=True)
+    ok["hmm"] = same_bp(fh["breakpoints"], sh["breakpoints"]) and np.array_equal(fh["states"], sh["states"])
+    # config 5's gather: lists of different lengths, one of them beyond the first-round capacity
+    mine = np.arange(5 + 40_000 * (rank == world - 1) + 7 * rank, dtype=np.int32) + 1000 * rank
+    got = eng.allgather_lists(mine)
+    ok["allgather_lists"] = all(np.array_equal(g, np.arange(5 + 40_000 * (r == world - 1) + 7 * r, dtype=np.int32) + 1000 * r)
+                                for r, g in enumerate(got))
+    buf = (np.arange(1_000_003, dtype=np.float32) * (1 if rank == world - 1 else 0))
+    eng.broadcast(buf, world - 1)
+    ok["broadcast"] = bool(np.array_equal(buf, np.arange(1_000_003, dtype=np.float32)))
+    info = {"bins": int(len(cov)), "breakpoints": sum(len(b) for b in full["breakpoints"]), "owners": shard["owner"].tolist(),
+            "fused_exchange_ms": x_ms}
+    return ok, info
+
+
+def main_torchrun(scale):
     import torch
     import torch.distributed as dist
-    from canvas_b200 import multi, native, synth
-    scale = float(sys.argv[1]) if len(sys.argv) > 1 else 0.25
+    from canvas_b200 import native
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     eng = native.Engine(local)
-    s = synth.make_sample(config=2, sample=3, scale=scale, n_events=60)
-    c = eng.clean(s.chrom, s.is_autosome, s.is_chr_y, s.start, s.stop, s.count, s.gc)  # replicated on every rank
-    off = synth.chrom_offsets(s.chrom[c["kept_index"]], len(s.names))
-    from canvas_b200 import textcodec
-    cov = textcodec.f2_roundtrip(c["count"])
-    ew = max(2000, int(100000 * scale))
-    full = eng.partition_wavelet(off, cov, is_germline=True, evenness_window=ew)
-    shard = multi.partition_wavelet_sharded(eng, off, cov, is_germline=True, evenness_window=ew)
-    ok_w = all(a.tolist() == b.tolist() for a, b in zip(full["breakpoints"], shard["breakpoints"]))
-    ok_w = ok_w and full["cv"] == shard["cv"] and np.array_equal(full["factor_of_three"], shard["factor_of_three"])
-    # the fused Clean + partition call, sharded: equals the single-GPU fused call
-    fused = eng.clean_partition_wavelet(s.chrom, s.is_autosome, s.is_chr_y, s.start, s.stop, s.count, s.gc, is_germline=True,
-                                        evenness_window=ew)
-    fs = multi.clean_partition_wavelet_sharded(eng, (s.chrom, s.is_autosome, s.is_chr_y, s.start, s.stop, s.count, s.gc),
-                                               np.bincount(s.chrom, minlength=len(s.names)), is_germline=True, evenness_window=ew)
-    ok_w = ok_w and all(a.tolist() == b.tolist() for a, b in zip(fused["breakpoints"], fs["breakpoints"]))
-    ok_w = ok_w and all(a.tolist() == b.tolist() for a, b in zip(fused["breakpoints"], full["breakpoints"]))
-    # CBS on a few chromosomes' worth of bins (permutation tests are heavier)
-    ncb = min(len(off) - 1, 6)
-    off_c = off[:ncb + 1]
-    cov_c = cov[:off_c[-1]]
-    full_c = eng.partition_cbs(off_c, cov_c)
-    shard_c = multi.partition_cbs_sharded(eng, off_c, cov_c)
-    ok_c = all(a["len"].tolist() == b["len"].tolist() for a, b in zip(full_c["segments"], shard_c["segments"]))
-    full_h = eng.partition_hmm(off, cov, per_sample=True)
-    shard_h = multi.partition_hmm_sharded(eng, off, cov, per_sample=True)
-    ok_h = all(a.tolist() == b.tolist() for a, b in zip(full_h["breakpoints"], shard_h["breakpoints"]))
-    flag = torch.tensor([int(ok_w), int(ok_c and ok_h)], device="cuda")
+    eng.comm_init_torch()
+    ok, info = checks(eng, rank, world, scale)
+    flag = torch.tensor([int(v) for v in ok.values()], device="cuda")
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0:
-        print("multi-gpu check: world", world, "bins", len(cov), "wavelet", bool(flag[0].item()), "cbs+hmm", bool(flag[1].item()),
-              "breakpoints", sum(len(b) for b in full["breakpoints"]), "cbs segments", sum(len(x["len"]) for x in full_c["segments"]),
-              "owners", shard["owner"].tolist())
+        print("multi-gpu check (one process per GPU): world", world, "nccl", native.load().cg_comm_nccl_version(),
+              {k: bool(f) for k, f in zip(ok, flag.tolist())}, info)
     dist.destroy_process_group()
     eng.close()
-    return 0 if (ok_w and ok_c and ok_h) else 1
+    return 0 if all(flag.tolist()) else 1
+
+
+def main_single_process(n, scale):
+    import ctypes as C
+    from canvas_b200 import native
+    engs = [native.Engine(i) for i in range(n)]
+    arr = (C.c_void_p * n)(*[e.h for e in engs])
+    rc = native.load().cg_comm_init_all(n, arr)
+    assert rc == 0, engs[0].lib.cg_last_error(engs[0].h)
+    res = [None] * n
+
+    def work(r):
+        try:
+            res[r] = checks(engs[r], r, n, scale)
+        except Exception as e:  # noqa
+            res[r] = ({"exception": False}, {"error": repr(e)})
+
+    th = [threading.Thread(target=work, args=(r,)) for r in range(n)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    good = all(all(r[0].values()) for r in res)
+    print("multi-gpu check (one process,", n, "contexts, one thread each):", [r[0] for r in res] if not good else res[0][0], res[0][1])
+    [e.close() for e in engs]
+    return 0 if good else 1
 
 
 if __name__ == "__main__":
-    sys.exit(main())
+    a = sys.argv[1:]
+    if a and a[0] == "--single-process":
+        sys.exit(main_single_process(int(a[1]), float(a[2]) if len(a) > 2 else 0.25))
+    sys.exit(main_torchrun(float(a[0]) if a else 0.25))

@@ -87,7 +87,14 @@ def loess():
 
 
 runs = {"fused": fused, "k8": k8, "cbs": cbs, "hmm": hmm, "bin": binning, "loess": loess}
+rc = 0
 for name, fn in runs.items():
     if what in ("all", name):
-        fn()
+        try:
+            fn()
+        except Exception:
+            import traceback
+            traceback.print_exc()
+            rc = 1
 eng.close()
+sys.exit(rc)
