@@ -226,13 +226,16 @@ __device__ unsigned long long block_radix_select_u64(const unsigned long long* k
         __syncthreads();
         if (threadIdx.x < 32) {
             const int lane = threadIdx.x;
+            // every lane reads the rank before the one owning lane rewrites it below (racecheck: the shuffles in between
+            // are the warp-level barrier that orders the two)
+            const unsigned r = (unsigned)s_rank;
             unsigned c[8], sum = 0;
 #pragma unroll
             for (int t = 0; t < 8; t++) { c[t] = s_h[lane * 8 + t]; sum += c[t]; }
             unsigned incl = sum;
             for (int o = 1; o < 32; o <<= 1) { const unsigned v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
             const unsigned excl = incl - sum;
-            const unsigned r = (unsigned)s_rank;
+            __syncwarp();
             if (r >= excl && r < excl + sum) {  // exactly one lane
                 unsigned run = excl;
 #pragma unroll

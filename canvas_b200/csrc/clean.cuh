@@ -165,10 +165,14 @@ __host__ __device__ inline double cg_pow10(int k) {  // literals instead of a pe
     }
 }
 
-__host__ __device__ inline double dotnet_f2_roundtrip(float v) {
-    if (v != v || v - v != 0.0f) return (double)v;  // NaN / +-Infinity survive as such
+// Hundredths of |v| as float.ToString("F2") prints them (seven significant digits first, then half-up to two decimals);
+// false for NaN / +-Infinity.  The .cleaned value CanvasPartition parses back is hundredths / 100 (IO.cs:21,
+// CanvasSegment.cs:1147): a correctly rounded decimal parse and one IEEE division give the same double.
+__host__ __device__ inline bool dotnet_f2_hundredths(float v, double& hundredths) {
+    hundredths = 0.0;
+    if (v != v || v - v != 0.0f) return false;
     double x = v < 0 ? -(double)v : (double)v;
-    if (x == 0.0) return 0.0;
+    if (x == 0.0) return true;
     int e = 0;  // 10^e <= x < 10^(e+1)
     if (x >= 1.0) { while (e < 18 && x >= cg_pow10(e + 1)) e++; }
     else { e = -1; while (e > -19 && x * cg_pow10(-e) < 1.0) e--; }
@@ -177,7 +181,6 @@ __host__ __device__ inline double dotnet_f2_roundtrip(float v) {
     double scaled = (6 - e >= 0) ? (6 - e < 20 ? x * cg_pow10(6 - e) : 0.0) : x / cg_pow10(e - 6);
     double d7 = rint(scaled);
     if (d7 >= 1e7) { d7 /= 10.0; e += 1; }
-    double hundredths;
     if (e >= 4) {
         hundredths = d7 * cg_pow10(e - 4 < 19 ? e - 4 : 19);
     } else {
@@ -200,6 +203,12 @@ __host__ __device__ inline double dotnet_f2_roundtrip(float v) {
             hundredths = (double)h;
         }
     }
+    return true;
+}
+
+__host__ __device__ inline double dotnet_f2_roundtrip(float v) {
+    double hundredths;
+    if (!dotnet_f2_hundredths(v, hundredths)) return (double)v;  // NaN / +-Infinity survive as such
     const double r = hundredths / 100.0;
     return v < 0 ? -r : r;
 }

@@ -67,11 +67,15 @@ int comm_attach(cg_ctx* ctx, ncclComm_t comm, int rank, int size) {
     c->comm = comm;
     c->rank = rank;
     c->size = size;
+    if (const char* e = getenv("CANVAS_COMM_PACK_INTS")) {
+        const long v = atol(e);
+        if (v >= CG_COMM_PACK_MIN && v <= (1 << 24)) c->pack_ints = (int)v;
+    }
     ctx->comm = c;
     CG_CUDA(ctx, cudaSetDevice(ctx->device));
     CG_CUDA(ctx, cudaEventCreate(&c->ev0));
     CG_CUDA(ctx, cudaEventCreate(&c->ev1));
-    return comm_reserve(ctx, CG_COMM_PACK_INTS);
+    return comm_reserve(ctx, (size_t)c->pack_ints);
 }
 
 }  // namespace
@@ -94,7 +98,7 @@ int comm_reserve(cg_ctx* ctx, size_t cap_ints) {
     if (!c) return cg_fail(ctx, CG_ERR_ARG, "no communicator: call cg_comm_init first");
     CG_CUDA(ctx, cudaSetDevice(ctx->device));
     if (!c->d_send) {
-        const size_t cap = CG_COMM_PACK_INTS;
+        const size_t cap = (size_t)c->pack_ints;
         CG_CUDA(ctx, cudaMalloc((void**)&c->d_send, cap * 4));
         CG_CUDA(ctx, cudaMalloc((void**)&c->d_recv, cap * 4 * (size_t)c->size));
         CG_CUDA(ctx, cudaMallocHost((void**)&c->h_recv, cap * 4 * (size_t)c->size));
@@ -102,7 +106,7 @@ int comm_reserve(cg_ctx* ctx, size_t cap_ints) {
         CG_CUDA(ctx, cudaMemset(c->d_send, 0, cap * 4));
         c->cap_ints = cap;
     }
-    if (cap_ints <= (size_t)CG_COMM_PACK_INTS || cap_ints <= c->cap2_ints) return CG_OK;
+    if (cap_ints <= (size_t)c->pack_ints || cap_ints <= c->cap2_ints) return CG_OK;
     if (c->d2_send) c->retired.push_back(c->d2_send);
     if (c->d2_recv) c->retired.push_back(c->d2_recv);
     c->d2_send = c->d2_recv = nullptr;
@@ -140,7 +144,7 @@ int comm_allgatherv(cg_ctx* ctx, const int32_t* local, int64_t n_local, const st
     CG_CUDA(ctx, cudaSetDevice(ctx->device));
     cudaStream_t s = ctx->stream;
     const int R = c->size;
-    const int CAP = CG_COMM_PACK_INTS;
+    const int CAP = c->pack_ints;
     int rc = comm_reserve(ctx, CAP);
     if (rc) return rc;
     if (n_local < 0 || n_local > 0x7ffffff0LL) return cg_fail(ctx, CG_ERR_ARG, "comm_allgatherv: bad list length");

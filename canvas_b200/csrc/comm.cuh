@@ -12,6 +12,7 @@
 #include "common.cuh"
 
 constexpr int CG_COMM_PACK_INTS = 16384;  // first-round capacity of a rank's packed list: [length, payload ...]
+constexpr int CG_COMM_PACK_MIN = 512;     // smallest capacity CANVAS_COMM_PACK_INTS may ask for (tests of the second round)
 
 struct CgNccl {
     void* lib = nullptr;
@@ -30,6 +31,7 @@ struct CgNccl {
 struct CgComm {
     ncclComm_t comm = nullptr;  // nullptr with size == 1: loopback (no NCCL call is made)
     int rank = 0, size = 1;
+    int pack_ints = CG_COMM_PACK_INTS;  // first-round capacity; CANVAS_COMM_PACK_INTS (same value on every rank) overrides it
     // first-round exchange buffers (device: send [cap], recv [size * cap]; pinned host mirrors), allocated once
     int32_t* d_send = nullptr;
     int32_t* d_recv = nullptr;

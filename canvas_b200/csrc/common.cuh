@@ -27,6 +27,8 @@ struct cg_ctx {
     int num_sms = CG_NUM_SMS_FALLBACK;
     cudaStream_t stream = nullptr;
     cudaStream_t copy_stream = nullptr;  // overlaps result downloads with later kernels
+    cudaStream_t side_stream = nullptr;  // kernels off the critical path (partition: evenness / factor-of-three statistics)
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     cudaEvent_t ev_mid = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     std::string err;

@@ -28,6 +28,8 @@ struct SelState {
     K* gprefix;                  // [nseg*SEL_G]  decided high bits of each group
     unsigned* hist;              // [nseg*SEL_G*256]
     int* seg_done;               // [nseg + 1] blocks that finished the current pass (slot nseg: whole grid)
+    unsigned* req_aux;           // [nseg*SEL_G*4] pair mode (see sel_resolve_segment): {count of the even key, count of the odd key,
+                                 //                rank inside the pair, 0} of the pair of keys that holds the requested rank
 };
 
 template <typename K>
@@ -39,6 +41,7 @@ inline size_t sel_state_bytes(int nseg) {
     s += arena_need((size_t)nseg * SEL_G, sizeof(K)) * 2;
     s += arena_need((size_t)nseg * SEL_G * SEL_BINS, sizeof(unsigned));
     s += arena_need(nseg + 1, sizeof(int));
+    s += arena_need((size_t)nseg * SEL_G * 4, sizeof(unsigned));
     return s;
 }
 
@@ -53,11 +56,12 @@ inline bool sel_state_alloc(cg_ctx* ctx, int nseg, SelState<K>& st) {
     st.gprefix = arena_take<K>(ctx, (size_t)nseg * SEL_G);
     st.hist = arena_take<unsigned>(ctx, (size_t)nseg * SEL_G * SEL_BINS);
     st.seg_done = arena_take<int>(ctx, nseg + 1);
-    return st.seg_done && st.nreq && st.ngrp && st.req_k && st.req_grp && st.req_key && st.gprefix && st.hist;
+    st.req_aux = arena_take<unsigned>(ctx, (size_t)nseg * SEL_G * 4);
+    return st.seg_done && st.req_aux && st.nreq && st.ngrp && st.req_k && st.req_grp && st.req_key && st.gprefix && st.hist;
 }
 
 template <typename K>
-__device__ void sel_resolve_segment(SelState<K>& st, int s, int shift, int last);
+__device__ void sel_resolve_segment(SelState<K>& st, int s, int shift, int last, int pair = 0);
 
 // After the caller filled nreq / req_k: one group per segment with an empty prefix.
 template <typename K>
@@ -216,7 +220,7 @@ struct SelWork {
 
 template <typename K, class View>
 __global__ void __launch_bounds__(256, 4) sel_hist_contig_kernel(View v, const SelWork* __restrict__ work, const int* __restrict__ seg_nwork,
-                                       SelState<K> st, int shift, int first, int last) {
+                                       SelState<K> st, int shift, int first, int last, int pair) {
     __shared__ unsigned s_hist[SEL_WSEG][SEL_G * SEL_BINS];
     __shared__ K s_prefix[SEL_WSEG][SEL_G];
     __shared__ int s_last_block[SEL_WSEG];
@@ -302,6 +306,51 @@ __global__ void __launch_bounds__(256, 4) sel_hist_contig_kernel(View v, const S
             o = span;  // the generic loop below has nothing left
         }
     }
+    if constexpr (sizeof(K) == 4) {
+        // integer keys (hundredths of the coverage): one 4-byte load per element feeds every segment of the work item.
+        // View: __device__ bool plain32(int seg, const uint32_t*& base, int& twice_centre, bool& has_centre) const;
+        //   key = base[i], or the distance class (|2 base[i] - twice_centre| << 1) | (2 base[i] > twice_centre)
+        const uint32_t* hp = nullptr;
+        int c2[SEL_WSEG] = {0, 0, 0};
+        bool has_centre = false;
+        bool plain = true;
+#pragma unroll
+        for (int a = 0; a < SEL_WSEG; a++)
+            if (ng[a] > 0) {
+                const uint32_t* base = nullptr;
+                bool hc = false;
+                if (!v.plain32(w.seg[a], base, c2[a], hc)) plain = false;
+                else if (hp && (hp != base || hc != has_centre)) plain = false;
+                else { hp = base; has_centre = hc; }
+            }
+        if (plain && hp) {
+            hp += w.lo;
+            auto feed = [&](uint32_t h) {
+                if (!has_centre) {
+#pragma unroll
+                    for (int a = 0; a < SEL_WSEG; a++)
+                        if (ng[a] > 0) update(a, (K)h);
+                } else {
+#pragma unroll
+                    for (int a = 0; a < SEL_WSEG; a++)
+                        if (ng[a] > 0) {
+                            const int t = 2 * (int)h - c2[a];
+                            update(a, (K)(((unsigned)abs(t) << 1) | (t > 0 ? 1u : 0u)));
+                        }
+                }
+            };
+            constexpr int SEL_U32 = 8;
+            for (; o + (SEL_U32 - 1) * bd < span; o += SEL_U32 * bd) {
+                uint32_t x[SEL_U32];
+#pragma unroll
+                for (int u = 0; u < SEL_U32; u++) x[u] = hp[o + u * bd];
+#pragma unroll
+                for (int u = 0; u < SEL_U32; u++) feed(x[u]);
+            }
+            for (; o < span; o += bd) feed(hp[o]);
+            o = span;
+        }
+    }
     for (; o < span; o += bd) {
 #pragma unroll
         for (int a = 0; a < SEL_WSEG; a++)
@@ -332,7 +381,7 @@ __global__ void __launch_bounds__(256, 4) sel_hist_contig_kernel(View v, const S
     const int wid = threadIdx.x >> 5;
     if (wid < SEL_WSEG && s_last_block[wid]) {
         __threadfence();
-        sel_resolve_segment<K>(st, w.seg[wid], shift, last);
+        sel_resolve_segment<K>(st, w.seg[wid], shift, last, pair);
         if ((threadIdx.x & 31) == 0) st.seg_done[w.seg[wid]] = 0;
     }
 }
@@ -343,8 +392,10 @@ __global__ void __launch_bounds__(256, 4) sel_hist_contig_kernel(View v, const S
 // ---------------------------------------------------------------------------------------------
 // Resolve one segment with one warp: walk the rows of its groups, move each request into the bucket
 // that holds its rank, regroup requests by their new prefix and clear the rows for the next pass.
+// pair != 0 (last pass only): keys 2j and 2j+1 form one class whose two members the caller orders itself (the two sides of a
+// distance class in the MAD wave); besides the key, the populations of both members and the rank inside the pair are recorded.
 template <typename K>
-__device__ void sel_resolve_segment(SelState<K>& st, int s, int shift, int last) {
+__device__ void sel_resolve_segment(SelState<K>& st, int s, int shift, int last, int pair) {
     const int lane = threadIdx.x & 31;
     const int nr = st.nreq[s];
     const int ng = st.ngrp[s];
@@ -401,6 +452,19 @@ __device__ void sel_resolve_segment(SelState<K>& st, int s, int shift, int last)
                     run += c[t];
                 }
             }
+            if (pair && last) {  // the pair (d & ~1, d | 1) lies inside the owner lane's eight bins
+                unsigned c0 = 0, c1 = 0, rin = 0;
+                if (lane == owner) {
+                    const int t0 = (d & 7) & ~1;
+#pragma unroll
+                    for (int t = 0; t < 8; t += 2)
+                        if (t == t0) { c0 = c[t]; c1 = c[t + 1]; }
+                    const unsigned long long cum_pair = (d & 1) ? cum - c0 : cum;
+                    rin = (unsigned)(k - cum_pair);
+                    unsigned* aux = st.req_aux + ((size_t)s * SEL_G + r) * 4;
+                    aux[0] = c0; aux[1] = c1; aux[2] = rin; aux[3] = 0u;
+                }
+            }
             d = __shfl_sync(0xffffffffu, d, owner);
             cum = __shfl_sync(0xffffffffu, cum, owner);
             rk[r] = k >= cum ? k - cum : 0ull;
@@ -449,14 +513,14 @@ inline void sel_run_scatter(cg_ctx* ctx, const View& v, SelState<K>& st, long lo
     }
 }
 
+// key_bits: keys are known to be below 2^key_bits (a multiple of 8): the passes over the constant leading digits are skipped
 template <typename K, class View>
 inline void sel_run_contig(cg_ctx* ctx, const View& v, const SelWork* work_dev, const int* seg_nwork_dev, int nwork,
-                           SelState<K>& st) {
-    const int bits = (int)sizeof(K) * 8;
+                           SelState<K>& st, int key_bits = (int)sizeof(K) * 8, int pair = 0) {
     CG_LAUNCH(ctx, sel_begin_kernel<K>, div_up(st.nseg + 1, 128), 128, 0, st);
     if (nwork <= 0) return;
-    for (int shift = bits - 8; shift >= 0; shift -= 8) {
-        int first = shift == bits - 8;
-        CG_LAUNCH(ctx, (sel_hist_contig_kernel<K, View>), nwork, 256, 0, v, work_dev, seg_nwork_dev, st, shift, first, shift == 0);
+    for (int shift = key_bits - 8; shift >= 0; shift -= 8) {
+        int first = shift == key_bits - 8;
+        CG_LAUNCH(ctx, (sel_hist_contig_kernel<K, View>), nwork, 256, 0, v, work_dev, seg_nwork_dev, st, shift, first, shift == 0, pair);
     }
 }

@@ -19,8 +19,11 @@ struct WvPlan {
     std::vector<long long> off;
     WvSegTable t{};
     std::vector<long long> seg_len;
-    std::vector<SelWork> work;       // select work list (coverage windows, chromosomes, f3 pools)
+    std::vector<SelWork> work;       // select work list (coverage windows, chromosomes, f3 pools, evenness / ratio lists)
     std::vector<int> seg_nwork;      // work items of every segment
+    // the same items as two lists: coverage pieces (integer-key select on the main stream) and the rest (factor-of-three
+    // pools, evenness and ratio lists: double keys, side stream).  The combined list serves the all-double fallback.
+    size_t n_work_cov = 0;           // work[0 .. n_work_cov) are the coverage pieces
     std::vector<WvEvWork> ev_work;
     std::vector<WvScanTile> tiles;
     std::vector<int> tile_first;
@@ -97,6 +100,7 @@ void make_plan(WvPlan& pl, int n_chrom, const int64_t* chrom_off, int window) {
             add_work(pl.work, t.base_chrom + c, o + a, o + std::min(b, len), seg10, seg100);
         }
     }
+    pl.n_work_cov = pl.work.size();
     // factor-of-three cascade
     std::vector<long long> cur_len(n_chrom), cur_off(n_chrom);
     for (int c = 0; c < n_chrom; c++) { cur_len[c] = pl.off[c + 1] - pl.off[c]; cur_off[c] = pl.off[c]; }
@@ -157,6 +161,11 @@ struct WvDev {
     double* pz;
     // scalars
     SelState<uint64_t> sel;
+    SelState<uint32_t> sel32;   // integer-key select over the coverage segments (hundredths)
+    uint32_t* hq;               // hundredths of the coverage
+    int* m2;                    // per segment: twice the median in hundredths
+    unsigned* hq_bad;           // != 0: some coverage value is not a plain non-negative hundredth -> double keys
+    unsigned long long* ratio_keys;  // order statistics of the per-window MAD / median ratios: [0..5] 10 000-bin windows, [6..7] evenness-size windows
     long long* seg_len;
     SelWork* work;
     int* seg_nwork;
@@ -245,6 +254,7 @@ size_t wv_workspace_bytes(const WvPlan& pl) {
     size_t s = 0;
     s += arena_need(N, 8) + arena_need(C + 1, 8) + arena_need(C + 1, 1) + arena_need(N + C + 1, 8);
     s += sel_state_bytes<uint64_t>(pl.t.nseg) + arena_need(pl.t.nseg, 8);
+    s += sel_state_bytes<uint32_t>(pl.t.nseg) + arena_need(N + 1, 4) + arena_need(pl.t.nseg, 4) + arena_need(64, 4) + arena_need(16, 8);
     s += arena_need(pl.t.nseg + 1, 4) + arena_need(pl.work.size() + pl.work.size() / 8 + 64, sizeof(SelWork)) + arena_need(pl.ev_work.size() + 1, sizeof(WvEvWork));
     s += arena_need(pl.tiles.size() + 1, sizeof(WvScanTile)) + arena_need(C + 2, 4) + arena_need(pl.tiles.size() + 1, 8);
     s += arena_need(WV_F3_LEVELS, sizeof(WvF3Level));
@@ -262,7 +272,7 @@ size_t wv_workspace_bytes(const WvPlan& pl) {
     return s + (1 << 16);
 }
 
-int wv_alloc(cg_ctx* ctx, const WvPlan& pl, WvDev& d, double* cov_dev_existing) {
+int wv_alloc(cg_ctx* ctx, const WvPlan& pl, WvDev& d, double* cov_dev_existing, uint32_t* hq_existing = nullptr) {
     const size_t N = (size_t)pl.N, C = (size_t)pl.n_chrom;
     d.cov = cov_dev_existing ? cov_dev_existing : arena_take<double>(ctx, N);
     // plan tables uploaded by wv_enqueue: one contiguous block [d.off, d.plan_end) so that a single copy from a
@@ -281,6 +291,12 @@ int wv_alloc(cg_ctx* ctx, const WvPlan& pl, WvDev& d, double* cov_dev_existing) 
     d.plan_end = ctx->arena + ctx->arena_off;
     d.pz = arena_take<double>(ctx, N + C + 1);
     bool ok = sel_state_alloc<uint64_t>(ctx, pl.t.nseg, d.sel);
+    ok = sel_state_alloc<uint32_t>(ctx, pl.t.nseg, d.sel32) && ok;
+    d.hq = hq_existing ? hq_existing : arena_take<uint32_t>(ctx, N + 1);
+    d.m2 = arena_take<int>(ctx, pl.t.nseg);
+    d.hq_bad = arena_take<unsigned>(ctx, 64);
+    d.ratio_keys = arena_take<unsigned long long>(ctx, 16);
+    ok = ok && d.hq && d.m2 && d.hq_bad && d.ratio_keys;
     d.tsum = arena_take<double>(ctx, pl.tiles.size() + 1);
     d.tmed = arena_take<double>(ctx, pl.f3_total + 1);
     d.cmad = arena_take<double>(ctx, pl.f3_total + 1);
@@ -338,9 +354,9 @@ int wv_alloc(cg_ctx* ctx, const WvPlan& pl, WvDev& d, double* cov_dev_existing) 
 // be enqueued before the final plan is known (fused call: while the host still waits for the Clean results).
 // One kernel fills all nine regions (separate memsets cost a few microseconds of stream latency each).
 struct WvFillTable {
-    void* ptr[10];
-    unsigned long long words[10];  // 32-bit words
-    unsigned value[10];
+    void* ptr[12];
+    unsigned long long words[12];  // 32-bit words
+    unsigned value[12];
     int n;
 };
 
@@ -367,6 +383,7 @@ int wv_clear(cg_ctx* ctx, WvDev& d) {
     };
     add(d.ctl, sizeof(WvCtl), 0u);
     add(d.sel.hist, (size_t)d.cap_nseg * SEL_G * SEL_BINS * sizeof(unsigned), 0u);
+    add(d.sel32.hist, (size_t)d.cap_nseg * SEL_G * SEL_BINS * sizeof(unsigned), 0u);
     add(d.lvlcnt, (size_t)(d.cap_N + 1) * sizeof(unsigned), 0u);
     add(d.depth, (C + 1) * sizeof(int), 0u);
     add(d.big, (size_t)UH_QCAP * sizeof(UhBigTask), 0xffffffffu);
@@ -407,7 +424,7 @@ __global__ void wv_device_offsets_kernel(const unsigned* __restrict__ chrom_cnt,
 }
 
 int wv_enqueue(cg_ctx* ctx, const cg_wavelet_opts* o, const WvPlan& pl, WvDev& d, const unsigned char* selected_host,
-               bool rq_index_done = false, int* comm_pack = nullptr) {
+               bool rq_index_done = false, int* comm_pack = nullptr, bool use_int = false) {
     cudaStream_t s = ctx->stream;
     const int C = pl.n_chrom;
     const WvSegTable& t = pl.t;
@@ -416,6 +433,7 @@ int wv_enqueue(cg_ctx* ctx, const cg_wavelet_opts* o, const WvPlan& pl, WvDev& d
         pl.rq_ntiles > d.cap_rq || C != d.cap_C)
         return cg_fail(ctx, CG_ERR_CAPACITY, "partition: plan exceeds the workspace it was allocated for");
     d.sel.nseg = t.nseg;
+    d.sel32.nseg = t.nseg;
     // ---- plan tables: packed into the pinned staging block with the device layout, one copy
     {
         char* base = (char*)d.off;
@@ -449,7 +467,7 @@ int wv_enqueue(cg_ctx* ctx, const cg_wavelet_opts* o, const WvPlan& pl, WvDev& d
         CG_CUDA(ctx, cudaMemcpyAsync(base, h, bytes, cudaMemcpyHostToDevice, s));
     }
     if (pl.N == 0) {
-        if (comm_pack) CG_LAUNCH(ctx, wv_pack_comm_kernel, 1, 256, 0, d.n_bp, d.bp, d.off, C, comm_pack, CG_COMM_PACK_INTS);
+        if (comm_pack) CG_LAUNCH(ctx, wv_pack_comm_kernel, 1, 256, 0, d.n_bp, d.bp, d.off, C, comm_pack, ctx->comm->pack_ints);
         return CG_OK;
     }
 
@@ -474,55 +492,95 @@ int wv_enqueue(cg_ctx* ctx, const cg_wavelet_opts* o, const WvPlan& pl, WvDev& d
         wv_enqueue_rq_index(ctx, d, C, pl.rq_ntiles);
         CG_TL(ctx, "rq index");
     }
-    // ---- evenness per window (coverage only: early, for the same reason)
-    if (!pl.ev_work.empty())
-        CG_LAUNCH(ctx, wv_evenness_kernel, (int)pl.ev_work.size(), 1024, 0, d.cov, d.ev_work, d.ev10, d.ev100, d.ctl);
-    CG_TL(ctx, "evenness");
-    // ---- prefix sums
     const int ntiles = (int)pl.tiles.size();
-    if (ntiles > 0) {
-        CG_LAUNCH(ctx, wv_scan_tile_sum_kernel, ntiles, 256, 0, d.cov, d.tiles, d.tsum);
-        CG_LAUNCH(ctx, wv_scan_tile_offsets_kernel, div_up(C, 64), 64, 0, d.tsum, d.tile_first, C);
-        CG_LAUNCH(ctx, wv_scan_apply_kernel, ntiles, 256, 0, d.cov, d.tiles, d.tsum, d.off, d.pz);
-    }
-    CG_TL(ctx, "scan");
-    // ---- factor-of-three cascade
     int max_len = 1;
     for (int c = 0; c < C; c++) max_len = std::max<long long>(max_len, pl.off[c + 1] - pl.off[c]);
-    for (int r = 0; r < pl.f3_levels_run; r++) {
-        if (pl.f3_cnt[r] == 0) break;
-        long long per = std::max<long long>(1, max_len / 3);
-        for (int q = 0; q < r; q++) per = std::max<long long>(1, per / 3);
-        dim3 grid((unsigned)std::min<long long>(256, (per + 255) / 256), (unsigned)C);
-        CG_LAUNCH(ctx, wv_triplet_kernel, grid, 256, 0, r == 0 ? d.cov : d.tmed, d.tmed, d.cmad, d.f3lv + r);
-    }
-    CG_TL(ctx, "triplets");
-    // ---- order statistics, three dependent waves
     const int nwork = (int)pl.work.size();
     const int rq_grid = div_up(t.nseg, 128);
     PartView pv{d.cov, d.cmad, d.ev10, d.ev100, d.r10, d.r100, nullptr, t};
-    CG_LAUNCH(ctx, wv_request_kernel, rq_grid, 128, 0, d.sel, sp, d.ctl, 1);
-    sel_run_contig<uint64_t, PartView>(ctx, pv, d.work, d.seg_nwork, nwork, d.sel);
-    CG_TL(ctx, "wave1 medians");
-    CG_LAUNCH(ctx, wv_median_finish_kernel, rq_grid, 128, 0, d.sel, d.med);
-    CG_LAUNCH(ctx, wv_evenness_finish_kernel, 1, 1, 0, d.sel, t, d.ctl);
-    CG_LAUNCH(ctx, wv_f3_finish_kernel, 1, 1, 0, sp, d.med, d.ctl);
-    PartView pv2 = pv;
-    pv2.center = d.med;
-    CG_LAUNCH(ctx, wv_request_kernel, rq_grid, 128, 0, d.sel, sp, d.ctl, 2);
-    sel_run_contig<uint64_t, PartView>(ctx, pv2, d.work, d.seg_nwork, nwork, d.sel);
-    CG_TL(ctx, "wave2 mads");
-    CG_LAUNCH(ctx, wv_median_finish_kernel, rq_grid, 128, 0, d.sel, d.mad);
+    auto enqueue_evenness = [&]() {
+        if (!pl.ev_work.empty())
+            CG_LAUNCH(ctx, wv_evenness_kernel, (int)pl.ev_work.size(), 1024, 0, d.cov, d.ev_work, d.ev10, d.ev100, d.ctl);
+    };
+    auto enqueue_scan = [&]() {
+        if (ntiles > 0) {
+            CG_LAUNCH(ctx, wv_scan_tile_sum_kernel, ntiles, 256, 0, d.cov, d.tiles, d.tsum);
+            CG_LAUNCH(ctx, wv_scan_tile_offsets_kernel, div_up(C, 64), 64, 0, d.tsum, d.tile_first, C);
+            CG_LAUNCH(ctx, wv_scan_apply_kernel, ntiles, 256, 0, d.cov, d.tiles, d.tsum, d.off, d.pz);
+        }
+    };
+    auto enqueue_triplets = [&]() {
+        for (int r = 0; r < pl.f3_levels_run; r++) {
+            if (pl.f3_cnt[r] == 0) break;
+            long long per = std::max<long long>(1, max_len / 3);
+            for (int q = 0; q < r; q++) per = std::max<long long>(1, per / 3);
+            dim3 grid((unsigned)std::min<long long>(256, (per + 255) / 256), (unsigned)C);
+            CG_LAUNCH(ctx, wv_triplet_kernel, grid, 256, 0, r == 0 ? d.cov : d.tmed, d.tmed, d.cmad, d.f3lv + r);
+        }
+    };
+    if (use_int) {
+        // ---- side stream: everything that only feeds reported scalars (evenness score, factor-of-three list) — per-window
+        // evenness, triplet cascade, their order statistics on double keys.  Joined before the results are packed.
+        cudaStream_t main_s = ctx->stream;
+        CG_CUDA(ctx, cudaEventRecord(ctx->ev_fork, main_s));
+        CG_CUDA(ctx, cudaStreamWaitEvent(ctx->side_stream, ctx->ev_fork, 0));
+        ctx->stream = ctx->side_stream;  // CG_LAUNCH and the select drivers enqueue on ctx->stream
+        enqueue_evenness();
+        enqueue_triplets();
+        CG_LAUNCH(ctx, wv_request_kernel, rq_grid, 128, 0, d.sel, sp, d.ctl, 1, 1);
+        sel_run_contig<uint64_t, PartView>(ctx, pv, d.work + pl.n_work_cov, d.seg_nwork, nwork - (int)pl.n_work_cov, d.sel);
+        CG_LAUNCH(ctx, wv_median_finish_kernel, rq_grid, 128, 0, d.sel, d.med);
+        CG_LAUNCH(ctx, wv_evenness_finish_kernel, 1, 1, 0, d.sel, t, d.ctl);
+        CG_LAUNCH(ctx, wv_f3_finish_kernel, 1, 1, 0, sp, d.med, d.ctl);
+        CG_CUDA(ctx, cudaEventRecord(ctx->ev_join, ctx->side_stream));
+        ctx->stream = main_s;
+        // ---- main stream: prefix sums, then medians and MADs of the coverage windows / chromosomes on integer hundredths
+        enqueue_scan();
+        CG_TL(ctx, "scan");
+        CovView32 cv1{d.hq, nullptr}, cv2{d.hq, d.m2};
+        CG_LAUNCH(ctx, wv_request32_kernel, rq_grid, 128, 0, d.sel32, sp, 1);
+        sel_run_contig<uint32_t, CovView32>(ctx, cv1, d.work, d.seg_nwork, (int)pl.n_work_cov, d.sel32, 24, 0);
+        CG_LAUNCH(ctx, wv_median_finish32_kernel, rq_grid, 128, 0, d.sel32, d.med, d.m2);
+        CG_TL(ctx, "wave1 medians");
+        CG_LAUNCH(ctx, wv_request32_kernel, rq_grid, 128, 0, d.sel32, sp, 2);
+        sel_run_contig<uint32_t, CovView32>(ctx, cv2, d.work, d.seg_nwork, (int)pl.n_work_cov, d.sel32, 24, 1);
+        CG_LAUNCH(ctx, wv_mad_finish32_kernel, rq_grid, 128, 0, d.sel32, d.med, d.m2, d.mad);
+        CG_TL(ctx, "wave2 mads");
+    } else {
+        // ---- evenness per window (coverage only: early, so that the device has work while the host launches the rest)
+        enqueue_evenness();
+        CG_TL(ctx, "evenness");
+        enqueue_scan();
+        CG_TL(ctx, "scan");
+        enqueue_triplets();
+        CG_TL(ctx, "triplets");
+        // ---- order statistics on double keys, dependent waves
+        CG_LAUNCH(ctx, wv_request_kernel, rq_grid, 128, 0, d.sel, sp, d.ctl, 1, 0);
+        sel_run_contig<uint64_t, PartView>(ctx, pv, d.work, d.seg_nwork, nwork, d.sel);
+        CG_TL(ctx, "wave1 medians");
+        CG_LAUNCH(ctx, wv_median_finish_kernel, rq_grid, 128, 0, d.sel, d.med);
+        CG_LAUNCH(ctx, wv_evenness_finish_kernel, 1, 1, 0, d.sel, t, d.ctl);
+        CG_LAUNCH(ctx, wv_f3_finish_kernel, 1, 1, 0, sp, d.med, d.ctl);
+        PartView pv2 = pv;
+        pv2.center = d.med;
+        CG_LAUNCH(ctx, wv_request_kernel, rq_grid, 128, 0, d.sel, sp, d.ctl, 2, 0);
+        sel_run_contig<uint64_t, PartView>(ctx, pv2, d.work, d.seg_nwork, nwork, d.sel);
+        CG_TL(ctx, "wave2 mads");
+        CG_LAUNCH(ctx, wv_median_finish_kernel, rq_grid, 128, 0, d.sel, d.mad);
+    }
     if (pl.cv_possible) {
         if (t.base_chrom > 0) CG_LAUNCH(ctx, wv_ratio_kernel, div_up(t.base_chrom, 128), 128, 0, t, d.med, d.mad, d.r10, d.r100);
         if (t.n_w10 <= WV_RATIO_SORT_MAX && t.n_w100 <= WV_RATIO_SORT_MAX) {
-            CG_LAUNCH(ctx, wv_ratio_stats_kernel, 2, 1024, 0, d.sel, sp, d.r10, d.r100);
+            CG_LAUNCH(ctx, wv_ratio_stats_kernel, 2, 1024, 0, d.ratio_keys, sp, d.r10, d.r100);
         } else {
-            CG_LAUNCH(ctx, wv_request_kernel, rq_grid, 128, 0, d.sel, sp, d.ctl, 3);
+            // more windows than one CTA sorts: the select engine on double keys (after the side stream is done with its state)
+            if (use_int) CG_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
+            CG_LAUNCH(ctx, wv_request_kernel, rq_grid, 128, 0, d.sel, sp, d.ctl, 3, 0);
             sel_run_contig<uint64_t, PartView>(ctx, pv, d.work, d.seg_nwork, nwork, d.sel);
+            CG_LAUNCH(ctx, wv_ratio_keys_from_select_kernel, 1, 32, 0, d.sel, t, d.ratio_keys);
         }
     }
-    CG_LAUNCH(ctx, wv_cv_sigma_kernel, 1, 128, 0, d.sel, sp, d.med, d.mad, d.off, d.ctl, d.sigma, d.cand_thr);
+    CG_LAUNCH(ctx, wv_cv_sigma_kernel, 1, 128, 0, d.ratio_keys, sp, d.med, d.mad, d.off, d.ctl, d.sigma, d.cand_thr);
 
     CG_TL(ctx, "wave3 + cv");
     cudaEventRecord(ctx->stage_ev[3], s);
@@ -595,8 +653,9 @@ int wv_enqueue(cg_ctx* ctx, const cg_wavelet_opts* o, const WvPlan& pl, WvDev& d
     }
     CG_TL(ctx, "uh_finish");
     cudaEventRecord(ctx->stage_ev[7], s);
+    if (use_int) CG_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));  // evenness / factor-of-three scalars are in the control block
     CG_LAUNCH(ctx, wv_pack_kernel, 1, 256, 0, d.n_bp, d.depth, d.bp, d.off, C, d.pack);
-    if (comm_pack) CG_LAUNCH(ctx, wv_pack_comm_kernel, 1, 256, 0, d.n_bp, d.bp, d.off, C, comm_pack, CG_COMM_PACK_INTS);
+    if (comm_pack) CG_LAUNCH(ctx, wv_pack_comm_kernel, 1, 256, 0, d.n_bp, d.bp, d.off, C, comm_pack, ctx->comm->pack_ints);
     return CG_OK;
 }
 
@@ -761,7 +820,19 @@ static int partition_wavelet_impl(cg_ctx* ctx, const cg_wavelet_opts* opts, int 
     CG_CUDA(ctx, cudaEventRecord(ctx->ev0, s));
     rc = wv_clear(ctx, d);
     if (rc) return rc;
-    rc = wv_enqueue(ctx, opts, pl, d, sel.data(), false, exchange ? ctx->comm->d_send : nullptr);
+    // integer keys for the order statistics when every coverage value is a plain two-decimal number (what the .cleaned
+    // text holds); the host needs that verdict before it enqueues the select passes
+    bool use_int = false;
+    if (pl.N > 0 && !getenv("CANVAS_NO_INT_KEYS")) {
+        CG_CUDA(ctx, cudaMemsetAsync(d.hq_bad, 0, 4, s));
+        CG_LAUNCH(ctx, wv_hundredths_kernel, std::max(1, std::min(div_up(pl.N, 256), ctx->num_sms * 8)), 256, 0, d.cov, pl.N, d.hq, d.hq_bad);
+        unsigned* h_bad = (unsigned*)(ctx->pinned + 8192);
+        CG_CUDA(ctx, cudaMemcpyAsync(h_bad, d.hq_bad, 4, cudaMemcpyDeviceToHost, s));
+        CG_CUDA(ctx, cudaStreamSynchronize(s));
+        use_int = *h_bad == 0u;
+    }
+    ctx->stats[15] = use_int ? 1.0 : 0.0;
+    rc = wv_enqueue(ctx, opts, pl, d, sel.data(), false, exchange ? ctx->comm->d_send : nullptr, use_int);
     if (rc) { cudaStreamSynchronize(s); return rc; }
     CG_CUDA(ctx, cudaEventRecord(ctx->ev1, s));
     rc = wv_collect(ctx, pl, d, n_bp, bp, evenness, evenness_ok, cv, cv_has_value, factor_of_three, exchange);
@@ -798,18 +869,28 @@ extern "C" int cg_partition_wavelet(cg_ctx* ctx, const cg_wavelet_opts* opts, in
 }
 
 // coverage for the partition stage = .cleaned round trip of the cleaned counts; per-chromosome bin counts
+// ... and the integer hundredths themselves (keys of the partition's order statistics); chrom_cnt[256] is raised when a
+// value cannot take the integer path (negative, not finite, or beyond WV_HQ_SAT)
 __global__ void fused_coverage_kernel(const float* __restrict__ count_out, const int32_t* __restrict__ kept,
                                       const uint8_t* __restrict__ chrom_in, const CleanCtl* __restrict__ ctl,
-                                      double* __restrict__ cov, unsigned* __restrict__ chrom_cnt) {
+                                      double* __restrict__ cov, uint32_t* __restrict__ hq, unsigned* __restrict__ chrom_cnt) {
     const int n = ctl->n_out;
     const int n_round = ((n + 31) / 32) * 32;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += gridDim.x * blockDim.x) {
         const bool ok = i < n;
         int c = 0;
+        bool bad = false;
         if (ok) {
-            cov[i] = dotnet_f2_roundtrip(count_out[i]);
+            const float v = count_out[i];
+            double hundredths;
+            const bool finite = dotnet_f2_hundredths(v, hundredths);
+            const double r = hundredths / 100.0;
+            cov[i] = !finite ? (double)v : (v < 0 ? -r : r);
+            bad = !finite || v < 0 || !(hundredths < (double)WV_HQ_SAT);
+            hq[i] = bad ? WV_HQ_SAT : (uint32_t)hundredths;
             c = chrom_in[kept[i]];
         }
+        if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) atomicOr(&chrom_cnt[256], 1u);
         const unsigned act = __ballot_sync(0xffffffffu, ok);
         if (ok) {
             const unsigned m = __match_any_sync(act, c);
@@ -865,7 +946,7 @@ static int clean_partition_wavelet_impl(cg_ctx* ctx, const cg_clean_opts* copts,
     WvPlan worst;
     make_plan(worst, n_chrom, in_off.data(), wopts->evenness_window);
     const bool loess = copts->gc_norm && copts->gc_mode != 0;
-    size_t need = clean_workspace_bytes(n, n_chrom, loess) + arena_need(n, 8) + arena_need(256, 4) + wv_workspace_bytes(worst);
+    size_t need = clean_workspace_bytes(n, n_chrom, loess) + arena_need(n, 8) + arena_need(n + 1, 4) + arena_need(264, 4) + wv_workspace_bytes(worst);
     need += need / 16;
     int rc = arena_reserve(ctx, need);
     if (rc) return rc;
@@ -878,8 +959,9 @@ static int clean_partition_wavelet_impl(cg_ctx* ctx, const cg_clean_opts* copts,
         for (int c = 0; c < n_chrom; c++) d.max_chrom_bins = std::max<int64_t>(d.max_chrom_bins, in_off[c + 1] - in_off[c]);
     }
     double* cov = arena_take<double>(ctx, n);
-    unsigned* chrom_cnt = arena_take<unsigned>(ctx, 256);
-    if (!cov || !chrom_cnt) return cg_fail(ctx, CG_ERR_CUDA, "arena exhausted");
+    uint32_t* hq = arena_take<uint32_t>(ctx, n + 1);
+    unsigned* chrom_cnt = arena_take<unsigned>(ctx, 264);  // [256]: a coverage value that cannot take the integer-key path
+    if (!cov || !hq || !chrom_cnt) return cg_fail(ctx, CG_ERR_CUDA, "arena exhausted");
     cudaStream_t s = ctx->stream;
     CG_CUDA(ctx, cudaMemcpyAsync(d.chrom, chrom, n, cudaMemcpyHostToDevice, s));
     CG_CUDA(ctx, cudaMemcpyAsync(d.gc, gc, n, cudaMemcpyHostToDevice, s));
@@ -890,7 +972,7 @@ static int clean_partition_wavelet_impl(cg_ctx* ctx, const cg_clean_opts* copts,
     if (n_chrom > 0) CG_CUDA(ctx, cudaMemcpyAsync(d.is_auto, chrom_is_autosome, n_chrom, cudaMemcpyHostToDevice, s));
     CG_CUDA(ctx, cudaMemsetAsync(d.is_chry, 0, 256, s));
     if (n_chrom > 0 && chrom_is_chrY) CG_CUDA(ctx, cudaMemcpyAsync(d.is_chry, chrom_is_chrY, n_chrom, cudaMemcpyHostToDevice, s));
-    CG_CUDA(ctx, cudaMemsetAsync(chrom_cnt, 0, 256 * 4, s));
+    CG_CUDA(ctx, cudaMemsetAsync(chrom_cnt, 0, 264 * 4, s));
     CgTimeline tl;
     tl.begin(s);
     ctx->tl = tl.on ? &tl : nullptr;
@@ -898,17 +980,17 @@ static int clean_partition_wavelet_impl(cg_ctx* ctx, const cg_clean_opts* copts,
     rc = clean_enqueue(ctx, copts, d);
     if (rc) { cudaStreamSynchronize(s); return rc; }
     CG_LAUNCH(ctx, fused_coverage_kernel, std::max(1, std::min(div_up(n, 256), ctx->num_sms * 8)), 256, 0, d.count_out,
-              d.kept, d.chrom, d.ctl, cov, chrom_cnt);
+              d.kept, d.chrom, d.ctl, cov, hq, chrom_cnt);
     CG_TL(ctx, "coverage f2");
     CleanCtl* h = (CleanCtl*)ctx->pinned;
     unsigned* h_cnt = (unsigned*)(ctx->pinned + 8192);
     CG_CUDA(ctx, cudaMemcpyAsync(h, d.ctl, sizeof(CleanCtl), cudaMemcpyDeviceToHost, s));
-    CG_CUDA(ctx, cudaMemcpyAsync(h_cnt, chrom_cnt, 256 * 4, cudaMemcpyDeviceToHost, s));
+    CG_CUDA(ctx, cudaMemcpyAsync(h_cnt, chrom_cnt, 264 * 4, cudaMemcpyDeviceToHost, s));
     CG_CUDA(ctx, cudaEventRecord(ctx->ev_mid, s));
     // partition workspace sized for the input lengths (an upper bound of the cleaned ones); its accumulators are
     // cleared on the device while the host waits for the per-chromosome survivor counts
     WvDev wd;
-    rc = wv_alloc(ctx, worst, wd, cov);
+    rc = wv_alloc(ctx, worst, wd, cov, hq);
     if (rc) { cudaStreamSynchronize(s); return rc; }
     rc = wv_clear(ctx, wd);
     if (rc) { cudaStreamSynchronize(s); return rc; }
@@ -956,7 +1038,9 @@ static int clean_partition_wavelet_impl(cg_ctx* ctx, const cg_clean_opts* copts,
     for (int c = 0; c <= n_chrom; c++) chrom_off_out[c] = off[c];
     WvPlan pl;
     make_plan(pl, n_chrom, off.data(), wopts->evenness_window);
-    rc = wv_enqueue(ctx, wopts, pl, wd, sel.data(), n_chrom > 0, exchange ? ctx->comm->d_send : nullptr);
+    const bool use_int = h_cnt[256] == 0u && !getenv("CANVAS_NO_INT_KEYS");
+    ctx->stats[15] = use_int ? 1.0 : 0.0;
+    rc = wv_enqueue(ctx, wopts, pl, wd, sel.data(), n_chrom > 0, exchange ? ctx->comm->d_send : nullptr, use_int);
     if (rc) { cudaStreamSynchronize(s); cudaStreamSynchronize(ctx->copy_stream); return rc; }
     CG_CUDA(ctx, cudaEventRecord(ctx->ev1, s));
     rc = wv_collect(ctx, pl, wd, n_bp, bp, evenness, evenness_ok, cv, cv_has_value, factor_of_three, exchange);

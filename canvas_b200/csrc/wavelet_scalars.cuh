@@ -51,6 +51,50 @@ struct PartView {
     }
 };
 
+// ---------------------------------------------------------------------------------------------
+// Integer keys.  The coverage CanvasPartition reads is hundredths / 100 by construction of the .cleaned text (IO.cs:21), so
+// the medians and MADs of the coverage windows and chromosomes (Segmentation.cs:309-347, WaveletSegmentation.cs:406-417) are
+// selected on the integer hundredths: keys below 2^24, three 8-bit digit passes instead of eight over the doubles, and the
+// doubles are rebuilt from the selected integers (h / 100.0 is the very double the text parses to).  MAD wave: the integer
+// distance |2h - m2| (m2 = the sum of the two middle hundredths = twice the median) orders the doubles |x - median| except
+// INSIDE one distance class, where the bins above and below the median can give two different doubles; the key carries the
+// side in its lowest bit and the class that holds the requested rank is resolved from the populations of its two sides
+// (CPU prototype: tools/hundredths_select_study.py, profiles/r03r_*).
+// ---------------------------------------------------------------------------------------------
+constexpr uint32_t WV_HQ_SAT = (1u << 22) - 1;  // hundredths from here on (coverage >= 41943.03) do not take the integer path
+
+struct CovView32 {
+    const uint32_t* hq;  // hundredths per bin
+    const int* m2;       // per segment: twice the median in hundredths (MAD wave); nullptr in the median wave
+    __device__ bool get(long long i, int seg, uint32_t& key) const {
+        const uint32_t h = hq[i];
+        if (!m2) { key = h; return true; }
+        const int t = 2 * (int)h - m2[seg];
+        key = ((unsigned)abs(t) << 1) | (t > 0 ? 1u : 0u);
+        return true;
+    }
+    __device__ bool plain32(int seg, const uint32_t*& base, int& twice_centre, bool& has_centre) const {
+        base = hq;
+        has_centre = m2 != nullptr;
+        twice_centre = has_centre ? m2[seg] : 0;
+        return true;
+    }
+};
+
+// coverage (already two-decimal doubles) -> hundredths; anything that is not exactly a non-negative hundredth below the
+// saturation bound raises the flag and the caller keeps the double keys
+__global__ void wv_hundredths_kernel(const double* __restrict__ cov, long long n, uint32_t* __restrict__ hq, unsigned* __restrict__ bad) {
+    bool any_bad = false;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const double x = cov[i];
+        const double h = rint(__dmul_rn(x, 100.0));
+        const bool ok = h >= 0.0 && h < (double)WV_HQ_SAT && __ddiv_rn(h, 100.0) == x && !(x == 0.0 && signbit(x));
+        hq[i] = ok ? (uint32_t)h : WV_HQ_SAT;
+        any_bad = any_bad || !ok;
+    }
+    if (__any_sync(0xffffffffu, any_bad) && (threadIdx.x & 31) == 0) atomicOr(bad, 1u);
+}
+
 struct WvScalarParams {
     WvSegTable t;
     const long long* seg_len;  // [nseg] host-known lengths (0 for the ev/ratio kinds)
@@ -105,11 +149,13 @@ __device__ inline void wv_quartile_values(unsigned long long n, const float* v, 
 // wave 1: medians of coverage windows + chromosomes, of the factor-of-three CMAD pools, and the
 // evenness order statistics; wave 2: MADs (centre = wave-1 median); wave 3: the float statistics of
 // the per-window MAD/median ratios.
-__global__ void wv_request_kernel(SelState<uint64_t> st, WvScalarParams p, const WvCtl* ctl, int wave) {
+// skip_cov: the coverage segments (windows, chromosomes) are served by the integer-key select (wv_request32_kernel)
+__global__ void wv_request_kernel(SelState<uint64_t> st, WvScalarParams p, const WvCtl* ctl, int wave, int skip_cov) {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= st.nseg) return;
     const WvSegTable& t = p.t;
     st.nreq[s] = 0;
+    if (skip_cov && s < t.base_f3) return;
     unsigned long long* k = st.req_k + (size_t)s * SEL_G;
     if (wave == 1) {
         if (s < t.base_f3) {
@@ -147,6 +193,58 @@ __global__ void wv_median_finish_kernel(SelState<uint64_t> st, double* __restric
     const uint64_t ka = st.req_key[s * SEL_G + 0], kb = st.req_key[s * SEL_G + 1];
     const double a = f64_unkey(ka), b = f64_unkey(kb);
     out[s] = ka == kb ? a : __ddiv_rn(__dadd_rn(a, b), 2.0);
+}
+
+// integer path: median requests for the coverage segments only (windows + chromosomes); wave as in wv_request_kernel
+__global__ void wv_request32_kernel(SelState<uint32_t> st, WvScalarParams p, int wave) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= st.nseg) return;
+    const WvSegTable& t = p.t;
+    st.nreq[s] = 0;
+    if (s >= t.base_f3) return;
+    if (wave == 2) {
+        const bool window_seg = s < t.base_chrom;
+        if (window_seg != (p.cv_possible != 0)) return;
+    }
+    const long long n = p.seg_len[s];
+    if (n > 0) { st.nreq[s] = 2; median_pair((unsigned long long)n, st.req_k + (size_t)s * SEL_G); }
+}
+
+// medians from the selected hundredths: SortedList<double>.Median() of the doubles h / 100
+__global__ void wv_median_finish32_kernel(SelState<uint32_t> st, double* __restrict__ med, int* __restrict__ m2) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= st.nseg) return;
+    if (st.nreq[s] != 2) return;
+    const uint32_t ha = st.req_key[s * SEL_G + 0], hb = st.req_key[s * SEL_G + 1];
+    const double a = __ddiv_rn((double)ha, 100.0), b = __ddiv_rn((double)hb, 100.0);
+    med[s] = ha == hb ? a : __ddiv_rn(__dadd_rn(a, b), 2.0);
+    m2[s] = (int)(ha + hb);
+}
+
+// MADs from the selected distance classes.  A request ended on key (d << 1 | side); its class holds c0 bins below the median
+// (hundredths (m2 - d) / 2) and c1 above ((m2 + d) / 2), and the requested rank is r inside the class: the smaller of the two
+// doubles |h / 100 - median| comes first.
+__global__ void wv_mad_finish32_kernel(SelState<uint32_t> st, const double* __restrict__ med, const int* __restrict__ m2,
+                                       double* __restrict__ mad) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= st.nseg) return;
+    if (st.nreq[s] != 2) return;
+    const double centre = med[s];
+    const int mm = m2[s];
+    double v[2];
+    for (int r = 0; r < 2; r++) {
+        const uint32_t key = st.req_key[s * SEL_G + r];
+        const unsigned* aux = st.req_aux + ((size_t)s * SEL_G + r) * 4;
+        const int d = (int)(key >> 1);
+        const unsigned c0 = aux[0], c1 = aux[1], rin = aux[2];
+        const double v_dn = fabs(__dsub_rn(__ddiv_rn((double)((mm - d) / 2), 100.0), centre));
+        const double v_up = fabs(__dsub_rn(__ddiv_rn((double)((mm + d) / 2), 100.0), centre));
+        if (c0 == 0u) v[r] = v_up;
+        else if (c1 == 0u) v[r] = v_dn;
+        else if (v_dn <= v_up) v[r] = rin < c0 ? v_dn : v_up;
+        else v[r] = rin < c1 ? v_up : v_dn;
+    }
+    mad[s] = v[0] == v[1] ? v[0] : __ddiv_rn(__dadd_rn(v[0], v[1]), 2.0);
 }
 
 // evenness order statistics are consumed right after wave 1 (the select state is reused by wave 2)
@@ -193,13 +291,12 @@ __global__ void wv_ratio_kernel(WvSegTable t, const double* __restrict__ med, co
 // the keys in shared memory (bitonic) and writes the requested order statistics where the select engine would
 // have left them (quartile ranks of the 10 000-bin windows, median pair of the evenness-size windows).
 constexpr int WV_RATIO_SORT_MAX = 4096;
-__global__ void __launch_bounds__(1024) wv_ratio_stats_kernel(SelState<uint64_t> st, WvScalarParams p, const float* __restrict__ r10,
-                                                              const float* __restrict__ r100) {
+__global__ void __launch_bounds__(1024) wv_ratio_stats_kernel(unsigned long long* __restrict__ ratio_keys, WvScalarParams p,
+                                                              const float* __restrict__ r10, const float* __restrict__ r100) {
     __shared__ unsigned long long s_k[WV_RATIO_SORT_MAX];
     const WvSegTable& t = p.t;
     const bool ten = blockIdx.x == 0;
     const int n = ten ? t.n_w10 : t.n_w100;
-    const int seg = ten ? t.base_r10 : t.base_r100;
     const float* src = ten ? r10 : r100;
     if (!p.cv_possible) return;
     if (ten && !(p.window > WV_WINDOW_IQR && n >= 2)) return;
@@ -225,12 +322,19 @@ __global__ void __launch_bounds__(1024) wv_ratio_stats_kernel(SelState<uint64_t>
         int nr;
         if (ten) { nr = 6; wv_quartile_ranks((unsigned long long)n, rk); }
         else { nr = 2; median_pair((unsigned long long)n, rk); }
-        for (int r = 0; r < nr; r++) st.req_key[(size_t)seg * SEL_G + r] = s_k[rk[r] < (unsigned long long)n ? rk[r] : n - 1];
+        for (int r = 0; r < nr; r++) ratio_keys[(ten ? 0 : 6) + r] = s_k[rk[r] < (unsigned long long)n ? rk[r] : n - 1];
     }
 }
 
+// wave 3 through the select engine (more windows than wv_ratio_stats_kernel sorts): its keys to where the CV step reads them
+__global__ void wv_ratio_keys_from_select_kernel(SelState<uint64_t> st, WvSegTable t, unsigned long long* __restrict__ ratio_keys) {
+    const int r = threadIdx.x;
+    if (r < 6) ratio_keys[r] = st.req_key[(size_t)t.base_r10 * SEL_G + r];
+    else if (r < 8) ratio_keys[r] = st.req_key[(size_t)t.base_r100 * SEL_G + (r - 6)];
+}
+
 // CV decision (Segmentation.cs:309-327) and per-chromosome thresholds (WaveletSegmentation.cs:406-417)
-__global__ void wv_cv_sigma_kernel(SelState<uint64_t> st, WvScalarParams p, const double* __restrict__ med,
+__global__ void wv_cv_sigma_kernel(const unsigned long long* __restrict__ ratio_keys, WvScalarParams p, const double* __restrict__ med,
                                    const double* __restrict__ mad, const long long* __restrict__ off, WvCtl* ctl,
                                    double* __restrict__ sigma, double* __restrict__ cand_thr) {
     __shared__ double s_cv;
@@ -244,14 +348,14 @@ __global__ void wv_cv_sigma_kernel(SelState<uint64_t> st, WvScalarParams p, cons
             bool done = false;
             if (p.window > WV_WINDOW_IQR && t.n_w10 >= 2) {
                 float v[6], q[3];
-                for (int r = 0; r < 6; r++) v[r] = (float)f64_unkey(st.req_key[t.base_r10 * SEL_G + r]);
+                for (int r = 0; r < 6; r++) v[r] = (float)f64_unkey(ratio_keys[r]);
                 wv_quartile_values(t.n_w10, v, q);
                 if ((double)__fdiv_rn(__fsub_rn(q[2], q[0]), q[1]) > 0.015) { cv = (double)q[0]; done = true; }
             }
             if (!done) {
                 if (t.n_w100 >= 1) {
-                    const float a = (float)f64_unkey(st.req_key[t.base_r100 * SEL_G + 0]);
-                    const float b = (float)f64_unkey(st.req_key[t.base_r100 * SEL_G + 1]);
+                    const float a = (float)f64_unkey(ratio_keys[6]);
+                    const float b = (float)f64_unkey(ratio_keys[7]);
                     cv = (t.n_w100 & 1) ? (double)a : (double)__fdiv_rn(__fadd_rn(a, b), 2.0f);
                 } else {
                     cv = 0.0;  // Median of an empty list: unreachable for WGS-shaped input

@@ -49,16 +49,23 @@ def test_wavelet_sharded_equals_plain(eng):
     assert eng.last_exchange_ms >= 0
 
 
-def test_wavelet_sharded_more_breakpoints_than_the_first_round_holds(eng):
-    # a staircase with a step every 12 bins: ~25 000 breakpoints, beyond the 16 383 ints of the fixed-capacity round
+def test_wavelet_sharded_more_breakpoints_than_the_first_round_holds(monkeypatch):
+    # first-round capacity lowered to 512 ints (CANVAS_COMM_PACK_INTS): ~1000 breakpoints travel in the exact second round
+    monkeypatch.setenv("CANVAS_COMM_PACK_INTS", "512")
+    e = native.Engine(0)
+    e.comm_init(1, 0)
     rng = np.random.default_rng(3)
     n = 300_000
-    cov = np.round(100.0 + 60.0 * ((np.arange(n) // 12) % 2) + rng.normal(0, 0.5, n), 2)
+    lev = rng.choice([100., 2000., 4000., 8000., 16000.], n // 15 + 1)
+    cov = np.round(np.repeat(lev, 15)[:n] + rng.normal(0, 0.5, n), 2)
     off = np.array([0, 200_000, n])
-    plain = eng.partition_wavelet(off, cov, evenness_window=20000)
-    shard = eng.partition_wavelet(off, cov, evenness_window=20000, sharded=True)
-    assert sum(len(b) for b in plain["breakpoints"]) > 17_000
+    plain = e.partition_wavelet(off, cov, evenness_window=20000)
+    shard = e.partition_wavelet(off, cov, evenness_window=20000, sharded=True)
+    assert sum(len(b) for b in plain["breakpoints"]) > 600
     _same_bp(plain["breakpoints"], shard["breakpoints"])
+    big = np.arange(5000, dtype=np.int32)
+    assert np.array_equal(e.allgather_lists(big)[0], big)
+    e.close()
 
 
 def test_cbs_and_hmm_sharded_equal_plain(eng):

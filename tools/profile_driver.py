@@ -10,6 +10,11 @@ what = sys.argv[3] if len(sys.argv) > 3 else "both"
 eng = native.Engine(0)
 s = synth.make_sample(config=2, scale=scale)
 for it in range(iters):
+    if what == "fused":
+        r = eng.clean_partition_wavelet(s.chrom, s.is_autosome, s.is_chr_y, s.start, s.stop, s.count, s.gc, is_germline=True)
+        print("fused kernels ms", eng.last_kernel_ms, "launches", eng.last_launches, "bp", sum(len(b) for b in r["breakpoints"]),
+              "stages", eng.last_stage_ms())
+        continue
     if what in ("both", "clean"):
         r = eng.clean(s.chrom, s.is_autosome, s.is_chr_y, s.start, s.stop, s.count, s.gc)
         print("clean kernels ms", eng.last_kernel_ms, "launches", eng.last_launches, "kept", len(r["kept_index"]))

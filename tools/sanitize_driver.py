@@ -32,7 +32,7 @@ def fused():
 
 
 def k8():
-    n, batch = 300_007, 3
+    n, batch = 300_008, 3  # cg_normalize_apply takes n in multiples of 4
     count = rng.poisson(100, (batch, n)).astype(np.float32)
     gc = rng.integers(0, 101, (batch, n)).astype(np.uint8)
     med = rng.uniform(50, 150, (batch, 101))
