@@ -4,6 +4,8 @@
 extern "C" int cg_create(int device, cg_ctx** out) {
     if (!out) return CG_ERR_ARG;
     *out = nullptr;
+    // one hardware queue per chromosome stream of the partition (only effective if no CUDA context exists yet)
+    setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0);
     int count = 0;
     if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0 || device < 0 || device >= count)
         return CG_ERR_CUDA;  // no CPU fallback: the engine needs a CUDA device
@@ -51,6 +53,9 @@ extern "C" void cg_destroy(cg_ctx* ctx) {
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     if (ctx->ev_mid) cudaEventDestroy(ctx->ev_mid);
+    for (cudaStream_t st : ctx->chrom_streams) { cudaStreamSynchronize(st); cudaStreamDestroy(st); }
+    for (cudaEvent_t ev : ctx->chrom_ev) cudaEventDestroy(ev);
+    if (ctx->ev_fork2) cudaEventDestroy(ctx->ev_fork2);
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
     if (ctx->side_stream) { cudaStreamSynchronize(ctx->side_stream); cudaStreamDestroy(ctx->side_stream); }

@@ -75,7 +75,7 @@ int comm_attach(cg_ctx* ctx, ncclComm_t comm, int rank, int size) {
     CG_CUDA(ctx, cudaSetDevice(ctx->device));
     CG_CUDA(ctx, cudaEventCreate(&c->ev0));
     CG_CUDA(ctx, cudaEventCreate(&c->ev1));
-    return comm_reserve(ctx, (size_t)c->pack_ints);
+    return comm_reserve(ctx, 0);
 }
 
 }  // namespace
@@ -106,7 +106,7 @@ int comm_reserve(cg_ctx* ctx, size_t cap_ints) {
         CG_CUDA(ctx, cudaMemset(c->d_send, 0, cap * 4));
         c->cap_ints = cap;
     }
-    if (cap_ints <= (size_t)c->pack_ints || cap_ints <= c->cap2_ints) return CG_OK;
+    if (cap_ints == 0 || cap_ints <= c->cap2_ints) return CG_OK;  // cap_ints: what the second round has to hold per rank
     if (c->d2_send) c->retired.push_back(c->d2_send);
     if (c->d2_recv) c->retired.push_back(c->d2_recv);
     c->d2_send = c->d2_recv = nullptr;
@@ -145,7 +145,7 @@ int comm_allgatherv(cg_ctx* ctx, const int32_t* local, int64_t n_local, const st
     cudaStream_t s = ctx->stream;
     const int R = c->size;
     const int CAP = c->pack_ints;
-    int rc = comm_reserve(ctx, CAP);
+    int rc = comm_reserve(ctx, 0);
     if (rc) return rc;
     if (n_local < 0 || n_local > 0x7ffffff0LL) return cg_fail(ctx, CG_ERR_ARG, "comm_allgatherv: bad list length");
     if (local) {

@@ -48,7 +48,7 @@ struct CgComm {
 };
 
 const CgNccl* cg_nccl(std::string* err);                       // nullptr + message when the library cannot be bound
-int comm_reserve(cg_ctx* ctx, size_t cap_ints);                // buffers for lists of up to cap_ints ints per rank
+int comm_reserve(cg_ctx* ctx, size_t cap_ints);                // first-round buffers; second-round buffers for cap_ints ints per rank when > 0
 // Greedy longest-processing-time-first: heaviest unit first onto the least loaded rank (ties: lower rank, earlier unit).
 void comm_assign_lpt(int n_units, const int64_t* weight, int n_ranks, int32_t* owner);
 // All-gather of one int32 list per rank.  The local list is either on the host (`local`) or already packed on the device

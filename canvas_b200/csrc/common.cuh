@@ -29,6 +29,11 @@ struct cg_ctx {
     cudaStream_t copy_stream = nullptr;  // overlaps result downloads with later kernels
     cudaStream_t side_stream = nullptr;  // kernels off the critical path (partition: evenness / factor-of-three statistics)
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    // partition: one stream per chromosome pipeline (decomposition stages + finish), created on first use
+    std::vector<cudaStream_t> chrom_streams;
+    std::vector<cudaEvent_t> chrom_ev;
+    cudaEvent_t ev_fork2 = nullptr;
+    bool uh_attrs_set = false;
     cudaEvent_t ev_mid = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     std::string err;
@@ -60,6 +65,25 @@ struct cg_ctx {
     std::vector<CgGraphEntry> clean_graphs;  // Clean pipeline graphs (clean.cu), dropped when the arena moves
     CgComm* comm = nullptr;
 };
+
+constexpr size_t CG_CHROM_STREAMS = 32;
+inline int cg_chrom_streams(cg_ctx* ctx, int n) {
+    while ((int)ctx->chrom_streams.size() < n) {
+        cudaStream_t st = nullptr;
+        cudaEvent_t ev = nullptr;
+        if (cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess) {
+            ctx->err = "cannot create the per-chromosome streams";
+            return CG_ERR_CUDA;
+        }
+        ctx->chrom_streams.push_back(st);
+        ctx->chrom_ev.push_back(ev);
+    }
+    if (!ctx->ev_fork2 && cudaEventCreateWithFlags(&ctx->ev_fork2, cudaEventDisableTiming) != cudaSuccess) {
+        ctx->err = "cannot create an event";
+        return CG_ERR_CUDA;
+    }
+    return CG_OK;
+}
 
 inline void cg_graphs_clear(cg_ctx* ctx) {
     for (auto& g : ctx->clean_graphs) cudaGraphExecDestroy(g.exec);

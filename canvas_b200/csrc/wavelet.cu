@@ -36,6 +36,7 @@ struct WvPlan {
     int f3_levels_run = 0;
     int window = 100000;
     int cv_possible = 0;
+    std::vector<UhChromPlan> cplan;  // per-chromosome slices of the decomposition's rings and lists
 };
 
 constexpr long long SEL_CHUNK = 8192;
@@ -152,6 +153,22 @@ void make_plan(WvPlan& pl, int n_chrom, const int64_t* chrom_off, int window) {
     for (int c = 0; c < n_chrom; c++)
         pl.rq_tfirst[c + 1] = pl.rq_tfirst[c] + (int)((pl.off[c + 1] - pl.off[c] + RQ_TILE - 1) / RQ_TILE);
     pl.rq_ntiles = pl.rq_tfirst[n_chrom];
+    // decomposition: every chromosome owns a slice of the ring and of each list.  A node of stage M / S / T has more than
+    // UH_SMALL_MAX / UH_TINY_MAX / 1 bins and the roots of one stage are disjoint, which bounds the list lengths; big nodes
+    // (> UH_MID_MAX bins) are disjoint too, so a small ring holds every big node that can be pending at one time.
+    pl.cplan.assign(std::max(n_chrom, 1), UhChromPlan{});
+    int ring = 0, mid = 0, small = 0, tiny = 0, cand = 0;
+    for (int c = 0; c < n_chrom; c++) {
+        const long long len = pl.off[c + 1] - pl.off[c];
+        UhChromPlan& q = pl.cplan[c];
+        int rc = 8;
+        while (rc < 2 * (len / UH_MID_MAX + 2)) rc <<= 1;
+        q.ring_base = ring; q.ring_cap = rc; ring += rc;
+        q.mid_base = mid; q.mid_cap = (int)(len / UH_SMALL_MAX + 64); mid += q.mid_cap;
+        q.small_base = small; q.small_cap = (int)(len / UH_TINY_MAX + 64); small += q.small_cap;
+        q.tiny_base = tiny; q.tiny_cap = (int)(len / 2 + 64); tiny += q.tiny_cap;
+        q.cand_base = cand; q.cand_cap = (int)(len / 4 + 256); cand += q.cand_cap;
+    }
 }
 
 struct WvDev {
@@ -186,6 +203,8 @@ struct WvDev {
     UhTask *mid, *small;
     UhTinyTask* tiny;
     int mid_cap, small_cap, tiny_cap;
+    UhChromCtl* cc;     // [C] queue counters of the per-chromosome pipelines
+    UhChromPlan* cp;    // [C] (plan table, uploaded with the others)
     UhCand* cand;
     int cand_cap;
     // finish scratch
@@ -212,8 +231,14 @@ struct WvDev {
 // [0, C) n_bp, [C, 2C) tree depth, [2C] total breakpoints, then the lists in chromosome order while they fit.
 constexpr int WV_PACK_INTS = 16384;
 __global__ void __launch_bounds__(256) wv_pack_kernel(const int* __restrict__ n_bp, const int* __restrict__ depth, const int* __restrict__ bp,
-                                                      const long long* __restrict__ off, int C, int* __restrict__ pack) {
+                                                      const long long* __restrict__ off, int C, int* __restrict__ pack,
+                                                      const UhChromCtl* __restrict__ cc, WvCtl* ctl) {
     __shared__ int s_at[WV_MAX_CHROM + 1];
+    if (threadIdx.x == 32) {
+        unsigned long long tot = 0;
+        for (int c = 0; c < C; c++) tot += (unsigned long long)cc[c].cand_count_.v;
+        ctl->cand_total = tot;
+    }
     if (threadIdx.x == 0) {
         int run = 0;
         for (int c = 0; c < C; c++) { s_at[c] = run; run += n_bp[c]; }
@@ -262,9 +287,10 @@ size_t wv_workspace_bytes(const WvPlan& pl) {
     s += arena_need(pl.t.n_w10 + 1, 4) + arena_need(pl.t.n_w100 + 1, 4);
     s += arena_need(pl.t.nseg, 8) * 2 + arena_need(C + 1, 8) * 2 + arena_need(32, 8) + arena_need(1, sizeof(WvCtl));
     s += arena_need(N + 1, 4) + arena_need(C + 1, 4);
-    s += arena_need(UH_QCAP, sizeof(UhBigTask)) + arena_need(N / UH_SMALL_MAX + C + 64, sizeof(UhTask)) +
-         arena_need(N / UH_TINY_MAX + C + 64, sizeof(UhTask)) + arena_need(N / 2 + C + 64, sizeof(UhTinyTask));
-    s += arena_need(N / 4 + 4096, sizeof(UhCand));
+    s += arena_need(UH_QCAP, sizeof(UhBigTask)) + arena_need(N / UH_SMALL_MAX + 64 * C + 64, sizeof(UhTask)) +
+         arena_need(N / UH_TINY_MAX + 64 * C + 64, sizeof(UhTask)) + arena_need(N / 2 + 64 * C + 64, sizeof(UhTinyTask));
+    s += arena_need(N / 4 + 256 * C + 4096, sizeof(UhCand));
+    s += arena_need(C + 1, sizeof(UhChromCtl)) + arena_need(C + 1, sizeof(UhChromPlan));
     s += arena_need(N + 1, 4) * 5 + arena_need(N + 1, 8) * 2 + arena_need(N / 32 + C + 2, 4);
     s += arena_need(C + 1, 4) + arena_need(N + 1, 4);
     s += arena_need((C + 1) * RQ_BUCKETS, 8) + arena_need(N + 1, 8) + arena_need((size_t)(pl.rq_ntiles + 1) * RQ_BUCKETS, 2) * 2;
@@ -288,6 +314,7 @@ int wv_alloc(cg_ctx* ctx, const WvPlan& pl, WvDev& d, double* cov_dev_existing, 
     d.f3lv = arena_take<WvF3Level>(ctx, WV_F3_LEVELS);
     d.rq_tfirst = arena_take<int>(ctx, C + 2);
     d.log3 = arena_take<double>(ctx, 32);
+    d.cp = arena_take<UhChromPlan>(ctx, C + 1);
     d.plan_end = ctx->arena + ctx->arena_off;
     d.pz = arena_take<double>(ctx, N + C + 1);
     bool ok = sel_state_alloc<uint64_t>(ctx, pl.t.nseg, d.sel);
@@ -314,14 +341,15 @@ int wv_alloc(cg_ctx* ctx, const WvPlan& pl, WvDev& d, double* cov_dev_existing, 
     d.big = arena_take<UhBigTask>(ctx, UH_QCAP);
     // a node of stage M / S / T has more than UH_SMALL_MAX / UH_TINY_MAX / 1 bins and the roots of one
     // stage are disjoint, which bounds the list lengths
-    d.mid_cap = (int)(N / UH_SMALL_MAX + C + 64);
+    d.mid_cap = (int)(N / UH_SMALL_MAX + 64 * C + 64);
     d.mid = arena_take<UhTask>(ctx, d.mid_cap);
-    d.small_cap = (int)(N / UH_TINY_MAX + C + 64);
+    d.small_cap = (int)(N / UH_TINY_MAX + 64 * C + 64);
     d.small = arena_take<UhTask>(ctx, d.small_cap);
-    d.tiny_cap = (int)(N / 2 + C + 64);
+    d.tiny_cap = (int)(N / 2 + 64 * C + 64);
     d.tiny = arena_take<UhTinyTask>(ctx, d.tiny_cap);
-    d.cand_cap = (int)(N / 4 + 4096);
+    d.cand_cap = (int)(N / 4 + 256 * C + 4096);
     d.cand = arena_take<UhCand>(ctx, d.cand_cap);
+    d.cc = arena_take<UhChromCtl>(ctx, C + 1);
     d.lvl_idx = arena_take<int>(ctx, N + 1);
     d.sv = arena_take<int>(ctx, N + 1);
     d.piece = arena_take<int>(ctx, N + 1);
@@ -343,7 +371,7 @@ int wv_alloc(cg_ctx* ctx, const WvPlan& pl, WvDev& d, double* cov_dev_existing, 
     ok = ok && d.rq_spl && d.rq_sorted && d.rq_hist && d.rq_tstart && d.rq_cum && d.rq_tfirst;
     ok = ok && d.cov && d.off && d.selected && d.pz && d.seg_len && d.work && d.seg_nwork && d.ev_work && d.tiles && d.tile_first &&
          d.tsum && d.f3lv && d.tmed && d.cmad && d.ev10 && d.ev100 && d.r10 && d.r100 && d.med && d.mad && d.sigma &&
-         d.cand_thr && d.log3 && d.ctl && d.pack && d.lvlcnt && d.depth && d.big && d.mid && d.small && d.tiny && d.cand && d.lvl_idx &&
+         d.cand_thr && d.log3 && d.ctl && d.pack && d.lvlcnt && d.depth && d.big && d.mid && d.small && d.tiny && d.cand && d.cc && d.cp && d.lvl_idx &&
          d.sv && d.piece && d.prelim && d.lvl_first && d.svkey && d.rec && d.bitmap && d.n_bp && d.bp;
     d.cap_N = pl.N; d.cap_nseg = pl.t.nseg; d.cap_work = pl.work.size() + pl.work.size() / 8 + 63; d.cap_ev = pl.ev_work.size(); d.cap_tiles = pl.tiles.size();
     d.cap_f3 = pl.f3_total; d.cap_w10 = pl.t.n_w10; d.cap_w100 = pl.t.n_w100; d.cap_rq = pl.rq_ntiles; d.cap_C = pl.n_chrom;
@@ -387,10 +415,11 @@ int wv_clear(cg_ctx* ctx, WvDev& d) {
     add(d.lvlcnt, (size_t)(d.cap_N + 1) * sizeof(unsigned), 0u);
     add(d.depth, (C + 1) * sizeof(int), 0u);
     add(d.big, (size_t)UH_QCAP * sizeof(UhBigTask), 0xffffffffu);
+    add(d.cc, (C + 1) * sizeof(UhChromCtl), 0u);
     add(d.n_bp, (C + 1) * sizeof(int), 0u);
     add(d.med, (size_t)d.cap_nseg * 8, 0u);
     add(d.mad, (size_t)d.cap_nseg * 8, 0u);
-    static_assert(sizeof(WvCtl) % 4 == 0 && sizeof(UhBigTask) % 4 == 0, "fill regions are whole 32-bit words");
+    static_assert(sizeof(WvCtl) % 4 == 0 && sizeof(UhBigTask) % 4 == 0 && sizeof(UhChromCtl) % 4 == 0, "fill regions are whole 32-bit words");
     CG_LAUNCH(ctx, wv_fill_kernel, ctx->num_sms * 4, 256, 0, t);
     // t_first = all ones (a minimum is taken over it); it lies inside the control block cleared above
     CG_CUDA(ctx, cudaMemsetAsync(&d.ctl->t_first, 0xff, sizeof(unsigned long long), ctx->stream));
@@ -459,6 +488,7 @@ int wv_enqueue(cg_ctx* ctx, const cg_wavelet_opts* o, const WvPlan& pl, WvDev& d
         put(d.tile_first, pl.tile_first.data(), (size_t)(C + 1) * 4);
         put(d.f3lv, pl.f3lv, sizeof(WvF3Level) * WV_F3_LEVELS);
         put(d.rq_tfirst, pl.rq_tfirst.data(), (size_t)(C + 1) * 4);
+        put(d.cp, pl.cplan.data(), (size_t)C * sizeof(UhChromPlan));
         // ceil(log(3^k) / log(3)) as the host's libm evaluates it (WaveletSegmentation.cs:224)
         double log3_tab[32] = {0};
         double pw = 1.0;
@@ -586,58 +616,12 @@ int wv_enqueue(cg_ctx* ctx, const cg_wavelet_opts* o, const WvPlan& pl, WvDev& d
     cudaEventRecord(ctx->stage_ev[3], s);
     cudaEventRecord(ctx->stage_ev[4], s);
     ctx->stage_used[2] = true;
-    // ---- decomposition
+    // ---- decomposition + finish: one pipeline per chromosome, each on its own stream (largest chromosomes first)
     UhParams up;
     up.x = d.cov; up.pz = d.pz; up.off = d.off; up.cand_thr = d.cand_thr; up.lvlcnt = d.lvlcnt;
-    up.big = d.big; up.mid = d.mid; up.mid_cap = d.mid_cap; up.small = d.small; up.small_cap = d.small_cap; up.tiny = d.tiny;
-    up.tiny_cap = d.tiny_cap;
-    up.cand = d.cand; up.cand_cap = d.cand_cap; up.ctl = d.ctl;
-    CG_LAUNCH(ctx, uh_seed_kernel, 1, 256, 0, up, d.selected, C, o->min_size);
-    {
-        // kernel A: as many co-resident clusters as the device takes (the grid must stay resident: idle
-        // clusters wait on the task ring)
-        cudaLaunchConfig_t cfg = {};
-        cfg.blockDim = dim3(UH_THREADS);
-        cfg.dynamicSmemBytes = 0;
-        cfg.stream = s;
-        cudaLaunchAttribute attr[1];
-        attr[0].id = cudaLaunchAttributeClusterDimension;
-        attr[0].val.clusterDim.x = UH_CLUSTER; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-        cfg.attrs = attr;
-        cfg.numAttrs = 1;
-        cfg.gridDim = dim3(UH_CLUSTER * 64);
-        int ncl = 0;
-        if (cudaOccupancyMaxActiveClusters(&ncl, uh_chain_kernel, &cfg) != cudaSuccess || ncl < 1) { cudaGetLastError(); ncl = ctx->num_sms / UH_CLUSTER / 2; }
-        if (ncl > 64) ncl = 64;
-        if (ncl < 1) ncl = 1;
-        cfg.gridDim = dim3(UH_CLUSTER * ncl);
-        cudaError_t le = cudaLaunchKernelEx(&cfg, uh_chain_kernel, up);
-        if (le != cudaSuccess) return cg_fail(ctx, CG_ERR_CUDA, std::string("uh_chain_kernel launch: ") + cudaGetErrorString(le));
-        ctx->launches++;
-        // stages M, S, T: each consumes the list the earlier stages filled
-        int occ = 0;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, uh_mid_kernel, UH_MID_THREADS, 0);
-        if (occ < 1) occ = 1;
-        CG_TL(ctx, "uh_chain");
-        CG_LAUNCH(ctx, uh_mid_kernel, ctx->num_sms * std::min(occ, 4), UH_MID_THREADS, 0, up);
-        const size_t uh_smem = sizeof(UhWarpScratch) * (UH_SMALL_THREADS / 32);
-        cudaFuncSetAttribute(uh_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)uh_smem);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, uh_small_kernel, UH_SMALL_THREADS, uh_smem);
-        if (occ < 1) occ = 1;
-        CG_TL(ctx, "uh_mid");
-        CG_LAUNCH(ctx, uh_small_kernel, ctx->num_sms * std::min(occ, 6), UH_SMALL_THREADS, uh_smem, up);
-        CG_TL(ctx, "uh_small");
-        CG_LAUNCH(ctx, uh_tiny_table_kernel, UH_TINY_MAX - 1, UH_TINY_MAX, 0, d.tiny_tab);
-        CG_LAUNCH(ctx, uh_tiny_kernel, ctx->num_sms * 16, 128, 0, up, d.tiny_tab);
-        if (C > 0) CG_LAUNCH(ctx, uh_depth_kernel, dim3(32, C), 256, 0, d.lvlcnt, d.off, d.depth);
-    }
-    CG_TL(ctx, "uh_tiny + depth");
-    cudaEventRecord(ctx->stage_ev[5], s);
-    cudaEventRecord(ctx->stage_ev[6], s);
-    ctx->stage_used[3] = true;
-    // ---- per-chromosome finish
+    up.big = d.big; up.mid = d.mid; up.small = d.small; up.tiny = d.tiny; up.cand = d.cand; up.cc = d.cc; up.cp = d.cp; up.ctl = d.ctl;
     FinParams fp;
-    fp.x = d.cov; fp.pz = d.pz; fp.off = d.off; fp.selected = d.selected; fp.cand = d.cand; fp.ctl = d.ctl;
+    fp.x = d.cov; fp.pz = d.pz; fp.off = d.off; fp.selected = d.selected; fp.cand = d.cand; fp.cc = d.cc; fp.cp = d.cp; fp.ctl = d.ctl;
     fp.lvlcnt = d.lvlcnt; fp.depth = d.depth; fp.sigma = d.sigma; fp.chrom_median = d.med + t.base_chrom;
     fp.log3_scale_tab = d.log3;
     fp.rq.spl = d.rq_spl; fp.rq.hist = d.rq_hist; fp.rq.tstart = d.rq_tstart; fp.rq.cum = d.rq_cum; fp.rq.sorted = d.rq_sorted;
@@ -647,14 +631,72 @@ int wv_enqueue(cg_ctx* ctx, const cg_wavelet_opts* o, const WvPlan& pl, WvDev& d
     fp.is_germline = o->is_germline; fp.min_size = o->min_size; fp.n_chrom = C; fp.pad = 0;
     fp.lvl_idx = d.lvl_idx; fp.sv = d.sv; fp.svkey = d.svkey; fp.bitmap = d.bitmap; fp.piece = d.piece; fp.rec = d.rec;
     fp.prelim = d.prelim; fp.lvl_first = d.lvl_first; fp.n_bp = d.n_bp; fp.bp = d.bp;
-    if (C > 0) {
-        cudaFuncSetAttribute(uh_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fin_smem_bytes());
-        CG_LAUNCH(ctx, uh_finish_kernel, C, FIN_THREADS, fin_smem_bytes(), fp);
+    {
+        const UhChromPlan& last = pl.cplan[C - 1];
+        if (last.ring_base + last.ring_cap > UH_QCAP || last.mid_base + last.mid_cap > d.mid_cap || last.small_base + last.small_cap > d.small_cap ||
+            last.tiny_base + last.tiny_cap > d.tiny_cap || last.cand_base + last.cand_cap > d.cand_cap)
+            return cg_fail(ctx, CG_ERR_CAPACITY, "partition: per-chromosome queues exceed the workspace");
     }
-    CG_TL(ctx, "uh_finish");
+    CG_LAUNCH(ctx, uh_seed_kernel, div_up(C, 128), 128, 0, up, d.selected, C, o->min_size);
+    CG_LAUNCH(ctx, uh_tiny_table_kernel, UH_TINY_MAX - 1, UH_TINY_MAX, 0, d.tiny_tab);
+    const size_t uh_smem = sizeof(UhWarpScratch) * (UH_SMALL_THREADS / 32);
+    if (!ctx->uh_attrs_set) {
+        cudaFuncSetAttribute(uh_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)uh_smem);
+        cudaFuncSetAttribute(uh_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fin_smem_bytes());
+        ctx->uh_attrs_set = true;
+    }
+    std::vector<int> order;
+    for (int c = 0; c < C; c++) {
+        const long long len = pl.off[c + 1] - pl.off[c];
+        if (selected_host[c] && len > o->min_size && len >= 2) order.push_back(c);
+    }
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return pl.off[a + 1] - pl.off[a] > pl.off[b + 1] - pl.off[b]; });
+    const int n_streams = (int)std::min<size_t>(order.size(), CG_CHROM_STREAMS);
+    int rc_streams = cg_chrom_streams(ctx, n_streams);
+    if (rc_streams) return rc_streams;
+    CG_CUDA(ctx, cudaEventRecord(ctx->ev_fork2, s));
+    for (size_t k = 0; k < order.size(); k++) {
+        const int c = order[k];
+        const long long len = pl.off[c + 1] - pl.off[c];
+        cudaStream_t cs = ctx->chrom_streams[k % n_streams];
+        if (k < (size_t)n_streams) CG_CUDA(ctx, cudaStreamWaitEvent(cs, ctx->ev_fork2, 0));
+        ctx->stream = cs;  // CG_LAUNCH enqueues on ctx->stream
+        if (len > UH_MID_MAX) {
+            // chains of big nodes: clusters wait on the chromosome's ring, any one of them can finish the work alone
+            cudaLaunchConfig_t cfg = {};
+            cfg.blockDim = dim3(UH_THREADS);
+            cfg.dynamicSmemBytes = 0;
+            cfg.stream = cs;
+            cudaLaunchAttribute attr[1];
+            attr[0].id = cudaLaunchAttributeClusterDimension;
+            attr[0].val.clusterDim.x = UH_CLUSTER; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+            cfg.attrs = attr;
+            cfg.numAttrs = 1;
+            cfg.gridDim = dim3(UH_CLUSTER * (len > 100000 ? 2 : 1));
+            cudaError_t le = cudaLaunchKernelEx(&cfg, uh_chain_kernel, up, c);
+            if (le != cudaSuccess) { ctx->stream = s; return cg_fail(ctx, CG_ERR_CUDA, std::string("uh_chain_kernel launch: ") + cudaGetErrorString(le)); }
+            ctx->launches++;
+        }
+        if (len > UH_SMALL_MAX)
+            CG_LAUNCH(ctx, uh_mid_kernel, (int)std::min<long long>(64, std::max<long long>(1, len / 2048)), UH_MID_THREADS, 0, up, c);
+        if (len > UH_TINY_MAX)
+            CG_LAUNCH(ctx, uh_small_kernel, (int)std::min<long long>(ctx->num_sms, std::max<long long>(1, len / 1024)), UH_SMALL_THREADS, uh_smem, up, c);
+        CG_LAUNCH(ctx, uh_tiny_kernel, (int)std::min<long long>(ctx->num_sms, std::max<long long>(1, len / 1024)), 128, 0, up, d.tiny_tab, c);
+        CG_LAUNCH(ctx, uh_depth_kernel, (int)std::min<long long>(32, std::max<long long>(1, len / 4096)), 256, 0, d.lvlcnt, d.off, d.depth, c);
+        CG_LAUNCH(ctx, uh_finish_kernel, 1, FIN_THREADS, fin_smem_bytes(), fp, c);
+    }
+    ctx->stream = s;
+    for (int k = 0; k < n_streams; k++) {
+        CG_CUDA(ctx, cudaEventRecord(ctx->chrom_ev[k], ctx->chrom_streams[k]));
+        CG_CUDA(ctx, cudaStreamWaitEvent(s, ctx->chrom_ev[k], 0));
+    }
+    CG_TL(ctx, "decompose + finish");
+    cudaEventRecord(ctx->stage_ev[5], s);
+    cudaEventRecord(ctx->stage_ev[6], s);
+    ctx->stage_used[3] = true;
     cudaEventRecord(ctx->stage_ev[7], s);
     if (use_int) CG_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));  // evenness / factor-of-three scalars are in the control block
-    CG_LAUNCH(ctx, wv_pack_kernel, 1, 256, 0, d.n_bp, d.depth, d.bp, d.off, C, d.pack);
+    CG_LAUNCH(ctx, wv_pack_kernel, 1, 256, 0, d.n_bp, d.depth, d.bp, d.off, C, d.pack, d.cc, d.ctl);
     if (comm_pack) CG_LAUNCH(ctx, wv_pack_comm_kernel, 1, 256, 0, d.n_bp, d.bp, d.off, C, comm_pack, ctx->comm->pack_ints);
     return CG_OK;
 }
@@ -697,7 +739,7 @@ int wv_collect(cg_ctx* ctx, const WvPlan& pl, WvDev& d, int32_t* n_bp, int32_t* 
     if (h->overflow_.v) return cg_fail(ctx, CG_ERR_CAPACITY, "partition: internal queue capacity exceeded");
     ctx->stats[0] = (double)(h->visits_big + h->visits_small + h->visits_tiny);
     ctx->stats[1] = (double)(h->nodes_big + h->nodes_small + h->nodes_tiny);
-    ctx->stats[2] = (double)h->cand_count_.v;
+    ctx->stats[2] = (double)h->cand_total;
     ctx->stats[3] = (double)pl.N;
     const int* h_nbp = h_pack;
     for (int c = 0; c < C; c++) n_bp[c] = h_nbp[c];

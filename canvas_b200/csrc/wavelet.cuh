@@ -25,7 +25,7 @@ constexpr int UH_MID_THREADS = 256;
 constexpr int UH_SMALL_THREADS = 256;
 constexpr int UH_THREADS = 512;
 constexpr int UH_CLUSTER = 8;        // CTAs (SMs) cooperating on one chain of big nodes
-constexpr int UH_QCAP = 1 << 16;    // ticket ring capacity
+constexpr int UH_QCAP = 1 << 16;    // total capacity of the ticket rings (every chromosome owns a power-of-two slice)
 
 // Segment kinds of the partition select table (see wavelet.cu)
 struct WvSegTable {
@@ -60,11 +60,26 @@ struct UhCand {  // node whose coefficient may survive the hard threshold
 struct alignas(128) WvPadU64 { unsigned long long v; unsigned long long pad[15]; };
 struct alignas(128) WvPadI32 { int v; int pad[31]; };
 
-struct WvCtl {
-    // queues
+// Every chromosome runs its own pipeline (chain -> mid -> small -> tiny -> finish on its own stream), so that its later
+// stages and its finish start as soon as ITS tree is ready while other chromosomes are still decomposing.  Queue state and
+// list slices are therefore per chromosome.
+struct UhChromCtl {
     WvPadU64 q_head_, q_tail_;
-    WvPadI32 small_head_, small_tail_, outstanding_, big_done_, overflow_, cand_count_;
-    WvPadI32 mid_head_, mid_tail_, tiny_tail_;
+    WvPadI32 outstanding_, big_done_;
+    WvPadI32 mid_head_, mid_tail_, small_head_, small_tail_, tiny_tail_, cand_count_;
+};
+
+struct UhChromPlan {      // slices of the shared arrays, filled by the host from the chromosome lengths
+    int ring_base, ring_cap;   // ring_cap is a power of two
+    int mid_base, mid_cap;
+    int small_base, small_cap;
+    int tiny_base, tiny_cap;
+    int cand_base, cand_cap;
+    int pad[2];
+};
+
+struct WvCtl {
+    WvPadI32 overflow_;
     // scalars
     int cv_has_value, evenness_ok;
     double cv, evenness;
@@ -74,9 +89,8 @@ struct WvCtl {
     // statistics (bench / DESIGN): bin visits of the decomposition and node counts per tier
     unsigned long long visits_big, visits_small, visits_tiny;
     unsigned long long nodes_big, nodes_small, nodes_tiny;
-    // timeline of the decomposition kernel (%globaltimer, ns)
+    unsigned long long cand_total;
+    // timeline of the decomposition kernels (%globaltimer, ns)
     unsigned long long t_first, t_big_done, t_last;
     unsigned long long multi_chunk_nodes, queue_hops;
-    // big-worker time accounting (ns, summed over workers) and node latencies
-    unsigned long long ns_wait, ns_work, ns_node_lat_sum, ns_node_lat_max, n_node_lat, ns_inline_sum, n_inline;
 };

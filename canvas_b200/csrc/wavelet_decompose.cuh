@@ -23,6 +23,11 @@
 // A run of exact zeros is emitted at once as the reference's one-bin-per-level comb.  Nodes are not
 // stored: only per-level node counts (HardThresh's germline weights need them) and the few nodes
 // whose coefficient can survive the threshold ("candidates").
+//
+// Every kernel works on ONE chromosome (argument c): the host runs the four stages of a chromosome back to back on that
+// chromosome's stream, followed by its finish kernel, and the chromosomes' pipelines run side by side — a stage of one
+// chromosome no longer waits for the slowest chromosome of the stage before it.  Queue counters and list slices are per
+// chromosome (UhChromCtl / UhChromPlan).
 #pragma once
 #include <cooperative_groups.h>
 
@@ -34,33 +39,42 @@ struct UhParams {
     const long long* off;    // [n_chrom + 1]
     const double* cand_thr;  // [n_chrom]
     unsigned* lvlcnt;        // [N]: node count of level l of chromosome c at off[c] + l
-    UhBigTask* big;          // stage A ring [UH_QCAP]; c < 0 = empty
-    UhTask* mid;             // stage M list
-    int mid_cap;
-    UhTask* small;           // stage S list
-    int small_cap;
-    UhTinyTask* tiny;        // stage T list
-    int tiny_cap;
-    UhCand* cand;
-    int cand_cap;
+    UhBigTask* big;          // stage A rings [UH_QCAP], one slice per chromosome; c < 0 = empty slot
+    UhTask* mid;             // stage M lists, one slice per chromosome
+    UhTask* small;           // stage S lists
+    UhTinyTask* tiny;        // stage T lists
+    UhCand* cand;            // candidate lists
+    UhChromCtl* cc;          // [n_chrom] queue counters
+    const UhChromPlan* cp;   // [n_chrom] slices of the arrays above
     WvCtl* ctl;
 };
 
 __device__ inline void uh_emit_candidate(const UhParams& p, int c, int level, int s, int b, int e, double coef) {
     if (fabs(coef) <= p.cand_thr[c]) return;  // NaN falls through on purpose (never zeroed by HardThresh)
-    const int i = atomicAdd(&p.ctl->cand_count_.v, 1);
-    if (i >= p.cand_cap) { p.ctl->overflow_.v = 1; return; }
+    const UhChromPlan& cp = p.cp[c];
+    const int i = atomicAdd(&p.cc[c].cand_count_.v, 1);
+    if (i >= cp.cand_cap) { p.ctl->overflow_.v = 1; return; }
     UhCand k;
     k.key = ((unsigned long long)c << 56) | ((unsigned long long)level << 32) | (unsigned)s;
     k.s = s; k.b = b; k.e = e; k.level = level; k.c = c; k.pad = 0; k.coef = coef;
-    p.cand[i] = k;
+    p.cand[cp.cand_base + i] = k;
+}
+
+// Can the node's coefficient exceed the candidate threshold at all?  score = D^2 / (a b) of the chosen split, and
+// coef^2 = score * n / scale^2 with scale = max(0.5, mean / 200): three multiplications instead of the square root and two
+// divisions of the exact coefficient, which only the few nodes that pass (or a NaN) still compute.  The factor leaves the
+// rounding of the exact formula far inside the margin.
+__device__ inline bool uh_may_be_candidate(double score, double nn, double mu, double thr2) {
+    const double sc = fmax(0.5, mu * 0.005);
+    return !(score * nn < 0.999999 * thr2 * sc * sc);
 }
 
 // Stage-A ring: a producer reserves a position with one atomicAdd, fills the slot and publishes it by
 // storing the chromosome id last; a consumer reserves a position the same way and waits for it.
 __device__ inline void uh_push_big(const UhParams& p, int c, int s, int e, int level, double base, double endv) {
-    const unsigned long long pos = atomicAdd(&p.ctl->q_tail_.v, 1ull);
-    UhBigTask* t = p.big + (pos & (UH_QCAP - 1));
+    const UhChromPlan& cp = p.cp[c];
+    const unsigned long long pos = atomicAdd(&p.cc[c].q_tail_.v, 1ull);
+    UhBigTask* t = p.big + cp.ring_base + (int)(pos & (unsigned long long)(cp.ring_cap - 1));
     while (*(volatile int*)&t->c >= 0) __nanosleep(64);  // slot still held by an unconsumed task (ring wrapped)
     t->s = s; t->e = e; t->level = level; t->base = base; t->endv = endv;
     __threadfence();
@@ -162,7 +176,7 @@ struct UhMail {
 };
 
 __global__ void __cluster_dims__(UH_CLUSTER, 1, 1) __launch_bounds__(UH_THREADS, 2)
-uh_chain_kernel(UhParams p) {
+uh_chain_kernel(UhParams p, int c_self) {
     namespace cg = cooperative_groups;
     cg::cluster_group cluster = cg::this_cluster();
     const int crank = (int)cluster.block_rank();
@@ -174,6 +188,12 @@ uh_chain_kernel(UhParams p) {
     __shared__ UhOutBuf<UhTask, 32> s_mid_out, s_small_out;
     __shared__ UhOutBuf<UhTinyTask, 32> s_tiny_out;
     WvCtl* ctl = p.ctl;
+    UhChromCtl* cc = p.cc + c_self;
+    const UhChromPlan cp = p.cp[c_self];
+    UhTask* const mid_list = p.mid + cp.mid_base;
+    UhTask* const small_list = p.small + cp.small_base;
+    UhTinyTask* const tiny_list = p.tiny + cp.tiny_base;
+    const double thr2 = p.cand_thr[c_self] * p.cand_thr[c_self];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const double* __restrict__ pz = p.pz;
     unsigned long long v_big = 0, n_big = 0;
@@ -190,14 +210,14 @@ uh_chain_kernel(UhParams p) {
         // ---- the leader CTA takes a big task; everybody reads it from the leader's shared memory
         if (crank == 0 && threadIdx.x == 0) {
             int c = -1;
-            const unsigned long long pos = atomicAdd(&ctl->q_head_.v, 1ull);
-            UhBigTask* t = p.big + (pos & (UH_QCAP - 1));
+            const unsigned long long pos = atomicAdd(&cc->q_head_.v, 1ull);
+            UhBigTask* t = p.big + cp.ring_base + (int)(pos & (unsigned long long)(cp.ring_cap - 1));
             volatile int* ready = &t->c;
             unsigned polls = 0;
             for (;;) {
                 c = *ready;
                 if (c >= 0) break;
-                if ((++polls & 3u) == 0u && (*(volatile int*)&ctl->big_done_.v || *(volatile int*)&ctl->overflow_.v)) {
+                if ((++polls & 3u) == 0u && (*(volatile int*)&cc->big_done_.v || *(volatile int*)&ctl->overflow_.v)) {
                     __threadfence();
                     c = *ready;
                     break;
@@ -286,21 +306,21 @@ uh_chain_kernel(UhParams p) {
             const bool cont_right = rbig && !cont_left;
             if (crank == 0 && threadIdx.x == 32) {
                 atomicAdd(&p.lvlcnt[loff + level], 1u);
-                uh_emit_candidate(p, c, level, s, s + fm, e, uh_coef_from(fv, base, T, n, fm));
+                if (uh_may_be_candidate(fbest, nn, mu, thr2)) uh_emit_candidate(p, c, level, s, s + fm, e, uh_coef_from(fv, base, T, n, fm));
                 n_big++;
             }
             if (crank == 0 && threadIdx.x == 0) {
                 // children that are not continued: other big child -> ring, the rest -> stage lists
-                if (lbig && !cont_left) { atomicAdd(&ctl->outstanding_.v, 1); uh_push_big(p, c, ls, le, level + 1, base, fv); }
-                if (rbig && !cont_right) { atomicAdd(&ctl->outstanding_.v, 1); uh_push_big(p, c, rs, re, level + 1, fv, endv); }
+                if (lbig && !cont_left) { atomicAdd(&cc->outstanding_.v, 1); uh_push_big(p, c, ls, le, level + 1, base, fv); }
+                if (rbig && !cont_right) { atomicAdd(&cc->outstanding_.v, 1); uh_push_big(p, c, rs, re, level + 1, fv, endv); }
                 const UhTask tl = {c, ls, le, level + 1, base, fv}, tr = {c, rs, re, level + 1, fv, endv};
-                if (lt_ == UH_TIER_MID) uh_buf_push(s_mid_out, tl, p.mid, p.mid_cap, &ctl->mid_tail_.v, ctl);
-                if (rt_ == UH_TIER_MID) uh_buf_push(s_mid_out, tr, p.mid, p.mid_cap, &ctl->mid_tail_.v, ctl);
-                if (lt_ == UH_TIER_SMALL) uh_buf_push(s_small_out, tl, p.small, p.small_cap, &ctl->small_tail_.v, ctl);
-                if (rt_ == UH_TIER_SMALL) uh_buf_push(s_small_out, tr, p.small, p.small_cap, &ctl->small_tail_.v, ctl);
+                if (lt_ == UH_TIER_MID) uh_buf_push(s_mid_out, tl, mid_list, cp.mid_cap, &cc->mid_tail_.v, ctl);
+                if (rt_ == UH_TIER_MID) uh_buf_push(s_mid_out, tr, mid_list, cp.mid_cap, &cc->mid_tail_.v, ctl);
+                if (lt_ == UH_TIER_SMALL) uh_buf_push(s_small_out, tl, small_list, cp.small_cap, &cc->small_tail_.v, ctl);
+                if (rt_ == UH_TIER_SMALL) uh_buf_push(s_small_out, tr, small_list, cp.small_cap, &cc->small_tail_.v, ctl);
                 const UhTinyTask yl = {c, ls, le, level + 1}, yr = {c, rs, re, level + 1};
-                if (lt_ == UH_TIER_TINY) uh_buf_push(s_tiny_out, yl, p.tiny, p.tiny_cap, &ctl->tiny_tail_.v, ctl);
-                if (rt_ == UH_TIER_TINY) uh_buf_push(s_tiny_out, yr, p.tiny, p.tiny_cap, &ctl->tiny_tail_.v, ctl);
+                if (lt_ == UH_TIER_TINY) uh_buf_push(s_tiny_out, yl, tiny_list, cp.tiny_cap, &cc->tiny_tail_.v, ctl);
+                if (rt_ == UH_TIER_TINY) uh_buf_push(s_tiny_out, yr, tiny_list, cp.tiny_cap, &cc->tiny_tail_.v, ctl);
             }
             if (cont_left) { e = le; endv = fv; level++; }
             else if (cont_right) { s = rs; base = fv; level++; }
@@ -309,20 +329,20 @@ uh_chain_kernel(UhParams p) {
         // ---- chain finished: one big task less
         if (crank == 0 && threadIdx.x == 0) {
             __threadfence();
-            const int now = atomicSub(&ctl->outstanding_.v, 1) - 1;
+            const int now = atomicSub(&cc->outstanding_.v, 1) - 1;
             if (now == 0) {
                 __threadfence();
-                *(volatile int*)&ctl->big_done_.v = 1;
+                *(volatile int*)&cc->big_done_.v = 1;
                 unsigned long long t;
                 asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
-                ctl->t_big_done = t;
+                atomicMax(&ctl->t_big_done, t);
             }
         }
     }
     if (crank == 0 && threadIdx.x == 0) {
-        uh_buf_flush(s_mid_out, p.mid, p.mid_cap, &ctl->mid_tail_.v, ctl);
-        uh_buf_flush(s_small_out, p.small, p.small_cap, &ctl->small_tail_.v, ctl);
-        uh_buf_flush(s_tiny_out, p.tiny, p.tiny_cap, &ctl->tiny_tail_.v, ctl);
+        uh_buf_flush(s_mid_out, mid_list, cp.mid_cap, &cc->mid_tail_.v, ctl);
+        uh_buf_flush(s_small_out, small_list, cp.small_cap, &cc->small_tail_.v, ctl);
+        uh_buf_flush(s_tiny_out, tiny_list, cp.tiny_cap, &cc->tiny_tail_.v, ctl);
     }
     if (v_big) atomicAdd(&ctl->visits_big, v_big);
     if (n_big) atomicAdd(&ctl->nodes_big, n_big);
@@ -334,7 +354,7 @@ uh_chain_kernel(UhParams p) {
 constexpr int UH_MID_STACK = 32;
 
 __global__ void __launch_bounds__(UH_MID_THREADS, 4)
-uh_mid_kernel(UhParams p) {
+uh_mid_kernel(UhParams p, int c_self) {
     __shared__ UhTask s_stack[UH_MID_STACK];
     __shared__ double s_ws[2][UH_MID_THREADS / 32], s_wv[2][UH_MID_THREADS / 32];
     __shared__ int s_wm2[2][UH_MID_THREADS / 32];
@@ -342,16 +362,22 @@ uh_mid_kernel(UhParams p) {
     __shared__ UhOutBuf<UhTinyTask, 32> s_tiny_out;
     __shared__ int s_idx;
     WvCtl* ctl = p.ctl;
+    UhChromCtl* cc = p.cc + c_self;
+    const UhChromPlan cp = p.cp[c_self];
+    const UhTask* const mid_list = p.mid + cp.mid_base;
+    UhTask* const small_list = p.small + cp.small_base;
+    UhTinyTask* const tiny_list = p.tiny + cp.tiny_base;
+    const double thr2 = p.cand_thr[c_self] * p.cand_thr[c_self];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const double* __restrict__ pz = p.pz;
     unsigned long long v_mid = 0, n_mid = 0;
-    const int total = min(*(volatile int*)&ctl->mid_tail_.v, p.mid_cap);
+    const int total = min(*(volatile int*)&cc->mid_tail_.v, cp.mid_cap);
     if (threadIdx.x == 0) { s_small_out.count = 0; s_tiny_out.count = 0; }
     int parity = 0;
     for (;;) {
         if (threadIdx.x == 0) {
-            s_idx = atomicAdd(&ctl->mid_head_.v, 1);
-            if (s_idx < total) s_stack[0] = p.mid[s_idx];
+            s_idx = atomicAdd(&cc->mid_head_.v, 1);
+            if (s_idx < total) s_stack[0] = mid_list[s_idx];
         }
         __syncthreads();
         if (s_idx >= total) break;
@@ -401,7 +427,7 @@ uh_mid_kernel(UhParams p) {
             const bool lmid = lt_ >= UH_TIER_MID, rmid = rt_ >= UH_TIER_MID;  // a child of a mid node is never BIG
             if (threadIdx.x == 32) {
                 atomicAdd(&p.lvlcnt[loff + level], 1u);
-                uh_emit_candidate(p, c, level, s, s + fm, e, uh_coef_from(fv, base, T, n, fm));
+                if (uh_may_be_candidate(fbest, nn, mu, thr2)) uh_emit_candidate(p, c, level, s, s + fm, e, uh_coef_from(fv, base, T, n, fm));
                 n_mid++;
             }
             if (threadIdx.x == 0) {
@@ -410,11 +436,11 @@ uh_mid_kernel(UhParams p) {
                 int q = sp;
                 if (ln >= rn) { if (lmid) s_stack[q++] = tl; if (rmid) s_stack[q++] = tr; }
                 else { if (rmid) s_stack[q++] = tr; if (lmid) s_stack[q++] = tl; }
-                if (lt_ == UH_TIER_SMALL) uh_buf_push(s_small_out, tl, p.small, p.small_cap, &ctl->small_tail_.v, ctl);
-                if (rt_ == UH_TIER_SMALL) uh_buf_push(s_small_out, tr, p.small, p.small_cap, &ctl->small_tail_.v, ctl);
+                if (lt_ == UH_TIER_SMALL) uh_buf_push(s_small_out, tl, small_list, cp.small_cap, &cc->small_tail_.v, ctl);
+                if (rt_ == UH_TIER_SMALL) uh_buf_push(s_small_out, tr, small_list, cp.small_cap, &cc->small_tail_.v, ctl);
                 const UhTinyTask yl = {c, ls, le, level + 1}, yr = {c, rs, re, level + 1};
-                if (lt_ == UH_TIER_TINY) uh_buf_push(s_tiny_out, yl, p.tiny, p.tiny_cap, &ctl->tiny_tail_.v, ctl);
-                if (rt_ == UH_TIER_TINY) uh_buf_push(s_tiny_out, yr, p.tiny, p.tiny_cap, &ctl->tiny_tail_.v, ctl);
+                if (lt_ == UH_TIER_TINY) uh_buf_push(s_tiny_out, yl, tiny_list, cp.tiny_cap, &cc->tiny_tail_.v, ctl);
+                if (rt_ == UH_TIER_TINY) uh_buf_push(s_tiny_out, yr, tiny_list, cp.tiny_cap, &cc->tiny_tail_.v, ctl);
             }
             sp += (lmid ? 1 : 0) + (rmid ? 1 : 0);
             __syncthreads();  // thread 0's stack writes before the next pop
@@ -422,8 +448,8 @@ uh_mid_kernel(UhParams p) {
         __syncthreads();
     }
     if (threadIdx.x == 0) {
-        uh_buf_flush(s_small_out, p.small, p.small_cap, &ctl->small_tail_.v, ctl);
-        uh_buf_flush(s_tiny_out, p.tiny, p.tiny_cap, &ctl->tiny_tail_.v, ctl);
+        uh_buf_flush(s_small_out, small_list, cp.small_cap, &cc->small_tail_.v, ctl);
+        uh_buf_flush(s_tiny_out, tiny_list, cp.tiny_cap, &cc->tiny_tail_.v, ctl);
     }
     if (v_mid) atomicAdd(&ctl->visits_big, v_mid);
     if (n_mid) atomicAdd(&ctl->nodes_big, n_mid);
@@ -435,31 +461,34 @@ uh_mid_kernel(UhParams p) {
 constexpr int UH_WARP_STACK = 16;
 
 struct UhWarpScratch {
-    unsigned lvl[UH_SMALL_MAX];  // node count per level relative to the task's level
     UhTask st[UH_WARP_STACK];
     UhOutBuf<UhTinyTask, 32> tiny_out;
 };
 
 __global__ void __launch_bounds__(UH_SMALL_THREADS, 4)
-uh_small_kernel(UhParams p) {
+uh_small_kernel(UhParams p, int c_self) {
     extern __shared__ __align__(16) unsigned char uh_smem[];
     UhWarpScratch& ws = reinterpret_cast<UhWarpScratch*>(uh_smem)[threadIdx.x >> 5];
     WvCtl* ctl = p.ctl;
+    UhChromCtl* cc = p.cc + c_self;
+    const UhChromPlan cp = p.cp[c_self];
+    const UhTask* const small_list = p.small + cp.small_base;
+    UhTinyTask* const tiny_list = p.tiny + cp.tiny_base;
+    const double thr2 = p.cand_thr[c_self] * p.cand_thr[c_self];
     const int lane = threadIdx.x & 31;
+    const int c = c_self;
+    const long long p0 = p.off[c] + c;
+    unsigned* const lvl = p.lvlcnt + p.off[c];  // level counts go straight to L2 (one RED per node)
     const double* __restrict__ pz = p.pz;
     unsigned long long v_small = 0, n_small = 0;
-    const int total = min(*(volatile int*)&ctl->small_tail_.v, p.small_cap);
+    const int total = min(*(volatile int*)&cc->small_tail_.v, cp.small_cap);
     if (lane == 0) ws.tiny_out.count = 0;
     for (;;) {
         int idx = 0;
-        if (lane == 0) idx = atomicAdd(&ctl->small_head_.v, 1);
+        if (lane == 0) idx = atomicAdd(&cc->small_head_.v, 1);
         idx = __shfl_sync(0xffffffffu, idx, 0);
         if (idx >= total) break;
-        const UhTask root = p.small[idx];
-        const int c = root.c, L0 = root.level;
-        const long long p0 = p.off[c] + c;
-        for (int t = lane; t < UH_SMALL_MAX; t += 32) ws.lvl[t] = 0u;
-        if (lane == 0) ws.st[0] = root;
+        if (lane == 0) ws.st[0] = small_list[idx];
         __syncwarp();
         int sp = 1;
         while (sp > 0) {
@@ -482,7 +511,7 @@ uh_small_kernel(UhParams p) {
             const double fv = __shfl_sync(0xffffffffu, bv, own ? __ffs(own) - 1 : 0);
             if (lane == 0) v_small += (unsigned long long)n;
             if (best == 0.0 || best_m == 0x7fffffff) {
-                for (int k = lane; k < n - 1; k += 32) atomicAdd(&ws.lvl[level - L0 + k], 1u);
+                for (int k = lane; k < n - 1; k += 32) atomicAdd(&lvl[level + k], 1u);
                 if (lane == 0) n_small += (unsigned long long)(n - 1);
                 __syncwarp();
                 continue;
@@ -492,10 +521,10 @@ uh_small_kernel(UhParams p) {
             const int ln = le - ls + 1, rn = re - rs + 1;
             const int lt_ = uh_tier(ln), rt_ = uh_tier(rn);
             const bool lsm = lt_ >= UH_TIER_SMALL, rsm = rt_ >= UH_TIER_SMALL;
-            // the serial part is spread over two lanes: 0 pushes, 1 emits
+            // the serial part is spread over two lanes: 0 pushes, 1 counts the node and emits the (rare) candidate
             if (lane == 1) {
-                atomicAdd(&ws.lvl[level - L0], 1u);
-                uh_emit_candidate(p, c, level, s, s + fm, e, uh_coef_from(fv, base, T, n, fm));
+                atomicAdd(&lvl[level], 1u);
+                if (uh_may_be_candidate(best, nn, mu, thr2)) uh_emit_candidate(p, c, level, s, s + fm, e, uh_coef_from(fv, base, T, n, fm));
                 n_small++;
             }
             if (lane == 0) {
@@ -504,20 +533,14 @@ uh_small_kernel(UhParams p) {
                 if (ln >= rn) { if (lsm) ws.st[q++] = tl; if (rsm) ws.st[q++] = tr; }
                 else { if (rsm) ws.st[q++] = tr; if (lsm) ws.st[q++] = tl; }
                 const UhTinyTask yl = {c, ls, le, level + 1}, yr = {c, rs, re, level + 1};
-                if (lt_ == UH_TIER_TINY) uh_buf_push(ws.tiny_out, yl, p.tiny, p.tiny_cap, &ctl->tiny_tail_.v, ctl);
-                if (rt_ == UH_TIER_TINY) uh_buf_push(ws.tiny_out, yr, p.tiny, p.tiny_cap, &ctl->tiny_tail_.v, ctl);
+                if (lt_ == UH_TIER_TINY) uh_buf_push(ws.tiny_out, yl, tiny_list, cp.tiny_cap, &cc->tiny_tail_.v, ctl);
+                if (rt_ == UH_TIER_TINY) uh_buf_push(ws.tiny_out, yr, tiny_list, cp.tiny_cap, &cc->tiny_tail_.v, ctl);
             }
             sp += (lsm ? 1 : 0) + (rsm ? 1 : 0);
             __syncwarp();
         }
-        // flush the level counts of this subtree
-        for (int t = lane; t < UH_SMALL_MAX; t += 32) {
-            const unsigned v = ws.lvl[t];
-            if (v) atomicAdd(&p.lvlcnt[p.off[c] + L0 + t], v);
-        }
-        __syncwarp();
     }
-    if (lane == 0) uh_buf_flush(ws.tiny_out, p.tiny, p.tiny_cap, &ctl->tiny_tail_.v, ctl);
+    if (lane == 0) uh_buf_flush(ws.tiny_out, tiny_list, cp.tiny_cap, &cc->tiny_tail_.v, ctl);
     if (v_small) atomicAdd(&ctl->visits_small, v_small);
     if (n_small) atomicAdd(&ctl->nodes_small, n_small);
 }
@@ -553,7 +576,7 @@ __global__ void uh_tiny_table_kernel(UhTinyTab* tab) {
 }
 
 __global__ void __launch_bounds__(128)
-uh_tiny_kernel(UhParams p, const UhTinyTab* __restrict__ gtab) {
+uh_tiny_kernel(UhParams p, const UhTinyTab* __restrict__ gtab, int c_self) {
     __shared__ UhTinyTab s_tab;
     {
         const double* src = reinterpret_cast<const double*>(gtab);
@@ -562,11 +585,13 @@ uh_tiny_kernel(UhParams p, const UhTinyTab* __restrict__ gtab) {
     }
     __syncthreads();
     WvCtl* ctl = p.ctl;
-    const int total = min(*(volatile int*)&ctl->tiny_tail_.v, p.tiny_cap);
+    const UhChromPlan cp = p.cp[c_self];
+    const UhTinyTask* const tiny_list = p.tiny + cp.tiny_base;
+    const int total = min(*(volatile int*)&p.cc[c_self].tiny_tail_.v, cp.tiny_cap);
     unsigned visits = 0, nodes = 0;
     for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
-        const UhTinyTask root = p.tiny[idx];
-        const int c = root.c;
+        const UhTinyTask root = tiny_list[idx];
+        const int c = c_self;
         const double* __restrict__ xc = p.x + p.off[c];
         unsigned* __restrict__ lv = p.lvlcnt + p.off[c];
         int st_s[6], st_e[6], st_l[6];
@@ -627,8 +652,7 @@ uh_tiny_kernel(UhParams p, const UhTinyTab* __restrict__ gtab) {
 }
 
 // number of levels of every chromosome = highest level with a node + 1 (depth[] zeroed by the host)
-__global__ void uh_depth_kernel(const unsigned* __restrict__ lvlcnt, const long long* __restrict__ off, int* __restrict__ depth) {
-    const int c = blockIdx.y;
+__global__ void uh_depth_kernel(const unsigned* __restrict__ lvlcnt, const long long* __restrict__ off, int* __restrict__ depth, int c) {
     const long long o = off[c];
     const int n = (int)(off[c + 1] - o);
     int mx = 0;
@@ -640,11 +664,12 @@ __global__ void uh_depth_kernel(const unsigned* __restrict__ lvlcnt, const long 
 
 // seeds: one root per selected chromosome with more than min_size bins (one thread per chromosome)
 __global__ void uh_seed_kernel(UhParams p, const unsigned char* __restrict__ selected, int n_chrom, int min_size) {
-    __shared__ int s_big;
-    if (threadIdx.x == 0) s_big = 0;
-    __syncthreads();
-    WvCtl* ctl = p.ctl;
-    for (int c = threadIdx.x; c < n_chrom; c += blockDim.x) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+        atomicMin(&p.ctl->t_first, t);
+    }
+    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < n_chrom; c += gridDim.x * blockDim.x) {
         const long long len = p.off[c + 1] - p.off[c];
         if (!selected[c] || len <= (long long)min_size || len < 2) continue;
         const int e = (int)len - 1;
@@ -652,21 +677,17 @@ __global__ void uh_seed_kernel(UhParams p, const unsigned char* __restrict__ sel
         const double base = p.pz[p0], endv = p.pz[p0 + e + 1];
         const int tier = uh_tier(e + 1);
         if (tier == UH_TIER_BIG) {
-            atomicAdd(&s_big, 1);
-            atomicAdd(&ctl->outstanding_.v, 1);
+            atomicAdd(&p.cc[c].outstanding_.v, 1);
             uh_push_big(p, c, 0, e, 0, base, endv);
         } else if (tier == UH_TIER_MID) {
-            const int i = atomicAdd(&ctl->mid_tail_.v, 1);
-            if (i < p.mid_cap) p.mid[i] = UhTask{c, 0, e, 0, base, endv};
+            const int i = atomicAdd(&p.cc[c].mid_tail_.v, 1);
+            if (i < p.cp[c].mid_cap) p.mid[p.cp[c].mid_base + i] = UhTask{c, 0, e, 0, base, endv};
         } else if (tier == UH_TIER_SMALL) {
-            const int i = atomicAdd(&ctl->small_tail_.v, 1);
-            if (i < p.small_cap) p.small[i] = UhTask{c, 0, e, 0, base, endv};
+            const int i = atomicAdd(&p.cc[c].small_tail_.v, 1);
+            if (i < p.cp[c].small_cap) p.small[p.cp[c].small_base + i] = UhTask{c, 0, e, 0, base, endv};
         } else if (tier == UH_TIER_TINY) {
-            const int i = atomicAdd(&ctl->tiny_tail_.v, 1);
-            if (i < p.tiny_cap) p.tiny[i] = UhTinyTask{c, 0, e, 0};
+            const int i = atomicAdd(&p.cc[c].tiny_tail_.v, 1);
+            if (i < p.cp[c].tiny_cap) p.tiny[p.cp[c].tiny_base + i] = UhTinyTask{c, 0, e, 0};
         }
     }
-    __syncthreads();
-    // no big node at all: stage A has nothing to wait for
-    if (threadIdx.x == 0 && s_big == 0) { __threadfence(); *(volatile int*)&ctl->big_done_.v = 1; }
 }

@@ -16,7 +16,9 @@ struct FinParams {
     const double* pz;          // prefix sums (for the smooth term)
     const long long* off;
     const unsigned char* selected;
-    const UhCand* cand;
+    const UhCand* cand;        // candidate lists, one slice per chromosome (cp[c].cand_base, cc[c].cand_count_)
+    const UhChromCtl* cc;
+    const UhChromPlan* cp;
     const WvCtl* ctl;
     const unsigned* lvlcnt;
     const int* depth;
@@ -816,18 +818,18 @@ __device__ void fin_bitonic(unsigned long long* key, int* val, int n2) {
         if (threadIdx.x == 0 && p.phase_ns) {                                                \
             unsigned long long t__;                                                          \
             asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t__));                          \
-            p.phase_ns[(size_t)blockIdx.x * 8 + (k)] = t__;                                  \
+            p.phase_ns[(size_t)(c_first + blockIdx.x) * 8 + (k)] = t__;                                  \
         }                                                                                    \
     } while (0)
 
 __global__ void __launch_bounds__(FIN_THREADS, 1)
-uh_finish_kernel(FinParams p) {
+uh_finish_kernel(FinParams p, int c_first) {
     extern __shared__ __align__(16) unsigned char fin_smem[];
     BmsState& s_bms = *reinterpret_cast<BmsState*>(fin_smem);
     unsigned long long* s_key = reinterpret_cast<unsigned long long*>(fin_smem + ((sizeof(BmsState) + 15) & ~(size_t)15));
     int* s_val = reinterpret_cast<int*>(s_key + FIN_SORT_SMEM);
     unsigned long long* s_spl = reinterpret_cast<unsigned long long*>(s_val + FIN_SORT_SMEM);
-    const int c = blockIdx.x;
+    const int c = c_first + blockIdx.x;
     const long long o = p.off[c];
     const int n = (int)(p.off[c + 1] - o);
     if (threadIdx.x == 0) p.n_bp[c] = 0;
@@ -854,7 +856,8 @@ uh_finish_kernel(FinParams p) {
         rqc.cum = p.rq.cum + (size_t)(tf + c) * RQ_BUCKETS;
         rqc.sorted = p.rq.sorted + o;
     }
-    const int ncand_all = min(p.ctl->cand_count_.v, 0x7fffffff);
+    const UhCand* __restrict__ cand = p.cand + p.cp[c].cand_base;
+    const int ncand_all = min(p.cc[c].cand_count_.v, p.cp[c].cand_cap);
 
     if (threadIdx.x == 0) { s_bms.dbg_ok = s_bms.dbg_fallback = s_bms.dbg_na_sum = s_bms.dbg_na_max = 0; }
     FIN_STAMP(0);
@@ -896,8 +899,8 @@ uh_finish_kernel(FinParams p) {
     for (int base = 0; base < ncand_all; base += blockDim.x) {
         const int i = base + threadIdx.x;
         bool keep = false;
-        if (i < ncand_all && p.cand[i].c == c) {
-            const UhCand k = p.cand[i];
+        if (i < ncand_all) {
+            const UhCand k = cand[i];
             double w = 1.0;
             if (p.is_germline) w = __dadd_rn(__ddiv_rn(__dmul_rn((double)(lvl_idx[k.level] + 1), 1.0 - 0.8), (double)T), 0.8);
             const double thr = __dmul_rn(__dmul_rn(__dmul_rn(2.0, sigma), w), root);
@@ -907,7 +910,7 @@ uh_finish_kernel(FinParams p) {
         const int ex = fin_block_scan(keep ? 1 : 0, total);
         if (keep) {
             sv[K + ex] = i;
-            svkey[K + ex] = ((unsigned long long)p.cand[i].level << 32) | (unsigned)p.cand[i].s;
+            svkey[K + ex] = ((unsigned long long)cand[i].level << 32) | (unsigned)cand[i].s;
         }
         K += total;
     }
@@ -951,7 +954,7 @@ uh_finish_kernel(FinParams p) {
     __syncthreads();
     if (threadIdx.x == 0) atomicOr(&bitmap[0], 1u);
     for (int i = threadIdx.x; i < K; i += blockDim.x) {
-        const UhCand k = p.cand[sv[i]];
+        const UhCand k = cand[sv[i]];
         const int q[3] = {k.s, k.b + 1, k.e + 1};
         for (int t = 0; t < 3; t++)
             if (q[t] > 0 && q[t] < n) atomicOr(&bitmap[q[t] >> 5], 1u << (q[t] & 31));
@@ -1003,7 +1006,7 @@ uh_finish_kernel(FinParams p) {
                     if ((int)(svkey[mid] & 0xffffffffu) <= q) a = mid + 1; else b = mid;
                 }
                 if (a == lo) continue;
-                const UhCand k = p.cand[sv[a - 1]];
+                const UhCand k = cand[sv[a - 1]];
                 if (q > k.e) continue;
                 const double nn = (double)(k.e - k.s + 1), m = (double)(k.b - k.s + 1);
                 const double v = q <= k.b ? sqrt(__dsub_rn(__ddiv_rn(1.0, m), __ddiv_rn(1.0, nn)))
@@ -1113,8 +1116,8 @@ uh_finish_kernel(FinParams p) {
     }
     FIN_STAMP(5);
     if (threadIdx.x == 0 && p.phase_ns) {
-        p.phase_ns[(size_t)blockIdx.x * 8 + 6] = (s_bms.dbg_fallback << 32) | s_bms.dbg_ok;
-        p.phase_ns[(size_t)blockIdx.x * 8 + 7] = (s_bms.dbg_na_max << 32) | s_bms.dbg_na_sum;
+        p.phase_ns[(size_t)(c_first + blockIdx.x) * 8 + 6] = (s_bms.dbg_fallback << 32) | s_bms.dbg_ok;
+        p.phase_ns[(size_t)(c_first + blockIdx.x) * 8 + 7] = (s_bms.dbg_na_max << 32) | s_bms.dbg_na_sum;
     }
     if (threadIdx.x == 0) p.n_bp[c] = nb;
 }

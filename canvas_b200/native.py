@@ -8,6 +8,10 @@ import os
 
 import numpy as np
 
+# the partition runs one stream per chromosome pipeline: let the driver give every one of them its own hardware queue
+# (read when the CUDA context is created, so it has to be in the environment before the first CUDA call of the process)
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "_build", "libcanvasgpu.so")
 
@@ -372,7 +376,7 @@ class Engine:
                 "visits_big": out[4], "visits_small": out[5], "visits_tiny": out[6],
                 "nodes_big": out[7], "nodes_small": out[8], "nodes_tiny": out[9],
                 "big_phase_ms": out[10], "decompose_span_ms": out[11], "multi_chunk_nodes": out[12],
-                "queue_hops": out[13], "max_depth": out[14]}
+                "queue_hops": out[13], "max_depth": out[14], "integer_keys": bool(out[15])}
 
     # ------------------------------------------------------------------ CanvasClean
     def clean(self, chrom, is_autosome, is_chr_y, start, stop, count, gc, size_filter=True,
