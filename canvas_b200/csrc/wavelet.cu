@@ -167,7 +167,7 @@ void make_plan(WvPlan& pl, int n_chrom, const int64_t* chrom_off, int window) {
         q.mid_base = mid; q.mid_cap = (int)(len / UH_SMALL_MAX + 64); mid += q.mid_cap;
         q.small_base = small; q.small_cap = (int)(len / UH_TINY_MAX + 64); small += q.small_cap;
         q.tiny_base = tiny; q.tiny_cap = (int)(len / 2 + 64); tiny += q.tiny_cap;
-        q.cand_base = cand; q.cand_cap = (int)(len / 4 + 256); cand += q.cand_cap;
+        q.cand_base = cand; q.cand_cap = (int)(len / 4 + 4096); cand += q.cand_cap;
     }
 }
 
@@ -219,6 +219,7 @@ struct WvDev {
     unsigned* rq_cum;
     int* rq_tfirst;
     unsigned long long* phase_ns;
+    unsigned long long* tl_ns;  // debug timeline of the decomposition stages, [C][16]
     UhTinyTab* tiny_tab;
     int* pack;  // results packed for one download: n_bp[C], depth[C], total, then the breakpoint lists back to back
     // sizes the arrays were allocated for (wv_alloc); a plan run on them must not exceed any
@@ -289,12 +290,12 @@ size_t wv_workspace_bytes(const WvPlan& pl) {
     s += arena_need(N + 1, 4) + arena_need(C + 1, 4);
     s += arena_need(UH_QCAP, sizeof(UhBigTask)) + arena_need(N / UH_SMALL_MAX + 64 * C + 64, sizeof(UhTask)) +
          arena_need(N / UH_TINY_MAX + 64 * C + 64, sizeof(UhTask)) + arena_need(N / 2 + 64 * C + 64, sizeof(UhTinyTask));
-    s += arena_need(N / 4 + 256 * C + 4096, sizeof(UhCand));
+    s += arena_need(N / 4 + 4096 * C + 4096, sizeof(UhCand));
     s += arena_need(C + 1, sizeof(UhChromCtl)) + arena_need(C + 1, sizeof(UhChromPlan));
     s += arena_need(N + 1, 4) * 5 + arena_need(N + 1, 8) * 2 + arena_need(N / 32 + C + 2, 4);
     s += arena_need(C + 1, 4) + arena_need(N + 1, 4);
     s += arena_need((C + 1) * RQ_BUCKETS, 8) + arena_need(N + 1, 8) + arena_need((size_t)(pl.rq_ntiles + 1) * RQ_BUCKETS, 2) * 2;
-    s += arena_need((size_t)(pl.rq_ntiles + C + 2) * RQ_BUCKETS, 4) + arena_need(C + 2, 4) + arena_need((C + 1) * 8, 8) + arena_need(1, sizeof(UhTinyTab)) + arena_need(WV_PACK_INTS, 4);
+    s += arena_need((size_t)(pl.rq_ntiles + C + 2) * RQ_BUCKETS, 4) + arena_need(C + 2, 4) + arena_need((C + 1) * 8, 8) + arena_need((C + 1) * 16, 8) + arena_need(1, sizeof(UhTinyTab)) + arena_need(WV_PACK_INTS, 4);
     return s + (1 << 16);
 }
 
@@ -347,7 +348,7 @@ int wv_alloc(cg_ctx* ctx, const WvPlan& pl, WvDev& d, double* cov_dev_existing, 
     d.small = arena_take<UhTask>(ctx, d.small_cap);
     d.tiny_cap = (int)(N / 2 + 64 * C + 64);
     d.tiny = arena_take<UhTinyTask>(ctx, d.tiny_cap);
-    d.cand_cap = (int)(N / 4 + 256 * C + 4096);
+    d.cand_cap = (int)(N / 4 + 4096 * C + 4096);
     d.cand = arena_take<UhCand>(ctx, d.cand_cap);
     d.cc = arena_take<UhChromCtl>(ctx, C + 1);
     d.lvl_idx = arena_take<int>(ctx, N + 1);
@@ -366,6 +367,7 @@ int wv_alloc(cg_ctx* ctx, const WvPlan& pl, WvDev& d, double* cov_dev_existing, 
     d.rq_tstart = arena_take<unsigned short>(ctx, (size_t)(pl.rq_ntiles + 1) * RQ_BUCKETS);
     d.rq_cum = arena_take<unsigned>(ctx, (size_t)(pl.rq_ntiles + C + 2) * RQ_BUCKETS);
     d.phase_ns = arena_take<unsigned long long>(ctx, (C + 1) * 8);
+    d.tl_ns = arena_take<unsigned long long>(ctx, (C + 1) * 16);
     d.pack = arena_take<int>(ctx, WV_PACK_INTS);
     d.tiny_tab = arena_take<UhTinyTab>(ctx, 1);
     ok = ok && d.rq_spl && d.rq_sorted && d.rq_hist && d.rq_tstart && d.rq_cum && d.rq_tfirst;
@@ -628,6 +630,8 @@ int wv_enqueue(cg_ctx* ctx, const cg_wavelet_opts* o, const WvPlan& pl, WvDev& d
     fp.rq.tfirst = d.rq_tfirst;
     fp.phase_ns = getenv("CANVAS_DEBUG") ? d.phase_ns : nullptr;
     if (fp.phase_ns) cudaMemsetAsync(d.phase_ns, 0, (size_t)(C + 1) * 64, s);
+    up.tl_ns = fp.phase_ns && d.tl_ns ? d.tl_ns : nullptr;
+    if (up.tl_ns) cudaMemsetAsync(d.tl_ns, 0, (size_t)(C + 1) * 128, s);
     fp.is_germline = o->is_germline; fp.min_size = o->min_size; fp.n_chrom = C; fp.pad = 0;
     fp.lvl_idx = d.lvl_idx; fp.sv = d.sv; fp.svkey = d.svkey; fp.bitmap = d.bitmap; fp.piece = d.piece; fp.rec = d.rec;
     fp.prelim = d.prelim; fp.lvl_first = d.lvl_first; fp.n_bp = d.n_bp; fp.bp = d.bp;
@@ -744,8 +748,24 @@ int wv_collect(cg_ctx* ctx, const WvPlan& pl, WvDev& d, int32_t* n_bp, int32_t* 
     const int* h_nbp = h_pack;
     for (int c = 0; c < C; c++) n_bp[c] = h_nbp[c];
     if (getenv("CANVAS_DEBUG")) {
-        std::vector<unsigned long long> ph((size_t)(pl.n_chrom + 1) * 8, 0);
+        std::vector<unsigned long long> ph((size_t)(pl.n_chrom + 1) * 8, 0), tn((size_t)(pl.n_chrom + 1) * 16, 0);
         cudaMemcpy(ph.data(), d.phase_ns, ph.size() * 8, cudaMemcpyDeviceToHost);
+        cudaMemcpy(tn.data(), d.tl_ns, tn.size() * 8, cudaMemcpyDeviceToHost);
+        {
+            // pipeline of every chromosome: start (relative to the first decomposition kernel) and duration of each stage, us
+            const unsigned long long t0 = h->t_first;
+            for (int c = 0; c < pl.n_chrom; c++) {
+                const unsigned long long* q = tn.data() + (size_t)c * 16;
+                const unsigned long long* f = ph.data() + (size_t)c * 8;
+                if (!q[1] && !q[3] && !q[5] && !q[7]) continue;
+                auto rel = [&](unsigned long long t) { return t > t0 ? (double)(t - t0) * 1e-3 : 0.0; };
+                fprintf(stderr, "[pipe] chr %2d n=%7lld | chain %7.1f +%7.1f | mid %7.1f +%7.1f | small %7.1f +%7.1f | tiny %7.1f +%7.1f | finish %7.1f +%7.1f us\n", c,
+                        (long long)(pl.off[c + 1] - pl.off[c]),
+                        q[1] ? rel(~q[0]) : 0.0, q[1] ? (double)(q[1] - ~q[0]) * 1e-3 : 0.0, q[3] ? rel(~q[2]) : 0.0, q[3] ? (double)(q[3] - ~q[2]) * 1e-3 : 0.0,
+                        q[5] ? rel(~q[4]) : 0.0, q[5] ? (double)(q[5] - ~q[4]) * 1e-3 : 0.0, q[7] ? rel(~q[6]) : 0.0, q[7] ? (double)(q[7] - ~q[6]) * 1e-3 : 0.0,
+                        f[0] ? rel(f[0]) : 0.0, f[0] && f[5] > f[0] ? (double)(f[5] - f[0]) * 1e-3 : 0.0);
+            }
+        }
         for (int c = 0; c < pl.n_chrom; c++) {
             const unsigned long long* q = ph.data() + (size_t)c * 8;
             if (!q[0]) continue;

@@ -47,7 +47,16 @@ struct UhParams {
     UhChromCtl* cc;          // [n_chrom] queue counters
     const UhChromPlan* cp;   // [n_chrom] slices of the arrays above
     WvCtl* ctl;
+    unsigned long long* tl_ns;  // debug timeline (nullable): [n_chrom][16], per stage k: [2k] = ~(earliest start), [2k+1] = latest end
 };
+
+// debug timeline of the per-chromosome pipelines (CANVAS_DEBUG): called by one thread per block
+__device__ inline void uh_stamp(unsigned long long* tl, int c, int stage, bool end) {
+    if (!tl) return;
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    atomicMax(&tl[(size_t)c * 16 + 2 * stage + (end ? 1 : 0)], end ? t : ~t);
+}
 
 __device__ inline void uh_emit_candidate(const UhParams& p, int c, int level, int s, int b, int e, double coef) {
     if (fabs(coef) <= p.cand_thr[c]) return;  // NaN falls through on purpose (never zeroed by HardThresh)
@@ -199,6 +208,7 @@ uh_chain_kernel(UhParams p, int c_self) {
     unsigned long long v_big = 0, n_big = 0;
     if (threadIdx.x == 0) {
         s_mid_out.count = 0; s_small_out.count = 0; s_tiny_out.count = 0;
+        uh_stamp(p.tl_ns, c_self, 0, false);
         if (crank == 0) {
             unsigned long long t;
             asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
@@ -346,6 +356,7 @@ uh_chain_kernel(UhParams p, int c_self) {
     }
     if (v_big) atomicAdd(&ctl->visits_big, v_big);
     if (n_big) atomicAdd(&ctl->nodes_big, n_big);
+    if (threadIdx.x == 0) uh_stamp(p.tl_ns, c_self, 0, true);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -372,7 +383,7 @@ uh_mid_kernel(UhParams p, int c_self) {
     const double* __restrict__ pz = p.pz;
     unsigned long long v_mid = 0, n_mid = 0;
     const int total = min(*(volatile int*)&cc->mid_tail_.v, cp.mid_cap);
-    if (threadIdx.x == 0) { s_small_out.count = 0; s_tiny_out.count = 0; }
+    if (threadIdx.x == 0) { s_small_out.count = 0; s_tiny_out.count = 0; uh_stamp(p.tl_ns, c_self, 1, false); }
     int parity = 0;
     for (;;) {
         if (threadIdx.x == 0) {
@@ -453,6 +464,7 @@ uh_mid_kernel(UhParams p, int c_self) {
     }
     if (v_mid) atomicAdd(&ctl->visits_big, v_mid);
     if (n_mid) atomicAdd(&ctl->nodes_big, n_mid);
+    if (threadIdx.x == 0) uh_stamp(p.tl_ns, c_self, 1, true);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -483,6 +495,7 @@ uh_small_kernel(UhParams p, int c_self) {
     unsigned long long v_small = 0, n_small = 0;
     const int total = min(*(volatile int*)&cc->small_tail_.v, cp.small_cap);
     if (lane == 0) ws.tiny_out.count = 0;
+    if (threadIdx.x == 0) uh_stamp(p.tl_ns, c_self, 2, false);
     for (;;) {
         int idx = 0;
         if (lane == 0) idx = atomicAdd(&cc->small_head_.v, 1);
@@ -543,6 +556,7 @@ uh_small_kernel(UhParams p, int c_self) {
     if (lane == 0) uh_buf_flush(ws.tiny_out, tiny_list, cp.tiny_cap, &cc->tiny_tail_.v, ctl);
     if (v_small) atomicAdd(&ctl->visits_small, v_small);
     if (n_small) atomicAdd(&ctl->nodes_small, n_small);
+    if (lane == 0) uh_stamp(p.tl_ns, c_self, 2, true);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -585,6 +599,7 @@ uh_tiny_kernel(UhParams p, const UhTinyTab* __restrict__ gtab, int c_self) {
     }
     __syncthreads();
     WvCtl* ctl = p.ctl;
+    if (threadIdx.x == 0) uh_stamp(p.tl_ns, c_self, 3, false);
     const UhChromPlan cp = p.cp[c_self];
     const UhTinyTask* const tiny_list = p.tiny + cp.tiny_base;
     const int total = min(*(volatile int*)&p.cc[c_self].tiny_tail_.v, cp.tiny_cap);
@@ -648,6 +663,7 @@ uh_tiny_kernel(UhParams p, const UhTinyTab* __restrict__ gtab, int c_self) {
         unsigned long long t;
         asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
         atomicMax(&ctl->t_last, t);
+        uh_stamp(p.tl_ns, c_self, 3, true);
     }
 }
 
