@@ -98,74 +98,247 @@ __global__ void bin_tile_scan_kernel(const unsigned* __restrict__ tile_cnt, int 
     }
 }
 
-// end position of bin k = position of the ((k+1) * bin_size)-th possible position (:611-612)
-__global__ void bin_end_kernel(const unsigned long long* __restrict__ bits, long long nwords, long long len,
-                               const unsigned long long* __restrict__ tile_off, int ntiles, int bin_size,
-                               const BinCtl* __restrict__ ctl, int max_bins, int* __restrict__ end_pos) {
-    const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    const int nb = min(ctl->n_bins, max_bins);
-    if (k >= nb) return;
-    const unsigned long long target = (unsigned long long)(k + 1) * (unsigned long long)bin_size;  // 1-based rank
-    int lo = 0, hi = ntiles - 1;  // last tile with tile_off < target
-    while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (tile_off[mid] < target) lo = mid; else hi = mid - 1; }
-    unsigned long long need = target - tile_off[lo];
+// end position of bin k = position of the ((k+1) * bin_size)-th possible position (:611-612).  One block per tile of the
+// bitmap: the tile's masked words and their running popcount are staged in shared memory, then every bin that ends inside
+// the tile finds its word by binary search there and its bit with __fns.
+__global__ void __launch_bounds__(256) bin_end_tile_kernel(const unsigned long long* __restrict__ bits, long long nwords, long long len,
+                                                          const unsigned long long* __restrict__ tile_off, int bin_size,
+                                                          const BinCtl* __restrict__ ctl, int max_bins, int* __restrict__ end_pos) {
+    __shared__ unsigned long long s_w[BIN_TILE_WORDS];
+    __shared__ unsigned s_pre[BIN_TILE_WORDS];  // possible positions of the tile before word i
+    __shared__ unsigned s_warp[8];
+    const int t = blockIdx.x;
+    const unsigned long long lo_rank = tile_off[t], hi_rank = tile_off[t + 1];
+    const unsigned long long B = (unsigned long long)bin_size;
+    const long long nb = min(ctl->n_bins, max_bins);
+    const long long k_first = (long long)(lo_rank / B);               // first bin whose closing rank (k+1) B lies beyond lo_rank
+    const long long k_last = min((long long)(hi_rank / B) - 1, nb - 1);  // last bin whose closing rank is <= hi_rank
+    if (k_last < k_first) return;
     const unsigned long long first = min(ctl->first_pos, (unsigned long long)len);
-    long long w = (long long)lo * BIN_TILE_WORDS;
-    unsigned long long word = 0;
-    for (int i = 0; i < BIN_TILE_WORDS; i++, w++) {
-        word = masked_word(bits, w, nwords, first, len);
-        const unsigned c = __popcll(word);
-        if (need <= c) break;
-        need -= c;
+    const long long w0 = (long long)t * BIN_TILE_WORDS;
+    // each thread owns four consecutive words: popcounts, then a block-wide exclusive scan
+    unsigned c4[4], run = 0;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const int i = threadIdx.x * 4 + j;
+        const unsigned long long w = masked_word(bits, w0 + i, nwords, first, len);
+        s_w[i] = w;
+        c4[j] = (unsigned)__popcll(w);
+        run += c4[j];
     }
-    // position of the need-th set bit of `word`
-    for (unsigned long long r = 1; r < need; r++) word &= word - 1;
-    end_pos[k] = (int)(w * 64 + (__ffsll((long long)word) - 1));
-}
-
-// per-bin sums, one warp per bin: count = sum of min(10, hits) over possible positions (:618-625),
-// gc = (int)(100f * GC / nucleotides) with every base counted as a nucleotide (:592-593, :638)
-__global__ void bin_sum_kernel(const unsigned char* __restrict__ hits, const unsigned long long* __restrict__ bits,
-                               const char* __restrict__ bases, const BinCtl* __restrict__ ctl, const int* __restrict__ end_pos,
-                               int max_bins, int32_t* __restrict__ start, int32_t* __restrict__ stop, int32_t* __restrict__ count,
-                               unsigned char* __restrict__ gc) {
-    const int k = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
-    const int nb = min(ctl->n_bins, max_bins);
-    if (k >= nb) return;
-    const int s = k == 0 ? (int)ctl->first_pos : end_pos[k - 1] + 1;
-    const int e = end_pos[k];  // inclusive
-    unsigned obs = 0, gcc = 0;
-    for (int p = s + lane; p <= e; p += 32) {
-        const char b = bases[p];
-        gcc += (b == 'C' || b == 'c' || b == 'G' || b == 'g');
-        if ((bits[p >> 6] >> (p & 63)) & 1ull) obs += min(10u, (unsigned)hits[p]);
-    }
-    obs = __reduce_add_sync(0xffffffffu, obs);
-    gcc = __reduce_add_sync(0xffffffffu, gcc);
-    if (lane == 0) {
-        start[k] = s;
-        stop[k] = e + 1;  // "pos + 1 to conform to bed specification" (:652)
-        count[k] = (int)obs;
-        gc[k] = (unsigned char)(int)__fdiv_rn(__fmul_rn(100.0f, (float)gcc), (float)(e - s + 1));
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    unsigned incl = run;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const unsigned v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+    if (lane == 31) s_warp[wid] = incl;
+    __syncthreads();
+    unsigned base = incl - run;
+    for (int k = 0; k < wid; k++) base += s_warp[k];
+#pragma unroll
+    for (int j = 0; j < 4; j++) { s_pre[threadIdx.x * 4 + j] = base; base += c4[j]; }
+    __syncthreads();
+    for (long long k = k_first + threadIdx.x; k <= k_last; k += blockDim.x) {
+        const unsigned need = (unsigned)((unsigned long long)(k + 1) * B - lo_rank);  // 1-based rank inside the tile
+        int lo = 0, hi = BIN_TILE_WORDS - 1;  // last word with s_pre < need
+        while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (s_pre[mid] < need) lo = mid; else hi = mid - 1; }
+        const unsigned long long w = s_w[lo];
+        unsigned r = need - s_pre[lo];  // r-th set bit of w
+        const unsigned wl = (unsigned)w, wh = (unsigned)(w >> 32);
+        const unsigned cl = (unsigned)__popc(wl);
+        const int bit = r <= cl ? (int)__fns(wl, 0, (int)r) : 32 + (int)__fns(wh, 0, (int)(r - cl));
+        end_pos[k] = (int)((w0 + lo) * 64 + bit);
     }
 }
 
-// GCContentWeighted (:626-636): float accumulation in position order, Math.Round (half to even)
-__global__ void bin_sum_weighted_kernel(const unsigned char* __restrict__ hits, const unsigned long long* __restrict__ bits,
-                                        const unsigned char* __restrict__ read_gc, const float* __restrict__ obs_vs_exp,
-                                        const BinCtl* __restrict__ ctl, const int* __restrict__ end_pos, int max_bins,
-                                        int32_t* __restrict__ count) {
+// Per-bin sums in one streaming pass over the positions (TruncatedDynamicRange count :618-625 and the G/C bases of :592-593):
+// a block takes 4096 consecutive positions, a thread 16 of them (one 128-bit load of hits and of bases, 16 bits of the
+// bitmap); bin ends that fall inside the tile are marked in a shared bitmap, a block scan of their counts tells every
+// thread the bin of its first position, four positions are summed at a time with byte-wise SIMD, and the per-bin partial
+// sums go through shared-memory accumulators to integer atomics in global memory (integers: any order gives the same sums).
+constexpr int BIN_ACC_THREADS = 256;
+constexpr int BIN_ACC_TILE = BIN_ACC_THREADS * 16;
+constexpr int BIN_ACC_LOCAL = 1024;  // bins of one tile accumulated in shared memory (more go straight to global atomics)
+
+__device__ inline void bin_acc_add(unsigned* s_obs, unsigned* s_gc, unsigned* g_obs, unsigned* g_gc, long long k_lo, long long bin, long long nb,
+                                   unsigned obs, unsigned gcv) {
+    if (bin >= nb || (obs | gcv) == 0u) return;
+    const long long loc = bin - k_lo;
+    if (loc < BIN_ACC_LOCAL) {
+        if (obs) atomicAdd(&s_obs[loc], obs);
+        if (gcv) atomicAdd(&s_gc[loc], gcv);
+    } else {
+        if (obs) atomicAdd(&g_obs[bin], obs);
+        if (gcv) atomicAdd(&g_gc[bin], gcv);
+    }
+}
+
+// four positions at once: h = four hit counts, b = four bases, m4 = their four possible bits
+__device__ inline void bin_quad(unsigned h, unsigned b, unsigned m4, unsigned& obs, unsigned& gcv) {
+    const unsigned mask = ((m4 * 0x00204081u) & 0x01010101u) * 0xffu;  // bit j -> byte j = 0xff
+    obs += __vsadu4(__vminu4(h, 0x0a0a0a0au) & mask, 0u);
+    const unsigned x = b | 0x20202020u;
+    gcv += (unsigned)__popc((__vcmpeq4(x, 0x63636363u) | __vcmpeq4(x, 0x67676767u)) & 0x01010101u);
+}
+
+__global__ void __launch_bounds__(BIN_ACC_THREADS) bin_accum_kernel(const unsigned char* __restrict__ hits, const unsigned long long* __restrict__ bits,
+                                                                   const char* __restrict__ bases, long long nwords, long long len,
+                                                                   const BinCtl* __restrict__ ctl, const int* __restrict__ end_pos, int max_bins,
+                                                                   unsigned* __restrict__ g_obs, unsigned* __restrict__ g_gc) {
+    __shared__ unsigned s_flag[BIN_ACC_TILE / 32];
+    __shared__ unsigned s_obs[BIN_ACC_LOCAL], s_gc[BIN_ACC_LOCAL];
+    __shared__ unsigned s_warp[BIN_ACC_THREADS / 32];
+    __shared__ long long s_k[2];
+    const long long nb = min(ctl->n_bins, max_bins);
+    if (nb <= 0) return;
+    const long long tile_start = (long long)blockIdx.x * BIN_ACC_TILE;
+    const long long tile_end = min(tile_start + BIN_ACC_TILE, len);
+    if (tile_start > (long long)end_pos[nb - 1]) return;  // past the last complete bin
+    if (threadIdx.x < 2) {
+        // first bin whose end is >= tile_start (threadIdx 0) / >= tile_end (threadIdx 1)
+        const long long target = threadIdx.x == 0 ? tile_start : tile_end;
+        long long lo = 0, hi = nb;
+        while (lo < hi) { const long long mid = (lo + hi) >> 1; if ((long long)end_pos[mid] < target) lo = mid + 1; else hi = mid; }
+        s_k[threadIdx.x] = lo;
+    }
+    for (int i = threadIdx.x; i < BIN_ACC_TILE / 32; i += blockDim.x) s_flag[i] = 0u;
+    for (int i = threadIdx.x; i < BIN_ACC_LOCAL; i += blockDim.x) { s_obs[i] = 0u; s_gc[i] = 0u; }
+    __syncthreads();
+    const long long k_lo = s_k[0], k_hi = s_k[1];  // bins k_lo .. k_hi - 1 end inside the tile
+    for (long long k = k_lo + threadIdx.x; k < k_hi; k += blockDim.x) {
+        const int r = (int)((long long)end_pos[k] - tile_start);
+        atomicOr(&s_flag[r >> 5], 1u << (r & 31));
+    }
+    __syncthreads();
+    // ends inside this thread's 16 positions; position p belongs to bin k_lo + (ends of the tile before p)
+    const unsigned f16 = (s_flag[threadIdx.x >> 1] >> (16 * (threadIdx.x & 1))) & 0xffffu;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const unsigned mine = (unsigned)__popc(f16);
+    unsigned incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const unsigned v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+    if (lane == 31) s_warp[wid] = incl;
+    __syncthreads();
+    unsigned before = incl - mine;
+    for (int k = 0; k < wid; k++) before += s_warp[k];
+    long long bin = k_lo + before;
+    const long long p0 = tile_start + (long long)threadIdx.x * 16;
+    unsigned obs = 0, gcv = 0;
+    if (p0 < len && bin < nb) {
+        const unsigned long long first = min(ctl->first_pos, (unsigned long long)len);
+        const unsigned m16 = (unsigned)(masked_word(bits, p0 >> 6, nwords, first, len) >> (p0 & 63)) & 0xffffu;
+        if (p0 + 16 <= len) {
+            const uint4 h4 = *reinterpret_cast<const uint4*>(hits + p0);
+            const uint4 b4 = *reinterpret_cast<const uint4*>(bases + p0);
+            const unsigned hq[4] = {h4.x, h4.y, h4.z, h4.w}, bq[4] = {b4.x, b4.y, b4.z, b4.w};
+            if (f16 == 0u) {
+#pragma unroll
+                for (int q = 0; q < 4; q++) bin_quad(hq[q], bq[q], (m16 >> (4 * q)) & 0xfu, obs, gcv);
+            } else {
+                // a bin closes inside these 16 positions: position by position
+#pragma unroll
+                for (int q = 0; q < 4; q++)
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        const int i = 4 * q + j;
+                        const unsigned h = (hq[q] >> (8 * j)) & 0xffu, b = ((bq[q] >> (8 * j)) & 0xffu) | 0x20u;
+                        if ((m16 >> i) & 1u) obs += min(10u, h);
+                        gcv += (b == 0x63u || b == 0x67u) ? 1u : 0u;
+                        if ((f16 >> i) & 1u) {
+                            bin_acc_add(s_obs, s_gc, g_obs, g_gc, k_lo, bin, nb, obs, gcv);
+                            obs = 0; gcv = 0; bin++;
+                        }
+                    }
+            }
+        } else {
+            for (int i = 0; i < 16 && p0 + i < len; i++) {  // ragged end of the chromosome
+                const unsigned h = hits[p0 + i], b = (unsigned)(unsigned char)bases[p0 + i] | 0x20u;
+                if ((m16 >> i) & 1u) obs += min(10u, h);
+                gcv += (b == 0x63u || b == 0x67u) ? 1u : 0u;
+                if ((f16 >> i) & 1u) {
+                    bin_acc_add(s_obs, s_gc, g_obs, g_gc, k_lo, bin, nb, obs, gcv);
+                    obs = 0; gcv = 0; bin++;
+                }
+            }
+        }
+    }
+    // what is left belongs to `bin`; lanes of a warp mostly share it: one shared-memory atomic per distinct bin of the warp
+    {
+        const bool live = bin < nb && (obs | gcv) != 0u;
+        unsigned todo = __ballot_sync(0xffffffffu, live);
+        while (todo) {
+            const int leader = __ffs(todo) - 1;
+            const long long lb = __shfl_sync(0xffffffffu, bin, leader);
+            const bool same = live && bin == lb;
+            const unsigned grp = __ballot_sync(0xffffffffu, same);
+            const unsigned so = __reduce_add_sync(0xffffffffu, same ? obs : 0u);
+            const unsigned sg = __reduce_add_sync(0xffffffffu, same ? gcv : 0u);
+            if (lane == leader) bin_acc_add(s_obs, s_gc, g_obs, g_gc, k_lo, lb, nb, so, sg);
+            todo &= ~grp;
+        }
+    }
+    __syncthreads();
+    const long long nloc = min((long long)BIN_ACC_LOCAL, min(k_hi + 1, nb) - k_lo);
+    for (int i = threadIdx.x; i < nloc; i += blockDim.x) {
+        const unsigned o = s_obs[i], g = s_gc[i];
+        if (o) atomicAdd(&g_obs[k_lo + i], o);
+        if (g) atomicAdd(&g_gc[k_lo + i], g);
+    }
+}
+
+// bin coordinates, count and GC percentage from the accumulated sums: gc = (int)(100f * GC / nucleotides) with every base
+// counted as a nucleotide (:592-593, :638); stop = end + 1 "to conform to bed specification" (:652)
+__global__ void bin_finalize_kernel(const BinCtl* __restrict__ ctl, const int* __restrict__ end_pos, int max_bins, const unsigned* __restrict__ g_obs,
+                                    const unsigned* __restrict__ g_gc, int32_t* __restrict__ start, int32_t* __restrict__ stop,
+                                    int32_t* __restrict__ count, unsigned char* __restrict__ gc) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     const int nb = min(ctl->n_bins, max_bins);
     if (k >= nb) return;
     const int s = k == 0 ? (int)ctl->first_pos : end_pos[k - 1] + 1;
     const int e = end_pos[k];
+    start[k] = s;
+    stop[k] = e + 1;
+    count[k] = (int)g_obs[k];
+    gc[k] = (unsigned char)(int)__fdiv_rn(__fmul_rn(100.0f, (float)g_gc[k]), (float)(e - s + 1));
+}
+
+// GCContentWeighted (:626-636): float accumulation in position order, Math.Round (half to even).  One warp per bin reads the
+// positions coalesced (a lane per position, four rows in flight); terms that are exactly zero cannot change the running sum,
+// the others are added one by one in position order by every lane alike.
+__global__ void __launch_bounds__(256) bin_sum_weighted_kernel(const unsigned char* __restrict__ hits, const unsigned long long* __restrict__ bits,
+                                                               const unsigned char* __restrict__ read_gc, const float* __restrict__ obs_vs_exp,
+                                                               const BinCtl* __restrict__ ctl, const int* __restrict__ end_pos, int max_bins,
+                                                               int32_t* __restrict__ count) {
+    __shared__ float s_ratio[128];
+    for (int i = threadIdx.x; i < 128; i += blockDim.x) s_ratio[i] = i < 101 ? obs_vs_exp[i] : 1.0f;
+    __syncthreads();
+    const int k = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    const int nb = min(ctl->n_bins, max_bins);
+    if (k >= nb) return;
+    const int s = k == 0 ? (int)ctl->first_pos : end_pos[k - 1] + 1;
+    const int e = end_pos[k];
     float acc = 0.0f;
-    for (int p = s; p <= e; p++)
-        if ((bits[p >> 6] >> (p & 63)) & 1ull)
-            acc = __fadd_rn(acc, fminf(10.0f, __fdiv_rn((float)hits[p], obs_vs_exp[read_gc[p]])));
-    count[k] = (int)rint((double)acc);
+    constexpr int U = 4;
+    for (int base = s; base <= e; base += 32 * U) {
+        float term[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const int p = base + 32 * u + lane;
+            term[u] = 0.0f;
+            if (p <= e && ((bits[p >> 6] >> (p & 63)) & 1ull))
+                term[u] = fminf(10.0f, __fdiv_rn((float)hits[p], s_ratio[min((int)read_gc[p], 127)]));
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            unsigned nz = __ballot_sync(0xffffffffu, !(term[u] == 0.0f));
+            while (nz) {
+                const int l = __ffs(nz) - 1;
+                acc = __fadd_rn(acc, __shfl_sync(0xffffffffu, term[u], l));
+                nz &= nz - 1;
+            }
+        }
+    }
+    if (lane == 0) count[k] = (int)rint((double)acc);
 }
 
 // FragmentBinner.cs:296-311 + FindBestBin :353-371: first bin whose Stop is right of the fragment start,
@@ -343,7 +516,7 @@ extern "C" int cg_bin_hits(cg_ctx* ctx, int64_t chr_len, const uint8_t* hits, co
     const int ntiles = (int)((nwords + BIN_TILE_WORDS - 1) / BIN_TILE_WORDS);
     const long long cap = std::min<long long>(max_bins, chr_len / bin_size + 1);
     size_t need = arena_need(chr_len, 1) * 3 + arena_need(nwords, 8) + arena_need(ntiles + 1, 4) + arena_need(ntiles + 2, 8) +
-                  arena_need(cap + 1, 4) * 4 + arena_need(cap + 1, 1) + arena_need(256, 4) + arena_need(1, sizeof(BinCtl)) + (1 << 16);
+                  arena_need(cap + 1, 4) * 6 + arena_need(cap + 1, 1) + arena_need(256, 4) + arena_need(1, sizeof(BinCtl)) + (1 << 16);
     int rc = arena_reserve(ctx, need);
     if (rc) return rc;
     unsigned char* d_hits = arena_take<unsigned char>(ctx, chr_len);
@@ -357,9 +530,11 @@ extern "C" int cg_bin_hits(cg_ctx* ctx, int64_t chr_len, const uint8_t* hits, co
     int32_t* d_stop = arena_take<int32_t>(ctx, cap + 1);
     int32_t* d_count = arena_take<int32_t>(ctx, cap + 1);
     unsigned char* d_gc = arena_take<unsigned char>(ctx, cap + 1);
+    unsigned* d_obs = arena_take<unsigned>(ctx, cap + 1);
+    unsigned* d_gcc = arena_take<unsigned>(ctx, cap + 1);
     float* d_ratio = arena_take<float>(ctx, 256);
     BinCtl* d_ctl = arena_take<BinCtl>(ctx, 1);
-    if (!d_hits || !d_bases || !d_rgc || !d_bits || !d_tcnt || !d_toff || !d_end || !d_start || !d_stop || !d_count || !d_gc || !d_ratio || !d_ctl)
+    if (!d_hits || !d_bases || !d_rgc || !d_bits || !d_tcnt || !d_toff || !d_end || !d_start || !d_stop || !d_count || !d_gc || !d_obs || !d_gcc || !d_ratio || !d_ctl)
         return cg_fail(ctx, CG_ERR_CUDA, "cg_bin_hits: device arena exhausted");
     cudaStream_t s = ctx->stream;
     CG_CUDA(ctx, cudaMemcpyAsync(d_hits, hits, chr_len, cudaMemcpyHostToDevice, s));
@@ -375,12 +550,14 @@ extern "C" int cg_bin_hits(cg_ctx* ctx, int64_t chr_len, const uint8_t* hits, co
     CG_LAUNCH(ctx, bin_tile_count_kernel, ntiles, 256, 0, d_bits, nwords, (long long)chr_len, d_ctl, d_tcnt);
     CG_LAUNCH(ctx, bin_tile_scan_kernel, 1, 1024, 0, d_tcnt, ntiles, d_toff, bin_size, d_ctl);
     if (cap > 0) {
-        CG_LAUNCH(ctx, bin_end_kernel, div_up(cap, 128), 128, 0, d_bits, nwords, (long long)chr_len, d_toff, ntiles, bin_size, d_ctl,
-                  (int)cap, d_end);
-        CG_LAUNCH(ctx, bin_sum_kernel, div_up(cap * 32, 256), 256, 0, d_hits, d_bits, d_bases, d_ctl, d_end, (int)cap, d_start, d_stop,
-                  d_count, d_gc);
+        CG_CUDA(ctx, cudaMemsetAsync(d_obs, 0, (size_t)(cap + 1) * 4, s));
+        CG_CUDA(ctx, cudaMemsetAsync(d_gcc, 0, (size_t)(cap + 1) * 4, s));
+        CG_LAUNCH(ctx, bin_end_tile_kernel, ntiles, 256, 0, d_bits, nwords, (long long)chr_len, d_toff, bin_size, d_ctl, (int)cap, d_end);
+        CG_LAUNCH(ctx, bin_accum_kernel, div_up(chr_len, BIN_ACC_TILE), BIN_ACC_THREADS, 0, d_hits, d_bits, d_bases, nwords, (long long)chr_len,
+                  d_ctl, d_end, (int)cap, d_obs, d_gcc);
+        CG_LAUNCH(ctx, bin_finalize_kernel, div_up(cap, 256), 256, 0, d_ctl, d_end, (int)cap, d_obs, d_gcc, d_start, d_stop, d_count, d_gc);
         if (mode == 1)
-            CG_LAUNCH(ctx, bin_sum_weighted_kernel, div_up(cap, 128), 128, 0, d_hits, d_bits, d_rgc, d_ratio, d_ctl, d_end, (int)cap, d_count);
+            CG_LAUNCH(ctx, bin_sum_weighted_kernel, div_up(cap * 32, 256), 256, 0, d_hits, d_bits, d_rgc, d_ratio, d_ctl, d_end, (int)cap, d_count);
     }
     CG_CUDA(ctx, cudaEventRecord(ctx->ev1, s));
     BinCtl* h = (BinCtl*)ctx->pinned;

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -63,15 +64,22 @@ struct cg_ctx {
     size_t aux_cap = 0;
     CgTimeline* tl = nullptr;  // debug timeline of the current call (CANVAS_DEBUG)
     std::vector<CgGraphEntry> clean_graphs;  // Clean pipeline graphs (clean.cu), dropped when the arena moves
+    std::vector<CgGraphEntry> part_graphs;   // partition: per-chromosome pipelines (wavelet.cu); exec == nullptr: shape seen once
     CgComm* comm = nullptr;
 };
 
 constexpr size_t CG_CHROM_STREAMS = 32;
 inline int cg_chrom_streams(cg_ctx* ctx, int n) {
+    int prio_lo = 0, prio_hi = 0;  // numerically lower = more urgent
+    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
     while ((int)ctx->chrom_streams.size() < n) {
         cudaStream_t st = nullptr;
         cudaEvent_t ev = nullptr;
-        if (cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess) {
+        // streams are handed out to the chromosomes in order of decreasing length: the longest chromosomes (whose finish
+        // stage ends the partition) get their blocks scheduled first when pipelines compete for the SMs
+        const int k = (int)ctx->chrom_streams.size();
+        const int prio = std::min(prio_lo, prio_hi + k / 4);
+        if (cudaStreamCreateWithPriority(&st, cudaStreamNonBlocking, prio) != cudaSuccess || cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess) {
             ctx->err = "cannot create the per-chromosome streams";
             return CG_ERR_CUDA;
         }
@@ -88,6 +96,9 @@ inline int cg_chrom_streams(cg_ctx* ctx, int n) {
 inline void cg_graphs_clear(cg_ctx* ctx) {
     for (auto& g : ctx->clean_graphs) cudaGraphExecDestroy(g.exec);
     ctx->clean_graphs.clear();
+    for (auto& g : ctx->part_graphs)
+        if (g.exec) cudaGraphExecDestroy(g.exec);
+    ctx->part_graphs.clear();
 }
 
 inline int cg_fail(cg_ctx* ctx, int code, const std::string& msg) {

@@ -223,6 +223,7 @@ struct WvDev {
     UhTinyTab* tiny_tab;
     int* pack;  // results packed for one download: n_bp[C], depth[C], total, then the breakpoint lists back to back
     // sizes the arrays were allocated for (wv_alloc); a plan run on them must not exceed any
+    const long long* alloc_off;  // host: chromosome offsets of the plan the workspace was allocated for (an upper bound of every later plan)
     long long cap_N;
     size_t cap_work, cap_ev, cap_tiles;
     int cap_nseg, cap_f3, cap_w10, cap_w100, cap_rq, cap_C;
@@ -375,6 +376,7 @@ int wv_alloc(cg_ctx* ctx, const WvPlan& pl, WvDev& d, double* cov_dev_existing, 
          d.tsum && d.f3lv && d.tmed && d.cmad && d.ev10 && d.ev100 && d.r10 && d.r100 && d.med && d.mad && d.sigma &&
          d.cand_thr && d.log3 && d.ctl && d.pack && d.lvlcnt && d.depth && d.big && d.mid && d.small && d.tiny && d.cand && d.cc && d.cp && d.lvl_idx &&
          d.sv && d.piece && d.prelim && d.lvl_first && d.svkey && d.rec && d.bitmap && d.n_bp && d.bp;
+    d.alloc_off = pl.off.data();
     d.cap_N = pl.N; d.cap_nseg = pl.t.nseg; d.cap_work = pl.work.size() + pl.work.size() / 8 + 63; d.cap_ev = pl.ev_work.size(); d.cap_tiles = pl.tiles.size();
     d.cap_f3 = pl.f3_total; d.cap_w10 = pl.t.n_w10; d.cap_w100 = pl.t.n_w100; d.cap_rq = pl.rq_ntiles; d.cap_C = pl.n_chrom;
     return ok ? CG_OK : cg_fail(ctx, CG_ERR_CUDA, "partition: device arena exhausted");
@@ -641,58 +643,118 @@ int wv_enqueue(cg_ctx* ctx, const cg_wavelet_opts* o, const WvPlan& pl, WvDev& d
             last.tiny_base + last.tiny_cap > d.tiny_cap || last.cand_base + last.cand_cap > d.cand_cap)
             return cg_fail(ctx, CG_ERR_CAPACITY, "partition: per-chromosome queues exceed the workspace");
     }
-    CG_LAUNCH(ctx, uh_seed_kernel, div_up(C, 128), 128, 0, up, d.selected, C, o->min_size);
-    CG_LAUNCH(ctx, uh_tiny_table_kernel, UH_TINY_MAX - 1, UH_TINY_MAX, 0, d.tiny_tab);
     const size_t uh_smem = sizeof(UhWarpScratch) * (UH_SMALL_THREADS / 32);
     if (!ctx->uh_attrs_set) {
         cudaFuncSetAttribute(uh_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)uh_smem);
         cudaFuncSetAttribute(uh_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fin_smem_bytes());
         ctx->uh_attrs_set = true;
     }
-    std::vector<int> order;
-    for (int c = 0; c < C; c++) {
-        const long long len = pl.off[c + 1] - pl.off[c];
-        if (selected_host[c] && len > o->min_size && len >= 2) order.push_back(c);
-    }
-    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return pl.off[a + 1] - pl.off[a] > pl.off[b + 1] - pl.off[b]; });
-    const int n_streams = (int)std::min<size_t>(order.size(), CG_CHROM_STREAMS);
-    int rc_streams = cg_chrom_streams(ctx, n_streams);
-    if (rc_streams) return rc_streams;
-    CG_CUDA(ctx, cudaEventRecord(ctx->ev_fork2, s));
-    for (size_t k = 0; k < order.size(); k++) {
-        const int c = order[k];
-        const long long len = pl.off[c + 1] - pl.off[c];
-        cudaStream_t cs = ctx->chrom_streams[k % n_streams];
-        if (k < (size_t)n_streams) CG_CUDA(ctx, cudaStreamWaitEvent(cs, ctx->ev_fork2, 0));
-        ctx->stream = cs;  // CG_LAUNCH enqueues on ctx->stream
-        if (len > UH_MID_MAX) {
-            // chains of big nodes: clusters wait on the chromosome's ring, any one of them can finish the work alone
-            cudaLaunchConfig_t cfg = {};
-            cfg.blockDim = dim3(UH_THREADS);
-            cfg.dynamicSmemBytes = 0;
-            cfg.stream = cs;
-            cudaLaunchAttribute attr[1];
-            attr[0].id = cudaLaunchAttributeClusterDimension;
-            attr[0].val.clusterDim.x = UH_CLUSTER; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-            cfg.attrs = attr;
-            cfg.numAttrs = 1;
-            cfg.gridDim = dim3(UH_CLUSTER * (len > 100000 ? 2 : 1));
-            cudaError_t le = cudaLaunchKernelEx(&cfg, uh_chain_kernel, up, c);
-            if (le != cudaSuccess) { ctx->stream = s; return cg_fail(ctx, CG_ERR_CUDA, std::string("uh_chain_kernel launch: ") + cudaGetErrorString(le)); }
-            ctx->launches++;
+    // The launch sequence of the pipelines depends on the chromosome lengths only through grid sizes and through which
+    // stages a chromosome needs; with the lengths the workspace was allocated for (the INPUT lengths in the fused call: the
+    // same for every sample binned on the same reference) it is the same for every call of that shape, so it is captured
+    // once into a CUDA graph and replayed: one launch instead of ~150, every chromosome's first kernel starts at once, and
+    // ranks that share a host no longer queue behind each other's launches.  A shape is captured the second time it is seen.
+    auto enqueue_pipelines = [&](const long long* loff, cudaStream_t root) -> int {
+        std::vector<int> order;
+        for (int c = 0; c < C; c++) {
+            const long long len = loff[c + 1] - loff[c];
+            if (selected_host[c] && len > o->min_size && len >= 2) order.push_back(c);
         }
-        if (len > UH_SMALL_MAX)
-            CG_LAUNCH(ctx, uh_mid_kernel, (int)std::min<long long>(64, std::max<long long>(1, len / 2048)), UH_MID_THREADS, 0, up, c);
-        if (len > UH_TINY_MAX)
-            CG_LAUNCH(ctx, uh_small_kernel, (int)std::min<long long>(ctx->num_sms, std::max<long long>(1, len / 1024)), UH_SMALL_THREADS, uh_smem, up, c);
-        CG_LAUNCH(ctx, uh_tiny_kernel, (int)std::min<long long>(ctx->num_sms, std::max<long long>(1, len / 1024)), 128, 0, up, d.tiny_tab, c);
-        CG_LAUNCH(ctx, uh_depth_kernel, (int)std::min<long long>(32, std::max<long long>(1, len / 4096)), 256, 0, d.lvlcnt, d.off, d.depth, c);
-        CG_LAUNCH(ctx, uh_finish_kernel, 1, FIN_THREADS, fin_smem_bytes(), fp, c);
+        std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return loff[a + 1] - loff[a] > loff[b + 1] - loff[b]; });
+        const int n_streams = (int)std::min<size_t>(order.size(), CG_CHROM_STREAMS);
+        int rc_streams = cg_chrom_streams(ctx, n_streams);
+        if (rc_streams) return rc_streams;
+        CG_LAUNCH(ctx, uh_seed_kernel, div_up(C, 128), 128, 0, up, d.selected, C, o->min_size);
+        CG_LAUNCH(ctx, uh_tiny_table_kernel, UH_TINY_MAX - 1, UH_TINY_MAX, 0, d.tiny_tab);
+        CG_CUDA(ctx, cudaEventRecord(ctx->ev_fork2, root));
+        for (size_t k = 0; k < order.size(); k++) {
+            const int c = order[k];
+            const long long len = loff[c + 1] - loff[c];
+            cudaStream_t cs = ctx->chrom_streams[k % n_streams];
+            if (k < (size_t)n_streams) CG_CUDA(ctx, cudaStreamWaitEvent(cs, ctx->ev_fork2, 0));
+            ctx->stream = cs;  // CG_LAUNCH enqueues on ctx->stream
+            if (len > UH_MID_MAX) {
+                // chains of big nodes: clusters wait on the chromosome's ring, any one of them can finish the work alone
+                cudaLaunchConfig_t cfg = {};
+                cfg.blockDim = dim3(UH_THREADS);
+                cfg.dynamicSmemBytes = 0;
+                cfg.stream = cs;
+                cudaLaunchAttribute attr[1];
+                attr[0].id = cudaLaunchAttributeClusterDimension;
+                attr[0].val.clusterDim.x = UH_CLUSTER; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+                cfg.attrs = attr;
+                cfg.numAttrs = 1;
+                cfg.gridDim = dim3(UH_CLUSTER * (len > 100000 ? 2 : 1));
+                cudaError_t le = cudaLaunchKernelEx(&cfg, uh_chain_kernel, up, c);
+                if (le != cudaSuccess) { ctx->stream = root; return cg_fail(ctx, CG_ERR_CUDA, std::string("uh_chain_kernel launch: ") + cudaGetErrorString(le)); }
+                ctx->launches++;
+            }
+            if (len > UH_SMALL_MAX)
+                CG_LAUNCH(ctx, uh_mid_kernel, (int)std::min<long long>(64, std::max<long long>(1, len / 2048)), UH_MID_THREADS, 0, up, c);
+            if (len > UH_TINY_MAX)
+                CG_LAUNCH(ctx, uh_small_kernel, (int)std::min<long long>(ctx->num_sms, std::max<long long>(1, len / 1024)), UH_SMALL_THREADS, uh_smem, up, c);
+            CG_LAUNCH(ctx, uh_tiny_kernel, (int)std::min<long long>(ctx->num_sms, std::max<long long>(1, len / 1024)), 128, 0, up, d.tiny_tab, c);
+            CG_LAUNCH(ctx, uh_depth_kernel, (int)std::min<long long>(32, std::max<long long>(1, len / 4096)), 256, 0, d.lvlcnt, d.off, d.depth, c);
+            CG_LAUNCH(ctx, uh_finish_kernel, 1, FIN_THREADS, fin_smem_bytes(), fp, c);
+        }
+        ctx->stream = root;
+        for (int k = 0; k < n_streams; k++) {
+            CG_CUDA(ctx, cudaEventRecord(ctx->chrom_ev[k], ctx->chrom_streams[k]));
+            CG_CUDA(ctx, cudaStreamWaitEvent(root, ctx->chrom_ev[k], 0));
+        }
+        return CG_OK;
+    };
+    bool replayed = false;
+    if (!fp.phase_ns && !getenv("CANVAS_NO_GRAPH")) {
+        CgGraphEntry want{};
+        unsigned long long hl = 1469598103934665603ull, hs = 1469598103934665603ull;  // FNV-1a of the launch lengths / the mask
+        for (int c = 0; c <= C; c++) { hl ^= (unsigned long long)d.alloc_off[c]; hl *= 1099511628211ull; }
+        for (int c = 0; c < C; c++) { hs ^= (unsigned long long)(selected_host[c] ? 1 : 0) + 2; hs *= 1099511628211ull; }
+        const long long key[12] = {(long long)(uintptr_t)ctx->arena, (long long)(uintptr_t)d.cov, (long long)(uintptr_t)d.ctl,
+                                   (long long)(uintptr_t)d.cc, (long long)(uintptr_t)d.bp, C, o->min_size, o->is_germline, (long long)hl,
+                                   (long long)hs, (long long)(uintptr_t)d.rq_sorted, (long long)(uintptr_t)d.tiny_tab};
+        for (int i = 0; i < 12; i++) want.key[i] = key[i];
+        CgGraphEntry* hit = nullptr;
+        for (auto& g : ctx->part_graphs)
+            if (!memcmp(g.key, want.key, sizeof(want.key))) { hit = &g; break; }
+        if (!hit) {  // first sighting of this shape: remember it, launch directly below
+            if (ctx->part_graphs.size() >= 16) {
+                for (auto& g : ctx->part_graphs)
+                    if (g.exec) cudaGraphExecDestroy(g.exec);
+                ctx->part_graphs.clear();
+            }
+            want.exec = nullptr;
+            ctx->part_graphs.push_back(want);
+        } else {
+            if (!hit->exec) {
+                const int launches_before = ctx->launches;
+                cudaGraph_t graph = nullptr;
+                if (cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+                    const int rc_cap = enqueue_pipelines(d.alloc_off, s);
+                    const cudaError_t ce = cudaStreamEndCapture(s, &graph);
+                    hit->launches = ctx->launches - launches_before;
+                    ctx->launches = launches_before;
+                    if (rc_cap == CG_OK && ce == cudaSuccess && graph) {
+                        if (cudaGraphInstantiate(&hit->exec, graph, 0) != cudaSuccess) hit->exec = nullptr;
+                    }
+                    if (graph) cudaGraphDestroy(graph);
+                    cudaGetLastError();
+                    ctx->launch_err = cudaSuccess;
+                } else {
+                    cudaGetLastError();
+                }
+            }
+            if (hit->exec) {
+                const cudaError_t le = cudaGraphLaunch(hit->exec, s);
+                if (le != cudaSuccess) return cg_fail(ctx, CG_ERR_CUDA, std::string("partition: graph launch failed: ") + cudaGetErrorString(le));
+                ctx->launches += hit->launches;
+                replayed = true;
+            }
+        }
     }
-    ctx->stream = s;
-    for (int k = 0; k < n_streams; k++) {
-        CG_CUDA(ctx, cudaEventRecord(ctx->chrom_ev[k], ctx->chrom_streams[k]));
-        CG_CUDA(ctx, cudaStreamWaitEvent(s, ctx->chrom_ev[k], 0));
+    if (!replayed) {
+        const int rc_p = enqueue_pipelines(pl.off.data(), s);
+        if (rc_p) return rc_p;
     }
     CG_TL(ctx, "decompose + finish");
     cudaEventRecord(ctx->stage_ev[5], s);

@@ -687,11 +687,15 @@ __global__ void uh_seed_kernel(UhParams p, const unsigned char* __restrict__ sel
     }
     for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < n_chrom; c += gridDim.x * blockDim.x) {
         const long long len = p.off[c + 1] - p.off[c];
-        if (!selected[c] || len <= (long long)min_size || len < 2) continue;
+        const bool run = selected[c] && len > (long long)min_size && len >= 2;
+        const int tier = run ? uh_tier((int)len) : UH_TIER_NONE;
+        // a chain kernel may have been launched for this chromosome on the strength of an upper bound of its length
+        // (launch sequences are cached per input shape): without a big root it has nothing to wait for
+        if (tier != UH_TIER_BIG) *(volatile int*)&p.cc[c].big_done_.v = 1;
+        if (!run) continue;
         const int e = (int)len - 1;
         const long long p0 = p.off[c] + c;
         const double base = p.pz[p0], endv = p.pz[p0 + e + 1];
-        const int tier = uh_tier(e + 1);
         if (tier == UH_TIER_BIG) {
             atomicAdd(&p.cc[c].outstanding_.v, 1);
             uh_push_big(p, c, 0, e, 0, base, endv);

@@ -12,3 +12,4 @@ print({k: d[k] for k in ("value", "ms_per_step", "stages_ms", "gpu_launches")}, 
 PY
 CANVAS_DEBUG=1 timeout 300 python tools/profile_driver.py 1.0 3 fused > $out/${tag}_timeline.txt 2>&1
 grep "\[pipe\]" $out/${tag}_timeline.txt | tail -24 | cut -c1-200
+if [ -n "$3" ]; then bash -c "$3"; fi
