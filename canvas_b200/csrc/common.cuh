@@ -29,7 +29,7 @@ struct cg_ctx {
     cudaStream_t stream = nullptr;
     cudaStream_t copy_stream = nullptr;  // overlaps result downloads with later kernels
     cudaStream_t side_stream = nullptr;  // kernels off the critical path (partition: evenness / factor-of-three statistics)
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_rq = nullptr;
     // partition: one stream per chromosome pipeline (decomposition stages + finish), created on first use
     std::vector<cudaStream_t> chrom_streams;
     std::vector<cudaEvent_t> chrom_ev;

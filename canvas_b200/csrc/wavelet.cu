@@ -218,6 +218,10 @@ struct WvDev {
     unsigned short *rq_hist, *rq_tstart;
     unsigned* rq_cum;
     int* rq_tfirst;
+    // fused call: the index is built on the side stream from device-side offsets, before the plan tables are uploaded
+    long long* rq_off2;
+    int* rq_tfirst2;
+    unsigned char* rq_sel2;
     unsigned long long* phase_ns;
     unsigned long long* tl_ns;  // debug timeline of the decomposition stages, [C][16]
     UhTinyTab* tiny_tab;
@@ -296,7 +300,7 @@ size_t wv_workspace_bytes(const WvPlan& pl) {
     s += arena_need(N + 1, 4) * 5 + arena_need(N + 1, 8) * 2 + arena_need(N / 32 + C + 2, 4);
     s += arena_need(C + 1, 4) + arena_need(N + 1, 4);
     s += arena_need((C + 1) * RQ_BUCKETS, 8) + arena_need(N + 1, 8) + arena_need((size_t)(pl.rq_ntiles + 1) * RQ_BUCKETS, 2) * 2;
-    s += arena_need((size_t)(pl.rq_ntiles + C + 2) * RQ_BUCKETS, 4) + arena_need(C + 2, 4) + arena_need((C + 1) * 8, 8) + arena_need((C + 1) * 16, 8) + arena_need(1, sizeof(UhTinyTab)) + arena_need(WV_PACK_INTS, 4);
+    s += arena_need((size_t)(pl.rq_ntiles + C + 2) * RQ_BUCKETS, 4) + arena_need(C + 2, 4) + arena_need((C + 1) * 8, 8) + arena_need((C + 1) * 16, 8) + arena_need(1, sizeof(UhTinyTab)) + arena_need(WV_PACK_INTS, 4) + arena_need(C + 2, 8) + arena_need(C + 2, 4) + arena_need(C + 2, 1);
     return s + (1 << 16);
 }
 
@@ -370,6 +374,10 @@ int wv_alloc(cg_ctx* ctx, const WvPlan& pl, WvDev& d, double* cov_dev_existing, 
     d.phase_ns = arena_take<unsigned long long>(ctx, (C + 1) * 8);
     d.tl_ns = arena_take<unsigned long long>(ctx, (C + 1) * 16);
     d.pack = arena_take<int>(ctx, WV_PACK_INTS);
+    d.rq_off2 = arena_take<long long>(ctx, C + 2);
+    d.rq_tfirst2 = arena_take<int>(ctx, C + 2);
+    d.rq_sel2 = arena_take<unsigned char>(ctx, C + 2);
+    ok = ok && d.rq_off2 && d.rq_tfirst2 && d.rq_sel2;
     d.tiny_tab = arena_take<UhTinyTab>(ctx, 1);
     ok = ok && d.rq_spl && d.rq_sorted && d.rq_hist && d.rq_tstart && d.rq_cum && d.rq_tfirst;
     ok = ok && d.cov && d.off && d.selected && d.pz && d.seg_len && d.work && d.seg_nwork && d.ev_work && d.tiles && d.tile_first &&
@@ -431,12 +439,13 @@ int wv_clear(cg_ctx* ctx, WvDev& d) {
 }
 
 // The range-quantile index of the finish stage needs only the coverage and the chromosome offsets.
-static void wv_enqueue_rq_index(cg_ctx* ctx, WvDev& d, int C, int rq_ntiles_upper) {
+static void wv_enqueue_rq_index(cg_ctx* ctx, WvDev& d, int C, int rq_ntiles_upper, const long long* off, const int* tfirst,
+                                const unsigned char* selected) {
     if (rq_ntiles_upper <= 0 || C <= 0) return;
-    CG_LAUNCH(ctx, rq_splitter_kernel, C, 1024, 0, d.cov, d.off, d.selected, d.rq_spl);
-    CG_LAUNCH(ctx, rq_tile_kernel, rq_ntiles_upper, RQ_TILE, 0, d.cov, d.off, d.rq_tfirst, C, d.selected, d.rq_spl, d.rq_hist,
+    CG_LAUNCH(ctx, rq_splitter_kernel, C, 1024, 0, d.cov, off, selected, d.rq_spl);
+    CG_LAUNCH(ctx, rq_tile_kernel, rq_ntiles_upper, RQ_TILE, 0, d.cov, off, tfirst, C, selected, d.rq_spl, d.rq_hist,
               d.rq_tstart, d.rq_sorted);
-    CG_LAUNCH(ctx, rq_cumulate_kernel, C, RQ_BUCKETS, 0, d.rq_tfirst, d.selected, d.rq_hist, d.rq_cum);
+    CG_LAUNCH(ctx, rq_cumulate_kernel, C, RQ_BUCKETS, 0, tfirst, selected, d.rq_hist, d.rq_cum);
 }
 
 // chromosome offsets and first index tiles from the per-chromosome bin counts, on the device (fused call: lets the index
@@ -523,7 +532,7 @@ int wv_enqueue(cg_ctx* ctx, const cg_wavelet_opts* o, const WvPlan& pl, WvDev& d
     // ---- range-quantile index for the medians of the finish stage: needs only the coverage, and is enqueued first so
     // that the device has work while the host is still launching the many small kernels of the scalars
     if (!rq_index_done) {
-        wv_enqueue_rq_index(ctx, d, C, pl.rq_ntiles);
+        wv_enqueue_rq_index(ctx, d, C, pl.rq_ntiles, d.off, d.rq_tfirst, d.selected);
         CG_TL(ctx, "rq index");
     }
     const int ntiles = (int)pl.tiles.size();
@@ -704,6 +713,7 @@ int wv_enqueue(cg_ctx* ctx, const cg_wavelet_opts* o, const WvPlan& pl, WvDev& d
         }
         return CG_OK;
     };
+    if (rq_index_done) CG_CUDA(ctx, cudaStreamWaitEvent(s, ctx->ev_rq, 0));  // built on the side stream (fused call)
     bool replayed = false;
     if (!fp.phase_ns && !getenv("CANVAS_NO_GRAPH")) {
         CgGraphEntry want{};
@@ -1129,11 +1139,16 @@ static int clean_partition_wavelet_impl(cg_ctx* ctx, const cg_clean_opts* copts,
     } else if (chrom_selected)
         for (int c = 0; c < n_chrom; c++) sel[c] = chrom_selected[c] ? 1 : 0;
     if (n_chrom > 0) {
-        CG_CUDA(ctx, cudaMemcpyAsync(wd.selected, sel.data(), n_chrom, cudaMemcpyHostToDevice, s));
-        CG_LAUNCH(ctx, wv_device_offsets_kernel, 1, 32, 0, chrom_cnt, n_chrom, wd.off, wd.rq_tfirst);
-        wv_enqueue_rq_index(ctx, wd, n_chrom, worst.rq_ntiles);
+        // ... on the side stream, from its own copies of the offsets: the finish stage needs it a millisecond from now
+        CG_CUDA(ctx, cudaStreamWaitEvent(ctx->side_stream, ctx->ev_mid, 0));
+        ctx->stream = ctx->side_stream;
+        cudaMemcpyAsync(wd.rq_sel2, sel.data(), n_chrom, cudaMemcpyHostToDevice, ctx->side_stream);
+        CG_LAUNCH(ctx, wv_device_offsets_kernel, 1, 32, 0, chrom_cnt, n_chrom, wd.rq_off2, wd.rq_tfirst2);
+        wv_enqueue_rq_index(ctx, wd, n_chrom, worst.rq_ntiles, wd.rq_off2, wd.rq_tfirst2, wd.rq_sel2);
+        ctx->stream = s;
+        CG_CUDA(ctx, cudaEventRecord(ctx->ev_rq, ctx->side_stream));
     }
-    CG_TL(ctx, "clears + rq index");
+    CG_TL(ctx, "clears");
     cudaEventRecord(ctx->gap_ev, s);
     ctx->gap_used = true;
     {
