@@ -1,17 +1,20 @@
 #!/usr/bin/env python
-"""Headline benchmark: Mbins/s through CanvasClean + CanvasPartition (wavelets) on a synthetic
-3.1 M-bin germline WGS coverage array (BASELINE.json config 2), 1..8 GPUs, one sample per GPU.
+"""Headline benchmark: Mbins/s through CanvasClean + CanvasPartition on synthetic WGS coverage arrays (BASELINE.json).
 
-  python bench.py --gpus 1 --steps 5 --warmup 3
-  python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
-         --master-port P bench.py --gpus N --steps K --warmup W
-  python bench.py --impl reference ...      # CPU restatement of the reference on the host cores
+  python bench.py --gpus 1 --steps 5 --warmup 3              # config 2: one 3.1 M-bin germline sample on one B200
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+         bench.py --gpus N --steps K --warmup W               # config 5: one sample per GPU + NCCL gather of segment lists
+  python bench.py --config 3 | --config 4 [...]               # tumour/normal pair on one GPU | trio, (sample, chromosome) units over N GPUs
+  python bench.py --impl reference [...]                      # the same workload on the host cores (C++ restatement of the reference)
 
-One JSON line on stdout (rank 0).  `value` = bins of all ranks / device time of the kernels with the
-inputs already resident in HBM (CUDA events on the library's launch stream); `e2e` = the same metric
-through the C-ABI call with pinned HOST buffers (H2D + kernels + D2H, wall clock around the
-synchronous call, max over ranks); `roofline` = Unbalanced-Haar decomposition kernel against the
-measured HBM copy bandwidth; `cpu_baseline` = oracle (C++ restatement of the reference) on this box.
+One JSON line on stdout (rank 0).  `value` = bins of all ranks / device time of the kernels with the inputs already resident
+in HBM (CUDA events on the library's launch stream, max over ranks); `e2e` = the same metric through the C-ABI call with
+pinned HOST buffers (H2D + kernels + D2H + the exchange, wall clock around the synchronous calls, max over ranks);
+`roofline` = the Unbalanced-Haar decomposition against the measured HBM copy bandwidth; `cpu_baseline` = the oracle on this
+box's cores.  At N > 1 the line also carries `per_rank` (stage times of every rank), `strong_scaling_single_sample` (ONE
+sample, chromosomes LPT-sharded over the ranks inside cg_clean_partition_wavelet_sharded) and `config4` (the trio chain).
+Every exchange goes through the library's own NCCL communicator (cg_comm_*); torch.distributed only carries the 128-byte
+NCCL id, the barriers and the max-over-ranks of the timings.
 """
 import argparse
 import json
@@ -29,8 +32,16 @@ sys.path.insert(0, ROOT)
 
 METRIC = "Mbins/s through Clean+Partition on 3M-bin WGS array"
 UNIT = "Mbins/s"
-WORKLOAD = ("config2 germline-WGS 30x synthetic, ~3.1M x 1kb bins: CanvasClean (-g -s -r, local-SD metric, "
-            "MedianByGC) + CanvasPartition wavelets (-g); one sample per GPU")
+WORKLOADS = {
+    2: ("config2 germline-WGS 30x synthetic, ~3.1M x 1kb bins: CanvasClean (-g -s -r, local-SD metric, MedianByGC) + "
+        "CanvasPartition wavelets (-g); one sample per GPU"),
+    3: ("config3 somatic-WGS tumour/normal pair, 2 x ~3.1M bins on one GPU: CanvasClean + CanvasPartition wavelets "
+        "(somatic thresholds) per sample"),
+    4: ("config4 SmallPedigree-WGS trio, 3 x ~3.1M bins: CanvasClean per sample (once, on rank s mod N) -> NCCL broadcast -> "
+        "common-bin merge -> PerSampleHMM over (sample, chromosome) units LPT-sharded across the GPUs -> NCCL gather"),
+    5: ("config5 batch of independent 30x WGS samples (config-2 pipeline), one per GPU, NCCL all-gather of the per-sample "
+        "segment lists"),
+}
 
 
 def peaks():
@@ -77,9 +88,10 @@ class ClockSampler(threading.Thread):
                 "samples": len(self.samples)}
 
 
-def run_oracle_once(s, threads):
-    """The reference path on the CPU: CanvasClean (single thread, as the reference) -> .cleaned text
-    round trip -> CanvasPartition wavelets with one thread per chromosome up to `threads`."""
+# ---------------------------------------------------------------------------------------------------------------- CPU arm
+def oracle_sample(s, threads, germline=True):
+    """The reference path of one sample on the CPU: CanvasClean (single thread, as the reference) -> .cleaned text round
+    trip -> CanvasPartition wavelets with one thread per chromosome up to `threads`."""
     from canvas_b200 import synth
     from oracle import pyoracle as ora
     t0 = time.perf_counter()
@@ -88,10 +100,82 @@ def run_oracle_once(s, threads):
     off = synth.chrom_offsets(s.chrom[r["kept_index"]], len(s.names))
     cov = ora.f2_roundtrip(r["count"])
     t2 = time.perf_counter()
-    p = ora.partition_wavelet(off, cov, is_germline=True, n_threads=threads)
+    p = ora.partition_wavelet(off, cov, is_germline=germline, n_threads=threads)
     t3 = time.perf_counter()
-    return {"clean_s": t1 - t0, "partition_s": t3 - t2, "total_s": (t1 - t0) + (t3 - t2),
-            "breakpoints": sum(len(b) for b in p["breakpoints"])}
+    return {"clean_s": t1 - t0, "partition_s": t3 - t2, "breakpoints": sum(len(b) for b in p["breakpoints"])}
+
+
+def oracle_trio(samples, threads):
+    """Config 4 on the CPU: Clean per sample (one thread each, side by side as separate CanvasClean processes would run),
+    dictionary merge of the common bins, PerSampleHMM per sample with one thread per chromosome."""
+    from concurrent.futures import ThreadPoolExecutor
+    from canvas_b200 import pedigree, synth, textcodec
+    from oracle import pyoracle as ora
+    pos = pedigree.bin_positions(samples[0])
+    t0 = time.perf_counter()
+    with ThreadPoolExecutor(max_workers=min(len(samples), threads)) as ex:
+        cl = list(ex.map(lambda s: ora.clean(s.chrom, s.is_autosome, s.is_chr_y, s.start, s.stop, s.count, s.gc), samples))
+    t1 = time.perf_counter()
+    cleaned = [(s.chrom[c["kept_index"]], pos[c["kept_index"]], (pos[c["kept_index"]] + 1000).astype(np.int32), c["count"])
+               for s, c in zip(samples, cl)]
+    m = ora.merge_common_bins_np(cleaned)
+    ch0 = cleaned[0][0][m["kept_index"]]
+    off = synth.chrom_offsets(ch0, len(samples[0].names))
+    t2 = time.perf_counter()
+    nbp = 0
+    for k in range(len(samples)):
+        cov = textcodec.float_default_roundtrip(m["count"][k])
+        nbp += sum(len(b) for b in ora.partition_hmm(off, cov, per_sample=True, n_threads=threads)["breakpoints"])
+    t3 = time.perf_counter()
+    return {"clean_s": t1 - t0, "merge_s": t2 - t1, "partition_s": t3 - t2, "breakpoints": nbp}
+
+
+def run_reference(args, config, n_samples, K, W):
+    """`--impl reference`: the C++ restatement of the reference on every host core, same workload as the GPU arm."""
+    from concurrent.futures import ThreadPoolExecutor
+    from canvas_b200 import synth
+    threads = os.cpu_count() or 1
+    if config == 4:
+        samples = [synth.make_sample(config=4, sample=k, scale=args.scale, n_events=60) for k in range(3)]
+        step = lambda: oracle_trio(samples, threads)  # noqa: E731
+        how = ("the trio per step: Clean of the three samples side by side (one thread each), dictionary merge, "
+               "PerSampleHMM with one thread per chromosome")
+    else:
+        if config == 3:
+            samples = [synth.make_sample(config=3, sample=k, scale=args.scale, n_events=150, tumour=(k == 0)) for k in range(2)]
+            how = "tumour and normal per step, side by side: Clean 1 thread per sample, Partition 1 thread per chromosome"
+        else:
+            samples = [synth.make_sample(config=2, sample=k, scale=args.scale) for k in range(n_samples)]
+            how = (f"{n_samples} full config-2 sample(s) per step, side by side (Clean on 1 thread per sample as the reference, "
+                   "Partition one thread per chromosome)")
+        workers = min(len(samples), threads)
+        per = max(1, threads // workers)
+
+        def step():
+            with ThreadPoolExecutor(max_workers=workers) as ex:
+                rs = list(ex.map(lambda s: oracle_sample(s, per, germline=(config != 3)), samples))
+            return {"clean_s": max(r["clean_s"] for r in rs), "partition_s": max(r["partition_s"] for r in rs),
+                    "breakpoints": sum(r["breakpoints"] for r in rs)}
+    nb = sum(len(s) for s in samples)
+    for _ in range(W):
+        step()
+    walls, parts = [], []
+    for _ in range(K):
+        t0 = time.perf_counter()
+        parts.append(step())
+        walls.append(time.perf_counter() - t0)
+    sec = sum(walls) / K
+    v = nb / sec / 1e6
+    return {"metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": K, "warmup": W,
+            "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "strong" if config == 4 else "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic", "impl": "reference",
+            "config": {"workload": WORKLOADS[config], "bins_per_sample": len(samples[0]), "samples": len(samples)},
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
+                             "sample": how + "; C++ restatement of the reference (the C# build needs private NuGet feeds)"},
+            "clean_ms": 1e3 * sum(x["clean_s"] for x in parts) / K,
+            "partition_ms": 1e3 * sum(x["partition_s"] for x in parts) / K,
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
 
 
 _REAL_STDOUT = None
@@ -116,169 +200,225 @@ def _emit(line):
         os.write(_REAL_STDOUT, data)
 
 
+def pack_segments(breakpoints):
+    """(chromosome, breakpoint) pairs of one sample as a flat int32 list."""
+    if not any(len(b) for b in breakpoints):
+        return np.zeros(0, np.int32)
+    return np.concatenate([np.stack([np.full(len(b), c, np.int32), b.astype(np.int32)], 1).ravel()
+                           for c, b in enumerate(breakpoints) if len(b)])
+
+
+def effective_config(args, world):
+    return args.config or (2 if max(world, args.gpus) == 1 else 5)
+
+
+# ---------------------------------------------------------------------------------------------------------------- GPU arm
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="canvas_b200", choices=["canvas_b200", "reference"])
+    ap.add_argument("--config", type=int, default=0, choices=[0, 2, 3, 4, 5],
+                    help="BASELINE.json configuration (default: 2 on one GPU, 5 = one config-2 sample per GPU on several)")
     ap.add_argument("--scale", type=float, default=1.0, help="shrink the genome (debugging only; 1.0 = BASELINE config)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="N > 1: skip the strong-scaling and config-4 side measurements")
     args = ap.parse_args()
     W = max(args.warmup, 0)
     K = max(args.steps, 1)
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    config = effective_config(args, world)
     from canvas_b200 import synth
     _claim_stdout()
 
-    # ------------------------------------------------------------------ reference arm (CPU)
     if args.impl == "reference":
         if rank != 0:
             return 0
-        threads = os.cpu_count() or 1
-        s = synth.make_sample(config=2, sample=0, scale=args.scale)
-        nb = len(s)
-        for _ in range(max(W, 0)):
-            run_oracle_once(s, threads)
-        t = []
-        for _ in range(K):
-            t.append(run_oracle_once(s, threads))
-        sec = sum(x["total_s"] for x in t) / K
-        v = nb / sec / 1e6
-        line = {"metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": K, "warmup": W,
-                "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "f64", "data": "synthetic", "impl": "reference",
-                "config": {"workload": WORKLOAD, "bins_per_sample": nb, "samples": 1},
-                "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
-                                 "sample": "one full config-2 sample per step (Clean on 1 thread as the reference, "
-                                           "Partition one thread per chromosome); C++ restatement, the C# build "
-                                           "needs private NuGet feeds"},
-                "clean_ms": 1e3 * sum(x["clean_s"] for x in t) / K,
-                "partition_ms": 1e3 * sum(x["partition_s"] for x in t) / K,
-                "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-                "gpu_launches": 0}
-        _emit(line)
+        n_samples = max(world, args.gpus) if config in (2, 5) else 1
+        _emit(run_reference(args, config, n_samples, K, W))
         return 0
 
-    # ------------------------------------------------------------------ GPU arm
     import torch
     import torch.distributed as dist
-    from canvas_b200 import native
+    from canvas_b200 import native, pedigree
+    torch.cuda.set_device(local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # NCCL's version / debug lines must not mix with the JSON line on stdout
-        torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    else:
-        torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     eng = native.Engine(local_rank)
-    s = synth.make_sample(config=2, sample=rank, scale=args.scale)
-    nb = len(s)
-    nc = len(s.names)
+    if world > 1:
+        eng.comm_init_torch()  # the library's own NCCL communicator; torch only hands the id around
+    else:
+        eng.comm_init(1, 0)
     pin = eng.pinned
-    inp = dict(chrom=pin.array(s.chrom), start=pin.array(s.start), stop=pin.array(s.stop), count=pin.array(s.count),
-               gc=pin.array(s.gc))
-    out = (pin.empty(nb, np.int32), pin.empty(nb, np.float32), pin.empty(max(nc, 1), np.int32), pin.empty(nb, np.int32))
-    h2d = nb * (1 + 4 + 4 + 4 + 1)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
-    SEG_CAP = 8192
-    seg_local = torch.zeros(SEG_CAP, dtype=torch.int32, device=dev)
-    seg_all = torch.zeros(SEG_CAP * world, dtype=torch.int32, device=dev) if world > 1 else None
+    W = max(W, 3)  # timing rules: at least three warm-up steps
 
-    e2e_s = []
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    def max_over_ranks(vals):
+        t = torch.tensor(vals, dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.tolist()
+
+    def sum_over_ranks(v):
+        t = torch.tensor([v], dtype=torch.int64, device=dev)
+        if world > 1:
+            dist.all_reduce(t)
+        return int(t.item())
+
+    def pinned_sample(s):
+        return dict(chrom=pin.array(s.chrom), start=pin.array(s.start), stop=pin.array(s.stop), count=pin.array(s.count),
+                    gc=pin.array(s.gc))
+
+    def timed(step, n_steps):
+        """n_steps timed steps between barriers; L2 flushed before every step; per-step wall seconds (the flush is outside)."""
+        walls = []
+        barrier()
+        for _ in range(n_steps):
+            flush.fill_(1)
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+            t = time.perf_counter()
+            step()
+            walls.append(time.perf_counter() - t)
+        barrier()
+        return walls
+
+    line_extra = {}
+
+    # ------------------------------------------------------------------ config 4: the trio chain
+    def run_config4(n_warm, n_steps):
+        trio = [synth.make_sample(config=4, sample=k, scale=args.scale, n_events=60) for k in range(3)]
+        pos = pedigree.bin_positions(trio[0])
+        tm, res = {}, {}
+
+        def step():
+            res["r"] = pedigree.trio_segments(eng, trio, pos=pos, sharded=world > 1, timings=tm if res.get("timed") else None)
+        for _ in range(n_warm):
+            step()
+        res["timed"] = True
+        walls = timed(step, n_steps)
+        wall_ms, kern_ms = max_over_ranks([1e3 * sum(walls) / n_steps, tm.get("kernel_ms", 0.0) / n_steps])
+        bins = sum(len(s) for s in trio)
+        return {"workload": WORKLOADS[4], "bins": bins, "common_bins": res["r"]["n_common"],
+                "breakpoints": int(sum(len(b) for per in res["r"]["breakpoints"] for b in per)),
+                "ms_per_step": wall_ms, "Mbins_per_s": bins / wall_ms / 1e3,
+                "kernel_ms_max_rank": kern_ms, "Mbins_per_s_kernels": bins / kern_ms / 1e3 if kern_ms > 0 else None,
+                "phases_ms_rank0": {k: v / n_steps for k, v in tm.items() if k not in ("kernel_ms", "launches")},
+                "launches_rank0": tm.get("launches", 0) // max(n_steps, 1),
+                "h2d_bytes": 14 * len(trio[0]) * (3 if world == 1 else 1),
+                "timing": "wall clock around the chain of C-ABI calls, host buffers in and out, max over ranks"}
+
+    if config == 4:
+        sampler = ClockSampler(local_rank)
+        if rank == 0:
+            sampler.start()
+        c4 = run_config4(W, K)
+        clocks = sampler.summary() if rank == 0 else None
+        if rank == 0:
+            line = {"metric": METRIC, "value": c4["Mbins_per_s_kernels"], "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+                    "ms_per_step": c4["kernel_ms_max_rank"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                    "dtype": "f64", "data": "synthetic",
+                    "config": {"workload": WORKLOADS[4], "bins_per_sample": c4["bins"] // 3, "samples": 3,
+                               "l2": "flushed between steps (256 MiB device write)", "parallelism": f"(sample, chromosome) units x{world}"},
+                    "e2e": {"value": c4["Mbins_per_s"], "unit": UNIT, "ms_per_step": c4["ms_per_step"],
+                            "h2d_bytes_per_step": c4["h2d_bytes"], "d2h_bytes_per_step": 8 * c4["common_bins"] * 3, "timing": c4["timing"]},
+                    "gpu_launches": c4["launches_rank0"] * K, "config4": c4, "clocks": clocks, "device": eng.describe()}
+            _emit(line)
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    # ------------------------------------------------------------------ configs 2 / 5 (one germline sample per GPU) and 3 (pair)
+    if config == 3:
+        samples = [synth.make_sample(config=3, sample=k, scale=args.scale, n_events=150, tumour=(k == 0)) for k in range(2)]
+        germline = False
+    else:
+        samples = [synth.make_sample(config=2, sample=rank, scale=args.scale)]
+        germline = True
+    nb = sum(len(s) for s in samples)
+    nc = len(samples[0].names)
+    inps = [pinned_sample(s) for s in samples]
+    outs = [(pin.empty(len(s), np.int32), pin.empty(len(s), np.float32), pin.empty(max(nc, 1), np.int32), pin.empty(len(s), np.int32))
+            for s in samples]
+    h2d = nb * (1 + 4 + 4 + 4 + 1)
+    acc = {"dev_ms": [], "launches": 0, "stages": {}, "pstats": None, "d2h": 0, "x_ms": 0.0, "last": None}
 
     def step():
-        flush.fill_(1)
-        torch.cuda.synchronize()
-        t_call = time.perf_counter()
-        r = eng.clean_partition_wavelet(inp["chrom"], s.is_autosome, s.is_chr_y, inp["start"], inp["stop"],
-                                        inp["count"], inp["gc"], is_germline=True, out=out)
-        nbp = sum(len(b) for b in r["breakpoints"])
+        dev_ms, d2h = 0.0, 0
+        r = None
+        for s, inp, out in zip(samples, inps, outs):
+            r = eng.clean_partition_wavelet(inp["chrom"], s.is_autosome, s.is_chr_y, inp["start"], inp["stop"], inp["count"],
+                                            inp["gc"], is_germline=germline, out=out)
+            dev_ms += eng.last_kernel_ms
+            acc["launches"] += eng.last_launches
+            for k, v in eng.last_stage_ms().items():
+                acc["stages"][k] = acc["stages"].get(k, 0.0) + v
+            acc["pstats"] = eng.last_partition_stats()
+            nbp = sum(len(b) for b in r["breakpoints"])
+            d2h += len(r["kept_index"]) * 8 + nbp * 4 + nc * 4 + 4096
+            acc["last"] = r
         if world > 1:
-            # config 5: gather the per-sample segment lists (chromosome, breakpoint) on every rank
-            flat = np.zeros(SEG_CAP, np.int32)
-            flat[0] = nbp
-            k = 1
-            for c, b in enumerate(r["breakpoints"]):
-                m = min(len(b), (SEG_CAP - k) // 2)
-                flat[k:k + 2 * m:2] = c
-                flat[k + 1:k + 2 * m:2] = b[:m]
-                k += 2 * m
-            seg_local.copy_(torch.from_numpy(flat))
-            dist.all_gather_into_tensor(seg_all, seg_local)
-            torch.cuda.synchronize()
-        e2e_s.append(time.perf_counter() - t_call)  # the synchronous call: H2D + kernels + D2H (+ the gather)
-        return r, nbp
+            # config 5: the per-sample segment lists of every rank, on every rank (cg_comm_allgather_lists)
+            acc["all"] = eng.allgather_lists(pack_segments(r["breakpoints"]))
+            acc["x_ms"] += eng.last_exchange_ms
+        acc["dev_ms"].append(dev_ms)
+        acc["d2h"] = d2h
 
-    W = max(W, 3)  # timing rules: at least three warm-up steps
     for _ in range(W):
         step()
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
+    acc.update(dev_ms=[], launches=0, stages={}, x_ms=0.0)
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    dev_ms, launches, stage_acc, visits, d2h = [], 0, {}, 0.0, 0
-    e2e_s.clear()
-    t0 = time.perf_counter()
-    for _ in range(K):
-        r, nbp = step()
-        dev_ms.append(eng.last_kernel_ms)
-        launches += eng.last_launches
-        for k, v in eng.last_stage_ms().items():
-            stage_acc[k] = stage_acc.get(k, 0.0) + v
-        pstats = eng.last_partition_stats()
-        visits = pstats["visits"]
-        d2h = len(r["kept_index"]) * 8 + nbp * 4 + nc * 4 + 4096
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    t1 = time.perf_counter()
+    walls = timed(step, K)
     clocks = sampler.summary() if rank == 0 else None
-    loop_ms = (t1 - t0) * 1e3 / K  # includes the L2 flush between steps
-    wall_ms = sum(e2e_s) * 1e3 / K
-    kern_ms = sum(dev_ms) / K
-    del loop_ms
-    tt = torch.tensor([wall_ms, kern_ms], dtype=torch.float64, device=dev)
+    my_wall, my_kern = 1e3 * sum(walls) / K, sum(acc["dev_ms"]) / K
+    wall_ms, kern_ms = max_over_ranks([my_wall, my_kern])
+    total_bins = sum_over_ranks(nb)
+    r = acc["last"]
+    pstats = acc["pstats"]
+    stages = {k: v / K for k, v in acc["stages"].items()}
+    per_rank = None
     if world > 1:
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-    wall_ms, kern_ms = tt.tolist()
-    total_bins = nb * world if world == 1 else None
-    if world > 1:
-        nbt = torch.tensor([nb], dtype=torch.int64, device=dev)
-        dist.all_reduce(nbt)
-        total_bins = int(nbt.item())
+        mine = {"rank": rank, "device_ms": my_kern, "e2e_ms": my_wall, "stages_ms": stages, "exchange_ms": acc["x_ms"] / K,
+                "l_eff": pstats["visits"] / max(1, len(r["kept_index"])), "launches_per_step": acc["launches"] // K,
+                "breakpoints": int(sum(len(b) for b in r["breakpoints"]))}
+        per_rank = [None] * world
+        dist.all_gather_object(per_rank, mine)
     strong = None
-    if world > 1:
-        # the same path on ONE sample with its chromosomes sharded over the ranks: Clean and the
-        # genome-wide scalars replicated, each rank segments its LPT share, one all-gather of breakpoints
-        from canvas_b200 import multi
-        s0 = synth.make_sample(config=2, sample=0, scale=args.scale)
-        in0 = dict(chrom=pin.array(s0.chrom), start=pin.array(s0.start), stop=pin.array(s0.stop), count=pin.array(s0.count),
-                   gc=pin.array(s0.gc))
-        lens0 = np.bincount(s0.chrom, minlength=len(s0.names))
-        ts = []
-        for it in range(W + K):
-            flush.fill_(1)
-            torch.cuda.synchronize()
-            dist.barrier()
-            ta = time.perf_counter()
-            p0 = multi.clean_partition_wavelet_sharded(
-                eng, (in0["chrom"], s0.is_autosome, s0.is_chr_y, in0["start"], in0["stop"], in0["count"], in0["gc"]), lens0,
-                is_germline=True, out=out)
-            torch.cuda.synchronize()
-            if it >= W:
-                ts.append(time.perf_counter() - ta)
-        tst = torch.tensor([sum(ts) / len(ts)], dtype=torch.float64, device=dev)
-        dist.all_reduce(tst, op=dist.ReduceOp.MAX)
-        strong = {"what": "ONE config-2 sample: Clean + scalars replicated, chromosomes LPT-sharded over the ranks, one "
-                          "all-gather of breakpoints; wall clock of the fused C-ABI call incl. H2D/D2H, max over ranks",
-                  "ms_per_sample": tst.item() * 1e3, "Mbins_per_s": len(s0) / tst.item() / 1e6,
-                  "breakpoints": sum(len(b) for b in p0["breakpoints"])}
+    if world > 1 and not args.no_extras:
+        # ONE sample with its chromosomes sharded over the ranks (SURVEY.md 8e), entirely inside the C-ABI: Clean and the
+        # genome-wide scalars on every rank, each rank segments its LPT share, one NCCL all-gather of breakpoints
+        s0 = samples[0] if rank == 0 else synth.make_sample(config=2, sample=0, scale=args.scale)
+        in0 = inps[0] if rank == 0 else pinned_sample(s0)
+        res = {"k": 0.0}
+
+        def sstep():
+            res["r"] = eng.clean_partition_wavelet(in0["chrom"], s0.is_autosome, s0.is_chr_y, in0["start"], in0["stop"], in0["count"],
+                                                   in0["gc"], is_germline=True, out=outs[0], sharded=True)
+            res["k"] += eng.last_kernel_ms
+        for _ in range(W):
+            sstep()
+        res["k"] = 0.0
+        sw = timed(sstep, K)
+        s_wall, s_kern = max_over_ranks([1e3 * sum(sw) / K, res["k"] / K])
+        strong = {"what": "ONE config-2 sample through cg_clean_partition_wavelet_sharded: Clean + scalars on every rank, chromosomes "
+                          "LPT-sharded, one NCCL all-gather of breakpoints inside the call; wall clock incl. H2D/D2H, max over ranks",
+                  "ms_per_sample": s_wall, "Mbins_per_s": len(s0) / s_wall / 1e3, "device_ms": s_kern,
+                  "breakpoints": int(sum(len(b) for b in res["r"]["breakpoints"])), "exchange_ms": eng.last_exchange_ms}
+        line_extra["config4"] = run_config4(2, 3)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -289,50 +429,54 @@ def main():
     tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")  # dram bytes per launch from the committed ncu --set full captures
     if os.path.exists(tp):
         traffic = json.load(open(tp))
-    stages = {k: v / K for k, v in stage_acc.items()}
+    visits = pstats["visits"]
     # the chromosomes' pipelines (decomposition stages + finish) overlap: the decomposition's own span is the device-side
     # timestamp from its first kernel to its last tiny-stage thread (partition_stats), not a stage bracket
     dec_ms = pstats.get("decompose_span_ms", 0.0) or stages.get("decompose", -1.0)
-    alg_bytes = 8.0 * visits  # one f64 prefix sum read per bin visit (SURVEY.md §8d: 8 * L_eff B/bin)
+    alg_bytes = 8.0 * visits  # one f64 prefix sum read per bin visit (SURVEY.md 8d: 8 * L_eff B/bin)
     achieved = alg_bytes / (dec_ms * 1e-3) / 1e9 if dec_ms > 0 else None
     line = {"metric": METRIC, "value": total_bins / (kern_ms * 1e-3) / 1e6, "unit": UNIT, "n_gpus": world, "steps": K,
             "warmup": W, "ms_per_step": kern_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "bins_per_sample": nb, "samples": world,
+            "config": {"workload": WORKLOADS[config], "bins_per_sample": len(samples[0]), "samples": world * len(samples),
                        "l2": "flushed between steps (256 MiB device write)", "parallelism": f"sample-per-gpu x{world}",
-                       "exchange": "NCCL all-gather of per-sample segment lists" if world > 1 else "none"},
+                       "exchange": "cg_comm_allgather_lists (NCCL all-gather inside libcanvasgpu) of per-sample segment lists" if world > 1 else "none"},
             "e2e": {"value": total_bins / (wall_ms * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": wall_ms,
-                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "timing": "wall clock around the synchronous C-ABI call with pinned host buffers, max over ranks"},
-            "gpu_launches": launches,
+                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": acc["d2h"],
+                    "timing": "wall clock around the synchronous C-ABI call(s) with pinned host buffers (+ the exchange), max over ranks"},
+            "gpu_launches": acc["launches"],
             "stages_ms": stages, "partition_stats": pstats,
             "roofline": {"kernel": "Unbalanced-Haar decomposition (uh_chain + uh_mid + uh_small + uh_tiny kernels, one pipeline per chromosome)",
                          "bound": "hbm", "achieved": achieved, "peak": hbm,
                          "unit": "GB/s", "frac": (achieved / hbm) if achieved else None,
                          "traffic": traffic.get("uh_decompose"), "traffic_source": traffic.get("source"),
                          "peak_source": peak_src, "algorithmic_bytes": alg_bytes,
-                         "l_eff": visits / max(1, len(r["kept_index"])),
-                         "note": "the prefix sums (24 MB) stay in L2: DRAM traffic (cold-cache ncu, each of the four stage kernels "
-                                 "re-reading them once) is ~1/%d of the algorithmic bytes; the stage is bound by the dependent "
-                                 "chain of big nodes, not by HBM" % max(1, round(alg_bytes / max(1, traffic.get("uh_decompose", 1))))},
+                         "l_eff": visits / max(1, len(r["kept_index"])), "ms": dec_ms,
+                         "note": "the prefix sums (24 MB) stay in L2: DRAM traffic (cold-cache ncu) is ~1/%d of the algorithmic bytes; the stage "
+                                 "is bound by dependent chains of tree nodes, not by HBM" % max(1, round(alg_bytes / max(1, traffic.get("uh_decompose", 1))))},
             "clocks": clocks, "device": eng.describe()}
     # Clean / Partition totals against the HBM roofline with SURVEY.md 8(d)'s accounting: Clean = 101 B per input bin,
     # wavelet Partition = 8 * L_eff + 72 B per cleaned bin
     kept = max(1, len(r["kept_index"]))
     l_eff = visits / kept
+    n_s = len(samples)
     part_ms = sum(stages.get(k, 0.0) for k in ("scalars", "decompose", "finish"))
     totals = {}
-    for name, nbytes, ms in (("clean", 101.0 * nb, stages.get("clean", 0.0)), ("partition_wavelet", (8.0 * l_eff + 72.0) * kept, part_ms)):
+    for name, nbytes, ms in (("clean", 101.0 * nb, stages.get("clean", 0.0)), ("partition_wavelet", (8.0 * l_eff + 72.0) * kept * n_s, part_ms)):
         if ms > 0:
             ach = nbytes / (ms * 1e-3) / 1e9
             totals[name] = {"algorithmic_bytes": nbytes, "ms": ms, "achieved": ach, "unit": "GB/s", "frac": ach / hbm}
     line["roofline_totals"] = totals
-    # K8 normalise stream on batches larger than L2 (the kernel BASELINE.json's roofline target names):
-    # 8 samples = config 5 (223 MB), 16 samples (446 MB) and 32 samples (892 MB)
+    if per_rank is not None:
+        line["per_rank"] = per_rank
     if strong is not None:
         line["strong_scaling_single_sample"] = strong
+    line.update(line_extra)
+    # K8 normalise stream on batches larger than L2 (the kernel BASELINE.json's roofline target names):
+    # 8 samples = config 5 (223 MB), 16 samples (446 MB) and 32 samples (892 MB)
     try:
-        n16 = (nb // 16) * 16
+        s = samples[0]
+        n16 = (len(s) // 16) * 16
         rng = np.random.default_rng(1)
         for batch, key in ((8, "roofline_normalize"), (16, "roofline_normalize_16"), (32, "roofline_normalize_32")):
             cnt = np.tile(s.count[:n16], (batch, 1))
@@ -350,10 +494,12 @@ def main():
         line["roofline_normalize"] = {"error": str(e)}
     if world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
-        o = run_oracle_once(s, threads)
-        line["cpu_baseline"] = {"value": nb / o["total_s"] / 1e6, "unit": UNIT, "cores": threads, "kind": "port",
-                                "sample": "one full config-2 sample (Clean 1 thread, Partition 1 thread per chromosome)",
-                                "clean_ms": o["clean_s"] * 1e3, "partition_ms": o["partition_s"] * 1e3}
+        t0 = time.perf_counter()
+        os_ = [oracle_sample(s, threads, germline=germline) for s in samples]
+        sec = time.perf_counter() - t0
+        line["cpu_baseline"] = {"value": nb / sec / 1e6, "unit": UNIT, "cores": threads, "kind": "port",
+                                "sample": f"{len(samples)} full sample(s) of this workload (Clean 1 thread, Partition 1 thread per chromosome)",
+                                "clean_ms": sum(o["clean_s"] for o in os_) * 1e3, "partition_ms": sum(o["partition_s"] for o in os_) * 1e3}
     _emit(line)
     if world > 1:
         dist.destroy_process_group()

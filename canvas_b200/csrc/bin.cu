@@ -23,13 +23,28 @@ __global__ void bin_init_kernel(BinCtl* ctl) {
     ctl->n_bins = 0;
 }
 
-// "Skip past leading Ns": the first position whose base is not a lower-case 'n' (:582-583)
-__global__ void bin_first_base_kernel(const char* __restrict__ bases, long long len, BinCtl* ctl) {
-    const long long stride = (long long)gridDim.x * blockDim.x;
+// "Skip past leading Ns": the first position whose base is not a lower-case 'n' (:582-583).  Threads take 16 bases per
+// step; a thread stops as soon as its position lies beyond the best answer so far.
+__global__ void __launch_bounds__(256) bin_first_base_kernel(const char* __restrict__ bases, long long len, BinCtl* ctl) {
+    const long long stride = (long long)gridDim.x * blockDim.x * 16;
     unsigned long long best = ~0ull;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += stride) {
-        if (bases[i] != 'n') { best = (unsigned long long)i; break; }
+    for (long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 16; i < len; i += stride) {
         if ((unsigned long long)i > *(volatile unsigned long long*)&ctl->first_pos) break;
+        if (i + 16 <= len) {
+            const uint4 v = *reinterpret_cast<const uint4*>(bases + i);
+            const unsigned w[4] = {v.x, v.y, v.z, v.w};
+            int at = -1;
+#pragma unroll
+            for (int q = 3; q >= 0; q--) {
+                const unsigned ne = ~__vcmpeq4(w[q], 0x6e6e6e6eu);  // 0xff where the base is not 'n'
+                if (ne) at = 4 * q + ((__ffs((int)ne) - 1) >> 3);
+            }
+            if (at >= 0) { best = (unsigned long long)(i + at); break; }
+        } else {
+            for (long long j = i; j < len; j++)
+                if (bases[j] != 'n') { best = (unsigned long long)j; break; }
+            break;
+        }
     }
     if (best != ~0ull) atomicMin(&ctl->first_pos, best);
 }
@@ -180,6 +195,21 @@ __device__ inline void bin_quad(unsigned h, unsigned b, unsigned m4, unsigned& o
     gcv += (unsigned)__popc((__vcmpeq4(x, 0x63636363u) | __vcmpeq4(x, 0x67676767u)) & 0x01010101u);
 }
 
+// first index k of the ascending array a[0..n) with a[k] >= target (n if none): one warp, 32 probes per round
+__device__ inline long long warp_lower_bound(const int* __restrict__ a, long long n, long long target, int lane) {
+    long long lo = 0, hi = n;
+    while (hi > lo) {
+        const long long step = (hi - lo + 31) / 32;
+        const long long idx = lo + (long long)(lane + 1) * step - 1;
+        const bool less = idx < hi && (long long)a[idx] < target;
+        const int cnt = __popc(__ballot_sync(0xffffffffu, less));  // the probes are ascending: a prefix of them is below the target
+        const long long nlo = lo + (long long)cnt * step;
+        hi = min(hi, lo + (long long)(cnt + 1) * step - 1);
+        lo = nlo;
+    }
+    return lo;
+}
+
 __global__ void __launch_bounds__(BIN_ACC_THREADS) bin_accum_kernel(const unsigned char* __restrict__ hits, const unsigned long long* __restrict__ bits,
                                                                    const char* __restrict__ bases, long long nwords, long long len,
                                                                    const BinCtl* __restrict__ ctl, const int* __restrict__ end_pos, int max_bins,
@@ -192,18 +222,28 @@ __global__ void __launch_bounds__(BIN_ACC_THREADS) bin_accum_kernel(const unsign
     if (nb <= 0) return;
     const long long tile_start = (long long)blockIdx.x * BIN_ACC_TILE;
     const long long tile_end = min(tile_start + BIN_ACC_TILE, len);
-    if (tile_start > (long long)end_pos[nb - 1]) return;  // past the last complete bin
-    if (threadIdx.x < 2) {
-        // first bin whose end is >= tile_start (threadIdx 0) / >= tile_end (threadIdx 1)
-        const long long target = threadIdx.x == 0 ? tile_start : tile_end;
-        long long lo = 0, hi = nb;
-        while (lo < hi) { const long long mid = (lo + hi) >> 1; if ((long long)end_pos[mid] < target) lo = mid + 1; else hi = mid; }
-        s_k[threadIdx.x] = lo;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const long long p0 = tile_start + (long long)threadIdx.x * 16;
+    // the loads of this thread's 16 positions do not depend on the bin lookup: issue them first
+    const bool whole = p0 + 16 <= len;
+    uint4 h4 = make_uint4(0u, 0u, 0u, 0u), b4 = make_uint4(0u, 0u, 0u, 0u);
+    unsigned long long mword = 0ull;
+    if (whole) {
+        h4 = *reinterpret_cast<const uint4*>(hits + p0);
+        b4 = *reinterpret_cast<const uint4*>(bases + p0);
+    }
+    if (p0 < len) mword = masked_word(bits, p0 >> 6, nwords, min(ctl->first_pos, (unsigned long long)len), len);
+    // bins that end inside the tile: warp 0 finds the first bin whose end is >= tile_start, warp 1 the first with end >= tile_end
+    if (wid < 2) {
+        const long long k = warp_lower_bound(end_pos, nb, wid == 0 ? tile_start : tile_end, lane);
+        if (lane == 0) s_k[wid] = k;
     }
     for (int i = threadIdx.x; i < BIN_ACC_TILE / 32; i += blockDim.x) s_flag[i] = 0u;
-    for (int i = threadIdx.x; i < BIN_ACC_LOCAL; i += blockDim.x) { s_obs[i] = 0u; s_gc[i] = 0u; }
     __syncthreads();
-    const long long k_lo = s_k[0], k_hi = s_k[1];  // bins k_lo .. k_hi - 1 end inside the tile
+    const long long k_lo = s_k[0], k_hi = s_k[1];  // bins k_lo .. k_hi - 1 end inside the tile, bin k_hi continues past it
+    if (k_lo >= nb) return;                         // the whole tile lies past the last complete bin
+    const long long nloc = min((long long)BIN_ACC_LOCAL, min(k_hi + 1, nb) - k_lo);
+    for (int i = threadIdx.x; i < nloc; i += blockDim.x) { s_obs[i] = 0u; s_gc[i] = 0u; }
     for (long long k = k_lo + threadIdx.x; k < k_hi; k += blockDim.x) {
         const int r = (int)((long long)end_pos[k] - tile_start);
         atomicOr(&s_flag[r >> 5], 1u << (r & 31));
@@ -211,7 +251,6 @@ __global__ void __launch_bounds__(BIN_ACC_THREADS) bin_accum_kernel(const unsign
     __syncthreads();
     // ends inside this thread's 16 positions; position p belongs to bin k_lo + (ends of the tile before p)
     const unsigned f16 = (s_flag[threadIdx.x >> 1] >> (16 * (threadIdx.x & 1))) & 0xffffu;
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const unsigned mine = (unsigned)__popc(f16);
     unsigned incl = mine;
 #pragma unroll
@@ -221,14 +260,10 @@ __global__ void __launch_bounds__(BIN_ACC_THREADS) bin_accum_kernel(const unsign
     unsigned before = incl - mine;
     for (int k = 0; k < wid; k++) before += s_warp[k];
     long long bin = k_lo + before;
-    const long long p0 = tile_start + (long long)threadIdx.x * 16;
     unsigned obs = 0, gcv = 0;
     if (p0 < len && bin < nb) {
-        const unsigned long long first = min(ctl->first_pos, (unsigned long long)len);
-        const unsigned m16 = (unsigned)(masked_word(bits, p0 >> 6, nwords, first, len) >> (p0 & 63)) & 0xffffu;
-        if (p0 + 16 <= len) {
-            const uint4 h4 = *reinterpret_cast<const uint4*>(hits + p0);
-            const uint4 b4 = *reinterpret_cast<const uint4*>(bases + p0);
+        const unsigned m16 = (unsigned)(mword >> (p0 & 63)) & 0xffffu;
+        if (whole) {
             const unsigned hq[4] = {h4.x, h4.y, h4.z, h4.w}, bq[4] = {b4.x, b4.y, b4.z, b4.w};
             if (f16 == 0u) {
 #pragma unroll
@@ -277,7 +312,6 @@ __global__ void __launch_bounds__(BIN_ACC_THREADS) bin_accum_kernel(const unsign
         }
     }
     __syncthreads();
-    const long long nloc = min((long long)BIN_ACC_LOCAL, min(k_hi + 1, nb) - k_lo);
     for (int i = threadIdx.x; i < nloc; i += blockDim.x) {
         const unsigned o = s_obs[i], g = s_gc[i];
         if (o) atomicAdd(&g_obs[k_lo + i], o);

@@ -347,14 +347,16 @@ def test_write_partitioned_text(tmp_path):
                                          "chr2\t0\t1000\t100\t2\nchr2\t1000\t2000\t95.02\t2\nchr2\t2000\t3000\tNaN\t2\n")
 
 
-def test_bench_reference_arm_contract():
-    # `bench.py --impl reference` needs no GPU: one JSON line with the contract's keys (a shrunken genome keeps it to seconds)
+@pytest.mark.parametrize("extra,samples", [([], 1), (["--gpus", "2"], 2), (["--config", "3"], 2), (["--config", "4"], 3)])
+def test_bench_reference_arm_contract(extra, samples):
+    # `bench.py --impl reference` needs no GPU: one JSON line with the contract's keys (a shrunken genome keeps it to seconds);
+    # it processes as many samples as the GPU arm of the same command line (one per GPU, the pair, the trio)
     import json
     import subprocess
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     p = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
-                        "--scale", "0.05"], capture_output=True, text=True, timeout=300)
+                        "--scale", "0.05"] + extra, capture_output=True, text=True, timeout=300)
     assert p.returncode == 0, p.stderr[-2000:]
     lines = [ln for ln in p.stdout.splitlines() if ln.strip()]
     assert len(lines) == 1
@@ -364,4 +366,22 @@ def test_bench_reference_arm_contract():
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     for k in ("metric", "n_gpus", "steps", "warmup", "ms_per_step", "scaling", "vs_baseline", "dtype", "data", "config"):
         assert k in d, k
-    assert "workload" in d["config"]
+    assert "workload" in d["config"] and d["config"]["samples"] == samples
+
+
+def test_numpy_merge_equals_the_dictionary_merge():
+    # the CPU arm of config 4 uses the column-array merge; it must select what Utilities.MergeMultiSampleCleanedBedFile selects
+    from oracle import pyoracle as ora
+    rng = np.random.default_rng(8)
+    samples = []
+    for k in range(3):
+        keep = rng.random(600) > 0.15
+        chrom = np.repeat(np.arange(3), 200)[keep].astype(np.uint8)
+        start = (np.tile(np.arange(200), 3) * 1000)[keep].astype(np.int32)
+        samples.append((chrom, start, (start + 1000 + k).astype(np.int32), rng.normal(100, 10, keep.sum()).astype(np.float32)))
+    want = ora.merge_multi_sample_cleaned([[(int(c), int(a), int(b), float(v)) for c, a, b, v in zip(*s)] for s in samples])
+    got = ora.merge_common_bins_np(samples)
+    assert len(want) == len(got["kept_index"]) > 100
+    c0, a0 = samples[0][0][got["kept_index"]], samples[0][1][got["kept_index"]]
+    assert [(w[0], w[1], w[2]) for w in want] == list(zip(c0.tolist(), a0.tolist(), got["stop"].tolist()))
+    assert np.array_equal(np.array([w[3] for w in want], np.float32).T, got["count"])
