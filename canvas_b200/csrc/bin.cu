@@ -171,7 +171,8 @@ __global__ void __launch_bounds__(256) bin_end_tile_kernel(const unsigned long l
 // thread the bin of its first position, four positions are summed at a time with byte-wise SIMD, and the per-bin partial
 // sums go through shared-memory accumulators to integer atomics in global memory (integers: any order gives the same sums).
 constexpr int BIN_ACC_THREADS = 256;
-constexpr int BIN_ACC_TILE = BIN_ACC_THREADS * 16;
+constexpr int BIN_ACC_PER_THREAD = 32;  // positions per thread: two 128-bit loads of hits and of bases, 32 bits of the bitmap
+constexpr int BIN_ACC_TILE = BIN_ACC_THREADS * BIN_ACC_PER_THREAD;
 constexpr int BIN_ACC_LOCAL = 1024;  // bins of one tile accumulated in shared memory (more go straight to global atomics)
 
 __device__ inline void bin_acc_add(unsigned* s_obs, unsigned* s_gc, unsigned* g_obs, unsigned* g_gc, long long k_lo, long long bin, long long nb,
@@ -195,63 +196,59 @@ __device__ inline void bin_quad(unsigned h, unsigned b, unsigned m4, unsigned& o
     gcv += (unsigned)__popc((__vcmpeq4(x, 0x63636363u) | __vcmpeq4(x, 0x67676767u)) & 0x01010101u);
 }
 
-// first index k of the ascending array a[0..n) with a[k] >= target (n if none): one warp, 32 probes per round
-__device__ inline long long warp_lower_bound(const int* __restrict__ a, long long n, long long target, int lane) {
-    long long lo = 0, hi = n;
-    while (hi > lo) {
-        const long long step = (hi - lo + 31) / 32;
-        const long long idx = lo + (long long)(lane + 1) * step - 1;
-        const bool less = idx < hi && (long long)a[idx] < target;
-        const int cnt = __popc(__ballot_sync(0xffffffffu, less));  // the probes are ascending: a prefix of them is below the target
-        const long long nlo = lo + (long long)cnt * step;
-        hi = min(hi, lo + (long long)(cnt + 1) * step - 1);
-        lo = nlo;
-    }
-    return lo;
+// first bin of every tile of the streaming pass: tile_first[t] = number of bins that end before position t * BIN_ACC_TILE.
+// Bin k is that bin for the tiles whose start lies in (end[k-1], end[k]]; thread nb fills the tiles past the last bin.
+__global__ void bin_tile_first_kernel(const BinCtl* __restrict__ ctl, const int* __restrict__ end_pos, int max_bins, long long n_tiles,
+                                      int* __restrict__ tile_first) {
+    const long long nb = min(ctl->n_bins, max_bins);
+    const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k > nb) return;
+    const long long prev = k == 0 ? -1 : (long long)end_pos[k - 1];
+    const long long t_lo = prev < 0 ? 0 : prev / BIN_ACC_TILE + 1;
+    const long long t_hi = k == nb ? n_tiles : (long long)end_pos[k] / BIN_ACC_TILE;  // inclusive
+    for (long long t = t_lo; t <= t_hi && t <= n_tiles; t++) tile_first[t] = (int)k;
 }
 
 __global__ void __launch_bounds__(BIN_ACC_THREADS) bin_accum_kernel(const unsigned char* __restrict__ hits, const unsigned long long* __restrict__ bits,
                                                                    const char* __restrict__ bases, long long nwords, long long len,
                                                                    const BinCtl* __restrict__ ctl, const int* __restrict__ end_pos, int max_bins,
-                                                                   unsigned* __restrict__ g_obs, unsigned* __restrict__ g_gc) {
-    __shared__ unsigned s_flag[BIN_ACC_TILE / 32];
+                                                                   const int* __restrict__ tile_first, unsigned* __restrict__ g_obs,
+                                                                   unsigned* __restrict__ g_gc) {
+    __shared__ unsigned s_flag[BIN_ACC_THREADS];  // one word of end flags per thread (32 positions)
     __shared__ unsigned s_obs[BIN_ACC_LOCAL], s_gc[BIN_ACC_LOCAL];
     __shared__ unsigned s_warp[BIN_ACC_THREADS / 32];
-    __shared__ long long s_k[2];
     const long long nb = min(ctl->n_bins, max_bins);
     if (nb <= 0) return;
     const long long tile_start = (long long)blockIdx.x * BIN_ACC_TILE;
-    const long long tile_end = min(tile_start + BIN_ACC_TILE, len);
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const long long p0 = tile_start + (long long)threadIdx.x * 16;
-    // the loads of this thread's 16 positions do not depend on the bin lookup: issue them first
-    const bool whole = p0 + 16 <= len;
-    uint4 h4 = make_uint4(0u, 0u, 0u, 0u), b4 = make_uint4(0u, 0u, 0u, 0u);
-    unsigned long long mword = 0ull;
+    const long long p0 = tile_start + (long long)threadIdx.x * BIN_ACC_PER_THREAD;
+    // bins k_lo .. k_hi - 1 end inside the tile, bin k_hi continues past it
+    const long long k_lo = tile_first[blockIdx.x], k_hi = tile_first[blockIdx.x + 1];
+    if (k_lo >= nb) return;  // the whole tile lies past the last complete bin
+    // the loads of this thread's 32 positions do not depend on the bin lookup: issue them first
+    const bool whole = p0 + BIN_ACC_PER_THREAD <= len;
+    uint4 h4[2], b4[2];
+    h4[0] = h4[1] = b4[0] = b4[1] = make_uint4(0u, 0u, 0u, 0u);
     if (whole) {
-        h4 = *reinterpret_cast<const uint4*>(hits + p0);
-        b4 = *reinterpret_cast<const uint4*>(bases + p0);
+        h4[0] = *reinterpret_cast<const uint4*>(hits + p0);
+        h4[1] = *reinterpret_cast<const uint4*>(hits + p0 + 16);
+        b4[0] = *reinterpret_cast<const uint4*>(bases + p0);
+        b4[1] = *reinterpret_cast<const uint4*>(bases + p0 + 16);
     }
-    if (p0 < len) mword = masked_word(bits, p0 >> 6, nwords, min(ctl->first_pos, (unsigned long long)len), len);
-    // bins that end inside the tile: warp 0 finds the first bin whose end is >= tile_start, warp 1 the first with end >= tile_end
-    if (wid < 2) {
-        const long long k = warp_lower_bound(end_pos, nb, wid == 0 ? tile_start : tile_end, lane);
-        if (lane == 0) s_k[wid] = k;
-    }
-    for (int i = threadIdx.x; i < BIN_ACC_TILE / 32; i += blockDim.x) s_flag[i] = 0u;
-    __syncthreads();
-    const long long k_lo = s_k[0], k_hi = s_k[1];  // bins k_lo .. k_hi - 1 end inside the tile, bin k_hi continues past it
-    if (k_lo >= nb) return;                         // the whole tile lies past the last complete bin
+    unsigned m32 = 0u;
+    if (p0 < len) m32 = (unsigned)(masked_word(bits, p0 >> 6, nwords, min(ctl->first_pos, (unsigned long long)len), len) >> (p0 & 63));
+    s_flag[threadIdx.x] = 0u;
     const long long nloc = min((long long)BIN_ACC_LOCAL, min(k_hi + 1, nb) - k_lo);
     for (int i = threadIdx.x; i < nloc; i += blockDim.x) { s_obs[i] = 0u; s_gc[i] = 0u; }
+    __syncthreads();
     for (long long k = k_lo + threadIdx.x; k < k_hi; k += blockDim.x) {
         const int r = (int)((long long)end_pos[k] - tile_start);
         atomicOr(&s_flag[r >> 5], 1u << (r & 31));
     }
     __syncthreads();
-    // ends inside this thread's 16 positions; position p belongs to bin k_lo + (ends of the tile before p)
-    const unsigned f16 = (s_flag[threadIdx.x >> 1] >> (16 * (threadIdx.x & 1))) & 0xffffu;
-    const unsigned mine = (unsigned)__popc(f16);
+    // ends inside this thread's positions; position p belongs to bin k_lo + (ends of the tile before p)
+    const unsigned f32 = s_flag[threadIdx.x];
+    const unsigned mine = (unsigned)__popc(f32);
     unsigned incl = mine;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) { const unsigned v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
@@ -262,34 +259,38 @@ __global__ void __launch_bounds__(BIN_ACC_THREADS) bin_accum_kernel(const unsign
     long long bin = k_lo + before;
     unsigned obs = 0, gcv = 0;
     if (p0 < len && bin < nb) {
-        const unsigned m16 = (unsigned)(mword >> (p0 & 63)) & 0xffffu;
         if (whole) {
-            const unsigned hq[4] = {h4.x, h4.y, h4.z, h4.w}, bq[4] = {b4.x, b4.y, b4.z, b4.w};
-            if (f16 == 0u) {
 #pragma unroll
-                for (int q = 0; q < 4; q++) bin_quad(hq[q], bq[q], (m16 >> (4 * q)) & 0xfu, obs, gcv);
-            } else {
-                // a bin closes inside these 16 positions: position by position
+            for (int half = 0; half < 2; half++) {
+                const unsigned hq[4] = {h4[half].x, h4[half].y, h4[half].z, h4[half].w};
+                const unsigned bq[4] = {b4[half].x, b4[half].y, b4[half].z, b4[half].w};
+                const unsigned m16 = (m32 >> (16 * half)) & 0xffffu, f16 = (f32 >> (16 * half)) & 0xffffu;
+                if (f16 == 0u) {
 #pragma unroll
-                for (int q = 0; q < 4; q++)
+                    for (int q = 0; q < 4; q++) bin_quad(hq[q], bq[q], (m16 >> (4 * q)) & 0xfu, obs, gcv);
+                } else {
+                    // a bin closes inside these 16 positions: position by position
 #pragma unroll
-                    for (int j = 0; j < 4; j++) {
-                        const int i = 4 * q + j;
-                        const unsigned h = (hq[q] >> (8 * j)) & 0xffu, b = ((bq[q] >> (8 * j)) & 0xffu) | 0x20u;
-                        if ((m16 >> i) & 1u) obs += min(10u, h);
-                        gcv += (b == 0x63u || b == 0x67u) ? 1u : 0u;
-                        if ((f16 >> i) & 1u) {
-                            bin_acc_add(s_obs, s_gc, g_obs, g_gc, k_lo, bin, nb, obs, gcv);
-                            obs = 0; gcv = 0; bin++;
+                    for (int q = 0; q < 4; q++)
+#pragma unroll
+                        for (int j = 0; j < 4; j++) {
+                            const int i = 4 * q + j;
+                            const unsigned h = (hq[q] >> (8 * j)) & 0xffu, b = ((bq[q] >> (8 * j)) & 0xffu) | 0x20u;
+                            if ((m16 >> i) & 1u) obs += min(10u, h);
+                            gcv += (b == 0x63u || b == 0x67u) ? 1u : 0u;
+                            if ((f16 >> i) & 1u) {
+                                bin_acc_add(s_obs, s_gc, g_obs, g_gc, k_lo, bin, nb, obs, gcv);
+                                obs = 0; gcv = 0; bin++;
+                            }
                         }
-                    }
+                }
             }
         } else {
-            for (int i = 0; i < 16 && p0 + i < len; i++) {  // ragged end of the chromosome
+            for (int i = 0; i < BIN_ACC_PER_THREAD && p0 + i < len; i++) {  // ragged end of the chromosome
                 const unsigned h = hits[p0 + i], b = (unsigned)(unsigned char)bases[p0 + i] | 0x20u;
-                if ((m16 >> i) & 1u) obs += min(10u, h);
+                if ((m32 >> i) & 1u) obs += min(10u, h);
                 gcv += (b == 0x63u || b == 0x67u) ? 1u : 0u;
-                if ((f16 >> i) & 1u) {
+                if ((f32 >> i) & 1u) {
                     bin_acc_add(s_obs, s_gc, g_obs, g_gc, k_lo, bin, nb, obs, gcv);
                     obs = 0; gcv = 0; bin++;
                 }
@@ -550,7 +551,8 @@ extern "C" int cg_bin_hits(cg_ctx* ctx, int64_t chr_len, const uint8_t* hits, co
     const int ntiles = (int)((nwords + BIN_TILE_WORDS - 1) / BIN_TILE_WORDS);
     const long long cap = std::min<long long>(max_bins, chr_len / bin_size + 1);
     size_t need = arena_need(chr_len, 1) * 3 + arena_need(nwords, 8) + arena_need(ntiles + 1, 4) + arena_need(ntiles + 2, 8) +
-                  arena_need(cap + 1, 4) * 6 + arena_need(cap + 1, 1) + arena_need(256, 4) + arena_need(1, sizeof(BinCtl)) + (1 << 16);
+                  arena_need(cap + 1, 4) * 6 + arena_need(cap + 1, 1) + arena_need(256, 4) + arena_need(1, sizeof(BinCtl)) +
+                  arena_need(chr_len / BIN_ACC_TILE + 4, 4) + (1 << 16);
     int rc = arena_reserve(ctx, need);
     if (rc) return rc;
     unsigned char* d_hits = arena_take<unsigned char>(ctx, chr_len);
@@ -566,9 +568,11 @@ extern "C" int cg_bin_hits(cg_ctx* ctx, int64_t chr_len, const uint8_t* hits, co
     unsigned char* d_gc = arena_take<unsigned char>(ctx, cap + 1);
     unsigned* d_obs = arena_take<unsigned>(ctx, cap + 1);
     unsigned* d_gcc = arena_take<unsigned>(ctx, cap + 1);
+    const long long n_acc_tiles = div_up(chr_len, BIN_ACC_TILE);
+    int* d_tfirst = arena_take<int>(ctx, n_acc_tiles + 2);
     float* d_ratio = arena_take<float>(ctx, 256);
     BinCtl* d_ctl = arena_take<BinCtl>(ctx, 1);
-    if (!d_hits || !d_bases || !d_rgc || !d_bits || !d_tcnt || !d_toff || !d_end || !d_start || !d_stop || !d_count || !d_gc || !d_obs || !d_gcc || !d_ratio || !d_ctl)
+    if (!d_hits || !d_bases || !d_rgc || !d_bits || !d_tcnt || !d_toff || !d_end || !d_start || !d_stop || !d_count || !d_gc || !d_obs || !d_gcc || !d_tfirst || !d_ratio || !d_ctl)
         return cg_fail(ctx, CG_ERR_CUDA, "cg_bin_hits: device arena exhausted");
     cudaStream_t s = ctx->stream;
     CG_CUDA(ctx, cudaMemcpyAsync(d_hits, hits, chr_len, cudaMemcpyHostToDevice, s));
@@ -587,8 +591,9 @@ extern "C" int cg_bin_hits(cg_ctx* ctx, int64_t chr_len, const uint8_t* hits, co
         CG_CUDA(ctx, cudaMemsetAsync(d_obs, 0, (size_t)(cap + 1) * 4, s));
         CG_CUDA(ctx, cudaMemsetAsync(d_gcc, 0, (size_t)(cap + 1) * 4, s));
         CG_LAUNCH(ctx, bin_end_tile_kernel, ntiles, 256, 0, d_bits, nwords, (long long)chr_len, d_toff, bin_size, d_ctl, (int)cap, d_end);
-        CG_LAUNCH(ctx, bin_accum_kernel, div_up(chr_len, BIN_ACC_TILE), BIN_ACC_THREADS, 0, d_hits, d_bits, d_bases, nwords, (long long)chr_len,
-                  d_ctl, d_end, (int)cap, d_obs, d_gcc);
+        CG_LAUNCH(ctx, bin_tile_first_kernel, div_up(cap + 1, 256), 256, 0, d_ctl, d_end, (int)cap, n_acc_tiles, d_tfirst);
+        CG_LAUNCH(ctx, bin_accum_kernel, (int)n_acc_tiles, BIN_ACC_THREADS, 0, d_hits, d_bits, d_bases, nwords, (long long)chr_len,
+                  d_ctl, d_end, (int)cap, d_tfirst, d_obs, d_gcc);
         CG_LAUNCH(ctx, bin_finalize_kernel, div_up(cap, 256), 256, 0, d_ctl, d_end, (int)cap, d_obs, d_gcc, d_start, d_stop, d_count, d_gc);
         if (mode == 1)
             CG_LAUNCH(ctx, bin_sum_weighted_kernel, div_up(cap * 32, 256), 256, 0, d_hits, d_bits, d_rgc, d_ratio, d_ctl, d_end, (int)cap, d_count);

@@ -84,6 +84,136 @@ __global__ void __launch_bounds__(256) read_gc_kernel(const unsigned* __restrict
     }
 }
 
+// The same in one streaming pass when the longest read (mean * cutoff bases) fits a shared-memory halo: a block takes 8192
+// positions, turns their bases plus the halo into a G/C bitmap with a running popcount per word (shared memory), and every
+// thread computes the read GC of 32 consecutive positions from two bitmap lookups.  Neighbouring positions share all but two
+// bases of their reads, so the GC bin changes slowly along a thread's run and the histogram updates are run-length
+// aggregated (one shared-memory atomic per run instead of one per position).  Traffic = the algorithmic 5 B / position.
+constexpr int RG_THREADS = 256;
+constexpr int RG_PER = 32;
+constexpr int RG_TILE = RG_THREADS * RG_PER;
+constexpr int RG_HALO_MAX = 8192;
+constexpr int RG_WORDS = (RG_TILE + RG_HALO_MAX) / 32 + 2;
+
+__global__ void __launch_bounds__(RG_THREADS) read_gc_tile_kernel(const char* __restrict__ bases, const short* __restrict__ frag_len,
+                                                                 const unsigned char* __restrict__ hits, long long len, int mean_frag, int cutoff,
+                                                                 unsigned char* __restrict__ read_gc, unsigned long long* __restrict__ expected,
+                                                                 unsigned long long* __restrict__ observed) {
+    __shared__ unsigned s_bits[RG_WORDS];
+    __shared__ unsigned s_pre[RG_WORDS];
+    __shared__ unsigned s_warp[RG_THREADS / 32];
+    __shared__ unsigned s_exp[GC_READ_BINS], s_obs[GC_READ_BINS];
+    const int cap = mean_frag * cutoff;
+    const long long limit = len - (long long)cap - 1;  // pos < Bases.Length - mean * cutoff - 1 (:469)
+    const long long tile_start = (long long)blockIdx.x * RG_TILE;
+    const int span = (int)(min(len, tile_start + RG_TILE + cap) - tile_start);  // bases this tile's reads can touch
+    const int nwords = (span + 31) / 32 + 1;
+    for (int t = threadIdx.x; t < GC_READ_BINS; t += blockDim.x) s_exp[t] = s_obs[t] = 0u;
+    // ---- G/C bitmap of [tile_start, tile_start + span): 16 bases per 128-bit load -> 16 bits
+    unsigned short* s_half = reinterpret_cast<unsigned short*>(s_bits);
+    for (int i = threadIdx.x * 16; i < nwords * 32; i += RG_THREADS * 16) {
+        unsigned bits16 = 0u;
+        if (i + 16 <= span) {
+            const uint4 v = *reinterpret_cast<const uint4*>(bases + tile_start + i);
+            const unsigned w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const unsigned x = w[q] | 0x20202020u;
+                const unsigned eq = (__vcmpeq4(x, 0x63636363u) | __vcmpeq4(x, 0x67676767u)) & 0x01010101u;
+                bits16 |= ((eq * 0x10204080u) >> 28) << (4 * q);  // bit 0 of byte j -> bit j
+            }
+        } else {
+            for (int j = 0; j < 16 && i + j < span; j++) bits16 |= (unsigned)is_gc(bases[tile_start + i + j]) << j;
+        }
+        s_half[i >> 4] = (unsigned short)bits16;
+    }
+    __syncthreads();
+    // ---- s_pre[w] = G/C bases before word w
+    {
+        constexpr int WPT = (RG_WORDS + RG_THREADS - 1) / RG_THREADS;
+        unsigned c[WPT], run = 0;
+#pragma unroll
+        for (int j = 0; j < WPT; j++) {
+            const int w = threadIdx.x * WPT + j;
+            c[j] = w < nwords ? (unsigned)__popc(s_bits[w]) : 0u;
+            run += c[j];
+        }
+        const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+        unsigned incl = run;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const unsigned v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+        if (lane == 31) s_warp[wid] = incl;
+        __syncthreads();
+        unsigned base = incl - run;
+        for (int k = 0; k < wid; k++) base += s_warp[k];
+#pragma unroll
+        for (int j = 0; j < WPT; j++) {
+            const int w = threadIdx.x * WPT + j;
+            if (w < RG_WORDS) s_pre[w] = base;
+            base += c[j];
+        }
+    }
+    __syncthreads();
+    // ---- 32 consecutive positions per thread
+    const int a0 = threadIdx.x * RG_PER;
+    const long long p0 = tile_start + a0;
+    if (p0 < len) {
+        const bool whole = p0 + RG_PER <= len;
+        unsigned fw[16], hw[8], out[8];  // 32 lengths (two per word), 32 hit counts, 32 results
+        if (whole) {
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const uint4 v = *reinterpret_cast<const uint4*>(frag_len + p0 + 8 * q);
+                fw[4 * q] = v.x; fw[4 * q + 1] = v.y; fw[4 * q + 2] = v.z; fw[4 * q + 3] = v.w;
+            }
+#pragma unroll
+            for (int q = 0; q < 2; q++) {
+                const uint4 v = *reinterpret_cast<const uint4*>(hits + p0 + 16 * q);
+                hw[4 * q] = v.x; hw[4 * q + 1] = v.y; hw[4 * q + 2] = v.z; hw[4 * q + 3] = v.w;
+            }
+        }
+        int run_g = -1;
+        unsigned run_n = 0, run_h = 0;
+        auto count_before = [&](int a) { return s_pre[a >> 5] + (unsigned)__popc(s_bits[a >> 5] & ((1u << (a & 31)) - 1u)); };
+#pragma unroll
+        for (int i = 0; i < RG_PER; i++) {
+            const long long pos = p0 + i;
+            if (!whole && pos >= len) break;
+            const int f = whole ? (int)(short)((fw[i >> 1] >> (16 * (i & 1))) & 0xffffu) : (int)frag_len[pos];
+            const unsigned h = whole ? (hw[i >> 2] >> (8 * (i & 3))) & 0xffu : (unsigned)hits[pos];
+            int g = 0;
+            if (pos < limit) {
+                const int cur = f == 0 ? mean_frag : min(f, cap);  // Convert.ToInt16(Math.Min(length, mean * cutoff))
+                if (cur > 0) {
+                    const unsigned cnt = count_before(a0 + i + cur) - count_before(a0 + i);  // G/C bases of [pos, pos + cur)
+                    g = (int)min((100u * cnt) / (unsigned)cur, (unsigned)GC_READ_BINS);
+                }
+            }
+            if (whole) {
+                if ((i & 3) == 0) out[i >> 2] = 0u;
+                out[i >> 2] |= (unsigned)g << (8 * (i & 3));
+            } else {
+                read_gc[pos] = (unsigned char)g;
+            }
+            if (g == run_g) { run_n++; run_h += h; }
+            else {
+                if (run_n) { atomicAdd(&s_exp[run_g], run_n); if (run_h) atomicAdd(&s_obs[run_g], run_h); }
+                run_g = g; run_n = 1u; run_h = h;
+            }
+        }
+        if (run_n) { atomicAdd(&s_exp[run_g], run_n); if (run_h) atomicAdd(&s_obs[run_g], run_h); }
+        if (whole) {
+            *reinterpret_cast<uint4*>(read_gc + p0) = make_uint4(out[0], out[1], out[2], out[3]);
+            *reinterpret_cast<uint4*>(read_gc + p0 + 16) = make_uint4(out[4], out[5], out[6], out[7]);
+        }
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < GC_READ_BINS; t += blockDim.x) {
+        if (s_exp[t]) atomicAdd(&expected[t], (unsigned long long)s_exp[t]);
+        if (s_obs[t]) atomicAdd(&observed[t], (unsigned long long)s_obs[t]);
+    }
+}
+
 __global__ void __launch_bounds__(256) frag_stats_kernel(const short* __restrict__ frag_len, long long len, unsigned long long* __restrict__ out) {
     unsigned long long sum = 0, cnt = 0;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += (long long)gridDim.x * blockDim.x) {
@@ -170,11 +300,17 @@ extern "C" int cg_bin_read_gc(cg_ctx* ctx, int64_t len, const char* bases, const
     CG_CUDA(ctx, cudaMemsetAsync(d_exp, 0, GC_READ_BINS * 8, s));
     CG_CUDA(ctx, cudaMemsetAsync(d_obs, 0, GC_READ_BINS * 8, s));
     CG_CUDA(ctx, cudaEventRecord(ctx->ev0, s));
-    CG_LAUNCH(ctx, gc_tile_count_kernel, ntiles, GCT_THREADS, 0, d_bases, (long long)len, d_tiles);
-    CG_LAUNCH(ctx, compact_scan_kernel, 1, 1024, 0, d_tiles, ntiles, d_total);
-    CG_LAUNCH(ctx, gc_prefix_kernel, ntiles, GCT_THREADS, 0, d_bases, (long long)len, d_tiles, d_prefix);
-    CG_LAUNCH(ctx, read_gc_kernel, (int)div_up((long long)len, 8192LL), 256, 0, d_prefix, d_f, d_hits, (long long)len, mean_frag, cutoff, d_gc,
-              d_exp, d_obs);
+    if (mean_frag * cutoff <= RG_HALO_MAX) {
+        // the longest read fits the shared-memory halo: one streaming pass, no prefix array
+        CG_LAUNCH(ctx, read_gc_tile_kernel, (int)div_up((long long)len, (long long)RG_TILE), RG_THREADS, 0, d_bases, d_f, d_hits, (long long)len,
+                  mean_frag, cutoff, d_gc, d_exp, d_obs);
+    } else {
+        CG_LAUNCH(ctx, gc_tile_count_kernel, ntiles, GCT_THREADS, 0, d_bases, (long long)len, d_tiles);
+        CG_LAUNCH(ctx, compact_scan_kernel, 1, 1024, 0, d_tiles, ntiles, d_total);
+        CG_LAUNCH(ctx, gc_prefix_kernel, ntiles, GCT_THREADS, 0, d_bases, (long long)len, d_tiles, d_prefix);
+        CG_LAUNCH(ctx, read_gc_kernel, (int)div_up((long long)len, 8192LL), 256, 0, d_prefix, d_f, d_hits, (long long)len, mean_frag, cutoff, d_gc,
+                  d_exp, d_obs);
+    }
     CG_CUDA(ctx, cudaEventRecord(ctx->ev1, s));
     unsigned long long h_exp[GC_READ_BINS], h_obs[GC_READ_BINS];
     CG_CUDA(ctx, cudaMemcpyAsync(read_gc, d_gc, (size_t)len, cudaMemcpyDeviceToHost, s));

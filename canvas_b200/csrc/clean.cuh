@@ -213,6 +213,23 @@ __host__ __device__ inline double dotnet_f2_roundtrip(float v) {
     return v < 0 ? -r : r;
 }
 
+// float.ToString() (".NET Core 2.0: G7") followed by Convert.ToDouble — what the merged four-column .cleaned file of the
+// pedigree workflow does to a count (CanvasRunner.cs:895-897): seven significant digits d7 at decimal shift k, parsed back
+// as the double nearest to d7 / 10^k (one IEEE division of two exactly representable numbers).
+__host__ __device__ inline double dotnet_g7_roundtrip(float v) {
+    if (v != v || v - v != 0.0f) return (double)v;
+    const double x = v < 0 ? -(double)v : (double)v;
+    if (x == 0.0) return 0.0;
+    int e = 0;  // 10^e <= x < 10^(e+1)
+    if (x >= 1.0) { while (e < 18 && x >= cg_pow10(e + 1)) e++; }
+    else { e = -1; while (e > -19 && x * cg_pow10(-e) < 1.0) e--; }
+    const int k = 6 - e;
+    const double p = cg_pow10(k >= 0 ? (k < 19 ? k : 19) : (-k < 19 ? -k : 19));
+    const double d7 = rint(k >= 0 ? x * p : x / p);
+    const double r = k >= 0 ? d7 / p : d7 * p;
+    return v < 0 ? -r : r;
+}
+
 struct LoessDev;
 
 // Device-side buffers of one cg_clean call (slices of the ctx arena).

@@ -23,6 +23,7 @@
 #include <cstdlib>
 #include <vector>
 
+#include "clean.cuh"
 #include "select.cuh"
 
 namespace {
@@ -642,9 +643,18 @@ float f32_from_key(uint32_t k) { return f32_unkey(k); }
 
 }  // namespace
 
-extern "C" int cg_partition_hmm_shard(cg_ctx* ctx, const cg_hmm_opts* o, int n_samples, int n_chrom, const int64_t* chrom_off,
-                                      const double* coverage, const uint8_t* chrom_selected, int32_t* n_bp, int32_t* bp,
-                                      uint8_t* states_out) {
+// float counts -> the doubles CanvasPartition would parse from the text file that carries them (text_mode 1: "{F2}" of the
+// .cleaned file, 2: float.ToString() of the pedigree workflow's merged file, 0: plain widening)
+__global__ void hmm_counts_to_coverage_kernel(const float* __restrict__ count, long long n, int text_mode, double* __restrict__ cov) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const float v = count[i];
+        cov[i] = text_mode == 1 ? dotnet_f2_roundtrip(v) : (text_mode == 2 ? dotnet_g7_roundtrip(v) : (double)v);
+    }
+}
+
+static int partition_hmm_impl(cg_ctx* ctx, const cg_hmm_opts* o, int n_samples, int n_chrom, const int64_t* chrom_off,
+                              const double* coverage, const float* count32, int text_mode, const uint8_t* chrom_selected, int32_t* n_bp,
+                              int32_t* bp, uint8_t* states_out) {
     if (!ctx) return CG_ERR_ARG;
     if (!o || !chrom_off || !n_bp || n_chrom < 0 || n_chrom > HMM_MAX_CHROM || n_samples < 1)
         return cg_fail(ctx, CG_ERR_ARG, "cg_partition_hmm: bad argument");
@@ -665,7 +675,7 @@ extern "C" int cg_partition_hmm_shard(cg_ctx* ctx, const cg_hmm_opts* o, int n_s
     for (int i = 0; i < 4; i++) ctx->stage_used[i] = false;
     ctx->gap_used = false;
     if (N == 0) return CG_OK;
-    if (!coverage || !bp) return cg_fail(ctx, CG_ERR_ARG, "cg_partition_hmm: null array");
+    if ((!coverage && !count32) || !bp) return cg_fail(ctx, CG_ERR_ARG, "cg_partition_hmm: null array");
     if (N > 0x7fff0000LL) return cg_fail(ctx, CG_ERR_UNSUPPORTED, "cg_partition_hmm: too many bins");
     CG_CUDA(ctx, cudaSetDevice(ctx->device));
     const bool debug = getenv("CANVAS_DEBUG") != nullptr;
@@ -755,7 +765,16 @@ extern "C" int cg_partition_hmm_shard(cg_ctx* ctx, const cg_hmm_opts* o, int n_s
         !d_grp || !d_gmats || !d_gvec || !d_gmap || !d_grp_end || !d_blk_end || !d_blk_cnt || !d_blk_off || !d_end_state || !d_nbp || !d_ctl || !d_var)
         return cg_fail(ctx, CG_ERR_CUDA, "cg_partition_hmm: device arena exhausted");
     cudaStream_t s = ctx->stream;
-    CG_CUDA(ctx, cudaMemcpyAsync(d_cov, coverage, (size_t)S * N * 8, cudaMemcpyHostToDevice, s));
+    if (coverage) {
+        CG_CUDA(ctx, cudaMemcpyAsync(d_cov, coverage, (size_t)S * N * 8, cudaMemcpyHostToDevice, s));
+    } else {
+        // float counts: half the bytes over PCIe, the text round trip happens here (staged in the emission table's space)
+        float* d_cnt = reinterpret_cast<float*>(d_le);
+        static_assert(HMM_NS * 8 >= HMM_MAX_SAMPLES * 4, "the float staging area fits the emission table");
+        CG_CUDA(ctx, cudaMemcpyAsync(d_cnt, count32, (size_t)S * N * 4, cudaMemcpyHostToDevice, s));
+        hmm_counts_to_coverage_kernel<<<std::max(1, std::min(div_up((long long)S * N, 256), ctx->num_sms * 8)), 256, 0, s>>>(d_cnt, (long long)S * N, text_mode, d_cov);
+        ctx->launches++;
+    }
     CG_CUDA(ctx, cudaMemcpyAsync(d_ci, ci.data(), (size_t)C * sizeof(HmmChromInfo), cudaMemcpyHostToDevice, s));
     CG_CUDA(ctx, cudaMemsetAsync(d_ctl, 0, sizeof(HmmCtl), s));
     CG_CUDA(ctx, cudaMemsetAsync(d_states, 0, N, s));
@@ -946,6 +965,21 @@ extern "C" int cg_partition_hmm_shard(cg_ctx* ctx, const cg_hmm_opts* o, int n_s
     ctx->stats[2] = (double)L;
     ctx->stats[3] = (double)N;
     return CG_OK;
+}
+
+extern "C" int cg_partition_hmm_shard(cg_ctx* ctx, const cg_hmm_opts* o, int n_samples, int n_chrom, const int64_t* chrom_off,
+                                      const double* coverage, const uint8_t* chrom_selected, int32_t* n_bp, int32_t* bp,
+                                      uint8_t* states_out) {
+    if (ctx && !coverage && n_chrom > 0 && chrom_off && chrom_off[n_chrom] > 0) return cg_fail(ctx, CG_ERR_ARG, "cg_partition_hmm: null array");
+    return partition_hmm_impl(ctx, o, n_samples, n_chrom, chrom_off, coverage, nullptr, 0, chrom_selected, n_bp, bp, states_out);
+}
+
+extern "C" int cg_partition_hmm_counts(cg_ctx* ctx, const cg_hmm_opts* o, int n_samples, int n_chrom, const int64_t* chrom_off,
+                                       const float* count, int text_mode, const uint8_t* chrom_selected, int32_t* n_bp, int32_t* bp,
+                                       uint8_t* states_out) {
+    if (ctx && (text_mode < 0 || text_mode > 2)) return cg_fail(ctx, CG_ERR_ARG, "cg_partition_hmm_counts: text_mode must be 0, 1 or 2");
+    if (ctx && !count && n_chrom > 0 && chrom_off && chrom_off[n_chrom] > 0) return cg_fail(ctx, CG_ERR_ARG, "cg_partition_hmm: null array");
+    return partition_hmm_impl(ctx, o, n_samples, n_chrom, chrom_off, nullptr, count, text_mode, chrom_selected, n_bp, bp, states_out);
 }
 
 extern "C" int cg_partition_hmm(cg_ctx* ctx, const cg_hmm_opts* o, int n_samples, int n_chrom, const int64_t* chrom_off,

@@ -50,11 +50,18 @@ def unpack_breakpoints(buffers, n_chrom):
 
 
 def all_gather_breakpoints(breakpoints, n_chrom, capacity=16384, device=None):
-    """One collective: every rank contributes the breakpoints of its chromosomes, every rank gets all."""
+    """Every rank contributes the breakpoints of its chromosomes, every rank gets all.  The buffer size is agreed
+    collectively first (all_reduce MAX of what each rank needs): a rank whose lists outgrow the default capacity makes
+    EVERY rank use the larger buffer, instead of raising alone and leaving the others waiting in the all-gather.
+    (The product path does this inside the library: cg_*_sharded / cg_comm_allgather_lists; this torch.distributed form
+    serves the CPU tests of the host logic.)"""
     import torch
     import torch.distributed as dist
     world = dist.get_world_size()
     dev = device if device is not None else ("cuda" if dist.get_backend() == "nccl" else "cpu")
+    need = torch.tensor([1 + 2 * sum(len(b) for b in breakpoints)], dtype=torch.int64, device=dev)
+    dist.all_reduce(need, op=dist.ReduceOp.MAX)
+    capacity = max(int(capacity), int(need.item()))
     local = torch.from_numpy(pack_breakpoints(breakpoints, capacity)).to(dev)
     gathered = torch.empty(world * capacity, dtype=torch.int32, device=dev)
     dist.all_gather_into_tensor(gathered, local)

@@ -79,6 +79,8 @@ SIGNATURES = {
     "cg_partition_hmm": (C.c_int, [C.c_void_p, _P(HmmOpts), C.c_int, C.c_int, _P(_i64), _P(_f64), _P(_i32), _P(_i32), _P(_u8)]),
     "cg_partition_hmm_shard": (C.c_int, [C.c_void_p, _P(HmmOpts), C.c_int, C.c_int, _P(_i64), _P(_f64), _P(_u8), _P(_i32),
                                          _P(_i32), _P(_u8)]),
+    "cg_partition_hmm_counts": (C.c_int, [C.c_void_p, _P(HmmOpts), C.c_int, C.c_int, _P(_i64), _P(_f32), C.c_int, _P(_u8), _P(_i32),
+                                          _P(_i32), _P(_u8)]),
     "cg_merge_common_bins": (C.c_int, [C.c_void_p, C.c_int, _P(_i64), _P(C.c_void_p), _P(C.c_void_p), _P(C.c_void_p),
                                        _P(C.c_void_p), _P(_i64), _P(_i32), _P(_i32), _P(_f32)]),
     "cg_smooth": (C.c_int, [C.c_void_p, C.c_int, C.c_int, _P(_i64), _P(_f32), _P(_i64), _P(_f32)]),
@@ -585,6 +587,26 @@ class Engine:
             mask = np.ascontiguousarray(chrom_selected, np.uint8)
             rc = self.lib.cg_partition_hmm_shard(self.h, C.byref(o), ns, nc, _ptr(off, _i64), _ptr(cov, _f64), _ptr(mask, _u8),
                                                  _ptr(n_bp, _i32), _ptr(bp, _i32), _ptr(states, _u8))
+        self._check(rc)
+        return {"breakpoints": [bp[off[c]:off[c] + n_bp[c]].copy() for c in range(nc)], "states": states[:n],
+                "kernel_ms": self.lib.cg_last_kernel_ms(self.h), "launches": self.lib.cg_last_launches(self.h)}
+
+    def partition_hmm_counts(self, chrom_off, count, text_mode=2, per_sample=True, min_size=10, chrom_selected=None):
+        """cg_partition_hmm_counts: float counts in, the .cleaned text round trip (1 = F2, 2 = float.ToString(), 0 = none) on
+        the device.  count: [N] or [n_samples, N] float32."""
+        off = np.ascontiguousarray(chrom_off, np.int64)
+        cnt = np.ascontiguousarray(np.atleast_2d(np.asarray(count, np.float32)))
+        ns, n = cnt.shape
+        nc = len(off) - 1
+        if nc > 0 and n != int(off[-1]):
+            raise ValueError("count length does not match the chromosome offsets")
+        o = HmmOpts(5, int(per_sample), min_size, 0)
+        n_bp = np.zeros(max(nc, 1), np.int32)
+        bp = np.zeros(max(n, 1), np.int32)
+        states = np.zeros(max(n, 1), np.uint8)
+        mask = None if chrom_selected is None else np.ascontiguousarray(chrom_selected, np.uint8)
+        rc = self.lib.cg_partition_hmm_counts(self.h, C.byref(o), ns, nc, _ptr(off, _i64), _ptr(cnt, _f32), int(text_mode),
+                                              None if mask is None else _ptr(mask, _u8), _ptr(n_bp, _i32), _ptr(bp, _i32), _ptr(states, _u8))
         self._check(rc)
         return {"breakpoints": [bp[off[c]:off[c] + n_bp[c]].copy() for c in range(nc)], "states": states[:n],
                 "kernel_ms": self.lib.cg_last_kernel_ms(self.h), "launches": self.lib.cg_last_launches(self.h)}

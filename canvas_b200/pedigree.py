@@ -11,7 +11,7 @@ whole result on every rank.
 """
 import numpy as np
 
-from . import native, synth, textcodec
+from . import native, synth
 
 
 def bin_positions(sample):
@@ -77,8 +77,8 @@ def trio_segments(eng, samples, pos=None, sharded=False, timings=None):
         if not mask.any():
             local.append([np.zeros(0, np.int32)] * nc)
             continue
-        cov = textcodec.float_default_roundtrip(m["count"][s])  # the merged file prints float.ToString()
-        r = eng.partition_hmm(off, cov, per_sample=True, chrom_selected=None if world == 1 else mask)
+        # the merged file prints float.ToString(): text_mode 2 reproduces that round trip on the device
+        r = eng.partition_hmm_counts(off, m["count"][s], text_mode=2, per_sample=True, chrom_selected=None if world == 1 else mask)
         kernel_ms += r["kernel_ms"]
         launches += r["launches"]
         local.append(r["breakpoints"])

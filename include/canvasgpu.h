@@ -220,6 +220,15 @@ int cg_partition_hmm_shard(cg_ctx* ctx, const cg_hmm_opts* opts, int n_samples, 
                            const double* coverage, const uint8_t* chrom_selected, int32_t* n_bp, int32_t* bp,
                            uint8_t* states);
 
+/* The same from the float counts of the .cleaned table, with the text round trip that stands between CanvasClean and
+ * CanvasPartition applied on the device: text_mode 1 = "{3:F2}" + Convert.ToDouble (IO.cs:21, CanvasSegment.cs:1147),
+ * 2 = float.ToString() of the pedigree workflow's merged four-column file (CanvasRunner.cs:895-897), 0 = plain widening.
+ * count is [n_samples][N]; chrom_selected may be NULL (every chromosome).  Half the bytes cross PCIe and the host does
+ * not format / parse three million numbers per sample. */
+int cg_partition_hmm_counts(cg_ctx* ctx, const cg_hmm_opts* opts, int n_samples, int n_chrom, const int64_t* chrom_off,
+                            const float* count, int text_mode, const uint8_t* chrom_selected, int32_t* n_bp, int32_t* bp,
+                            uint8_t* states);
+
 /* ---------------------------------------------------------------------------------------------
  * Multi-GPU: chromosomes are independent once the genome-wide scalars exist, so every rank
  * segments the chromosomes a longest-processing-time-first assignment gives it, and ONE NCCL all-gather over NVLink

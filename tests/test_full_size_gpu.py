@@ -97,9 +97,16 @@ def test_config4_trio_clean_merge_hmm(engine):
         pick = np.arange(0, len(ch0), 9973)
         assert [lut[(int(ch0[i]), int(st0[i]))] for i in pick] == m["count"][k][pick].tolist()
     off = synth.chrom_offsets(ch0, len(samples[0].names))
+    # the chain bench.py's config 4 times (canvas_b200/pedigree.py: Clean -> merge -> cg_partition_hmm_counts with the
+    # float.ToString() round trip on the device) against the oracle fed with the host's emulation of that text
+    from canvas_b200 import pedigree
+    engine.comm_init(1, 0)
+    chain = pedigree.trio_segments(engine, samples, pos=pos.astype(np.int32))
+    assert chain["n_common"] == len(common) and np.array_equal(chain["chrom_off"], off)
     for k in range(3):
         cov = textcodec.float_default_roundtrip(m["count"][k])  # the merged file prints float.ToString()
         got = engine.partition_hmm(off, cov, per_sample=True)
         want = ora.partition_hmm(off, cov, per_sample=True, n_threads=16)
         assert np.array_equal(got["states"], want["states"])
         assert all(a.tolist() == b.tolist() for a, b in zip(got["breakpoints"], want["breakpoints"]))
+        assert all(a.tolist() == b.tolist() for a, b in zip(chain["breakpoints"][k], want["breakpoints"]))

@@ -107,3 +107,23 @@ def test_edge_cases(engine):
     assert e.value.code == native.CG_ERR_ARG
     with pytest.raises(native.CanvasGpuError):
         engine.partition_hmm(np.array([0, 20]), np.concatenate([np.full(19, 50.0), [np.nan]]))
+
+
+def test_counts_entry_point_reproduces_the_text_round_trips(engine):
+    # cg_partition_hmm_counts: float counts in, the .cleaned text round trip on the device — same paths as the double entry
+    # point fed with the host's emulation of float.ToString("F2") / float.ToString()
+    rng = np.random.default_rng(12)
+    lens = [30000, 257, 9000]
+    off = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    cn = np.repeat(rng.choice([1, 2, 3], 40), sum(lens) // 40 + 1)[:sum(lens)]
+    cnt = (rng.poisson(50.0 * cn) * rng.uniform(0.97, 1.03, sum(lens))).astype(np.float32)
+    cnt[::977] = 0.0
+    cnt[5::1201] *= 1e-3  # small values: other decimal exponents
+    for mode, conv in ((1, textcodec.f2_roundtrip), (2, textcodec.float_default_roundtrip), (0, lambda v: v.astype(np.float64))):
+        want = engine.partition_hmm(off, conv(cnt), per_sample=True)
+        got = engine.partition_hmm_counts(off, cnt, text_mode=mode, per_sample=True)
+        _same(got, want)
+    mask = np.array([1, 0, 1], np.uint8)
+    want = engine.partition_hmm(off, textcodec.float_default_roundtrip(cnt), per_sample=True, chrom_selected=mask)
+    got = engine.partition_hmm_counts(off, cnt, text_mode=2, per_sample=True, chrom_selected=mask)
+    assert all(a.tolist() == b.tolist() for a, b in zip(got["breakpoints"], want["breakpoints"]))

@@ -106,3 +106,42 @@ def test_partition_hmm_sharded_world2():
     ret = mgr.dict()
     mp.spawn(_hmm_worker, args=(2, port, ret), nprocs=2, join=True)
     assert ret[0] and ret[1]
+
+
+def _overflow_worker(rank, world, port, ret):
+    import torch.distributed as dist
+    sys.path.insert(0, ROOT)
+    from canvas_b200 import multi
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    # rank 1 alone holds more breakpoints than the capacity both ranks were given: the size is agreed collectively, so
+    # nobody raises on its own and nobody is left waiting in the all-gather
+    truth = [np.arange(3, dtype=np.int32), np.arange(500, dtype=np.int32) * 2]
+    mine = [truth[c] if c == rank else np.zeros(0, np.int32) for c in range(2)]
+    got = multi.all_gather_breakpoints(mine, 2, capacity=64, device="cpu")
+    ret[rank] = all(g.tolist() == t.tolist() for g, t in zip(got, truth))
+    dist.destroy_process_group()
+
+
+def test_all_gather_breakpoints_beyond_the_default_capacity_world2():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    mgr = mp.get_context("spawn").Manager()
+    ret = mgr.dict()
+    mp.spawn(_overflow_worker, args=(2, port, ret), nprocs=2, join=True)
+    assert ret[0] and ret[1]
+
+
+def test_library_lpt_equals_the_python_one():
+    # cg_shard_assign (host code of the library, what the *_sharded entry points use) against multi.assign_chromosomes_lpt
+    sys.path.insert(0, ROOT)
+    from canvas_b200 import multi, native
+    rng = np.random.default_rng(2)
+    for world in (1, 2, 3, 8):
+        for n in (0, 1, 5, 24, 72, 300):
+            w = rng.integers(0, 250000, n)
+            w[rng.random(n) < 0.2] = 1000  # ties
+            assert native.shard_assign(w, world).tolist() == multi.assign_chromosomes_lpt(w, world).tolist()
