@@ -300,11 +300,13 @@ def main():
     # ------------------------------------------------------------------ config 4: the trio chain
     def run_config4(n_warm, n_steps):
         trio = [synth.make_sample(config=4, sample=k, scale=args.scale, n_events=60) for k in range(3)]
-        pos = pedigree.bin_positions(trio[0])
+        for t in trio:  # page-locked input columns, as in the other configurations
+            t.chrom, t.start, t.stop, t.count, t.gc = (pin.array(a) for a in (t.chrom, t.start, t.stop, t.count, t.gc))
         tm, res = {}, {}
+        layout_off = synth.chrom_offsets(trio[0].chrom, len(trio[0].names))
 
         def step():
-            res["r"] = pedigree.trio_segments(eng, trio, pos=pos, sharded=world > 1, timings=tm if res.get("timed") else None)
+            res["r"] = pedigree.trio_segments(eng, trio, sharded=world > 1, timings=tm if res.get("timed") else None, layout_off=layout_off)
         for _ in range(n_warm):
             step()
         res["timed"] = True

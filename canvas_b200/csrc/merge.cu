@@ -197,3 +197,135 @@ extern "C" int cg_merge_common_bins(cg_ctx* ctx, int n_samples, const int64_t* n
     }
     return CG_OK;
 }
+
+// ---------------------------------------------------------------------------------------------
+// cg_merge_kept_indices: the same merge for samples cleaned from ONE bin layout.  A pedigree is binned once
+// (CanvasRunner.cs:846-870 hands the same bin definitions to every sample's CanvasBin), so a bin is identified by its
+// index in that layout and cg_clean's kept_index lists are already the keys: a position table per sample
+// (layout index -> row in that sample's list) replaces the key columns and the binary searches, and the host no longer
+// gathers chromosome / start / stop columns per sample.
+// ---------------------------------------------------------------------------------------------
+namespace {
+
+struct KeptCols {
+    const int32_t* kept[MERGE_MAX_SAMPLES];
+    const float* count[MERGE_MAX_SAMPLES];
+    int* pos[MERGE_MAX_SAMPLES];  // [n_bins] row of the bin in sample s, -1 when that sample dropped it
+    int n[MERGE_MAX_SAMPLES];
+    int S;
+};
+
+__global__ void kept_scatter_kernel(const int32_t* __restrict__ kept, int n, int n_bins, int* __restrict__ pos, MergeCtl* ctl) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int b = kept[i];
+        if (b < 0 || b >= n_bins || (i > 0 && kept[i - 1] >= b)) { ctl->unsorted = 1; continue; }
+        pos[b] = i;
+    }
+}
+
+struct KeptPred {
+    KeptCols c;
+    __device__ bool operator()(int i) const {
+        const int b = c.kept[0][i];
+        for (int s = 1; s < c.S; s++)
+            if (c.pos[s][b] < 0) return false;
+        return true;
+    }
+};
+
+struct KeptEmit {
+    KeptCols c;
+    int32_t* common;
+    float* count_out;  // [S][n0]
+    __device__ void operator()(int src, int dst) const {
+        const int n0 = c.n[0];
+        const int b = c.kept[0][src];
+        common[dst] = b;
+        count_out[dst] = c.count[0][src];
+        for (int s = 1; s < c.S; s++) count_out[(size_t)s * n0 + dst] = c.count[s][c.pos[s][b]];
+    }
+};
+
+}  // namespace
+
+extern "C" int cg_merge_kept_indices(cg_ctx* ctx, int64_t n_bins, int n_samples, const int64_t* n_kept, const int32_t* const* kept,
+                                     const float* const* count, int64_t* n_out, int32_t* common_index, float* count_out) {
+    if (!ctx) return CG_ERR_ARG;
+    if (n_samples < 1 || n_bins < 0 || n_bins > 0x7fff0000LL || !n_kept || !kept || !count || !n_out)
+        return cg_fail(ctx, CG_ERR_ARG, "cg_merge_kept_indices: bad argument");
+    if (n_samples > MERGE_MAX_SAMPLES) return cg_fail(ctx, CG_ERR_UNSUPPORTED, "cg_merge_kept_indices: at most 8 samples");
+    const int S = n_samples;
+    for (int s = 0; s < S; s++) {
+        if (n_kept[s] < 0 || n_kept[s] > n_bins) return cg_fail(ctx, CG_ERR_ARG, "cg_merge_kept_indices: bad list length");
+        if (n_kept[s] > 0 && (!kept[s] || !count[s])) return cg_fail(ctx, CG_ERR_ARG, "cg_merge_kept_indices: null column");
+    }
+    *n_out = 0;
+    ctx->launches = 0;
+    ctx->tl = nullptr;
+    ctx->launch_err = cudaSuccess;
+    ctx->last_kernel_ms = 0;
+    for (int i = 0; i < 4; i++) ctx->stage_used[i] = false;
+    ctx->gap_used = false;
+    const int n0 = (int)n_kept[0];
+    if (n0 == 0) return CG_OK;
+    if (!common_index || !count_out) return cg_fail(ctx, CG_ERR_ARG, "cg_merge_kept_indices: null output");
+    CG_CUDA(ctx, cudaSetDevice(ctx->device));
+    size_t need = arena_need(1, sizeof(MergeCtl)) + arena_need(n0 / CMP_TILE + 2, 4) + arena_need((size_t)S * n0, 4) + arena_need(n0, 4) + (1u << 16);
+    for (int s = 0; s < S; s++) need += arena_need(n_kept[s], 4) * 2 + arena_need(n_bins + 1, 4);
+    int rc = arena_reserve(ctx, need);
+    if (rc) return rc;
+    MergeCtl* ctl = arena_take<MergeCtl>(ctx, 1);
+    int* tiles = arena_take<int>(ctx, n0 / CMP_TILE + 2);
+    float* d_count_out = arena_take<float>(ctx, (size_t)S * n0);
+    int32_t* d_common = arena_take<int32_t>(ctx, n0);
+    if (!ctl || !tiles || !d_count_out || !d_common) return cg_fail(ctx, CG_ERR_CUDA, "arena exhausted");
+    cudaStream_t st = ctx->stream;
+    KeptCols cols;
+    memset(&cols, 0, sizeof(cols));
+    cols.S = S;
+    MergeCtl h0 = {n0, 0, 0, 0, 0};
+    CG_CUDA(ctx, cudaMemcpyAsync(ctl, &h0, sizeof(MergeCtl), cudaMemcpyHostToDevice, st));
+    for (int s = 0; s < S; s++) {
+        const size_t m = (size_t)n_kept[s];
+        int32_t* d_kept = arena_take<int32_t>(ctx, m);
+        float* d_count = arena_take<float>(ctx, m);
+        int* d_pos = arena_take<int>(ctx, n_bins + 1);
+        if (!d_kept || !d_count || !d_pos) return cg_fail(ctx, CG_ERR_CUDA, "arena exhausted");
+        if (m > 0) {
+            CG_CUDA(ctx, cudaMemcpyAsync(d_kept, kept[s], m * 4, cudaMemcpyHostToDevice, st));
+            CG_CUDA(ctx, cudaMemcpyAsync(d_count, count[s], m * 4, cudaMemcpyHostToDevice, st));
+        }
+        cols.kept[s] = d_kept; cols.count[s] = d_count; cols.pos[s] = d_pos; cols.n[s] = (int)m;
+    }
+    CG_CUDA(ctx, cudaEventRecord(ctx->ev0, st));
+    for (int s = 0; s < S; s++) {
+        if (s > 0) CG_CUDA(ctx, cudaMemsetAsync(cols.pos[s], 0xff, (size_t)(n_bins + 1) * 4, st));
+        if (n_kept[s] > 0)
+            CG_LAUNCH(ctx, kept_scatter_kernel, std::max(1, std::min(div_up(n_kept[s], 256), ctx->num_sms * 8)), 256, 0, cols.kept[s],
+                      (int)n_kept[s], (int)n_bins, cols.pos[s], ctl);
+    }
+    {
+        KeptPred p{cols};
+        KeptEmit e{cols, d_common, d_count_out};
+        compact_run(ctx, p, e, &ctl->n0, n0, tiles, &ctl->n_out);
+    }
+    CG_CUDA(ctx, cudaEventRecord(ctx->ev1, st));
+    MergeCtl* h = (MergeCtl*)ctx->pinned;
+    CG_CUDA(ctx, cudaMemcpyAsync(h, ctl, sizeof(MergeCtl), cudaMemcpyDeviceToHost, st));
+    CG_CUDA(ctx, cudaStreamSynchronize(st));
+    CG_CUDA(ctx, cudaGetLastError());
+    CG_CHECK_LAUNCHES(ctx);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+    ctx->last_kernel_ms = ms;
+    if (h->unsorted) return cg_fail(ctx, CG_ERR_UNSORTED, "cg_merge_kept_indices: every list must be strictly increasing indices into the layout");
+    const int m = h->n_out;
+    *n_out = m;
+    if (m > 0) {
+        CG_CUDA(ctx, cudaMemcpyAsync(common_index, d_common, (size_t)m * 4, cudaMemcpyDeviceToHost, st));
+        for (int s = 0; s < S; s++)
+            CG_CUDA(ctx, cudaMemcpyAsync(count_out + (size_t)s * n0, d_count_out + (size_t)s * n0, (size_t)m * 4, cudaMemcpyDeviceToHost, st));
+        CG_CUDA(ctx, cudaStreamSynchronize(st));
+    }
+    return CG_OK;
+}

@@ -663,6 +663,7 @@ int wv_enqueue(cg_ctx* ctx, const cg_wavelet_opts* o, const WvPlan& pl, WvDev& d
     // same for every sample binned on the same reference) it is the same for every call of that shape, so it is captured
     // once into a CUDA graph and replayed: one launch instead of ~150, every chromosome's first kernel starts at once, and
     // ranks that share a host no longer queue behind each other's launches.  A shape is captured the second time it is seen.
+    static const int mid_threads = getenv("CANVAS_MID_THREADS") ? atoi(getenv("CANVAS_MID_THREADS")) : UH_MID_THREADS;
     auto enqueue_pipelines = [&](const long long* loff, cudaStream_t root) -> int {
         std::vector<int> order;
         for (int c = 0; c < C; c++) {
@@ -699,7 +700,12 @@ int wv_enqueue(cg_ctx* ctx, const cg_wavelet_opts* o, const WvPlan& pl, WvDev& d
                 ctx->launches++;
             }
             if (len > UH_SMALL_MAX)
-                CG_LAUNCH(ctx, uh_mid_kernel, (int)std::min<long long>(64, std::max<long long>(1, len / 2048)), UH_MID_THREADS, 0, up, c);
+            {
+                const int mid_grid = (int)std::min<long long>(64, std::max<long long>(1, len / 2048));
+                if (mid_threads >= 1024) CG_LAUNCH(ctx, (uh_mid_kernel<1024, 16>), mid_grid, 1024, 0, up, c);
+                else if (mid_threads >= 512) CG_LAUNCH(ctx, (uh_mid_kernel<512, 16>), mid_grid, 512, 0, up, c);
+                else CG_LAUNCH(ctx, (uh_mid_kernel<256, 8>), mid_grid, 256, 0, up, c);
+            }
             if (len > UH_TINY_MAX)
                 CG_LAUNCH(ctx, uh_small_kernel, (int)std::min<long long>(ctx->num_sms, std::max<long long>(1, len / 1024)), UH_SMALL_THREADS, uh_smem, up, c);
             CG_LAUNCH(ctx, uh_tiny_kernel, (int)std::min<long long>(ctx->num_sms, std::max<long long>(1, len / 1024)), 128, 0, up, d.tiny_tab, c);

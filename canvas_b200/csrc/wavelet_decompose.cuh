@@ -364,11 +364,14 @@ uh_chain_kernel(UhParams p, int c_self) {
 // ---------------------------------------------------------------------------------------------
 constexpr int UH_MID_STACK = 32;
 
-__global__ void __launch_bounds__(UH_MID_THREADS, 4)
+// NT threads per CTA: a mid node is one round of loads for every thread when NT * U covers it; the subtree is a chain of
+// dependent nodes, so the stage is bound by the latency of a node, not by throughput
+template <int NT, int U>
+__global__ void __launch_bounds__(NT, NT >= 1024 ? 1 : (NT >= 512 ? 2 : 4))
 uh_mid_kernel(UhParams p, int c_self) {
     __shared__ UhTask s_stack[UH_MID_STACK];
-    __shared__ double s_ws[2][UH_MID_THREADS / 32], s_wv[2][UH_MID_THREADS / 32];
-    __shared__ int s_wm2[2][UH_MID_THREADS / 32];
+    __shared__ double s_ws[2][NT / 32], s_wv[2][NT / 32];
+    __shared__ int s_wm2[2][NT / 32];
     __shared__ UhOutBuf<UhTask, 32> s_small_out;
     __shared__ UhOutBuf<UhTinyTask, 32> s_tiny_out;
     __shared__ int s_idx;
@@ -407,7 +410,7 @@ uh_mid_kernel(UhParams p, int c_self) {
             const double mu = T / nn;
             double bnum = -1.0, bden = 1.0, bv = 0.0;
             int bm = 0x7fffffff;
-            uh_scan<UH_MID_THREADS, 8>(pz + p0 + s + 1, 0, n - 1, threadIdx.x, base, mu, nn, bnum, bden, bm, bv);
+            uh_scan<NT, U>(pz + p0 + s + 1, 0, n - 1, threadIdx.x, base, mu, nn, bnum, bden, bm, bv);
             double best = bnum >= 0.0 ? bnum / bden : -1.0;
             int best_m = bm;
             warp_argmax(best, best_m);
@@ -420,7 +423,7 @@ uh_mid_kernel(UhParams p, int c_self) {
             double fbest = s_ws[parity][0], fv = s_wv[parity][0];
             int fm = s_wm2[parity][0];
 #pragma unroll
-            for (int w = 1; w < UH_MID_THREADS / 32; w++) {
+            for (int w = 1; w < NT / 32; w++) {
                 const double sc = s_ws[parity][w];
                 const int mm = s_wm2[parity][w];
                 if (sc > fbest || (sc == fbest && mm < fm)) { fbest = sc; fm = mm; fv = s_wv[parity][w]; }
@@ -428,7 +431,7 @@ uh_mid_kernel(UhParams p, int c_self) {
             parity ^= 1;
             if (threadIdx.x == 0) v_mid += (unsigned long long)n;
             if (fbest == 0.0 || fm == 0x7fffffff) {
-                for (int k = threadIdx.x; k < n - 1; k += UH_MID_THREADS) atomicAdd(&p.lvlcnt[loff + level + k], 1u);
+                for (int k = threadIdx.x; k < n - 1; k += NT) atomicAdd(&p.lvlcnt[loff + level + k], 1u);
                 if (threadIdx.x == 0) n_mid += (unsigned long long)(n - 1);
                 continue;
             }

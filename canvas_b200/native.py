@@ -83,6 +83,7 @@ SIGNATURES = {
                                           _P(_i32), _P(_u8)]),
     "cg_merge_common_bins": (C.c_int, [C.c_void_p, C.c_int, _P(_i64), _P(C.c_void_p), _P(C.c_void_p), _P(C.c_void_p),
                                        _P(C.c_void_p), _P(_i64), _P(_i32), _P(_i32), _P(_f32)]),
+    "cg_merge_kept_indices": (C.c_int, [C.c_void_p, _i64, C.c_int, _P(_i64), _P(C.c_void_p), _P(C.c_void_p), _P(_i64), _P(_i32), _P(_f32)]),
     "cg_smooth": (C.c_int, [C.c_void_p, C.c_int, C.c_int, _P(_i64), _P(_f32), _P(_i64), _P(_f32)]),
     "cg_format_bins": (_i64, [_i64, C.c_int, _P(C.c_char_p), _P(_u8), _P(_i32), _P(_i32), _P(_f32), _P(_u8), C.c_int,
                               C.c_char_p, _i64, C.c_int]),
@@ -629,6 +630,24 @@ class Engine:
         k = m.value
         return {"kept_index": kept[:k].copy(), "stop": stop[:k].copy(), "count": cnt[:ns, :k].copy(),
                 "kernel_ms": self.lib.cg_last_kernel_ms(self.h)}
+
+    def merge_kept_indices(self, n_bins, kept_lists, count_lists):
+        """cg_merge_kept_indices: samples cleaned from one bin layout — kept_index / count of every sample in, the indices
+        (into the layout) of the bins every sample kept and counts [n_samples, n_common] out."""
+        ns = len(kept_lists)
+        kept = [np.ascontiguousarray(k, np.int32) for k in kept_lists]
+        cnt = [np.ascontiguousarray(c, np.float32) for c in count_lists]
+        n = np.array([len(k) for k in kept], np.int64)
+        n0 = max(int(n[0]), 1)
+        kp = (C.c_void_p * ns)(*[k.ctypes.data for k in kept])
+        cp = (C.c_void_p * ns)(*[c.ctypes.data for c in cnt])
+        common = np.zeros(n0, np.int32)
+        out = np.zeros((ns, n0), np.float32)
+        n_out = _i64(0)
+        self._check(self.lib.cg_merge_kept_indices(self.h, int(n_bins), ns, _ptr(n, _i64), kp, cp, C.byref(n_out), _ptr(common, _i32),
+                                                   _ptr(out, _f32)))
+        m = n_out.value
+        return {"common_index": common[:m], "count": out[:, :m], "kernel_ms": self.lib.cg_last_kernel_ms(self.h)}
 
     def smooth(self, chrom_off, count, max_half_window):
         """RepeatedMedianSmoother.Smooth per chromosome: list of smoothed count arrays (possibly shorter than the input)."""

@@ -21,15 +21,13 @@ def bin_positions(sample):
     return ((np.arange(len(sample)) - off[sample.chrom]) * 1000).astype(np.int32)
 
 
-def trio_segments(eng, samples, pos=None, sharded=False, timings=None):
+def trio_segments(eng, samples, sharded=False, timings=None, layout_off=None):
     """samples: synth samples of one pedigree (shared bin layout).  Returns {"breakpoints": [sample][chrom] arrays,
     "chrom_off": offsets of the common bins, "n_common": int, "owner": [sample][chrom] rank of every unit}."""
     import time
     S = len(samples)
     nc = len(samples[0].names)
     rank, world = (eng.comm_rank, eng.comm_size) if sharded else (0, 1)
-    if pos is None:
-        pos = bin_positions(samples[0])
     kernel_ms, launches = 0.0, 0
     t0 = time.perf_counter()
     # ---- CanvasClean, each sample once
@@ -48,7 +46,7 @@ def trio_segments(eng, samples, pos=None, sharded=False, timings=None):
             n_out[s] = len(r["kept_index"])
         got = eng.allgather_lists(n_out)
         n_out = np.max(np.stack(got), axis=0)
-    cleaned = []
+    kept_lists, count_lists = [], []
     for s in range(S):
         if world > 1:
             root = s % world
@@ -58,15 +56,18 @@ def trio_segments(eng, samples, pos=None, sharded=False, timings=None):
             cnt = eng.broadcast(cnt, root)
         else:
             kept, cnt = mine[s]["kept_index"], mine[s]["count"]
-        sm = samples[s]
-        cleaned.append((sm.chrom[kept], pos[kept], (pos[kept] + 1000).astype(np.int32), cnt))
+        kept_lists.append(kept)
+        count_lists.append(cnt)
     t2 = time.perf_counter()
-    # ---- bins common to every sample (every rank: a few binary searches per bin)
-    m = eng.merge_common_bins(cleaned)
+    # ---- bins common to every sample (every rank).  The samples share one bin layout, so cg_clean's kept_index lists are
+    # the keys (cg_merge_kept_indices); the general, coordinate-keyed form is cg_merge_common_bins
+    m = eng.merge_kept_indices(len(samples[0]), kept_lists, count_lists)
     kernel_ms += m["kernel_ms"]
     launches += eng.last_launches
-    ch0 = cleaned[0][0][m["kept_index"]]
-    off = synth.chrom_offsets(ch0, nc)
+    if layout_off is None:
+        layout_off = synth.chrom_offsets(samples[0].chrom, nc)
+    off = np.searchsorted(m["common_index"], layout_off).astype(np.int64)  # common bins are in layout order
+    n_common = int(len(m["common_index"]))
     t3 = time.perf_counter()
     # ---- PerSampleHMM, (sample, chromosome) units over the ranks
     lens = np.diff(off)
@@ -106,4 +107,4 @@ def trio_segments(eng, samples, pos=None, sharded=False, timings=None):
             timings[k] = timings.get(k, 0.0) + v * 1e3
         timings["kernel_ms"] = timings.get("kernel_ms", 0.0) + kernel_ms
         timings["launches"] = timings.get("launches", 0) + launches
-    return {"breakpoints": bps, "chrom_off": off, "n_common": int(len(ch0)), "owner": owner}
+    return {"breakpoints": bps, "chrom_off": off, "n_common": n_common, "common_index": m["common_index"], "owner": owner}

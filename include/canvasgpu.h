@@ -300,6 +300,14 @@ int cg_merge_common_bins(cg_ctx* ctx, int n_samples, const int64_t* n, const uin
                          const int32_t* const* start, const int32_t* const* stop, const float* const* count,
                          int64_t* n_out, int32_t* kept_index, int32_t* stop_out, float* count_out);
 
+/* The same merge for samples cleaned from ONE bin layout (a pedigree is binned once, so a bin is identified by its index
+ * in that layout): kept[s][0 .. n_kept[s]) = cg_clean's kept_index of sample s (strictly increasing indices below n_bins),
+ * count[s] its normalised counts.  Outputs, capacity n_kept[0]: *n_out common bins, common_index[k] their indices in the
+ * layout (ascending = the first sample's order), count_out[s * n_kept[0] + k] sample s's count of common bin k.  The
+ * coordinates of the common bins are layout columns the host already holds; nothing is gathered per sample. */
+int cg_merge_kept_indices(cg_ctx* ctx, int64_t n_bins, int n_samples, const int64_t* n_kept, const int32_t* const* kept,
+                          const float* const* count, int64_t* n_out, int32_t* common_index, float* count_out);
+
 /* ---------------------------------------------------------------------------------------------
  * CanvasSmooth — RepeatedMedianSmoother.Smooth (CanvasSmooth/CanvasSmooth.cs:44-77) over every chromosome:
  * Utilities.MedianFilter (CanvasCommon/Utilities.cs:767-791) with half windows 1 .. max_half_window, each pass on

@@ -82,9 +82,11 @@ def test_config4_trio_clean_merge_hmm(engine):
     # a pedigree shares one bin layout; the synthetic oversized bins push the generator's own coordinates past int32
     # at full scale, so the file coordinates are rebuilt from the bin index (1 kb bins)
     pos = (np.arange(len(samples[0])) - synth.chrom_offsets(samples[0].chrom, len(samples[0].names))[samples[0].chrom]) * 1000
+    cleaned_index = []
     for s in samples:
         c = engine.clean(s.chrom, s.is_autosome, s.is_chr_y, s.start, s.stop, s.count, s.gc)
         k = c["kept_index"]
+        cleaned_index.append(k)
         cleaned.append((s.chrom[k], pos[k].astype(np.int32), (pos[k] + 1000).astype(np.int32), c["count"]))
     m = engine.merge_common_bins(cleaned)
     keys = [set(zip(ch.tolist(), st.tolist())) for ch, st, _, _ in cleaned]
@@ -101,8 +103,10 @@ def test_config4_trio_clean_merge_hmm(engine):
     # float.ToString() round trip on the device) against the oracle fed with the host's emulation of that text
     from canvas_b200 import pedigree
     engine.comm_init(1, 0)
-    chain = pedigree.trio_segments(engine, samples, pos=pos.astype(np.int32))
+    chain = pedigree.trio_segments(engine, samples)
     assert chain["n_common"] == len(common) and np.array_equal(chain["chrom_off"], off)
+    # the index-keyed merge of the chain selects the bins the coordinate-keyed merge selects
+    assert np.array_equal(chain["common_index"], cleaned_index[0][m["kept_index"]])
     for k in range(3):
         cov = textcodec.float_default_roundtrip(m["count"][k])  # the merged file prints float.ToString()
         got = engine.partition_hmm(off, cov, per_sample=True)
