@@ -196,6 +196,15 @@ __device__ inline void bin_quad(unsigned h, unsigned b, unsigned m4, unsigned& o
     gcv += (unsigned)__popc((__vcmpeq4(x, 0x63636363u) | __vcmpeq4(x, 0x67676767u)) & 0x01010101u);
 }
 
+// the same restricted to the positions of the quad selected by the 4-bit mask `part`
+__device__ inline void bin_quad_part(unsigned h, unsigned b, unsigned m4, unsigned part, unsigned& obs, unsigned& gcv) {
+    const unsigned pmask = ((part * 0x00204081u) & 0x01010101u) * 0xffu;
+    const unsigned mask = ((m4 * 0x00204081u) & 0x01010101u) * 0xffu & pmask;
+    obs += __vsadu4(__vminu4(h, 0x0a0a0a0au) & mask, 0u);
+    const unsigned x = b | 0x20202020u;
+    gcv += (unsigned)__popc((__vcmpeq4(x, 0x63636363u) | __vcmpeq4(x, 0x67676767u)) & 0x01010101u & pmask);
+}
+
 // first bin of every tile of the streaming pass: tile_first[t] = number of bins that end before position t * BIN_ACC_TILE.
 // Bin k is that bin for the tiles whose start lies in (end[k-1], end[k]]; thread nb fills the tiles past the last bin.
 __global__ void bin_tile_first_kernel(const BinCtl* __restrict__ ctl, const int* __restrict__ end_pos, int max_bins, long long n_tiles,
@@ -269,20 +278,31 @@ __global__ void __launch_bounds__(BIN_ACC_THREADS) bin_accum_kernel(const unsign
 #pragma unroll
                     for (int q = 0; q < 4; q++) bin_quad(hq[q], bq[q], (m16 >> (4 * q)) & 0xfu, obs, gcv);
                 } else {
-                    // a bin closes inside these 16 positions: position by position
+                    // a bin closes inside these 16 positions (one thread in thirty, but most warps have such a thread, so this
+                    // branch has to stay short): quads without an end as above, a quad with one end as two masked halves
 #pragma unroll
-                    for (int q = 0; q < 4; q++)
-#pragma unroll
-                        for (int j = 0; j < 4; j++) {
-                            const int i = 4 * q + j;
-                            const unsigned h = (hq[q] >> (8 * j)) & 0xffu, b = ((bq[q] >> (8 * j)) & 0xffu) | 0x20u;
-                            if ((m16 >> i) & 1u) obs += min(10u, h);
-                            gcv += (b == 0x63u || b == 0x67u) ? 1u : 0u;
-                            if ((f16 >> i) & 1u) {
-                                bin_acc_add(s_obs, s_gc, g_obs, g_gc, k_lo, bin, nb, obs, gcv);
-                                obs = 0; gcv = 0; bin++;
+                    for (int q = 0; q < 4; q++) {
+                        const unsigned fq = (f16 >> (4 * q)) & 0xfu, mq = (m16 >> (4 * q)) & 0xfu;
+                        if (fq == 0u) {
+                            bin_quad(hq[q], bq[q], mq, obs, gcv);
+                        } else if ((fq & (fq - 1u)) == 0u) {
+                            const unsigned upto = (fq << 1) - 1u;  // positions of the quad up to and including the end
+                            bin_quad_part(hq[q], bq[q], mq, upto, obs, gcv);
+                            bin_acc_add(s_obs, s_gc, g_obs, g_gc, k_lo, bin, nb, obs, gcv);
+                            obs = 0; gcv = 0; bin++;
+                            bin_quad_part(hq[q], bq[q], mq, ~upto & 0xfu, obs, gcv);
+                        } else {
+                            for (int j = 0; j < 4; j++) {  // bins shorter than four positions
+                                const unsigned h = (hq[q] >> (8 * j)) & 0xffu, b = ((bq[q] >> (8 * j)) & 0xffu) | 0x20u;
+                                if ((mq >> j) & 1u) obs += min(10u, h);
+                                gcv += (b == 0x63u || b == 0x67u) ? 1u : 0u;
+                                if ((fq >> j) & 1u) {
+                                    bin_acc_add(s_obs, s_gc, g_obs, g_gc, k_lo, bin, nb, obs, gcv);
+                                    obs = 0; gcv = 0; bin++;
+                                }
                             }
                         }
+                    }
                 }
             }
         } else {

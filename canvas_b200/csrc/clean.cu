@@ -520,7 +520,7 @@ __global__ void __launch_bounds__(256) gc_weighted_kernel(const float* __restric
         s_total = (int)min(total, (long long)0x7fffffff);
         s_cnt = 0;
         s_go = total <= WQ_CAP ? 1 : 0;
-        if (!s_go) ctl->need_weighted = 1;  // more neighbours than the shared-memory sorter holds: reported as unsupported
+        if (!s_go) ctl->wq_big[g] = 1;  // more neighbours than the shared-memory sorter holds: gc_weighted_big_kernel takes the bucket
     }
     __syncthreads();
     if (!s_go) return;
@@ -566,6 +566,114 @@ __global__ void __launch_bounds__(256) gc_weighted_kernel(const float* __restric
         }
         if (mode == 0) ctl->med[g] = q[1];
         else { ctl->q2[g] = (float)q[1]; ctl->iqr[g] = (float)(q[2] - q[0]); }
+    }
+}
+
+// The same for the buckets gc_weighted_kernel left (one neighbouring bucket alone can hold tens of thousands of bins, and
+// the reference collects all of them, CanvasClean.cs:107-132): one CTA works through them one after the other with the keys
+// in global scratch — block-wide bitonic sort, then the cumulative weights as a block scan.  Sums of the weights 2^-r are
+// exact in double whatever their order, so the scan gives the reference's running sums; the reference's loop keeps the
+// LAST value whose cumulative share is <= p, and since the shares ascend that is the largest index that satisfies it.
+__global__ void __launch_bounds__(1024) gc_weighted_big_kernel(const float* __restrict__ count2, const uint8_t* __restrict__ gc2,
+                                                               const uint8_t* __restrict__ chrom2, const uint8_t* __restrict__ alive,
+                                                               const uint8_t* __restrict__ is_auto, CleanCtl* ctl, int mode, const int* enabled,
+                                                               unsigned long long* __restrict__ key, long long key_cap) {
+    __shared__ signed char s_rad[GC_BINS];
+    __shared__ int s_total, s_cnt;
+    __shared__ double s_w[32];
+    __shared__ int s_i[3][32];
+    if (!*enabled) return;
+    const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
+    for (int g = 0; g < GC_BINS; g++) {
+        if (!ctl->wq_big[g]) continue;  // uniform
+        __syncthreads();
+        if (t < GC_BINS) s_rad[t] = -1;
+        __syncthreads();
+        if (t == 0) {
+            long long total = 0;
+            int r = 0;
+            while (total < MIN_BINS_PER_GC) {
+                const int hi = g + r, lo = g - r;
+                if (hi >= GC_BINS && lo < 0) break;
+                if (hi < GC_BINS) { s_rad[hi] = (signed char)r; total += alive_auto_count(ctl, hi); }
+                if (lo != hi && lo >= 0) { s_rad[lo] = (signed char)r; total += alive_auto_count(ctl, lo); }
+                r++;
+            }
+            s_total = (int)min(total, (long long)0x7fffffff);
+            s_cnt = 0;
+        }
+        __syncthreads();
+        const int T = s_total;
+        long long pad = 1;
+        while (pad < T) pad <<= 1;
+        if (pad > key_cap) {  // cannot happen: the scratch holds every bin
+            if (t == 0) { ctl->need_weighted = 1; ctl->wq_big[g] = 0; }
+            continue;
+        }
+        for (long long k = t; k < pad; k += blockDim.x) key[k] = ~0ull;
+        __syncthreads();
+        const int n2 = ctl->n2;
+        for (int i = t; i < n2; i += blockDim.x) {
+            const int r = s_rad[gc2[i]];
+            if (r >= 0 && alive[i] && is_auto[chrom2[i]]) {
+                const int slot = atomicAdd(&s_cnt, 1);
+                if (slot < pad) key[slot] = ((unsigned long long)f32_key(count2[i]) << 8) | (unsigned long long)r;
+            }
+        }
+        __syncthreads();
+        for (long long k = 2; k <= pad; k <<= 1)
+            for (long long j = k >> 1; j > 0; j >>= 1) {
+                for (long long i = t; i < pad; i += blockDim.x) {
+                    const long long l = i ^ j;
+                    if (l > i) {
+                        const bool up = (i & k) == 0;
+                        const unsigned long long a = key[i], b = key[l];
+                        if ((a > b) == up) { key[i] = b; key[l] = a; }
+                    }
+                }
+                __syncthreads();
+            }
+        // cumulative weights: a contiguous chunk per thread, block scan of the chunk sums
+        const int chunk = (T + (int)blockDim.x - 1) / (int)blockDim.x;
+        const int c0 = min(T, t * chunk), c1 = min(T, c0 + chunk);
+        double mine = 0.0;
+        for (int i = c0; i < c1; i++) mine += ldexp(1.0, -(int)(key[i] & 0xffull));
+        double incl = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const double v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+        if (lane == 31) s_w[wid] = incl;
+        __syncthreads();
+        double before = incl - mine, all = 0.0;
+        for (int k = 0; k < (int)(blockDim.x >> 5); k++) { if (k < wid) before += s_w[k]; all += s_w[k]; }
+        const double total_w = (double)(float)all;  // Enumerable.Sum over float weights returns a float
+        const double probs[3] = {0.25, 0.5, 0.75};
+        int last[3] = {-1, -1, -1};
+        double cw = before;
+        for (int i = c0; i < c1; i++) {
+            cw += ldexp(1.0, -(int)(key[i] & 0xffull));
+            const double cp = cw / total_w;
+#pragma unroll
+            for (int p = 0; p < 3; p++)
+                if (cp <= probs[p]) last[p] = i;
+        }
+#pragma unroll
+        for (int p = 0; p < 3; p++) {
+            const int m = (int)__reduce_max_sync(0xffffffffu, (unsigned)(last[p] + 1));
+            if (lane == 0) s_i[p][wid] = m;
+        }
+        __syncthreads();
+        if (t == 0) {
+            double q[3];
+            for (int p = 0; p < 3; p++) {
+                int m = 0;
+                for (int k = 0; k < (int)(blockDim.x >> 5); k++) m = max(m, s_i[p][k]);
+                q[p] = m > 0 ? (double)f32_unkey((uint32_t)(key[m - 1] >> 8)) : 0.0;
+            }
+            if (mode == 0) ctl->med[g] = q[1];
+            else { ctl->q2[g] = (float)q[1]; ctl->iqr[g] = (float)(q[2] - q[0]); }
+            ctl->wq_big[g] = 0;
+        }
+        __syncthreads();
     }
 }
 
@@ -625,6 +733,12 @@ struct EmitOut {
 // ---------------------------------------------------------------------------------------------
 // Device-side pipeline (shared by cg_clean and cg_clean_partition_wavelet)
 // ---------------------------------------------------------------------------------------------
+static long long wq_scratch_keys(int64_t n) {  // a power of two that holds every bin
+    long long p = 1;
+    while (p < n) p <<= 1;
+    return p;
+}
+
 size_t clean_workspace_bytes(int64_t n, int n_chrom, bool loess) {
     size_t s = 0;
     s += arena_need(n, 1) * 2 + arena_need(n, 4) * 3;          // inputs
@@ -633,6 +747,7 @@ size_t clean_workspace_bytes(int64_t n, int n_chrom, bool loess) {
     s += arena_need(n / LOCAL_SD_WINDOW + 2, 8) + arena_need(n / LOCAL_SD_WINDOW + 2, 1);
     s += arena_need(n, 4) * 2;                                  // outputs
     s += arena_need(n / CMP_TILE + 2, 4);
+    s += arena_need(wq_scratch_keys(n), 8);                     // weighted quantiles beyond the shared-memory sorter
     s += arena_need(1, sizeof(CleanCtl)) + arena_need(256, 1) * 2 + arena_need(256, 4) + arena_need(256, 8) * 2;
     s += sel_state_bytes<uint32_t>(1) + sel_state_bytes<uint32_t>(GC_SEGS) + sel_state_bytes<uint64_t>(std::max(n_chrom, 1));
     if (loess) s += loess_workspace_bytes(n);
@@ -661,6 +776,8 @@ int clean_alloc(cg_ctx* ctx, int64_t n, int n_chrom, CleanDev& d, bool loess) {
     d.kept = arena_take<int32_t>(ctx, n);
     d.count_out = arena_take<float>(ctx, n);
     d.tiles = arena_take<int>(ctx, n / CMP_TILE + 2);
+    d.wq_cap = wq_scratch_keys(n);
+    d.wq_key = arena_take<unsigned long long>(ctx, (size_t)d.wq_cap);
     d.ctl = arena_take<CleanCtl>(ctx, 1);
     d.is_auto = arena_take<uint8_t>(ctx, 256);
     d.is_chry = arena_take<uint8_t>(ctx, 256);
@@ -669,7 +786,7 @@ int clean_alloc(cg_ctx* ctx, int64_t n, int n_chrom, CleanDev& d, bool loess) {
     d.wmad = arena_take<double>(ctx, 256);
     bool ok = d.chrom && d.gc && d.start && d.stop && d.count && d.chrom1 && d.gc1 && d.count1 && d.orig1 &&
               d.chrom2 && d.gc2 && d.alive && d.count2 && d.orig2 && d.wsd && d.wchrom && d.kept &&
-              d.count_out && d.tiles && d.ctl && d.is_auto && d.is_chry && d.wcnt && d.wmed && d.wmad;
+              d.count_out && d.tiles && d.wq_key && d.ctl && d.is_auto && d.is_chry && d.wcnt && d.wmed && d.wmad;
     ok = ok && sel_state_alloc<uint32_t>(ctx, 1, d.sel_size) && sel_state_alloc<uint32_t>(ctx, GC_SEGS, d.sel_gc) &&
          sel_state_alloc<uint64_t>(ctx, std::max(n_chrom, 1), d.sel_win);
     if (ok && loess) {
@@ -816,6 +933,7 @@ static int clean_enqueue_body(cg_ctx* ctx, const cg_clean_opts* o, CleanDev& d) 
             sel_run_scatter<uint32_t, GcCountView>(ctx, gv, d.sel_gc, n);
             CG_LAUNCH(ctx, gc_median_finish_kernel, 1, 128, 0, d.sel_gc, ctl, &ctl->do_norm);
             CG_LAUNCH(ctx, gc_weighted_kernel, GC_BINS, 256, WQ_CAP * 8, d.count2, d.gc2, d.chrom2, d.alive, d.is_auto, ctl, 0, &ctl->do_norm);
+            CG_LAUNCH(ctx, gc_weighted_big_kernel, 1, 1024, 0, d.count2, d.gc2, d.chrom2, d.alive, d.is_auto, ctl, 0, &ctl->do_norm, d.wq_key, d.wq_cap);
             CG_LAUNCH(ctx, normalize_apply_bulk_kernel, dim3(grid_k8, 1), K8_THREADS, k8_smem_bytes(), d.count2, d.gc2, d.alive, d.count2,
                       &ctl->n2, 0LL, ctl->med, &ctl->global_median, &ctl->do_norm, 0LL);
         }
@@ -827,6 +945,7 @@ static int clean_enqueue_body(cg_ctx* ctx, const cg_clean_opts* o, CleanDev& d) 
             sel_run_scatter<uint32_t, GcCountView>(ctx, gq, d.sel_gc, n);
             CG_LAUNCH(ctx, gc_quartile_finish_kernel, 1, 128, 0, d.sel_gc, ctl, &ctl->do_variance);
             CG_LAUNCH(ctx, gc_weighted_kernel, GC_BINS, 256, WQ_CAP * 8, d.count2, d.gc2, d.chrom2, d.alive, d.is_auto, ctl, 1, &ctl->do_variance);
+            CG_LAUNCH(ctx, gc_weighted_big_kernel, 1, 1024, 0, d.count2, d.gc2, d.chrom2, d.alive, d.is_auto, ctl, 1, &ctl->do_variance, d.wq_key, d.wq_cap);
             CG_LAUNCH(ctx, variance_decide_kernel, 1, 1, 0, ctl);
             CG_LAUNCH(ctx, variance_apply_kernel, grid_stream, 256, 0, d.count2, d.gc2, d.alive, ctl);
             // second normalisation when the rescale fired (:516-517)
@@ -838,6 +957,7 @@ static int clean_enqueue_body(cg_ctx* ctx, const cg_clean_opts* o, CleanDev& d) 
                 sel_run_scatter<uint32_t, GcCountView>(ctx, gm, d.sel_gc, n);
                 CG_LAUNCH(ctx, gc_median_finish_kernel, 1, 128, 0, d.sel_gc, ctl, &ctl->variance_fired);
                 CG_LAUNCH(ctx, gc_weighted_kernel, GC_BINS, 256, WQ_CAP * 8, d.count2, d.gc2, d.chrom2, d.alive, d.is_auto, ctl, 0, &ctl->variance_fired);
+                CG_LAUNCH(ctx, gc_weighted_big_kernel, 1, 1024, 0, d.count2, d.gc2, d.chrom2, d.alive, d.is_auto, ctl, 0, &ctl->variance_fired, d.wq_key, d.wq_cap);
                 CG_LAUNCH(ctx, normalize_apply_bulk_kernel, dim3(grid_k8, 1), K8_THREADS, k8_smem_bytes(), d.count2, d.gc2, d.alive,
                           d.count2, &ctl->n2, 0LL, ctl->med, &ctl->global_median, &ctl->variance_fired, 0LL);
             }

@@ -42,6 +42,7 @@ struct CleanCtl {
     double med[GC_BINS];          // per-GC median (NormalizeByGC) ; <= 0 disables the bucket
     float q2[GC_BINS];            // per-GC quartile 2 (NormalizeVarianceByGC localQuartiles.Item2)
     float iqr[GC_BINS];           // per-GC IQR (localIQR), -1 for an empty bucket
+    int wq_big[GC_BINS];          // buckets whose weighted quantiles need more neighbours than the shared-memory sorter holds
 };
 
 // Block-wide exclusive scan of one int per thread (blockDim.x <= 1024); returns the exclusive prefix
@@ -259,6 +260,8 @@ struct CleanDev {
     float* count_out;
     // scratch / control
     int* tiles;
+    unsigned long long* wq_key;  // scratch of gc_weighted_big_kernel: wq_cap keys (a power of two >= n)
+    long long wq_cap;
     CleanCtl* ctl;
     uint8_t* is_auto;
     uint8_t* is_chry;
