@@ -980,7 +980,8 @@ extern "C" int cg_clean(cg_ctx* ctx, const cg_clean_opts* opts, int64_t n, const
                         int64_t* n_out, int32_t* kept_index, float* count_out, double* local_sd,
                         int* gc_norm_skipped) {
     if (!ctx) return CG_ERR_ARG;
-    if (!opts || n < 0 || n > 0x7fff0000LL || n_chrom < 0 || n_chrom > 256 || !n_out || !local_sd || !gc_norm_skipped)
+    if (n_chrom > 256) return cg_fail(ctx, CG_ERR_UNSUPPORTED, "cg_clean: more than 256 chromosomes (contigs): this build addresses chromosomes with 8-bit ids (see DESIGN.md, Limits)");
+    if (!opts || n < 0 || n > 0x7fff0000LL || n_chrom < 0 || !n_out || !local_sd || !gc_norm_skipped)
         return cg_fail(ctx, CG_ERR_ARG, "cg_clean: bad argument");
     ctx->launches = 0;
     ctx->tl = nullptr;

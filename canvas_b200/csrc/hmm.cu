@@ -656,7 +656,8 @@ static int partition_hmm_impl(cg_ctx* ctx, const cg_hmm_opts* o, int n_samples, 
                               const double* coverage, const float* count32, int text_mode, const uint8_t* chrom_selected, int32_t* n_bp,
                               int32_t* bp, uint8_t* states_out) {
     if (!ctx) return CG_ERR_ARG;
-    if (!o || !chrom_off || !n_bp || n_chrom < 0 || n_chrom > HMM_MAX_CHROM || n_samples < 1)
+    if (n_chrom > HMM_MAX_CHROM) return cg_fail(ctx, CG_ERR_UNSUPPORTED, "cg_partition_hmm: more than 256 chromosomes (contigs): this build addresses chromosomes with 8-bit ids (see DESIGN.md, Limits)");
+    if (!o || !chrom_off || !n_bp || n_chrom < 0 || n_samples < 1)
         return cg_fail(ctx, CG_ERR_ARG, "cg_partition_hmm: bad argument");
     if (n_samples > HMM_MAX_SAMPLES) return cg_fail(ctx, CG_ERR_UNSUPPORTED, "cg_partition_hmm: at most 4 samples are segmented jointly");
     if (o->n_states != HMM_NS) return cg_fail(ctx, CG_ERR_UNSUPPORTED, "cg_partition_hmm: the reference model has 5 hidden states");

@@ -902,7 +902,8 @@ int wv_collect(cg_ctx* ctx, const WvPlan& pl, WvDev& d, int32_t* n_bp, int32_t* 
 }
 
 int check_args(cg_ctx* ctx, const cg_wavelet_opts* opts, int n_chrom, const int64_t* chrom_off) {
-    if (!opts || n_chrom < 0 || n_chrom > WV_MAX_CHROM || !chrom_off) return cg_fail(ctx, CG_ERR_ARG, "partition: bad argument");
+    if (n_chrom > WV_MAX_CHROM) return cg_fail(ctx, CG_ERR_UNSUPPORTED, "cg_partition_wavelet: more than 256 chromosomes (contigs): this build addresses chromosomes with 8-bit ids (see DESIGN.md, Limits)");
+    if (!opts || n_chrom < 0 || !chrom_off) return cg_fail(ctx, CG_ERR_ARG, "partition: bad argument");
     if (opts->evenness_window <= 0) return cg_fail(ctx, CG_ERR_ARG, "partition: evenness_window must be positive");
     if (chrom_off[0] != 0) return cg_fail(ctx, CG_ERR_ARG, "partition: chrom_off[0] must be 0");
     for (int c = 0; c < n_chrom; c++)
@@ -1050,7 +1051,8 @@ static int clean_partition_wavelet_impl(cg_ctx* ctx, const cg_clean_opts* copts,
                                         bool exchange, int32_t* owner) {
     if (!ctx) return CG_ERR_ARG;
     if (exchange && !ctx->comm) return cg_fail(ctx, CG_ERR_ARG, "cg_clean_partition_wavelet_sharded: no communicator (cg_comm_init)");
-    if (!copts || !wopts || n < 0 || n > 0x7fff0000LL || n_chrom < 0 || n_chrom > WV_MAX_CHROM || !n_out || !local_sd ||
+    if (n_chrom > WV_MAX_CHROM) return cg_fail(ctx, CG_ERR_UNSUPPORTED, "cg_clean_partition_wavelet: more than 256 chromosomes (contigs): this build addresses chromosomes with 8-bit ids (see DESIGN.md, Limits)");
+    if (!copts || !wopts || n < 0 || n > 0x7fff0000LL || n_chrom < 0 || !n_out || !local_sd ||
         !gc_norm_skipped || !chrom_off_out || !n_bp || !evenness || !evenness_ok || !cv || !cv_has_value || !factor_of_three)
         return cg_fail(ctx, CG_ERR_ARG, "cg_clean_partition_wavelet: bad argument");
     if (wopts->evenness_window <= 0) return cg_fail(ctx, CG_ERR_ARG, "partition: evenness_window must be positive");

@@ -886,7 +886,10 @@ uh_finish_kernel(FinParams p, int c_first) {
             for (int l = threadIdx.x; l < T; l += blockDim.x) { lvl_idx[l] = l; gcnt[l] = lvlcnt[l]; }
             __syncthreads();
             const int cap = n / 3;
-            level_sort_parallel(LevelSorter{lvl_idx, gcnt}, T, piece, prelim, cap, s_sort_counts);
+            // large sub-arrays are partitioned by the whole block here too (stop positions in the survivor scratch, which
+            // is not in use yet): a run of a few thousand exact zeros (chrY of a female sample) makes the tree that deep,
+            // and one thread partitioning thousands of levels out of L2 took 1.6 ms
+            level_sort_parallel(LevelSorter{lvl_idx, gcnt}, T, piece, prelim, cap, s_sort_counts, sv, reinterpret_cast<int*>(svkey));
         }
     }
     __syncthreads();

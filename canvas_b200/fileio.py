@@ -419,19 +419,43 @@ def read_cleaned_columns(path):
     return chrom, np.array(start, np.int32), np.array(stop, np.int32), np.array(count, np.float32)
 
 
+def _runs(chrom):
+    """Chromosome names of a column in order of first appearance."""
+    out, seen = [], set()
+    for c in chrom:
+        if c not in seen:
+            seen.add(c)
+            out.append(c)
+    return out
+
+
+def merge_chromosome_orders(orders):
+    """One chromosome order that every file's own order is a subsequence of (when such an order exists): ids assigned from
+    it make every sample's (id, start) key column ascending, which cg_merge_common_bins requires.  Numbering by first
+    appearance over the files does not: a chromosome that the first file lost completely (chrY filtered out of the mother)
+    but a later file still has mid-genome would get the highest id and make that later file non-monotone.  A name not seen
+    before is inserted right after the file's previous chromosome."""
+    merged = []
+    for order in orders:
+        at = 0
+        for c in order:
+            if c in merged:
+                at = merged.index(c) + 1
+            else:
+                merged.insert(at, c)
+                at += 1
+    return merged
+
+
 def normalize_canvas_clean(engine, cleaned_paths):
     """CanvasRunner.NormalizeCanvasClean (CanvasRunner.cs:883-903): rewrite every sample's .cleaned file with the bins
     common to all samples — four columns, the count printed by float.ToString().  The set intersection runs on the
     GPU (cg_merge_common_bins); rows must be in (chromosome, start) order, which CanvasClean's output is."""
     cols = [read_cleaned_columns(p) for p in cleaned_paths]
-    names = []
-    for chrom, _, _, _ in cols:  # chromosome ids by first appearance over all files (the reference's HashSet order)
-        for c in chrom:
-            if not names or (c != names[-1] and c not in names):
-                names.append(c)
+    names = merge_chromosome_orders([_runs(chrom) for chrom, _, _, _ in cols])
     ids = {c: i for i, c in enumerate(names)}
     if len(names) > 256:
-        raise ValueError("more than 256 chromosomes")
+        raise ValueError("more than 256 chromosomes (contigs): this build addresses chromosomes with 8-bit ids (DESIGN.md, Limits)")
     samples = [(np.array([ids[c] for c in chrom], np.uint8), a, b, v) for chrom, a, b, v in cols]
     r = engine.merge_common_bins(samples)
     chrom0 = cols[0][0]

@@ -212,7 +212,8 @@ def parse_bins(text, n_threads=0):
     if n == -2:
         raise ValueError("malformed line in bin file")
     if n == -3:
-        raise ValueError("more than 256 chromosome runs")
+        raise ValueError("more than 256 chromosome runs (contigs, or chromosomes that reappear later in the file): this build "
+                         "addresses chromosomes with 8-bit ids (DESIGN.md, Limits)")
     if n < 0 or n > cap:
         raise CanvasGpuError(CG_ERR_ARG, "cg_parse_bins failed")
     parts = names.raw.split(b"\0")[:n_names.value]
@@ -710,6 +711,10 @@ class Engine:
         share (the enumeration stops at the shorter one): kept bin indices, ratios, counts."""
         a = np.ascontiguousarray(sample, np.float32)
         b = np.ascontiguousarray(reference, np.float32)
+        if len(a) != len(b) and mode == "lsnorm":
+            # the reference takes each median over its whole file and only then enumerates up to the shorter one
+            # (LSNormRatioCalculator.cs:28-36); medians over truncated lists would silently differ
+            raise CanvasGpuError(CG_ERR_UNSUPPORTED, "normalize_ratio (lsnorm): sample and reference bin lists of different length")
         n = min(len(a), len(b))
         on = None if on_target is None else np.ascontiguousarray(on_target, np.uint8)
         pl = None if ploidy is None else np.ascontiguousarray(ploidy, np.int32)

@@ -385,3 +385,23 @@ def test_numpy_merge_equals_the_dictionary_merge():
     c0, a0 = samples[0][0][got["kept_index"]], samples[0][1][got["kept_index"]]
     assert [(w[0], w[1], w[2]) for w in want] == list(zip(c0.tolist(), a0.tolist(), got["stop"].tolist()))
     assert np.array_equal(np.array([w[3] for w in want], np.float32).T, got["count"])
+
+
+def test_chromosome_order_merged_over_pedigree_files():
+    # ids by first appearance over all files break the (id, start) order when the first file lost a whole chromosome that a
+    # later file still has mid-genome; the merged order keeps every file ascending
+    m = fileio.merge_chromosome_orders([["chr1", "chr2", "chrX"], ["chr1", "chr2", "chr3", "chrX", "chrY"], ["chr2", "chr3", "chrY"]])
+    assert m == ["chr1", "chr2", "chr3", "chrX", "chrY"]
+    for order in (["chr1", "chr2", "chrX"], ["chr1", "chr2", "chr3", "chrX", "chrY"], ["chr2", "chr3", "chrY"]):
+        idx = [m.index(c) for c in order]
+        assert idx == sorted(idx)
+    assert fileio.merge_chromosome_orders([[], ["a"], ["b", "a"]]) == ["b", "a"]
+
+
+def test_more_than_256_contigs_is_reported_not_garbled(tmp_path):
+    # the chromosome cap (8-bit ids) is a documented limit: the readers say so instead of failing somewhere downstream
+    lines = "".join(f"contig{c}\t0\t1000\t100.00\t40\n" for c in range(300))
+    p = tmp_path / "many.binned"
+    p.write_bytes(fileio.gzip_bytes(lines.encode()))
+    with pytest.raises(ValueError, match="256 chromosome"):
+        fileio.read_binned(str(p))
