@@ -224,6 +224,7 @@ struct WvDev {
     unsigned char* rq_sel2;
     unsigned long long* phase_ns;
     unsigned long long* tl_ns;  // debug timeline of the decomposition stages, [C][16]
+    unsigned long long* task_dbg;  // debug: per mid task (chromosome, bins, nodes, ns)
     UhTinyTab* tiny_tab;
     int* pack;  // results packed for one download: n_bp[C], depth[C], total, then the breakpoint lists back to back
     // sizes the arrays were allocated for (wv_alloc); a plan run on them must not exceed any
@@ -300,7 +301,7 @@ size_t wv_workspace_bytes(const WvPlan& pl) {
     s += arena_need(N + 1, 4) * 5 + arena_need(N + 1, 8) * 2 + arena_need(N / 32 + C + 2, 4);
     s += arena_need(C + 1, 4) + arena_need(N + 1, 4);
     s += arena_need((C + 1) * RQ_BUCKETS, 8) + arena_need(N + 1, 8) + arena_need((size_t)(pl.rq_ntiles + 1) * RQ_BUCKETS, 2) * 2;
-    s += arena_need((size_t)(pl.rq_ntiles + C + 2) * RQ_BUCKETS, 4) + arena_need(C + 2, 4) + arena_need((C + 1) * 8, 8) + arena_need((C + 1) * 16, 8) + arena_need(1, sizeof(UhTinyTab)) + arena_need(WV_PACK_INTS, 4) + arena_need(C + 2, 8) + arena_need(C + 2, 4) + arena_need(C + 2, 1);
+    s += arena_need((size_t)(pl.rq_ntiles + C + 2) * RQ_BUCKETS, 4) + arena_need(C + 2, 4) + arena_need((C + 1) * 8, 8) + arena_need((C + 1) * 16, 8) + arena_need(2 * UH_TASK_DBG_CAP + 2, 8) + arena_need(1, sizeof(UhTinyTab)) + arena_need(WV_PACK_INTS, 4) + arena_need(C + 2, 8) + arena_need(C + 2, 4) + arena_need(C + 2, 1);
     return s + (1 << 16);
 }
 
@@ -373,6 +374,7 @@ int wv_alloc(cg_ctx* ctx, const WvPlan& pl, WvDev& d, double* cov_dev_existing, 
     d.rq_cum = arena_take<unsigned>(ctx, (size_t)(pl.rq_ntiles + C + 2) * RQ_BUCKETS);
     d.phase_ns = arena_take<unsigned long long>(ctx, (C + 1) * 8);
     d.tl_ns = arena_take<unsigned long long>(ctx, (C + 1) * 16);
+    d.task_dbg = arena_take<unsigned long long>(ctx, 2 * UH_TASK_DBG_CAP + 2);
     d.pack = arena_take<int>(ctx, WV_PACK_INTS);
     d.rq_off2 = arena_take<long long>(ctx, C + 2);
     d.rq_tfirst2 = arena_take<int>(ctx, C + 2);
@@ -643,6 +645,8 @@ int wv_enqueue(cg_ctx* ctx, const cg_wavelet_opts* o, const WvPlan& pl, WvDev& d
     if (fp.phase_ns) cudaMemsetAsync(d.phase_ns, 0, (size_t)(C + 1) * 64, s);
     up.tl_ns = fp.phase_ns && d.tl_ns ? d.tl_ns : nullptr;
     if (up.tl_ns) cudaMemsetAsync(d.tl_ns, 0, (size_t)(C + 1) * 128, s);
+    up.task_dbg = up.tl_ns && d.task_dbg ? d.task_dbg : nullptr;
+    if (up.task_dbg) cudaMemsetAsync(d.task_dbg, 0, 8, s);
     fp.is_germline = o->is_germline; fp.min_size = o->min_size; fp.n_chrom = C; fp.pad = 0;
     fp.lvl_idx = d.lvl_idx; fp.sv = d.sv; fp.svkey = d.svkey; fp.bitmap = d.bitmap; fp.piece = d.piece; fp.rec = d.rec;
     fp.prelim = d.prelim; fp.lvl_first = d.lvl_first; fp.n_bp = d.n_bp; fp.bp = d.bp;
@@ -829,6 +833,23 @@ int wv_collect(cg_ctx* ctx, const WvPlan& pl, WvDev& d, int32_t* n_bp, int32_t* 
         std::vector<unsigned long long> ph((size_t)(pl.n_chrom + 1) * 8, 0), tn((size_t)(pl.n_chrom + 1) * 16, 0);
         cudaMemcpy(ph.data(), d.phase_ns, ph.size() * 8, cudaMemcpyDeviceToHost);
         cudaMemcpy(tn.data(), d.tl_ns, tn.size() * 8, cudaMemcpyDeviceToHost);
+        if (d.task_dbg) {
+            // the slowest mid-stage subtrees: a stage ends with its slowest CTA
+            std::vector<unsigned long long> td(2 * UH_TASK_DBG_CAP + 2, 0);
+            cudaMemcpy(td.data(), d.task_dbg, td.size() * 8, cudaMemcpyDeviceToHost);
+            const size_t cnt = (size_t)std::min<unsigned long long>(td[0], UH_TASK_DBG_CAP);
+            std::vector<size_t> idx(cnt);
+            for (size_t i = 0; i < cnt; i++) idx[i] = i;
+            std::sort(idx.begin(), idx.end(), [&](size_t a, size_t b) { return (td[2 + 2 * a] & 0xffffffffull) > (td[2 + 2 * b] & 0xffffffffull); });
+            double tot = 0;
+            for (size_t i = 0; i < cnt; i++) tot += (double)(td[2 + 2 * i] & 0xffffffffull);
+            fprintf(stderr, "[mid] %zu subtrees, %.1f us of CTA time in total; slowest:\n", cnt, tot * 1e-3);
+            for (size_t k = 0; k < std::min<size_t>(cnt, 12); k++) {
+                const size_t i = idx[k];
+                fprintf(stderr, "[mid]   chr %2llu bins %6llu nodes %5llu %8.1f us\n", td[1 + 2 * i] >> 32, td[1 + 2 * i] & 0xffffffffull,
+                        td[2 + 2 * i] >> 32, (double)(td[2 + 2 * i] & 0xffffffffull) * 1e-3);
+            }
+        }
         {
             // pipeline of every chromosome: start (relative to the first decomposition kernel) and duration of each stage, us
             const unsigned long long t0 = h->t_first;

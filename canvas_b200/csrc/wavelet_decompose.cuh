@@ -48,7 +48,9 @@ struct UhParams {
     const UhChromPlan* cp;   // [n_chrom] slices of the arrays above
     WvCtl* ctl;
     unsigned long long* tl_ns;  // debug timeline (nullable): [n_chrom][16], per stage k: [2k] = ~(earliest start), [2k+1] = latest end
+    unsigned long long* task_dbg;  // debug (nullable): [0] = entries used, then per mid task {chrom << 32 | bins, nodes << 32 | ns}
 };
+constexpr int UH_TASK_DBG_CAP = 16384;
 
 // debug timeline of the per-chromosome pipelines (CANVAS_DEBUG): called by one thread per block
 __device__ inline void uh_stamp(unsigned long long* tl, int c, int stage, bool end) {
@@ -395,6 +397,10 @@ uh_mid_kernel(UhParams p, int c_self) {
         }
         __syncthreads();
         if (s_idx >= total) break;
+        unsigned long long dbg_t0 = 0;
+        unsigned dbg_nodes = 0;
+        const int dbg_bins = s_stack[0].e - s_stack[0].s + 1;
+        if (p.task_dbg && threadIdx.x == 0) asm volatile("mov.u64 %0, %globaltimer;" : "=l"(dbg_t0));
         // every thread mirrors the stack pointer; thread 0 alone writes the stack
         int sp = 1;
         while (sp > 0) {
@@ -429,7 +435,7 @@ uh_mid_kernel(UhParams p, int c_self) {
                 if (sc > fbest || (sc == fbest && mm < fm)) { fbest = sc; fm = mm; fv = s_wv[parity][w]; }
             }
             parity ^= 1;
-            if (threadIdx.x == 0) v_mid += (unsigned long long)n;
+            if (threadIdx.x == 0) { v_mid += (unsigned long long)n; dbg_nodes++; }
             if (fbest == 0.0 || fm == 0x7fffffff) {
                 for (int k = threadIdx.x; k < n - 1; k += NT) atomicAdd(&p.lvlcnt[loff + level + k], 1u);
                 if (threadIdx.x == 0) n_mid += (unsigned long long)(n - 1);
@@ -458,6 +464,15 @@ uh_mid_kernel(UhParams p, int c_self) {
             }
             sp += (lmid ? 1 : 0) + (rmid ? 1 : 0);
             __syncthreads();  // thread 0's stack writes before the next pop
+        }
+        if (p.task_dbg && threadIdx.x == 0) {
+            unsigned long long t1;
+            asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t1));
+            const unsigned long long i = atomicAdd(&p.task_dbg[0], 1ull);
+            if (i < UH_TASK_DBG_CAP) {
+                p.task_dbg[1 + 2 * i] = ((unsigned long long)c_self << 32) | (unsigned)dbg_bins;
+                p.task_dbg[2 + 2 * i] = ((unsigned long long)dbg_nodes << 32) | (unsigned)min(t1 - dbg_t0, 0xffffffffull);
+            }
         }
         __syncthreads();
     }

@@ -77,7 +77,12 @@ def test_ratio_special_values(eng):
             assert np.array_equal(want[k], got[k], equal_nan=True), (mode, k)
     assert len(eng.normalize_ratio(np.zeros(0), np.zeros(0))["ratio"]) == 0
     # the shorter list ends the enumeration (eSampleBins.MoveNext() && eReferenceBins.MoveNext())
-    assert len(eng.normalize_ratio(np.ones(10), np.ones(4))["ratio"]) == 4
+    assert len(eng.normalize_ratio(np.ones(10), np.ones(4), mode="raw")["ratio"]) == 4
+    # ... but LSNorm takes each median over its WHOLE file first (LSNormRatioCalculator.cs:28-36): lists of different
+    # length are refused rather than normalised with medians of truncated lists
+    with pytest.raises(native.CanvasGpuError) as e:
+        eng.normalize_ratio(np.ones(10), np.ones(4), mode="lsnorm")
+    assert e.value.code == native.CG_ERR_UNSUPPORTED
 
 
 @pytest.mark.parametrize("s,n,masked", [(2, 1000, False), (6, 200001, True), (3, 3100000, False), (4, 5, False)])
