@@ -659,6 +659,9 @@ int wv_enqueue(cg_ctx* ctx, const cg_wavelet_opts* o, const WvPlan& pl, WvDev& d
     const size_t uh_smem = sizeof(UhWarpScratch) * (UH_SMALL_THREADS / 32);
     if (!ctx->uh_attrs_set) {
         cudaFuncSetAttribute(uh_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)uh_smem);
+        cudaFuncSetAttribute(uh_mid_kernel<1024, 4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((UH_MID_MAX + 2) * sizeof(double)));
+        cudaFuncSetAttribute(uh_mid_kernel<512, 4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((UH_MID_MAX + 2) * sizeof(double)));
+        cudaFuncSetAttribute(uh_mid_kernel<256, 4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((UH_MID_MAX + 2) * sizeof(double)));
         cudaFuncSetAttribute(uh_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fin_smem_bytes());
         ctx->uh_attrs_set = true;
     }
@@ -668,6 +671,7 @@ int wv_enqueue(cg_ctx* ctx, const cg_wavelet_opts* o, const WvPlan& pl, WvDev& d
     // once into a CUDA graph and replayed: one launch instead of ~150, every chromosome's first kernel starts at once, and
     // ranks that share a host no longer queue behind each other's launches.  A shape is captured the second time it is seen.
     static const int mid_threads = getenv("CANVAS_MID_THREADS") ? atoi(getenv("CANVAS_MID_THREADS")) : UH_MID_THREADS;
+    const size_t mid_smem = (size_t)(UH_MID_MAX + 2) * sizeof(double);
     auto enqueue_pipelines = [&](const long long* loff, cudaStream_t root) -> int {
         std::vector<int> order;
         for (int c = 0; c < C; c++) {
@@ -705,10 +709,15 @@ int wv_enqueue(cg_ctx* ctx, const cg_wavelet_opts* o, const WvPlan& pl, WvDev& d
             }
             if (len > UH_SMALL_MAX)
             {
-                const int mid_grid = (int)std::min<long long>(64, std::max<long long>(1, len / 2048));
-                if (mid_threads >= 1024) CG_LAUNCH(ctx, (uh_mid_kernel<1024, 16>), mid_grid, 1024, 0, up, c);
-                else if (mid_threads >= 512) CG_LAUNCH(ctx, (uh_mid_kernel<512, 16>), mid_grid, 512, 0, up, c);
-                else CG_LAUNCH(ctx, (uh_mid_kernel<256, 8>), mid_grid, 256, 0, up, c);
+                if (mid_threads > 0) {  // subtree staged in shared memory (default)
+                    const int mid_grid = (int)std::min<long long>(32, std::max<long long>(1, len / 8192));
+                    if (mid_threads >= 1024) CG_LAUNCH(ctx, (uh_mid_kernel<1024, 4, true>), mid_grid, 1024, mid_smem, up, c);
+                    else if (mid_threads >= 512) CG_LAUNCH(ctx, (uh_mid_kernel<512, 4, true>), mid_grid, 512, mid_smem, up, c);
+                    else CG_LAUNCH(ctx, (uh_mid_kernel<256, 4, true>), mid_grid, 256, mid_smem, up, c);
+                } else {                // CANVAS_MID_THREADS=0: every node straight from L2 (the earlier form, kept for A/B runs)
+                    const int mid_grid = (int)std::min<long long>(64, std::max<long long>(1, len / 2048));
+                    CG_LAUNCH(ctx, (uh_mid_kernel<256, 8, false>), mid_grid, 256, 0, up, c);
+                }
             }
             if (len > UH_TINY_MAX)
                 CG_LAUNCH(ctx, uh_small_kernel, (int)std::min<long long>(ctx->num_sms, std::max<long long>(1, len / 1024)), UH_SMALL_THREADS, uh_smem, up, c);

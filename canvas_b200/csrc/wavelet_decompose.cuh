@@ -135,14 +135,15 @@ __device__ inline void warp_argmax(double& score, int& m) {
 
 // Scan split positions [m_lo, m_hi) of a node with NT cooperating threads, U loads in flight each.
 // Candidates are compared inside a thread by cross-multiplication (no division in the loop).
-template <int NT, int U>
+// GLOBAL = false: q points into shared memory (a subtree's prefix sums staged there).
+template <int NT, int U, bool GLOBAL = true>
 __device__ inline void uh_scan(const double* __restrict__ q, int m_lo, int m_hi, int tid, double base, double mu, double nn,
                                double& bnum, double& bden, int& bm, double& bv) {
     int m = m_lo + tid;
     for (; m + (U - 1) * NT < m_hi; m += U * NT) {
         double v[U];
 #pragma unroll
-        for (int u = 0; u < U; u++) v[u] = __ldg(q + m + u * NT);
+        for (int u = 0; u < U; u++) v[u] = GLOBAL ? __ldg(q + m + u * NT) : q[m + u * NT];
 #pragma unroll
         for (int u = 0; u < U; u++) {
             const double a = (double)(m + u * NT + 1);
@@ -152,7 +153,7 @@ __device__ inline void uh_scan(const double* __restrict__ q, int m_lo, int m_hi,
         }
     }
     for (; m < m_hi; m += NT) {
-        const double vv = __ldg(q + m);
+        const double vv = GLOBAL ? __ldg(q + m) : q[m];
         const double a = (double)(m + 1);
         const double D = fma(-a, mu, vv - base);
         const double num = D * D, den = a * (nn - a);
@@ -366,11 +367,14 @@ uh_chain_kernel(UhParams p, int c_self) {
 // ---------------------------------------------------------------------------------------------
 constexpr int UH_MID_STACK = 32;
 
-// NT threads per CTA: a mid node is one round of loads for every thread when NT * U covers it; the subtree is a chain of
-// dependent nodes, so the stage is bound by the latency of a node, not by throughput
-template <int NT, int U>
+// A chromosome has only a dozen or two of these subtrees, and the big ones are chains of 100-200 dependent nodes of
+// 10-16 thousand bins each (noise splits peel a few hundred bins off a node), so the stage lasts as long as its slowest
+// chain and a node costs what one SM can pull out of L2 (~100 GB/s: 1.5-5 us).  STAGED: the subtree's prefix sums (at most
+// UH_MID_MAX + 1 doubles = 128 KB) are copied to shared memory once and every node of the subtree scans them there.
+template <int NT, int U, bool STAGED>
 __global__ void __launch_bounds__(NT, NT >= 1024 ? 1 : (NT >= 512 ? 2 : 4))
 uh_mid_kernel(UhParams p, int c_self) {
+    extern __shared__ __align__(16) double s_pz[];  // STAGED: prefix sums of the current subtree, s_pz[0] = the one before its first bin
     __shared__ UhTask s_stack[UH_MID_STACK];
     __shared__ double s_ws[2][NT / 32], s_wv[2][NT / 32];
     __shared__ int s_wm2[2][NT / 32];
@@ -401,6 +405,12 @@ uh_mid_kernel(UhParams p, int c_self) {
         unsigned dbg_nodes = 0;
         const int dbg_bins = s_stack[0].e - s_stack[0].s + 1;
         if (p.task_dbg && threadIdx.x == 0) asm volatile("mov.u64 %0, %globaltimer;" : "=l"(dbg_t0));
+        const int root_s = s_stack[0].s;
+        if (STAGED) {
+            const double* __restrict__ src = pz + (p.off[s_stack[0].c] + s_stack[0].c) + root_s;
+            for (int i = threadIdx.x; i <= dbg_bins; i += NT) s_pz[i] = __ldg(src + i);
+            __syncthreads();
+        }
         // every thread mirrors the stack pointer; thread 0 alone writes the stack
         int sp = 1;
         while (sp > 0) {
@@ -416,7 +426,8 @@ uh_mid_kernel(UhParams p, int c_self) {
             const double mu = T / nn;
             double bnum = -1.0, bden = 1.0, bv = 0.0;
             int bm = 0x7fffffff;
-            uh_scan<NT, U>(pz + p0 + s + 1, 0, n - 1, threadIdx.x, base, mu, nn, bnum, bden, bm, bv);
+            if (STAGED) uh_scan<NT, U, false>(s_pz + (s - root_s) + 1, 0, n - 1, threadIdx.x, base, mu, nn, bnum, bden, bm, bv);
+            else uh_scan<NT, U>(pz + p0 + s + 1, 0, n - 1, threadIdx.x, base, mu, nn, bnum, bden, bm, bv);
             double best = bnum >= 0.0 ? bnum / bden : -1.0;
             int best_m = bm;
             warp_argmax(best, best_m);

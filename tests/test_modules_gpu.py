@@ -30,10 +30,14 @@ def test_clean_then_partition_on_files(tmp_path, engine):
     # expected .cleaned: oracle on what the reader parses back from the .binned text
     sb = fileio.read_binned(binned)
     o = ora.clean(sb.chrom, sb.is_autosome, sb.is_chr_y, sb.start, sb.stop, sb.count, sb.gc)
-    exp = str(tmp_path / "exp.cleaned")
     k = o["kept_index"]
-    fileio.write_binned(exp, sb.names, sb.chrom[k], sb.start[k], sb.stop[k], o["count"], sb.gc[k])
-    assert gzip.open(cleaned, "rt").read() == gzip.open(exp, "rt").read()
+    # expected text without the product's formatters: the oracle's string-based F2 rounding (oracle/clean.cpp
+    # ora_f2_roundtrip: seven significant digits, then half-up on the decimal string) gives the two-decimal value, and
+    # Python's own %.2f prints a two-decimal double exactly
+    f2 = ora.f2_roundtrip(o["count"])
+    exp_text = "".join(f"{sb.names[c]}\t{a}\t{b}\t{'%.2f' % v}\t{g}\n" for c, a, b, v, g in
+                       zip(sb.chrom[k].tolist(), sb.start[k].tolist(), sb.stop[k].tolist(), f2.tolist(), sb.gc[k].tolist()))
+    assert gzip.open(cleaned, "rt").read() == exp_text
     assert fileio.read_metric(lsd, "localSD") == float(fileio.dotnet_double(o["local_sd"]))
 
     assert modules.main(["CanvasPartition", "-i", cleaned, "-v", vaf, "-o", part, "-r", str(tmp_path), "-g",
@@ -44,9 +48,18 @@ def test_clean_then_partition_on_files(tmp_path, engine):
     p = ora.partition_wavelet(off, np.concatenate([cov[c] for c in order]), is_germline=True, evenness_window=6000,
                               n_threads=4)
     seg = {c: fileio.derive_segments(p["breakpoints"][i], lens[i], start[c], end[c]) for i, c in enumerate(order)}
+    # expected .partitioned text, again without the product's writer: double.ToString() of a two-decimal coverage is its
+    # shortest decimal form (Segmentation.cs:247), i.e. %.2f with trailing zeros dropped
+    segs = fileio.post_process_segments(order, seg, start, end, cov)
+    got_rows = [ln.split("\t") for ln in gzip.open(part, "rt").read().splitlines()]
+    exp_rows = []
+    for c in order:
+        for a, b, v in zip(start[c].tolist(), end[c].tolist(), cov[c].tolist()):
+            exp_rows.append([c, str(a), str(b), ("%.2f" % v).rstrip("0").rstrip(".")])
+    assert [r[:4] for r in got_rows] == exp_rows
     expected = str(tmp_path / "exp.partitioned")
-    fileio.write_partitioned(expected, order, fileio.post_process_segments(order, seg, start, end, cov))
-    assert gzip.open(part, "rt").read() == gzip.open(expected, "rt").read()
+    fileio.write_partitioned(expected, order, segs)
+    assert [r[4] for r in got_rows] == [ln.split("\t")[4] for ln in gzip.open(expected, "rt").read().splitlines()]
     got_ev = fileio.read_metric(evn, "evenness")
     assert abs(got_ev - p["evenness"]) <= 1e-9 * abs(p["evenness"])
     ids = [int(l.split("\t")[4]) for l in gzip.open(part, "rt").read().splitlines()]
