@@ -224,6 +224,8 @@ def main():
     ap.add_argument("--scale", type=float, default=1.0, help="shrink the genome (debugging only; 1.0 = BASELINE config)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="N > 1: skip the strong-scaling and config-4 side measurements")
+    ap.add_argument("--method", default="wavelets", choices=["wavelets", "cbs"],
+                    help="segmentation method of the Partition stage (cbs: one GPU, config 2; Clean and Partition as two calls)")
     args = ap.parse_args()
     W = max(args.warmup, 0)
     K = max(args.steps, 1)
@@ -321,6 +323,65 @@ def main():
                 "launches_rank0": tm.get("launches", 0) // max(n_steps, 1),
                 "h2d_bytes": 14 * len(trio[0]) * (3 if world == 1 else 1),
                 "timing": "wall clock around the chain of C-ABI calls, host buffers in and out, max over ranks"}
+
+    # ------------------------------------------------------------------ CanvasPartition -m CBS on the config-2 sample
+    if args.method == "cbs":
+        s = synth.make_sample(config=2, sample=0, scale=args.scale)
+        inp = pinned_sample(s)
+        acc = {"clean": 0.0, "cbs": 0.0, "launches": 0}
+        res = {}
+
+        def step():
+            c = eng.clean(inp["chrom"], s.is_autosome, s.is_chr_y, inp["start"], inp["stop"], inp["count"], inp["gc"])
+            acc["clean"] += eng.last_kernel_ms
+            acc["launches"] += eng.last_launches
+            off = synth.chrom_offsets(s.chrom[c["kept_index"]], len(s.names))
+            from canvas_b200 import textcodec
+            r = eng.partition_cbs(off, textcodec.f2_roundtrip(c["count"]))
+            acc["cbs"] += r["kernel_ms"]
+            acc["launches"] += 1
+            res["r"], res["bins"] = r, len(c["kept_index"])
+        eng.cbs_boundary()
+        for _ in range(W):
+            step()
+        acc.update(clean=0.0, cbs=0.0, launches=0)
+        sampler = ClockSampler(local_rank)
+        sampler.start()
+        walls = timed(step, K)
+        clocks = sampler.summary()
+        r = res["r"]
+        kern_ms = (acc["clean"] + acc["cbs"]) / K
+        wall_ms = 1e3 * sum(walls) / K
+        hbm, peak_src = peaks()
+        # a test on n bins reads the partial sums once and shuffles + scans them once per executed permutation
+        alg = 16.0 * (r["perm_steps"] + r["edge_steps"] + res["bins"])
+        line = {"metric": METRIC, "value": len(s) / kern_ms / 1e3, "unit": UNIT, "n_gpus": 1, "steps": K, "warmup": W, "ms_per_step": kern_ms,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": WORKLOADS[2].replace("wavelets (-g)", "-m CBS (hybrid p-values, 10000 permutations)"), "bins_per_sample": len(s),
+                           "samples": 1, "l2": "flushed between steps (256 MiB device write)", "method": "cbs"},
+                "e2e": {"value": len(s) / wall_ms / 1e3, "unit": UNIT, "ms_per_step": wall_ms, "h2d_bytes_per_step": 14 * len(s) + 8 * res["bins"],
+                        "d2h_bytes_per_step": 8 * res["bins"] + 12 * sum(len(x["len"]) for x in r["segments"]),
+                        "timing": "wall clock around cg_clean + the host's .cleaned round trip + cg_partition_cbs, pinned inputs"},
+                "gpu_launches": acc["launches"], "stages_ms": {"clean": acc["clean"] / K, "cbs": acc["cbs"] / K},
+                "cbs": {"tests": r["tests"], "permutations": r["perms"], "permuted_bins": r["perm_steps"], "edge_draws": r["edge_steps"],
+                        "segments": int(sum(len(x["len"]) for x in r["segments"])), "phase_ms_slowest_chromosome": r["phase_ms"]},
+                "roofline": {"kernel": "cbs_kernel (one cluster per chromosome)", "bound": "hbm", "achieved": alg / (acc["cbs"] / K * 1e-3) / 1e9,
+                             "peak": hbm, "unit": "GB/s", "frac": alg / (acc["cbs"] / K * 1e-3) / 1e9 / hbm, "traffic": None,
+                             "algorithmic_bytes": alg, "peak_source": peak_src,
+                             "note": "16 B x (permuted bins + edge draws + bins): dependent Fisher-Yates chains and the MT19937 stream bound it, not HBM"},
+                "clocks": clocks, "device": eng.describe()}
+        if not args.no_cpu_baseline:
+            from oracle import pyoracle as ora
+            threads = os.cpu_count() or 1
+            c = ora.clean(s.chrom, s.is_autosome, s.is_chr_y, s.start, s.stop, s.count, s.gc)
+            off = synth.chrom_offsets(s.chrom[c["kept_index"]], len(s.names))
+            t0 = time.perf_counter()
+            ora.partition_cbs(off, ora.f2_roundtrip(c["count"]), n_threads=threads)
+            sec = time.perf_counter() - t0
+            line["cpu_baseline"] = {"value": res["bins"] / sec / 1e6, "unit": UNIT, "cores": threads, "kind": "port",
+                                    "sample": "CBS of the full cleaned config-2 sample, one thread per chromosome", "partition_ms": sec * 1e3}
+        _emit(line)
+        return 0
 
     if config == 4:
         sampler = ClockSampler(local_rank)

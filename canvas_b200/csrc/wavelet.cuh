@@ -21,7 +21,7 @@ constexpr int WV_SCAN_TILE = 2048;
 constexpr int UH_MID_MAX = 16384;   // nodes above this size: stage A (thread-block clusters)
 constexpr int UH_SMALL_MAX = 1024;  // nodes up to this size: a whole subtree is done by one warp (stage S)
 constexpr int UH_TINY_MAX = 16;     // nodes up to this size: sequential reference recurrence per thread (stage T)
-constexpr int UH_MID_THREADS = 512;  // default CTA size of the mid stage (CANVAS_MID_THREADS: 256 / 512 / 1024, 0 = unstaged form)
+constexpr int UH_MID_THREADS = 0;    // mid stage: 0 = every node straight from L2, 256 threads (default); CANVAS_MID_THREADS=256 / 512 / 1024 = subtree staged in shared memory (A/B: profiles/rd2o_*, no gain)
 constexpr int UH_SMALL_THREADS = 256;
 constexpr int UH_THREADS = 512;
 constexpr int UH_CLUSTER = 8;        // CTAs (SMs) cooperating on one chain of big nodes

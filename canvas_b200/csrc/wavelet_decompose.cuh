@@ -502,7 +502,6 @@ uh_mid_kernel(UhParams p, int c_self) {
 constexpr int UH_WARP_STACK = 16;
 
 struct UhWarpScratch {
-    double pz[UH_SMALL_MAX + 2];  // prefix sums of the warp's current subtree: pz[0] = the one before its first bin
     UhTask st[UH_WARP_STACK];
     UhOutBuf<UhTinyTask, 32> tiny_out;
 };
@@ -531,15 +530,9 @@ uh_small_kernel(UhParams p, int c_self) {
         if (lane == 0) idx = atomicAdd(&cc->small_head_.v, 1);
         idx = __shfl_sync(0xffffffffu, idx, 0);
         if (idx >= total) break;
-        const UhTask root = small_list[idx];
-        if (lane == 0) ws.st[0] = root;
-        // the subtree is a chain of a few dozen dependent nodes of a few hundred bins: its prefix sums (<= 1025 doubles) are
-        // staged in shared memory once, so that a node costs a shared-memory scan instead of an L2 round trip
-        {
-            const double* __restrict__ src = pz + p0 + root.s;
-            const int cnt = root.e - root.s + 2;
-            for (int i = lane; i < cnt; i += 32) ws.pz[i] = __ldg(src + i);
-        }
+        // (staging the subtree's prefix sums in shared memory, as the mid stage can, was measured here too: 75 KB per CTA cost
+        // more occupancy than the L2 round trips it saved — profiles/rd2p_*)
+        if (lane == 0) ws.st[0] = small_list[idx];
         __syncwarp();
         int sp = 1;
         while (sp > 0) {
@@ -554,7 +547,7 @@ uh_small_kernel(UhParams p, int c_self) {
             const double mu = T / nn;
             double bnum = -1.0, bden = 1.0, bv = 0.0;
             int bm = 0x7fffffff;
-            uh_scan<32, 4, false>(ws.pz + (s - root.s) + 1, 0, n - 1, lane, base, mu, nn, bnum, bden, bm, bv);
+            uh_scan<32, 4>(pz + p0 + s + 1, 0, n - 1, lane, base, mu, nn, bnum, bden, bm, bv);
             double best = bnum >= 0.0 ? bnum / bden : -1.0;
             int best_m = bm;
             warp_argmax(best, best_m);

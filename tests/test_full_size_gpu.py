@@ -114,3 +114,38 @@ def test_config4_trio_clean_merge_hmm(engine):
         assert np.array_equal(got["states"], want["states"])
         assert all(a.tolist() == b.tolist() for a, b in zip(got["breakpoints"], want["breakpoints"]))
         assert all(a.tolist() == b.tolist() for a, b in zip(chain["breakpoints"][k], want["breakpoints"]))
+
+
+def test_config2_cbs_whole_genome(engine):
+    # CanvasPartition -m CBS on the whole cleaned config-2 sample (3.0 M bins, ~34 000 permutations): identical segments, means
+    # and random-stream consumption as the oracle's DNAcopy restatement on every chromosome
+    s = synth.make_sample(config=2, sample=0)
+    c = engine.clean(s.chrom, s.is_autosome, s.is_chr_y, s.start, s.stop, s.count, s.gc)
+    off = synth.chrom_offsets(s.chrom[c["kept_index"]], len(s.names))
+    cov = textcodec.f2_roundtrip(c["count"])
+    got = engine.partition_cbs(off, cov)
+    want = ora.partition_cbs(off, cov, n_threads=16)
+    for ci, (w, g) in enumerate(zip(want["segments"], got["segments"])):
+        assert np.array_equal(w["len"], g["len"]) and np.array_equal(w["mean"], g["mean"]), ci
+    for k in ("tests", "perms", "perm_steps", "edge_steps"):
+        assert want[k] == got[k], k
+    assert got["perms"] > 10000
+
+
+def test_config2_loess_mode_full_size(engine, golden_dir):
+    # CanvasClean -m LOESS on the whole config-2 sample.  The oracle needs two minutes for it (its golden-section search
+    # evaluates O(n) fits per step), so its full-size result is a committed fixture (tools/make_golden_loess_full.py): the
+    # kept bins as a SHA-256, every 997th normalised count, the local-SD metric.  Kept bins exact, values within the
+    # north star's 1e-5 (sums of ~3 M terms are grouped differently on the device; the oracle itself is pinned by
+    # TestLoessInterpolator)
+    import hashlib
+    import json
+    import os
+    g = json.load(open(os.path.join(golden_dir, "loess_config2_full.json")))
+    s = synth.make_sample(config=g["config"], sample=g["sample"])
+    assert len(s) == g["bins"]
+    a = engine.clean(s.chrom, s.is_autosome, s.is_chr_y, s.start, s.stop, s.count, s.gc, gc_mode=1)
+    assert len(a["kept_index"]) == g["kept"]
+    assert hashlib.sha256(np.ascontiguousarray(a["kept_index"], np.int32).tobytes()).hexdigest() == g["kept_sha256"]
+    assert np.allclose(a["count"][::g["step"]], np.array(g["counts"], np.float32), rtol=1e-5, atol=0)
+    assert abs(a["local_sd"] - g["local_sd"]) <= 1e-5 * abs(g["local_sd"])
