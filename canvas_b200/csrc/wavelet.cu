@@ -531,6 +531,12 @@ int wv_enqueue(cg_ctx* ctx, const cg_wavelet_opts* o, const WvPlan& pl, WvDev& d
     CG_TL(ctx, "host wait + plan");
     cudaEventRecord(ctx->stage_ev[2], s);
     ctx->stage_used[1] = true;
+    const bool dbg_on = getenv("CANVAS_DEBUG") != nullptr;
+    if (dbg_on) {  // debug timelines of the pipelines: cleared before anything that may stamp them
+        cudaMemsetAsync(d.phase_ns, 0, (size_t)(C + 1) * 64, s);
+        if (d.tl_ns) cudaMemsetAsync(d.tl_ns, 0, (size_t)(C + 1) * 128, s);
+        if (d.task_dbg) cudaMemsetAsync(d.task_dbg, 0, 8, s);
+    }
     // ---- range-quantile index for the medians of the finish stage: needs only the coverage, and is enqueued first so
     // that the device has work while the host is still launching the many small kernels of the scalars
     if (!rq_index_done) {
@@ -581,6 +587,7 @@ int wv_enqueue(cg_ctx* ctx, const cg_wavelet_opts* o, const WvPlan& pl, WvDev& d
         ctx->stream = main_s;
         // ---- main stream: prefix sums, then medians and MADs of the coverage windows / chromosomes on integer hundredths
         enqueue_scan();
+        CG_CUDA(ctx, cudaEventRecord(ctx->ev_scan, ctx->stream));  // the decomposition's chains and mid stage need nothing else
         CG_TL(ctx, "scan");
         CovView32 cv1{d.hq, nullptr}, cv2{d.hq, d.m2};
         CG_LAUNCH(ctx, wv_request32_kernel, rq_grid, 128, 0, d.sel32, sp, 1);
@@ -596,6 +603,7 @@ int wv_enqueue(cg_ctx* ctx, const cg_wavelet_opts* o, const WvPlan& pl, WvDev& d
         enqueue_evenness();
         CG_TL(ctx, "evenness");
         enqueue_scan();
+        CG_CUDA(ctx, cudaEventRecord(ctx->ev_scan, ctx->stream));
         CG_TL(ctx, "scan");
         enqueue_triplets();
         CG_TL(ctx, "triplets");
@@ -629,8 +637,15 @@ int wv_enqueue(cg_ctx* ctx, const cg_wavelet_opts* o, const WvPlan& pl, WvDev& d
 
     CG_TL(ctx, "wave3 + cv");
     cudaEventRecord(ctx->stage_ev[3], s);
-    cudaEventRecord(ctx->stage_ev[4], s);
+    CG_CUDA(ctx, cudaEventRecord(ctx->ev_thr, s));  // thresholds (sigma, cand_thr) exist: the small / tiny stages and the finish may run
     ctx->stage_used[2] = true;
+    // The chromosome pipelines run on their own root stream from the moment the prefix sums exist: chains and the mid stage
+    // record EVERY node as a candidate (a few hundred per chromosome; the finish stage applies the real threshold anyway),
+    // so they need no threshold and overlap the order statistics above; a chromosome's small stage waits for ev_thr.
+    cudaStream_t pipe = ctx->pipe_stream;
+    CG_CUDA(ctx, cudaStreamWaitEvent(pipe, ctx->ev_scan, 0));
+    if (rq_index_done) CG_CUDA(ctx, cudaStreamWaitEvent(pipe, ctx->ev_rq, 0));  // built on the side stream (fused call)
+    cudaEventRecord(ctx->stage_ev[4], pipe);
     // ---- decomposition + finish: one pipeline per chromosome, each on its own stream (largest chromosomes first)
     UhParams up;
     up.x = d.cov; up.pz = d.pz; up.off = d.off; up.cand_thr = d.cand_thr; up.lvlcnt = d.lvlcnt;
@@ -641,12 +656,9 @@ int wv_enqueue(cg_ctx* ctx, const cg_wavelet_opts* o, const WvPlan& pl, WvDev& d
     fp.log3_scale_tab = d.log3;
     fp.rq.spl = d.rq_spl; fp.rq.hist = d.rq_hist; fp.rq.tstart = d.rq_tstart; fp.rq.cum = d.rq_cum; fp.rq.sorted = d.rq_sorted;
     fp.rq.tfirst = d.rq_tfirst;
-    fp.phase_ns = getenv("CANVAS_DEBUG") ? d.phase_ns : nullptr;
-    if (fp.phase_ns) cudaMemsetAsync(d.phase_ns, 0, (size_t)(C + 1) * 64, s);
+    fp.phase_ns = dbg_on ? d.phase_ns : nullptr;
     up.tl_ns = fp.phase_ns && d.tl_ns ? d.tl_ns : nullptr;
-    if (up.tl_ns) cudaMemsetAsync(d.tl_ns, 0, (size_t)(C + 1) * 128, s);
     up.task_dbg = up.tl_ns && d.task_dbg ? d.task_dbg : nullptr;
-    if (up.task_dbg) cudaMemsetAsync(d.task_dbg, 0, 8, s);
     fp.is_germline = o->is_germline; fp.min_size = o->min_size; fp.n_chrom = C; fp.pad = 0;
     fp.lvl_idx = d.lvl_idx; fp.sv = d.sv; fp.svkey = d.svkey; fp.bitmap = d.bitmap; fp.piece = d.piece; fp.rec = d.rec;
     fp.prelim = d.prelim; fp.lvl_first = d.lvl_first; fp.n_bp = d.n_bp; fp.bp = d.bp;
@@ -672,7 +684,7 @@ int wv_enqueue(cg_ctx* ctx, const cg_wavelet_opts* o, const WvPlan& pl, WvDev& d
     // ranks that share a host no longer queue behind each other's launches.  A shape is captured the second time it is seen.
     static const int mid_threads = getenv("CANVAS_MID_THREADS") ? atoi(getenv("CANVAS_MID_THREADS")) : UH_MID_THREADS;
     const size_t mid_smem = (size_t)(UH_MID_MAX + 2) * sizeof(double);
-    auto enqueue_pipelines = [&](const long long* loff, cudaStream_t root) -> int {
+    auto enqueue_pipelines = [&](const long long* loff, cudaStream_t root, bool capturing) -> int {
         std::vector<int> order;
         for (int c = 0; c < C; c++) {
             const long long len = loff[c + 1] - loff[c];
@@ -682,6 +694,7 @@ int wv_enqueue(cg_ctx* ctx, const cg_wavelet_opts* o, const WvPlan& pl, WvDev& d
         const int n_streams = (int)std::min<size_t>(order.size(), CG_CHROM_STREAMS);
         int rc_streams = cg_chrom_streams(ctx, n_streams);
         if (rc_streams) return rc_streams;
+        ctx->stream = root;
         CG_LAUNCH(ctx, uh_seed_kernel, div_up(C, 128), 128, 0, up, d.selected, C, o->min_size);
         CG_LAUNCH(ctx, uh_tiny_table_kernel, UH_TINY_MAX - 1, UH_TINY_MAX, 0, d.tiny_tab);
         CG_CUDA(ctx, cudaEventRecord(ctx->ev_fork2, root));
@@ -704,7 +717,7 @@ int wv_enqueue(cg_ctx* ctx, const cg_wavelet_opts* o, const WvPlan& pl, WvDev& d
                 cfg.numAttrs = 1;
                 cfg.gridDim = dim3(UH_CLUSTER * (len > 100000 ? 2 : 1));
                 cudaError_t le = cudaLaunchKernelEx(&cfg, uh_chain_kernel, up, c);
-                if (le != cudaSuccess) { ctx->stream = root; return cg_fail(ctx, CG_ERR_CUDA, std::string("uh_chain_kernel launch: ") + cudaGetErrorString(le)); }
+                if (le != cudaSuccess) { ctx->stream = s; return cg_fail(ctx, CG_ERR_CUDA, std::string("uh_chain_kernel launch: ") + cudaGetErrorString(le)); }
                 ctx->launches++;
             }
             if (len > UH_SMALL_MAX)
@@ -719,20 +732,21 @@ int wv_enqueue(cg_ctx* ctx, const cg_wavelet_opts* o, const WvPlan& pl, WvDev& d
                     CG_LAUNCH(ctx, (uh_mid_kernel<256, 8, false>), mid_grid, 256, 0, up, c);
                 }
             }
+            // thresholds: recorded on the main stream before this enqueue started (an external event for a captured sequence)
+            CG_CUDA(ctx, cudaStreamWaitEvent(cs, ctx->ev_thr, capturing ? cudaEventWaitExternal : 0));
             if (len > UH_TINY_MAX)
                 CG_LAUNCH(ctx, uh_small_kernel, (int)std::min<long long>(ctx->num_sms, std::max<long long>(1, len / 1024)), UH_SMALL_THREADS, uh_smem, up, c);
             CG_LAUNCH(ctx, uh_tiny_kernel, (int)std::min<long long>(ctx->num_sms, std::max<long long>(1, len / 1024)), 128, 0, up, d.tiny_tab, c);
             CG_LAUNCH(ctx, uh_depth_kernel, (int)std::min<long long>(32, std::max<long long>(1, len / 4096)), 256, 0, d.lvlcnt, d.off, d.depth, c);
             CG_LAUNCH(ctx, uh_finish_kernel, 1, FIN_THREADS, fin_smem_bytes(), fp, c);
         }
-        ctx->stream = root;
+        ctx->stream = s;
         for (int k = 0; k < n_streams; k++) {
             CG_CUDA(ctx, cudaEventRecord(ctx->chrom_ev[k], ctx->chrom_streams[k]));
             CG_CUDA(ctx, cudaStreamWaitEvent(root, ctx->chrom_ev[k], 0));
         }
         return CG_OK;
     };
-    if (rq_index_done) CG_CUDA(ctx, cudaStreamWaitEvent(s, ctx->ev_rq, 0));  // built on the side stream (fused call)
     bool replayed = false;
     if (!fp.phase_ns && !getenv("CANVAS_NO_GRAPH")) {
         CgGraphEntry want{};
@@ -758,9 +772,10 @@ int wv_enqueue(cg_ctx* ctx, const cg_wavelet_opts* o, const WvPlan& pl, WvDev& d
             if (!hit->exec) {
                 const int launches_before = ctx->launches;
                 cudaGraph_t graph = nullptr;
-                if (cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
-                    const int rc_cap = enqueue_pipelines(d.alloc_off, s);
-                    const cudaError_t ce = cudaStreamEndCapture(s, &graph);
+                if (cudaStreamBeginCapture(pipe, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+                    const int rc_cap = enqueue_pipelines(d.alloc_off, pipe, true);
+                    ctx->stream = s;
+                    const cudaError_t ce = cudaStreamEndCapture(pipe, &graph);
                     hit->launches = ctx->launches - launches_before;
                     ctx->launches = launches_before;
                     if (rc_cap == CG_OK && ce == cudaSuccess && graph) {
@@ -774,7 +789,7 @@ int wv_enqueue(cg_ctx* ctx, const cg_wavelet_opts* o, const WvPlan& pl, WvDev& d
                 }
             }
             if (hit->exec) {
-                const cudaError_t le = cudaGraphLaunch(hit->exec, s);
+                const cudaError_t le = cudaGraphLaunch(hit->exec, pipe);
                 if (le != cudaSuccess) return cg_fail(ctx, CG_ERR_CUDA, std::string("partition: graph launch failed: ") + cudaGetErrorString(le));
                 ctx->launches += hit->launches;
                 replayed = true;
@@ -782,9 +797,12 @@ int wv_enqueue(cg_ctx* ctx, const cg_wavelet_opts* o, const WvPlan& pl, WvDev& d
         }
     }
     if (!replayed) {
-        const int rc_p = enqueue_pipelines(pl.off.data(), s);
+        const int rc_p = enqueue_pipelines(pl.off.data(), pipe, false);
+        ctx->stream = s;
         if (rc_p) return rc_p;
     }
+    CG_CUDA(ctx, cudaEventRecord(ctx->ev_pipe, pipe));
+    CG_CUDA(ctx, cudaStreamWaitEvent(s, ctx->ev_pipe, 0));
     CG_TL(ctx, "decompose + finish");
     cudaEventRecord(ctx->stage_ev[5], s);
     cudaEventRecord(ctx->stage_ev[6], s);

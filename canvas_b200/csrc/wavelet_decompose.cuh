@@ -71,6 +71,18 @@ __device__ inline void uh_emit_candidate(const UhParams& p, int c, int level, in
     p.cand[cp.cand_base + i] = k;
 }
 
+// Chains and the mid stage run before the thresholds exist (they overlap the order statistics that produce them): every one of
+// their nodes — a few hundred per chromosome — is recorded, and the finish stage applies the real threshold as to any candidate.
+__device__ inline void uh_emit_candidate_always(const UhParams& p, int c, int level, int s, int b, int e, double coef) {
+    const UhChromPlan& cp = p.cp[c];
+    const int i = atomicAdd(&p.cc[c].cand_count_.v, 1);
+    if (i >= cp.cand_cap) { p.ctl->overflow_.v = 1; return; }
+    UhCand k;
+    k.key = ((unsigned long long)c << 56) | ((unsigned long long)level << 32) | (unsigned)s;
+    k.s = s; k.b = b; k.e = e; k.level = level; k.c = c; k.pad = 0; k.coef = coef;
+    p.cand[cp.cand_base + i] = k;
+}
+
 // Can the node's coefficient exceed the candidate threshold at all?  score = D^2 / (a b) of the chosen split, and
 // coef^2 = score * n / scale^2 with scale = max(0.5, mean / 200): three multiplications instead of the square root and two
 // divisions of the exact coefficient, which only the few nodes that pass (or a NaN) still compute.  The factor leaves the
@@ -205,7 +217,6 @@ uh_chain_kernel(UhParams p, int c_self) {
     UhTask* const mid_list = p.mid + cp.mid_base;
     UhTask* const small_list = p.small + cp.small_base;
     UhTinyTask* const tiny_list = p.tiny + cp.tiny_base;
-    const double thr2 = p.cand_thr[c_self] * p.cand_thr[c_self];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const double* __restrict__ pz = p.pz;
     unsigned long long v_big = 0, n_big = 0;
@@ -319,7 +330,7 @@ uh_chain_kernel(UhParams p, int c_self) {
             const bool cont_right = rbig && !cont_left;
             if (crank == 0 && threadIdx.x == 32) {
                 atomicAdd(&p.lvlcnt[loff + level], 1u);
-                if (uh_may_be_candidate(fbest, nn, mu, thr2)) uh_emit_candidate(p, c, level, s, s + fm, e, uh_coef_from(fv, base, T, n, fm));
+                uh_emit_candidate_always(p, c, level, s, s + fm, e, uh_coef_from(fv, base, T, n, fm));
                 n_big++;
             }
             if (crank == 0 && threadIdx.x == 0) {
@@ -387,7 +398,6 @@ uh_mid_kernel(UhParams p, int c_self) {
     const UhTask* const mid_list = p.mid + cp.mid_base;
     UhTask* const small_list = p.small + cp.small_base;
     UhTinyTask* const tiny_list = p.tiny + cp.tiny_base;
-    const double thr2 = p.cand_thr[c_self] * p.cand_thr[c_self];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const double* __restrict__ pz = p.pz;
     unsigned long long v_mid = 0, n_mid = 0;
@@ -458,7 +468,7 @@ uh_mid_kernel(UhParams p, int c_self) {
             const bool lmid = lt_ >= UH_TIER_MID, rmid = rt_ >= UH_TIER_MID;  // a child of a mid node is never BIG
             if (threadIdx.x == 32) {
                 atomicAdd(&p.lvlcnt[loff + level], 1u);
-                if (uh_may_be_candidate(fbest, nn, mu, thr2)) uh_emit_candidate(p, c, level, s, s + fm, e, uh_coef_from(fv, base, T, n, fm));
+                uh_emit_candidate_always(p, c, level, s, s + fm, e, uh_coef_from(fv, base, T, n, fm));
                 n_mid++;
             }
             if (threadIdx.x == 0) {
