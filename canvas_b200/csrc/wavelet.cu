@@ -6,6 +6,7 @@
 #include "clean.cuh"
 #include "comm.cuh"
 #include "wavelet.cuh"
+#include <chrono>
 #include "wavelet_decompose.cuh"
 #include "wavelet_finish.cuh"
 #include "wavelet_rqindex.cuh"
@@ -1125,6 +1126,10 @@ static int clean_partition_wavelet_impl(cg_ctx* ctx, const cg_clean_opts* copts,
     if (!chrom || !start || !stop || !count || !gc || !kept_index || !count_out || !bp || !chrom_is_autosome)
         return cg_fail(ctx, CG_ERR_ARG, "cg_clean_partition_wavelet: null array");
     CG_CUDA(ctx, cudaSetDevice(ctx->device));
+    static const bool host_times = getenv("CANVAS_HOST_TIMES") != nullptr;  // where the HOST thread spends the call (stderr)
+    double ht[8] = {0};
+    auto now_us = []() { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    ht[0] = now_us();
     // chromosome runs of the input (ids are non-decreasing; the device validates that): binary search
     std::vector<int64_t> in_off(n_chrom + 1, 0);
     for (int c = 0; c < n_chrom; c++) {
@@ -1205,6 +1210,7 @@ static int clean_partition_wavelet_impl(cg_ctx* ctx, const cg_clean_opts* copts,
         CG_CUDA(ctx, cudaEventRecord(ctx->ev_rq, ctx->side_stream));
     }
     CG_TL(ctx, "clears");
+    ht[1] = now_us();
     cudaEventRecord(ctx->gap_ev, s);
     ctx->gap_used = true;
     {
@@ -1214,6 +1220,7 @@ static int clean_partition_wavelet_impl(cg_ctx* ctx, const cg_clean_opts* copts,
         while ((q = cudaEventQuery(ctx->ev_mid)) == cudaErrorNotReady) {}
         if (q != cudaSuccess) return cg_fail(ctx, CG_ERR_CUDA, std::string("cg_clean_partition_wavelet: ") + cudaGetErrorString(q));
     }
+    ht[2] = now_us();
     CG_CUDA(ctx, cudaGetLastError());
     CG_CHECK_LAUNCHES(ctx);
     if (h->unsorted) return cg_fail(ctx, CG_ERR_UNSORTED, "cg_clean: chromosome ids must form non-decreasing runs and GC must be 0..100");
@@ -1235,10 +1242,16 @@ static int clean_partition_wavelet_impl(cg_ctx* ctx, const cg_clean_opts* copts,
     make_plan(pl, n_chrom, off.data(), wopts->evenness_window);
     const bool use_int = h_cnt[256] == 0u && !getenv("CANVAS_NO_INT_KEYS");
     ctx->stats[15] = use_int ? 1.0 : 0.0;
+    ht[3] = now_us();
     rc = wv_enqueue(ctx, wopts, pl, wd, sel.data(), n_chrom > 0, exchange ? ctx->comm->d_send : nullptr, use_int);
     if (rc) { cudaStreamSynchronize(s); cudaStreamSynchronize(ctx->copy_stream); return rc; }
     CG_CUDA(ctx, cudaEventRecord(ctx->ev1, s));
+    ht[4] = now_us();
     rc = wv_collect(ctx, pl, wd, n_bp, bp, evenness, evenness_ok, cv, cv_has_value, factor_of_three, exchange);
+    ht[5] = now_us();
+    if (host_times)
+        fprintf(stderr, "[host] enqueue copies+clean+index %.0f us | wait for counts %.0f | plan %.0f | enqueue partition %.0f | wait+collect %.0f\n",
+                ht[1] - ht[0], ht[2] - ht[1], ht[3] - ht[2], ht[4] - ht[3], ht[5] - ht[4]);
     tl.print("fused");
     ctx->tl = nullptr;
     CG_CUDA(ctx, cudaStreamSynchronize(ctx->copy_stream));
