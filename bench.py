@@ -303,27 +303,43 @@ def main():
     # ------------------------------------------------------------------ config 4: the trio chain
     def run_config4(n_warm, n_steps):
         trio = [synth.make_sample(config=4, sample=k, scale=args.scale, n_events=60) for k in range(3)]
-        for t in trio:  # page-locked input columns, as in the other configurations
-            t.chrom, t.start, t.stop, t.count, t.gc = (pin.array(a) for a in (t.chrom, t.start, t.stop, t.count, t.gc))
+        t0 = trio[0]
+        n4, S4 = len(t0), len(trio)
+        # page-locked layout columns and counts in, page-locked result tables out, as in the other configurations; a rank
+        # only holds the counts of the samples it cleans (sample s on rank s mod N)
+        lay = dict(chrom=pin.array(t0.chrom), start=pin.array(t0.start), stop=pin.array(t0.stop), gc=pin.array(t0.gc))
+        cols = [pin.array(t.count) if k % world == rank else None for k, t in enumerate(trio)]
+        out = (pin.empty(n4, np.int32), pin.empty(S4 * n4, np.float32).reshape(S4, n4), pin.empty(S4 * n4, np.int32).reshape(S4, n4))
         tm, res = {}, {}
-        layout_off = synth.chrom_offsets(trio[0].chrom, len(trio[0].names))
 
         def step():
-            res["r"] = pedigree.trio_segments(eng, trio, sharded=world > 1, timings=tm if res.get("timed") else None, layout_off=layout_off)
+            r = eng.pedigree_hmm(lay["chrom"], t0.is_autosome, t0.is_chr_y, lay["start"], lay["stop"], cols, lay["gc"],
+                                 sharded=world > 1, out=out)
+            res["r"] = r
+            if res.get("timed"):
+                for k, v in r["phases_ms"].items():
+                    tm[k] = tm.get(k, 0.0) + v
+                for k in ("kernel_ms", "launches", "nccl_ms"):
+                    tm[k] = tm.get(k, 0.0) + r[k]
         for _ in range(n_warm):
             step()
         res["timed"] = True
         walls = timed(step, n_steps)
         wall_ms, kern_ms = max_over_ranks([1e3 * sum(walls) / n_steps, tm.get("kernel_ms", 0.0) / n_steps])
-        bins = sum(len(s) for s in trio)
-        return {"workload": WORKLOADS[4], "bins": bins, "common_bins": res["r"]["n_common"],
-                "breakpoints": int(sum(len(b) for per in res["r"]["breakpoints"] for b in per)),
+        bins = S4 * n4
+        r = res["r"]
+        mine = sum(1 for k in range(S4) if k % world == rank)
+        return {"workload": WORKLOADS[4], "bins": bins, "common_bins": r["n_common"],
+                "breakpoints": int(sum(len(b) for per in r["breakpoints"] for b in per)),
                 "ms_per_step": wall_ms, "Mbins_per_s": bins / wall_ms / 1e3,
                 "kernel_ms_max_rank": kern_ms, "Mbins_per_s_kernels": bins / kern_ms / 1e3 if kern_ms > 0 else None,
-                "phases_ms_rank0": {k: v / n_steps for k, v in tm.items() if k not in ("kernel_ms", "launches")},
-                "launches_rank0": tm.get("launches", 0) // max(n_steps, 1),
-                "h2d_bytes": 14 * len(trio[0]) * (3 if world == 1 else 1),
-                "timing": "wall clock around the chain of C-ABI calls, host buffers in and out, max over ranks"}
+                "phases_ms_rank0": {k: v / n_steps for k, v in tm.items() if k not in ("kernel_ms", "launches", "nccl_ms")},
+                "nccl_ms_rank0": tm.get("nccl_ms", 0.0) / n_steps,
+                "launches_rank0": int(tm.get("launches", 0)) // max(n_steps, 1),
+                "units_per_rank": np.bincount(r["owner"].ravel(), minlength=world).tolist(),
+                "h2d_bytes": (10 * n4 + 4 * n4 * mine) if mine else 0, "d2h_bytes": 4 * r["n_common"] * (S4 + 1) + 4 * int(sum(len(b) for per in r["breakpoints"] for b in per)),
+                "call": "cg_pedigree_hmm (one device-resident call: Clean per sample, common bins, PerSampleHMM per sample)",
+                "timing": "wall clock around the C-ABI call, page-locked host buffers in and out, max over ranks"}
 
     # ------------------------------------------------------------------ CanvasPartition -m CBS on the config-2 sample
     if args.method == "cbs":
@@ -397,7 +413,7 @@ def main():
                     "config": {"workload": WORKLOADS[4], "bins_per_sample": c4["bins"] // 3, "samples": 3,
                                "l2": "flushed between steps (256 MiB device write)", "parallelism": f"(sample, chromosome) units x{world}"},
                     "e2e": {"value": c4["Mbins_per_s"], "unit": UNIT, "ms_per_step": c4["ms_per_step"],
-                            "h2d_bytes_per_step": c4["h2d_bytes"], "d2h_bytes_per_step": 8 * c4["common_bins"] * 3, "timing": c4["timing"]},
+                            "h2d_bytes_per_step": c4["h2d_bytes"], "d2h_bytes_per_step": c4["d2h_bytes"], "timing": c4["timing"]},
                     "gpu_launches": c4["launches_rank0"] * K, "config4": c4, "clocks": clocks, "device": eng.describe()}
             _emit(line)
         if world > 1:

@@ -12,7 +12,7 @@ ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 OUT_DIR = os.path.join(HERE, "_build")
 LIB = os.path.join(OUT_DIR, "libcanvasgpu.so")
-SOURCES = ["capi.cu", "clean.cu", "wavelet.cu", "bin.cu", "cbs.cu", "hmm.cu", "merge.cu", "smooth.cu", "codec.cu", "normalize.cu", "bin_gc.cu", "comm.cu"]
+SOURCES = ["capi.cu", "clean.cu", "wavelet.cu", "bin.cu", "cbs.cu", "hmm.cu", "merge.cu", "smooth.cu", "codec.cu", "normalize.cu", "bin_gc.cu", "comm.cu", "pedigree.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     # the reference computes in IEEE double/float without fused multiply-add (.NET RyuJIT);

@@ -53,6 +53,7 @@ extern "C" void cg_destroy(cg_ctx* ctx) {
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
     if (ctx->plan_pinned) cudaFreeHost(ctx->plan_pinned);
     if (ctx->aux) cudaFree(ctx->aux);
+    if (ctx->ped) cudaFree(ctx->ped);
     for (int i = 0; i < 8; i++)
         if (ctx->stage_ev[i]) cudaEventDestroy(ctx->stage_ev[i]);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);

@@ -40,12 +40,7 @@ void load_nccl() {
         g_nccl = n;
 }
 
-#define CG_NCCL(ctx, nc, call)                                                                                     \
-    do {                                                                                                           \
-        ncclResult_t r__ = (call);                                                                                 \
-        if (r__ != ncclSuccess)                                                                                    \
-            return cg_fail(ctx, CG_ERR_CUDA, std::string(#call) + ": " + (nc)->GetErrorString(r__));               \
-    } while (0)
+
 
 void comm_free_buffers(CgComm* c) {
     if (c->d_send) cudaFree(c->d_send);

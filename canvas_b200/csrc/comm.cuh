@@ -47,6 +47,13 @@ struct CgComm {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 };
 
+#define CG_NCCL(ctx, nc, call)                                                                                     \
+    do {                                                                                                           \
+        ncclResult_t r__ = (call);                                                                                 \
+        if (r__ != ncclSuccess)                                                                                    \
+            return cg_fail(ctx, CG_ERR_CUDA, std::string(#call) + ": " + (nc)->GetErrorString(r__));               \
+    } while (0)
+
 const CgNccl* cg_nccl(std::string* err);                       // nullptr + message when the library cannot be bound
 int comm_reserve(cg_ctx* ctx, size_t cap_ints);                // first-round buffers; second-round buffers for cap_ints ints per rank when > 0
 // Greedy longest-processing-time-first: heaviest unit first onto the least loaded rank (ties: lower rank, earlier unit).

@@ -64,6 +64,9 @@ struct cg_ctx {
     // second device block for tables whose size is only known in the middle of a call (HMM emission tables)
     char* aux = nullptr;
     size_t aux_cap = 0;
+    // third device block: what the pedigree chain keeps between its stages (cleaned lists of every sample, merged counts)
+    char* ped = nullptr;
+    size_t ped_cap = 0;
     CgTimeline* tl = nullptr;  // debug timeline of the current call (CANVAS_DEBUG)
     std::vector<CgGraphEntry> clean_graphs;  // Clean pipeline graphs (clean.cu), dropped when the arena moves
     std::vector<CgGraphEntry> part_graphs;   // partition: per-chromosome pipelines (wavelet.cu); exec == nullptr: shape seen once

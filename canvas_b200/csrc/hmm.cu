@@ -652,9 +652,10 @@ __global__ void hmm_counts_to_coverage_kernel(const float* __restrict__ count, l
     }
 }
 
+// count32_on_device: the float counts already sit in this GPU's memory (the pedigree chain, pedigree.cu)
 static int partition_hmm_impl(cg_ctx* ctx, const cg_hmm_opts* o, int n_samples, int n_chrom, const int64_t* chrom_off,
                               const double* coverage, const float* count32, int text_mode, const uint8_t* chrom_selected, int32_t* n_bp,
-                              int32_t* bp, uint8_t* states_out) {
+                              int32_t* bp, uint8_t* states_out, bool count32_on_device = false) {
     if (!ctx) return CG_ERR_ARG;
     if (n_chrom > HMM_MAX_CHROM) return cg_fail(ctx, CG_ERR_UNSUPPORTED, "cg_partition_hmm: more than 256 chromosomes (contigs): this build addresses chromosomes with 8-bit ids (see DESIGN.md, Limits)");
     if (!o || !chrom_off || !n_bp || n_chrom < 0 || n_samples < 1)
@@ -772,8 +773,8 @@ static int partition_hmm_impl(cg_ctx* ctx, const cg_hmm_opts* o, int n_samples, 
         // float counts: half the bytes over PCIe, the text round trip happens here (staged in the emission table's space)
         float* d_cnt = reinterpret_cast<float*>(d_le);
         static_assert(HMM_NS * 8 >= HMM_MAX_SAMPLES * 4, "the float staging area fits the emission table");
-        CG_CUDA(ctx, cudaMemcpyAsync(d_cnt, count32, (size_t)S * N * 4, cudaMemcpyHostToDevice, s));
-        hmm_counts_to_coverage_kernel<<<std::max(1, std::min(div_up((long long)S * N, 256), ctx->num_sms * 8)), 256, 0, s>>>(d_cnt, (long long)S * N, text_mode, d_cov);
+        if (!count32_on_device) CG_CUDA(ctx, cudaMemcpyAsync(d_cnt, count32, (size_t)S * N * 4, cudaMemcpyHostToDevice, s));
+        hmm_counts_to_coverage_kernel<<<std::max(1, std::min(div_up((long long)S * N, 256), ctx->num_sms * 8)), 256, 0, s>>>(count32_on_device ? count32 : d_cnt, (long long)S * N, text_mode, d_cov);
         ctx->launches++;
     }
     CG_CUDA(ctx, cudaMemcpyAsync(d_ci, ci.data(), (size_t)C * sizeof(HmmChromInfo), cudaMemcpyHostToDevice, s));
@@ -812,7 +813,11 @@ static int partition_hmm_impl(cg_ctx* ctx, const cg_hmm_opts* o, int n_samples, 
                 if ((N - 1) % 4 == 0) { q1 = (v[2] * 0.25f) + (v[3] * 0.75f); q3 = (v[4] * 0.75f) + (v[5] * 0.25f); }
                 else { q1 = (v[2] * 0.75f) + (v[3] * 0.25f); q3 = (v[4] * 0.25f) + (v[5] * 0.75f); }
             }
-            if (N < 2) { q1 = q3 = 0; q2 = N == 1 ? (float)coverage[(size_t)sm * N] : 0; }
+            if (N < 2) {
+                double only = 0;  // a one-bin genome: its own value is the median (read back: the coverage may have been built on the device)
+                if (N == 1) { CG_CUDA(ctx, cudaMemcpy(&only, d_cov + (size_t)sm * N, 8, cudaMemcpyDeviceToHost)); }
+                q1 = q3 = 0; q2 = (float)only;
+            }
             const float iqr = q3 - q1;
             for (int c = 0; c < C; c++) {
                 haploid[(size_t)sm * C + c] = (double)q2 / 2.0;
@@ -981,6 +986,12 @@ extern "C" int cg_partition_hmm_counts(cg_ctx* ctx, const cg_hmm_opts* o, int n_
     if (ctx && (text_mode < 0 || text_mode > 2)) return cg_fail(ctx, CG_ERR_ARG, "cg_partition_hmm_counts: text_mode must be 0, 1 or 2");
     if (ctx && !count && n_chrom > 0 && chrom_off && chrom_off[n_chrom] > 0) return cg_fail(ctx, CG_ERR_ARG, "cg_partition_hmm: null array");
     return partition_hmm_impl(ctx, o, n_samples, n_chrom, chrom_off, nullptr, count, text_mode, chrom_selected, n_bp, bp, states_out);
+}
+
+// One sample of the pedigree chain: float counts in device memory, results to the host (pedigree.cu).
+int hmm_partition_device_counts(cg_ctx* ctx, const cg_hmm_opts* o, int n_chrom, const int64_t* chrom_off, const float* d_count,
+                                int text_mode, const uint8_t* chrom_selected, int32_t* n_bp, int32_t* bp) {
+    return partition_hmm_impl(ctx, o, 1, n_chrom, chrom_off, nullptr, d_count, text_mode, chrom_selected, n_bp, bp, nullptr, true);
 }
 
 extern "C" int cg_partition_hmm(cg_ctx* ctx, const cg_hmm_opts* o, int n_samples, int n_chrom, const int64_t* chrom_off,

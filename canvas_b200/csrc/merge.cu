@@ -248,8 +248,11 @@ struct KeptEmit {
 
 }  // namespace
 
-extern "C" int cg_merge_kept_indices(cg_ctx* ctx, int64_t n_bins, int n_samples, const int64_t* n_kept, const int32_t* const* kept,
-                                     const float* const* count, int64_t* n_out, int32_t* common_index, float* count_out) {
+// on_device: the lists and the outputs are device memory of this GPU (the pedigree chain, pedigree.cu) — nothing is staged,
+// count_out rows are `out_stride` floats apart.  Otherwise host memory in and out, rows n_kept[0] apart (the C-ABI form).
+int merge_kept_lists(cg_ctx* ctx, int64_t n_bins, int n_samples, const int64_t* n_kept, const int32_t* const* kept,
+                     const float* const* count, int64_t* n_out, int32_t* common_index, float* count_out, bool on_device,
+                     size_t out_stride) {
     if (!ctx) return CG_ERR_ARG;
     if (n_samples < 1 || n_bins < 0 || n_bins > 0x7fff0000LL || !n_kept || !kept || !count || !n_out)
         return cg_fail(ctx, CG_ERR_ARG, "cg_merge_kept_indices: bad argument");
@@ -279,6 +282,7 @@ extern "C" int cg_merge_kept_indices(cg_ctx* ctx, int64_t n_bins, int n_samples,
     float* d_count_out = arena_take<float>(ctx, (size_t)S * n0);
     int32_t* d_common = arena_take<int32_t>(ctx, n0);
     if (!ctl || !tiles || !d_count_out || !d_common) return cg_fail(ctx, CG_ERR_CUDA, "arena exhausted");
+    if (!on_device) out_stride = (size_t)n0;
     cudaStream_t st = ctx->stream;
     KeptCols cols;
     memset(&cols, 0, sizeof(cols));
@@ -291,11 +295,11 @@ extern "C" int cg_merge_kept_indices(cg_ctx* ctx, int64_t n_bins, int n_samples,
         float* d_count = arena_take<float>(ctx, m);
         int* d_pos = arena_take<int>(ctx, n_bins + 1);
         if (!d_kept || !d_count || !d_pos) return cg_fail(ctx, CG_ERR_CUDA, "arena exhausted");
-        if (m > 0) {
+        if (m > 0 && !on_device) {
             CG_CUDA(ctx, cudaMemcpyAsync(d_kept, kept[s], m * 4, cudaMemcpyHostToDevice, st));
             CG_CUDA(ctx, cudaMemcpyAsync(d_count, count[s], m * 4, cudaMemcpyHostToDevice, st));
         }
-        cols.kept[s] = d_kept; cols.count[s] = d_count; cols.pos[s] = d_pos; cols.n[s] = (int)m;
+        cols.kept[s] = on_device ? kept[s] : d_kept; cols.count[s] = on_device ? count[s] : d_count; cols.pos[s] = d_pos; cols.n[s] = (int)m;
     }
     CG_CUDA(ctx, cudaEventRecord(ctx->ev0, st));
     for (int s = 0; s < S; s++) {
@@ -322,10 +326,16 @@ extern "C" int cg_merge_kept_indices(cg_ctx* ctx, int64_t n_bins, int n_samples,
     const int m = h->n_out;
     *n_out = m;
     if (m > 0) {
-        CG_CUDA(ctx, cudaMemcpyAsync(common_index, d_common, (size_t)m * 4, cudaMemcpyDeviceToHost, st));
+        const cudaMemcpyKind kind = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+        CG_CUDA(ctx, cudaMemcpyAsync(common_index, d_common, (size_t)m * 4, kind, st));
         for (int s = 0; s < S; s++)
-            CG_CUDA(ctx, cudaMemcpyAsync(count_out + (size_t)s * n0, d_count_out + (size_t)s * n0, (size_t)m * 4, cudaMemcpyDeviceToHost, st));
+            CG_CUDA(ctx, cudaMemcpyAsync(count_out + (size_t)s * out_stride, d_count_out + (size_t)s * n0, (size_t)m * 4, kind, st));
         CG_CUDA(ctx, cudaStreamSynchronize(st));
     }
     return CG_OK;
+}
+
+extern "C" int cg_merge_kept_indices(cg_ctx* ctx, int64_t n_bins, int n_samples, const int64_t* n_kept, const int32_t* const* kept,
+                                     const float* const* count, int64_t* n_out, int32_t* common_index, float* count_out) {
+    return merge_kept_lists(ctx, n_bins, n_samples, n_kept, kept, count, n_out, common_index, count_out, false, 0);
 }

@@ -84,6 +84,9 @@ SIGNATURES = {
     "cg_merge_common_bins": (C.c_int, [C.c_void_p, C.c_int, _P(_i64), _P(C.c_void_p), _P(C.c_void_p), _P(C.c_void_p),
                                        _P(C.c_void_p), _P(_i64), _P(_i32), _P(_i32), _P(_f32)]),
     "cg_merge_kept_indices": (C.c_int, [C.c_void_p, _i64, C.c_int, _P(_i64), _P(C.c_void_p), _P(C.c_void_p), _P(_i64), _P(_i32), _P(_f32)]),
+    "cg_pedigree_hmm": (C.c_int, [C.c_void_p, _P(CleanOpts), _P(HmmOpts), C.c_int, _i64, _P(_u8), _P(_u8), _P(_u8), C.c_int, _P(_i32), _P(_i32),
+                                  _P(C.c_void_p), _P(_u8), C.c_int, _P(_i64), _P(_f64), _P(C.c_int), _P(_i64), _P(_i32), _P(_f32), _P(_i64),
+                                  _P(_i32), _P(_i32), _P(_i32)]),
     "cg_smooth": (C.c_int, [C.c_void_p, C.c_int, C.c_int, _P(_i64), _P(_f32), _P(_i64), _P(_f32)]),
     "cg_format_bins": (_i64, [_i64, C.c_int, _P(C.c_char_p), _P(_u8), _P(_i32), _P(_i32), _P(_f32), _P(_u8), C.c_int,
                               C.c_char_p, _i64, C.c_int]),
@@ -641,6 +644,57 @@ class Engine:
         self._check(rc)
         return {"breakpoints": [bp[off[c]:off[c] + n_bp[c]].copy() for c in range(nc)], "states": states[:n],
                 "kernel_ms": self.lib.cg_last_kernel_ms(self.h), "launches": self.lib.cg_last_launches(self.h)}
+
+    def pedigree_hmm(self, chrom, is_autosome, is_chr_y, start, stop, counts, gc, sharded=False, min_size=10, out=None,
+                     size_filter=True, outlier_filter=True, gc_norm=True, gc_mode=0, want_local_sd=True, min_bins_per_gc=100):
+        """cg_pedigree_hmm: CanvasClean per sample -> common bins -> PerSampleHMM per sample, device resident (one call).
+        counts: one float32 array per sample over the shared layout (None allowed for samples another rank cleans when
+        sharded).  out: optional (common_index i32[n], count f32[S, n], bp i32[S, n]) buffers, e.g. page-locked."""
+        chrom = np.ascontiguousarray(chrom, np.uint8)
+        n = len(chrom)
+        is_autosome = np.ascontiguousarray(is_autosome, np.uint8)
+        is_chr_y = np.ascontiguousarray(is_chr_y, np.uint8)
+        start = np.ascontiguousarray(start, np.int32)
+        stop = np.ascontiguousarray(stop, np.int32)
+        gc = np.ascontiguousarray(gc, np.uint8)
+        cols = [None if c is None else np.ascontiguousarray(c, np.float32) for c in counts]
+        S, nc = len(cols), len(is_autosome)
+        for c in cols:
+            if c is not None and len(c) != n:
+                raise ValueError("every sample's counts must cover the shared bin layout")
+        ptrs = (C.c_void_p * S)(*[None if c is None else c.ctypes.data for c in cols])
+        co = CleanOpts(int(size_filter), int(outlier_filter), int(gc_norm), int(gc_mode), int(want_local_sd), int(min_bins_per_gc))
+        ho = HmmOpts(5, 1, min_size, 0)
+        if out is None:
+            common = np.empty(max(n, 1), np.int32)
+            cnt = np.empty((S, max(n, 1)), np.float32)
+            bp = np.empty((S, max(n, 1)), np.int32)
+        else:
+            common, cnt, bp = out
+        n_kept = np.zeros(S, np.int64)
+        lsd = np.zeros(S, np.float64)
+        skipped = np.zeros(S, np.int32)
+        n_common = _i64(0)
+        off = np.zeros(nc + 1, np.int64)
+        n_bp = np.zeros((S, max(nc, 1)), np.int32)
+        owner = np.zeros((S, max(nc, 1)), np.int32)
+        rc = self.lib.cg_pedigree_hmm(self.h, C.byref(co), C.byref(ho), S, n, _ptr(chrom, _u8), _ptr(is_autosome, _u8), _ptr(is_chr_y, _u8),
+                                      nc, _ptr(start, _i32), _ptr(stop, _i32), ptrs, _ptr(gc, _u8), int(bool(sharded)), _ptr(n_kept, _i64),
+                                      _ptr(lsd, _f64), skipped.ctypes.data_as(_P(C.c_int)), C.byref(n_common), _ptr(common, _i32),
+                                      _ptr(cnt, _f32), _ptr(off, _i64), _ptr(n_bp, _i32), _ptr(bp, _i32), _ptr(owner, _i32))
+        self._check(rc)
+        m = n_common.value
+        st = self.last_partition_stats_raw()
+        return {"breakpoints": [[bp[s, off[c]:off[c] + n_bp[s, c]].copy() for c in range(nc)] for s in range(S)],
+                "chrom_off": off, "n_common": m, "common_index": common[:m], "count": cnt[:, :m], "n_kept": n_kept,
+                "local_sd": lsd, "gc_norm_skipped": skipped.astype(bool), "owner": owner[:, :nc],
+                "phases_ms": {"clean": st[0], "broadcast": st[1], "merge": st[2], "hmm": st[3], "gather": st[4]},
+                "kernel_ms": st[5], "launches": int(st[6]), "nccl_ms": st[7]}
+
+    def last_partition_stats_raw(self):
+        buf = (C.c_double * 16)()
+        self.lib.cg_last_partition_stats(self.h, buf, 16)
+        return list(buf)
 
     def merge_common_bins(self, samples):
         """MergeMultiSampleCleanedBedFile: samples = [(chrom_id u8, start i32, stop i32, count f32), ...] ordered by

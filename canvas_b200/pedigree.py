@@ -2,6 +2,11 @@
 (reference Canvas/CanvasRunner.cs:883-937: CanvasClean per sample :883-893, NormalizeCanvasClean / Utilities.
 MergeMultiSampleCleanedBedFile :895-903 + CanvasCommon/Utilities.cs:834-920, CanvasPartition -m PerSampleHMM :927).
 
+The product call for this chain is Engine.pedigree_hmm = cg_pedigree_hmm (csrc/pedigree.cu): ONE device-resident call that keeps
+the cleaned lists in HBM between the stages.  trio_segments below drives the same stages one C-ABI call at a time through
+host memory — the form a host that wants the intermediate files would use, and the cross-check of the one-call chain in the
+tests.
+
 One GPU: every step on the one engine.  N ranks (BASELINE config 4: "chromosomes sharded across 8 x B200"): sample s is
 cleaned ONCE, on rank s mod N, and its cleaned bins are broadcast over NCCL (cg_comm_broadcast) instead of repeating Clean
 on every rank; the common-bin merge is cheap and runs on every rank; the 3 x 24 (sample, chromosome) units of the HMM are

@@ -309,6 +309,29 @@ int cg_merge_kept_indices(cg_ctx* ctx, int64_t n_bins, int n_samples, const int6
                           const float* const* count, int64_t* n_out, int32_t* common_index, float* count_out);
 
 /* ---------------------------------------------------------------------------------------------
+ * The SmallPedigree chain in one call, device resident: CanvasClean per sample (Canvas/CanvasRunner.cs:883-893) ->
+ * bins common to every sample (CanvasRunner.cs:895-903, CanvasCommon/Utilities.cs:834-920) -> CanvasPartition
+ * -m PerSampleHMM per sample (CanvasRunner.cs:927, CanvasPartition/HiddenMarkovModelsRunner.cs:23-109).  The samples of a
+ * pedigree share one bin layout (chrom/start/stop/gc, n bins; CanvasRunner.cs:846-870); count[s] are sample s's counts.
+ * The cleaned lists never leave the GPU between the stages: the layout is uploaded once, each sample adds 4 B/bin.
+ * sharded != 0 (communicator of R ranks, every rank makes the same call): sample s is cleaned on rank s mod R (count[s]
+ * may be NULL elsewhere), cleaned lists move GPU to GPU over NCCL, the n_samples x n_chrom (sample, chromosome) units of the
+ * HMM are assigned longest-first (cg_shard_assign on the common-bin counts, tiled per sample) and one all-gather completes
+ * the result on EVERY rank.  owner (may be NULL): [n_samples][n_chrom] rank of every unit.
+ * Outputs: n_kept / local_sd / gc_norm_skipped [n_samples] as cg_clean reports them; *n_common, common_index[k] (capacity
+ * n) = layout index of common bin k, count_out[s * n + k] = sample s's cleaned count of it (what the merged .cleaned file
+ * prints with float.ToString()); chrom_off_out[n_chrom + 1] offsets of the chromosomes among the common bins;
+ * n_bp[s * n_chrom + c] breakpoints of (s, c) at bp[s * n + chrom_off_out[c] ...], as cg_partition_hmm numbers them.
+ * cg_last_partition_stats: [0..4] wall ms of clean / exchange of cleaned lists / merge / HMM / gather on this rank,
+ * [5] kernel ms, [6] launches, [7] device ms of the NCCL calls.
+ * ------------------------------------------------------------------------------------------- */
+int cg_pedigree_hmm(cg_ctx* ctx, const cg_clean_opts* copts, const cg_hmm_opts* hopts, int n_samples, int64_t n,
+                    const uint8_t* chrom, const uint8_t* chrom_is_autosome, const uint8_t* chrom_is_chrY, int n_chrom,
+                    const int32_t* start, const int32_t* stop, const float* const* count, const uint8_t* gc, int sharded,
+                    int64_t* n_kept, double* local_sd, int* gc_norm_skipped, int64_t* n_common, int32_t* common_index,
+                    float* count_out, int64_t* chrom_off_out, int32_t* n_bp, int32_t* bp, int32_t* owner);
+
+/* ---------------------------------------------------------------------------------------------
  * CanvasSmooth — RepeatedMedianSmoother.Smooth (CanvasSmooth/CanvasSmooth.cs:44-77) over every chromosome:
  * Utilities.MedianFilter (CanvasCommon/Utilities.cs:767-791) with half windows 1 .. max_half_window, each pass on
  * the previous output.  count is all chromosomes concatenated (chrom_off[n_chrom + 1]).  n_out[c] smoothed counts of

@@ -90,3 +90,55 @@ def test_allgather_lists_and_empty_input(eng):
     r = eng.clean_partition_wavelet(np.zeros(0, np.uint8), np.ones(2, np.uint8), np.zeros(2, np.uint8), np.zeros(0, np.int32),
                                     np.zeros(0, np.int32), np.zeros(0, np.float32), np.zeros(0, np.uint8), sharded=True)
     assert len(r["kept_index"]) == 0 and all(len(b) == 0 for b in r["breakpoints"])
+
+
+def test_pedigree_chain_one_call_equals_the_staged_chain(eng):
+    # cg_pedigree_hmm (Clean x S -> common bins -> PerSampleHMM, device resident) against the same stages called one by one
+    # through host memory, and against the oracle; with and without the (loopback) communicator
+    from oracle import pyoracle as ora
+    trio = [synth.make_sample(config=4, sample=k, scale=0.04, n_events=40) for k in range(3)]
+    t0 = trio[0]
+    one = eng.pedigree_hmm(t0.chrom, t0.is_autosome, t0.is_chr_y, t0.start, t0.stop, [t.count for t in trio], t0.gc)
+    cleaned = [eng.clean(t.chrom, t.is_autosome, t.is_chr_y, t.start, t.stop, t.count, t.gc) for t in trio]
+    for k, c in enumerate(cleaned):
+        o = ora.clean(trio[k].chrom, trio[k].is_autosome, trio[k].is_chr_y, trio[k].start, trio[k].stop, trio[k].count, trio[k].gc)
+        assert np.array_equal(c["kept_index"], o["kept_index"])
+        assert one["n_kept"][k] == len(c["kept_index"]) and one["local_sd"][k] == c["local_sd"] == o["local_sd"]
+    m = eng.merge_kept_indices(len(t0), [c["kept_index"].copy() for c in cleaned], [c["count"].copy() for c in cleaned])
+    assert one["n_common"] == len(m["common_index"]) > 1000
+    assert np.array_equal(one["common_index"], m["common_index"])
+    assert np.array_equal(one["count"].view(np.uint32), m["count"].view(np.uint32))
+    off = np.searchsorted(m["common_index"], synth.chrom_offsets(t0.chrom, len(t0.names))).astype(np.int64)
+    assert np.array_equal(one["chrom_off"], off)
+    total = 0
+    for k in range(3):
+        want = ora.partition_hmm(off, textcodec.float_default_roundtrip(m["count"][k]), per_sample=True, n_threads=4)
+        _same_bp(one["breakpoints"][k], want["breakpoints"])
+        total += sum(len(b) for b in want["breakpoints"])
+    assert total > 20
+    loop = eng.pedigree_hmm(t0.chrom, t0.is_autosome, t0.is_chr_y, t0.start, t0.stop, [t.count for t in trio], t0.gc, sharded=True)
+    assert loop["n_common"] == one["n_common"] and set(loop["owner"].ravel().tolist()) == {0}
+    for k in range(3):
+        _same_bp(loop["breakpoints"][k], one["breakpoints"][k])
+
+
+def test_pedigree_chain_edge_cases(eng):
+    t = synth.make_sample(config=4, sample=0, scale=0.02, n_events=10)
+    # one sample: the "common" bins are its own cleaned bins
+    one = eng.pedigree_hmm(t.chrom, t.is_autosome, t.is_chr_y, t.start, t.stop, [t.count], t.gc)
+    c = eng.clean(t.chrom, t.is_autosome, t.is_chr_y, t.start, t.stop, t.count, t.gc)
+    assert np.array_equal(one["common_index"], c["kept_index"]) and np.array_equal(one["count"][0].view(np.uint32), c["count"].view(np.uint32))
+    # empty layout
+    z = np.zeros(0, np.int32)
+    e = eng.pedigree_hmm(np.zeros(0, np.uint8), t.is_autosome, t.is_chr_y, z, z, [np.zeros(0, np.float32)] * 2, np.zeros(0, np.uint8))
+    assert e["n_common"] == 0 and all(len(b) == 0 for per in e["breakpoints"] for b in per) and e["gc_norm_skipped"].all()
+    # a sample this GPU has to clean must come with its counts
+    with pytest.raises(native.CanvasGpuError) as err:
+        eng.pedigree_hmm(t.chrom, t.is_autosome, t.is_chr_y, t.start, t.stop, [t.count, None], t.gc)
+    assert err.value.code == native.CG_ERR_ARG
+    # unsorted chromosome ids are refused as in cg_clean
+    bad = t.chrom.copy()
+    bad[10] = bad.max()
+    with pytest.raises(native.CanvasGpuError) as err:
+        eng.pedigree_hmm(bad, t.is_autosome, t.is_chr_y, t.start, t.stop, [t.count], t.gc)
+    assert err.value.code == native.CG_ERR_UNSORTED

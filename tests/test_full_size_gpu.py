@@ -114,6 +114,15 @@ def test_config4_trio_clean_merge_hmm(engine):
         assert np.array_equal(got["states"], want["states"])
         assert all(a.tolist() == b.tolist() for a, b in zip(got["breakpoints"], want["breakpoints"]))
         assert all(a.tolist() == b.tolist() for a, b in zip(chain["breakpoints"][k], want["breakpoints"]))
+    # the same chain as ONE device-resident call (cg_pedigree_hmm): cleaned lists never leave the GPU between the stages
+    s0 = samples[0]
+    one = engine.pedigree_hmm(s0.chrom, s0.is_autosome, s0.is_chr_y, s0.start, s0.stop, [s.count for s in samples], s0.gc)
+    assert one["n_common"] == len(common) and np.array_equal(one["chrom_off"], off)
+    assert np.array_equal(one["common_index"], chain["common_index"])
+    assert np.array_equal(one["count"].view(np.uint32), m["count"].view(np.uint32))
+    assert one["n_kept"].tolist() == [len(k) for k in cleaned_index]
+    for k in range(3):
+        assert all(a.tolist() == b.tolist() for a, b in zip(one["breakpoints"][k], chain["breakpoints"][k]))
 
 
 def test_config2_cbs_whole_genome(engine):

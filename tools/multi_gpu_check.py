@@ -63,7 +63,22 @@ def checks(eng, rank, world, scale):
     buf = (np.arange(1_000_003, dtype=np.float32) * (1 if rank == world - 1 else 0))
     eng.broadcast(buf, world - 1)
     ok["broadcast"] = bool(np.array_equal(buf, np.arange(1_000_003, dtype=np.float32)))
+    # the pedigree chain (config 4): Clean once per sample on rank s mod R, GPU-to-GPU broadcast of the cleaned lists, merge,
+    # (sample, chromosome) units of the HMM over the ranks, one all-gather -- must equal the one-GPU chain on every rank
+    trio = [synth.make_sample(config=4, sample=k, scale=scale, n_events=40) for k in range(3)]
+    t0 = trio[0]
+    cols = [t.count for t in trio]
+    p1 = eng.pedigree_hmm(t0.chrom, t0.is_autosome, t0.is_chr_y, t0.start, t0.stop, cols, t0.gc)
+    # a rank only needs the counts of the samples it cleans
+    mine_cols = [c if k % world == rank else None for k, c in enumerate(cols)]
+    pn = eng.pedigree_hmm(t0.chrom, t0.is_autosome, t0.is_chr_y, t0.start, t0.stop, mine_cols, t0.gc, sharded=True)
+    ok["pedigree"] = (p1["n_common"] == pn["n_common"] and np.array_equal(p1["common_index"], pn["common_index"])
+                      and np.array_equal(p1["count"].view(np.uint32), pn["count"].view(np.uint32))
+                      and p1["n_kept"].tolist() == pn["n_kept"].tolist() and p1["local_sd"].tolist() == pn["local_sd"].tolist()
+                      and all(same_bp(a, b) for a, b in zip(p1["breakpoints"], pn["breakpoints"]))
+                      and sum(len(b) for per in p1["breakpoints"] for b in per) > 0)
     info = {"bins": int(len(cov)), "breakpoints": sum(len(b) for b in full["breakpoints"]), "owners": shard["owner"].tolist(),
+            "pedigree_units_per_rank": np.bincount(pn["owner"].ravel(), minlength=world).tolist(),
             "fused_exchange_ms": x_ms}
     return ok, info
 
