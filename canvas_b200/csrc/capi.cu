@@ -54,6 +54,11 @@ extern "C" void cg_destroy(cg_ctx* ctx) {
     if (ctx->plan_pinned) cudaFreeHost(ctx->plan_pinned);
     if (ctx->aux) cudaFree(ctx->aux);
     if (ctx->ped) cudaFree(ctx->ped);
+    if (ctx->prefetch_stream) { cudaStreamSynchronize(ctx->prefetch_stream); cudaStreamDestroy(ctx->prefetch_stream); }
+    for (CgStageSlot& sl : ctx->stage) {
+        if (sl.base) cudaFree(sl.base);
+        if (sl.ready) cudaEventDestroy(sl.ready);
+    }
     for (int i = 0; i < 8; i++)
         if (ctx->stage_ev[i]) cudaEventDestroy(ctx->stage_ev[i]);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
@@ -106,4 +111,47 @@ extern "C" void* cg_host_alloc(size_t bytes) {
 }
 extern "C" void cg_host_free(void* p) {
     if (p) cudaFreeHost(p);
+}
+
+// ---------------------------------------------------------------------------------------------
+// cg_prefetch_bins: the next sample's columns cross PCIe while the current call's kernels run
+// ---------------------------------------------------------------------------------------------
+extern "C" int cg_prefetch_bins(cg_ctx* ctx, int64_t n, const uint8_t* chrom, const int32_t* start, const int32_t* stop,
+                                const float* count, const uint8_t* gc) {
+    if (!ctx) return CG_ERR_ARG;
+    if (n < 0 || n > 0x7fff0000LL) return cg_fail(ctx, CG_ERR_ARG, "cg_prefetch_bins: bad length");
+    if (n == 0) return CG_OK;
+    if (!chrom || !start || !stop || !count || !gc) return cg_fail(ctx, CG_ERR_ARG, "cg_prefetch_bins: null array");
+    CG_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (!ctx->prefetch_stream) CG_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->prefetch_stream, cudaStreamNonBlocking));
+    // a free slot if there is one, else the older staged copy is given up: with one prefetch per call the slots alternate, and
+    // the slot the next call reads is never the one being filled (calls are synchronous: nothing reads a slot right now)
+    CgStageSlot* sl = !ctx->stage[0].staged ? &ctx->stage[0] : !ctx->stage[1].staged ? &ctx->stage[1]
+                      : (ctx->stage[0].seq < ctx->stage[1].seq ? &ctx->stage[0] : &ctx->stage[1]);
+    const size_t n_al = ((size_t)n + 255) & ~(size_t)255;
+    const size_t need = n_al * 14;
+    if (need > sl->cap) {
+        if (sl->base) { CG_CUDA(ctx, cudaStreamSynchronize(ctx->prefetch_stream)); CG_CUDA(ctx, cudaFree(sl->base)); sl->base = nullptr; sl->cap = 0; }
+        CG_CUDA(ctx, cudaMalloc((void**)&sl->base, need + (need >> 4)));
+        sl->cap = need + (need >> 4);
+    }
+    if (!sl->ready) CG_CUDA(ctx, cudaEventCreateWithFlags(&sl->ready, cudaEventDisableTiming));
+    sl->start = (int32_t*)sl->base;
+    sl->stop = (int32_t*)(sl->base + n_al * 4);
+    sl->count = (float*)(sl->base + n_al * 8);
+    sl->chrom = (uint8_t*)(sl->base + n_al * 12);
+    sl->gc = (uint8_t*)(sl->base + n_al * 13);
+    cudaStream_t ps = ctx->prefetch_stream;
+    sl->staged = false;
+    CG_CUDA(ctx, cudaMemcpyAsync(sl->start, start, (size_t)n * 4, cudaMemcpyHostToDevice, ps));
+    CG_CUDA(ctx, cudaMemcpyAsync(sl->stop, stop, (size_t)n * 4, cudaMemcpyHostToDevice, ps));
+    CG_CUDA(ctx, cudaMemcpyAsync(sl->count, count, (size_t)n * 4, cudaMemcpyHostToDevice, ps));
+    CG_CUDA(ctx, cudaMemcpyAsync(sl->chrom, chrom, (size_t)n, cudaMemcpyHostToDevice, ps));
+    CG_CUDA(ctx, cudaMemcpyAsync(sl->gc, gc, (size_t)n, cudaMemcpyHostToDevice, ps));
+    CG_CUDA(ctx, cudaEventRecord(sl->ready, ps));
+    sl->n = n;
+    sl->key[0] = chrom; sl->key[1] = start; sl->key[2] = stop; sl->key[3] = count; sl->key[4] = gc;
+    sl->seq = ++ctx->stage_seq;
+    sl->staged = true;
+    return CG_OK;
 }

@@ -23,6 +23,20 @@ struct CgGraphEntry {
     cudaGraphExec_t exec;
     int launches;
 };
+// Input columns of a sample staged ahead of the call that consumes them (cg_prefetch_bins)
+struct CgStageSlot {
+    char* base = nullptr;
+    size_t cap = 0;
+    int64_t n = 0;
+    const void* key[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // the host arrays the columns were copied from
+    cudaEvent_t ready = nullptr;
+    bool staged = false;
+    unsigned long long seq = 0;  // order of staging: the oldest matching copy is consumed first
+    uint8_t *chrom = nullptr, *gc = nullptr;
+    int32_t *start = nullptr, *stop = nullptr;
+    float* count = nullptr;
+};
+
 struct cg_ctx {
     int device = 0;
     int num_sms = CG_NUM_SMS_FALLBACK;
@@ -67,6 +81,10 @@ struct cg_ctx {
     // third device block: what the pedigree chain keeps between its stages (cleaned lists of every sample, merged counts)
     char* ped = nullptr;
     size_t ped_cap = 0;
+    // two staging slots for prefetched inputs: one is read by the running call while the other fills
+    CgStageSlot stage[2];
+    unsigned long long stage_seq = 0;
+    cudaStream_t prefetch_stream = nullptr;
     CgTimeline* tl = nullptr;  // debug timeline of the current call (CANVAS_DEBUG)
     std::vector<CgGraphEntry> clean_graphs;  // Clean pipeline graphs (clean.cu), dropped when the arena moves
     std::vector<CgGraphEntry> part_graphs;   // partition: per-chromosome pipelines (wavelet.cu); exec == nullptr: shape seen once
@@ -119,6 +137,17 @@ inline int cg_fail(cg_ctx* ctx, int code, const std::string& msg) {
                            std::string(#call) + ": " + cudaGetErrorString(e__) + " (" +      \
                                __FILE__ + ":" + std::to_string(__LINE__) + ")");             \
     } while (0)
+
+// The staged copy of exactly these host arrays, if cg_prefetch_bins was called for them (consumed by the caller)
+inline CgStageSlot* cg_stage_find(cg_ctx* ctx, int64_t n, const void* chrom, const void* start, const void* stop, const void* count,
+                                  const void* gc) {
+    CgStageSlot* hit = nullptr;
+    for (CgStageSlot& sl : ctx->stage)
+        if (sl.staged && sl.n == n && sl.key[0] == chrom && sl.key[1] == start && sl.key[2] == stop && sl.key[3] == count && sl.key[4] == gc &&
+            (!hit || sl.seq < hit->seq))
+            hit = &sl;
+    return hit;
+}
 
 // Arena: one cudaMalloc, bump allocation, 256-byte aligned.  reserve() is called once per API call
 // with the worst-case footprint, take() hands out slices.

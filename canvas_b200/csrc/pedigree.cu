@@ -86,7 +86,7 @@ extern "C" int cg_pedigree_hmm(cg_ctx* ctx, const cg_clean_opts* copts, const cg
     for (int c = 0; c <= C; c++) chrom_off_out[c] = 0;
     *n_common = 0;
     if (owner) for (int i = 0; i < S * C; i++) owner[i] = 0;
-    for (int i = 0; i < 16; i++) ctx->stats[i] = 0;
+    double phase[8] = {0};  // the stages below reuse ctx->stats; the chain's own figures are written at the end
     bool any_mine = false;
     for (int s = 0; s < S; s++) any_mine = any_mine || (s % R == me);
     int rc_local = CG_OK;
@@ -203,7 +203,7 @@ extern "C" int cg_pedigree_hmm(cg_ctx* ctx, const cg_clean_opts* copts, const cg
         return CG_OK;
     };
     if (rc_local == CG_OK) rc_local = clean_mine();
-    ctx->stats[0] = ms_since(t_phase);
+    phase[0] = ms_since(t_phase);
 
     // ---- every sample's cleaned list on every rank
     if (exchange) {
@@ -252,11 +252,11 @@ extern "C" int cg_pedigree_hmm(cg_ctx* ctx, const cg_clean_opts* copts, const cg
             float ms = 0;
             cudaEventElapsedTime(&ms, ctx->comm->ev0, ctx->comm->ev1);
             ctx->comm->last_exchange_ms = ms;
-            ctx->stats[7] = ms;
+            phase[7] = ms;
         }
     }
     for (int s = 0; s < S; s++) { n_kept[s] = info[s].m; local_sd[s] = info[s].local_sd; gc_norm_skipped[s] = info[s].skipped; }
-    ctx->stats[1] = ms_since(t_phase);
+    phase[1] = ms_since(t_phase);
     if (n == 0) return CG_OK;
 
     // ---- bins common to every sample (every rank)
@@ -285,7 +285,7 @@ extern "C" int cg_pedigree_hmm(cg_ctx* ctx, const cg_clean_opts* copts, const cg
         CG_CUDA(ctx, cudaStreamSynchronize(st));
     }
     for (int c = 0; c <= C; c++) chrom_off_out[c] = off[c];
-    ctx->stats[2] = ms_since(t_phase);
+    phase[2] = ms_since(t_phase);
 
     // ---- PerSampleHMM: the S x C (sample, chromosome) units, longest first over the ranks
     std::vector<int32_t> own((size_t)S * C, 0);
@@ -309,7 +309,7 @@ extern "C" int cg_pedigree_hmm(cg_ctx* ctx, const cg_clean_opts* copts, const cg
         kernel_ms += ctx->last_kernel_ms;
         launches += ctx->launches;
     }
-    ctx->stats[3] = ms_since(t_phase);
+    phase[3] = ms_since(t_phase);
     if (rc_hmm != CG_OK && !exchange) { cudaStreamSynchronize(ctx->copy_stream); return rc_hmm; }
 
     // ---- one all-gather of the packed lists: [sample, chromosome, count, breakpoints ...] per unit
@@ -347,12 +347,13 @@ extern "C" int cg_pedigree_hmm(cg_ctx* ctx, const cg_clean_opts* copts, const cg
             }
             at += (size_t)counts[r];
         }
-        ctx->stats[7] += ctx->comm->last_exchange_ms;
+        phase[7] += ctx->comm->last_exchange_ms;
     }
     CG_CUDA(ctx, cudaStreamSynchronize(ctx->copy_stream));
-    ctx->stats[4] = ms_since(t_phase);
-    ctx->stats[5] = kernel_ms;
-    ctx->stats[6] = (double)launches;
+    phase[4] = ms_since(t_phase);
+    phase[5] = kernel_ms;
+    phase[6] = (double)launches;
+    for (int i = 0; i < 16; i++) ctx->stats[i] = i < 8 ? phase[i] : 0.0;
     ctx->last_kernel_ms = kernel_ms;
     ctx->launches = launches;
     return CG_OK;

@@ -84,6 +84,7 @@ SIGNATURES = {
     "cg_merge_common_bins": (C.c_int, [C.c_void_p, C.c_int, _P(_i64), _P(C.c_void_p), _P(C.c_void_p), _P(C.c_void_p),
                                        _P(C.c_void_p), _P(_i64), _P(_i32), _P(_i32), _P(_f32)]),
     "cg_merge_kept_indices": (C.c_int, [C.c_void_p, _i64, C.c_int, _P(_i64), _P(C.c_void_p), _P(C.c_void_p), _P(_i64), _P(_i32), _P(_f32)]),
+    "cg_prefetch_bins": (C.c_int, [C.c_void_p, _i64, _P(_u8), _P(_i32), _P(_i32), _P(_f32), _P(_u8)]),
     "cg_pedigree_hmm": (C.c_int, [C.c_void_p, _P(CleanOpts), _P(HmmOpts), C.c_int, _i64, _P(_u8), _P(_u8), _P(_u8), C.c_int, _P(_i32), _P(_i32),
                                   _P(C.c_void_p), _P(_u8), C.c_int, _P(_i64), _P(_f64), _P(C.c_int), _P(_i64), _P(_i32), _P(_f32), _P(_i64),
                                   _P(_i32), _P(_i32), _P(_i32)]),
@@ -644,6 +645,15 @@ class Engine:
         self._check(rc)
         return {"breakpoints": [bp[off[c]:off[c] + n_bp[c]].copy() for c in range(nc)], "states": states[:n],
                 "kernel_ms": self.lib.cg_last_kernel_ms(self.h), "launches": self.lib.cg_last_launches(self.h)}
+
+    def prefetch_bins(self, chrom, start, stop, count, gc):
+        """cg_prefetch_bins: stage these columns on the device while the current call computes; the next clean /
+        clean_partition_wavelet call given the SAME arrays (contiguous, right dtypes, ideally page-locked) consumes them."""
+        for a, t in ((chrom, np.uint8), (start, np.int32), (stop, np.int32), (count, np.float32), (gc, np.uint8)):
+            if not (isinstance(a, np.ndarray) and a.dtype == t and a.flags.c_contiguous):
+                raise ValueError("prefetch_bins needs the contiguous typed arrays the later call will be given")
+        self._check(self.lib.cg_prefetch_bins(self.h, len(count), _ptr(chrom, _u8), _ptr(start, _i32), _ptr(stop, _i32),
+                                              _ptr(count, _f32), _ptr(gc, _u8)))
 
     def pedigree_hmm(self, chrom, is_autosome, is_chr_y, start, stop, counts, gc, sharded=False, min_size=10, out=None,
                      size_filter=True, outlier_filter=True, gc_norm=True, gc_mode=0, want_local_sd=True, min_bins_per_gc=100):

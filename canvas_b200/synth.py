@@ -53,6 +53,9 @@ def make_sample(config=2, sample=0, chromosomes=None, bin_size=1000, scale=1.0, 
     """One synthetic .binned array.  `scale` shrinks every chromosome (tests); `chromosomes`
     restricts to a subset of names (config 1 = ['chr20'])."""
     rng = np.random.default_rng(20240601 + 1000 * config + sample)
+    # config 4 is a pedigree: its samples are binned on ONE layout (CanvasRunner.cs:846-870 hands the same bin definitions to
+    # every sample), so coordinates and GC content come from a generator the sample index does not touch
+    lrng = np.random.default_rng(20240601 + 1000 * config + 999) if config == 4 else rng
     chroms = [(n, l) for n, l in HG19 if chromosomes is None or n in chromosomes]
     names = [n for n, _ in chroms]
     cols = {k: [] for k in ("chrom", "start", "stop", "count", "gc")}
@@ -65,17 +68,17 @@ def make_sample(config=2, sample=0, chromosomes=None, bin_size=1000, scale=1.0, 
         mid = nb // 2
         big = np.arange(mid - n_big // 2, mid - n_big // 2 + n_big)
         big = big[(big >= 0) & (big < nb)]
-        extra = np.exp(rng.uniform(np.log(5e3), np.log(3e6), size=len(big))).astype(np.int64)
+        extra = np.exp(lrng.uniform(np.log(5e3), np.log(3e6), size=len(big))).astype(np.int64)
         shift = np.zeros(nb, np.int64)
         shift[big] = extra
         cum = np.cumsum(shift)
         start = start + cum - shift
         stop = stop + cum
         # GC: autocorrelated N(41, 6)
-        white = rng.normal(0, 1, nb + 24)
+        white = lrng.normal(0, 1, nb + 24)
         kernel = np.ones(25) / np.sqrt(25)
         smooth = np.convolve(white, kernel, mode="valid")[:nb]
-        gcv = 41 + 6 * (0.8 * smooth + 0.6 * rng.normal(0, 1, nb))
+        gcv = 41 + 6 * (0.8 * smooth + 0.6 * lrng.normal(0, 1, nb))
         gc = np.clip(np.rint(gcv), 0, 100).astype(np.int64)
         bias = np.clip(1 - 8e-4 * (gc - 45.0) ** 2, 0.3, 1.1)
         cn = np.full(nb, 2.0 if is_autosome(name) else 1.0)

@@ -308,6 +308,15 @@ int cg_merge_common_bins(cg_ctx* ctx, int n_samples, const int64_t* n, const uin
 int cg_merge_kept_indices(cg_ctx* ctx, int64_t n_bins, int n_samples, const int64_t* n_kept, const int32_t* const* kept,
                           const float* const* count, int64_t* n_out, int32_t* common_index, float* count_out);
 
+/* Software pipelining across calls (a cohort run processes sample after sample): start copying the NEXT sample's columns into
+ * a staging slot of the device while the call for the current sample computes.  Returns at once.  The next cg_clean /
+ * cg_clean_partition_wavelet* call that is given exactly these arrays (same pointers, same n) reads the staged columns and
+ * copies nothing; the arrays must stay unchanged (and, for the copy to overlap, page-locked: cg_host_alloc) until then.  Two
+ * slots: one prefetch per call keeps one slot filling while the other is read.  Replaces nothing in the reference (its
+ * modules read their input files before they compute); it hides the 14 B/bin upload that the file read was. */
+int cg_prefetch_bins(cg_ctx* ctx, int64_t n, const uint8_t* chrom, const int32_t* start, const int32_t* stop, const float* count,
+                     const uint8_t* gc);
+
 /* ---------------------------------------------------------------------------------------------
  * The SmallPedigree chain in one call, device resident: CanvasClean per sample (Canvas/CanvasRunner.cs:883-893) ->
  * bins common to every sample (CanvasRunner.cs:895-903, CanvasCommon/Utilities.cs:834-920) -> CanvasPartition
