@@ -255,6 +255,7 @@ extern "C" int cg_pedigree_hmm(cg_ctx* ctx, const cg_clean_opts* copts, const cg
             phase[7] = ms;
         }
     }
+    if (rc_local != CG_OK) return rc_local;  // (with an exchange every rank has left above, together)
     for (int s = 0; s < S; s++) { n_kept[s] = info[s].m; local_sd[s] = info[s].local_sd; gc_norm_skipped[s] = info[s].skipped; }
     phase[1] = ms_since(t_phase);
     if (n == 0) return CG_OK;
@@ -288,12 +289,23 @@ extern "C" int cg_pedigree_hmm(cg_ctx* ctx, const cg_clean_opts* copts, const cg
     phase[2] = ms_since(t_phase);
 
     // ---- PerSampleHMM: the S x C (sample, chromosome) units, longest first over the ranks
+    // Every HMM call carries a fixed cost (whole-genome quartiles, emission table, three host syncs: ~1 ms) next to ~0.5 ms of
+    // per-chromosome work for a whole sample, so a rank should touch as few samples as possible: with R >= S the ranks r with
+    // r mod S == s form sample s's group and share its chromosomes longest-first; with R < S whole samples go round robin.
     std::vector<int32_t> own((size_t)S * C, 0);
     if (C > 0) {
-        std::vector<int64_t> w((size_t)S * C);
-        for (int s = 0; s < S; s++)
-            for (int c = 0; c < C; c++) w[(size_t)s * C + c] = off[c + 1] - off[c];
-        comm_assign_lpt(S * C, w.data(), R, own.data());
+        std::vector<int64_t> w((size_t)C);
+        for (int c = 0; c < C; c++) w[c] = off[c + 1] - off[c];
+        for (int s = 0; s < S; s++) {
+            if (R < S) {
+                for (int c = 0; c < C; c++) own[(size_t)s * C + c] = s % R;
+                continue;
+            }
+            const int group = (R - s + S - 1) / S;  // ranks s, s + S, s + 2 S, ... below R
+            std::vector<int32_t> in_group((size_t)C);
+            comm_assign_lpt(C, w.data(), group, in_group.data());
+            for (int c = 0; c < C; c++) own[(size_t)s * C + c] = s + S * in_group[c];
+        }
     }
     if (owner) for (int i = 0; i < S * C; i++) owner[i] = own[i];
     int rc_hmm = CG_OK;

@@ -325,8 +325,9 @@ int cg_prefetch_bins(cg_ctx* ctx, int64_t n, const uint8_t* chrom, const int32_t
  * The cleaned lists never leave the GPU between the stages: the layout is uploaded once, each sample adds 4 B/bin.
  * sharded != 0 (communicator of R ranks, every rank makes the same call): sample s is cleaned on rank s mod R (count[s]
  * may be NULL elsewhere), cleaned lists move GPU to GPU over NCCL, the n_samples x n_chrom (sample, chromosome) units of the
- * HMM are assigned longest-first (cg_shard_assign on the common-bin counts, tiled per sample) and one all-gather completes
- * the result on EVERY rank.  owner (may be NULL): [n_samples][n_chrom] rank of every unit.
+ * HMM are spread so that a rank touches as few samples as possible (R >= n_samples: the ranks r with r mod n_samples == s share
+ * sample s's chromosomes longest-first; R < n_samples: whole samples round robin) and one all-gather completes the result on
+ * EVERY rank.  owner (may be NULL): [n_samples][n_chrom] rank of every unit.
  * Outputs: n_kept / local_sd / gc_norm_skipped [n_samples] as cg_clean reports them; *n_common, common_index[k] (capacity
  * n) = layout index of common bin k, count_out[s * n + k] = sample s's cleaned count of it (what the merged .cleaned file
  * prints with float.ToString()); chrom_off_out[n_chrom + 1] offsets of the chromosomes among the common bins;

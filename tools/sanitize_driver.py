@@ -1,7 +1,7 @@
 """Small inputs through every kernel family, for compute-sanitizer (memcheck / racecheck / synccheck / initcheck).
 Results are still compared with the oracle where that is cheap, so a sanitizer run also proves the instrumented
 kernels computed the right thing.
-Usage (GPU box): compute-sanitizer --tool memcheck python tools/sanitize_driver.py [fused|k8|cbs|hmm|bin|loess|all]"""
+Usage (GPU box): compute-sanitizer --tool memcheck python tools/sanitize_driver.py [fused|k8|cbs|hmm|bin|loess|pedigree|all]"""
 import os
 import sys
 
@@ -86,7 +86,26 @@ def loess():
     print("loess ok")
 
 
-runs = {"fused": fused, "k8": k8, "cbs": cbs, "hmm": hmm, "bin": binning, "loess": loess}
+def pedigree():
+    # the device-resident trio chain (loopback communicator) and a prefetched fused call
+    eng.comm_init(1, 0)
+    trio = [synth.make_sample(config=4, sample=k, scale=scale, n_events=20) for k in range(3)]
+    t0 = trio[0]
+    one = eng.pedigree_hmm(t0.chrom, t0.is_autosome, t0.is_chr_y, t0.start, t0.stop, [t.count for t in trio], t0.gc, sharded=True)
+    c = [ora.clean(t.chrom, t.is_autosome, t.is_chr_y, t.start, t.stop, t.count, t.gc) for t in trio]
+    assert [len(x["kept_index"]) for x in c] == one["n_kept"].tolist()
+    common = np.intersect1d(np.intersect1d(c[0]["kept_index"], c[1]["kept_index"]), c[2]["kept_index"])
+    assert np.array_equal(common, one["common_index"])
+    cols = [np.ascontiguousarray(a, d) for a, d in ((t0.chrom, np.uint8), (t0.start, np.int32), (t0.stop, np.int32), (t0.count, np.float32), (t0.gc, np.uint8))]
+    plain = eng.clean_partition_wavelet(cols[0], t0.is_autosome, t0.is_chr_y, cols[1], cols[2], cols[3], cols[4], evenness_window=2000)
+    for _ in range(2):
+        eng.prefetch_bins(*cols)
+        pre = eng.clean_partition_wavelet(cols[0], t0.is_autosome, t0.is_chr_y, cols[1], cols[2], cols[3], cols[4], evenness_window=2000)
+        assert all(a.tolist() == b.tolist() for a, b in zip(plain["breakpoints"], pre["breakpoints"]))
+    print("pedigree + prefetch ok: common bins", one["n_common"])
+
+
+runs = {"pedigree": pedigree, "fused": fused, "k8": k8, "cbs": cbs, "hmm": hmm, "bin": binning, "loess": loess}
 rc = 0
 for name, fn in runs.items():
     if what in ("all", name):
