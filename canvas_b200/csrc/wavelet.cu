@@ -223,6 +223,9 @@ struct WvDev {
     long long* rq_off2;
     int* rq_tfirst2;
     unsigned char* rq_sel2;
+    // fused call: the prefix sums are computed before the host knows the cleaned lengths (tile grid of the input lengths)
+    int* e_tile_c;
+    int* e_tile_first;
     unsigned long long* phase_ns;
     unsigned long long* tl_ns;  // debug timeline of the decomposition stages, [C][16]
     unsigned long long* task_dbg;  // debug: per mid task (chromosome, bins, nodes, ns)
@@ -303,6 +306,7 @@ size_t wv_workspace_bytes(const WvPlan& pl) {
     s += arena_need(C + 1, 4) + arena_need(N + 1, 4);
     s += arena_need((C + 1) * RQ_BUCKETS, 8) + arena_need(N + 1, 8) + arena_need((size_t)(pl.rq_ntiles + 1) * RQ_BUCKETS, 2) * 2;
     s += arena_need((size_t)(pl.rq_ntiles + C + 2) * RQ_BUCKETS, 4) + arena_need(C + 2, 4) + arena_need((C + 1) * 8, 8) + arena_need((C + 1) * 16, 8) + arena_need(2 * UH_TASK_DBG_CAP + 2, 8) + arena_need(1, sizeof(UhTinyTab)) + arena_need(WV_PACK_INTS, 4) + arena_need(C + 2, 8) + arena_need(C + 2, 4) + arena_need(C + 2, 1);
+    s += arena_need(pl.tiles.size() + 1, 4) + arena_need(C + 2, 4);
     return s + (1 << 16);
 }
 
@@ -381,6 +385,9 @@ int wv_alloc(cg_ctx* ctx, const WvPlan& pl, WvDev& d, double* cov_dev_existing, 
     d.rq_tfirst2 = arena_take<int>(ctx, C + 2);
     d.rq_sel2 = arena_take<unsigned char>(ctx, C + 2);
     ok = ok && d.rq_off2 && d.rq_tfirst2 && d.rq_sel2;
+    d.e_tile_c = arena_take<int>(ctx, pl.tiles.size() + 1);
+    d.e_tile_first = arena_take<int>(ctx, C + 2);
+    ok = ok && d.e_tile_c && d.e_tile_first;
     d.tiny_tab = arena_take<UhTinyTab>(ctx, 1);
     ok = ok && d.rq_spl && d.rq_sorted && d.rq_hist && d.rq_tstart && d.rq_cum && d.rq_tfirst;
     ok = ok && d.cov && d.off && d.selected && d.pz && d.seg_len && d.work && d.seg_nwork && d.ev_work && d.tiles && d.tile_first &&
@@ -469,7 +476,7 @@ __global__ void wv_device_offsets_kernel(const unsigned* __restrict__ chrom_cnt,
 }
 
 int wv_enqueue(cg_ctx* ctx, const cg_wavelet_opts* o, const WvPlan& pl, WvDev& d, const unsigned char* selected_host,
-               bool rq_index_done = false, int* comm_pack = nullptr, bool use_int = false) {
+               bool rq_index_done = false, int* comm_pack = nullptr, bool use_int = false, bool scan_done = false) {
     cudaStream_t s = ctx->stream;
     const int C = pl.n_chrom;
     const WvSegTable& t = pl.t;
@@ -554,11 +561,12 @@ int wv_enqueue(cg_ctx* ctx, const cg_wavelet_opts* o, const WvPlan& pl, WvDev& d
         if (!pl.ev_work.empty())
             CG_LAUNCH(ctx, wv_evenness_kernel, (int)pl.ev_work.size(), 1024, 0, d.cov, d.ev_work, d.ev10, d.ev100, d.ctl);
     };
-    auto enqueue_scan = [&]() {
-        if (ntiles > 0) {
-            CG_LAUNCH(ctx, wv_scan_tile_sum_kernel, ntiles, 256, 0, d.cov, d.tiles, d.tsum);
+    auto enqueue_scan = [&]() {  // (fused call: already done, from device-side offsets, while the host waited for the counts)
+        if (ntiles > 0 && !scan_done) {
+            const WvScanSrc src{d.tiles, nullptr, nullptr, nullptr};
+            CG_LAUNCH(ctx, wv_scan_tile_sum_kernel, ntiles, 256, 0, d.cov, src, d.tsum);
             CG_LAUNCH(ctx, wv_scan_tile_offsets_kernel, div_up(C, 64), 64, 0, d.tsum, d.tile_first, C);
-            CG_LAUNCH(ctx, wv_scan_apply_kernel, ntiles, 256, 0, d.cov, d.tiles, d.tsum, d.off, d.pz);
+            CG_LAUNCH(ctx, wv_scan_apply_kernel, ntiles, 256, 0, d.cov, src, d.tsum, d.off, d.pz);
         }
     };
     auto enqueue_triplets = [&]() {
@@ -588,7 +596,7 @@ int wv_enqueue(cg_ctx* ctx, const cg_wavelet_opts* o, const WvPlan& pl, WvDev& d
         ctx->stream = main_s;
         // ---- main stream: prefix sums, then medians and MADs of the coverage windows / chromosomes on integer hundredths
         enqueue_scan();
-        CG_CUDA(ctx, cudaEventRecord(ctx->ev_scan, ctx->stream));  // the decomposition's chains and mid stage need nothing else
+        if (!scan_done) CG_CUDA(ctx, cudaEventRecord(ctx->ev_scan, ctx->stream));  // the decomposition's chains and mid stage need nothing else
         CG_TL(ctx, "scan");
         CovView32 cv1{d.hq, nullptr}, cv2{d.hq, d.m2};
         CG_LAUNCH(ctx, wv_request32_kernel, rq_grid, 128, 0, d.sel32, sp, 1);
@@ -604,7 +612,7 @@ int wv_enqueue(cg_ctx* ctx, const cg_wavelet_opts* o, const WvPlan& pl, WvDev& d
         enqueue_evenness();
         CG_TL(ctx, "evenness");
         enqueue_scan();
-        CG_CUDA(ctx, cudaEventRecord(ctx->ev_scan, ctx->stream));
+        if (!scan_done) CG_CUDA(ctx, cudaEventRecord(ctx->ev_scan, ctx->stream));
         CG_TL(ctx, "scan");
         enqueue_triplets();
         CG_TL(ctx, "triplets");
@@ -754,6 +762,8 @@ int wv_enqueue(cg_ctx* ctx, const cg_wavelet_opts* o, const WvPlan& pl, WvDev& d
         unsigned long long hl = 1469598103934665603ull, hs = 1469598103934665603ull;  // FNV-1a of the launch lengths / the mask
         for (int c = 0; c <= C; c++) { hl ^= (unsigned long long)d.alloc_off[c]; hl *= 1099511628211ull; }
         for (int c = 0; c < C; c++) { hs ^= (unsigned long long)(selected_host[c] ? 1 : 0) + 2; hs *= 1099511628211ull; }
+        // the finish kernels take a pointer into the median table that depends on the number of windows of THIS plan
+        hs ^= (unsigned long long)t.base_chrom + 0x9e3779b97f4a7c15ull; hs *= 1099511628211ull;
         const long long key[12] = {(long long)(uintptr_t)ctx->arena, (long long)(uintptr_t)d.cov, (long long)(uintptr_t)d.ctl,
                                    (long long)(uintptr_t)d.cc, (long long)(uintptr_t)d.bp, C, o->min_size, o->is_germline, (long long)hl,
                                    (long long)hs, (long long)(uintptr_t)d.rq_sorted, (long long)(uintptr_t)d.tiny_tab};
@@ -1206,17 +1216,43 @@ static int clean_partition_wavelet_impl(cg_ctx* ctx, const cg_clean_opts* copts,
         for (int c = 0; c < n_chrom; c++) { sel[c] = own[c] == ctx->comm->rank; if (owner) owner[c] = own[c]; }
     } else if (chrom_selected)
         for (int c = 0; c < n_chrom; c++) sel[c] = chrom_selected[c] ? 1 : 0;
+    bool scan_done = false;
     if (n_chrom > 0) {
-        // ... on the side stream, from its own copies of the offsets: the finish stage needs it a millisecond from now
-        CG_CUDA(ctx, cudaStreamWaitEvent(ctx->side_stream, ctx->ev_mid, 0));
+        // chromosome offsets of the cleaned list, on the device: the index and the prefix sums need nothing else from the plan
+        CG_LAUNCH(ctx, wv_device_offsets_kernel, 1, 32, 0, chrom_cnt, n_chrom, wd.rq_off2, wd.rq_tfirst2);
+        CG_CUDA(ctx, cudaEventRecord(ctx->ev_off, s));
+        // ... the index on the side stream: the finish stage needs it a millisecond from now
+        CG_CUDA(ctx, cudaStreamWaitEvent(ctx->side_stream, ctx->ev_off, 0));
         ctx->stream = ctx->side_stream;
         cudaMemcpyAsync(wd.rq_sel2, sel.data(), n_chrom, cudaMemcpyHostToDevice, ctx->side_stream);
-        CG_LAUNCH(ctx, wv_device_offsets_kernel, 1, 32, 0, chrom_cnt, n_chrom, wd.rq_off2, wd.rq_tfirst2);
         wv_enqueue_rq_index(ctx, wd, n_chrom, worst.rq_ntiles, wd.rq_off2, wd.rq_tfirst2, wd.rq_sel2);
         ctx->stream = s;
         CG_CUDA(ctx, cudaEventRecord(ctx->ev_rq, ctx->side_stream));
+        CG_TL(ctx, "clears");
+        // ... and the prefix sums on this stream, while the host waits for the counts and plans: the tile grid is laid out for
+        // the input lengths and every tile clips itself against the device-side offsets (same tile boundaries relative to a
+        // chromosome's first bin as the host's table, hence the same sums)
+        const size_t nt = worst.tiles.size();
+        const size_t early_bytes = (nt + (size_t)n_chrom + 2) * 4;
+        constexpr size_t EARLY_AT = 128u << 10;  // second half of the pinned scalar block (the first holds the downloads)
+        if (nt > 0 && EARLY_AT + early_bytes <= ctx->pinned_cap && !getenv("CANVAS_NO_EARLY_SCAN")) {
+            int* h_tc = (int*)(ctx->pinned + EARLY_AT);
+            int* h_tf = h_tc + nt;
+            for (size_t k = 0; k < nt; k++) h_tc[k] = worst.tiles[k].c;
+            for (int c = 0; c <= n_chrom; c++) h_tf[c] = worst.tile_first[c];
+            CG_CUDA(ctx, cudaMemcpyAsync(wd.e_tile_c, h_tc, nt * 4, cudaMemcpyHostToDevice, s));
+            CG_CUDA(ctx, cudaMemcpyAsync(wd.e_tile_first, h_tf, (size_t)(n_chrom + 1) * 4, cudaMemcpyHostToDevice, s));
+            const WvScanSrc src{nullptr, wd.e_tile_c, wd.e_tile_first, wd.rq_off2};
+            CG_LAUNCH(ctx, wv_scan_tile_sum_kernel, (int)nt, 256, 0, wd.cov, src, wd.tsum);
+            CG_LAUNCH(ctx, wv_scan_tile_offsets_kernel, div_up(n_chrom, 64), 64, 0, wd.tsum, wd.e_tile_first, n_chrom);
+            CG_LAUNCH(ctx, wv_scan_apply_kernel, (int)nt, 256, 0, wd.cov, src, wd.tsum, wd.rq_off2, wd.pz);
+            CG_CUDA(ctx, cudaEventRecord(ctx->ev_scan, s));
+            scan_done = true;
+            CG_TL(ctx, "prefix sums (early)");
+        }
+    } else {
+        CG_TL(ctx, "clears");
     }
-    CG_TL(ctx, "clears");
     ht[1] = now_us();
     cudaEventRecord(ctx->gap_ev, s);
     ctx->gap_used = true;
@@ -1250,7 +1286,7 @@ static int clean_partition_wavelet_impl(cg_ctx* ctx, const cg_clean_opts* copts,
     const bool use_int = h_cnt[256] == 0u && !getenv("CANVAS_NO_INT_KEYS");
     ctx->stats[15] = use_int ? 1.0 : 0.0;
     ht[3] = now_us();
-    rc = wv_enqueue(ctx, wopts, pl, wd, sel.data(), n_chrom > 0, exchange ? ctx->comm->d_send : nullptr, use_int);
+    rc = wv_enqueue(ctx, wopts, pl, wd, sel.data(), n_chrom > 0, exchange ? ctx->comm->d_send : nullptr, use_int, scan_done);
     if (rc) { cudaStreamSynchronize(s); cudaStreamSynchronize(ctx->copy_stream); return rc; }
     CG_CUDA(ctx, cudaEventRecord(ctx->ev1, s));
     ht[4] = now_us();

@@ -72,15 +72,30 @@ __device__ inline void uh_emit_candidate(const UhParams& p, int c, int level, in
 }
 
 // Chains and the mid stage run before the thresholds exist (they overlap the order statistics that produce them): every one of
-// their nodes — a few hundred per chromosome — is recorded, and the finish stage applies the real threshold as to any candidate.
-__device__ inline void uh_emit_candidate_always(const UhParams& p, int c, int level, int s, int b, int e, double coef) {
-    const UhChromPlan& cp = p.cp[c];
-    const int i = atomicAdd(&p.cc[c].cand_count_.v, 1);
-    if (i >= cp.cand_cap) { p.ctl->overflow_.v = 1; return; }
+// their nodes — a few hundred per chromosome — is recorded, and the finish stage applies the real threshold as to any candidate
+// ... without stalling the node loop on the slot counter: the atomic that reserves a slot takes a round trip to L2 (~0.5 us,
+// a sixth of a node), so the record of node i waits in registers and is written when node i+1 is emitted — by then the slot
+// index has long arrived.  The last record is flushed when the kernel ends.
+struct UhPendingCand {
     UhCand k;
-    k.key = ((unsigned long long)c << 56) | ((unsigned long long)level << 32) | (unsigned)s;
-    k.s = s; k.b = b; k.e = e; k.level = level; k.c = c; k.pad = 0; k.coef = coef;
-    p.cand[cp.cand_base + i] = k;
+    int slot;
+    bool has;
+};
+
+__device__ inline void uh_cand_flush(const UhParams& p, const UhChromPlan& cp, UhPendingCand& pc) {
+    if (!pc.has) return;
+    if (pc.slot >= cp.cand_cap) p.ctl->overflow_.v = 1;
+    else p.cand[cp.cand_base + pc.slot] = pc.k;
+    pc.has = false;
+}
+
+__device__ inline void uh_cand_defer(const UhParams& p, UhChromCtl* cc, const UhChromPlan& cp, UhPendingCand& pc, int c, int level,
+                                     int s, int b, int e, double coef) {
+    uh_cand_flush(p, cp, pc);
+    pc.k.key = ((unsigned long long)c << 56) | ((unsigned long long)level << 32) | (unsigned)s;
+    pc.k.s = s; pc.k.b = b; pc.k.e = e; pc.k.level = level; pc.k.c = c; pc.k.pad = 0; pc.k.coef = coef;
+    pc.slot = atomicAdd(&cc->cand_count_.v, 1);
+    pc.has = true;
 }
 
 // Can the node's coefficient exceed the candidate threshold at all?  score = D^2 / (a b) of the chosen split, and
@@ -220,6 +235,8 @@ uh_chain_kernel(UhParams p, int c_self) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const double* __restrict__ pz = p.pz;
     unsigned long long v_big = 0, n_big = 0;
+    UhPendingCand pend;
+    pend.has = false;
     if (threadIdx.x == 0) {
         s_mid_out.count = 0; s_small_out.count = 0; s_tiny_out.count = 0;
         uh_stamp(p.tl_ns, c_self, 0, false);
@@ -330,7 +347,7 @@ uh_chain_kernel(UhParams p, int c_self) {
             const bool cont_right = rbig && !cont_left;
             if (crank == 0 && threadIdx.x == 32) {
                 atomicAdd(&p.lvlcnt[loff + level], 1u);
-                uh_emit_candidate_always(p, c, level, s, s + fm, e, uh_coef_from(fv, base, T, n, fm));
+                uh_cand_defer(p, cc, cp, pend, c, level, s, s + fm, e, uh_coef_from(fv, base, T, n, fm));
                 n_big++;
             }
             if (crank == 0 && threadIdx.x == 0) {
@@ -368,6 +385,7 @@ uh_chain_kernel(UhParams p, int c_self) {
         uh_buf_flush(s_small_out, small_list, cp.small_cap, &cc->small_tail_.v, ctl);
         uh_buf_flush(s_tiny_out, tiny_list, cp.tiny_cap, &cc->tiny_tail_.v, ctl);
     }
+    uh_cand_flush(p, cp, pend);
     if (v_big) atomicAdd(&ctl->visits_big, v_big);
     if (n_big) atomicAdd(&ctl->nodes_big, n_big);
     if (threadIdx.x == 0) uh_stamp(p.tl_ns, c_self, 0, true);
@@ -401,6 +419,8 @@ uh_mid_kernel(UhParams p, int c_self) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const double* __restrict__ pz = p.pz;
     unsigned long long v_mid = 0, n_mid = 0;
+    UhPendingCand pend;
+    pend.has = false;
     const int total = min(*(volatile int*)&cc->mid_tail_.v, cp.mid_cap);
     if (threadIdx.x == 0) { s_small_out.count = 0; s_tiny_out.count = 0; uh_stamp(p.tl_ns, c_self, 1, false); }
     int parity = 0;
@@ -468,7 +488,7 @@ uh_mid_kernel(UhParams p, int c_self) {
             const bool lmid = lt_ >= UH_TIER_MID, rmid = rt_ >= UH_TIER_MID;  // a child of a mid node is never BIG
             if (threadIdx.x == 32) {
                 atomicAdd(&p.lvlcnt[loff + level], 1u);
-                uh_emit_candidate_always(p, c, level, s, s + fm, e, uh_coef_from(fv, base, T, n, fm));
+                uh_cand_defer(p, cc, cp, pend, c, level, s, s + fm, e, uh_coef_from(fv, base, T, n, fm));
                 n_mid++;
             }
             if (threadIdx.x == 0) {
@@ -501,6 +521,7 @@ uh_mid_kernel(UhParams p, int c_self) {
         uh_buf_flush(s_small_out, small_list, cp.small_cap, &cc->small_tail_.v, ctl);
         uh_buf_flush(s_tiny_out, tiny_list, cp.tiny_cap, &cc->tiny_tail_.v, ctl);
     }
+    uh_cand_flush(p, cp, pend);
     if (v_mid) atomicAdd(&ctl->visits_big, v_mid);
     if (n_mid) atomicAdd(&ctl->nodes_big, n_mid);
     if (threadIdx.x == 0) uh_stamp(p.tl_ns, c_self, 1, true);

@@ -514,9 +514,32 @@ struct WvScanTile {
     int c;         // chromosome
 };
 
-__global__ void wv_scan_tile_sum_kernel(const double* __restrict__ cov, const WvScanTile* __restrict__ tiles,
+// Where a scan tile lies: either the host's table (tiles of the final plan), or — fused call, before the host knows the
+// cleaned lengths — tile k of chromosome c by position: the tile grid is laid out for the INPUT lengths (tile_c, tile_first)
+// and clipped against the device-side offsets of the cleaned list.  Tile boundaries relative to a chromosome's first bin are
+// the same in both forms, so the sums are grouped identically.
+struct WvScanSrc {
+    const WvScanTile* tiles;
+    const int* tile_c;
+    const int* tile_first;
+    const long long* off;
+};
+
+__device__ inline WvScanTile wv_scan_tile_get(const WvScanSrc& s, int b) {
+    if (s.tiles) return s.tiles[b];
+    const int c = s.tile_c[b];
+    const long long lo = s.off[c] + (long long)(b - s.tile_first[c]) * WV_SCAN_TILE;
+    const long long len = s.off[c + 1] - lo;
+    WvScanTile t;
+    t.lo = lo;
+    t.len = (int)(len < 0 ? 0 : (len > WV_SCAN_TILE ? WV_SCAN_TILE : len));
+    t.c = c;
+    return t;
+}
+
+__global__ void wv_scan_tile_sum_kernel(const double* __restrict__ cov, WvScanSrc src,
                                         double* __restrict__ tsum) {
-    const WvScanTile t = tiles[blockIdx.x];
+    const WvScanTile t = wv_scan_tile_get(src, blockIdx.x);
     double part = 0.0;
     for (int i = threadIdx.x; i < t.len; i += blockDim.x) part += cov[t.lo + i];
     const double s = block_sum_double(part);
@@ -537,10 +560,10 @@ __global__ void wv_scan_tile_offsets_kernel(double* __restrict__ tsum, const int
 }
 
 __global__ void __launch_bounds__(256)
-wv_scan_apply_kernel(const double* __restrict__ cov, const WvScanTile* __restrict__ tiles,
+wv_scan_apply_kernel(const double* __restrict__ cov, WvScanSrc src,
                      const double* __restrict__ toff, const long long* __restrict__ off, double* __restrict__ pz) {
     __shared__ double s_w[8];
-    const WvScanTile t = tiles[blockIdx.x];
+    const WvScanTile t = wv_scan_tile_get(src, blockIdx.x);
     constexpr int ITEMS = WV_SCAN_TILE / 256;
     const int first = threadIdx.x * ITEMS;
     double v[ITEMS];

@@ -49,18 +49,22 @@ void cg_host_free(void* p);
  * host<->device copies; and the number of kernel launches it made. */
 double cg_last_kernel_ms(cg_ctx* ctx);
 int cg_last_launches(cg_ctx* ctx);
-/* Device time (ms) of one stage of the last call: 0 Clean pipeline, 1 partition scalars + prefix sums,
- * 2 Unbalanced-Haar decomposition kernel, 3 per-chromosome finish kernel (threshold, reconstruction,
- * healing, refinement).  -1 when the stage did not run.  Fused call only: 4 = from the end of Clean to the end of
- * the work enqueued before the mid-call wait (coverage round trip, clears, range-quantile index), 5 = from there to the
- * start of the scalars (device idle while the host plans the partition, plus the plan upload). */
+/* Device time (ms) between the events that bracket one stage of the last call: 0 Clean pipeline, 1 partition prefix sums +
+ * order statistics + thresholds, 2 the per-chromosome pipelines (Unbalanced-Haar decomposition stages and the finish of every
+ * chromosome, from the seed kernel to the last finish), 3 packing of the results.  -1 when the stage did not run.  Stages 1
+ * and 2 OVERLAP: the pipelines start as soon as the prefix sums exist and run beside the order statistics, so the stage times
+ * add up to more than cg_last_kernel_ms.  Fused call only: 4 = from the end of Clean to the end of the work enqueued before
+ * the mid-call wait (coverage round trip, clears), 5 = from there to the start of the prefix sums (main stream idle while the
+ * host plans the partition — the range-quantile index is built on a side stream meanwhile — plus the plan upload). */
 double cg_last_stage_ms(cg_ctx* ctx, int stage);
 /* Work counters of the last partition call: out[0] = bin visits of the decomposition (sum over tree
- * nodes of their length: L_eff * N), out[1] = tree nodes, out[2] = candidate nodes kept for the
- * threshold, out[3] = bins, out[4..6] = bin visits of the big / warp / per-thread tiers, out[7..9] = nodes of
- * those tiers, out[10] / out[11] = ms from the start of the decomposition kernel to the end of its big-node
- * phase / to its end, out[12] = multi-chunk nodes, out[13] = nodes that went through the ticket ring,
- * out[14] = deepest tree.  Returns the number of values written (<= min(n, 16)). */
+ * nodes of their length: L_eff * N), out[1] = tree nodes, out[2] = candidate nodes recorded for the threshold (every chain /
+ * mid-stage node + the small / tiny nodes above the candidate threshold), out[3] = bins, out[4..6] = bin visits of the
+ * big (chain + mid) / warp / per-thread tiers, out[7..9] = nodes of those tiers, out[10] / out[11] = ms (device %globaltimer)
+ * from the first decomposition kernel to the last chain node / to the last tiny-stage thread of any chromosome, out[12],
+ * out[13] = unused (0), out[14] = deepest tree, out[15] = 1 when the order statistics ran on integer hundredths (0: a coverage
+ * value was not a two-decimal number below 2^22 / 100 and the f64 keys were used).
+ * After cg_pedigree_hmm: the phase figures listed there.  Returns the number of values written (<= min(n, 16)). */
 int cg_last_partition_stats(cg_ctx* ctx, double* out, int n);
 
 /* ---------------------------------------------------------------------------------------------
