@@ -89,6 +89,7 @@ struct cg_ctx {
     std::vector<CgGraphEntry> clean_graphs;  // Clean pipeline graphs (clean.cu), dropped when the arena moves
     std::vector<CgGraphEntry> part_graphs;   // partition: per-chromosome pipelines (wavelet.cu); exec == nullptr: shape seen once
     CgComm* comm = nullptr;
+    double host_ts[8] = {0};  // CANVAS_HOST_TIMES: host clock (us) at points inside the partition enqueue
 };
 
 constexpr size_t CG_CHROM_STREAMS = 32;

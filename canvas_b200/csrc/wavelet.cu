@@ -475,6 +475,10 @@ __global__ void wv_device_offsets_kernel(const unsigned* __restrict__ chrom_cnt,
     rq_tfirst[C] = t;
 }
 
+static inline double wv_now_us() {
+    return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
 int wv_enqueue(cg_ctx* ctx, const cg_wavelet_opts* o, const WvPlan& pl, WvDev& d, const unsigned char* selected_host,
                bool rq_index_done = false, int* comm_pack = nullptr, bool use_int = false, bool scan_done = false) {
     cudaStream_t s = ctx->stream;
@@ -537,6 +541,7 @@ int wv_enqueue(cg_ctx* ctx, const cg_wavelet_opts* o, const WvPlan& pl, WvDev& d
     sp.thr_upper = o->thr_upper;
 
     CG_TL(ctx, "host wait + plan");
+    ctx->host_ts[0] = wv_now_us();
     cudaEventRecord(ctx->stage_ev[2], s);
     ctx->stage_used[1] = true;
     const bool dbg_on = getenv("CANVAS_DEBUG") != nullptr;
@@ -578,11 +583,13 @@ int wv_enqueue(cg_ctx* ctx, const cg_wavelet_opts* o, const WvPlan& pl, WvDev& d
             CG_LAUNCH(ctx, wv_triplet_kernel, grid, 256, 0, r == 0 ? d.cov : d.tmed, d.tmed, d.cmad, d.f3lv + r);
         }
     };
-    if (use_int) {
-        // ---- side stream: everything that only feeds reported scalars (evenness score, factor-of-three list) — per-window
-        // evenness, triplet cascade, their order statistics on double keys.  Joined before the results are packed.
+    // ---- side stream: everything that only feeds reported scalars (evenness score, factor-of-three list) — per-window
+    // evenness, triplet cascade, their order statistics on double keys.  Joined before the results are packed.  It is
+    // ENQUEUED after the chromosome pipelines have been launched (its ~35 launches cost the host 0.1 ms, and the pipelines can
+    // only be launched once the thresholds' event is recorded) unless the ratio statistics below need its select state.
+    const bool side_first = use_int && pl.cv_possible && !(t.n_w10 <= WV_RATIO_SORT_MAX && t.n_w100 <= WV_RATIO_SORT_MAX);
+    auto enqueue_side = [&]() -> int {
         cudaStream_t main_s = ctx->stream;
-        CG_CUDA(ctx, cudaEventRecord(ctx->ev_fork, main_s));
         CG_CUDA(ctx, cudaStreamWaitEvent(ctx->side_stream, ctx->ev_fork, 0));
         ctx->stream = ctx->side_stream;  // CG_LAUNCH and the select drivers enqueue on ctx->stream
         enqueue_evenness();
@@ -594,6 +601,11 @@ int wv_enqueue(cg_ctx* ctx, const cg_wavelet_opts* o, const WvPlan& pl, WvDev& d
         CG_LAUNCH(ctx, wv_f3_finish_kernel, 1, 1, 0, sp, d.med, d.ctl);
         CG_CUDA(ctx, cudaEventRecord(ctx->ev_join, ctx->side_stream));
         ctx->stream = main_s;
+        return CG_OK;
+    };
+    if (use_int) {
+        CG_CUDA(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream));  // plan tables are up: the side stream may start from here
+        if (side_first) { const int rc_s = enqueue_side(); if (rc_s) return rc_s; }
         // ---- main stream: prefix sums, then medians and MADs of the coverage windows / chromosomes on integer hundredths
         enqueue_scan();
         if (!scan_done) CG_CUDA(ctx, cudaEventRecord(ctx->ev_scan, ctx->stream));  // the decomposition's chains and mid stage need nothing else
@@ -645,6 +657,7 @@ int wv_enqueue(cg_ctx* ctx, const cg_wavelet_opts* o, const WvPlan& pl, WvDev& d
     CG_LAUNCH(ctx, wv_cv_sigma_kernel, 1, 128, 0, d.ratio_keys, sp, d.med, d.mad, d.off, d.ctl, d.sigma, d.cand_thr);
 
     CG_TL(ctx, "wave3 + cv");
+    ctx->host_ts[1] = wv_now_us();
     cudaEventRecord(ctx->stage_ev[3], s);
     CG_CUDA(ctx, cudaEventRecord(ctx->ev_thr, s));  // thresholds (sigma, cand_thr) exist: the small / tiny stages and the finish may run
     ctx->stage_used[2] = true;
@@ -812,6 +825,8 @@ int wv_enqueue(cg_ctx* ctx, const cg_wavelet_opts* o, const WvPlan& pl, WvDev& d
         ctx->stream = s;
         if (rc_p) return rc_p;
     }
+    ctx->host_ts[2] = wv_now_us();
+    if (use_int && !side_first) { const int rc_s = enqueue_side(); if (rc_s) return rc_s; }
     CG_CUDA(ctx, cudaEventRecord(ctx->ev_pipe, pipe));
     CG_CUDA(ctx, cudaStreamWaitEvent(s, ctx->ev_pipe, 0));
     CG_TL(ctx, "decompose + finish");
@@ -1293,8 +1308,10 @@ static int clean_partition_wavelet_impl(cg_ctx* ctx, const cg_clean_opts* copts,
     rc = wv_collect(ctx, pl, wd, n_bp, bp, evenness, evenness_ok, cv, cv_has_value, factor_of_three, exchange);
     ht[5] = now_us();
     if (host_times)
-        fprintf(stderr, "[host] enqueue copies+clean+index %.0f us | wait for counts %.0f | plan %.0f | enqueue partition %.0f | wait+collect %.0f\n",
-                ht[1] - ht[0], ht[2] - ht[1], ht[3] - ht[2], ht[4] - ht[3], ht[5] - ht[4]);
+        fprintf(stderr, "[host] enqueue copies+clean+index %.0f us | wait for counts %.0f | plan %.0f | enqueue partition %.0f (plan tables up %.0f, "
+                        "order statistics enqueued %.0f, pipelines launched %.0f) | wait+collect %.0f\n",
+                ht[1] - ht[0], ht[2] - ht[1], ht[3] - ht[2], ht[4] - ht[3], ctx->host_ts[0] - ht[3], ctx->host_ts[1] - ht[3],
+                ctx->host_ts[2] - ht[3], ht[5] - ht[4]);
     tl.print("fused");
     ctx->tl = nullptr;
     CG_CUDA(ctx, cudaStreamSynchronize(ctx->copy_stream));
