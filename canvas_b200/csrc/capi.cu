@@ -29,6 +29,7 @@ extern "C" int cg_create(int device, cg_ctx** out) {
         cudaEventCreateWithFlags(&ctx->ev_thr, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&ctx->ev_pipe, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&ctx->ev_off, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->ev_plan, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&ctx->ev_mid, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess ||
         cudaMallocHost((void**)&ctx->pinned, 1 << 18) != cudaSuccess) {
@@ -75,6 +76,7 @@ extern "C" void cg_destroy(cg_ctx* ctx) {
     if (ctx->ev_thr) cudaEventDestroy(ctx->ev_thr);
     if (ctx->ev_pipe) cudaEventDestroy(ctx->ev_pipe);
     if (ctx->ev_off) cudaEventDestroy(ctx->ev_off);
+    if (ctx->ev_plan) cudaEventDestroy(ctx->ev_plan);
     if (ctx->pipe_stream) { cudaStreamSynchronize(ctx->pipe_stream); cudaStreamDestroy(ctx->pipe_stream); }
     if (ctx->side_stream) { cudaStreamSynchronize(ctx->side_stream); cudaStreamDestroy(ctx->side_stream); }
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);

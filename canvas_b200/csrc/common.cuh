@@ -45,7 +45,7 @@ struct cg_ctx {
     cudaStream_t side_stream = nullptr;  // kernels off the critical path (partition: evenness / factor-of-three statistics)
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_rq = nullptr;
     cudaStream_t pipe_stream = nullptr;  // root of the per-chromosome pipelines of the partition
-    cudaEvent_t ev_scan = nullptr, ev_thr = nullptr, ev_pipe = nullptr, ev_off = nullptr;
+    cudaEvent_t ev_scan = nullptr, ev_thr = nullptr, ev_pipe = nullptr, ev_off = nullptr, ev_plan = nullptr;
     // partition: one stream per chromosome pipeline (decomposition stages + finish), created on first use
     std::vector<cudaStream_t> chrom_streams;
     std::vector<cudaEvent_t> chrom_ev;

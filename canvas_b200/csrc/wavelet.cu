@@ -522,6 +522,7 @@ int wv_enqueue(cg_ctx* ctx, const cg_wavelet_opts* o, const WvPlan& pl, WvDev& d
         for (int k = 0; k < 20; k++) { log3_tab[k] = std::ceil(std::log(pw) / std::log(3.0)); pw *= 3.0; }
         put(d.log3, log3_tab, 20 * 8);
         CG_CUDA(ctx, cudaMemcpyAsync(base, h, bytes, cudaMemcpyHostToDevice, s));
+        CG_CUDA(ctx, cudaEventRecord(ctx->ev_plan, s));  // offsets, slices and masks are on the device: the pipelines read them
     }
     if (pl.N == 0) {
         if (comm_pack) CG_LAUNCH(ctx, wv_pack_comm_kernel, 1, 256, 0, d.n_bp, d.bp, d.off, C, comm_pack, ctx->comm->pack_ints);
@@ -583,11 +584,12 @@ int wv_enqueue(cg_ctx* ctx, const cg_wavelet_opts* o, const WvPlan& pl, WvDev& d
             CG_LAUNCH(ctx, wv_triplet_kernel, grid, 256, 0, r == 0 ? d.cov : d.tmed, d.tmed, d.cmad, d.f3lv + r);
         }
     };
-    // ---- side stream: everything that only feeds reported scalars (evenness score, factor-of-three list) — per-window
-    // evenness, triplet cascade, their order statistics on double keys.  Joined before the results are packed.  It is
-    // ENQUEUED after the chromosome pipelines have been launched (its ~35 launches cost the host 0.1 ms, and the pipelines can
-    // only be launched once the thresholds' event is recorded) unless the ratio statistics below need its select state.
-    const bool side_first = use_int && pl.cv_possible && !(t.n_w10 <= WV_RATIO_SORT_MAX && t.n_w100 <= WV_RATIO_SORT_MAX);
+    // ---- side stream: the evenness score and the factor-of-three list (per-window evenness, triplet cascade, their order
+    // statistics on double keys).  The finish stage of every chromosome reads the factor-of-three list (germline refinement),
+    // so the pipelines wait for ev_join before their finish kernels; the results are packed after it as well.
+    // (Enqueueing this block AFTER the pipelines' launch was measured — the pipelines start 0.1 ms earlier — and lost: 3.20 ms
+    // against 3.03, the side kernels then compete with the chains instead of running in the host's shadow; profiles/rd2z_*.)
+    const bool side_first = use_int;
     auto enqueue_side = [&]() -> int {
         cudaStream_t main_s = ctx->stream;
         CG_CUDA(ctx, cudaStreamWaitEvent(ctx->side_stream, ctx->ev_fork, 0));
@@ -666,6 +668,7 @@ int wv_enqueue(cg_ctx* ctx, const cg_wavelet_opts* o, const WvPlan& pl, WvDev& d
     // so they need no threshold and overlap the order statistics above; a chromosome's small stage waits for ev_thr.
     cudaStream_t pipe = ctx->pipe_stream;
     CG_CUDA(ctx, cudaStreamWaitEvent(pipe, ctx->ev_scan, 0));
+    CG_CUDA(ctx, cudaStreamWaitEvent(pipe, ctx->ev_plan, 0));  // (the prefix sums of the fused call are older than the plan upload)
     if (rq_index_done) CG_CUDA(ctx, cudaStreamWaitEvent(pipe, ctx->ev_rq, 0));  // built on the side stream (fused call)
     cudaEventRecord(ctx->stage_ev[4], pipe);
     // ---- decomposition + finish: one pipeline per chromosome, each on its own stream (largest chromosomes first)
@@ -760,6 +763,8 @@ int wv_enqueue(cg_ctx* ctx, const cg_wavelet_opts* o, const WvPlan& pl, WvDev& d
                 CG_LAUNCH(ctx, uh_small_kernel, (int)std::min<long long>(ctx->num_sms, std::max<long long>(1, len / 1024)), UH_SMALL_THREADS, uh_smem, up, c);
             CG_LAUNCH(ctx, uh_tiny_kernel, (int)std::min<long long>(ctx->num_sms, std::max<long long>(1, len / 1024)), 128, 0, up, d.tiny_tab, c);
             CG_LAUNCH(ctx, uh_depth_kernel, (int)std::min<long long>(32, std::max<long long>(1, len / 4096)), 256, 0, d.lvlcnt, d.off, d.depth, c);
+            // the factor-of-three list comes from the side stream (recorded before this enqueue started)
+            if (use_int) CG_CUDA(ctx, cudaStreamWaitEvent(cs, ctx->ev_join, capturing ? cudaEventWaitExternal : 0));
             CG_LAUNCH(ctx, uh_finish_kernel, 1, FIN_THREADS, fin_smem_bytes(), fp, c);
         }
         ctx->stream = s;
@@ -777,6 +782,7 @@ int wv_enqueue(cg_ctx* ctx, const cg_wavelet_opts* o, const WvPlan& pl, WvDev& d
         for (int c = 0; c < C; c++) { hs ^= (unsigned long long)(selected_host[c] ? 1 : 0) + 2; hs *= 1099511628211ull; }
         // the finish kernels take a pointer into the median table that depends on the number of windows of THIS plan
         hs ^= (unsigned long long)t.base_chrom + 0x9e3779b97f4a7c15ull; hs *= 1099511628211ull;
+        hs ^= use_int ? 0x51ull : 0x15ull; hs *= 1099511628211ull;  // the integer-key form has one more event wait per chromosome
         const long long key[12] = {(long long)(uintptr_t)ctx->arena, (long long)(uintptr_t)d.cov, (long long)(uintptr_t)d.ctl,
                                    (long long)(uintptr_t)d.cc, (long long)(uintptr_t)d.bp, C, o->min_size, o->is_germline, (long long)hl,
                                    (long long)hs, (long long)(uintptr_t)d.rq_sorted, (long long)(uintptr_t)d.tiny_tab};
