@@ -25,6 +25,7 @@ extern "C" int cg_create(int device, cg_ctx** out) {
         cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&ctx->ev_rq, cudaEventDisableTiming) != cudaSuccess ||
         cudaStreamCreateWithFlags(&ctx->pipe_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&ctx->plan_stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreateWithFlags(&ctx->ev_scan, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&ctx->ev_thr, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&ctx->ev_pipe, cudaEventDisableTiming) != cudaSuccess ||
@@ -78,6 +79,7 @@ extern "C" void cg_destroy(cg_ctx* ctx) {
     if (ctx->ev_off) cudaEventDestroy(ctx->ev_off);
     if (ctx->ev_plan) cudaEventDestroy(ctx->ev_plan);
     if (ctx->pipe_stream) { cudaStreamSynchronize(ctx->pipe_stream); cudaStreamDestroy(ctx->pipe_stream); }
+    if (ctx->plan_stream) { cudaStreamSynchronize(ctx->plan_stream); cudaStreamDestroy(ctx->plan_stream); }
     if (ctx->side_stream) { cudaStreamSynchronize(ctx->side_stream); cudaStreamDestroy(ctx->side_stream); }
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);

@@ -85,6 +85,7 @@ struct cg_ctx {
     CgStageSlot stage[2];
     unsigned long long stage_seq = 0;
     cudaStream_t prefetch_stream = nullptr;
+    cudaStream_t plan_stream = nullptr;  // upload of the partition's plan tables: not queued behind kernels or the result downloads
     CgTimeline* tl = nullptr;  // debug timeline of the current call (CANVAS_DEBUG)
     std::vector<CgGraphEntry> clean_graphs;  // Clean pipeline graphs (clean.cu), dropped when the arena moves
     std::vector<CgGraphEntry> part_graphs;   // partition: per-chromosome pipelines (wavelet.cu); exec == nullptr: shape seen once

@@ -521,8 +521,13 @@ int wv_enqueue(cg_ctx* ctx, const cg_wavelet_opts* o, const WvPlan& pl, WvDev& d
         double pw = 1.0;
         for (int k = 0; k < 20; k++) { log3_tab[k] = std::ceil(std::log(pw) / std::log(3.0)); pw *= 3.0; }
         put(d.log3, log3_tab, 20 * 8);
-        CG_CUDA(ctx, cudaMemcpyAsync(base, h, bytes, cudaMemcpyHostToDevice, s));
-        CG_CUDA(ctx, cudaEventRecord(ctx->ev_plan, s));  // offsets, slices and masks are on the device: the pipelines read them
+        // on its own stream: in the fused call the main stream is still computing the prefix sums when the host gets here, and
+        // a copy queued behind those kernels would hold the order statistics and the pipelines back by its own latency
+        static const bool plan_inline = getenv("CANVAS_PLAN_INLINE") != nullptr;
+        cudaStream_t ps = plan_inline ? s : ctx->plan_stream;
+        CG_CUDA(ctx, cudaMemcpyAsync(base, h, bytes, cudaMemcpyHostToDevice, ps));
+        CG_CUDA(ctx, cudaEventRecord(ctx->ev_plan, ps));  // offsets, slices and masks are on the device: the pipelines read them
+        if (!plan_inline) CG_CUDA(ctx, cudaStreamWaitEvent(s, ctx->ev_plan, 0));
     }
     if (pl.N == 0) {
         if (comm_pack) CG_LAUNCH(ctx, wv_pack_comm_kernel, 1, 256, 0, d.n_bp, d.bp, d.off, C, comm_pack, ctx->comm->pack_ints);
@@ -584,6 +589,189 @@ int wv_enqueue(cg_ctx* ctx, const cg_wavelet_opts* o, const WvPlan& pl, WvDev& d
             CG_LAUNCH(ctx, wv_triplet_kernel, grid, 256, 0, r == 0 ? d.cov : d.tmed, d.tmed, d.cmad, d.f3lv + r);
         }
     };
+    cudaStream_t pipe = ctx->pipe_stream;
+    // ---- decomposition + finish: one pipeline per chromosome, each on its own stream (largest chromosomes first)
+    UhParams up;
+    up.x = d.cov; up.pz = d.pz; up.off = d.off; up.cand_thr = d.cand_thr; up.lvlcnt = d.lvlcnt;
+    up.big = d.big; up.mid = d.mid; up.small = d.small; up.tiny = d.tiny; up.cand = d.cand; up.cc = d.cc; up.cp = d.cp; up.ctl = d.ctl;
+    FinParams fp;
+    fp.x = d.cov; fp.pz = d.pz; fp.off = d.off; fp.selected = d.selected; fp.cand = d.cand; fp.cc = d.cc; fp.cp = d.cp; fp.ctl = d.ctl;
+    fp.lvlcnt = d.lvlcnt; fp.depth = d.depth; fp.sigma = d.sigma; fp.chrom_median = d.med + t.base_chrom;
+    fp.log3_scale_tab = d.log3;
+    fp.rq.spl = d.rq_spl; fp.rq.hist = d.rq_hist; fp.rq.tstart = d.rq_tstart; fp.rq.cum = d.rq_cum; fp.rq.sorted = d.rq_sorted;
+    fp.rq.tfirst = d.rq_tfirst;
+    fp.phase_ns = dbg_on ? d.phase_ns : nullptr;
+    up.tl_ns = fp.phase_ns && d.tl_ns ? d.tl_ns : nullptr;
+    up.task_dbg = up.tl_ns && d.task_dbg ? d.task_dbg : nullptr;
+    fp.is_germline = o->is_germline; fp.min_size = o->min_size; fp.n_chrom = C; fp.pad = 0;
+    fp.lvl_idx = d.lvl_idx; fp.sv = d.sv; fp.svkey = d.svkey; fp.bitmap = d.bitmap; fp.piece = d.piece; fp.rec = d.rec;
+    fp.prelim = d.prelim; fp.lvl_first = d.lvl_first; fp.n_bp = d.n_bp; fp.bp = d.bp;
+    {
+        const UhChromPlan& last = pl.cplan[C - 1];
+        if (last.ring_base + last.ring_cap > UH_QCAP || last.mid_base + last.mid_cap > d.mid_cap || last.small_base + last.small_cap > d.small_cap ||
+            last.tiny_base + last.tiny_cap > d.tiny_cap || last.cand_base + last.cand_cap > d.cand_cap)
+            return cg_fail(ctx, CG_ERR_CAPACITY, "partition: per-chromosome queues exceed the workspace");
+    }
+    const size_t uh_smem = sizeof(UhWarpScratch) * (UH_SMALL_THREADS / 32);
+    if (!ctx->uh_attrs_set) {
+        cudaFuncSetAttribute(uh_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)uh_smem);
+        cudaFuncSetAttribute(uh_mid_kernel<1024, 4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((UH_MID_MAX + 2) * sizeof(double)));
+        cudaFuncSetAttribute(uh_mid_kernel<512, 4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((UH_MID_MAX + 2) * sizeof(double)));
+        cudaFuncSetAttribute(uh_mid_kernel<256, 4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((UH_MID_MAX + 2) * sizeof(double)));
+        cudaFuncSetAttribute(uh_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fin_smem_bytes());
+        ctx->uh_attrs_set = true;
+    }
+    // The launch sequence of the pipelines depends on the chromosome lengths only through grid sizes and through which
+    // stages a chromosome needs; with the lengths the workspace was allocated for (the INPUT lengths in the fused call: the
+    // same for every sample binned on the same reference) it is the same for every call of that shape, so it is captured
+    // once into a CUDA graph and replayed: one launch instead of ~150, every chromosome's first kernel starts at once, and
+    // ranks that share a host no longer queue behind each other's launches.  A shape is captured the second time it is seen.
+    static const int mid_threads = getenv("CANVAS_MID_THREADS") ? atoi(getenv("CANVAS_MID_THREADS")) : UH_MID_THREADS;
+    const size_t mid_smem = (size_t)(UH_MID_MAX + 2) * sizeof(double);
+    // part 0: a chromosome's whole pipeline; 1: seed + chains + mid stage only (need the prefix sums, nothing else);
+    // 2: small / tiny stages, depth and finish only (stream-ordered after part 1 by the caller, thresholds known)
+    auto enqueue_pipelines = [&](const long long* loff, cudaStream_t root, bool capturing, int part) -> int {
+        std::vector<int> order;
+        for (int c = 0; c < C; c++) {
+            const long long len = loff[c + 1] - loff[c];
+            if (selected_host[c] && len > o->min_size && len >= 2) order.push_back(c);
+        }
+        std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return loff[a + 1] - loff[a] > loff[b + 1] - loff[b]; });
+        const int n_streams = (int)std::min<size_t>(order.size(), CG_CHROM_STREAMS);
+        int rc_streams = cg_chrom_streams(ctx, n_streams);
+        if (rc_streams) return rc_streams;
+        ctx->stream = root;
+        if (part != 2) {
+            CG_LAUNCH(ctx, uh_seed_kernel, div_up(C, 128), 128, 0, up, d.selected, C, o->min_size);
+            CG_LAUNCH(ctx, uh_tiny_table_kernel, UH_TINY_MAX - 1, UH_TINY_MAX, 0, d.tiny_tab);
+        }
+        CG_CUDA(ctx, cudaEventRecord(ctx->ev_fork2, root));
+        for (size_t k = 0; k < order.size(); k++) {
+            const int c = order[k];
+            const long long len = loff[c + 1] - loff[c];
+            cudaStream_t cs = ctx->chrom_streams[k % n_streams];
+            if (k < (size_t)n_streams) CG_CUDA(ctx, cudaStreamWaitEvent(cs, ctx->ev_fork2, 0));
+            ctx->stream = cs;  // CG_LAUNCH enqueues on ctx->stream
+            if (part != 2 && len > UH_MID_MAX) {
+                // chains of big nodes: clusters wait on the chromosome's ring, any one of them can finish the work alone
+                cudaLaunchConfig_t cfg = {};
+                cfg.blockDim = dim3(UH_THREADS);
+                cfg.dynamicSmemBytes = 0;
+                cfg.stream = cs;
+                cudaLaunchAttribute attr[1];
+                attr[0].id = cudaLaunchAttributeClusterDimension;
+                attr[0].val.clusterDim.x = UH_CLUSTER; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+                cfg.attrs = attr;
+                cfg.numAttrs = 1;
+                cfg.gridDim = dim3(UH_CLUSTER * (len > 100000 ? 2 : 1));
+                cudaError_t le = cudaLaunchKernelEx(&cfg, uh_chain_kernel, up, c);
+                if (le != cudaSuccess) { ctx->stream = s; return cg_fail(ctx, CG_ERR_CUDA, std::string("uh_chain_kernel launch: ") + cudaGetErrorString(le)); }
+                ctx->launches++;
+            }
+            if (part != 2 && len > UH_SMALL_MAX)
+            {
+                if (mid_threads > 0) {  // subtree staged in shared memory (default)
+                    const int mid_grid = (int)std::min<long long>(32, std::max<long long>(1, len / 8192));
+                    if (mid_threads >= 1024) CG_LAUNCH(ctx, (uh_mid_kernel<1024, 4, true>), mid_grid, 1024, mid_smem, up, c);
+                    else if (mid_threads >= 512) CG_LAUNCH(ctx, (uh_mid_kernel<512, 4, true>), mid_grid, 512, mid_smem, up, c);
+                    else CG_LAUNCH(ctx, (uh_mid_kernel<256, 4, true>), mid_grid, 256, mid_smem, up, c);
+                } else {                // CANVAS_MID_THREADS=0: every node straight from L2 (the earlier form, kept for A/B runs)
+                    const int mid_grid = (int)std::min<long long>(64, std::max<long long>(1, len / 2048));
+                    CG_LAUNCH(ctx, (uh_mid_kernel<256, 8, false>), mid_grid, 256, 0, up, c);
+                }
+            }
+            if (part == 1) continue;
+            // thresholds: recorded on the main stream before this enqueue started (an external event for a captured sequence;
+            // part 2 is launched behind stream-level waits instead)
+            if (part == 0) CG_CUDA(ctx, cudaStreamWaitEvent(cs, ctx->ev_thr, capturing ? cudaEventWaitExternal : 0));
+            if (len > UH_TINY_MAX)
+                CG_LAUNCH(ctx, uh_small_kernel, (int)std::min<long long>(ctx->num_sms, std::max<long long>(1, len / 1024)), UH_SMALL_THREADS, uh_smem, up, c);
+            CG_LAUNCH(ctx, uh_tiny_kernel, (int)std::min<long long>(ctx->num_sms, std::max<long long>(1, len / 1024)), 128, 0, up, d.tiny_tab, c);
+            CG_LAUNCH(ctx, uh_depth_kernel, (int)std::min<long long>(32, std::max<long long>(1, len / 4096)), 256, 0, d.lvlcnt, d.off, d.depth, c);
+            // the factor-of-three list comes from the side stream (recorded before this enqueue started)
+            static const bool no_join_wait = getenv("CANVAS_X_NO_JOIN_WAIT") != nullptr;  // measurement only: drops a needed ordering
+            if (part == 0 && use_int && !no_join_wait) CG_CUDA(ctx, cudaStreamWaitEvent(cs, ctx->ev_join, capturing ? cudaEventWaitExternal : 0));
+            CG_LAUNCH(ctx, uh_finish_kernel, 1, FIN_THREADS, fin_smem_bytes(), fp, c);
+        }
+        ctx->stream = s;
+        for (int k = 0; k < n_streams; k++) {
+            CG_CUDA(ctx, cudaEventRecord(ctx->chrom_ev[k], ctx->chrom_streams[k]));
+            CG_CUDA(ctx, cudaStreamWaitEvent(root, ctx->chrom_ev[k], 0));
+        }
+        return CG_OK;
+    };
+    auto launch_part = [&](int part) -> int {
+        bool replayed = false;
+        if (!fp.phase_ns && !getenv("CANVAS_NO_GRAPH")) {
+            CgGraphEntry want{};
+            unsigned long long hl = 1469598103934665603ull, hs = 1469598103934665603ull;  // FNV-1a of the launch lengths / the mask
+            for (int c = 0; c <= C; c++) { hl ^= (unsigned long long)d.alloc_off[c]; hl *= 1099511628211ull; }
+            for (int c = 0; c < C; c++) { hs ^= (unsigned long long)(selected_host[c] ? 1 : 0) + 2; hs *= 1099511628211ull; }
+            // the finish kernels take a pointer into the median table that depends on the number of windows of THIS plan
+            hs ^= (unsigned long long)t.base_chrom + 0x9e3779b97f4a7c15ull; hs *= 1099511628211ull;
+            hs ^= (use_int ? 0x51ull : 0x15ull) + 0x100ull * (unsigned)part; hs *= 1099511628211ull;  // the integer-key form has one more event wait per chromosome
+            const long long key[12] = {(long long)(uintptr_t)ctx->arena, (long long)(uintptr_t)d.cov, (long long)(uintptr_t)d.ctl,
+                                       (long long)(uintptr_t)d.cc, (long long)(uintptr_t)d.bp, C, o->min_size, o->is_germline, (long long)hl,
+                                       (long long)hs, (long long)(uintptr_t)d.rq_sorted, (long long)(uintptr_t)d.tiny_tab};
+            for (int i = 0; i < 12; i++) want.key[i] = key[i];
+            CgGraphEntry* hit = nullptr;
+            for (auto& g : ctx->part_graphs)
+                if (!memcmp(g.key, want.key, sizeof(want.key))) { hit = &g; break; }
+            if (!hit) {  // first sighting of this shape: remember it, launch directly below
+                if (ctx->part_graphs.size() >= 16) {
+                    for (auto& g : ctx->part_graphs)
+                        if (g.exec) cudaGraphExecDestroy(g.exec);
+                    ctx->part_graphs.clear();
+                }
+                want.exec = nullptr;
+                ctx->part_graphs.push_back(want);
+            } else {
+                if (!hit->exec) {
+                    const int launches_before = ctx->launches;
+                    cudaGraph_t graph = nullptr;
+                    if (cudaStreamBeginCapture(pipe, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+                        const int rc_cap = enqueue_pipelines(d.alloc_off, pipe, true, part);
+                        ctx->stream = s;
+                        const cudaError_t ce = cudaStreamEndCapture(pipe, &graph);
+                        hit->launches = ctx->launches - launches_before;
+                        ctx->launches = launches_before;
+                        if (rc_cap == CG_OK && ce == cudaSuccess && graph) {
+                            if (cudaGraphInstantiate(&hit->exec, graph, 0) != cudaSuccess) hit->exec = nullptr;
+                        }
+                        if (graph) cudaGraphDestroy(graph);
+                        cudaGetLastError();
+                        ctx->launch_err = cudaSuccess;
+                    } else {
+                        cudaGetLastError();
+                    }
+                }
+                if (hit->exec) {
+                    const cudaError_t le = cudaGraphLaunch(hit->exec, pipe);
+                    if (le != cudaSuccess) return cg_fail(ctx, CG_ERR_CUDA, std::string("partition: graph launch failed: ") + cudaGetErrorString(le));
+                    ctx->launches += hit->launches;
+                    replayed = true;
+                }
+            }
+        }
+        if (!replayed) {
+            const int rc_p = enqueue_pipelines(pl.off.data(), pipe, false, part);
+            ctx->stream = s;
+            if (rc_p) return rc_p;
+        }
+        return CG_OK;
+    };
+    // With the prefix sums already there (fused call) the first half of every pipeline — seed, chains, mid stage — is launched
+    // BEFORE the host enqueues the ~60 kernels of the order statistics (0.2 ms of host time); the second half follows once the
+    // thresholds' event is recorded, stream-ordered behind the first.  CANVAS_SPLIT_PIPE=0 keeps one launch after the statistics.
+    static const bool split_env = !(getenv("CANVAS_SPLIT_PIPE") && atoi(getenv("CANVAS_SPLIT_PIPE")) == 0);
+    const bool split_pipe = split_env && scan_done && !dbg_on;
+    if (split_pipe) {
+        CG_CUDA(ctx, cudaStreamWaitEvent(pipe, ctx->ev_scan, 0));
+        CG_CUDA(ctx, cudaStreamWaitEvent(pipe, ctx->ev_plan, 0));
+        cudaEventRecord(ctx->stage_ev[4], pipe);
+        const int rc_l = launch_part(1);
+        if (rc_l) return rc_l;
+    }
     // ---- side stream: the evenness score and the factor-of-three list (per-window evenness, triplet cascade, their order
     // statistics on double keys).  The finish stage of every chromosome reads the factor-of-three list (germline refinement),
     // so the pipelines wait for ev_join before their finish kernels; the results are packed after it as well.
@@ -666,170 +854,20 @@ int wv_enqueue(cg_ctx* ctx, const cg_wavelet_opts* o, const WvPlan& pl, WvDev& d
     // The chromosome pipelines run on their own root stream from the moment the prefix sums exist: chains and the mid stage
     // record EVERY node as a candidate (a few hundred per chromosome; the finish stage applies the real threshold anyway),
     // so they need no threshold and overlap the order statistics above; a chromosome's small stage waits for ev_thr.
-    cudaStream_t pipe = ctx->pipe_stream;
-    CG_CUDA(ctx, cudaStreamWaitEvent(pipe, ctx->ev_scan, 0));
-    CG_CUDA(ctx, cudaStreamWaitEvent(pipe, ctx->ev_plan, 0));  // (the prefix sums of the fused call are older than the plan upload)
-    if (rq_index_done) CG_CUDA(ctx, cudaStreamWaitEvent(pipe, ctx->ev_rq, 0));  // built on the side stream (fused call)
-    cudaEventRecord(ctx->stage_ev[4], pipe);
-    // ---- decomposition + finish: one pipeline per chromosome, each on its own stream (largest chromosomes first)
-    UhParams up;
-    up.x = d.cov; up.pz = d.pz; up.off = d.off; up.cand_thr = d.cand_thr; up.lvlcnt = d.lvlcnt;
-    up.big = d.big; up.mid = d.mid; up.small = d.small; up.tiny = d.tiny; up.cand = d.cand; up.cc = d.cc; up.cp = d.cp; up.ctl = d.ctl;
-    FinParams fp;
-    fp.x = d.cov; fp.pz = d.pz; fp.off = d.off; fp.selected = d.selected; fp.cand = d.cand; fp.cc = d.cc; fp.cp = d.cp; fp.ctl = d.ctl;
-    fp.lvlcnt = d.lvlcnt; fp.depth = d.depth; fp.sigma = d.sigma; fp.chrom_median = d.med + t.base_chrom;
-    fp.log3_scale_tab = d.log3;
-    fp.rq.spl = d.rq_spl; fp.rq.hist = d.rq_hist; fp.rq.tstart = d.rq_tstart; fp.rq.cum = d.rq_cum; fp.rq.sorted = d.rq_sorted;
-    fp.rq.tfirst = d.rq_tfirst;
-    fp.phase_ns = dbg_on ? d.phase_ns : nullptr;
-    up.tl_ns = fp.phase_ns && d.tl_ns ? d.tl_ns : nullptr;
-    up.task_dbg = up.tl_ns && d.task_dbg ? d.task_dbg : nullptr;
-    fp.is_germline = o->is_germline; fp.min_size = o->min_size; fp.n_chrom = C; fp.pad = 0;
-    fp.lvl_idx = d.lvl_idx; fp.sv = d.sv; fp.svkey = d.svkey; fp.bitmap = d.bitmap; fp.piece = d.piece; fp.rec = d.rec;
-    fp.prelim = d.prelim; fp.lvl_first = d.lvl_first; fp.n_bp = d.n_bp; fp.bp = d.bp;
-    {
-        const UhChromPlan& last = pl.cplan[C - 1];
-        if (last.ring_base + last.ring_cap > UH_QCAP || last.mid_base + last.mid_cap > d.mid_cap || last.small_base + last.small_cap > d.small_cap ||
-            last.tiny_base + last.tiny_cap > d.tiny_cap || last.cand_base + last.cand_cap > d.cand_cap)
-            return cg_fail(ctx, CG_ERR_CAPACITY, "partition: per-chromosome queues exceed the workspace");
-    }
-    const size_t uh_smem = sizeof(UhWarpScratch) * (UH_SMALL_THREADS / 32);
-    if (!ctx->uh_attrs_set) {
-        cudaFuncSetAttribute(uh_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)uh_smem);
-        cudaFuncSetAttribute(uh_mid_kernel<1024, 4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((UH_MID_MAX + 2) * sizeof(double)));
-        cudaFuncSetAttribute(uh_mid_kernel<512, 4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((UH_MID_MAX + 2) * sizeof(double)));
-        cudaFuncSetAttribute(uh_mid_kernel<256, 4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((UH_MID_MAX + 2) * sizeof(double)));
-        cudaFuncSetAttribute(uh_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fin_smem_bytes());
-        ctx->uh_attrs_set = true;
-    }
-    // The launch sequence of the pipelines depends on the chromosome lengths only through grid sizes and through which
-    // stages a chromosome needs; with the lengths the workspace was allocated for (the INPUT lengths in the fused call: the
-    // same for every sample binned on the same reference) it is the same for every call of that shape, so it is captured
-    // once into a CUDA graph and replayed: one launch instead of ~150, every chromosome's first kernel starts at once, and
-    // ranks that share a host no longer queue behind each other's launches.  A shape is captured the second time it is seen.
-    static const int mid_threads = getenv("CANVAS_MID_THREADS") ? atoi(getenv("CANVAS_MID_THREADS")) : UH_MID_THREADS;
-    const size_t mid_smem = (size_t)(UH_MID_MAX + 2) * sizeof(double);
-    auto enqueue_pipelines = [&](const long long* loff, cudaStream_t root, bool capturing) -> int {
-        std::vector<int> order;
-        for (int c = 0; c < C; c++) {
-            const long long len = loff[c + 1] - loff[c];
-            if (selected_host[c] && len > o->min_size && len >= 2) order.push_back(c);
-        }
-        std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return loff[a + 1] - loff[a] > loff[b + 1] - loff[b]; });
-        const int n_streams = (int)std::min<size_t>(order.size(), CG_CHROM_STREAMS);
-        int rc_streams = cg_chrom_streams(ctx, n_streams);
-        if (rc_streams) return rc_streams;
-        ctx->stream = root;
-        CG_LAUNCH(ctx, uh_seed_kernel, div_up(C, 128), 128, 0, up, d.selected, C, o->min_size);
-        CG_LAUNCH(ctx, uh_tiny_table_kernel, UH_TINY_MAX - 1, UH_TINY_MAX, 0, d.tiny_tab);
-        CG_CUDA(ctx, cudaEventRecord(ctx->ev_fork2, root));
-        for (size_t k = 0; k < order.size(); k++) {
-            const int c = order[k];
-            const long long len = loff[c + 1] - loff[c];
-            cudaStream_t cs = ctx->chrom_streams[k % n_streams];
-            if (k < (size_t)n_streams) CG_CUDA(ctx, cudaStreamWaitEvent(cs, ctx->ev_fork2, 0));
-            ctx->stream = cs;  // CG_LAUNCH enqueues on ctx->stream
-            if (len > UH_MID_MAX) {
-                // chains of big nodes: clusters wait on the chromosome's ring, any one of them can finish the work alone
-                cudaLaunchConfig_t cfg = {};
-                cfg.blockDim = dim3(UH_THREADS);
-                cfg.dynamicSmemBytes = 0;
-                cfg.stream = cs;
-                cudaLaunchAttribute attr[1];
-                attr[0].id = cudaLaunchAttributeClusterDimension;
-                attr[0].val.clusterDim.x = UH_CLUSTER; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-                cfg.attrs = attr;
-                cfg.numAttrs = 1;
-                cfg.gridDim = dim3(UH_CLUSTER * (len > 100000 ? 2 : 1));
-                cudaError_t le = cudaLaunchKernelEx(&cfg, uh_chain_kernel, up, c);
-                if (le != cudaSuccess) { ctx->stream = s; return cg_fail(ctx, CG_ERR_CUDA, std::string("uh_chain_kernel launch: ") + cudaGetErrorString(le)); }
-                ctx->launches++;
-            }
-            if (len > UH_SMALL_MAX)
-            {
-                if (mid_threads > 0) {  // subtree staged in shared memory (default)
-                    const int mid_grid = (int)std::min<long long>(32, std::max<long long>(1, len / 8192));
-                    if (mid_threads >= 1024) CG_LAUNCH(ctx, (uh_mid_kernel<1024, 4, true>), mid_grid, 1024, mid_smem, up, c);
-                    else if (mid_threads >= 512) CG_LAUNCH(ctx, (uh_mid_kernel<512, 4, true>), mid_grid, 512, mid_smem, up, c);
-                    else CG_LAUNCH(ctx, (uh_mid_kernel<256, 4, true>), mid_grid, 256, mid_smem, up, c);
-                } else {                // CANVAS_MID_THREADS=0: every node straight from L2 (the earlier form, kept for A/B runs)
-                    const int mid_grid = (int)std::min<long long>(64, std::max<long long>(1, len / 2048));
-                    CG_LAUNCH(ctx, (uh_mid_kernel<256, 8, false>), mid_grid, 256, 0, up, c);
-                }
-            }
-            // thresholds: recorded on the main stream before this enqueue started (an external event for a captured sequence)
-            CG_CUDA(ctx, cudaStreamWaitEvent(cs, ctx->ev_thr, capturing ? cudaEventWaitExternal : 0));
-            if (len > UH_TINY_MAX)
-                CG_LAUNCH(ctx, uh_small_kernel, (int)std::min<long long>(ctx->num_sms, std::max<long long>(1, len / 1024)), UH_SMALL_THREADS, uh_smem, up, c);
-            CG_LAUNCH(ctx, uh_tiny_kernel, (int)std::min<long long>(ctx->num_sms, std::max<long long>(1, len / 1024)), 128, 0, up, d.tiny_tab, c);
-            CG_LAUNCH(ctx, uh_depth_kernel, (int)std::min<long long>(32, std::max<long long>(1, len / 4096)), 256, 0, d.lvlcnt, d.off, d.depth, c);
-            // the factor-of-three list comes from the side stream (recorded before this enqueue started)
-            if (use_int) CG_CUDA(ctx, cudaStreamWaitEvent(cs, ctx->ev_join, capturing ? cudaEventWaitExternal : 0));
-            CG_LAUNCH(ctx, uh_finish_kernel, 1, FIN_THREADS, fin_smem_bytes(), fp, c);
-        }
-        ctx->stream = s;
-        for (int k = 0; k < n_streams; k++) {
-            CG_CUDA(ctx, cudaEventRecord(ctx->chrom_ev[k], ctx->chrom_streams[k]));
-            CG_CUDA(ctx, cudaStreamWaitEvent(root, ctx->chrom_ev[k], 0));
-        }
-        return CG_OK;
-    };
-    bool replayed = false;
-    if (!fp.phase_ns && !getenv("CANVAS_NO_GRAPH")) {
-        CgGraphEntry want{};
-        unsigned long long hl = 1469598103934665603ull, hs = 1469598103934665603ull;  // FNV-1a of the launch lengths / the mask
-        for (int c = 0; c <= C; c++) { hl ^= (unsigned long long)d.alloc_off[c]; hl *= 1099511628211ull; }
-        for (int c = 0; c < C; c++) { hs ^= (unsigned long long)(selected_host[c] ? 1 : 0) + 2; hs *= 1099511628211ull; }
-        // the finish kernels take a pointer into the median table that depends on the number of windows of THIS plan
-        hs ^= (unsigned long long)t.base_chrom + 0x9e3779b97f4a7c15ull; hs *= 1099511628211ull;
-        hs ^= use_int ? 0x51ull : 0x15ull; hs *= 1099511628211ull;  // the integer-key form has one more event wait per chromosome
-        const long long key[12] = {(long long)(uintptr_t)ctx->arena, (long long)(uintptr_t)d.cov, (long long)(uintptr_t)d.ctl,
-                                   (long long)(uintptr_t)d.cc, (long long)(uintptr_t)d.bp, C, o->min_size, o->is_germline, (long long)hl,
-                                   (long long)hs, (long long)(uintptr_t)d.rq_sorted, (long long)(uintptr_t)d.tiny_tab};
-        for (int i = 0; i < 12; i++) want.key[i] = key[i];
-        CgGraphEntry* hit = nullptr;
-        for (auto& g : ctx->part_graphs)
-            if (!memcmp(g.key, want.key, sizeof(want.key))) { hit = &g; break; }
-        if (!hit) {  // first sighting of this shape: remember it, launch directly below
-            if (ctx->part_graphs.size() >= 16) {
-                for (auto& g : ctx->part_graphs)
-                    if (g.exec) cudaGraphExecDestroy(g.exec);
-                ctx->part_graphs.clear();
-            }
-            want.exec = nullptr;
-            ctx->part_graphs.push_back(want);
-        } else {
-            if (!hit->exec) {
-                const int launches_before = ctx->launches;
-                cudaGraph_t graph = nullptr;
-                if (cudaStreamBeginCapture(pipe, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
-                    const int rc_cap = enqueue_pipelines(d.alloc_off, pipe, true);
-                    ctx->stream = s;
-                    const cudaError_t ce = cudaStreamEndCapture(pipe, &graph);
-                    hit->launches = ctx->launches - launches_before;
-                    ctx->launches = launches_before;
-                    if (rc_cap == CG_OK && ce == cudaSuccess && graph) {
-                        if (cudaGraphInstantiate(&hit->exec, graph, 0) != cudaSuccess) hit->exec = nullptr;
-                    }
-                    if (graph) cudaGraphDestroy(graph);
-                    cudaGetLastError();
-                    ctx->launch_err = cudaSuccess;
-                } else {
-                    cudaGetLastError();
-                }
-            }
-            if (hit->exec) {
-                const cudaError_t le = cudaGraphLaunch(hit->exec, pipe);
-                if (le != cudaSuccess) return cg_fail(ctx, CG_ERR_CUDA, std::string("partition: graph launch failed: ") + cudaGetErrorString(le));
-                ctx->launches += hit->launches;
-                replayed = true;
-            }
-        }
-    }
-    if (!replayed) {
-        const int rc_p = enqueue_pipelines(pl.off.data(), pipe, false);
-        ctx->stream = s;
-        if (rc_p) return rc_p;
+    if (!split_pipe) {
+        CG_CUDA(ctx, cudaStreamWaitEvent(pipe, ctx->ev_scan, 0));
+        CG_CUDA(ctx, cudaStreamWaitEvent(pipe, ctx->ev_plan, 0));  // (the prefix sums of the fused call are older than the plan upload)
+        if (rq_index_done) CG_CUDA(ctx, cudaStreamWaitEvent(pipe, ctx->ev_rq, 0));  // built on the side stream (fused call)
+        cudaEventRecord(ctx->stage_ev[4], pipe);
+        const int rc_l = launch_part(0);
+        if (rc_l) return rc_l;
+    } else {
+        // second half: thresholds and the factor-of-three list exist (events recorded above), the index is built
+        CG_CUDA(ctx, cudaStreamWaitEvent(pipe, ctx->ev_thr, 0));
+        if (use_int) CG_CUDA(ctx, cudaStreamWaitEvent(pipe, ctx->ev_join, 0));
+        if (rq_index_done) CG_CUDA(ctx, cudaStreamWaitEvent(pipe, ctx->ev_rq, 0));
+        const int rc_l = launch_part(2);
+        if (rc_l) return rc_l;
     }
     ctx->host_ts[2] = wv_now_us();
     if (use_int && !side_first) { const int rc_s = enqueue_side(); if (rc_s) return rc_s; }
