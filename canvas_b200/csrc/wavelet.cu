@@ -760,10 +760,12 @@ int wv_enqueue(cg_ctx* ctx, const cg_wavelet_opts* o, const WvPlan& pl, WvDev& d
         }
         return CG_OK;
     };
-    // With the prefix sums already there (fused call) the first half of every pipeline — seed, chains, mid stage — is launched
-    // BEFORE the host enqueues the ~60 kernels of the order statistics (0.2 ms of host time); the second half follows once the
-    // thresholds' event is recorded, stream-ordered behind the first.  CANVAS_SPLIT_PIPE=0 keeps one launch after the statistics.
-    static const bool split_env = !(getenv("CANVAS_SPLIT_PIPE") && atoi(getenv("CANVAS_SPLIT_PIPE")) == 0);
+    // Experiment, off by default (CANVAS_SPLIT_PIPE=1): with the prefix sums already there (fused call) the first half of every
+    // pipeline — seed, chains, mid stage — is launched BEFORE the host enqueues the ~60 kernels of the order statistics (0.2 ms
+    // of host time) and the second half once the thresholds' event is recorded, stream-ordered behind the first.  Measured
+    // 3.44 ms against 3.10 (profiles/rd2ad_split_pipelines_ab.txt): the barrier between the halves costs more than the earlier
+    // start gains — a short chromosome's small stage must not wait for the longest chromosome's chain.
+    static const bool split_env = getenv("CANVAS_SPLIT_PIPE") && atoi(getenv("CANVAS_SPLIT_PIPE")) != 0;
     const bool split_pipe = split_env && scan_done && !dbg_on;
     if (split_pipe) {
         CG_CUDA(ctx, cudaStreamWaitEvent(pipe, ctx->ev_scan, 0));
