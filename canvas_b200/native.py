@@ -698,7 +698,7 @@ class Engine:
         return {"breakpoints": [[bp[s, off[c]:off[c] + n_bp[s, c]].copy() for c in range(nc)] for s in range(S)],
                 "chrom_off": off, "n_common": m, "common_index": common[:m], "count": cnt[:, :m], "n_kept": n_kept,
                 "local_sd": lsd, "gc_norm_skipped": skipped.astype(bool), "owner": owner[:, :nc],
-                "phases_ms": {"clean": st[0], "broadcast": st[1], "merge": st[2], "hmm": st[3], "gather": st[4]},
+                "phases_ms": {"clean": st[0], "broadcast": st[1], "merge": st[2], "hmm": st[3], "gather": st[4], "download": st[8]},
                 "kernel_ms": st[5], "launches": int(st[6]), "nccl_ms": st[7]}
 
     def last_partition_stats_raw(self):

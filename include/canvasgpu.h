@@ -337,7 +337,7 @@ int cg_prefetch_bins(cg_ctx* ctx, int64_t n, const uint8_t* chrom, const int32_t
  * prints with float.ToString()); chrom_off_out[n_chrom + 1] offsets of the chromosomes among the common bins;
  * n_bp[s * n_chrom + c] breakpoints of (s, c) at bp[s * n + chrom_off_out[c] ...], as cg_partition_hmm numbers them.
  * cg_last_partition_stats: [0..4] wall ms of clean / exchange of cleaned lists / merge / HMM / gather on this rank,
- * [5] kernel ms, [6] launches, [7] device ms of the NCCL calls.
+ * [5] kernel ms, [6] launches, [7] device ms of the NCCL calls, [8] wall ms of the final download of the merged table.
  * ------------------------------------------------------------------------------------------- */
 int cg_pedigree_hmm(cg_ctx* ctx, const cg_clean_opts* copts, const cg_hmm_opts* hopts, int n_samples, int64_t n,
                     const uint8_t* chrom, const uint8_t* chrom_is_autosome, const uint8_t* chrom_is_chrY, int n_chrom,
