@@ -127,6 +127,11 @@ void comm_assign_lpt(int n_units, const int64_t* weight, int n_ranks, int32_t* o
     }
 }
 
+static __global__ void comm_lengths_kernel(const int32_t* __restrict__ d_recv, int32_t* __restrict__ h_recv, int cap, int n_ranks) {
+    for (int r = threadIdx.x; r < n_ranks; r += blockDim.x) h_recv[(size_t)r * cap] = d_recv[(size_t)r * cap];
+    __threadfence_system();
+}
+
 int comm_allgatherv(cg_ctx* ctx, const int32_t* local, int64_t n_local, const std::function<const int32_t*()>& fetch_local_full,
                     std::vector<int64_t>& counts, std::vector<int32_t>& all) {
     CgComm* c = ctx->comm;
@@ -155,7 +160,9 @@ int comm_allgatherv(cg_ctx* ctx, const int32_t* local, int64_t n_local, const st
     else CG_CUDA(ctx, cudaMemcpyAsync(c->d_recv, c->d_send, (size_t)CAP * 4, cudaMemcpyDeviceToDevice, s));
     CG_CUDA(ctx, cudaEventRecord(c->ev1, s));
     // lengths first (one strided copy), then exactly the used part of every rank's block
-    CG_CUDA(ctx, cudaMemcpy2DAsync(c->h_recv, (size_t)CAP * 4, c->d_recv, (size_t)CAP * 4, 4, (size_t)R, cudaMemcpyDeviceToHost, s));
+    // (read back by kernel stores into the page-locked mirror, not by the copy engine: see cg_readback_small)
+    comm_lengths_kernel<<<1, 64, 0, s>>>(c->d_recv, c->h_recv, (int)CAP, R);
+    CG_CUDA(ctx, cudaGetLastError());
     CG_CUDA(ctx, cudaStreamSynchronize(s));
     counts.assign(R, 0);
     int64_t maxn = 0, total = 0;
@@ -172,8 +179,7 @@ int comm_allgatherv(cg_ctx* ctx, const int32_t* local, int64_t n_local, const st
     if (maxn <= CAP - 1) {
         for (int r = 0; r < R; r++)
             if (counts[r] > 0)
-                CG_CUDA(ctx, cudaMemcpyAsync(c->h_recv + (size_t)r * CAP + 1, c->d_recv + (size_t)r * CAP + 1, (size_t)counts[r] * 4,
-                                             cudaMemcpyDeviceToHost, s));
+                CG_CUDA(ctx, cg_readback_small(s, c->h_recv + (size_t)r * CAP + 1, c->d_recv + (size_t)r * CAP + 1, (size_t)counts[r] * 4));
         CG_CUDA(ctx, cudaStreamSynchronize(s));
         size_t at = 0;
         for (int r = 0; r < R; r++) {

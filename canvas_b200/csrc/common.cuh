@@ -195,6 +195,23 @@ inline T* arena_take(cg_ctx* ctx, size_t count) {
 
 inline size_t arena_need(size_t count, size_t elem) { return ((count * elem + 255) & ~(size_t)255); }
 
+// A few words from device memory into PAGE-LOCKED host memory, written by a kernel instead of the copy engine: a small
+// device-to-host cudaMemcpyAsync queues behind whatever large download is in flight in that direction (the pedigree chain
+// sends 48 MB home while its HMM stage reads scalars back: 4.6 ms instead of 1.2 on an 8-rank host), a store over PCIe from an
+// SM does not.  dst must come from cudaMallocHost / cg_host_alloc; both pointers 4-byte aligned.
+static __global__ void cg_small_copy_kernel(const unsigned* __restrict__ src, unsigned* __restrict__ dst, int words) {
+    for (int i = threadIdx.x; i < words; i += blockDim.x) dst[i] = src[i];
+    __threadfence_system();
+}
+inline cudaError_t cg_readback_small(cudaStream_t s, void* pinned_dst, const void* dev_src, size_t bytes) {
+    if (bytes == 0) return cudaSuccess;
+    cg_small_copy_kernel<<<1, 256, 0, s>>>(static_cast<const unsigned*>(dev_src), static_cast<unsigned*>(pinned_dst), (int)((bytes + 3) / 4));
+    return cudaGetLastError();
+}
+constexpr size_t CG_PINNED_SMALL_AT = 72u << 10;   // [72 KiB, 80 KiB) of ctx->pinned: scalars read back by cg_readback_small
+constexpr size_t CG_PINNED_LIST_AT = 80u << 10;    // [80 KiB, 128 KiB): short result lists read back the same way
+constexpr size_t CG_PINNED_LIST_BYTES = 48u << 10;
+
 // ---------------------------------------------------------------------------------------------
 // Order-preserving key maps.  .NET orders NaN below every number (Double.CompareTo), so NaN maps
 // to key 0, which no other value produces.

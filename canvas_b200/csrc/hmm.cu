@@ -795,8 +795,10 @@ static int partition_hmm_impl(cg_ctx* ctx, const cg_hmm_opts* o, int n_samples, 
         CG_LAUNCH(ctx, hmm_quartile_request_kernel, div_up(nseg_q, 32), 32, 0, sel_q, N);
         QuartView qv{d_cov, N, S};
         sel_run_scatter<uint32_t, QuartView>(ctx, qv, sel_q, (long long)S * N);
-        std::vector<uint32_t> keys((size_t)nseg_q * SEL_G);
-        CG_CUDA(ctx, cudaMemcpyAsync(keys.data(), sel_q.req_key, keys.size() * 4, cudaMemcpyDeviceToHost, s));
+        static_assert(HMM_MAX_SAMPLES * SEL_G * 4 <= 1024, "quartile keys fit their pinned slot");
+        const uint32_t* keys = reinterpret_cast<const uint32_t*>(ctx->pinned + CG_PINNED_SMALL_AT);
+        CG_CUDA(ctx, cg_readback_small(s, ctx->pinned + CG_PINNED_SMALL_AT, sel_q.req_key, (size_t)nseg_q * SEL_G * 4));
+        ctx->launches++;
         CG_CUDA(ctx, cudaStreamSynchronize(s));
         for (int sm = 0; sm < S; sm++) {
             float v[6] = {0, 0, 0, 0, 0, 0};
@@ -941,8 +943,11 @@ static int partition_hmm_impl(cg_ctx* ctx, const cg_hmm_opts* o, int n_samples, 
         } else {
             CG_LAUNCH(ctx, hmm_sequential_kernel, C, 1, 0, d_le, d_ci, C, log_start, ls, lo, d_back, d_states, d_nbp, d_bp);
         }
-        CG_CUDA(ctx, cudaMemcpyAsync(&h_ctl, d_ctl, sizeof(HmmCtl), cudaMemcpyDeviceToHost, s));
+        static_assert(sizeof(HmmCtl) % 4 == 0 && sizeof(HmmCtl) <= 256, "control block fits its pinned slot");
+        CG_CUDA(ctx, cg_readback_small(s, ctx->pinned + CG_PINNED_SMALL_AT + 1024, d_ctl, sizeof(HmmCtl)));
+        ctx->launches++;
         CG_CUDA(ctx, cudaStreamSynchronize(s));
+        memcpy(&h_ctl, ctx->pinned + CG_PINNED_SMALL_AT + 1024, sizeof(HmmCtl));
         if (sequential || !h_ctl.degenerate) break;
         sequential = true;  // a score reached Double.MinValue: only the strictly sequential order reproduces the reference
     }
@@ -950,16 +955,35 @@ static int partition_hmm_impl(cg_ctx* ctx, const cg_hmm_opts* o, int n_samples, 
     CG_CUDA(ctx, cudaEventRecord(ctx->ev1, s));
     dbg("viterbi");
     // ---- results
-    std::vector<int> h_nbp((size_t)C + 1, 0);
-    CG_CUDA(ctx, cudaMemcpyAsync(h_nbp.data(), d_nbp, (size_t)C * 4, cudaMemcpyDeviceToHost, s));
+    static_assert(HMM_MAX_CHROM * 4 <= 2048, "breakpoint counts fit their pinned slot");
+    const int* h_nbp = reinterpret_cast<const int*>(ctx->pinned + CG_PINNED_SMALL_AT + 2048);
+    CG_CUDA(ctx, cg_readback_small(s, ctx->pinned + CG_PINNED_SMALL_AT + 2048, d_nbp, (size_t)C * 4));
+    ctx->launches++;
     CG_CUDA(ctx, cudaStreamSynchronize(s));
-    for (int c = 0; c < C; c++) {
-        n_bp[c] = h_nbp[(size_t)c];
-        if (n_bp[c] > 0)
-            CG_CUDA(ctx, cudaMemcpyAsync(bp + chrom_off[c], d_bp + chrom_off[c], (size_t)n_bp[c] * 4, cudaMemcpyDeviceToHost, s));
+    long long total_bp = 0;
+    for (int c = 0; c < C; c++) { n_bp[c] = h_nbp[c]; total_bp += n_bp[c] > 0 ? n_bp[c] : 0; }
+    if (total_bp * 4 <= (long long)CG_PINNED_LIST_BYTES) {
+        // short lists (the usual case): through the page-locked block, written by kernels (see cg_readback_small)
+        int* stage = reinterpret_cast<int*>(ctx->pinned + CG_PINNED_LIST_AT);
+        long long at = 0;
+        for (int c = 0; c < C; c++)
+            if (n_bp[c] > 0) {
+                CG_CUDA(ctx, cg_readback_small(s, stage + at, d_bp + chrom_off[c], (size_t)n_bp[c] * 4));
+                ctx->launches++;
+                at += n_bp[c];
+            }
+        if (states_out) CG_CUDA(ctx, cudaMemcpyAsync(states_out, d_states, (size_t)N, cudaMemcpyDeviceToHost, s));
+        CG_CUDA(ctx, cudaStreamSynchronize(s));
+        at = 0;
+        for (int c = 0; c < C; c++)
+            if (n_bp[c] > 0) { memcpy(bp + chrom_off[c], stage + at, (size_t)n_bp[c] * 4); at += n_bp[c]; }
+    } else {
+        for (int c = 0; c < C; c++)
+            if (n_bp[c] > 0)
+                CG_CUDA(ctx, cudaMemcpyAsync(bp + chrom_off[c], d_bp + chrom_off[c], (size_t)n_bp[c] * 4, cudaMemcpyDeviceToHost, s));
+        if (states_out) CG_CUDA(ctx, cudaMemcpyAsync(states_out, d_states, (size_t)N, cudaMemcpyDeviceToHost, s));
+        CG_CUDA(ctx, cudaStreamSynchronize(s));
     }
-    if (states_out) CG_CUDA(ctx, cudaMemcpyAsync(states_out, d_states, (size_t)N, cudaMemcpyDeviceToHost, s));
-    CG_CUDA(ctx, cudaStreamSynchronize(s));
     CG_CUDA(ctx, cudaGetLastError());
     CG_CHECK_LAUNCHES(ctx);
     if (h_ctl.bad_value) return cg_fail(ctx, CG_ERR_ARG, "cg_partition_hmm: coverage must be finite and non-negative (Convert.ToInt32 / the emission table index throw in the reference)");

@@ -278,15 +278,15 @@ extern "C" int cg_pedigree_hmm(cg_ctx* ctx, const cg_clean_opts* copts, const cg
         launches++;
         CG_CUDA(ctx, cudaMemcpyAsync(off.data(), p_off, (size_t)(C + 1) * 8, cudaMemcpyDeviceToHost, st));
         CG_CUDA(ctx, cudaStreamSynchronize(st));
-    }
-    // The merged table (4 (S + 1) bytes per common bin) goes home LAST: the HMM and the gather read their few scalars back
-    // with small device-to-host copies, and those would queue behind 48 MB on the one copy engine of that direction
-    // (measured: the HMM stage of a rank took 4.6 ms instead of 1.2 with the download started here).
-    auto download_merged = [&]() -> int {
-        if (m_common <= 0) return CG_OK;
+        // The merged table (4 (S + 1) bytes per common bin, 48 MB for a trio) goes home on the copy stream while the HMM runs.
+        // The HMM and the gather read their scalars and short lists back with kernel stores into page-locked memory
+        // (cg_readback_small): small copies would queue behind this download on the copy engine of that direction
+        // (measured on an 8-rank host: the HMM stage of a rank took 4.6 ms instead of 1.2).
         CG_CUDA(ctx, cudaMemcpyAsync(common_index, p_common, (size_t)m_common * 4, cudaMemcpyDeviceToHost, ctx->copy_stream));
         for (int s = 0; s < S; s++)
             CG_CUDA(ctx, cudaMemcpyAsync(count_out + (size_t)s * n, p_cnt_m + (size_t)s * n_al, (size_t)m_common * 4, cudaMemcpyDeviceToHost, ctx->copy_stream));
+    }
+    auto download_merged = [&]() -> int {  // wait for it
         CG_CUDA(ctx, cudaStreamSynchronize(ctx->copy_stream));
         return CG_OK;
     };
@@ -327,7 +327,7 @@ extern "C" int cg_pedigree_hmm(cg_ctx* ctx, const cg_clean_opts* copts, const cg
         launches += ctx->launches;
     }
     phase[3] = ms_since(t_phase);
-    if (rc_hmm != CG_OK && !exchange) return rc_hmm;
+    if (rc_hmm != CG_OK && !exchange) { cudaStreamSynchronize(ctx->copy_stream); return rc_hmm; }
 
     // ---- one all-gather of the packed lists: [sample, chromosome, count, breakpoints ...] per unit
     if (exchange) {
@@ -345,16 +345,17 @@ extern "C" int cg_pedigree_hmm(cg_ctx* ctx, const cg_clean_opts* copts, const cg
         std::vector<int64_t> counts;
         std::vector<int32_t> all;
         int rc = comm_allgatherv(ctx, mine.data(), (int64_t)mine.size(), nullptr, counts, all);
-        if (rc_hmm != CG_OK) { ctx->err = hmm_err; return rc_hmm; }
-        if (rc) return rc;
+        if (rc_hmm != CG_OK) { ctx->err = hmm_err; cudaStreamSynchronize(ctx->copy_stream); return rc_hmm; }
+        if (rc) { cudaStreamSynchronize(ctx->copy_stream); return rc; }
         size_t at = 0;
         for (int r = 0; r < R; r++) {
             const int32_t* p = all.data() + at;
-            if (counts[r] < 1 || p[0] != 0) return cg_fail(ctx, CG_ERR_CUDA, "cg_pedigree_hmm: rank " + std::to_string(r) + " failed in its HMM stage");
+            if (counts[r] < 1 || p[0] != 0) { cudaStreamSynchronize(ctx->copy_stream); return cg_fail(ctx, CG_ERR_CUDA, "cg_pedigree_hmm: rank " + std::to_string(r) + " failed in its HMM stage"); }
             int64_t k = 1;
             while (k + 3 <= counts[r]) {
                 const int s = p[k], c = p[k + 1], cnt = p[k + 2];
                 if (s < 0 || s >= S || c < 0 || c >= C || cnt < 0 || k + 3 + cnt > counts[r] || cnt > off[c + 1] - off[c]) {
+                    cudaStreamSynchronize(ctx->copy_stream);
                     return cg_fail(ctx, CG_ERR_CUDA, "cg_pedigree_hmm: corrupt exchange");
                 }
                 n_bp[(size_t)s * C + c] = cnt;
