@@ -313,8 +313,9 @@ def main():
         tm, res = {}, {}
 
         def step():
+            # rank 0 writes the merged .cleaned files: it alone downloads the merged table; every rank gets all breakpoints
             r = eng.pedigree_hmm(lay["chrom"], t0.is_autosome, t0.is_chr_y, lay["start"], lay["stop"], cols, lay["gc"],
-                                 sharded=world > 1, out=out)
+                                 sharded=world > 1, out=out, want_tables=rank == 0)
             res["r"] = r
             if res.get("timed"):
                 for k, v in r["phases_ms"].items():
@@ -337,7 +338,8 @@ def main():
                 "nccl_ms_rank0": tm.get("nccl_ms", 0.0) / n_steps,
                 "launches_rank0": int(tm.get("launches", 0)) // max(n_steps, 1),
                 "units_per_rank": np.bincount(r["owner"].ravel(), minlength=world).tolist(),
-                "h2d_bytes": (10 * n4 + 4 * n4 * mine) if mine else 0, "d2h_bytes": 4 * r["n_common"] * (S4 + 1) + 4 * int(sum(len(b) for per in r["breakpoints"] for b in per)),
+                "h2d_bytes": (10 * n4 + 4 * n4 * mine) if mine else 0,
+                "d2h_bytes": (4 * r["n_common"] * (S4 + 1) if rank == 0 else 0) + 4 * int(sum(len(b) for per in r["breakpoints"] for b in per)),
                 "call": "cg_pedigree_hmm (one device-resident call: Clean per sample, common bins, PerSampleHMM per sample)",
                 "timing": "wall clock around the C-ABI call, page-locked host buffers in and out, max over ranks"}
 

@@ -90,8 +90,9 @@ extern "C" int cg_pedigree_hmm(cg_ctx* ctx, const cg_clean_opts* copts, const cg
     bool any_mine = false;
     for (int s = 0; s < S; s++) any_mine = any_mine || (s % R == me);
     int rc_local = CG_OK;
-    if (n > 0 && (!chrom || !start || !stop || !gc || !common_index || !count_out || !bp || (C > 0 && !chrom_is_autosome)))
+    if (n > 0 && (!chrom || !start || !stop || !gc || !bp || (C > 0 && !chrom_is_autosome) || (!common_index != !count_out)))
         rc_local = cg_fail(ctx, CG_ERR_ARG, "cg_pedigree_hmm: null array");
+    const bool want_tables = common_index && count_out;  // a rank that does not write the merged .cleaned files skips 4 (S + 1) B/bin of download
     for (int s = 0; s < S && rc_local == CG_OK && n > 0; s++)
         if (s % R == me && !count[s]) rc_local = cg_fail(ctx, CG_ERR_ARG, "cg_pedigree_hmm: null counts of a sample this rank cleans");
     if (rc_local != CG_OK && !exchange) return rc_local;
@@ -282,9 +283,11 @@ extern "C" int cg_pedigree_hmm(cg_ctx* ctx, const cg_clean_opts* copts, const cg
         // The HMM and the gather read their scalars and short lists back with kernel stores into page-locked memory
         // (cg_readback_small): small copies would queue behind this download on the copy engine of that direction
         // (measured on an 8-rank host: the HMM stage of a rank took 4.6 ms instead of 1.2).
-        CG_CUDA(ctx, cudaMemcpyAsync(common_index, p_common, (size_t)m_common * 4, cudaMemcpyDeviceToHost, ctx->copy_stream));
-        for (int s = 0; s < S; s++)
-            CG_CUDA(ctx, cudaMemcpyAsync(count_out + (size_t)s * n, p_cnt_m + (size_t)s * n_al, (size_t)m_common * 4, cudaMemcpyDeviceToHost, ctx->copy_stream));
+        if (want_tables) {
+            CG_CUDA(ctx, cudaMemcpyAsync(common_index, p_common, (size_t)m_common * 4, cudaMemcpyDeviceToHost, ctx->copy_stream));
+            for (int s = 0; s < S; s++)
+                CG_CUDA(ctx, cudaMemcpyAsync(count_out + (size_t)s * n, p_cnt_m + (size_t)s * n_al, (size_t)m_common * 4, cudaMemcpyDeviceToHost, ctx->copy_stream));
+        }
     }
     auto download_merged = [&]() -> int {  // wait for it
         CG_CUDA(ctx, cudaStreamSynchronize(ctx->copy_stream));

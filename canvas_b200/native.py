@@ -655,11 +655,12 @@ class Engine:
         self._check(self.lib.cg_prefetch_bins(self.h, len(count), _ptr(chrom, _u8), _ptr(start, _i32), _ptr(stop, _i32),
                                               _ptr(count, _f32), _ptr(gc, _u8)))
 
-    def pedigree_hmm(self, chrom, is_autosome, is_chr_y, start, stop, counts, gc, sharded=False, min_size=10, out=None,
+    def pedigree_hmm(self, chrom, is_autosome, is_chr_y, start, stop, counts, gc, sharded=False, min_size=10, out=None, want_tables=True,
                      size_filter=True, outlier_filter=True, gc_norm=True, gc_mode=0, want_local_sd=True, min_bins_per_gc=100):
         """cg_pedigree_hmm: CanvasClean per sample -> common bins -> PerSampleHMM per sample, device resident (one call).
         counts: one float32 array per sample over the shared layout (None allowed for samples another rank cleans when
-        sharded).  out: optional (common_index i32[n], count f32[S, n], bp i32[S, n]) buffers, e.g. page-locked."""
+        sharded).  out: optional (common_index i32[n], count f32[S, n], bp i32[S, n]) buffers, e.g. page-locked.
+        want_tables=False: this rank does not need the merged table (common_index / count stay None, nothing is downloaded)."""
         chrom = np.ascontiguousarray(chrom, np.uint8)
         n = len(chrom)
         is_autosome = np.ascontiguousarray(is_autosome, np.uint8)
@@ -690,13 +691,15 @@ class Engine:
         owner = np.zeros((S, max(nc, 1)), np.int32)
         rc = self.lib.cg_pedigree_hmm(self.h, C.byref(co), C.byref(ho), S, n, _ptr(chrom, _u8), _ptr(is_autosome, _u8), _ptr(is_chr_y, _u8),
                                       nc, _ptr(start, _i32), _ptr(stop, _i32), ptrs, _ptr(gc, _u8), int(bool(sharded)), _ptr(n_kept, _i64),
-                                      _ptr(lsd, _f64), skipped.ctypes.data_as(_P(C.c_int)), C.byref(n_common), _ptr(common, _i32),
-                                      _ptr(cnt, _f32), _ptr(off, _i64), _ptr(n_bp, _i32), _ptr(bp, _i32), _ptr(owner, _i32))
+                                      _ptr(lsd, _f64), skipped.ctypes.data_as(_P(C.c_int)), C.byref(n_common),
+                                      _ptr(common, _i32) if want_tables else None, _ptr(cnt, _f32) if want_tables else None,
+                                      _ptr(off, _i64), _ptr(n_bp, _i32), _ptr(bp, _i32), _ptr(owner, _i32))
         self._check(rc)
         m = n_common.value
         st = self.last_partition_stats_raw()
         return {"breakpoints": [[bp[s, off[c]:off[c] + n_bp[s, c]].copy() for c in range(nc)] for s in range(S)],
-                "chrom_off": off, "n_common": m, "common_index": common[:m], "count": cnt[:, :m], "n_kept": n_kept,
+                "chrom_off": off, "n_common": m, "common_index": common[:m] if want_tables else None,
+                "count": cnt[:, :m] if want_tables else None, "n_kept": n_kept,
                 "local_sd": lsd, "gc_norm_skipped": skipped.astype(bool), "owner": owner[:, :nc],
                 "phases_ms": {"clean": st[0], "broadcast": st[1], "merge": st[2], "hmm": st[3], "gather": st[4], "download": st[8]},
                 "kernel_ms": st[5], "launches": int(st[6]), "nccl_ms": st[7]}

@@ -334,7 +334,8 @@ int cg_prefetch_bins(cg_ctx* ctx, int64_t n, const uint8_t* chrom, const int32_t
  * EVERY rank.  owner (may be NULL): [n_samples][n_chrom] rank of every unit.
  * Outputs: n_kept / local_sd / gc_norm_skipped [n_samples] as cg_clean reports them; *n_common, common_index[k] (capacity
  * n) = layout index of common bin k, count_out[s * n + k] = sample s's cleaned count of it (what the merged .cleaned file
- * prints with float.ToString()); chrom_off_out[n_chrom + 1] offsets of the chromosomes among the common bins;
+ * prints with float.ToString()) — both may be NULL together on a rank that does not write those files: the table is
+ * 4 (n_samples + 1) bytes per bin, and N ranks downloading it through one host's PCIe root compete with each other; chrom_off_out[n_chrom + 1] offsets of the chromosomes among the common bins;
  * n_bp[s * n_chrom + c] breakpoints of (s, c) at bp[s * n + chrom_off_out[c] ...], as cg_partition_hmm numbers them.
  * cg_last_partition_stats: [0..4] wall ms of clean / exchange of cleaned lists / merge / HMM / gather on this rank,
  * [5] kernel ms, [6] launches, [7] device ms of the NCCL calls, [8] wall ms of the final download of the merged table.

@@ -128,6 +128,10 @@ def test_pedigree_chain_edge_cases(eng):
     one = eng.pedigree_hmm(t.chrom, t.is_autosome, t.is_chr_y, t.start, t.stop, [t.count], t.gc)
     c = eng.clean(t.chrom, t.is_autosome, t.is_chr_y, t.start, t.stop, t.count, t.gc)
     assert np.array_equal(one["common_index"], c["kept_index"]) and np.array_equal(one["count"][0].view(np.uint32), c["count"].view(np.uint32))
+    # a rank that does not write the merged files skips the table download: same breakpoints, no tables
+    lean = eng.pedigree_hmm(t.chrom, t.is_autosome, t.is_chr_y, t.start, t.stop, [t.count], t.gc, want_tables=False)
+    assert lean["common_index"] is None and lean["count"] is None and lean["n_common"] == one["n_common"]
+    _same_bp(lean["breakpoints"][0], one["breakpoints"][0])
     # empty layout
     z = np.zeros(0, np.int32)
     e = eng.pedigree_hmm(np.zeros(0, np.uint8), t.is_autosome, t.is_chr_y, z, z, [np.zeros(0, np.float32)] * 2, np.zeros(0, np.uint8))
