@@ -196,3 +196,32 @@ def test_prefetched_inputs_give_the_same_result(engine):
     assert np.array_equal(c1["kept_index"], rb["kept_index"]) and np.array_equal(c1["count"].view(np.uint32), rb["count"].view(np.uint32))
     with pytest.raises(ValueError):
         engine.prefetch_bins(a.chrom.astype(np.int64), ca["start"], ca["stop"], ca["count"], ca["gc"])
+
+
+def test_graph_replay_across_samples_of_one_layout(engine):
+    # The pipelines' CUDA graph is keyed on the INPUT chromosome lengths: every sample binned on one layout replays the graph
+    # captured for the first two, with its own cleaned lengths read from device memory.  Three samples of one layout, visited
+    # repeatedly in mixed order (with and without prefetch), must each keep reproducing the oracle's result.
+    samples = [synth.make_sample(config=2, sample=10 + k, scale=0.04, n_events=50 + 10 * k) for k in range(3)]
+    assert all(len(s) == len(samples[0]) for s in samples)
+    want = []
+    for s in samples:
+        o = ora.clean(s.chrom, s.is_autosome, s.is_chr_y, s.start, s.stop, s.count, s.gc)
+        off = synth.chrom_offsets(s.chrom[o["kept_index"]], len(s.names))
+        p = ora.partition_wavelet(off, ora.f2_roundtrip(o["count"]), is_germline=True, evenness_window=5000, n_threads=4)
+        want.append((o, p))
+    assert len({len(o["kept_index"]) for o, _ in want}) == 3  # the cleaned lengths differ: the replayed graph sees new offsets
+    cols = [dict(chrom=np.ascontiguousarray(s.chrom, np.uint8), start=np.ascontiguousarray(s.start, np.int32),
+                 stop=np.ascontiguousarray(s.stop, np.int32), count=np.ascontiguousarray(s.count, np.float32),
+                 gc=np.ascontiguousarray(s.gc, np.uint8)) for s in samples]
+    order = [0, 1, 2, 2, 0, 1, 0, 2, 1, 1, 0]
+    for step, k in enumerate(order):
+        s, c = samples[k], cols[k]
+        if step % 3 == 1:
+            engine.prefetch_bins(c["chrom"], c["start"], c["stop"], c["count"], c["gc"])
+        r = engine.clean_partition_wavelet(c["chrom"], s.is_autosome, s.is_chr_y, c["start"], c["stop"], c["count"], c["gc"],
+                                           is_germline=True, evenness_window=5000)
+        o, p = want[k]
+        assert np.array_equal(r["kept_index"], o["kept_index"]), (step, k)
+        assert np.array_equal(r["count"].view(np.uint32), o["count"].view(np.uint32)), (step, k)
+        _compare(r, p, f"step {step} sample {k}")
