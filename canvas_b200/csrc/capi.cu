@@ -158,6 +158,7 @@ extern "C" int cg_prefetch_bins(cg_ctx* ctx, int64_t n, const uint8_t* chrom, co
     sl->n = n;
     sl->key[0] = chrom; sl->key[1] = start; sl->key[2] = stop; sl->key[3] = count; sl->key[4] = gc;
     sl->seq = ++ctx->stage_seq;
+    sl->age = 0;
     sl->staged = true;
     return CG_OK;
 }

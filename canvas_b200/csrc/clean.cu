@@ -1017,11 +1017,10 @@ extern "C" int cg_clean(cg_ctx* ctx, const cg_clean_opts* opts, int64_t n, const
         d.max_chrom_bins = prev == n ? longest : -1;
     }
     cudaStream_t s = ctx->stream;
-    if (CgStageSlot* sl = cg_stage_find(ctx, n, chrom, start, stop, count, gc)) {
+    if (CgStageSlot* sl = cg_stage_take(ctx, n, chrom, start, stop, count, gc)) {
         // staged by cg_prefetch_bins while the previous call ran: read the columns where they are
         CG_CUDA(ctx, cudaStreamWaitEvent(s, sl->ready, 0));
         d.chrom = sl->chrom; d.gc = sl->gc; d.start = sl->start; d.stop = sl->stop; d.count = sl->count;
-        sl->staged = false;
     } else {
         CG_CUDA(ctx, cudaMemcpyAsync(d.chrom, chrom, n, cudaMemcpyHostToDevice, s));
         CG_CUDA(ctx, cudaMemcpyAsync(d.gc, gc, n, cudaMemcpyHostToDevice, s));

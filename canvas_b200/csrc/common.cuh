@@ -32,6 +32,7 @@ struct CgStageSlot {
     cudaEvent_t ready = nullptr;
     bool staged = false;
     unsigned long long seq = 0;  // order of staging: the oldest matching copy is consumed first
+    int age = 0;                 // calls that passed it by: a copy nobody asks for is dropped after the second one
     uint8_t *chrom = nullptr, *gc = nullptr;
     int32_t *start = nullptr, *stop = nullptr;
     float* count = nullptr;
@@ -148,6 +149,19 @@ inline CgStageSlot* cg_stage_find(cg_ctx* ctx, int64_t n, const void* chrom, con
         if (sl.staged && sl.n == n && sl.key[0] == chrom && sl.key[1] == start && sl.key[2] == stop && sl.key[3] == count && sl.key[4] == gc &&
             (!hit || sl.seq < hit->seq))
             hit = &sl;
+    return hit;
+}
+
+// The call that consumes staged columns: takes the oldest matching copy (nullptr: none, copy as usual).  Every other staged
+// copy grows older; one that two calls in a row did not ask for is dropped, so that a forgotten prefetch cannot be matched much
+// later by a host buffer that has been refilled in the meantime.  (In a pipeline — prefetch next, call current — a copy is
+// passed by exactly once.)
+inline CgStageSlot* cg_stage_take(cg_ctx* ctx, int64_t n, const void* chrom, const void* start, const void* stop, const void* count,
+                                  const void* gc) {
+    CgStageSlot* hit = cg_stage_find(ctx, n, chrom, start, stop, count, gc);
+    for (CgStageSlot& sl : ctx->stage)
+        if (sl.staged && &sl != hit && ++sl.age >= 2) sl.staged = false;
+    if (hit) hit->staged = false;
     return hit;
 }
 

@@ -1228,11 +1228,10 @@ static int clean_partition_wavelet_impl(cg_ctx* ctx, const cg_clean_opts* copts,
     unsigned* chrom_cnt = arena_take<unsigned>(ctx, 264);  // [256]: a coverage value that cannot take the integer-key path
     if (!cov || !hq || !chrom_cnt) return cg_fail(ctx, CG_ERR_CUDA, "arena exhausted");
     cudaStream_t s = ctx->stream;
-    if (CgStageSlot* sl = cg_stage_find(ctx, n, chrom, start, stop, count, gc)) {
+    if (CgStageSlot* sl = cg_stage_take(ctx, n, chrom, start, stop, count, gc)) {
         // staged by cg_prefetch_bins while the previous call ran: read the columns where they are
         CG_CUDA(ctx, cudaStreamWaitEvent(s, sl->ready, 0));
         d.chrom = sl->chrom; d.gc = sl->gc; d.start = sl->start; d.stop = sl->stop; d.count = sl->count;
-        sl->staged = false;
     } else {
         CG_CUDA(ctx, cudaMemcpyAsync(d.chrom, chrom, n, cudaMemcpyHostToDevice, s));
         CG_CUDA(ctx, cudaMemcpyAsync(d.gc, gc, n, cudaMemcpyHostToDevice, s));

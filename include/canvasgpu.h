@@ -316,7 +316,8 @@ int cg_merge_kept_indices(cg_ctx* ctx, int64_t n_bins, int n_samples, const int6
  * a staging slot of the device while the call for the current sample computes.  Returns at once.  The next cg_clean /
  * cg_clean_partition_wavelet* call that is given exactly these arrays (same pointers, same n) reads the staged columns and
  * copies nothing; the arrays must stay unchanged (and, for the copy to overlap, page-locked: cg_host_alloc) until then.  Two
- * slots: one prefetch per call keeps one slot filling while the other is read.  Replaces nothing in the reference (its
+ * slots: one prefetch per call keeps one slot filling while the other is read; a staged copy that two calls in a row did not
+ * ask for is dropped.  Replaces nothing in the reference (its
  * modules read their input files before they compute); it hides the 14 B/bin upload that the file read was. */
 int cg_prefetch_bins(cg_ctx* ctx, int64_t n, const uint8_t* chrom, const int32_t* start, const int32_t* stop, const float* count,
                      const uint8_t* gc);
