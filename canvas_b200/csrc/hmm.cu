@@ -121,6 +121,28 @@ __global__ void hmm_median_request_kernel(SelState<uint64_t> st, const HmmChromI
     st.nreq[seg] = 2;
 }
 
+// block and group tables of one chromosome from its range (one CTA per chromosome)
+__global__ void hmm_tables_kernel(const HmmChromInfo* __restrict__ ci, HmmBlk* __restrict__ blk, HmmGrp* __restrict__ grp) {
+    const int c = blockIdx.x;
+    const HmmChromInfo h = ci[c];
+    for (int k = threadIdx.x; k < h.n_blk; k += blockDim.x) {
+        HmmBlk b;
+        b.t0 = h.a + 1 + (long long)k * HMM_BLOCK;
+        b.t1 = b.t0 + HMM_BLOCK < h.b ? b.t0 + HMM_BLOCK : h.b;
+        b.chrom = c;
+        b.last = b.t1 == h.b;
+        blk[h.first_blk + k] = b;
+    }
+    for (int k = threadIdx.x; k < h.n_grp; k += blockDim.x) {
+        HmmGrp g;
+        g.b0 = h.first_blk + k * HMM_GROUP;
+        g.b1 = g.b0 + HMM_GROUP < h.first_blk + h.n_blk ? g.b0 + HMM_GROUP : h.first_blk + h.n_blk;
+        g.chrom = c;
+        g.pad = 0;
+        grp[h.first_grp + k] = g;
+    }
+}
+
 __global__ void hmm_chrom_id_kernel(const HmmChromInfo* __restrict__ ci, int C, long long N, uint8_t* __restrict__ chrom_id) {
     for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < N; t += (long long)gridDim.x * blockDim.x) {
         int lo = 0, hi = C - 1;
@@ -692,39 +714,26 @@ static int partition_hmm_impl(cg_ctx* ctx, const cg_hmm_opts* o, int n_samples, 
     dbg("validate");
 
     // ---- chromosomes and blocks
+    // (the block and group tables themselves — 47 000 blocks for a 3 M-bin genome — are filled on the device from these
+    // per-chromosome ranges: hmm_tables_kernel)
     std::vector<HmmChromInfo> ci((size_t)C);
-    std::vector<HmmBlk> blks;
+    long long n_blk_ll = 0;
+    int n_grp = 0, max_chrom_grp = 1;
     for (int c = 0; c < C; c++) {
         HmmChromInfo& h = ci[(size_t)c];
         h.a = chrom_off[c]; h.b = chrom_off[c + 1];
         const long long n = h.b - h.a;
         h.active = (n > o->min_size && n >= 1 && (!chrom_selected || chrom_selected[c])) ? 1 : 0;
-        h.first_blk = (int)blks.size();
-        h.n_blk = 0; h.tab = 0; h.max_thr = 0;
-        if (h.active)
-            for (long long t = h.a + 1; t < h.b; t += HMM_BLOCK) {
-                HmmBlk b;
-                b.t0 = t; b.t1 = std::min<long long>(h.b, t + HMM_BLOCK); b.chrom = c; b.last = b.t1 == h.b;
-                blks.push_back(b);
-                h.n_blk++;
-            }
-    }
-    const int n_blk = (int)blks.size();
-    std::vector<HmmGrp> grps;
-    int max_chrom_grp = 1;
-    for (int c = 0; c < C; c++) {
-        HmmChromInfo& h = ci[(size_t)c];
-        h.first_grp = (int)grps.size();
-        h.n_grp = 0;
-        for (int b = h.first_blk; b < h.first_blk + h.n_blk; b += HMM_GROUP) {
-            HmmGrp g;
-            g.b0 = b; g.b1 = std::min(h.first_blk + h.n_blk, b + HMM_GROUP); g.chrom = c; g.pad = 0;
-            grps.push_back(g);
-            h.n_grp++;
-        }
+        h.first_blk = (int)n_blk_ll;
+        h.tab = 0; h.max_thr = 0;
+        h.n_blk = (h.active && n > 1) ? (int)((n - 1 + HMM_BLOCK - 1) / HMM_BLOCK) : 0;  // blocks of bins a+1 .. b-1
+        n_blk_ll += h.n_blk;
+        h.first_grp = n_grp;
+        h.n_grp = (h.n_blk + HMM_GROUP - 1) / HMM_GROUP;
+        n_grp += h.n_grp;
         max_chrom_grp = std::max(max_chrom_grp, h.n_grp);
     }
-    const int n_grp = (int)grps.size();
+    const int n_blk = (int)n_blk_ll;
     if ((size_t)max_chrom_grp * 200 > 200 * 1024) return cg_fail(ctx, CG_ERR_UNSUPPORTED, "cg_partition_hmm: chromosome too long");
 
     // ---- workspace
@@ -905,8 +914,7 @@ static int partition_hmm_impl(cg_ctx* ctx, const cg_hmm_opts* o, int n_samples, 
     dbg("tables");
     CG_CUDA(ctx, cudaMemcpyAsync(d_tab, tab.data(), tab.size() * 8, cudaMemcpyHostToDevice, s));
     CG_CUDA(ctx, cudaMemcpyAsync(d_ci, ci.data(), (size_t)C * sizeof(HmmChromInfo), cudaMemcpyHostToDevice, s));
-    if (n_blk > 0) CG_CUDA(ctx, cudaMemcpyAsync(d_blk, blks.data(), (size_t)n_blk * sizeof(HmmBlk), cudaMemcpyHostToDevice, s));
-    if (n_grp > 0) CG_CUDA(ctx, cudaMemcpyAsync(d_grp, grps.data(), (size_t)n_grp * sizeof(HmmGrp), cudaMemcpyHostToDevice, s));
+    if (n_blk > 0) CG_LAUNCH(ctx, hmm_tables_kernel, C, 256, 0, d_ci, d_blk, d_grp);
     const double self_t = 0.99;
     const double ls = std::log(self_t), lo = std::log((1.0 - self_t) / (HMM_NS - 1));
     const double log_start = std::log((double)(1.0f / HMM_NS));
