@@ -57,6 +57,7 @@ extern "C" void cg_destroy(cg_ctx* ctx) {
     if (ctx->plan_pinned) cudaFreeHost(ctx->plan_pinned);
     if (ctx->aux) cudaFree(ctx->aux);
     if (ctx->ped) cudaFree(ctx->ped);
+    for (cudaEvent_t ev : ctx->ped_ev) if (ev) cudaEventDestroy(ev);
     if (ctx->prefetch_stream) { cudaStreamSynchronize(ctx->prefetch_stream); cudaStreamDestroy(ctx->prefetch_stream); }
     for (CgStageSlot& sl : ctx->stage) {
         if (sl.base) cudaFree(sl.base);

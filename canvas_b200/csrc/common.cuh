@@ -82,6 +82,7 @@ struct cg_ctx {
     // third device block: what the pedigree chain keeps between its stages (cleaned lists of every sample, merged counts)
     char* ped = nullptr;
     size_t ped_cap = 0;
+    std::vector<cudaEvent_t> ped_ev;  // per sample: its input counts are on the device
     // two staging slots for prefetched inputs: one is read by the running call while the other fills
     CgStageSlot stage[2];
     unsigned long long stage_seq = 0;

@@ -104,9 +104,10 @@ extern "C" int cg_pedigree_hmm(cg_ctx* ctx, const cg_clean_opts* copts, const cg
 
     // ---- the block that outlives the stages
     const size_t n_al = ((size_t)n + 63) & ~(size_t)63;
-    size_t ped_bytes = n_al * (4 * (size_t)S * 3 + 4 + 1 + 1 + 4 + 4) + (size_t)(C + 1) * 16 + 4096;
+    size_t ped_bytes = n_al * (4 * (size_t)S * 4 + 4 + 1 + 1 + 4 + 4) + (size_t)(C + 1) * 16 + 4096;
     int32_t* p_kept[PED_MAX_SAMPLES];
     float* p_cnt[PED_MAX_SAMPLES];
+    float* p_raw[PED_MAX_SAMPLES];  // the samples' input counts, uploaded ahead of their Clean
     int32_t* p_common = nullptr;
     float* p_cnt_m = nullptr;
     int32_t *p_start = nullptr, *p_stop = nullptr;
@@ -120,6 +121,7 @@ extern "C" int cg_pedigree_hmm(cg_ctx* ctx, const cg_clean_opts* copts, const cg
             for (int s = 0; s < S; s++) { p_kept[s] = (int32_t*)b; b += n_al * 4; }
             for (int s = 0; s < S; s++) { p_cnt[s] = (float*)b; b += n_al * 4; }
             p_cnt_m = (float*)b; b += n_al * 4 * S;
+            for (int s = 0; s < S; s++) { p_raw[s] = (float*)b; b += n_al * 4; }
             p_common = (int32_t*)b; b += n_al * 4;
             p_start = (int32_t*)b; b += n_al * 4;
             p_stop = (int32_t*)b; b += n_al * 4;
@@ -150,6 +152,17 @@ extern "C" int cg_pedigree_hmm(cg_ctx* ctx, const cg_clean_opts* copts, const cg
         CG_CUDA(ctx, cudaMemcpyAsync(p_gc, gc, (size_t)n, cudaMemcpyHostToDevice, st));
         CG_CUDA(ctx, cudaMemcpyAsync(p_start, start, (size_t)n * 4, cudaMemcpyHostToDevice, st));
         CG_CUDA(ctx, cudaMemcpyAsync(p_stop, stop, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+        // every count column of this rank goes up front, on the copy stream: sample k's upload overlaps the Clean of sample k-1
+        if (ctx->ped_ev.size() < (size_t)S) {
+            const size_t have = ctx->ped_ev.size();
+            ctx->ped_ev.resize((size_t)S, nullptr);
+            for (size_t k = have; k < (size_t)S; k++) CG_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ped_ev[k], cudaEventDisableTiming));
+        }
+        for (int s = 0; s < S; s++) {
+            if (s % R != me) continue;
+            CG_CUDA(ctx, cudaMemcpyAsync(p_raw[s], count[s], (size_t)n * 4, cudaMemcpyHostToDevice, ctx->copy_stream));
+            CG_CUDA(ctx, cudaEventRecord(ctx->ped_ev[s], ctx->copy_stream));
+        }
         const bool loess = copts->gc_norm && copts->gc_mode != 0;
         for (int s = 0; s < S; s++) {
             if (s % R != me) continue;
@@ -172,7 +185,8 @@ extern "C" int cg_pedigree_hmm(cg_ctx* ctx, const cg_clean_opts* copts, const cg
             CG_CUDA(ctx, cudaMemcpyAsync(d.gc, p_gc, (size_t)n, cudaMemcpyDeviceToDevice, st));
             CG_CUDA(ctx, cudaMemcpyAsync(d.start, p_start, (size_t)n * 4, cudaMemcpyDeviceToDevice, st));
             CG_CUDA(ctx, cudaMemcpyAsync(d.stop, p_stop, (size_t)n * 4, cudaMemcpyDeviceToDevice, st));
-            CG_CUDA(ctx, cudaMemcpyAsync(d.count, count[s], (size_t)n * 4, cudaMemcpyHostToDevice, st));
+            CG_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ped_ev[s], 0));
+            CG_CUDA(ctx, cudaMemcpyAsync(d.count, p_raw[s], (size_t)n * 4, cudaMemcpyDeviceToDevice, st));
             CG_CUDA(ctx, cudaMemsetAsync(d.is_auto, 0, 256, st));
             if (C > 0) CG_CUDA(ctx, cudaMemcpyAsync(d.is_auto, chrom_is_autosome, C, cudaMemcpyHostToDevice, st));
             CG_CUDA(ctx, cudaMemsetAsync(d.is_chry, 0, 256, st));
@@ -204,6 +218,7 @@ extern "C" int cg_pedigree_hmm(cg_ctx* ctx, const cg_clean_opts* copts, const cg
         return CG_OK;
     };
     if (rc_local == CG_OK) rc_local = clean_mine();
+    if (rc_local != CG_OK && ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);  // uploads of the caller's columns may still be in flight
     phase[0] = ms_since(t_phase);
 
     // ---- every sample's cleaned list on every rank
