@@ -259,6 +259,7 @@ def main():
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # NCCL's version / debug lines must not mix with the JSON line on stdout
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     dev = torch.device("cuda", local_rank)
+    all_cpus = os.sched_getaffinity(0)
     eng = native.Engine(local_rank, bind_numa=True)  # CPU cores and page-locked buffers on the GPU's own socket
     if world > 1:
         eng.comm_init_torch()  # the library's own NCCL communicator; torch only hands the id around
@@ -399,6 +400,7 @@ def main():
         if not args.no_cpu_baseline:
             from oracle import pyoracle as ora
             threads = os.cpu_count() or 1
+            os.sched_setaffinity(0, all_cpus)  # the CPU baseline gets every core of the box
             c = ora.clean(s.chrom, s.is_autosome, s.is_chr_y, s.start, s.stop, s.count, s.gc)
             off = synth.chrom_offsets(s.chrom[c["kept_index"]], len(s.names))
             t0 = time.perf_counter()
@@ -602,6 +604,7 @@ def main():
         line["roofline_normalize"] = {"error": str(e)}
     if world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
+        os.sched_setaffinity(0, all_cpus)  # the CPU baseline gets every core of the box, not only the GPU's socket
         o = oracle_samples(samples, threads, germline=germline)
         line["cpu_baseline"] = {"value": nb / o["timed_s"] / 1e6, "unit": UNIT, "cores": threads, "kind": "port",
                                 "sample": f"{len(samples)} full sample(s) of this workload (Clean 1 thread per sample, Partition 1 thread per chromosome; "
