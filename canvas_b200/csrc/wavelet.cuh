@@ -1,13 +1,16 @@
 // CanvasPartition (wavelets) on the device — shared declarations.
 //
 // Reference: Src/Canvas/CanvasPartition/{WaveletsRunner,WaveletSegmentation,Segmentation}.cs.
-// Pipeline (all on ctx->stream, no host round trip until the results are copied back):
-//   1. genome-wide scalars: coverage variability (CV), factor-of-three CMADs, evenness score,
-//      per-chromosome median / MAD  -> per-chromosome threshold sigma
-//   2. per-chromosome prefix sums of the coverage
-//   3. Unbalanced-Haar decomposition: one persistent kernel, dynamic node queue (uh_decompose_kernel)
-//   4. per chromosome: hard threshold, reconstruction on the surviving nodes, healing of bad
+// One call, no host round trip between its stages (the fused Clean + Partition call waits once, for the per-chromosome
+// survivor counts of Clean):
+//   1. per-chromosome prefix sums of the coverage (main stream; in the fused call before the host has planned)
+//   2. genome-wide scalars: per-chromosome / per-window medians and MADs on integer hundredths -> coverage variability (CV),
+//      per-chromosome threshold sigma (main stream); factor-of-three CMADs and evenness score (side stream)
+//   3. Unbalanced-Haar decomposition, one pipeline per chromosome on its own stream: chains of big nodes (thread-block
+//      clusters) -> mid subtrees (one CTA each) -> small subtrees (one warp each) -> tiny subtrees (one thread each)
+//   4. per chromosome, as soon as ITS tree is done: hard threshold, reconstruction on the surviving nodes, healing of bad
 //      splits, germline refinement (uh_finish_kernel)
+// The stream / event / graph structure is drawn in DESIGN.md §3.
 #pragma once
 #include "common.cuh"
 #include "select.cuh"

@@ -1,9 +1,11 @@
-"""Multi-GPU plumbing of the partition stage (one process per GPU, torch.distributed).
+"""torch.distributed form of the partition stage's multi-GPU exchange — for the CPU (gloo) tests of the host logic only.
 
-Chromosomes are independent once the genome-wide scalars exist: every rank computes
-the scalars on the full coverage (replicated, microseconds), segments only the chromosomes assigned
-to it (longest-processing-time-first by bin count) and ONE all-gather of a fixed-capacity int32 buffer
-reassembles the genome-wide breakpoint list on every rank.  There is no other exchange on the path.
+The PRODUCT path does this inside the library (csrc/comm.cu: cg_comm_init + cg_*_sharded, NCCL bound with dlopen; the
+Python binding is Engine.comm_init / sharded=True).  The logic is the same and is what tests/test_multi_cpu.py pins with
+world-size-2 gloo runs: chromosomes are independent once the genome-wide scalars exist, so every rank
+computes the scalars on the full coverage (replicated, microseconds), segments only the chromosomes assigned to it
+(longest-processing-time-first by bin count) and ONE all-gather reassembles the genome-wide breakpoint list on every
+rank; the buffer size is agreed collectively first, so a rank with long lists cannot leave the others waiting.
 """
 import numpy as np
 
