@@ -387,6 +387,22 @@ def post_process_segments(order, seg_by_chr, start, end, cov, excluded=None, max
     return out
 
 
+def segment_extent(seg):
+    """SegmentWithBins.Start / End (Models/SegmentWithBins.cs:38-52): smallest start and largest end over the bins, in
+    whatever order they were added."""
+    return min(a for a, _, _ in seg["bins"]), max(b for _, b, _ in seg["bins"])
+
+
+def segment_median_coverage(seg):
+    """SegmentWithBins.MedianCoverage (Models/SegmentWithBins.cs:18-21): MathNet Statistics.Median of the bins' coverage —
+    the mean of the two middle values for an even count (pinned by SegmentWithBinsTests.AddBinTest)."""
+    v = sorted(c for _, _, c in seg["bins"])
+    if not v:
+        return float("nan")
+    m = len(v) // 2
+    return v[m] if len(v) % 2 else (v[m - 1] + v[m]) / 2.0
+
+
 def write_partitioned(path, order, segments):
     """SegmentationInput.WriteCanvasPartitionResults (Segmentation.cs:235-252)."""
     buf = io.StringIO()

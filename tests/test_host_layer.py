@@ -416,3 +416,18 @@ def test_bind_host_near_gpu_is_only_a_hint():
     after = os.sched_getaffinity(0)
     assert cpus is None or (set(cpus) == after and after <= before)
     os.sched_setaffinity(0, before)
+
+
+def test_segment_with_bins_reference_vector():
+    # SegmentWithBinsTests.AddBinTest (CanvasTest/CanvasPartition/SegmentWithBinsTests.cs:22-46): extent and median coverage
+    # after every AddBin, and independence of the insertion order
+    from canvas_b200 import fileio
+    b1, b2, b3 = (100, 2000, 10.0), (2500, 3000, 5.0), (5000, 8000, 45.0)
+    seg = {"id": 1, "bins": [b1]}
+    assert fileio.segment_extent(seg) == (100, 2000) and fileio.segment_median_coverage(seg) == 10 and len(seg["bins"]) == 1
+    seg["bins"].append(b2)
+    assert fileio.segment_extent(seg) == (100, 3000) and fileio.segment_median_coverage(seg) == 7.5
+    seg["bins"].append(b3)
+    assert fileio.segment_extent(seg) == (100, 8000) and fileio.segment_median_coverage(seg) == 10 and len(seg["bins"]) == 3
+    other = {"id": 1, "bins": [b1, b3, b2]}
+    assert fileio.segment_extent(other) == (100, 8000) and fileio.segment_median_coverage(other) == 10
