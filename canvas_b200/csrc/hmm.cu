@@ -651,9 +651,10 @@ double factorial_ln(int x) {
     return gamma_ln((double)x + 1.0);
 }
 
-// DistributionUtilities.NegativeBinomialWrapper (Distributions.cs:206-217)
+// DistributionUtilities.NegativeBinomialWrapper (CanvasCommon/DistributionUtilities.cs:51-69, called by
+// MultivariateNegativeBinomial, Distributions.cs:33): the clumping parameter has a floor of 2 on this path
 void negative_binomial(double mean, double variance, int len, double* density) {
-    const double r = std::pow(std::max(mean, 0.1), 2) / (std::max(variance, mean * 1.2) - mean);
+    const double r = std::max(2.0, std::pow(std::max(mean, 0.1), 2) / (std::max(variance, mean * 1.2) - mean));
     for (int x = 0; x < len; x++) {
         const double t = std::exp(std::log(std::pow(1 + mean / r, -r)) + std::log(std::pow(mean / (mean + r), x)) + gamma_ln(r + x) -
                                   factorial_ln(x) - gamma_ln(r));

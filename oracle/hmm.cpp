@@ -6,7 +6,8 @@
 //                                                         emission set-up, Viterbi, breakpoints where the state changes
 //   CanvasPartition/HiddenMarkovModelsRunner.cs:111-163  InitializeNegativeBinomialEmission, RemoveOutliers
 //   CanvasPartition/Distributions.cs:29-36,62-76         MultivariateNegativeBinomial
-//   CanvasPartition/Distributions.cs:187-217             GetGenotypeCombinations, NegativeBinomialWrapper
+//   CanvasPartition/Distributions.cs:187-204             GetGenotypeCombinations
+//   CanvasCommon/DistributionUtilities.cs:51-69          NegativeBinomialWrapper (the one MultivariateNegativeBinomial calls)
 //   CanvasPartition/Distributions.cs:257-323             NegativeBinomialMixture.EstimateViterbiLikelihood
 //   CanvasPartition/HMM.cs:25-52,62-130                  transition matrix, BestPathViterbi
 //   CanvasCommon/Utilities.cs:290-302,340-344,361-419    Variance, Median, Quartiles
@@ -67,10 +68,13 @@ double factorial_ln(int x) {
 // Convert.ToInt32(double): round half to even
 int to_int32(double v) { return (int)std::nearbyint(v); }
 
-// Distributions.cs:206-217
+// CanvasCommon/DistributionUtilities.cs:51-69 — the wrapper MultivariateNegativeBinomial calls (Distributions.cs:33), with its
+// floor of 2 on the clumping parameter (adjustClumpingParameter is false on this path); CanvasPartition's own copy without
+// the floor (Distributions.cs:206-217) has no caller.  Pinned by DistributionUtilitiesTests.cs:39-49.
 std::vector<double> negative_binomial_wrapper(double mean, double variance, int max_value) {
     std::vector<double> density((size_t)std::max(max_value, 0), 0.0);
     double r = std::pow(std::max(mean, 0.1), 2) / (std::max(variance, mean * 1.2) - mean);
+    r = std::max(2.0, r);
     for (int x = 0; x < max_value; x++) {
         double t = std::exp(std::log(std::pow(1 + mean / r, -r)) + std::log(std::pow(mean / (mean + r), x)) + gamma_ln(r + x) -
                             factorial_ln(x) - gamma_ln(r));

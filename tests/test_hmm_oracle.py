@@ -20,7 +20,9 @@ def test_negative_binomial_is_a_density_with_the_requested_mean():
         d = ora.negative_binomial(mean, var, 4000)
         assert abs(d.sum() - 1.0) < 1e-9
         assert abs((d * np.arange(len(d))).sum() - mean) < 1e-6 * mean
-        v_eff = max(var, 1.2 * mean)  # NegativeBinomialWrapper's variance floor (Distributions.cs:209)
+        # NegativeBinomialWrapper's variance floor and its floor of 2 on the clumping parameter (DistributionUtilities.cs:59-60)
+        k = max(2.0, mean * mean / (max(var, 1.2 * mean) - mean))
+        v_eff = mean + mean * mean / k
         assert abs((d * (np.arange(len(d)) - mean) ** 2).sum() - v_eff) < 1e-6 * v_eff
 
 
@@ -124,3 +126,24 @@ def test_joint_three_samples_runs_and_shares_breakpoints():
     r = ora.partition_hmm(np.array([0, n]), x, per_sample=False)
     bps = r["breakpoints"][0].tolist()
     assert any(abs(b - 5000) <= 3 for b in bps) and any(abs(b - 5600) <= 3 for b in bps)
+
+
+def test_negative_binomial_reference_vector():
+    # DistributionUtilitiesTests.TestNegativeBinomialWrapperMaxDensityEqualsMean (CanvasTest/DistributionUtilitiesTests.cs:39-49):
+    # mean = variance = 50 over 200 values -> the density peaks at index 49 (the variance floor 1.2 * mean applies)
+    d = ora.negative_binomial(50.0, 50.0, 200)
+    assert len(d) == 200 and int(np.argmax(d)) == 49
+    assert abs(float(np.sum(d)) - 1.0) < 1e-9
+
+
+def test_genotype_arrangements_reference_vectors():
+    # DistributionUtilitiesTests.TestGetGenotypeCombinations(+SingleSample) (:13-37): every assignment of {altCN, 2} to the
+    # samples except "all diploid"; for altCN == 2 the one all-diploid arrangement.  The oracle and the kernels enumerate them
+    # as bit masks (bit s set: sample s is diploid) — this is that enumeration, spelled out
+    def arrangements(n_samples, alt):
+        full = (1 << n_samples) - 1
+        masks = [m for m in range(1 << n_samples) if (m == full) == (alt == 2)]
+        return sorted([2 if (m >> s) & 1 else alt for s in range(n_samples)] for m in masks)
+    assert arrangements(2, 1) == [[1, 1], [1, 2], [2, 1]]
+    assert arrangements(1, 1) == [[1]]
+    assert arrangements(3, 2) == [[2, 2, 2]]
