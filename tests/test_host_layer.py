@@ -431,3 +431,18 @@ def test_segment_with_bins_reference_vector():
     assert fileio.segment_extent(seg) == (100, 8000) and fileio.segment_median_coverage(seg) == 10 and len(seg["bins"]) == 3
     other = {"id": 1, "bins": [b1, b3, b2]}
     assert fileio.segment_extent(other) == (100, 8000) and fileio.segment_median_coverage(other) == 10
+
+
+def test_mode_parsers_reference_vectors():
+    # TestUtilities.TestParseCanvasNormalizeMode(+_WithBadString) (CanvasTest/TestUtilities.cs:12-31) and the sibling parser of
+    # CanvasClean's -m (CanvasCommon/Utilities.cs:91-102): case-insensitive, trimmed, unknown names throw
+    import pytest
+    from canvas_b200 import modules
+    for text, want in (("weightedaverage", "weightedaverage"), ("WeightedAverage", "weightedaverage"), ("bestlr2", "bestlr2"),
+                       ("BestLR2", "bestlr2"), ("pca", "pca"), ("PCA", "pca"), (" PCA ", "pca")):
+        assert modules.parse_canvas_normalize_mode(text) == want
+    with pytest.raises(ValueError):
+        modules.parse_canvas_normalize_mode("badmode")
+    assert modules.parse_gc_normalization_mode("MedianByGC") == "medianbygc" and modules.parse_gc_normalization_mode("LOESS ") == "loess"
+    with pytest.raises(ValueError):
+        modules.parse_gc_normalization_mode("median")
